@@ -1,0 +1,264 @@
+/*
+ * playrho_b200.h -- C ABI of the B200-native, device-resident PlayRho world ("CudaWorld").
+ *
+ * This is the drop-in boundary for the per-step collision-and-solve pipeline
+ *   Step(AabbTreeWorld&, const StepConf&)          Library/source/playrho/d2/AabbTreeWorld.cpp:2144
+ * A C++17 host type (playrho_b200/host/CudaWorld.hpp) implements the 52 ADL free functions that
+ * playrho::d2::detail::WorldModel<T> (Library/include/playrho/d2/detail/WorldModel.hpp:36-370)
+ * forwards to, and calls ONLY the functions below. Plain pointers and sizes, no C++/torch types,
+ * never throws; every function returns PR_OK (0) or a negative pr_status; pr_last_error() gives
+ * the message. A handle is single-threaded like the reference world (AabbTreeWorld.hpp:866-875).
+ *
+ * All reals are IEEE binary32 (playrho::Real = float, Library/include/playrho/Real.hpp:69).
+ * Ids are 32-bit here; the 16-bit stock ids of the reference are a host-shim concern.
+ */
+#ifndef PLAYRHO_B200_H
+#define PLAYRHO_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PR_ABI_VERSION 1
+#define PR_INVALID_ID 0xFFFFFFFFu
+#define PR_INVALID_VERTEX 255u /* playrho::InvalidVertex, Settings.hpp:87-90 */
+
+typedef enum pr_status {
+    PR_OK = 0,
+    PR_ERR_INVALID_ARGUMENT = -1, /* playrho::InvalidArgument */
+    PR_ERR_OUT_OF_RANGE = -2,     /* playrho::OutOfRange      */
+    PR_ERR_WRONG_STATE = -3,      /* playrho::WrongState (world locked) */
+    PR_ERR_LENGTH = -4,           /* playrho::LengthError (capacity) */
+    PR_ERR_CUDA = -5,             /* CUDA runtime failure; message has cudaGetErrorString */
+    PR_ERR_UNSUPPORTED = -6       /* e.g. joint type the device solver does not know */
+} pr_status;
+
+typedef struct pr_vec2 { float x, y; } pr_vec2;
+
+/* --- body flags: bit-identical to Body::Flag, Library/include/playrho/d2/Body.hpp:440-474 --- */
+enum {
+    PR_BODY_DESTROYED = 0x0001, PR_BODY_AWAKE = 0x0002, PR_BODY_AUTOSLEEP = 0x0004,
+    PR_BODY_IMPENETRABLE = 0x0008, PR_BODY_FIXED_ROTATION = 0x0010, PR_BODY_ENABLED = 0x0020,
+    PR_BODY_VELOCITY = 0x0080 /* speedable */, PR_BODY_ACCELERATION = 0x0100 /* accelerable */,
+    PR_BODY_MASS_DIRTY = 0x0200
+};
+/* --- contact flags: bit-identical to Contact::Flag, Library/include/playrho/Contact.hpp:285-310 --- */
+enum {
+    PR_CONTACT_TOUCHING = 0x01, PR_CONTACT_ENABLED = 0x02, PR_CONTACT_FILTER = 0x04,
+    PR_CONTACT_TOI = 0x08, PR_CONTACT_DIRTY = 0x10, PR_CONTACT_SENSOR = 0x20,
+    PR_CONTACT_DESTROYED = 0x40, PR_CONTACT_IMPENETRABLE = 0x80
+};
+/* Manifold::Type, Library/include/playrho/d2/Manifold.hpp:96-126 */
+enum { PR_MANIFOLD_UNSET = 0, PR_MANIFOLD_CIRCLES = 1, PR_MANIFOLD_FACE_A = 2, PR_MANIFOLD_FACE_B = 3 };
+/* ContactFeature::Type, Library/include/playrho/ContactFeature.hpp:44-48 */
+enum { PR_CF_VERTEX = 0, PR_CF_FACE = 1 };
+
+/* State of one Body (Body.hpp private block). One row per body id. */
+typedef struct pr_body {
+    float xf_px, xf_py, xf_qc, xf_qs; /* m_xf: p and q=(cos,sin)               */
+    float pos0_x, pos0_y, pos0_a;      /* m_sweep.pos0 (linear, angular)        */
+    float pos1_x, pos1_y, pos1_a;      /* m_sweep.pos1                          */
+    float lc_x, lc_y;                  /* m_sweep.localCenter                   */
+    float alpha0;                      /* m_sweep.alpha0                        */
+    float vel_x, vel_y, vel_w;         /* m_linearVelocity, m_angularVelocity   */
+    float acc_x, acc_y, acc_w;         /* m_linearAcceleration, m_angularAcc... */
+    float inv_mass, inv_rot_i;         /* m_invMass, m_invRotI                  */
+    float lin_damp, ang_damp;          /* m_linearDamping, m_angularDamping     */
+    float under_active_time;           /* m_underActiveTime                     */
+    uint32_t flags;                    /* PR_BODY_*                             */
+} pr_body;
+
+/* One convex child of a shape == DistanceProxy{vertexRadius,count,vertices,normals}
+ * (Library/include/playrho/d2/DistanceProxy.hpp:51-151). vertex_offset indexes the vertex /
+ * normal arrays passed with it (disk: 1 vertex, no normal needed -- pass anything). */
+typedef struct pr_child {
+    uint32_t vertex_offset;
+    uint32_t vertex_count; /* 1..254 */
+    float vertex_radius;
+} pr_child;
+
+/* Per-shape data the step needs (ShapeConf.hpp:45-51, Filter.hpp). */
+typedef struct pr_shape {
+    float friction, restitution, density;
+    uint16_t filter_category, filter_mask;
+    int16_t filter_group;
+    uint16_t is_sensor;
+    uint32_t child_offset; /* into the pr_child array passed with it */
+    uint32_t child_count;
+} pr_shape;
+
+/* RevoluteJointConf (Library/include/playrho/d2/RevoluteJointConf.hpp) -- the one joint type the
+ * device solver runs. Solver-written fields are readable back. */
+typedef struct pr_revolute_joint {
+    uint32_t body_a, body_b;
+    uint32_t collide_connected;
+    pr_vec2 local_anchor_a, local_anchor_b;
+    float impulse_x, impulse_y, impulse_z;
+    float angular_motor_impulse;
+    float reference_angle;
+    uint32_t enable_limit, enable_motor;
+    float lower_angle, upper_angle;
+    float motor_speed, max_motor_torque;
+    uint32_t limit_state;
+} pr_revolute_joint;
+
+/* ContactFeature packed little-endian: typeA | indexA<<8 | typeB<<16 | indexB<<24 */
+typedef uint32_t pr_contact_feature;
+
+/* Manifold (Library/include/playrho/d2/Manifold.hpp:133-160,411-418): 64 B, one row per contact id */
+typedef struct pr_manifold {
+    float ln_x, ln_y;         /* m_localNormal (face types)                      */
+    float lp_x, lp_y;         /* m_localPoint                                    */
+    float p0_x, p0_y, p1_x, p1_y; /* points[i].localPoint                        */
+    float jn0, jt0, jn1, jt1; /* points[i].normalImpulse / tangentImpulse        */
+    pr_contact_feature cf0, cf1;
+    uint32_t type;            /* PR_MANIFOLD_*                                   */
+    uint32_t count;           /* GetPointCount()                                 */
+} pr_manifold;
+
+/* Contact (Library/include/playrho/Contact.hpp:312-341) + its ContactKey */
+typedef struct pr_contact {
+    uint32_t id;                            /* ContactID (pool index)            */
+    uint32_t key_min, key_max;              /* ContactKey = proxy (tree leaf) ids */
+    uint32_t body_a, shape_a, child_a;      /* Contactable A                     */
+    uint32_t body_b, shape_b, child_b;      /* Contactable B                     */
+    float friction, restitution, tangent_speed;
+    float toi;
+    uint32_t toi_count;
+    uint32_t flags;                         /* PR_CONTACT_*                      */
+} pr_contact;
+
+/* Proxy == DynamicTree leaf: Contactable + fat AABB (DynamicTree.hpp TreeNode) */
+typedef struct pr_proxy {
+    uint32_t tree_id; /* id the reference's DynamicTree would have given this leaf */
+    uint32_t body, shape, child;
+    float min_x, min_y, max_x, max_y; /* fat AABB */
+} pr_proxy;
+
+/* StepConf (Library/include/playrho/StepConf.hpp:163-391), same field meaning and defaults;
+ * pr_step_conf_default() fills the reference's defaults. Angles in radians. */
+typedef struct pr_step_conf {
+    float delta_time, dt_ratio;
+    float min_still_time_to_sleep, linear_slop, angular_slop;
+    float reg_resolution_rate, reg_min_separation, reg_min_momentum;
+    float toi_resolution_rate, toi_min_separation, toi_min_momentum;
+    float target_depth, tolerance, velocity_threshold;
+    float max_translation, max_rotation, max_linear_correction, max_angular_correction;
+    float linear_sleep_tolerance, angular_sleep_tolerance;
+    float displace_multiplier, aabb_extension, max_circles_ratio;
+    uint32_t reg_velocity_iters, reg_position_iters, toi_velocity_iters, toi_position_iters;
+    uint32_t max_toi_root_iters, max_toi_iters, max_distance_iters, max_sub_steps;
+    uint32_t do_warm_start, do_toi, do_blocksolve;
+} pr_step_conf;
+
+/* StepStats (Library/include/playrho/StepStats.hpp): pre / reg / toi */
+typedef struct pr_step_stats {
+    struct { uint32_t proxies_created, proxies_moved, contacts_destroyed, contacts_added,
+                      contacts_updated, contacts_skipped; } pre;
+    struct { float min_separation, max_inc_impulse;
+             uint32_t islands_found, islands_solved, contacts_added, bodies_slept, proxies_moved,
+                      sum_pos_iters, sum_vel_iters, contacts_updated, contacts_skipped,
+                      max_island_bodies; } reg;
+    struct { float min_separation, max_inc_impulse;
+             uint32_t islands_found, islands_solved, contacts_found, contacts_at_max_sub_steps,
+                      contacts_updated_toi, contacts_updated_touching, contacts_skipped_touching,
+                      contacts_added, proxies_moved, sum_pos_iters, sum_vel_iters,
+                      max_dist_iters, max_toi_iters, max_root_iters; } toi;
+} pr_step_stats;
+
+/* WorldConf (Library/include/playrho/d2/WorldConf.hpp) + device arena sizes (0 = grow on demand) */
+typedef struct pr_world_conf {
+    float min_vertex_radius, max_vertex_radius; /* GetVertexRadiusInterval */
+    uint32_t body_capacity, proxy_capacity, contact_capacity, vertex_capacity;
+    int32_t device; /* CUDA device ordinal, -1 = current */
+} pr_world_conf;
+
+typedef struct pr_counts {
+    uint32_t bodies, shapes, children, vertices, proxies, contacts, joints;
+    uint32_t contact_id_range; /* GetContactRange(): size of the contact pool incl. free slots */
+    uint32_t tree_node_capacity, tree_leaf_count;
+} pr_counts;
+
+/* Per-step device-side accounting used for the roofline figure */
+typedef struct pr_step_profile {
+    uint32_t n_awake, p_total, p_moved, c_total, c_dirty, c_touching, n_colors, n_islands;
+    uint32_t vel_iters, pos_iters, candidate_pairs, kernel_launches;
+    float ms_total;            /* CUDA-event time of the whole step on the world's stream */
+    float ms_stage[16];        /* see PR_STAGE_* */
+} pr_step_profile;
+enum { PR_STAGE_PRE = 0, PR_STAGE_ISLANDS, PR_STAGE_INTEGRATE, PR_STAGE_SETUP, PR_STAGE_COLOR,
+       PR_STAGE_VELOCITY, PR_STAGE_POSITION, PR_STAGE_WRITEBACK, PR_STAGE_SYNC, PR_STAGE_NARROW,
+       PR_STAGE_BVH, PR_STAGE_QUERY, PR_STAGE_ADD, PR_STAGE_TOI, PR_STAGE_COUNT };
+
+typedef struct pr_world pr_world; /* opaque */
+
+/* ---- lifetime (replaces AabbTreeWorld ctor/copy/Clear: AabbTreeWorld.cpp:780-1017) ---- */
+int pr_abi_version(void);
+void pr_world_conf_default(pr_world_conf* conf);
+void pr_step_conf_default(pr_step_conf* conf);          /* StepConf{} defaults */
+int pr_create(const pr_world_conf* conf, pr_world** out);
+int pr_destroy(pr_world* w);
+int pr_clone(const pr_world* w, pr_world** out);        /* WorldModel::Clone_, WorldModel.hpp:96-99 */
+int pr_clear(pr_world* w);                              /* Clear(AabbTreeWorld&), AabbTreeWorld.cpp:949 */
+const char* pr_last_error(const pr_world* w);           /* w may be NULL: last create error */
+
+/* ---- population (CreateShape :1234, CreateBody :1019, CreateJoint :1132) ----
+ * Bulk, flattened: shapes[i].child_offset/children[j].vertex_offset index the arrays given here.
+ * Ids are returned in first_id.. first_id+n-1 (pool append order; creation-only pools). */
+int pr_create_shapes(pr_world* w, uint32_t n, const pr_shape* shapes, const pr_child* children,
+                     uint32_t n_children, const pr_vec2* vertices, const pr_vec2* normals,
+                     uint32_t n_vertices, uint32_t* first_id);
+/* shape_offsets has n+1 entries into shape_ids (CSR): the ShapeIDs attached to each body.
+ * Queues (body,shape) for proxy creation at the next Step like m_fixturesForProxies (:1019-1060). */
+int pr_create_bodies(pr_world* w, uint32_t n, const pr_body* bodies, const uint32_t* shape_offsets,
+                     const uint32_t* shape_ids, uint32_t* first_id);
+int pr_create_revolute_joints(pr_world* w, uint32_t n, const pr_revolute_joint* joints,
+                              uint32_t* first_id);
+
+/* ---- dirty-row upload / download (SetBody :2723 / GetBody; value semantics) ---- */
+int pr_set_bodies(pr_world* w, uint32_t n, const uint32_t* ids, const pr_body* rows);
+int pr_get_bodies(const pr_world* w, uint32_t first, uint32_t n, pr_body* rows);
+int pr_get_revolute_joints(const pr_world* w, uint32_t first, uint32_t n, pr_revolute_joint* rows);
+int pr_get_counts(const pr_world* w, pr_counts* out);
+/* contacts in m_contacts order (creation order), manifolds[i] belongs to contacts[i] */
+int pr_get_contacts(const pr_world* w, uint32_t cap, pr_contact* contacts, pr_manifold* manifolds,
+                    uint32_t* n_out);
+int pr_get_proxies(const pr_world* w, uint32_t cap, pr_proxy* proxies, uint32_t* n_out);
+/* whole-state restore for stage-parity tests and clone-from-host: replaces every proxy's fat AABB
+ * and the complete contact list (ids, flags, manifolds incl. stored impulses). */
+int pr_load_state(pr_world* w, uint32_t n_bodies, const pr_body* bodies, uint32_t n_proxies,
+                  const pr_proxy* proxies, uint32_t n_contacts, const pr_contact* contacts,
+                  const pr_manifold* manifolds, float inv_dt0);
+
+/* ---- the hot path: Step(AabbTreeWorld&, const StepConf&), AabbTreeWorld.cpp:2144-2219 ---- */
+int pr_step(pr_world* w, const pr_step_conf* conf, pr_step_stats* stats_out);
+/* the constraint order the last regular-phase solve used (colour-sorted):
+ * contact ids in solve order, their colour and island label. For the parity oracle. */
+int pr_get_solve_order(const pr_world* w, uint32_t cap, uint32_t* contact_ids, uint32_t* colors,
+                       uint32_t* n_out);
+int pr_get_step_profile(const pr_world* w, pr_step_profile* out);
+int pr_shift_origin(pr_world* w, float x, float y);     /* ShiftOrigin :2221 */
+float pr_get_inv_dt0(const pr_world* w);                /* GetInvDeltaTime */
+
+/* ---- stage entry point for known-answer tests: CollideShapes (Manifold.cpp:393) over arrays ----
+ * pair i collides child a_child[i] under xf_a[i] (px,py,c,s) with child b_child[i] under xf_b[i]. */
+int pr_collide_shapes(int device, uint32_t n, const pr_child* children, uint32_t n_children,
+                      const pr_vec2* vertices, const pr_vec2* normals, uint32_t n_vertices,
+                      const uint32_t* a_child, const float* xf_a, const uint32_t* b_child,
+                      const float* xf_b, float linear_slop, float max_circles_ratio,
+                      pr_manifold* out);
+
+/* ---- batched independent worlds (config 5; no reference API, additive: SURVEY §8(b)) ---- */
+typedef struct pr_batch pr_batch;
+int pr_batch_create(const pr_world_conf* conf, uint32_t n_worlds, pr_batch** out);
+int pr_batch_destroy(pr_batch* b);
+pr_world* pr_batch_world(pr_batch* b, uint32_t i);      /* borrow world i for population */
+int pr_batch_step(pr_batch* b, const pr_step_conf* conf, pr_step_stats* stats_sum_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLAYRHO_B200_H */

@@ -1,0 +1,673 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY. Not product code; never linked into
+// libplayrho_b200.so. A C-ABI shim of OURS over the UNMODIFIED reference library (compiled from
+// /root/reference by oracle/Makefile into oracle/_ref/libPlayRho{,32}.a) so that python tests and
+// bench.py's cpu_baseline leg can (a) build scenes with the reference's own shape/mass code,
+// (b) run the reference's Step, (c) dump its state in the POD layout of include/playrho_b200.h,
+// (d) call the reference's pure stage functions (CollideShapes, ...) on flat arrays.
+// Only the reference's PUBLIC API is used (playrho/d2/World*.hpp, Manifold.hpp, ...).
+#include <playrho/d2/BasicAPI.hpp>
+#include <playrho/d2/AabbTreeWorld.hpp>
+#include <playrho/d2/DynamicTree.hpp>
+#include <playrho/d2/Manifold.hpp>
+#include <playrho/d2/DistanceProxy.hpp>
+#include <playrho/d2/WorldManifold.hpp>
+#include <playrho/d2/RevoluteJointConf.hpp>
+#include <playrho/d2/TimeOfImpact.hpp>
+#include <playrho/ToiConf.hpp>
+#include <playrho/ToiOutput.hpp>
+
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../include/playrho_b200.h"
+
+using namespace playrho;
+using namespace playrho::d2;
+
+namespace {
+
+struct RefWorld {
+    World world;
+    std::string error;
+    explicit RefWorld(const WorldConf& c) : world{c} {}
+};
+
+StepConf ToStepConf(const pr_step_conf& c)
+{
+    StepConf s;
+    s.deltaTime = c.delta_time;
+    s.dtRatio = c.dt_ratio;
+    s.minStillTimeToSleep = c.min_still_time_to_sleep;
+    s.linearSlop = c.linear_slop;
+    s.angularSlop = c.angular_slop;
+    s.regResolutionRate = c.reg_resolution_rate;
+    s.regMinSeparation = c.reg_min_separation;
+    s.regMinMomentum = c.reg_min_momentum;
+    s.toiResolutionRate = c.toi_resolution_rate;
+    s.toiMinSeparation = c.toi_min_separation;
+    s.toiMinMomentum = c.toi_min_momentum;
+    s.targetDepth = c.target_depth;
+    s.tolerance = c.tolerance;
+    s.velocityThreshold = c.velocity_threshold;
+    s.maxTranslation = c.max_translation;
+    s.maxRotation = c.max_rotation;
+    s.maxLinearCorrection = c.max_linear_correction;
+    s.maxAngularCorrection = c.max_angular_correction;
+    s.linearSleepTolerance = c.linear_sleep_tolerance;
+    s.angularSleepTolerance = c.angular_sleep_tolerance;
+    s.displaceMultiplier = c.displace_multiplier;
+    s.aabbExtension = c.aabb_extension;
+    s.maxCirclesRatio = c.max_circles_ratio;
+    s.regVelocityIters = static_cast<StepConf::iteration_type>(c.reg_velocity_iters);
+    s.regPositionIters = static_cast<StepConf::iteration_type>(c.reg_position_iters);
+    s.toiVelocityIters = static_cast<StepConf::iteration_type>(c.toi_velocity_iters);
+    s.toiPositionIters = static_cast<StepConf::iteration_type>(c.toi_position_iters);
+    s.maxToiRootIters = static_cast<StepConf::iteration_type>(c.max_toi_root_iters);
+    s.maxToiIters = static_cast<StepConf::iteration_type>(c.max_toi_iters);
+    s.maxDistanceIters = static_cast<StepConf::iteration_type>(c.max_distance_iters);
+    s.maxSubSteps = static_cast<StepConf::iteration_type>(c.max_sub_steps);
+    s.doWarmStart = c.do_warm_start != 0;
+    s.doToi = c.do_toi != 0;
+    s.doBlocksolve = c.do_blocksolve != 0;
+    return s;
+}
+
+void FromStepConf(const StepConf& s, pr_step_conf& c)
+{
+    c.delta_time = s.deltaTime;
+    c.dt_ratio = s.dtRatio;
+    c.min_still_time_to_sleep = s.minStillTimeToSleep;
+    c.linear_slop = s.linearSlop;
+    c.angular_slop = s.angularSlop;
+    c.reg_resolution_rate = s.regResolutionRate;
+    c.reg_min_separation = s.regMinSeparation;
+    c.reg_min_momentum = s.regMinMomentum;
+    c.toi_resolution_rate = s.toiResolutionRate;
+    c.toi_min_separation = s.toiMinSeparation;
+    c.toi_min_momentum = s.toiMinMomentum;
+    c.target_depth = s.targetDepth;
+    c.tolerance = s.tolerance;
+    c.velocity_threshold = s.velocityThreshold;
+    c.max_translation = s.maxTranslation;
+    c.max_rotation = s.maxRotation;
+    c.max_linear_correction = s.maxLinearCorrection;
+    c.max_angular_correction = s.maxAngularCorrection;
+    c.linear_sleep_tolerance = s.linearSleepTolerance;
+    c.angular_sleep_tolerance = s.angularSleepTolerance;
+    c.displace_multiplier = s.displaceMultiplier;
+    c.aabb_extension = s.aabbExtension;
+    c.max_circles_ratio = s.maxCirclesRatio;
+    c.reg_velocity_iters = s.regVelocityIters;
+    c.reg_position_iters = s.regPositionIters;
+    c.toi_velocity_iters = s.toiVelocityIters;
+    c.toi_position_iters = s.toiPositionIters;
+    c.max_toi_root_iters = s.maxToiRootIters;
+    c.max_toi_iters = s.maxToiIters;
+    c.max_distance_iters = s.maxDistanceIters;
+    c.max_sub_steps = s.maxSubSteps;
+    c.do_warm_start = s.doWarmStart;
+    c.do_toi = s.doToi;
+    c.do_blocksolve = s.doBlocksolve;
+}
+
+void FromStats(const StepStats& s, pr_step_stats& o)
+{
+    std::memset(&o, 0, sizeof(o));
+    o.pre.proxies_created = s.pre.proxiesCreated;
+    o.pre.proxies_moved = s.pre.proxiesMoved;
+    o.pre.contacts_destroyed = s.pre.contactsDestroyed;
+    o.pre.contacts_added = s.pre.contactsAdded;
+    o.pre.contacts_updated = s.pre.contactsUpdated;
+    o.pre.contacts_skipped = s.pre.contactsSkipped;
+    o.reg.min_separation = s.reg.minSeparation;
+    o.reg.max_inc_impulse = s.reg.maxIncImpulse;
+    o.reg.islands_found = s.reg.islandsFound;
+    o.reg.islands_solved = s.reg.islandsSolved;
+    o.reg.contacts_added = s.reg.contactsAdded;
+    o.reg.bodies_slept = s.reg.bodiesSlept;
+    o.reg.proxies_moved = s.reg.proxiesMoved;
+    o.reg.sum_pos_iters = s.reg.sumPosIters;
+    o.reg.sum_vel_iters = s.reg.sumVelIters;
+    o.reg.contacts_updated = s.reg.contactsUpdated;
+    o.reg.contacts_skipped = s.reg.contactsSkipped;
+    o.reg.max_island_bodies = s.reg.maxIslandBodies;
+    o.toi.min_separation = s.toi.minSeparation;
+    o.toi.max_inc_impulse = s.toi.maxIncImpulse;
+    o.toi.islands_found = s.toi.islandsFound;
+    o.toi.islands_solved = s.toi.islandsSolved;
+    o.toi.contacts_found = s.toi.contactsFound;
+    o.toi.contacts_at_max_sub_steps = s.toi.contactsAtMaxSubSteps;
+    o.toi.contacts_updated_toi = s.toi.contactsUpdatedToi;
+    o.toi.contacts_updated_touching = s.toi.contactsUpdatedTouching;
+    o.toi.contacts_skipped_touching = s.toi.contactsSkippedTouching;
+    o.toi.contacts_added = s.toi.contactsAdded;
+    o.toi.proxies_moved = s.toi.proxiesMoved;
+    o.toi.sum_pos_iters = s.toi.sumPosIters;
+    o.toi.sum_vel_iters = s.toi.sumVelIters;
+    o.toi.max_dist_iters = s.toi.maxDistIters;
+    o.toi.max_toi_iters = s.toi.maxToiIters;
+    o.toi.max_root_iters = s.toi.maxRootIters;
+}
+
+template <class Conf>
+Conf& ApplyCommon(Conf& conf, float friction, float restitution, float density, int sensor,
+                  unsigned cat, unsigned mask, int group)
+{
+    conf.UseFriction(friction).UseRestitution(restitution).UseDensity(density * 1_kgpm2);
+    conf.UseIsSensor(sensor != 0);
+    Filter f;
+    f.categoryBits = static_cast<Filter::bits_type>(cat);
+    f.maskBits = static_cast<Filter::bits_type>(mask);
+    f.groupIndex = static_cast<Filter::index_type>(group);
+    conf.UseFilter(f);
+    return conf;
+}
+
+pr_contact_feature Pack(const ContactFeature& cf)
+{
+    return static_cast<uint32_t>(cf.typeA) | (static_cast<uint32_t>(cf.indexA) << 8) |
+           (static_cast<uint32_t>(cf.typeB) << 16) | (static_cast<uint32_t>(cf.indexB) << 24);
+}
+
+void FromManifold(const Manifold& m, pr_manifold& o)
+{
+    std::memset(&o, 0, sizeof(o));
+    o.type = static_cast<uint32_t>(m.GetType());
+    o.count = m.GetPointCount();
+    o.cf0 = o.cf1 = Pack(ContactFeature{});
+    if (o.type == Manifold::e_unset) {
+        return;
+    }
+    if (o.type != Manifold::e_circles) {
+        const auto ln = m.GetLocalNormal();
+        o.ln_x = ln.GetX();
+        o.ln_y = ln.GetY();
+    }
+    const auto lp = m.GetLocalPoint();
+    o.lp_x = GetX(lp);
+    o.lp_y = GetY(lp);
+    if (o.count > 0) {
+        const auto& p = m.GetPoint(0);
+        o.p0_x = GetX(p.localPoint);
+        o.p0_y = GetY(p.localPoint);
+        o.jn0 = p.normalImpulse;
+        o.jt0 = p.tangentImpulse;
+        o.cf0 = Pack(p.contactFeature);
+    }
+    if (o.count > 1) {
+        const auto& p = m.GetPoint(1);
+        o.p1_x = GetX(p.localPoint);
+        o.p1_y = GetY(p.localPoint);
+        o.jn1 = p.normalImpulse;
+        o.jt1 = p.tangentImpulse;
+        o.cf1 = Pack(p.contactFeature);
+    }
+}
+
+void FromBody(const Body& b, pr_body& o)
+{
+    const auto xf = GetTransformation(b);
+    const auto& sw = GetSweep(b);
+    const auto v = GetVelocity(b);
+    o.xf_px = GetX(xf.p);
+    o.xf_py = GetY(xf.p);
+    o.xf_qc = xf.q.GetX();
+    o.xf_qs = xf.q.GetY();
+    o.pos0_x = GetX(sw.pos0.linear);
+    o.pos0_y = GetY(sw.pos0.linear);
+    o.pos0_a = sw.pos0.angular;
+    o.pos1_x = GetX(sw.pos1.linear);
+    o.pos1_y = GetY(sw.pos1.linear);
+    o.pos1_a = sw.pos1.angular;
+    o.lc_x = GetX(sw.localCenter);
+    o.lc_y = GetY(sw.localCenter);
+    o.alpha0 = sw.alpha0;
+    o.vel_x = GetX(v.linear);
+    o.vel_y = GetY(v.linear);
+    o.vel_w = v.angular;
+    o.acc_x = GetX(GetLinearAcceleration(b));
+    o.acc_y = GetY(GetLinearAcceleration(b));
+    o.acc_w = GetAngularAcceleration(b);
+    o.inv_mass = GetInvMass(b);
+    o.inv_rot_i = GetInvRotInertia(b);
+    o.lin_damp = GetLinearDamping(b);
+    o.ang_damp = GetAngularDamping(b);
+    o.under_active_time = GetUnderActiveTime(b);
+    uint32_t f = 0;
+    if (IsDestroyed(b)) f |= PR_BODY_DESTROYED;
+    if (IsAwake(b)) f |= PR_BODY_AWAKE;
+    if (IsSleepingAllowed(b)) f |= PR_BODY_AUTOSLEEP;
+    if (IsImpenetrable(b)) f |= PR_BODY_IMPENETRABLE;
+    if (IsFixedRotation(b)) f |= PR_BODY_FIXED_ROTATION;
+    if (IsEnabled(b)) f |= PR_BODY_ENABLED;
+    if (IsSpeedable(b)) f |= PR_BODY_VELOCITY;
+    if (IsAccelerable(b)) f |= PR_BODY_ACCELERATION;
+    if (IsMassDataDirty(b)) f |= PR_BODY_MASS_DIRTY;
+    o.flags = f;
+}
+
+template <class ID>
+ID MakeId(uint32_t v)
+{
+    return static_cast<ID>(static_cast<typename ID::underlying_type>(v));
+}
+
+} // namespace
+
+extern "C" {
+
+int ref_ids_are_32bit(void) { return sizeof(BodyID) == 4; }
+
+void ref_step_conf_default(pr_step_conf* out) { FromStepConf(StepConf{}, *out); }
+
+void* ref_world_create(float minVertexRadius, float maxVertexRadius)
+{
+    try {
+        auto conf = WorldConf{};
+        if (minVertexRadius > 0 && maxVertexRadius > 0) {
+            conf.vertexRadius = Interval<Positive<Length>>{Positive<Length>{minVertexRadius},
+                                                           Positive<Length>{maxVertexRadius}};
+        }
+        return new RefWorld(conf);
+    } catch (...) {
+        return nullptr;
+    }
+}
+
+void ref_world_destroy(void* h) { delete static_cast<RefWorld*>(h); }
+
+const char* ref_last_error(void* h) { return static_cast<RefWorld*>(h)->error.c_str(); }
+
+#define REF_TRY(h) auto* rw = static_cast<RefWorld*>(h); try {
+#define REF_CATCH(bad) } catch (const std::exception& e) { rw->error = e.what(); return bad; }
+
+uint32_t ref_add_disk(void* h, float radius, float lx, float ly, float friction, float restitution,
+                      float density, int sensor, unsigned cat, unsigned mask, int group)
+{
+    REF_TRY(h)
+    auto conf = DiskShapeConf{};
+    conf.UseRadius(radius).UseLocation(Length2{lx, ly});
+    ApplyCommon(conf, friction, restitution, density, sensor, cat, mask, group);
+    return to_underlying(CreateShape(rw->world, conf));
+    REF_CATCH(PR_INVALID_ID)
+}
+
+// Polygon through PolygonShapeConf::Set (convex hull, like any user of the reference would)
+uint32_t ref_add_polygon(void* h, const float* xy, uint32_t n, float vertexRadius, float friction,
+                         float restitution, float density, int sensor, unsigned cat, unsigned mask,
+                         int group)
+{
+    REF_TRY(h)
+    std::vector<Length2> pts;
+    for (uint32_t i = 0; i < n; ++i) pts.push_back(Length2{xy[2 * i], xy[2 * i + 1]});
+    auto conf = PolygonShapeConf{};
+    if (vertexRadius > 0) conf.UseVertexRadius(vertexRadius);
+    conf.Set(Span<const Length2>(pts.data(), pts.size()));
+    ApplyCommon(conf, friction, restitution, density, sensor, cat, mask, group);
+    return to_underlying(CreateShape(rw->world, conf));
+    REF_CATCH(PR_INVALID_ID)
+}
+
+uint32_t ref_add_box(void* h, float hx, float hy, float cx, float cy, float angle,
+                     float vertexRadius, float friction, float restitution, float density,
+                     int sensor, unsigned cat, unsigned mask, int group)
+{
+    REF_TRY(h)
+    auto conf = PolygonShapeConf{};
+    if (vertexRadius > 0) conf.UseVertexRadius(vertexRadius);
+    if (cx == 0 && cy == 0 && angle == 0) conf.SetAsBox(hx, hy);
+    else conf.SetAsBox(hx, hy, Length2{cx, cy}, angle);
+    ApplyCommon(conf, friction, restitution, density, sensor, cat, mask, group);
+    return to_underlying(CreateShape(rw->world, conf));
+    REF_CATCH(PR_INVALID_ID)
+}
+
+uint32_t ref_add_edge(void* h, float x0, float y0, float x1, float y1, float vertexRadius,
+                      float friction, float restitution, float density, int sensor, unsigned cat,
+                      unsigned mask, int group)
+{
+    REF_TRY(h)
+    auto conf = EdgeShapeConf{};
+    if (vertexRadius > 0) conf.UseVertexRadius(vertexRadius);
+    conf.Set(Length2{x0, y0}, Length2{x1, y1});
+    ApplyCommon(conf, friction, restitution, density, sensor, cat, mask, group);
+    return to_underlying(CreateShape(rw->world, conf));
+    REF_CATCH(PR_INVALID_ID)
+}
+
+uint32_t ref_add_chain(void* h, const float* xy, uint32_t n, float vertexRadius, float friction,
+                       float restitution, float density, int sensor, unsigned cat, unsigned mask,
+                       int group)
+{
+    REF_TRY(h)
+    std::vector<Length2> pts;
+    for (uint32_t i = 0; i < n; ++i) pts.push_back(Length2{xy[2 * i], xy[2 * i + 1]});
+    auto conf = ChainShapeConf{};
+    if (vertexRadius > 0) conf.UseVertexRadius(vertexRadius);
+    conf.Set(pts);
+    ApplyCommon(conf, friction, restitution, density, sensor, cat, mask, group);
+    return to_underlying(CreateShape(rw->world, conf));
+    REF_CATCH(PR_INVALID_ID)
+}
+
+// type: 0 static, 1 kinematic, 2 dynamic (BodyType.hpp). bits: 1 bullet, 2 fixedRotation,
+// 4 disallow sleep, 8 start asleep, 16 disabled
+uint32_t ref_add_body(void* h, int type, float x, float y, float angle, float vx, float vy, float w,
+                      float ax, float ay, float aw, float linDamp, float angDamp, unsigned bits,
+                      const uint32_t* shapes, uint32_t nshapes)
+{
+    REF_TRY(h)
+    auto bc = BodyConf{};
+    bc.Use(type == 0 ? BodyType::Static : type == 1 ? BodyType::Kinematic : BodyType::Dynamic);
+    bc.UseLocation(Length2{x, y}).UseAngle(angle);
+    bc.UseLinearVelocity(LinearVelocity2{vx, vy}).UseAngularVelocity(w);
+    bc.UseLinearAcceleration(LinearAcceleration2{ax, ay}).UseAngularAcceleration(aw);
+    bc.UseLinearDamping(linDamp).UseAngularDamping(angDamp);
+    bc.UseBullet((bits & 1u) != 0).UseFixedRotation((bits & 2u) != 0);
+    bc.UseAllowSleep((bits & 4u) == 0).UseAwake((bits & 8u) == 0).UseEnabled((bits & 16u) == 0);
+    for (uint32_t i = 0; i < nshapes; ++i) bc.Use(MakeId<ShapeID>(shapes[i]));
+    return to_underlying(CreateBody(rw->world, bc));
+    REF_CATCH(PR_INVALID_ID)
+}
+
+uint32_t ref_add_revolute(void* h, uint32_t bodyA, uint32_t bodyB, float ax, float ay,
+                          int enableMotor, float motorSpeed, float maxMotorTorque,
+                          int collideConnected)
+{
+    REF_TRY(h)
+    auto jc = GetRevoluteJointConf(rw->world, MakeId<BodyID>(bodyA), MakeId<BodyID>(bodyB),
+                                   Length2{ax, ay});
+    jc.enableMotor = enableMotor != 0;
+    jc.motorSpeed = motorSpeed;
+    jc.maxMotorTorque = maxMotorTorque;
+    jc.collideConnected = collideConnected != 0;
+    return to_underlying(CreateJoint(rw->world, jc));
+    REF_CATCH(PR_INVALID_ID)
+}
+
+int ref_set_body_velocity(void* h, uint32_t body, float vx, float vy, float w)
+{
+    REF_TRY(h)
+    SetVelocity(rw->world, MakeId<BodyID>(body), Velocity{LinearVelocity2{vx, vy}, w});
+    return 0;
+    REF_CATCH(-1)
+}
+
+int ref_set_body_transform(void* h, uint32_t body, float x, float y, float angle)
+{
+    REF_TRY(h)
+    SetTransform(rw->world, MakeId<BodyID>(body), Length2{x, y}, angle);
+    return 0;
+    REF_CATCH(-1)
+}
+
+int ref_step(void* h, const pr_step_conf* conf, pr_step_stats* stats)
+{
+    REF_TRY(h)
+    const auto s = Step(rw->world, ToStepConf(*conf));
+    if (stats) FromStats(s, *stats);
+    return 0;
+    REF_CATCH(-1)
+}
+
+// steps n times; returns wall seconds spent inside Step() (cpu_baseline)
+double ref_step_timed(void* h, const pr_step_conf* conf, uint32_t n, pr_step_stats* last)
+{
+    auto* rw = static_cast<RefWorld*>(h);
+    const auto sc = ToStepConf(*conf);
+    StepStats s;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t i = 0; i < n; ++i) s = Step(rw->world, sc);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (last) FromStats(s, *last);
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int ref_get_counts(void* h, pr_counts* out)
+{
+    REF_TRY(h)
+    std::memset(out, 0, sizeof(*out));
+    out->bodies = static_cast<uint32_t>(GetBodyRange(rw->world));
+    out->shapes = static_cast<uint32_t>(GetShapeRange(rw->world));
+    out->joints = static_cast<uint32_t>(GetJointRange(rw->world));
+    out->contacts = static_cast<uint32_t>(GetContacts(rw->world).size());
+    out->contact_id_range = static_cast<uint32_t>(GetContactRange(rw->world));
+    const auto& tree = GetTree(rw->world);
+    out->proxies = tree.GetLeafCount();
+    out->tree_leaf_count = tree.GetLeafCount();
+    out->tree_node_capacity = tree.GetNodeCapacity();
+    uint32_t nchild = 0, nvert = 0;
+    for (uint32_t s = 0; s < out->shapes; ++s) {
+        const auto& shape = GetShape(rw->world, MakeId<ShapeID>(s));
+        const auto cc = GetChildCount(shape);
+        nchild += cc;
+        for (ChildCounter c = 0; c < cc; ++c) nvert += GetChild(shape, c).GetVertexCount();
+    }
+    out->children = nchild;
+    out->vertices = nvert;
+    return 0;
+    REF_CATCH(-1)
+}
+
+// Flatten every shape: SURVEY F7 (each child is a DistanceProxy{radius,count,vertices,normals})
+int ref_export_shapes(void* h, pr_shape* shapes, pr_child* children, pr_vec2* verts, pr_vec2* normals)
+{
+    REF_TRY(h)
+    const auto ns = static_cast<uint32_t>(GetShapeRange(rw->world));
+    uint32_t ci = 0, vi = 0;
+    for (uint32_t s = 0; s < ns; ++s) {
+        const auto& shape = GetShape(rw->world, MakeId<ShapeID>(s));
+        auto& o = shapes[s];
+        o.friction = GetFriction(shape);
+        o.restitution = GetRestitution(shape);
+        o.density = GetDensity(shape);
+        const auto f = GetFilter(shape);
+        o.filter_category = f.categoryBits;
+        o.filter_mask = f.maskBits;
+        o.filter_group = f.groupIndex;
+        o.is_sensor = IsSensor(shape) ? 1 : 0;
+        o.child_offset = ci;
+        o.child_count = GetChildCount(shape);
+        for (ChildCounter c = 0; c < o.child_count; ++c) {
+            const auto dp = GetChild(shape, c);
+            children[ci].vertex_offset = vi;
+            children[ci].vertex_count = dp.GetVertexCount();
+            children[ci].vertex_radius = dp.GetVertexRadius();
+            for (VertexCounter v = 0; v < dp.GetVertexCount(); ++v) {
+                verts[vi] = pr_vec2{GetX(dp.GetVertex(v)), GetY(dp.GetVertex(v))};
+                if (dp.GetVertexCount() > 1) {
+                    normals[vi] = pr_vec2{dp.GetNormal(v).GetX(), dp.GetNormal(v).GetY()};
+                } else {
+                    normals[vi] = pr_vec2{0, 0};
+                }
+                ++vi;
+            }
+            ++ci;
+        }
+    }
+    return 0;
+    REF_CATCH(-1)
+}
+
+int ref_export_bodies(void* h, pr_body* bodies)
+{
+    REF_TRY(h)
+    const auto nb = static_cast<uint32_t>(GetBodyRange(rw->world));
+    for (uint32_t b = 0; b < nb; ++b) FromBody(GetBody(rw->world, MakeId<BodyID>(b)), bodies[b]);
+    return 0;
+    REF_CATCH(-1)
+}
+
+// CSR of shape ids per body; offsets has nb+1 entries
+int ref_export_body_shapes(void* h, uint32_t* offsets, uint32_t* shape_ids, uint32_t cap)
+{
+    REF_TRY(h)
+    const auto nb = static_cast<uint32_t>(GetBodyRange(rw->world));
+    uint32_t k = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+        offsets[b] = k;
+        for (const auto& s : GetShapes(rw->world, MakeId<BodyID>(b))) {
+            if (k < cap) shape_ids[k] = to_underlying(s);
+            ++k;
+        }
+    }
+    offsets[nb] = k;
+    return static_cast<int>(k);
+    REF_CATCH(-1)
+}
+
+int ref_export_proxies(void* h, pr_proxy* out, uint32_t cap)
+{
+    REF_TRY(h)
+    const auto& tree = GetTree(rw->world);
+    uint32_t n = 0;
+    for (DynamicTree::Size i = 0; i < tree.GetNodeCapacity(); ++i) {
+        if (DynamicTree::IsLeaf(tree.GetHeight(i))) {
+            if (n < cap) {
+                const auto leaf = tree.GetLeafData(i);
+                const auto aabb = tree.GetAABB(i);
+                out[n].tree_id = i;
+                out[n].body = to_underlying(leaf.bodyId);
+                out[n].shape = to_underlying(leaf.shapeId);
+                out[n].child = leaf.childId;
+                out[n].min_x = aabb.ranges[0].GetMin();
+                out[n].max_x = aabb.ranges[0].GetMax();
+                out[n].min_y = aabb.ranges[1].GetMin();
+                out[n].max_y = aabb.ranges[1].GetMax();
+            }
+            ++n;
+        }
+    }
+    return static_cast<int>(n);
+    REF_CATCH(-1)
+}
+
+int ref_export_contacts(void* h, pr_contact* out, pr_manifold* manifolds, uint32_t cap)
+{
+    REF_TRY(h)
+    const auto contacts = GetContacts(rw->world);
+    uint32_t n = 0;
+    for (const auto& kc : contacts) {
+        if (n < cap) {
+            const auto key = std::get<ContactKey>(kc);
+            const auto id = std::get<ContactID>(kc);
+            const auto& c = GetContact(rw->world, id);
+            auto& o = out[n];
+            o.id = to_underlying(id);
+            o.key_min = key.GetMin();
+            o.key_max = key.GetMax();
+            o.body_a = to_underlying(GetBodyA(c));
+            o.shape_a = to_underlying(GetShapeA(c));
+            o.child_a = GetChildIndexA(c);
+            o.body_b = to_underlying(GetBodyB(c));
+            o.shape_b = to_underlying(GetShapeB(c));
+            o.child_b = GetChildIndexB(c);
+            o.friction = GetFriction(c);
+            o.restitution = GetRestitution(c);
+            o.tangent_speed = GetTangentSpeed(c);
+            o.toi = HasValidToi(c) ? static_cast<float>(*GetToi(c)) : 1.0f;
+            o.toi_count = GetToiCount(c);
+            uint32_t f = 0;
+            if (IsTouching(c)) f |= PR_CONTACT_TOUCHING;
+            if (IsEnabled(c)) f |= PR_CONTACT_ENABLED;
+            if (NeedsFiltering(c)) f |= PR_CONTACT_FILTER;
+            if (HasValidToi(c)) f |= PR_CONTACT_TOI;
+            if (NeedsUpdating(c)) f |= PR_CONTACT_DIRTY;
+            if (IsSensor(c)) f |= PR_CONTACT_SENSOR;
+            if (IsDestroyed(c)) f |= PR_CONTACT_DESTROYED;
+            if (IsImpenetrable(c)) f |= PR_CONTACT_IMPENETRABLE;
+            o.flags = f;
+            if (manifolds) FromManifold(GetManifold(rw->world, id), manifolds[n]);
+        }
+        ++n;
+    }
+    return static_cast<int>(n);
+    REF_CATCH(-1)
+}
+
+float ref_get_inv_dt0(void* h) { return GetInvDeltaTime(static_cast<RefWorld*>(h)->world); }
+
+// ---- stage functions of the reference on flat arrays ----
+
+// CollideShapes (Manifold.cpp:393) for n pairs of children
+int ref_collide_shapes(uint32_t n, const pr_child* children, const pr_vec2* verts,
+                       const pr_vec2* normals, const uint32_t* a_child, const float* xf_a,
+                       const uint32_t* b_child, const float* xf_b, float linearSlop,
+                       float maxCirclesRatio, pr_manifold* out)
+{
+    static_assert(sizeof(Length2) == sizeof(pr_vec2), "layout");
+    static_assert(sizeof(UnitVec) == sizeof(pr_vec2), "layout");
+    auto conf = Manifold::Conf{};
+    conf.linearSlop = linearSlop;
+    conf.maxCirclesRatio = maxCirclesRatio;
+    for (uint32_t i = 0; i < n; ++i) {
+        const auto& ca = children[a_child[i]];
+        const auto& cb = children[b_child[i]];
+        const auto pa = DistanceProxy{ca.vertex_radius, static_cast<VertexCounter>(ca.vertex_count),
+            reinterpret_cast<const Length2*>(verts + ca.vertex_offset),
+            reinterpret_cast<const UnitVec*>(normals + ca.vertex_offset)};
+        const auto pb = DistanceProxy{cb.vertex_radius, static_cast<VertexCounter>(cb.vertex_count),
+            reinterpret_cast<const Length2*>(verts + cb.vertex_offset),
+            reinterpret_cast<const UnitVec*>(normals + cb.vertex_offset)};
+        const float* a = xf_a + 4 * i;
+        const float* b = xf_b + 4 * i;
+        const auto qa = UnitVec::Get(a[2], a[3]).first; // exact when (c,s) already unit: see below
+        const auto qb = UnitVec::Get(b[2], b[3]).first;
+        (void)qa; (void)qb;
+        // Build the transformation from raw (c,s) bits without renormalising:
+        Transformation xa, xb;
+        xa.p = Length2{a[0], a[1]};
+        xb.p = Length2{b[0], b[1]};
+        std::memcpy(static_cast<void*>(&xa.q), a + 2, sizeof(float) * 2);
+        std::memcpy(static_cast<void*>(&xb.q), b + 2, sizeof(float) * 2);
+        FromManifold(CollideShapes(pa, xa, pb, xb, conf), out[i]);
+    }
+    return 0;
+}
+
+// UnitVec::Get(angle) == {cos, sin} as the reference computes it (UnitVec.cpp:27-30)
+void ref_unitvec_from_angle(uint32_t n, const float* angles, float* cs)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        const auto u = UnitVec::Get(Angle{angles[i]});
+        cs[2 * i] = u.GetX();
+        cs[2 * i + 1] = u.GetY();
+    }
+}
+
+// GetToiViaSat (TimeOfImpact.cpp:35) on flat arrays: sweeps as 8 floats
+// (pos0 x,y,a, pos1 x,y,a, lc x,y); alpha0 = 0. out: time, state, toi_iters, max_dist, max_root
+int ref_toi(uint32_t n, const pr_child* children, const pr_vec2* verts, const pr_vec2* normals,
+            const uint32_t* a_child, const float* sweep_a, const uint32_t* b_child,
+            const float* sweep_b, const pr_step_conf* sc, float* out_time, int32_t* out_state,
+            uint32_t* out_iters)
+{
+    const auto conf = GetToiConf(ToStepConf(*sc));
+    for (uint32_t i = 0; i < n; ++i) {
+        const auto& ca = children[a_child[i]];
+        const auto& cb = children[b_child[i]];
+        const auto pa = DistanceProxy{ca.vertex_radius, static_cast<VertexCounter>(ca.vertex_count),
+            reinterpret_cast<const Length2*>(verts + ca.vertex_offset),
+            reinterpret_cast<const UnitVec*>(normals + ca.vertex_offset)};
+        const auto pb = DistanceProxy{cb.vertex_radius, static_cast<VertexCounter>(cb.vertex_count),
+            reinterpret_cast<const Length2*>(verts + cb.vertex_offset),
+            reinterpret_cast<const UnitVec*>(normals + cb.vertex_offset)};
+        const float* a = sweep_a + 8 * i;
+        const float* b = sweep_b + 8 * i;
+        const auto sa = Sweep{Position{Length2{a[0], a[1]}, a[2]}, Position{Length2{a[3], a[4]}, a[5]},
+                              Length2{a[6], a[7]}};
+        const auto sb = Sweep{Position{Length2{b[0], b[1]}, b[2]}, Position{Length2{b[3], b[4]}, b[5]},
+                              Length2{b[6], b[7]}};
+        const auto o = GetToiViaSat(pa, sa, pb, sb, conf);
+        out_time[i] = o.time;
+        out_state[i] = static_cast<int32_t>(o.state);
+        out_iters[3 * i + 0] = o.stats.toi_iters;
+        out_iters[3 * i + 1] = o.stats.max_dist_iters;
+        out_iters[3 * i + 2] = o.stats.max_root_iters;
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,25 @@
+// orc_toi.h -- TEST INFRASTRUCTURE ONLY (oracle restatement): GJK distance, TOI and revolute joint.
+#ifndef ORC_TOI_H
+#define ORC_TOI_H
+#include "orc_math.h"
+namespace orc {
+
+// TestOverlap(proxyA, xfA, proxyB, xfB, conf), Distance.cpp:205-230: returns squared-area-like
+// signed value; >= 0 means overlapping.
+float test_overlap(const Proxy& a, Xf xfA, const Proxy& b, Xf xfB, uint32_t maxIters);
+
+struct ToiOut { float time; int state; uint32_t toi_iters, max_dist_iters, max_root_iters; };
+struct Sweep { Pos pos0, pos1; V2 lc; float alpha0; };
+// GetToiViaSat, TimeOfImpact.cpp:35-251
+ToiOut toi_via_sat(const Proxy& a, const Sweep& sA, const Proxy& b, const Sweep& sB, const pr_step_conf& conf);
+
+struct JointSolverConf { float dt, dtRatio; bool warmStart; float linearSlop, angularSlop, maxLinearCorrection, maxAngularCorrection; };
+struct RevoluteWork { V2 rA{0, 0}, rB{0, 0}; float mass[9] = {0}; float angularMass = 0; };
+void revolute_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
+                            float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c);
+bool revolute_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& velA,
+                             float imB, float iiB, Vel& velB, const JointSolverConf& c);
+bool revolute_solve_position(const pr_revolute_joint& j, float imA, float iiA, V2 lcA, Pos& posA,
+                             float imB, float iiB, V2 lcB, Pos& posB, const JointSolverConf& c);
+} // namespace orc
+#endif

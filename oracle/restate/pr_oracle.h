@@ -1,0 +1,67 @@
+/*
+ * pr_oracle.h -- TEST INFRASTRUCTURE ONLY (oracle). Never linked into or called by the product.
+ *
+ * C API of the plain, serial C++ restatement of the reference's Step pipeline
+ * (Library/source/playrho/d2/AabbTreeWorld.cpp:2144 and what it calls). It uses the POD layouts
+ * of include/playrho_b200.h so the same arrays can be fed to the oracle, to the real reference
+ * (oracle/ref_harness.cpp) and to the CUDA world.
+ *
+ * PINNING: tests/test_oracle_pin.py checks this restatement bit-for-bit against the real reference
+ * (oracle/_ref, built from /root/reference by oracle/Makefile) on HelloWorld (incl. the reference's
+ * golden ExpectedOutput.txt), pyramid, disk-box, mixed-polygon and chain scenes over whole
+ * trajectories, and against known-answer vectors from UnitTests/CollideShapes.cpp.
+ */
+#ifndef PR_ORACLE_H
+#define PR_ORACLE_H
+#include "../../include/playrho_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_world orc_world;
+
+orc_world* orc_create(void);
+void orc_destroy(orc_world* w);
+const char* orc_last_error(const orc_world* w);
+int orc_create_shapes(orc_world* w, uint32_t n, const pr_shape* shapes, const pr_child* children,
+                      uint32_t n_children, const pr_vec2* vertices, const pr_vec2* normals,
+                      uint32_t n_vertices);
+int orc_create_bodies(orc_world* w, uint32_t n, const pr_body* bodies,
+                      const uint32_t* shape_offsets, const uint32_t* shape_ids);
+int orc_create_revolute_joints(orc_world* w, uint32_t n, const pr_revolute_joint* joints);
+int orc_set_bodies(orc_world* w, uint32_t n, const uint32_t* ids, const pr_body* rows);
+int orc_load_state(orc_world* w, uint32_t n_bodies, const pr_body* bodies, uint32_t n_proxies,
+                   const pr_proxy* proxies, uint32_t n_contacts, const pr_contact* contacts,
+                   const pr_manifold* manifolds, float inv_dt0);
+/* order == NULL: the reference's native constraint order (island DFS order).
+ * order != NULL: n_order contact ids; within each island, constraints are solved in the relative
+ * order they appear in `order` (the GPU's colour-sorted order) -- "the reference solver fed the
+ * same colour-sorted constraint order" (BASELINE.json north_star). */
+int orc_step(orc_world* w, const pr_step_conf* conf, pr_step_stats* stats, const uint32_t* order,
+             uint32_t n_order);
+int orc_get_counts(const orc_world* w, pr_counts* out);
+int orc_get_bodies(const orc_world* w, uint32_t first, uint32_t n, pr_body* rows);
+int orc_get_contacts(const orc_world* w, uint32_t cap, pr_contact* contacts, pr_manifold* manifolds,
+                     uint32_t* n_out);
+int orc_get_proxies(const orc_world* w, uint32_t cap, pr_proxy* proxies, uint32_t* n_out);
+int orc_get_revolute_joints(const orc_world* w, uint32_t first, uint32_t n, pr_revolute_joint* rows);
+float orc_get_inv_dt0(const orc_world* w);
+
+/* stage functions on flat arrays */
+int orc_collide_shapes(uint32_t n, const pr_child* children, const pr_vec2* verts,
+                       const pr_vec2* normals, const uint32_t* a_child, const float* xf_a,
+                       const uint32_t* b_child, const float* xf_b, float linear_slop,
+                       float max_circles_ratio, pr_manifold* out);
+void orc_step_conf_default(pr_step_conf* c);
+int orc_toi(uint32_t n, const pr_child* children, const pr_vec2* verts, const pr_vec2* normals,
+            const uint32_t* a_child, const float* sweep_a, const uint32_t* b_child,
+            const float* sweep_b, const pr_step_conf* sc, float* out_time, int32_t* out_state,
+            uint32_t* out_iters);
+/* the glibc-2.39 sincosf restatement that the CUDA side ports (checked against libm here) */
+void orc_sincosf_restated(uint32_t n, const float* x, float* cs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,329 @@
+"""ctypes wrappers (TEST INFRASTRUCTURE) over
+  - oracle/_ref/libref_harness{,32}.so : the real reference, built by oracle/Makefile
+  - oracle/libpr_oracle.so             : the C++ restatement
+Both speak the POD layouts of include/playrho_b200.h (playrho_b200/abi.py)."""
+import ctypes as C
+import os
+import numpy as np
+
+from playrho_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
+REF32_SO = os.path.join(ROOT, "oracle", "_ref", "libref_harness32.so")
+ORC_SO = os.path.join(ROOT, "oracle", "libpr_oracle.so")
+
+vp, u32, f32, i32 = C.c_void_p, C.c_uint32, C.c_float, C.c_int
+
+
+def have_ref(ids32=False):
+    return os.path.exists(REF32_SO if ids32 else REF_SO)
+
+
+def have_oracle():
+    return os.path.exists(ORC_SO)
+
+
+_libs = {}
+
+
+def _ref_lib(ids32=False):
+    key = "ref32" if ids32 else "ref"
+    if key not in _libs:
+        lib = C.CDLL(REF32_SO if ids32 else REF_SO)
+        lib.ref_world_create.restype = vp
+        lib.ref_world_create.argtypes = [f32, f32]
+        lib.ref_world_destroy.argtypes = [vp]
+        lib.ref_last_error.restype = C.c_char_p
+        lib.ref_last_error.argtypes = [vp]
+        common = [f32, f32, f32, i32, C.c_uint, C.c_uint, i32]
+        lib.ref_add_disk.restype = u32
+        lib.ref_add_disk.argtypes = [vp, f32, f32, f32] + common
+        lib.ref_add_polygon.restype = u32
+        lib.ref_add_polygon.argtypes = [vp, vp, u32, f32] + common
+        lib.ref_add_box.restype = u32
+        lib.ref_add_box.argtypes = [vp, f32, f32, f32, f32, f32, f32] + common
+        lib.ref_add_edge.restype = u32
+        lib.ref_add_edge.argtypes = [vp, f32, f32, f32, f32, f32] + common
+        lib.ref_add_chain.restype = u32
+        lib.ref_add_chain.argtypes = [vp, vp, u32, f32] + common
+        lib.ref_add_body.restype = u32
+        lib.ref_add_body.argtypes = [vp, i32] + [f32] * 11 + [C.c_uint, vp, u32]
+        lib.ref_add_revolute.restype = u32
+        lib.ref_add_revolute.argtypes = [vp, u32, u32, f32, f32, i32, f32, f32, i32]
+        lib.ref_set_body_velocity.argtypes = [vp, u32, f32, f32, f32]
+        lib.ref_set_body_transform.argtypes = [vp, u32, f32, f32, f32]
+        lib.ref_step.argtypes = [vp, vp, vp]
+        lib.ref_step_timed.restype = C.c_double
+        lib.ref_step_timed.argtypes = [vp, vp, u32, vp]
+        lib.ref_get_counts.argtypes = [vp, vp]
+        lib.ref_export_shapes.argtypes = [vp, vp, vp, vp, vp]
+        lib.ref_export_bodies.argtypes = [vp, vp]
+        lib.ref_export_body_shapes.argtypes = [vp, vp, vp, u32]
+        lib.ref_export_proxies.argtypes = [vp, vp, u32]
+        lib.ref_export_contacts.argtypes = [vp, vp, vp, u32]
+        lib.ref_get_inv_dt0.restype = f32
+        lib.ref_get_inv_dt0.argtypes = [vp]
+        lib.ref_collide_shapes.argtypes = [u32, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp]
+        lib.ref_unitvec_from_angle.argtypes = [u32, vp, vp]
+        lib.ref_toi.argtypes = [u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.ref_step_conf_default.argtypes = [vp]
+        _libs[key] = lib
+    return _libs[key]
+
+
+def _orc_lib():
+    if "orc" not in _libs:
+        lib = C.CDLL(ORC_SO)
+        lib.orc_create.restype = vp
+        lib.orc_destroy.argtypes = [vp]
+        lib.orc_last_error.restype = C.c_char_p
+        lib.orc_last_error.argtypes = [vp]
+        lib.orc_create_shapes.argtypes = [vp, u32, vp, vp, u32, vp, vp, u32]
+        lib.orc_create_bodies.argtypes = [vp, u32, vp, vp, vp]
+        lib.orc_create_revolute_joints.argtypes = [vp, u32, vp]
+        lib.orc_set_bodies.argtypes = [vp, u32, vp, vp]
+        lib.orc_load_state.argtypes = [vp, u32, vp, u32, vp, u32, vp, vp, f32]
+        lib.orc_step.argtypes = [vp, vp, vp, vp, u32]
+        lib.orc_get_counts.argtypes = [vp, vp]
+        lib.orc_get_bodies.argtypes = [vp, u32, u32, vp]
+        lib.orc_get_contacts.argtypes = [vp, u32, vp, vp, vp]
+        lib.orc_get_proxies.argtypes = [vp, u32, vp, vp]
+        lib.orc_get_revolute_joints.argtypes = [vp, u32, u32, vp]
+        lib.orc_get_inv_dt0.restype = f32
+        lib.orc_get_inv_dt0.argtypes = [vp]
+        lib.orc_collide_shapes.argtypes = [u32, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp]
+        lib.orc_step_conf_default.argtypes = [vp]
+        lib.orc_toi.argtypes = [u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.orc_sincosf_restated.argtypes = [u32, vp, vp]
+        _libs["orc"] = lib
+    return _libs["orc"]
+
+
+def default_step_conf(**kw):
+    c = abi.one(abi.STEP_CONF)
+    _orc_lib().orc_step_conf_default(abi.ptr(c))
+    for k, v in kw.items():
+        c[k] = v
+    return c
+
+
+STATIC, KINEMATIC, DYNAMIC = 0, 1, 2
+
+
+class RefWorld:
+    """The real reference world (playrho::d2::World{AabbTreeWorld}) behind oracle/ref_harness.cpp."""
+
+    def __init__(self, ids32=False, min_vr=0.0, max_vr=0.0):
+        self.lib = _ref_lib(ids32)
+        self.h = self.lib.ref_world_create(min_vr, max_vr)
+        assert self.h
+
+    def close(self):
+        if self.h:
+            self.lib.ref_world_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _chk(self, r):
+        if r == 0xFFFFFFFF or r == -1:
+            raise RuntimeError(self.lib.ref_last_error(self.h).decode())
+        return r
+
+    @staticmethod
+    def _common(friction, restitution, density, sensor, cat, mask, group):
+        return (friction, restitution, density, int(sensor), cat, mask, group)
+
+    def add_disk(self, radius, loc=(0.0, 0.0), friction=0.2, restitution=0.0, density=0.0,
+                 sensor=False, cat=1, mask=0xFFFF, group=0):
+        return self._chk(self.lib.ref_add_disk(self.h, radius, loc[0], loc[1],
+                                               *self._common(friction, restitution, density, sensor, cat, mask, group)))
+
+    def add_polygon(self, pts, vertex_radius=0.0, friction=0.2, restitution=0.0, density=0.0,
+                    sensor=False, cat=1, mask=0xFFFF, group=0):
+        xy = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1)
+        return self._chk(self.lib.ref_add_polygon(self.h, abi.ptr(xy), len(xy) // 2, vertex_radius,
+                                                  *self._common(friction, restitution, density, sensor, cat, mask, group)))
+
+    def add_box(self, hx, hy, center=(0.0, 0.0), angle=0.0, vertex_radius=0.0, friction=0.2,
+                restitution=0.0, density=0.0, sensor=False, cat=1, mask=0xFFFF, group=0):
+        return self._chk(self.lib.ref_add_box(self.h, hx, hy, center[0], center[1], angle, vertex_radius,
+                                              *self._common(friction, restitution, density, sensor, cat, mask, group)))
+
+    def add_edge(self, p0, p1, vertex_radius=0.0, friction=0.2, restitution=0.0, density=0.0,
+                 sensor=False, cat=1, mask=0xFFFF, group=0):
+        return self._chk(self.lib.ref_add_edge(self.h, p0[0], p0[1], p1[0], p1[1], vertex_radius,
+                                               *self._common(friction, restitution, density, sensor, cat, mask, group)))
+
+    def add_chain(self, pts, vertex_radius=0.0, friction=0.2, restitution=0.0, density=0.0,
+                  sensor=False, cat=1, mask=0xFFFF, group=0):
+        xy = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1)
+        return self._chk(self.lib.ref_add_chain(self.h, abi.ptr(xy), len(xy) // 2, vertex_radius,
+                                                *self._common(friction, restitution, density, sensor, cat, mask, group)))
+
+    def add_body(self, btype, pos=(0.0, 0.0), angle=0.0, vel=(0.0, 0.0), w=0.0, acc=(0.0, 0.0),
+                 aw=0.0, lin_damp=0.0, ang_damp=0.0, bullet=False, fixed_rotation=False,
+                 allow_sleep=True, awake=True, enabled=True, shapes=()):
+        bits = (1 if bullet else 0) | (2 if fixed_rotation else 0) | (0 if allow_sleep else 4) | \
+               (0 if awake else 8) | (0 if enabled else 16)
+        sh = np.asarray(list(shapes), dtype=np.uint32)
+        return self._chk(self.lib.ref_add_body(self.h, btype, pos[0], pos[1], angle, vel[0], vel[1], w,
+                                               acc[0], acc[1], aw, lin_damp, ang_damp, bits,
+                                               abi.ptr(sh) if len(sh) else None, len(sh)))
+
+    def add_revolute(self, body_a, body_b, anchor, enable_motor=False, motor_speed=0.0,
+                     max_motor_torque=0.0, collide_connected=False):
+        return self._chk(self.lib.ref_add_revolute(self.h, body_a, body_b, anchor[0], anchor[1],
+                                                   int(enable_motor), motor_speed, max_motor_torque,
+                                                   int(collide_connected)))
+
+    def step(self, conf):
+        st = abi.one(abi.STEP_STATS)
+        self._chk(self.lib.ref_step(self.h, abi.ptr(conf), abi.ptr(st)))
+        return st[0]
+
+    def step_timed(self, conf, n):
+        st = abi.one(abi.STEP_STATS)
+        secs = self.lib.ref_step_timed(self.h, abi.ptr(conf), n, abi.ptr(st))
+        return secs, st[0]
+
+    def counts(self):
+        c = abi.one(abi.COUNTS)
+        self._chk(self.lib.ref_get_counts(self.h, abi.ptr(c)))
+        return c[0]
+
+    def export_scene(self):
+        """Flattened shapes + bodies + body->shape CSR, the input of pr_create_* / orc_create_*."""
+        n = self.counts()
+        shapes = np.zeros(n["shapes"], abi.SHAPE)
+        children = np.zeros(n["children"], abi.CHILD)
+        verts = np.zeros(max(1, n["vertices"]), abi.VEC2)
+        normals = np.zeros(max(1, n["vertices"]), abi.VEC2)
+        self._chk(self.lib.ref_export_shapes(self.h, abi.ptr(shapes), abi.ptr(children), abi.ptr(verts), abi.ptr(normals)))
+        bodies = self.bodies()
+        offs = np.zeros(n["bodies"] + 1, np.uint32)
+        cap = max(1, int(n["bodies"]) * 4 + 16)
+        ids = np.zeros(cap, np.uint32)
+        k = self.lib.ref_export_body_shapes(self.h, abi.ptr(offs), abi.ptr(ids), cap)
+        assert 0 <= k <= cap
+        return dict(shapes=shapes, children=children, verts=verts[:n["vertices"]], normals=normals[:n["vertices"]],
+                    bodies=bodies, shape_offsets=offs, shape_ids=ids[:k])
+
+    def bodies(self):
+        n = self.counts()
+        bodies = np.zeros(n["bodies"], abi.BODY)
+        self._chk(self.lib.ref_export_bodies(self.h, abi.ptr(bodies)))
+        return bodies
+
+    def proxies(self):
+        n = self.counts()
+        out = np.zeros(max(1, n["proxies"]), abi.PROXY)
+        k = self.lib.ref_export_proxies(self.h, abi.ptr(out), len(out))
+        return out[:k]
+
+    def contacts(self):
+        n = self.counts()
+        cs = np.zeros(max(1, n["contacts"]), abi.CONTACT)
+        ms = np.zeros(max(1, n["contacts"]), abi.MANIFOLD)
+        k = self.lib.ref_export_contacts(self.h, abi.ptr(cs), abi.ptr(ms), len(cs))
+        return cs[:k], ms[:k]
+
+    def inv_dt0(self):
+        return self.lib.ref_get_inv_dt0(self.h)
+
+
+class OracleWorld:
+    """The C++ restatement (oracle/restate)."""
+
+    def __init__(self, scene=None):
+        self.lib = _orc_lib()
+        self.h = self.lib.orc_create()
+        if scene is not None:
+            self.create(scene)
+
+    def close(self):
+        if self.h:
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def create(self, sc):
+        self.lib.orc_create_shapes(self.h, len(sc["shapes"]), abi.ptr(sc["shapes"]), abi.ptr(sc["children"]),
+                                   len(sc["children"]), abi.ptr(sc["verts"]), abi.ptr(sc["normals"]), len(sc["verts"]))
+        self.lib.orc_create_bodies(self.h, len(sc["bodies"]), abi.ptr(sc["bodies"]), abi.ptr(sc["shape_offsets"]),
+                                   abi.ptr(sc["shape_ids"]))
+        if "joints" in sc and len(sc["joints"]):
+            self.lib.orc_create_revolute_joints(self.h, len(sc["joints"]), abi.ptr(sc["joints"]))
+
+    def step(self, conf, order=None):
+        st = abi.one(abi.STEP_STATS)
+        if order is not None:
+            order = np.ascontiguousarray(order, dtype=np.uint32)
+        r = self.lib.orc_step(self.h, abi.ptr(conf), abi.ptr(st), abi.ptr(order) if order is not None else None,
+                              0 if order is None else len(order))
+        if r != 0:
+            raise RuntimeError(self.lib.orc_last_error(self.h).decode())
+        return st[0]
+
+    def counts(self):
+        c = abi.one(abi.COUNTS)
+        self.lib.orc_get_counts(self.h, abi.ptr(c))
+        return c[0]
+
+    def bodies(self):
+        n = self.counts()["bodies"]
+        out = np.zeros(n, abi.BODY)
+        self.lib.orc_get_bodies(self.h, 0, n, abi.ptr(out))
+        return out
+
+    def contacts(self):
+        n = max(1, int(self.counts()["contacts"]))
+        cs, ms = np.zeros(n, abi.CONTACT), np.zeros(n, abi.MANIFOLD)
+        k = C.c_uint32(0)
+        self.lib.orc_get_contacts(self.h, n, abi.ptr(cs), abi.ptr(ms), C.byref(k))
+        return cs[:k.value], ms[:k.value]
+
+    def proxies(self):
+        n = max(1, int(self.counts()["proxies"]))
+        out = np.zeros(n, abi.PROXY)
+        k = C.c_uint32(0)
+        self.lib.orc_get_proxies(self.h, n, abi.ptr(out), C.byref(k))
+        return out[:k.value]
+
+    def load_state(self, bodies, proxies, contacts, manifolds, inv_dt0):
+        r = self.lib.orc_load_state(self.h, len(bodies), abi.ptr(bodies), len(proxies), abi.ptr(proxies),
+                                    len(contacts), abi.ptr(contacts), abi.ptr(manifolds), inv_dt0)
+        if r != 0:
+            raise RuntimeError(self.lib.orc_last_error(self.h).decode())
+
+    def inv_dt0(self):
+        return self.lib.orc_get_inv_dt0(self.h)
+
+
+def bits_equal(a, b):
+    """Bitwise equality of two structured arrays (NaN-safe, -0 != +0)."""
+    return a.shape == b.shape and a.tobytes() == b.tobytes()
+
+
+def diff_fields(a, b, limit=5):
+    """Human-readable list of differing (row, field) for structured arrays."""
+    out = []
+    if a.shape != b.shape:
+        return ["shape %s vs %s" % (a.shape, b.shape)]
+    for name in a.dtype.names:
+        av, bv = a[name], b[name]
+        if av.dtype.names:
+            out += ["%s.%s" % (name, s) for s in diff_fields(av, bv, limit)]
+            continue
+        ai = av.view(np.uint32) if av.dtype.itemsize == 4 else av
+        bi = bv.view(np.uint32) if bv.dtype.itemsize == 4 else bv
+        bad = np.nonzero(ai != bi)[0]
+        for r in bad[:limit]:
+            out.append("row %d %s: %r vs %r" % (r, name, av[r], bv[r]))
+        if len(bad) > limit:
+            out.append("... %d rows differ in %s" % (len(bad), name))
+    return out
