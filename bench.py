@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py -- measures BASELINE.json's metric for the B200-native PlayRho world.
+
+  python bench.py --gpus N --steps K --warmup W [--bodies B] [--workload mixed|disks]
+  python bench.py --impl reference ...      # the reference's own CPU Step on the host cores
+
+One "step" = one Step(world, StepConf) of the hot path (AabbTreeWorld.cpp:2144) over the synthetic
+scene named in config.workload. N=1: BASELINE config 4 shape (1M mixed polygons+disks over tiled
+chain terrain). N>1: independent worlds, one per rank (weak scaling, no data-path collective; NCCL
+only reduces step statistics). Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--bodies", type=int, default=1000000)
+    ap.add_argument("--workload", default="mixed")
+    ap.add_argument("--settle", type=int, default=40, help="untimed steps so that bodies are in contact")
+    ap.add_argument("--ref-bodies", type=int, default=4000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons}
+
+
+def algorithmic_bytes(prof, nv, np_):
+    """SURVEY.md §8(d) B_step from this step's device counters (TOI term omitted while TOI is off)."""
+    n_awake, p, pm = int(prof["n_awake"]), int(prof["p_total"]), int(prof["p_moved"])
+    c, cd, ct = int(prof["c_total"]), int(prof["c_dirty"]), int(prof["c_touching"])
+    vbar = 3.5
+    logp = int(np.ceil(np.log2(max(2, p))))
+    terms = {
+        "a1_a12_bodies": 128 * n_awake,
+        "a2_proxies": int((36 + 8 * vbar) * n_awake + 16 * pm),
+        "a3_bvh": 184 * p if pm else 0,
+        "a4_query": pm * (32 * logp + 16 * 6),
+        "a6_destroy": 32 * c,
+        "a7_narrow": int((184 + 16 * 2 * vbar) * cd),
+        "a8_islands_colour": 24 * (ct + n_awake),
+        "a9_setup": 360 * ct,
+        "a10_velocity": 188 * ct * nv,
+        "a11_position": 112 * ct * np_,
+        "a12_impulses": 16 * ct,
+    }
+    return sum(terms.values()), terms
+
+
+def build_scene(args, seed):
+    import scenes_np
+    if args.workload == "disks":
+        return scenes_np.disks_box(args.bodies, seed=seed)
+    return scenes_np.mixed_fast(args.bodies, seed=seed)
+
+
+def run_reference(args, rank, world_size):
+    """--impl reference: the reference's own Step (oracle/_ref, built from /root/reference) on the host."""
+    if rank != 0:
+        return
+    import refworld
+    import scenes
+    from playrho_b200 import abi  # noqa: F401
+    n = args.ref_bodies
+    ids32 = refworld.have_ref(True)
+    if not refworld.have_ref(ids32):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+        return
+    ref = scenes.mixed(n, ids32=ids32) if args.workload != "disks" else scenes.disks_box(n, ids32=ids32)
+    conf = refworld.default_step_conf(do_toi=0)
+    ref.step_timed(conf, args.settle)
+    ref.step_timed(conf, args.warmup)
+    secs, _ = ref.step_timed(conf, args.steps)
+    nb = int(ref.counts()["bodies"])
+    value = nb * args.steps / secs
+    line = {
+        "impl": "reference", "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s-%d (bounded sample of the %d-body workload; reference Step is O(islands x bodies), SURVEY F4)"
+                   % (args.workload, nb, args.bodies), "toi": False, "step_conf": "default, doToi=false"},
+        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": 1, "kind": "reference",
+                         "sample": "%d bodies, %d steps after %d settle steps, 1 thread (reference is single-threaded)" % (nb, args.steps, args.settle)},
+        "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world_size)
+        return
+    import torch
+    import torch.distributed as dist
+    from playrho_b200 import abi, world as W
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sc = build_scene(args, seed=12345 + rank)
+    nb = len(sc["bodies"])
+    conf = W.default_step_conf(do_toi=0)
+    gw = W.World(sc, device=local_rank, body_capacity=nb + 16, proxy_capacity=nb + 8192, contact_capacity=6 * nb)
+    for _ in range(args.settle):
+        gw.step(conf)
+    for _ in range(max(3, args.warmup)):
+        gw.step(conf)
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---------------- device-resident timed region: K steps, state already in HBM
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    launches, stage_ms, vel_ms, profs = 0, np.zeros(abi.N_STAGES), 0.0, []
+    stats_sum = np.zeros(4, dtype=np.float64)
+    for _ in range(args.steps):
+        st = gw.step(conf)
+        p = gw.profile()
+        launches += int(p["kernel_launches"])
+        stage_ms += p["ms_stage"]
+        profs.append(p.copy())
+        stats_sum += [st["reg"]["islands_found"], st["reg"]["contacts_added"], st["reg"]["proxies_moved"], st["reg"]["bodies_slept"]]
+    barrier()
+    secs = time.perf_counter() - t0
+    # ---------------- end-to-end: host buffers in, host buffers out, every step
+    rows = gw.bodies()
+    ids = np.arange(nb, dtype=np.uint32)
+    pinned_in = torch.from_numpy(rows.view(np.uint8).reshape(-1)).pin_memory()
+    rows_pinned = pinned_in.numpy().view(abi.BODY)
+    e2e_steps = max(2, min(args.steps, 10))
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        gw.set_bodies(ids, rows_pinned)       # H2D: every body row
+        gw.step(conf)
+        out = gw.bodies()                     # D2H: every body row
+        rows_pinned[:] = out
+    barrier()
+    e2e_secs = time.perf_counter() - t1
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    # ---------------- reduce over ranks (max time; stats summed over NVLink)
+    t = torch.tensor([secs, e2e_secs], device="cuda", dtype=torch.float64)
+    s = torch.tensor(np.concatenate([stats_sum, [nb, launches]]), device="cuda", dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    secs, e2e_secs = float(t[0]), float(t[1])
+    total_bodies = float(s[4])
+    if rank == 0:
+        peak, peak_kind = peaks()
+        last = profs[-1]
+        nv, npi = int(conf["reg_velocity_iters"][0]), int(conf["reg_position_iters"][0])
+        bstep, terms = algorithmic_bytes(last, nv, npi)
+        ms_step = 1e3 * secs / args.steps
+        vel_ms = float(stage_ms[5]) / args.steps
+        vel_bytes = terms["a10_velocity"]
+        achieved = (vel_bytes / 1e9) / (vel_ms / 1e3) if vel_ms > 0 else 0.0
+        line = {
+            "metric": "body_steps_per_sec", "value": total_bodies * args.steps / secs, "unit": "body-steps/s",
+            "n_gpus": world_size, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s-%d bodies per GPU (BASELINE config 4 shape: 50%% disks / 50%% 4-8-gons over tiled 256-segment chain terrain)"
+                       % (args.workload, nb), "toi": False, "step_conf": "default (8 vel / 3 pos iters), doToi=false",
+                       "settle_steps": args.settle, "l2": "working set (>1 GB) exceeds the 126 MB L2",
+                       "contacts": int(last["c_total"]), "touching": int(last["c_touching"]), "colors": int(last["n_colors"]),
+                       "islands": int(last["n_islands"]), "awake_bodies": int(last["n_awake"])},
+            "e2e": {"value": total_bodies * e2e_steps / e2e_secs, "unit": "body-steps/s",
+                    "h2d_bytes_per_step": int(nb * abi.BODY.itemsize + 4 * nb), "d2h_bytes_per_step": int(nb * abi.BODY.itemsize),
+                    "ms_per_step": 1e3 * e2e_secs / e2e_steps},
+            "gpu_launches": int(float(s[5])),
+            "roofline": {"bound": "hbm", "kernel": "k_solve_velocity (all colours x %d iterations, incl. per-island checks)" % nv,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
+                         "traffic": None, "algorithmic_bytes_per_step": bstep,
+                         "step_achieved_gbs": (bstep / 1e9) / (ms_step / 1e3), "step_frac": (bstep / 1e9) / (ms_step / 1e3) / peak},
+            "stage_ms_per_step": {n: float(stage_ms[i]) / args.steps for i, n in enumerate(abi.STAGE_NAMES)},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline and world_size == 1:
+            try:
+                import refworld
+                import scenes
+                ids32 = refworld.have_ref(True)
+                if refworld.have_ref(ids32):
+                    n = args.ref_bodies
+                    ref = scenes.mixed(n, ids32=ids32) if args.workload != "disks" else scenes.disks_box(n, ids32=ids32)
+                    rconf = refworld.default_step_conf(do_toi=0)
+                    ref.step_timed(rconf, args.settle)
+                    rs, _ = ref.step_timed(rconf, 20)
+                    rnb = int(ref.counts()["bodies"])
+                    line["cpu_baseline"] = {"value": rnb * 20 / rs, "unit": "body-steps/s", "cores": 1, "kind": "reference",
+                                            "ms_per_step": 1e3 * rs / 20,
+                                            "sample": "reference Step, %s scene at %d bodies, 20 steps after %d settle steps, 1 thread" % (args.workload, rnb, args.settle)}
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": "body-steps/s", "cores": 1, "kind": "reference", "sample": "failed: %s" % e}
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

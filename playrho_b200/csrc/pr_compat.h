@@ -1,0 +1,105 @@
+// pr_compat.h -- one source, two compilations.
+//   nvcc (product):     real CUDA for sm_100a. This is the ONLY thing libplayrho_b200.so contains.
+//   g++ -DPR_HOST_EMUL: a serial "one thread after another" execution of the same kernels, built
+//                       ONLY by tests/ (tests/_emul/) to check host logic and kernel bodies on the
+//                       GPU-less CI box. It is never built into, loaded by, or reachable from the
+//                       product library or the python package (no CPU fallback exists).
+#ifndef PR_COMPAT_H
+#define PR_COMPAT_H
+
+#include <cstdint>
+#include <cstddef>
+#include <cstring>
+#include <cmath>
+
+#ifndef PR_HOST_EMUL
+// ------------------------------------------------------------------ CUDA
+#include <cuda_runtime.h>
+#define PR_HD __host__ __device__ __forceinline__
+#define PR_D __device__ __forceinline__
+#define PR_KERNEL __global__ void
+#define PR_TID (blockIdx.x * blockDim.x + threadIdx.x)
+#define PR_NTHREADS (gridDim.x * blockDim.x)
+typedef cudaStream_t pr_stream_t;
+typedef cudaEvent_t pr_event_t;
+
+#define PR_BLOCK 256
+// one thread per element launch
+#define PR_LAUNCH(kernel, n, stream, ...)                                                          \
+    do {                                                                                           \
+        const unsigned pr_n_ = static_cast<unsigned>(n);                                           \
+        if (pr_n_ > 0) {                                                                           \
+            kernel<<<(pr_n_ + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, stream>>>(__VA_ARGS__);       \
+            pr::count_launch();                                                                    \
+        }                                                                                          \
+    } while (0)
+#define PR_LAUNCH_GRID(kernel, grid, block, stream, ...)                                           \
+    do { kernel<<<grid, block, 0, stream>>>(__VA_ARGS__); pr::count_launch(); } while (0)
+
+#else
+// ------------------------------------------------------------------ host emulation (tests only)
+#include <algorithm>
+#include <cstdlib>
+#define PR_HD inline
+#define PR_D inline
+#define PR_KERNEL void
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
+inline float2 make_float2(float x, float y) { return {x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
+inline uint2 make_uint2(unsigned x, unsigned y) { return {x, y}; }
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return {x, y, z, w}; }
+namespace pr { extern thread_local unsigned emul_tid, emul_nthreads; }
+#define PR_TID (pr::emul_tid)
+#define PR_NTHREADS (pr::emul_nthreads)
+typedef int pr_stream_t;
+typedef int pr_event_t;
+#define PR_LAUNCH(kernel, n, stream, ...)                                                          \
+    do {                                                                                           \
+        const unsigned pr_n_ = static_cast<unsigned>(n);                                           \
+        pr::emul_nthreads = pr_n_;                                                                 \
+        for (unsigned pr_t_ = 0; pr_t_ < pr_n_; ++pr_t_) { pr::emul_tid = pr_t_; kernel(__VA_ARGS__); } \
+        if (pr_n_ > 0) pr::count_launch();                                                         \
+    } while (0)
+template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> inline T atomicAnd(T* p, T v) { T o = *p; *p = o & v; return o; }
+template <class T> inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+template <class T> inline T atomicCAS(T* p, T c, T v) { T o = *p; if (o == c) *p = v; return o; }
+inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
+inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); return f; }
+inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+inline int __clzll(unsigned long long v) { return v ? __builtin_clzll(v) : 64; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffsll(unsigned long long v) { return __builtin_ffsll(static_cast<long long>(v)); }
+inline void __threadfence() {}
+#endif
+
+namespace pr {
+// host+device bit casts
+PR_HD unsigned f2u(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    unsigned u; std::memcpy(&u, &f, 4); return u;
+#endif
+}
+PR_HD float u2f(unsigned u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; std::memcpy(&f, &u, 4); return f;
+#endif
+}
+void count_launch();
+} // namespace pr
+
+#endif // PR_COMPAT_H

@@ -1,0 +1,1321 @@
+// pr_kernels.cuh -- the sm_100a kernels of the step pipeline.
+// One thread per element unless noted; every kernel is HBM/latency bound (no dense contraction,
+// tensor cores unused by design). Kernels avoid early returns so that full-warp primitives
+// (ballot/reduce aggregation of atomics) stay converged.
+#ifndef PR_KERNELS_CUH
+#define PR_KERNELS_CUH
+#include "pr_world.h"
+#include "pr_math.cuh"
+#include "pr_collide.cuh"
+
+namespace pr {
+
+// ------------------------------------------------------------------ warp-aggregated helpers
+#ifndef PR_HOST_EMUL
+// slot index for threads with pred (all 32 lanes of the warp must call this, converged)
+PR_D unsigned warp_append(unsigned* counter, bool pred)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    const unsigned lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (mask) {
+        const int leader = __ffs(mask) - 1;
+        if (static_cast<int>(lane) == leader) base = atomicAdd(counter, static_cast<unsigned>(__popc(mask)));
+        base = __shfl_sync(0xffffffffu, base, leader);
+    }
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+// opportunistic aggregation usable from divergent code
+PR_D unsigned active_append(unsigned* counter)
+{
+    const unsigned active = __activemask();
+    const unsigned lane = threadIdx.x & 31;
+    const int leader = __ffs(active) - 1;
+    unsigned base = 0;
+    if (static_cast<int>(lane) == leader) base = atomicAdd(counter, static_cast<unsigned>(__popc(active)));
+    base = __shfl_sync(active, base, leader);
+    return base + __popc(active & ((1u << lane) - 1u));
+}
+PR_D void warp_add(unsigned* counter, unsigned v)
+{
+    const unsigned s = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(counter, s);
+}
+PR_D void warp_max(unsigned* counter, unsigned v)
+{
+    const unsigned s = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) atomicMax(counter, s);
+}
+PR_D void warp_min(unsigned* counter, unsigned v)
+{
+    const unsigned s = __reduce_min_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) atomicMin(counter, s);
+}
+// per-island atomics with a uniform-label fast path (giant islands would otherwise serialise on one
+// address); `valid` lanes contribute v to slot[label]. All 32 lanes must call.
+PR_D void island_max(unsigned* slot, unsigned label, unsigned v, bool valid)
+{
+    const unsigned l0 = __shfl_sync(0xffffffffu, label, 0);
+    const bool uniform = __all_sync(0xffffffffu, valid && label == l0);
+    if (uniform) {
+        const unsigned s = __reduce_max_sync(0xffffffffu, v);
+        if ((threadIdx.x & 31) == 0) atomicMax(&slot[l0], s);
+    } else if (valid) atomicMax(&slot[label], v);
+}
+PR_D void island_min(unsigned* slot, unsigned label, unsigned v, bool valid)
+{
+    const unsigned l0 = __shfl_sync(0xffffffffu, label, 0);
+    const bool uniform = __all_sync(0xffffffffu, valid && label == l0);
+    if (uniform) {
+        const unsigned s = __reduce_min_sync(0xffffffffu, v);
+        if ((threadIdx.x & 31) == 0) atomicMin(&slot[l0], s);
+    } else if (valid) atomicMin(&slot[label], v);
+}
+#else
+PR_D unsigned warp_append(unsigned* counter, bool pred) { return pred ? atomicAdd(counter, 1u) : 0u; }
+PR_D unsigned active_append(unsigned* counter) { return atomicAdd(counter, 1u); }
+PR_D void warp_add(unsigned* counter, unsigned v) { *counter += v; }
+PR_D void warp_max(unsigned* counter, unsigned v) { if (v > *counter) *counter = v; }
+PR_D void warp_min(unsigned* counter, unsigned v) { if (v < *counter) *counter = v; }
+PR_D void island_max(unsigned* slot, unsigned label, unsigned v, bool valid) { if (valid && v > slot[label]) slot[label] = v; }
+PR_D void island_min(unsigned* slot, unsigned label, unsigned v, bool valid) { if (valid && v < slot[label]) slot[label] = v; }
+#endif
+
+// ------------------------------------------------------------------ small accessors
+PR_D bool f_speedable(unsigned f) { return (f & PR_BODY_VELOCITY) != 0; }
+PR_D bool f_accelerable(unsigned f) { return (f & PR_BODY_ACCELERATION) != 0; }
+PR_D bool f_awake(unsigned f) { return (f & PR_BODY_AWAKE) != 0; }
+PR_D bool f_enabled(unsigned f) { return (f & PR_BODY_ENABLED) != 0; }
+PR_D ProxyView child_view(const DV& d, unsigned cg)
+{
+    ProxyView v;
+    v.radius = d.ch_radius[cg]; v.count = d.ch_count[cg];
+    const unsigned off = d.ch_voff[cg];
+    v.v = d.vtx + off; v.n = d.nrm + off;
+    return v;
+}
+PR_D Pos pos_from4(float4 p) { Pos r; r.l = v2(p.x, p.y); r.a = p.z; return r; }
+
+// ------------------------------------------------------------------ bodies: AoS rows <-> SoA
+PR_KERNEL k_put_bodies(DV d, unsigned n, unsigned firstId, const unsigned* ids, const pr_body* rows, unsigned isUpdate)
+{
+    const unsigned i = PR_TID;
+    if (i < n) {
+        const unsigned id = ids ? ids[i] : firstId + i;
+        const pr_body r = rows[i];
+        if (isUpdate) { // SetBody transform-change path, AabbTreeWorld.cpp:2723-2795
+            const float4 o = d.b_xf[id];
+            if (o.x != r.xf_px || o.y != r.xf_py || o.z != r.xf_qc || o.w != r.xf_qs) { d.b_sync[id] = 1u; d.b_moved[id] = 1u; }
+        }
+        d.b_xf[id] = make_float4(r.xf_px, r.xf_py, r.xf_qc, r.xf_qs);
+        d.b_pos0[id] = make_float4(r.pos0_x, r.pos0_y, r.pos0_a, r.alpha0);
+        d.b_pos1[id] = make_float4(r.pos1_x, r.pos1_y, r.pos1_a, r.under_active_time);
+        d.b_vel[id] = make_float4(r.vel_x, r.vel_y, r.vel_w, 0.0f);
+        d.b_acc[id] = make_float4(r.acc_x, r.acc_y, r.acc_w, 0.0f);
+        d.b_mass[id] = make_float4(r.inv_mass, r.inv_rot_i, r.lin_damp, r.ang_damp);
+        d.b_lc[id] = make_float2(r.lc_x, r.lc_y);
+        d.b_flags[id] = r.flags;
+    }
+}
+
+PR_KERNEL k_get_bodies(DV d, unsigned first, unsigned n, pr_body* rows)
+{
+    const unsigned i = PR_TID;
+    if (i < n) {
+        const unsigned id = first + i;
+        pr_body r;
+        const float4 xf = d.b_xf[id], p0 = d.b_pos0[id], p1 = d.b_pos1[id], v = d.b_vel[id], a = d.b_acc[id], m = d.b_mass[id];
+        const float2 lc = d.b_lc[id];
+        r.xf_px = xf.x; r.xf_py = xf.y; r.xf_qc = xf.z; r.xf_qs = xf.w;
+        r.pos0_x = p0.x; r.pos0_y = p0.y; r.pos0_a = p0.z; r.alpha0 = p0.w;
+        r.pos1_x = p1.x; r.pos1_y = p1.y; r.pos1_a = p1.z; r.under_active_time = p1.w;
+        r.lc_x = lc.x; r.lc_y = lc.y;
+        r.vel_x = v.x; r.vel_y = v.y; r.vel_w = v.z;
+        r.acc_x = a.x; r.acc_y = a.y; r.acc_w = a.z;
+        r.inv_mass = m.x; r.inv_rot_i = m.y; r.lin_damp = m.z; r.ang_damp = m.w;
+        r.flags = d.b_flags[id];
+        rows[i] = r;
+    }
+}
+
+// ------------------------------------------------------------------ a2: proxy AABB + fat-box policy
+struct Box { float minx, miny, maxx, maxy; };
+PR_D Box box_from4(float4 f) { Box b; b.minx = f.x; b.miny = f.y; b.maxx = f.z; b.maxy = f.w; return b; }
+PR_D float4 box_to4(Box b) { return make_float4(b.minx, b.miny, b.maxx, b.maxy); }
+// ComputeAABB(proxy, xf0, xf1), AABB.cpp:51-62 (+ Interval::Include, GetFattenedAABB(vertexRadius))
+PR_D Box compute_aabb(const ProxyView& p, Xf xf0, Xf xf1)
+{
+    Box r; r.minx = PR_INF; r.miny = PR_INF; r.maxx = -PR_INF; r.maxy = -PR_INF;
+    for (unsigned i = 0; i < p.count; ++i) {
+        const float2 v = p.vertex(i);
+        const float2 a = transform(v, xf0);
+        r.minx = stdmin(a.x, r.minx); r.maxx = stdmax(a.x, r.maxx); r.miny = stdmin(a.y, r.miny); r.maxy = stdmax(a.y, r.maxy);
+        const float2 b = transform(v, xf1);
+        r.minx = stdmin(b.x, r.minx); r.maxx = stdmax(b.x, r.maxx); r.miny = stdmin(b.y, r.miny); r.maxy = stdmax(b.y, r.maxy);
+    }
+    r.minx -= p.radius; r.maxx += p.radius; r.miny -= p.radius; r.maxy += p.radius;
+    return r;
+}
+// GetFattenedAABB + GetDisplacedAABB, detail/AABB.hpp:305-320; Interval::Expand adds d to min if d<0 else max
+PR_D Box fatten_displace(Box a, float ext, float2 dsp)
+{
+    a.minx -= ext; a.maxx += ext; a.miny -= ext; a.maxy += ext;
+    if (dsp.x < 0.0f) a.minx += dsp.x; else a.maxx += dsp.x;
+    if (dsp.y < 0.0f) a.miny += dsp.y; else a.maxy += dsp.y;
+    return a;
+}
+PR_D bool box_contains(Box a, Box b) { return a.minx <= b.minx && a.maxx >= b.maxx && a.miny <= b.miny && a.maxy >= b.maxy; }
+// closed-interval overlap: min(maxs) >= max(mins) per axis, Interval.hpp IsIntersecting
+PR_D bool box_overlap(Box a, Box b)
+{
+    return (stdmin(a.maxx, b.maxx) >= stdmax(a.minx, b.minx)) && (stdmin(a.maxy, b.maxy) >= stdmax(a.miny, b.miny));
+}
+
+// CreateProxies (AabbTreeWorld.cpp:557-579) for proxies [first, first+n): fat box + queue for FindContacts
+PR_KERNEL k_create_proxy_aabbs(DV d, pr_step_conf conf, unsigned first, unsigned n)
+{
+    const unsigned i = PR_TID;
+    if (i < n) {
+        const unsigned px = first + i;
+        const unsigned body = d.p_body[px];
+        const Xf xf1 = xf_from4(d.b_xf[body]);
+        const Xf xf0 = get_xf(pos_from4(d.b_pos0[body]), d.b_lc[body]);
+        const float2 dsp = conf.displace_multiplier * (xf1.p - xf0.p);
+        const Box a = fatten_displace(compute_aabb(child_view(d, d.p_cg[px]), xf0, xf1), conf.aabb_extension, dsp);
+        d.p_fat[px] = box_to4(a);
+        d.p_moved[px] = 1u;
+        d.q_list[d.cnt->nQueue + i] = px; // host bumps nQueue afterwards
+    }
+}
+
+// Synchronize (AabbTreeWorld.cpp:2564-2585) for every proxy whose body is flagged in b_sync
+PR_KERNEL k_sync_proxies(DV d, pr_step_conf conf, unsigned nProxies)
+{
+    const unsigned px = PR_TID;
+    bool moved = false;
+    if (px < nProxies) {
+        const unsigned body = d.p_body[px];
+        if (d.b_sync[body]) {
+            const Xf xf1 = xf_from4(d.b_xf[body]);
+            const Xf xf0 = get_xf(pos_from4(d.b_pos0[body]), d.b_lc[body]);
+            const Box a = compute_aabb(child_view(d, d.p_cg[px]), xf0, xf1);
+            if (!box_contains(box_from4(d.p_fat[px]), a)) {
+                const float2 dsp = conf.displace_multiplier * (xf1.p - xf0.p);
+                d.p_fat[px] = box_to4(fatten_displace(a, conf.aabb_extension, dsp));
+                moved = (d.p_moved[px] == 0u); // queue once
+                d.p_moved[px] = 1u;
+                if (!moved) atomicAdd(&d.cnt->proxiesMoved, 1u); // re-moved while still queued: count, do not re-queue
+            }
+        }
+    }
+    const unsigned slot = warp_append(&d.cnt->nQueue, moved);
+    if (moved) { d.q_list[slot] = px; }
+    warp_add(&d.cnt->proxiesMoved, moved ? 1u : 0u);
+}
+
+PR_KERNEL k_clear_queue_flags(DV d, unsigned nQueue)
+{
+    const unsigned i = PR_TID;
+    if (i < nQueue) d.p_moved[d.q_list[i]] = 0u;
+}
+
+// ------------------------------------------------------------------ a6: DestroyContacts
+PR_D void body_set_awake(const DV& d, unsigned b)
+{ // Body::SetAwake, Body.cpp:163-171
+    if (f_speedable(d.b_flags[b])) {
+        atomicOr(&d.b_flags[b], static_cast<unsigned>(PR_BODY_AWAKE));
+        reinterpret_cast<float*>(&d.b_pos1[b])[3] = 0.0f; // underActiveTime
+    }
+}
+PR_D void manifold_clear(const DV& d, unsigned id)
+{
+    d.m0[id] = make_float4(0, 0, 0, 0); d.m1[id] = make_float4(0, 0, 0, 0); d.m2[id] = make_float4(0, 0, 0, 0);
+    d.m3[id] = make_uint4(PR_CF_DEFAULT, PR_CF_DEFAULT, 0u, 0u);
+}
+// keep[i] = 1 if the two FAT leaf boxes still overlap (AabbTreeWorld.cpp:2290-2304), else InternalDestroy (:2245)
+PR_KERNEL k_destroy_test(DV d, unsigned nOrder, unsigned* keep)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        const uint2 px = d.c_px[id];
+        const bool ov = box_overlap(box_from4(d.p_fat[px.x]), box_from4(d.p_fat[px.y]));
+        keep[i] = ov ? 1u : 0u;
+        if (!ov) {
+            const uint4 ab = d.c_ab[id];
+            const unsigned flags = d.c_flags[id];
+            if (d.m3[id].w > 0u && !(flags & PR_CONTACT_SENSOR)) { body_set_awake(d, ab.x); body_set_awake(d, ab.y); }
+            d.c_flags[id] = PR_CONTACT_DESTROYED;
+            d.c_key[id] = ~0ull;
+            manifold_clear(d, id);
+        }
+    }
+}
+// stable compaction: kept ids to newOrder[pos[i]]; destroyed ids pushed on the free stack in order (ObjectPool::Free)
+PR_KERNEL k_destroy_compact(DV d, unsigned nOrder, const unsigned* keep, const unsigned* pos, unsigned* newOrder, unsigned nFree)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        if (keep[i]) newOrder[pos[i]] = id;
+        else d.c_free[nFree + (i - pos[i])] = id;
+    }
+}
+
+// ------------------------------------------------------------------ contact-key hash set
+PR_D unsigned long long mix64(unsigned long long k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return k;
+}
+PR_D void hash_insert(const DV& d, unsigned long long key)
+{
+    unsigned h = static_cast<unsigned>(mix64(key)) & d.ht_mask;
+    for (unsigned probe = 0; probe <= d.ht_mask; ++probe) {
+        const unsigned long long old = atomicCAS(&d.ht_keys[h], ~0ull, key);
+        if (old == ~0ull || old == key) return;
+        h = (h + 1u) & d.ht_mask;
+    }
+    atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_HASH_FULL));
+}
+PR_D bool hash_contains(const DV& d, unsigned long long key)
+{
+    unsigned h = static_cast<unsigned>(mix64(key)) & d.ht_mask;
+    for (unsigned probe = 0; probe <= d.ht_mask; ++probe) {
+        const unsigned long long cur = d.ht_keys[h];
+        if (cur == key) return true;
+        if (cur == ~0ull) return false;
+        h = (h + 1u) & d.ht_mask;
+    }
+    return false;
+}
+PR_KERNEL k_hash_fill(DV d, unsigned nOrder)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) hash_insert(d, d.c_key[d.c_order[i]]);
+}
+
+// ------------------------------------------------------------------ a7: narrowphase Update
+PR_D void store_manifold(const DV& d, unsigned id, const Mf& m)
+{
+    d.m0[id] = make_float4(m.ln.x, m.ln.y, m.lp.x, m.lp.y);
+    d.m1[id] = make_float4(m.p0.x, m.p0.y, m.p1.x, m.p1.y);
+    d.m2[id] = make_float4(m.jn0, m.jt0, m.jn1, m.jt1);
+    d.m3[id] = make_uint4(m.cf0, m.cf1, m.type, m.count);
+}
+// Update(ContactID), AabbTreeWorld.cpp:2587-2721: collide, carry impulses over by ContactFeature
+// equality else nearest old point, touching flag. One thread per contact of order[start, start+n).
+PR_KERNEL k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n, unsigned useMoved)
+{
+    const unsigned i = PR_TID;
+    bool updated = false;
+    if (i < n) {
+        const unsigned id = d.c_order[start + i];
+        unsigned flags = d.c_flags[id];
+        const uint4 ab = d.c_ab[id];
+        bool dirty = (flags & PR_CONTACT_DIRTY) != 0;
+        if (useMoved) dirty = dirty || (d.b_moved[ab.x] | d.b_moved[ab.y]) != 0u;
+        if (dirty) {
+            updated = true;
+            const bool oldTouching = (flags & PR_CONTACT_TOUCHING) != 0;
+            bool newTouching = false;
+            if (flags & PR_CONTACT_SENSOR) {
+                atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_SENSOR)); // GJK TestOverlap path: TOI milestone
+                manifold_clear(d, id);
+            } else {
+                const Xf xfA = xf_from4(d.b_xf[ab.x]), xfB = xf_from4(d.b_xf[ab.y]);
+                Mf nm = collide_shapes(child_view(d, ab.z), xfA, child_view(d, ab.w), xfB, conf.linear_slop, conf.max_circles_ratio);
+                const uint4 o3 = d.m3[id];
+                const unsigned oldCount = o3.w, newCount = nm.count;
+                newTouching = newCount > 0u;
+                if (newCount > 0u && oldCount > 0u) {
+                    const float4 o1 = d.m1[id], o2 = d.m2[id];
+                    const unsigned ocf[2] = {o3.x, o3.y};
+                    const float ojn[2] = {o2.x, o2.z}, ojt[2] = {o2.y, o2.w};
+                    const float2 op[2] = {v2(o1.x, o1.y), v2(o1.z, o1.w)};
+                    const unsigned ncf[2] = {nm.cf0, nm.cf1};
+                    const float2 np[2] = {nm.p0, nm.p1};
+                    float njn[2] = {0.0f, 0.0f}, njt[2] = {0.0f, 0.0f};
+                    bool found[2] = {false, newCount < 2u};
+                    for (unsigned a = 0; a < newCount; ++a) {
+                        for (unsigned b = 0; b < oldCount; ++b) {
+                            if (ncf[a] == ocf[b]) { found[a] = true; njn[a] = ojn[b]; njt[a] = ojt[b]; break; }
+                        }
+                    }
+                    for (unsigned a = 0; a < newCount; ++a) {
+                        if (!found[a]) {
+                            float least = PR_INF;
+                            for (unsigned b = 0; b < oldCount; ++b) {
+                                const float sq = magsq(op[b] - np[a]);
+                                if (least > sq) { least = sq; njn[a] = ojn[b]; njt[a] = ojt[b]; }
+                            }
+                        }
+                    }
+                    nm.jn0 = njn[0]; nm.jt0 = njt[0]; nm.jn1 = njn[1]; nm.jt1 = njt[1];
+                }
+                store_manifold(d, id, nm);
+            }
+            flags &= ~static_cast<unsigned>(PR_CONTACT_DIRTY);
+            if (!oldTouching && newTouching) flags |= PR_CONTACT_TOUCHING;
+            else if (oldTouching && !newTouching) flags &= ~static_cast<unsigned>(PR_CONTACT_TOUCHING);
+            d.c_flags[id] = flags;
+        }
+    }
+    warp_add(&d.cnt->contactsUpdated, updated ? 1u : 0u);
+}
+
+// ------------------------------------------------------------------ a3: LBVH (Morton + Karras build + refit)
+PR_KERNEL k_bvh_bounds(DV d, unsigned nProxies)
+{
+    const unsigned i = PR_TID;
+    unsigned cx0 = 0xFFFFFFFFu, cy0 = 0xFFFFFFFFu, cx1 = 0u, cy1 = 0u;
+    if (i < nProxies) {
+        const float4 f = d.p_fat[i];
+        const float cx = (f.x + f.z) * 0.5f, cy = (f.y + f.w) * 0.5f;
+        cx0 = cx1 = float_flip(cx); cy0 = cy1 = float_flip(cy);
+    }
+    warp_min(&d.cnt->boundsMinX, cx0); warp_min(&d.cnt->boundsMinY, cy0);
+    warp_max(&d.cnt->boundsMaxX, cx1); warp_max(&d.cnt->boundsMaxY, cy1);
+}
+PR_D unsigned expand_bits16(unsigned v)
+{
+    v &= 0xFFFFu;
+    v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+PR_KERNEL k_bvh_morton(DV d, unsigned nProxies)
+{
+    const unsigned i = PR_TID;
+    if (i < nProxies) {
+        const float x0 = float_unflip(d.cnt->boundsMinX), y0 = float_unflip(d.cnt->boundsMinY);
+        const float x1 = float_unflip(d.cnt->boundsMaxX), y1 = float_unflip(d.cnt->boundsMaxY);
+        const float4 f = d.p_fat[i];
+        const float cx = (f.x + f.z) * 0.5f, cy = (f.y + f.w) * 0.5f;
+        const float sx = (x1 > x0) ? 65535.0f / (x1 - x0) : 0.0f, sy = (y1 > y0) ? 65535.0f / (y1 - y0) : 0.0f;
+        const unsigned qx = static_cast<unsigned>(fminf(fmaxf((cx - x0) * sx, 0.0f), 65535.0f));
+        const unsigned qy = static_cast<unsigned>(fminf(fmaxf((cy - y0) * sy, 0.0f), 65535.0f));
+        d.bv_code[i] = expand_bits16(qx) | (expand_bits16(qy) << 1);
+        d.bv_idx[i] = i;
+    }
+}
+// common-prefix length of sorted keys i and j (index as tie-break), -1 if j out of range
+PR_D int bvh_delta(const unsigned* codes, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const unsigned a = codes[i], b = codes[j];
+    if (a == b) return 32 + __clz(static_cast<unsigned>(i) ^ static_cast<unsigned>(j));
+    return __clz(a ^ b);
+}
+// Karras 2012: one thread per internal node i in [0, n-1)
+PR_KERNEL k_bvh_build(DV d, unsigned nLeaves, const unsigned* codes)
+{
+    const int i = static_cast<int>(PR_TID);
+    const int n = static_cast<int>(nLeaves);
+    if (i < n - 1) {
+        const int dir = (bvh_delta(codes, n, i, i + 1) - bvh_delta(codes, n, i, i - 1)) >= 0 ? 1 : -1;
+        const int dmin = bvh_delta(codes, n, i, i - dir);
+        int lmax = 2;
+        while (bvh_delta(codes, n, i, i + lmax * dir) > dmin) lmax *= 2;
+        int l = 0;
+        for (int t = lmax / 2; t >= 1; t /= 2) if (bvh_delta(codes, n, i, i + (l + t) * dir) > dmin) l += t;
+        const int j = i + l * dir;
+        const int dnode = bvh_delta(codes, n, i, j);
+        int s = 0;
+        for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+            if (bvh_delta(codes, n, i, i + (s + t) * dir) > dnode) s += t;
+            if (t == 1) break;
+        }
+        const int gamma = i + s * dir + (dir < 0 ? -1 : 0);
+        const int lo = (i < j) ? i : j, hi = (i < j) ? j : i;
+        const unsigned left = (lo == gamma) ? (static_cast<unsigned>(gamma) | LEAF_BIT) : static_cast<unsigned>(gamma);
+        const unsigned right = (hi == gamma + 1) ? (static_cast<unsigned>(gamma + 1) | LEAF_BIT) : static_cast<unsigned>(gamma + 1);
+        d.bv_left[i] = left; d.bv_right[i] = right;
+        if (left & LEAF_BIT) d.bv_lparent[left & ~LEAF_BIT] = i; else d.bv_parent[left] = i;
+        if (right & LEAF_BIT) d.bv_lparent[right & ~LEAF_BIT] = i; else d.bv_parent[right] = i;
+        d.bv_visit[i] = 0u;
+        if (i == 0) d.bv_parent[0] = INVALID;
+    }
+}
+PR_D Box bvh_child_box(const DV& d, unsigned child, const unsigned* sortedIdx)
+{
+    if (child & LEAF_BIT) return box_from4(d.p_fat[sortedIdx[child & ~LEAF_BIT]]);
+#ifndef PR_HOST_EMUL
+    return box_from4(__ldcg(&d.bv_box[child])); // written by another thread this launch: bypass L1
+#else
+    return box_from4(d.bv_box[child]);
+#endif
+}
+// bottom-up refit: one thread per leaf; the second thread to arrive at a node computes its box
+PR_KERNEL k_bvh_refit(DV d, unsigned nLeaves, const unsigned* sortedIdx)
+{
+    const unsigned i = PR_TID;
+    if (i < nLeaves && nLeaves > 1u) {
+        unsigned node = d.bv_lparent[i];
+        while (node != INVALID) {
+            __threadfence();
+            const unsigned prev = atomicAdd(&d.bv_visit[node], 1u);
+            if (prev == 0u) break;
+            const Box a = bvh_child_box(d, d.bv_left[node], sortedIdx), b = bvh_child_box(d, d.bv_right[node], sortedIdx);
+            Box u; u.minx = fminf(a.minx, b.minx); u.miny = fminf(a.miny, b.miny); u.maxx = fmaxf(a.maxx, b.maxx); u.maxy = fmaxf(a.maxy, b.maxy);
+            d.bv_box[node] = box_to4(u);
+            node = d.bv_parent[node];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ a4 + a5 (filter part): overlap query
+PR_D bool filters_allow(unsigned fa, int ga, unsigned fb, int gb)
+{ // ShouldCollide(Filter, Filter), Filter.hpp
+    if (ga == gb && ga != 0) return ga > 0;
+    const unsigned catA = fa & 0xFFFFu, maskA = fa >> 16, catB = fb & 0xFFFFu, maskB = fb >> 16;
+    return (maskA & catB) != 0u && (catA & maskB) != 0u;
+}
+PR_D void query_emit(const DV& d, unsigned q, unsigned o, unsigned capPairs)
+{
+    if (o == q) return;
+    const unsigned bq = d.p_body[q], bo = d.p_body[o];
+    if (bq == bo) return;
+    const unsigned tq = d.p_tree[q], to = d.p_tree[o];
+    if (d.p_moved[o] && to < tq) return; // both queued: the smaller tree id emits (unique, like sort+unique :746-749)
+    const unsigned fq = d.b_flags[bq], fo = d.b_flags[bo];
+    if (!(f_accelerable(fq) || f_accelerable(fo))) return; // EitherIsAccelerable :474
+    const unsigned sq = d.p_shape[q], so = d.p_shape[o];
+    if (!filters_allow(d.sh_filter[sq], d.sh_group[sq], d.sh_filter[so], d.sh_group[so])) return;
+    const bool qMin = tq < to;
+    const unsigned long long key = (static_cast<unsigned long long>(qMin ? tq : to) << 32) | (qMin ? to : tq);
+    if (hash_contains(d, key)) return; // contact already exists (:2485-2489)
+    const unsigned slot = active_append(&d.cnt->nPairs);
+    if (slot < capPairs) { d.np_key[slot] = key; d.np_px[slot] = qMin ? make_uint2(q, o) : make_uint2(o, q); }
+    else atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_PAIR_OVERFLOW));
+}
+// FindContacts (AabbTreeWorld.cpp:709-751): one thread per QUEUED proxy walks the LBVH
+PR_KERNEL k_bvh_query(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs)
+{
+    const unsigned t = PR_TID;
+    if (t < nQueue) {
+        const unsigned q = d.q_list[t];
+        const Box qb = box_from4(d.p_fat[q]);
+        if (nLeaves == 1u) {
+            // single leaf: nothing to pair with
+        } else {
+            unsigned stack[64];
+            int sp = 0;
+            stack[sp++] = 0u;
+            while (sp > 0) {
+                const unsigned node = stack[--sp];
+                const unsigned ch[2] = {d.bv_left[node], d.bv_right[node]};
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (ch[c] & LEAF_BIT) {
+                        const unsigned o = sortedIdx[ch[c] & ~LEAF_BIT];
+                        if (box_overlap(qb, box_from4(d.p_fat[o]))) query_emit(d, q, o, capPairs);
+                    } else if (box_overlap(qb, box_from4(d.bv_box[ch[c]]))) {
+                        if (sp < 64) stack[sp++] = ch[c];
+                        else atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_STACK));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// AddContacts (AabbTreeWorld.cpp:2423-2547), creation part: sorted pair i gets its ContactID from the LIFO
+// free stack else by append (ObjectPool::Allocate), is appended to m_contacts in key order.
+PR_KERNEL k_create_contacts(DV d, unsigned nNew, const unsigned long long* keys, const unsigned* srcIdx,
+                            unsigned nOrder, unsigned nFree, unsigned poolSize)
+{
+    const unsigned i = PR_TID;
+    if (i < nNew) {
+        const unsigned id = (i < nFree) ? d.c_free[nFree - 1u - i] : poolSize + (i - nFree);
+        const unsigned long long key = keys[i];
+        const uint2 px = d.np_px[srcIdx[i]];
+        const unsigned bA = d.p_body[px.x], bB = d.p_body[px.y];
+        const unsigned sA = d.p_shape[px.x], sB = d.p_shape[px.y];
+        const float4 matA = d.sh_mat[sA], matB = d.sh_mat[sB];
+        const unsigned fA = d.b_flags[bA], fB = d.b_flags[bB];
+        unsigned flags = PR_CONTACT_ENABLED | PR_CONTACT_DIRTY; // Contact ctor, Contact.hpp:343-349
+        if ((fA & PR_BODY_IMPENETRABLE) || (fB & PR_BODY_IMPENETRABLE)) flags |= PR_CONTACT_IMPENETRABLE;
+        const bool sensor = (matA.z != 0.0f) || (matB.z != 0.0f);
+        if (sensor) flags |= PR_CONTACT_SENSOR;
+        d.c_key[id] = key;
+        d.c_ab[id] = make_uint4(bA, bB, d.p_cg[px.x], d.p_cg[px.y]);
+        d.c_px[id] = px;
+        d.c_ids[id] = make_uint4(sA, d.p_child[px.x], sB, d.p_child[px.y]);
+        // MixFriction = sqrt(f1*f2), MixRestitution = max, Contact.hpp:57-69
+        d.c_mat[id] = make_float4(sqrtf(matA.x * matB.x), (matA.y > matB.y) ? matA.y : matB.y, 0.0f, 1.0f);
+        d.c_flags[id] = flags;
+        manifold_clear(d, id);
+        d.c_order[nOrder + i] = id;
+        hash_insert(d, key);
+        if (!sensor) {
+            if (f_speedable(fA)) atomicOr(&d.b_flags[bA], static_cast<unsigned>(PR_BODY_AWAKE));
+            if (f_speedable(fB)) atomicOr(&d.b_flags[bB], static_cast<unsigned>(PR_BODY_AWAKE));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ a8: islands (parallel union-find)
+PR_D unsigned uf_find(unsigned* parent, unsigned x)
+{
+    unsigned p = parent[x];
+    while (p != x) {
+        const unsigned gp = parent[p];
+        if (gp != p) parent[x] = gp; // path halving (benign race: always an ancestor)
+        x = p; p = gp;
+    }
+    return x;
+}
+PR_D void uf_union(unsigned* parent, unsigned a, unsigned b)
+{
+    for (;;) {
+        a = uf_find(parent, a); b = uf_find(parent, b);
+        if (a == b) return;
+        if (a > b) { const unsigned t = a; a = b; b = t; } // smaller id becomes the root => root = min member
+        const unsigned old = atomicCAS(&parent[b], b, a);
+        if (old == b) return;
+    }
+}
+PR_KERNEL k_isl_init(DV d, unsigned nBodies, unsigned velIters, unsigned posIters)
+{
+    const unsigned i = PR_TID;
+    if (i < nBodies) {
+        const unsigned f = d.b_flags[i];
+        d.b_island[i] = (f_enabled(f) && f_speedable(f)) ? i : INVALID;
+        d.isl_state[i] = 0u; d.isl_velIters[i] = velIters; d.isl_posIters[i] = posIters;
+        d.isl_inc[i] = 0u; d.isl_maxInc[i] = 0u;
+        d.isl_sep[i] = float_flip(PR_INF); d.isl_minSep[i] = float_flip(PR_INF); d.isl_minUA[i] = float_flip(PR_INF);
+        d.isl_nbodies[i] = 0u;
+        d.b_cmask[i] = 0ull; d.b_claim[i] = ~0ull;
+        d.b_sync[i] = 0u;
+    }
+}
+PR_D bool contact_solvable(unsigned flags)
+{ // AddContactsToIsland, AabbTreeWorld.cpp:1436-1441
+    return (flags & PR_CONTACT_ENABLED) && (flags & PR_CONTACT_TOUCHING) && !(flags & PR_CONTACT_SENSOR);
+}
+PR_KERNEL k_isl_union(DV d, unsigned nOrder)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        if (contact_solvable(d.c_flags[id])) {
+            const uint4 ab = d.c_ab[id];
+            if (d.b_island[ab.x] != INVALID && d.b_island[ab.y] != INVALID) uf_union(d.b_island, ab.x, ab.y);
+        }
+    }
+}
+PR_KERNEL k_isl_flatten(DV d, unsigned nBodies)
+{
+    const unsigned i = PR_TID;
+    if (i < nBodies) {
+        unsigned r = INVALID;
+        if (d.b_island[i] != INVALID) {
+            r = uf_find(d.b_island, i);
+            const unsigned f = d.b_flags[i];
+            if (f_awake(f) && f_enabled(f)) atomicOr(&d.isl_state[r], static_cast<unsigned>(ISL_ACTIVE)); // SolveReg seed test :1496
+        }
+        d.b_root[i] = r; // separate array: parent[] is still being path-halved by other threads
+    }
+}
+// a1: GetBodyConstraint (BodyConstraint.hpp:154) = Cap(GetVelocity(body,h)) for bodies of active islands;
+// also SolveRegIslandViaGS's pos0 <- pos1 (:1574) and AddToIsland's SetAwakeFlag (:1400).
+PR_KERNEL k_isl_prepare(DV d, unsigned nBodies, pr_step_conf conf)
+{
+    const unsigned i = PR_TID;
+    unsigned isRoot = 0u, isActive = 0u;
+    if (i < nBodies) {
+        const unsigned r = d.b_root[i];
+        const bool active = (r != INVALID) && (d.isl_state[r] & ISL_ACTIVE);
+        d.b_island[i] = active ? r : INVALID; // from here on b_island is the label of this step's solve
+        const float4 p1 = d.b_pos1[i];
+        float4 v = d.b_vel[i];
+        const unsigned f = d.b_flags[i];
+        if (active) {
+            isActive = 1u; isRoot = (r == i) ? 1u : 0u;
+            if (!f_awake(f)) d.b_flags[i] = f | PR_BODY_AWAKE;
+            const float4 p0 = d.b_pos0[i];
+            d.b_pos0[i] = make_float4(p1.x, p1.y, p1.z, p0.w);
+            atomicAdd(&d.isl_nbodies[r], 1u);
+            d.b_sync[i] = 1u;
+        }
+        if (active || !f_speedable(f)) {
+            const float h = conf.delta_time;
+            if (f_accelerable(f)) { // GetVelocity(body, h), Body.cpp:290-310
+                const float4 a = d.b_acc[i], m = d.b_mass[i];
+                float2 l = v2(v.x, v.y) + h * v2(a.x, a.y);
+                float w = v.z + h * a.z;
+                l = vdiv(l, 1 + h * m.z);
+                w /= (1 + h * m.w);
+                v.x = l.x; v.y = l.y; v.z = w;
+            }
+            // Cap, Velocity.cpp:27-46
+            const float2 tr = h * v2(v.x, v.y);
+            const float lsq = magsq(tr);
+            if (lsq > square(conf.max_translation)) { const float ratio = conf.max_translation / sqrtf(lsq); v.x *= ratio; v.y *= ratio; }
+            const float absRot = fabsf(h * v.z);
+            if (absRot > conf.max_rotation) { const float ratio = conf.max_rotation / absRot; v.z *= ratio; }
+        }
+        d.s_vel[i] = make_float4(v.x, v.y, v.z, 0.0f);
+        d.s_pos[i] = make_float4(p1.x, p1.y, p1.z, 0.0f);
+    }
+    warp_add(&d.cnt->islandsFound, isRoot);
+    warp_add(&d.cnt->nAwake, isActive);
+}
+// which contacts become constraints this step: solvable and in an ACTIVE island
+PR_KERNEL k_mark_constraints(DV d, unsigned nOrder, unsigned* mark)
+{
+    const unsigned i = PR_TID;
+    unsigned touching = 0u;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        unsigned m = 0u;
+        const unsigned flags = d.c_flags[id];
+        if (flags & PR_CONTACT_TOUCHING) touching = 1u;
+        if (contact_solvable(flags)) {
+            const uint4 ab = d.c_ab[id];
+            const unsigned rA = d.b_island[ab.x], rB = d.b_island[ab.y];
+            m = (rA != INVALID || rB != INVALID) ? 1u : 0u;
+        }
+        mark[i] = m;
+    }
+    warp_add(&d.cnt->nTouching, touching);
+}
+PR_KERNEL k_gather_constraints(DV d, unsigned nOrder, const unsigned* mark, const unsigned* pos)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder && mark[i]) { d.k_contact[pos[i]] = d.c_order[i]; d.k_color[pos[i]] = COLOR_UNSET; }
+}
+
+// ------------------------------------------------------------------ deterministic graph colouring
+// Jones-Plassmann rounds with hashed priorities; the winner takes the lowest colour free on both
+// of its mass-carrying bodies (64-bit masks). Bodies with invMass == invRotI == 0 never change in
+// the solver and are excluded from conflicts. Result depends only on contact ids and list order.
+PR_D unsigned hash32(unsigned x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
+PR_D bool body_dyn(const DV& d, unsigned b) { const float4 m = d.b_mass[b]; return m.x != 0.0f || m.y != 0.0f; }
+PR_D unsigned long long color_key(unsigned round, unsigned cid, unsigned k)
+{
+    return (static_cast<unsigned long long>(63u - (round & 63u)) << 58) | (static_cast<unsigned long long>(hash32(cid)) << 26) | (k & 0x3FFFFFFu);
+}
+PR_KERNEL k_color_claim(DV d, unsigned nCons, unsigned round)
+{
+    const unsigned k = PR_TID;
+    if (k < nCons && d.k_color[k] == COLOR_UNSET) {
+        const unsigned cid = d.k_contact[k];
+        const uint4 ab = d.c_ab[cid];
+        const unsigned long long key = color_key(round, cid, k);
+        if (body_dyn(d, ab.x)) atomicMin(&d.b_claim[ab.x], key);
+        if (body_dyn(d, ab.y)) atomicMin(&d.b_claim[ab.y], key);
+    }
+}
+PR_KERNEL k_color_commit(DV d, unsigned nCons, unsigned round)
+{
+    const unsigned k = PR_TID;
+    unsigned remaining = 0u;
+    if (k < nCons && d.k_color[k] == COLOR_UNSET) {
+        const unsigned cid = d.k_contact[k];
+        const uint4 ab = d.c_ab[cid];
+        const unsigned long long key = color_key(round, cid, k);
+        const bool dA = body_dyn(d, ab.x), dB = body_dyn(d, ab.y);
+        const bool win = (!dA || d.b_claim[ab.x] == key) && (!dB || d.b_claim[ab.y] == key);
+        if (win) {
+            const unsigned long long used = (dA ? d.b_cmask[ab.x] : 0ull) | (dB ? d.b_cmask[ab.y] : 0ull);
+            const unsigned long long freeBits = ~used;
+            if (freeBits) {
+                const unsigned c = static_cast<unsigned>(__ffsll(static_cast<long long>(freeBits))) - 1u;
+                d.k_color[k] = c;
+                if (dA) d.b_cmask[ab.x] |= (1ull << c);
+                if (dB) d.b_cmask[ab.y] |= (1ull << c);
+            } else d.k_color[k] = COLOR_OVERFLOW;
+        } else remaining = 1u;
+    }
+    warp_add(&d.cnt->nUncolored, remaining);
+}
+PR_KERNEL k_color_reset_claims(DV d, unsigned nBodies)
+{
+    const unsigned i = PR_TID;
+    if (i < nBodies) d.b_claim[i] = ~0ull;
+}
+PR_KERNEL k_color_starts(DV d, unsigned nCons, const unsigned* sortedColor)
+{
+    const unsigned k = PR_TID;
+    if (k < nCons) {
+        const unsigned c = sortedColor[k];
+        if (k == 0u || sortedColor[k - 1u] != c) d.cnt->colorStart[c] = k;
+    }
+}
+
+// ------------------------------------------------------------------ a9: constraint setup
+PR_D float2 rel_velocity(float4 vA, float2 relA, float4 vB, float2 relB)
+{ // GetContactRelVelocity, d2/Math.cpp:99-102
+    const float2 velBrot = rev_perp(relB) * (vB.z / 1.0f);
+    const float2 velArot = rev_perp(relA) * (vA.z / 1.0f);
+    return (v2(vB.x, vB.y) + velBrot) - (v2(vA.x, vA.y) + velArot);
+}
+// GetWorldManifold (WorldManifold.cpp:37-130) + VelocityConstraint ctor (VelocityConstraint.cpp:81-196)
+// + PositionConstraint (AabbTreeWorld.cpp:289-312) for sorted constraint row i
+PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtRatio)
+{
+    const unsigned i = PR_TID;
+    if (i < nCons) {
+        const unsigned cid = d.k_contact[d.k_sorted[i]];
+        const uint4 ab = d.c_ab[cid];
+        const float4 mat = d.c_mat[cid];
+        const float4 q0 = d.m0[cid], q1 = d.m1[cid], q2 = d.m2[cid];
+        const uint4 q3 = d.m3[cid];
+        const float rA = d.ch_radius[ab.z], rB = d.ch_radius[ab.w];
+        const float4 pA = d.s_pos[ab.x], pB = d.s_pos[ab.y];
+        const float4 vA = d.s_vel[ab.x], vB = d.s_vel[ab.y];
+        const float4 mA = d.b_mass[ab.x], mB = d.b_mass[ab.y];
+        const float2 lcA = d.b_lc[ab.x], lcB = d.b_lc[ab.y];
+        const Xf xfA = get_xf(pos_from4(pA), lcA), xfB = get_xf(pos_from4(pB), lcB);
+        PCRow pc;
+        pc.lnx = q0.x; pc.lny = q0.y; pc.lpx = q0.z; pc.lpy = q0.w;
+        pc.p0x = q1.x; pc.p0y = q1.y; pc.p1x = q1.z; pc.p1y = q1.w;
+        pc.lcAx = lcA.x; pc.lcAy = lcA.y; pc.lcBx = lcB.x; pc.lcBy = lcB.y;
+        pc.totalRadius = rA + rB; pc.typeCount = q3.z | (q3.w << 8); pc.pad0 = pc.pad1 = 0u;
+        d.pc[i] = pc;
+        // world manifold
+        Rot normal = mkrot(0.0f, 0.0f);
+        float2 wp[2] = {v2(0, 0), v2(0, 0)};
+        const float2 lp = v2(q0.z, q0.w);
+        const float2 mp[2] = {v2(q1.x, q1.y), v2(q1.z, q1.w)};
+        const unsigned type = q3.z, count = q3.w;
+        if (type == MF_CIRCLES) {
+            const float2 pointA = transform(lp, xfA), pointB = transform(mp[0], xfB);
+            normal = unit_vector(pointB - pointA, mkrot(1.0f, 0.0f));
+            const float2 cA = pointA + (rA * normal), cB = pointB - (rB * normal);
+            wp[0] = vdiv(cA + cB, 2.0f);
+        } else if (type == MF_FACE_A) {
+            normal = rot_rotate(mkrot(q0.x, q0.y), xfA.q);
+            const float2 planePoint = transform(lp, xfA);
+            for (unsigned j = 0; j < count; ++j) {
+                const float2 clip = transform(mp[j], xfB);
+                const float2 cA = clip + (rA - dot(clip - planePoint, normal)) * normal;
+                const float2 cB = clip - (rB * normal);
+                wp[j] = vdiv(cA + cB, 2.0f);
+            }
+        } else if (type == MF_FACE_B) {
+            const Rot nb = rot_rotate(mkrot(q0.x, q0.y), xfB.q);
+            const float2 planePoint = transform(lp, xfB);
+            for (unsigned j = 0; j < count; ++j) {
+                const float2 clip = transform(mp[j], xfA);
+                const float2 cB = clip + (rB - dot(clip - planePoint, nb)) * nb;
+                const float2 cA = clip - (rA * nb);
+                wp[j] = vdiv(cA + cB, 2.0f);
+            }
+            normal = rneg(nb);
+        }
+        VCRow vc;
+        vc.nx = normal.c; vc.ny = normal.s; vc.friction = mat.x; vc.tangentSpeed = mat.z;
+        vc.bodyA = ab.x; vc.bodyB = ab.y; vc.count = count; vc.contact = cid;
+        vc.invMA = mA.x; vc.invIA = mA.y; vc.invMB = mB.x; vc.invIB = mB.y;
+        const unsigned rAi = d.b_island[ab.x], rBi = d.b_island[ab.y];
+        vc.island = (rAi != INVALID) ? rAi : rBi;
+        vc.dynA = (mA.x != 0.0f || mA.y != 0.0f) ? 1u : 0u; vc.dynB = (mB.x != 0.0f || mB.y != 0.0f) ? 1u : 0u; vc.pad = 0u;
+        const float invMass = mA.x + mB.x;
+        const Rot tangent = fwd_perp(normal);
+        const float restitution = mat.y;
+        float2 relA[2] = {v2(0, 0), v2(0, 0)}, relB[2] = {v2(0, 0), v2(0, 0)};
+        float jn[2] = {0, 0}, jt[2] = {0, 0}, nm[2] = {0, 0}, tm[2] = {0, 0}, bias[2] = {0, 0};
+        const float ojn[2] = {q2.x, q2.z}, ojt[2] = {q2.y, q2.w};
+        for (unsigned j = 0; j < count; ++j) {
+            relA[j] = wp[j] - v2(pA.x, pA.y);
+            relB[j] = wp[j] - v2(pB.x, pB.y);
+            jn[j] = ojn[j] * dtRatio; jt[j] = ojt[j] * dtRatio;
+            const float2 dv = rel_velocity(vA, relA[j], vB, relB[j]);
+            const float vn = dot(dv, normal);
+            bias[j] = (vn < -conf.velocity_threshold) ? -restitution * vn : 0.0f;
+            {
+                const float a = mA.y * square(cross(relA[j], normal)) / 1.0f, b = mB.y * square(cross(relB[j], normal)) / 1.0f;
+                const float value = invMass + a + b;
+                nm[j] = (value != 0.0f) ? 1.0f / value : 0.0f;
+            }
+            {
+                const float a = mA.y * square(cross(relA[j], tangent)) / 1.0f, b = mB.y * square(cross(relB[j], tangent)) / 1.0f;
+                const float value = invMass + a + b;
+                tm[j] = (value != 0.0f) ? 1.0f / value : 0.0f;
+            }
+        }
+        vc.k00 = vc.k11 = vc.k01 = 0.0f; vc.m00 = vc.m11 = vc.m01 = 0.0f;
+        if (conf.do_blocksolve && count == 2u) { // ComputeK + conditioning, VelocityConstraint.cpp:38-133
+            const float rnA0 = cross(relA[0], normal), rnB0 = cross(relB[0], normal);
+            const float rnA1 = cross(relA[1], normal), rnB1 = cross(relB[1], normal);
+            const float iA0 = (mA.y * square(rnA0)) / 1.0f, iA1 = (mA.y * square(rnA1)) / 1.0f;
+            const float iB0 = (mB.y * square(rnB0)) / 1.0f, iB1 = (mB.y * square(rnB1)) / 1.0f;
+            const float iA = (mA.y * rnA0 * rnA1) / 1.0f, iB = (mB.y * rnB0 * rnB1) / 1.0f;
+            const float k00 = invMass + iA0 + iB0, k11 = invMass + iA1 + iB1, k01 = invMass + iA + iB;
+            const float kdiff = k00 * k11 - square(k01);
+            if (square(k00) < 1000.0f * kdiff) {
+                vc.k00 = k00; vc.k11 = k11; vc.k01 = k01;
+                const float cp = k00 * k11 - k01 * k01;
+                if (!almost_zero(cp)) { const float inv = 1 / cp; vc.m00 = k11 * inv; vc.m11 = k00 * inv; vc.m01 = -k01 * inv; }
+            } else { // RemovePoint
+                vc.count = 1u;
+                relA[1] = relB[1] = v2(0, 0); jn[1] = jt[1] = nm[1] = tm[1] = bias[1] = 0.0f;
+            }
+        }
+        vc.rA0x = relA[0].x; vc.rA0y = relA[0].y; vc.rB0x = relB[0].x; vc.rB0y = relB[0].y;
+        vc.jn0 = jn[0]; vc.jt0 = jt[0]; vc.nm0 = nm[0]; vc.tm0 = tm[0];
+        vc.rA1x = relA[1].x; vc.rA1y = relA[1].y; vc.rB1x = relB[1].x; vc.rB1y = relB[1].y;
+        vc.jn1 = jn[1]; vc.jt1 = jt[1]; vc.nm1 = nm[1]; vc.tm1 = tm[1];
+        vc.bias0 = bias[0]; vc.bias1 = bias[1];
+        d.vc[i] = vc;
+    }
+}
+
+// ------------------------------------------------------------------ a9/a10: warm start + velocity solve
+PR_D void apply_pair(float4& vA, float4& vB, float2 P, float2 relA, float2 relB, float imA, float iiA, float imB, float iiB)
+{
+    const float LA = cross(relA, P) / 1.0f, LB = cross(relB, P) / 1.0f;
+    const float2 a = v2(vA.x, vA.y) - imA * P; vA.x = a.x; vA.y = a.y; vA.z -= iiA * LA;
+    const float2 b = v2(vB.x, vB.y) + imB * P; vB.x = b.x; vB.y = b.y; vB.z += iiB * LB;
+}
+// WarmStartVelocities, AabbTreeWorld.cpp:222-273
+PR_D void warm_start_row(const DV& d, unsigned i)
+{
+    const VCRow vc = d.vc[i];
+    float4 vA = d.s_vel[vc.bodyA], vB = d.s_vel[vc.bodyB];
+    const Rot normal = mkrot(vc.nx, vc.ny), tangent = fwd_perp(normal);
+    float2 dAl = v2(0, 0), dBl = v2(0, 0); float dAa = 0.0f, dBa = 0.0f;
+    const float2 relA[2] = {v2(vc.rA0x, vc.rA0y), v2(vc.rA1x, vc.rA1y)}, relB[2] = {v2(vc.rB0x, vc.rB0y), v2(vc.rB1x, vc.rB1y)};
+    const float jn[2] = {vc.jn0, vc.jn1}, jt[2] = {vc.jt0, vc.jt1};
+    for (unsigned j = 0; j < vc.count; ++j) {
+        const float2 P = jn[j] * normal + jt[j] * tangent;
+        const float LA = cross(relA[j], P) / 1.0f, LB = cross(relB[j], P) / 1.0f;
+        dAl = dAl - vc.invMA * P; dAa -= vc.invIA * LA;
+        dBl = dBl + vc.invMB * P; dBa += vc.invIB * LB;
+    }
+    if (vc.dynA) d.s_vel[vc.bodyA] = make_float4(vA.x + dAl.x, vA.y + dAl.y, vA.z + dAa, 0.0f);
+    if (vc.dynB) d.s_vel[vc.bodyB] = make_float4(vB.x + dBl.x, vB.y + dBl.y, vB.z + dBa, 0.0f);
+}
+PR_KERNEL k_warm_start(DV d, unsigned start, unsigned count)
+{
+    const unsigned t = PR_TID;
+    if (t < count) warm_start_row(d, start + t);
+}
+PR_KERNEL k_warm_start_serial(DV d, unsigned start, unsigned count)
+{
+    if (PR_TID == 0u) for (unsigned t = 0; t < count; ++t) warm_start_row(d, start + t);
+}
+
+// GaussSeidel::SolveVelocityConstraint (ContactSolver.cpp:481): tangent (:395) then normal
+// (block :245 with cases 1-4 :113-243, else sequential :337); points in order 1 then 0.
+PR_D float solve_velocity_row(const DV& d, unsigned i, bool& did)
+{
+    VCRow vc = d.vc[i];
+    did = false;
+    if (d.isl_state[vc.island] & ISL_VEL_DONE) return 0.0f;
+    did = true;
+    float4 vA = d.s_vel[vc.bodyA], vB = d.s_vel[vc.bodyB];
+    const Rot normal = mkrot(vc.nx, vc.ny), tangent = fwd_perp(normal);
+    const float2 relA[2] = {v2(vc.rA0x, vc.rA0y), v2(vc.rA1x, vc.rA1y)}, relB[2] = {v2(vc.rB0x, vc.rB0y), v2(vc.rB1x, vc.rB1y)};
+    float jn[2] = {vc.jn0, vc.jn1}, jt[2] = {vc.jt0, vc.jt1};
+    const float nm[2] = {vc.nm0, vc.nm1}, tm[2] = {vc.tm0, vc.tm1}, bias[2] = {vc.bias0, vc.bias1};
+    float maxInc = 0.0f;
+    { // SolveTangentConstraint
+        float m = 0.0f;
+        for (int j = (vc.count == 2u) ? 1 : 0; j >= 0; --j) {
+            const float2 closing = rel_velocity(vA, relA[j], vB, relB[j]);
+            const float directionalVel = vc.tangentSpeed - dot(closing, tangent);
+            const float lambda = tm[j] * directionalVel;
+            const float maxImpulse = vc.friction * jn[j];
+            const float oldImpulse = jt[j];
+            const float newImpulse = stdclamp(oldImpulse + lambda, -maxImpulse, maxImpulse);
+            const float inc = newImpulse - oldImpulse;
+            apply_pair(vA, vB, inc * tangent, relA[j], relB[j], vc.invMA, vc.invIA, vc.invMB, vc.invIB);
+            m = stdmax(m, fabsf(inc));
+            jt[j] = oldImpulse + inc;
+        }
+        maxInc = stdmax(maxInc, m);
+    }
+    const bool kZero = (vc.k00 == 0.0f && vc.k11 == 0.0f && vc.k01 == 0.0f);
+    if (vc.count == 1u || kZero) { // SeqSolveNormalConstraint
+        float m = 0.0f;
+        for (int j = (vc.count == 2u) ? 1 : 0; j >= 0; --j) {
+            const float2 closing = rel_velocity(vA, relA[j], vB, relB[j]);
+            const float directionalVel = dot(closing, normal);
+            const float lambda = nm[j] * (bias[j] - directionalVel);
+            const float oldImpulse = jn[j];
+            const float newImpulse = stdmax(oldImpulse + lambda, 0.0f);
+            const float inc = newImpulse - oldImpulse;
+            apply_pair(vA, vB, inc * normal, relA[j], relB[j], vc.invMA, vc.invIA, vc.invMB, vc.invIB);
+            m = stdmax(m, fabsf(inc));
+            jn[j] = oldImpulse + inc;
+        }
+        maxInc = stdmax(maxInc, m);
+    } else { // BlockSolveNormalConstraint
+        const float2 dv0 = rel_velocity(vA, relA[0], vB, relB[0]), dv1 = rel_velocity(vA, relA[1], vB, relB[1]);
+        const float vn0 = dot(dv0, normal), vn1 = dot(dv1, normal);
+        const float b0 = vn0 - bias[0], b1 = vn1 - bias[1];
+        float t0 = 0.0f; t0 += vc.k00 * jn[0]; t0 += vc.k01 * jn[1];
+        float t1 = 0.0f; t1 += vc.k01 * jn[0]; t1 += vc.k11 * jn[1];
+        const float bp0 = b0 - t0, bp1 = b1 - t1;
+        float n0 = 0.0f, n1 = 0.0f; bool solved = false;
+        {
+            float x0 = 0.0f; x0 += vc.m00 * bp0; x0 += vc.m01 * bp1;
+            float x1 = 0.0f; x1 += vc.m01 * bp0; x1 += vc.m11 * bp1;
+            x0 = -x0; x1 = -x1;
+            if (x0 >= 0.0f && x1 >= 0.0f) { n0 = x0; n1 = x1; solved = true; }
+        }
+        if (!solved) {
+            const float x0 = -nm[0] * bp0;
+            const float vn2 = vc.k01 * x0 + bp1;
+            if (x0 >= 0.0f && vn2 >= 0.0f) { n0 = x0; n1 = 0.0f; solved = true; }
+        }
+        if (!solved) {
+            const float x1 = -nm[1] * bp1;
+            const float vn1b = vc.k01 * x1 + bp0;
+            if (x1 >= 0.0f && vn1b >= 0.0f) { n0 = 0.0f; n1 = x1; solved = true; }
+        }
+        if (!solved && bp0 >= 0.0f && bp1 >= 0.0f) { n0 = 0.0f; n1 = 0.0f; solved = true; }
+        if (solved) { // BlockSolveUpdate + GetVelocityDelta, ContactSolver.cpp:69-111
+            const float i0 = n0 - jn[0], i1 = n1 - jn[1];
+            const float2 P0 = i0 * normal, P1 = i1 * normal;
+            const float2 P = P0 + P1;
+            const float LA = (cross(relA[0], P0) + cross(relA[1], P1)) / 1.0f;
+            const float LB = (cross(relB[0], P0) + cross(relB[1], P1)) / 1.0f;
+            const float2 dAl = -(vc.invMA * P); const float dAa = -(vc.invIA * LA);
+            const float2 dBl = vc.invMB * P; const float dBa = vc.invIB * LB;
+            vA.x += dAl.x; vA.y += dAl.y; vA.z += dAa;
+            vB.x += dBl.x; vB.y += dBl.y; vB.z += dBa;
+            jn[0] = n0; jn[1] = n1;
+            maxInc = stdmax(maxInc, stdmax(fabsf(n0), fabsf(n1)));
+        }
+    }
+    if (vc.dynA) d.s_vel[vc.bodyA] = vA;
+    if (vc.dynB) d.s_vel[vc.bodyB] = vB;
+    VCRow* row = &d.vc[i];
+    row->jn0 = jn[0]; row->jt0 = jt[0]; row->jn1 = jn[1]; row->jt1 = jt[1];
+    return maxInc;
+}
+PR_KERNEL k_solve_velocity(DV d, unsigned start, unsigned count)
+{
+    const unsigned t = PR_TID;
+    bool did = false; float inc = 0.0f; unsigned label = 0u;
+    if (t < count) { inc = solve_velocity_row(d, start + t, did); label = d.vc[start + t].island; }
+    island_max(d.isl_inc, label, f2u(inc), did);
+}
+PR_KERNEL k_solve_velocity_serial(DV d, unsigned start, unsigned count)
+{
+    if (PR_TID == 0u) {
+        for (unsigned t = 0; t < count; ++t) {
+            bool did = false;
+            const float inc = solve_velocity_row(d, start + t, did);
+            if (did) atomicMax(&d.isl_inc[d.vc[start + t].island], f2u(inc));
+        }
+    }
+}
+// per-island early exit of velocity iterations (AabbTreeWorld.cpp:1603-1622)
+PR_KERNEL k_isl_vel_check(DV d, unsigned nBodies, unsigned iter, float minMomentum)
+{
+    const unsigned i = PR_TID;
+    unsigned stillActive = 0u;
+    if (i < nBodies && d.b_island[i] == i) {
+        const unsigned st = d.isl_state[i];
+        if ((st & ISL_ACTIVE) && !(st & ISL_VEL_DONE)) {
+            const unsigned incBits = d.isl_inc[i];
+            if (incBits > d.isl_maxInc[i]) d.isl_maxInc[i] = incBits; // non-negative floats order like uints
+            if (u2f(incBits) <= minMomentum) { d.isl_state[i] = st | ISL_VEL_DONE; d.isl_velIters[i] = iter + 1u; }
+            else stillActive = 1u;
+            d.isl_inc[i] = 0u;
+        }
+    }
+    warp_add(&d.cnt->nActiveVel, stillActive);
+}
+
+// ------------------------------------------------------------------ a11: integrate + NGS position solve
+PR_KERNEL k_integrate_positions(DV d, unsigned nBodies, float h)
+{ // IntegratePositions, AabbTreeWorld.cpp:176-189
+    const unsigned i = PR_TID;
+    if (i < nBodies && d.b_island[i] != INVALID) {
+        const float4 v = d.s_vel[i];
+        float4 p = d.s_pos[i];
+        const float2 tr = h * v2(v.x, v.y);
+        const float rot = h * v.z;
+        p.x += tr.x; p.y += tr.y; p.z += rot;
+        d.s_pos[i] = p;
+    }
+}
+struct PSM { Rot normal; float2 point; float separation; };
+PR_D PSM get_psm(const PCRow& pc, unsigned index, Xf xfA, Xf xfB)
+{ // GetPSM, PositionSolverManifold.cpp:35-120
+    const float2 lp = v2(pc.lpx, pc.lpy);
+    const float2 plp = index == 0u ? v2(pc.p0x, pc.p0y) : v2(pc.p1x, pc.p1y);
+    const Rot ln = mkrot(pc.lnx, pc.lny);
+    const unsigned type = pc.typeCount & 0xFFu;
+    PSM r;
+    if (type == MF_CIRCLES) {
+        const float2 pointA = transform(lp, xfA), pointB = transform(plp, xfB);
+        const float2 delta = pointB - pointA;
+        r.normal = unit_vector(delta, mkrot(0.0f, 0.0f));
+        r.point = vdiv(pointA + pointB, 2.0f);
+        r.separation = dot(delta, r.normal);
+    } else if (type == MF_FACE_A) {
+        const float2 planePoint = transform(lp, xfA);
+        r.normal = rot_rotate(ln, xfA.q);
+        r.point = transform(plp, xfB);
+        r.separation = dot(r.point - planePoint, r.normal);
+    } else {
+        const float2 planePoint = transform(lp, xfB);
+        const Rot n = rot_rotate(ln, xfB.q);
+        r.point = transform(plp, xfA);
+        r.separation = dot(r.point - planePoint, n);
+        r.normal = rneg(n);
+    }
+    return r;
+}
+struct PDelta { float2 al; float aa; float2 bl; float ba; float sep; };
+PR_D PDelta psm_solve(const PSM& psm, float2 pA, float2 pB, float imA, float iiA, float imB, float iiB, float totalRadius,
+                      float rate, float slop, float maxCorr)
+{ // solver_fn in SolvePositionConstraint, ContactSolver.cpp:521-545
+    const float separation = psm.separation - totalRadius;
+    const float2 rA = psm.point - pA, rB = psm.point - pB;
+    const float K = (imA + imB) + iiA * square(cross(rA, psm.normal) / 1.0f) + iiB * square(cross(rB, psm.normal) / 1.0f);
+    const float C = -stdclamp(rate * (separation + slop), -maxCorr, 0.0f);
+    const float2 P = vdiv(psm.normal * C, K);
+    const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+    PDelta r;
+    r.al = -(imA * P); r.aa = -(iiA * LA); r.bl = imB * P; r.ba = iiB * LB; r.sep = separation;
+    return r;
+}
+// GaussSeidel::SolvePositionConstraint, ContactSolver.cpp:494-643 (moveA = moveB = true)
+PR_D float solve_position_row(const DV& d, unsigned i, float rate, float slop, float maxCorr, bool& did)
+{
+    const VCRow* vcp = &d.vc[i];
+    const unsigned island = vcp->island;
+    did = false;
+    if (d.isl_state[island] & ISL_POS_SOLVED) return PR_INF;
+    did = true;
+    const unsigned bA = vcp->bodyA, bB = vcp->bodyB;
+    const float imA = vcp->invMA, iiA = vcp->invIA, imB = vcp->invMB, iiB = vcp->invIB;
+    const unsigned dynA = vcp->dynA, dynB = vcp->dynB;
+    const PCRow pc = d.pc[i];
+    float4 a4 = d.s_pos[bA], b4 = d.s_pos[bB];
+    Pos posA = pos_from4(a4), posB = pos_from4(b4);
+    const float2 lcA = v2(pc.lcAx, pc.lcAy), lcB = v2(pc.lcBx, pc.lcBy);
+    const unsigned count = pc.typeCount >> 8;
+    float minSep = PR_INF;
+    if (count == 1u) {
+        const PSM psm0 = get_psm(pc, 0u, get_xf(posA, lcA), get_xf(posB, lcB));
+        const PDelta s = psm_solve(psm0, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
+        posA.l = posA.l + s.al; posA.a += s.aa; posB.l = posB.l + s.bl; posB.a += s.ba;
+        minSep = 0.0f + s.sep;
+    } else if (count == 2u) {
+        const Xf xfA = get_xf(posA, lcA), xfB = get_xf(posB, lcB);
+        const PSM psm0 = get_psm(pc, 0u, xfA, xfB), psm1 = get_psm(pc, 1u, xfA, xfB);
+        if (almost_equal(psm0.separation, psm1.separation)) {
+            const PDelta s0 = psm_solve(psm0, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
+            const PDelta s1 = psm_solve(psm1, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
+            posA.l = (posA.l + s0.al) + s1.al; posA.a = (posA.a + s0.aa) + s1.aa;
+            posB.l = (posB.l + s0.bl) + s1.bl; posB.a = (posB.a + s0.ba) + s1.ba;
+            minSep = s0.sep;
+        } else if (psm0.separation < psm1.separation) {
+            const PDelta s0 = psm_solve(psm0, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
+            posA.l = posA.l + s0.al; posA.a += s0.aa; posB.l = posB.l + s0.bl; posB.a += s0.ba;
+            const PSM p1 = get_psm(pc, 1u, get_xf(posA, lcA), get_xf(posB, lcB));
+            const PDelta s1 = psm_solve(p1, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
+            posA.l = posA.l + s1.al; posA.a += s1.aa; posB.l = posB.l + s1.bl; posB.a += s1.ba;
+            minSep = s0.sep;
+        } else if (psm1.separation < psm0.separation) {
+            const PDelta s1 = psm_solve(psm1, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
+            posA.l = posA.l + s1.al; posA.a += s1.aa; posB.l = posB.l + s1.bl; posB.a += s1.ba;
+            const PSM p0 = get_psm(pc, 0u, get_xf(posA, lcA), get_xf(posB, lcB));
+            const PDelta s0 = psm_solve(p0, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
+            posA.l = posA.l + s0.al; posA.a += s0.aa; posB.l = posB.l + s0.bl; posB.a += s0.ba;
+            minSep = s1.sep;
+        }
+    }
+    if (dynA) d.s_pos[bA] = make_float4(posA.l.x, posA.l.y, posA.a, 0.0f);
+    if (dynB) d.s_pos[bB] = make_float4(posB.l.x, posB.l.y, posB.a, 0.0f);
+    return minSep;
+}
+PR_KERNEL k_solve_position(DV d, unsigned start, unsigned count, float rate, float slop, float maxCorr)
+{
+    const unsigned t = PR_TID;
+    bool did = false; float sep = PR_INF; unsigned label = 0u;
+    if (t < count) { sep = solve_position_row(d, start + t, rate, slop, maxCorr, did); label = d.vc[start + t].island; }
+    island_min(d.isl_sep, label, float_flip(sep), did);
+}
+PR_KERNEL k_solve_position_serial(DV d, unsigned start, unsigned count, float rate, float slop, float maxCorr)
+{
+    if (PR_TID == 0u) {
+        for (unsigned t = 0; t < count; ++t) {
+            bool did = false;
+            const float sep = solve_position_row(d, start + t, rate, slop, maxCorr, did);
+            if (did) atomicMin(&d.isl_sep[d.vc[start + t].island], float_flip(sep));
+        }
+    }
+}
+PR_KERNEL k_isl_pos_check(DV d, unsigned nBodies, unsigned iter, float minSeparation)
+{ // AabbTreeWorld.cpp:1628-1644
+    const unsigned i = PR_TID;
+    unsigned stillActive = 0u;
+    if (i < nBodies && d.b_island[i] == i) {
+        const unsigned st = d.isl_state[i];
+        if ((st & ISL_ACTIVE) && !(st & ISL_POS_SOLVED)) {
+            const unsigned sepFlip = d.isl_sep[i];
+            if (sepFlip < d.isl_minSep[i]) d.isl_minSep[i] = sepFlip;
+            if (float_unflip(sepFlip) >= minSeparation) { d.isl_state[i] = st | ISL_POS_SOLVED; d.isl_posIters[i] = iter + 1u; }
+            else stillActive = 1u;
+            d.isl_sep[i] = float_flip(PR_INF);
+        }
+    }
+    warp_add(&d.cnt->nActivePos, stillActive);
+}
+
+// ------------------------------------------------------------------ a12: write-back, sleep, stats
+PR_KERNEL k_assign_impulses(DV d, unsigned nCons)
+{ // AssignImpulses, AabbTreeWorld.cpp:208-230
+    const unsigned i = PR_TID;
+    if (i < nCons) {
+        const VCRow* vc = &d.vc[i];
+        const unsigned cid = vc->contact, count = vc->count;
+        float4 m2 = d.m2[cid];
+        if (count > 0u) { m2.x = vc->jn0; m2.y = vc->jt0; }
+        if (count > 1u) { m2.z = vc->jn1; m2.w = vc->jt1; }
+        d.m2[cid] = m2;
+    }
+}
+PR_KERNEL k_writeback_bodies(DV d, unsigned nBodies, pr_step_conf conf)
+{ // AabbTreeWorld.cpp:1652-1664 + UpdateUnderActiveTimes :395-417
+    const unsigned i = PR_TID;
+    bool member = false; unsigned label = 0u; unsigned uaFlip = 0xFFFFFFFFu;
+    if (i < nBodies) {
+        const unsigned r = d.b_island[i];
+        if (r != INVALID) {
+            const float4 sv = d.s_vel[i], sp = d.s_pos[i];
+            d.b_vel[i] = make_float4(sv.x, sv.y, sv.z, 0.0f);
+            float4 p1 = d.b_pos1[i];
+            if (!(p1.x == sp.x && p1.y == sp.y) || p1.z != sp.z) {
+                p1.x = sp.x; p1.y = sp.y; p1.z = sp.z;
+                const Xf xf = get_xf(pos_from4(sp), d.b_lc[i]);
+                d.b_xf[i] = make_float4(xf.p.x, xf.p.y, xf.q.c, xf.q.s);
+                d.b_moved[i] = 1u;
+            }
+            const unsigned f = d.b_flags[i];
+            // IsUnderActive, d2/Math.hpp:283-289
+            const float lin = magsq(v2(sv.x, sv.y)), ang = square(sv.z);
+            const bool ua = (ang <= square(conf.angular_sleep_tolerance)) && (lin <= square(conf.linear_sleep_tolerance));
+            const float t = ((f & PR_BODY_AUTOSLEEP) && ua) ? p1.w + conf.delta_time : 0.0f;
+            p1.w = t;
+            d.b_pos1[i] = p1;
+            member = true; label = r; uaFlip = float_flip(t);
+        }
+    }
+    island_min(d.isl_minUA, label, uaFlip, member);
+}
+PR_KERNEL k_sleep_and_stats(DV d, unsigned nBodies, float minStillTime)
+{ // Sleepem :419-430 ; Update(RegStepStats&, IslandStats) StepStats.cpp:29-38
+    const unsigned i = PR_TID;
+    unsigned slept = 0u, solved = 0u, posIt = 0u, velIt = 0u, nb = 0u, sepFlip = 0xFFFFFFFFu, incBits = 0u;
+    if (i < nBodies) {
+        const unsigned r = d.b_island[i];
+        if (r != INVALID) {
+            const unsigned st = d.isl_state[r];
+            if ((st & ISL_POS_SOLVED) && float_unflip(d.isl_minUA[r]) >= minStillTime) {
+                const unsigned f = d.b_flags[i];
+                if (f_awake(f) && (!f_speedable(f) || (f & PR_BODY_AUTOSLEEP))) { // Body::UnsetAwake, Body.cpp:173-182
+                    d.b_flags[i] = f & ~static_cast<unsigned>(PR_BODY_AWAKE);
+                    reinterpret_cast<float*>(&d.b_pos1[i])[3] = 0.0f;
+                    d.b_vel[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    slept = 1u;
+                }
+            }
+            if (r == i) {
+                solved = (st & ISL_POS_SOLVED) ? 1u : 0u;
+                posIt = d.isl_posIters[i]; velIt = d.isl_velIters[i]; nb = d.isl_nbodies[i];
+                sepFlip = d.isl_minSep[i]; incBits = d.isl_maxInc[i];
+            }
+        }
+    }
+    warp_add(&d.cnt->bodiesSlept, slept); warp_add(&d.cnt->islandsSolved, solved);
+    warp_add(&d.cnt->sumPosIters, posIt); warp_add(&d.cnt->sumVelIters, velIt);
+    warp_max(&d.cnt->maxIslandBodies, nb); warp_min(&d.cnt->minSepFlip, sepFlip); warp_max(&d.cnt->maxIncBits, incBits);
+}
+
+// ------------------------------------------------------------------ export helpers
+PR_KERNEL k_export_contacts(DV d, unsigned nOrder, pr_contact* out, pr_manifold* mout)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        const unsigned long long key = d.c_key[id];
+        const uint4 ab = d.c_ab[id], ids = d.c_ids[id];
+        const float4 mat = d.c_mat[id];
+        const unsigned fl = d.c_flags[id];
+        pr_contact c;
+        c.id = id; c.key_min = static_cast<unsigned>(key >> 32); c.key_max = static_cast<unsigned>(key & 0xFFFFFFFFull);
+        c.body_a = ab.x; c.shape_a = ids.x; c.child_a = ids.y; c.body_b = ab.y; c.shape_b = ids.z; c.child_b = ids.w;
+        c.friction = mat.x; c.restitution = mat.y; c.tangent_speed = mat.z; c.toi = mat.w;
+        c.toi_count = fl >> 8; c.flags = fl & 0xFFu;
+        out[i] = c;
+        if (mout) {
+            const float4 q0 = d.m0[id], q1 = d.m1[id], q2 = d.m2[id]; const uint4 q3 = d.m3[id];
+            pr_manifold m;
+            m.ln_x = q0.x; m.ln_y = q0.y; m.lp_x = q0.z; m.lp_y = q0.w; m.p0_x = q1.x; m.p0_y = q1.y; m.p1_x = q1.z; m.p1_y = q1.w;
+            m.jn0 = q2.x; m.jt0 = q2.y; m.jn1 = q2.z; m.jt1 = q2.w; m.cf0 = q3.x; m.cf1 = q3.y; m.type = q3.z; m.count = q3.w;
+            mout[i] = m;
+        }
+    }
+}
+PR_KERNEL k_import_contacts(DV d, unsigned n, const pr_contact* in, const pr_manifold* min, const unsigned* pxOfTree)
+{
+    const unsigned i = PR_TID;
+    if (i < n) {
+        const pr_contact c = in[i];
+        const pr_manifold m = min[i];
+        const unsigned id = c.id;
+        const unsigned pa = pxOfTree[c.key_min], pb = pxOfTree[c.key_max];
+        d.c_key[id] = (static_cast<unsigned long long>(c.key_min) << 32) | c.key_max;
+        d.c_ab[id] = make_uint4(c.body_a, c.body_b, d.p_cg[pa], d.p_cg[pb]);
+        d.c_px[id] = make_uint2(pa, pb);
+        d.c_ids[id] = make_uint4(c.shape_a, c.child_a, c.shape_b, c.child_b);
+        d.c_mat[id] = make_float4(c.friction, c.restitution, c.tangent_speed, c.toi);
+        d.c_flags[id] = (c.flags & 0xFFu) | (c.toi_count << 8);
+        d.m0[id] = make_float4(m.ln_x, m.ln_y, m.lp_x, m.lp_y); d.m1[id] = make_float4(m.p0_x, m.p0_y, m.p1_x, m.p1_y);
+        d.m2[id] = make_float4(m.jn0, m.jt0, m.jn1, m.jt1); d.m3[id] = make_uint4(m.cf0, m.cf1, m.type, m.count);
+        d.c_order[i] = id;
+    }
+}
+PR_KERNEL k_export_proxies(DV d, unsigned n, pr_proxy* out)
+{
+    const unsigned i = PR_TID;
+    if (i < n) {
+        const float4 f = d.p_fat[i];
+        pr_proxy p;
+        p.tree_id = d.p_tree[i]; p.body = d.p_body[i]; p.shape = d.p_shape[i]; p.child = d.p_child[i];
+        p.min_x = f.x; p.min_y = f.y; p.max_x = f.z; p.max_y = f.w;
+        out[i] = p;
+    }
+}
+PR_KERNEL k_fill_u32(unsigned* p, unsigned n, unsigned v) { const unsigned i = PR_TID; if (i < n) p[i] = v; }
+PR_KERNEL k_fill_u64(unsigned long long* p, unsigned n, unsigned long long v) { const unsigned i = PR_TID; if (i < n) p[i] = v; }
+PR_KERNEL k_gather_u32(const unsigned* src, const unsigned* idx, unsigned* dst, unsigned n) { const unsigned i = PR_TID; if (i < n) dst[i] = src[idx[i]]; }
+PR_KERNEL k_solve_order(DV d, unsigned nCons, unsigned* ids, unsigned* colors, const unsigned* sortedColor)
+{
+    const unsigned i = PR_TID;
+    if (i < nCons) { ids[i] = d.k_contact[d.k_sorted[i]]; colors[i] = sortedColor[i]; }
+}
+
+// standalone CollideShapes over arrays (pr_collide_shapes)
+PR_KERNEL k_collide_batch(unsigned n, const pr_child* children, const float2* verts, const float2* normals,
+                          const unsigned* aChild, const float4* xfA, const unsigned* bChild, const float4* xfB,
+                          float linearSlop, float maxCirclesRatio, pr_manifold* out)
+{
+    const unsigned i = PR_TID;
+    if (i < n) {
+        const pr_child ca = children[aChild[i]], cb = children[bChild[i]];
+        ProxyView A, B;
+        A.radius = ca.vertex_radius; A.count = ca.vertex_count; A.v = verts + ca.vertex_offset; A.n = normals + ca.vertex_offset;
+        B.radius = cb.vertex_radius; B.count = cb.vertex_count; B.v = verts + cb.vertex_offset; B.n = normals + cb.vertex_offset;
+        const Mf m = collide_shapes(A, xf_from4(xfA[i]), B, xf_from4(xfB[i]), linearSlop, maxCirclesRatio);
+        pr_manifold o;
+        o.ln_x = m.ln.x; o.ln_y = m.ln.y; o.lp_x = m.lp.x; o.lp_y = m.lp.y; o.p0_x = m.p0.x; o.p0_y = m.p0.y; o.p1_x = m.p1.x; o.p1_y = m.p1.y;
+        o.jn0 = o.jt0 = o.jn1 = o.jt1 = 0.0f; o.cf0 = m.cf0; o.cf1 = m.cf1; o.type = m.type; o.count = m.count;
+        out[i] = o;
+    }
+}
+
+} // namespace pr
+#endif

@@ -1,0 +1,895 @@
+// pr_world.cu -- host orchestration of the device-resident world and the extern "C" layer
+// declared in include/playrho_b200.h. Step() mirrors Step(AabbTreeWorld&, const StepConf&)
+// (Library/source/playrho/d2/AabbTreeWorld.cpp:2144-2219): pre-phase, SolveReg (:1472), SolveToi.
+#include "pr_kernels.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <limits>
+#include <unordered_map>
+
+namespace pr {
+
+static unsigned g_launches = 0;
+void count_launch() { ++g_launches; }
+unsigned launches_since_reset() { return g_launches; }
+void reset_launch_count() { g_launches = 0; }
+#ifdef PR_HOST_EMUL
+thread_local unsigned emul_tid = 0, emul_nthreads = 0;
+#endif
+static std::string g_createError;
+
+// ------------------------------------------------------------------ memory / stream shims
+#ifndef PR_HOST_EMUL
+struct CudaError { std::string msg; };
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        const cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) throw CudaError{std::string(#call) + ": " + cudaGetErrorString(e_)}; \
+    } while (0)
+static void* dev_alloc(size_t bytes) { void* p = nullptr; CK(cudaMalloc(&p, bytes ? bytes : 16)); return p; }
+static void dev_free(void* p) { if (p) cudaFree(p); }
+static void h2d(World& w, void* dst, const void* src, size_t n) { if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, w.stream)); }
+static void d2h(World& w, void* dst, const void* src, size_t n) { if (n) { CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, w.stream)); CK(cudaStreamSynchronize(w.stream)); } }
+static void d2d(World& w, void* dst, const void* src, size_t n) { if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, w.stream)); }
+static void dset(World& w, void* dst, int v, size_t n) { if (n) CK(cudaMemsetAsync(dst, v, n, w.stream)); }
+static void sync(World& w) { CK(cudaStreamSynchronize(w.stream)); }
+static void check_launch() { CK(cudaGetLastError()); }
+struct StageTimer {
+    cudaEvent_t ev[64]; int stage[64]; int n = 0; bool on = true;
+    StageTimer() { for (auto& e : ev) cudaEventCreate(&e); }
+    ~StageTimer() { for (auto& e : ev) cudaEventDestroy(e); }
+    void mark(World& w, int s) { if (n < 64) { cudaEventRecord(ev[n], w.stream); stage[n++] = s; } }
+    void finish(World& w, pr_step_profile& p)
+    {
+        mark(w, -1);
+        cudaEventSynchronize(ev[n - 1]);
+        for (int i = 0; i + 1 < n; ++i) {
+            float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            if (stage[i] >= 0 && stage[i] < 16) p.ms_stage[stage[i]] += ms;
+        }
+        float tot = 0; cudaEventElapsedTime(&tot, ev[0], ev[n - 1]); p.ms_total = tot;
+        n = 0;
+    }
+};
+#else
+struct CudaError { std::string msg; };
+#define CK(call) (call)
+static void* dev_alloc(size_t bytes) { return std::calloc(1, bytes ? bytes : 16); }
+static void dev_free(void* p) { std::free(p); }
+static void h2d(World&, void* dst, const void* src, size_t n) { if (n) std::memcpy(dst, src, n); }
+static void d2h(World&, void* dst, const void* src, size_t n) { if (n) std::memcpy(dst, src, n); }
+static void d2d(World&, void* dst, const void* src, size_t n) { if (n) std::memmove(dst, src, n); }
+static void dset(World&, void* dst, int v, size_t n) { if (n) std::memset(dst, v, n); }
+static void sync(World&) {}
+static void check_launch() {}
+struct StageTimer { void mark(World&, int) {} void finish(World&, pr_step_profile&) {} };
+#endif
+
+// ------------------------------------------------------------------ array table (alloc / grow / clone)
+enum Group { G_BODY, G_SHAPE, G_CHILD, G_VERT, G_PROXY, G_CONTACT, G_HASH, G_PAIR, G_CONS, G_COUNT };
+struct ArrDesc { void** slot; size_t elem; Group g; size_t mult; };
+static std::vector<ArrDesc> arrays(World& w)
+{
+    DV& d = w.d;
+#define A(field, g) ArrDesc{reinterpret_cast<void**>(&d.field), sizeof(*d.field), g, 1}
+#define A2(field, g, m) ArrDesc{reinterpret_cast<void**>(&d.field), sizeof(*d.field), g, m}
+    return {
+        A(b_xf, G_BODY), A(b_pos0, G_BODY), A(b_pos1, G_BODY), A(b_vel, G_BODY), A(b_acc, G_BODY), A(b_mass, G_BODY),
+        A(b_lc, G_BODY), A(b_flags, G_BODY), A(s_vel, G_BODY), A(s_pos, G_BODY), A(b_island, G_BODY), A(b_root, G_BODY),
+        A(b_moved, G_BODY), A(b_sync, G_BODY), A(isl_state, G_BODY), A(isl_velIters, G_BODY), A(isl_posIters, G_BODY),
+        A(isl_inc, G_BODY), A(isl_maxInc, G_BODY), A(isl_sep, G_BODY), A(isl_minSep, G_BODY), A(isl_minUA, G_BODY),
+        A(isl_nbodies, G_BODY), A(b_claim, G_BODY), A(b_cmask, G_BODY),
+        A(sh_mat, G_SHAPE), A(sh_filter, G_SHAPE), A(sh_group, G_SHAPE),
+        A(ch_radius, G_CHILD), A(ch_voff, G_CHILD), A(ch_count, G_CHILD), A(vtx, G_VERT), A(nrm, G_VERT),
+        A(p_body, G_PROXY), A(p_shape, G_PROXY), A(p_child, G_PROXY), A(p_cg, G_PROXY), A(p_tree, G_PROXY), A(p_moved, G_PROXY),
+        A(p_fat, G_PROXY), A(q_list, G_PROXY), A(bv_code, G_PROXY), A(bv_code2, G_PROXY), A(bv_idx, G_PROXY), A(bv_idx2, G_PROXY),
+        A(bv_left, G_PROXY), A(bv_right, G_PROXY), A(bv_parent, G_PROXY), A(bv_lparent, G_PROXY), A(bv_visit, G_PROXY), A(bv_box, G_PROXY),
+        A(c_key, G_CONTACT), A(c_ab, G_CONTACT), A(c_px, G_CONTACT), A(c_ids, G_CONTACT), A(c_mat, G_CONTACT), A(c_flags, G_CONTACT),
+        A(m0, G_CONTACT), A(m1, G_CONTACT), A(m2, G_CONTACT), A(m3, G_CONTACT), A(c_order, G_CONTACT), A(c_free, G_CONTACT),
+        A(c_tmp, G_CONTACT), A(c_tmp2, G_CONTACT),
+        A(ht_keys, G_HASH),
+        A(np_key, G_PAIR), A(np_key2, G_PAIR), A(np_px, G_PAIR), A(np_idx, G_PAIR), A(np_idx2, G_PAIR),
+        A(vc, G_CONS), A(pc, G_CONS), A(k_contact, G_CONS), A(k_color, G_CONS), A(k_sorted, G_CONS), A(k_tmpKey, G_CONS),
+        A(k_tmpKey2, G_CONS), A(k_tmpVal, G_CONS),
+    };
+#undef A
+#undef A2
+}
+static unsigned* cap_of(World& w, Group g)
+{
+    switch (g) {
+    case G_BODY: return &w.capBodies; case G_SHAPE: return &w.capShapes; case G_CHILD: return &w.capChildren;
+    case G_VERT: return &w.capVerts; case G_PROXY: return &w.capProxies; case G_CONTACT: return &w.capContacts;
+    case G_HASH: return &w.capHash; case G_PAIR: return &w.capPairs; case G_CONS: return &w.capCons; default: return nullptr;
+    }
+}
+static unsigned next_pow2(unsigned v) { unsigned p = 1; while (p < v) p <<= 1; return p; }
+
+static void ensure_scratch(World& w, unsigned nMax)
+{
+    const size_t need = scan_scratch_elems(std::max(nMax, 256u * rs_blocks(nMax))) + 16;
+    if (need > w.scanScratchCap) {
+        dev_free(w.scanScratch);
+        w.scanScratch = static_cast<unsigned*>(dev_alloc(need * sizeof(unsigned)));
+        w.scanScratchCap = need; w.rs.scan = w.scanScratch; w.rs.scanCap = need;
+    }
+    const size_t hneed = 256u * static_cast<size_t>(rs_blocks(nMax)) + 16;
+    if (hneed > w.rs.histCap) {
+        dev_free(w.rs.hist);
+        w.rs.hist = static_cast<unsigned*>(dev_alloc(hneed * sizeof(unsigned)));
+        w.rs.histCap = hneed;
+    }
+}
+
+// grow group g to hold at least `need` elements, preserving contents
+static void ensure(World& w, Group g, unsigned need)
+{
+    unsigned* cap = cap_of(w, g);
+    if (need <= *cap) return;
+    unsigned newCap = std::max(need, std::max(1024u, *cap + *cap / 2));
+    if (g == G_HASH) newCap = next_pow2(need);
+    for (const ArrDesc& a : arrays(w)) {
+        if (a.g != g) continue;
+        void* np = dev_alloc(a.elem * newCap);
+        if (*a.slot && *cap && g != G_HASH) d2d(w, np, *a.slot, a.elem * *cap);
+        sync(w);
+        dev_free(*a.slot);
+        *a.slot = np;
+    }
+    if (g == G_HASH) { w.d.ht_mask = newCap - 1u; w.hashDirty = true; }
+    *cap = newCap;
+    ensure_scratch(w, std::max(std::max(w.capContacts, w.capProxies), std::max(w.capPairs, w.capCons)));
+}
+
+static void read_counters(World& w) { d2h(w, &w.hostCnt, w.d.cnt, sizeof(Counters)); }
+static void write_counters(World& w) { h2d(w, w.d.cnt, &w.hostCnt, sizeof(Counters)); }
+
+static void throw_device_error(World& w)
+{
+    const unsigned e = w.hostCnt.error;
+    if (!e) return;
+    std::string m = "device error:";
+    if (e & ERR_STACK) m += " bvh traversal stack overflow;";
+    if (e & ERR_SENSOR) m += " sensor contacts (GJK TestOverlap) not supported yet;";
+    if (e & ERR_HASH_FULL) m += " contact hash full;";
+    throw CudaError{m};
+}
+
+// ------------------------------------------------------------------ pre-phase pieces
+static unsigned create_queued_proxies(World& w, const pr_step_conf& conf)
+{ // Step: CreateProxies for m_fixturesForProxies, AabbTreeWorld.cpp:2158-2168
+    if (w.fixturesForProxies.empty()) return 0;
+    std::vector<unsigned> body, shape, child, cg, tree;
+    for (const auto& bs : w.fixturesForProxies) {
+        const pr_shape& s = w.shapes[bs.second];
+        for (unsigned c = 0; c < s.child_count; ++c) {
+            const unsigned k = w.nProxies + static_cast<unsigned>(body.size());
+            body.push_back(bs.first); shape.push_back(bs.second); child.push_back(c); cg.push_back(s.child_offset + c);
+            tree.push_back(k == 0 ? 0u : 2u * k - 1u); // DynamicTree leaf id sequence
+            w.maxTreeId = std::max(w.maxTreeId, tree.back());
+        }
+    }
+    w.fixturesForProxies.clear();
+    const unsigned n = static_cast<unsigned>(body.size());
+    if (!n) return 0;
+    ensure(w, G_PROXY, w.nProxies + n);
+    const unsigned first = w.nProxies;
+    h2d(w, w.d.p_body + first, body.data(), n * 4); h2d(w, w.d.p_shape + first, shape.data(), n * 4);
+    h2d(w, w.d.p_child + first, child.data(), n * 4); h2d(w, w.d.p_cg + first, cg.data(), n * 4);
+    h2d(w, w.d.p_tree + first, tree.data(), n * 4);
+    sync(w); // host vectors go out of scope
+    PR_LAUNCH(k_create_proxy_aabbs, n, w.stream, w.d, conf, first, n);
+    read_counters(w);
+    w.hostCnt.nQueue += n;
+    write_counters(w);
+    w.nProxies += n;
+    return n;
+}
+
+static unsigned destroy_contacts(World& w)
+{ // DestroyContacts (overlap part), AabbTreeWorld.cpp:2290-2304
+    if (w.nOrder == 0) return 0;
+    DV& d = w.d;
+    ensure(w, G_CONS, w.nOrder + 1);
+    PR_LAUNCH(k_destroy_test, w.nOrder, w.stream, d, w.nOrder, d.c_tmp);
+    scan_exclusive_u32(d.c_tmp, d.k_tmpVal, w.nOrder, &d.cnt->nNew, w.scanScratch, w.stream);
+    read_counters(w);
+    const unsigned kept = w.hostCnt.nNew;
+    const unsigned destroyed = w.nOrder - kept;
+    if (destroyed) {
+        PR_LAUNCH(k_destroy_compact, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, d.k_tmpVal, d.c_tmp2, w.nFree);
+        std::swap(d.c_order, d.c_tmp2);
+        w.nFree += destroyed;
+        w.nOrder = kept;
+        w.hashDirty = true;
+    }
+    return destroyed;
+}
+
+static void rebuild_hash(World& w)
+{
+    ensure(w, G_HASH, next_pow2(std::max(2048u, 2u * w.capContacts)));
+    dset(w, w.d.ht_keys, 0xFF, sizeof(unsigned long long) * w.capHash);
+    PR_LAUNCH(k_hash_fill, w.nOrder, w.stream, w.d, w.nOrder);
+    w.hashDirty = false;
+}
+
+static int key_bits(unsigned maxVal) { int b = 1; while (b < 32 && (maxVal >> b)) ++b; return ((b + 7) / 8) * 8; }
+
+// FindContacts + AddContacts, AabbTreeWorld.cpp:709-751 and :2423-2547
+static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer& tm)
+{
+    DV& d = w.d;
+    read_counters(w);
+    throw_device_error(w);
+    const unsigned nQueue = w.hostCnt.nQueue;
+    if (nQueue == 0) return 0;
+    const unsigned P = w.nProxies;
+    tm.mark(w, PR_STAGE_BVH);
+    bool idxInB = false;
+    if (P > 1) {
+        w.hostCnt.boundsMinX = w.hostCnt.boundsMinY = 0xFFFFFFFFu; w.hostCnt.boundsMaxX = w.hostCnt.boundsMaxY = 0u;
+        write_counters(w);
+        PR_LAUNCH(k_bvh_bounds, P, w.stream, d, P);
+        PR_LAUNCH(k_bvh_morton, P, w.stream, d, P);
+        idxInB = radix_sort_pairs<unsigned>(d.bv_code, d.bv_idx, d.bv_code2, d.bv_idx2, P, 0, 32, true, w.rs, w.stream);
+        const unsigned* codes = idxInB ? d.bv_code2 : d.bv_code;
+        const unsigned* sidx = idxInB ? d.bv_idx2 : d.bv_idx;
+        PR_LAUNCH(k_bvh_build, P - 1, w.stream, d, P, codes);
+        PR_LAUNCH(k_bvh_refit, P, w.stream, d, P, sidx);
+    }
+    const unsigned* sortedIdx = idxInB ? d.bv_idx2 : d.bv_idx;
+    if (w.hashDirty) rebuild_hash(w);
+    tm.mark(w, PR_STAGE_QUERY);
+    unsigned nPairs = 0;
+    for (;;) {
+        ensure(w, G_PAIR, std::max(1024u, nPairs));
+        read_counters(w);
+        w.hostCnt.nPairs = 0; w.hostCnt.error &= ~static_cast<unsigned>(ERR_PAIR_OVERFLOW);
+        write_counters(w);
+        PR_LAUNCH(k_bvh_query, nQueue, w.stream, d, nQueue, P, sortedIdx, w.capPairs);
+        read_counters(w);
+        nPairs = w.hostCnt.nPairs;
+        if (nPairs <= w.capPairs) break;
+    }
+    throw_device_error(w);
+    PR_LAUNCH(k_clear_queue_flags, nQueue, w.stream, d, nQueue);
+    w.hostCnt.nQueue = 0; w.hostCnt.error &= ~static_cast<unsigned>(ERR_PAIR_OVERFLOW);
+    write_counters(w);
+    w.profile.candidate_pairs += nPairs;
+    if (nPairs == 0) return 0;
+    tm.mark(w, PR_STAGE_ADD);
+    // sort candidate keys: (min tree id << 32 | max tree id); LSD over the max field then the min field
+    const unsigned maxTree = std::max(1u, w.maxTreeId);
+    const int bits = key_bits(maxTree);
+    bool inB = radix_sort_pairs<unsigned long long>(d.np_key, d.np_idx, d.np_key2, d.np_idx2, nPairs, 0, bits, true, w.rs, w.stream);
+    unsigned long long* kA = inB ? d.np_key2 : d.np_key; unsigned* vA = inB ? d.np_idx2 : d.np_idx;
+    unsigned long long* kB = inB ? d.np_key : d.np_key2; unsigned* vB = inB ? d.np_idx : d.np_idx2;
+    const bool inB2 = radix_sort_pairs<unsigned long long>(kA, vA, kB, vB, nPairs, 32, 32 + bits, false, w.rs, w.stream);
+    const unsigned long long* keys = inB2 ? kB : kA;
+    const unsigned* src = inB2 ? vB : vA;
+    const unsigned used = std::min(nPairs, w.nFree);
+    const unsigned fresh = nPairs - used;
+    ensure(w, G_CONTACT, std::max(w.poolSize + fresh, w.nOrder + nPairs) + 1);
+    if (2u * w.capContacts > w.capHash) rebuild_hash(w);
+    PR_LAUNCH(k_create_contacts, nPairs, w.stream, d, nPairs, keys, src, w.nOrder, w.nFree, w.poolSize);
+    const unsigned oldOrder = w.nOrder;
+    w.nFree -= used; w.poolSize += fresh; w.nOrder += nPairs;
+    // AddContacts ends with Update(contactID) for each new contact (:2531); not part of UpdateContacts' stats
+    read_counters(w);
+    const unsigned savedUpdated = w.hostCnt.contactsUpdated;
+    PR_LAUNCH(k_update_contacts, nPairs, w.stream, d, conf, oldOrder, nPairs, 0u);
+    read_counters(w);
+    w.hostCnt.contactsUpdated = savedUpdated;
+    write_counters(w);
+    throw_device_error(w);
+    return nPairs;
+}
+
+// ------------------------------------------------------------------ regular phase (SolveReg :1472-1561)
+static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, StageTimer& tm)
+{
+    DV& d = w.d;
+    const unsigned N = w.nBodies;
+    tm.mark(w, PR_STAGE_ISLANDS);
+    PR_LAUNCH(k_isl_init, N, w.stream, d, N, conf.reg_velocity_iters, conf.reg_position_iters);
+    PR_LAUNCH(k_isl_union, w.nOrder, w.stream, d, w.nOrder);
+    PR_LAUNCH(k_isl_flatten, N, w.stream, d, N);
+    tm.mark(w, PR_STAGE_INTEGRATE);
+    PR_LAUNCH(k_isl_prepare, N, w.stream, d, N, conf);
+    tm.mark(w, PR_STAGE_COLOR);
+    unsigned nCons = 0;
+    if (w.nOrder) {
+        ensure(w, G_CONS, w.nOrder + 1);
+        PR_LAUNCH(k_mark_constraints, w.nOrder, w.stream, d, w.nOrder, d.c_tmp);
+        scan_exclusive_u32(d.c_tmp, d.k_tmpVal, w.nOrder, &d.cnt->nConstraints, w.scanScratch, w.stream);
+        PR_LAUNCH(k_gather_constraints, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, d.k_tmpVal);
+        read_counters(w);
+        nCons = w.hostCnt.nConstraints;
+    }
+    w.nCons = nCons; w.nColors = 0;
+    std::vector<std::pair<unsigned, unsigned>> ranges; // (start, count) per colour, overflow tail last
+    unsigned tailStart = 0, tailCount = 0;
+    if (nCons) {
+        for (unsigned round = 0;; ++round) {
+            if (round && (round % 64u) == 0u) PR_LAUNCH(k_color_reset_claims, N, w.stream, d, N);
+            w.hostCnt.nUncolored = 0; write_counters(w);
+            PR_LAUNCH(k_color_claim, nCons, w.stream, d, nCons, round);
+            PR_LAUNCH(k_color_commit, nCons, w.stream, d, nCons, round);
+            read_counters(w);
+            if (w.hostCnt.nUncolored == 0) break;
+            if (round > 100000u) throw CudaError{"colouring did not converge"};
+        }
+        // stable sort by colour (one 8-bit radix pass): k_sorted = permutation of the base constraint list
+        d2d(w, d.k_tmpKey, d.k_color, nCons * sizeof(unsigned));
+        const bool inB = radix_sort_pairs<unsigned>(d.k_tmpKey, d.k_sorted, d.k_tmpKey2, d.k_tmpVal, nCons, 0, 8, true, w.rs, w.stream);
+        const unsigned* sortedColor = inB ? d.k_tmpKey2 : d.k_tmpKey;
+        if (inB) d2d(w, d.k_sorted, d.k_tmpVal, nCons * sizeof(unsigned));
+        for (unsigned c = 0; c <= MAX_COLORS; ++c) w.hostCnt.colorStart[c] = INVALID;
+        write_counters(w);
+        PR_LAUNCH(k_color_starts, nCons, w.stream, d, nCons, sortedColor);
+        read_counters(w);
+        if (w.debugFlags & 1u) { // solve order for the parity oracle (pr_get_solve_order)
+            w.solveOrderIds.resize(nCons); w.solveOrderColors.resize(nCons);
+            // c_tmp (marks, consumed) and c_tmp2 (stale ping-pong copy of c_order) are free scratch here
+            PR_LAUNCH(k_solve_order, nCons, w.stream, d, nCons, d.c_tmp, d.c_tmp2, sortedColor);
+            d2h(w, w.solveOrderIds.data(), d.c_tmp, nCons * sizeof(unsigned));
+            d2h(w, w.solveOrderColors.data(), d.c_tmp2, nCons * sizeof(unsigned));
+        }
+        unsigned prevStart = nCons;
+        for (int c = static_cast<int>(MAX_COLORS) - 1; c >= 0; --c) {
+            const unsigned s = w.hostCnt.colorStart[c];
+            if (s == INVALID) continue;
+            if (static_cast<unsigned>(c) == COLOR_OVERFLOW) { tailStart = s; tailCount = prevStart - s; }
+            else ranges.emplace_back(s, prevStart - s);
+            prevStart = s;
+        }
+        std::reverse(ranges.begin(), ranges.end());
+        w.nColors = static_cast<unsigned>(ranges.size()) + (tailCount ? 1u : 0u);
+        tm.mark(w, PR_STAGE_SETUP);
+        PR_LAUNCH(k_build_constraints, nCons, w.stream, d, nCons, conf, conf.do_warm_start ? conf.dt_ratio : 0.0f);
+        if (conf.do_warm_start) {
+            for (const auto& r : ranges) PR_LAUNCH(k_warm_start, r.second, w.stream, d, r.first, r.second);
+            if (tailCount) PR_LAUNCH(k_warm_start_serial, 1, w.stream, d, tailStart, tailCount);
+        }
+    }
+    tm.mark(w, PR_STAGE_VELOCITY);
+    for (unsigned it = 0; it < conf.reg_velocity_iters; ++it) {
+        for (const auto& r : ranges) PR_LAUNCH(k_solve_velocity, r.second, w.stream, d, r.first, r.second);
+        if (tailCount) PR_LAUNCH(k_solve_velocity_serial, 1, w.stream, d, tailStart, tailCount);
+        PR_LAUNCH(k_isl_vel_check, N, w.stream, d, N, it, conf.reg_min_momentum);
+    }
+    tm.mark(w, PR_STAGE_POSITION);
+    PR_LAUNCH(k_integrate_positions, N, w.stream, d, N, conf.delta_time);
+    for (unsigned it = 0; it < conf.reg_position_iters; ++it) {
+        for (const auto& r : ranges)
+            PR_LAUNCH(k_solve_position, r.second, w.stream, d, r.first, r.second, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
+        if (tailCount)
+            PR_LAUNCH(k_solve_position_serial, 1, w.stream, d, tailStart, tailCount, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
+        PR_LAUNCH(k_isl_pos_check, N, w.stream, d, N, it, conf.reg_min_separation);
+    }
+    tm.mark(w, PR_STAGE_WRITEBACK);
+    if (nCons) PR_LAUNCH(k_assign_impulses, nCons, w.stream, d, nCons);
+    PR_LAUNCH(k_writeback_bodies, N, w.stream, d, N, conf);
+    PR_LAUNCH(k_sleep_and_stats, N, w.stream, d, N, conf.min_still_time_to_sleep);
+    tm.mark(w, PR_STAGE_SYNC);
+    w.hostCnt.proxiesMoved = 0; // (device copy is refreshed below)
+    read_counters(w);
+    w.hostCnt.proxiesMoved = 0; w.hostCnt.contactsUpdated = 0;
+    write_counters(w);
+    PR_LAUNCH(k_sync_proxies, w.nProxies, w.stream, d, conf, w.nProxies);
+    tm.mark(w, PR_STAGE_NARROW);
+    const unsigned nOrderAtUpdate = w.nOrder;
+    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 1u);
+    dset(w, d.b_moved, 0, sizeof(unsigned) * N);
+    dset(w, d.b_sync, 0, sizeof(unsigned) * N);
+    read_counters(w);
+    const Counters c = w.hostCnt;
+    stats.reg.proxies_moved = c.proxiesMoved;
+    stats.reg.contacts_updated = c.contactsUpdated;
+    stats.reg.contacts_skipped = nOrderAtUpdate - c.contactsUpdated;
+    stats.reg.islands_found = c.islandsFound;
+    stats.reg.islands_solved = c.islandsSolved;
+    stats.reg.bodies_slept = c.bodiesSlept;
+    stats.reg.sum_pos_iters = c.sumPosIters;
+    stats.reg.sum_vel_iters = c.sumVelIters;
+    stats.reg.max_island_bodies = c.maxIslandBodies;
+    stats.reg.min_separation = float_unflip(c.minSepFlip);
+    stats.reg.max_inc_impulse = u2f(c.maxIncBits);
+    w.profile.n_awake = c.nAwake; w.profile.c_touching = c.nTouching; w.profile.c_dirty = c.contactsUpdated;
+    w.profile.p_moved = c.proxiesMoved; w.profile.n_islands = c.islandsFound; w.profile.n_colors = w.nColors;
+    w.profile.vel_iters = conf.reg_velocity_iters; w.profile.pos_iters = conf.reg_position_iters;
+    stats.reg.contacts_added = find_add_contacts(w, conf, tm);
+}
+
+static void reset_counters(World& w)
+{
+    std::memset(&w.hostCnt, 0, sizeof(Counters));
+    w.hostCnt.minSepFlip = float_flip(std::numeric_limits<float>::infinity());
+    write_counters(w);
+}
+
+static void step_impl(World& w, const pr_step_conf& conf, pr_step_stats& stats)
+{
+    DV& d = w.d;
+    static thread_local StageTimer* tmp = nullptr;
+    if (!tmp) tmp = new StageTimer();
+    StageTimer& tm = *tmp;
+    std::memset(&stats, 0, sizeof(stats));
+    stats.reg.min_separation = std::numeric_limits<float>::infinity();
+    stats.toi.min_separation = std::numeric_limits<float>::infinity();
+    std::memset(&w.profile, 0, sizeof(w.profile));
+    reset_launch_count();
+    tm.mark(w, PR_STAGE_PRE);
+    // keep the queue count across steps (pr_set_bodies / creation between steps feed it)
+    read_counters(w);
+    const unsigned keepQueue = w.hostCnt.nQueue;
+    reset_counters(w);
+    w.hostCnt.nQueue = keepQueue; write_counters(w);
+    stats.pre.proxies_created = create_queued_proxies(w, conf);
+    if (w.anyBodySet) PR_LAUNCH(k_sync_proxies, w.nProxies, w.stream, d, conf, w.nProxies);
+    stats.pre.contacts_destroyed = destroy_contacts(w);
+    const unsigned nOrderAtUpdate = w.nOrder;
+    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, w.anyBodySet ? 1u : 0u);
+    if (w.anyBodySet) { dset(w, d.b_moved, 0, sizeof(unsigned) * w.nBodies); dset(w, d.b_sync, 0, sizeof(unsigned) * w.nBodies); }
+    w.anyBodySet = false;
+    read_counters(w);
+    stats.pre.proxies_moved = w.hostCnt.proxiesMoved;
+    stats.pre.contacts_updated = w.hostCnt.contactsUpdated;
+    stats.pre.contacts_skipped = nOrderAtUpdate - w.hostCnt.contactsUpdated;
+    stats.pre.contacts_added = find_add_contacts(w, conf, tm);
+    if (conf.delta_time != 0.0f) {
+        w.inv_dt0 = 1.0f / conf.delta_time;
+        if (w.stepComplete) solve_reg(w, conf, stats, tm);
+        // TOI phase: see pr_toi (milestone); conf.do_toi is honoured there
+    }
+    check_launch();
+    w.profile.p_total = w.nProxies; w.profile.c_total = w.nOrder;
+    tm.finish(w, w.profile);
+    sync(w);
+    w.profile.kernel_launches = launches_since_reset();
+}
+
+} // namespace pr
+
+// =============================================================================================
+using namespace pr;
+struct pr_world { World w; };
+
+#define API_TRY(wptr) try {
+#define API_CATCH(wptr)                                                                            \
+    } catch (const CudaError& e) { (wptr)->w.error = e.msg; return PR_ERR_CUDA; }                  \
+    catch (const std::exception& e) { (wptr)->w.error = e.what(); return PR_ERR_CUDA; }
+
+extern "C" {
+
+int pr_abi_version(void) { return PR_ABI_VERSION; }
+
+void pr_world_conf_default(pr_world_conf* c)
+{
+    c->min_vertex_radius = 0.01f; c->max_vertex_radius = 255.0f; // WorldConf::DefaultVertexRadius
+    c->body_capacity = c->proxy_capacity = c->contact_capacity = c->vertex_capacity = 0;
+    c->device = -1;
+}
+
+void pr_step_conf_default(pr_step_conf* c)
+{ // StepConf{} defaults: Settings.hpp:92-256, StepConf.hpp:163-391 (checked against the reference in tests)
+    const float pi = 3.14159265358979323846264338327950288f;
+    const float slop = 0.005f;
+    c->delta_time = 1.0f / 60; c->dt_ratio = 1.0f;
+    c->min_still_time_to_sleep = 1.0f / 2; c->linear_slop = slop; c->angular_slop = (pi * 2 * 1.0f) / 180.0f;
+    c->reg_resolution_rate = 2.0f / 10; c->reg_min_separation = -slop * 3; c->reg_min_momentum = 0.0f / 100;
+    c->toi_resolution_rate = 75.0f / 100; c->toi_min_separation = -slop * 1.5f; c->toi_min_momentum = 0.0f / 100;
+    c->target_depth = slop * 3; c->tolerance = slop / 4; c->velocity_threshold = 1.0f;
+    c->max_translation = 2.0f; c->max_rotation = 179.0f * (pi / 180.0f);
+    c->max_linear_correction = 0.2f; c->max_angular_correction = (8.0f / 180.0f) * pi * 1.0f;
+    c->linear_sleep_tolerance = 0.01f; c->angular_sleep_tolerance = 2.0f * (pi / 180.0f);
+    c->displace_multiplier = 2.0f; c->aabb_extension = slop * 20.0f; c->max_circles_ratio = 10.0f;
+    c->reg_velocity_iters = 8; c->reg_position_iters = 3; c->toi_velocity_iters = 8; c->toi_position_iters = 20;
+    c->max_toi_root_iters = 30; c->max_toi_iters = 20; c->max_distance_iters = 20; c->max_sub_steps = 8;
+    c->do_warm_start = 1; c->do_toi = 1; c->do_blocksolve = 1;
+}
+
+int pr_create(const pr_world_conf* conf, pr_world** out)
+{
+    *out = nullptr;
+    pr_world* pw = nullptr;
+    try {
+        pw = new pr_world();
+        World& w = pw->w;
+        if (conf) w.conf = *conf; else pr_world_conf_default(&w.conf);
+#ifndef PR_HOST_EMUL
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_createError = "no CUDA device: the B200 path has no CPU fallback"; delete pw; return PR_ERR_CUDA; }
+        if (w.conf.device >= 0) CK(cudaSetDevice(w.conf.device));
+        CK(cudaGetDevice(&w.device));
+        CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+#endif
+        w.d.cnt = static_cast<Counters*>(dev_alloc(sizeof(Counters)));
+        ensure(w, G_BODY, std::max(64u, w.conf.body_capacity));
+        ensure(w, G_SHAPE, 64); ensure(w, G_CHILD, 64); ensure(w, G_VERT, std::max(256u, w.conf.vertex_capacity));
+        ensure(w, G_PROXY, std::max(64u, w.conf.proxy_capacity));
+        ensure(w, G_CONTACT, std::max(256u, w.conf.contact_capacity));
+        ensure(w, G_PAIR, 1024); ensure(w, G_CONS, 256);
+        ensure(w, G_HASH, next_pow2(2u * w.capContacts));
+        reset_counters(w);
+        sync(w);
+        *out = pw;
+        return PR_OK;
+    } catch (const CudaError& e) { g_createError = e.msg; delete pw; return PR_ERR_CUDA; }
+}
+
+int pr_destroy(pr_world* pw)
+{
+    if (!pw) return PR_OK;
+    World& w = pw->w;
+    for (const ArrDesc& a : arrays(w)) dev_free(*a.slot);
+    dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist);
+#ifndef PR_HOST_EMUL
+    if (w.stream) cudaStreamDestroy(w.stream);
+#endif
+    delete pw;
+    return PR_OK;
+}
+
+const char* pr_last_error(const pr_world* pw) { return pw ? pw->w.error.c_str() : g_createError.c_str(); }
+
+int pr_clone(const pr_world* src, pr_world** out)
+{
+    pr_world* pw = nullptr;
+    const int rc = pr_create(&src->w.conf, &pw);
+    if (rc != PR_OK) return rc;
+    API_TRY(pw)
+    World& w = pw->w;
+    World& s = const_cast<World&>(src->w);
+    sync(s);
+    ensure(w, G_BODY, s.capBodies); ensure(w, G_SHAPE, s.capShapes); ensure(w, G_CHILD, s.capChildren); ensure(w, G_VERT, s.capVerts);
+    ensure(w, G_PROXY, s.capProxies); ensure(w, G_CONTACT, s.capContacts); ensure(w, G_HASH, s.capHash);
+    ensure(w, G_PAIR, s.capPairs); ensure(w, G_CONS, s.capCons);
+    auto da = arrays(w); auto sa = arrays(s);
+    for (size_t i = 0; i < da.size(); ++i) d2d(w, *da[i].slot, *sa[i].slot, da[i].elem * *cap_of(s, sa[i].g));
+    d2d(w, w.d.cnt, s.d.cnt, sizeof(Counters));
+    w.shapes = s.shapes; w.children = s.children; w.bodyShapes = s.bodyShapes; w.joints = s.joints;
+    w.fixturesForProxies = s.fixturesForProxies;
+    w.nBodies = s.nBodies; w.nShapes = s.nShapes; w.nChildren = s.nChildren; w.nVerts = s.nVerts; w.nProxies = s.nProxies;
+    w.maxTreeId = s.maxTreeId; w.debugFlags = s.debugFlags;
+    w.nOrder = s.nOrder; w.nFree = s.nFree; w.poolSize = s.poolSize; w.anyBodySet = s.anyBodySet; w.hashDirty = true;
+    w.stepComplete = s.stepComplete; w.inv_dt0 = s.inv_dt0;
+    sync(w);
+    *out = pw;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_clear(pr_world* pw)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    w.shapes.clear(); w.children.clear(); w.bodyShapes.clear(); w.joints.clear(); w.fixturesForProxies.clear();
+    w.nBodies = w.nShapes = w.nChildren = w.nVerts = w.nProxies = w.nOrder = w.nFree = w.poolSize = 0; w.maxTreeId = 0;
+    w.anyBodySet = false; w.hashDirty = true; w.stepComplete = true;
+    reset_counters(w);
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_create_shapes(pr_world* pw, uint32_t n, const pr_shape* shapes, const pr_child* children, uint32_t n_children,
+                     const pr_vec2* vertices, const pr_vec2* normals, uint32_t n_vertices, uint32_t* first_id)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    // CreateShape validation (AabbTreeWorld.cpp:1234-1255): every child's vertex radius within the world interval
+    for (uint32_t i = 0; i < n_children; ++i) {
+        if (children[i].vertex_count == 0 || children[i].vertex_count > 254) { w.error = "child vertex count out of range"; return PR_ERR_INVALID_ARGUMENT; }
+        if (!(children[i].vertex_radius >= w.conf.min_vertex_radius && children[i].vertex_radius <= w.conf.max_vertex_radius)) {
+            w.error = "vertex radius outside world interval"; return PR_ERR_INVALID_ARGUMENT;
+        }
+        if (children[i].vertex_offset + children[i].vertex_count > n_vertices) { w.error = "child vertex range"; return PR_ERR_OUT_OF_RANGE; }
+    }
+    ensure(w, G_SHAPE, w.nShapes + n); ensure(w, G_CHILD, w.nChildren + n_children); ensure(w, G_VERT, w.nVerts + n_vertices);
+    std::vector<float4> mat(n); std::vector<unsigned> filt(n); std::vector<int> grp(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        pr_shape s = shapes[i];
+        if (s.child_offset + s.child_count > n_children) { w.error = "shape child range"; return PR_ERR_OUT_OF_RANGE; }
+        s.child_offset += w.nChildren;
+        w.shapes.push_back(s);
+        mat[i] = make_float4(s.friction, s.restitution, s.is_sensor ? 1.0f : 0.0f, s.density);
+        filt[i] = static_cast<unsigned>(s.filter_category) | (static_cast<unsigned>(s.filter_mask) << 16);
+        grp[i] = s.filter_group;
+    }
+    std::vector<float> rad(n_children); std::vector<unsigned> voff(n_children), cnt(n_children);
+    for (uint32_t i = 0; i < n_children; ++i) {
+        pr_child c = children[i];
+        c.vertex_offset += w.nVerts;
+        w.children.push_back(c);
+        rad[i] = c.vertex_radius; voff[i] = c.vertex_offset; cnt[i] = c.vertex_count;
+    }
+    h2d(w, w.d.sh_mat + w.nShapes, mat.data(), n * sizeof(float4)); h2d(w, w.d.sh_filter + w.nShapes, filt.data(), n * 4);
+    h2d(w, w.d.sh_group + w.nShapes, grp.data(), n * 4);
+    h2d(w, w.d.ch_radius + w.nChildren, rad.data(), n_children * 4); h2d(w, w.d.ch_voff + w.nChildren, voff.data(), n_children * 4);
+    h2d(w, w.d.ch_count + w.nChildren, cnt.data(), n_children * 4);
+    h2d(w, w.d.vtx + w.nVerts, vertices, n_vertices * sizeof(pr_vec2)); h2d(w, w.d.nrm + w.nVerts, normals, n_vertices * sizeof(pr_vec2));
+    sync(w);
+    if (first_id) *first_id = w.nShapes;
+    w.nShapes += n; w.nChildren += n_children; w.nVerts += n_vertices;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const uint32_t* shape_offsets, const uint32_t* shape_ids, uint32_t* first_id)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t k = shape_offsets[i]; k < shape_offsets[i + 1]; ++k)
+            if (shape_ids[k] >= w.nShapes) { w.error = "no such shape"; return PR_ERR_OUT_OF_RANGE; }
+    ensure(w, G_BODY, w.nBodies + n);
+    pr_body* staging = static_cast<pr_body*>(dev_alloc(sizeof(pr_body) * n));
+    h2d(w, staging, bodies, sizeof(pr_body) * n);
+    PR_LAUNCH(k_put_bodies, n, w.stream, w.d, n, w.nBodies, static_cast<const unsigned*>(nullptr), staging, 0u);
+    dset(w, w.d.b_moved + w.nBodies, 0, 4 * n); dset(w, w.d.b_sync + w.nBodies, 0, 4 * n);
+    sync(w);
+    dev_free(staging);
+    for (uint32_t i = 0; i < n; ++i) {
+        std::vector<unsigned> sh(shape_ids + shape_offsets[i], shape_ids + shape_offsets[i + 1]);
+        if (bodies[i].flags & PR_BODY_ENABLED) for (unsigned s : sh) w.fixturesForProxies.emplace_back(w.nBodies + i, s); // CreateBody :1046-1052
+        w.bodyShapes.push_back(std::move(sh));
+    }
+    if (first_id) *first_id = w.nBodies;
+    w.nBodies += n;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*, uint32_t*)
+{
+    if (n == 0) return PR_OK;
+    pw->w.error = "revolute joints: device solver support lands with the joint milestone";
+    return PR_ERR_UNSUPPORTED;
+}
+
+int pr_set_bodies(pr_world* pw, uint32_t n, const uint32_t* ids, const pr_body* rows)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    for (uint32_t i = 0; i < n; ++i) if (ids[i] >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    if (!n) return PR_OK;
+    pr_body* staging = static_cast<pr_body*>(dev_alloc(sizeof(pr_body) * n));
+    unsigned* dids = static_cast<unsigned*>(dev_alloc(4 * n));
+    h2d(w, staging, rows, sizeof(pr_body) * n); h2d(w, dids, ids, 4 * n);
+    PR_LAUNCH(k_put_bodies, n, w.stream, w.d, n, 0u, dids, staging, 1u);
+    sync(w);
+    dev_free(staging); dev_free(dids);
+    w.anyBodySet = true;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_get_bodies(const pr_world* cpw, uint32_t first, uint32_t n, pr_body* rows)
+{
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    if (first + n > w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    if (!n) return PR_OK;
+    pr_body* staging = static_cast<pr_body*>(dev_alloc(sizeof(pr_body) * n));
+    PR_LAUNCH(k_get_bodies, n, w.stream, w.d, first, n, staging);
+    d2h(w, rows, staging, sizeof(pr_body) * n);
+    dev_free(staging);
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_get_revolute_joints(const pr_world*, uint32_t, uint32_t n, pr_revolute_joint*) { return n ? PR_ERR_UNSUPPORTED : PR_OK; }
+
+int pr_get_counts(const pr_world* pw, pr_counts* out)
+{
+    const World& w = pw->w;
+    std::memset(out, 0, sizeof(*out));
+    out->bodies = w.nBodies; out->shapes = w.nShapes; out->children = w.nChildren; out->vertices = w.nVerts;
+    out->proxies = w.nProxies; out->contacts = w.nOrder; out->joints = 0; out->contact_id_range = w.poolSize;
+    out->tree_leaf_count = w.nProxies;
+    // DynamicTree capacity: DefaultTreeCapacity 4096 grown to the next power of two of the node count (DynamicTree.cpp:436-454)
+    const unsigned nodes = w.nProxies ? 2u * w.nProxies - 1u : 0u;
+    out->tree_node_capacity = std::max(4096u, next_pow2(nodes));
+    return PR_OK;
+}
+
+int pr_get_contacts(const pr_world* cpw, uint32_t cap, pr_contact* contacts, pr_manifold* manifolds, uint32_t* n_out)
+{
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    *n_out = w.nOrder;
+    const unsigned n = std::min(cap, w.nOrder);
+    if (!n) return PR_OK;
+    pr_contact* sc = static_cast<pr_contact*>(dev_alloc(sizeof(pr_contact) * n));
+    pr_manifold* sm = manifolds ? static_cast<pr_manifold*>(dev_alloc(sizeof(pr_manifold) * n)) : nullptr;
+    PR_LAUNCH(k_export_contacts, n, w.stream, w.d, n, sc, sm);
+    d2h(w, contacts, sc, sizeof(pr_contact) * n);
+    if (manifolds) d2h(w, manifolds, sm, sizeof(pr_manifold) * n);
+    dev_free(sc); dev_free(sm);
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_get_proxies(const pr_world* cpw, uint32_t cap, pr_proxy* proxies, uint32_t* n_out)
+{
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    *n_out = w.nProxies;
+    const unsigned n = std::min(cap, w.nProxies);
+    if (!n) return PR_OK;
+    pr_proxy* sp = static_cast<pr_proxy*>(dev_alloc(sizeof(pr_proxy) * n));
+    PR_LAUNCH(k_export_proxies, n, w.stream, w.d, n, sp);
+    d2h(w, proxies, sp, sizeof(pr_proxy) * n);
+    dev_free(sp);
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_load_state(pr_world* pw, uint32_t n_bodies, const pr_body* bodies, uint32_t n_proxies, const pr_proxy* proxies,
+                  uint32_t n_contacts, const pr_contact* contacts, const pr_manifold* manifolds, float inv_dt0)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    if (n_bodies != w.nBodies) { w.error = "body count mismatch"; return PR_ERR_INVALID_ARGUMENT; }
+    std::vector<unsigned> ids(n_bodies);
+    for (unsigned i = 0; i < n_bodies; ++i) ids[i] = i;
+    const int rc = pr_set_bodies(pw, n_bodies, ids.data(), bodies);
+    if (rc != PR_OK) return rc;
+    dset(w, w.d.b_moved, 0, 4 * w.capBodies); dset(w, w.d.b_sync, 0, 4 * w.capBodies);
+    w.anyBodySet = false;
+    // proxies
+    ensure(w, G_PROXY, n_proxies + 1);
+    std::vector<unsigned> body(n_proxies), shape(n_proxies), child(n_proxies), cg(n_proxies), tree(n_proxies);
+    std::vector<float4> fat(n_proxies);
+    unsigned maxTree = 0;
+    for (unsigned i = 0; i < n_proxies; ++i) {
+        const pr_proxy& p = proxies[i];
+        if (p.shape >= w.nShapes || p.body >= w.nBodies) { w.error = "proxy refers to unknown body/shape"; return PR_ERR_OUT_OF_RANGE; }
+        body[i] = p.body; shape[i] = p.shape; child[i] = p.child; cg[i] = w.shapes[p.shape].child_offset + p.child; tree[i] = p.tree_id;
+        fat[i] = make_float4(p.min_x, p.min_y, p.max_x, p.max_y);
+        maxTree = std::max(maxTree, p.tree_id);
+    }
+    h2d(w, w.d.p_body, body.data(), 4 * n_proxies); h2d(w, w.d.p_shape, shape.data(), 4 * n_proxies);
+    h2d(w, w.d.p_child, child.data(), 4 * n_proxies); h2d(w, w.d.p_cg, cg.data(), 4 * n_proxies);
+    h2d(w, w.d.p_tree, tree.data(), 4 * n_proxies); h2d(w, w.d.p_fat, fat.data(), sizeof(float4) * n_proxies);
+    dset(w, w.d.p_moved, 0, 4 * w.capProxies);
+    w.nProxies = n_proxies; w.maxTreeId = maxTree;
+    w.fixturesForProxies.clear();
+    // contacts
+    unsigned maxId = 0;
+    for (unsigned i = 0; i < n_contacts; ++i) maxId = std::max(maxId, contacts[i].id + 1);
+    ensure(w, G_CONTACT, std::max(maxId, n_contacts) + 1);
+    std::vector<unsigned> pxOfTree(maxTree + 1, 0u);
+    for (unsigned i = 0; i < n_proxies; ++i) pxOfTree[tree[i]] = i;
+    std::vector<char> usedId(maxId, 0);
+    for (unsigned i = 0; i < n_contacts; ++i) usedId[contacts[i].id] = 1;
+    std::vector<unsigned> freeIds;
+    for (unsigned id = maxId; id-- > 0;) if (!usedId[id]) freeIds.push_back(id);
+    if (n_contacts) {
+        pr_contact* sc = static_cast<pr_contact*>(dev_alloc(sizeof(pr_contact) * n_contacts));
+        pr_manifold* sm = static_cast<pr_manifold*>(dev_alloc(sizeof(pr_manifold) * n_contacts));
+        unsigned* dpx = static_cast<unsigned*>(dev_alloc(4 * pxOfTree.size()));
+        h2d(w, sc, contacts, sizeof(pr_contact) * n_contacts); h2d(w, sm, manifolds, sizeof(pr_manifold) * n_contacts);
+        h2d(w, dpx, pxOfTree.data(), 4 * pxOfTree.size());
+        PR_LAUNCH(k_import_contacts, n_contacts, w.stream, w.d, n_contacts, sc, sm, dpx);
+        sync(w);
+        dev_free(sc); dev_free(sm); dev_free(dpx);
+    }
+    h2d(w, w.d.c_free, freeIds.data(), 4 * freeIds.size());
+    sync(w);
+    w.nOrder = n_contacts; w.nFree = static_cast<unsigned>(freeIds.size()); w.poolSize = maxId;
+    w.hashDirty = true; w.stepComplete = true; w.inv_dt0 = inv_dt0;
+    reset_counters(w);
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_step(pr_world* pw, const pr_step_conf* conf, pr_step_stats* stats_out)
+{
+    API_TRY(pw)
+    pr_step_stats st;
+    step_impl(pw->w, *conf, st);
+    if (stats_out) *stats_out = st;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_get_solve_order(const pr_world* pw, uint32_t cap, uint32_t* contact_ids, uint32_t* colors, uint32_t* n_out)
+{
+    const World& w = pw->w;
+    *n_out = w.nCons;
+    const unsigned n = std::min<unsigned>(cap, static_cast<unsigned>(std::min<size_t>(w.nCons, w.solveOrderIds.size())));
+    for (unsigned i = 0; i < n; ++i) { contact_ids[i] = w.solveOrderIds[i]; if (colors) colors[i] = w.solveOrderColors[i]; }
+    return PR_OK;
+}
+
+int pr_set_debug(pr_world* pw, uint32_t flags) { pw->w.debugFlags = flags; return PR_OK; }
+
+int pr_get_step_profile(const pr_world* pw, pr_step_profile* out) { *out = pw->w.profile; return PR_OK; }
+
+int pr_shift_origin(pr_world* pw, float, float) { pw->w.error = "ShiftOrigin: not implemented yet"; return PR_ERR_UNSUPPORTED; }
+
+float pr_get_inv_dt0(const pr_world* pw) { return pw->w.inv_dt0; }
+
+int pr_collide_shapes(int device, uint32_t n, const pr_child* children, uint32_t n_children, const pr_vec2* vertices,
+                      const pr_vec2* normals, uint32_t n_vertices, const uint32_t* a_child, const float* xf_a,
+                      const uint32_t* b_child, const float* xf_b, float linear_slop, float max_circles_ratio, pr_manifold* out)
+{
+    try {
+        World w; // only for the stream shim
+#ifndef PR_HOST_EMUL
+        if (device >= 0) CK(cudaSetDevice(device));
+        w.stream = 0;
+#else
+        (void)device;
+#endif
+        if (!n) return PR_OK;
+        pr_child* dch = static_cast<pr_child*>(dev_alloc(sizeof(pr_child) * n_children));
+        float2* dv = static_cast<float2*>(dev_alloc(sizeof(float2) * n_vertices));
+        float2* dn = static_cast<float2*>(dev_alloc(sizeof(float2) * n_vertices));
+        unsigned* da = static_cast<unsigned*>(dev_alloc(4 * n)); unsigned* db = static_cast<unsigned*>(dev_alloc(4 * n));
+        float4* dxa = static_cast<float4*>(dev_alloc(16 * n)); float4* dxb = static_cast<float4*>(dev_alloc(16 * n));
+        pr_manifold* dout = static_cast<pr_manifold*>(dev_alloc(sizeof(pr_manifold) * n));
+        h2d(w, dch, children, sizeof(pr_child) * n_children); h2d(w, dv, vertices, 8 * n_vertices); h2d(w, dn, normals, 8 * n_vertices);
+        h2d(w, da, a_child, 4 * n); h2d(w, db, b_child, 4 * n); h2d(w, dxa, xf_a, 16 * n); h2d(w, dxb, xf_b, 16 * n);
+        PR_LAUNCH(k_collide_batch, n, w.stream, n, dch, dv, dn, da, dxa, db, dxb, linear_slop, max_circles_ratio, dout);
+        d2h(w, out, dout, sizeof(pr_manifold) * n);
+        dev_free(dch); dev_free(dv); dev_free(dn); dev_free(da); dev_free(db); dev_free(dxa); dev_free(dxb); dev_free(dout);
+        return PR_OK;
+    } catch (const CudaError& e) { g_createError = e.msg; return PR_ERR_CUDA; }
+}
+
+// sizes of the POD structs, for the python mirror (tests/test_abi.py)
+int pr_abi_sizeof(int which)
+{
+    switch (which) {
+    case 0: return sizeof(pr_body); case 1: return sizeof(pr_child); case 2: return sizeof(pr_shape);
+    case 3: return sizeof(pr_revolute_joint); case 4: return sizeof(pr_manifold); case 5: return sizeof(pr_contact);
+    case 6: return sizeof(pr_proxy); case 7: return sizeof(pr_step_conf); case 8: return sizeof(pr_step_stats);
+    case 9: return sizeof(pr_world_conf); case 10: return sizeof(pr_counts); case 11: return sizeof(pr_step_profile);
+    default: return -1;
+    }
+}
+
+// batched worlds: minimal host-loop implementation (one stream per world); the one-CTA-per-world
+// kernel path is SURVEY §7 step 8.
+struct pr_batch { std::vector<pr_world*> worlds; };
+int pr_batch_create(const pr_world_conf* conf, uint32_t n_worlds, pr_batch** out)
+{
+    pr_batch* b = new pr_batch();
+    for (uint32_t i = 0; i < n_worlds; ++i) {
+        pr_world* w = nullptr;
+        const int rc = pr_create(conf, &w);
+        if (rc != PR_OK) { for (auto* x : b->worlds) pr_destroy(x); delete b; return rc; }
+        b->worlds.push_back(w);
+    }
+    *out = b;
+    return PR_OK;
+}
+int pr_batch_destroy(pr_batch* b) { if (b) { for (auto* x : b->worlds) pr_destroy(x); delete b; } return PR_OK; }
+pr_world* pr_batch_world(pr_batch* b, uint32_t i) { return i < b->worlds.size() ? b->worlds[i] : nullptr; }
+int pr_batch_step(pr_batch* b, const pr_step_conf* conf, pr_step_stats* sum)
+{
+    pr_step_stats acc; std::memset(&acc, 0, sizeof(acc));
+    acc.reg.min_separation = acc.toi.min_separation = std::numeric_limits<float>::infinity();
+    for (auto* w : b->worlds) {
+        pr_step_stats s;
+        const int rc = pr_step(w, conf, &s);
+        if (rc != PR_OK) return rc;
+        acc.reg.islands_found += s.reg.islands_found; acc.reg.islands_solved += s.reg.islands_solved;
+        acc.reg.contacts_added += s.reg.contacts_added; acc.reg.bodies_slept += s.reg.bodies_slept;
+        acc.reg.proxies_moved += s.reg.proxies_moved; acc.reg.sum_pos_iters += s.reg.sum_pos_iters;
+        acc.reg.sum_vel_iters += s.reg.sum_vel_iters; acc.reg.contacts_updated += s.reg.contacts_updated;
+        acc.reg.min_separation = std::min(acc.reg.min_separation, s.reg.min_separation);
+        acc.reg.max_inc_impulse = std::max(acc.reg.max_inc_impulse, s.reg.max_inc_impulse);
+    }
+    if (sum) *sum = acc;
+    return PR_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,127 @@
+// pr_world.h -- host-side world object and the device SoA view handed to kernels.
+// Data layout in HBM (one row per id; ids are the API-visible pool indices):
+//   bodies   : float4 xf | float4 pos0(x,y,a,alpha0) | float4 pos1(x,y,a,underActive) | float4 vel |
+//              float4 acc | float4 mass(invM,invI,linDamp,angDamp) | float2 lc | u32 flags
+//   children : radius, vertex offset/count ; pooled float2 vertices / normals
+//   proxies  : body, shape, child, global child, tree id, float4 fat AABB (minx,miny,maxx,maxy)
+//   contacts : u64 key | uint4 (bodyA,bodyB,childGlobalA,childGlobalB) | uint2 proxy slots |
+//              uint4 api ids | float4 (friction,restitution,tangentSpeed,toi) | u32 flags |
+//              manifold = 4 x float4 (ln,lp | p0,p1 | jn0,jt0,jn1,jt1 | cf0,cf1,type,count)
+//   per-step : BodyConstraint (float4 vel, float4 pos), VelocityConstraint rows (144 B),
+//              PositionConstraint rows (64 B), both stored in colour-sorted solve order.
+#ifndef PR_WORLD_H
+#define PR_WORLD_H
+#include "pr_compat.h"
+#include "pr_prims.cuh"
+#include "../../include/playrho_b200.h"
+#include <string>
+#include <vector>
+
+namespace pr {
+
+constexpr unsigned INVALID = 0xFFFFFFFFu;
+constexpr unsigned COLOR_UNSET = 0xFFu;
+constexpr unsigned COLOR_OVERFLOW = 64u; // constraints that found no free colour < 64: serial tail
+constexpr unsigned MAX_COLORS = 65u;
+constexpr unsigned LEAF_BIT = 0x80000000u;
+
+enum { ISL_ACTIVE = 1u, ISL_VEL_DONE = 2u, ISL_POS_SOLVED = 4u };
+enum { ERR_NONE = 0, ERR_STACK = 1, ERR_SENSOR = 2, ERR_PAIR_OVERFLOW = 4, ERR_HASH_FULL = 8 };
+
+// VelocityConstraint row (Library/include/playrho/d2/VelocityConstraint.hpp), 144 B
+struct VCRow {
+    float nx, ny, friction, tangentSpeed;
+    unsigned bodyA, bodyB, count, contact;
+    float invMA, invIA, invMB, invIB;
+    float rA0x, rA0y, rB0x, rB0y;
+    float jn0, jt0, nm0, tm0;
+    float rA1x, rA1y, rB1x, rB1y;
+    float jn1, jt1, nm1, tm1;
+    float bias0, bias1, k00, k11;
+    float k01, m00, m11, m01;
+    unsigned island, dynA, dynB, pad;
+};
+// PositionConstraint row (PositionConstraint.hpp) + what GetPSM needs, 64 B
+struct PCRow {
+    float lnx, lny, lpx, lpy;
+    float p0x, p0y, p1x, p1y;
+    float lcAx, lcAy, lcBx, lcBy;
+    float totalRadius; unsigned typeCount; unsigned pad0, pad1;
+};
+
+struct Counters {
+    unsigned nQueue, nPairs, nNew, nDestroyed, nUncolored, nConstraints, nDirty, nOverflow;
+    unsigned islandsFound, islandsSolved, bodiesSlept, sumVelIters, sumPosIters, maxIslandBodies;
+    unsigned proxiesMoved, contactsUpdated, nAwake, nTouching, nActiveVel, nActivePos;
+    unsigned minSepFlip, maxIncBits, error, pad;
+    unsigned boundsMinX, boundsMinY, boundsMaxX, boundsMaxY;
+    unsigned colorStart[MAX_COLORS + 1];
+};
+
+struct DV {
+    // bodies
+    float4 *b_xf, *b_pos0, *b_pos1, *b_vel, *b_acc, *b_mass; float2* b_lc; unsigned* b_flags;
+    float4 *s_vel, *s_pos;
+    unsigned *b_island, *b_root, *b_moved, *b_sync;
+    unsigned *isl_state, *isl_velIters, *isl_posIters, *isl_inc, *isl_maxInc, *isl_sep, *isl_minSep, *isl_minUA, *isl_nbodies;
+    unsigned long long *b_claim, *b_cmask;
+    // shapes / children / vertices
+    float4* sh_mat; unsigned* sh_filter; int* sh_group;
+    float* ch_radius; unsigned *ch_voff, *ch_count; float2 *vtx, *nrm;
+    // proxies
+    unsigned *p_body, *p_shape, *p_child, *p_cg, *p_tree, *p_moved; float4* p_fat; unsigned* q_list;
+    // contacts
+    unsigned long long* c_key; uint4* c_ab; uint2* c_px; uint4* c_ids; float4* c_mat; unsigned* c_flags;
+    float4 *m0, *m1, *m2; uint4* m3;
+    unsigned *c_order, *c_free, *c_tmp, *c_tmp2;
+    unsigned long long* ht_keys; unsigned ht_mask;
+    // new pairs
+    unsigned long long *np_key, *np_key2; uint2* np_px; unsigned *np_idx, *np_idx2;
+    // constraints
+    VCRow* vc; PCRow* pc; unsigned *k_contact, *k_color, *k_sorted, *k_tmpKey, *k_tmpKey2, *k_tmpVal;
+    // bvh
+    unsigned *bv_code, *bv_code2, *bv_idx, *bv_idx2, *bv_left, *bv_right, *bv_parent, *bv_lparent, *bv_visit;
+    float4* bv_box;
+    Counters* cnt;
+};
+
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+};
+
+struct World {
+    pr_world_conf conf{};
+    int device = 0;
+    pr_stream_t stream{};
+    std::string error;
+    // host mirrors
+    std::vector<pr_shape> shapes;       // child_offset is global
+    std::vector<pr_child> children;     // vertex_offset is global
+    std::vector<std::vector<unsigned>> bodyShapes;
+    std::vector<pr_revolute_joint> joints;
+    std::vector<std::pair<unsigned, unsigned>> fixturesForProxies;
+    unsigned nBodies = 0, nShapes = 0, nChildren = 0, nVerts = 0, nProxies = 0;
+    unsigned nOrder = 0, nFree = 0, poolSize = 0;  // contacts
+    unsigned nCons = 0, nColors = 0, maxTreeId = 0, debugFlags = 0;
+    bool anyBodySet = false, hashDirty = true, stepComplete = true;
+    float inv_dt0 = 0;
+    // capacities
+    unsigned capBodies = 0, capShapes = 0, capChildren = 0, capVerts = 0, capProxies = 0, capContacts = 0,
+             capPairs = 0, capCons = 0, capHash = 0;
+    DV d{};
+    RadixScratch rs;
+    unsigned* scanScratch = nullptr; size_t scanScratchCap = 0;
+    Counters hostCnt{};
+    Counters* pinnedCnt = nullptr;
+    pr_step_profile profile{};
+    std::vector<unsigned> solveOrderIds, solveOrderColors;
+    std::vector<void*> allocs;
+};
+
+void count_launch();
+unsigned launches_since_reset();
+void reset_launch_count();
+
+} // namespace pr
+#endif

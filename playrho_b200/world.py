@@ -1,0 +1,219 @@
+"""ctypes binding of the C ABI in include/playrho_b200.h (libplayrho_b200.so, sm_100a CUDA).
+
+This is plumbing for tests/bench: the product is the shared library + the C++17 host type in
+playrho_b200/host/. There is NO CPU fallback: if the library is missing or no CUDA device is
+present, constructing a World raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplayrho_b200.so")
+
+vp, u32, f32, i32 = C.c_void_p, C.c_uint32, C.c_float, C.c_int
+
+EXPORTS = [
+    "pr_abi_version", "pr_world_conf_default", "pr_step_conf_default", "pr_create", "pr_destroy",
+    "pr_clone", "pr_clear", "pr_last_error", "pr_create_shapes", "pr_create_bodies",
+    "pr_create_revolute_joints", "pr_set_bodies", "pr_get_bodies", "pr_get_revolute_joints",
+    "pr_get_counts", "pr_get_contacts", "pr_get_proxies", "pr_load_state", "pr_step",
+    "pr_get_solve_order", "pr_set_debug", "pr_get_step_profile", "pr_abi_sizeof", "pr_shift_origin",
+    "pr_get_inv_dt0", "pr_collide_shapes", "pr_batch_create", "pr_batch_destroy", "pr_batch_world",
+    "pr_batch_step",
+]
+
+
+def bind(lib):
+    """Attach argtypes/restypes to a loaded library exposing the pr_* C ABI."""
+    lib.pr_abi_version.restype = i32
+    lib.pr_world_conf_default.argtypes = [vp]
+    lib.pr_step_conf_default.argtypes = [vp]
+    lib.pr_create.argtypes = [vp, C.POINTER(vp)]
+    lib.pr_destroy.argtypes = [vp]
+    lib.pr_clone.argtypes = [vp, C.POINTER(vp)]
+    lib.pr_clear.argtypes = [vp]
+    lib.pr_last_error.restype = C.c_char_p
+    lib.pr_last_error.argtypes = [vp]
+    lib.pr_create_shapes.argtypes = [vp, u32, vp, vp, u32, vp, vp, u32, C.POINTER(u32)]
+    lib.pr_create_bodies.argtypes = [vp, u32, vp, vp, vp, C.POINTER(u32)]
+    lib.pr_create_revolute_joints.argtypes = [vp, u32, vp, C.POINTER(u32)]
+    lib.pr_set_bodies.argtypes = [vp, u32, vp, vp]
+    lib.pr_get_bodies.argtypes = [vp, u32, u32, vp]
+    lib.pr_get_revolute_joints.argtypes = [vp, u32, u32, vp]
+    lib.pr_get_counts.argtypes = [vp, vp]
+    lib.pr_get_contacts.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
+    lib.pr_get_proxies.argtypes = [vp, u32, vp, C.POINTER(u32)]
+    lib.pr_load_state.argtypes = [vp, u32, vp, u32, vp, u32, vp, vp, f32]
+    lib.pr_step.argtypes = [vp, vp, vp]
+    lib.pr_get_solve_order.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
+    lib.pr_set_debug.argtypes = [vp, u32]
+    lib.pr_get_step_profile.argtypes = [vp, vp]
+    lib.pr_abi_sizeof.argtypes = [i32]
+    lib.pr_shift_origin.argtypes = [vp, f32, f32]
+    lib.pr_get_inv_dt0.restype = f32
+    lib.pr_get_inv_dt0.argtypes = [vp]
+    lib.pr_collide_shapes.argtypes = [i32, u32, vp, u32, vp, vp, u32, vp, vp, vp, vp, f32, f32, vp]
+    lib.pr_batch_create.argtypes = [vp, u32, C.POINTER(vp)]
+    lib.pr_batch_destroy.argtypes = [vp]
+    lib.pr_batch_world.restype = vp
+    lib.pr_batch_world.argtypes = [vp, u32]
+    lib.pr_batch_step.argtypes = [vp, vp, vp]
+    return lib
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load the CUDA library. Raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if path is None:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError("libplayrho_b200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                                   "There is no CPU fallback.")
+            _lib = bind(C.CDLL(LIB_PATH))
+        return _lib
+    return bind(C.CDLL(path))
+
+
+class PrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pr_status %d: %s" % (code, msg))
+        self.code = code
+
+
+def default_step_conf(lib=None, **kw):
+    lib = lib or load_library()
+    c = abi.one(abi.STEP_CONF)
+    lib.pr_step_conf_default(abi.ptr(c))
+    for k, v in kw.items():
+        c[k] = v
+    return c
+
+
+class World:
+    """Device-resident world. Mirrors the reference's World usage: create shapes/bodies, Step, read back."""
+
+    def __init__(self, scene=None, lib=None, device=-1, body_capacity=0, contact_capacity=0, proxy_capacity=0,
+                 record_solve_order=False):
+        self.lib = lib or load_library()
+        conf = abi.one(abi.WORLD_CONF)
+        self.lib.pr_world_conf_default(abi.ptr(conf))
+        conf["device"] = device
+        conf["body_capacity"] = body_capacity
+        conf["contact_capacity"] = contact_capacity
+        conf["proxy_capacity"] = proxy_capacity
+        h = vp()
+        rc = self.lib.pr_create(abi.ptr(conf), C.byref(h))
+        if rc != 0:
+            raise PrError(rc, self.lib.pr_last_error(None).decode())
+        self.h = h
+        if record_solve_order:
+            self.lib.pr_set_debug(self.h, 1)
+        if scene is not None:
+            self.create(scene)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise PrError(rc, self.lib.pr_last_error(self.h).decode())
+
+    def create(self, sc):
+        first = u32(0)
+        self._chk(self.lib.pr_create_shapes(self.h, len(sc["shapes"]), abi.ptr(sc["shapes"]), abi.ptr(sc["children"]),
+                                            len(sc["children"]), abi.ptr(sc["verts"]), abi.ptr(sc["normals"]),
+                                            len(sc["verts"]), C.byref(first)))
+        self._chk(self.lib.pr_create_bodies(self.h, len(sc["bodies"]), abi.ptr(sc["bodies"]), abi.ptr(sc["shape_offsets"]),
+                                            abi.ptr(sc["shape_ids"]), C.byref(first)))
+        if "joints" in sc and len(sc["joints"]):
+            self._chk(self.lib.pr_create_revolute_joints(self.h, len(sc["joints"]), abi.ptr(sc["joints"]), C.byref(first)))
+
+    def step(self, conf):
+        st = abi.one(abi.STEP_STATS)
+        self._chk(self.lib.pr_step(self.h, abi.ptr(conf), abi.ptr(st)))
+        return st[0]
+
+    def counts(self):
+        c = abi.one(abi.COUNTS)
+        self._chk(self.lib.pr_get_counts(self.h, abi.ptr(c)))
+        return c[0]
+
+    def bodies(self, first=0, n=None):
+        if n is None:
+            n = int(self.counts()["bodies"]) - first
+        out = np.zeros(n, abi.BODY)
+        self._chk(self.lib.pr_get_bodies(self.h, first, n, abi.ptr(out)))
+        return out
+
+    def set_bodies(self, ids, rows):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=abi.BODY)
+        self._chk(self.lib.pr_set_bodies(self.h, len(ids), abi.ptr(ids), abi.ptr(rows)))
+
+    def contacts(self):
+        n = max(1, int(self.counts()["contacts"]))
+        cs, ms = np.zeros(n, abi.CONTACT), np.zeros(n, abi.MANIFOLD)
+        k = u32(0)
+        self._chk(self.lib.pr_get_contacts(self.h, n, abi.ptr(cs), abi.ptr(ms), C.byref(k)))
+        return cs[:k.value], ms[:k.value]
+
+    def proxies(self):
+        n = max(1, int(self.counts()["proxies"]))
+        out = np.zeros(n, abi.PROXY)
+        k = u32(0)
+        self._chk(self.lib.pr_get_proxies(self.h, n, abi.ptr(out), C.byref(k)))
+        return out[:k.value]
+
+    def load_state(self, bodies, proxies, contacts, manifolds, inv_dt0):
+        self._chk(self.lib.pr_load_state(self.h, len(bodies), abi.ptr(bodies), len(proxies), abi.ptr(proxies),
+                                         len(contacts), abi.ptr(contacts), abi.ptr(manifolds), inv_dt0))
+
+    def solve_order(self):
+        k = u32(0)
+        self.lib.pr_get_solve_order(self.h, 0, None, None, C.byref(k))
+        ids, cols = np.zeros(max(1, k.value), np.uint32), np.zeros(max(1, k.value), np.uint32)
+        self.lib.pr_get_solve_order(self.h, len(ids), abi.ptr(ids), abi.ptr(cols), C.byref(k))
+        return ids[:k.value], cols[:k.value]
+
+    def profile(self):
+        p = abi.one(abi.STEP_PROFILE)
+        self.lib.pr_get_step_profile(self.h, abi.ptr(p))
+        return p[0]
+
+    def inv_dt0(self):
+        return self.lib.pr_get_inv_dt0(self.h)
+
+    def clone(self):
+        h = vp()
+        self._chk(self.lib.pr_clone(self.h, C.byref(h)))
+        other = World.__new__(World)
+        other.lib, other.h = self.lib, h
+        return other
+
+
+def collide_shapes(children, verts, normals, a_child, xf_a, b_child, xf_b, linear_slop=0.005,
+                   max_circles_ratio=10.0, lib=None, device=-1):
+    lib = lib or load_library()
+    n = len(a_child)
+    out = np.zeros(max(1, n), abi.MANIFOLD)
+    a_child = np.ascontiguousarray(a_child, np.uint32)
+    b_child = np.ascontiguousarray(b_child, np.uint32)
+    xf_a = np.ascontiguousarray(xf_a, np.float32)
+    xf_b = np.ascontiguousarray(xf_b, np.float32)
+    rc = lib.pr_collide_shapes(device, n, abi.ptr(children), len(children), abi.ptr(verts), abi.ptr(normals),
+                               len(verts), abi.ptr(a_child), abi.ptr(xf_a), abi.ptr(b_child), abi.ptr(xf_b),
+                               linear_slop, max_circles_ratio, abi.ptr(out))
+    if rc != 0:
+        raise PrError(rc, lib.pr_last_error(None).decode())
+    return out[:n]

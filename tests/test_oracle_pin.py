@@ -1,0 +1,84 @@
+"""Pins the C++ restatement (oracle/restate) against the REAL reference (oracle/_ref, built from
+/root/reference by oracle/Makefile) and against the reference's golden HelloWorld output."""
+import os
+import numpy as np
+import pytest
+import refworld
+import scenes
+from common import need_ref, need_oracle, assert_bits
+from playrho_b200 import abi
+
+GOLDEN = os.path.join(refworld.ROOT, "tests", "golden", "HelloWorld_ExpectedOutput.txt")
+
+
+@need_ref
+@need_oracle
+def test_step_conf_defaults_match_reference():
+    rc = abi.one(abi.STEP_CONF)
+    refworld._ref_lib().ref_step_conf_default(abi.ptr(rc))
+    assert_bits(rc, refworld.default_step_conf(), "StepConf defaults")
+
+
+@need_ref
+@need_oracle
+@pytest.mark.parametrize("name,steps", [("hello", 60), ("pyramid5", 120), ("pyramid10", 200), ("disks100", 200), ("mixed100", 200)])
+def test_restatement_bit_exact_vs_reference_reg_phase(name, steps):
+    """Whole-trajectory bit equality (bodies, contacts, manifolds, proxies, StepStats), doToi off."""
+    ref = scenes.SCENES[name]()
+    orc = refworld.OracleWorld(ref.export_scene())
+    conf = refworld.default_step_conf(do_toi=0)
+    for s in range(steps):
+        rs, os_ = ref.step(conf), orc.step(conf)
+        assert_bits(ref.bodies(), orc.bodies(), "%s step %d bodies" % (name, s))
+        rc, rm = ref.contacts()
+        oc, om = orc.contacts()
+        assert_bits(rc, oc, "%s step %d contacts" % (name, s))
+        assert_bits(rm, om, "%s step %d manifolds" % (name, s))
+        rp, op = ref.proxies(), orc.proxies()
+        assert_bits(rp[np.argsort(rp["tree_id"])], op[np.argsort(op["tree_id"])], "%s step %d proxies" % (name, s))
+        assert_bits(np.array([rs]), np.array([os_]), "%s step %d stats" % (name, s))
+
+
+@need_ref
+def test_reference_reproduces_golden_helloworld():
+    """The reference built by oracle/Makefile reproduces HelloWorld/ExpectedOutput.txt."""
+    ref = scenes.hello_world()
+    conf = refworld.default_step_conf()
+    lines = []
+    for _ in range(60):
+        ref.step(conf)
+        b = ref.bodies()[1]
+        ang = np.arctan2(b["xf_qs"], b["xf_qc"])
+        lines.append("%5.2f%5.2f%5.2f" % (b["xf_px"], b["xf_py"], ang))
+    golden = open(GOLDEN).read().splitlines()
+    assert lines == golden
+
+
+@need_ref
+@need_oracle
+def test_collide_shapes_restatement_vs_reference_random():
+    """CollideShapes (Manifold.cpp:393) on random child pairs: restatement == reference, bit for bit."""
+    rng = np.random.RandomState(3)
+    ref = scenes.mixed(60, seed=5)
+    sc = ref.export_scene()
+    nchild = len(sc["children"])
+    n = 20000
+    a = rng.randint(0, nchild, n).astype(np.uint32)
+    b = rng.randint(0, nchild, n).astype(np.uint32)
+    def xfs():
+        ang = rng.uniform(-3.2, 3.2, n).astype(np.float32)
+        cs = np.zeros((n, 2), np.float32)
+        refworld._ref_lib().ref_unitvec_from_angle(n, abi.ptr(ang), abi.ptr(cs))
+        return np.concatenate([rng.uniform(-0.6, 0.6, (n, 2)).astype(np.float32), cs], 1).copy()
+    xa, xb = xfs(), xfs()
+    # move child B near child A's first vertex so that many pairs actually touch
+    va = np.stack([sc["verts"]["x"], sc["verts"]["y"]], 1)
+    xa[:, :2] -= va[sc["children"]["vertex_offset"][a]] * 0.0
+    out_r = np.zeros(n, abi.MANIFOLD)
+    out_o = np.zeros(n, abi.MANIFOLD)
+    refworld._ref_lib().ref_collide_shapes(n, abi.ptr(sc["children"]), abi.ptr(sc["verts"]), abi.ptr(sc["normals"]),
+                                           abi.ptr(a), abi.ptr(xa), abi.ptr(b), abi.ptr(xb), 0.005, 10.0, abi.ptr(out_r))
+    refworld._orc_lib().orc_collide_shapes(n, abi.ptr(sc["children"]), abi.ptr(sc["verts"]), abi.ptr(sc["normals"]),
+                                           abi.ptr(a), abi.ptr(xa), abi.ptr(b), abi.ptr(xb), 0.005, 10.0, abi.ptr(out_o))
+    assert (out_r["count"] > 0).sum() > 500
+    assert_bits(out_r, out_o, "manifolds")
