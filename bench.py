@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--settle", type=int, default=40, help="untimed steps so that bodies are in contact")
     ap.add_argument("--ref-bodies", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -166,7 +167,8 @@ def main():
     sampler.start()
     # ---------------- device-resident timed region: K steps, state already in HBM
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.cuda_profiler:
+        torch.cuda.profiler.start()
     t0 = time.perf_counter()
     launches, stage_ms, vel_ms, profs = 0, np.zeros(abi.N_STAGES), 0.0, []
     stats_sum = np.zeros(4, dtype=np.float64)
@@ -179,6 +181,8 @@ def main():
         stats_sum += [st["reg"]["islands_found"], st["reg"]["contacts_added"], st["reg"]["proxies_moved"], st["reg"]["bodies_slept"]]
     barrier()
     secs = time.perf_counter() - t0
+    if args.cuda_profiler:
+        torch.cuda.profiler.stop()
     # ---------------- end-to-end: host buffers in, host buffers out, every step
     rows = gw.bodies()
     ids = np.arange(nb, dtype=np.uint32)

@@ -314,6 +314,11 @@ def diff_fields(a, b, limit=5):
     out = []
     if a.shape != b.shape:
         return ["shape %s vs %s" % (a.shape, b.shape)]
+    if a.dtype.names is None:
+        ai = a.view(np.uint32) if a.dtype.itemsize == 4 else a
+        bi = b.view(np.uint32) if b.dtype.itemsize == 4 else b
+        bad = np.nonzero(ai != bi)[0]
+        return ["row %d: %r vs %r" % (r, a[r], b[r]) for r in bad[:limit]] + (["... %d rows differ" % len(bad)] if len(bad) > limit else [])
     for name in a.dtype.names:
         av, bv = a[name], b[name]
         if av.dtype.names:
