@@ -1,8 +1,337 @@
-// orc_toi.cpp -- TEST INFRASTRUCTURE ONLY (oracle restatement). STUBS: filled in by the TOI milestone.
+// orc_toi.cpp -- TEST INFRASTRUCTURE ONLY (oracle restatement): GJK Distance (Distance.cpp, Simplex.cpp),
+// SeparationScenario.cpp and GetToiViaSat (TimeOfImpact.cpp). Revolute joint: still a stub.
+#include <algorithm>
 #include "orc_toi.h"
 namespace orc {
-float test_overlap(const Proxy&, Xf, const Proxy&, Xf, uint32_t) { return -1.0f; }
-ToiOut toi_via_sat(const Proxy&, const Sweep&, const Proxy&, const Sweep&, const pr_step_conf&) { return {1.0f, 0, 0, 0, 0}; }
+namespace {
+
+constexpr uint32_t kInvalidVertex = 255u; // InvalidVertex, Settings.hpp:87-90
+constexpr float kInfF = std::numeric_limits<float>::infinity();
+
+// SimplexEdge, SimplexEdge.hpp: world points of one vertex of A and one of B, with their indices
+struct SEdge { V2 wA; uint32_t iA; V2 wB; uint32_t iB; };
+inline V2 delta(const SEdge& e) { return e.wB - e.wA; } // GetPointDelta, SimplexEdge.hpp:84-87
+struct SEdges { SEdge e[3]; uint32_t n = 0; };
+struct Simplex { SEdges edges; float coef[3] = {0, 0, 0}; };
+struct IndexPair { uint32_t a = kInvalidVertex, b = kInvalidVertex; };
+inline bool operator==(IndexPair x, IndexPair y) { return x.a == y.a && x.b == y.b; }
+struct IndexPair3 { IndexPair p[3]; };
+inline uint32_t num_valid(const IndexPair3& ip)
+{ // GetNumValidIndices, IndexPair.hpp:66-72
+    const IndexPair inv;
+    return (ip.p[0] == inv ? 0u : 1u) + (ip.p[1] == inv ? 0u : 1u) + (ip.p[2] == inv ? 0u : 1u);
+}
+struct Cache { float metric = 0.0f; IndexPair3 indices; };
+
+// GetSimplexEdge, Distance.cpp:37-44
+inline SEdge simplex_edge(const Proxy& a, Xf xfA, uint32_t iA, const Proxy& b, Xf xfB, uint32_t iB)
+{
+    return {transform(a.vertex(iA), xfA), iA, transform(b.vertex(iB), xfB), iB};
+}
+// GetIndexPairs, Simplex.cpp:27-42
+inline IndexPair3 index_pairs(const SEdges& s)
+{
+    IndexPair3 r;
+    for (uint32_t i = 0; i < s.n; ++i) r.p[i] = {s.e[i].iA, s.e[i].iB};
+    return r;
+}
+// Simplex::CalcMetric, Simplex.cpp:218-238
+inline float calc_metric(const SEdges& s)
+{
+    if (s.n == 2) return std::sqrt(magsq(delta(s.e[1]) - delta(s.e[0])));
+    if (s.n == 3) return cross(delta(s.e[1]) - delta(s.e[0]), delta(s.e[2]) - delta(s.e[0]));
+    return 0.0f;
+}
+// CalcSearchDirection, Simplex.cpp:44-62
+inline V2 search_direction(const SEdges& s)
+{
+    if (s.n == 1) return -delta(s.e[0]);
+    if (s.n == 2) {
+        const V2 e12 = delta(s.e[1]) - delta(s.e[0]);
+        const V2 e0 = delta(s.e[0]);
+        const float sgn = cross(e12, -e0);
+        return (sgn > 0.0f) ? V2{-e12.y, e12.x} : V2{e12.y, -e12.x};
+    }
+    return {0.0f, 0.0f};
+}
+// Simplex::Get(s0, s1), Simplex.cpp:69-116
+inline Simplex simplex2(const SEdge& s0, const SEdge& s1)
+{
+    Simplex r;
+    const V2 w1 = delta(s0), w2 = delta(s1);
+    const V2 e12 = w2 - w1;
+    const float d12_2 = -dot(w1, e12);
+    if (d12_2 <= 0.0f) { r.edges.e[0] = s0; r.edges.n = 1; r.coef[0] = 1.0f; return r; }
+    const float d12_1 = dot(w2, e12);
+    if (d12_1 <= 0.0f) { r.edges.e[0] = s1; r.edges.n = 1; r.coef[0] = 1.0f; return r; }
+    const float inv_sum = 1.0f / (d12_1 + d12_2);
+    r.edges.e[0] = s0; r.edges.e[1] = s1; r.edges.n = 2; r.coef[0] = d12_1 * inv_sum; r.coef[1] = d12_2 * inv_sum;
+    return r;
+}
+// Simplex::Get(s0, s1, s2), Simplex.cpp:118-199
+inline Simplex simplex3(const SEdge& s0, const SEdge& s1, const SEdge& s2)
+{
+    Simplex r;
+    auto one = [&](const SEdge& s) { r.edges.e[0] = s; r.edges.n = 1; r.coef[0] = 1.0f; return r; };
+    auto two = [&](const SEdge& a, const SEdge& b, float ca, float cb) {
+        r.edges.e[0] = a; r.edges.e[1] = b; r.edges.n = 2; r.coef[0] = ca; r.coef[1] = cb; return r;
+    };
+    const V2 w1 = delta(s0), w2 = delta(s1), w3 = delta(s2);
+    const V2 e12 = w2 - w1;
+    const float d12_1 = dot(w2, e12), d12_2 = -dot(w1, e12);
+    const V2 e13 = w3 - w1;
+    const float d13_1 = dot(w3, e13), d13_2 = -dot(w1, e13);
+    const V2 e23 = w3 - w2;
+    const float d23_1 = dot(w3, e23), d23_2 = -dot(w2, e23);
+    if (d12_2 <= 0.0f && d13_2 <= 0.0f) return one(s0);
+    if (d12_1 <= 0.0f && d23_2 <= 0.0f) return one(s1);
+    if (d13_1 <= 0.0f && d23_1 <= 0.0f) return one(s2);
+    const float n123 = cross(e12, e13);
+    const float d123_3 = n123 * cross(w1, w2);
+    if (d12_1 > 0.0f && d12_2 > 0.0f && d123_3 <= 0.0f) {
+        const float inv_sum = 1.0f / (d12_1 + d12_2);
+        return two(s0, s1, d12_1 * inv_sum, d12_2 * inv_sum);
+    }
+    const float d123_2 = n123 * cross(w3, w1);
+    if (d13_1 > 0.0f && d13_2 > 0.0f && d123_2 <= 0.0f) {
+        const float inv_sum = 1.0f / (d13_1 + d13_2);
+        return two(s0, s2, d13_1 * inv_sum, d13_2 * inv_sum);
+    }
+    const float d123_1 = n123 * cross(w2, w3);
+    if (d23_1 > 0.0f && d23_2 > 0.0f && d123_1 <= 0.0f) {
+        const float inv_sum = 1.0f / (d23_1 + d23_2);
+        return two(s2, s1, d23_2 * inv_sum, d23_1 * inv_sum); // note the swapped order, Simplex.cpp:193
+    }
+    const float inv_sum = 1.0f / (d123_1 + d123_2 + d123_3);
+    r.edges.e[0] = s0; r.edges.e[1] = s1; r.edges.e[2] = s2; r.edges.n = 3;
+    r.coef[0] = d123_1 * inv_sum; r.coef[1] = d123_2 * inv_sum; r.coef[2] = d123_3 * inv_sum;
+    return r;
+}
+inline Simplex simplex_get(const SEdges& s)
+{ // Simplex::Get(edges), Simplex.cpp:201-216
+    if (s.n == 1) { Simplex r; r.edges = s; r.coef[0] = 1.0f; return r; }
+    if (s.n == 2) return simplex2(s.e[0], s.e[1]);
+    if (s.n == 3) return simplex3(s.e[0], s.e[1], s.e[2]);
+    return Simplex{};
+}
+// GetSupportIndex, DistanceProxy.hpp:232-249 (first strict maximum of Dot(vertex, dir))
+inline uint32_t support_index(const Proxy& p, V2 dir)
+{
+    uint32_t index = kInvalidVertex;
+    float maxValue = -kInfF;
+    for (uint32_t i = 0; i < p.count; ++i) {
+        const float value = dot(p.vertex(i), dir);
+        if (maxValue < value) { maxValue = value; index = i; }
+    }
+    return index;
+}
+enum DistState { D_Unknown, D_UnfitSearchDir, D_HitMaxIters, D_MaxPoints, D_DuplicateIndexPair };
+struct DistOut { Simplex simplex; uint32_t iterations; int state; };
+
+// Distance, Distance.cpp:100-203
+DistOut distance(const Proxy& a, Xf xfA, const Proxy& b, Xf xfB, const Cache& cache, uint32_t maxIters)
+{
+    IndexPair3 saved = cache.indices;
+    SEdges edges;
+    const uint32_t count = num_valid(saved);
+    for (uint32_t i = 0; i < count; ++i) edges.e[i] = simplex_edge(a, xfA, saved.p[i].a, b, xfB, saved.p[i].b);
+    edges.n = count;
+    if (edges.n > 1) {
+        const float metric1 = cache.metric;
+        const float metric2 = calc_metric(edges);
+        if ((metric2 < (metric1 / 2)) || (metric2 > (metric1 * 2)) || (metric2 < 0) || almost_zero(metric2)) edges.n = 0;
+    }
+    if (edges.n == 0) {
+        edges.e[0] = simplex_edge(a, xfA, 0, b, xfB, 0); edges.n = 1;
+        saved = IndexPair3{}; saved.p[0] = {0, 0};
+    }
+    Simplex simplex;
+    int state = D_HitMaxIters;
+    uint32_t iter = 0;
+    while (iter < maxIters) {
+        ++iter;
+        simplex = simplex_get(edges);
+        edges = simplex.edges;
+        if (edges.n == 3) { state = D_MaxPoints; break; }
+        const V2 d = search_direction(edges);
+        if (almost_zero(magsq(d))) { state = D_UnfitSearchDir; break; }
+        const uint32_t indexA = support_index(a, inv_rotate(-d, xfA.q));
+        const uint32_t indexB = support_index(b, inv_rotate(d, xfB.q));
+        const IndexPair key{indexA, indexB};
+        if (saved.p[0] == key || saved.p[1] == key || saved.p[2] == key) { state = D_DuplicateIndexPair; break; }
+        edges.e[edges.n++] = simplex_edge(a, xfA, indexA, b, xfB, indexB);
+        saved = index_pairs(edges);
+    }
+    return {simplex, iter, state};
+}
+// GetWitnessPoints, Distance.cpp:72-94, and |pB - pA|^2
+inline float witness_dist_sq(const Simplex& s)
+{
+    V2 pA{0, 0}, pB{0, 0};
+    for (uint32_t i = 0; i < s.edges.n; ++i) {
+        pA = pA + s.edges.e[i].wA * s.coef[i];
+        pB = pB + s.edges.e[i].wB * s.coef[i];
+    }
+    return magsq(pB - pA);
+}
+
+// SeparationScenario.cpp: type 0 = points, 1 = faceA, 2 = faceB
+struct Scenario { int type; Rot axis; V2 localPoint; };
+// GetSeparationScenario, SeparationScenario.cpp:138-190
+Scenario separation_scenario(const IndexPair3& idx, const Proxy& a, Xf xfA, const Proxy& b, Xf xfB)
+{
+    const Rot zero{0.0f, 0.0f};
+    const uint32_t n = num_valid(idx);
+    if (n >= 2 && idx.p[0].a == idx.p[1].a) { // FaceB: two points on B, one on A
+        const V2 b1 = b.vertex(idx.p[0].b), b2 = b.vertex(idx.p[1].b);
+        const V2 e = b2 - b1;
+        const Rot axis = unit_vector(V2{e.y, -e.x}, zero);
+        const Rot normal = rot_rotate(axis, xfB.q);
+        const V2 localPoint = (b1 + b2) / 2.0f;
+        const V2 pointB = transform(localPoint, xfB);
+        const V2 pointA = transform(a.vertex(idx.p[0].a), xfA);
+        const V2 dp = pointA - pointB;
+        return {2, (dot(dp, normal) < 0.0f) ? -axis : axis, localPoint};
+    }
+    if (n >= 2) { // FaceA
+        const V2 a1 = a.vertex(idx.p[0].a), a2 = a.vertex(idx.p[1].a);
+        const V2 e = a2 - a1;
+        const Rot axis = unit_vector(V2{e.y, -e.x}, zero);
+        const Rot normal = rot_rotate(axis, xfA.q);
+        const V2 localPoint = (a1 + a2) / 2.0f;
+        const V2 pointA = transform(localPoint, xfA);
+        const V2 pointB = transform(b.vertex(idx.p[0].b), xfB);
+        const V2 dp = pointB - pointA;
+        return {1, (dot(dp, normal) < 0.0f) ? -axis : axis, localPoint};
+    }
+    const V2 pointA = transform(a.vertex(idx.p[0].a), xfA);
+    const V2 pointB = transform(b.vertex(idx.p[0].b), xfB);
+    return {0, unit_vector(pointB - pointA, zero), {0, 0}};
+}
+struct MinSep { float distance; IndexPair ip; };
+// FindMinSeparation, SeparationScenario.cpp:29-74
+MinSep find_min_separation(const Scenario& s, const Proxy& a, Xf xfA, const Proxy& b, Xf xfB)
+{
+    if (s.type == 0) {
+        const V2 ax = rotv(s.axis);
+        const uint32_t iA = support_index(a, inv_rotate(ax, xfA.q));
+        const uint32_t iB = support_index(b, inv_rotate(-ax, xfB.q));
+        const V2 pA = transform(a.vertex(iA), xfA), pB = transform(b.vertex(iB), xfB);
+        return {dot(pB - pA, s.axis), {iA, iB}};
+    }
+    if (s.type == 1) {
+        const Rot normal = rot_rotate(s.axis, xfA.q);
+        const V2 pA = transform(s.localPoint, xfA);
+        const uint32_t iB = support_index(b, inv_rotate(-rotv(normal), xfB.q));
+        const V2 pB = transform(b.vertex(iB), xfB);
+        return {dot(pB - pA, normal), {kInvalidVertex, iB}};
+    }
+    const Rot normal = rot_rotate(s.axis, xfB.q);
+    const uint32_t iA = support_index(a, inv_rotate(-rotv(normal), xfA.q));
+    const V2 pA = transform(a.vertex(iA), xfA);
+    const V2 pB = transform(s.localPoint, xfB);
+    return {dot(pA - pB, normal), {iA, kInvalidVertex}};
+}
+// Evaluate, SeparationScenario.cpp:76-114
+float evaluate(const Scenario& s, const Proxy& a, Xf xfA, const Proxy& b, Xf xfB, IndexPair ip)
+{
+    if (s.type == 0) {
+        const V2 pA = transform(a.vertex(ip.a), xfA), pB = transform(b.vertex(ip.b), xfB);
+        return dot(pB - pA, s.axis);
+    }
+    if (s.type == 1) {
+        const Rot normal = rot_rotate(s.axis, xfA.q);
+        const V2 pA = transform(s.localPoint, xfA), pB = transform(b.vertex(ip.b), xfB);
+        return dot(pB - pA, normal);
+    }
+    const Rot normal = rot_rotate(s.axis, xfB.q);
+    const V2 pB = transform(s.localPoint, xfB), pA = transform(a.vertex(ip.a), xfA);
+    return dot(pA - pB, normal);
+}
+// GetTransformation(sweep, beta), d2/Math.hpp:251-254
+inline Xf sweep_xf(const Sweep& s, float beta) { return get_xf(lerp_pos(s.pos0, s.pos1, beta), s.lc); }
+
+} // namespace
+
+// TestOverlap, Distance.cpp:205-218 (default-constructed simplex cache)
+float test_overlap(const Proxy& a, Xf xfA, const Proxy& b, Xf xfB, uint32_t maxIters)
+{
+    const DistOut d = distance(a, xfA, b, xfB, Cache{}, maxIters);
+    const float distSq = witness_dist_sq(d.simplex);
+    const float totalRadiusSq = square(a.radius + b.radius);
+    return totalRadiusSq - distSq;
+}
+
+// GetToiViaSat, TimeOfImpact.cpp:35-251. States follow ToiOutput::State (ToiOutput.hpp:73-140).
+ToiOut toi_via_sat(const Proxy& a, const Sweep& sA, const Proxy& b, const Sweep& sB, const pr_step_conf& conf)
+{
+    enum { e_unknown, e_touching, e_separated, e_overlapped, e_maxRootIters, e_nextAfter, e_maxToiIters,
+           e_belowMinTarget, e_maxDistIters, e_targetDepthExceedsTotalRadius, e_minTargetSquaredOverflow,
+           e_maxTargetSquaredOverflow, e_notFinite };
+    ToiOut out{0.0f, e_unknown, 0, 0, 0};
+    const float timeMax = 1.0f; // GetToiConf, ToiConf.cpp:26-35
+    const float totalRadius = a.radius + b.radius;
+    if (conf.target_depth > totalRadius) { out.state = e_targetDepthExceedsTotalRadius; return out; }
+    const float target = totalRadius - conf.target_depth;
+    const float maxTarget = std::max(target + conf.tolerance, 0.0f);
+    const float minTarget = std::max(target - conf.tolerance, 0.0f);
+    const float minTargetSquared = square(minTarget);
+    if (!std::isfinite(minTargetSquared) && std::isfinite(minTarget)) { out.state = e_minTargetSquaredOverflow; return out; }
+    const float maxTargetSquared = square(maxTarget);
+    if (!std::isfinite(maxTargetSquared) && std::isfinite(maxTarget)) { out.state = e_maxTargetSquaredOverflow; return out; }
+    float timeLo = 0.0f;
+    Xf loA = sweep_xf(sA, timeLo), loB = sweep_xf(sB, timeLo);
+    Cache cache;
+    auto done = [&](float t, int st) { out.time = t; out.state = st; return out; };
+    while (out.toi_iters < conf.max_toi_iters) {
+        const DistOut dinfo = distance(a, loA, b, loB, cache, conf.max_distance_iters);
+        ++out.toi_iters;
+        out.max_dist_iters = std::max(out.max_dist_iters, dinfo.iterations);
+        if (dinfo.state == D_HitMaxIters) return done(timeLo, e_maxDistIters);
+        cache.metric = calc_metric(dinfo.simplex.edges);
+        cache.indices = index_pairs(dinfo.simplex.edges);
+        const float distSquared = witness_dist_sq(dinfo.simplex);
+        if (distSquared < minTargetSquared) return done(timeLo, e_overlapped);
+        if (distSquared <= maxTargetSquared) return done(timeLo, e_touching);
+        const Scenario fcn = separation_scenario(cache.indices, a, loA, b, loB);
+        float timeHi = timeMax;
+        Xf hiA = sweep_xf(sA, timeHi), hiB = sweep_xf(sB, timeHi);
+        for (uint32_t pbIter = 0; pbIter < 254u; ++pbIter) { // MaxShapeVertices, Settings.hpp
+            const MinSep hiMin = find_min_separation(fcn, a, hiA, b, hiB);
+            if (hiMin.distance > maxTarget) return done(timeHi, e_separated);
+            if (hiMin.distance >= minTarget) {
+                if (timeHi == timeLo) return done(timeHi, e_separated);
+                timeLo = timeHi; loA = hiA; loB = hiB;
+                break;
+            }
+            const float loEval = evaluate(fcn, a, loA, b, loB, hiMin.ip);
+            if (loEval <= maxTarget) return done(timeLo, (loEval < minTarget) ? e_belowMinTarget : e_touching);
+            float a1 = timeLo, a2 = timeHi, s1 = loEval, s2 = hiMin.distance;
+            uint32_t roots = 0;
+            float t = timeLo;
+            for (;;) {
+                if (roots == conf.max_toi_root_iters) {
+                    out.max_root_iters = std::max(out.max_root_iters, roots);
+                    return done(t, e_maxRootIters);
+                }
+                if (std::nextafter(a1, a2) >= a2) {
+                    out.max_root_iters = std::max(out.max_root_iters, roots);
+                    return done(t, e_nextAfter);
+                }
+                // Secant / Bisect, Math.hpp:92-108
+                t = (roots % 2u) ? (a1 + (target - s1) * (a2 - a1) / (s2 - s1)) : ((a1 + a2) / 2);
+                ++roots;
+                const Xf tA = sweep_xf(sA, t), tB = sweep_xf(sB, t);
+                const float s = evaluate(fcn, a, tA, b, tB, hiMin.ip);
+                if (std::fabs(s - target) <= conf.tolerance) { timeHi = t; hiA = tA; hiB = tB; break; }
+                if (s > target) { a1 = t; s1 = s; } else { a2 = t; s2 = s; }
+            }
+            out.max_root_iters = std::max(out.max_root_iters, roots);
+        }
+    }
+    return done(timeLo, e_maxToiIters);
+}
+
 void revolute_init_velocity(pr_revolute_joint&, RevoluteWork&, float, float, V2, Pos, Vel&, float, float, V2, Pos, Vel&, const JointSolverConf&) {}
 bool revolute_solve_velocity(pr_revolute_joint&, RevoluteWork&, float, float, Vel&, float, float, Vel&, const JointSolverConf&) { return true; }
 bool revolute_solve_position(const pr_revolute_joint&, float, float, V2, Pos&, float, float, V2, Pos&, const JointSolverConf&) { return true; }

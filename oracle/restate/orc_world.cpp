@@ -73,6 +73,7 @@ struct orc_world {
     std::vector<uint32_t> bodiesForSync;
     std::vector<char> islandedBodies, islandedContacts, islandedJoints;
     bool stepComplete = true;
+    bool subStepping = false;
     float inv_dt0 = 0;
     std::string error;
 

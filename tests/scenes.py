@@ -101,7 +101,40 @@ def tumbler(n_squares=40, seed=12345, ids32=False):
     return w
 
 
+def shooter(n=60, seed=4, ids32=False, sensor=True):
+    """TOI stress: closed edge box, fast random bodies (some bullets), a spinning kinematic bar and a
+    static sensor disk (exercises GetToiViaSat, SolveToi mini-islands, bullet-vs-dynamic TOI, TestOverlap)."""
+    rng = np.random.RandomState(seed)
+    w = RefWorld(ids32)
+    W = 14.0
+    edges = [w.add_edge((0.0, 0.0), (W, 0.0)), w.add_edge((W, 0.0), (W, W)), w.add_edge((W, W), (0.0, W)),
+             w.add_edge((0.0, W), (0.0, 0.0))]
+    w.add_body(STATIC, shapes=edges)
+    bar = w.add_box(2.5, 0.2, density=1.0)
+    w.add_body(KINEMATIC, pos=(W / 2, W / 2), w=2.5, shapes=[bar])
+    if sensor:
+        sd = w.add_disk(1.5, sensor=True)
+        w.add_body(STATIC, pos=(3.0, 3.0), shapes=[sd])
+    side = int(np.ceil(np.sqrt(n)))
+    for k in range(n):
+        i, j = k % side, k // side
+        pos = (1.0 + i * (W - 2.0) / side + rng.uniform(-0.05, 0.05), 1.0 + j * (W - 2.0) / side + rng.uniform(-0.05, 0.05))
+        r = rng.uniform(0.15, 0.4)
+        if rng.rand() < 0.5:
+            sh = w.add_disk(r, density=1.0, restitution=rng.uniform(0, 0.6))
+        else:
+            kk = rng.randint(3, 8)
+            ang = np.sort(rng.uniform(0, 2 * np.pi, kk))
+            sh = w.add_polygon(np.stack([r * np.cos(ang), r * np.sin(ang)], 1), density=1.0, restitution=rng.uniform(0, 0.4))
+        sp = rng.uniform(5, 60)
+        th = rng.uniform(0, 2 * np.pi)
+        w.add_body(DYNAMIC, pos=pos, angle=rng.uniform(-3, 3), vel=(sp * np.cos(th), sp * np.sin(th)), w=rng.uniform(-20, 20),
+                   acc=GRAVITY, bullet=bool(rng.rand() < 0.3), shapes=[sh])
+    return w
+
+
 SCENES = {
+    "shooter": shooter,
     "hello": hello_world,
     "pyramid5": lambda **k: pyramid(5, **k),
     "pyramid10": lambda **k: pyramid(10, **k),

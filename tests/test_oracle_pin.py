@@ -40,6 +40,43 @@ def test_restatement_bit_exact_vs_reference_reg_phase(name, steps):
 
 
 @need_ref
+@need_oracle
+@pytest.mark.parametrize("name,steps", [("hello", 60), ("pyramid5", 150), ("pyramid10", 200), ("disks100", 250), ("mixed100", 250), ("shooter", 300)])
+def test_restatement_bit_exact_vs_reference_with_toi(name, steps):
+    """Default StepConf (doToi on): SolveToi (AabbTreeWorld.cpp:1752-2142), GetToiViaSat, GJK Distance."""
+    ref = scenes.SCENES[name]()
+    orc = refworld.OracleWorld(ref.export_scene())
+    conf = refworld.default_step_conf()
+    events = 0
+    for s in range(steps):
+        rs, os_ = ref.step(conf), orc.step(conf)
+        events += int(rs["toi"]["contacts_found"])
+        assert_bits(np.array([rs]), np.array([os_]), "%s step %d stats" % (name, s))
+        assert_bits(ref.bodies(), orc.bodies(), "%s step %d bodies" % (name, s))
+        rc, rm = ref.contacts()
+        oc, om = orc.contacts()
+        assert_bits(rc, oc, "%s step %d contacts" % (name, s))
+        assert_bits(rm, om, "%s step %d manifolds" % (name, s))
+        rp, op = ref.proxies(), orc.proxies()
+        assert_bits(rp[np.argsort(rp["tree_id"])], op[np.argsort(op["tree_id"])], "%s step %d proxies" % (name, s))
+    assert events > 0, "scene never produced a TOI event"
+
+
+@need_ref
+@need_oracle
+def test_restatement_reproduces_golden_helloworld():
+    """The restatement itself (default StepConf, TOI on) prints HelloWorld/ExpectedOutput.txt."""
+    orc = refworld.OracleWorld(scenes.hello_world().export_scene())
+    conf = refworld.default_step_conf()
+    lines = []
+    for _ in range(60):
+        orc.step(conf)
+        b = orc.bodies()[1]
+        lines.append("%5.2f%5.2f%5.2f" % (b["xf_px"], b["xf_py"], np.arctan2(b["xf_qs"], b["xf_qc"])))
+    assert lines == open(GOLDEN).read().splitlines()
+
+
+@need_ref
 def test_reference_reproduces_golden_helloworld():
     """The reference built by oracle/Makefile reproduces HelloWorld/ExpectedOutput.txt."""
     ref = scenes.hello_world()
@@ -82,3 +119,41 @@ def test_collide_shapes_restatement_vs_reference_random():
                                            abi.ptr(a), abi.ptr(xa), abi.ptr(b), abi.ptr(xb), 0.005, 10.0, abi.ptr(out_o))
     assert (out_r["count"] > 0).sum() > 500
     assert_bits(out_r, out_o, "manifolds")
+
+
+def random_sweeps(rng, n, spread=1.5, move=2.0, spin=3.0):
+    """(n, 8) float32 sweeps: pos0 x,y,a ; pos1 x,y,a ; local centre x,y."""
+    p0 = rng.uniform(-spread, spread, (n, 2)); a0 = rng.uniform(-3.2, 3.2, (n, 1))
+    d = rng.uniform(-move, move, (n, 2)); da = rng.uniform(-spin, spin, (n, 1))
+    lc = rng.uniform(-0.1, 0.1, (n, 2))
+    return np.concatenate([p0, a0, p0 + d, a0 + da, lc], 1).astype(np.float32).copy()
+
+
+@need_ref
+@need_oracle
+def test_toi_restatement_vs_reference_random():
+    """GetToiViaSat (TimeOfImpact.cpp:35) incl. GJK Distance / Simplex / SeparationScenario on random
+    child pairs and sweeps: time, state and the three iteration statistics bit-for-bit."""
+    rng = np.random.RandomState(11)
+    sc = scenes.mixed(60, seed=5).export_scene()
+    nchild = len(sc["children"])
+    n = 30000
+    a = rng.randint(0, nchild, n).astype(np.uint32)
+    b = rng.randint(0, nchild, n).astype(np.uint32)
+    sa, sb = random_sweeps(rng, n), random_sweeps(rng, n)
+    # a third of the pairs start far apart and fly towards each other
+    sb[: n // 3, 0] += 3.0; sb[: n // 3, 3] -= 3.0
+    conf = refworld.default_step_conf()
+    outs = []
+    for lib, fn in ((refworld._ref_lib(), "ref_toi"), (refworld._orc_lib(), "orc_toi")):
+        t = np.zeros(n, np.float32); st = np.zeros(n, np.int32); it = np.zeros((n, 3), np.uint32)
+        getattr(lib, fn)(n, abi.ptr(sc["children"]), abi.ptr(sc["verts"]), abi.ptr(sc["normals"]), abi.ptr(a), abi.ptr(sa),
+                         abi.ptr(b), abi.ptr(sb), abi.ptr(conf), abi.ptr(t), abi.ptr(st), abi.ptr(it))
+        outs.append((t, st, it))
+    (rt, rs, ri), (ot, os_, oi) = outs
+    states = set(int(s) for s in np.unique(rs))
+    assert {1, 2, 3} <= states, states  # touching, separated, overlapped all occur
+    assert (rs == 1).sum() > 1000
+    assert np.array_equal(rs, os_), np.nonzero(rs != os_)[0][:10]
+    assert_bits(rt, ot, "toi time")
+    assert np.array_equal(ri, oi)
