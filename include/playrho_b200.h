@@ -186,6 +186,7 @@ typedef struct pr_counts {
 typedef struct pr_step_profile {
     uint32_t n_awake, p_total, p_moved, c_total, c_dirty, c_touching, n_colors, n_islands;
     uint32_t vel_iters, pos_iters, candidate_pairs, kernel_launches;
+    uint32_t toi_rounds, toi_events; /* TOI phase: kernel rounds run and TOI events solved (SolveToi loop turns) */
     float ms_total;            /* CUDA-event time of the whole step on the world's stream */
     float ms_stage[16];        /* see PR_STAGE_* */
 } pr_step_profile;
@@ -244,6 +245,16 @@ int pr_set_debug(pr_world* w, uint32_t flags);
 int pr_get_step_profile(const pr_world* w, pr_step_profile* out);
 int pr_abi_sizeof(int which); /* sizeof of the POD structs above, for foreign-language mirrors */
 int pr_shift_origin(pr_world* w, float x, float y);     /* ShiftOrigin :2221 */
+/* TOI event scheduling (SolveToi loop, AabbTreeWorld.cpp:1752-1831):
+ *   PR_TOI_SERIAL_EXACT  one event per round in the reference's order (global soonest first): bit-exact
+ *   PR_TOI_PARALLEL      every locally-soonest event whose bodies and contact neighbours are disjoint
+ *                        from all sooner events runs in the same round (default; drift vs the serial
+ *                        order is reported by the tests, not gated -- BASELINE.json north_star) */
+enum { PR_TOI_SERIAL_EXACT = 0, PR_TOI_PARALLEL = 1 };
+int pr_set_toi_mode(pr_world* w, uint32_t mode);
+int pr_set_sub_stepping(pr_world* w, uint32_t flag);    /* SetSubStepping, AabbTreeWorld.hpp */
+int pr_get_sub_stepping(const pr_world* w);             /* GetSubStepping */
+int pr_is_step_complete(const pr_world* w);             /* IsStepComplete */
 float pr_get_inv_dt0(const pr_world* w);                /* GetInvDeltaTime */
 
 /* ---- stage entry point for known-answer tests: CollideShapes (Manifold.cpp:393) over arrays ----
@@ -253,6 +264,15 @@ int pr_collide_shapes(int device, uint32_t n, const pr_child* children, uint32_t
                       const uint32_t* a_child, const float* xf_a, const uint32_t* b_child,
                       const float* xf_b, float linear_slop, float max_circles_ratio,
                       pr_manifold* out);
+
+/* GetToiViaSat (TimeOfImpact.cpp:35) over arrays: sweeps are 8 floats (pos0 x,y,a | pos1 x,y,a | local
+ * centre x,y), alpha0 = 0; out_iters has 3 entries per pair: toi_iters, max_dist_iters, max_root_iters;
+ * out_state is ToiOutput::State (ToiOutput.hpp:73). */
+int pr_toi_batch(int device, uint32_t n, const pr_child* children, uint32_t n_children,
+                 const pr_vec2* vertices, const pr_vec2* normals, uint32_t n_vertices,
+                 const uint32_t* a_child, const float* sweep_a, const uint32_t* b_child,
+                 const float* sweep_b, const pr_step_conf* conf, float* out_time, int32_t* out_state,
+                 uint32_t* out_iters);
 
 /* ---- batched independent worlds (config 5; no reference API, additive: SURVEY §8(b)) ---- */
 typedef struct pr_batch pr_batch;

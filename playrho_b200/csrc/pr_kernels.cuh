@@ -7,6 +7,7 @@
 #include "pr_world.h"
 #include "pr_math.cuh"
 #include "pr_collide.cuh"
+#include "pr_toi.cuh"
 
 namespace pr {
 
@@ -303,63 +304,65 @@ PR_D void store_manifold(const DV& d, unsigned id, const Mf& m)
     d.m2[id] = make_float4(m.jn0, m.jt0, m.jn1, m.jt1);
     d.m3[id] = make_uint4(m.cf0, m.cf1, m.type, m.count);
 }
-// Update(ContactID), AabbTreeWorld.cpp:2587-2721: collide, carry impulses over by ContactFeature
-// equality else nearest old point, touching flag. One thread per contact of order[start, start+n).
+// Update(ContactID), AabbTreeWorld.cpp:2587-2721: collide (or sensor TestOverlap), carry impulses over by
+// ContactFeature equality else nearest old point, touching flag. Called with the contact's flags word.
+PR_D void update_contact(const DV& d, const pr_step_conf& conf, unsigned id, unsigned flags)
+{
+    const uint4 ab = d.c_ab[id];
+    const bool oldTouching = (flags & PR_CONTACT_TOUCHING) != 0;
+    bool newTouching = false;
+    const Xf xfA = xf_from4(d.b_xf[ab.x]), xfB = xf_from4(d.b_xf[ab.y]);
+    if (flags & PR_CONTACT_SENSOR) { // TestOverlap(...) >= 0, AabbTreeWorld.cpp:2622-2626
+        newTouching = gjk_test_overlap(child_view(d, ab.z), xfA, child_view(d, ab.w), xfB, conf.max_distance_iters) >= 0.0f;
+        manifold_clear(d, id);
+    } else {
+        Mf nm = collide_shapes(child_view(d, ab.z), xfA, child_view(d, ab.w), xfB, conf.linear_slop, conf.max_circles_ratio);
+        const uint4 o3 = d.m3[id];
+        const unsigned oldCount = o3.w, newCount = nm.count;
+        newTouching = newCount > 0u;
+        if (newCount > 0u && oldCount > 0u) {
+            const float4 o1 = d.m1[id], o2 = d.m2[id];
+            const unsigned ocf[2] = {o3.x, o3.y};
+            const float ojn[2] = {o2.x, o2.z}, ojt[2] = {o2.y, o2.w};
+            const float2 op[2] = {v2(o1.x, o1.y), v2(o1.z, o1.w)};
+            const unsigned ncf[2] = {nm.cf0, nm.cf1};
+            const float2 np[2] = {nm.p0, nm.p1};
+            float njn[2] = {0.0f, 0.0f}, njt[2] = {0.0f, 0.0f};
+            bool found[2] = {false, newCount < 2u};
+            for (unsigned a = 0; a < newCount; ++a) {
+                for (unsigned b = 0; b < oldCount; ++b) {
+                    if (ncf[a] == ocf[b]) { found[a] = true; njn[a] = ojn[b]; njt[a] = ojt[b]; break; }
+                }
+            }
+            for (unsigned a = 0; a < newCount; ++a) {
+                if (!found[a]) {
+                    float least = PR_INF;
+                    for (unsigned b = 0; b < oldCount; ++b) {
+                        const float sq = magsq(op[b] - np[a]);
+                        if (least > sq) { least = sq; njn[a] = ojn[b]; njt[a] = ojt[b]; }
+                    }
+                }
+            }
+            nm.jn0 = njn[0]; nm.jt0 = njt[0]; nm.jn1 = njn[1]; nm.jt1 = njt[1];
+        }
+        store_manifold(d, id, nm);
+    }
+    flags &= ~static_cast<unsigned>(PR_CONTACT_DIRTY);
+    if (!oldTouching && newTouching) flags |= PR_CONTACT_TOUCHING;
+    else if (oldTouching && !newTouching) flags &= ~static_cast<unsigned>(PR_CONTACT_TOUCHING);
+    d.c_flags[id] = flags;
+}
+// UpdateContacts (AabbTreeWorld.cpp:2333-2421): one thread per contact of order[start, start+n)
 PR_KERNEL k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n, unsigned useMoved)
 {
     const unsigned i = PR_TID;
     bool updated = false;
     if (i < n) {
         const unsigned id = d.c_order[start + i];
-        unsigned flags = d.c_flags[id];
-        const uint4 ab = d.c_ab[id];
+        const unsigned flags = d.c_flags[id];
         bool dirty = (flags & PR_CONTACT_DIRTY) != 0;
-        if (useMoved) dirty = dirty || (d.b_moved[ab.x] | d.b_moved[ab.y]) != 0u;
-        if (dirty) {
-            updated = true;
-            const bool oldTouching = (flags & PR_CONTACT_TOUCHING) != 0;
-            bool newTouching = false;
-            if (flags & PR_CONTACT_SENSOR) {
-                atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_SENSOR)); // GJK TestOverlap path: TOI milestone
-                manifold_clear(d, id);
-            } else {
-                const Xf xfA = xf_from4(d.b_xf[ab.x]), xfB = xf_from4(d.b_xf[ab.y]);
-                Mf nm = collide_shapes(child_view(d, ab.z), xfA, child_view(d, ab.w), xfB, conf.linear_slop, conf.max_circles_ratio);
-                const uint4 o3 = d.m3[id];
-                const unsigned oldCount = o3.w, newCount = nm.count;
-                newTouching = newCount > 0u;
-                if (newCount > 0u && oldCount > 0u) {
-                    const float4 o1 = d.m1[id], o2 = d.m2[id];
-                    const unsigned ocf[2] = {o3.x, o3.y};
-                    const float ojn[2] = {o2.x, o2.z}, ojt[2] = {o2.y, o2.w};
-                    const float2 op[2] = {v2(o1.x, o1.y), v2(o1.z, o1.w)};
-                    const unsigned ncf[2] = {nm.cf0, nm.cf1};
-                    const float2 np[2] = {nm.p0, nm.p1};
-                    float njn[2] = {0.0f, 0.0f}, njt[2] = {0.0f, 0.0f};
-                    bool found[2] = {false, newCount < 2u};
-                    for (unsigned a = 0; a < newCount; ++a) {
-                        for (unsigned b = 0; b < oldCount; ++b) {
-                            if (ncf[a] == ocf[b]) { found[a] = true; njn[a] = ojn[b]; njt[a] = ojt[b]; break; }
-                        }
-                    }
-                    for (unsigned a = 0; a < newCount; ++a) {
-                        if (!found[a]) {
-                            float least = PR_INF;
-                            for (unsigned b = 0; b < oldCount; ++b) {
-                                const float sq = magsq(op[b] - np[a]);
-                                if (least > sq) { least = sq; njn[a] = ojn[b]; njt[a] = ojt[b]; }
-                            }
-                        }
-                    }
-                    nm.jn0 = njn[0]; nm.jt0 = njt[0]; nm.jn1 = njn[1]; nm.jt1 = njt[1];
-                }
-                store_manifold(d, id, nm);
-            }
-            flags &= ~static_cast<unsigned>(PR_CONTACT_DIRTY);
-            if (!oldTouching && newTouching) flags |= PR_CONTACT_TOUCHING;
-            else if (oldTouching && !newTouching) flags &= ~static_cast<unsigned>(PR_CONTACT_TOUCHING);
-            d.c_flags[id] = flags;
-        }
+        if (useMoved) { const uint4 ab = d.c_ab[id]; dirty = dirty || (d.b_moved[ab.x] | d.b_moved[ab.y]) != 0u; }
+        if (dirty) { updated = true; update_contact(d, conf, id, flags); }
     }
     warp_add(&d.cnt->contactsUpdated, updated ? 1u : 0u);
 }
@@ -545,6 +548,7 @@ PR_KERNEL k_create_contacts(DV d, unsigned nNew, const unsigned long long* keys,
         // MixFriction = sqrt(f1*f2), MixRestitution = max, Contact.hpp:57-69
         d.c_mat[id] = make_float4(sqrtf(matA.x * matB.x), (matA.y > matB.y) ? matA.y : matB.y, 0.0f, 1.0f);
         d.c_flags[id] = flags;
+        d.c_toiIsl[id] = 0u;
         manifold_clear(d, id);
         d.c_order[nOrder + i] = id;
         hash_insert(d, key);
@@ -618,6 +622,25 @@ PR_KERNEL k_isl_flatten(DV d, unsigned nBodies)
         d.b_root[i] = r; // separate array: parent[] is still being path-halved by other threads
     }
 }
+// GetBodyConstraint's velocity (BodyConstraint.hpp:154-164): Cap(GetVelocity(body, h))
+PR_D float4 body_constraint_velocity(const DV& d, unsigned i, float4 v, unsigned f, float h, const pr_step_conf& conf)
+{
+    if (f_accelerable(f)) { // GetVelocity(body, h), Body.cpp:290-310
+        const float4 a = d.b_acc[i], m = d.b_mass[i];
+        float2 l = v2(v.x, v.y) + h * v2(a.x, a.y);
+        float w = v.z + h * a.z;
+        l = vdiv(l, 1 + h * m.z);
+        w /= (1 + h * m.w);
+        v.x = l.x; v.y = l.y; v.z = w;
+    }
+    // Cap, Velocity.cpp:27-46
+    const float2 tr = h * v2(v.x, v.y);
+    const float lsq = magsq(tr);
+    if (lsq > square(conf.max_translation)) { const float ratio = conf.max_translation / sqrtf(lsq); v.x *= ratio; v.y *= ratio; }
+    const float absRot = fabsf(h * v.z);
+    if (absRot > conf.max_rotation) { const float ratio = conf.max_rotation / absRot; v.z *= ratio; }
+    return v;
+}
 // a1: GetBodyConstraint (BodyConstraint.hpp:154) = Cap(GetVelocity(body,h)) for bodies of active islands;
 // also SolveRegIslandViaGS's pos0 <- pos1 (:1574) and AddToIsland's SetAwakeFlag (:1400).
 PR_KERNEL k_isl_prepare(DV d, unsigned nBodies, pr_step_conf conf)
@@ -639,23 +662,7 @@ PR_KERNEL k_isl_prepare(DV d, unsigned nBodies, pr_step_conf conf)
             atomicAdd(&d.isl_nbodies[r], 1u);
             d.b_sync[i] = 1u;
         }
-        if (active || !f_speedable(f)) {
-            const float h = conf.delta_time;
-            if (f_accelerable(f)) { // GetVelocity(body, h), Body.cpp:290-310
-                const float4 a = d.b_acc[i], m = d.b_mass[i];
-                float2 l = v2(v.x, v.y) + h * v2(a.x, a.y);
-                float w = v.z + h * a.z;
-                l = vdiv(l, 1 + h * m.z);
-                w /= (1 + h * m.w);
-                v.x = l.x; v.y = l.y; v.z = w;
-            }
-            // Cap, Velocity.cpp:27-46
-            const float2 tr = h * v2(v.x, v.y);
-            const float lsq = magsq(tr);
-            if (lsq > square(conf.max_translation)) { const float ratio = conf.max_translation / sqrtf(lsq); v.x *= ratio; v.y *= ratio; }
-            const float absRot = fabsf(h * v.z);
-            if (absRot > conf.max_rotation) { const float ratio = conf.max_rotation / absRot; v.z *= ratio; }
-        }
+        if (active || !f_speedable(f)) v = body_constraint_velocity(d, i, v, f, conf.delta_time, conf);
         d.s_vel[i] = make_float4(v.x, v.y, v.z, 0.0f);
         d.s_pos[i] = make_float4(p1.x, p1.y, p1.z, 0.0f);
     }
@@ -754,11 +761,9 @@ PR_D float2 rel_velocity(float4 vA, float2 relA, float4 vB, float2 relB)
 }
 // GetWorldManifold (WorldManifold.cpp:37-130) + VelocityConstraint ctor (VelocityConstraint.cpp:81-196)
 // + PositionConstraint (AabbTreeWorld.cpp:289-312) for sorted constraint row i
-PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtRatio)
+PR_D void build_constraint_rows(const DV& d, unsigned cid, unsigned i, const pr_step_conf& conf, float dtRatio, unsigned islandLabel)
 {
-    const unsigned i = PR_TID;
-    if (i < nCons) {
-        const unsigned cid = d.k_contact[d.k_sorted[i]];
+    {
         const uint4 ab = d.c_ab[cid];
         const float4 mat = d.c_mat[cid];
         const float4 q0 = d.m0[cid], q1 = d.m1[cid], q2 = d.m2[cid];
@@ -810,8 +815,7 @@ PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtR
         vc.nx = normal.c; vc.ny = normal.s; vc.friction = mat.x; vc.tangentSpeed = mat.z;
         vc.bodyA = ab.x; vc.bodyB = ab.y; vc.count = count; vc.contact = cid;
         vc.invMA = mA.x; vc.invIA = mA.y; vc.invMB = mB.x; vc.invIB = mB.y;
-        const unsigned rAi = d.b_island[ab.x], rBi = d.b_island[ab.y];
-        vc.island = (rAi != INVALID) ? rAi : rBi;
+        vc.island = islandLabel;
         vc.dynA = (mA.x != 0.0f || mA.y != 0.0f) ? 1u : 0u; vc.dynB = (mB.x != 0.0f || mB.y != 0.0f) ? 1u : 0u; vc.pad = 0u;
         const float invMass = mA.x + mB.x;
         const Rot tangent = fwd_perp(normal);
@@ -863,6 +867,16 @@ PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtR
         d.vc[i] = vc;
     }
 }
+PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtRatio)
+{
+    const unsigned i = PR_TID;
+    if (i < nCons) {
+        const unsigned cid = d.k_contact[d.k_sorted[i]];
+        const uint4 ab = d.c_ab[cid];
+        const unsigned rAi = d.b_island[ab.x], rBi = d.b_island[ab.y];
+        build_constraint_rows(d, cid, i, conf, dtRatio, (rAi != INVALID) ? rAi : rBi);
+    }
+}
 
 // ------------------------------------------------------------------ a9/a10: warm start + velocity solve
 PR_D void apply_pair(float4& vA, float4& vB, float2 P, float2 relA, float2 relB, float imA, float iiA, float imB, float iiB)
@@ -901,11 +915,11 @@ PR_KERNEL k_warm_start_serial(DV d, unsigned start, unsigned count)
 
 // GaussSeidel::SolveVelocityConstraint (ContactSolver.cpp:481): tangent (:395) then normal
 // (block :245 with cases 1-4 :113-243, else sequential :337); points in order 1 then 0.
-PR_D float solve_velocity_row(const DV& d, unsigned i, bool& did)
+PR_D float solve_velocity_row(const DV& d, unsigned i, bool& did, bool checkIsland = true)
 {
     VCRow vc = d.vc[i];
     did = false;
-    if (d.isl_state[vc.island] & ISL_VEL_DONE) return 0.0f;
+    if (checkIsland && (d.isl_state[vc.island] & ISL_VEL_DONE)) return 0.0f;
     did = true;
     float4 vA = d.s_vel[vc.bodyA], vB = d.s_vel[vc.bodyB];
     const Rot normal = mkrot(vc.nx, vc.ny), tangent = fwd_perp(normal);
@@ -1080,12 +1094,12 @@ PR_D PDelta psm_solve(const PSM& psm, float2 pA, float2 pB, float imA, float iiA
     return r;
 }
 // GaussSeidel::SolvePositionConstraint, ContactSolver.cpp:494-643 (moveA = moveB = true)
-PR_D float solve_position_row(const DV& d, unsigned i, float rate, float slop, float maxCorr, bool& did)
+PR_D float solve_position_row(const DV& d, unsigned i, float rate, float slop, float maxCorr, bool& did, bool checkIsland = true)
 {
     const VCRow* vcp = &d.vc[i];
     const unsigned island = vcp->island;
     did = false;
-    if (d.isl_state[island] & ISL_POS_SOLVED) return PR_INF;
+    if (checkIsland && (d.isl_state[island] & ISL_POS_SOLVED)) return PR_INF;
     did = true;
     const unsigned bA = vcp->bodyA, bB = vcp->bodyB;
     const float imA = vcp->invMA, iiA = vcp->invIA, imB = vcp->invMB, iiB = vcp->invIB;
@@ -1275,6 +1289,7 @@ PR_KERNEL k_import_contacts(DV d, unsigned n, const pr_contact* in, const pr_man
         d.c_flags[id] = (c.flags & 0xFFu) | (c.toi_count << 8);
         d.m0[id] = make_float4(m.ln_x, m.ln_y, m.lp_x, m.lp_y); d.m1[id] = make_float4(m.p0_x, m.p0_y, m.p1_x, m.p1_y);
         d.m2[id] = make_float4(m.jn0, m.jt0, m.jn1, m.jt1); d.m3[id] = make_uint4(m.cf0, m.cf1, m.type, m.count);
+        d.c_toiIsl[id] = 0u;
         d.c_order[i] = id;
     }
 }
@@ -1318,4 +1333,5 @@ PR_KERNEL k_collide_batch(unsigned n, const pr_child* children, const float2* ve
 }
 
 } // namespace pr
+#include "pr_toi_phase.cuh"
 #endif

@@ -1,0 +1,453 @@
+// pr_toi_phase.cuh -- device TOI phase: SolveToi(conf) and callees, AabbTreeWorld.cpp:1684-2142.
+//
+// The reference loop is serial: compute contact TOIs, take the globally soonest, advance its two
+// bodies, build a mini island from their contact lists, solve it, re-synchronise, repeat.
+// Here each loop turn is one ROUND of kernels over device-resident state:
+//   k_toi_alpha / k_toi_advance_bodies / k_toi_compute   UpdateContactTOIs (:1684) for every contact
+//                                                        without a valid TOI, one thread per contact
+//   k_toi_claim / k_toi_select                           GetSoonestContact (:2870) -> event list
+//   k_toi_solve                                          SolveToi(contact) (:1833), ProcessContactsForTOI
+//                                                        (:2060), SolveToiViaGS (:1957): ONE thread per
+//                                                        event walks the bodies' contact lists in
+//                                                        m_contacts order and solves the mini island
+//   k_sync_proxies + FindContacts/AddContacts            (:1797-1817)
+// mode 0 (serial-exact): one event per round = the reference's order, results bit-identical.
+// mode 1 (parallel): every event that is the soonest among all events touching its bodies or their
+//   contact neighbours runs in the same round (their body sets are disjoint, so they commute with
+//   each other; an event that an earlier one would have influenced through a chain of later events is
+//   the documented source of drift -- BASELINE north_star: "drift reported, not gated").
+#ifndef PR_TOI_PHASE_CUH
+#define PR_TOI_PHASE_CUH
+
+namespace pr {
+
+// ------------------------------------------------------------------ body -> contact adjacency (m_bodyContacts)
+PR_KERNEL k_adj_count(DV d, unsigned nOrder)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        d.c_pos[id] = i;
+        const uint4 ab = d.c_ab[id];
+        atomicAdd(&d.adj_cnt[ab.x], 1u);
+        atomicAdd(&d.adj_cnt[ab.y], 1u);
+    }
+}
+PR_KERNEL k_adj_fill(DV d, unsigned nOrder)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        const uint4 ab = d.c_ab[id];
+        d.adj_list[d.adj_off[ab.x] + atomicAdd(&d.adj_cnt[ab.x], 1u)] = id;
+        d.adj_list[d.adj_off[ab.y] + atomicAdd(&d.adj_cnt[ab.y], 1u)] = id;
+    }
+}
+// per speedable body: order its segment like m_bodyContacts (append order == m_contacts order)
+PR_KERNEL k_adj_sort(DV d, unsigned nBodies)
+{
+    const unsigned b = PR_TID;
+    if (b < nBodies && f_speedable(d.b_flags[b])) {
+        const unsigned lo = d.adj_off[b], hi = d.adj_off[b + 1u];
+        for (unsigned i = lo + 1u; i < hi; ++i) {
+            const unsigned id = d.adj_list[i];
+            const unsigned key = d.c_pos[id];
+            unsigned j = i;
+            while (j > lo && d.c_pos[d.adj_list[j - 1u]] > key) { d.adj_list[j] = d.adj_list[j - 1u]; --j; }
+            d.adj_list[j] = id;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ UpdateContactTOIs (:1684-1750)
+PR_D bool toi_eligible(const DV& d, unsigned flags, uint4 ab, unsigned maxSubSteps, bool& atMax)
+{
+    atMax = false;
+    if (flags & PR_CONTACT_TOI) return false;
+    if (!(flags & PR_CONTACT_ENABLED) || (flags & PR_CONTACT_SENSOR) || !(flags & PR_CONTACT_IMPENETRABLE)) return false;
+    if ((flags >> 8) >= maxSubSteps) { atMax = true; return false; }
+    return f_awake(d.b_flags[ab.x]) || f_awake(d.b_flags[ab.y]);
+}
+PR_KERNEL k_toi_round_init(DV d, unsigned nBodies)
+{
+    const unsigned i = PR_TID;
+    if (i < nBodies) { d.b_toiAlpha[i] = f2u(d.b_pos0[i].w); d.b_claim[i] = ~0ull; }
+}
+// alpha0 = max(alphaA, alphaB) of every contact about to get a TOI (:1717): raise both bodies' targets
+PR_KERNEL k_toi_alpha(DV d, unsigned nOrder, unsigned maxSubSteps)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        const uint4 ab = d.c_ab[id];
+        bool atMax;
+        if (toi_eligible(d, d.c_flags[id], ab, maxSubSteps, atMax)) {
+            const float a0 = stdmax(d.b_pos0[ab.x].w, d.b_pos0[ab.y].w);
+            atomicMax(&d.b_toiAlpha[ab.x], f2u(a0)); // alpha in [0,1): non-negative floats order like uints
+            atomicMax(&d.b_toiAlpha[ab.y], f2u(a0));
+        }
+    }
+}
+PR_D void advance0(float4& p0, float4 p1, float alpha)
+{ // Advance0(Sweep, alpha), Sweep.cpp:30-34
+    const float beta = (alpha - p0.w) / (1.0f - p0.w);
+    Pos a; a.l = v2(p0.x, p0.y); a.a = p0.z;
+    Pos b; b.l = v2(p1.x, p1.y); b.a = p1.z;
+    const Pos r = lerp_pos(a, b, beta);
+    p0 = make_float4(r.l.x, r.l.y, r.a, alpha);
+}
+PR_KERNEL k_toi_advance_bodies(DV d, unsigned nBodies)
+{
+    const unsigned i = PR_TID;
+    if (i < nBodies) {
+        float4 p0 = d.b_pos0[i];
+        const float t = u2f(d.b_toiAlpha[i]);
+        if (t != p0.w) { advance0(p0, d.b_pos1[i], t); d.b_pos0[i] = p0; }
+    }
+}
+PR_D float normalized_angle(float value)
+{ // GetNormalized(Angle), Math.cpp:30-93 (trunc variant)
+    const float pi = 3.14159265358979323846264338327950288f;
+    const float twoPi = 2.0f * pi;
+    const float rTwoPi = 1.0f / twoPi;
+    float a = value;
+    a = a - truncf(a * rTwoPi) * twoPi;
+    if (a >= pi) a -= pi * 2;
+    else if (a < -pi) a += pi * 2;
+    return a;
+}
+PR_D SweepD normalized_sweep(float4 p0, float4 p1, float2 lc)
+{ // GetNormalized(Sweep), d2/Math.hpp:160-167
+    SweepD s;
+    s.pos0.l = v2(p0.x, p0.y); s.pos1.l = v2(p1.x, p1.y); s.lc = lc;
+    const float pos0a = normalized_angle(p0.z);
+    const float dd = p0.z - pos0a;
+    s.pos0.a = pos0a;
+    s.pos1.a = p1.z - dd;
+    return s;
+}
+PR_D unsigned long long toi_key(float toi, unsigned pos) { return (static_cast<unsigned long long>(f2u(toi)) << 32) | pos; }
+
+PR_KERNEL k_toi_compute(DV d, pr_step_conf conf, unsigned nOrder)
+{
+    const unsigned i = PR_TID;
+    unsigned atMaxCount = 0u, updated = 0u, distIt = 0u, toiIt = 0u, rootIt = 0u;
+    unsigned long long key = ~0ull;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        unsigned flags = d.c_flags[id];
+        const uint4 ab = d.c_ab[id];
+        bool atMax;
+        float toi = d.c_mat[id].w;
+        if (toi_eligible(d, flags, ab, conf.max_sub_steps, atMax)) {
+            float4 p0A = d.b_pos0[ab.x], p0B = d.b_pos0[ab.y];
+            const float4 p1A = d.b_pos1[ab.x], p1B = d.b_pos1[ab.y];
+            const float alpha0 = stdmax(p0A.w, p0B.w);
+            if (p0A.w != alpha0) advance0(p0A, p1A, alpha0); // not stored: only reachable in parallel mode
+            if (p0B.w != alpha0) advance0(p0B, p1B, alpha0);
+            const SweepD sA = normalized_sweep(p0A, p1A, d.b_lc[ab.x]), sB = normalized_sweep(p0B, p1B, d.b_lc[ab.y]);
+            const ToiResult out = toi_via_sat(child_view(d, ab.z), sA, child_view(d, ab.w), sB, conf.target_depth, conf.tolerance,
+                                              conf.max_toi_iters, conf.max_toi_root_iters, conf.max_distance_iters);
+            toi = (out.state == TOI_TOUCHING) ? stdmin(alpha0 + (1.0f - alpha0) * out.time, 1.0f) : 1.0f; // :1740
+            reinterpret_cast<float*>(&d.c_mat[id])[3] = toi;
+            flags |= PR_CONTACT_TOI;
+            d.c_flags[id] = flags;
+            updated = 1u; distIt = out.maxDistIters; toiIt = out.toiIters; rootIt = out.maxRootIters;
+        } else if (atMax) atMaxCount = 1u;
+        if ((flags & PR_CONTACT_TOI) && toi < 1.0f) key = toi_key(toi, i); // GetSoonestContact candidates
+    }
+    warp_add(&d.cnt->toiAtMaxSub, atMaxCount); warp_add(&d.cnt->toiUpdated, updated);
+    warp_max(&d.cnt->toiMaxDistIters, distIt); warp_max(&d.cnt->toiMaxToiIters, toiIt); warp_max(&d.cnt->toiMaxRootIters, rootIt);
+    if (key != ~0ull) atomicMin(&d.cnt->toiMinKey, key);
+}
+
+// ------------------------------------------------------------------ event selection
+template <class F> PR_D void toi_for_each_claim_body(const DV& d, uint4 ab, F&& fn)
+{
+    const unsigned two[2] = {ab.x, ab.y};
+    for (int s = 0; s < 2; ++s) {
+        const unsigned b = two[s];
+        const unsigned f = d.b_flags[b];
+        if (f_speedable(f)) fn(b);
+        if (f_accelerable(f)) {
+            for (unsigned k = d.adj_off[b]; k < d.adj_off[b + 1u]; ++k) {
+                const uint4 o = d.c_ab[d.adj_list[k]];
+                const unsigned other = (o.x == b) ? o.y : o.x;
+                if (f_speedable(d.b_flags[other])) fn(other);
+            }
+        }
+    }
+}
+PR_KERNEL k_toi_claim(DV d, unsigned nOrder)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        const float toi = d.c_mat[id].w;
+        if ((d.c_flags[id] & PR_CONTACT_TOI) && toi < 1.0f) {
+            const unsigned long long key = toi_key(toi, i);
+            toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { atomicMin(&d.b_claim[b], key); });
+        }
+    }
+}
+PR_KERNEL k_toi_select(DV d, unsigned nOrder, unsigned parallel)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        const float toi = d.c_mat[id].w;
+        if ((d.c_flags[id] & PR_CONTACT_TOI) && toi < 1.0f) {
+            const unsigned long long key = toi_key(toi, i);
+            bool win;
+            if (parallel) {
+                win = true;
+                toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { if (d.b_claim[b] != key) win = false; });
+            } else win = (key == d.cnt->toiMinKey);
+            if (win) d.toi_events[atomicAdd(&d.cnt->toiEvents, 1u)] = id;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ SolveToi(contact) (:1833-1955)
+PR_D void toi_flag_body_contacts(const DV& d, unsigned b)
+{ // FlagForUpdating(m_bodyContacts[b]), :459-465
+    for (unsigned k = d.adj_off[b]; k < d.adj_off[b + 1u]; ++k) atomicOr(&d.c_flags[d.adj_list[k]], static_cast<unsigned>(PR_CONTACT_DIRTY));
+}
+struct SweepBk { float4 p0, p1, xf; };
+PR_D SweepBk toi_backup(const DV& d, unsigned b) { SweepBk s; s.p0 = d.b_pos0[b]; s.p1 = d.b_pos1[b]; s.xf = d.b_xf[b]; return s; }
+PR_D void toi_restore(const DV& d, unsigned b, const SweepBk& s)
+{ // Body::SetSweep, Body.hpp:697-702 (m_xf = GetTransform1(sweep): the same bits it had)
+    d.b_pos0[b] = s.p0;
+    float4 p1 = d.b_pos1[b]; p1.x = s.p1.x; p1.y = s.p1.y; p1.z = s.p1.z; d.b_pos1[b] = p1;
+    d.b_xf[b] = s.xf;
+}
+PR_D bool pos_differs(float4 a, float4 b) { return !(a.x == b.x && a.y == b.y) || a.z != b.z; }
+// Advance(Body&, toi), Body.hpp:1004-1009; returns whether pos0 or pos1 changed (:1866, :2095)
+PR_D bool toi_advance_body(const DV& d, unsigned b, float toi)
+{
+    float4 p0 = d.b_pos0[b];
+    float4 p1 = d.b_pos1[b];
+    const float4 o0 = p0, o1 = p1;
+    advance0(p0, p1, toi);
+    p1.x = p0.x; p1.y = p0.y; p1.z = p0.z;
+    d.b_pos0[b] = p0; d.b_pos1[b] = p1;
+    Pos p; p.l = v2(p1.x, p1.y); p.a = p1.z;
+    const Xf xf = get_xf(p, d.b_lc[b]);
+    d.b_xf[b] = make_float4(xf.p.x, xf.p.y, xf.q.c, xf.q.s);
+    return pos_differs(p0, o0) || pos_differs(p1, o1);
+}
+struct ToiIsland { unsigned base, nB, nC; };
+PR_D bool toi_body_islanded(const DV& d, const ToiIsland& isl, unsigned b, bool speedable)
+{
+    if (speedable) return d.b_toiIsl[b] != 0u;
+    for (unsigned k = 0; k < isl.nB; ++k) if (d.toi_islBodies[isl.base + k] == b) return true; // non-speedable: this event's list
+    return false;
+}
+// ProcessContactsForTOI, :2060-2142
+PR_D void toi_process_contacts(const DV& d, const pr_step_conf& conf, unsigned id, ToiIsland& isl, float toi, bool exactMode,
+                               unsigned& updatedN, unsigned& skippedN)
+{
+    const bool bodyImpenetrable = (d.b_flags[id] & PR_BODY_IMPENETRABLE) != 0u;
+    for (unsigned k = d.adj_off[id]; k < d.adj_off[id + 1u]; ++k) {
+        const unsigned cid = d.adj_list[k];
+        if (d.c_toiIsl[cid]) continue;
+        unsigned cf = d.c_flags[cid];
+        if (cf & PR_CONTACT_SENSOR) continue;
+        const uint4 ab = d.c_ab[cid];
+        const unsigned other = (ab.x == id) ? ab.y : ab.x;
+        const unsigned of = d.b_flags[other];
+        if (!(bodyImpenetrable || (of & PR_BODY_IMPENETRABLE))) continue;
+        const bool otherSpeedable = f_speedable(of);
+        const bool otherIslanded = toi_body_islanded(d, isl, other, otherSpeedable);
+        const SweepBk backup = toi_backup(d, other);
+        const bool touchOther = !otherIslanded && (otherSpeedable || exactMode);
+        if (touchOther) {
+            if (toi_advance_body(d, other, toi)) toi_flag_body_contacts(d, other);
+        }
+        cf = d.c_flags[cid];
+        if (cf & PR_CONTACT_DIRTY) { update_contact(d, conf, cid, cf); ++updatedN; }
+        else ++skippedN;
+        cf = d.c_flags[cid];
+        if (!(cf & PR_CONTACT_ENABLED) || !(cf & PR_CONTACT_TOUCHING)) {
+            if (touchOther) toi_restore(d, other, backup);
+            continue;
+        }
+        d.toi_islContacts[isl.base + isl.nC++] = cid;
+        d.c_toiIsl[cid] = 1u;
+        if (!otherIslanded) {
+            if (otherSpeedable) { atomicOr(&d.b_flags[other], static_cast<unsigned>(PR_BODY_AWAKE)); d.b_toiIsl[other] = 1u; }
+            d.toi_islBodies[isl.base + isl.nB++] = other;
+        }
+    }
+}
+
+PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactMode)
+{
+    const unsigned e = PR_TID;
+    if (e >= nEvents) return;
+    const unsigned cid = d.toi_events[e];
+    const uint4 ab = d.c_ab[cid];
+    const unsigned A = ab.x, B = ab.y;
+    const float toi = d.c_mat[cid].w;
+    unsigned numUpdated = 0u, numSkipped = 0u;
+    const unsigned fA = d.b_flags[A], fB = d.b_flags[B];
+    {
+        const SweepBk bkA = toi_backup(d, A), bkB = toi_backup(d, B);
+        const bool touchA = f_speedable(fA) || exactMode, touchB = f_speedable(fB) || exactMode;
+        if (touchA && toi_advance_body(d, A, toi)) toi_flag_body_contacts(d, A);
+        if (touchB && toi_advance_body(d, B, toi)) toi_flag_body_contacts(d, B);
+        unsigned cf = d.c_flags[cid];
+        if (cf & PR_CONTACT_DIRTY) { update_contact(d, conf, cid, cf); ++numUpdated; }
+        cf = d.c_flags[cid];
+        cf &= ~static_cast<unsigned>(PR_CONTACT_TOI); // SetToi(contact, {})
+        cf += 0x100u;                                  // IncrementToiCount
+        d.c_flags[cid] = cf;
+        reinterpret_cast<float*>(&d.c_mat[cid])[3] = 1.0f;
+        if (!(cf & PR_CONTACT_ENABLED) || !(cf & PR_CONTACT_TOUCHING)) {
+            if (touchA) toi_restore(d, A, bkA);
+            if (touchB) toi_restore(d, B, bkB);
+            atomicAdd(&d.cnt->toiUpdTouching, numUpdated);
+            atomicAdd(&d.cnt->toiSkipTouching, numUpdated ? 0u : 1u);
+            return;
+        }
+    }
+    if (f_speedable(fA)) atomicOr(&d.b_flags[A], static_cast<unsigned>(PR_BODY_AWAKE));
+    if (f_speedable(fB)) atomicOr(&d.b_flags[B], static_cast<unsigned>(PR_BODY_AWAKE));
+    ToiIsland isl;
+    const unsigned need = 2u + (d.adj_off[A + 1u] - d.adj_off[A]) + (d.adj_off[B + 1u] - d.adj_off[B]);
+    isl.base = atomicAdd(&d.cnt->toiScratchTop, need);
+    isl.nB = 2u; isl.nC = 1u;
+    d.toi_islBodies[isl.base] = A; d.toi_islBodies[isl.base + 1u] = B; d.toi_islContacts[isl.base] = cid;
+    if (f_speedable(fA)) d.b_toiIsl[A] = 1u;
+    if (f_speedable(fB)) d.b_toiIsl[B] = 1u;
+    d.c_toiIsl[cid] = 1u;
+    if (f_accelerable(fA)) toi_process_contacts(d, conf, A, isl, toi, exactMode != 0u, numUpdated, numSkipped);
+    if (f_accelerable(fB)) toi_process_contacts(d, conf, B, isl, toi, exactMode != 0u, numUpdated, numSkipped);
+
+    // ---- SolveToiViaGS (:1957-2058) with subConf.deltaTime = (1 - toi) * deltaTime (:1952-1953)
+    pr_step_conf sub = conf;
+    sub.delta_time = (1.0f - toi) * conf.delta_time;
+    for (unsigned k = 0; k < isl.nB; ++k) { // GetBodyConstraints(h = 0)
+        const unsigned b = d.toi_islBodies[isl.base + k];
+        const float4 p1 = d.b_pos1[b];
+        d.s_vel[b] = body_constraint_velocity(d, b, d.b_vel[b], d.b_flags[b], 0.0f, sub);
+        d.s_vel[b].w = 0.0f;
+        d.s_pos[b] = make_float4(p1.x, p1.y, p1.z, 0.0f);
+    }
+    for (unsigned j = 0; j < isl.nC; ++j) build_constraint_rows(d, d.toi_islContacts[isl.base + j], isl.base + j, sub, 0.0f, 0u);
+    float minSepAll = PR_INF;
+    unsigned positionIters = conf.toi_position_iters;
+    unsigned solved = 0u;
+    for (unsigned it = 0; it < conf.toi_position_iters; ++it) {
+        float minSeparation = PR_INF;
+        for (unsigned j = 0; j < isl.nC; ++j) {
+            bool did;
+            minSeparation = stdmin(minSeparation, solve_position_row(d, isl.base + j, conf.toi_resolution_rate, conf.linear_slop,
+                                                                     conf.max_linear_correction, did, false));
+        }
+        minSepAll = stdmin(minSepAll, minSeparation);
+        if (minSeparation >= conf.toi_min_separation) { positionIters = it + 1u; solved = 1u; break; }
+    }
+    for (unsigned k = 0; k < isl.nB; ++k) { // "leap of faith": pos0 <- solved position (:2006-2012)
+        const unsigned b = d.toi_islBodies[isl.base + k];
+        if (f_speedable(d.b_flags[b])) {
+            const float4 sp = d.s_pos[b];
+            float4 p0 = d.b_pos0[b]; p0.x = sp.x; p0.y = sp.y; p0.z = sp.z; d.b_pos0[b] = p0;
+        }
+    }
+    for (unsigned j = 0; j < isl.nC; ++j) build_constraint_rows(d, d.toi_islContacts[isl.base + j], isl.base + j, sub, 0.0f, 0u);
+    unsigned velocityIters = conf.toi_velocity_iters;
+    float maxIncAll = 0.0f;
+    for (unsigned it = 0; it < conf.toi_velocity_iters; ++it) {
+        float newInc = 0.0f;
+        for (unsigned j = 0; j < isl.nC; ++j) { bool did; newInc = stdmax(newInc, solve_velocity_row(d, isl.base + j, did, false)); }
+        if (newInc <= conf.toi_min_momentum) { velocityIters = it + 1u; break; }
+        maxIncAll = stdmax(maxIncAll, newInc);
+    }
+    const float h = sub.delta_time;
+    for (unsigned k = 0; k < isl.nB; ++k) { // IntegratePositions + write-back (:2042-2052)
+        const unsigned b = d.toi_islBodies[isl.base + k];
+        const unsigned f = d.b_flags[b];
+        if (!f_speedable(f)) continue;
+        const float4 v = d.s_vel[b];
+        float4 sp = d.s_pos[b];
+        const float2 tr = h * v2(v.x, v.y);
+        const float rot = h * v.z;
+        sp.x += tr.x; sp.y += tr.y; sp.z += rot;
+        d.b_vel[b] = make_float4(v.x, v.y, v.z, 0.0f);
+        float4 p1 = d.b_pos1[b];
+        if (pos_differs(p1, sp)) {
+            p1.x = sp.x; p1.y = sp.y; p1.z = sp.z;
+            d.b_pos1[b] = p1;
+            Pos p; p.l = v2(sp.x, sp.y); p.a = sp.z;
+            const Xf xf = get_xf(p, d.b_lc[b]);
+            d.b_xf[b] = make_float4(xf.p.x, xf.p.y, xf.q.c, xf.q.s);
+            toi_flag_body_contacts(d, b);
+        }
+    }
+    // ---- :1797-1811: reset island flags; accelerable bodies get their proxies synchronised and their contacts' TOIs reset
+    for (unsigned k = 0; k < isl.nB; ++k) {
+        const unsigned b = d.toi_islBodies[isl.base + k];
+        const unsigned f = d.b_flags[b];
+        if (f_speedable(f)) d.b_toiIsl[b] = 0u;
+        if (f_accelerable(f)) {
+            d.b_sync[b] = 1u;
+            for (unsigned q = d.adj_off[b]; q < d.adj_off[b + 1u]; ++q) {
+                const unsigned c2 = d.adj_list[q];
+                atomicAnd(&d.c_flags[c2], ~static_cast<unsigned>(PR_CONTACT_TOI));
+                reinterpret_cast<float*>(&d.c_mat[c2])[3] = 1.0f;
+                d.c_toiIsl[c2] = 0u;
+            }
+        }
+    }
+    atomicMin(&d.cnt->toiMinSepFlip, float_flip(minSepAll));
+    atomicMax(&d.cnt->toiMaxIncBits, f2u(maxIncAll));
+    atomicAdd(&d.cnt->toiIslandsSolved, solved);
+    atomicAdd(&d.cnt->toiSumPosIters, positionIters);
+    atomicAdd(&d.cnt->toiSumVelIters, velocityIters);
+    atomicAdd(&d.cnt->toiIslandsFound, (positionIters > 0u || velocityIters > 0u) ? 1u : 0u);
+    atomicAdd(&d.cnt->toiUpdTouching, numUpdated);
+    atomicAdd(&d.cnt->toiSkipTouching, numSkipped);
+}
+
+// no event left (:1768-1777): ResetBodiesForSolveTOI, ResetContactsForSolveTOI
+PR_KERNEL k_toi_finish_bodies(DV d, unsigned nBodies)
+{
+    const unsigned i = PR_TID;
+    if (i < nBodies) { reinterpret_cast<float*>(&d.b_pos0[i])[3] = 0.0f; d.b_toiIsl[i] = 0u; }
+}
+PR_KERNEL k_toi_finish_contacts(DV d, unsigned nOrder)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        d.c_flags[id] = d.c_flags[id] & 0xFFu & ~static_cast<unsigned>(PR_CONTACT_TOI); // SetToi({}) + SetToiCount(0)
+        reinterpret_cast<float*>(&d.c_mat[id])[3] = 1.0f;
+        d.c_toiIsl[id] = 0u;
+    }
+}
+
+// standalone GetToiViaSat over arrays (pr_toi_batch): sweeps as 8 floats pos0 x,y,a | pos1 x,y,a | lc x,y
+PR_KERNEL k_toi_batch(unsigned n, const pr_child* children, const float2* verts, const float2* normals, const unsigned* aChild,
+                      const float* sweepA, const unsigned* bChild, const float* sweepB, pr_step_conf conf, float* outTime,
+                      int* outState, unsigned* outIters)
+{
+    const unsigned i = PR_TID;
+    if (i < n) {
+        const pr_child ca = children[aChild[i]], cb = children[bChild[i]];
+        ProxyView A, B;
+        A.radius = ca.vertex_radius; A.count = ca.vertex_count; A.v = verts + ca.vertex_offset; A.n = normals + ca.vertex_offset;
+        B.radius = cb.vertex_radius; B.count = cb.vertex_count; B.v = verts + cb.vertex_offset; B.n = normals + cb.vertex_offset;
+        const float* a = sweepA + 8u * i; const float* b = sweepB + 8u * i;
+        SweepD sA, sB;
+        sA.pos0.l = v2(a[0], a[1]); sA.pos0.a = a[2]; sA.pos1.l = v2(a[3], a[4]); sA.pos1.a = a[5]; sA.lc = v2(a[6], a[7]);
+        sB.pos0.l = v2(b[0], b[1]); sB.pos0.a = b[2]; sB.pos1.l = v2(b[3], b[4]); sB.pos1.a = b[5]; sB.lc = v2(b[6], b[7]);
+        const ToiResult r = toi_via_sat(A, sA, B, sB, conf.target_depth, conf.tolerance, conf.max_toi_iters, conf.max_toi_root_iters,
+                                        conf.max_distance_iters);
+        outTime[i] = r.time; outState[i] = r.state;
+        outIters[3u * i] = r.toiIters; outIters[3u * i + 1u] = r.maxDistIters; outIters[3u * i + 2u] = r.maxRootIters;
+    }
+}
+
+} // namespace pr
+#endif

@@ -67,7 +67,7 @@ struct StageTimer { void mark(World&, int) {} void finish(World&, pr_step_profil
 #endif
 
 // ------------------------------------------------------------------ array table (alloc / grow / clone)
-enum Group { G_BODY, G_SHAPE, G_CHILD, G_VERT, G_PROXY, G_CONTACT, G_HASH, G_PAIR, G_CONS, G_COUNT };
+enum Group { G_BODY, G_SHAPE, G_CHILD, G_VERT, G_PROXY, G_CONTACT, G_HASH, G_PAIR, G_CONS, G_ADJ, G_COUNT };
 struct ArrDesc { void** slot; size_t elem; Group g; size_t mult; };
 static std::vector<ArrDesc> arrays(World& w)
 {
@@ -80,6 +80,9 @@ static std::vector<ArrDesc> arrays(World& w)
         A(b_moved, G_BODY), A(b_sync, G_BODY), A(isl_state, G_BODY), A(isl_velIters, G_BODY), A(isl_posIters, G_BODY),
         A(isl_inc, G_BODY), A(isl_maxInc, G_BODY), A(isl_sep, G_BODY), A(isl_minSep, G_BODY), A(isl_minUA, G_BODY),
         A(isl_nbodies, G_BODY), A(b_claim, G_BODY), A(b_cmask, G_BODY),
+        A(adj_off, G_BODY), A(adj_cnt, G_BODY), A(b_toiIsl, G_BODY), A(b_toiAlpha, G_BODY),
+        A(c_pos, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT),
+        A(adj_list, G_ADJ), A(toi_islBodies, G_ADJ), A(toi_islContacts, G_ADJ),
         A(sh_mat, G_SHAPE), A(sh_filter, G_SHAPE), A(sh_group, G_SHAPE),
         A(ch_radius, G_CHILD), A(ch_voff, G_CHILD), A(ch_count, G_CHILD), A(vtx, G_VERT), A(nrm, G_VERT),
         A(p_body, G_PROXY), A(p_shape, G_PROXY), A(p_child, G_PROXY), A(p_cg, G_PROXY), A(p_tree, G_PROXY), A(p_moved, G_PROXY),
@@ -101,7 +104,8 @@ static unsigned* cap_of(World& w, Group g)
     switch (g) {
     case G_BODY: return &w.capBodies; case G_SHAPE: return &w.capShapes; case G_CHILD: return &w.capChildren;
     case G_VERT: return &w.capVerts; case G_PROXY: return &w.capProxies; case G_CONTACT: return &w.capContacts;
-    case G_HASH: return &w.capHash; case G_PAIR: return &w.capPairs; case G_CONS: return &w.capCons; default: return nullptr;
+    case G_HASH: return &w.capHash; case G_PAIR: return &w.capPairs; case G_CONS: return &w.capCons; case G_ADJ: return &w.capAdj;
+    default: return nullptr;
     }
 }
 static unsigned next_pow2(unsigned v) { unsigned p = 1; while (p < v) p <<= 1; return p; }
@@ -139,7 +143,7 @@ static void ensure(World& w, Group g, unsigned need)
     }
     if (g == G_HASH) { w.d.ht_mask = newCap - 1u; w.hashDirty = true; }
     *cap = newCap;
-    ensure_scratch(w, std::max(std::max(w.capContacts, w.capProxies), std::max(w.capPairs, w.capCons)));
+    ensure_scratch(w, std::max(std::max(std::max(w.capContacts, w.capProxies), std::max(w.capPairs, w.capCons)), std::max(w.capBodies, w.capAdj)));
 }
 
 static void read_counters(World& w) { d2h(w, &w.hostCnt, w.d.cnt, sizeof(Counters)); }
@@ -202,7 +206,7 @@ static unsigned destroy_contacts(World& w)
         std::swap(d.c_order, d.c_tmp2);
         w.nFree += destroyed;
         w.nOrder = kept;
-        w.hashDirty = true;
+        w.hashDirty = true; w.adjValid = false;
     }
     return destroyed;
 }
@@ -275,7 +279,7 @@ static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer
     if (2u * w.capContacts > w.capHash) rebuild_hash(w);
     PR_LAUNCH(k_create_contacts, nPairs, w.stream, d, nPairs, keys, src, w.nOrder, w.nFree, w.poolSize);
     const unsigned oldOrder = w.nOrder;
-    w.nFree -= used; w.poolSize += fresh; w.nOrder += nPairs;
+    w.nFree -= used; w.poolSize += fresh; w.nOrder += nPairs; w.adjValid = false;
     // AddContacts ends with Update(contactID) for each new contact (:2531); not part of UpdateContacts' stats
     read_counters(w);
     const unsigned savedUpdated = w.hostCnt.contactsUpdated;
@@ -403,6 +407,91 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     stats.reg.contacts_added = find_add_contacts(w, conf, tm);
 }
 
+// ------------------------------------------------------------------ TOI phase (SolveToi :1752-1831)
+// m_bodyContacts as CSR: count, scan, fill, then order each speedable body's segment by m_contacts position
+static void build_adjacency(World& w)
+{
+    DV& d = w.d;
+    const unsigned N = w.nBodies;
+    ensure(w, G_BODY, N + 1);
+    ensure(w, G_ADJ, 2u * w.nOrder + 2u * N + 64u);
+    dset(w, d.adj_cnt, 0, sizeof(unsigned) * N);
+    PR_LAUNCH(k_adj_count, w.nOrder, w.stream, d, w.nOrder);
+    scan_exclusive_u32(d.adj_cnt, d.adj_off, N, d.adj_off + N, w.scanScratch, w.stream);
+    dset(w, d.adj_cnt, 0, sizeof(unsigned) * N);
+    PR_LAUNCH(k_adj_fill, w.nOrder, w.stream, d, w.nOrder);
+    PR_LAUNCH(k_adj_sort, N, w.stream, d, N);
+    w.adjValid = true;
+}
+
+static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, StageTimer& tm)
+{
+    DV& d = w.d;
+    const unsigned N = w.nBodies;
+    tm.mark(w, PR_STAGE_TOI);
+    auto& st = stats.toi;
+    read_counters(w);
+    w.hostCnt.toiAtMaxSub = w.hostCnt.toiUpdated = w.hostCnt.toiMaxDistIters = w.hostCnt.toiMaxToiIters = w.hostCnt.toiMaxRootIters = 0;
+    w.hostCnt.toiMinSepFlip = float_flip(std::numeric_limits<float>::infinity());
+    w.hostCnt.toiMaxIncBits = 0; w.hostCnt.toiIslandsSolved = w.hostCnt.toiSumPosIters = w.hostCnt.toiSumVelIters = 0;
+    w.hostCnt.toiIslandsFound = w.hostCnt.toiUpdTouching = w.hostCnt.toiSkipTouching = 0;
+    w.hostCnt.proxiesMoved = 0; w.hostCnt.contactsUpdated = 0;
+    const bool exact = (w.toiMode == 0u);
+    unsigned rounds = 0;
+    for (;;) {
+        if (w.nOrder == 0) { // nothing can have a TOI
+            w.stepComplete = true;
+            write_counters(w);
+            PR_LAUNCH(k_toi_finish_bodies, N, w.stream, d, N);
+            break;
+        }
+        if (!w.adjValid) { write_counters(w); build_adjacency(w); read_counters(w); }
+        ensure(w, G_CONS, 2u * w.nOrder + 2u * N + 64u); // island rows (VC/PC scratch) of all events of one round
+        w.hostCnt.toiMinKey = ~0ull; w.hostCnt.toiEvents = 0; w.hostCnt.toiScratchTop = 0;
+        write_counters(w);
+        PR_LAUNCH(k_toi_round_init, N, w.stream, d, N);
+        PR_LAUNCH(k_toi_alpha, w.nOrder, w.stream, d, w.nOrder, conf.max_sub_steps);
+        PR_LAUNCH(k_toi_advance_bodies, N, w.stream, d, N);
+        PR_LAUNCH(k_toi_compute, w.nOrder, w.stream, d, conf, w.nOrder);
+        if (!exact) PR_LAUNCH(k_toi_claim, w.nOrder, w.stream, d, w.nOrder);
+        PR_LAUNCH(k_toi_select, w.nOrder, w.stream, d, w.nOrder, exact ? 0u : 1u);
+        read_counters(w);
+        const unsigned nEvents = w.hostCnt.toiEvents;
+        if (nEvents == 0) { // :1768-1777
+            w.stepComplete = true;
+            PR_LAUNCH(k_toi_finish_bodies, N, w.stream, d, N);
+            PR_LAUNCH(k_toi_finish_contacts, w.nOrder, w.stream, d, w.nOrder);
+            break;
+        }
+        ++rounds;
+        st.contacts_found += nEvents;
+        PR_LAUNCH(k_toi_solve, nEvents, w.stream, d, conf, nEvents, exact ? 1u : 0u);
+        PR_LAUNCH(k_sync_proxies, w.nProxies, w.stream, d, conf, w.nProxies);
+        dset(w, d.b_sync, 0, sizeof(unsigned) * N);
+        st.contacts_added += find_add_contacts(w, conf, tm); // leaves hostCnt == device counters
+        tm.mark(w, PR_STAGE_TOI);
+        if (w.subStepping) { w.stepComplete = false; break; }
+    }
+    // final UpdateContacts (:1825-1827)
+    read_counters(w);
+    const unsigned movedToi = w.hostCnt.proxiesMoved;
+    w.hostCnt.contactsUpdated = 0;
+    write_counters(w);
+    const unsigned nOrderAtUpdate = w.nOrder;
+    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 0u);
+    read_counters(w);
+    const Counters c = w.hostCnt;
+    st.contacts_at_max_sub_steps = c.toiAtMaxSub; st.contacts_updated_toi = c.toiUpdated;
+    st.max_dist_iters = c.toiMaxDistIters; st.max_toi_iters = c.toiMaxToiIters; st.max_root_iters = c.toiMaxRootIters;
+    st.min_separation = float_unflip(c.toiMinSepFlip); st.max_inc_impulse = u2f(c.toiMaxIncBits);
+    st.islands_found = c.toiIslandsFound; st.islands_solved = c.toiIslandsSolved;
+    st.sum_pos_iters = c.toiSumPosIters; st.sum_vel_iters = c.toiSumVelIters;
+    st.contacts_updated_touching = c.toiUpdTouching + c.contactsUpdated;
+    st.contacts_skipped_touching = c.toiSkipTouching + (nOrderAtUpdate - c.contactsUpdated);
+    st.proxies_moved = movedToi;
+    w.profile.toi_rounds = rounds; w.profile.toi_events = st.contacts_found;
+}
+
 static void reset_counters(World& w)
 {
     std::memset(&w.hostCnt, 0, sizeof(Counters));
@@ -442,7 +531,7 @@ static void step_impl(World& w, const pr_step_conf& conf, pr_step_stats& stats)
     if (conf.delta_time != 0.0f) {
         w.inv_dt0 = 1.0f / conf.delta_time;
         if (w.stepComplete) solve_reg(w, conf, stats, tm);
-        // TOI phase: see pr_toi (milestone); conf.do_toi is honoured there
+        if (conf.do_toi) solve_toi(w, conf, stats, tm);
     }
     check_launch();
     w.profile.p_total = w.nProxies; w.profile.c_total = w.nOrder;
@@ -511,7 +600,7 @@ int pr_create(const pr_world_conf* conf, pr_world** out)
         ensure(w, G_SHAPE, 64); ensure(w, G_CHILD, 64); ensure(w, G_VERT, std::max(256u, w.conf.vertex_capacity));
         ensure(w, G_PROXY, std::max(64u, w.conf.proxy_capacity));
         ensure(w, G_CONTACT, std::max(256u, w.conf.contact_capacity));
-        ensure(w, G_PAIR, 1024); ensure(w, G_CONS, 256);
+        ensure(w, G_PAIR, 1024); ensure(w, G_CONS, 256); ensure(w, G_ADJ, 256);
         ensure(w, G_HASH, next_pow2(2u * w.capContacts));
         reset_counters(w);
         sync(w);
@@ -546,7 +635,7 @@ int pr_clone(const pr_world* src, pr_world** out)
     sync(s);
     ensure(w, G_BODY, s.capBodies); ensure(w, G_SHAPE, s.capShapes); ensure(w, G_CHILD, s.capChildren); ensure(w, G_VERT, s.capVerts);
     ensure(w, G_PROXY, s.capProxies); ensure(w, G_CONTACT, s.capContacts); ensure(w, G_HASH, s.capHash);
-    ensure(w, G_PAIR, s.capPairs); ensure(w, G_CONS, s.capCons);
+    ensure(w, G_PAIR, s.capPairs); ensure(w, G_CONS, s.capCons); ensure(w, G_ADJ, s.capAdj);
     auto da = arrays(w); auto sa = arrays(s);
     for (size_t i = 0; i < da.size(); ++i) d2d(w, *da[i].slot, *sa[i].slot, da[i].elem * *cap_of(s, sa[i].g));
     d2d(w, w.d.cnt, s.d.cnt, sizeof(Counters));
@@ -555,7 +644,8 @@ int pr_clone(const pr_world* src, pr_world** out)
     w.nBodies = s.nBodies; w.nShapes = s.nShapes; w.nChildren = s.nChildren; w.nVerts = s.nVerts; w.nProxies = s.nProxies;
     w.maxTreeId = s.maxTreeId; w.debugFlags = s.debugFlags;
     w.nOrder = s.nOrder; w.nFree = s.nFree; w.poolSize = s.poolSize; w.anyBodySet = s.anyBodySet; w.hashDirty = true;
-    w.stepComplete = s.stepComplete; w.inv_dt0 = s.inv_dt0;
+    w.stepComplete = s.stepComplete; w.inv_dt0 = s.inv_dt0; w.subStepping = s.subStepping; w.toiMode = s.toiMode;
+    w.adjValid = false;
     sync(w);
     *out = pw;
     return PR_OK;
@@ -568,7 +658,7 @@ int pr_clear(pr_world* pw)
     World& w = pw->w;
     w.shapes.clear(); w.children.clear(); w.bodyShapes.clear(); w.joints.clear(); w.fixturesForProxies.clear();
     w.nBodies = w.nShapes = w.nChildren = w.nVerts = w.nProxies = w.nOrder = w.nFree = w.poolSize = 0; w.maxTreeId = 0;
-    w.anyBodySet = false; w.hashDirty = true; w.stepComplete = true;
+    w.anyBodySet = false; w.hashDirty = true; w.adjValid = false; w.stepComplete = true;
     reset_counters(w);
     return PR_OK;
     API_CATCH(pw)
@@ -783,7 +873,7 @@ int pr_load_state(pr_world* pw, uint32_t n_bodies, const pr_body* bodies, uint32
     h2d(w, w.d.c_free, freeIds.data(), 4 * freeIds.size());
     sync(w);
     w.nOrder = n_contacts; w.nFree = static_cast<unsigned>(freeIds.size()); w.poolSize = maxId;
-    w.hashDirty = true; w.stepComplete = true; w.inv_dt0 = inv_dt0;
+    w.hashDirty = true; w.adjValid = false; w.stepComplete = true; w.inv_dt0 = inv_dt0;
     reset_counters(w);
     return PR_OK;
     API_CATCH(pw)
@@ -815,6 +905,47 @@ int pr_get_step_profile(const pr_world* pw, pr_step_profile* out) { *out = pw->w
 int pr_shift_origin(pr_world* pw, float, float) { pw->w.error = "ShiftOrigin: not implemented yet"; return PR_ERR_UNSUPPORTED; }
 
 float pr_get_inv_dt0(const pr_world* pw) { return pw->w.inv_dt0; }
+
+int pr_set_toi_mode(pr_world* pw, uint32_t mode)
+{
+    if (mode > PR_TOI_PARALLEL) { pw->w.error = "unknown TOI mode"; return PR_ERR_INVALID_ARGUMENT; }
+    pw->w.toiMode = mode;
+    return PR_OK;
+}
+int pr_set_sub_stepping(pr_world* pw, uint32_t flag) { pw->w.subStepping = flag != 0; return PR_OK; }
+int pr_get_sub_stepping(const pr_world* pw) { return pw->w.subStepping ? 1 : 0; }
+int pr_is_step_complete(const pr_world* pw) { return pw->w.stepComplete ? 1 : 0; }
+
+int pr_toi_batch(int device, uint32_t n, const pr_child* children, uint32_t n_children, const pr_vec2* vertices,
+                 const pr_vec2* normals, uint32_t n_vertices, const uint32_t* a_child, const float* sweep_a,
+                 const uint32_t* b_child, const float* sweep_b, const pr_step_conf* conf, float* out_time,
+                 int32_t* out_state, uint32_t* out_iters)
+{
+    try {
+        World w; // only for the stream shim
+#ifndef PR_HOST_EMUL
+        if (device >= 0) CK(cudaSetDevice(device));
+        w.stream = 0;
+#else
+        (void)device;
+#endif
+        if (!n) return PR_OK;
+        pr_child* dch = static_cast<pr_child*>(dev_alloc(sizeof(pr_child) * n_children));
+        float2* dv = static_cast<float2*>(dev_alloc(sizeof(float2) * n_vertices));
+        float2* dn = static_cast<float2*>(dev_alloc(sizeof(float2) * n_vertices));
+        unsigned* da = static_cast<unsigned*>(dev_alloc(4 * n)); unsigned* db = static_cast<unsigned*>(dev_alloc(4 * n));
+        float* dsa = static_cast<float*>(dev_alloc(32 * n)); float* dsb = static_cast<float*>(dev_alloc(32 * n));
+        float* dt = static_cast<float*>(dev_alloc(4 * n)); int* dst = static_cast<int*>(dev_alloc(4 * n));
+        unsigned* dit = static_cast<unsigned*>(dev_alloc(12 * n));
+        h2d(w, dch, children, sizeof(pr_child) * n_children); h2d(w, dv, vertices, 8 * n_vertices); h2d(w, dn, normals, 8 * n_vertices);
+        h2d(w, da, a_child, 4 * n); h2d(w, db, b_child, 4 * n); h2d(w, dsa, sweep_a, 32 * n); h2d(w, dsb, sweep_b, 32 * n);
+        PR_LAUNCH(k_toi_batch, n, w.stream, n, dch, dv, dn, da, dsa, db, dsb, *conf, dt, dst, dit);
+        d2h(w, out_time, dt, 4 * n); d2h(w, out_state, dst, 4 * n); d2h(w, out_iters, dit, 12 * n);
+        dev_free(dch); dev_free(dv); dev_free(dn); dev_free(da); dev_free(db); dev_free(dsa); dev_free(dsb);
+        dev_free(dt); dev_free(dst); dev_free(dit);
+        return PR_OK;
+    } catch (const CudaError& e) { g_createError = e.msg; return PR_ERR_CUDA; }
+}
 
 int pr_collide_shapes(int device, uint32_t n, const pr_child* children, uint32_t n_children, const pr_vec2* vertices,
                       const pr_vec2* normals, uint32_t n_vertices, const uint32_t* a_child, const float* xf_a,

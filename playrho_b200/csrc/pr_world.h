@@ -50,6 +50,10 @@ struct PCRow {
 };
 
 struct Counters {
+    unsigned long long toiMinKey; // (toi bits << 32 | position in m_contacts) of the soonest contact, GetSoonestContact
+    unsigned toiEvents, toiScratchTop, toiAtMaxSub, toiUpdated, toiMaxDistIters, toiMaxToiIters, toiMaxRootIters;
+    unsigned toiMinSepFlip, toiMaxIncBits, toiIslandsSolved, toiSumPosIters, toiSumVelIters, toiIslandsFound;
+    unsigned toiUpdTouching, toiSkipTouching, toiPad;
     unsigned nQueue, nPairs, nNew, nDestroyed, nUncolored, nConstraints, nDirty, nOverflow;
     unsigned islandsFound, islandsSolved, bodiesSlept, sumVelIters, sumPosIters, maxIslandBodies;
     unsigned proxiesMoved, contactsUpdated, nAwake, nTouching, nActiveVel, nActivePos;
@@ -74,6 +78,8 @@ struct DV {
     unsigned long long* c_key; uint4* c_ab; uint2* c_px; uint4* c_ids; float4* c_mat; unsigned* c_flags;
     float4 *m0, *m1, *m2; uint4* m3;
     unsigned *c_order, *c_free, *c_tmp, *c_tmp2;
+    // TOI phase: body -> contact adjacency (m_bodyContacts) as CSR, islanded flags, event list, island scratch
+    unsigned *adj_off, *adj_cnt, *adj_list, *c_pos, *b_toiIsl, *c_toiIsl, *b_toiAlpha, *toi_events, *toi_islBodies, *toi_islContacts;
     unsigned long long* ht_keys; unsigned ht_mask;
     // new pairs
     unsigned long long *np_key, *np_key2; uint2* np_px; unsigned *np_idx, *np_idx2;
@@ -105,10 +111,12 @@ struct World {
     unsigned nOrder = 0, nFree = 0, poolSize = 0;  // contacts
     unsigned nCons = 0, nColors = 0, maxTreeId = 0, debugFlags = 0;
     bool anyBodySet = false, hashDirty = true, stepComplete = true;
+    bool subStepping = false, adjValid = false;
+    unsigned toiMode = 1; // PR_TOI_PARALLEL (default) or PR_TOI_SERIAL_EXACT (reference order)
     float inv_dt0 = 0;
     // capacities
     unsigned capBodies = 0, capShapes = 0, capChildren = 0, capVerts = 0, capProxies = 0, capContacts = 0,
-             capPairs = 0, capCons = 0, capHash = 0;
+             capPairs = 0, capCons = 0, capHash = 0, capAdj = 0;
     DV d{};
     RadixScratch rs;
     unsigned* scanScratch = nullptr; size_t scanScratchCap = 0;

@@ -21,7 +21,8 @@ EXPORTS = [
     "pr_create_revolute_joints", "pr_set_bodies", "pr_get_bodies", "pr_get_revolute_joints",
     "pr_get_counts", "pr_get_contacts", "pr_get_proxies", "pr_load_state", "pr_step",
     "pr_get_solve_order", "pr_set_debug", "pr_get_step_profile", "pr_abi_sizeof", "pr_shift_origin",
-    "pr_get_inv_dt0", "pr_collide_shapes", "pr_batch_create", "pr_batch_destroy", "pr_batch_world",
+    "pr_get_inv_dt0", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
+    "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_world",
     "pr_batch_step",
 ]
 
@@ -56,6 +57,11 @@ def bind(lib):
     lib.pr_get_inv_dt0.restype = f32
     lib.pr_get_inv_dt0.argtypes = [vp]
     lib.pr_collide_shapes.argtypes = [i32, u32, vp, u32, vp, vp, u32, vp, vp, vp, vp, f32, f32, vp]
+    lib.pr_set_toi_mode.argtypes = [vp, u32]
+    lib.pr_set_sub_stepping.argtypes = [vp, u32]
+    lib.pr_get_sub_stepping.argtypes = [vp]
+    lib.pr_is_step_complete.argtypes = [vp]
+    lib.pr_toi_batch.argtypes = [i32, u32, vp, u32, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.pr_batch_create.argtypes = [vp, u32, C.POINTER(vp)]
     lib.pr_batch_destroy.argtypes = [vp]
     lib.pr_batch_world.restype = vp
@@ -194,12 +200,36 @@ class World:
     def inv_dt0(self):
         return self.lib.pr_get_inv_dt0(self.h)
 
+    def set_toi_mode(self, mode):
+        """0 = serial-exact (reference event order, bit-exact), 1 = parallel independent events."""
+        self._chk(self.lib.pr_set_toi_mode(self.h, mode))
+
+    def set_sub_stepping(self, flag):
+        self._chk(self.lib.pr_set_sub_stepping(self.h, 1 if flag else 0))
+
+    def is_step_complete(self):
+        return bool(self.lib.pr_is_step_complete(self.h))
+
     def clone(self):
         h = vp()
         self._chk(self.lib.pr_clone(self.h, C.byref(h)))
         other = World.__new__(World)
         other.lib, other.h = self.lib, h
         return other
+
+
+def toi_batch(children, verts, normals, a_child, sweep_a, b_child, sweep_b, conf, lib=None, device=-1):
+    """GetToiViaSat on arrays through the C ABI (pr_toi_batch)."""
+    lib = lib or load_library()
+    n = len(a_child)
+    t, st, it = np.zeros(n, np.float32), np.zeros(n, np.int32), np.zeros((n, 3), np.uint32)
+    rc = lib.pr_toi_batch(device, n, abi.ptr(children), len(children), abi.ptr(verts), abi.ptr(normals), len(verts),
+                          abi.ptr(np.ascontiguousarray(a_child, np.uint32)), abi.ptr(np.ascontiguousarray(sweep_a, np.float32)),
+                          abi.ptr(np.ascontiguousarray(b_child, np.uint32)), abi.ptr(np.ascontiguousarray(sweep_b, np.float32)),
+                          abi.ptr(conf), abi.ptr(t), abi.ptr(st), abi.ptr(it))
+    if rc != 0:
+        raise PrError(rc, lib.pr_last_error(None).decode())
+    return t, st, it
 
 
 def collide_shapes(children, verts, normals, a_child, xf_a, b_child, xf_b, linear_slop=0.005,

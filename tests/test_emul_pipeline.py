@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import refworld
 import scenes_np
-from common import need_oracle, need_emul, emul_lib, run_vs_oracle
+from common import need_oracle, need_emul, need_ref, emul_lib, run_vs_oracle
 from playrho_b200 import world as W
 
 
@@ -20,6 +20,45 @@ from playrho_b200 import world as W
 def test_emulated_device_pipeline_bit_exact(name, builder, steps):
     gs, ncontacts, prof = run_vs_oracle(builder(), steps, lib=emul_lib())
     assert ncontacts > 0
+
+
+@need_oracle
+@need_emul
+@pytest.mark.parametrize("name,builder,steps", [
+    ("disks64", lambda: scenes_np.disks_box(64, seed=7), 120),
+    ("pyramid6", lambda: scenes_np.pyramid(6), 150),
+    ("mixed80", lambda: scenes_np.mixed(80, seed=11, tile_segments=16, tile_width=8.0), 150),
+])
+def test_emulated_device_pipeline_with_toi_bit_exact(name, builder, steps):
+    """Default StepConf (doToi on), serial-exact TOI event order: reg + TOI phases vs the oracle."""
+    gs, ncontacts, prof = run_vs_oracle(builder(), steps, lib=emul_lib(), conf=refworld.default_step_conf())
+    assert ncontacts > 0
+
+
+@need_oracle
+@need_emul
+@need_ref
+def test_emulated_device_pipeline_shooter_toi_bit_exact():
+    """Fast bodies, bullets, a spinning kinematic bar and a sensor: hundreds of TOI events."""
+    import scenes
+    sc = scenes.shooter().export_scene()
+    conf = refworld.default_step_conf()
+    gw = W.World(sc, lib=emul_lib(), record_solve_order=True)
+    gw.set_toi_mode(0)
+    orc = refworld.OracleWorld(sc)
+    events = 0
+    for s in range(200):
+        gs = gw.step(conf)
+        os_ = orc.step(conf, order=gw.solve_order()[0])
+        events += int(gs["toi"]["contacts_found"])
+        gsa, osa = np.array([gs]), np.array([os_])
+        gsa["reg"]["max_island_bodies"] = osa["reg"]["max_island_bodies"]
+        assert refworld.bits_equal(gsa, osa), "step %d stats: %s" % (s, refworld.diff_fields(gsa, osa))
+        assert refworld.bits_equal(gw.bodies(), orc.bodies()), "step %d bodies: %s" % (s, refworld.diff_fields(gw.bodies(), orc.bodies()))
+        gc, gm = gw.contacts(); oc, om = orc.contacts()
+        assert refworld.bits_equal(gc, oc), "step %d contacts: %s" % (s, refworld.diff_fields(gc, oc))
+        assert refworld.bits_equal(gm, om), "step %d manifolds: %s" % (s, refworld.diff_fields(gm, om))
+    assert events > 100
 
 
 @need_oracle

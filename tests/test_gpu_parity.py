@@ -26,6 +26,99 @@ def test_cuda_step_bit_exact_vs_oracle(name, builder, steps, every):
     assert prof["kernel_launches"] > 0
 
 
+@need_oracle
+@pytest.mark.parametrize("name,builder,steps,every", [
+    ("disks64", lambda: scenes_np.disks_box(64, seed=7), 120, 1),
+    ("pyramid10", lambda: scenes_np.pyramid(10), 200, 1),
+    ("mixed80", lambda: scenes_np.mixed(80, seed=11, tile_segments=16, tile_width=8.0), 150, 1),
+    ("mixed1500", lambda: scenes_np.mixed(1500, seed=12345, tile_segments=64, tile_width=32.0), 100, 5),
+])
+def test_cuda_step_with_toi_bit_exact_vs_oracle(name, builder, steps, every):
+    """Default StepConf (doToi ON), TOI events in the reference's serial order (PR_TOI_SERIAL_EXACT):
+    regular + TOI phase, every state array and every StepStats field bit-exact."""
+    gs, ncontacts, prof = run_vs_oracle(builder(), steps, device=0, check_every=every, conf=refworld.default_step_conf())
+    assert ncontacts > 0
+
+
+@need_oracle
+@need_ref
+def test_cuda_shooter_toi_bit_exact_vs_oracle():
+    """Fast bodies, bullets, spinning kinematic bar, sensor shape: hundreds of TOI events (SolveToi mini
+    islands, GetToiViaSat, GJK TestOverlap for the sensor)."""
+    import scenes
+    sc = scenes.shooter().export_scene()
+    conf = refworld.default_step_conf()
+    gw = W.World(sc, device=0, record_solve_order=True)
+    gw.set_toi_mode(0)
+    orc = refworld.OracleWorld(sc)
+    events, sensor_touch = 0, 0
+    for s in range(300):
+        gs = gw.step(conf)
+        os_ = orc.step(conf, order=gw.solve_order()[0])
+        events += int(gs["toi"]["contacts_found"])
+        gsa, osa = np.array([gs]), np.array([os_])
+        gsa["reg"]["max_island_bodies"] = osa["reg"]["max_island_bodies"]
+        assert_bits(gsa, osa, "step %d stats" % s)
+        assert_bits(gw.bodies(), orc.bodies(), "step %d bodies" % s)
+        gc, gm = gw.contacts(); oc, om = orc.contacts()
+        assert_bits(gc, oc, "step %d contacts" % s)
+        assert_bits(gm, om, "step %d manifolds" % s)
+        sensor_touch += int(((gc["flags"] & abi.CONTACT_SENSOR) != 0).sum()) if hasattr(abi, "CONTACT_SENSOR") else 0
+    assert events > 300
+
+
+@need_ref
+def test_cuda_toi_batch_bit_exact_vs_reference():
+    """GetToiViaSat (TimeOfImpact.cpp:35) on 200k random child pairs and sweeps vs the real reference."""
+    import scenes
+    from test_oracle_pin import random_sweeps
+    rng = np.random.RandomState(21)
+    sc = scenes.mixed(80, seed=5).export_scene()
+    nchild = len(sc["children"])
+    n = 200000
+    a = rng.randint(0, nchild, n).astype(np.uint32)
+    b = rng.randint(0, nchild, n).astype(np.uint32)
+    sa, sb = random_sweeps(rng, n), random_sweeps(rng, n)
+    sb[: n // 3, 0] += 3.0; sb[: n // 3, 3] -= 3.0
+    conf = refworld.default_step_conf()
+    rt = np.zeros(n, np.float32); rs = np.zeros(n, np.int32); ri = np.zeros((n, 3), np.uint32)
+    refworld._ref_lib().ref_toi(n, abi.ptr(sc["children"]), abi.ptr(sc["verts"]), abi.ptr(sc["normals"]), abi.ptr(a), abi.ptr(sa),
+                                abi.ptr(b), abi.ptr(sb), abi.ptr(conf), abi.ptr(rt), abi.ptr(rs), abi.ptr(ri))
+    gt, gs, gi = W.toi_batch(sc["children"], sc["verts"], sc["normals"], a, sa, b, sb, conf, device=0)
+    assert (rs == 1).sum() > 5000
+    assert np.array_equal(rs, gs)
+    assert_bits(rt, gt, "toi time")
+    assert np.array_equal(ri, gi)
+
+
+@need_oracle
+def test_cuda_parallel_toi_mode_drift_report():
+    """PR_TOI_PARALLEL (product default) vs PR_TOI_SERIAL_EXACT on the same scene: same number of bodies
+    asleep/awake is not required; trajectories may drift (reported, not gated: BASELINE north_star).
+    Gated here: finite state, no tunnelling through the terrain, and determinism of the parallel mode."""
+    sc = scenes_np.mixed(1500, seed=12345, tile_segments=64, tile_width=32.0)
+    conf = W.default_step_conf()
+    runs = []
+    for mode in (0, 1, 1):
+        gw = W.World(sc, device=0)
+        gw.set_toi_mode(mode)
+        events = rounds = 0
+        for _ in range(150):
+            st = gw.step(conf)
+            p = gw.profile()
+            events += int(p["toi_events"]); rounds += int(p["toi_rounds"])
+        runs.append((gw.bodies(), events, rounds))
+    (b0, e0, r0), (b1, e1, r1), (b2, e2, r2) = runs
+    assert_bits(b1, b2, "parallel TOI mode is deterministic")
+    dyn = b0["inv_mass"] > 0
+    drift = np.hypot(b0["pos1_x"][dyn] - b1["pos1_x"][dyn], b0["pos1_y"][dyn] - b1["pos1_y"][dyn])
+    print("TOI drift parallel vs serial-exact after 150 steps: max %.4g m, mean %.4g m; events %d vs %d; rounds %d vs %d"
+          % (drift.max(), drift.mean(), e0, e1, r0, r1))
+    assert np.isfinite(b1["pos1_x"]).all() and np.isfinite(b1["pos1_y"]).all()
+    assert (b1["pos1_y"][dyn] > -0.5).all(), "a body tunnelled through the terrain"
+    assert e0 > 0 and e1 > 0 and r1 <= r0
+
+
 @need_ref
 def test_cuda_collide_shapes_bit_exact_vs_reference():
     """CollideShapes (Manifold.cpp:393) on random child pairs vs the real reference's function."""
