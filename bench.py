@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--settle", type=int, default=40, help="untimed steps so that bodies are in contact")
     ap.add_argument("--ref-bodies", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-toi", action="store_true", help="StepConf.doToi=false (default: TOI enabled as BASELINE config 4 says)")
+    ap.add_argument("--toi-mode", type=int, default=1, help="1 = parallel independent TOI events (product default), 0 = serial-exact")
     ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     return ap.parse_args()
 
@@ -116,7 +118,7 @@ def run_reference(args, rank, world_size):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
         return
     ref = scenes.mixed(n, ids32=ids32) if args.workload != "disks" else scenes.disks_box(n, ids32=ids32)
-    conf = refworld.default_step_conf(do_toi=0)
+    conf = refworld.default_step_conf(do_toi=0 if args.no_toi else 1)
     ref.step_timed(conf, args.settle)
     ref.step_timed(conf, args.warmup)
     secs, _ = ref.step_timed(conf, args.steps)
@@ -127,7 +129,7 @@ def run_reference(args, rank, world_size):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s-%d (bounded sample of the %d-body workload; reference Step is O(islands x bodies), SURVEY F4)"
-                   % (args.workload, nb, args.bodies), "toi": False, "step_conf": "default, doToi=false"},
+                   % (args.workload, nb, args.bodies), "toi": not args.no_toi, "step_conf": "default StepConf (8 vel / 3 pos iters)"},
         "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": 1, "kind": "reference",
                          "sample": "%d bodies, %d steps after %d settle steps, 1 thread (reference is single-threaded)" % (nb, args.steps, args.settle)},
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -151,8 +153,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sc = build_scene(args, seed=12345 + rank)
     nb = len(sc["bodies"])
-    conf = W.default_step_conf(do_toi=0)
+    conf = W.default_step_conf(do_toi=0 if args.no_toi else 1)
     gw = W.World(sc, device=local_rank, body_capacity=nb + 16, proxy_capacity=nb + 8192, contact_capacity=6 * nb)
+    gw.set_toi_mode(args.toi_mode)
     for _ in range(args.settle):
         gw.step(conf)
     for _ in range(max(3, args.warmup)):
@@ -222,7 +225,9 @@ def main():
             "n_gpus": world_size, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s-%d bodies per GPU (BASELINE config 4 shape: 50%% disks / 50%% 4-8-gons over tiled 256-segment chain terrain)"
-                       % (args.workload, nb), "toi": False, "step_conf": "default (8 vel / 3 pos iters), doToi=false",
+                       % (args.workload, nb), "toi": not args.no_toi, "toi_mode": "parallel" if args.toi_mode else "serial-exact",
+                       "toi_events_per_step": float(np.mean([p["toi_events"] for p in profs])), "toi_rounds_per_step": float(np.mean([p["toi_rounds"] for p in profs])),
+                       "step_conf": "default StepConf (8 vel / 3 pos iters, doToi=%s)" % (not args.no_toi),
                        "settle_steps": args.settle, "l2": "working set (>1 GB) exceeds the 126 MB L2",
                        "contacts": int(last["c_total"]), "touching": int(last["c_touching"]), "colors": int(last["n_colors"]),
                        "islands": int(last["n_islands"]), "awake_bodies": int(last["n_awake"])},
@@ -245,7 +250,7 @@ def main():
                 if refworld.have_ref(ids32):
                     n = args.ref_bodies
                     ref = scenes.mixed(n, ids32=ids32) if args.workload != "disks" else scenes.disks_box(n, ids32=ids32)
-                    rconf = refworld.default_step_conf(do_toi=0)
+                    rconf = refworld.default_step_conf(do_toi=0 if args.no_toi else 1)
                     ref.step_timed(rconf, args.settle)
                     rs, _ = ref.step_timed(rconf, 20)
                     rnb = int(ref.counts()["bodies"])
