@@ -192,7 +192,7 @@ typedef struct pr_step_profile {
 } pr_step_profile;
 enum { PR_STAGE_PRE = 0, PR_STAGE_ISLANDS, PR_STAGE_INTEGRATE, PR_STAGE_SETUP, PR_STAGE_COLOR,
        PR_STAGE_VELOCITY, PR_STAGE_POSITION, PR_STAGE_WRITEBACK, PR_STAGE_SYNC, PR_STAGE_NARROW,
-       PR_STAGE_BVH, PR_STAGE_QUERY, PR_STAGE_ADD, PR_STAGE_TOI, PR_STAGE_COUNT };
+       PR_STAGE_BVH, PR_STAGE_QUERY, PR_STAGE_ADD, PR_STAGE_TOI, PR_STAGE_TOI_SOLVE, PR_STAGE_COUNT };
 
 typedef struct pr_world pr_world; /* opaque */
 

@@ -78,7 +78,7 @@ STEP_PROFILE = np.dtype([(n, u4) for n in ("n_awake", "p_total", "p_moved", "c_t
                                            "pos_iters", "candidate_pairs", "kernel_launches", "toi_rounds", "toi_events")] +
                         [("ms_total", f4), ("ms_stage", f4, (N_STAGES,))])
 STAGE_NAMES = ["pre", "islands", "integrate", "setup", "color", "velocity", "position", "writeback",
-               "sync", "narrow", "bvh", "query", "add", "toi"]
+               "sync", "narrow", "bvh", "query", "add", "toi", "toi_solve"]
 
 # body / contact flag bits (include/playrho_b200.h)
 BODY_DESTROYED, BODY_AWAKE, BODY_AUTOSLEEP, BODY_IMPENETRABLE = 0x1, 0x2, 0x4, 0x8

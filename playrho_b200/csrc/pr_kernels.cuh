@@ -107,6 +107,8 @@ PR_KERNEL k_put_bodies(DV d, unsigned n, unsigned firstId, const unsigned* ids, 
         if (isUpdate) { // SetBody transform-change path, AabbTreeWorld.cpp:2723-2795
             const float4 o = d.b_xf[id];
             if (o.x != r.xf_px || o.y != r.xf_py || o.z != r.xf_qc || o.w != r.xf_qs) { d.b_sync[id] = 1u; d.b_moved[id] = 1u; }
+            const float4 om = d.b_mass[id];
+            if ((om.x != 0.0f || om.y != 0.0f) != (r.inv_mass != 0.0f || r.inv_rot_i != 0.0f)) d.cnt->recolorFlag = 1u;
         }
         d.b_xf[id] = make_float4(r.xf_px, r.xf_py, r.xf_qc, r.xf_qs);
         d.b_pos0[id] = make_float4(r.pos0_x, r.pos0_y, r.pos0_a, r.alpha0);
@@ -220,49 +222,6 @@ PR_KERNEL k_clear_queue_flags(DV d, unsigned nQueue)
     if (i < nQueue) d.p_moved[d.q_list[i]] = 0u;
 }
 
-// ------------------------------------------------------------------ a6: DestroyContacts
-PR_D void body_set_awake(const DV& d, unsigned b)
-{ // Body::SetAwake, Body.cpp:163-171
-    if (f_speedable(d.b_flags[b])) {
-        atomicOr(&d.b_flags[b], static_cast<unsigned>(PR_BODY_AWAKE));
-        reinterpret_cast<float*>(&d.b_pos1[b])[3] = 0.0f; // underActiveTime
-    }
-}
-PR_D void manifold_clear(const DV& d, unsigned id)
-{
-    d.m0[id] = make_float4(0, 0, 0, 0); d.m1[id] = make_float4(0, 0, 0, 0); d.m2[id] = make_float4(0, 0, 0, 0);
-    d.m3[id] = make_uint4(PR_CF_DEFAULT, PR_CF_DEFAULT, 0u, 0u);
-}
-// keep[i] = 1 if the two FAT leaf boxes still overlap (AabbTreeWorld.cpp:2290-2304), else InternalDestroy (:2245)
-PR_KERNEL k_destroy_test(DV d, unsigned nOrder, unsigned* keep)
-{
-    const unsigned i = PR_TID;
-    if (i < nOrder) {
-        const unsigned id = d.c_order[i];
-        const uint2 px = d.c_px[id];
-        const bool ov = box_overlap(box_from4(d.p_fat[px.x]), box_from4(d.p_fat[px.y]));
-        keep[i] = ov ? 1u : 0u;
-        if (!ov) {
-            const uint4 ab = d.c_ab[id];
-            const unsigned flags = d.c_flags[id];
-            if (d.m3[id].w > 0u && !(flags & PR_CONTACT_SENSOR)) { body_set_awake(d, ab.x); body_set_awake(d, ab.y); }
-            d.c_flags[id] = PR_CONTACT_DESTROYED;
-            d.c_key[id] = ~0ull;
-            manifold_clear(d, id);
-        }
-    }
-}
-// stable compaction: kept ids to newOrder[pos[i]]; destroyed ids pushed on the free stack in order (ObjectPool::Free)
-PR_KERNEL k_destroy_compact(DV d, unsigned nOrder, const unsigned* keep, const unsigned* pos, unsigned* newOrder, unsigned nFree)
-{
-    const unsigned i = PR_TID;
-    if (i < nOrder) {
-        const unsigned id = d.c_order[i];
-        if (keep[i]) newOrder[pos[i]] = id;
-        else d.c_free[nFree + (i - pos[i])] = id;
-    }
-}
-
 // ------------------------------------------------------------------ contact-key hash set
 PR_D unsigned long long mix64(unsigned long long k)
 {
@@ -279,6 +238,18 @@ PR_D void hash_insert(const DV& d, unsigned long long key)
     }
     atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_HASH_FULL));
 }
+// removal leaves a tombstone (probe chains stay intact); the host rebuilds the table when live + dead > half
+#define PR_HASH_TOMB (~0ull - 1ull)
+PR_D void hash_remove(const DV& d, unsigned long long key)
+{
+    unsigned h = static_cast<unsigned>(mix64(key)) & d.ht_mask;
+    for (unsigned probe = 0; probe <= d.ht_mask; ++probe) {
+        const unsigned long long cur = d.ht_keys[h];
+        if (cur == key) { d.ht_keys[h] = PR_HASH_TOMB; return; }
+        if (cur == ~0ull) return;
+        h = (h + 1u) & d.ht_mask;
+    }
+}
 PR_D bool hash_contains(const DV& d, unsigned long long key)
 {
     unsigned h = static_cast<unsigned>(mix64(key)) & d.ht_mask;
@@ -294,6 +265,50 @@ PR_KERNEL k_hash_fill(DV d, unsigned nOrder)
 {
     const unsigned i = PR_TID;
     if (i < nOrder) hash_insert(d, d.c_key[d.c_order[i]]);
+}
+
+// ------------------------------------------------------------------ a6: DestroyContacts
+PR_D void body_set_awake(const DV& d, unsigned b)
+{ // Body::SetAwake, Body.cpp:163-171
+    if (f_speedable(d.b_flags[b])) {
+        atomicOr(&d.b_flags[b], static_cast<unsigned>(PR_BODY_AWAKE));
+        reinterpret_cast<float*>(&d.b_pos1[b])[3] = 0.0f; // underActiveTime
+    }
+}
+PR_D void manifold_clear(const DV& d, unsigned id)
+{
+    d.m0[id] = make_float4(0, 0, 0, 0); d.m1[id] = make_float4(0, 0, 0, 0); d.m2[id] = make_float4(0, 0, 0, 0);
+    d.m3[id] = make_uint4(PR_CF_DEFAULT, PR_CF_DEFAULT, 0u, 0u);
+}
+// keep[i] = 1 if the two FAT leaf boxes still overlap (AabbTreeWorld.cpp:2290-2304), else InternalDestroy (:2245)
+PR_KERNEL k_destroy_test(DV d, unsigned nOrder, unsigned* keep, unsigned hashLive)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        const uint2 px = d.c_px[id];
+        const bool ov = box_overlap(box_from4(d.p_fat[px.x]), box_from4(d.p_fat[px.y]));
+        keep[i] = ov ? 1u : 0u;
+        if (!ov) {
+            const uint4 ab = d.c_ab[id];
+            const unsigned flags = d.c_flags[id];
+            if (d.m3[id].w > 0u && !(flags & PR_CONTACT_SENSOR)) { body_set_awake(d, ab.x); body_set_awake(d, ab.y); }
+            d.c_flags[id] = PR_CONTACT_DESTROYED;
+            if (hashLive) hash_remove(d, d.c_key[id]);
+            d.c_key[id] = ~0ull;
+            manifold_clear(d, id);
+        }
+    }
+}
+// stable compaction: kept ids to newOrder[pos[i]]; destroyed ids pushed on the free stack in order (ObjectPool::Free)
+PR_KERNEL k_destroy_compact(DV d, unsigned nOrder, const unsigned* keep, const unsigned* pos, unsigned* newOrder, unsigned nFree)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        if (keep[i]) newOrder[pos[i]] = id;
+        else d.c_free[nFree + (i - pos[i])] = id;
+    }
 }
 
 // ------------------------------------------------------------------ a7: narrowphase Update
@@ -353,7 +368,7 @@ PR_D void update_contact(const DV& d, const pr_step_conf& conf, unsigned id, uns
     d.c_flags[id] = flags;
 }
 // UpdateContacts (AabbTreeWorld.cpp:2333-2421): one thread per contact of order[start, start+n)
-PR_KERNEL k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n, unsigned useMoved)
+PR_KERNEL k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n, unsigned useMoved, unsigned countIt)
 {
     const unsigned i = PR_TID;
     bool updated = false;
@@ -364,7 +379,7 @@ PR_KERNEL k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n,
         if (useMoved) { const uint4 ab = d.c_ab[id]; dirty = dirty || (d.b_moved[ab.x] | d.b_moved[ab.y]) != 0u; }
         if (dirty) { updated = true; update_contact(d, conf, id, flags); }
     }
-    warp_add(&d.cnt->contactsUpdated, updated ? 1u : 0u);
+    warp_add(&d.cnt->contactsUpdated, (updated && countIt) ? 1u : 0u);
 }
 
 // ------------------------------------------------------------------ a3: LBVH (Morton + Karras build + refit)
@@ -453,6 +468,7 @@ PR_D Box bvh_child_box(const DV& d, unsigned child, const unsigned* sortedIdx)
 PR_KERNEL k_bvh_refit(DV d, unsigned nLeaves, const unsigned* sortedIdx)
 {
     const unsigned i = PR_TID;
+    if (i < nLeaves) d.bv_leafOf[sortedIdx[i]] = i;
     if (i < nLeaves && nLeaves > 1u) {
         unsigned node = d.bv_lparent[i];
         while (node != INVALID) {
@@ -462,6 +478,46 @@ PR_KERNEL k_bvh_refit(DV d, unsigned nLeaves, const unsigned* sortedIdx)
             const Box a = bvh_child_box(d, d.bv_left[node], sortedIdx), b = bvh_child_box(d, d.bv_right[node], sortedIdx);
             Box u; u.minx = fminf(a.minx, b.minx); u.miny = fminf(a.miny, b.miny); u.maxx = fmaxf(a.maxx, b.maxx); u.maxy = fmaxf(a.maxy, b.maxy);
             d.bv_box[node] = box_to4(u);
+            node = d.bv_parent[node];
+        }
+    }
+}
+
+// Incremental refit: when only a few proxies got a new fat box (a TOI round, a quiet regular step) the
+// tree topology is kept and every ancestor box of a moved leaf is GROWN with float atomics (boxes never
+// shrink between full rebuilds, so the tree stays a valid, slightly looser, bounding hierarchy).
+PR_D void atomic_min_f(float* addr, float v)
+{
+#ifndef PR_HOST_EMUL
+    v += 0.0f; // -0 -> +0
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+#else
+    if (v < *addr) *addr = v;
+#endif
+}
+PR_D void atomic_max_f(float* addr, float v)
+{
+#ifndef PR_HOST_EMUL
+    v += 0.0f; // -0 -> +0
+    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+#else
+    if (v > *addr) *addr = v;
+#endif
+}
+PR_KERNEL k_bvh_refit_moved(DV d, unsigned nQueue, unsigned nLeaves)
+{
+    const unsigned t = PR_TID;
+    if (t < nQueue && nLeaves > 1u) {
+        const unsigned q = d.q_list[t];
+        const float4 f = d.p_fat[q];
+        unsigned node = d.bv_lparent[d.bv_leafOf[q]];
+        while (node != INVALID) {
+            float* b = reinterpret_cast<float*>(&d.bv_box[node]);
+            const float4 cur = d.bv_box[node];
+            if (cur.x <= f.x && cur.y <= f.y && cur.z >= f.z && cur.w >= f.w) break; // already inside: so are all ancestors
+            atomic_min_f(b + 0, f.x); atomic_min_f(b + 1, f.y); atomic_max_f(b + 2, f.z); atomic_max_f(b + 3, f.w);
             node = d.bv_parent[node];
         }
     }
@@ -525,8 +581,10 @@ PR_KERNEL k_bvh_query(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* s
 
 // AddContacts (AabbTreeWorld.cpp:2423-2547), creation part: sorted pair i gets its ContactID from the LIFO
 // free stack else by append (ObjectPool::Allocate), is appended to m_contacts in key order.
+PR_D void adj_append(const DV& d, unsigned b, unsigned id);
+PR_D bool toi_static_eligible(unsigned flags);
 PR_KERNEL k_create_contacts(DV d, unsigned nNew, const unsigned long long* keys, const unsigned* srcIdx,
-                            unsigned nOrder, unsigned nFree, unsigned poolSize)
+                            unsigned nOrder, unsigned nFree, unsigned poolSize, unsigned adjLive)
 {
     const unsigned i = PR_TID;
     if (i < nNew) {
@@ -548,9 +606,14 @@ PR_KERNEL k_create_contacts(DV d, unsigned nNew, const unsigned long long* keys,
         // MixFriction = sqrt(f1*f2), MixRestitution = max, Contact.hpp:57-69
         d.c_mat[id] = make_float4(sqrtf(matA.x * matB.x), (matA.y > matB.y) ? matA.y : matB.y, 0.0f, 1.0f);
         d.c_flags[id] = flags;
-        d.c_toiIsl[id] = 0u;
+        d.c_toiIsl[id] = 0u; d.c_color[id] = COLOR_UNSET;
         manifold_clear(d, id);
         d.c_order[nOrder + i] = id;
+        if (adjLive) { // the TOI phase's tables are live: m_bodyContacts push_back + TOI candidate list
+            d.c_pos[id] = nOrder + i;
+            adj_append(d, bA, id); adj_append(d, bB, id);
+            if (toi_static_eligible(flags)) d.toi_list[atomicAdd(&d.cnt->toiListN, 1u)] = id;
+        }
         hash_insert(d, key);
         if (!sensor) {
             if (f_speedable(fA)) atomicOr(&d.b_flags[bA], static_cast<unsigned>(PR_BODY_AWAKE));
@@ -669,7 +732,8 @@ PR_KERNEL k_isl_prepare(DV d, unsigned nBodies, pr_step_conf conf)
     warp_add(&d.cnt->islandsFound, isRoot);
     warp_add(&d.cnt->nAwake, isActive);
 }
-// which contacts become constraints this step: solvable and in an ACTIVE island
+// which contacts become constraints this step: solvable and in an ACTIVE island. A contact that is not a
+// constraint this step loses its persistent colour (it was not in the conflict masks of this step's colouring).
 PR_KERNEL k_mark_constraints(DV d, unsigned nOrder, unsigned* mark)
 {
     const unsigned i = PR_TID;
@@ -685,56 +749,90 @@ PR_KERNEL k_mark_constraints(DV d, unsigned nOrder, unsigned* mark)
             m = (rA != INVALID || rB != INVALID) ? 1u : 0u;
         }
         mark[i] = m;
+        if (!m) d.c_color[id] = COLOR_UNSET;
     }
     warp_add(&d.cnt->nTouching, touching);
 }
-PR_KERNEL k_gather_constraints(DV d, unsigned nOrder, const unsigned* mark, const unsigned* pos)
+PR_KERNEL k_gather_constraints(DV d, unsigned nOrder, const unsigned* mark, const unsigned* pos, unsigned recolorAll)
 {
     const unsigned i = PR_TID;
-    if (i < nOrder && mark[i]) { d.k_contact[pos[i]] = d.c_order[i]; d.k_color[pos[i]] = COLOR_UNSET; }
+    if (i < nOrder && mark[i]) {
+        const unsigned id = d.c_order[i];
+        d.k_contact[pos[i]] = id;
+        d.k_color[pos[i]] = recolorAll ? COLOR_UNSET : d.c_color[id];
+    }
 }
 
 // ------------------------------------------------------------------ deterministic graph colouring
-// Jones-Plassmann rounds with hashed priorities; the winner takes the lowest colour free on both
-// of its mass-carrying bodies (64-bit masks). Bodies with invMass == invRotI == 0 never change in
-// the solver and are excluded from conflicts. Result depends only on contact ids and list order.
+// Colours are PERSISTENT per contact: a constraint that was a constraint last step keeps its colour (a
+// subset of a conflict-free set is conflict-free), so each step only colours the NEW constraints:
+//   k_color_keep   : kept colours -> per-body 64-bit masks; uncoloured constraints -> work list
+//   k_color_claim / k_color_commit : Jones-Plassmann rounds with hashed priorities over the work list;
+//                    the winner takes the lowest colour free on both of its mass-carrying bodies.
+// Bodies with invMass == invRotI == 0 never change in the solver and are excluded from conflicts.
+// The result depends only on contact ids, list order and the world's own history (clones copy it).
 PR_D unsigned hash32(unsigned x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
 PR_D bool body_dyn(const DV& d, unsigned b) { const float4 m = d.b_mass[b]; return m.x != 0.0f || m.y != 0.0f; }
 PR_D unsigned long long color_key(unsigned round, unsigned cid, unsigned k)
 {
     return (static_cast<unsigned long long>(63u - (round & 63u)) << 58) | (static_cast<unsigned long long>(hash32(cid)) << 26) | (k & 0x3FFFFFFu);
 }
-PR_KERNEL k_color_claim(DV d, unsigned nCons, unsigned round)
+PR_KERNEL k_color_keep(DV d, unsigned nBound)
 {
     const unsigned k = PR_TID;
-    if (k < nCons && d.k_color[k] == COLOR_UNSET) {
-        const unsigned cid = d.k_contact[k];
-        const uint4 ab = d.c_ab[cid];
-        const unsigned long long key = color_key(round, cid, k);
-        if (body_dyn(d, ab.x)) atomicMin(&d.b_claim[ab.x], key);
-        if (body_dyn(d, ab.y)) atomicMin(&d.b_claim[ab.y], key);
+    bool todo = false;
+    if (k < nBound && k < d.cnt->nConstraints) {
+        const unsigned c = d.k_color[k];
+        if (c == COLOR_UNSET) todo = true;
+        else if (c < 64u) {
+            const uint4 ab = d.c_ab[d.k_contact[k]];
+            if (body_dyn(d, ab.x)) atomicOr(&d.b_cmask[ab.x], 1ull << c);
+            if (body_dyn(d, ab.y)) atomicOr(&d.b_cmask[ab.y], 1ull << c);
+        }
+    }
+    const unsigned slot = warp_append(&d.cnt->nColorWork, todo);
+    if (todo) d.k_ulist[slot] = k;
+}
+PR_KERNEL k_color_claim(DV d, unsigned nWork, unsigned round)
+{
+    const unsigned t = PR_TID;
+    if (t == 0u) d.cnt->nUncolored = 0u; // (k_color_commit of this round counts what is left)
+    if (t < nWork) {
+        const unsigned k = d.k_ulist[t];
+        if (d.k_color[k] == COLOR_UNSET) {
+            const unsigned cid = d.k_contact[k];
+            const uint4 ab = d.c_ab[cid];
+            const unsigned long long key = color_key(round, cid, k);
+            if (body_dyn(d, ab.x)) atomicMin(&d.b_claim[ab.x], key);
+            if (body_dyn(d, ab.y)) atomicMin(&d.b_claim[ab.y], key);
+        }
     }
 }
-PR_KERNEL k_color_commit(DV d, unsigned nCons, unsigned round)
+PR_KERNEL k_color_commit(DV d, unsigned nWork, unsigned round)
 {
-    const unsigned k = PR_TID;
+    const unsigned t = PR_TID;
     unsigned remaining = 0u;
-    if (k < nCons && d.k_color[k] == COLOR_UNSET) {
-        const unsigned cid = d.k_contact[k];
-        const uint4 ab = d.c_ab[cid];
-        const unsigned long long key = color_key(round, cid, k);
-        const bool dA = body_dyn(d, ab.x), dB = body_dyn(d, ab.y);
-        const bool win = (!dA || d.b_claim[ab.x] == key) && (!dB || d.b_claim[ab.y] == key);
-        if (win) {
-            const unsigned long long used = (dA ? d.b_cmask[ab.x] : 0ull) | (dB ? d.b_cmask[ab.y] : 0ull);
-            const unsigned long long freeBits = ~used;
-            if (freeBits) {
-                const unsigned c = static_cast<unsigned>(__ffsll(static_cast<long long>(freeBits))) - 1u;
+    if (t < nWork) {
+        const unsigned k = d.k_ulist[t];
+        if (d.k_color[k] == COLOR_UNSET) {
+            const unsigned cid = d.k_contact[k];
+            const uint4 ab = d.c_ab[cid];
+            const unsigned long long key = color_key(round, cid, k);
+            const bool dA = body_dyn(d, ab.x), dB = body_dyn(d, ab.y);
+            const bool win = (!dA || d.b_claim[ab.x] == key) && (!dB || d.b_claim[ab.y] == key);
+            if (win) {
+                const unsigned long long used = (dA ? d.b_cmask[ab.x] : 0ull) | (dB ? d.b_cmask[ab.y] : 0ull);
+                const unsigned long long freeBits = ~used;
+                unsigned c = COLOR_OVERFLOW;
+                if (freeBits) {
+                    c = static_cast<unsigned>(__ffsll(static_cast<long long>(freeBits))) - 1u;
+                    if (dA) d.b_cmask[ab.x] |= (1ull << c);
+                    if (dB) d.b_cmask[ab.y] |= (1ull << c);
+                }
                 d.k_color[k] = c;
-                if (dA) d.b_cmask[ab.x] |= (1ull << c);
-                if (dB) d.b_cmask[ab.y] |= (1ull << c);
-            } else d.k_color[k] = COLOR_OVERFLOW;
-        } else remaining = 1u;
+                d.c_color[cid] = c;
+            } else remaining = 1u;
+        }
     }
     warp_add(&d.cnt->nUncolored, remaining);
 }
@@ -1289,7 +1387,7 @@ PR_KERNEL k_import_contacts(DV d, unsigned n, const pr_contact* in, const pr_man
         d.c_flags[id] = (c.flags & 0xFFu) | (c.toi_count << 8);
         d.m0[id] = make_float4(m.ln_x, m.ln_y, m.lp_x, m.lp_y); d.m1[id] = make_float4(m.p0_x, m.p0_y, m.p1_x, m.p1_y);
         d.m2[id] = make_float4(m.jn0, m.jt0, m.jn1, m.jt1); d.m3[id] = make_uint4(m.cf0, m.cf1, m.type, m.count);
-        d.c_toiIsl[id] = 0u;
+        d.c_toiIsl[id] = 0u; d.c_color[id] = COLOR_UNSET;
         d.c_order[i] = id;
     }
 }

@@ -199,6 +199,41 @@ inline bool radix_sort_pairs(K* keysA, unsigned* valsA, K* keysB, unsigned* vals
     return !inA;
 }
 
+// ---------------------------------------------------------------- small sort (one block)
+// Sorts up to SMALL_SORT_MAX unique 64-bit keys (full-key order) with their element indices as values,
+// in shared memory with a bitonic network: the latency path for the few candidate pairs a TOI round or
+// a quiet regular step produces (the tiled radix sort above needs 3 launches per 8-bit pass).
+constexpr unsigned SMALL_SORT_MAX = 2048;
+__global__ void k_sort_pairs_small(const unsigned long long* __restrict__ keysIn, unsigned long long* __restrict__ keysOut,
+                                   unsigned* __restrict__ valsOut, unsigned n)
+{
+    __shared__ unsigned long long k[SMALL_SORT_MAX];
+    __shared__ unsigned v[SMALL_SORT_MAX];
+    for (unsigned i = threadIdx.x; i < SMALL_SORT_MAX; i += blockDim.x) {
+        k[i] = (i < n) ? keysIn[i] : ~0ull;
+        v[i] = i;
+    }
+    __syncthreads();
+    for (unsigned size = 2; size <= SMALL_SORT_MAX; size <<= 1) {
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned t = threadIdx.x; t < SMALL_SORT_MAX / 2; t += blockDim.x) {
+                const unsigned lo = 2u * t - (t & (stride - 1u));
+                const unsigned hi = lo + stride;
+                const bool asc = ((lo & size) == 0u);
+                const unsigned long long a = k[lo], b = k[hi];
+                if ((a > b) == asc) { k[lo] = b; k[hi] = a; const unsigned tv = v[lo]; v[lo] = v[hi]; v[hi] = tv; }
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) { keysOut[i] = k[i]; valsOut[i] = v[i]; }
+}
+inline void sort_pairs_small(const unsigned long long* keysIn, unsigned long long* keysOut, unsigned* valsOut, unsigned n,
+                             cudaStream_t stream)
+{
+    if (n) PR_LAUNCH_GRID(k_sort_pairs_small, 1, 1024, stream, keysIn, keysOut, valsOut, n);
+}
+
 #else // ---------------------------------------------------------------- host emulation
 } // namespace pr
 #include <vector>
@@ -233,6 +268,19 @@ inline bool radix_sort_pairs(K* keysA, unsigned* valsA, K* keysB, unsigned* vals
     for (unsigned i = 0; i < n; ++i) { keysA[i] = k[i]; valsA[i] = v[i]; }
     count_launch();
     return false;
+}
+
+constexpr unsigned SMALL_SORT_MAX = 2048;
+inline void sort_pairs_small(const unsigned long long* keysIn, unsigned long long* keysOut, unsigned* valsOut, unsigned n,
+                             pr_stream_t)
+{
+    std::vector<unsigned> idx(n);
+    for (unsigned i = 0; i < n; ++i) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](unsigned a, unsigned b) { return keysIn[a] < keysIn[b]; });
+    std::vector<unsigned long long> k(n);
+    for (unsigned i = 0; i < n; ++i) k[i] = keysIn[idx[i]];
+    for (unsigned i = 0; i < n; ++i) { keysOut[i] = k[i]; valsOut[i] = idx[i]; }
+    if (n) count_launch();
 }
 #endif
 

@@ -22,15 +22,36 @@
 namespace pr {
 
 // ------------------------------------------------------------------ body -> contact adjacency (m_bodyContacts)
+// CSR over SPEEDABLE bodies only (lists of static bodies are never walked: ProcessContactsForTOI runs
+// for accelerable bodies, FlagForUpdating only for bodies that moved). Every segment has slack so
+// contacts created during the TOI rounds are appended in place (k_create_contacts); segments are kept in
+// m_contacts order by an insertion sort (whole table at build time, per body before an event walks it).
+PR_D bool toi_static_eligible(unsigned flags)
+{ // the flag part of UpdateContactTOIs' filter (:1696) that never changes during a step
+    return (flags & PR_CONTACT_ENABLED) && !(flags & PR_CONTACT_SENSOR) && (flags & PR_CONTACT_IMPENETRABLE);
+}
 PR_KERNEL k_adj_count(DV d, unsigned nOrder)
 {
     const unsigned i = PR_TID;
+    bool listed = false; unsigned id = 0u;
     if (i < nOrder) {
-        const unsigned id = d.c_order[i];
+        id = d.c_order[i];
         d.c_pos[id] = i;
         const uint4 ab = d.c_ab[id];
-        atomicAdd(&d.adj_cnt[ab.x], 1u);
-        atomicAdd(&d.adj_cnt[ab.y], 1u);
+        if (f_speedable(d.b_flags[ab.x])) atomicAdd(&d.adj_cnt[ab.x], 1u);
+        if (f_speedable(d.b_flags[ab.y])) atomicAdd(&d.adj_cnt[ab.y], 1u);
+        listed = toi_static_eligible(d.c_flags[id]);
+    }
+    const unsigned slot = warp_append(&d.cnt->toiListN, listed);
+    if (listed) d.toi_list[slot] = id;
+}
+PR_KERNEL k_adj_cap(DV d, unsigned nBodies)
+{
+    const unsigned b = PR_TID;
+    if (b < nBodies) {
+        const unsigned c = d.adj_cnt[b];
+        d.adj_cnt[b] = f_speedable(d.b_flags[b]) ? c + ((c >> 2) > 4u ? (c >> 2) : 4u) : 0u; // capacity (scan input)
+        d.adj_n[b] = 0u;
     }
 }
 PR_KERNEL k_adj_fill(DV d, unsigned nOrder)
@@ -39,23 +60,38 @@ PR_KERNEL k_adj_fill(DV d, unsigned nOrder)
     if (i < nOrder) {
         const unsigned id = d.c_order[i];
         const uint4 ab = d.c_ab[id];
-        d.adj_list[d.adj_off[ab.x] + atomicAdd(&d.adj_cnt[ab.x], 1u)] = id;
-        d.adj_list[d.adj_off[ab.y] + atomicAdd(&d.adj_cnt[ab.y], 1u)] = id;
+        if (f_speedable(d.b_flags[ab.x])) d.adj_list[d.adj_off[ab.x] + atomicAdd(&d.adj_n[ab.x], 1u)] = id;
+        if (f_speedable(d.b_flags[ab.y])) d.adj_list[d.adj_off[ab.y] + atomicAdd(&d.adj_n[ab.y], 1u)] = id;
     }
 }
-// per speedable body: order its segment like m_bodyContacts (append order == m_contacts order)
+PR_D unsigned adj_end(const DV& d, unsigned b)
+{
+    const unsigned lo = d.adj_off[b], cap = d.adj_off[b + 1u] - lo, n = d.adj_n[b];
+    return lo + (n < cap ? n : cap);
+}
+PR_D void adj_sort_body(const DV& d, unsigned b)
+{
+    const unsigned lo = d.adj_off[b], hi = adj_end(d, b);
+    for (unsigned i = lo + 1u; i < hi; ++i) {
+        const unsigned id = d.adj_list[i];
+        const unsigned key = d.c_pos[id];
+        unsigned j = i;
+        while (j > lo && d.c_pos[d.adj_list[j - 1u]] > key) { d.adj_list[j] = d.adj_list[j - 1u]; --j; }
+        d.adj_list[j] = id;
+    }
+}
 PR_KERNEL k_adj_sort(DV d, unsigned nBodies)
 {
     const unsigned b = PR_TID;
-    if (b < nBodies && f_speedable(d.b_flags[b])) {
-        const unsigned lo = d.adj_off[b], hi = d.adj_off[b + 1u];
-        for (unsigned i = lo + 1u; i < hi; ++i) {
-            const unsigned id = d.adj_list[i];
-            const unsigned key = d.c_pos[id];
-            unsigned j = i;
-            while (j > lo && d.c_pos[d.adj_list[j - 1u]] > key) { d.adj_list[j] = d.adj_list[j - 1u]; --j; }
-            d.adj_list[j] = id;
-        }
+    if (b < nBodies && f_speedable(d.b_flags[b])) adj_sort_body(d, b);
+}
+// AddContacts' m_bodyContacts push_back (:2520-2523) for a contact created while the table is live
+PR_D void adj_append(const DV& d, unsigned b, unsigned id)
+{
+    if (f_speedable(d.b_flags[b])) {
+        const unsigned slot = d.adj_off[b] + atomicAdd(&d.adj_n[b], 1u);
+        if (slot < d.adj_off[b + 1u]) d.adj_list[slot] = id;
+        else atomicOr(&d.cnt->adjOverflow, 1u); // host rebuilds the table before its next use
     }
 }
 
@@ -68,17 +104,22 @@ PR_D bool toi_eligible(const DV& d, unsigned flags, uint4 ab, unsigned maxSubSte
     if ((flags >> 8) >= maxSubSteps) { atMax = true; return false; }
     return f_awake(d.b_flags[ab.x]) || f_awake(d.b_flags[ab.y]);
 }
-PR_KERNEL k_toi_round_init(DV d, unsigned nBodies)
+PR_KERNEL k_toi_phase_init(DV d, unsigned nBodies)
 {
     const unsigned i = PR_TID;
-    if (i < nBodies) { d.b_toiAlpha[i] = f2u(d.b_pos0[i].w); d.b_claim[i] = ~0ull; }
+    if (i < nBodies) { d.b_toiAlpha[i] = f2u(d.b_pos0[i].w); d.b_claim[i] = ~0ull; d.b_toiStamp[i] = 0u; d.b_toiIsl[i] = 0u; }
 }
-// alpha0 = max(alphaA, alphaB) of every contact about to get a TOI (:1717): raise both bodies' targets
-PR_KERNEL k_toi_alpha(DV d, unsigned nOrder, unsigned maxSubSteps)
+PR_KERNEL k_toi_round_reset(DV d)
+{
+    if (PR_TID == 0u) { d.cnt->toiMinKey = ~0ull; d.cnt->toiEvents = 0u; d.cnt->toiScratchTop = 0u; d.cnt->syncN = 0u; }
+}
+// alpha0 = max(alphaA, alphaB) of every contact about to get a TOI (:1717): raise both bodies' targets.
+// Invariant outside k_toi_alpha..k_toi_advance: b_toiAlpha[b] == bits(alpha0 of b).
+PR_KERNEL k_toi_alpha(DV d, unsigned maxSubSteps)
 {
     const unsigned i = PR_TID;
-    if (i < nOrder) {
-        const unsigned id = d.c_order[i];
+    if (i < d.cnt->toiListN) {
+        const unsigned id = d.toi_list[i];
         const uint4 ab = d.c_ab[id];
         bool atMax;
         if (toi_eligible(d, d.c_flags[id], ab, maxSubSteps, atMax)) {
@@ -96,13 +137,25 @@ PR_D void advance0(float4& p0, float4 p1, float alpha)
     const Pos r = lerp_pos(a, b, beta);
     p0 = make_float4(r.l.x, r.l.y, r.a, alpha);
 }
-PR_KERNEL k_toi_advance_bodies(DV d, unsigned nBodies)
+// Advance0(bA, alpha0); Advance0(bB, alpha0) (:1718-1719): once per body per round (stamp = round id)
+PR_KERNEL k_toi_advance(DV d, unsigned maxSubSteps, unsigned round)
 {
     const unsigned i = PR_TID;
-    if (i < nBodies) {
-        float4 p0 = d.b_pos0[i];
-        const float t = u2f(d.b_toiAlpha[i]);
-        if (t != p0.w) { advance0(p0, d.b_pos1[i], t); d.b_pos0[i] = p0; }
+    if (i < d.cnt->toiListN) {
+        const unsigned id = d.toi_list[i];
+        const uint4 ab = d.c_ab[id];
+        bool atMax;
+        if (toi_eligible(d, d.c_flags[id], ab, maxSubSteps, atMax)) {
+            const unsigned two[2] = {ab.x, ab.y};
+            for (int s = 0; s < 2; ++s) {
+                const unsigned b = two[s];
+                const unsigned t = d.b_toiAlpha[b];
+                if (atomicExch(&d.b_toiStamp[b], round) != round) {
+                    float4 p0 = d.b_pos0[b];
+                    if (f2u(p0.w) != t) { advance0(p0, d.b_pos1[b], u2f(t)); d.b_pos0[b] = p0; }
+                }
+            }
+        }
     }
 }
 PR_D float normalized_angle(float value)
@@ -128,13 +181,13 @@ PR_D SweepD normalized_sweep(float4 p0, float4 p1, float2 lc)
 }
 PR_D unsigned long long toi_key(float toi, unsigned pos) { return (static_cast<unsigned long long>(f2u(toi)) << 32) | pos; }
 
-PR_KERNEL k_toi_compute(DV d, pr_step_conf conf, unsigned nOrder)
+PR_KERNEL k_toi_compute(DV d, pr_step_conf conf)
 {
     const unsigned i = PR_TID;
     unsigned atMaxCount = 0u, updated = 0u, distIt = 0u, toiIt = 0u, rootIt = 0u;
     unsigned long long key = ~0ull;
-    if (i < nOrder) {
-        const unsigned id = d.c_order[i];
+    if (i < d.cnt->toiListN) {
+        const unsigned id = d.toi_list[i];
         unsigned flags = d.c_flags[id];
         const uint4 ab = d.c_ab[id];
         bool atMax;
@@ -154,7 +207,7 @@ PR_KERNEL k_toi_compute(DV d, pr_step_conf conf, unsigned nOrder)
             d.c_flags[id] = flags;
             updated = 1u; distIt = out.maxDistIters; toiIt = out.toiIters; rootIt = out.maxRootIters;
         } else if (atMax) atMaxCount = 1u;
-        if ((flags & PR_CONTACT_TOI) && toi < 1.0f) key = toi_key(toi, i); // GetSoonestContact candidates
+        if ((flags & PR_CONTACT_TOI) && toi < 1.0f) key = toi_key(toi, d.c_pos[id]); // GetSoonestContact candidates
     }
     warp_add(&d.cnt->toiAtMaxSub, atMaxCount); warp_add(&d.cnt->toiUpdated, updated);
     warp_max(&d.cnt->toiMaxDistIters, distIt); warp_max(&d.cnt->toiMaxToiIters, toiIt); warp_max(&d.cnt->toiMaxRootIters, rootIt);
@@ -170,7 +223,7 @@ template <class F> PR_D void toi_for_each_claim_body(const DV& d, uint4 ab, F&& 
         const unsigned f = d.b_flags[b];
         if (f_speedable(f)) fn(b);
         if (f_accelerable(f)) {
-            for (unsigned k = d.adj_off[b]; k < d.adj_off[b + 1u]; ++k) {
+            for (unsigned k = d.adj_off[b], ke = adj_end(d, b); k < ke; ++k) {
                 const uint4 o = d.c_ab[d.adj_list[k]];
                 const unsigned other = (o.x == b) ? o.y : o.x;
                 if (f_speedable(d.b_flags[other])) fn(other);
@@ -178,26 +231,35 @@ template <class F> PR_D void toi_for_each_claim_body(const DV& d, uint4 ab, F&& 
         }
     }
 }
-PR_KERNEL k_toi_claim(DV d, unsigned nOrder)
+PR_KERNEL k_toi_claim(DV d)
 {
     const unsigned i = PR_TID;
-    if (i < nOrder) {
-        const unsigned id = d.c_order[i];
+    if (i < d.cnt->toiListN) {
+        const unsigned id = d.toi_list[i];
         const float toi = d.c_mat[id].w;
         if ((d.c_flags[id] & PR_CONTACT_TOI) && toi < 1.0f) {
-            const unsigned long long key = toi_key(toi, i);
+            const unsigned long long key = toi_key(toi, d.c_pos[id]);
             toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { atomicMin(&d.b_claim[b], key); });
         }
     }
 }
-PR_KERNEL k_toi_select(DV d, unsigned nOrder, unsigned parallel)
+PR_KERNEL k_toi_unclaim(DV d)
 {
     const unsigned i = PR_TID;
-    if (i < nOrder) {
-        const unsigned id = d.c_order[i];
+    if (i < d.cnt->toiListN) {
+        const unsigned id = d.toi_list[i];
+        if ((d.c_flags[id] & PR_CONTACT_TOI) && d.c_mat[id].w < 1.0f)
+            toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { d.b_claim[b] = ~0ull; });
+    }
+}
+PR_KERNEL k_toi_select(DV d, unsigned parallel)
+{
+    const unsigned i = PR_TID;
+    if (i < d.cnt->toiListN) {
+        const unsigned id = d.toi_list[i];
         const float toi = d.c_mat[id].w;
         if ((d.c_flags[id] & PR_CONTACT_TOI) && toi < 1.0f) {
-            const unsigned long long key = toi_key(toi, i);
+            const unsigned long long key = toi_key(toi, d.c_pos[id]);
             bool win;
             if (parallel) {
                 win = true;
@@ -211,13 +273,13 @@ PR_KERNEL k_toi_select(DV d, unsigned nOrder, unsigned parallel)
 // ------------------------------------------------------------------ SolveToi(contact) (:1833-1955)
 PR_D void toi_flag_body_contacts(const DV& d, unsigned b)
 { // FlagForUpdating(m_bodyContacts[b]), :459-465
-    for (unsigned k = d.adj_off[b]; k < d.adj_off[b + 1u]; ++k) atomicOr(&d.c_flags[d.adj_list[k]], static_cast<unsigned>(PR_CONTACT_DIRTY));
+    for (unsigned k = d.adj_off[b], ke = adj_end(d, b); k < ke; ++k) atomicOr(&d.c_flags[d.adj_list[k]], static_cast<unsigned>(PR_CONTACT_DIRTY));
 }
 struct SweepBk { float4 p0, p1, xf; };
 PR_D SweepBk toi_backup(const DV& d, unsigned b) { SweepBk s; s.p0 = d.b_pos0[b]; s.p1 = d.b_pos1[b]; s.xf = d.b_xf[b]; return s; }
 PR_D void toi_restore(const DV& d, unsigned b, const SweepBk& s)
 { // Body::SetSweep, Body.hpp:697-702 (m_xf = GetTransform1(sweep): the same bits it had)
-    d.b_pos0[b] = s.p0;
+    d.b_pos0[b] = s.p0; d.b_toiAlpha[b] = f2u(s.p0.w);
     float4 p1 = d.b_pos1[b]; p1.x = s.p1.x; p1.y = s.p1.y; p1.z = s.p1.z; d.b_pos1[b] = p1;
     d.b_xf[b] = s.xf;
 }
@@ -230,7 +292,7 @@ PR_D bool toi_advance_body(const DV& d, unsigned b, float toi)
     const float4 o0 = p0, o1 = p1;
     advance0(p0, p1, toi);
     p1.x = p0.x; p1.y = p0.y; p1.z = p0.z;
-    d.b_pos0[b] = p0; d.b_pos1[b] = p1;
+    d.b_pos0[b] = p0; d.b_pos1[b] = p1; d.b_toiAlpha[b] = f2u(toi);
     Pos p; p.l = v2(p1.x, p1.y); p.a = p1.z;
     const Xf xf = get_xf(p, d.b_lc[b]);
     d.b_xf[b] = make_float4(xf.p.x, xf.p.y, xf.q.c, xf.q.s);
@@ -248,7 +310,8 @@ PR_D void toi_process_contacts(const DV& d, const pr_step_conf& conf, unsigned i
                                unsigned& updatedN, unsigned& skippedN)
 {
     const bool bodyImpenetrable = (d.b_flags[id] & PR_BODY_IMPENETRABLE) != 0u;
-    for (unsigned k = d.adj_off[id]; k < d.adj_off[id + 1u]; ++k) {
+    adj_sort_body(d, id); // contacts appended since the table was built go to their m_bodyContacts position
+    for (unsigned k = d.adj_off[id], ke = adj_end(d, id); k < ke; ++k) {
         const unsigned cid = d.adj_list[k];
         if (d.c_toiIsl[cid]) continue;
         unsigned cf = d.c_flags[cid];
@@ -281,7 +344,7 @@ PR_D void toi_process_contacts(const DV& d, const pr_step_conf& conf, unsigned i
     }
 }
 
-PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactMode)
+PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactMode, unsigned scratchCap)
 {
     const unsigned e = PR_TID;
     if (e >= nEvents) return;
@@ -291,6 +354,16 @@ PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactM
     const float toi = d.c_mat[cid].w;
     unsigned numUpdated = 0u, numSkipped = 0u;
     const unsigned fA = d.b_flags[A], fB = d.b_flags[B];
+    // island scratch (body list, contact list, VC/PC rows): sized by the two contact lists. An event that does
+    // not fit this round's arena is left untouched (still the soonest of its neighbourhood) for the next round.
+    ToiIsland isl;
+    const unsigned need = 2u + (f_speedable(fA) ? d.adj_n[A] : 0u) + (f_speedable(fB) ? d.adj_n[B] : 0u);
+    isl.base = atomicAdd(&d.cnt->toiScratchTop, need);
+    if (isl.base + need > scratchCap) {
+        if (isl.base == 0u) atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_TOI_SCRATCH));
+        atomicAdd(&d.cnt->toiDeferred, 1u);
+        return;
+    }
     {
         const SweepBk bkA = toi_backup(d, A), bkB = toi_backup(d, B);
         const bool touchA = f_speedable(fA) || exactMode, touchB = f_speedable(fB) || exactMode;
@@ -313,9 +386,6 @@ PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactM
     }
     if (f_speedable(fA)) atomicOr(&d.b_flags[A], static_cast<unsigned>(PR_BODY_AWAKE));
     if (f_speedable(fB)) atomicOr(&d.b_flags[B], static_cast<unsigned>(PR_BODY_AWAKE));
-    ToiIsland isl;
-    const unsigned need = 2u + (d.adj_off[A + 1u] - d.adj_off[A]) + (d.adj_off[B + 1u] - d.adj_off[B]);
-    isl.base = atomicAdd(&d.cnt->toiScratchTop, need);
     isl.nB = 2u; isl.nC = 1u;
     d.toi_islBodies[isl.base] = A; d.toi_islBodies[isl.base + 1u] = B; d.toi_islContacts[isl.base] = cid;
     if (f_speedable(fA)) d.b_toiIsl[A] = 1u;
@@ -391,8 +461,8 @@ PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactM
         const unsigned f = d.b_flags[b];
         if (f_speedable(f)) d.b_toiIsl[b] = 0u;
         if (f_accelerable(f)) {
-            d.b_sync[b] = 1u;
-            for (unsigned q = d.adj_off[b]; q < d.adj_off[b + 1u]; ++q) {
+            d.sync_list[atomicAdd(&d.cnt->syncN, 1u)] = b;
+            for (unsigned q = d.adj_off[b], qe = adj_end(d, b); q < qe; ++q) {
                 const unsigned c2 = d.adj_list[q];
                 atomicAnd(&d.c_flags[c2], ~static_cast<unsigned>(PR_CONTACT_TOI));
                 reinterpret_cast<float*>(&d.c_mat[c2])[3] = 1.0f;
@@ -414,16 +484,35 @@ PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactM
 PR_KERNEL k_toi_finish_bodies(DV d, unsigned nBodies)
 {
     const unsigned i = PR_TID;
-    if (i < nBodies) { reinterpret_cast<float*>(&d.b_pos0[i])[3] = 0.0f; d.b_toiIsl[i] = 0u; }
+    if (i < nBodies) { reinterpret_cast<float*>(&d.b_pos0[i])[3] = 0.0f; d.b_toiAlpha[i] = 0u; }
 }
-PR_KERNEL k_toi_finish_contacts(DV d, unsigned nOrder)
-{
+PR_KERNEL k_toi_finish_contacts(DV d)
+{ // only contacts on the TOI list can carry a TOI or a TOI count
     const unsigned i = PR_TID;
-    if (i < nOrder) {
-        const unsigned id = d.c_order[i];
+    if (i < d.cnt->toiListN) {
+        const unsigned id = d.toi_list[i];
         d.c_flags[id] = d.c_flags[id] & 0xFFu & ~static_cast<unsigned>(PR_CONTACT_TOI); // SetToi({}) + SetToiCount(0)
         reinterpret_cast<float*>(&d.c_mat[id])[3] = 1.0f;
-        d.c_toiIsl[id] = 0u;
+    }
+}
+// Synchronize (:2564-2585) for the bodies the round's events listed (:1800-1805): grid-stride over sync_list
+PR_KERNEL k_sync_body_proxies(DV d, pr_step_conf conf)
+{
+    const unsigned n = d.cnt->syncN;
+    for (unsigned i = PR_TID; i < n; i += PR_NTHREADS) {
+        const unsigned body = d.sync_list[i];
+        const Xf xf1 = xf_from4(d.b_xf[body]);
+        const Xf xf0 = get_xf(pos_from4(d.b_pos0[body]), d.b_lc[body]);
+        const float2 dsp = conf.displace_multiplier * (xf1.p - xf0.p);
+        for (unsigned k = d.bp_off[body]; k < d.bp_off[body + 1u]; ++k) {
+            const unsigned px = d.bp_list[k];
+            const Box a = compute_aabb(child_view(d, d.p_cg[px]), xf0, xf1);
+            if (!box_contains(box_from4(d.p_fat[px]), a)) {
+                d.p_fat[px] = box_to4(fatten_displace(a, conf.aabb_extension, dsp));
+                if (d.p_moved[px] == 0u) { d.p_moved[px] = 1u; d.q_list[atomicAdd(&d.cnt->nQueue, 1u)] = px; }
+                atomicAdd(&d.cnt->proxiesMoved, 1u);
+            }
+        }
     }
 }
 

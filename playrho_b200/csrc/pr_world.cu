@@ -36,10 +36,11 @@ static void dset(World& w, void* dst, int v, size_t n) { if (n) CK(cudaMemsetAsy
 static void sync(World& w) { CK(cudaStreamSynchronize(w.stream)); }
 static void check_launch() { CK(cudaGetLastError()); }
 struct StageTimer {
-    cudaEvent_t ev[64]; int stage[64]; int n = 0; bool on = true;
+    static constexpr int MAXEV = 2048;
+    cudaEvent_t ev[MAXEV]; int stage[MAXEV]; int n = 0; bool on = true;
     StageTimer() { for (auto& e : ev) cudaEventCreate(&e); }
     ~StageTimer() { for (auto& e : ev) cudaEventDestroy(e); }
-    void mark(World& w, int s) { if (n < 64) { cudaEventRecord(ev[n], w.stream); stage[n++] = s; } }
+    void mark(World& w, int s) { if (n < MAXEV - 1) { cudaEventRecord(ev[n], w.stream); stage[n++] = s; } }
     void finish(World& w, pr_step_profile& p)
     {
         mark(w, -1);
@@ -80,8 +81,9 @@ static std::vector<ArrDesc> arrays(World& w)
         A(b_moved, G_BODY), A(b_sync, G_BODY), A(isl_state, G_BODY), A(isl_velIters, G_BODY), A(isl_posIters, G_BODY),
         A(isl_inc, G_BODY), A(isl_maxInc, G_BODY), A(isl_sep, G_BODY), A(isl_minSep, G_BODY), A(isl_minUA, G_BODY),
         A(isl_nbodies, G_BODY), A(b_claim, G_BODY), A(b_cmask, G_BODY),
-        A(adj_off, G_BODY), A(adj_cnt, G_BODY), A(b_toiIsl, G_BODY), A(b_toiAlpha, G_BODY),
-        A(c_pos, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT),
+        A(adj_off, G_BODY), A(adj_cnt, G_BODY), A(adj_n, G_BODY), A(b_toiIsl, G_BODY), A(b_toiAlpha, G_BODY), A(b_toiStamp, G_BODY),
+        A(sync_list, G_BODY), A(bp_off, G_BODY), A(bp_list, G_PROXY), A(bv_leafOf, G_PROXY),
+        A(c_pos, G_CONTACT), A(c_color, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT), A(toi_list, G_CONTACT),
         A(adj_list, G_ADJ), A(toi_islBodies, G_ADJ), A(toi_islContacts, G_ADJ),
         A(sh_mat, G_SHAPE), A(sh_filter, G_SHAPE), A(sh_group, G_SHAPE),
         A(ch_radius, G_CHILD), A(ch_voff, G_CHILD), A(ch_count, G_CHILD), A(vtx, G_VERT), A(nrm, G_VERT),
@@ -94,7 +96,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(ht_keys, G_HASH),
         A(np_key, G_PAIR), A(np_key2, G_PAIR), A(np_px, G_PAIR), A(np_idx, G_PAIR), A(np_idx2, G_PAIR),
         A(vc, G_CONS), A(pc, G_CONS), A(k_contact, G_CONS), A(k_color, G_CONS), A(k_sorted, G_CONS), A(k_tmpKey, G_CONS),
-        A(k_tmpKey2, G_CONS), A(k_tmpVal, G_CONS),
+        A(k_tmpKey2, G_CONS), A(k_tmpVal, G_CONS), A(k_ulist, G_CONS),
     };
 #undef A
 #undef A2
@@ -157,6 +159,7 @@ static void throw_device_error(World& w)
     if (e & ERR_STACK) m += " bvh traversal stack overflow;";
     if (e & ERR_SENSOR) m += " sensor contacts (GJK TestOverlap) not supported yet;";
     if (e & ERR_HASH_FULL) m += " contact hash full;";
+    if (e & ERR_TOI_SCRATCH) m += " one TOI island needs more scratch rows than the arena holds;";
     throw CudaError{m};
 }
 
@@ -170,6 +173,8 @@ static unsigned create_queued_proxies(World& w, const pr_step_conf& conf)
         for (unsigned c = 0; c < s.child_count; ++c) {
             const unsigned k = w.nProxies + static_cast<unsigned>(body.size());
             body.push_back(bs.first); shape.push_back(bs.second); child.push_back(c); cg.push_back(s.child_offset + c);
+            if (w.bodyProxies.size() <= bs.first) w.bodyProxies.resize(bs.first + 1u);
+            w.bodyProxies[bs.first].push_back(k);
             tree.push_back(k == 0 ? 0u : 2u * k - 1u); // DynamicTree leaf id sequence
             w.maxTreeId = std::max(w.maxTreeId, tree.back());
         }
@@ -188,7 +193,26 @@ static unsigned create_queued_proxies(World& w, const pr_step_conf& conf)
     w.hostCnt.nQueue += n;
     write_counters(w);
     w.nProxies += n;
+    w.bpDirty = true; w.bvhValid = false;
     return n;
+}
+
+// body -> proxy CSR (m_bodyProxies) for the TOI rounds' per-body Synchronize
+static void upload_body_proxies(World& w)
+{
+    if (!w.bpDirty) return;
+    const unsigned N = w.nBodies;
+    ensure(w, G_BODY, N + 1);
+    std::vector<unsigned> off(N + 1, 0u), list;
+    list.reserve(w.nProxies);
+    for (unsigned b = 0; b < N; ++b) {
+        off[b] = static_cast<unsigned>(list.size());
+        if (b < w.bodyProxies.size()) list.insert(list.end(), w.bodyProxies[b].begin(), w.bodyProxies[b].end());
+    }
+    off[N] = static_cast<unsigned>(list.size());
+    h2d(w, w.d.bp_off, off.data(), 4 * (N + 1)); h2d(w, w.d.bp_list, list.data(), 4 * list.size());
+    sync(w);
+    w.bpDirty = false;
 }
 
 static unsigned destroy_contacts(World& w)
@@ -196,7 +220,7 @@ static unsigned destroy_contacts(World& w)
     if (w.nOrder == 0) return 0;
     DV& d = w.d;
     ensure(w, G_CONS, w.nOrder + 1);
-    PR_LAUNCH(k_destroy_test, w.nOrder, w.stream, d, w.nOrder, d.c_tmp);
+    PR_LAUNCH(k_destroy_test, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, w.hashDirty ? 0u : 1u);
     scan_exclusive_u32(d.c_tmp, d.k_tmpVal, w.nOrder, &d.cnt->nNew, w.scanScratch, w.stream);
     read_counters(w);
     const unsigned kept = w.hostCnt.nNew;
@@ -206,23 +230,24 @@ static unsigned destroy_contacts(World& w)
         std::swap(d.c_order, d.c_tmp2);
         w.nFree += destroyed;
         w.nOrder = kept;
-        w.hashDirty = true; w.adjValid = false;
+        w.hashTombs += destroyed; w.adjValid = false;
+        if (2ull * (static_cast<unsigned long long>(w.nOrder) + w.hashTombs) > w.capHash) w.hashDirty = true;
     }
     return destroyed;
 }
 
 static void rebuild_hash(World& w)
 {
-    ensure(w, G_HASH, next_pow2(std::max(2048u, 2u * w.capContacts)));
+    ensure(w, G_HASH, next_pow2(std::max(2048u, 4u * w.capContacts)));
     dset(w, w.d.ht_keys, 0xFF, sizeof(unsigned long long) * w.capHash);
     PR_LAUNCH(k_hash_fill, w.nOrder, w.stream, w.d, w.nOrder);
-    w.hashDirty = false;
+    w.hashDirty = false; w.hashTombs = 0;
 }
 
 static int key_bits(unsigned maxVal) { int b = 1; while (b < 32 && (maxVal >> b)) ++b; return ((b + 7) / 8) * 8; }
 
 // FindContacts + AddContacts, AabbTreeWorld.cpp:709-751 and :2423-2547
-static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer& tm)
+static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer& tm, bool toiRound = false)
 {
     DV& d = w.d;
     read_counters(w);
@@ -231,28 +256,31 @@ static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer
     if (nQueue == 0) return 0;
     const unsigned P = w.nProxies;
     tm.mark(w, PR_STAGE_BVH);
-    bool idxInB = false;
-    if (P > 1) {
+    // few moved proxies and an intact tree: grow the ancestors' boxes in place instead of rebuilding
+    const bool refit = w.bvhValid && w.bvhLeaves == P && P > 1 && 8ull * nQueue < P && w.bvhRefits < 256u;
+    if (refit) {
+        PR_LAUNCH(k_bvh_refit_moved, nQueue, w.stream, d, nQueue, P);
+        ++w.bvhRefits;
+    } else if (P > 1) {
         w.hostCnt.boundsMinX = w.hostCnt.boundsMinY = 0xFFFFFFFFu; w.hostCnt.boundsMaxX = w.hostCnt.boundsMaxY = 0u;
         write_counters(w);
         PR_LAUNCH(k_bvh_bounds, P, w.stream, d, P);
         PR_LAUNCH(k_bvh_morton, P, w.stream, d, P);
-        idxInB = radix_sort_pairs<unsigned>(d.bv_code, d.bv_idx, d.bv_code2, d.bv_idx2, P, 0, 32, true, w.rs, w.stream);
+        const bool idxInB = radix_sort_pairs<unsigned>(d.bv_code, d.bv_idx, d.bv_code2, d.bv_idx2, P, 0, 32, true, w.rs, w.stream);
         const unsigned* codes = idxInB ? d.bv_code2 : d.bv_code;
-        const unsigned* sidx = idxInB ? d.bv_idx2 : d.bv_idx;
+        w.bvhSortedIdx = idxInB ? d.bv_idx2 : d.bv_idx;
         PR_LAUNCH(k_bvh_build, P - 1, w.stream, d, P, codes);
-        PR_LAUNCH(k_bvh_refit, P, w.stream, d, P, sidx);
+        PR_LAUNCH(k_bvh_refit, P, w.stream, d, P, w.bvhSortedIdx);
+        w.bvhValid = true; w.bvhLeaves = P; w.bvhRefits = 0;
     }
-    const unsigned* sortedIdx = idxInB ? d.bv_idx2 : d.bv_idx;
     if (w.hashDirty) rebuild_hash(w);
     tm.mark(w, PR_STAGE_QUERY);
     unsigned nPairs = 0;
-    for (;;) {
+    for (;;) { // (hostCnt mirrors the device counters here: refreshed by the read above / at the loop's end)
         ensure(w, G_PAIR, std::max(1024u, nPairs));
-        read_counters(w);
         w.hostCnt.nPairs = 0; w.hostCnt.error &= ~static_cast<unsigned>(ERR_PAIR_OVERFLOW);
         write_counters(w);
-        PR_LAUNCH(k_bvh_query, nQueue, w.stream, d, nQueue, P, sortedIdx, w.capPairs);
+        PR_LAUNCH(k_bvh_query, nQueue, w.stream, d, nQueue, P, w.bvhSortedIdx, w.capPairs);
         read_counters(w);
         nPairs = w.hostCnt.nPairs;
         if (nPairs <= w.capPairs) break;
@@ -264,30 +292,35 @@ static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer
     w.profile.candidate_pairs += nPairs;
     if (nPairs == 0) return 0;
     tm.mark(w, PR_STAGE_ADD);
-    // sort candidate keys: (min tree id << 32 | max tree id); LSD over the max field then the min field
-    const unsigned maxTree = std::max(1u, w.maxTreeId);
-    const int bits = key_bits(maxTree);
-    bool inB = radix_sort_pairs<unsigned long long>(d.np_key, d.np_idx, d.np_key2, d.np_idx2, nPairs, 0, bits, true, w.rs, w.stream);
-    unsigned long long* kA = inB ? d.np_key2 : d.np_key; unsigned* vA = inB ? d.np_idx2 : d.np_idx;
-    unsigned long long* kB = inB ? d.np_key : d.np_key2; unsigned* vB = inB ? d.np_idx : d.np_idx2;
-    const bool inB2 = radix_sort_pairs<unsigned long long>(kA, vA, kB, vB, nPairs, 32, 32 + bits, false, w.rs, w.stream);
-    const unsigned long long* keys = inB2 ? kB : kA;
-    const unsigned* src = inB2 ? vB : vA;
+    // sort candidate keys (min tree id << 32 | max tree id) like FindContacts' std::sort (:746)
+    const unsigned long long* keys; const unsigned* src;
+    if (nPairs <= SMALL_SORT_MAX) { // one-block bitonic sort: the TOI rounds' and quiet steps' latency path
+        sort_pairs_small(d.np_key, d.np_key2, d.np_idx2, nPairs, w.stream);
+        keys = d.np_key2; src = d.np_idx2;
+    } else { // LSD radix over the max field then the min field
+        const unsigned maxTree = std::max(1u, w.maxTreeId);
+        const int bits = key_bits(maxTree);
+        const bool inB = radix_sort_pairs<unsigned long long>(d.np_key, d.np_idx, d.np_key2, d.np_idx2, nPairs, 0, bits, true, w.rs, w.stream);
+        unsigned long long* kA = inB ? d.np_key2 : d.np_key; unsigned* vA = inB ? d.np_idx2 : d.np_idx;
+        unsigned long long* kB = inB ? d.np_key : d.np_key2; unsigned* vB = inB ? d.np_idx : d.np_idx2;
+        const bool inB2 = radix_sort_pairs<unsigned long long>(kA, vA, kB, vB, nPairs, 32, 32 + bits, false, w.rs, w.stream);
+        keys = inB2 ? kB : kA; src = inB2 ? vB : vA;
+    }
     const unsigned used = std::min(nPairs, w.nFree);
     const unsigned fresh = nPairs - used;
     ensure(w, G_CONTACT, std::max(w.poolSize + fresh, w.nOrder + nPairs) + 1);
-    if (2u * w.capContacts > w.capHash) rebuild_hash(w);
-    PR_LAUNCH(k_create_contacts, nPairs, w.stream, d, nPairs, keys, src, w.nOrder, w.nFree, w.poolSize);
+    if (2ull * (static_cast<unsigned long long>(w.nOrder) + nPairs + w.hashTombs) > w.capHash) rebuild_hash(w);
+    const bool adjLive = toiRound && w.adjValid;
+    if (adjLive) ensure(w, G_ADJ, 2u * (w.nOrder + nPairs) + 2u * w.nBodies + 64u);
+    PR_LAUNCH(k_create_contacts, nPairs, w.stream, d, nPairs, keys, src, w.nOrder, w.nFree, w.poolSize, adjLive ? 1u : 0u);
     const unsigned oldOrder = w.nOrder;
-    w.nFree -= used; w.poolSize += fresh; w.nOrder += nPairs; w.adjValid = false;
+    w.nFree -= used; w.poolSize += fresh; w.nOrder += nPairs;
+    if (adjLive) w.toiListBound += nPairs; else w.adjValid = false;
     // AddContacts ends with Update(contactID) for each new contact (:2531); not part of UpdateContacts' stats
+    PR_LAUNCH(k_update_contacts, nPairs, w.stream, d, conf, oldOrder, nPairs, 0u, 0u);
     read_counters(w);
-    const unsigned savedUpdated = w.hostCnt.contactsUpdated;
-    PR_LAUNCH(k_update_contacts, nPairs, w.stream, d, conf, oldOrder, nPairs, 0u);
-    read_counters(w);
-    w.hostCnt.contactsUpdated = savedUpdated;
-    write_counters(w);
     throw_device_error(w);
+    if (w.hostCnt.adjOverflow) { w.adjValid = false; w.hostCnt.adjOverflow = 0; write_counters(w); }
     return nPairs;
 }
 
@@ -308,7 +341,8 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         ensure(w, G_CONS, w.nOrder + 1);
         PR_LAUNCH(k_mark_constraints, w.nOrder, w.stream, d, w.nOrder, d.c_tmp);
         scan_exclusive_u32(d.c_tmp, d.k_tmpVal, w.nOrder, &d.cnt->nConstraints, w.scanScratch, w.stream);
-        PR_LAUNCH(k_gather_constraints, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, d.k_tmpVal);
+        PR_LAUNCH(k_gather_constraints, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, d.k_tmpVal, w.recolorAll ? 1u : 0u);
+        PR_LAUNCH(k_color_keep, w.nOrder, w.stream, d, w.nOrder); // nColorWork was zeroed by reset_counters at step start
         read_counters(w);
         nCons = w.hostCnt.nConstraints;
     }
@@ -316,14 +350,19 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     std::vector<std::pair<unsigned, unsigned>> ranges; // (start, count) per colour, overflow tail last
     unsigned tailStart = 0, tailCount = 0;
     if (nCons) {
-        for (unsigned round = 0;; ++round) {
-            if (round && (round % 64u) == 0u) PR_LAUNCH(k_color_reset_claims, N, w.stream, d, N);
-            w.hostCnt.nUncolored = 0; write_counters(w);
-            PR_LAUNCH(k_color_claim, nCons, w.stream, d, nCons, round);
-            PR_LAUNCH(k_color_commit, nCons, w.stream, d, nCons, round);
-            read_counters(w);
-            if (w.hostCnt.nUncolored == 0) break;
-            if (round > 100000u) throw CudaError{"colouring did not converge"};
+        const unsigned nWork = w.hostCnt.nColorWork;
+        w.recolorAll = false;
+        if (nWork) {
+            for (unsigned round = 0;; ++round) {
+                if (round && (round % 64u) == 0u) PR_LAUNCH(k_color_reset_claims, N, w.stream, d, N);
+                PR_LAUNCH(k_color_claim, nWork, w.stream, d, nWork, round);
+                PR_LAUNCH(k_color_commit, nWork, w.stream, d, nWork, round);
+                if ((round & 3u) == 3u || nWork < 64u) { // look at the remaining count every 4th round only
+                    read_counters(w);
+                    if (w.hostCnt.nUncolored == 0) break;
+                }
+                if (round > 100000u) throw CudaError{"colouring did not converge"};
+            }
         }
         // stable sort by colour (one 8-bit radix pass): k_sorted = permutation of the base constraint list
         d2d(w, d.k_tmpKey, d.k_color, nCons * sizeof(unsigned));
@@ -351,6 +390,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         }
         std::reverse(ranges.begin(), ranges.end());
         w.nColors = static_cast<unsigned>(ranges.size()) + (tailCount ? 1u : 0u);
+        if (w.nColors > 40u) w.recolorAll = true; // persistent colours fragmented: colour from scratch next step
         tm.mark(w, PR_STAGE_SETUP);
         PR_LAUNCH(k_build_constraints, nCons, w.stream, d, nCons, conf, conf.do_warm_start ? conf.dt_ratio : 0.0f);
         if (conf.do_warm_start) {
@@ -385,7 +425,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     PR_LAUNCH(k_sync_proxies, w.nProxies, w.stream, d, conf, w.nProxies);
     tm.mark(w, PR_STAGE_NARROW);
     const unsigned nOrderAtUpdate = w.nOrder;
-    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 1u);
+    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 1u, 1u);
     dset(w, d.b_moved, 0, sizeof(unsigned) * N);
     dset(w, d.b_sync, 0, sizeof(unsigned) * N);
     read_counters(w);
@@ -410,17 +450,22 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
 // ------------------------------------------------------------------ TOI phase (SolveToi :1752-1831)
 // m_bodyContacts as CSR: count, scan, fill, then order each speedable body's segment by m_contacts position
 static void build_adjacency(World& w)
-{
+{ // leaves hostCnt mirroring the device counters
     DV& d = w.d;
     const unsigned N = w.nBodies;
     ensure(w, G_BODY, N + 1);
-    ensure(w, G_ADJ, 2u * w.nOrder + 2u * N + 64u);
+    ensure(w, G_ADJ, 2u * w.nOrder + 2u * w.nOrder / 4u + 8u * N + 64u);
     dset(w, d.adj_cnt, 0, sizeof(unsigned) * N);
+    read_counters(w);
+    w.hostCnt.toiListN = 0; w.hostCnt.adjOverflow = 0;
+    write_counters(w);
     PR_LAUNCH(k_adj_count, w.nOrder, w.stream, d, w.nOrder);
+    PR_LAUNCH(k_adj_cap, N, w.stream, d, N);
     scan_exclusive_u32(d.adj_cnt, d.adj_off, N, d.adj_off + N, w.scanScratch, w.stream);
-    dset(w, d.adj_cnt, 0, sizeof(unsigned) * N);
     PR_LAUNCH(k_adj_fill, w.nOrder, w.stream, d, w.nOrder);
     PR_LAUNCH(k_adj_sort, N, w.stream, d, N);
+    read_counters(w);
+    w.toiListBound = w.hostCnt.toiListN;
     w.adjValid = true;
 }
 
@@ -435,42 +480,48 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     w.hostCnt.toiMinSepFlip = float_flip(std::numeric_limits<float>::infinity());
     w.hostCnt.toiMaxIncBits = 0; w.hostCnt.toiIslandsSolved = w.hostCnt.toiSumPosIters = w.hostCnt.toiSumVelIters = 0;
     w.hostCnt.toiIslandsFound = w.hostCnt.toiUpdTouching = w.hostCnt.toiSkipTouching = 0;
-    w.hostCnt.proxiesMoved = 0; w.hostCnt.contactsUpdated = 0;
+    w.hostCnt.proxiesMoved = 0; w.hostCnt.contactsUpdated = 0; w.hostCnt.toiDeferred = 0;
+    write_counters(w);
     const bool exact = (w.toiMode == 0u);
-    unsigned rounds = 0;
+    unsigned rounds = 0, round = 0;
+    upload_body_proxies(w);
+    PR_LAUNCH(k_toi_phase_init, N, w.stream, d, N);
     for (;;) {
-        if (w.nOrder == 0) { // nothing can have a TOI
-            w.stepComplete = true;
-            write_counters(w);
-            PR_LAUNCH(k_toi_finish_bodies, N, w.stream, d, N);
-            break;
+        if (w.nOrder == 0) { w.stepComplete = true; break; } // nothing can have a TOI
+        if (!w.adjValid) build_adjacency(w);
+        ensure(w, G_CONS, std::min(2u * w.nOrder, w.nOrder + (1u << 20)) + 64u); // island rows (VC/PC scratch) of one round's events
+        const unsigned scratchCap = std::min(w.capCons, w.capAdj);
+        const unsigned nList = w.toiListBound; // >= device toiListN (kernels re-check against it)
+        ++round;
+        if (nList) {
+            PR_LAUNCH(k_toi_round_reset, 1, w.stream, d);
+            PR_LAUNCH(k_toi_alpha, nList, w.stream, d, conf.max_sub_steps);
+            PR_LAUNCH(k_toi_advance, nList, w.stream, d, conf.max_sub_steps, round);
+            PR_LAUNCH(k_toi_compute, nList, w.stream, d, conf);
+            if (!exact) PR_LAUNCH(k_toi_claim, nList, w.stream, d);
+            PR_LAUNCH(k_toi_select, nList, w.stream, d, exact ? 0u : 1u);
+            if (!exact) PR_LAUNCH(k_toi_unclaim, nList, w.stream, d);
         }
-        if (!w.adjValid) { write_counters(w); build_adjacency(w); read_counters(w); }
-        ensure(w, G_CONS, 2u * w.nOrder + 2u * N + 64u); // island rows (VC/PC scratch) of all events of one round
-        w.hostCnt.toiMinKey = ~0ull; w.hostCnt.toiEvents = 0; w.hostCnt.toiScratchTop = 0;
-        write_counters(w);
-        PR_LAUNCH(k_toi_round_init, N, w.stream, d, N);
-        PR_LAUNCH(k_toi_alpha, w.nOrder, w.stream, d, w.nOrder, conf.max_sub_steps);
-        PR_LAUNCH(k_toi_advance_bodies, N, w.stream, d, N);
-        PR_LAUNCH(k_toi_compute, w.nOrder, w.stream, d, conf, w.nOrder);
-        if (!exact) PR_LAUNCH(k_toi_claim, w.nOrder, w.stream, d, w.nOrder);
-        PR_LAUNCH(k_toi_select, w.nOrder, w.stream, d, w.nOrder, exact ? 0u : 1u);
         read_counters(w);
-        const unsigned nEvents = w.hostCnt.toiEvents;
+        const unsigned nEvents = nList ? w.hostCnt.toiEvents : 0u;
         if (nEvents == 0) { // :1768-1777
             w.stepComplete = true;
-            PR_LAUNCH(k_toi_finish_bodies, N, w.stream, d, N);
-            PR_LAUNCH(k_toi_finish_contacts, w.nOrder, w.stream, d, w.nOrder);
+            if (rounds || w.toiAlphaDirty) { PR_LAUNCH(k_toi_finish_bodies, N, w.stream, d, N); w.toiAlphaDirty = false; }
+            if (nList) PR_LAUNCH(k_toi_finish_contacts, nList, w.stream, d);
             break;
         }
         ++rounds;
-        st.contacts_found += nEvents;
-        PR_LAUNCH(k_toi_solve, nEvents, w.stream, d, conf, nEvents, exact ? 1u : 0u);
-        PR_LAUNCH(k_sync_proxies, w.nProxies, w.stream, d, conf, w.nProxies);
-        dset(w, d.b_sync, 0, sizeof(unsigned) * N);
-        st.contacts_added += find_add_contacts(w, conf, tm); // leaves hostCnt == device counters
+        tm.mark(w, PR_STAGE_TOI_SOLVE);
+        st.contacts_found += nEvents; // (events deferred for lack of scratch are subtracted below)
+        PR_LAUNCH(k_toi_solve, nEvents, w.stream, d, conf, nEvents, exact ? 1u : 0u, scratchCap);
+#ifndef PR_HOST_EMUL
+        PR_LAUNCH_GRID(k_sync_body_proxies, 148, PR_BLOCK, w.stream, d, conf);
+#else
+        PR_LAUNCH(k_sync_body_proxies, 1, w.stream, d, conf);
+#endif
+        st.contacts_added += find_add_contacts(w, conf, tm, true);
         tm.mark(w, PR_STAGE_TOI);
-        if (w.subStepping) { w.stepComplete = false; break; }
+        if (w.subStepping) { w.stepComplete = false; w.toiAlphaDirty = true; break; }
     }
     // final UpdateContacts (:1825-1827)
     read_counters(w);
@@ -478,7 +529,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     w.hostCnt.contactsUpdated = 0;
     write_counters(w);
     const unsigned nOrderAtUpdate = w.nOrder;
-    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 0u);
+    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 0u, 1u);
     read_counters(w);
     const Counters c = w.hostCnt;
     st.contacts_at_max_sub_steps = c.toiAtMaxSub; st.contacts_updated_toi = c.toiUpdated;
@@ -489,6 +540,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     st.contacts_updated_touching = c.toiUpdTouching + c.contactsUpdated;
     st.contacts_skipped_touching = c.toiSkipTouching + (nOrderAtUpdate - c.contactsUpdated);
     st.proxies_moved = movedToi;
+    st.contacts_found -= c.toiDeferred;
     w.profile.toi_rounds = rounds; w.profile.toi_events = st.contacts_found;
 }
 
@@ -513,14 +565,15 @@ static void step_impl(World& w, const pr_step_conf& conf, pr_step_stats& stats)
     tm.mark(w, PR_STAGE_PRE);
     // keep the queue count across steps (pr_set_bodies / creation between steps feed it)
     read_counters(w);
-    const unsigned keepQueue = w.hostCnt.nQueue;
+    const unsigned keepQueue = w.hostCnt.nQueue, keepToiList = w.hostCnt.toiListN; // state that outlives a step
+    if (w.hostCnt.recolorFlag) w.recolorAll = true; // a SetBody changed which bodies carry mass: conflict sets changed
     reset_counters(w);
-    w.hostCnt.nQueue = keepQueue; write_counters(w);
+    w.hostCnt.nQueue = keepQueue; w.hostCnt.toiListN = keepToiList; write_counters(w);
     stats.pre.proxies_created = create_queued_proxies(w, conf);
     if (w.anyBodySet) PR_LAUNCH(k_sync_proxies, w.nProxies, w.stream, d, conf, w.nProxies);
     stats.pre.contacts_destroyed = destroy_contacts(w);
     const unsigned nOrderAtUpdate = w.nOrder;
-    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, w.anyBodySet ? 1u : 0u);
+    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, w.anyBodySet ? 1u : 0u, 1u);
     if (w.anyBodySet) { dset(w, d.b_moved, 0, sizeof(unsigned) * w.nBodies); dset(w, d.b_sync, 0, sizeof(unsigned) * w.nBodies); }
     w.anyBodySet = false;
     read_counters(w);
@@ -640,7 +693,8 @@ int pr_clone(const pr_world* src, pr_world** out)
     for (size_t i = 0; i < da.size(); ++i) d2d(w, *da[i].slot, *sa[i].slot, da[i].elem * *cap_of(s, sa[i].g));
     d2d(w, w.d.cnt, s.d.cnt, sizeof(Counters));
     w.shapes = s.shapes; w.children = s.children; w.bodyShapes = s.bodyShapes; w.joints = s.joints;
-    w.fixturesForProxies = s.fixturesForProxies;
+    w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies;
+    w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll;
     w.nBodies = s.nBodies; w.nShapes = s.nShapes; w.nChildren = s.nChildren; w.nVerts = s.nVerts; w.nProxies = s.nProxies;
     w.maxTreeId = s.maxTreeId; w.debugFlags = s.debugFlags;
     w.nOrder = s.nOrder; w.nFree = s.nFree; w.poolSize = s.poolSize; w.anyBodySet = s.anyBodySet; w.hashDirty = true;
@@ -657,6 +711,7 @@ int pr_clear(pr_world* pw)
     API_TRY(pw)
     World& w = pw->w;
     w.shapes.clear(); w.children.clear(); w.bodyShapes.clear(); w.joints.clear(); w.fixturesForProxies.clear();
+    w.bodyProxies.clear(); w.bpDirty = true; w.bvhValid = false; w.hashTombs = 0; w.toiAlphaDirty = true;
     w.nBodies = w.nShapes = w.nChildren = w.nVerts = w.nProxies = w.nOrder = w.nFree = w.poolSize = 0; w.maxTreeId = 0;
     w.anyBodySet = false; w.hashDirty = true; w.adjValid = false; w.stepComplete = true;
     reset_counters(w);
@@ -728,6 +783,7 @@ int pr_create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const uint
     }
     if (first_id) *first_id = w.nBodies;
     w.nBodies += n;
+    w.adjValid = false; w.bpDirty = true; w.toiAlphaDirty = true;
     return PR_OK;
     API_CATCH(pw)
 }
@@ -751,7 +807,7 @@ int pr_set_bodies(pr_world* pw, uint32_t n, const uint32_t* ids, const pr_body* 
     PR_LAUNCH(k_put_bodies, n, w.stream, w.d, n, 0u, dids, staging, 1u);
     sync(w);
     dev_free(staging); dev_free(dids);
-    w.anyBodySet = true;
+    w.anyBodySet = true; w.toiAlphaDirty = true;
     return PR_OK;
     API_CATCH(pw)
 }
@@ -849,6 +905,9 @@ int pr_load_state(pr_world* pw, uint32_t n_bodies, const pr_body* bodies, uint32
     h2d(w, w.d.p_tree, tree.data(), 4 * n_proxies); h2d(w, w.d.p_fat, fat.data(), sizeof(float4) * n_proxies);
     dset(w, w.d.p_moved, 0, 4 * w.capProxies);
     w.nProxies = n_proxies; w.maxTreeId = maxTree;
+    w.bodyProxies.assign(w.nBodies, {});
+    for (unsigned i = 0; i < n_proxies; ++i) w.bodyProxies[body[i]].push_back(i);
+    w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true;
     w.fixturesForProxies.clear();
     // contacts
     unsigned maxId = 0;
@@ -873,7 +932,7 @@ int pr_load_state(pr_world* pw, uint32_t n_bodies, const pr_body* bodies, uint32
     h2d(w, w.d.c_free, freeIds.data(), 4 * freeIds.size());
     sync(w);
     w.nOrder = n_contacts; w.nFree = static_cast<unsigned>(freeIds.size()); w.poolSize = maxId;
-    w.hashDirty = true; w.adjValid = false; w.stepComplete = true; w.inv_dt0 = inv_dt0;
+    w.hashDirty = true; w.adjValid = false; w.stepComplete = true; w.inv_dt0 = inv_dt0; w.recolorAll = true;
     reset_counters(w);
     return PR_OK;
     API_CATCH(pw)

@@ -26,7 +26,7 @@ constexpr unsigned MAX_COLORS = 65u;
 constexpr unsigned LEAF_BIT = 0x80000000u;
 
 enum { ISL_ACTIVE = 1u, ISL_VEL_DONE = 2u, ISL_POS_SOLVED = 4u };
-enum { ERR_NONE = 0, ERR_STACK = 1, ERR_SENSOR = 2, ERR_PAIR_OVERFLOW = 4, ERR_HASH_FULL = 8 };
+enum { ERR_NONE = 0, ERR_STACK = 1, ERR_SENSOR = 2, ERR_PAIR_OVERFLOW = 4, ERR_HASH_FULL = 8, ERR_TOI_SCRATCH = 16 };
 
 // VelocityConstraint row (Library/include/playrho/d2/VelocityConstraint.hpp), 144 B
 struct VCRow {
@@ -53,8 +53,8 @@ struct Counters {
     unsigned long long toiMinKey; // (toi bits << 32 | position in m_contacts) of the soonest contact, GetSoonestContact
     unsigned toiEvents, toiScratchTop, toiAtMaxSub, toiUpdated, toiMaxDistIters, toiMaxToiIters, toiMaxRootIters;
     unsigned toiMinSepFlip, toiMaxIncBits, toiIslandsSolved, toiSumPosIters, toiSumVelIters, toiIslandsFound;
-    unsigned toiUpdTouching, toiSkipTouching, toiPad;
-    unsigned nQueue, nPairs, nNew, nDestroyed, nUncolored, nConstraints, nDirty, nOverflow;
+    unsigned toiUpdTouching, toiSkipTouching, toiListN, syncN, adjOverflow, toiDeferred, recolorFlag, toiPad;
+    unsigned nQueue, nPairs, nNew, nDestroyed, nUncolored, nConstraints, nDirty, nColorWork;
     unsigned islandsFound, islandsSolved, bodiesSlept, sumVelIters, sumPosIters, maxIslandBodies;
     unsigned proxiesMoved, contactsUpdated, nAwake, nTouching, nActiveVel, nActivePos;
     unsigned minSepFlip, maxIncBits, error, pad;
@@ -79,14 +79,18 @@ struct DV {
     float4 *m0, *m1, *m2; uint4* m3;
     unsigned *c_order, *c_free, *c_tmp, *c_tmp2;
     // TOI phase: body -> contact adjacency (m_bodyContacts) as CSR, islanded flags, event list, island scratch
-    unsigned *adj_off, *adj_cnt, *adj_list, *c_pos, *b_toiIsl, *c_toiIsl, *b_toiAlpha, *toi_events, *toi_islBodies, *toi_islContacts;
+    // (adjacency covers speedable bodies only, each segment has slack for contacts added during the TOI rounds)
+    unsigned *adj_off, *adj_cnt, *adj_n, *adj_list, *c_pos, *b_toiIsl, *c_toiIsl, *b_toiAlpha, *b_toiStamp, *toi_events, *toi_islBodies,
+        *toi_islContacts, *toi_list, *sync_list;
+    unsigned *bp_off, *bp_list; // body -> proxy CSR (m_bodyProxies)
     unsigned long long* ht_keys; unsigned ht_mask;
     // new pairs
     unsigned long long *np_key, *np_key2; uint2* np_px; unsigned *np_idx, *np_idx2;
     // constraints
-    VCRow* vc; PCRow* pc; unsigned *k_contact, *k_color, *k_sorted, *k_tmpKey, *k_tmpKey2, *k_tmpVal;
+    VCRow* vc; PCRow* pc; unsigned *k_contact, *k_color, *k_sorted, *k_tmpKey, *k_tmpKey2, *k_tmpVal, *k_ulist;
+    unsigned* c_color; // persistent colour per contact
     // bvh
-    unsigned *bv_code, *bv_code2, *bv_idx, *bv_idx2, *bv_left, *bv_right, *bv_parent, *bv_lparent, *bv_visit;
+    unsigned *bv_code, *bv_code2, *bv_idx, *bv_idx2, *bv_left, *bv_right, *bv_parent, *bv_lparent, *bv_visit, *bv_leafOf;
     float4* bv_box;
     Counters* cnt;
 };
@@ -111,7 +115,11 @@ struct World {
     unsigned nOrder = 0, nFree = 0, poolSize = 0;  // contacts
     unsigned nCons = 0, nColors = 0, maxTreeId = 0, debugFlags = 0;
     bool anyBodySet = false, hashDirty = true, stepComplete = true;
-    bool subStepping = false, adjValid = false;
+    bool recolorAll = true;
+    bool subStepping = false, adjValid = false, bvhValid = false, bpDirty = true, toiAlphaDirty = true;
+    unsigned bvhLeaves = 0, bvhRefits = 0, hashTombs = 0, toiListBound = 0;
+    const unsigned* bvhSortedIdx = nullptr;
+    std::vector<std::vector<unsigned>> bodyProxies; // m_bodyProxies
     unsigned toiMode = 1; // PR_TOI_PARALLEL (default) or PR_TOI_SERIAL_EXACT (reference order)
     float inv_dt0 = 0;
     // capacities
