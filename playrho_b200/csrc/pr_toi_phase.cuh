@@ -222,11 +222,15 @@ template <class F> PR_D void toi_for_each_claim_body(const DV& d, uint4 ab, F&& 
         const unsigned b = two[s];
         const unsigned f = d.b_flags[b];
         if (f_speedable(f)) fn(b);
-        if (f_accelerable(f)) {
+        if (f_accelerable(f)) { // the bodies ProcessContactsForTOI(b) can advance / read (:2079-2087): same filter
+            const bool bodyImpenetrable = (f & PR_BODY_IMPENETRABLE) != 0u;
             for (unsigned k = d.adj_off[b], ke = adj_end(d, b); k < ke; ++k) {
-                const uint4 o = d.c_ab[d.adj_list[k]];
+                const unsigned c2 = d.adj_list[k];
+                if (d.c_flags[c2] & PR_CONTACT_SENSOR) continue;
+                const uint4 o = d.c_ab[c2];
                 const unsigned other = (o.x == b) ? o.y : o.x;
-                if (f_speedable(d.b_flags[other])) fn(other);
+                const unsigned of = d.b_flags[other];
+                if (f_speedable(of) && (bodyImpenetrable || (of & PR_BODY_IMPENETRABLE))) fn(other);
             }
         }
     }
@@ -346,8 +350,10 @@ PR_D void toi_process_contacts(const DV& d, const pr_step_conf& conf, unsigned i
 
 PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactMode, unsigned scratchCap)
 {
-    const unsigned e = PR_TID;
-    if (e >= nEvents) return;
+    // one WARP per event, lane 0 working: events take wildly different paths (island sizes, manifold cases,
+    // iteration counts), so packing 32 of them into one warp serialises them (measured: 3.5 active lanes)
+    const unsigned e = PR_TID >> 5;
+    if ((PR_TID & 31u) != 0u || e >= nEvents) return;
     const unsigned cid = d.toi_events[e];
     const uint4 ab = d.c_ab[cid];
     const unsigned A = ab.x, B = ab.y;

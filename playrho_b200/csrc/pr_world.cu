@@ -513,7 +513,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         ++rounds;
         tm.mark(w, PR_STAGE_TOI_SOLVE);
         st.contacts_found += nEvents; // (events deferred for lack of scratch are subtracted below)
-        PR_LAUNCH(k_toi_solve, nEvents, w.stream, d, conf, nEvents, exact ? 1u : 0u, scratchCap);
+        PR_LAUNCH(k_toi_solve, 32u * nEvents, w.stream, d, conf, nEvents, exact ? 1u : 0u, scratchCap);
 #ifndef PR_HOST_EMUL
         PR_LAUNCH_GRID(k_sync_body_proxies, 148, PR_BLOCK, w.stream, d, conf);
 #else
