@@ -549,11 +549,15 @@ PR_D void query_emit(const DV& d, unsigned q, unsigned o, unsigned capPairs)
     else atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_PAIR_OVERFLOW));
 }
 // FindContacts (AabbTreeWorld.cpp:709-751): one thread per QUEUED proxy walks the LBVH
-PR_KERNEL k_bvh_query(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs)
+// mortonOrder != 0 (used right after a full rebuild, when most proxies are queued): thread t takes the t-th
+// leaf in Morton order if it is queued, so that the lanes of a warp walk neighbouring parts of the tree.
+PR_KERNEL k_bvh_query(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs, unsigned mortonOrder)
 {
     const unsigned t = PR_TID;
-    if (t < nQueue) {
-        const unsigned q = d.q_list[t];
+    unsigned q = INVALID;
+    if (mortonOrder) { if (t < nLeaves) { const unsigned c = sortedIdx[t]; if (d.p_moved[c]) q = c; } }
+    else if (t < nQueue) q = d.q_list[t];
+    if (q != INVALID) {
         const Box qb = box_from4(d.p_fat[q]);
         if (nLeaves == 1u) {
             // single leaf: nothing to pair with
@@ -581,7 +585,7 @@ PR_KERNEL k_bvh_query(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* s
 
 // AddContacts (AabbTreeWorld.cpp:2423-2547), creation part: sorted pair i gets its ContactID from the LIFO
 // free stack else by append (ObjectPool::Allocate), is appended to m_contacts in key order.
-PR_D void adj_append(const DV& d, unsigned b, unsigned id);
+PR_D void adj_append(const DV& d, unsigned b, unsigned id, bool eligible);
 PR_D bool toi_static_eligible(unsigned flags);
 PR_KERNEL k_create_contacts(DV d, unsigned nNew, const unsigned long long* keys, const unsigned* srcIdx,
                             unsigned nOrder, unsigned nFree, unsigned poolSize, unsigned adjLive)
@@ -611,8 +615,9 @@ PR_KERNEL k_create_contacts(DV d, unsigned nNew, const unsigned long long* keys,
         d.c_order[nOrder + i] = id;
         if (adjLive) { // the TOI phase's tables are live: m_bodyContacts push_back + TOI candidate list
             d.c_pos[id] = nOrder + i;
-            adj_append(d, bA, id); adj_append(d, bB, id);
-            if (toi_static_eligible(flags)) d.toi_list[atomicAdd(&d.cnt->toiListN, 1u)] = id;
+            const bool eligible = toi_static_eligible(flags);
+            adj_append(d, bA, id, eligible); adj_append(d, bB, id, eligible);
+            if (eligible) d.toi_list[atomicAdd(&d.cnt->toiListN, 1u)] = id;
         }
         hash_insert(d, key);
         if (!sensor) {
@@ -857,6 +862,70 @@ PR_D float2 rel_velocity(float4 vA, float2 relA, float4 vB, float2 relB)
     const float2 velArot = rev_perp(relA) * (vA.z / 1.0f);
     return (v2(vB.x, vB.y) + velBrot) - (v2(vA.x, vA.y) + velArot);
 }
+// ---- constraint rows in SoA planes (pr_world.h): plane k holds bytes [16k, 16k+16) of the logical row
+//   vc0 nx ny friction tangentSpeed | vc1 bodyA bodyB count|dynA<<8|dynB<<9 contact | vc2 invMA invIA invMB invIB
+//   vc3 rA0 rB0 | vc4 rA1 rB1 | vc5 nm0 tm0 nm1 tm1 | vc6 bias0 bias1 k00 k11 | vc7 k01 m00 m11 m01
+//   vc8 jn0 jt0 jn1 jt1 (the only plane the velocity iterations write) | vc_island
+//   pc0 ln lp | pc1 p0 p1 | pc2 lcA lcB | pc3 totalRadius typeCount
+PR_D void vc_store(const DV& d, unsigned i, const VCRow& v)
+{
+    d.vc0[i] = make_float4(v.nx, v.ny, v.friction, v.tangentSpeed);
+    d.vc1[i] = make_float4(u2f(v.bodyA), u2f(v.bodyB), u2f(v.count | (v.dynA << 8) | (v.dynB << 9)), u2f(v.contact));
+    d.vc2[i] = make_float4(v.invMA, v.invIA, v.invMB, v.invIB);
+    d.vc3[i] = make_float4(v.rA0x, v.rA0y, v.rB0x, v.rB0y);
+    d.vc4[i] = make_float4(v.rA1x, v.rA1y, v.rB1x, v.rB1y);
+    d.vc5[i] = make_float4(v.nm0, v.tm0, v.nm1, v.tm1);
+    d.vc6[i] = make_float4(v.bias0, v.bias1, v.k00, v.k11);
+    d.vc7[i] = make_float4(v.k01, v.m00, v.m11, v.m01);
+    d.vc8[i] = make_float4(v.jn0, v.jt0, v.jn1, v.jt1);
+    d.vc_island[i] = v.island;
+}
+PR_D void vc_load_head(const DV& d, unsigned i, VCRow& v)
+{
+    const float4 a = d.vc1[i], b = d.vc2[i];
+    v.bodyA = f2u(a.x); v.bodyB = f2u(a.y); v.contact = f2u(a.w);
+    const unsigned cf = f2u(a.z);
+    v.count = cf & 0xFFu; v.dynA = (cf >> 8) & 1u; v.dynB = (cf >> 9) & 1u; v.pad = 0u;
+    v.invMA = b.x; v.invIA = b.y; v.invMB = b.z; v.invIB = b.w;
+    v.island = d.vc_island[i];
+}
+PR_D VCRow vc_load(const DV& d, unsigned i)
+{
+    VCRow v;
+    vc_load_head(d, i, v);
+    const float4 a = d.vc0[i], c = d.vc3[i], e = d.vc5[i], f = d.vc6[i], h = d.vc8[i];
+    v.nx = a.x; v.ny = a.y; v.friction = a.z; v.tangentSpeed = a.w;
+    v.rA0x = c.x; v.rA0y = c.y; v.rB0x = c.z; v.rB0y = c.w;
+    v.nm0 = e.x; v.tm0 = e.y; v.nm1 = e.z; v.tm1 = e.w;
+    v.bias0 = f.x; v.bias1 = f.y; v.k00 = f.z; v.k11 = f.w;
+    v.jn0 = h.x; v.jt0 = h.y; v.jn1 = h.z; v.jt1 = h.w;
+    if (v.count == 2u) { // second point and the block-solver matrices only exist for two-point rows
+        const float4 dd = d.vc4[i], g = d.vc7[i];
+        v.rA1x = dd.x; v.rA1y = dd.y; v.rB1x = dd.z; v.rB1y = dd.w;
+        v.k01 = g.x; v.m00 = g.y; v.m11 = g.z; v.m01 = g.w;
+    } else {
+        v.rA1x = v.rA1y = v.rB1x = v.rB1y = 0.0f; v.k01 = v.m00 = v.m11 = v.m01 = 0.0f;
+    }
+    return v;
+}
+PR_D void pc_store(const DV& d, unsigned i, const PCRow& p)
+{
+    d.pc0[i] = make_float4(p.lnx, p.lny, p.lpx, p.lpy);
+    d.pc1[i] = make_float4(p.p0x, p.p0y, p.p1x, p.p1y);
+    d.pc2[i] = make_float4(p.lcAx, p.lcAy, p.lcBx, p.lcBy);
+    d.pc3[i] = make_float4(p.totalRadius, u2f(p.typeCount), 0.0f, 0.0f);
+}
+PR_D PCRow pc_load(const DV& d, unsigned i)
+{
+    PCRow p;
+    const float4 a = d.pc0[i], b = d.pc1[i], c = d.pc2[i], e = d.pc3[i];
+    p.lnx = a.x; p.lny = a.y; p.lpx = a.z; p.lpy = a.w;
+    p.p0x = b.x; p.p0y = b.y; p.p1x = b.z; p.p1y = b.w;
+    p.lcAx = c.x; p.lcAy = c.y; p.lcBx = c.z; p.lcBy = c.w;
+    p.totalRadius = e.x; p.typeCount = f2u(e.y); p.pad0 = p.pad1 = 0u;
+    return p;
+}
+
 // GetWorldManifold (WorldManifold.cpp:37-130) + VelocityConstraint ctor (VelocityConstraint.cpp:81-196)
 // + PositionConstraint (AabbTreeWorld.cpp:289-312) for sorted constraint row i
 PR_D void build_constraint_rows(const DV& d, unsigned cid, unsigned i, const pr_step_conf& conf, float dtRatio, unsigned islandLabel)
@@ -877,7 +946,7 @@ PR_D void build_constraint_rows(const DV& d, unsigned cid, unsigned i, const pr_
         pc.p0x = q1.x; pc.p0y = q1.y; pc.p1x = q1.z; pc.p1y = q1.w;
         pc.lcAx = lcA.x; pc.lcAy = lcA.y; pc.lcBx = lcB.x; pc.lcBy = lcB.y;
         pc.totalRadius = rA + rB; pc.typeCount = q3.z | (q3.w << 8); pc.pad0 = pc.pad1 = 0u;
-        d.pc[i] = pc;
+        pc_store(d, i, pc);
         // world manifold
         Rot normal = mkrot(0.0f, 0.0f);
         float2 wp[2] = {v2(0, 0), v2(0, 0)};
@@ -962,7 +1031,7 @@ PR_D void build_constraint_rows(const DV& d, unsigned cid, unsigned i, const pr_
         vc.rA1x = relA[1].x; vc.rA1y = relA[1].y; vc.rB1x = relB[1].x; vc.rB1y = relB[1].y;
         vc.jn1 = jn[1]; vc.jt1 = jt[1]; vc.nm1 = nm[1]; vc.tm1 = tm[1];
         vc.bias0 = bias[0]; vc.bias1 = bias[1];
-        d.vc[i] = vc;
+        vc_store(d, i, vc);
     }
 }
 PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtRatio)
@@ -986,7 +1055,7 @@ PR_D void apply_pair(float4& vA, float4& vB, float2 P, float2 relA, float2 relB,
 // WarmStartVelocities, AabbTreeWorld.cpp:222-273
 PR_D void warm_start_row(const DV& d, unsigned i)
 {
-    const VCRow vc = d.vc[i];
+    const VCRow vc = vc_load(d, i);
     float4 vA = d.s_vel[vc.bodyA], vB = d.s_vel[vc.bodyB];
     const Rot normal = mkrot(vc.nx, vc.ny), tangent = fwd_perp(normal);
     float2 dAl = v2(0, 0), dBl = v2(0, 0); float dAa = 0.0f, dBa = 0.0f;
@@ -1015,7 +1084,7 @@ PR_KERNEL k_warm_start_serial(DV d, unsigned start, unsigned count)
 // (block :245 with cases 1-4 :113-243, else sequential :337); points in order 1 then 0.
 PR_D float solve_velocity_row(const DV& d, unsigned i, bool& did, bool checkIsland = true)
 {
-    VCRow vc = d.vc[i];
+    VCRow vc = vc_load(d, i);
     did = false;
     if (checkIsland && (d.isl_state[vc.island] & ISL_VEL_DONE)) return 0.0f;
     did = true;
@@ -1097,15 +1166,14 @@ PR_D float solve_velocity_row(const DV& d, unsigned i, bool& did, bool checkIsla
     }
     if (vc.dynA) d.s_vel[vc.bodyA] = vA;
     if (vc.dynB) d.s_vel[vc.bodyB] = vB;
-    VCRow* row = &d.vc[i];
-    row->jn0 = jn[0]; row->jt0 = jt[0]; row->jn1 = jn[1]; row->jt1 = jt[1];
+    d.vc8[i] = make_float4(jn[0], jt[0], jn[1], jt[1]);
     return maxInc;
 }
 PR_KERNEL k_solve_velocity(DV d, unsigned start, unsigned count)
 {
     const unsigned t = PR_TID;
     bool did = false; float inc = 0.0f; unsigned label = 0u;
-    if (t < count) { inc = solve_velocity_row(d, start + t, did); label = d.vc[start + t].island; }
+    if (t < count) { inc = solve_velocity_row(d, start + t, did); label = d.vc_island[start + t]; }
     island_max(d.isl_inc, label, f2u(inc), did);
 }
 PR_KERNEL k_solve_velocity_serial(DV d, unsigned start, unsigned count)
@@ -1114,7 +1182,7 @@ PR_KERNEL k_solve_velocity_serial(DV d, unsigned start, unsigned count)
         for (unsigned t = 0; t < count; ++t) {
             bool did = false;
             const float inc = solve_velocity_row(d, start + t, did);
-            if (did) atomicMax(&d.isl_inc[d.vc[start + t].island], f2u(inc));
+            if (did) atomicMax(&d.isl_inc[d.vc_island[start + t]], f2u(inc));
         }
     }
 }
@@ -1194,7 +1262,8 @@ PR_D PDelta psm_solve(const PSM& psm, float2 pA, float2 pB, float imA, float iiA
 // GaussSeidel::SolvePositionConstraint, ContactSolver.cpp:494-643 (moveA = moveB = true)
 PR_D float solve_position_row(const DV& d, unsigned i, float rate, float slop, float maxCorr, bool& did, bool checkIsland = true)
 {
-    const VCRow* vcp = &d.vc[i];
+    VCRow vch; vc_load_head(d, i, vch);
+    const VCRow* vcp = &vch;
     const unsigned island = vcp->island;
     did = false;
     if (checkIsland && (d.isl_state[island] & ISL_POS_SOLVED)) return PR_INF;
@@ -1202,7 +1271,7 @@ PR_D float solve_position_row(const DV& d, unsigned i, float rate, float slop, f
     const unsigned bA = vcp->bodyA, bB = vcp->bodyB;
     const float imA = vcp->invMA, iiA = vcp->invIA, imB = vcp->invMB, iiB = vcp->invIB;
     const unsigned dynA = vcp->dynA, dynB = vcp->dynB;
-    const PCRow pc = d.pc[i];
+    const PCRow pc = pc_load(d, i);
     float4 a4 = d.s_pos[bA], b4 = d.s_pos[bB];
     Pos posA = pos_from4(a4), posB = pos_from4(b4);
     const float2 lcA = v2(pc.lcAx, pc.lcAy), lcB = v2(pc.lcBx, pc.lcBy);
@@ -1246,7 +1315,7 @@ PR_KERNEL k_solve_position(DV d, unsigned start, unsigned count, float rate, flo
 {
     const unsigned t = PR_TID;
     bool did = false; float sep = PR_INF; unsigned label = 0u;
-    if (t < count) { sep = solve_position_row(d, start + t, rate, slop, maxCorr, did); label = d.vc[start + t].island; }
+    if (t < count) { sep = solve_position_row(d, start + t, rate, slop, maxCorr, did); label = d.vc_island[start + t]; }
     island_min(d.isl_sep, label, float_flip(sep), did);
 }
 PR_KERNEL k_solve_position_serial(DV d, unsigned start, unsigned count, float rate, float slop, float maxCorr)
@@ -1255,7 +1324,7 @@ PR_KERNEL k_solve_position_serial(DV d, unsigned start, unsigned count, float ra
         for (unsigned t = 0; t < count; ++t) {
             bool did = false;
             const float sep = solve_position_row(d, start + t, rate, slop, maxCorr, did);
-            if (did) atomicMin(&d.isl_sep[d.vc[start + t].island], float_flip(sep));
+            if (did) atomicMin(&d.isl_sep[d.vc_island[start + t]], float_flip(sep));
         }
     }
 }
@@ -1281,11 +1350,11 @@ PR_KERNEL k_assign_impulses(DV d, unsigned nCons)
 { // AssignImpulses, AabbTreeWorld.cpp:208-230
     const unsigned i = PR_TID;
     if (i < nCons) {
-        const VCRow* vc = &d.vc[i];
-        const unsigned cid = vc->contact, count = vc->count;
+        const float4 head = d.vc1[i], imp = d.vc8[i];
+        const unsigned cid = f2u(head.w), count = f2u(head.z) & 0xFFu;
         float4 m2 = d.m2[cid];
-        if (count > 0u) { m2.x = vc->jn0; m2.y = vc->jt0; }
-        if (count > 1u) { m2.z = vc->jn1; m2.w = vc->jt1; }
+        if (count > 0u) { m2.x = imp.x; m2.y = imp.y; }
+        if (count > 1u) { m2.z = imp.z; m2.w = imp.w; }
         d.m2[cid] = m2;
     }
 }

@@ -22,35 +22,49 @@
 namespace pr {
 
 // ------------------------------------------------------------------ body -> contact adjacency (m_bodyContacts)
-// CSR over SPEEDABLE bodies only (lists of static bodies are never walked: ProcessContactsForTOI runs
-// for accelerable bodies, FlagForUpdating only for bodies that moved). Every segment has slack so
-// contacts created during the TOI rounds are appended in place (k_create_contacts); segments are kept in
-// m_contacts order by an insertion sort (whole table at build time, per body before an event walks it).
+// CSR over the set R of speedable bodies that own a TOI-candidate (impenetrable, non-sensor) contact: only
+// those can be advanced, walked (ProcessContactsForTOI) or flagged (FlagForUpdating) by a TOI event; a
+// 1M-body pile has a few thousand of them. Every segment has slack so contacts created during the TOI rounds
+// are appended in place (k_create_contacts); a body's segment is put into m_contacts order by an insertion
+// sort right before an event walks it (adj_sort_body).
 PR_D bool toi_static_eligible(unsigned flags)
 { // the flag part of UpdateContactTOIs' filter (:1696) that never changes during a step
     return (flags & PR_CONTACT_ENABLED) && !(flags & PR_CONTACT_SENSOR) && (flags & PR_CONTACT_IMPENETRABLE);
 }
-PR_KERNEL k_adj_count(DV d, unsigned nOrder)
+// pass 1: m_contacts position, TOI candidate list, and the set R of speedable bodies that own at least one
+// candidate contact -- only those bodies can ever be advanced, walked or flagged by a TOI event
+PR_KERNEL k_toi_list_build(DV d, unsigned nOrder)
 {
     const unsigned i = PR_TID;
     bool listed = false; unsigned id = 0u;
     if (i < nOrder) {
         id = d.c_order[i];
         d.c_pos[id] = i;
-        const uint4 ab = d.c_ab[id];
-        if (f_speedable(d.b_flags[ab.x])) atomicAdd(&d.adj_cnt[ab.x], 1u);
-        if (f_speedable(d.b_flags[ab.y])) atomicAdd(&d.adj_cnt[ab.y], 1u);
         listed = toi_static_eligible(d.c_flags[id]);
+        if (listed) {
+            const uint4 ab = d.c_ab[id];
+            if (f_speedable(d.b_flags[ab.x])) d.b_inR[ab.x] = 1u;
+            if (f_speedable(d.b_flags[ab.y])) d.b_inR[ab.y] = 1u;
+        }
     }
     const unsigned slot = warp_append(&d.cnt->toiListN, listed);
     if (listed) d.toi_list[slot] = id;
+}
+PR_KERNEL k_adj_count(DV d, unsigned nOrder)
+{
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const uint4 ab = d.c_ab[d.c_order[i]];
+        if (d.b_inR[ab.x]) atomicAdd(&d.adj_cnt[ab.x], 1u);
+        if (d.b_inR[ab.y]) atomicAdd(&d.adj_cnt[ab.y], 1u);
+    }
 }
 PR_KERNEL k_adj_cap(DV d, unsigned nBodies)
 {
     const unsigned b = PR_TID;
     if (b < nBodies) {
         const unsigned c = d.adj_cnt[b];
-        d.adj_cnt[b] = f_speedable(d.b_flags[b]) ? c + ((c >> 2) > 4u ? (c >> 2) : 4u) : 0u; // capacity (scan input)
+        d.adj_cnt[b] = d.b_inR[b] ? c + ((c >> 2) > 4u ? (c >> 2) : 4u) : 0u; // capacity (scan input)
         d.adj_n[b] = 0u;
     }
 }
@@ -60,8 +74,8 @@ PR_KERNEL k_adj_fill(DV d, unsigned nOrder)
     if (i < nOrder) {
         const unsigned id = d.c_order[i];
         const uint4 ab = d.c_ab[id];
-        if (f_speedable(d.b_flags[ab.x])) d.adj_list[d.adj_off[ab.x] + atomicAdd(&d.adj_n[ab.x], 1u)] = id;
-        if (f_speedable(d.b_flags[ab.y])) d.adj_list[d.adj_off[ab.y] + atomicAdd(&d.adj_n[ab.y], 1u)] = id;
+        if (d.b_inR[ab.x]) d.adj_list[d.adj_off[ab.x] + atomicAdd(&d.adj_n[ab.x], 1u)] = id;
+        if (d.b_inR[ab.y]) d.adj_list[d.adj_off[ab.y] + atomicAdd(&d.adj_n[ab.y], 1u)] = id;
     }
 }
 PR_D unsigned adj_end(const DV& d, unsigned b)
@@ -86,13 +100,13 @@ PR_KERNEL k_adj_sort(DV d, unsigned nBodies)
     if (b < nBodies && f_speedable(d.b_flags[b])) adj_sort_body(d, b);
 }
 // AddContacts' m_bodyContacts push_back (:2520-2523) for a contact created while the table is live
-PR_D void adj_append(const DV& d, unsigned b, unsigned id)
+PR_D void adj_append(const DV& d, unsigned b, unsigned id, bool eligible)
 {
-    if (f_speedable(d.b_flags[b])) {
+    if (d.b_inR[b]) {
         const unsigned slot = d.adj_off[b] + atomicAdd(&d.adj_n[b], 1u);
         if (slot < d.adj_off[b + 1u]) d.adj_list[slot] = id;
         else atomicOr(&d.cnt->adjOverflow, 1u); // host rebuilds the table before its next use
-    }
+    } else if (eligible && f_speedable(d.b_flags[b])) atomicOr(&d.cnt->adjOverflow, 1u); // b joins R: rebuild
 }
 
 // ------------------------------------------------------------------ UpdateContactTOIs (:1684-1750)

@@ -81,7 +81,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(b_moved, G_BODY), A(b_sync, G_BODY), A(isl_state, G_BODY), A(isl_velIters, G_BODY), A(isl_posIters, G_BODY),
         A(isl_inc, G_BODY), A(isl_maxInc, G_BODY), A(isl_sep, G_BODY), A(isl_minSep, G_BODY), A(isl_minUA, G_BODY),
         A(isl_nbodies, G_BODY), A(b_claim, G_BODY), A(b_cmask, G_BODY),
-        A(adj_off, G_BODY), A(adj_cnt, G_BODY), A(adj_n, G_BODY), A(b_toiIsl, G_BODY), A(b_toiAlpha, G_BODY), A(b_toiStamp, G_BODY),
+        A(adj_off, G_BODY), A(adj_cnt, G_BODY), A(adj_n, G_BODY), A(b_toiIsl, G_BODY), A(b_toiAlpha, G_BODY), A(b_toiStamp, G_BODY), A(b_inR, G_BODY),
         A(sync_list, G_BODY), A(bp_off, G_BODY), A(bp_list, G_PROXY), A(bv_leafOf, G_PROXY),
         A(c_pos, G_CONTACT), A(c_color, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT), A(toi_list, G_CONTACT),
         A(adj_list, G_ADJ), A(toi_islBodies, G_ADJ), A(toi_islContacts, G_ADJ),
@@ -95,7 +95,8 @@ static std::vector<ArrDesc> arrays(World& w)
         A(c_tmp, G_CONTACT), A(c_tmp2, G_CONTACT),
         A(ht_keys, G_HASH),
         A(np_key, G_PAIR), A(np_key2, G_PAIR), A(np_px, G_PAIR), A(np_idx, G_PAIR), A(np_idx2, G_PAIR),
-        A(vc, G_CONS), A(pc, G_CONS), A(k_contact, G_CONS), A(k_color, G_CONS), A(k_sorted, G_CONS), A(k_tmpKey, G_CONS),
+        A(vc0, G_CONS), A(vc1, G_CONS), A(vc2, G_CONS), A(vc3, G_CONS), A(vc4, G_CONS), A(vc5, G_CONS), A(vc6, G_CONS), A(vc7, G_CONS),
+        A(vc8, G_CONS), A(vc_island, G_CONS), A(pc0, G_CONS), A(pc1, G_CONS), A(pc2, G_CONS), A(pc3, G_CONS), A(k_contact, G_CONS), A(k_color, G_CONS), A(k_sorted, G_CONS), A(k_tmpKey, G_CONS),
         A(k_tmpKey2, G_CONS), A(k_tmpVal, G_CONS), A(k_ulist, G_CONS),
     };
 #undef A
@@ -280,7 +281,8 @@ static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer
         ensure(w, G_PAIR, std::max(1024u, nPairs));
         w.hostCnt.nPairs = 0; w.hostCnt.error &= ~static_cast<unsigned>(ERR_PAIR_OVERFLOW);
         write_counters(w);
-        PR_LAUNCH(k_bvh_query, nQueue, w.stream, d, nQueue, P, w.bvhSortedIdx, w.capPairs);
+        const bool morton = !refit && P > 1 && 4ull * nQueue >= P;
+        PR_LAUNCH(k_bvh_query, morton ? P : nQueue, w.stream, d, nQueue, P, w.bvhSortedIdx, w.capPairs, morton ? 1u : 0u);
         read_counters(w);
         nPairs = w.hostCnt.nPairs;
         if (nPairs <= w.capPairs) break;
@@ -456,14 +458,15 @@ static void build_adjacency(World& w)
     ensure(w, G_BODY, N + 1);
     ensure(w, G_ADJ, 2u * w.nOrder + 2u * w.nOrder / 4u + 8u * N + 64u);
     dset(w, d.adj_cnt, 0, sizeof(unsigned) * N);
+    dset(w, d.b_inR, 0, sizeof(unsigned) * N);
     read_counters(w);
     w.hostCnt.toiListN = 0; w.hostCnt.adjOverflow = 0;
     write_counters(w);
+    PR_LAUNCH(k_toi_list_build, w.nOrder, w.stream, d, w.nOrder);
     PR_LAUNCH(k_adj_count, w.nOrder, w.stream, d, w.nOrder);
     PR_LAUNCH(k_adj_cap, N, w.stream, d, N);
     scan_exclusive_u32(d.adj_cnt, d.adj_off, N, d.adj_off + N, w.scanScratch, w.stream);
     PR_LAUNCH(k_adj_fill, w.nOrder, w.stream, d, w.nOrder);
-    PR_LAUNCH(k_adj_sort, N, w.stream, d, N);
     read_counters(w);
     w.toiListBound = w.hostCnt.toiListN;
     w.adjValid = true;

@@ -80,14 +80,18 @@ struct DV {
     unsigned *c_order, *c_free, *c_tmp, *c_tmp2;
     // TOI phase: body -> contact adjacency (m_bodyContacts) as CSR, islanded flags, event list, island scratch
     // (adjacency covers speedable bodies only, each segment has slack for contacts added during the TOI rounds)
-    unsigned *adj_off, *adj_cnt, *adj_n, *adj_list, *c_pos, *b_toiIsl, *c_toiIsl, *b_toiAlpha, *b_toiStamp, *toi_events, *toi_islBodies,
+    unsigned *adj_off, *adj_cnt, *adj_n, *adj_list, *c_pos, *b_toiIsl, *c_toiIsl, *b_toiAlpha, *b_toiStamp, *b_inR, *toi_events, *toi_islBodies,
         *toi_islContacts, *toi_list, *sync_list;
     unsigned *bp_off, *bp_list; // body -> proxy CSR (m_bodyProxies)
     unsigned long long* ht_keys; unsigned ht_mask;
     // new pairs
     unsigned long long *np_key, *np_key2; uint2* np_px; unsigned *np_idx, *np_idx2;
     // constraints
-    VCRow* vc; PCRow* pc; unsigned *k_contact, *k_color, *k_sorted, *k_tmpKey, *k_tmpKey2, *k_tmpVal, *k_ulist;
+    // constraint rows, structure-of-arrays (one float4 plane per 16 B of VCRow / PCRow so that a warp's access to
+    // 32 consecutive rows is one coalesced 512 B transaction): see vc_load / vc_store in pr_kernels.cuh
+    float4 *vc0, *vc1, *vc2, *vc3, *vc4, *vc5, *vc6, *vc7, *vc8; unsigned* vc_island;
+    float4 *pc0, *pc1, *pc2, *pc3;
+    unsigned *k_contact, *k_color, *k_sorted, *k_tmpKey, *k_tmpKey2, *k_tmpVal, *k_ulist;
     unsigned* c_color; // persistent colour per contact
     // bvh
     unsigned *bv_code, *bv_code2, *bv_idx, *bv_idx2, *bv_left, *bv_right, *bv_parent, *bv_lparent, *bv_visit, *bv_leafOf;
