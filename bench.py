@@ -189,16 +189,18 @@ def main():
     # ---------------- end-to-end: host buffers in, host buffers out, every step
     rows = gw.bodies()
     ids = np.arange(nb, dtype=np.uint32)
-    pinned_in = torch.from_numpy(rows.view(np.uint8).reshape(-1)).pin_memory()
-    rows_pinned = pinned_in.numpy().view(abi.BODY)
+    pinned_in = torch.from_numpy(rows.view(np.uint8).reshape(-1).copy()).pin_memory()
+    pinned_out = torch.empty_like(pinned_in).pin_memory()
+    rows_in = pinned_in.numpy().view(abi.BODY)
+    rows_out = pinned_out.numpy().view(abi.BODY)
     e2e_steps = max(2, min(args.steps, 10))
     barrier()
     t1 = time.perf_counter()
     for _ in range(e2e_steps):
-        gw.set_bodies(ids, rows_pinned)       # H2D: every body row
+        gw.set_bodies(ids, rows_in)           # H2D: every body row, from pinned host memory
         gw.step(conf)
-        out = gw.bodies()                     # D2H: every body row
-        rows_pinned[:] = out
+        gw.bodies_into(rows_out)              # D2H: every body row, into pinned host memory
+        rows_in, rows_out = rows_out, rows_in # next step uploads what this step produced
     barrier()
     e2e_secs = time.perf_counter() - t1
     sampler.stop_flag = True

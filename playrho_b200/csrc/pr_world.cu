@@ -149,8 +149,42 @@ static void ensure(World& w, Group g, unsigned need)
     ensure_scratch(w, std::max(std::max(std::max(w.capContacts, w.capProxies), std::max(w.capPairs, w.capCons)), std::max(w.capBodies, w.capAdj)));
 }
 
+#ifndef PR_HOST_EMUL
+// counters travel through pinned host memory: one D2H + stream sync per read, and a ring of pinned slots for
+// the asynchronous H2D writes (a slot is reused only after >= one intervening read, i.e. a stream sync)
+static void* stage_buf(World& w, int which, size_t bytes)
+{
+    if (bytes > w.stageCap[which]) {
+        sync(w);
+        dev_free(w.stageBuf[which]);
+        w.stageBuf[which] = dev_alloc(bytes + bytes / 4);
+        w.stageCap[which] = bytes + bytes / 4;
+    }
+    return w.stageBuf[which];
+}
+static void read_counters(World& w)
+{
+    CK(cudaMemcpyAsync(&w.pinnedCnt[0], w.d.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaStreamSynchronize(w.stream));
+    w.hostCnt = w.pinnedCnt[0];
+    w.pinnedNext = 1; // everything queued before this point has executed: all write slots are free again
+}
+static void write_counters(World& w)
+{
+    if (w.pinnedNext >= World::PINNED_SLOTS) { CK(cudaStreamSynchronize(w.stream)); w.pinnedNext = 1; }
+    Counters* slot = &w.pinnedCnt[w.pinnedNext++];
+    *slot = w.hostCnt;
+    CK(cudaMemcpyAsync(w.d.cnt, slot, sizeof(Counters), cudaMemcpyHostToDevice, w.stream));
+}
+#else
+static void* stage_buf(World& w, int which, size_t bytes)
+{
+    if (bytes > w.stageCap[which]) { dev_free(w.stageBuf[which]); w.stageBuf[which] = dev_alloc(bytes); w.stageCap[which] = bytes; }
+    return w.stageBuf[which];
+}
 static void read_counters(World& w) { d2h(w, &w.hostCnt, w.d.cnt, sizeof(Counters)); }
 static void write_counters(World& w) { h2d(w, w.d.cnt, &w.hostCnt, sizeof(Counters)); }
+#endif
 
 static void throw_device_error(World& w)
 {
@@ -652,6 +686,9 @@ int pr_create(const pr_world_conf* conf, pr_world** out)
         CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
 #endif
         w.d.cnt = static_cast<Counters*>(dev_alloc(sizeof(Counters)));
+#ifndef PR_HOST_EMUL
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&w.pinnedCnt), sizeof(Counters) * World::PINNED_SLOTS, cudaHostAllocDefault));
+#endif
         ensure(w, G_BODY, std::max(64u, w.conf.body_capacity));
         ensure(w, G_SHAPE, 64); ensure(w, G_CHILD, 64); ensure(w, G_VERT, std::max(256u, w.conf.vertex_capacity));
         ensure(w, G_PROXY, std::max(64u, w.conf.proxy_capacity));
@@ -670,9 +707,10 @@ int pr_destroy(pr_world* pw)
     if (!pw) return PR_OK;
     World& w = pw->w;
     for (const ArrDesc& a : arrays(w)) dev_free(*a.slot);
-    dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist);
+    dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist); dev_free(w.stageBuf[0]); dev_free(w.stageBuf[1]);
 #ifndef PR_HOST_EMUL
     if (w.stream) cudaStreamDestroy(w.stream);
+    if (w.pinnedCnt) cudaFreeHost(w.pinnedCnt);
 #endif
     delete pw;
     return PR_OK;
@@ -804,12 +842,11 @@ int pr_set_bodies(pr_world* pw, uint32_t n, const uint32_t* ids, const pr_body* 
     World& w = pw->w;
     for (uint32_t i = 0; i < n; ++i) if (ids[i] >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
     if (!n) return PR_OK;
-    pr_body* staging = static_cast<pr_body*>(dev_alloc(sizeof(pr_body) * n));
-    unsigned* dids = static_cast<unsigned*>(dev_alloc(4 * n));
+    pr_body* staging = static_cast<pr_body*>(stage_buf(w, 0, sizeof(pr_body) * n));
+    unsigned* dids = static_cast<unsigned*>(stage_buf(w, 1, 4 * n));
     h2d(w, staging, rows, sizeof(pr_body) * n); h2d(w, dids, ids, 4 * n);
     PR_LAUNCH(k_put_bodies, n, w.stream, w.d, n, 0u, dids, staging, 1u);
-    sync(w);
-    dev_free(staging); dev_free(dids);
+    sync(w); // the caller's rows / ids may be reused once we return
     w.anyBodySet = true; w.toiAlphaDirty = true;
     return PR_OK;
     API_CATCH(pw)
@@ -822,10 +859,9 @@ int pr_get_bodies(const pr_world* cpw, uint32_t first, uint32_t n, pr_body* rows
     World& w = pw->w;
     if (first + n > w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
     if (!n) return PR_OK;
-    pr_body* staging = static_cast<pr_body*>(dev_alloc(sizeof(pr_body) * n));
+    pr_body* staging = static_cast<pr_body*>(stage_buf(w, 0, sizeof(pr_body) * n));
     PR_LAUNCH(k_get_bodies, n, w.stream, w.d, first, n, staging);
     d2h(w, rows, staging, sizeof(pr_body) * n);
-    dev_free(staging);
     return PR_OK;
     API_CATCH(pw)
 }

@@ -133,10 +133,12 @@ struct World {
     RadixScratch rs;
     unsigned* scanScratch = nullptr; size_t scanScratchCap = 0;
     Counters hostCnt{};
-    Counters* pinnedCnt = nullptr;
+    static constexpr unsigned PINNED_SLOTS = 64;
+    Counters* pinnedCnt = nullptr; unsigned pinnedNext = 1;
     pr_step_profile profile{};
     std::vector<unsigned> solveOrderIds, solveOrderColors;
     std::vector<void*> allocs;
+    void* stageBuf[2] = {nullptr, nullptr}; size_t stageCap[2] = {0, 0}; // persistent device staging for row upload/download
 };
 
 void count_launch();

@@ -1,0 +1,584 @@
+// CudaWorld.cpp -- host shim of the B200-native world (see CudaWorld.hpp). Calls ONLY the C ABI of
+// include/playrho_b200.h; mirrors the argument checks and exception types of AabbTreeWorld
+// (Library/source/playrho/d2/AabbTreeWorld.cpp, lines cited per function).
+#include "CudaWorld.hpp"
+#include "../../include/playrho_b200.h"
+
+#include <playrho/InvalidArgument.hpp>
+#include <playrho/LengthError.hpp>
+#include <playrho/OutOfRange.hpp>
+#include <playrho/WrongState.hpp>
+#include <playrho/d2/DistanceProxy.hpp>
+#include <playrho/d2/RevoluteJointConf.hpp>
+#include <playrho/to_underlying.hpp>
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
+
+namespace playrho::b200 {
+
+namespace {
+constexpr auto worldIsLockedMsg = "world is locked";
+constexpr auto noSuchBodyMsg = "no such body";
+constexpr auto noSuchShapeMsg = "no such shape";
+constexpr auto noSuchJointMsg = "no such joint";
+constexpr auto noSuchContactMsg = "no such contact";
+constexpr auto unsupportedMsg = "operation not supported by the B200 device world yet";
+
+template <class ID>
+ID MakeId(std::uint32_t v) { return static_cast<ID>(static_cast<typename ID::underlying_type>(v)); }
+
+template <class Container, class ID>
+auto& AtId(Container& c, ID id, const char* msg)
+{
+    const auto i = static_cast<std::size_t>(to_underlying(id));
+    if (i >= c.size()) throw OutOfRange<ID>{id, msg}; // At(...), AabbTreeWorld.cpp:163-174
+    return c[i];
+}
+
+pr_contact_feature Pack(const ContactFeature& cf)
+{
+    return static_cast<std::uint32_t>(cf.typeA) | (static_cast<std::uint32_t>(cf.indexA) << 8) |
+           (static_cast<std::uint32_t>(cf.typeB) << 16) | (static_cast<std::uint32_t>(cf.indexB) << 24);
+}
+ContactFeature Unpack(pr_contact_feature v)
+{
+    return ContactFeature{static_cast<ContactFeature::Type>(v & 0xFFu), static_cast<ContactFeature::Index>((v >> 8) & 0xFFu),
+                          static_cast<ContactFeature::Type>((v >> 16) & 0xFFu), static_cast<ContactFeature::Index>((v >> 24) & 0xFFu)};
+}
+
+// Body value -> device row (Body.hpp private block; flags bit-identical to Body::Flag)
+pr_body ToRow(const Body& b)
+{
+    pr_body o{};
+    const auto xf = GetTransformation(b);
+    const auto& sw = GetSweep(b);
+    const auto v = GetVelocity(b);
+    o.xf_px = GetX(xf.p); o.xf_py = GetY(xf.p); o.xf_qc = xf.q.GetX(); o.xf_qs = xf.q.GetY();
+    o.pos0_x = GetX(sw.pos0.linear); o.pos0_y = GetY(sw.pos0.linear); o.pos0_a = sw.pos0.angular;
+    o.pos1_x = GetX(sw.pos1.linear); o.pos1_y = GetY(sw.pos1.linear); o.pos1_a = sw.pos1.angular;
+    o.lc_x = GetX(sw.localCenter); o.lc_y = GetY(sw.localCenter);
+    o.alpha0 = sw.alpha0;
+    o.vel_x = GetX(v.linear); o.vel_y = GetY(v.linear); o.vel_w = v.angular;
+    o.acc_x = GetX(GetLinearAcceleration(b)); o.acc_y = GetY(GetLinearAcceleration(b)); o.acc_w = GetAngularAcceleration(b);
+    o.inv_mass = GetInvMass(b); o.inv_rot_i = GetInvRotInertia(b);
+    o.lin_damp = GetLinearDamping(b); o.ang_damp = GetAngularDamping(b);
+    o.under_active_time = GetUnderActiveTime(b);
+    std::uint32_t f = 0;
+    if (IsDestroyed(b)) f |= PR_BODY_DESTROYED;
+    if (IsAwake(b)) f |= PR_BODY_AWAKE;
+    if (IsSleepingAllowed(b)) f |= PR_BODY_AUTOSLEEP;
+    if (IsImpenetrable(b)) f |= PR_BODY_IMPENETRABLE;
+    if (IsFixedRotation(b)) f |= PR_BODY_FIXED_ROTATION;
+    if (IsEnabled(b)) f |= PR_BODY_ENABLED;
+    if (IsSpeedable(b)) f |= PR_BODY_VELOCITY;
+    if (IsAccelerable(b)) f |= PR_BODY_ACCELERATION;
+    if (IsMassDataDirty(b)) f |= PR_BODY_MASS_DIRTY;
+    o.flags = f;
+    return o;
+}
+
+// device row -> Body value: only what a Step can change (sweep, transform, velocity, awake, timer)
+void FromRow(const pr_body& r, Body& b)
+{
+    auto sweep = Sweep{Position{Length2{r.pos0_x, r.pos0_y}, Angle{r.pos0_a}}, Position{Length2{r.pos1_x, r.pos1_y}, Angle{r.pos1_a}},
+                       Length2{r.lc_x, r.lc_y}, ZeroToUnderOneFF<Real>(r.alpha0)};
+    b.SetSweep(sweep); // (recomputes the transformation from pos1 with the same libm sincos the device restates)
+    b.JustSetVelocity(Velocity{LinearVelocity2{r.vel_x, r.vel_y}, AngularVelocity{r.vel_w}});
+    if (r.flags & PR_BODY_AWAKE) b.SetAwakeFlag(); else b.UnsetAwakeFlag();
+    b.SetUnderActiveTime(Time{r.under_active_time});
+}
+
+pr_step_conf ToConf(const StepConf& s)
+{
+    pr_step_conf c{};
+    c.delta_time = s.deltaTime; c.dt_ratio = s.dtRatio;
+    c.min_still_time_to_sleep = s.minStillTimeToSleep; c.linear_slop = s.linearSlop; c.angular_slop = s.angularSlop;
+    c.reg_resolution_rate = s.regResolutionRate; c.reg_min_separation = s.regMinSeparation; c.reg_min_momentum = s.regMinMomentum;
+    c.toi_resolution_rate = s.toiResolutionRate; c.toi_min_separation = s.toiMinSeparation; c.toi_min_momentum = s.toiMinMomentum;
+    c.target_depth = s.targetDepth; c.tolerance = s.tolerance; c.velocity_threshold = s.velocityThreshold;
+    c.max_translation = s.maxTranslation; c.max_rotation = s.maxRotation;
+    c.max_linear_correction = s.maxLinearCorrection; c.max_angular_correction = s.maxAngularCorrection;
+    c.linear_sleep_tolerance = s.linearSleepTolerance; c.angular_sleep_tolerance = s.angularSleepTolerance;
+    c.displace_multiplier = s.displaceMultiplier; c.aabb_extension = s.aabbExtension; c.max_circles_ratio = s.maxCirclesRatio;
+    c.reg_velocity_iters = s.regVelocityIters; c.reg_position_iters = s.regPositionIters;
+    c.toi_velocity_iters = s.toiVelocityIters; c.toi_position_iters = s.toiPositionIters;
+    c.max_toi_root_iters = s.maxToiRootIters; c.max_toi_iters = s.maxToiIters; c.max_distance_iters = s.maxDistanceIters;
+    c.max_sub_steps = s.maxSubSteps;
+    c.do_warm_start = s.doWarmStart; c.do_toi = s.doToi; c.do_blocksolve = s.doBlocksolve;
+    return c;
+}
+
+template <class T, class U> T Narrow(U v) { return static_cast<T>(v); }
+
+StepStats ToStats(const pr_step_stats& o)
+{
+    StepStats s;
+    using PC = decltype(s.pre.proxiesCreated);
+    s.pre.proxiesCreated = Narrow<PC>(o.pre.proxies_created); s.pre.proxiesMoved = Narrow<PC>(o.pre.proxies_moved);
+    s.pre.contactsDestroyed = Narrow<PC>(o.pre.contacts_destroyed); s.pre.contactsAdded = Narrow<PC>(o.pre.contacts_added);
+    s.pre.contactsUpdated = Narrow<PC>(o.pre.contacts_updated); s.pre.contactsSkipped = Narrow<PC>(o.pre.contacts_skipped);
+    s.reg.minSeparation = o.reg.min_separation; s.reg.maxIncImpulse = o.reg.max_inc_impulse;
+    using RC = decltype(s.reg.islandsFound);
+    s.reg.islandsFound = Narrow<RC>(o.reg.islands_found); s.reg.islandsSolved = Narrow<RC>(o.reg.islands_solved);
+    s.reg.contactsAdded = Narrow<RC>(o.reg.contacts_added); s.reg.bodiesSlept = Narrow<RC>(o.reg.bodies_slept);
+    s.reg.proxiesMoved = Narrow<RC>(o.reg.proxies_moved); s.reg.sumPosIters = Narrow<RC>(o.reg.sum_pos_iters);
+    s.reg.sumVelIters = Narrow<RC>(o.reg.sum_vel_iters); s.reg.contactsUpdated = Narrow<RC>(o.reg.contacts_updated);
+    s.reg.contactsSkipped = Narrow<RC>(o.reg.contacts_skipped);
+    s.reg.maxIslandBodies = Narrow<decltype(s.reg.maxIslandBodies)>(o.reg.max_island_bodies);
+    s.toi.minSeparation = o.toi.min_separation; s.toi.maxIncImpulse = o.toi.max_inc_impulse;
+    using TC = decltype(s.toi.islandsFound);
+    s.toi.islandsFound = Narrow<TC>(o.toi.islands_found); s.toi.islandsSolved = Narrow<TC>(o.toi.islands_solved);
+    s.toi.contactsFound = Narrow<TC>(o.toi.contacts_found); s.toi.contactsAtMaxSubSteps = Narrow<TC>(o.toi.contacts_at_max_sub_steps);
+    s.toi.contactsUpdatedToi = Narrow<TC>(o.toi.contacts_updated_toi);
+    s.toi.contactsUpdatedTouching = Narrow<TC>(o.toi.contacts_updated_touching);
+    s.toi.contactsSkippedTouching = Narrow<TC>(o.toi.contacts_skipped_touching);
+    s.toi.contactsAdded = Narrow<TC>(o.toi.contacts_added); s.toi.proxiesMoved = Narrow<TC>(o.toi.proxies_moved);
+    s.toi.sumPosIters = Narrow<TC>(o.toi.sum_pos_iters); s.toi.sumVelIters = Narrow<TC>(o.toi.sum_vel_iters);
+    s.toi.maxDistIters = Narrow<decltype(s.toi.maxDistIters)>(o.toi.max_dist_iters);
+    s.toi.maxToiIters = Narrow<decltype(s.toi.maxToiIters)>(o.toi.max_toi_iters);
+    s.toi.maxRootIters = Narrow<decltype(s.toi.maxRootIters)>(o.toi.max_root_iters);
+    return s;
+}
+
+Manifold ToManifold(const pr_manifold& m)
+{
+    using P = Manifold::Point;
+    const auto pt = [&](int k) {
+        return k == 0 ? P{Length2{m.p0_x, m.p0_y}, Unpack(m.cf0), Momentum{m.jn0}, Momentum{m.jt0}}
+                      : P{Length2{m.p1_x, m.p1_y}, Unpack(m.cf1), Momentum{m.jn1}, Momentum{m.jt1}};
+    };
+    const auto ln = [&]() { // stored local normal is already unit length: rebuild the UnitVec from its raw bits
+        UnitVec u; const float raw[2] = {m.ln_x, m.ln_y};
+        static_assert(sizeof(UnitVec) == sizeof(raw), "UnitVec layout");
+        std::memcpy(static_cast<void*>(&u), raw, sizeof(raw));
+        return u;
+    };
+    const auto lp = Length2{m.lp_x, m.lp_y};
+    switch (m.type) {
+    case PR_MANIFOLD_CIRCLES: {
+        const auto cf = Unpack(m.cf0);
+        auto r = Manifold::GetForCircles(lp, cf.indexA, Length2{m.p0_x, m.p0_y}, cf.indexB);
+        r.SetImpulses(0, Momentum{m.jn0}, Momentum{m.jt0});
+        return r;
+    }
+    case PR_MANIFOLD_FACE_A:
+        if (m.count == 0) return Manifold::GetForFaceA(ln(), lp);
+        if (m.count == 1) return Manifold::GetForFaceA(ln(), lp, pt(0));
+        return Manifold::GetForFaceA(ln(), lp, pt(0), pt(1));
+    case PR_MANIFOLD_FACE_B:
+        if (m.count == 0) return Manifold::GetForFaceB(ln(), lp);
+        if (m.count == 1) return Manifold::GetForFaceB(ln(), lp, pt(0));
+        return Manifold::GetForFaceB(ln(), lp, pt(0), pt(1));
+    default: break;
+    }
+    return Manifold{};
+}
+
+Contact ToContact(const pr_contact& c)
+{
+    auto r = Contact{Contactable{MakeId<BodyID>(c.body_a), MakeId<ShapeID>(c.shape_a), static_cast<ChildCounter>(c.child_a)},
+                     Contactable{MakeId<BodyID>(c.body_b), MakeId<ShapeID>(c.shape_b), static_cast<ChildCounter>(c.child_b)}};
+    r.SetFriction(c.friction); r.SetRestitution(c.restitution); r.SetTangentSpeed(c.tangent_speed);
+    if (c.flags & PR_CONTACT_TOUCHING) r.SetTouching(); else r.UnsetTouching();
+    if (c.flags & PR_CONTACT_ENABLED) r.SetEnabled(); else r.UnsetEnabled();
+    if (c.flags & PR_CONTACT_FILTER) r.FlagForFiltering(); else r.UnflagForFiltering();
+    if (c.flags & PR_CONTACT_DIRTY) r.FlagForUpdating(); else r.UnflagForUpdating();
+    if (c.flags & PR_CONTACT_SENSOR) r.SetSensor(); else r.UnsetSensor();
+    if (c.flags & PR_CONTACT_IMPENETRABLE) r.SetImpenetrable(); else r.UnsetImpenetrable();
+    if (c.flags & PR_CONTACT_TOI) r.SetToi({UnitIntervalFF<Real>(c.toi)}); else r.SetToi({});
+    r.SetToiCount(static_cast<Contact::substep_type>(c.toi_count));
+    return r;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct CudaWorld::Impl {
+    pr_world* h = nullptr;
+    WorldConf conf;
+    unsigned toiMode = PR_TOI_PARALLEL;
+    bool locked = false;
+    // host mirrors of entity values
+    mutable std::vector<Body> bodies;
+    std::vector<char> bodyDirty;   // host value newer than the device row
+    bool anyBodyDirty = false;
+    mutable bool bodiesStale = false; // device rows newer than the host values (after a Step)
+    std::vector<Shape> shapes;
+    std::vector<Joint> joints;
+    // lazily downloaded contact state
+    mutable bool contactsStale = true;
+    mutable std::vector<KeyedContactID> contactIds;            // m_contacts order
+    mutable std::vector<Contact> contactBuf;                   // indexed by ContactID
+    mutable std::vector<Manifold> manifoldBuf;
+    mutable std::vector<char> contactLive;
+    mutable std::vector<std::vector<std::tuple<ContactKey, ContactID>>> bodyContacts;
+    // lazily materialised DynamicTree (GetTree): leaves created in tree-id order replay the id sequence
+    mutable bool treeStale = true;
+    mutable DynamicTree tree;
+    // listeners (stored only)
+    ShapeFunction shapeDestruction; BodyShapeFunction detach; JointFunction jointDestruction;
+    ContactFunction beginContact, endContact; ContactManifoldFunction preSolve; ContactImpulsesFunction postSolve;
+
+    void check(int rc, const char* what) const
+    {
+        if (rc == PR_OK) return;
+        const std::string msg = std::string(what) + ": " + (h ? pr_last_error(h) : pr_last_error(nullptr));
+        switch (rc) {
+        case PR_ERR_INVALID_ARGUMENT: throw InvalidArgument(msg.c_str());
+        case PR_ERR_OUT_OF_RANGE: throw std::out_of_range(msg);
+        case PR_ERR_WRONG_STATE: throw WrongState(msg.c_str());
+        case PR_ERR_LENGTH: throw LengthError(msg.c_str());
+        case PR_ERR_UNSUPPORTED: throw InvalidArgument(msg.c_str());
+        default: throw std::runtime_error(msg);
+        }
+    }
+    void create(const WorldConf& c)
+    {
+        conf = c;
+        pr_world_conf wc;
+        pr_world_conf_default(&wc);
+        wc.min_vertex_radius = static_cast<float>(Real(c.vertexRadius.GetMin()));
+        wc.max_vertex_radius = static_cast<float>(Real(c.vertexRadius.GetMax()));
+        wc.contact_capacity = c.contactCapacity;
+        wc.proxy_capacity = c.proxyCapacity;
+        check(pr_create(&wc, &h), "pr_create");
+        pr_set_toi_mode(h, toiMode);
+    }
+    void refreshBodies() const
+    { // device rows -> host values, once after each Step
+        if (!bodiesStale) return;
+        std::vector<pr_body> rows(bodies.size());
+        if (!rows.empty()) check(pr_get_bodies(h, 0, static_cast<std::uint32_t>(rows.size()), rows.data()), "pr_get_bodies");
+        for (std::size_t i = 0; i < rows.size(); ++i) if (!bodyDirty[i]) FromRow(rows[i], bodies[i]);
+        bodiesStale = false;
+    }
+    void uploadDirtyBodies()
+    {
+        if (!anyBodyDirty) return;
+        std::vector<std::uint32_t> ids; std::vector<pr_body> rows;
+        for (std::size_t i = 0; i < bodies.size(); ++i) if (bodyDirty[i]) { ids.push_back(static_cast<std::uint32_t>(i)); rows.push_back(ToRow(bodies[i])); bodyDirty[i] = 0; }
+        if (!ids.empty()) check(pr_set_bodies(h, static_cast<std::uint32_t>(ids.size()), ids.data(), rows.data()), "pr_set_bodies");
+        anyBodyDirty = false;
+    }
+    void refreshContacts() const
+    {
+        if (!contactsStale) return;
+        pr_counts n{};
+        pr_get_counts(h, &n);
+        std::vector<pr_contact> cs(std::max<std::uint32_t>(1u, n.contacts));
+        std::vector<pr_manifold> ms(cs.size());
+        std::uint32_t k = 0;
+        check(pr_get_contacts(h, static_cast<std::uint32_t>(cs.size()), cs.data(), ms.data(), &k), "pr_get_contacts");
+        contactIds.clear();
+        contactBuf.assign(n.contact_id_range, Contact{});
+        manifoldBuf.assign(n.contact_id_range, Manifold{});
+        contactLive.assign(n.contact_id_range, 0);
+        bodyContacts.assign(bodies.size(), {});
+        for (std::uint32_t i = 0; i < k; ++i) {
+            const auto key = ContactKey{static_cast<ContactCounter>(cs[i].key_min), static_cast<ContactCounter>(cs[i].key_max)};
+            const auto id = MakeId<ContactID>(cs[i].id);
+            contactIds.emplace_back(key, id);
+            contactBuf[cs[i].id] = ToContact(cs[i]);
+            manifoldBuf[cs[i].id] = ToManifold(ms[i]);
+            contactLive[cs[i].id] = 1;
+            bodyContacts[cs[i].body_a].emplace_back(key, id); // m_bodyContacts: append order == m_contacts order
+            bodyContacts[cs[i].body_b].emplace_back(key, id);
+        }
+        contactsStale = false;
+    }
+    void mutated() { contactsStale = true; treeStale = true; }
+};
+
+CudaWorld::CudaWorld(const WorldConf& conf) : m{new Impl} {
+    try { m->create(conf); } catch (...) { delete m; m = nullptr; throw; }
+}
+CudaWorld::CudaWorld(const CudaWorld& o) : m{new Impl}
+{
+    try {
+        o.m->refreshBodies();
+        const_cast<CudaWorld&>(o).m->uploadDirtyBodies();
+        m->conf = o.m->conf; m->toiMode = o.m->toiMode;
+        m->check(pr_clone(o.m->h, &m->h), "pr_clone");
+        m->bodies = o.m->bodies; m->bodyDirty = o.m->bodyDirty; m->anyBodyDirty = o.m->anyBodyDirty;
+        m->bodiesStale = false; m->shapes = o.m->shapes; m->joints = o.m->joints;
+        m->shapeDestruction = o.m->shapeDestruction; m->detach = o.m->detach; m->jointDestruction = o.m->jointDestruction;
+        m->beginContact = o.m->beginContact; m->endContact = o.m->endContact; m->preSolve = o.m->preSolve; m->postSolve = o.m->postSolve;
+    } catch (...) { if (m->h) pr_destroy(m->h); delete m; m = nullptr; throw; }
+}
+CudaWorld::CudaWorld(CudaWorld&& o) noexcept : m{o.m} { o.m = nullptr; }
+CudaWorld& CudaWorld::operator=(const CudaWorld& o) { if (this != &o) { CudaWorld tmp{o}; std::swap(m, tmp.m); } return *this; }
+CudaWorld& CudaWorld::operator=(CudaWorld&& o) noexcept { if (this != &o) { std::swap(m, o.m); } return *this; }
+CudaWorld::~CudaWorld() noexcept { if (m) { if (m->h) pr_destroy(m->h); delete m; } }
+void CudaWorld::SetToiMode(ToiMode mode) { m->toiMode = static_cast<unsigned>(mode); m->check(pr_set_toi_mode(m->h, m->toiMode), "pr_set_toi_mode"); }
+
+bool operator==(const CudaWorld& a, const CudaWorld& b)
+{ // like AabbTreeWorld's operator== (:927-947): essential state + same touching contacts
+    if (a.m == b.m) return true;
+    if (!a.m || !b.m) return false;
+    a.m->refreshBodies(); b.m->refreshBodies();
+    if (a.m->bodies.size() != b.m->bodies.size() || a.m->shapes.size() != b.m->shapes.size()) return false;
+    for (std::size_t i = 0; i < a.m->bodies.size(); ++i) if (!(a.m->bodies[i] == b.m->bodies[i])) return false;
+    for (std::size_t i = 0; i < a.m->shapes.size(); ++i) if (!(a.m->shapes[i] == b.m->shapes[i])) return false;
+    a.m->refreshContacts(); b.m->refreshContacts();
+    if (a.m->contactIds.size() != b.m->contactIds.size()) return false;
+    for (std::size_t i = 0; i < a.m->contactIds.size(); ++i) {
+        const auto ia = to_underlying(std::get<ContactID>(a.m->contactIds[i])), ib = to_underlying(std::get<ContactID>(b.m->contactIds[i]));
+        if (a.m->contactBuf[ia].IsTouching() != b.m->contactBuf[ib].IsTouching()) return false;
+    }
+    return true;
+}
+bool operator!=(const CudaWorld& a, const CudaWorld& b) { return !(a == b); }
+
+// ---- listeners
+void SetShapeDestructionListener(CudaWorld& w, ShapeFunction l) noexcept { w.m->shapeDestruction = std::move(l); }
+void SetDetachListener(CudaWorld& w, BodyShapeFunction l) noexcept { w.m->detach = std::move(l); }
+void SetJointDestructionListener(CudaWorld& w, JointFunction l) noexcept { w.m->jointDestruction = std::move(l); }
+void SetBeginContactListener(CudaWorld& w, ContactFunction l) noexcept { w.m->beginContact = std::move(l); }
+void SetEndContactListener(CudaWorld& w, ContactFunction l) noexcept { w.m->endContact = std::move(l); }
+void SetPreSolveContactListener(CudaWorld& w, ContactManifoldFunction l) noexcept { w.m->preSolve = std::move(l); }
+void SetPostSolveContactListener(CudaWorld& w, ContactImpulsesFunction l) noexcept { w.m->postSolve = std::move(l); }
+
+// ---- miscellaneous
+std::optional<pmr::StatsResource::Stats> GetResourceStats(const CudaWorld&) noexcept { return {}; }
+
+void Clear(CudaWorld& w) noexcept
+{ // Clear(AabbTreeWorld&), :949-1017 (destruction listeners are told about joints and shapes first)
+    if (!w.m || !w.m->h) return;
+    try {
+        if (w.m->shapeDestruction) for (std::size_t i = 0; i < w.m->shapes.size(); ++i) w.m->shapeDestruction(MakeId<ShapeID>(static_cast<std::uint32_t>(i)));
+    } catch (...) {}
+    pr_clear(w.m->h);
+    w.m->bodies.clear(); w.m->bodyDirty.clear(); w.m->anyBodyDirty = false; w.m->bodiesStale = false;
+    w.m->shapes.clear(); w.m->joints.clear();
+    w.m->mutated();
+}
+
+StepStats Step(CudaWorld& w, const StepConf& conf)
+{ // Step(AabbTreeWorld&, const StepConf&), :2144-2219
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    w.m->refreshBodies();       // (host values the user may still read-modify-write must be current)
+    w.m->uploadDirtyBodies();
+    const pr_step_conf c = ToConf(conf);
+    pr_step_stats st{};
+    w.m->locked = true;
+    const int rc = pr_step(w.m->h, &c, &st);
+    w.m->locked = false;
+    w.m->check(rc, "pr_step");
+    w.m->bodiesStale = true;
+    w.m->mutated();
+    return ToStats(st);
+}
+bool IsStepComplete(const CudaWorld& w) noexcept { return pr_is_step_complete(w.m->h) != 0; }
+bool GetSubStepping(const CudaWorld& w) noexcept { return pr_get_sub_stepping(w.m->h) != 0; }
+void SetSubStepping(CudaWorld& w, bool flag) noexcept { pr_set_sub_stepping(w.m->h, flag ? 1u : 0u); }
+bool IsLocked(const CudaWorld& w) noexcept { return w.m->locked; }
+void ShiftOrigin(CudaWorld& w, const Length2&)
+{
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    throw InvalidArgument(unsupportedMsg);
+}
+Interval<Positive<Length>> GetVertexRadiusInterval(const CudaWorld& w) noexcept { return w.m->conf.vertexRadius; }
+Frequency GetInvDeltaTime(const CudaWorld& w) noexcept { return Frequency{pr_get_inv_dt0(w.m->h)}; }
+
+const DynamicTree& GetTree(const CudaWorld& w) noexcept
+{ // materialised on demand from the device's fat AABBs; leaf ids replay DynamicTree's allocation
+    try {
+        if (w.m->treeStale) {
+            pr_counts n{};
+            pr_get_counts(w.m->h, &n);
+            std::vector<pr_proxy> px(std::max<std::uint32_t>(1u, n.proxies));
+            std::uint32_t k = 0;
+            pr_get_proxies(w.m->h, static_cast<std::uint32_t>(px.size()), px.data(), &k);
+            px.resize(k);
+            std::sort(px.begin(), px.end(), [](const pr_proxy& a, const pr_proxy& b) { return a.tree_id < b.tree_id; });
+            w.m->tree = DynamicTree{w.m->conf.treeCapacity};
+            for (const auto& p : px) {
+                const auto aabb = AABB{Length2{p.min_x, p.min_y}, Length2{p.max_x, p.max_y}};
+                w.m->tree.CreateLeaf(aabb, Contactable{MakeId<BodyID>(p.body), MakeId<ShapeID>(p.shape), static_cast<ChildCounter>(p.child)});
+            }
+            w.m->treeStale = false;
+        }
+    } catch (...) {}
+    return w.m->tree;
+}
+
+// ---- bodies
+BodyCounter GetBodyRange(const CudaWorld& w) noexcept { return static_cast<BodyCounter>(w.m->bodies.size()); }
+std::vector<BodyID> GetBodies(const CudaWorld& w)
+{
+    std::vector<BodyID> r; r.reserve(w.m->bodies.size());
+    for (std::size_t i = 0; i < w.m->bodies.size(); ++i) r.push_back(MakeId<BodyID>(static_cast<std::uint32_t>(i)));
+    return r;
+}
+std::vector<BodyID> GetBodiesForProxies(const CudaWorld&) { return {}; }
+
+BodyID CreateBody(CudaWorld& w, Body body)
+{ // CreateBody(AabbTreeWorld&, Body), :1019-1060
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    if (w.m->bodies.size() >= MaxBodies) throw LengthError("CreateBody: operation would exceed MaxBodies");
+    for (const auto& sid : body.GetShapes()) (void)AtId(w.m->shapes, sid, noSuchShapeMsg); // :1030 validates shape ids
+    const pr_body row = ToRow(body);
+    std::vector<std::uint32_t> sh;
+    for (const auto& sid : body.GetShapes()) sh.push_back(static_cast<std::uint32_t>(to_underlying(sid)));
+    const std::uint32_t offs[2] = {0u, static_cast<std::uint32_t>(sh.size())};
+    const std::uint32_t dummy = 0;
+    std::uint32_t first = 0;
+    w.m->check(pr_create_bodies(w.m->h, 1, &row, offs, sh.empty() ? &dummy : sh.data(), &first), "pr_create_bodies");
+    w.m->bodies.push_back(std::move(body));
+    w.m->bodyDirty.push_back(0);
+    w.m->mutated();
+    return MakeId<BodyID>(first);
+}
+Body GetBody(const CudaWorld& w, BodyID id)
+{
+    (void)AtId(w.m->bodies, id, noSuchBodyMsg);
+    w.m->refreshBodies();
+    return w.m->bodies[to_underlying(id)];
+}
+void SetBody(CudaWorld& w, BodyID id, Body value)
+{ // SetBody(AabbTreeWorld&, BodyID, Body), :2723-2795
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    auto& elem = AtId(w.m->bodies, id, noSuchBodyMsg);
+    w.m->refreshBodies();
+    if (IsDestroyed(elem)) throw WasDestroyed{id, "ID is destroyed"};
+    if (IsDestroyed(value)) throw InvalidArgument("cannot change is-destroyed value");
+    for (const auto& sid : value.GetShapes()) (void)AtId(w.m->shapes, sid, noSuchShapeMsg);
+    // what the device world cannot follow yet: changes that create/destroy proxies or contacts
+    if (GetType(elem) != GetType(value) || elem.GetShapes() != value.GetShapes() || IsEnabled(elem) != IsEnabled(value)) {
+        throw InvalidArgument(unsupportedMsg);
+    }
+    elem = std::move(value);
+    w.m->bodyDirty[to_underlying(id)] = 1;
+    w.m->anyBodyDirty = true;
+    w.m->mutated();
+}
+void Destroy(CudaWorld& w, BodyID id)
+{
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    (void)AtId(w.m->bodies, id, noSuchBodyMsg);
+    throw InvalidArgument(unsupportedMsg);
+}
+std::vector<std::pair<BodyID, JointID>> GetJoints(const CudaWorld& w, BodyID id) { (void)AtId(w.m->bodies, id, noSuchBodyMsg); return {}; }
+std::vector<std::tuple<ContactKey, ContactID>> GetContacts(const CudaWorld& w, BodyID id)
+{
+    (void)AtId(w.m->bodies, id, noSuchBodyMsg);
+    w.m->refreshContacts();
+    return w.m->bodyContacts[to_underlying(id)];
+}
+std::vector<ShapeID> GetShapes(const CudaWorld& w, BodyID id) { return AtId(w.m->bodies, id, noSuchBodyMsg).GetShapes(); }
+
+// ---- joints (the device solver runs none yet: SURVEY F8 / a15)
+JointCounter GetJointRange(const CudaWorld& w) noexcept { return static_cast<JointCounter>(w.m->joints.size()); }
+std::vector<JointID> GetJoints(const CudaWorld&) { return {}; }
+JointID CreateJoint(CudaWorld& w, Joint def)
+{
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
+    throw InvalidArgument(unsupportedMsg);
+}
+Joint GetJoint(const CudaWorld& w, JointID id) { return AtId(w.m->joints, id, noSuchJointMsg); }
+void SetJoint(CudaWorld& w, JointID id, Joint)
+{
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    (void)AtId(w.m->joints, id, noSuchJointMsg);
+    throw InvalidArgument(unsupportedMsg);
+}
+void Destroy(CudaWorld& w, JointID id)
+{
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    (void)AtId(w.m->joints, id, noSuchJointMsg);
+    throw InvalidArgument(unsupportedMsg);
+}
+
+// ---- shapes
+ShapeCounter GetShapeRange(const CudaWorld& w) noexcept { return static_cast<ShapeCounter>(w.m->shapes.size()); }
+ShapeID CreateShape(CudaWorld& w, Shape def)
+{ // CreateShape(AabbTreeWorld&, Shape), :1234-1260; every child flattens to a DistanceProxy
+    if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
+    const auto vmin = w.m->conf.vertexRadius.GetMin();
+    const auto vmax = w.m->conf.vertexRadius.GetMax();
+    const auto nChildren = GetChildCount(def);
+    pr_shape s{};
+    s.friction = static_cast<float>(Real(GetFriction(def))); s.restitution = GetRestitution(def);
+    s.density = static_cast<float>(Real(GetDensity(def)));
+    const auto f = GetFilter(def);
+    s.filter_category = f.categoryBits; s.filter_mask = f.maskBits; s.filter_group = f.groupIndex;
+    s.is_sensor = IsSensor(def) ? 1 : 0;
+    s.child_offset = 0; s.child_count = nChildren;
+    std::vector<pr_child> children; std::vector<pr_vec2> verts, normals;
+    for (ChildCounter c = 0; c < nChildren; ++c) {
+        const auto dp = GetChild(def, c);
+        const auto vr = dp.GetVertexRadius();
+        if (!(vr >= vmin)) throw InvalidArgument("CreateShape: vertex radius < min");
+        if (!(vr <= vmax)) throw InvalidArgument("CreateShape: vertex radius > max");
+        pr_child ch{};
+        ch.vertex_offset = static_cast<std::uint32_t>(verts.size()); ch.vertex_count = dp.GetVertexCount(); ch.vertex_radius = vr;
+        for (VertexCounter v = 0; v < dp.GetVertexCount(); ++v) {
+            verts.push_back(pr_vec2{GetX(dp.GetVertex(v)), GetY(dp.GetVertex(v))});
+            normals.push_back(dp.GetVertexCount() > 1 ? pr_vec2{dp.GetNormal(v).GetX(), dp.GetNormal(v).GetY()} : pr_vec2{0, 0});
+        }
+        children.push_back(ch);
+    }
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    if (w.m->shapes.size() >= MaxShapes) throw LengthError("CreateShape: operation would exceed MaxShapes");
+    std::uint32_t first = 0;
+    const pr_child noChild{}; const pr_vec2 noVert{};
+    w.m->check(pr_create_shapes(w.m->h, 1, &s, children.empty() ? &noChild : children.data(), static_cast<std::uint32_t>(children.size()),
+                                verts.empty() ? &noVert : verts.data(), normals.empty() ? &noVert : normals.data(),
+                                static_cast<std::uint32_t>(verts.size()), &first), "pr_create_shapes");
+    w.m->shapes.push_back(std::move(def));
+    return MakeId<ShapeID>(first);
+}
+Shape GetShape(const CudaWorld& w, ShapeID id) { return AtId(w.m->shapes, id, noSuchShapeMsg); }
+void SetShape(CudaWorld& w, ShapeID id, Shape def)
+{
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    (void)AtId(w.m->shapes, id, noSuchShapeMsg);
+    if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
+    throw InvalidArgument(unsupportedMsg);
+}
+void Destroy(CudaWorld& w, ShapeID id)
+{
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    (void)AtId(w.m->shapes, id, noSuchShapeMsg);
+    throw InvalidArgument(unsupportedMsg);
+}
+
+// ---- contacts
+ContactCounter GetContactRange(const CudaWorld& w) noexcept
+{
+    pr_counts n{};
+    pr_get_counts(w.m->h, &n);
+    return static_cast<ContactCounter>(n.contact_id_range);
+}
+std::vector<KeyedContactID> GetContacts(const CudaWorld& w) { w.m->refreshContacts(); return w.m->contactIds; }
+Contact GetContact(const CudaWorld& w, ContactID id)
+{
+    w.m->refreshContacts();
+    return AtId(w.m->contactBuf, id, noSuchContactMsg);
+}
+void SetContact(CudaWorld& w, ContactID id, Contact)
+{
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    w.m->refreshContacts();
+    (void)AtId(w.m->contactBuf, id, noSuchContactMsg);
+    throw InvalidArgument(unsupportedMsg);
+}
+Manifold GetManifold(const CudaWorld& w, ContactID id)
+{
+    w.m->refreshContacts();
+    return AtId(w.m->manifoldBuf, id, "no such manifold");
+}
+void SetManifold(CudaWorld& w, ContactID id, const Manifold&)
+{
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    w.m->refreshContacts();
+    (void)AtId(w.m->manifoldBuf, id, "no such manifold");
+    throw InvalidArgument(unsupportedMsg);
+}
+
+} // namespace playrho::b200

@@ -167,6 +167,11 @@ class World:
         rows = np.ascontiguousarray(rows, dtype=abi.BODY)
         self._chk(self.lib.pr_set_bodies(self.h, len(ids), abi.ptr(ids), abi.ptr(rows)))
 
+    def bodies_into(self, out, first=0):
+        """Download body rows into a caller-owned (e.g. pinned) abi.BODY array."""
+        self._chk(self.lib.pr_get_bodies(self.h, first, len(out), abi.ptr(out)))
+        return out
+
     def contacts(self):
         n = max(1, int(self.counts()["contacts"]))
         cs, ms = np.zeros(n, abi.CONTACT), np.zeros(n, abi.MANIFOLD)
