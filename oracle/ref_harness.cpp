@@ -387,6 +387,31 @@ uint32_t ref_add_revolute(void* h, uint32_t bodyA, uint32_t bodyB, float ax, flo
     REF_CATCH(PR_INVALID_ID)
 }
 
+// every joint as a pr_revolute_joint (only revolute joints exist in the scenes built through this harness)
+int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
+{
+    REF_TRY(h)
+    const auto n = static_cast<uint32_t>(GetJointRange(rw->world));
+    for (uint32_t i = 0; i < n && i < cap; ++i) {
+        const auto jc = TypeCast<RevoluteJointConf>(GetJoint(rw->world, MakeId<JointID>(i)));
+        auto& o = out[i];
+        std::memset(&o, 0, sizeof(o));
+        o.body_a = to_underlying(jc.bodyA); o.body_b = to_underlying(jc.bodyB);
+        o.collide_connected = jc.collideConnected ? 1u : 0u;
+        o.local_anchor_a = pr_vec2{GetX(jc.localAnchorA), GetY(jc.localAnchorA)};
+        o.local_anchor_b = pr_vec2{GetX(jc.localAnchorB), GetY(jc.localAnchorB)};
+        o.impulse_x = GetX(jc.impulse); o.impulse_y = GetY(jc.impulse); o.impulse_z = GetZ(jc.impulse);
+        o.angular_motor_impulse = jc.angularMotorImpulse;
+        o.reference_angle = jc.referenceAngle;
+        o.enable_limit = jc.enableLimit ? 1u : 0u; o.enable_motor = jc.enableMotor ? 1u : 0u;
+        o.lower_angle = jc.lowerAngle; o.upper_angle = jc.upperAngle;
+        o.motor_speed = jc.motorSpeed; o.max_motor_torque = jc.maxMotorTorque;
+        o.limit_state = static_cast<uint32_t>(jc.limitState);
+    }
+    return static_cast<int>(n);
+    REF_CATCH(-1)
+}
+
 int ref_set_body_velocity(void* h, uint32_t body, float vx, float vy, float w)
 {
     REF_TRY(h)

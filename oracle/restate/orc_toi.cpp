@@ -1,5 +1,5 @@
 // orc_toi.cpp -- TEST INFRASTRUCTURE ONLY (oracle restatement): GJK Distance (Distance.cpp, Simplex.cpp),
-// SeparationScenario.cpp and GetToiViaSat (TimeOfImpact.cpp). Revolute joint: still a stub.
+// SeparationScenario.cpp, GetToiViaSat (TimeOfImpact.cpp) and the revolute joint (RevoluteJointConf.cpp).
 #include <algorithm>
 #include "orc_toi.h"
 namespace orc {
@@ -332,9 +332,192 @@ ToiOut toi_via_sat(const Proxy& a, const Sweep& sA, const Proxy& b, const Sweep&
     return done(timeLo, e_maxToiIters);
 }
 
-void revolute_init_velocity(pr_revolute_joint&, RevoluteWork&, float, float, V2, Pos, Vel&, float, float, V2, Pos, Vel&, const JointSolverConf&) {}
-bool revolute_solve_velocity(pr_revolute_joint&, RevoluteWork&, float, float, Vel&, float, float, Vel&, const JointSolverConf&) { return true; }
-bool revolute_solve_position(const pr_revolute_joint&, float, float, V2, Pos&, float, float, V2, Pos&, const JointSolverConf&) { return true; }
+namespace {
+// Mat33 is three column vectors ex, ey, ez (GetX(GetY(m)) == ey.x); stored here as m[3*col + row]
+inline float m33(const float* m, int col, int row) { return m[3 * col + row]; }
+struct V3 { float x, y, z; };
+inline float dot3(V3 a, V3 b) { float r = 0.0f; r += a.x * b.x; r += a.y * b.y; r += a.z * b.z; return r; } // Math.hpp:320
+inline V3 cross3(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; } // Math.hpp:397
+inline V3 col(const float* m, int c) { return {m[3 * c], m[3 * c + 1], m[3 * c + 2]}; }
+// Solve33, Math.hpp:447-456
+inline V3 solve33(const float* m, V3 b)
+{
+    const float dp = dot3(col(m, 0), cross3(col(m, 1), col(m, 2)));
+    const float det = (dp != 0) ? (1 / dp) : dp;
+    return {det * dot3(b, cross3(col(m, 1), col(m, 2))), det * dot3(col(m, 0), cross3(b, col(m, 2))),
+            det * dot3(col(m, 0), cross3(col(m, 1), b))};
+}
+// Solve22, Math.hpp:462-474
+inline V2 solve22(const float* m, V2 b)
+{
+    const float matXX = m33(m, 0, 0), matXY = m33(m, 1, 0), matYX = m33(m, 0, 1), matYY = m33(m, 1, 1);
+    const float cp = matXX * matYY - matXY * matYX;
+    const float det = (cp != 0) ? (1 / cp) : cp;
+    return {det * (matYY * b.x - matXY * b.y), det * (matXX * b.y - matYX * b.x)};
+}
+enum { LS_INACTIVE = 0, LS_AT_LOWER = 1, LS_AT_UPPER = 2, LS_EQUAL = 3 }; // LimitState.hpp:32-45
+} // namespace
+
+// InitVelocity(RevoluteJointConf&, ...), RevoluteJointConf.cpp:127-226
+void revolute_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
+                            float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
+{
+    const float aA = posA.a, aB = posB.a;
+    const Rot qA = rot_from_angle(aA), qB = rot_from_angle(aB);
+    wk.rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    wk.rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    const float totInvI = iiA + iiB;
+    const bool fixedRotation = (totInvI == 0.0f);
+    { // GetMat33, RevoluteJointConf.cpp:35-62
+        const V2 rA = wk.rA, rB = wk.rB;
+        const float exx = imA + (square(rA.y) * iiA / 1.0f) + imB + (square(rB.y) * iiB / 1.0f);
+        const float eyx = (-rA.y * rA.x * iiA / 1.0f) + (-rB.y * rB.x * iiB / 1.0f);
+        const float ezx = (-rA.y * iiA * 1.0f / 1.0f) + (-rB.y * iiB * 1.0f / 1.0f);
+        const float eyy = imA + (square(rA.x) * iiA / 1.0f) + imB + (square(rB.x) * iiB / 1.0f);
+        const float ezy = (rA.x * iiA * 1.0f / 1.0f) + (rB.x * iiB * 1.0f / 1.0f);
+        float* m = wk.mass;
+        m[0] = exx; m[3] = eyx; m[6] = ezx;   // GetX(GetX), GetX(GetY), GetX(GetZ)
+        m[1] = m[3]; m[4] = eyy; m[7] = ezy;  // GetY(GetX) = GetX(GetY), GetY(GetY), GetY(GetZ)
+        m[2] = m[6]; m[5] = m[7]; m[8] = totInvI;
+    }
+    wk.angularMass = (totInvI > 0.0f) ? (1.0f / totInvI) : 0.0f;
+    if (!j.enable_motor || fixedRotation) j.angular_motor_impulse = 0.0f;
+    if (j.enable_limit && !fixedRotation) {
+        const float jointAngle = aB - aA - j.reference_angle;
+        if (std::fabs(j.upper_angle - j.lower_angle) < (c.angularSlop * 2)) j.limit_state = LS_EQUAL;
+        else if (jointAngle <= j.lower_angle) {
+            if (j.limit_state != LS_AT_LOWER) { j.limit_state = LS_AT_LOWER; j.impulse_z = 0; }
+        } else if (jointAngle >= j.upper_angle) {
+            if (j.limit_state != LS_AT_UPPER) { j.limit_state = LS_AT_UPPER; j.impulse_z = 0; }
+        } else { j.limit_state = LS_INACTIVE; j.impulse_z = 0; }
+    } else j.limit_state = LS_INACTIVE;
+    if (c.warmStart) {
+        j.impulse_x *= c.dtRatio; j.impulse_y *= c.dtRatio; j.impulse_z *= c.dtRatio;
+        j.angular_motor_impulse *= c.dtRatio;
+        const V2 P{j.impulse_x * 1.0f, j.impulse_y * 1.0f};
+        const float L = j.angular_motor_impulse + (j.impulse_z * 1.0f * 1.0f / (1.0f * 1.0f));
+        const float LA = cross(wk.rA, P) / 1.0f + L;
+        const float LB = cross(wk.rB, P) / 1.0f + L;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    } else {
+        j.impulse_x = j.impulse_y = j.impulse_z = 0.0f;
+        j.angular_motor_impulse = 0.0f;
+    }
+}
+
+// SolveVelocity(RevoluteJointConf&, ...), RevoluteJointConf.cpp:228-331; returns "no change"
+bool revolute_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& vA, float imB, float iiB,
+                             Vel& vB, const JointSolverConf& c)
+{
+    const Vel oldA = vA, oldB = vB;
+    Vel velA = vA, velB = vB;
+    const bool fixedRotation = (iiA + iiB == 0.0f);
+    if (j.enable_motor && (j.limit_state != LS_EQUAL) && !fixedRotation) {
+        const float impulse = -wk.angularMass * (velB.a - velA.a - j.motor_speed);
+        const float oldImpulse = j.angular_motor_impulse;
+        const float maxImpulse = c.dt * j.max_motor_torque;
+        j.angular_motor_impulse = std::clamp(j.angular_motor_impulse + impulse, -maxImpulse, maxImpulse);
+        const float incImpulse = j.angular_motor_impulse - oldImpulse;
+        velA.a -= iiA * incImpulse;
+        velB.a += iiB * incImpulse;
+    }
+    const V2 vb = velB.l + rev_perp(wk.rB) * (velB.a / 1.0f);
+    const V2 va = velA.l + rev_perp(wk.rA) * (velA.a / 1.0f);
+    const V2 vDelta = vb - va;
+    if (j.enable_limit && (j.limit_state != LS_INACTIVE) && !fixedRotation) {
+        const V3 Cdot{vDelta.x / 1.0f, vDelta.y / 1.0f, (velB.a - velA.a) / 1.0f};
+        const V3 s = solve33(wk.mass, Cdot);
+        V3 impulse{-s.x, -s.y, -s.z};
+        auto updateImpulse = [&](V3& imp) -> V3 {
+            const V2 zcol{m33(wk.mass, 2, 0), m33(wk.mass, 2, 1)};
+            const V2 rhs = -V2{vDelta.x / 1.0f, vDelta.y / 1.0f} + j.impulse_z * zcol;
+            const V2 reduced = solve22(wk.mass, rhs);
+            imp = {reduced.x, reduced.y, -j.impulse_z};
+            return {j.impulse_x + reduced.x, j.impulse_y + reduced.y, 0.0f};
+        };
+        V3 acc{j.impulse_x, j.impulse_y, j.impulse_z};
+        if (j.limit_state == LS_AT_LOWER) {
+            const float newZ = j.impulse_z + impulse.z;
+            acc = (newZ < 0) ? updateImpulse(impulse) : V3{acc.x + impulse.x, acc.y + impulse.y, acc.z + impulse.z};
+        } else if (j.limit_state == LS_AT_UPPER) {
+            const float newZ = j.impulse_z + impulse.z;
+            acc = (newZ > 0) ? updateImpulse(impulse) : V3{acc.x + impulse.x, acc.y + impulse.y, acc.z + impulse.z};
+        } else acc = {acc.x + impulse.x, acc.y + impulse.y, acc.z + impulse.z};
+        j.impulse_x = acc.x; j.impulse_y = acc.y; j.impulse_z = acc.z;
+        const V2 P{impulse.x * 1.0f, impulse.y * 1.0f};
+        const float L = impulse.z * 1.0f * 1.0f / (1.0f * 1.0f);
+        const float LA = cross(wk.rA, P) / 1.0f + L;
+        const float LB = cross(wk.rB, P) / 1.0f + L;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    } else {
+        const V2 impulse = solve22(wk.mass, -V2{vDelta.x / 1.0f, vDelta.y / 1.0f});
+        j.impulse_x += impulse.x; j.impulse_y += impulse.y;
+        const V2 P{impulse.x * 1.0f, impulse.y * 1.0f};
+        const float LA = cross(wk.rA, P) / 1.0f, LB = cross(wk.rB, P) / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    }
+    const bool changed = (velA.l != oldA.l) || (velA.a != oldA.a) || (velB.l != oldB.l) || (velB.a != oldB.a);
+    if (changed) { vA = velA; vB = velB; return false; }
+    return true;
+}
+
+// SolvePosition(const RevoluteJointConf&, ...), RevoluteJointConf.cpp:333-435
+bool revolute_solve_position(const pr_revolute_joint& j, float imA, float iiA, V2 lcA, Pos& pA, float imB, float iiB, V2 lcB,
+                             Pos& pB, const JointSolverConf& c)
+{
+    Pos posA = pA, posB = pB;
+    const bool fixedRotation = ((iiA + iiB) == 0.0f);
+    float angularError = 0.0f;
+    if (j.enable_limit && (j.limit_state != LS_INACTIVE) && !fixedRotation) {
+        const float totInvI = iiA + iiB;
+        const float angularMass = (totInvI > 0.0f) ? (1.0f / totInvI) : 0.0f; // object.angularMass as set by InitVelocity
+        const float angle = posB.a - posA.a - j.reference_angle;
+        float limitImpulse = 0.0f;
+        if (j.limit_state == LS_AT_LOWER) {
+            float C = angle - j.lower_angle;
+            angularError = -C;
+            C = std::clamp(C + c.angularSlop, -c.maxAngularCorrection, 0.0f);
+            limitImpulse = -angularMass * C;
+        } else if (j.limit_state == LS_AT_UPPER) {
+            float C = angle - j.upper_angle;
+            angularError = C;
+            C = std::clamp(C - c.angularSlop, 0.0f, c.maxAngularCorrection);
+            limitImpulse = -angularMass * C;
+        } else {
+            const float C = std::clamp(angle - j.lower_angle, -c.maxAngularCorrection, c.maxAngularCorrection);
+            limitImpulse = -angularMass * C;
+            angularError = std::fabs(C);
+        }
+        posA.a -= iiA * limitImpulse;
+        posB.a += iiB * limitImpulse;
+    }
+    float positionError = 0.0f;
+    {
+        const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+        const V2 rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+        const V2 rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+        const V2 C = (posB.l + rB) - (posA.l + rA);
+        positionError = magsq(C);
+        const float exx = imA + (iiA * square(rA.y) / 1.0f) + imB + (iiB * square(rB.y) / 1.0f);
+        const float exy = (-iiA * rA.x * rA.y / 1.0f) + (-iiB * rB.x * rB.y / 1.0f);
+        const float eyy = imA + (iiA * square(rA.x) / 1.0f) + imB + (iiB * square(rB.x) / 1.0f);
+        // Solve(Matrix22 K, C), Math.hpp:414-426, with K = {{exx, exy}, {exy, eyy}}
+        const float cp = exx * eyy - exy * exy; // Cross(get<0>(mat), get<1>(mat))
+        V2 sol{0.0f, 0.0f};
+        if (!almost_zero(cp)) {
+            const float inverse = 1 / cp;
+            sol = {(eyy * C.x - exy * C.y) * inverse, (exx * C.y - exy * C.x) * inverse};
+        }
+        const V2 P = -sol;
+        posA.l = posA.l - imA * P; posA.a -= iiA * cross(rA, P) / 1.0f;
+        posB.l = posB.l + imB * P; posB.a += iiB * cross(rB, P) / 1.0f;
+    }
+    pA = posA; pB = posB;
+    return (positionError <= square(c.linearSlop)) && (angularError <= c.angularSlop);
+}
 }
 
 #include "pr_oracle.h"

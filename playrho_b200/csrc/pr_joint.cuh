@@ -1,0 +1,246 @@
+// pr_joint.cuh -- the revolute joint on the device: InitVelocity / SolveVelocity / SolvePosition
+// of Library/source/playrho/d2/RevoluteJointConf.cpp:127-435 (GetMat33 :35-62, Solve33 / Solve22 Math.hpp:447-474),
+// one thread per joint. Joints run before the contact colours in every velocity iteration and after them in
+// every position iteration, exactly where SolveRegIslandViaGS calls them (AabbTreeWorld.cpp:1597-1644).
+// When two joints share a speedable body the host launches these kernels with ONE thread that walks the joints
+// in id order (a valid Gauss-Seidel order); otherwise one thread per joint.
+#ifndef PR_JOINT_CUH
+#define PR_JOINT_CUH
+
+namespace pr {
+
+struct V3 { float x, y, z; };
+PR_D float dot3(V3 a, V3 b) { float r = 0.0f; r += a.x * b.x; r += a.y * b.y; r += a.z * b.z; return r; }
+PR_D V3 cross3(V3 a, V3 b) { V3 r; r.x = a.y * b.z - a.z * b.y; r.y = a.z * b.x - a.x * b.z; r.z = a.x * b.y - a.y * b.x; return r; }
+PR_D V3 mcol(const float* m, int c) { V3 r; r.x = m[3 * c]; r.y = m[3 * c + 1]; r.z = m[3 * c + 2]; return r; }
+PR_D V3 solve33(const float* m, V3 b)
+{
+    const float dp = dot3(mcol(m, 0), cross3(mcol(m, 1), mcol(m, 2)));
+    const float det = (dp != 0) ? (1 / dp) : dp;
+    V3 r;
+    r.x = det * dot3(b, cross3(mcol(m, 1), mcol(m, 2)));
+    r.y = det * dot3(mcol(m, 0), cross3(b, mcol(m, 2)));
+    r.z = det * dot3(mcol(m, 0), cross3(mcol(m, 1), b));
+    return r;
+}
+PR_D float2 solve22(const float* m, float2 b)
+{
+    const float matXX = m[0], matXY = m[3], matYX = m[1], matYY = m[4];
+    const float cp = matXX * matYY - matXY * matYX;
+    const float det = (cp != 0) ? (1 / cp) : cp;
+    return v2(det * (matYY * b.x - matXY * b.y), det * (matXX * b.y - matYX * b.x));
+}
+enum { LS_INACTIVE = 0, LS_AT_LOWER = 1, LS_AT_UPPER = 2, LS_EQUAL = 3 };
+
+// the island a joint is solved with: the active island of either of its bodies (AddToIsland :1443-1466);
+// INVALID when no active island reached it or the other body is disabled
+PR_D unsigned joint_island(const DV& d, const pr_revolute_joint& j)
+{
+    const unsigned ia = d.b_island[j.body_a], ib = d.b_island[j.body_b];
+    if (ia != INVALID) return f_enabled(d.b_flags[j.body_b]) ? ia : INVALID;
+    if (ib != INVALID) return f_enabled(d.b_flags[j.body_a]) ? ib : INVALID;
+    return INVALID;
+}
+
+PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf)
+{
+    pr_revolute_joint j = d.jt[ji];
+    JointWork wk;
+    wk.island = joint_island(d, j);
+    if (wk.island == INVALID) { d.jt_work[ji] = wk; return; }
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 pA = d.s_pos[j.body_a], pB = d.s_pos[j.body_b];
+    float4 velA = d.s_vel[j.body_a], velB = d.s_vel[j.body_b];
+    const float aA = pA.z, aB = pB.z;
+    const Rot qA = rot_from_angle(aA), qB = rot_from_angle(aB);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    wk.rAx = rA.x; wk.rAy = rA.y; wk.rBx = rB.x; wk.rBy = rB.y;
+    const float totInvI = iiA + iiB;
+    const bool fixedRotation = (totInvI == 0.0f);
+    {
+        const float exx = imA + (square(rA.y) * iiA / 1.0f) + imB + (square(rB.y) * iiB / 1.0f);
+        const float eyx = (-rA.y * rA.x * iiA / 1.0f) + (-rB.y * rB.x * iiB / 1.0f);
+        const float ezx = (-rA.y * iiA * 1.0f / 1.0f) + (-rB.y * iiB * 1.0f / 1.0f);
+        const float eyy = imA + (square(rA.x) * iiA / 1.0f) + imB + (square(rB.x) * iiB / 1.0f);
+        const float ezy = (rA.x * iiA * 1.0f / 1.0f) + (rB.x * iiB * 1.0f / 1.0f);
+        float* m = wk.m;
+        m[0] = exx; m[3] = eyx; m[6] = ezx;
+        m[1] = m[3]; m[4] = eyy; m[7] = ezy;
+        m[2] = m[6]; m[5] = m[7]; m[8] = totInvI;
+    }
+    wk.angularMass = (totInvI > 0.0f) ? (1.0f / totInvI) : 0.0f;
+    if (!j.enable_motor || fixedRotation) j.angular_motor_impulse = 0.0f;
+    if (j.enable_limit && !fixedRotation) {
+        const float jointAngle = aB - aA - j.reference_angle;
+        if (fabsf(j.upper_angle - j.lower_angle) < (conf.angular_slop * 2)) j.limit_state = LS_EQUAL;
+        else if (jointAngle <= j.lower_angle) {
+            if (j.limit_state != LS_AT_LOWER) { j.limit_state = LS_AT_LOWER; j.impulse_z = 0; }
+        } else if (jointAngle >= j.upper_angle) {
+            if (j.limit_state != LS_AT_UPPER) { j.limit_state = LS_AT_UPPER; j.impulse_z = 0; }
+        } else { j.limit_state = LS_INACTIVE; j.impulse_z = 0; }
+    } else j.limit_state = LS_INACTIVE;
+    if (conf.do_warm_start) {
+        j.impulse_x *= conf.dt_ratio; j.impulse_y *= conf.dt_ratio; j.impulse_z *= conf.dt_ratio;
+        j.angular_motor_impulse *= conf.dt_ratio;
+        const float2 P = v2(j.impulse_x * 1.0f, j.impulse_y * 1.0f);
+        const float L = j.angular_motor_impulse + (j.impulse_z * 1.0f * 1.0f / (1.0f * 1.0f));
+        const float LA = cross(rA, P) / 1.0f + L;
+        const float LB = cross(rB, P) / 1.0f + L;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    } else {
+        j.impulse_x = j.impulse_y = j.impulse_z = 0.0f;
+        j.angular_motor_impulse = 0.0f;
+    }
+    d.s_vel[j.body_a] = velA; d.s_vel[j.body_b] = velB; // bodyConstraint.SetVelocity (:224-225)
+    d.jt[ji] = j;
+    d.jt_work[ji] = wk;
+}
+
+PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& conf)
+{
+    const JointWork wk = d.jt_work[ji];
+    if (wk.island == INVALID || (d.isl_state[wk.island] & ISL_VEL_DONE)) return;
+    pr_revolute_joint j = d.jt[ji];
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 oldA = d.s_vel[j.body_a], oldB = d.s_vel[j.body_b];
+    float4 velA = oldA, velB = oldB;
+    const float2 rA = v2(wk.rAx, wk.rAy), rB = v2(wk.rBx, wk.rBy);
+    const bool fixedRotation = (iiA + iiB == 0.0f);
+    if (j.enable_motor && (j.limit_state != LS_EQUAL) && !fixedRotation) {
+        const float impulse = -wk.angularMass * (velB.z - velA.z - j.motor_speed);
+        const float oldImpulse = j.angular_motor_impulse;
+        const float maxImpulse = conf.delta_time * j.max_motor_torque;
+        j.angular_motor_impulse = stdclamp(j.angular_motor_impulse + impulse, -maxImpulse, maxImpulse);
+        const float incImpulse = j.angular_motor_impulse - oldImpulse;
+        velA.z -= iiA * incImpulse;
+        velB.z += iiB * incImpulse;
+    }
+    const float2 vb = v2(velB.x, velB.y) + rev_perp(rB) * (velB.z / 1.0f);
+    const float2 va = v2(velA.x, velA.y) + rev_perp(rA) * (velA.z / 1.0f);
+    const float2 vDelta = vb - va;
+    if (j.enable_limit && (j.limit_state != LS_INACTIVE) && !fixedRotation) {
+        V3 Cdot; Cdot.x = vDelta.x / 1.0f; Cdot.y = vDelta.y / 1.0f; Cdot.z = (velB.z - velA.z) / 1.0f;
+        const V3 s = solve33(wk.m, Cdot);
+        V3 impulse; impulse.x = -s.x; impulse.y = -s.y; impulse.z = -s.z;
+        V3 acc; acc.x = j.impulse_x; acc.y = j.impulse_y; acc.z = j.impulse_z;
+        const float newZ = j.impulse_z + impulse.z;
+        const bool reduce = (j.limit_state == LS_AT_LOWER && newZ < 0) || (j.limit_state == LS_AT_UPPER && newZ > 0);
+        if (reduce) { // UpdateImpulse lambda (:277-285)
+            const float2 zcol = v2(wk.m[6], wk.m[7]);
+            const float2 rhs = -v2(vDelta.x / 1.0f, vDelta.y / 1.0f) + j.impulse_z * zcol;
+            const float2 reduced = solve22(wk.m, rhs);
+            impulse.x = reduced.x; impulse.y = reduced.y; impulse.z = -j.impulse_z;
+            acc.x = j.impulse_x + reduced.x; acc.y = j.impulse_y + reduced.y; acc.z = 0.0f;
+        } else { acc.x += impulse.x; acc.y += impulse.y; acc.z += impulse.z; }
+        j.impulse_x = acc.x; j.impulse_y = acc.y; j.impulse_z = acc.z;
+        const float2 P = v2(impulse.x * 1.0f, impulse.y * 1.0f);
+        const float L = impulse.z * 1.0f * 1.0f / (1.0f * 1.0f);
+        const float LA = cross(rA, P) / 1.0f + L;
+        const float LB = cross(rB, P) / 1.0f + L;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    } else {
+        const float2 impulse = solve22(wk.m, -v2(vDelta.x / 1.0f, vDelta.y / 1.0f));
+        j.impulse_x += impulse.x; j.impulse_y += impulse.y;
+        const float2 P = v2(impulse.x * 1.0f, impulse.y * 1.0f);
+        const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    }
+    d.jt[ji] = j;
+    const bool changed = velA.x != oldA.x || velA.y != oldA.y || velA.z != oldA.z || velB.x != oldB.x || velB.y != oldB.y || velB.z != oldB.z;
+    if (changed) {
+        d.s_vel[j.body_a] = velA; d.s_vel[j.body_b] = velB;
+        d.isl_jflag[wk.island] = 1u; // jointsOkay = false for this island this iteration (:1604-1608)
+    }
+}
+
+PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& conf)
+{
+    const JointWork wk = d.jt_work[ji];
+    if (wk.island == INVALID || (d.isl_state[wk.island] & ISL_POS_SOLVED)) return;
+    const pr_revolute_joint j = d.jt[ji];
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    float4 posA = d.s_pos[j.body_a], posB = d.s_pos[j.body_b];
+    const bool fixedRotation = ((iiA + iiB) == 0.0f);
+    float angularError = 0.0f;
+    if (j.enable_limit && (j.limit_state != LS_INACTIVE) && !fixedRotation) {
+        const float angle = posB.z - posA.z - j.reference_angle;
+        float limitImpulse = 0.0f;
+        if (j.limit_state == LS_AT_LOWER) {
+            float C = angle - j.lower_angle;
+            angularError = -C;
+            C = stdclamp(C + conf.angular_slop, -conf.max_angular_correction, 0.0f);
+            limitImpulse = -wk.angularMass * C;
+        } else if (j.limit_state == LS_AT_UPPER) {
+            float C = angle - j.upper_angle;
+            angularError = C;
+            C = stdclamp(C - conf.angular_slop, 0.0f, conf.max_angular_correction);
+            limitImpulse = -wk.angularMass * C;
+        } else {
+            const float C = stdclamp(angle - j.lower_angle, -conf.max_angular_correction, conf.max_angular_correction);
+            limitImpulse = -wk.angularMass * C;
+            angularError = fabsf(C);
+        }
+        posA.z -= iiA * limitImpulse;
+        posB.z += iiB * limitImpulse;
+    }
+    float positionError = 0.0f;
+    {
+        const Rot qA = rot_from_angle(posA.z), qB = rot_from_angle(posB.z);
+        const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+        const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+        const float2 C = (v2(posB.x, posB.y) + rB) - (v2(posA.x, posA.y) + rA);
+        positionError = magsq(C);
+        const float exx = imA + (iiA * square(rA.y) / 1.0f) + imB + (iiB * square(rB.y) / 1.0f);
+        const float exy = (-iiA * rA.x * rA.y / 1.0f) + (-iiB * rB.x * rB.y / 1.0f);
+        const float eyy = imA + (iiA * square(rA.x) / 1.0f) + imB + (iiB * square(rB.x) / 1.0f);
+        const float cp = exx * eyy - exy * exy; // Solve(Matrix22, Vector2), Math.hpp:414-426
+        float2 sol = v2(0.0f, 0.0f);
+        if (!almost_zero(cp)) {
+            const float inverse = 1 / cp;
+            sol = v2((eyy * C.x - exy * C.y) * inverse, (exx * C.y - exy * C.x) * inverse);
+        }
+        const float2 P = -sol;
+        const float2 la = v2(posA.x, posA.y) - imA * P; posA.x = la.x; posA.y = la.y; posA.z -= iiA * cross(rA, P) / 1.0f;
+        const float2 lb = v2(posB.x, posB.y) + imB * P; posB.x = lb.x; posB.y = lb.y; posB.z += iiB * cross(rB, P) / 1.0f;
+    }
+    d.s_pos[j.body_a] = posA; d.s_pos[j.body_b] = posB;
+    const bool ok = (positionError <= square(conf.linear_slop)) && (angularError <= conf.angular_slop);
+    if (!ok) d.isl_jflag[wk.island] = 1u;
+}
+
+// phase: 0 = InitVelocity, 1 = SolveVelocity, 2 = SolvePosition. serial != 0: one thread walks all joints.
+PR_KERNEL k_joints(DV d, pr_step_conf conf, unsigned nJoints, unsigned phase, unsigned serial)
+{
+    const unsigned t = PR_TID;
+    const unsigned lo = serial ? 0u : t, hi = serial ? (t == 0u ? nJoints : 0u) : (t < nJoints ? t + 1u : 0u);
+    for (unsigned ji = lo; ji < hi; ++ji) {
+        if (phase == 0u) joint_init_velocity(d, ji, conf);
+        else if (phase == 1u) joint_solve_velocity(d, ji, conf);
+        else joint_solve_position(d, ji, conf);
+    }
+}
+// islands: a joint links its two bodies (AddToIsland :1443-1466) when both can be island members
+PR_KERNEL k_isl_union_joints(DV d, unsigned nJoints)
+{
+    const unsigned i = PR_TID;
+    if (i < nJoints) {
+        const unsigned a = d.jt[i].body_a, b = d.jt[i].body_b;
+        if (d.b_island[a] != INVALID && d.b_island[b] != INVALID) uf_union(d.b_island, a, b);
+    }
+}
+// Add(JointID) wakes both bodies (AabbTreeWorld.cpp:1159-1180)
+PR_KERNEL k_joint_wake(DV d, unsigned first, unsigned n)
+{
+    const unsigned i = PR_TID;
+    if (i < n) { body_set_awake(d, d.jt[first + i].body_a); body_set_awake(d, d.jt[first + i].body_b); }
+}
+
+} // namespace pr
+#endif

@@ -540,6 +540,12 @@ PR_D void query_emit(const DV& d, unsigned q, unsigned o, unsigned capPairs)
     const unsigned fq = d.b_flags[bq], fo = d.b_flags[bo];
     if (!(f_accelerable(fq) || f_accelerable(fo))) return; // EitherIsAccelerable :474
     const unsigned sq = d.p_shape[q], so = d.p_shape[o];
+    if (d.nNcPairs) { // ShouldCollide(joints): a joint with collideConnected == false links the two bodies (:479-490)
+        const unsigned long long bk = (static_cast<unsigned long long>(bq < bo ? bq : bo) << 32) | (bq < bo ? bo : bq);
+        unsigned lo = 0u, hi = d.nNcPairs;
+        while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (d.nc_pairs[mid] < bk) lo = mid + 1u; else hi = mid; }
+        if (lo < d.nNcPairs && d.nc_pairs[lo] == bk) return;
+    }
     if (!filters_allow(d.sh_filter[sq], d.sh_group[sq], d.sh_filter[so], d.sh_group[so])) return;
     const bool qMin = tq < to;
     const unsigned long long key = (static_cast<unsigned long long>(qMin ? tq : to) << 32) | (qMin ? to : tq);
@@ -655,7 +661,7 @@ PR_KERNEL k_isl_init(DV d, unsigned nBodies, unsigned velIters, unsigned posIter
         const unsigned f = d.b_flags[i];
         d.b_island[i] = (f_enabled(f) && f_speedable(f)) ? i : INVALID;
         d.isl_state[i] = 0u; d.isl_velIters[i] = velIters; d.isl_posIters[i] = posIters;
-        d.isl_inc[i] = 0u; d.isl_maxInc[i] = 0u;
+        d.isl_inc[i] = 0u; d.isl_maxInc[i] = 0u; d.isl_jflag[i] = 0u;
         d.isl_sep[i] = float_flip(PR_INF); d.isl_minSep[i] = float_flip(PR_INF); d.isl_minUA[i] = float_flip(PR_INF);
         d.isl_nbodies[i] = 0u;
         d.b_cmask[i] = 0ull; d.b_claim[i] = ~0ull;
@@ -690,6 +696,9 @@ PR_KERNEL k_isl_flatten(DV d, unsigned nBodies)
         d.b_root[i] = r; // separate array: parent[] is still being path-halved by other threads
     }
 }
+} // namespace pr
+#include "pr_joint.cuh"
+namespace pr {
 // GetBodyConstraint's velocity (BodyConstraint.hpp:154-164): Cap(GetVelocity(body, h))
 PR_D float4 body_constraint_velocity(const DV& d, unsigned i, float4 v, unsigned f, float h, const pr_step_conf& conf)
 {
@@ -1196,9 +1205,10 @@ PR_KERNEL k_isl_vel_check(DV d, unsigned nBodies, unsigned iter, float minMoment
         if ((st & ISL_ACTIVE) && !(st & ISL_VEL_DONE)) {
             const unsigned incBits = d.isl_inc[i];
             if (incBits > d.isl_maxInc[i]) d.isl_maxInc[i] = incBits; // non-negative floats order like uints
-            if (u2f(incBits) <= minMomentum) { d.isl_state[i] = st | ISL_VEL_DONE; d.isl_velIters[i] = iter + 1u; }
+            const bool jointsOkay = d.isl_jflag[i] == 0u; // every joint's SolveVelocity left the velocities unchanged
+            if (jointsOkay && u2f(incBits) <= minMomentum) { d.isl_state[i] = st | ISL_VEL_DONE; d.isl_velIters[i] = iter + 1u; }
             else stillActive = 1u;
-            d.isl_inc[i] = 0u;
+            d.isl_inc[i] = 0u; d.isl_jflag[i] = 0u;
         }
     }
     warp_add(&d.cnt->nActiveVel, stillActive);
@@ -1337,9 +1347,10 @@ PR_KERNEL k_isl_pos_check(DV d, unsigned nBodies, unsigned iter, float minSepara
         if ((st & ISL_ACTIVE) && !(st & ISL_POS_SOLVED)) {
             const unsigned sepFlip = d.isl_sep[i];
             if (sepFlip < d.isl_minSep[i]) d.isl_minSep[i] = sepFlip;
-            if (float_unflip(sepFlip) >= minSeparation) { d.isl_state[i] = st | ISL_POS_SOLVED; d.isl_posIters[i] = iter + 1u; }
+            const bool jointsOkay = d.isl_jflag[i] == 0u;
+            if (jointsOkay && float_unflip(sepFlip) >= minSeparation) { d.isl_state[i] = st | ISL_POS_SOLVED; d.isl_posIters[i] = iter + 1u; }
             else stillActive = 1u;
-            d.isl_sep[i] = float_flip(PR_INF);
+            d.isl_sep[i] = float_flip(PR_INF); d.isl_jflag[i] = 0u;
         }
     }
     warp_add(&d.cnt->nActivePos, stillActive);

@@ -68,7 +68,7 @@ struct StageTimer { void mark(World&, int) {} void finish(World&, pr_step_profil
 #endif
 
 // ------------------------------------------------------------------ array table (alloc / grow / clone)
-enum Group { G_BODY, G_SHAPE, G_CHILD, G_VERT, G_PROXY, G_CONTACT, G_HASH, G_PAIR, G_CONS, G_ADJ, G_COUNT };
+enum Group { G_BODY, G_SHAPE, G_CHILD, G_VERT, G_PROXY, G_CONTACT, G_HASH, G_PAIR, G_CONS, G_ADJ, G_JOINT, G_COUNT };
 struct ArrDesc { void** slot; size_t elem; Group g; size_t mult; };
 static std::vector<ArrDesc> arrays(World& w)
 {
@@ -85,6 +85,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(sync_list, G_BODY), A(bp_off, G_BODY), A(bp_list, G_PROXY), A(bv_leafOf, G_PROXY),
         A(c_pos, G_CONTACT), A(c_color, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT), A(toi_list, G_CONTACT),
         A(adj_list, G_ADJ), A(toi_islBodies, G_ADJ), A(toi_islContacts, G_ADJ),
+        A(jt, G_JOINT), A(jt_work, G_JOINT), A(nc_pairs, G_JOINT), A(isl_jflag, G_BODY),
         A(sh_mat, G_SHAPE), A(sh_filter, G_SHAPE), A(sh_group, G_SHAPE),
         A(ch_radius, G_CHILD), A(ch_voff, G_CHILD), A(ch_count, G_CHILD), A(vtx, G_VERT), A(nrm, G_VERT),
         A(p_body, G_PROXY), A(p_shape, G_PROXY), A(p_child, G_PROXY), A(p_cg, G_PROXY), A(p_tree, G_PROXY), A(p_moved, G_PROXY),
@@ -107,7 +108,7 @@ static unsigned* cap_of(World& w, Group g)
     switch (g) {
     case G_BODY: return &w.capBodies; case G_SHAPE: return &w.capShapes; case G_CHILD: return &w.capChildren;
     case G_VERT: return &w.capVerts; case G_PROXY: return &w.capProxies; case G_CONTACT: return &w.capContacts;
-    case G_HASH: return &w.capHash; case G_PAIR: return &w.capPairs; case G_CONS: return &w.capCons; case G_ADJ: return &w.capAdj;
+    case G_HASH: return &w.capHash; case G_PAIR: return &w.capPairs; case G_CONS: return &w.capCons; case G_ADJ: return &w.capAdj; case G_JOINT: return &w.capJoints;
     default: return nullptr;
     }
 }
@@ -368,6 +369,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     tm.mark(w, PR_STAGE_ISLANDS);
     PR_LAUNCH(k_isl_init, N, w.stream, d, N, conf.reg_velocity_iters, conf.reg_position_iters);
     PR_LAUNCH(k_isl_union, w.nOrder, w.stream, d, w.nOrder);
+    PR_LAUNCH(k_isl_union_joints, w.nJoints, w.stream, d, w.nJoints);
     PR_LAUNCH(k_isl_flatten, N, w.stream, d, N);
     tm.mark(w, PR_STAGE_INTEGRATE);
     PR_LAUNCH(k_isl_prepare, N, w.stream, d, N, conf);
@@ -434,8 +436,11 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             if (tailCount) PR_LAUNCH(k_warm_start_serial, 1, w.stream, d, tailStart, tailCount);
         }
     }
+    const unsigned jSerial = w.jointsSerial ? 1u : 0u, jThreads = w.jointsSerial ? (w.nJoints ? 1u : 0u) : w.nJoints;
+    PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 0u, jSerial); // InitVelocity after the contacts' warm start (:1597)
     tm.mark(w, PR_STAGE_VELOCITY);
     for (unsigned it = 0; it < conf.reg_velocity_iters; ++it) {
+        PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 1u, jSerial); // joints first (:1605-1608)
         for (const auto& r : ranges) PR_LAUNCH(k_solve_velocity, r.second, w.stream, d, r.first, r.second);
         if (tailCount) PR_LAUNCH(k_solve_velocity_serial, 1, w.stream, d, tailStart, tailCount);
         PR_LAUNCH(k_isl_vel_check, N, w.stream, d, N, it, conf.reg_min_momentum);
@@ -447,6 +452,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             PR_LAUNCH(k_solve_position, r.second, w.stream, d, r.first, r.second, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
         if (tailCount)
             PR_LAUNCH(k_solve_position_serial, 1, w.stream, d, tailStart, tailCount, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
+        PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 2u, jSerial); // joints after the contacts (:1634-1637)
         PR_LAUNCH(k_isl_pos_check, N, w.stream, d, N, it, conf.reg_min_separation);
     }
     tm.mark(w, PR_STAGE_WRITEBACK);
@@ -693,7 +699,7 @@ int pr_create(const pr_world_conf* conf, pr_world** out)
         ensure(w, G_SHAPE, 64); ensure(w, G_CHILD, 64); ensure(w, G_VERT, std::max(256u, w.conf.vertex_capacity));
         ensure(w, G_PROXY, std::max(64u, w.conf.proxy_capacity));
         ensure(w, G_CONTACT, std::max(256u, w.conf.contact_capacity));
-        ensure(w, G_PAIR, 1024); ensure(w, G_CONS, 256); ensure(w, G_ADJ, 256);
+        ensure(w, G_PAIR, 1024); ensure(w, G_CONS, 256); ensure(w, G_ADJ, 256); ensure(w, G_JOINT, 16);
         ensure(w, G_HASH, next_pow2(2u * w.capContacts));
         reset_counters(w);
         sync(w);
@@ -729,13 +735,14 @@ int pr_clone(const pr_world* src, pr_world** out)
     sync(s);
     ensure(w, G_BODY, s.capBodies); ensure(w, G_SHAPE, s.capShapes); ensure(w, G_CHILD, s.capChildren); ensure(w, G_VERT, s.capVerts);
     ensure(w, G_PROXY, s.capProxies); ensure(w, G_CONTACT, s.capContacts); ensure(w, G_HASH, s.capHash);
-    ensure(w, G_PAIR, s.capPairs); ensure(w, G_CONS, s.capCons); ensure(w, G_ADJ, s.capAdj);
+    ensure(w, G_PAIR, s.capPairs); ensure(w, G_CONS, s.capCons); ensure(w, G_ADJ, s.capAdj); ensure(w, G_JOINT, s.capJoints);
     auto da = arrays(w); auto sa = arrays(s);
     for (size_t i = 0; i < da.size(); ++i) d2d(w, *da[i].slot, *sa[i].slot, da[i].elem * *cap_of(s, sa[i].g));
     d2d(w, w.d.cnt, s.d.cnt, sizeof(Counters));
     w.shapes = s.shapes; w.children = s.children; w.bodyShapes = s.bodyShapes; w.joints = s.joints;
     w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies;
     w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll;
+    w.nJoints = s.nJoints; w.jointsSerial = s.jointsSerial; w.d.nNcPairs = s.d.nNcPairs;
     w.nBodies = s.nBodies; w.nShapes = s.nShapes; w.nChildren = s.nChildren; w.nVerts = s.nVerts; w.nProxies = s.nProxies;
     w.maxTreeId = s.maxTreeId; w.debugFlags = s.debugFlags;
     w.nOrder = s.nOrder; w.nFree = s.nFree; w.poolSize = s.poolSize; w.anyBodySet = s.anyBodySet; w.hashDirty = true;
@@ -753,6 +760,7 @@ int pr_clear(pr_world* pw)
     World& w = pw->w;
     w.shapes.clear(); w.children.clear(); w.bodyShapes.clear(); w.joints.clear(); w.fixturesForProxies.clear();
     w.bodyProxies.clear(); w.bpDirty = true; w.bvhValid = false; w.hashTombs = 0; w.toiAlphaDirty = true;
+    w.nJoints = 0; w.jointsSerial = false; w.d.nNcPairs = 0;
     w.nBodies = w.nShapes = w.nChildren = w.nVerts = w.nProxies = w.nOrder = w.nFree = w.poolSize = 0; w.maxTreeId = 0;
     w.anyBodySet = false; w.hashDirty = true; w.adjValid = false; w.stepComplete = true;
     reset_counters(w);
@@ -829,11 +837,36 @@ int pr_create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const uint
     API_CATCH(pw)
 }
 
-int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*, uint32_t*)
-{
+int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint* joints, uint32_t* first_id)
+{ // CreateJoint (:1132-1157) + Add(JointID) (:1159-1180) for RevoluteJointConf values
+    API_TRY(pw)
+    World& w = pw->w;
     if (n == 0) return PR_OK;
-    pw->w.error = "revolute joints: device solver support lands with the joint milestone";
-    return PR_ERR_UNSUPPORTED;
+    for (uint32_t i = 0; i < n; ++i)
+        if (joints[i].body_a >= w.nBodies || joints[i].body_b >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    w.joints.insert(w.joints.end(), joints, joints + n);
+    ensure(w, G_JOINT, w.nJoints + n + 1);
+    h2d(w, w.d.jt + w.nJoints, joints, sizeof(pr_revolute_joint) * n);
+    // joints that share a body cannot be solved by concurrent threads: fall back to one thread in id order
+    std::unordered_map<unsigned, unsigned> uses;
+    std::vector<unsigned long long> nc;
+    for (const auto& j : w.joints) {
+        ++uses[j.body_a]; ++uses[j.body_b];
+        if (!j.collide_connected) nc.push_back((static_cast<unsigned long long>(std::min(j.body_a, j.body_b)) << 32) | std::max(j.body_a, j.body_b));
+    }
+    w.jointsSerial = false;
+    for (const auto& u : uses) if (u.second > 1u) w.jointsSerial = true;
+    std::sort(nc.begin(), nc.end());
+    nc.erase(std::unique(nc.begin(), nc.end()), nc.end());
+    ensure(w, G_JOINT, static_cast<unsigned>(std::max<size_t>(nc.size(), w.nJoints + n) + 1));
+    h2d(w, w.d.nc_pairs, nc.data(), sizeof(unsigned long long) * nc.size());
+    w.d.nNcPairs = static_cast<unsigned>(nc.size());
+    PR_LAUNCH(k_joint_wake, n, w.stream, w.d, w.nJoints, n);
+    sync(w);
+    if (first_id) *first_id = w.nJoints;
+    w.nJoints += n;
+    return PR_OK;
+    API_CATCH(pw)
 }
 
 int pr_set_bodies(pr_world* pw, uint32_t n, const uint32_t* ids, const pr_body* rows)
@@ -866,14 +899,23 @@ int pr_get_bodies(const pr_world* cpw, uint32_t first, uint32_t n, pr_body* rows
     API_CATCH(pw)
 }
 
-int pr_get_revolute_joints(const pr_world*, uint32_t, uint32_t n, pr_revolute_joint*) { return n ? PR_ERR_UNSUPPORTED : PR_OK; }
+int pr_get_revolute_joints(const pr_world* cpw, uint32_t first, uint32_t n, pr_revolute_joint* rows)
+{
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    if (first + n > w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
+    d2h(w, rows, w.d.jt + first, sizeof(pr_revolute_joint) * n);
+    return PR_OK;
+    API_CATCH(pw)
+}
 
 int pr_get_counts(const pr_world* pw, pr_counts* out)
 {
     const World& w = pw->w;
     std::memset(out, 0, sizeof(*out));
     out->bodies = w.nBodies; out->shapes = w.nShapes; out->children = w.nChildren; out->vertices = w.nVerts;
-    out->proxies = w.nProxies; out->contacts = w.nOrder; out->joints = 0; out->contact_id_range = w.poolSize;
+    out->proxies = w.nProxies; out->contacts = w.nOrder; out->joints = w.nJoints; out->contact_id_range = w.poolSize;
     out->tree_leaf_count = w.nProxies;
     // DynamicTree capacity: DefaultTreeCapacity 4096 grown to the next power of two of the node count (DynamicTree.cpp:436-454)
     const unsigned nodes = w.nProxies ? 2u * w.nProxies - 1u : 0u;

@@ -49,6 +49,9 @@ struct PCRow {
     float totalRadius; unsigned typeCount; unsigned pad0, pad1;
 };
 
+// per-step work data of a revolute joint (RevoluteJointConf's rA, rB, mass, angularMass) + its island label
+struct JointWork { float rAx, rAy, rBx, rBy; float m[9]; float angularMass; unsigned island; unsigned pad; };
+
 struct Counters {
     unsigned long long toiMinKey; // (toi bits << 32 | position in m_contacts) of the soonest contact, GetSoonestContact
     unsigned toiEvents, toiScratchTop, toiAtMaxSub, toiUpdated, toiMaxDistIters, toiMaxToiIters, toiMaxRootIters;
@@ -67,6 +70,8 @@ struct DV {
     float4 *b_xf, *b_pos0, *b_pos1, *b_vel, *b_acc, *b_mass; float2* b_lc; unsigned* b_flags;
     float4 *s_vel, *s_pos;
     unsigned *b_island, *b_root, *b_moved, *b_sync;
+    pr_revolute_joint* jt; JointWork* jt_work; unsigned* isl_jflag; // revolute joints (a15)
+    unsigned long long* nc_pairs; unsigned nNcPairs;               // body pairs joined by a collideConnected=false joint
     unsigned *isl_state, *isl_velIters, *isl_posIters, *isl_inc, *isl_maxInc, *isl_sep, *isl_minSep, *isl_minUA, *isl_nbodies;
     unsigned long long *b_claim, *b_cmask;
     // shapes / children / vertices
@@ -128,7 +133,8 @@ struct World {
     float inv_dt0 = 0;
     // capacities
     unsigned capBodies = 0, capShapes = 0, capChildren = 0, capVerts = 0, capProxies = 0, capContacts = 0,
-             capPairs = 0, capCons = 0, capHash = 0, capAdj = 0;
+             capPairs = 0, capCons = 0, capHash = 0, capAdj = 0, capJoints = 0;
+    unsigned nJoints = 0; bool jointsSerial = false;
     DV d{};
     RadixScratch rs;
     unsigned* scanScratch = nullptr; size_t scanScratchCap = 0;

@@ -462,7 +462,17 @@ void Destroy(CudaWorld& w, BodyID id)
     (void)AtId(w.m->bodies, id, noSuchBodyMsg);
     throw InvalidArgument(unsupportedMsg);
 }
-std::vector<std::pair<BodyID, JointID>> GetJoints(const CudaWorld& w, BodyID id) { (void)AtId(w.m->bodies, id, noSuchBodyMsg); return {}; }
+std::vector<std::pair<BodyID, JointID>> GetJoints(const CudaWorld& w, BodyID id)
+{ // m_bodyJoints: (other body, joint) pairs
+    (void)AtId(w.m->bodies, id, noSuchBodyMsg);
+    std::vector<std::pair<BodyID, JointID>> r;
+    for (std::size_t i = 0; i < w.m->joints.size(); ++i) {
+        const auto a = GetBodyA(w.m->joints[i]), b = GetBodyB(w.m->joints[i]);
+        if (a == id) r.emplace_back(b, MakeId<JointID>(static_cast<std::uint32_t>(i)));
+        else if (b == id) r.emplace_back(a, MakeId<JointID>(static_cast<std::uint32_t>(i)));
+    }
+    return r;
+}
 std::vector<std::tuple<ContactKey, ContactID>> GetContacts(const CudaWorld& w, BodyID id)
 {
     (void)AtId(w.m->bodies, id, noSuchBodyMsg);
@@ -471,16 +481,52 @@ std::vector<std::tuple<ContactKey, ContactID>> GetContacts(const CudaWorld& w, B
 }
 std::vector<ShapeID> GetShapes(const CudaWorld& w, BodyID id) { return AtId(w.m->bodies, id, noSuchBodyMsg).GetShapes(); }
 
-// ---- joints (the device solver runs none yet: SURVEY F8 / a15)
+// ---- joints: the device solver runs RevoluteJointConf; other joint types are rejected
 JointCounter GetJointRange(const CudaWorld& w) noexcept { return static_cast<JointCounter>(w.m->joints.size()); }
-std::vector<JointID> GetJoints(const CudaWorld&) { return {}; }
-JointID CreateJoint(CudaWorld& w, Joint def)
+std::vector<JointID> GetJoints(const CudaWorld& w)
 {
-    if (w.m->locked) throw WrongState(worldIsLockedMsg);
-    if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
-    throw InvalidArgument(unsupportedMsg);
+    std::vector<JointID> r;
+    for (std::size_t i = 0; i < w.m->joints.size(); ++i) r.push_back(MakeId<JointID>(static_cast<std::uint32_t>(i)));
+    return r;
 }
-Joint GetJoint(const CudaWorld& w, JointID id) { return AtId(w.m->joints, id, noSuchJointMsg); }
+JointID CreateJoint(CudaWorld& w, Joint def)
+{ // CreateJoint(AabbTreeWorld&, Joint), :1132-1157
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    if (w.m->joints.size() >= MaxJoints) throw LengthError("CreateJoint: operation would exceed MaxJoints");
+    if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
+    if (GetType(def) != GetTypeID<RevoluteJointConf>()) throw InvalidArgument(unsupportedMsg);
+    const auto jc = TypeCast<RevoluteJointConf>(def);
+    (void)AtId(w.m->bodies, jc.bodyA, noSuchBodyMsg); (void)AtId(w.m->bodies, jc.bodyB, noSuchBodyMsg);
+    pr_revolute_joint o{};
+    o.body_a = static_cast<std::uint32_t>(to_underlying(jc.bodyA)); o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.collide_connected = jc.collideConnected ? 1u : 0u;
+    o.local_anchor_a = pr_vec2{GetX(jc.localAnchorA), GetY(jc.localAnchorA)};
+    o.local_anchor_b = pr_vec2{GetX(jc.localAnchorB), GetY(jc.localAnchorB)};
+    o.impulse_x = GetX(jc.impulse); o.impulse_y = GetY(jc.impulse); o.impulse_z = GetZ(jc.impulse);
+    o.angular_motor_impulse = jc.angularMotorImpulse; o.reference_angle = jc.referenceAngle;
+    o.enable_limit = jc.enableLimit ? 1u : 0u; o.enable_motor = jc.enableMotor ? 1u : 0u;
+    o.lower_angle = jc.lowerAngle; o.upper_angle = jc.upperAngle;
+    o.motor_speed = jc.motorSpeed; o.max_motor_torque = jc.maxMotorTorque;
+    o.limit_state = static_cast<std::uint32_t>(jc.limitState);
+    w.m->refreshBodies();       // Add(JointID) wakes both bodies on the device: keep the host values in step
+    w.m->uploadDirtyBodies();
+    std::uint32_t first = 0;
+    w.m->check(pr_create_revolute_joints(w.m->h, 1, &o, &first), "pr_create_revolute_joints");
+    w.m->joints.push_back(std::move(def));
+    w.m->bodiesStale = true;
+    return MakeId<JointID>(first);
+}
+Joint GetJoint(const CudaWorld& w, JointID id)
+{ // the solver-written fields (impulses, limit state) come back from the device
+    auto& elem = AtId(w.m->joints, id, noSuchJointMsg);
+    pr_revolute_joint r{};
+    w.m->check(pr_get_revolute_joints(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), 1, &r), "pr_get_revolute_joints");
+    auto jc = TypeCast<RevoluteJointConf>(elem);
+    jc.impulse = Vec3{r.impulse_x, r.impulse_y, r.impulse_z};
+    jc.angularMotorImpulse = r.angular_motor_impulse;
+    jc.limitState = static_cast<LimitState>(r.limit_state);
+    return Joint{jc};
+}
 void SetJoint(CudaWorld& w, JointID id, Joint)
 {
     if (w.m->locked) throw WrongState(worldIsLockedMsg);

@@ -167,6 +167,13 @@ class World:
         rows = np.ascontiguousarray(rows, dtype=abi.BODY)
         self._chk(self.lib.pr_set_bodies(self.h, len(ids), abi.ptr(ids), abi.ptr(rows)))
 
+    def joints(self):
+        n = int(self.counts()["joints"])
+        out = np.zeros(max(1, n), abi.REVOLUTE)
+        if n:
+            self._chk(self.lib.pr_get_revolute_joints(self.h, 0, n, abi.ptr(out)))
+        return out[:n]
+
     def bodies_into(self, out, first=0):
         """Download body rows into a caller-owned (e.g. pinned) abi.BODY array."""
         self._chk(self.lib.pr_get_bodies(self.h, first, len(out), abi.ptr(out)))

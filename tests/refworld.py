@@ -51,6 +51,7 @@ def _ref_lib(ids32=False):
         lib.ref_add_body.argtypes = [vp, i32] + [f32] * 11 + [C.c_uint, vp, u32]
         lib.ref_add_revolute.restype = u32
         lib.ref_add_revolute.argtypes = [vp, u32, u32, f32, f32, i32, f32, f32, i32]
+        lib.ref_export_revolute_joints.argtypes = [vp, vp, u32]
         lib.ref_set_body_velocity.argtypes = [vp, u32, f32, f32, f32]
         lib.ref_set_body_transform.argtypes = [vp, u32, f32, f32, f32]
         lib.ref_step.argtypes = [vp, vp, vp]
@@ -209,7 +210,12 @@ class RefWorld:
         k = self.lib.ref_export_body_shapes(self.h, abi.ptr(offs), abi.ptr(ids), cap)
         assert 0 <= k <= cap
         return dict(shapes=shapes, children=children, verts=verts[:n["vertices"]], normals=normals[:n["vertices"]],
-                    bodies=bodies, shape_offsets=offs, shape_ids=ids[:k])
+                    bodies=bodies, shape_offsets=offs, shape_ids=ids[:k], joints=self.joints())
+
+    def joints(self):
+        out = np.zeros(64, abi.REVOLUTE)
+        k = self.lib.ref_export_revolute_joints(self.h, abi.ptr(out), len(out))
+        return out[:max(0, k)].copy()
 
     def bodies(self):
         n = self.counts()
@@ -293,6 +299,12 @@ class OracleWorld:
         k = C.c_uint32(0)
         self.lib.orc_get_proxies(self.h, n, abi.ptr(out), C.byref(k))
         return out[:k.value]
+
+    def joints(self):
+        n = int(self.counts()["joints"])
+        out = np.zeros(max(1, n), abi.REVOLUTE)
+        self.lib.orc_get_revolute_joints(self.h, 0, n, abi.ptr(out))
+        return out[:n]
 
     def load_state(self, bodies, proxies, contacts, manifolds, inv_dt0):
         r = self.lib.orc_load_state(self.h, len(bodies), abi.ptr(bodies), len(proxies), abi.ptr(proxies),

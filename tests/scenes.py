@@ -135,6 +135,7 @@ def shooter(n=60, seed=4, ids32=False, sensor=True):
 
 SCENES = {
     "shooter": shooter,
+    "tumbler": lambda **k: tumbler(40, **k),
     "hello": hello_world,
     "pyramid5": lambda **k: pyramid(5, **k),
     "pyramid10": lambda **k: pyramid(10, **k),

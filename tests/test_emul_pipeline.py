@@ -63,6 +63,29 @@ def test_emulated_device_pipeline_shooter_toi_bit_exact():
 
 @need_oracle
 @need_emul
+@need_ref
+def test_emulated_tumbler_revolute_joint_bit_exact():
+    """Config 5 unit on the device pipeline: motorised revolute joint + enclosure + squares, default StepConf."""
+    import scenes
+    sc = scenes.tumbler(40).export_scene()
+    conf = refworld.default_step_conf()
+    gw = W.World(sc, lib=emul_lib(), record_solve_order=True)
+    gw.set_toi_mode(0)
+    orc = refworld.OracleWorld(sc)
+    for s in range(150):
+        gs = gw.step(conf)
+        os_ = orc.step(conf, order=gw.solve_order()[0])
+        gsa, osa = np.array([gs]), np.array([os_])
+        gsa["reg"]["max_island_bodies"] = osa["reg"]["max_island_bodies"]
+        assert refworld.bits_equal(gsa, osa), "step %d stats: %s" % (s, refworld.diff_fields(gsa, osa))
+        assert refworld.bits_equal(gw.bodies(), orc.bodies()), "step %d bodies: %s" % (s, refworld.diff_fields(gw.bodies(), orc.bodies()))
+        assert refworld.bits_equal(gw.joints(), orc.joints()), "step %d joints: %s" % (s, refworld.diff_fields(gw.joints(), orc.joints()))
+        gc, gm = gw.contacts(); oc, om = orc.contacts()
+        assert refworld.bits_equal(gc, oc) and refworld.bits_equal(gm, om), "step %d contacts" % s
+
+
+@need_oracle
+@need_emul
 def test_set_bodies_moves_proxies_and_flags_contacts():
     sc = scenes_np.disks_box(16, seed=3)
     lib = emul_lib()

@@ -67,6 +67,33 @@ def test_cuda_shooter_toi_bit_exact_vs_oracle():
     assert events > 300
 
 
+@need_oracle
+@need_ref
+def test_cuda_tumbler_revolute_joint_bit_exact_vs_oracle():
+    """Config 5 unit (Benchmark/BenchmarkMain.cpp:2614-2722): motorised revolute joint (RevoluteJointConf.cpp
+    :127-435) on a 4-box enclosure with 120 squares, default StepConf; joint impulses / limit state included."""
+    import scenes
+    sc = scenes.tumbler(120).export_scene()
+    conf = refworld.default_step_conf()
+    gw = W.World(sc, device=0, record_solve_order=True)
+    gw.set_toi_mode(0)
+    orc = refworld.OracleWorld(sc)
+    for s in range(300):
+        gs = gw.step(conf)
+        os_ = orc.step(conf, order=gw.solve_order()[0])
+        if s % 5 and s != 299:
+            continue
+        gsa, osa = np.array([gs]), np.array([os_])
+        gsa["reg"]["max_island_bodies"] = osa["reg"]["max_island_bodies"]
+        assert_bits(gsa, osa, "step %d stats" % s)
+        assert_bits(gw.bodies(), orc.bodies(), "step %d bodies" % s)
+        assert_bits(gw.joints(), orc.joints(), "step %d joints" % s)
+        gc, gm = gw.contacts(); oc, om = orc.contacts()
+        assert_bits(gc, oc, "step %d contacts" % s)
+        assert_bits(gm, om, "step %d manifolds" % s)
+    assert abs(float(gw.joints()[0]["angular_motor_impulse"])) > 0
+
+
 @need_ref
 def test_cuda_toi_batch_bit_exact_vs_reference():
     """GetToiViaSat (TimeOfImpact.cpp:35) on 200k random child pairs and sweeps vs the real reference."""

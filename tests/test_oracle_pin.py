@@ -64,6 +64,27 @@ def test_restatement_bit_exact_vs_reference_with_toi(name, steps):
 
 @need_ref
 @need_oracle
+def test_restatement_tumbler_revolute_joint_bit_exact_vs_reference():
+    """Config 5 unit: motorised revolute joint (RevoluteJointConf.cpp:127-435) driving a 4-box enclosure full of
+    squares, default StepConf (TOI on): bodies, contacts, manifolds, stats and the joint's solver-written
+    fields (impulse, motor impulse, limit state) bit for bit over 200 steps."""
+    ref = scenes.tumbler(40)
+    orc = refworld.OracleWorld(ref.export_scene())
+    conf = refworld.default_step_conf()
+    for s in range(200):
+        rs, os_ = ref.step(conf), orc.step(conf)
+        assert_bits(np.array([rs]), np.array([os_]), "tumbler step %d stats" % s)
+        assert_bits(ref.bodies(), orc.bodies(), "tumbler step %d bodies" % s)
+        rc, rm = ref.contacts()
+        oc, om = orc.contacts()
+        assert_bits(rc, oc, "tumbler step %d contacts" % s)
+        assert_bits(rm, om, "tumbler step %d manifolds" % s)
+        assert_bits(ref.joints(), orc.joints(), "tumbler step %d joints" % s)
+    assert len(rc) > 20
+
+
+@need_ref
+@need_oracle
 def test_restatement_reproduces_golden_helloworld():
     """The restatement itself (default StepConf, TOI on) prints HelloWorld/ExpectedOutput.txt."""
     orc = refworld.OracleWorld(scenes.hello_world().export_scene())
