@@ -1084,9 +1084,43 @@ PR_KERNEL k_warm_start(DV d, unsigned start, unsigned count)
     const unsigned t = PR_TID;
     if (t < count) warm_start_row(d, start + t);
 }
-PR_KERNEL k_warm_start_serial(DV d, unsigned start, unsigned count)
+// ---- colour-overflow tail (constraints that found no free colour < 64, e.g. the 65th+ contact of one body):
+// the tail is sorted by island label and solved by ONE THREAD PER ISLAND SEGMENT in list order -- a valid
+// Gauss-Seidel order inside each island, islands in parallel.
+PR_KERNEL k_tail_keys(DV d, unsigned tailStart, unsigned tailCount, unsigned* keys, unsigned* vals)
 {
-    if (PR_TID == 0u) for (unsigned t = 0; t < count; ++t) warm_start_row(d, start + t);
+    const unsigned t = PR_TID;
+    if (t < tailCount) {
+        const unsigned k = d.k_sorted[tailStart + t];
+        const uint4 ab = d.c_ab[d.k_contact[k]];
+        const unsigned ia = d.b_island[ab.x];
+        keys[t] = (ia != INVALID) ? ia : d.b_island[ab.y];
+        vals[t] = k;
+    }
+}
+PR_KERNEL k_tail_segments(DV d, unsigned tailStart, unsigned tailCount, const unsigned* keys, const unsigned* vals)
+{
+    const unsigned t = PR_TID;
+    bool head = false;
+    if (t < tailCount) {
+        d.k_sorted[tailStart + t] = vals[t];
+        head = (t == 0u) || (keys[t] != keys[t - 1u]);
+    }
+    const unsigned slot = warp_append(&d.cnt->nTailSegs, head);
+    if (head) d.k_ulist[slot] = t;
+}
+template <class F> PR_D void tail_for_each_row(const DV& d, unsigned tailStart, unsigned tailCount, unsigned nSegs, F&& fn)
+{
+    const unsigned s = PR_TID;
+    if (s < nSegs) {
+        unsigned t = d.k_ulist[s];
+        const unsigned label = d.vc_island[tailStart + t];
+        for (; t < tailCount && d.vc_island[tailStart + t] == label; ++t) fn(tailStart + t);
+    }
+}
+PR_KERNEL k_warm_start_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs)
+{
+    tail_for_each_row(d, tailStart, tailCount, nSegs, [&](unsigned row) { warm_start_row(d, row); });
 }
 
 // GaussSeidel::SolveVelocityConstraint (ContactSolver.cpp:481): tangent (:395) then normal
@@ -1185,15 +1219,13 @@ PR_KERNEL k_solve_velocity(DV d, unsigned start, unsigned count)
     if (t < count) { inc = solve_velocity_row(d, start + t, did); label = d.vc_island[start + t]; }
     island_max(d.isl_inc, label, f2u(inc), did);
 }
-PR_KERNEL k_solve_velocity_serial(DV d, unsigned start, unsigned count)
+PR_KERNEL k_solve_velocity_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs)
 {
-    if (PR_TID == 0u) {
-        for (unsigned t = 0; t < count; ++t) {
-            bool did = false;
-            const float inc = solve_velocity_row(d, start + t, did);
-            if (did) atomicMax(&d.isl_inc[d.vc_island[start + t]], f2u(inc));
-        }
-    }
+    tail_for_each_row(d, tailStart, tailCount, nSegs, [&](unsigned row) {
+        bool did = false;
+        const float inc = solve_velocity_row(d, row, did);
+        if (did) atomicMax(&d.isl_inc[d.vc_island[row]], f2u(inc));
+    });
 }
 // per-island early exit of velocity iterations (AabbTreeWorld.cpp:1603-1622)
 PR_KERNEL k_isl_vel_check(DV d, unsigned nBodies, unsigned iter, float minMomentum)
@@ -1328,15 +1360,13 @@ PR_KERNEL k_solve_position(DV d, unsigned start, unsigned count, float rate, flo
     if (t < count) { sep = solve_position_row(d, start + t, rate, slop, maxCorr, did); label = d.vc_island[start + t]; }
     island_min(d.isl_sep, label, float_flip(sep), did);
 }
-PR_KERNEL k_solve_position_serial(DV d, unsigned start, unsigned count, float rate, float slop, float maxCorr)
+PR_KERNEL k_solve_position_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs, float rate, float slop, float maxCorr)
 {
-    if (PR_TID == 0u) {
-        for (unsigned t = 0; t < count; ++t) {
-            bool did = false;
-            const float sep = solve_position_row(d, start + t, rate, slop, maxCorr, did);
-            if (did) atomicMin(&d.isl_sep[d.vc_island[start + t]], float_flip(sep));
-        }
-    }
+    tail_for_each_row(d, tailStart, tailCount, nSegs, [&](unsigned row) {
+        bool did = false;
+        const float sep = solve_position_row(d, row, rate, slop, maxCorr, did);
+        if (did) atomicMin(&d.isl_sep[d.vc_island[row]], float_flip(sep));
+    });
 }
 PR_KERNEL k_isl_pos_check(DV d, unsigned nBodies, unsigned iter, float minSeparation)
 { // AabbTreeWorld.cpp:1628-1644

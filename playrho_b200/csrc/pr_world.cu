@@ -386,7 +386,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     }
     w.nCons = nCons; w.nColors = 0;
     std::vector<std::pair<unsigned, unsigned>> ranges; // (start, count) per colour, overflow tail last
-    unsigned tailStart = 0, tailCount = 0;
+    unsigned tailStart = 0, tailCount = 0, nTailSegs = 0;
     if (nCons) {
         const unsigned nWork = w.hostCnt.nColorWork;
         w.recolorAll = false;
@@ -411,13 +411,6 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         write_counters(w);
         PR_LAUNCH(k_color_starts, nCons, w.stream, d, nCons, sortedColor);
         read_counters(w);
-        if (w.debugFlags & 1u) { // solve order for the parity oracle (pr_get_solve_order)
-            w.solveOrderIds.resize(nCons); w.solveOrderColors.resize(nCons);
-            // c_tmp (marks, consumed) and c_tmp2 (stale ping-pong copy of c_order) are free scratch here
-            PR_LAUNCH(k_solve_order, nCons, w.stream, d, nCons, d.c_tmp, d.c_tmp2, sortedColor);
-            d2h(w, w.solveOrderIds.data(), d.c_tmp, nCons * sizeof(unsigned));
-            d2h(w, w.solveOrderColors.data(), d.c_tmp2, nCons * sizeof(unsigned));
-        }
         unsigned prevStart = nCons;
         for (int c = static_cast<int>(MAX_COLORS) - 1; c >= 0; --c) {
             const unsigned s = w.hostCnt.colorStart[c];
@@ -427,13 +420,31 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             prevStart = s;
         }
         std::reverse(ranges.begin(), ranges.end());
+        if (tailCount) { // group the overflow tail by island: one thread per island segment solves it in list order
+            // (k_tmpKey / k_tmpKey2 hold the sorted colours only up to here; c_tmp / c_tmp2 are free scratch)
+            ensure(w, G_PAIR, tailCount);
+            PR_LAUNCH(k_tail_keys, tailCount, w.stream, d, tailStart, tailCount, d.c_tmp, d.c_tmp2);
+            const bool tb = radix_sort_pairs<unsigned>(d.c_tmp, d.c_tmp2, d.np_idx, d.np_idx2, tailCount, 0, key_bits(std::max(1u, N)), false, w.rs, w.stream);
+            w.hostCnt.nTailSegs = 0; write_counters(w);
+            PR_LAUNCH(k_tail_segments, tailCount, w.stream, d, tailStart, tailCount, tb ? d.np_idx : d.c_tmp, tb ? d.np_idx2 : d.c_tmp2);
+            read_counters(w);
+            nTailSegs = w.hostCnt.nTailSegs;
+        }
+        if (w.debugFlags & 1u) { // solve order for the parity oracle (pr_get_solve_order)
+            w.solveOrderIds.resize(nCons); w.solveOrderColors.resize(nCons);
+            // c_tmp (marks, consumed) and c_tmp2 (stale ping-pong copy of c_order) are free scratch here
+            PR_LAUNCH(k_solve_order, nCons, w.stream, d, nCons, d.c_tmp, d.c_tmp2, sortedColor);
+            d2h(w, w.solveOrderIds.data(), d.c_tmp, nCons * sizeof(unsigned));
+            d2h(w, w.solveOrderColors.data(), d.c_tmp2, nCons * sizeof(unsigned));
+        }
         w.nColors = static_cast<unsigned>(ranges.size()) + (tailCount ? 1u : 0u);
-        if (w.nColors > 40u) w.recolorAll = true; // persistent colours fragmented: colour from scratch next step
+        if (nWork == nCons) w.colorsAtFull = w.nColors; // (this step coloured everything from scratch)
+        else if (w.nColors > 24u && w.nColors > w.colorsAtFull + 8u) w.recolorAll = true; // persistent colours fragmented
         tm.mark(w, PR_STAGE_SETUP);
         PR_LAUNCH(k_build_constraints, nCons, w.stream, d, nCons, conf, conf.do_warm_start ? conf.dt_ratio : 0.0f);
         if (conf.do_warm_start) {
             for (const auto& r : ranges) PR_LAUNCH(k_warm_start, r.second, w.stream, d, r.first, r.second);
-            if (tailCount) PR_LAUNCH(k_warm_start_serial, 1, w.stream, d, tailStart, tailCount);
+            if (tailCount) PR_LAUNCH(k_warm_start_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
         }
     }
     const unsigned jSerial = w.jointsSerial ? 1u : 0u, jThreads = w.jointsSerial ? (w.nJoints ? 1u : 0u) : w.nJoints;
@@ -442,7 +453,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     for (unsigned it = 0; it < conf.reg_velocity_iters; ++it) {
         PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 1u, jSerial); // joints first (:1605-1608)
         for (const auto& r : ranges) PR_LAUNCH(k_solve_velocity, r.second, w.stream, d, r.first, r.second);
-        if (tailCount) PR_LAUNCH(k_solve_velocity_serial, 1, w.stream, d, tailStart, tailCount);
+        if (tailCount) PR_LAUNCH(k_solve_velocity_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
         PR_LAUNCH(k_isl_vel_check, N, w.stream, d, N, it, conf.reg_min_momentum);
     }
     tm.mark(w, PR_STAGE_POSITION);
@@ -451,7 +462,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         for (const auto& r : ranges)
             PR_LAUNCH(k_solve_position, r.second, w.stream, d, r.first, r.second, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
         if (tailCount)
-            PR_LAUNCH(k_solve_position_serial, 1, w.stream, d, tailStart, tailCount, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
+            PR_LAUNCH(k_solve_position_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
         PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 2u, jSerial); // joints after the contacts (:1634-1637)
         PR_LAUNCH(k_isl_pos_check, N, w.stream, d, N, it, conf.reg_min_separation);
     }

@@ -56,7 +56,7 @@ struct Counters {
     unsigned long long toiMinKey; // (toi bits << 32 | position in m_contacts) of the soonest contact, GetSoonestContact
     unsigned toiEvents, toiScratchTop, toiAtMaxSub, toiUpdated, toiMaxDistIters, toiMaxToiIters, toiMaxRootIters;
     unsigned toiMinSepFlip, toiMaxIncBits, toiIslandsSolved, toiSumPosIters, toiSumVelIters, toiIslandsFound;
-    unsigned toiUpdTouching, toiSkipTouching, toiListN, syncN, adjOverflow, toiDeferred, recolorFlag, toiPad;
+    unsigned toiUpdTouching, toiSkipTouching, toiListN, syncN, adjOverflow, toiDeferred, recolorFlag, nTailSegs;
     unsigned nQueue, nPairs, nNew, nDestroyed, nUncolored, nConstraints, nDirty, nColorWork;
     unsigned islandsFound, islandsSolved, bodiesSlept, sumVelIters, sumPosIters, maxIslandBodies;
     unsigned proxiesMoved, contactsUpdated, nAwake, nTouching, nActiveVel, nActivePos;
@@ -124,7 +124,7 @@ struct World {
     unsigned nOrder = 0, nFree = 0, poolSize = 0;  // contacts
     unsigned nCons = 0, nColors = 0, maxTreeId = 0, debugFlags = 0;
     bool anyBodySet = false, hashDirty = true, stepComplete = true;
-    bool recolorAll = true;
+    bool recolorAll = true; unsigned colorsAtFull = 0;
     bool subStepping = false, adjValid = false, bvhValid = false, bpDirty = true, toiAlphaDirty = true;
     unsigned bvhLeaves = 0, bvhRefits = 0, hashTombs = 0, toiListBound = 0;
     const unsigned* bvhSortedIdx = nullptr;
