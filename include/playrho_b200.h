@@ -274,12 +274,24 @@ int pr_toi_batch(int device, uint32_t n, const pr_child* children, uint32_t n_ch
                  const float* sweep_b, const pr_step_conf* conf, float* out_time, int32_t* out_state,
                  uint32_t* out_iters);
 
-/* ---- batched independent worlds (config 5; no reference API, additive: SURVEY §8(b)) ---- */
+/* ---- batched independent worlds (BASELINE config 5; no reference API, additive: SURVEY §8(b),(e)) ----
+ * n_worlds worlds that share nothing (World.hpp:652-656) live in ONE device arena: bodies carry a world
+ * index, the broadphase never pairs proxies of different worlds, and one pr_batch_step is one
+ * Step(world, conf) of every world -- each kernel launch is n_worlds wide. World w's bodies behave bit for
+ * bit like the same bodies in a reference world whose shapes carry a per-world collision Filter.
+ * pr_batch_arena() is an ordinary pr_world handle: create shapes (shared by all worlds) and joints on it,
+ * read bodies/contacts/joints back from it; body ids are arena-wide. Bodies are created with
+ * pr_batch_create_bodies (pr_create_bodies on the arena is PR_ERR_INVALID_ARGUMENT). Statistics returned by
+ * pr_batch_step are sums (min/max for the two float fields) over all worlds. */
 typedef struct pr_batch pr_batch;
 int pr_batch_create(const pr_world_conf* conf, uint32_t n_worlds, pr_batch** out);
 int pr_batch_destroy(pr_batch* b);
-pr_world* pr_batch_world(pr_batch* b, uint32_t i);      /* borrow world i for population */
+pr_world* pr_batch_arena(pr_batch* b);
+uint32_t pr_batch_world_count(const pr_batch* b);
+int pr_batch_create_bodies(pr_batch* b, uint32_t n, const pr_body* bodies, const uint32_t* world_index,
+                           const uint32_t* shape_offsets, const uint32_t* shape_ids, uint32_t* first_id);
 int pr_batch_step(pr_batch* b, const pr_step_conf* conf, pr_step_stats* stats_sum_out);
+int pr_batch_get_body_worlds(const pr_batch* b, uint32_t first, uint32_t n, uint32_t* world_index);
 
 #ifdef __cplusplus
 }

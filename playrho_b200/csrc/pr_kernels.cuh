@@ -413,7 +413,10 @@ PR_KERNEL k_bvh_morton(DV d, unsigned nProxies)
         const float sx = (x1 > x0) ? 65535.0f / (x1 - x0) : 0.0f, sy = (y1 > y0) ? 65535.0f / (y1 - y0) : 0.0f;
         const unsigned qx = static_cast<unsigned>(fminf(fmaxf((cx - x0) * sx, 0.0f), 65535.0f));
         const unsigned qy = static_cast<unsigned>(fminf(fmaxf((cy - y0) * sy, 0.0f), 65535.0f));
-        d.bv_code[i] = expand_bits16(qx) | (expand_bits16(qy) << 1);
+        unsigned code = expand_bits16(qx) | (expand_bits16(qy) << 1);
+        // batch arena: the world index is the key's prefix, so every world is its own subtree
+        if (d.nWorlds) code = (d.b_world[d.p_body[i]] << (32u - d.worldBits)) | (code >> d.worldBits);
+        d.bv_code[i] = code;
         d.bv_idx[i] = i;
     }
 }
@@ -452,6 +455,7 @@ PR_KERNEL k_bvh_build(DV d, unsigned nLeaves, const unsigned* codes)
         if (left & LEAF_BIT) d.bv_lparent[left & ~LEAF_BIT] = i; else d.bv_parent[left] = i;
         if (right & LEAF_BIT) d.bv_lparent[right & ~LEAF_BIT] = i; else d.bv_parent[right] = i;
         d.bv_visit[i] = 0u;
+        if (d.nWorlds) d.bv_wr[i] = make_uint2(codes[lo] >> (32u - d.worldBits), codes[hi] >> (32u - d.worldBits));
         if (i == 0) d.bv_parent[0] = INVALID;
     }
 }
@@ -535,6 +539,7 @@ PR_D void query_emit(const DV& d, unsigned q, unsigned o, unsigned capPairs)
     if (o == q) return;
     const unsigned bq = d.p_body[q], bo = d.p_body[o];
     if (bq == bo) return;
+    if (d.nWorlds && d.b_world[bq] != d.b_world[bo]) return; // batch arena: worlds share coordinates, never pairs
     const unsigned tq = d.p_tree[q], to = d.p_tree[o];
     if (d.p_moved[o] && to < tq) return; // both queued: the smaller tree id emits (unique, like sort+unique :746-749)
     const unsigned fq = d.b_flags[bq], fo = d.b_flags[bo];
@@ -554,6 +559,12 @@ PR_D void query_emit(const DV& d, unsigned q, unsigned o, unsigned capPairs)
     if (slot < capPairs) { d.np_key[slot] = key; d.np_px[slot] = qMin ? make_uint2(q, o) : make_uint2(o, q); }
     else atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_PAIR_OVERFLOW));
 }
+PR_D bool node_has_world(const DV& d, unsigned node, unsigned world)
+{ // batch arena: does internal node `node` cover leaves of world `world`? (always true for a plain world)
+    if (!d.nWorlds) return true;
+    const uint2 wr = d.bv_wr[node];
+    return world >= wr.x && world <= wr.y;
+}
 // FindContacts (AabbTreeWorld.cpp:709-751): one thread per QUEUED proxy walks the LBVH
 // mortonOrder != 0 (used right after a full rebuild, when most proxies are queued): thread t takes the t-th
 // leaf in Morton order if it is queued, so that the lanes of a warp walk neighbouring parts of the tree.
@@ -565,6 +576,7 @@ PR_KERNEL k_bvh_query(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* s
     else if (t < nQueue) q = d.q_list[t];
     if (q != INVALID) {
         const Box qb = box_from4(d.p_fat[q]);
+        const unsigned qw = d.nWorlds ? d.b_world[d.p_body[q]] : 0u;
         if (nLeaves == 1u) {
             // single leaf: nothing to pair with
         } else {
@@ -579,7 +591,7 @@ PR_KERNEL k_bvh_query(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* s
                     if (ch[c] & LEAF_BIT) {
                         const unsigned o = sortedIdx[ch[c] & ~LEAF_BIT];
                         if (box_overlap(qb, box_from4(d.p_fat[o]))) query_emit(d, q, o, capPairs);
-                    } else if (box_overlap(qb, box_from4(d.bv_box[ch[c]]))) {
+                    } else if (node_has_world(d, ch[c], qw) && box_overlap(qb, box_from4(d.bv_box[ch[c]]))) {
                         if (sp < 64) stack[sp++] = ch[c];
                         else atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_STACK));
                     }

@@ -82,7 +82,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(isl_inc, G_BODY), A(isl_maxInc, G_BODY), A(isl_sep, G_BODY), A(isl_minSep, G_BODY), A(isl_minUA, G_BODY),
         A(isl_nbodies, G_BODY), A(b_claim, G_BODY), A(b_cmask, G_BODY),
         A(adj_off, G_BODY), A(adj_cnt, G_BODY), A(adj_n, G_BODY), A(b_toiIsl, G_BODY), A(b_toiAlpha, G_BODY), A(b_toiStamp, G_BODY), A(b_inR, G_BODY),
-        A(sync_list, G_BODY), A(bp_off, G_BODY), A(bp_list, G_PROXY), A(bv_leafOf, G_PROXY),
+        A(sync_list, G_BODY), A(bp_off, G_BODY), A(bp_list, G_PROXY), A(bv_leafOf, G_PROXY), A(b_world, G_BODY), A(bv_wr, G_PROXY),
         A(c_pos, G_CONTACT), A(c_color, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT), A(toi_list, G_CONTACT),
         A(adj_list, G_ADJ), A(toi_islBodies, G_ADJ), A(toi_islContacts, G_ADJ),
         A(jt, G_JOINT), A(jt_work, G_JOINT), A(nc_pairs, G_JOINT), A(isl_jflag, G_BODY),
@@ -754,6 +754,7 @@ int pr_clone(const pr_world* src, pr_world** out)
     w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies;
     w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll;
     w.nJoints = s.nJoints; w.jointsSerial = s.jointsSerial; w.d.nNcPairs = s.d.nNcPairs;
+    w.d.nWorlds = s.d.nWorlds; w.d.worldBits = s.d.worldBits; w.bodyWorld = s.bodyWorld;
     w.nBodies = s.nBodies; w.nShapes = s.nShapes; w.nChildren = s.nChildren; w.nVerts = s.nVerts; w.nProxies = s.nProxies;
     w.maxTreeId = s.maxTreeId; w.debugFlags = s.debugFlags;
     w.nOrder = s.nOrder; w.nFree = s.nFree; w.poolSize = s.poolSize; w.anyBodySet = s.anyBodySet; w.hashDirty = true;
@@ -771,7 +772,7 @@ int pr_clear(pr_world* pw)
     World& w = pw->w;
     w.shapes.clear(); w.children.clear(); w.bodyShapes.clear(); w.joints.clear(); w.fixturesForProxies.clear();
     w.bodyProxies.clear(); w.bpDirty = true; w.bvhValid = false; w.hashTombs = 0; w.toiAlphaDirty = true;
-    w.nJoints = 0; w.jointsSerial = false; w.d.nNcPairs = 0;
+    w.nJoints = 0; w.jointsSerial = false; w.d.nNcPairs = 0; w.bodyWorld.clear();
     w.nBodies = w.nShapes = w.nChildren = w.nVerts = w.nProxies = w.nOrder = w.nFree = w.poolSize = 0; w.maxTreeId = 0;
     w.anyBodySet = false; w.hashDirty = true; w.adjValid = false; w.stepComplete = true;
     reset_counters(w);
@@ -822,10 +823,15 @@ int pr_create_shapes(pr_world* pw, uint32_t n, const pr_shape* shapes, const pr_
     API_CATCH(pw)
 }
 
-int pr_create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const uint32_t* shape_offsets, const uint32_t* shape_ids, uint32_t* first_id)
+static int create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const uint32_t* shape_offsets, const uint32_t* shape_ids,
+                         const uint32_t* world_index, uint32_t* first_id)
 {
     API_TRY(pw)
     World& w = pw->w;
+    if (w.d.nWorlds) { // batch arena: every body names the world it lives in
+        if (!world_index) { w.error = "batch arena: bodies are created with pr_batch_create_bodies (a world index per body)"; return PR_ERR_INVALID_ARGUMENT; }
+        for (uint32_t i = 0; i < n; ++i) if (world_index[i] >= w.d.nWorlds) { w.error = "no such world"; return PR_ERR_OUT_OF_RANGE; }
+    }
     for (uint32_t i = 0; i < n; ++i)
         for (uint32_t k = shape_offsets[i]; k < shape_offsets[i + 1]; ++k)
             if (shape_ids[k] >= w.nShapes) { w.error = "no such shape"; return PR_ERR_OUT_OF_RANGE; }
@@ -834,6 +840,7 @@ int pr_create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const uint
     h2d(w, staging, bodies, sizeof(pr_body) * n);
     PR_LAUNCH(k_put_bodies, n, w.stream, w.d, n, w.nBodies, static_cast<const unsigned*>(nullptr), staging, 0u);
     dset(w, w.d.b_moved + w.nBodies, 0, 4 * n); dset(w, w.d.b_sync + w.nBodies, 0, 4 * n);
+    if (w.d.nWorlds) { h2d(w, w.d.b_world + w.nBodies, world_index, 4 * n); w.bodyWorld.insert(w.bodyWorld.end(), world_index, world_index + n); }
     sync(w);
     dev_free(staging);
     for (uint32_t i = 0; i < n; ++i) {
@@ -848,6 +855,11 @@ int pr_create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const uint
     API_CATCH(pw)
 }
 
+int pr_create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const uint32_t* shape_offsets, const uint32_t* shape_ids, uint32_t* first_id)
+{
+    return create_bodies(pw, n, bodies, shape_offsets, shape_ids, nullptr, first_id);
+}
+
 int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint* joints, uint32_t* first_id)
 { // CreateJoint (:1132-1157) + Add(JointID) (:1159-1180) for RevoluteJointConf values
     API_TRY(pw)
@@ -855,6 +867,9 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
     if (n == 0) return PR_OK;
     for (uint32_t i = 0; i < n; ++i)
         if (joints[i].body_a >= w.nBodies || joints[i].body_b >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    if (w.d.nWorlds)
+        for (uint32_t i = 0; i < n; ++i)
+            if (w.bodyWorld[joints[i].body_a] != w.bodyWorld[joints[i].body_b]) { w.error = "joint between bodies of different worlds"; return PR_ERR_INVALID_ARGUMENT; }
     w.joints.insert(w.joints.end(), joints, joints + n);
     ensure(w, G_JOINT, w.nJoints + n + 1);
     h2d(w, w.d.jt + w.nJoints, joints, sizeof(pr_revolute_joint) * n);
@@ -1138,39 +1153,40 @@ int pr_abi_sizeof(int which)
     }
 }
 
-// batched worlds: minimal host-loop implementation (one stream per world); the one-CTA-per-world
-// kernel path is SURVEY §7 step 8.
-struct pr_batch { std::vector<pr_world*> worlds; };
+// Batched independent worlds (BASELINE config 5): all n_worlds worlds live in ONE device arena. Bodies carry their world
+// index; the index is the prefix of the LBVH sort key, so every world is its own subtree and a query never leaves
+// the queried proxy's world (k_bvh_query / query_emit). No contact ever joins two worlds, hence islands, colours, the
+// solver's per-island early exits, sleeping and TOI events are per world by construction, and one pr_step of the arena
+// is one Step of every world: each kernel launch is n_worlds wide instead of one launch train per world.
+struct pr_batch { pr_world* arena; uint32_t nWorlds; };
 int pr_batch_create(const pr_world_conf* conf, uint32_t n_worlds, pr_batch** out)
 {
+    *out = nullptr;
+    if (n_worlds == 0 || n_worlds > (1u << 20)) { g_createError = "pr_batch_create: n_worlds must be in 1..2^20"; return PR_ERR_INVALID_ARGUMENT; }
+    pr_world* a = nullptr;
+    const int rc = pr_create(conf, &a);
+    if (rc != PR_OK) return rc;
+    unsigned bits = 1; while ((1u << bits) < n_worlds) ++bits;
+    a->w.d.nWorlds = n_worlds; a->w.d.worldBits = bits;
     pr_batch* b = new pr_batch();
-    for (uint32_t i = 0; i < n_worlds; ++i) {
-        pr_world* w = nullptr;
-        const int rc = pr_create(conf, &w);
-        if (rc != PR_OK) { for (auto* x : b->worlds) pr_destroy(x); delete b; return rc; }
-        b->worlds.push_back(w);
-    }
+    b->arena = a; b->nWorlds = n_worlds;
     *out = b;
     return PR_OK;
 }
-int pr_batch_destroy(pr_batch* b) { if (b) { for (auto* x : b->worlds) pr_destroy(x); delete b; } return PR_OK; }
-pr_world* pr_batch_world(pr_batch* b, uint32_t i) { return i < b->worlds.size() ? b->worlds[i] : nullptr; }
-int pr_batch_step(pr_batch* b, const pr_step_conf* conf, pr_step_stats* sum)
+int pr_batch_destroy(pr_batch* b) { if (b) { pr_destroy(b->arena); delete b; } return PR_OK; }
+pr_world* pr_batch_arena(pr_batch* b) { return b ? b->arena : nullptr; }
+uint32_t pr_batch_world_count(const pr_batch* b) { return b ? b->nWorlds : 0u; }
+int pr_batch_create_bodies(pr_batch* b, uint32_t n, const pr_body* bodies, const uint32_t* world_index,
+                           const uint32_t* shape_offsets, const uint32_t* shape_ids, uint32_t* first_id)
 {
-    pr_step_stats acc; std::memset(&acc, 0, sizeof(acc));
-    acc.reg.min_separation = acc.toi.min_separation = std::numeric_limits<float>::infinity();
-    for (auto* w : b->worlds) {
-        pr_step_stats s;
-        const int rc = pr_step(w, conf, &s);
-        if (rc != PR_OK) return rc;
-        acc.reg.islands_found += s.reg.islands_found; acc.reg.islands_solved += s.reg.islands_solved;
-        acc.reg.contacts_added += s.reg.contacts_added; acc.reg.bodies_slept += s.reg.bodies_slept;
-        acc.reg.proxies_moved += s.reg.proxies_moved; acc.reg.sum_pos_iters += s.reg.sum_pos_iters;
-        acc.reg.sum_vel_iters += s.reg.sum_vel_iters; acc.reg.contacts_updated += s.reg.contacts_updated;
-        acc.reg.min_separation = std::min(acc.reg.min_separation, s.reg.min_separation);
-        acc.reg.max_inc_impulse = std::max(acc.reg.max_inc_impulse, s.reg.max_inc_impulse);
-    }
-    if (sum) *sum = acc;
+    return create_bodies(b->arena, n, bodies, shape_offsets, shape_ids, world_index, first_id);
+}
+int pr_batch_step(pr_batch* b, const pr_step_conf* conf, pr_step_stats* sum) { return pr_step(b->arena, conf, sum); }
+int pr_batch_get_body_worlds(const pr_batch* b, uint32_t first, uint32_t n, uint32_t* world_index)
+{
+    const World& w = b->arena->w;
+    if (first + n > w.nBodies) return PR_ERR_OUT_OF_RANGE;
+    std::memcpy(world_index, w.bodyWorld.data() + first, sizeof(uint32_t) * n);
     return PR_OK;
 }
 

@@ -101,6 +101,9 @@ struct DV {
     // bvh
     unsigned *bv_code, *bv_code2, *bv_idx, *bv_idx2, *bv_left, *bv_right, *bv_parent, *bv_lparent, *bv_visit, *bv_leafOf;
     float4* bv_box;
+    // batched independent worlds (config 5): every body carries the index of the world it lives in; the world index is
+    // the high bits of the LBVH sort key, so each internal node covers a contiguous world range [bv_wr.x, bv_wr.y]
+    unsigned* b_world; uint2* bv_wr; unsigned nWorlds, worldBits; // nWorlds == 0: a plain single world
     Counters* cnt;
 };
 
@@ -135,6 +138,7 @@ struct World {
     unsigned capBodies = 0, capShapes = 0, capChildren = 0, capVerts = 0, capProxies = 0, capContacts = 0,
              capPairs = 0, capCons = 0, capHash = 0, capAdj = 0, capJoints = 0;
     unsigned nJoints = 0; bool jointsSerial = false;
+    std::vector<unsigned> bodyWorld; // batch arena only: world index of each body
     DV d{};
     RadixScratch rs;
     unsigned* scanScratch = nullptr; size_t scanScratchCap = 0;

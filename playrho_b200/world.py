@@ -22,8 +22,8 @@ EXPORTS = [
     "pr_get_counts", "pr_get_contacts", "pr_get_proxies", "pr_load_state", "pr_step",
     "pr_get_solve_order", "pr_set_debug", "pr_get_step_profile", "pr_abi_sizeof", "pr_shift_origin",
     "pr_get_inv_dt0", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
-    "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_world",
-    "pr_batch_step",
+    "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
+    "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
 ]
 
 
@@ -64,9 +64,13 @@ def bind(lib):
     lib.pr_toi_batch.argtypes = [i32, u32, vp, u32, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.pr_batch_create.argtypes = [vp, u32, C.POINTER(vp)]
     lib.pr_batch_destroy.argtypes = [vp]
-    lib.pr_batch_world.restype = vp
-    lib.pr_batch_world.argtypes = [vp, u32]
+    lib.pr_batch_arena.restype = vp
+    lib.pr_batch_arena.argtypes = [vp]
+    lib.pr_batch_world_count.restype = u32
+    lib.pr_batch_world_count.argtypes = [vp]
+    lib.pr_batch_create_bodies.argtypes = [vp, u32, vp, vp, vp, vp, C.POINTER(u32)]
     lib.pr_batch_step.argtypes = [vp, vp, vp]
+    lib.pr_batch_get_body_worlds.argtypes = [vp, u32, u32, vp]
     return lib
 
 
@@ -228,6 +232,71 @@ class World:
         other = World.__new__(World)
         other.lib, other.h = self.lib, h
         return other
+
+
+class Batch(World):
+    """n_worlds independent worlds in one device arena (pr_batch_*, BASELINE config 5). The arena is an ordinary
+    world handle, so every World accessor works on it; body ids are arena-wide."""
+
+    def __init__(self, n_worlds, lib=None, device=-1, body_capacity=0, contact_capacity=0, proxy_capacity=0,
+                 record_solve_order=False):
+        self.lib = lib or load_library()
+        conf = abi.one(abi.WORLD_CONF)
+        self.lib.pr_world_conf_default(abi.ptr(conf))
+        conf["device"] = device
+        conf["body_capacity"] = body_capacity
+        conf["contact_capacity"] = contact_capacity
+        conf["proxy_capacity"] = proxy_capacity
+        b = vp()
+        rc = self.lib.pr_batch_create(abi.ptr(conf), n_worlds, C.byref(b))
+        if rc != 0:
+            raise PrError(rc, self.lib.pr_last_error(None).decode())
+        self.b = b
+        self.h = vp(self.lib.pr_batch_arena(b))
+        self.n_worlds = n_worlds
+        if record_solve_order:
+            self.lib.pr_set_debug(self.h, 1)
+
+    def close(self):
+        if getattr(self, "b", None):
+            self.lib.pr_batch_destroy(self.b)
+            self.b = None
+            self.h = None
+
+    def create_shapes(self, sc):
+        first = u32(0)
+        self._chk(self.lib.pr_create_shapes(self.h, len(sc["shapes"]), abi.ptr(sc["shapes"]), abi.ptr(sc["children"]),
+                                            len(sc["children"]), abi.ptr(sc["verts"]), abi.ptr(sc["normals"]),
+                                            len(sc["verts"]), C.byref(first)))
+        return first.value
+
+    def create_bodies(self, bodies, world_index, shape_offsets, shape_ids):
+        first = u32(0)
+        bodies = np.ascontiguousarray(bodies, dtype=abi.BODY)
+        world_index = np.ascontiguousarray(world_index, dtype=np.uint32)
+        shape_offsets = np.ascontiguousarray(shape_offsets, dtype=np.uint32)
+        shape_ids = np.ascontiguousarray(shape_ids, dtype=np.uint32)
+        assert len(world_index) == len(bodies) and len(shape_offsets) == len(bodies) + 1
+        self._chk(self.lib.pr_batch_create_bodies(self.b, len(bodies), abi.ptr(bodies), abi.ptr(world_index),
+                                                  abi.ptr(shape_offsets), abi.ptr(shape_ids), C.byref(first)))
+        return first.value
+
+    def create_joints(self, joints):
+        first = u32(0)
+        joints = np.ascontiguousarray(joints, dtype=abi.REVOLUTE)
+        self._chk(self.lib.pr_create_revolute_joints(self.h, len(joints), abi.ptr(joints), C.byref(first)))
+        return first.value
+
+    def step(self, conf):
+        st = abi.one(abi.STEP_STATS)
+        self._chk(self.lib.pr_batch_step(self.b, abi.ptr(conf), abi.ptr(st)))
+        return st[0]
+
+    def body_worlds(self):
+        n = int(self.counts()["bodies"])
+        out = np.zeros(max(1, n), np.uint32)
+        self._chk(self.lib.pr_batch_get_body_worlds(self.b, 0, n, abi.ptr(out)))
+        return out[:n]
 
 
 def toi_batch(children, verts, normals, a_child, sweep_a, b_child, sweep_b, conf, lib=None, device=-1):

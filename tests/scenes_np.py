@@ -286,3 +286,80 @@ def mixed_fast(n, seed=12345, tile_segments=256, tile_width=64.0, drop_height=2.
     return dict(shapes=np.concatenate([st["shapes"], shapes]), children=np.concatenate([st["children"], children]),
                 verts=np.concatenate([st["verts"], verts]), normals=np.concatenate([st["normals"], normals]),
                 bodies=np.concatenate([st["bodies"], bodies]), shape_offsets=offs, shape_ids=ids)
+
+
+def tumbler(n_squares=0, seed=12345, spread=4.0):
+    """Config 5 unit (Benchmark/BenchmarkMain.cpp:2614-2722, TumblerPlayRho): static anchor body, dynamic enclosure of
+    four 1 x 20 m boxes (density 5, sleeping not allowed) at (0,10) turned by a motorised revolute joint (0.05 pi rad/s,
+    maxMotorTorque 1e5), plus n_squares 0.25 m squares (density 1). The benchmark drops its squares one per step at
+    (0,10) (see tumbler_square_row); n_squares > 0 pre-places jittered squares for the tests."""
+    rng = np.random.RandomState(seed)
+    b = SceneBuilder()
+    g = b.body(0)
+
+    def wall(hx, hy, cx, cy):
+        return b.polygon([(cx + hx, cy - hy), (cx + hx, cy + hy), (cx - hx, cy + hy), (cx - hx, cy - hy)], density=5.0)
+    walls = [wall(0.5, 10.0, 10.0, 0.0), wall(0.5, 10.0, -10.0, 0.0), wall(10.0, 0.5, 0.0, 10.0), wall(10.0, 0.5, 0.0, -10.0)]
+    e = b.body(2, pos=(0.0, 10.0), allow_sleep=False, shapes=walls)  # (BodyConf default: no linear acceleration)
+    sq = b.box(0.125, 0.125, density=1.0)
+    for _ in range(n_squares):
+        b.body(2, pos=(rng.uniform(-spread, spread), 10.0 + rng.uniform(-spread, spread)), acc=GRAVITY, shapes=[sq])
+    sc = b.finish()
+    j = np.zeros(1, abi.REVOLUTE)
+    j["body_a"], j["body_b"] = g, e
+    j["local_anchor_a"]["x"], j["local_anchor_a"]["y"] = 0.0, 10.0
+    j["enable_motor"], j["motor_speed"], j["max_motor_torque"] = 1, np.float32(0.05 * np.pi), 1e5
+    sc["joints"] = j
+    sc["square_shape"] = sq
+    return sc
+
+
+def tumbler_step_conf(conf):
+    """TumblerPlayRho's StepConf (BenchmarkMain.cpp:2636-2657): the defaults except these two."""
+    conf["displace_multiplier"] = 4.0
+    conf["max_rotation"] = np.float32(0.5 * np.pi)
+    return conf
+
+
+def tumbler_square_row(sc):
+    """One AddSquare() body row (BenchmarkMain.cpp:2716-2722): a square at (0,10) with earthly gravity."""
+    b = SceneBuilder()
+    b.mass = [None] * sc["square_shape"] + [(0.0625 * 1.0, 0.0625 * (0.0625 + 0.0625) / 12.0, (0.0, 0.0))]
+    b.body(2, pos=(0.0, 10.0), acc=GRAVITY, shapes=[sc["square_shape"]])
+    return np.array(b.bodies, dtype=abi.BODY)
+
+
+def merge_worlds(scenes, layer_filters=False):
+    """Concatenate independent scenes into one arena scene (world-major body order). Returns (scene, world index of
+    each body). layer_filters=True gives world w's shapes the collision Filter {category = mask = 1 << w}: in a plain
+    (reference / oracle) world that is what keeps the worlds apart; the batch arena does not need it."""
+    out = dict(shapes=[], children=[], verts=[], normals=[], bodies=[], shape_ids=[], joints=[])
+    offs, world = [0], []
+    ns = nc = nv = nb = 0
+    for wi, sc in enumerate(scenes):
+        sh = sc["shapes"].copy()
+        sh["child_offset"] += nc
+        if layer_filters:
+            assert wi < 16
+            sh["filter_category"] = 1 << wi
+            sh["filter_mask"] = 1 << wi
+        ch = sc["children"].copy()
+        ch["vertex_offset"] += nv
+        out["shapes"].append(sh); out["children"].append(ch)
+        out["verts"].append(sc["verts"]); out["normals"].append(sc["normals"])
+        out["bodies"].append(sc["bodies"])
+        n_ids = int(sc["shape_offsets"][-1])
+        out["shape_ids"].append(sc["shape_ids"][:n_ids] + ns)
+        offs.extend((sc["shape_offsets"][1:].astype(np.int64) + offs[-1]).tolist())
+        if "joints" in sc and len(sc["joints"]):
+            j = sc["joints"].copy()
+            j["body_a"] += nb; j["body_b"] += nb
+            out["joints"].append(j)
+        world.extend([wi] * len(sc["bodies"]))
+        ns += len(sc["shapes"]); nc += len(sc["children"]); nv += len(sc["verts"]); nb += len(sc["bodies"])
+    merged = {k: np.concatenate(v) if len(v) else np.zeros(0, abi.REVOLUTE) for k, v in out.items()}
+    merged["shape_offsets"] = np.array(offs, dtype=np.uint32)
+    merged["shape_ids"] = merged["shape_ids"].astype(np.uint32)
+    if len(merged["shape_ids"]) == 0:
+        merged["shape_ids"] = np.zeros(1, np.uint32)
+    return merged, np.array(world, dtype=np.uint32)
