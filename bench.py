@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- measures BASELINE.json's metric for the B200-native PlayRho world.
 
-  python bench.py --gpus N --steps K --warmup W [--bodies B] [--workload mixed|disks]
+  python bench.py --gpus N --steps K --warmup W [--bodies B] [--workload mixed|disks|tumblers]
   python bench.py --impl reference ...      # the reference's own CPU Step on the host cores
 
 One "step" = one Step(world, StepConf) of the hot path (AabbTreeWorld.cpp:2144) over the synthetic
-scene named in config.workload. N=1: BASELINE config 4 shape (1M mixed polygons+disks over tiled
-chain terrain). N>1: independent worlds, one per rank (weak scaling, no data-path collective; NCCL
-only reduces step statistics). Prints ONE JSON line.
+scene named in config.workload. Default workload: BASELINE config 4 shape (1M mixed polygons+disks
+over tiled chain terrain), one such world per GPU (N>1: independent worlds, weak scaling, no data-path
+collective; NCCL only reduces step statistics). --workload tumblers: BASELINE config 5, --worlds
+(default 8192) independent 514-body tumbler worlds in one device arena per GPU, the worlds sharded
+across the N ranks (strong scaling). Prints ONE JSON line.
 """
 import argparse
 import json
@@ -32,7 +34,10 @@ def parse():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--bodies", type=int, default=1000000)
     ap.add_argument("--workload", default="mixed")
-    ap.add_argument("--settle", type=int, default=40, help="untimed steps so that bodies are in contact")
+    ap.add_argument("--settle", type=int, default=300, help="untimed steps so that the dropped bodies have piled up and are in contact")
+    ap.add_argument("--worlds", type=int, default=8192, help="tumblers: total number of independent worlds (sharded over the ranks)")
+    ap.add_argument("--squares", type=int, default=512, help="tumblers: squares added one per step per world before timing")
+    ap.add_argument("--ref-worlds", type=int, default=0, help="tumblers reference arm: worlds stepped on the host (default: one per host core)")
     ap.add_argument("--ref-bodies", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-toi", action="store_true", help="StepConf.doToi=false (default: TOI enabled as BASELINE config 4 says)")
@@ -76,6 +81,11 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_solve_velocity launch train (all colours x 8 iterations) from
+# the `ncu --set full` capture summarised under profiles/ (None until a capture of the current kernel exists)
+ROOFLINE_TRAFFIC = {}
+
+
 def algorithmic_bytes(prof, nv, np_):
     """SURVEY.md §8(d) B_step from this step's device counters (TOI term omitted while TOI is off)."""
     n_awake, p, pm = int(prof["n_awake"]), int(prof["p_total"]), int(prof["p_moved"])
@@ -105,36 +115,133 @@ def build_scene(args, seed):
     return scenes_np.mixed_fast(args.bodies, seed=seed)
 
 
+# ---------------------------------------------------------------- reference arm (CPU)
+def ref_scene(args, n):
+    import refworld
+    import scenes
+    ids32 = refworld.have_ref(True)
+    return scenes.mixed(n, ids32=ids32) if args.workload != "disks" else scenes.disks_box(n, ids32=ids32)
+
+
+def ref_tumbler_world(n_squares, conf):
+    """One TumblerPlayRho (Benchmark/BenchmarkMain.cpp:2614-2722) in the real reference: Step(); AddSquare() x n."""
+    import refworld
+    import scenes
+    w = scenes.tumbler(0)
+    sq = w.add_box(0.125, 0.125, density=1.0)
+    for _ in range(n_squares):
+        w.step(conf)
+        w.add_body(refworld.DYNAMIC, pos=(0.0, 10.0), acc=scenes.GRAVITY, shapes=[sq])
+    return w
+
+
+def time_reference_tumblers(args, steps, warmup):
+    """Reference Step on `cores` host threads, one independent tumbler world each (the reference is single-threaded
+    per world; ctypes releases the GIL inside ref_step_timed). Returns (body-steps/s, cores, bodies per world)."""
+    import refworld
+    import scenes_np
+    cores = args.ref_worlds or max(1, len(os.sched_getaffinity(0)))
+    conf = scenes_np.tumbler_step_conf(refworld.default_step_conf(do_toi=0 if args.no_toi else 1))
+    worlds = [None] * cores
+
+    def build(i):
+        worlds[i] = ref_tumbler_world(args.squares, conf)
+        worlds[i].step_timed(conf, warmup)
+    th = [threading.Thread(target=build, args=(i,)) for i in range(cores)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    secs = [0.0] * cores
+
+    def run(i):
+        secs[i] = worlds[i].step_timed(conf, steps)[0]
+    th = [threading.Thread(target=run, args=(i,)) for i in range(cores)]
+    t0 = time.perf_counter()
+    [t.start() for t in th]
+    [t.join() for t in th]
+    wall = time.perf_counter() - t0
+    nb = int(worlds[0].counts()["bodies"])
+    return cores * nb * steps / wall, cores, nb, wall
+
+
 def run_reference(args, rank, world_size):
     """--impl reference: the reference's own Step (oracle/_ref, built from /root/reference) on the host."""
     if rank != 0:
         return
     import refworld
-    import scenes
     from playrho_b200 import abi  # noqa: F401
-    n = args.ref_bodies
-    ids32 = refworld.have_ref(True)
-    if not refworld.have_ref(ids32):
+    if not refworld.have_ref(refworld.have_ref(True)):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
         return
-    ref = scenes.mixed(n, ids32=ids32) if args.workload != "disks" else scenes.disks_box(n, ids32=ids32)
-    conf = refworld.default_step_conf(do_toi=0 if args.no_toi else 1)
-    ref.step_timed(conf, args.settle)
-    ref.step_timed(conf, args.warmup)
-    secs, _ = ref.step_timed(conf, args.steps)
-    nb = int(ref.counts()["bodies"])
-    value = nb * args.steps / secs
+    if args.workload == "tumblers":
+        value, cores, nb, wall = time_reference_tumblers(args, args.steps, args.warmup)
+        ms = 1e3 * wall / args.steps
+        workload = "tumblers: %d independent %d-body tumbler worlds, one per host thread (bounded sample of the %d-world workload)" % (cores, nb, args.worlds)
+        sample = "%d worlds x %d bodies, %d steps after %d add-square steps, %d threads" % (cores, nb, args.steps, args.squares, cores)
+    else:
+        n = args.ref_bodies
+        ref = ref_scene(args, n)
+        conf = refworld.default_step_conf(do_toi=0 if args.no_toi else 1)
+        ref.step_timed(conf, args.settle)
+        ref.step_timed(conf, args.warmup)
+        secs, _ = ref.step_timed(conf, args.steps)
+        nb = int(ref.counts()["bodies"])
+        value, cores, ms = nb * args.steps / secs, 1, 1e3 * secs / args.steps
+        workload = "%s-%d (bounded sample of the %d-body workload; reference Step is O(islands x bodies), SURVEY F4)" % (args.workload, nb, args.bodies)
+        sample = "%d bodies, %d steps after %d settle steps, 1 thread (reference is single-threaded)" % (nb, args.steps, args.settle)
     line = {
         "impl": "reference", "metric": "body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s-%d (bounded sample of the %d-body workload; reference Step is O(islands x bodies), SURVEY F4)"
-                   % (args.workload, nb, args.bodies), "toi": not args.no_toi, "step_conf": "default StepConf (8 vel / 3 pos iters)"},
-        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": 1, "kind": "reference",
-                         "sample": "%d bodies, %d steps after %d settle steps, 1 thread (reference is single-threaded)" % (nb, args.steps, args.settle)},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "tumblers" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "toi": not args.no_toi, "step_conf": "default StepConf (8 vel / 3 pos iters)"},
+        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------- device worlds
+def make_mixed_world(args, W, rank, local_rank):
+    sc = build_scene(args, seed=12345 + rank)
+    nb = len(sc["bodies"])
+    gw = W.World(sc, device=local_rank, body_capacity=nb + 16, proxy_capacity=nb + 8192, contact_capacity=6 * nb)
+    conf = W.default_step_conf(do_toi=0 if args.no_toi else 1)
+    gw.set_toi_mode(args.toi_mode)
+    for _ in range(args.settle):
+        gw.step(conf)
+    desc = "%s-%d bodies per GPU (BASELINE config 4 shape: 50%% disks / 50%% 4-8-gons over tiled 256-segment chain terrain), " \
+           "state after %d settle steps (bodies piled up and in contact)" % (args.workload, nb, args.settle)
+    return gw, conf, desc, {"settle_steps": args.settle}
+
+
+def make_tumbler_arena(args, W, rank, world_size, local_rank):
+    """BASELINE config 5: this rank's share of --worlds tumbler worlds in one device arena; Step(); AddSquare() x --squares."""
+    import scenes_np
+    n_worlds = args.worlds // world_size + (1 if rank < args.worlds % world_size else 0)
+    unit = scenes_np.tumbler(0)
+    per = 2 + args.squares
+    gw = W.Batch(n_worlds, device=local_rank, body_capacity=n_worlds * per + 16, proxy_capacity=n_worlds * (4 + args.squares) + 64,
+                 contact_capacity=8 * n_worlds * args.squares)
+    gw.set_toi_mode(args.toi_mode)
+    gw.create_shapes(unit)  # the 5 shapes (4 enclosure walls + the square) are shared by every world
+    nu = len(unit["bodies"])
+    offs = np.concatenate([[0], (unit["shape_offsets"][1:][None, :] + int(unit["shape_offsets"][-1]) * np.arange(n_worlds)[:, None]).reshape(-1)])
+    n_ids = int(unit["shape_offsets"][-1])
+    gw.create_bodies(np.tile(unit["bodies"], n_worlds), np.repeat(np.arange(n_worlds), nu), offs, np.tile(unit["shape_ids"][:n_ids], n_worlds))
+    j = np.tile(unit["joints"], n_worlds)
+    j["body_a"] += (nu * np.arange(n_worlds)).astype(np.uint32)
+    j["body_b"] += (nu * np.arange(n_worlds)).astype(np.uint32)
+    gw.create_joints(j)
+    conf = scenes_np.tumbler_step_conf(W.default_step_conf(do_toi=0 if args.no_toi else 1))
+    row = scenes_np.tumbler_square_row(unit)
+    rows, wi = np.repeat(row, n_worlds), np.arange(n_worlds, dtype=np.uint32)
+    so, si = np.arange(n_worlds + 1, dtype=np.uint32), np.full(n_worlds, unit["square_shape"], np.uint32)
+    for _ in range(args.squares):
+        gw.step(conf)
+        gw.create_bodies(rows, wi, so, si)
+    desc = "tumblers: %d independent worlds (%d on this GPU, one device arena) x %d bodies (BASELINE config 5: enclosure on a " \
+           "motorised revolute joint + %d squares added one per step before timing, Benchmark/BenchmarkMain.cpp:2614-2759)" \
+           % (args.worlds, n_worlds, per, args.squares)
+    return gw, conf, desc, {"worlds": args.worlds, "worlds_per_gpu": n_worlds, "bodies_per_world": per}
 
 
 def main():
@@ -151,15 +258,16 @@ def main():
     torch.cuda.set_device(local_rank)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sc = build_scene(args, seed=12345 + rank)
-    nb = len(sc["bodies"])
-    conf = W.default_step_conf(do_toi=0 if args.no_toi else 1)
-    gw = W.World(sc, device=local_rank, body_capacity=nb + 16, proxy_capacity=nb + 8192, contact_capacity=6 * nb)
-    gw.set_toi_mode(args.toi_mode)
-    for _ in range(args.settle):
+    tumblers = args.workload == "tumblers"
+    if tumblers:
+        gw, conf, desc, extra = make_tumbler_arena(args, W, rank, world_size, local_rank)
+    else:
+        gw, conf, desc, extra = make_mixed_world(args, W, rank, local_rank)
+    nb = int(gw.counts()["bodies"])
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
         gw.step(conf)
-    for _ in range(max(3, args.warmup)):
-        gw.step(conf)
+    stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", local_rank))
 
     def barrier():
         if world_size > 1:
@@ -168,12 +276,14 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---------------- device-resident timed region: K steps, state already in HBM
+    # ---------------- device-resident timed region: K steps, state already in HBM; CUDA events on the world's stream
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if args.cuda_profiler:
         torch.cuda.profiler.start()
     t0 = time.perf_counter()
-    launches, stage_ms, vel_ms, profs = 0, np.zeros(abi.N_STAGES), 0.0, []
+    ev0.record(stream)
+    launches, stage_ms, profs = 0, np.zeros(abi.N_STAGES), []
     stats_sum = np.zeros(4, dtype=np.float64)
     for _ in range(args.steps):
         st = gw.step(conf)
@@ -182,8 +292,10 @@ def main():
         stage_ms += p["ms_stage"]
         profs.append(p.copy())
         stats_sum += [st["reg"]["islands_found"], st["reg"]["contacts_added"], st["reg"]["proxies_moved"], st["reg"]["bodies_slept"]]
+    ev1.record(stream)
     barrier()
-    secs = time.perf_counter() - t0
+    wall_secs = time.perf_counter() - t0
+    secs = ev0.elapsed_time(ev1) / 1e3
     if args.cuda_profiler:
         torch.cuda.profiler.stop()
     # ---------------- end-to-end: host buffers in, host buffers out, every step
@@ -194,24 +306,26 @@ def main():
     rows_in = pinned_in.numpy().view(abi.BODY)
     rows_out = pinned_out.numpy().view(abi.BODY)
     e2e_steps = max(2, min(args.steps, 10))
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    t1 = time.perf_counter()
+    ev2.record(stream)
     for _ in range(e2e_steps):
         gw.set_bodies(ids, rows_in)           # H2D: every body row, from pinned host memory
         gw.step(conf)
         gw.bodies_into(rows_out)              # D2H: every body row, into pinned host memory
         rows_in, rows_out = rows_out, rows_in # next step uploads what this step produced
+    ev3.record(stream)
     barrier()
-    e2e_secs = time.perf_counter() - t1
+    e2e_secs = ev2.elapsed_time(ev3) / 1e3
     sampler.stop_flag = True
     sampler.join(timeout=2)
     # ---------------- reduce over ranks (max time; stats summed over NVLink)
-    t = torch.tensor([secs, e2e_secs], device="cuda", dtype=torch.float64)
+    t = torch.tensor([secs, e2e_secs, wall_secs], device="cuda", dtype=torch.float64)
     s = torch.tensor(np.concatenate([stats_sum, [nb, launches]]), device="cuda", dtype=torch.float64)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-    secs, e2e_secs = float(t[0]), float(t[1])
+    secs, e2e_secs, wall_secs = float(t[0]), float(t[1]), float(t[2])
     total_bodies = float(s[4])
     if rank == 0:
         peak, peak_kind = peaks()
@@ -222,24 +336,28 @@ def main():
         vel_ms = float(stage_ms[5]) / args.steps
         vel_bytes = terms["a10_velocity"]
         achieved = (vel_bytes / 1e9) / (vel_ms / 1e3) if vel_ms > 0 else 0.0
+        cfg = {"workload": desc, "toi": not args.no_toi, "toi_mode": "parallel" if args.toi_mode else "serial-exact",
+               "toi_events_per_step": float(np.mean([p["toi_events"] for p in profs])), "toi_rounds_per_step": float(np.mean([p["toi_rounds"] for p in profs])),
+               "step_conf": "default StepConf (8 vel / 3 pos iters, doToi=%s)%s" % (not args.no_toi, " + TumblerPlayRho's displaceMultiplier 4, maxRotation pi/2" if tumblers else ""),
+               "l2": "working set (>1 GB) exceeds the 126 MB L2",
+               "contacts": int(last["c_total"]), "touching": int(last["c_touching"]), "colors": int(last["n_colors"]),
+               "islands": int(last["n_islands"]), "awake_bodies": int(last["n_awake"]),
+               "proxies": int(last["p_total"]), "proxies_moved": int(last["p_moved"]), "contacts_dirty": int(last["c_dirty"]),
+               "candidate_pairs": int(last["candidate_pairs"])}
+        cfg.update(extra)
         line = {
             "metric": "body_steps_per_sec", "value": total_bodies * args.steps / secs, "unit": "body-steps/s",
-            "n_gpus": world_size, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s-%d bodies per GPU (BASELINE config 4 shape: 50%% disks / 50%% 4-8-gons over tiled 256-segment chain terrain)"
-                       % (args.workload, nb), "toi": not args.no_toi, "toi_mode": "parallel" if args.toi_mode else "serial-exact",
-                       "toi_events_per_step": float(np.mean([p["toi_events"] for p in profs])), "toi_rounds_per_step": float(np.mean([p["toi_rounds"] for p in profs])),
-                       "step_conf": "default StepConf (8 vel / 3 pos iters, doToi=%s)" % (not args.no_toi),
-                       "settle_steps": args.settle, "l2": "working set (>1 GB) exceeds the 126 MB L2",
-                       "contacts": int(last["c_total"]), "touching": int(last["c_touching"]), "colors": int(last["n_colors"]),
-                       "islands": int(last["n_islands"]), "awake_bodies": int(last["n_awake"])},
+            "n_gpus": world_size, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "wall_ms_per_step": 1e3 * wall_secs / args.steps,
+            "higher_is_better": True, "scaling": "strong" if tumblers else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
             "e2e": {"value": total_bodies * e2e_steps / e2e_secs, "unit": "body-steps/s",
                     "h2d_bytes_per_step": int(nb * abi.BODY.itemsize + 4 * nb), "d2h_bytes_per_step": int(nb * abi.BODY.itemsize),
                     "ms_per_step": 1e3 * e2e_secs / e2e_steps},
             "gpu_launches": int(float(s[5])),
             "roofline": {"bound": "hbm", "kernel": "k_solve_velocity (all colours x %d iterations, incl. per-island checks)" % nv,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
-                         "traffic": None, "algorithmic_bytes_per_step": bstep,
+                         "traffic": ROOFLINE_TRAFFIC.get(args.workload), "algorithmic_bytes_per_launch_train": vel_bytes,
+                         "algorithmic_bytes_per_step": bstep,
                          "step_achieved_gbs": (bstep / 1e9) / (ms_step / 1e3), "step_frac": (bstep / 1e9) / (ms_step / 1e3) / peak},
             "stage_ms_per_step": {n: float(stage_ms[i]) / args.steps for i, n in enumerate(abi.STAGE_NAMES)},
             "clocks": sampler.summary(),
@@ -247,18 +365,20 @@ def main():
         if not args.no_cpu_baseline and world_size == 1:
             try:
                 import refworld
-                import scenes
-                ids32 = refworld.have_ref(True)
-                if refworld.have_ref(ids32):
-                    n = args.ref_bodies
-                    ref = scenes.mixed(n, ids32=ids32) if args.workload != "disks" else scenes.disks_box(n, ids32=ids32)
-                    rconf = refworld.default_step_conf(do_toi=0 if args.no_toi else 1)
-                    ref.step_timed(rconf, args.settle)
-                    rs, _ = ref.step_timed(rconf, 20)
-                    rnb = int(ref.counts()["bodies"])
-                    line["cpu_baseline"] = {"value": rnb * 20 / rs, "unit": "body-steps/s", "cores": 1, "kind": "reference",
-                                            "ms_per_step": 1e3 * rs / 20,
-                                            "sample": "reference Step, %s scene at %d bodies, 20 steps after %d settle steps, 1 thread" % (args.workload, rnb, args.settle)}
+                if refworld.have_ref(refworld.have_ref(True)):
+                    if tumblers:
+                        v, cores, rnb, wall = time_reference_tumblers(args, 20, 3)
+                        line["cpu_baseline"] = {"value": v, "unit": "body-steps/s", "cores": cores, "kind": "reference", "ms_per_step": 1e3 * wall / 20,
+                                                "sample": "reference Step, %d tumbler worlds x %d bodies (one per host thread), 20 steps after %d add-square steps" % (cores, rnb, args.squares)}
+                    else:
+                        ref = ref_scene(args, args.ref_bodies)
+                        rconf = refworld.default_step_conf(do_toi=0 if args.no_toi else 1)
+                        ref.step_timed(rconf, args.settle)
+                        rs, _ = ref.step_timed(rconf, 20)
+                        rnb = int(ref.counts()["bodies"])
+                        line["cpu_baseline"] = {"value": rnb * 20 / rs, "unit": "body-steps/s", "cores": 1, "kind": "reference",
+                                                "ms_per_step": 1e3 * rs / 20,
+                                                "sample": "reference Step, %s scene at %d bodies, 20 steps after %d settle steps, 1 thread" % (args.workload, rnb, args.settle)}
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "body-steps/s", "cores": 1, "kind": "reference", "sample": "failed: %s" % e}
         print(json.dumps(line))

@@ -256,6 +256,8 @@ int pr_set_sub_stepping(pr_world* w, uint32_t flag);    /* SetSubStepping, AabbT
 int pr_get_sub_stepping(const pr_world* w);             /* GetSubStepping */
 int pr_is_step_complete(const pr_world* w);             /* IsStepComplete */
 float pr_get_inv_dt0(const pr_world* w);                /* GetInvDeltaTime */
+/* the cudaStream_t every kernel and copy of this world is issued on (for the caller's CUDA events / ordering) */
+void* pr_get_stream(const pr_world* w);
 
 /* ---- stage entry point for known-answer tests: CollideShapes (Manifold.cpp:393) over arrays ----
  * pair i collides child a_child[i] under xf_a[i] (px,py,c,s) with child b_child[i] under xf_b[i]. */

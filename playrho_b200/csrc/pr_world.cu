@@ -1071,6 +1071,14 @@ int pr_get_step_profile(const pr_world* pw, pr_step_profile* out) { *out = pw->w
 int pr_shift_origin(pr_world* pw, float, float) { pw->w.error = "ShiftOrigin: not implemented yet"; return PR_ERR_UNSUPPORTED; }
 
 float pr_get_inv_dt0(const pr_world* pw) { return pw->w.inv_dt0; }
+void* pr_get_stream(const pr_world* pw)
+{
+#ifndef PR_HOST_EMUL
+    return reinterpret_cast<void*>(pw->w.stream);
+#else
+    return nullptr;
+#endif
+}
 
 int pr_set_toi_mode(pr_world* pw, uint32_t mode)
 {

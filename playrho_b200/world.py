@@ -21,7 +21,7 @@ EXPORTS = [
     "pr_create_revolute_joints", "pr_set_bodies", "pr_get_bodies", "pr_get_revolute_joints",
     "pr_get_counts", "pr_get_contacts", "pr_get_proxies", "pr_load_state", "pr_step",
     "pr_get_solve_order", "pr_set_debug", "pr_get_step_profile", "pr_abi_sizeof", "pr_shift_origin",
-    "pr_get_inv_dt0", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
+    "pr_get_inv_dt0", "pr_get_stream", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
     "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
 ]
@@ -56,6 +56,8 @@ def bind(lib):
     lib.pr_shift_origin.argtypes = [vp, f32, f32]
     lib.pr_get_inv_dt0.restype = f32
     lib.pr_get_inv_dt0.argtypes = [vp]
+    lib.pr_get_stream.restype = vp
+    lib.pr_get_stream.argtypes = [vp]
     lib.pr_collide_shapes.argtypes = [i32, u32, vp, u32, vp, vp, u32, vp, vp, vp, vp, f32, f32, vp]
     lib.pr_set_toi_mode.argtypes = [vp, u32]
     lib.pr_set_sub_stepping.argtypes = [vp, u32]
@@ -215,6 +217,10 @@ class World:
 
     def inv_dt0(self):
         return self.lib.pr_get_inv_dt0(self.h)
+
+    def stream(self):
+        """cudaStream_t (as an int) the world issues its work on; wrap with torch.cuda.ExternalStream for events."""
+        return self.lib.pr_get_stream(self.h) or 0
 
     def set_toi_mode(self, mode):
         """0 = serial-exact (reference event order, bit-exact), 1 = parallel independent events."""
