@@ -216,7 +216,8 @@ def make_mixed_world(args, W, rank, local_rank):
 def make_tumbler_arena(args, W, rank, world_size, local_rank):
     """BASELINE config 5: this rank's share of --worlds tumbler worlds in one device arena; Step(); AddSquare() x --squares."""
     import scenes_np
-    n_worlds = args.worlds // world_size + (1 if rank < args.worlds % world_size else 0)
+    from playrho_b200 import shard
+    _, n_worlds = shard.world_block(args.worlds, rank, world_size)  # this rank's contiguous block of worlds
     unit = scenes_np.tumbler(0)
     per = 2 + args.squares
     gw = W.Batch(n_worlds, device=local_rank, body_capacity=n_worlds * per + 16, proxy_capacity=n_worlds * (4 + args.squares) + 64,
@@ -283,7 +284,7 @@ def main():
         torch.cuda.profiler.start()
     t0 = time.perf_counter()
     ev0.record(stream)
-    launches, stage_ms, profs = 0, np.zeros(abi.N_STAGES), []
+    launches, stage_ms, profs, step_recs = 0, np.zeros(abi.N_STAGES), [], []
     stats_sum = np.zeros(4, dtype=np.float64)
     for _ in range(args.steps):
         st = gw.step(conf)
@@ -291,6 +292,7 @@ def main():
         launches += int(p["kernel_launches"])
         stage_ms += p["ms_stage"]
         profs.append(p.copy())
+        step_recs.append(st.copy())
         stats_sum += [st["reg"]["islands_found"], st["reg"]["contacts_added"], st["reg"]["proxies_moved"], st["reg"]["bodies_slept"]]
     ev1.record(stream)
     barrier()
@@ -326,6 +328,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
     secs, e2e_secs, wall_secs = float(t[0]), float(t[1]), float(t[2])
+    # the step statistics of all ranks, folded like StepStats.cpp:29-38 (the only NVLink traffic of the sharded path)
+    from playrho_b200 import shard
+    folded, _, _ = shard.reduce_step_stats(shard.fold_step_stats(step_recs), nb * args.steps, secs, device="cuda")
     total_bodies = float(s[4])
     if rank == 0:
         peak, peak_kind = peaks()
@@ -361,6 +366,11 @@ def main():
                          "step_achieved_gbs": (bstep / 1e9) / (ms_step / 1e3), "step_frac": (bstep / 1e9) / (ms_step / 1e3) / peak},
             "stage_ms_per_step": {n: float(stage_ms[i]) / args.steps for i, n in enumerate(abi.STAGE_NAMES)},
             "clocks": sampler.summary(),
+            "step_stats_all_ranks": {"islands_found": int(folded["reg"]["islands_found"]), "islands_solved": int(folded["reg"]["islands_solved"]),
+                                     "contacts_added": int(folded["reg"]["contacts_added"]) + int(folded["pre"]["contacts_added"]) + int(folded["toi"]["contacts_added"]),
+                                     "contacts_destroyed": int(folded["pre"]["contacts_destroyed"]), "bodies_slept": int(folded["reg"]["bodies_slept"]),
+                                     "toi_events": int(folded["toi"]["contacts_found"]), "min_separation": float(min(folded["reg"]["min_separation"], folded["toi"]["min_separation"])),
+                                     "max_inc_impulse": float(max(folded["reg"]["max_inc_impulse"], folded["toi"]["max_inc_impulse"]))},
         }
         if not args.no_cpu_baseline and world_size == 1:
             try:
