@@ -72,7 +72,58 @@ PR_D void island_min(unsigned* slot, unsigned label, unsigned v, bool valid)
         if ((threadIdx.x & 31) == 0) atomicMin(&slot[l0], s);
     } else if (valid) atomicMin(&slot[label], v);
 }
+// Block-aggregated counter updates: one global atomic per BLOCK (and none when it would not change the counter).
+// Every warp of a 1M-thread launch hitting the same few counter words serialises in one L2 slice (measured:
+// k_sleep_and_stats 105 us, k_isl_prepare 226 us for 1M bodies). All threads of the block must call, converged.
+PR_D void block_add(unsigned* counter, unsigned v)
+{
+    __shared__ unsigned acc;
+    if (threadIdx.x == 0) acc = 0u;
+    __syncthreads();
+    const unsigned s = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&acc, s);
+    __syncthreads();
+    if (threadIdx.x == 0 && acc) atomicAdd(counter, acc);
+    __syncthreads();
+}
+PR_D void block_max(unsigned* counter, unsigned v)
+{
+    __shared__ unsigned acc;
+    if (threadIdx.x == 0) acc = 0u;
+    __syncthreads();
+    const unsigned s = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && s) atomicMax(&acc, s);
+    __syncthreads();
+    if (threadIdx.x == 0 && acc > *reinterpret_cast<volatile unsigned*>(counter)) atomicMax(counter, acc); // (counter only grows)
+    __syncthreads();
+}
+PR_D void block_min(unsigned* counter, unsigned v)
+{
+    __shared__ unsigned acc;
+    if (threadIdx.x == 0) acc = 0xFFFFFFFFu;
+    __syncthreads();
+    const unsigned s = __reduce_min_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && s != 0xFFFFFFFFu) atomicMin(&acc, s);
+    __syncthreads();
+    if (threadIdx.x == 0 && acc < *reinterpret_cast<volatile unsigned*>(counter)) atomicMin(counter, acc); // (counter only shrinks)
+    __syncthreads();
+}
+// per-island add with the lanes of a warp that share a label combined first (a 100k-body island would otherwise
+// put 100k atomics on one word). Divergent callers allowed.
+PR_D void island_add_matched(unsigned* slot, unsigned label, unsigned v)
+{
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, label);
+    const unsigned lane = threadIdx.x & 31;
+    unsigned sum = 0u;
+    for (unsigned m = peers; m; m &= m - 1u) sum += __shfl_sync(peers, v, __ffs(m) - 1);
+    if (lane == static_cast<unsigned>(__ffs(peers) - 1)) atomicAdd(&slot[label], sum);
+}
 #else
+PR_D void block_add(unsigned* counter, unsigned v) { *counter += v; }
+PR_D void block_max(unsigned* counter, unsigned v) { if (v > *counter) *counter = v; }
+PR_D void block_min(unsigned* counter, unsigned v) { if (v < *counter) *counter = v; }
+PR_D void island_add_matched(unsigned* slot, unsigned label, unsigned v) { slot[label] += v; }
 PR_D unsigned warp_append(unsigned* counter, bool pred) { return pred ? atomicAdd(counter, 1u) : 0u; }
 PR_D unsigned active_append(unsigned* counter) { return atomicAdd(counter, 1u); }
 PR_D void warp_add(unsigned* counter, unsigned v) { *counter += v; }
@@ -379,7 +430,7 @@ PR_KERNEL k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n,
         if (useMoved) { const uint4 ab = d.c_ab[id]; dirty = dirty || (d.b_moved[ab.x] | d.b_moved[ab.y]) != 0u; }
         if (dirty) { updated = true; update_contact(d, conf, id, flags); }
     }
-    warp_add(&d.cnt->contactsUpdated, (updated && countIt) ? 1u : 0u);
+    block_add(&d.cnt->contactsUpdated, (updated && countIt) ? 1u : 0u);
 }
 
 // ------------------------------------------------------------------ a3: LBVH (Morton + Karras build + refit)
@@ -459,29 +510,37 @@ PR_KERNEL k_bvh_build(DV d, unsigned nLeaves, const unsigned* codes)
         if (i == 0) d.bv_parent[0] = INVALID;
     }
 }
-PR_D Box bvh_child_box(const DV& d, unsigned child, const unsigned* sortedIdx)
+// Node layout: internal node n keeps the boxes of its TWO CHILDREN (bv_cbox[n].l / .r) next to their links, so a
+// traversal step is ONE round of independent loads per level (links + both boxes) instead of link -> box chains;
+// a leaf child's box is a copy of its proxy's fat AABB (kept current by k_bvh_refit_moved).
+PR_D float4 ld_cg4(const float4* p)
 {
-    if (child & LEAF_BIT) return box_from4(d.p_fat[sortedIdx[child & ~LEAF_BIT]]);
 #ifndef PR_HOST_EMUL
-    return box_from4(__ldcg(&d.bv_box[child])); // written by another thread this launch: bypass L1
+    return __ldcg(p); // written by another thread of this launch: bypass L1
 #else
-    return box_from4(d.bv_box[child]);
+    return *p;
 #endif
 }
-// bottom-up refit: one thread per leaf; the second thread to arrive at a node computes its box
+// bottom-up refit: one thread per leaf carries its box upwards; at every node it stores the box into the slot of
+// the child it came from, and the second thread to arrive unions both slots and continues
 PR_KERNEL k_bvh_refit(DV d, unsigned nLeaves, const unsigned* sortedIdx)
 {
     const unsigned i = PR_TID;
     if (i < nLeaves) d.bv_leafOf[sortedIdx[i]] = i;
     if (i < nLeaves && nLeaves > 1u) {
+        float4 box = d.p_fat[sortedIdx[i]];
+        unsigned child = i | LEAF_BIT;
         unsigned node = d.bv_lparent[i];
         while (node != INVALID) {
+            const bool isLeft = d.bv_left[node] == child;
+            float4* slots = reinterpret_cast<float4*>(&d.bv_cbox[node]);
+            slots[isLeft ? 0 : 1] = box;
             __threadfence();
             const unsigned prev = atomicAdd(&d.bv_visit[node], 1u);
             if (prev == 0u) break;
-            const Box a = bvh_child_box(d, d.bv_left[node], sortedIdx), b = bvh_child_box(d, d.bv_right[node], sortedIdx);
-            Box u; u.minx = fminf(a.minx, b.minx); u.miny = fminf(a.miny, b.miny); u.maxx = fmaxf(a.maxx, b.maxx); u.maxy = fmaxf(a.maxy, b.maxy);
-            d.bv_box[node] = box_to4(u);
+            const float4 o = ld_cg4(&slots[isLeft ? 1 : 0]);
+            box = make_float4(fminf(box.x, o.x), fminf(box.y, o.y), fmaxf(box.z, o.z), fmaxf(box.w, o.w));
+            child = node;
             node = d.bv_parent[node];
         }
     }
@@ -516,13 +575,20 @@ PR_KERNEL k_bvh_refit_moved(DV d, unsigned nQueue, unsigned nLeaves)
     if (t < nQueue && nLeaves > 1u) {
         const unsigned q = d.q_list[t];
         const float4 f = d.p_fat[q];
-        unsigned node = d.bv_lparent[d.bv_leafOf[q]];
+        unsigned child = d.bv_leafOf[q] | LEAF_BIT;
+        unsigned node = d.bv_lparent[child & ~LEAF_BIT];
+        { // the leaf's own slot: an exact copy of its fat box (only this thread writes it)
+            float4* slots = reinterpret_cast<float4*>(&d.bv_cbox[node]);
+            slots[(d.bv_left[node] == child) ? 0 : 1] = f;
+            child = node; node = d.bv_parent[node];
+        }
         while (node != INVALID) {
-            float* b = reinterpret_cast<float*>(&d.bv_box[node]);
-            const float4 cur = d.bv_box[node];
+            float4* slot = reinterpret_cast<float4*>(&d.bv_cbox[node]) + ((d.bv_left[node] == child) ? 0 : 1);
+            const float4 cur = *slot;
             if (cur.x <= f.x && cur.y <= f.y && cur.z >= f.z && cur.w >= f.w) break; // already inside: so are all ancestors
+            float* b = reinterpret_cast<float*>(slot);
             atomic_min_f(b + 0, f.x); atomic_min_f(b + 1, f.y); atomic_max_f(b + 2, f.z); atomic_max_f(b + 3, f.w);
-            node = d.bv_parent[node];
+            child = node; node = d.bv_parent[node];
         }
     }
 }
@@ -565,41 +631,90 @@ PR_D bool node_has_world(const DV& d, unsigned node, unsigned world)
     const uint2 wr = d.bv_wr[node];
     return world >= wr.x && world <= wr.y;
 }
-// FindContacts (AabbTreeWorld.cpp:709-751): one thread per QUEUED proxy walks the LBVH
-// mortonOrder != 0 (used right after a full rebuild, when most proxies are queued): thread t takes the t-th
-// leaf in Morton order if it is queued, so that the lanes of a warp walk neighbouring parts of the tree.
+// FindContacts (AabbTreeWorld.cpp:709-751), dense queue: one thread per leaf in Morton order (a leaf that is not
+// queued idles), so that the lanes of a warp walk neighbouring parts of the tree. Used right after a full rebuild,
+// when most proxies are queued; also the only variant of the host-emulated test build.
 PR_KERNEL k_bvh_query(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs, unsigned mortonOrder)
 {
     const unsigned t = PR_TID;
     unsigned q = INVALID;
     if (mortonOrder) { if (t < nLeaves) { const unsigned c = sortedIdx[t]; if (d.p_moved[c]) q = c; } }
     else if (t < nQueue) q = d.q_list[t];
-    if (q != INVALID) {
+    if (q != INVALID && nLeaves > 1u) {
         const Box qb = box_from4(d.p_fat[q]);
         const unsigned qw = d.nWorlds ? d.b_world[d.p_body[q]] : 0u;
-        if (nLeaves == 1u) {
-            // single leaf: nothing to pair with
-        } else {
-            unsigned stack[64];
-            int sp = 0;
-            stack[sp++] = 0u;
-            while (sp > 0) {
-                const unsigned node = stack[--sp];
-                const unsigned ch[2] = {d.bv_left[node], d.bv_right[node]};
+        unsigned stack[64];
+        int sp = 0;
+        stack[sp++] = 0u;
+        while (sp > 0) {
+            const unsigned node = stack[--sp];
+            const unsigned ch[2] = {d.bv_left[node], d.bv_right[node]};
+            const CBox cb = d.bv_cbox[node];
+            const float4 bx[2] = {cb.l, cb.r};
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (ch[c] & LEAF_BIT) {
-                        const unsigned o = sortedIdx[ch[c] & ~LEAF_BIT];
-                        if (box_overlap(qb, box_from4(d.p_fat[o]))) query_emit(d, q, o, capPairs);
-                    } else if (node_has_world(d, ch[c], qw) && box_overlap(qb, box_from4(d.bv_box[ch[c]]))) {
-                        if (sp < 64) stack[sp++] = ch[c];
-                        else atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_STACK));
-                    }
+            for (int c = 0; c < 2; ++c) {
+                if (!box_overlap(qb, box_from4(bx[c]))) continue;
+                if (ch[c] & LEAF_BIT) query_emit(d, q, sortedIdx[ch[c] & ~LEAF_BIT], capPairs);
+                else if (node_has_world(d, ch[c], qw)) {
+                    if (sp < 64) stack[sp++] = ch[c];
+                    else atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_STACK));
                 }
             }
         }
     }
 }
+#ifndef PR_HOST_EMUL
+// Sparse queue (a settled step, a TOI round): the walk of ONE query is a chain of dependent loads ~100+ nodes long
+// (measured 150 us for a single query), so G lanes share a query: they pop up to G nodes of the query's stack (in
+// shared memory) at once, test both children of each, and push the survivors back with a ballot-ranked append. The
+// chain shrinks to ~tree depth. The visited leaf set -- hence the pair set -- is the same as the serial walk's.
+constexpr unsigned QG = 8u, QSTACK = 96u;
+PR_KERNEL k_bvh_query_coop(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs)
+{
+    __shared__ unsigned stk[PR_BLOCK / QG][QSTACK];
+    const unsigned lane = threadIdx.x & 31u, gl = lane & (QG - 1u);
+    const unsigned gmask = ((1u << QG) - 1u) << (lane & ~(QG - 1u));
+    const unsigned qi = PR_TID / QG;
+    if (qi >= nQueue || nLeaves <= 1u) return; // (whole groups leave together)
+    unsigned* st = stk[threadIdx.x / QG];
+    const unsigned q = d.q_list[qi];
+    const Box qb = box_from4(d.p_fat[q]);
+    const unsigned qw = d.nWorlds ? d.b_world[d.p_body[q]] : 0u;
+    if (gl == 0u) st[0] = 0u;
+    unsigned count = 1u;
+    __syncwarp(gmask);
+    while (count) {
+        const unsigned take = count < QG ? count : QG;
+        const unsigned node = (gl < take) ? st[count - 1u - gl] : INVALID;
+        __syncwarp(gmask);
+        count -= take;
+        unsigned push0 = INVALID, push1 = INVALID;
+        if (node != INVALID) {
+            const unsigned c0 = d.bv_left[node], c1 = d.bv_right[node];
+            const CBox cb = d.bv_cbox[node];
+            if (box_overlap(qb, box_from4(cb.l))) {
+                if (c0 & LEAF_BIT) query_emit(d, q, sortedIdx[c0 & ~LEAF_BIT], capPairs);
+                else if (node_has_world(d, c0, qw)) push0 = c0;
+            }
+            if (box_overlap(qb, box_from4(cb.r))) {
+                if (c1 & LEAF_BIT) query_emit(d, q, sortedIdx[c1 & ~LEAF_BIT], capPairs);
+                else if (node_has_world(d, c1, qw)) push1 = c1;
+            }
+        }
+        const unsigned b0 = __ballot_sync(gmask, push0 != INVALID) & gmask, b1 = __ballot_sync(gmask, push1 != INVALID) & gmask;
+        const unsigned below = (1u << lane) - 1u;
+        const unsigned n0 = __popc(b0), total = n0 + __popc(b1);
+        if (count + total > QSTACK) { // (uniform within the group) cannot happen for a balanced tree; reported, not silently dropped
+            if (gl == 0u) atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_STACK));
+            break;
+        }
+        if (push0 != INVALID) st[count + __popc(b0 & below)] = push0;
+        if (push1 != INVALID) st[count + n0 + __popc(b1 & below)] = push1;
+        count += total;
+        __syncwarp(gmask);
+    }
+}
+#endif
 
 // AddContacts (AabbTreeWorld.cpp:2423-2547), creation part: sorted pair i gets its ContactID from the LIFO
 // free stack else by append (ObjectPool::Allocate), is appended to m_contacts in key order.
@@ -703,7 +818,9 @@ PR_KERNEL k_isl_flatten(DV d, unsigned nBodies)
         if (d.b_island[i] != INVALID) {
             r = uf_find(d.b_island, i);
             const unsigned f = d.b_flags[i];
-            if (f_awake(f) && f_enabled(f)) atomicOr(&d.isl_state[r], static_cast<unsigned>(ISL_ACTIVE)); // SolveReg seed test :1496
+            // SolveReg seed test :1496 (the flag only ever gets set in this kernel: skip the atomic once it is visible)
+            if (f_awake(f) && f_enabled(f) && !(*reinterpret_cast<volatile unsigned*>(&d.isl_state[r]) & ISL_ACTIVE))
+                atomicOr(&d.isl_state[r], static_cast<unsigned>(ISL_ACTIVE));
         }
         d.b_root[i] = r; // separate array: parent[] is still being path-halved by other threads
     }
@@ -748,15 +865,15 @@ PR_KERNEL k_isl_prepare(DV d, unsigned nBodies, pr_step_conf conf)
             if (!f_awake(f)) d.b_flags[i] = f | PR_BODY_AWAKE;
             const float4 p0 = d.b_pos0[i];
             d.b_pos0[i] = make_float4(p1.x, p1.y, p1.z, p0.w);
-            atomicAdd(&d.isl_nbodies[r], 1u);
+            island_add_matched(d.isl_nbodies, r, 1u);
             d.b_sync[i] = 1u;
         }
         if (active || !f_speedable(f)) v = body_constraint_velocity(d, i, v, f, conf.delta_time, conf);
         d.s_vel[i] = make_float4(v.x, v.y, v.z, 0.0f);
         d.s_pos[i] = make_float4(p1.x, p1.y, p1.z, 0.0f);
     }
-    warp_add(&d.cnt->islandsFound, isRoot);
-    warp_add(&d.cnt->nAwake, isActive);
+    block_add(&d.cnt->islandsFound, isRoot);
+    block_add(&d.cnt->nAwake, isActive);
 }
 // which contacts become constraints this step: solvable and in an ACTIVE island. A contact that is not a
 // constraint this step loses its persistent colour (it was not in the conflict masks of this step's colouring).
@@ -777,7 +894,7 @@ PR_KERNEL k_mark_constraints(DV d, unsigned nOrder, unsigned* mark)
         mark[i] = m;
         if (!m) d.c_color[id] = COLOR_UNSET;
     }
-    warp_add(&d.cnt->nTouching, touching);
+    block_add(&d.cnt->nTouching, touching);
 }
 PR_KERNEL k_gather_constraints(DV d, unsigned nOrder, const unsigned* mark, const unsigned* pos, unsigned recolorAll)
 {
@@ -860,7 +977,7 @@ PR_KERNEL k_color_commit(DV d, unsigned nWork, unsigned round)
             } else remaining = 1u;
         }
     }
-    warp_add(&d.cnt->nUncolored, remaining);
+    block_add(&d.cnt->nUncolored, remaining);
 }
 PR_KERNEL k_color_reset_claims(DV d, unsigned nBodies)
 {
@@ -888,40 +1005,54 @@ PR_D float2 rel_velocity(float4 vA, float2 relA, float4 vB, float2 relB)
 //   vc3 rA0 rB0 | vc4 rA1 rB1 | vc5 nm0 tm0 nm1 tm1 | vc6 bias0 bias1 k00 k11 | vc7 k01 m00 m11 m01
 //   vc8 jn0 jt0 jn1 jt1 (the only plane the velocity iterations write) | vc_island
 //   pc0 ln lp | pc1 p0 p1 | pc2 lcA lcB | pc3 totalRadius typeCount
-PR_D void vc_store(const DV& d, unsigned i, const VCRow& v)
+// Row store: the planes of the constraint rows plus the BodyConstraint arrays they index. The regular phase keeps
+// them in HBM (rs_global); a TOI event's mini island keeps them in its warp's shared-memory slice (pr_toi_phase.cuh).
+struct RS {
+    float4 *vc0, *vc1, *vc2, *vc3, *vc4, *vc5, *vc6, *vc7, *vc8; unsigned* vc_island;
+    float4 *pc0, *pc1, *pc2, *pc3;
+    float4 *s_vel, *s_pos;
+};
+PR_D RS rs_global(const DV& d)
 {
-    d.vc0[i] = make_float4(v.nx, v.ny, v.friction, v.tangentSpeed);
-    d.vc1[i] = make_float4(u2f(v.bodyA), u2f(v.bodyB), u2f(v.count | (v.dynA << 8) | (v.dynB << 9)), u2f(v.contact));
-    d.vc2[i] = make_float4(v.invMA, v.invIA, v.invMB, v.invIB);
-    d.vc3[i] = make_float4(v.rA0x, v.rA0y, v.rB0x, v.rB0y);
-    d.vc4[i] = make_float4(v.rA1x, v.rA1y, v.rB1x, v.rB1y);
-    d.vc5[i] = make_float4(v.nm0, v.tm0, v.nm1, v.tm1);
-    d.vc6[i] = make_float4(v.bias0, v.bias1, v.k00, v.k11);
-    d.vc7[i] = make_float4(v.k01, v.m00, v.m11, v.m01);
-    d.vc8[i] = make_float4(v.jn0, v.jt0, v.jn1, v.jt1);
-    d.vc_island[i] = v.island;
+    RS r;
+    r.vc0 = d.vc0; r.vc1 = d.vc1; r.vc2 = d.vc2; r.vc3 = d.vc3; r.vc4 = d.vc4; r.vc5 = d.vc5; r.vc6 = d.vc6; r.vc7 = d.vc7; r.vc8 = d.vc8;
+    r.vc_island = d.vc_island; r.pc0 = d.pc0; r.pc1 = d.pc1; r.pc2 = d.pc2; r.pc3 = d.pc3; r.s_vel = d.s_vel; r.s_pos = d.s_pos;
+    return r;
 }
-PR_D void vc_load_head(const DV& d, unsigned i, VCRow& v)
+PR_D void vc_store(const RS& r, unsigned i, const VCRow& v)
 {
-    const float4 a = d.vc1[i], b = d.vc2[i];
+    r.vc0[i] = make_float4(v.nx, v.ny, v.friction, v.tangentSpeed);
+    r.vc1[i] = make_float4(u2f(v.bodyA), u2f(v.bodyB), u2f(v.count | (v.dynA << 8) | (v.dynB << 9)), u2f(v.contact));
+    r.vc2[i] = make_float4(v.invMA, v.invIA, v.invMB, v.invIB);
+    r.vc3[i] = make_float4(v.rA0x, v.rA0y, v.rB0x, v.rB0y);
+    r.vc4[i] = make_float4(v.rA1x, v.rA1y, v.rB1x, v.rB1y);
+    r.vc5[i] = make_float4(v.nm0, v.tm0, v.nm1, v.tm1);
+    r.vc6[i] = make_float4(v.bias0, v.bias1, v.k00, v.k11);
+    r.vc7[i] = make_float4(v.k01, v.m00, v.m11, v.m01);
+    r.vc8[i] = make_float4(v.jn0, v.jt0, v.jn1, v.jt1);
+    r.vc_island[i] = v.island;
+}
+PR_D void vc_load_head(const RS& r, unsigned i, VCRow& v)
+{
+    const float4 a = r.vc1[i], b = r.vc2[i];
     v.bodyA = f2u(a.x); v.bodyB = f2u(a.y); v.contact = f2u(a.w);
     const unsigned cf = f2u(a.z);
     v.count = cf & 0xFFu; v.dynA = (cf >> 8) & 1u; v.dynB = (cf >> 9) & 1u; v.pad = 0u;
     v.invMA = b.x; v.invIA = b.y; v.invMB = b.z; v.invIB = b.w;
-    v.island = d.vc_island[i];
+    v.island = r.vc_island[i];
 }
-PR_D VCRow vc_load(const DV& d, unsigned i)
+PR_D VCRow vc_load(const RS& r, unsigned i)
 {
     VCRow v;
-    vc_load_head(d, i, v);
-    const float4 a = d.vc0[i], c = d.vc3[i], e = d.vc5[i], f = d.vc6[i], h = d.vc8[i];
+    vc_load_head(r, i, v);
+    const float4 a = r.vc0[i], c = r.vc3[i], e = r.vc5[i], f = r.vc6[i], h = r.vc8[i];
     v.nx = a.x; v.ny = a.y; v.friction = a.z; v.tangentSpeed = a.w;
     v.rA0x = c.x; v.rA0y = c.y; v.rB0x = c.z; v.rB0y = c.w;
     v.nm0 = e.x; v.tm0 = e.y; v.nm1 = e.z; v.tm1 = e.w;
     v.bias0 = f.x; v.bias1 = f.y; v.k00 = f.z; v.k11 = f.w;
     v.jn0 = h.x; v.jt0 = h.y; v.jn1 = h.z; v.jt1 = h.w;
     if (v.count == 2u) { // second point and the block-solver matrices only exist for two-point rows
-        const float4 dd = d.vc4[i], g = d.vc7[i];
+        const float4 dd = r.vc4[i], g = r.vc7[i];
         v.rA1x = dd.x; v.rA1y = dd.y; v.rB1x = dd.z; v.rB1y = dd.w;
         v.k01 = g.x; v.m00 = g.y; v.m11 = g.z; v.m01 = g.w;
     } else {
@@ -929,17 +1060,17 @@ PR_D VCRow vc_load(const DV& d, unsigned i)
     }
     return v;
 }
-PR_D void pc_store(const DV& d, unsigned i, const PCRow& p)
+PR_D void pc_store(const RS& r, unsigned i, const PCRow& p)
 {
-    d.pc0[i] = make_float4(p.lnx, p.lny, p.lpx, p.lpy);
-    d.pc1[i] = make_float4(p.p0x, p.p0y, p.p1x, p.p1y);
-    d.pc2[i] = make_float4(p.lcAx, p.lcAy, p.lcBx, p.lcBy);
-    d.pc3[i] = make_float4(p.totalRadius, u2f(p.typeCount), 0.0f, 0.0f);
+    r.pc0[i] = make_float4(p.lnx, p.lny, p.lpx, p.lpy);
+    r.pc1[i] = make_float4(p.p0x, p.p0y, p.p1x, p.p1y);
+    r.pc2[i] = make_float4(p.lcAx, p.lcAy, p.lcBx, p.lcBy);
+    r.pc3[i] = make_float4(p.totalRadius, u2f(p.typeCount), 0.0f, 0.0f);
 }
-PR_D PCRow pc_load(const DV& d, unsigned i)
+PR_D PCRow pc_load(const RS& r, unsigned i)
 {
     PCRow p;
-    const float4 a = d.pc0[i], b = d.pc1[i], c = d.pc2[i], e = d.pc3[i];
+    const float4 a = r.pc0[i], b = r.pc1[i], c = r.pc2[i], e = r.pc3[i];
     p.lnx = a.x; p.lny = a.y; p.lpx = a.z; p.lpy = a.w;
     p.p0x = b.x; p.p0y = b.y; p.p1x = b.z; p.p1y = b.w;
     p.lcAx = c.x; p.lcAy = c.y; p.lcBx = c.z; p.lcBy = c.w;
@@ -949,7 +1080,10 @@ PR_D PCRow pc_load(const DV& d, unsigned i)
 
 // GetWorldManifold (WorldManifold.cpp:37-130) + VelocityConstraint ctor (VelocityConstraint.cpp:81-196)
 // + PositionConstraint (AabbTreeWorld.cpp:289-312) for sorted constraint row i
-PR_D void build_constraint_rows(const DV& d, unsigned cid, unsigned i, const pr_step_conf& conf, float dtRatio, unsigned islandLabel)
+// r: where the rows and the BodyConstraint arrays live (HBM for the regular phase, shared memory for a TOI mini island);
+// sA/sB: the two bodies' indices into r.s_vel / r.s_pos (the body ids themselves in the regular phase)
+PR_D void build_constraint_rows(const DV& d, const RS& r, unsigned cid, unsigned i, const pr_step_conf& conf, float dtRatio, unsigned islandLabel,
+                                unsigned sA, unsigned sB)
 {
     {
         const uint4 ab = d.c_ab[cid];
@@ -957,8 +1091,8 @@ PR_D void build_constraint_rows(const DV& d, unsigned cid, unsigned i, const pr_
         const float4 q0 = d.m0[cid], q1 = d.m1[cid], q2 = d.m2[cid];
         const uint4 q3 = d.m3[cid];
         const float rA = d.ch_radius[ab.z], rB = d.ch_radius[ab.w];
-        const float4 pA = d.s_pos[ab.x], pB = d.s_pos[ab.y];
-        const float4 vA = d.s_vel[ab.x], vB = d.s_vel[ab.y];
+        const float4 pA = r.s_pos[sA], pB = r.s_pos[sB];
+        const float4 vA = r.s_vel[sA], vB = r.s_vel[sB];
         const float4 mA = d.b_mass[ab.x], mB = d.b_mass[ab.y];
         const float2 lcA = d.b_lc[ab.x], lcB = d.b_lc[ab.y];
         const Xf xfA = get_xf(pos_from4(pA), lcA), xfB = get_xf(pos_from4(pB), lcB);
@@ -967,7 +1101,7 @@ PR_D void build_constraint_rows(const DV& d, unsigned cid, unsigned i, const pr_
         pc.p0x = q1.x; pc.p0y = q1.y; pc.p1x = q1.z; pc.p1y = q1.w;
         pc.lcAx = lcA.x; pc.lcAy = lcA.y; pc.lcBx = lcB.x; pc.lcBy = lcB.y;
         pc.totalRadius = rA + rB; pc.typeCount = q3.z | (q3.w << 8); pc.pad0 = pc.pad1 = 0u;
-        pc_store(d, i, pc);
+        pc_store(r, i, pc);
         // world manifold
         Rot normal = mkrot(0.0f, 0.0f);
         float2 wp[2] = {v2(0, 0), v2(0, 0)};
@@ -1001,7 +1135,7 @@ PR_D void build_constraint_rows(const DV& d, unsigned cid, unsigned i, const pr_
         }
         VCRow vc;
         vc.nx = normal.c; vc.ny = normal.s; vc.friction = mat.x; vc.tangentSpeed = mat.z;
-        vc.bodyA = ab.x; vc.bodyB = ab.y; vc.count = count; vc.contact = cid;
+        vc.bodyA = sA; vc.bodyB = sB; vc.count = count; vc.contact = cid;
         vc.invMA = mA.x; vc.invIA = mA.y; vc.invMB = mB.x; vc.invIB = mB.y;
         vc.island = islandLabel;
         vc.dynA = (mA.x != 0.0f || mA.y != 0.0f) ? 1u : 0u; vc.dynB = (mB.x != 0.0f || mB.y != 0.0f) ? 1u : 0u; vc.pad = 0u;
@@ -1052,7 +1186,7 @@ PR_D void build_constraint_rows(const DV& d, unsigned cid, unsigned i, const pr_
         vc.rA1x = relA[1].x; vc.rA1y = relA[1].y; vc.rB1x = relB[1].x; vc.rB1y = relB[1].y;
         vc.jn1 = jn[1]; vc.jt1 = jt[1]; vc.nm1 = nm[1]; vc.tm1 = tm[1];
         vc.bias0 = bias[0]; vc.bias1 = bias[1];
-        vc_store(d, i, vc);
+        vc_store(r, i, vc);
     }
 }
 PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtRatio)
@@ -1062,7 +1196,7 @@ PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtR
         const unsigned cid = d.k_contact[d.k_sorted[i]];
         const uint4 ab = d.c_ab[cid];
         const unsigned rAi = d.b_island[ab.x], rBi = d.b_island[ab.y];
-        build_constraint_rows(d, cid, i, conf, dtRatio, (rAi != INVALID) ? rAi : rBi);
+        build_constraint_rows(d, rs_global(d), cid, i, conf, dtRatio, (rAi != INVALID) ? rAi : rBi, ab.x, ab.y);
     }
 }
 
@@ -1074,10 +1208,10 @@ PR_D void apply_pair(float4& vA, float4& vB, float2 P, float2 relA, float2 relB,
     const float2 b = v2(vB.x, vB.y) + imB * P; vB.x = b.x; vB.y = b.y; vB.z += iiB * LB;
 }
 // WarmStartVelocities, AabbTreeWorld.cpp:222-273
-PR_D void warm_start_row(const DV& d, unsigned i)
+PR_D void warm_start_row(const RS& r, unsigned i)
 {
-    const VCRow vc = vc_load(d, i);
-    float4 vA = d.s_vel[vc.bodyA], vB = d.s_vel[vc.bodyB];
+    const VCRow vc = vc_load(r, i);
+    float4 vA = r.s_vel[vc.bodyA], vB = r.s_vel[vc.bodyB];
     const Rot normal = mkrot(vc.nx, vc.ny), tangent = fwd_perp(normal);
     float2 dAl = v2(0, 0), dBl = v2(0, 0); float dAa = 0.0f, dBa = 0.0f;
     const float2 relA[2] = {v2(vc.rA0x, vc.rA0y), v2(vc.rA1x, vc.rA1y)}, relB[2] = {v2(vc.rB0x, vc.rB0y), v2(vc.rB1x, vc.rB1y)};
@@ -1088,13 +1222,13 @@ PR_D void warm_start_row(const DV& d, unsigned i)
         dAl = dAl - vc.invMA * P; dAa -= vc.invIA * LA;
         dBl = dBl + vc.invMB * P; dBa += vc.invIB * LB;
     }
-    if (vc.dynA) d.s_vel[vc.bodyA] = make_float4(vA.x + dAl.x, vA.y + dAl.y, vA.z + dAa, 0.0f);
-    if (vc.dynB) d.s_vel[vc.bodyB] = make_float4(vB.x + dBl.x, vB.y + dBl.y, vB.z + dBa, 0.0f);
+    if (vc.dynA) r.s_vel[vc.bodyA] = make_float4(vA.x + dAl.x, vA.y + dAl.y, vA.z + dAa, 0.0f);
+    if (vc.dynB) r.s_vel[vc.bodyB] = make_float4(vB.x + dBl.x, vB.y + dBl.y, vB.z + dBa, 0.0f);
 }
 PR_KERNEL k_warm_start(DV d, unsigned start, unsigned count)
 {
     const unsigned t = PR_TID;
-    if (t < count) warm_start_row(d, start + t);
+    if (t < count) warm_start_row(rs_global(d), start + t);
 }
 // ---- colour-overflow tail (constraints that found no free colour < 64, e.g. the 65th+ contact of one body):
 // the tail is sorted by island label and solved by ONE THREAD PER ISLAND SEGMENT in list order -- a valid
@@ -1132,18 +1266,18 @@ template <class F> PR_D void tail_for_each_row(const DV& d, unsigned tailStart, 
 }
 PR_KERNEL k_warm_start_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs)
 {
-    tail_for_each_row(d, tailStart, tailCount, nSegs, [&](unsigned row) { warm_start_row(d, row); });
+    tail_for_each_row(d, tailStart, tailCount, nSegs, [&](unsigned row) { warm_start_row(rs_global(d), row); });
 }
 
 // GaussSeidel::SolveVelocityConstraint (ContactSolver.cpp:481): tangent (:395) then normal
 // (block :245 with cases 1-4 :113-243, else sequential :337); points in order 1 then 0.
-PR_D float solve_velocity_row(const DV& d, unsigned i, bool& did, bool checkIsland = true)
+PR_D float solve_velocity_row(const DV& d, const RS& r, unsigned i, bool& did, bool checkIsland = true)
 {
-    VCRow vc = vc_load(d, i);
+    VCRow vc = vc_load(r, i);
     did = false;
     if (checkIsland && (d.isl_state[vc.island] & ISL_VEL_DONE)) return 0.0f;
     did = true;
-    float4 vA = d.s_vel[vc.bodyA], vB = d.s_vel[vc.bodyB];
+    float4 vA = r.s_vel[vc.bodyA], vB = r.s_vel[vc.bodyB];
     const Rot normal = mkrot(vc.nx, vc.ny), tangent = fwd_perp(normal);
     const float2 relA[2] = {v2(vc.rA0x, vc.rA0y), v2(vc.rA1x, vc.rA1y)}, relB[2] = {v2(vc.rB0x, vc.rB0y), v2(vc.rB1x, vc.rB1y)};
     float jn[2] = {vc.jn0, vc.jn1}, jt[2] = {vc.jt0, vc.jt1};
@@ -1219,23 +1353,23 @@ PR_D float solve_velocity_row(const DV& d, unsigned i, bool& did, bool checkIsla
             maxInc = stdmax(maxInc, stdmax(fabsf(n0), fabsf(n1)));
         }
     }
-    if (vc.dynA) d.s_vel[vc.bodyA] = vA;
-    if (vc.dynB) d.s_vel[vc.bodyB] = vB;
-    d.vc8[i] = make_float4(jn[0], jt[0], jn[1], jt[1]);
+    if (vc.dynA) r.s_vel[vc.bodyA] = vA;
+    if (vc.dynB) r.s_vel[vc.bodyB] = vB;
+    r.vc8[i] = make_float4(jn[0], jt[0], jn[1], jt[1]);
     return maxInc;
 }
 PR_KERNEL k_solve_velocity(DV d, unsigned start, unsigned count)
 {
     const unsigned t = PR_TID;
     bool did = false; float inc = 0.0f; unsigned label = 0u;
-    if (t < count) { inc = solve_velocity_row(d, start + t, did); label = d.vc_island[start + t]; }
+    if (t < count) { inc = solve_velocity_row(d, rs_global(d), start + t, did); label = d.vc_island[start + t]; }
     island_max(d.isl_inc, label, f2u(inc), did);
 }
 PR_KERNEL k_solve_velocity_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs)
 {
     tail_for_each_row(d, tailStart, tailCount, nSegs, [&](unsigned row) {
         bool did = false;
-        const float inc = solve_velocity_row(d, row, did);
+        const float inc = solve_velocity_row(d, rs_global(d), row, did);
         if (did) atomicMax(&d.isl_inc[d.vc_island[row]], f2u(inc));
     });
 }
@@ -1255,7 +1389,7 @@ PR_KERNEL k_isl_vel_check(DV d, unsigned nBodies, unsigned iter, float minMoment
             d.isl_inc[i] = 0u; d.isl_jflag[i] = 0u;
         }
     }
-    warp_add(&d.cnt->nActiveVel, stillActive);
+    block_add(&d.cnt->nActiveVel, stillActive);
 }
 
 // ------------------------------------------------------------------ a11: integrate + NGS position solve
@@ -1314,9 +1448,9 @@ PR_D PDelta psm_solve(const PSM& psm, float2 pA, float2 pB, float imA, float iiA
     return r;
 }
 // GaussSeidel::SolvePositionConstraint, ContactSolver.cpp:494-643 (moveA = moveB = true)
-PR_D float solve_position_row(const DV& d, unsigned i, float rate, float slop, float maxCorr, bool& did, bool checkIsland = true)
+PR_D float solve_position_row(const DV& d, const RS& r, unsigned i, float rate, float slop, float maxCorr, bool& did, bool checkIsland = true)
 {
-    VCRow vch; vc_load_head(d, i, vch);
+    VCRow vch; vc_load_head(r, i, vch);
     const VCRow* vcp = &vch;
     const unsigned island = vcp->island;
     did = false;
@@ -1325,8 +1459,8 @@ PR_D float solve_position_row(const DV& d, unsigned i, float rate, float slop, f
     const unsigned bA = vcp->bodyA, bB = vcp->bodyB;
     const float imA = vcp->invMA, iiA = vcp->invIA, imB = vcp->invMB, iiB = vcp->invIB;
     const unsigned dynA = vcp->dynA, dynB = vcp->dynB;
-    const PCRow pc = pc_load(d, i);
-    float4 a4 = d.s_pos[bA], b4 = d.s_pos[bB];
+    const PCRow pc = pc_load(r, i);
+    float4 a4 = r.s_pos[bA], b4 = r.s_pos[bB];
     Pos posA = pos_from4(a4), posB = pos_from4(b4);
     const float2 lcA = v2(pc.lcAx, pc.lcAy), lcB = v2(pc.lcBx, pc.lcBy);
     const unsigned count = pc.typeCount >> 8;
@@ -1361,22 +1495,22 @@ PR_D float solve_position_row(const DV& d, unsigned i, float rate, float slop, f
             minSep = s1.sep;
         }
     }
-    if (dynA) d.s_pos[bA] = make_float4(posA.l.x, posA.l.y, posA.a, 0.0f);
-    if (dynB) d.s_pos[bB] = make_float4(posB.l.x, posB.l.y, posB.a, 0.0f);
+    if (dynA) r.s_pos[bA] = make_float4(posA.l.x, posA.l.y, posA.a, 0.0f);
+    if (dynB) r.s_pos[bB] = make_float4(posB.l.x, posB.l.y, posB.a, 0.0f);
     return minSep;
 }
 PR_KERNEL k_solve_position(DV d, unsigned start, unsigned count, float rate, float slop, float maxCorr)
 {
     const unsigned t = PR_TID;
     bool did = false; float sep = PR_INF; unsigned label = 0u;
-    if (t < count) { sep = solve_position_row(d, start + t, rate, slop, maxCorr, did); label = d.vc_island[start + t]; }
+    if (t < count) { sep = solve_position_row(d, rs_global(d), start + t, rate, slop, maxCorr, did); label = d.vc_island[start + t]; }
     island_min(d.isl_sep, label, float_flip(sep), did);
 }
 PR_KERNEL k_solve_position_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs, float rate, float slop, float maxCorr)
 {
     tail_for_each_row(d, tailStart, tailCount, nSegs, [&](unsigned row) {
         bool did = false;
-        const float sep = solve_position_row(d, row, rate, slop, maxCorr, did);
+        const float sep = solve_position_row(d, rs_global(d), row, rate, slop, maxCorr, did);
         if (did) atomicMin(&d.isl_sep[d.vc_island[row]], float_flip(sep));
     });
 }
@@ -1395,7 +1529,7 @@ PR_KERNEL k_isl_pos_check(DV d, unsigned nBodies, unsigned iter, float minSepara
             d.isl_sep[i] = float_flip(PR_INF); d.isl_jflag[i] = 0u;
         }
     }
-    warp_add(&d.cnt->nActivePos, stillActive);
+    block_add(&d.cnt->nActivePos, stillActive);
 }
 
 // ------------------------------------------------------------------ a12: write-back, sleep, stats
@@ -1463,9 +1597,9 @@ PR_KERNEL k_sleep_and_stats(DV d, unsigned nBodies, float minStillTime)
             }
         }
     }
-    warp_add(&d.cnt->bodiesSlept, slept); warp_add(&d.cnt->islandsSolved, solved);
-    warp_add(&d.cnt->sumPosIters, posIt); warp_add(&d.cnt->sumVelIters, velIt);
-    warp_max(&d.cnt->maxIslandBodies, nb); warp_min(&d.cnt->minSepFlip, sepFlip); warp_max(&d.cnt->maxIncBits, incBits);
+    block_add(&d.cnt->bodiesSlept, slept); block_add(&d.cnt->islandsSolved, solved);
+    block_add(&d.cnt->sumPosIters, posIt); block_add(&d.cnt->sumVelIters, velIt);
+    block_max(&d.cnt->maxIslandBodies, nb); block_min(&d.cnt->minSepFlip, sepFlip); block_max(&d.cnt->maxIncBits, incBits);
 }
 
 // ------------------------------------------------------------------ export helpers

@@ -362,12 +362,18 @@ PR_D void toi_process_contacts(const DV& d, const pr_step_conf& conf, unsigned i
     }
 }
 
-PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactMode, unsigned scratchCap)
+// A TOI event's mini island (rows + BodyConstraints) lives in the solving warp's slice of shared memory when it
+// fits: the NGS/GS iterations are a serial chain of dependent loads, and a chain through HBM/L2 costs ~0.5 us a
+// link. Larger islands fall back to the global scratch rows at isl.base.
+constexpr unsigned TOI_SM_NC = 16u, TOI_SM_NB = 16u;
+struct ToiSmem {
+    float4 rows[13][TOI_SM_NC];
+    float4 svel[TOI_SM_NB], spos[TOI_SM_NB];
+    unsigned island[TOI_SM_NC], bodies[TOI_SM_NB];
+};
+// SolveToi(contact) for event e (one thread; see k_toi_solve)
+PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, unsigned exactMode, unsigned scratchCap, ToiSmem* sm)
 {
-    // one WARP per event, lane 0 working: events take wildly different paths (island sizes, manifold cases,
-    // iteration counts), so packing 32 of them into one warp serialises them (measured: 3.5 active lanes)
-    const unsigned e = PR_TID >> 5;
-    if ((PR_TID & 31u) != 0u || e >= nEvents) return;
     const unsigned cid = d.toi_events[e];
     const uint4 ab = d.c_ab[cid];
     const unsigned A = ab.x, B = ab.y;
@@ -417,14 +423,41 @@ PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactM
     // ---- SolveToiViaGS (:1957-2058) with subConf.deltaTime = (1 - toi) * deltaTime (:1952-1953)
     pr_step_conf sub = conf;
     sub.delta_time = (1.0f - toi) * conf.delta_time;
+    const bool small = isl.nC <= TOI_SM_NC && isl.nB <= TOI_SM_NB;
+    RS r = rs_global(d);
+    unsigned row0 = isl.base;
+    if (small) {
+        r.vc0 = sm->rows[0]; r.vc1 = sm->rows[1]; r.vc2 = sm->rows[2]; r.vc3 = sm->rows[3]; r.vc4 = sm->rows[4];
+        r.vc5 = sm->rows[5]; r.vc6 = sm->rows[6]; r.vc7 = sm->rows[7]; r.vc8 = sm->rows[8]; r.vc_island = sm->island;
+        r.pc0 = sm->rows[9]; r.pc1 = sm->rows[10]; r.pc2 = sm->rows[11]; r.pc3 = sm->rows[12];
+        r.s_vel = sm->svel; r.s_pos = sm->spos;
+        row0 = 0u;
+        for (unsigned k = 0; k < isl.nB; ++k) sm->bodies[k] = d.toi_islBodies[isl.base + k];
+    }
+    // index of island body k (id b) in r.s_vel / r.s_pos, and of a contact's body there
+    auto slot_of_k = [&](unsigned k, unsigned b) { return small ? k : b; };
+    auto slot_of_body = [&](unsigned b) {
+        if (!small) return b;
+        unsigned k = 0u;
+        while (k + 1u < isl.nB && sm->bodies[k] != b) ++k;
+        return k;
+    };
+    auto build_rows = [&]() {
+        for (unsigned j = 0; j < isl.nC; ++j) {
+            const unsigned c2 = d.toi_islContacts[isl.base + j];
+            const uint4 ab2 = d.c_ab[c2];
+            build_constraint_rows(d, r, c2, row0 + j, sub, 0.0f, 0u, slot_of_body(ab2.x), slot_of_body(ab2.y));
+        }
+    };
     for (unsigned k = 0; k < isl.nB; ++k) { // GetBodyConstraints(h = 0)
         const unsigned b = d.toi_islBodies[isl.base + k];
         const float4 p1 = d.b_pos1[b];
-        d.s_vel[b] = body_constraint_velocity(d, b, d.b_vel[b], d.b_flags[b], 0.0f, sub);
-        d.s_vel[b].w = 0.0f;
-        d.s_pos[b] = make_float4(p1.x, p1.y, p1.z, 0.0f);
+        float4 v = body_constraint_velocity(d, b, d.b_vel[b], d.b_flags[b], 0.0f, sub);
+        v.w = 0.0f;
+        r.s_vel[slot_of_k(k, b)] = v;
+        r.s_pos[slot_of_k(k, b)] = make_float4(p1.x, p1.y, p1.z, 0.0f);
     }
-    for (unsigned j = 0; j < isl.nC; ++j) build_constraint_rows(d, d.toi_islContacts[isl.base + j], isl.base + j, sub, 0.0f, 0u);
+    build_rows();
     float minSepAll = PR_INF;
     unsigned positionIters = conf.toi_position_iters;
     unsigned solved = 0u;
@@ -432,7 +465,7 @@ PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactM
         float minSeparation = PR_INF;
         for (unsigned j = 0; j < isl.nC; ++j) {
             bool did;
-            minSeparation = stdmin(minSeparation, solve_position_row(d, isl.base + j, conf.toi_resolution_rate, conf.linear_slop,
+            minSeparation = stdmin(minSeparation, solve_position_row(d, r, row0 + j, conf.toi_resolution_rate, conf.linear_slop,
                                                                      conf.max_linear_correction, did, false));
         }
         minSepAll = stdmin(minSepAll, minSeparation);
@@ -441,16 +474,16 @@ PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactM
     for (unsigned k = 0; k < isl.nB; ++k) { // "leap of faith": pos0 <- solved position (:2006-2012)
         const unsigned b = d.toi_islBodies[isl.base + k];
         if (f_speedable(d.b_flags[b])) {
-            const float4 sp = d.s_pos[b];
+            const float4 sp = r.s_pos[slot_of_k(k, b)];
             float4 p0 = d.b_pos0[b]; p0.x = sp.x; p0.y = sp.y; p0.z = sp.z; d.b_pos0[b] = p0;
         }
     }
-    for (unsigned j = 0; j < isl.nC; ++j) build_constraint_rows(d, d.toi_islContacts[isl.base + j], isl.base + j, sub, 0.0f, 0u);
+    build_rows();
     unsigned velocityIters = conf.toi_velocity_iters;
     float maxIncAll = 0.0f;
     for (unsigned it = 0; it < conf.toi_velocity_iters; ++it) {
         float newInc = 0.0f;
-        for (unsigned j = 0; j < isl.nC; ++j) { bool did; newInc = stdmax(newInc, solve_velocity_row(d, isl.base + j, did, false)); }
+        for (unsigned j = 0; j < isl.nC; ++j) { bool did; newInc = stdmax(newInc, solve_velocity_row(d, r, row0 + j, did, false)); }
         if (newInc <= conf.toi_min_momentum) { velocityIters = it + 1u; break; }
         maxIncAll = stdmax(maxIncAll, newInc);
     }
@@ -459,8 +492,8 @@ PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactM
         const unsigned b = d.toi_islBodies[isl.base + k];
         const unsigned f = d.b_flags[b];
         if (!f_speedable(f)) continue;
-        const float4 v = d.s_vel[b];
-        float4 sp = d.s_pos[b];
+        const float4 v = r.s_vel[slot_of_k(k, b)];
+        float4 sp = r.s_pos[slot_of_k(k, b)];
         const float2 tr = h * v2(v.x, v.y);
         const float rot = h * v.z;
         sp.x += tr.x; sp.y += tr.y; sp.z += rot;
@@ -498,6 +531,22 @@ PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactM
     atomicAdd(&d.cnt->toiIslandsFound, (positionIters > 0u || velocityIters > 0u) ? 1u : 0u);
     atomicAdd(&d.cnt->toiUpdTouching, numUpdated);
     atomicAdd(&d.cnt->toiSkipTouching, numSkipped);
+}
+
+PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactMode, unsigned scratchCap)
+{
+    // one WARP per event, lane 0 working: events take wildly different paths (island sizes, manifold cases,
+    // iteration counts), so packing 32 of them into one warp serialises them (measured: 3.5 active lanes)
+#ifndef PR_HOST_EMUL
+    __shared__ ToiSmem sm[PR_BLOCK / 32];
+    ToiSmem* mine = &sm[threadIdx.x >> 5];
+#else
+    ToiSmem local;
+    ToiSmem* mine = &local;
+#endif
+    const unsigned e = PR_TID >> 5;
+    if ((PR_TID & 31u) != 0u || e >= nEvents) return;
+    toi_solve_event(d, conf, e, exactMode, scratchCap, mine);
 }
 
 // no event left (:1768-1777): ResetBodiesForSolveTOI, ResetContactsForSolveTOI

@@ -90,7 +90,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(ch_radius, G_CHILD), A(ch_voff, G_CHILD), A(ch_count, G_CHILD), A(vtx, G_VERT), A(nrm, G_VERT),
         A(p_body, G_PROXY), A(p_shape, G_PROXY), A(p_child, G_PROXY), A(p_cg, G_PROXY), A(p_tree, G_PROXY), A(p_moved, G_PROXY),
         A(p_fat, G_PROXY), A(q_list, G_PROXY), A(bv_code, G_PROXY), A(bv_code2, G_PROXY), A(bv_idx, G_PROXY), A(bv_idx2, G_PROXY),
-        A(bv_left, G_PROXY), A(bv_right, G_PROXY), A(bv_parent, G_PROXY), A(bv_lparent, G_PROXY), A(bv_visit, G_PROXY), A(bv_box, G_PROXY),
+        A(bv_left, G_PROXY), A(bv_right, G_PROXY), A(bv_parent, G_PROXY), A(bv_lparent, G_PROXY), A(bv_visit, G_PROXY), A(bv_cbox, G_PROXY),
         A(c_key, G_CONTACT), A(c_ab, G_CONTACT), A(c_px, G_CONTACT), A(c_ids, G_CONTACT), A(c_mat, G_CONTACT), A(c_flags, G_CONTACT),
         A(m0, G_CONTACT), A(m1, G_CONTACT), A(m2, G_CONTACT), A(m3, G_CONTACT), A(c_order, G_CONTACT), A(c_free, G_CONTACT),
         A(c_tmp, G_CONTACT), A(c_tmp2, G_CONTACT),
@@ -317,6 +317,10 @@ static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer
         w.hostCnt.nPairs = 0; w.hostCnt.error &= ~static_cast<unsigned>(ERR_PAIR_OVERFLOW);
         write_counters(w);
         const bool morton = !refit && P > 1 && 4ull * nQueue >= P;
+#ifndef PR_HOST_EMUL
+        if (!morton) PR_LAUNCH(k_bvh_query_coop, static_cast<unsigned long long>(nQueue) * QG, w.stream, d, nQueue, P, w.bvhSortedIdx, w.capPairs);
+        else
+#endif
         PR_LAUNCH(k_bvh_query, morton ? P : nQueue, w.stream, d, nQueue, P, w.bvhSortedIdx, w.capPairs, morton ? 1u : 0u);
         read_counters(w);
         nPairs = w.hostCnt.nPairs;

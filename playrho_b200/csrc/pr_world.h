@@ -52,6 +52,9 @@ struct PCRow {
 // per-step work data of a revolute joint (RevoluteJointConf's rA, rB, mass, angularMass) + its island label
 struct JointWork { float rAx, rAy, rBx, rBy; float m[9]; float angularMass; unsigned island; unsigned pad; };
 
+// the boxes of an LBVH node's two children, stored with the node
+struct CBox { float4 l, r; };
+
 struct Counters {
     unsigned long long toiMinKey; // (toi bits << 32 | position in m_contacts) of the soonest contact, GetSoonestContact
     unsigned toiEvents, toiScratchTop, toiAtMaxSub, toiUpdated, toiMaxDistIters, toiMaxToiIters, toiMaxRootIters;
@@ -100,7 +103,7 @@ struct DV {
     unsigned* c_color; // persistent colour per contact
     // bvh
     unsigned *bv_code, *bv_code2, *bv_idx, *bv_idx2, *bv_left, *bv_right, *bv_parent, *bv_lparent, *bv_visit, *bv_leafOf;
-    float4* bv_box;
+    CBox* bv_cbox; // per internal node: the boxes of its two children (see k_bvh_refit)
     // batched independent worlds (config 5): every body carries the index of the world it lives in; the world index is
     // the high bits of the LBVH sort key, so each internal node covers a contiguous world range [bv_wr.x, bv_wr.y]
     unsigned* b_world; uint2* bv_wr; unsigned nWorlds, worldBits; // nWorlds == 0: a plain single world
