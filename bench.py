@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-toi", action="store_true", help="StepConf.doToi=false (default: TOI enabled as BASELINE config 4 says)")
     ap.add_argument("--toi-mode", type=int, default=1, help="1 = parallel independent TOI events (product default), 0 = serial-exact")
+    ap.add_argument("--debug-flags", type=int, default=0, help="pr_set_debug flags (4 = plain narrowphase instead of the binned one)")
     ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     return ap.parse_args()
 
@@ -206,6 +207,8 @@ def make_mixed_world(args, W, rank, local_rank):
     gw = W.World(sc, device=local_rank, body_capacity=nb + 16, proxy_capacity=nb + 8192, contact_capacity=6 * nb)
     conf = W.default_step_conf(do_toi=0 if args.no_toi else 1)
     gw.set_toi_mode(args.toi_mode)
+    if args.debug_flags:
+        gw.lib.pr_set_debug(gw.h, args.debug_flags)
     for _ in range(args.settle):
         gw.step(conf)
     desc = "%s-%d bodies per GPU (BASELINE config 4 shape: 50%% disks / 50%% 4-8-gons over tiled 256-segment chain terrain), " \

@@ -372,8 +372,16 @@ struct ToiSmem {
     unsigned island[TOI_SM_NC], bodies[TOI_SM_NB];
 };
 // SolveToi(contact) for event e (one thread; see k_toi_solve)
+#ifdef PR_TOI_TIMING
+#define PR_TT(k) do { if (e == 0u) { const long long t_ = clock64(); atomicAdd(&d.cnt->dbg[k], static_cast<unsigned long long>(t_ - tt_)); tt_ = t_; } } while (0)
+#else
+#define PR_TT(k) do { } while (0)
+#endif
 PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, unsigned exactMode, unsigned scratchCap, ToiSmem* sm)
 {
+#ifdef PR_TOI_TIMING
+    long long tt_ = clock64();
+#endif
     const unsigned cid = d.toi_events[e];
     const uint4 ab = d.c_ab[cid];
     const unsigned A = ab.x, B = ab.y;
@@ -410,6 +418,7 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
             return;
         }
     }
+    PR_TT(0);
     if (f_speedable(fA)) atomicOr(&d.b_flags[A], static_cast<unsigned>(PR_BODY_AWAKE));
     if (f_speedable(fB)) atomicOr(&d.b_flags[B], static_cast<unsigned>(PR_BODY_AWAKE));
     isl.nB = 2u; isl.nC = 1u;
@@ -418,7 +427,9 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
     if (f_speedable(fB)) d.b_toiIsl[B] = 1u;
     d.c_toiIsl[cid] = 1u;
     if (f_accelerable(fA)) toi_process_contacts(d, conf, A, isl, toi, exactMode != 0u, numUpdated, numSkipped);
+    PR_TT(1);
     if (f_accelerable(fB)) toi_process_contacts(d, conf, B, isl, toi, exactMode != 0u, numUpdated, numSkipped);
+    PR_TT(2);
 
     // ---- SolveToiViaGS (:1957-2058) with subConf.deltaTime = (1 - toi) * deltaTime (:1952-1953)
     pr_step_conf sub = conf;
@@ -458,6 +469,7 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
         r.s_pos[slot_of_k(k, b)] = make_float4(p1.x, p1.y, p1.z, 0.0f);
     }
     build_rows();
+    PR_TT(3);
     float minSepAll = PR_INF;
     unsigned positionIters = conf.toi_position_iters;
     unsigned solved = 0u;
@@ -471,6 +483,7 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
         minSepAll = stdmin(minSepAll, minSeparation);
         if (minSeparation >= conf.toi_min_separation) { positionIters = it + 1u; solved = 1u; break; }
     }
+    PR_TT(4);
     for (unsigned k = 0; k < isl.nB; ++k) { // "leap of faith": pos0 <- solved position (:2006-2012)
         const unsigned b = d.toi_islBodies[isl.base + k];
         if (f_speedable(d.b_flags[b])) {
@@ -487,6 +500,7 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
         if (newInc <= conf.toi_min_momentum) { velocityIters = it + 1u; break; }
         maxIncAll = stdmax(maxIncAll, newInc);
     }
+    PR_TT(5);
     const float h = sub.delta_time;
     for (unsigned k = 0; k < isl.nB; ++k) { // IntegratePositions + write-back (:2042-2052)
         const unsigned b = d.toi_islBodies[isl.base + k];
@@ -523,6 +537,12 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
             }
         }
     }
+    PR_TT(6);
+#ifdef PR_TOI_TIMING
+    if (e == 0u) { atomicAdd(&d.cnt->dbg[8], 1ull); atomicAdd(&d.cnt->dbg[9], isl.nC); atomicAdd(&d.cnt->dbg[10], isl.nB);
+                   atomicAdd(&d.cnt->dbg[11], positionIters); atomicAdd(&d.cnt->dbg[12], velocityIters);
+                   atomicAdd(&d.cnt->dbg[13], numUpdated); atomicAdd(&d.cnt->dbg[14], numSkipped); }
+#endif
     atomicMin(&d.cnt->toiMinSepFlip, float_flip(minSepAll));
     atomicMax(&d.cnt->toiMaxIncBits, f2u(maxIncAll));
     atomicAdd(&d.cnt->toiIslandsSolved, solved);

@@ -482,7 +482,16 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     PR_LAUNCH(k_sync_proxies, w.nProxies, w.stream, d, conf, w.nProxies);
     tm.mark(w, PR_STAGE_NARROW);
     const unsigned nOrderAtUpdate = w.nOrder;
-    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 1u, 1u);
+    // Binned variant: opt-in only (debug bit 1). Measured at 4.4M contacts it LOSES to the plain kernel (1.02 vs 0.90 ms):
+    // homogeneous warps, but a warp's 32 contact ids are no longer consecutive, so every 16-byte row of the seven contact
+    // planes drags in a 32-byte sector of its own and the kernel turns bandwidth-bound. Kept for the record and the tests.
+    if ((w.debugFlags & 2u) && w.nOrder) {
+        ensure(w, G_CONS, w.nOrder + 1); // (k_tmpKey/k_tmpKey2/k_tmpVal and c_tmp are free scratch at this point of the step)
+        PR_LAUNCH(k_narrow_keys, w.nOrder, w.stream, d, w.nOrder, 1u, d.k_tmpKey, d.k_tmpVal);
+        const bool inB = radix_sort_pairs<unsigned>(d.k_tmpKey, d.k_tmpVal, d.k_tmpKey2, d.c_tmp, w.nOrder, 0, 8, false, w.rs, w.stream);
+        PR_LAUNCH(k_update_contacts_binned, w.nOrder, w.stream, d, conf, w.nOrder, inB ? d.k_tmpKey2 : d.k_tmpKey, inB ? d.c_tmp : d.k_tmpVal);
+    } else
+        PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 1u, 1u);
     dset(w, d.b_moved, 0, sizeof(unsigned) * N);
     dset(w, d.b_sync, 0, sizeof(unsigned) * N);
     read_counters(w);
@@ -600,6 +609,10 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     st.proxies_moved = movedToi;
     st.contacts_found -= c.toiDeferred;
     w.profile.toi_rounds = rounds; w.profile.toi_events = st.contacts_found;
+#ifdef PR_TOI_TIMING
+    std::fprintf(stderr, "toi_timing rounds=%u ev0=%llu | cyc: head %llu procA %llu procB %llu build %llu pos %llu vel %llu tailwb %llu | nC %llu nB %llu posIt %llu velIt %llu upd %llu skip %llu\n",
+                 rounds, c.dbg[8], c.dbg[0], c.dbg[1], c.dbg[2], c.dbg[3], c.dbg[4], c.dbg[5], c.dbg[6], c.dbg[9], c.dbg[10], c.dbg[11], c.dbg[12], c.dbg[13], c.dbg[14]);
+#endif
 }
 
 static void reset_counters(World& w)

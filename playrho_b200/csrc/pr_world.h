@@ -66,6 +66,9 @@ struct Counters {
     unsigned minSepFlip, maxIncBits, error, pad;
     unsigned boundsMinX, boundsMinY, boundsMaxX, boundsMaxY;
     unsigned colorStart[MAX_COLORS + 1];
+#ifdef PR_TOI_TIMING
+    unsigned long long dbg[16]; // profiling build only: clock64 deltas of the phases of toi_solve_event (event 0 of each round)
+#endif
 };
 
 struct DV {

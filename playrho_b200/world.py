@@ -11,7 +11,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplayrho_b200.so")
+# PLAYRHO_B200_LIB: an alternative build of the SAME CUDA library (e.g. a -DPR_TOI_TIMING profiling build)
+LIB_PATH = os.environ.get("PLAYRHO_B200_LIB") or os.path.join(_HERE, "libplayrho_b200.so")
 
 vp, u32, f32, i32 = C.c_void_p, C.c_uint32, C.c_float, C.c_int
 
@@ -111,7 +112,7 @@ class World:
     """Device-resident world. Mirrors the reference's World usage: create shapes/bodies, Step, read back."""
 
     def __init__(self, scene=None, lib=None, device=-1, body_capacity=0, contact_capacity=0, proxy_capacity=0,
-                 record_solve_order=False):
+                 record_solve_order=False, large_variants=False):
         self.lib = lib or load_library()
         conf = abi.one(abi.WORLD_CONF)
         self.lib.pr_world_conf_default(abi.ptr(conf))
@@ -124,8 +125,9 @@ class World:
         if rc != 0:
             raise PrError(rc, self.lib.pr_last_error(None).decode())
         self.h = h
-        if record_solve_order:
-            self.lib.pr_set_debug(self.h, 1)
+        # bit 0: record the solve order; bit 1: large-world kernel variants (binned narrowphase) at any size
+        if record_solve_order or large_variants:
+            self.lib.pr_set_debug(self.h, (1 if record_solve_order else 0) | (2 if large_variants else 0))
         if scene is not None:
             self.create(scene)
 

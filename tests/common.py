@@ -19,12 +19,12 @@ def assert_bits(a, b, what):
     assert refworld.bits_equal(a, b), "%s differ: %s" % (what, refworld.diff_fields(a, b))
 
 
-def run_vs_oracle(scene, steps, lib=None, conf=None, device=-1, check_every=1, toi_mode=0):
+def run_vs_oracle(scene, steps, lib=None, conf=None, device=-1, check_every=1, toi_mode=0, large_variants=False):
     """Step the device world and the oracle (fed the device's colour-sorted order) side by side and
     require BIT-EXACT bodies, contacts (ids, keys, flags), manifolds (points, feature ids, impulses),
     proxies (fat AABBs) and step statistics after every step."""
     conf = conf if conf is not None else refworld.default_step_conf(do_toi=0)
-    gw = W.World(scene, lib=lib, device=device, record_solve_order=True)
+    gw = W.World(scene, lib=lib, device=device, record_solve_order=True, large_variants=large_variants)
     gw.set_toi_mode(toi_mode)  # 0 = serial-exact: the reference's TOI event order
     orc = refworld.OracleWorld(scene)
     last = None

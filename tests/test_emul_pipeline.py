@@ -37,6 +37,16 @@ def test_emulated_device_pipeline_with_toi_bit_exact(name, builder, steps):
 
 @need_oracle
 @need_emul
+def test_emulated_binned_narrowphase_variant_bit_exact():
+    """The kernel variants large worlds take (narrowphase binned by shape-pair class through a radix pass) forced on a
+    small mixed scene: same bits as the oracle, TOI on."""
+    sc = scenes_np.mixed(80, seed=11, tile_segments=16, tile_width=8.0)
+    gs, ncontacts, prof = run_vs_oracle(sc, 150, lib=emul_lib(), conf=refworld.default_step_conf(), large_variants=True)
+    assert ncontacts > 0
+
+
+@need_oracle
+@need_emul
 @need_ref
 def test_emulated_device_pipeline_shooter_toi_bit_exact():
     """Fast bodies, bullets, a spinning kinematic bar and a sensor: hundreds of TOI events."""

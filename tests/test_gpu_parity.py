@@ -41,6 +41,16 @@ def test_cuda_step_with_toi_bit_exact_vs_oracle(name, builder, steps, every):
 
 
 @need_oracle
+def test_cuda_binned_narrowphase_variant_bit_exact_vs_oracle():
+    """The kernel variants large worlds take (binned narrowphase) forced on small scenes: same bits as the oracle."""
+    sc = scenes_np.mixed(1500, seed=12345, tile_segments=64, tile_width=32.0)
+    gs, ncontacts, prof = run_vs_oracle(sc, 100, device=0, check_every=5, conf=refworld.default_step_conf(), large_variants=True)
+    assert ncontacts > 0
+    gs, ncontacts, prof = run_vs_oracle(scenes_np.pyramid(10), 120, device=0, check_every=5, large_variants=True)
+    assert ncontacts > 0
+
+
+@need_oracle
 @need_ref
 def test_cuda_shooter_toi_bit_exact_vs_oracle():
     """Fast bodies, bullets, spinning kinematic bar, sensor shape: hundreds of TOI events (SolveToi mini
