@@ -607,28 +607,30 @@ PR_D void atomic_max_f(float* addr, float v)
     if (v > *addr) *addr = v;
 #endif
 }
+PR_D void bvh_refit_moved_one(const DV& d, unsigned t, unsigned nLeaves)
+{ // queue entry t
+    const unsigned q = d.q_list[t];
+    const float4 f = d.p_fat[q];
+    unsigned child = d.bv_leafOf[q] | LEAF_BIT;
+    unsigned node = d.bv_lparent[child & ~LEAF_BIT];
+    { // the leaf's own slot: an exact copy of its fat box (only this thread writes it)
+        float4* slots = reinterpret_cast<float4*>(&d.bv_cbox[node]);
+        slots[(d.bv_left[node] == child) ? 0 : 1] = f;
+        child = node; node = d.bv_parent[node];
+    }
+    while (node != INVALID) {
+        float4* slot = reinterpret_cast<float4*>(&d.bv_cbox[node]) + ((d.bv_left[node] == child) ? 0 : 1);
+        const float4 cur = *slot;
+        if (cur.x <= f.x && cur.y <= f.y && cur.z >= f.z && cur.w >= f.w) break; // already inside: so are all ancestors
+        float* b = reinterpret_cast<float*>(slot);
+        atomic_min_f(b + 0, f.x); atomic_min_f(b + 1, f.y); atomic_max_f(b + 2, f.z); atomic_max_f(b + 3, f.w);
+        child = node; node = d.bv_parent[node];
+    }
+}
 PR_KERNEL k_bvh_refit_moved(DV d, unsigned nQueue, unsigned nLeaves)
 {
     const unsigned t = PR_TID;
-    if (t < nQueue && nLeaves > 1u) {
-        const unsigned q = d.q_list[t];
-        const float4 f = d.p_fat[q];
-        unsigned child = d.bv_leafOf[q] | LEAF_BIT;
-        unsigned node = d.bv_lparent[child & ~LEAF_BIT];
-        { // the leaf's own slot: an exact copy of its fat box (only this thread writes it)
-            float4* slots = reinterpret_cast<float4*>(&d.bv_cbox[node]);
-            slots[(d.bv_left[node] == child) ? 0 : 1] = f;
-            child = node; node = d.bv_parent[node];
-        }
-        while (node != INVALID) {
-            float4* slot = reinterpret_cast<float4*>(&d.bv_cbox[node]) + ((d.bv_left[node] == child) ? 0 : 1);
-            const float4 cur = *slot;
-            if (cur.x <= f.x && cur.y <= f.y && cur.z >= f.z && cur.w >= f.w) break; // already inside: so are all ancestors
-            float* b = reinterpret_cast<float*>(slot);
-            atomic_min_f(b + 0, f.x); atomic_min_f(b + 1, f.y); atomic_max_f(b + 2, f.z); atomic_max_f(b + 3, f.w);
-            child = node; node = d.bv_parent[node];
-        }
-    }
+    if (t < nQueue && nLeaves > 1u) bvh_refit_moved_one(d, t, nLeaves);
 }
 
 // ------------------------------------------------------------------ a4 + a5 (filter part): overlap query
@@ -672,34 +674,36 @@ PR_D bool node_has_world(const DV& d, unsigned node, unsigned world)
 // FindContacts (AabbTreeWorld.cpp:709-751), dense queue: one thread per leaf in Morton order (a leaf that is not
 // queued idles), so that the lanes of a warp walk neighbouring parts of the tree. Used right after a full rebuild,
 // when most proxies are queued; also the only variant of the host-emulated test build.
+PR_D void bvh_query_serial(const DV& d, unsigned q, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs)
+{
+    const Box qb = box_from4(d.p_fat[q]);
+    const unsigned qw = d.nWorlds ? d.b_world[d.p_body[q]] : 0u;
+    unsigned stack[64];
+    int sp = 0;
+    stack[sp++] = 0u;
+    while (sp > 0) {
+        const unsigned node = stack[--sp];
+        const unsigned ch[2] = {d.bv_left[node], d.bv_right[node]};
+        const CBox cb = d.bv_cbox[node];
+        const float4 bx[2] = {cb.l, cb.r};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (!box_overlap(qb, box_from4(bx[c]))) continue;
+            if (ch[c] & LEAF_BIT) query_emit(d, q, sortedIdx[ch[c] & ~LEAF_BIT], capPairs);
+            else if (node_has_world(d, ch[c], qw)) {
+                if (sp < 64) stack[sp++] = ch[c];
+                else atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_STACK));
+            }
+        }
+    }
+}
 PR_KERNEL k_bvh_query(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs, unsigned mortonOrder)
 {
     const unsigned t = PR_TID;
     unsigned q = INVALID;
     if (mortonOrder) { if (t < nLeaves) { const unsigned c = sortedIdx[t]; if (d.p_moved[c]) q = c; } }
     else if (t < nQueue) q = d.q_list[t];
-    if (q != INVALID && nLeaves > 1u) {
-        const Box qb = box_from4(d.p_fat[q]);
-        const unsigned qw = d.nWorlds ? d.b_world[d.p_body[q]] : 0u;
-        unsigned stack[64];
-        int sp = 0;
-        stack[sp++] = 0u;
-        while (sp > 0) {
-            const unsigned node = stack[--sp];
-            const unsigned ch[2] = {d.bv_left[node], d.bv_right[node]};
-            const CBox cb = d.bv_cbox[node];
-            const float4 bx[2] = {cb.l, cb.r};
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (!box_overlap(qb, box_from4(bx[c]))) continue;
-                if (ch[c] & LEAF_BIT) query_emit(d, q, sortedIdx[ch[c] & ~LEAF_BIT], capPairs);
-                else if (node_has_world(d, ch[c], qw)) {
-                    if (sp < 64) stack[sp++] = ch[c];
-                    else atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_STACK));
-                }
-            }
-        }
-    }
+    if (q != INVALID && nLeaves > 1u) bvh_query_serial(d, q, nLeaves, sortedIdx, capPairs);
 }
 #ifndef PR_HOST_EMUL
 // Sparse queue (a settled step, a TOI round): the walk of ONE query is a chain of dependent loads ~100+ nodes long
@@ -707,15 +711,9 @@ PR_KERNEL k_bvh_query(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* s
 // shared memory) at once, test both children of each, and push the survivors back with a ballot-ranked append. The
 // chain shrinks to ~tree depth. The visited leaf set -- hence the pair set -- is the same as the serial walk's.
 constexpr unsigned QG = 8u, QSTACK = 96u;
-PR_KERNEL k_bvh_query_coop(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs)
+// one query by the QG lanes in gmask (gl = lane index inside the group); st = the group's stack in shared memory
+PR_D void bvh_query_group(const DV& d, unsigned q, const unsigned* sortedIdx, unsigned capPairs, unsigned* st, unsigned lane, unsigned gl, unsigned gmask)
 {
-    __shared__ unsigned stk[PR_BLOCK / QG][QSTACK];
-    const unsigned lane = threadIdx.x & 31u, gl = lane & (QG - 1u);
-    const unsigned gmask = ((1u << QG) - 1u) << (lane & ~(QG - 1u));
-    const unsigned qi = PR_TID / QG;
-    if (qi >= nQueue || nLeaves <= 1u) return; // (whole groups leave together)
-    unsigned* st = stk[threadIdx.x / QG];
-    const unsigned q = d.q_list[qi];
     const Box qb = box_from4(d.p_fat[q]);
     const unsigned qw = d.nWorlds ? d.b_world[d.p_body[q]] : 0u;
     if (gl == 0u) st[0] = 0u;
@@ -751,6 +749,16 @@ PR_KERNEL k_bvh_query_coop(DV d, unsigned nQueue, unsigned nLeaves, const unsign
         count += total;
         __syncwarp(gmask);
     }
+    __syncwarp(gmask);
+}
+PR_KERNEL k_bvh_query_coop(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs)
+{
+    __shared__ unsigned stk[PR_BLOCK / QG][QSTACK];
+    const unsigned lane = threadIdx.x & 31u, gl = lane & (QG - 1u);
+    const unsigned gmask = ((1u << QG) - 1u) << (lane & ~(QG - 1u));
+    const unsigned qi = PR_TID / QG;
+    if (qi >= nQueue || nLeaves <= 1u) return; // (whole groups leave together)
+    bvh_query_group(d, d.q_list[qi], sortedIdx, capPairs, stk[threadIdx.x / QG], lane, gl, gmask);
 }
 #endif
 
@@ -758,11 +766,10 @@ PR_KERNEL k_bvh_query_coop(DV d, unsigned nQueue, unsigned nLeaves, const unsign
 // free stack else by append (ObjectPool::Allocate), is appended to m_contacts in key order.
 PR_D void adj_append(const DV& d, unsigned b, unsigned id, bool eligible);
 PR_D bool toi_static_eligible(unsigned flags);
-PR_KERNEL k_create_contacts(DV d, unsigned nNew, const unsigned long long* keys, const unsigned* srcIdx,
-                            unsigned nOrder, unsigned nFree, unsigned poolSize, unsigned adjLive)
+PR_D void create_contact_one(const DV& d, unsigned i, const unsigned long long* keys, const unsigned* srcIdx,
+                              unsigned nOrder, unsigned nFree, unsigned poolSize, unsigned adjLive)
 {
-    const unsigned i = PR_TID;
-    if (i < nNew) {
+    {
         const unsigned id = (i < nFree) ? d.c_free[nFree - 1u - i] : poolSize + (i - nFree);
         const unsigned long long key = keys[i];
         const uint2 px = d.np_px[srcIdx[i]];
@@ -796,6 +803,12 @@ PR_KERNEL k_create_contacts(DV d, unsigned nNew, const unsigned long long* keys,
             if (f_speedable(fB)) atomicOr(&d.b_flags[bB], static_cast<unsigned>(PR_BODY_AWAKE));
         }
     }
+}
+PR_KERNEL k_create_contacts(DV d, unsigned nNew, const unsigned long long* keys, const unsigned* srcIdx,
+                            unsigned nOrder, unsigned nFree, unsigned poolSize, unsigned adjLive)
+{
+    const unsigned i = PR_TID;
+    if (i < nNew) create_contact_one(d, i, keys, srcIdx, nOrder, nFree, poolSize, adjLive);
 }
 
 // ------------------------------------------------------------------ a8: islands (parallel union-find)

@@ -123,15 +123,20 @@ PR_KERNEL k_toi_phase_init(DV d, unsigned nBodies)
     const unsigned i = PR_TID;
     if (i < nBodies) { d.b_toiAlpha[i] = f2u(d.b_pos0[i].w); d.b_claim[i] = ~0ull; d.b_toiStamp[i] = 0u; d.b_toiIsl[i] = 0u; }
 }
-PR_KERNEL k_toi_round_reset(DV d)
-{
-    if (PR_TID == 0u) { d.cnt->toiMinKey = ~0ull; d.cnt->toiEvents = 0u; d.cnt->toiScratchTop = 0u; d.cnt->syncN = 0u; }
-}
 // alpha0 = max(alphaA, alphaB) of every contact about to get a TOI (:1717): raise both bodies' targets.
 // Invariant outside k_toi_alpha..k_toi_advance: b_toiAlpha[b] == bits(alpha0 of b).
+// (thread 0 also opens the round: it resets the round's counters, or -- batched rounds -- halts the rest of the batch when
+// the previous round overflowed an adjacency segment or raised an error. A halt that becomes visible to only some threads of
+// THIS kernel is harmless: the atomicMax below is idempotent and k_toi_advance, which consumes it, is skipped.)
 PR_KERNEL k_toi_alpha(DV d, unsigned maxSubSteps)
 {
     const unsigned i = PR_TID;
+    if (d.cnt->toiHalt) return;
+    if (i == 0u) {
+        if (d.cnt->adjOverflow) d.cnt->toiHalt = TB_ADJ;
+        else if (d.cnt->error) d.cnt->toiHalt = TB_ERROR;
+        else { d.cnt->toiMinKey = ~0ull; d.cnt->toiEvents = 0u; d.cnt->toiScratchTop = 0u; d.cnt->syncN = 0u; }
+    }
     if (i < d.cnt->toiListN) {
         const unsigned id = d.toi_list[i];
         const uint4 ab = d.c_ab[id];
@@ -155,6 +160,7 @@ PR_D void advance0(float4& p0, float4 p1, float alpha)
 PR_KERNEL k_toi_advance(DV d, unsigned maxSubSteps, unsigned round)
 {
     const unsigned i = PR_TID;
+    if (d.cnt->toiHalt) return;
     if (i < d.cnt->toiListN) {
         const unsigned id = d.toi_list[i];
         const uint4 ab = d.c_ab[id];
@@ -200,7 +206,7 @@ PR_KERNEL k_toi_compute(DV d, pr_step_conf conf)
     const unsigned i = PR_TID;
     unsigned atMaxCount = 0u, updated = 0u, distIt = 0u, toiIt = 0u, rootIt = 0u;
     unsigned long long key = ~0ull;
-    if (i < d.cnt->toiListN) {
+    if (!d.cnt->toiHalt && i < d.cnt->toiListN) {
         const unsigned id = d.toi_list[i];
         unsigned flags = d.c_flags[id];
         const uint4 ab = d.c_ab[id];
@@ -252,6 +258,7 @@ template <class F> PR_D void toi_for_each_claim_body(const DV& d, uint4 ab, F&& 
 PR_KERNEL k_toi_claim(DV d)
 {
     const unsigned i = PR_TID;
+    if (d.cnt->toiHalt) return;
     if (i < d.cnt->toiListN) {
         const unsigned id = d.toi_list[i];
         const float toi = d.c_mat[id].w;
@@ -264,6 +271,7 @@ PR_KERNEL k_toi_claim(DV d)
 PR_KERNEL k_toi_unclaim(DV d)
 {
     const unsigned i = PR_TID;
+    if (d.cnt->toiHalt) return;
     if (i < d.cnt->toiListN) {
         const unsigned id = d.toi_list[i];
         if ((d.c_flags[id] & PR_CONTACT_TOI) && d.c_mat[id].w < 1.0f)
@@ -273,6 +281,7 @@ PR_KERNEL k_toi_unclaim(DV d)
 PR_KERNEL k_toi_select(DV d, unsigned parallel)
 {
     const unsigned i = PR_TID;
+    if (d.cnt->toiHalt) return;
     if (i < d.cnt->toiListN) {
         const unsigned id = d.toi_list[i];
         const float toi = d.c_mat[id].w;
@@ -587,6 +596,7 @@ PR_KERNEL k_toi_finish_contacts(DV d)
 // Synchronize (:2564-2585) for the bodies the round's events listed (:1800-1805): grid-stride over sync_list
 PR_KERNEL k_sync_body_proxies(DV d, pr_step_conf conf)
 {
+    if (d.cnt->toiHalt) return;
     const unsigned n = d.cnt->syncN;
     for (unsigned i = PR_TID; i < n; i += PR_NTHREADS) {
         const unsigned body = d.sync_list[i];
@@ -602,6 +612,131 @@ PR_KERNEL k_sync_body_proxies(DV d, pr_step_conf conf)
                 atomicAdd(&d.cnt->proxiesMoved, 1u);
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------ batched rounds (k_tb_*)
+// A round used to cost four device->host reads (events? queued proxies? candidate pairs? errors?) and the launch
+// bubbles behind them -- ~165 us of overhead around ~150 us of event solving, eight times a step. Here the host
+// enqueues SEVERAL rounds back to back with fixed launch shapes; every size lives in the device counters, every
+// kernel is a grid-stride loop over it, and cnt->toiHalt turns the rest of the batch into no-ops once a round finds
+// no event (TB_DONE) or meets something only the host can do (grow a buffer, rebuild the tree or the hash:
+// TB_HOST_FIND -- the round is then completed by the host's find_add_contacts -- or rebuild the adjacency: TB_ADJ).
+// The contact-pool bookkeeping (m_contacts size, free stack, pool size) is mirrored in the counters meanwhile.
+PR_KERNEL k_tb_solve(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratchCap)
+{
+#ifndef PR_HOST_EMUL
+    __shared__ ToiSmem sm[PR_BLOCK / 32];
+    ToiSmem* mine = &sm[threadIdx.x >> 5];
+#else
+    ToiSmem local;
+    ToiSmem* mine = &local;
+#endif
+    if (d.cnt->toiHalt) return;
+    const unsigned nEvents = d.cnt->toiEvents;
+    if (PR_TID == 0u) {
+        if (nEvents == 0u) d.cnt->toiHalt = TB_DONE; // :1768 (threads that miss this flip see nEvents == 0 and do nothing either)
+        else { d.cnt->tbRounds += 1u; d.cnt->tbFound += nEvents; }
+    }
+    if ((PR_TID & 31u) != 0u) return; // one warp per event, lane 0 working (see k_toi_solve)
+    for (unsigned e = PR_TID >> 5; e < nEvents; e += PR_NTHREADS >> 5) toi_solve_event(d, conf, e, exactMode, scratchCap, mine);
+}
+// FindContacts' tree update for the proxies the round's events moved; decides whether the host must take over
+PR_KERNEL k_tb_refit(DV d, unsigned nLeaves)
+{
+    if (d.cnt->toiHalt) return;
+    const unsigned nQ = d.cnt->nQueue;
+    const bool hostMust = nQ != 0u && 8ull * nQ >= nLeaves; // too many moved proxies for in-place refits: full rebuild
+    if (PR_TID == 0u) {
+        d.cnt->tbFindSkip = (nQ == 0u) ? 1u : 0u;
+        d.cnt->tbAddN = 0u;
+        if (nQ) { d.cnt->nPairs = 0u; d.cnt->error &= ~static_cast<unsigned>(ERR_PAIR_OVERFLOW); }
+        if (hostMust) d.cnt->toiHalt = TB_HOST_FIND;
+    }
+    if (hostMust) return;
+    for (unsigned t = PR_TID; t < nQ; t += PR_NTHREADS) bvh_refit_moved_one(d, t, nLeaves);
+}
+PR_KERNEL k_tb_query(DV d, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs)
+{
+    if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
+    const unsigned nQ = d.cnt->nQueue;
+#ifndef PR_HOST_EMUL
+    __shared__ unsigned stk[PR_BLOCK / QG][QSTACK];
+    const unsigned lane = threadIdx.x & 31u, gl = lane & (QG - 1u);
+    const unsigned gmask = ((1u << QG) - 1u) << (lane & ~(QG - 1u));
+    for (unsigned qi = PR_TID / QG; qi < nQ; qi += PR_NTHREADS / QG) // (a group's lanes share qi: they loop together)
+        bvh_query_group(d, d.q_list[qi], sortedIdx, capPairs, stk[threadIdx.x / QG], lane, gl, gmask);
+#else
+    for (unsigned t = PR_TID; t < nQ; t += PR_NTHREADS) bvh_query_serial(d, d.q_list[t], nLeaves, sortedIdx, capPairs);
+#endif
+}
+// end of FindContacts: can the device add this round's pairs itself? (every thread derives the same answer from counters
+// no thread of this kernel changes); if so un-queue the proxies
+PR_KERNEL k_tb_clear(DV d, unsigned capPairs, unsigned capContacts, unsigned capHash, unsigned hashTombs)
+{
+    if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
+    const unsigned nP = d.cnt->nPairs, order = d.cnt->devOrder, pool = d.cnt->devPool;
+    const bool hostMust = (d.cnt->error & ERR_PAIR_OVERFLOW) || nP > capPairs || nP > SMALL_SORT_MAX ||
+                          order + nP + 1u > capContacts || pool + nP + 1u > capContacts ||
+                          2ull * (static_cast<unsigned long long>(order) + nP + hashTombs) > capHash;
+    if (PR_TID == 0u) {
+        if (hostMust) d.cnt->toiHalt = TB_HOST_FIND;
+        else { d.cnt->tbAddN = nP; d.cnt->tbAddOld = order; d.cnt->tbPairs += nP; }
+    }
+    if (hostMust) return;
+    const unsigned nQ = d.cnt->nQueue;
+    for (unsigned t = PR_TID; t < nQ; t += PR_NTHREADS) d.p_moved[d.q_list[t]] = 0u;
+}
+// FindContacts' std::sort of the candidate keys (:746), one block (<= SMALL_SORT_MAX pairs, else the host took over)
+PR_KERNEL k_tb_sort(DV d)
+{
+    if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
+    const unsigned n = d.cnt->tbAddN;
+#ifndef PR_HOST_EMUL
+    __shared__ unsigned long long k[SMALL_SORT_MAX];
+    __shared__ unsigned v[SMALL_SORT_MAX];
+    if (threadIdx.x == 0u) d.cnt->nQueue = 0u;
+    if (n == 0u) return;
+    unsigned N = 32u;
+    while (N < n) N <<= 1;
+    for (unsigned i = threadIdx.x; i < N; i += blockDim.x) { k[i] = (i < n) ? d.np_key[i] : ~0ull; v[i] = i; }
+    __syncthreads();
+    for (unsigned size = 2; size <= N; size <<= 1) {
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned t = threadIdx.x; t < N / 2u; t += blockDim.x) {
+                const unsigned lo = 2u * t - (t & (stride - 1u));
+                const unsigned hi = lo + stride;
+                const bool asc = ((lo & size) == 0u);
+                const unsigned long long a = k[lo], b = k[hi];
+                if ((a > b) == asc) { k[lo] = b; k[hi] = a; const unsigned tv = v[lo]; v[lo] = v[hi]; v[hi] = tv; }
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) { d.np_key2[i] = k[i]; d.np_idx2[i] = v[i]; }
+#else
+    if (PR_TID != 0u) return;
+    d.cnt->nQueue = 0u;
+    sort_pairs_small(d.np_key, d.np_key2, d.np_idx2, n, 0);
+#endif
+}
+PR_KERNEL k_tb_create(DV d)
+{
+    if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
+    const unsigned n = d.cnt->tbAddN, order = d.cnt->devOrder, nFree = d.cnt->devFree, pool = d.cnt->devPool;
+    for (unsigned i = PR_TID; i < n; i += PR_NTHREADS) create_contact_one(d, i, d.np_key2, d.np_idx2, order, nFree, pool, 1u);
+}
+// AddContacts' Update(contactID) of the new contacts (:2531) + the pool bookkeeping of the round (thread 0: nobody in
+// this kernel reads what it writes)
+PR_KERNEL k_tb_update(DV d, pr_step_conf conf)
+{
+    if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
+    const unsigned n = d.cnt->tbAddN, old = d.cnt->tbAddOld;
+    for (unsigned i = PR_TID; i < n; i += PR_NTHREADS) { const unsigned id = d.c_order[old + i]; update_contact(d, conf, id, d.c_flags[id]); }
+    if (PR_TID == 0u && n) {
+        const unsigned nFree = d.cnt->devFree;
+        const unsigned used = n < nFree ? n : nFree;
+        d.cnt->devFree = nFree - used; d.cnt->devPool += n - used; d.cnt->devOrder += n; d.cnt->tbAdded += n;
     }
 }
 

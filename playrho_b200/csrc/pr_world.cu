@@ -557,11 +557,84 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         if (w.nOrder == 0) { w.stepComplete = true; break; } // nothing can have a TOI
         if (!w.adjValid) build_adjacency(w);
         ensure(w, G_CONS, std::min(2u * w.nOrder, w.nOrder + (1u << 20)) + 64u); // island rows (VC/PC scratch) of one round's events
+        const unsigned P = w.nProxies;
+        // ---- batched rounds: needs an intact tree to refit in place; otherwise one host-driven round (below)
+        const bool canBatch = w.bvhValid && w.bvhLeaves == P && P > 1; // (the refit budget is checked by the next regular step)
+        if (canBatch) {
+            if (w.hashDirty) rebuild_hash(w);
+            // rounds to enqueue: what the last step needed (+1: the round that finds nothing), a few at a time after that
+            const unsigned K = w.subStepping ? 1u : std::min(32u, rounds ? 4u : std::max(2u, w.toiRoundsHint + 1u));
+            ensure(w, G_PAIR, SMALL_SORT_MAX);
+            ensure(w, G_CONTACT, std::max(w.poolSize, w.nOrder) + K * SMALL_SORT_MAX + 2u);
+            if (2ull * (static_cast<unsigned long long>(w.nOrder) + K * SMALL_SORT_MAX + w.hashTombs) > w.capHash) rebuild_hash(w);
+            const unsigned scratchCap = std::min(w.capCons, w.capAdj);
+            read_counters(w);
+            throw_device_error(w);
+            w.hostCnt.toiHalt = TB_RUN; w.hostCnt.tbRounds = w.hostCnt.tbFound = w.hostCnt.tbAdded = w.hostCnt.tbPairs = 0u;
+            w.hostCnt.devOrder = w.nOrder; w.hostCnt.devFree = w.nFree; w.hostCnt.devPool = w.poolSize;
+            w.hostCnt.tbFindSkip = 1u; w.hostCnt.tbAddN = w.hostCnt.tbAddOld = 0u;
+            write_counters(w);
+            const unsigned listBound = w.toiListBound + K * SMALL_SORT_MAX; // contacts created by earlier rounds of the batch join the list
+            const unsigned solveWarps = std::min(592u * 8u, std::max(8u, listBound)); // (8 warps per 256-thread block)
+            for (unsigned k = 0; k < K; ++k) {
+                ++round;
+                PR_LAUNCH(k_toi_alpha, listBound, w.stream, d, conf.max_sub_steps);
+                PR_LAUNCH(k_toi_advance, listBound, w.stream, d, conf.max_sub_steps, round);
+                PR_LAUNCH(k_toi_compute, listBound, w.stream, d, conf);
+                if (!exact) PR_LAUNCH(k_toi_claim, listBound, w.stream, d);
+                PR_LAUNCH(k_toi_select, listBound, w.stream, d, exact ? 0u : 1u);
+                if (!exact) PR_LAUNCH(k_toi_unclaim, listBound, w.stream, d);
+                PR_LAUNCH(k_tb_solve, 32u * solveWarps, w.stream, d, conf, exact ? 1u : 0u, scratchCap);
+#ifndef PR_HOST_EMUL
+                PR_LAUNCH_GRID(k_sync_body_proxies, 148, PR_BLOCK, w.stream, d, conf);
+                PR_LAUNCH_GRID(k_tb_refit, 32, PR_BLOCK, w.stream, d, P);
+                PR_LAUNCH_GRID(k_tb_query, 148, PR_BLOCK, w.stream, d, P, w.bvhSortedIdx, w.capPairs);
+                PR_LAUNCH_GRID(k_tb_clear, 32, PR_BLOCK, w.stream, d, w.capPairs, w.capContacts, w.capHash, w.hashTombs);
+                PR_LAUNCH_GRID(k_tb_sort, 1, 1024, w.stream, d);
+                PR_LAUNCH_GRID(k_tb_create, 8, PR_BLOCK, w.stream, d);
+                PR_LAUNCH_GRID(k_tb_update, 8, PR_BLOCK, w.stream, d, conf);
+#else
+                PR_LAUNCH(k_sync_body_proxies, 1, w.stream, d, conf);
+                PR_LAUNCH(k_tb_refit, 2, w.stream, d, P);
+                PR_LAUNCH(k_tb_query, 2, w.stream, d, P, w.bvhSortedIdx, w.capPairs);
+                PR_LAUNCH(k_tb_clear, 2, w.stream, d, w.capPairs, w.capContacts, w.capHash, w.hashTombs);
+                PR_LAUNCH(k_tb_sort, 1, w.stream, d);
+                PR_LAUNCH(k_tb_create, 2, w.stream, d);
+                PR_LAUNCH(k_tb_update, 2, w.stream, d, conf);
+#endif
+            }
+            read_counters(w);
+            const Counters c = w.hostCnt;
+            round -= K - std::min(K, c.tbRounds + 1u); // (stamps only need to be unique; keep the count honest)
+            w.nOrder = c.devOrder; w.nFree = c.devFree; w.poolSize = c.devPool;
+            w.toiListBound += c.tbAdded; w.bvhRefits += c.tbRounds;
+            rounds += c.tbRounds;
+            st.contacts_found += c.tbFound; st.contacts_added += c.tbAdded;
+            w.profile.candidate_pairs += c.tbPairs;
+            const unsigned halt = c.toiHalt;
+            w.hostCnt.toiHalt = TB_RUN;
+            if (halt == TB_ERROR) { write_counters(w); throw_device_error(w); throw CudaError{"TOI rounds halted on a device error"}; }
+            if (halt == TB_ADJ || c.adjOverflow) { w.adjValid = false; w.hostCnt.adjOverflow = 0; }
+            write_counters(w);
+            if (halt == TB_HOST_FIND) { // the round's events are solved; its FindContacts/AddContacts needs the host (growth / rebuild)
+                tm.mark(w, PR_STAGE_TOI_SOLVE);
+                st.contacts_added += find_add_contacts(w, conf, tm, true);
+                tm.mark(w, PR_STAGE_TOI);
+            }
+            if (halt == TB_DONE) { // :1768-1777
+                w.stepComplete = true;
+                if (rounds || w.toiAlphaDirty) { PR_LAUNCH(k_toi_finish_bodies, N, w.stream, d, N); w.toiAlphaDirty = false; }
+                if (w.toiListBound) PR_LAUNCH(k_toi_finish_contacts, w.toiListBound, w.stream, d);
+                break;
+            }
+            if (w.subStepping && c.tbRounds) { w.stepComplete = false; w.toiAlphaDirty = true; break; }
+            continue;
+        }
+        // ---- one host-driven round (tree or hash about to be rebuilt)
         const unsigned scratchCap = std::min(w.capCons, w.capAdj);
         const unsigned nList = w.toiListBound; // >= device toiListN (kernels re-check against it)
         ++round;
         if (nList) {
-            PR_LAUNCH(k_toi_round_reset, 1, w.stream, d);
             PR_LAUNCH(k_toi_alpha, nList, w.stream, d, conf.max_sub_steps);
             PR_LAUNCH(k_toi_advance, nList, w.stream, d, conf.max_sub_steps, round);
             PR_LAUNCH(k_toi_compute, nList, w.stream, d, conf);
@@ -570,6 +643,8 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             if (!exact) PR_LAUNCH(k_toi_unclaim, nList, w.stream, d);
         }
         read_counters(w);
+        if (w.hostCnt.toiHalt == TB_ADJ) { w.adjValid = false; w.hostCnt.adjOverflow = 0; w.hostCnt.toiHalt = TB_RUN; write_counters(w); --round; continue; }
+        if (w.hostCnt.toiHalt == TB_ERROR) throw_device_error(w);
         const unsigned nEvents = nList ? w.hostCnt.toiEvents : 0u;
         if (nEvents == 0) { // :1768-1777
             w.stepComplete = true;
@@ -590,6 +665,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         tm.mark(w, PR_STAGE_TOI);
         if (w.subStepping) { w.stepComplete = false; w.toiAlphaDirty = true; break; }
     }
+    w.toiRoundsHint = rounds;
     // final UpdateContacts (:1825-1827)
     read_counters(w);
     const unsigned movedToi = w.hostCnt.proxiesMoved;

@@ -26,6 +26,7 @@ constexpr unsigned MAX_COLORS = 65u;
 constexpr unsigned LEAF_BIT = 0x80000000u;
 
 enum { ISL_ACTIVE = 1u, ISL_VEL_DONE = 2u, ISL_POS_SOLVED = 4u };
+enum { TB_RUN = 0, TB_DONE = 1, TB_HOST_FIND = 2, TB_ADJ = 3, TB_ERROR = 4 };
 enum { ERR_NONE = 0, ERR_STACK = 1, ERR_SENSOR = 2, ERR_PAIR_OVERFLOW = 4, ERR_HASH_FULL = 8, ERR_TOI_SCRATCH = 16 };
 
 // VelocityConstraint row (Library/include/playrho/d2/VelocityConstraint.hpp), 144 B
@@ -66,6 +67,12 @@ struct Counters {
     unsigned minSepFlip, maxIncBits, error, pad;
     unsigned boundsMinX, boundsMinY, boundsMaxX, boundsMaxY;
     unsigned colorStart[MAX_COLORS + 1];
+    // batched TOI rounds (pr_toi_phase.cuh, k_tb_*): the host enqueues several rounds without reading anything back;
+    // the contact-pool bookkeeping it normally keeps (World::nOrder/nFree/poolSize) is mirrored here meanwhile
+    unsigned toiHalt;       // TB_RUN, or why the remaining kernels of the batch turned into no-ops
+    unsigned tbRounds, tbFound, tbAdded, tbPairs; // totals of the batch
+    unsigned devOrder, devFree, devPool;          // m_contacts size, free-stack height, pool size
+    unsigned tbFindSkip, tbAddOld, tbAddN, tbPad;
 #ifdef PR_TOI_TIMING
     unsigned long long dbg[16]; // profiling build only: clock64 deltas of the phases of toi_solve_event (event 0 of each round)
 #endif
@@ -135,7 +142,7 @@ struct World {
     bool anyBodySet = false, hashDirty = true, stepComplete = true;
     bool recolorAll = true; unsigned colorsAtFull = 0;
     bool subStepping = false, adjValid = false, bvhValid = false, bpDirty = true, toiAlphaDirty = true;
-    unsigned bvhLeaves = 0, bvhRefits = 0, hashTombs = 0, toiListBound = 0;
+    unsigned bvhLeaves = 0, bvhRefits = 0, hashTombs = 0, toiListBound = 0, toiRoundsHint = 1;
     const unsigned* bvhSortedIdx = nullptr;
     std::vector<std::vector<unsigned>> bodyProxies; // m_bodyProxies
     unsigned toiMode = 1; // PR_TOI_PARALLEL (default) or PR_TOI_SERIAL_EXACT (reference order)
