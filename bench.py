@@ -82,8 +82,8 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_solve_velocity launch train (all colours x 8 iterations) from
-# the `ncu --set full` capture summarised under profiles/ (None until a capture of the current kernel exists)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE regular-phase k_update_contacts launch on this workload, from the
+# `ncu --set full` capture summarised under profiles/ (None until a capture of the current kernel exists)
 ROOFLINE_TRAFFIC = {}
 
 
@@ -341,9 +341,26 @@ def main():
         nv, npi = int(conf["reg_velocity_iters"][0]), int(conf["reg_position_iters"][0])
         bstep, terms = algorithmic_bytes(last, nv, npi)
         ms_step = 1e3 * secs / args.steps
-        vel_ms = float(stage_ms[5]) / args.steps
-        vel_bytes = terms["a10_velocity"]
-        achieved = (vel_bytes / 1e9) / (vel_ms / 1e3) if vel_ms > 0 else 0.0
+        stage = {n: float(stage_ms[i]) / args.steps for i, n in enumerate(abi.STAGE_NAMES)}
+        # dominant HBM-bound kernel: the regular phase's narrowphase launch (k_update_contacts over every contact of the
+        # world; one launch per step). Its CUDA-event time is the "narrow" stage (the launch + two 4 MB memsets).
+        dirty = float(np.mean([p["c_dirty"] for p in profs]))
+        narrow_bytes = (184 + 16 * 2 * 3.5) * dirty      # SURVEY §8(d) a7 term: (184 + 16 (vA + vB)) B per dirty contact
+        narrow_ms = stage["narrow"]
+        achieved = (narrow_bytes / 1e9) / (narrow_ms / 1e3) if narrow_ms > 0 else 0.0
+        vel_ms, vel_bytes = stage["velocity"], terms["a10_velocity"]
+        others = {
+            "k_solve_velocity (all colours x %d iterations + per-island checks)" % nv:
+                {"algorithmic_bytes": vel_bytes, "ms": vel_ms, "achieved": (vel_bytes / 1e9) / (vel_ms / 1e3) if vel_ms > 0 else 0.0},
+            "k_solve_position (all colours x %d iterations) + k_integrate_positions" % npi:
+                {"algorithmic_bytes": terms["a11_position"], "ms": stage["position"],
+                 "achieved": (terms["a11_position"] / 1e9) / (stage["position"] / 1e3) if stage["position"] > 0 else 0.0},
+            "k_build_constraints + warm start (setup)":
+                {"algorithmic_bytes": terms["a9_setup"], "ms": stage["setup"],
+                 "achieved": (terms["a9_setup"] / 1e9) / (stage["setup"] / 1e3) if stage["setup"] > 0 else 0.0},
+        }
+        for v in others.values():
+            v["frac"] = v["achieved"] / peak
         cfg = {"workload": desc, "toi": not args.no_toi, "toi_mode": "parallel" if args.toi_mode else "serial-exact",
                "toi_events_per_step": float(np.mean([p["toi_events"] for p in profs])), "toi_rounds_per_step": float(np.mean([p["toi_rounds"] for p in profs])),
                "step_conf": "default StepConf (8 vel / 3 pos iters, doToi=%s)%s" % (not args.no_toi, " + TumblerPlayRho's displaceMultiplier 4, maxRotation pi/2" if tumblers else ""),
@@ -362,12 +379,13 @@ def main():
                     "h2d_bytes_per_step": int(nb * abi.BODY.itemsize + 4 * nb), "d2h_bytes_per_step": int(nb * abi.BODY.itemsize),
                     "ms_per_step": 1e3 * e2e_secs / e2e_steps},
             "gpu_launches": int(float(s[5])),
-            "roofline": {"bound": "hbm", "kernel": "k_solve_velocity (all colours x %d iterations, incl. per-island checks)" % nv,
+            "roofline": {"bound": "hbm", "kernel": "k_update_contacts (regular-phase narrowphase: CollideShapes + impulse carry-over for every dirty contact, one launch per step)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
-                         "traffic": ROOFLINE_TRAFFIC.get(args.workload), "algorithmic_bytes_per_launch_train": vel_bytes,
-                         "algorithmic_bytes_per_step": bstep,
-                         "step_achieved_gbs": (bstep / 1e9) / (ms_step / 1e3), "step_frac": (bstep / 1e9) / (ms_step / 1e3) / peak},
-            "stage_ms_per_step": {n: float(stage_ms[i]) / args.steps for i, n in enumerate(abi.STAGE_NAMES)},
+                         "traffic": ROOFLINE_TRAFFIC.get(args.workload), "algorithmic_bytes_per_launch": narrow_bytes,
+                         "launch_ms": narrow_ms, "algorithmic_bytes_per_step": bstep,
+                         "step_achieved_gbs": (bstep / 1e9) / (ms_step / 1e3), "step_frac": (bstep / 1e9) / (ms_step / 1e3) / peak,
+                         "other_kernels": others},
+            "stage_ms_per_step": stage,
             "clocks": sampler.summary(),
             "step_stats_all_ranks": {"islands_found": int(folded["reg"]["islands_found"]), "islands_solved": int(folded["reg"]["islands_solved"]),
                                      "contacts_added": int(folded["reg"]["contacts_added"]) + int(folded["pre"]["contacts_added"]) + int(folded["toi"]["contacts_added"]),
