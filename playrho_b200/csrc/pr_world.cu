@@ -2,6 +2,7 @@
 // declared in include/playrho_b200.h. Step() mirrors Step(AabbTreeWorld&, const StepConf&)
 // (Library/source/playrho/d2/AabbTreeWorld.cpp:2144-2219): pre-phase, SolveReg (:1472), SolveToi.
 #include "pr_kernels.cuh"
+#include "pr_solve_fused.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -446,29 +447,65 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         else if (w.nColors > 24u && w.nColors > w.colorsAtFull + 8u) w.recolorAll = true; // persistent colours fragmented
         tm.mark(w, PR_STAGE_SETUP);
         PR_LAUNCH(k_build_constraints, nCons, w.stream, d, nCons, conf, conf.do_warm_start ? conf.dt_ratio : 0.0f);
-        if (conf.do_warm_start) {
+    }
+    const unsigned jSerial = w.jointsSerial ? 1u : 0u, jThreads = w.jointsSerial ? (w.nJoints ? 1u : 0u) : w.nJoints;
+    bool fused = false;
+#ifndef PR_HOST_EMUL
+    // The whole solve as ONE persistent cooperative kernel (pr_solve_fused.cuh): opt-in (debug bit 2). Measured on B200 it
+    // only ties the per-colour launches on the 1M mixed scene (1.62-1.67 vs 1.61 ms for warm start + 8 + 3 iterations: a
+    // grid barrier costs what a back-to-back launch costs, and a resident grid has fewer threads to hide the row -> body
+    // load chain) and loses on the 8192-tumbler arena (65 colours + overflow tail: 16.5 vs 10.8 ms).
+    if ((w.debugFlags & 4u) && ranges.size() <= MAX_COLORS) {
+        if (!w.fusedProbed) {
+            w.fusedProbed = true;
+            int coop = 0, sms = 0, perSm = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, w.device);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w.device);
+            if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_solve_fused, FUSED_BLOCK, 0) == cudaSuccess && perSm > 0) {
+                w.fusedGrid = static_cast<unsigned>(sms * perSm);
+                w.gridBar = static_cast<unsigned*>(dev_alloc(256));
+            }
+            cudaGetLastError();
+        }
+        if (w.fusedGrid) {
+            SolvePlan p{};
+            p.nColors = static_cast<unsigned>(ranges.size());
+            for (unsigned c = 0; c < p.nColors; ++c) { p.start[c] = ranges[c].first; p.count[c] = ranges[c].second; }
+            p.tailStart = tailStart; p.tailCount = tailCount; p.nTailSegs = nTailSegs;
+            p.nBodies = N; p.nJoints = w.nJoints; p.jointsSerial = jSerial; p.warmStart = (nCons && conf.do_warm_start) ? 1u : 0u;
+            tm.mark(w, PR_STAGE_VELOCITY);
+            CK(cudaMemsetAsync(w.gridBar, 0, sizeof(unsigned), w.stream));
+            pr_step_conf confCopy = conf;
+            void* args[] = {&d, &confCopy, &p, &w.gridBar};
+            const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_solve_fused), dim3(w.fusedGrid), dim3(FUSED_BLOCK), args, 0, w.stream);
+            if (e == cudaSuccess) { fused = true; count_launch(); }
+            else { cudaGetLastError(); w.fusedGrid = 0; } // fall back to one launch per colour from now on
+        }
+    }
+#endif
+    if (!fused) {
+        if (nCons && conf.do_warm_start) {
             for (const auto& r : ranges) PR_LAUNCH(k_warm_start, r.second, w.stream, d, r.first, r.second);
             if (tailCount) PR_LAUNCH(k_warm_start_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
         }
-    }
-    const unsigned jSerial = w.jointsSerial ? 1u : 0u, jThreads = w.jointsSerial ? (w.nJoints ? 1u : 0u) : w.nJoints;
-    PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 0u, jSerial); // InitVelocity after the contacts' warm start (:1597)
-    tm.mark(w, PR_STAGE_VELOCITY);
-    for (unsigned it = 0; it < conf.reg_velocity_iters; ++it) {
-        PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 1u, jSerial); // joints first (:1605-1608)
-        for (const auto& r : ranges) PR_LAUNCH(k_solve_velocity, r.second, w.stream, d, r.first, r.second);
-        if (tailCount) PR_LAUNCH(k_solve_velocity_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
-        PR_LAUNCH(k_isl_vel_check, N, w.stream, d, N, it, conf.reg_min_momentum);
-    }
-    tm.mark(w, PR_STAGE_POSITION);
-    PR_LAUNCH(k_integrate_positions, N, w.stream, d, N, conf.delta_time);
-    for (unsigned it = 0; it < conf.reg_position_iters; ++it) {
-        for (const auto& r : ranges)
-            PR_LAUNCH(k_solve_position, r.second, w.stream, d, r.first, r.second, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
-        if (tailCount)
-            PR_LAUNCH(k_solve_position_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
-        PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 2u, jSerial); // joints after the contacts (:1634-1637)
-        PR_LAUNCH(k_isl_pos_check, N, w.stream, d, N, it, conf.reg_min_separation);
+        PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 0u, jSerial); // InitVelocity after the contacts' warm start (:1597)
+        tm.mark(w, PR_STAGE_VELOCITY);
+        for (unsigned it = 0; it < conf.reg_velocity_iters; ++it) {
+            PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 1u, jSerial); // joints first (:1605-1608)
+            for (const auto& r : ranges) PR_LAUNCH(k_solve_velocity, r.second, w.stream, d, r.first, r.second);
+            if (tailCount) PR_LAUNCH(k_solve_velocity_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
+            PR_LAUNCH(k_isl_vel_check, N, w.stream, d, N, it, conf.reg_min_momentum);
+        }
+        tm.mark(w, PR_STAGE_POSITION);
+        PR_LAUNCH(k_integrate_positions, N, w.stream, d, N, conf.delta_time);
+        for (unsigned it = 0; it < conf.reg_position_iters; ++it) {
+            for (const auto& r : ranges)
+                PR_LAUNCH(k_solve_position, r.second, w.stream, d, r.first, r.second, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
+            if (tailCount)
+                PR_LAUNCH(k_solve_position_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
+            PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 2u, jSerial); // joints after the contacts (:1634-1637)
+            PR_LAUNCH(k_isl_pos_check, N, w.stream, d, N, it, conf.reg_min_separation);
+        }
     }
     tm.mark(w, PR_STAGE_WRITEBACK);
     if (nCons) PR_LAUNCH(k_assign_impulses, nCons, w.stream, d, nCons);

@@ -161,6 +161,7 @@ struct World {
     pr_step_profile profile{};
     std::vector<unsigned> solveOrderIds, solveOrderColors;
     std::vector<void*> allocs;
+    unsigned* gridBar = nullptr; unsigned fusedGrid = 0; bool fusedProbed = false; // persistent solver kernel (pr_solve_fused.cuh)
     void* stageBuf[2] = {nullptr, nullptr}; size_t stageCap[2] = {0, 0}; // persistent device staging for row upload/download
 };
 

@@ -125,9 +125,9 @@ class World:
         if rc != 0:
             raise PrError(rc, self.lib.pr_last_error(None).decode())
         self.h = h
-        # bit 0: record the solve order; bit 1: large-world kernel variants (binned narrowphase) at any size
+        # bit 0: record the solve order; bits 1,2: the opt-in kernel variants (binned narrowphase, persistent fused solver)
         if record_solve_order or large_variants:
-            self.lib.pr_set_debug(self.h, (1 if record_solve_order else 0) | (2 if large_variants else 0))
+            self.lib.pr_set_debug(self.h, (1 if record_solve_order else 0) | (6 if large_variants else 0))
         if scene is not None:
             self.create(scene)
 

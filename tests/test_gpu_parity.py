@@ -42,11 +42,15 @@ def test_cuda_step_with_toi_bit_exact_vs_oracle(name, builder, steps, every):
 
 @need_oracle
 def test_cuda_binned_narrowphase_variant_bit_exact_vs_oracle():
-    """The kernel variants large worlds take (binned narrowphase) forced on small scenes: same bits as the oracle."""
+    """The opt-in kernel variants (narrowphase binned by shape-pair class; the persistent cooperative solver kernel with
+    grid barriers between colours) on small scenes: same bits as the oracle, incl. joints and the colour-overflow tail."""
     sc = scenes_np.mixed(1500, seed=12345, tile_segments=64, tile_width=32.0)
     gs, ncontacts, prof = run_vs_oracle(sc, 100, device=0, check_every=5, conf=refworld.default_step_conf(), large_variants=True)
     assert ncontacts > 0
     gs, ncontacts, prof = run_vs_oracle(scenes_np.pyramid(10), 120, device=0, check_every=5, large_variants=True)
+    assert ncontacts > 0
+    conf = scenes_np.tumbler_step_conf(refworld.default_step_conf())
+    gs, ncontacts, prof = run_vs_oracle(scenes_np.tumbler(150), 150, device=0, check_every=10, conf=conf, large_variants=True)
     assert ncontacts > 0
 
 
