@@ -24,6 +24,12 @@ typedef cudaStream_t pr_stream_t;
 typedef cudaEvent_t pr_event_t;
 
 #define PR_BLOCK 256
+// warp-cooperative loops (a "warp" of the host emulation is one thread)
+#define PR_WARP 32u
+#define PR_LANE (threadIdx.x & 31u)
+#define PR_WARP_ID (PR_TID >> 5)
+#define PR_NWARPS (PR_NTHREADS >> 5)
+#define PR_WARP_ALL(p) (__all_sync(0xffffffffu, (p)) != 0)
 // one thread per element launch
 #define PR_LAUNCH(kernel, n, stream, ...)                                                          \
     do {                                                                                           \
@@ -54,6 +60,11 @@ inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return
 namespace pr { extern thread_local unsigned emul_tid, emul_nthreads; }
 #define PR_TID (pr::emul_tid)
 #define PR_NTHREADS (pr::emul_nthreads)
+#define PR_WARP 1u
+#define PR_LANE 0u
+#define PR_WARP_ID (pr::emul_tid)
+#define PR_NWARPS (pr::emul_nthreads)
+#define PR_WARP_ALL(p) (p)
 typedef int pr_stream_t;
 typedef int pr_event_t;
 #define PR_LAUNCH(kernel, n, stream, ...)                                                          \

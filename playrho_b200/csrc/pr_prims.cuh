@@ -92,6 +92,28 @@ __global__ void k_scan_apply(const unsigned* __restrict__ in, unsigned* __restri
     for (int i = 0; i < SCAN_ITEMS; ++i) { const unsigned j = base + i; if (j < n) out[j] = ex; ex += v[i]; }
 }
 
+// small inputs: ONE block walks the array in chunks of blockDim.x * SCAN_ITEMS with a running carry (one launch
+// instead of three; the radix passes over a few ten thousand candidate pairs scan 256 x ~100 counters each)
+constexpr unsigned SCAN_SMALL_MAX = 65536u;
+__global__ void k_scan_small(const unsigned* in, unsigned* out, unsigned n, unsigned* totalOut) // (in may alias out)
+{
+    __shared__ unsigned smem[33];
+    unsigned carry = 0;
+    for (unsigned chunk = 0; chunk < n; chunk += blockDim.x * SCAN_ITEMS) {
+        const unsigned base = chunk + threadIdx.x * SCAN_ITEMS;
+        unsigned v[SCAN_ITEMS];
+        unsigned sum = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) { const unsigned j = base + i; v[i] = (j < n) ? in[j] : 0u; sum += v[i]; }
+        unsigned total;
+        unsigned ex = block_excl_scan(sum, smem, &total) + carry;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) { const unsigned j = base + i; if (j < n) out[j] = ex; ex += v[i]; }
+        carry += total;
+    }
+    if (threadIdx.x == 0 && totalOut) *totalOut = carry;
+}
+
 // scratch must hold ceil(n / SCAN_TILE) uints. in may alias out. totalOut (device) may be null.
 inline void scan_exclusive_u32(const unsigned* in, unsigned* out, unsigned n, unsigned* totalOut,
                                unsigned* scratch, cudaStream_t stream)
@@ -100,6 +122,7 @@ inline void scan_exclusive_u32(const unsigned* in, unsigned* out, unsigned n, un
         if (totalOut) cudaMemsetAsync(totalOut, 0, sizeof(unsigned), stream);
         return;
     }
+    if (n <= SCAN_SMALL_MAX) { PR_LAUNCH_GRID(k_scan_small, 1, 1024, stream, in, out, n, totalOut); return; }
     const unsigned nTiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     PR_LAUNCH_GRID(k_scan_tile_sums, nTiles, SCAN_THREADS, stream, in, scratch, n);
     PR_LAUNCH_GRID(k_scan_tile_offsets, 1, SCAN_THREADS, stream, scratch, nTiles, totalOut);
@@ -112,15 +135,19 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_CHUNKS = 16;                       // chunks of RS_THREADS keys per block
 constexpr int RS_TILE = RS_THREADS * RS_CHUNKS;     // 4096 keys per block
 
-template <class K>
+// CHUNKS: chunks of RS_THREADS keys per block -- RS_CHUNKS for large inputs, RS_CHUNKS_SMALL for mid-size ones (a few ten
+// thousand keys on 4096-key tiles is a dozen blocks, each ranking 16 chunks one after another: 22 us per pass measured)
+constexpr int RS_CHUNKS_SMALL = 2;
+constexpr unsigned RS_SMALL_MAX = 262144u;
+template <class K, int CHUNKS>
 __global__ void k_rs_hist(const K* __restrict__ keys, unsigned n, int shift, unsigned* __restrict__ hist, unsigned nBlocks)
 {
     __shared__ unsigned h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
-    const unsigned base = blockIdx.x * RS_TILE;
+    const unsigned base = blockIdx.x * (CHUNKS * RS_THREADS);
 #pragma unroll 4
-    for (int c = 0; c < RS_CHUNKS; ++c) {
+    for (int c = 0; c < CHUNKS; ++c) {
         const unsigned j = base + c * RS_THREADS + threadIdx.x;
         if (j < n) atomicAdd(&h[static_cast<unsigned>(keys[j] >> shift) & 0xFFu], 1u);
     }
@@ -128,7 +155,7 @@ __global__ void k_rs_hist(const K* __restrict__ keys, unsigned n, int shift, uns
     hist[threadIdx.x * nBlocks + blockIdx.x] = h[threadIdx.x]; // digit-major so one scan gives offsets
 }
 
-template <class K>
+template <class K, int CHUNKS>
 __global__ void k_rs_scatter(const K* __restrict__ keysIn, const unsigned* __restrict__ valsIn,
                              K* __restrict__ keysOut, unsigned* __restrict__ valsOut, unsigned n, int shift,
                              const unsigned* __restrict__ offsets, unsigned nBlocks)
@@ -137,8 +164,8 @@ __global__ void k_rs_scatter(const K* __restrict__ keysIn, const unsigned* __res
     __shared__ unsigned warpCnt[RS_THREADS / 32][256];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     running[threadIdx.x] = offsets[threadIdx.x * nBlocks + blockIdx.x];
-    const unsigned base = blockIdx.x * RS_TILE;
-    for (int c = 0; c < RS_CHUNKS; ++c) {
+    const unsigned base = blockIdx.x * (CHUNKS * RS_THREADS);
+    for (int c = 0; c < CHUNKS; ++c) {
         if (base + c * RS_THREADS >= n) break;
 #pragma unroll
         for (int w = 0; w < RS_THREADS / 32; ++w) warpCnt[w][threadIdx.x] = 0;
@@ -181,7 +208,9 @@ inline bool radix_sort_pairs(K* keysA, unsigned* valsA, K* keysB, unsigned* vals
                              int endBit, bool valsAreIota, RadixScratch& s, cudaStream_t stream)
 {
     if (n == 0) return false;
-    const unsigned nBlocks = rs_blocks(n);
+    const unsigned smallBlocks = (n + RS_CHUNKS_SMALL * RS_THREADS - 1) / (RS_CHUNKS_SMALL * RS_THREADS);
+    const bool small = n <= RS_SMALL_MAX && 256ull * smallBlocks <= s.histCap;
+    const unsigned nBlocks = small ? smallBlocks : rs_blocks(n);
     bool inA = true;
     bool iota = valsAreIota;
     for (int shift = beginBit; shift < endBit; shift += 8) {
@@ -189,9 +218,12 @@ inline bool radix_sort_pairs(K* keysA, unsigned* valsA, K* keysB, unsigned* vals
         K* kout = inA ? keysB : keysA;
         unsigned* vin = inA ? valsA : valsB;
         unsigned* vout = inA ? valsB : valsA;
-        PR_LAUNCH_GRID(k_rs_hist<K>, nBlocks, RS_THREADS, stream, kin, n, shift, s.hist, nBlocks);
+        if (small) PR_LAUNCH_GRID((k_rs_hist<K, RS_CHUNKS_SMALL>), nBlocks, RS_THREADS, stream, kin, n, shift, s.hist, nBlocks);
+        else PR_LAUNCH_GRID((k_rs_hist<K, RS_CHUNKS>), nBlocks, RS_THREADS, stream, kin, n, shift, s.hist, nBlocks);
         scan_exclusive_u32(s.hist, s.hist, 256u * nBlocks, nullptr, s.scan, stream);
-        PR_LAUNCH_GRID(k_rs_scatter<K>, nBlocks, RS_THREADS, stream, kin, iota ? nullptr : vin, kout, vout, n, shift,
+        if (small) PR_LAUNCH_GRID((k_rs_scatter<K, RS_CHUNKS_SMALL>), nBlocks, RS_THREADS, stream, kin, iota ? nullptr : vin, kout, vout, n, shift,
+                                  s.hist, nBlocks);
+        else PR_LAUNCH_GRID((k_rs_scatter<K, RS_CHUNKS>), nBlocks, RS_THREADS, stream, kin, iota ? nullptr : vin, kout, vout, n, shift,
                        s.hist, nBlocks);
         iota = false;
         inA = !inA;

@@ -135,7 +135,7 @@ PR_KERNEL k_toi_alpha(DV d, unsigned maxSubSteps)
     if (i == 0u) {
         if (d.cnt->adjOverflow) d.cnt->toiHalt = TB_ADJ;
         else if (d.cnt->error) d.cnt->toiHalt = TB_ERROR;
-        else { d.cnt->toiMinKey = ~0ull; d.cnt->toiEvents = 0u; d.cnt->toiScratchTop = 0u; d.cnt->syncN = 0u; }
+        else { d.cnt->toiMinKey = ~0ull; d.cnt->toiEvents = 0u; d.cnt->toiScratchTop = 0u; d.cnt->syncN = 0u; d.cnt->toiCandN = 0u; }
     }
     if (i < d.cnt->toiListN) {
         const unsigned id = d.toi_list[i];
@@ -227,7 +227,10 @@ PR_KERNEL k_toi_compute(DV d, pr_step_conf conf)
             d.c_flags[id] = flags;
             updated = 1u; distIt = out.maxDistIters; toiIt = out.toiIters; rootIt = out.maxRootIters;
         } else if (atMax) atMaxCount = 1u;
-        if ((flags & PR_CONTACT_TOI) && toi < 1.0f) key = toi_key(toi, d.c_pos[id]); // GetSoonestContact candidates
+        if ((flags & PR_CONTACT_TOI) && toi < 1.0f) { // GetSoonestContact candidates: compacted for the selection kernels
+            key = toi_key(toi, d.c_pos[id]);
+            d.toi_cand[atomicAdd(&d.cnt->toiCandN, 1u)] = id;
+        }
     }
     warp_add(&d.cnt->toiAtMaxSub, atMaxCount); warp_add(&d.cnt->toiUpdated, updated);
     warp_max(&d.cnt->toiMaxDistIters, distIt); warp_max(&d.cnt->toiMaxToiIters, toiIt); warp_max(&d.cnt->toiMaxRootIters, rootIt);
@@ -235,16 +238,20 @@ PR_KERNEL k_toi_compute(DV d, pr_step_conf conf)
 }
 
 // ------------------------------------------------------------------ event selection
+// the bodies an event on contact (ab) can advance, walk or flag: its own two speedable bodies and, through the accelerable
+// ones' contact lists, the bodies ProcessContactsForTOI can advance / read (:2079-2087: same filter). One WARP per
+// candidate: the lanes take the adjacency entries (a body of a pile has 6-10 of them, each a chain of four dependent
+// loads -- one thread walking them all made these kernels 12 us each however few candidates there were).
 template <class F> PR_D void toi_for_each_claim_body(const DV& d, uint4 ab, F&& fn)
 {
     const unsigned two[2] = {ab.x, ab.y};
     for (int s = 0; s < 2; ++s) {
         const unsigned b = two[s];
         const unsigned f = d.b_flags[b];
-        if (f_speedable(f)) fn(b);
-        if (f_accelerable(f)) { // the bodies ProcessContactsForTOI(b) can advance / read (:2079-2087): same filter
+        if (f_speedable(f) && PR_LANE == 0u) fn(b);
+        if (f_accelerable(f)) {
             const bool bodyImpenetrable = (f & PR_BODY_IMPENETRABLE) != 0u;
-            for (unsigned k = d.adj_off[b], ke = adj_end(d, b); k < ke; ++k) {
+            for (unsigned k = d.adj_off[b] + PR_LANE, ke = adj_end(d, b); k < ke; k += PR_WARP) {
                 const unsigned c2 = d.adj_list[k];
                 if (d.c_flags[c2] & PR_CONTACT_SENSOR) continue;
                 const uint4 o = d.c_ab[c2];
@@ -257,43 +264,35 @@ template <class F> PR_D void toi_for_each_claim_body(const DV& d, uint4 ab, F&& 
 }
 PR_KERNEL k_toi_claim(DV d)
 {
-    const unsigned i = PR_TID;
     if (d.cnt->toiHalt) return;
-    if (i < d.cnt->toiListN) {
-        const unsigned id = d.toi_list[i];
-        const float toi = d.c_mat[id].w;
-        if ((d.c_flags[id] & PR_CONTACT_TOI) && toi < 1.0f) {
-            const unsigned long long key = toi_key(toi, d.c_pos[id]);
-            toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { atomicMin(&d.b_claim[b], key); });
-        }
+    const unsigned n = d.cnt->toiCandN;
+    for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS) {
+        const unsigned id = d.toi_cand[c];
+        const unsigned long long key = toi_key(d.c_mat[id].w, d.c_pos[id]);
+        toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { atomicMin(&d.b_claim[b], key); });
     }
 }
 PR_KERNEL k_toi_unclaim(DV d)
 {
-    const unsigned i = PR_TID;
     if (d.cnt->toiHalt) return;
-    if (i < d.cnt->toiListN) {
-        const unsigned id = d.toi_list[i];
-        if ((d.c_flags[id] & PR_CONTACT_TOI) && d.c_mat[id].w < 1.0f)
-            toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { d.b_claim[b] = ~0ull; });
-    }
+    const unsigned n = d.cnt->toiCandN;
+    for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS)
+        toi_for_each_claim_body(d, d.c_ab[d.toi_cand[c]], [&](unsigned b) { d.b_claim[b] = ~0ull; });
 }
 PR_KERNEL k_toi_select(DV d, unsigned parallel)
 {
-    const unsigned i = PR_TID;
     if (d.cnt->toiHalt) return;
-    if (i < d.cnt->toiListN) {
-        const unsigned id = d.toi_list[i];
-        const float toi = d.c_mat[id].w;
-        if ((d.c_flags[id] & PR_CONTACT_TOI) && toi < 1.0f) {
-            const unsigned long long key = toi_key(toi, d.c_pos[id]);
-            bool win;
-            if (parallel) {
-                win = true;
-                toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { if (d.b_claim[b] != key) win = false; });
-            } else win = (key == d.cnt->toiMinKey);
-            if (win) d.toi_events[atomicAdd(&d.cnt->toiEvents, 1u)] = id;
-        }
+    const unsigned n = d.cnt->toiCandN;
+    for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS) {
+        const unsigned id = d.toi_cand[c];
+        const unsigned long long key = toi_key(d.c_mat[id].w, d.c_pos[id]);
+        bool win;
+        if (parallel) {
+            bool mine = true;
+            toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { if (d.b_claim[b] != key) mine = false; });
+            win = PR_WARP_ALL(mine);
+        } else win = (key == d.cnt->toiMinKey);
+        if (win && PR_LANE == 0u) d.toi_events[atomicAdd(&d.cnt->toiEvents, 1u)] = id;
     }
 }
 

@@ -72,7 +72,7 @@ struct Counters {
     unsigned toiHalt;       // TB_RUN, or why the remaining kernels of the batch turned into no-ops
     unsigned tbRounds, tbFound, tbAdded, tbPairs; // totals of the batch
     unsigned devOrder, devFree, devPool;          // m_contacts size, free-stack height, pool size
-    unsigned tbFindSkip, tbAddOld, tbAddN, tbPad;
+    unsigned tbFindSkip, tbAddOld, tbAddN, toiCandN; // toiCandN: candidates (valid TOI < 1) of the round, see k_toi_compute
 #ifdef PR_TOI_TIMING
     unsigned long long dbg[16]; // profiling build only: clock64 deltas of the phases of toi_solve_event (event 0 of each round)
 #endif
@@ -99,7 +99,7 @@ struct DV {
     // TOI phase: body -> contact adjacency (m_bodyContacts) as CSR, islanded flags, event list, island scratch
     // (adjacency covers speedable bodies only, each segment has slack for contacts added during the TOI rounds)
     unsigned *adj_off, *adj_cnt, *adj_n, *adj_list, *c_pos, *b_toiIsl, *c_toiIsl, *b_toiAlpha, *b_toiStamp, *b_inR, *toi_events, *toi_islBodies,
-        *toi_islContacts, *toi_list, *sync_list;
+        *toi_islContacts, *toi_list, *toi_cand, *sync_list;
     unsigned *bp_off, *bp_list; // body -> proxy CSR (m_bodyProxies)
     unsigned long long* ht_keys; unsigned ht_mask;
     // new pairs
