@@ -29,7 +29,7 @@ import numpy as np  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--bodies", type=int, default=1000000)
@@ -55,11 +55,29 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed region. In-process NVML (nvidia_ml_py) every 20 ms; spawning
+    `nvidia-smi` instead (the fallback) takes a driver lock for tens of ms and showed up as +0.7 ms/step on the
+    host-interactive TOI phase in about one run out of three."""
+
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.how = index, [], False, "nvml"
 
-    def run(self):
+    def _nvml_loop(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        bits = [("hw_slowdown", pynvml.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", pynvml.nvmlClocksThrottleReasonSwPowerCap)]
+        while not self.stop_flag:
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.samples.append([str(sm), str(mx)] + ["Active" if (r & b) else "Not Active" for _, b in bits])
+            time.sleep(0.02)
+
+    def _smi_loop(self):
+        self.how = "nvidia-smi"
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
@@ -72,6 +90,12 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.2)
 
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
+
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
@@ -79,7 +103,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons}
+                "reasons": reasons, "samples": len(self.samples), "via": self.how}
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE regular-phase k_update_contacts launch on this workload, from the

@@ -669,36 +669,32 @@ PR_KERNEL k_tb_query(DV d, unsigned nLeaves, const unsigned* sortedIdx, unsigned
     for (unsigned t = PR_TID; t < nQ; t += PR_NTHREADS) bvh_query_serial(d, d.q_list[t], nLeaves, sortedIdx, capPairs);
 #endif
 }
-// end of FindContacts: can the device add this round's pairs itself? (every thread derives the same answer from counters
-// no thread of this kernel changes); if so un-queue the proxies
-PR_KERNEL k_tb_clear(DV d, unsigned capPairs, unsigned capContacts, unsigned capHash, unsigned hashTombs)
+// The rest of the round in ONE block (a TOI round adds at most a few hundred contacts; SMALL_SORT_MAX bounds it):
+//   decide  : can the device add this round's pairs itself? (every thread derives the same answer from counters that no
+//             thread changes before the decision is used); if so un-queue the proxies (end of FindContacts)
+//   sort    : FindContacts' std::sort of the candidate keys (:746), bitonic network in shared memory
+//   create  : AddContacts (:2423-2547) with ids from the mirrored pool bookkeeping
+//   update  : AddContacts' Update(contactID) of the new contacts (:2531), then the bookkeeping of the round
+// (four launches before; the block-wide barriers order the global writes of one stage before the reads of the next)
+constexpr unsigned TB_ADD_BLOCK = 512u;
+PR_KERNEL k_tb_add(DV d, pr_step_conf conf, unsigned capPairs, unsigned capContacts, unsigned capHash, unsigned hashTombs)
 {
     if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
-    const unsigned nP = d.cnt->nPairs, order = d.cnt->devOrder, pool = d.cnt->devPool;
+    const unsigned nP = d.cnt->nPairs, order = d.cnt->devOrder, pool = d.cnt->devPool, nFree = d.cnt->devFree, nQ = d.cnt->nQueue;
     const bool hostMust = (d.cnt->error & ERR_PAIR_OVERFLOW) || nP > capPairs || nP > SMALL_SORT_MAX ||
                           order + nP + 1u > capContacts || pool + nP + 1u > capContacts ||
                           2ull * (static_cast<unsigned long long>(order) + nP + hashTombs) > capHash;
-    if (PR_TID == 0u) {
-        if (hostMust) d.cnt->toiHalt = TB_HOST_FIND;
-        else { d.cnt->tbAddN = nP; d.cnt->tbAddOld = order; d.cnt->tbPairs += nP; }
-    }
-    if (hostMust) return;
-    const unsigned nQ = d.cnt->nQueue;
+    if (hostMust) { if (PR_TID == 0u) d.cnt->toiHalt = TB_HOST_FIND; return; }
     for (unsigned t = PR_TID; t < nQ; t += PR_NTHREADS) d.p_moved[d.q_list[t]] = 0u;
-}
-// FindContacts' std::sort of the candidate keys (:746), one block (<= SMALL_SORT_MAX pairs, else the host took over)
-PR_KERNEL k_tb_sort(DV d)
-{
-    if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
-    const unsigned n = d.cnt->tbAddN;
 #ifndef PR_HOST_EMUL
     __shared__ unsigned long long k[SMALL_SORT_MAX];
     __shared__ unsigned v[SMALL_SORT_MAX];
-    if (threadIdx.x == 0u) d.cnt->nQueue = 0u;
-    if (n == 0u) return;
+    __syncthreads();
+    if (threadIdx.x == 0u) { d.cnt->nQueue = 0u; d.cnt->tbPairs += nP; }
+    if (nP == 0u) return;
     unsigned N = 32u;
-    while (N < n) N <<= 1;
-    for (unsigned i = threadIdx.x; i < N; i += blockDim.x) { k[i] = (i < n) ? d.np_key[i] : ~0ull; v[i] = i; }
+    while (N < nP) N <<= 1;
+    for (unsigned i = threadIdx.x; i < N; i += blockDim.x) { k[i] = (i < nP) ? d.np_key[i] : ~0ull; v[i] = i; }
     __syncthreads();
     for (unsigned size = 2; size <= N; size <<= 1) {
         for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
@@ -712,30 +708,23 @@ PR_KERNEL k_tb_sort(DV d)
             __syncthreads();
         }
     }
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) { d.np_key2[i] = k[i]; d.np_idx2[i] = v[i]; }
+    for (unsigned i = threadIdx.x; i < nP; i += blockDim.x) { d.np_key2[i] = k[i]; d.np_idx2[i] = v[i]; }
+    __threadfence_block();
+    __syncthreads();
 #else
-    if (PR_TID != 0u) return;
-    d.cnt->nQueue = 0u;
-    sort_pairs_small(d.np_key, d.np_key2, d.np_idx2, n, 0);
+    d.cnt->nQueue = 0u; d.cnt->tbPairs += nP;
+    if (nP == 0u) return;
+    sort_pairs_small(d.np_key, d.np_key2, d.np_idx2, nP, 0);
 #endif
-}
-PR_KERNEL k_tb_create(DV d)
-{
-    if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
-    const unsigned n = d.cnt->tbAddN, order = d.cnt->devOrder, nFree = d.cnt->devFree, pool = d.cnt->devPool;
-    for (unsigned i = PR_TID; i < n; i += PR_NTHREADS) create_contact_one(d, i, d.np_key2, d.np_idx2, order, nFree, pool, 1u);
-}
-// AddContacts' Update(contactID) of the new contacts (:2531) + the pool bookkeeping of the round (thread 0: nobody in
-// this kernel reads what it writes)
-PR_KERNEL k_tb_update(DV d, pr_step_conf conf)
-{
-    if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
-    const unsigned n = d.cnt->tbAddN, old = d.cnt->tbAddOld;
-    for (unsigned i = PR_TID; i < n; i += PR_NTHREADS) { const unsigned id = d.c_order[old + i]; update_contact(d, conf, id, d.c_flags[id]); }
-    if (PR_TID == 0u && n) {
-        const unsigned nFree = d.cnt->devFree;
-        const unsigned used = n < nFree ? n : nFree;
-        d.cnt->devFree = nFree - used; d.cnt->devPool += n - used; d.cnt->devOrder += n; d.cnt->tbAdded += n;
+    for (unsigned i = PR_TID; i < nP; i += PR_NTHREADS) create_contact_one(d, i, d.np_key2, d.np_idx2, order, nFree, pool, 1u);
+#ifndef PR_HOST_EMUL
+    __threadfence_block();
+    __syncthreads();
+#endif
+    for (unsigned i = PR_TID; i < nP; i += PR_NTHREADS) { const unsigned id = d.c_order[order + i]; update_contact(d, conf, id, d.c_flags[id]); }
+    if (PR_TID == 0u) {
+        const unsigned used = nP < nFree ? nP : nFree;
+        d.cnt->devFree = nFree - used; d.cnt->devPool = pool + (nP - used); d.cnt->devOrder = order + nP; d.cnt->tbAdded += nP;
     }
 }
 

@@ -626,18 +626,12 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
                 PR_LAUNCH_GRID(k_sync_body_proxies, 148, PR_BLOCK, w.stream, d, conf);
                 PR_LAUNCH_GRID(k_tb_refit, 32, PR_BLOCK, w.stream, d, P);
                 PR_LAUNCH_GRID(k_tb_query, 148, PR_BLOCK, w.stream, d, P, w.bvhSortedIdx, w.capPairs);
-                PR_LAUNCH_GRID(k_tb_clear, 32, PR_BLOCK, w.stream, d, w.capPairs, w.capContacts, w.capHash, w.hashTombs);
-                PR_LAUNCH_GRID(k_tb_sort, 1, 1024, w.stream, d);
-                PR_LAUNCH_GRID(k_tb_create, 8, PR_BLOCK, w.stream, d);
-                PR_LAUNCH_GRID(k_tb_update, 8, PR_BLOCK, w.stream, d, conf);
+                PR_LAUNCH_GRID(k_tb_add, 1, TB_ADD_BLOCK, w.stream, d, conf, w.capPairs, w.capContacts, w.capHash, w.hashTombs);
 #else
                 PR_LAUNCH(k_sync_body_proxies, 1, w.stream, d, conf);
                 PR_LAUNCH(k_tb_refit, 2, w.stream, d, P);
                 PR_LAUNCH(k_tb_query, 2, w.stream, d, P, w.bvhSortedIdx, w.capPairs);
-                PR_LAUNCH(k_tb_clear, 2, w.stream, d, w.capPairs, w.capContacts, w.capHash, w.hashTombs);
-                PR_LAUNCH(k_tb_sort, 1, w.stream, d);
-                PR_LAUNCH(k_tb_create, 2, w.stream, d);
-                PR_LAUNCH(k_tb_update, 2, w.stream, d, conf);
+                PR_LAUNCH(k_tb_add, 1, w.stream, d, conf, w.capPairs, w.capContacts, w.capHash, w.hashTombs);
 #endif
             }
             read_counters(w);
@@ -1029,7 +1023,9 @@ int pr_set_bodies(pr_world* pw, uint32_t n, const uint32_t* ids, const pr_body* 
 {
     API_TRY(pw)
     World& w = pw->w;
-    for (uint32_t i = 0; i < n; ++i) if (ids[i] >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    uint32_t maxId = 0; // (branch-free so that it vectorises: a bulk SetBody of 1M rows spent ~1 ms in an early-exit loop here)
+    for (uint32_t i = 0; i < n; ++i) maxId = ids[i] > maxId ? ids[i] : maxId;
+    if (n && maxId >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
     if (!n) return PR_OK;
     pr_body* staging = static_cast<pr_body*>(stage_buf(w, 0, sizeof(pr_body) * n));
     unsigned* dids = static_cast<unsigned*>(stage_buf(w, 1, 4 * n));
