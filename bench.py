@@ -62,12 +62,21 @@ class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag, self.how = index, [], False, "nvml"
+        try:  # NVML is initialised HERE, long before the timed region: the first nvmlInit of a box stalls the driver for ~0.5 s
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml_handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml_max = pynvml.nvmlDeviceGetMaxClockInfo(self.nvml_handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(self.nvml_handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.nvml_handle)
+        except Exception:
+            self.nvml_handle = None
 
     def _nvml_loop(self):
         import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        if self.nvml_handle is None:
+            raise RuntimeError("no NVML")
+        h, mx = self.nvml_handle, self.nvml_max
         bits = [("hw_slowdown", pynvml.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonHwThermalSlowdown),
                 ("sw_thermal_slowdown", pynvml.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", pynvml.nvmlClocksThrottleReasonSwPowerCap)]
         while not self.stop_flag:
@@ -108,7 +117,7 @@ class ClockSampler(threading.Thread):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE regular-phase k_update_contacts launch on this workload, from the
 # `ncu --set full` capture summarised under profiles/ (None until a capture of the current kernel exists)
-ROOFLINE_TRAFFIC = {}
+ROOFLINE_TRAFFIC = {"mixed": int(1.149e9 + 0.2007e9)}  # profiles/r01d_ncu_full_mixed1m.txt, k_update_contacts (697 us row)
 
 
 def algorithmic_bytes(prof, nv, np_):
@@ -287,6 +296,7 @@ def main():
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     tumblers = args.workload == "tumblers"
+    sampler = ClockSampler(local_rank)  # (initialises NVML now; sampling starts with the timed region)
     if tumblers:
         gw, conf, desc, extra = make_tumbler_arena(args, W, rank, world_size, local_rank)
     else:
@@ -302,7 +312,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
     sampler.start()
     # ---------------- device-resident timed region: K steps, state already in HBM; CUDA events on the world's stream
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -413,6 +422,9 @@ def main():
                          "other_kernels": others},
             "stage_ms_per_step": stage,
             "clocks": sampler.summary(),
+            # per-step device times of rank 0 (pr_get_step_profile: CUDA events around each step's stages)
+            "step_ms_percentiles": {k: float(np.percentile([float(p["ms_total"]) for p in profs], q)) for k, q in (("p10", 10), ("p50", 50), ("p90", 90), ("max", 100))},
+            "toi_ms_percentiles": {k: float(np.percentile([float(p["ms_stage"][13]) + float(p["ms_stage"][14]) for p in profs], q)) for k, q in (("p10", 10), ("p50", 50), ("p90", 90), ("max", 100))},
             "step_stats_all_ranks": {"islands_found": int(folded["reg"]["islands_found"]), "islands_solved": int(folded["reg"]["islands_solved"]),
                                      "contacts_added": int(folded["reg"]["contacts_added"]) + int(folded["pre"]["contacts_added"]) + int(folded["toi"]["contacts_added"]),
                                      "contacts_destroyed": int(folded["pre"]["contacts_destroyed"]), "bodies_slept": int(folded["reg"]["bodies_slept"]),

@@ -1116,7 +1116,7 @@ PR_D void pc_store(const RS& r, unsigned i, const PCRow& p)
     r.pc0[i] = make_float4(p.lnx, p.lny, p.lpx, p.lpy);
     r.pc1[i] = make_float4(p.p0x, p.p0y, p.p1x, p.p1y);
     r.pc2[i] = make_float4(p.lcAx, p.lcAy, p.lcBx, p.lcBy);
-    r.pc3[i] = make_float4(p.totalRadius, u2f(p.typeCount), 0.0f, 0.0f);
+    r.pc3[i] = make_float4(p.totalRadius, u2f(p.typeCount), p.rotC, p.rotS);
 }
 PR_D PCRow pc_load(const RS& r, unsigned i)
 {
@@ -1125,7 +1125,7 @@ PR_D PCRow pc_load(const RS& r, unsigned i)
     p.lnx = a.x; p.lny = a.y; p.lpx = a.z; p.lpy = a.w;
     p.p0x = b.x; p.p0y = b.y; p.p1x = b.z; p.p1y = b.w;
     p.lcAx = c.x; p.lcAy = c.y; p.lcBx = c.z; p.lcBy = c.w;
-    p.totalRadius = e.x; p.typeCount = f2u(e.y); p.pad0 = p.pad1 = 0u;
+    p.totalRadius = e.x; p.typeCount = f2u(e.y); p.rotC = e.z; p.rotS = e.w;
     return p;
 }
 
@@ -1151,7 +1151,11 @@ PR_D void build_constraint_rows(const DV& d, const RS& r, unsigned cid, unsigned
         pc.lnx = q0.x; pc.lny = q0.y; pc.lpx = q0.z; pc.lpy = q0.w;
         pc.p0x = q1.x; pc.p0y = q1.y; pc.p1x = q1.z; pc.p1y = q1.w;
         pc.lcAx = lcA.x; pc.lcAy = lcA.y; pc.lcBx = lcB.x; pc.lcBy = lcB.y;
-        pc.totalRadius = rA + rB; pc.typeCount = q3.z | (q3.w << 8); pc.pad0 = pc.pad1 = 0u;
+        pc.totalRadius = rA + rB; pc.typeCount = q3.z | (q3.w << 8); pc.rotC = pc.rotS = 0.0f;
+        // a body that cannot move (no velocity flag) keeps its angle through the whole solve: its rotation, which the
+        // position iterations would recompute with sincosf for every row and iteration, is stored with the row
+        if (!f_speedable(d.b_flags[ab.x]) && mA.x == 0.0f && mA.y == 0.0f) { pc.typeCount |= 1u << 16; pc.rotC = xfA.q.c; pc.rotS = xfA.q.s; }
+        else if (!f_speedable(d.b_flags[ab.y]) && mB.x == 0.0f && mB.y == 0.0f) { pc.typeCount |= 1u << 17; pc.rotC = xfB.q.c; pc.rotS = xfB.q.s; }
         pc_store(r, i, pc);
         // world manifold
         Rot normal = mkrot(0.0f, 0.0f);
@@ -1515,15 +1519,20 @@ PR_D float solve_position_row(const DV& d, const RS& r, unsigned i, float rate, 
     did = true;
     Pos posA = pos_from4(a4), posB = pos_from4(b4);
     const float2 lcA = v2(pc.lcAx, pc.lcAy), lcB = v2(pc.lcBx, pc.lcBy);
-    const unsigned count = pc.typeCount >> 8;
+    const unsigned count = (pc.typeCount >> 8) & 0xFFu;
+    const bool fixedA = (pc.typeCount & (1u << 16)) != 0u, fixedB = (pc.typeCount & (1u << 17)) != 0u;
+    const Rot fixedRot = mkrot(pc.rotC, pc.rotS);
+    // GetTransformation(pos, lc) with the static body's UnitVec::Get(angle) taken from the row (same bits: same angle)
+    auto xf_a = [&](const Pos& p) { return fixedA ? get_xf(p.l, fixedRot, lcA) : get_xf(p, lcA); };
+    auto xf_b = [&](const Pos& p) { return fixedB ? get_xf(p.l, fixedRot, lcB) : get_xf(p, lcB); };
     float minSep = PR_INF;
     if (count == 1u) {
-        const PSM psm0 = get_psm(pc, 0u, get_xf(posA, lcA), get_xf(posB, lcB));
+        const PSM psm0 = get_psm(pc, 0u, xf_a(posA), xf_b(posB));
         const PDelta s = psm_solve(psm0, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
         posA.l = posA.l + s.al; posA.a += s.aa; posB.l = posB.l + s.bl; posB.a += s.ba;
         minSep = 0.0f + s.sep;
     } else if (count == 2u) {
-        const Xf xfA = get_xf(posA, lcA), xfB = get_xf(posB, lcB);
+        const Xf xfA = xf_a(posA), xfB = xf_b(posB);
         const PSM psm0 = get_psm(pc, 0u, xfA, xfB), psm1 = get_psm(pc, 1u, xfA, xfB);
         if (almost_equal(psm0.separation, psm1.separation)) {
             const PDelta s0 = psm_solve(psm0, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
@@ -1534,14 +1543,14 @@ PR_D float solve_position_row(const DV& d, const RS& r, unsigned i, float rate, 
         } else if (psm0.separation < psm1.separation) {
             const PDelta s0 = psm_solve(psm0, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
             posA.l = posA.l + s0.al; posA.a += s0.aa; posB.l = posB.l + s0.bl; posB.a += s0.ba;
-            const PSM p1 = get_psm(pc, 1u, get_xf(posA, lcA), get_xf(posB, lcB));
+            const PSM p1 = get_psm(pc, 1u, xf_a(posA), xf_b(posB));
             const PDelta s1 = psm_solve(p1, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
             posA.l = posA.l + s1.al; posA.a += s1.aa; posB.l = posB.l + s1.bl; posB.a += s1.ba;
             minSep = s0.sep;
         } else if (psm1.separation < psm0.separation) {
             const PDelta s1 = psm_solve(psm1, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
             posA.l = posA.l + s1.al; posA.a += s1.aa; posB.l = posB.l + s1.bl; posB.a += s1.ba;
-            const PSM p0 = get_psm(pc, 0u, get_xf(posA, lcA), get_xf(posB, lcB));
+            const PSM p0 = get_psm(pc, 0u, xf_a(posA), xf_b(posB));
             const PDelta s0 = psm_solve(p0, posA.l, posB.l, imA, iiA, imB, iiB, pc.totalRadius, rate, slop, maxCorr);
             posA.l = posA.l + s0.al; posA.a += s0.aa; posB.l = posB.l + s0.bl; posB.a += s0.ba;
             minSep = s1.sep;

@@ -47,7 +47,8 @@ struct PCRow {
     float lnx, lny, lpx, lpy;
     float p0x, p0y, p1x, p1y;
     float lcAx, lcAy, lcBx, lcBy;
-    float totalRadius; unsigned typeCount; unsigned pad0, pad1;
+    float totalRadius; unsigned typeCount; // type | count << 8 | (rotation of body A cached) << 16 | (of body B) << 17
+    float rotC, rotS;                      // UnitVec::Get(angle) of the row's STATIC body, if it has one (see solve_position_row)
 };
 
 // per-step work data of a revolute joint (RevoluteJointConf's rA, rB, mass, angularMass) + its island label
