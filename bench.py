@@ -99,6 +99,10 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.2)
 
+    def mark(self):
+        """Start of the timed region: forget the samples taken while warming up."""
+        self.samples = []
+
     def run(self):
         try:
             self._nvml_loop()
@@ -303,16 +307,27 @@ def main():
         gw, conf, desc, extra = make_mixed_world(args, W, rank, local_rank)
     nb = int(gw.counts()["bodies"])
     warmup = max(3, args.warmup)
+    # the sampling thread runs through the warm-up steps already: the first NVML queries of a thread on a fresh box were seen to
+    # stall the driver for ~1 s (one 1.29 s step in the first process of a box); its samples before the timed region are dropped
+    sampler.start()
+    stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", local_rank))
+    # everything the timed loop touches is used once while warming up (torch's lazy CUDA initialisation, event pools, profile reads)
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record(stream)
     for _ in range(warmup):
         gw.step(conf)
-    stream = torch.cuda.ExternalStream(gw.stream(), device=torch.device("cuda", local_rank))
+        gw.profile()
+    w1.record(stream)
+    torch.cuda.synchronize()
+    w0.elapsed_time(w1)
+    time.sleep(0.1)
 
     def barrier():
         if world_size > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler.start()
+    sampler.mark()
     # ---------------- device-resident timed region: K steps, state already in HBM; CUDA events on the world's stream
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
