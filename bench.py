@@ -351,6 +351,9 @@ def main():
     secs = ev0.elapsed_time(ev1) / 1e3
     if args.cuda_profiler:
         torch.cuda.profiler.stop()
+    if rank == 0:  # the slowest steps with their stage times (stderr): growth / rebuild steps show up here
+        for k in sorted(range(len(profs)), key=lambda k: -float(profs[k]["ms_total"]))[:3]:
+            print("slow step %d: %.2f ms colour rounds %d, buffer growths %d  %s" % (k, float(profs[k]["ms_total"]), int(profs[k]["color_rounds"]), int(profs[k]["grow_events"]), {n: round(float(profs[k]["ms_stage"][i]), 2) for i, n in enumerate(abi.STAGE_NAMES) if profs[k]["ms_stage"][i] > 0.3}), file=sys.stderr)
     # ---------------- end-to-end: host buffers in, host buffers out, every step
     rows = gw.bodies()
     ids = np.arange(nb, dtype=np.uint32)

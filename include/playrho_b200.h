@@ -187,6 +187,7 @@ typedef struct pr_step_profile {
     uint32_t n_awake, p_total, p_moved, c_total, c_dirty, c_touching, n_colors, n_islands;
     uint32_t vel_iters, pos_iters, candidate_pairs, kernel_launches;
     uint32_t toi_rounds, toi_events; /* TOI phase: kernel rounds run and TOI events solved (SolveToi loop turns) */
+    uint32_t color_rounds, grow_events; /* colouring rounds run; device buffers re-allocated (cudaMalloc/cudaFree) during the step */
     float ms_total;            /* CUDA-event time of the whole step on the world's stream */
     float ms_stage[16];        /* see PR_STAGE_* */
 } pr_step_profile;

@@ -75,7 +75,7 @@ COUNTS = np.dtype([(n, u4) for n in ("bodies", "shapes", "children", "vertices",
 N_STAGES = 16
 STEP_PROFILE = np.dtype([(n, u4) for n in ("n_awake", "p_total", "p_moved", "c_total", "c_dirty",
                                            "c_touching", "n_colors", "n_islands", "vel_iters",
-                                           "pos_iters", "candidate_pairs", "kernel_launches", "toi_rounds", "toi_events")] +
+                                           "pos_iters", "candidate_pairs", "kernel_launches", "toi_rounds", "toi_events", "color_rounds", "grow_events")] +
                         [("ms_total", f4), ("ms_stage", f4, (N_STAGES,))])
 STAGE_NAMES = ["pre", "islands", "integrate", "setup", "color", "velocity", "position", "writeback",
                "sync", "narrow", "bvh", "query", "add", "toi", "toi_solve"]

@@ -98,8 +98,9 @@ static std::vector<ArrDesc> arrays(World& w)
         A(ht_keys, G_HASH),
         A(np_key, G_PAIR), A(np_key2, G_PAIR), A(np_px, G_PAIR), A(np_idx, G_PAIR), A(np_idx2, G_PAIR),
         A(vc0, G_CONS), A(vc1, G_CONS), A(vc2, G_CONS), A(vc3, G_CONS), A(vc4, G_CONS), A(vc5, G_CONS), A(vc6, G_CONS), A(vc7, G_CONS),
-        A(vc8, G_CONS), A(vc_island, G_CONS), A(pc0, G_CONS), A(pc1, G_CONS), A(pc2, G_CONS), A(pc3, G_CONS), A(k_contact, G_CONS), A(k_color, G_CONS), A(k_sorted, G_CONS), A(k_tmpKey, G_CONS),
-        A(k_tmpKey2, G_CONS), A(k_tmpVal, G_CONS), A(k_ulist, G_CONS),
+        A(vc8, G_CONS), A(vc_island, G_CONS), A(pc0, G_CONS), A(pc1, G_CONS), A(pc2, G_CONS), A(pc3, G_CONS), A(k_sorted, G_CONS),
+        // per-contact scratch of the constraint-list build (sized like m_contacts: written before the constraint count is known)
+        A(k_contact, G_CONTACT), A(k_color, G_CONTACT), A(k_tmpKey, G_CONTACT), A(k_tmpKey2, G_CONTACT), A(k_tmpVal, G_CONTACT), A(k_ulist, G_CONTACT),
     };
 #undef A
 #undef A2
@@ -136,7 +137,8 @@ static void ensure(World& w, Group g, unsigned need)
 {
     unsigned* cap = cap_of(w, g);
     if (need <= *cap) return;
-    unsigned newCap = std::max(need, std::max(1024u, *cap + *cap / 2));
+    unsigned newCap = std::max(need + need / 8u, std::max(1024u, 2u * *cap)); // (growth is expensive: double, with headroom)
+    ++w.profile.grow_events;
     if (g == G_HASH) newCap = next_pow2(need);
     for (const ArrDesc& a : arrays(w)) {
         if (a.g != g) continue;
@@ -256,7 +258,7 @@ static unsigned destroy_contacts(World& w)
 { // DestroyContacts (overlap part), AabbTreeWorld.cpp:2290-2304
     if (w.nOrder == 0) return 0;
     DV& d = w.d;
-    ensure(w, G_CONS, w.nOrder + 1);
+    ensure(w, G_CONTACT, w.nOrder + 1);
     PR_LAUNCH(k_destroy_test, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, w.hashDirty ? 0u : 1u);
     scan_exclusive_u32(d.c_tmp, d.k_tmpVal, w.nOrder, &d.cnt->nNew, w.scanScratch, w.stream);
     read_counters(w);
@@ -381,13 +383,14 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     tm.mark(w, PR_STAGE_COLOR);
     unsigned nCons = 0;
     if (w.nOrder) {
-        ensure(w, G_CONS, w.nOrder + 1);
+        ensure(w, G_CONTACT, w.nOrder + 1);
         PR_LAUNCH(k_mark_constraints, w.nOrder, w.stream, d, w.nOrder, d.c_tmp);
         scan_exclusive_u32(d.c_tmp, d.k_tmpVal, w.nOrder, &d.cnt->nConstraints, w.scanScratch, w.stream);
         PR_LAUNCH(k_gather_constraints, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, d.k_tmpVal, w.recolorAll ? 1u : 0u);
         PR_LAUNCH(k_color_keep, w.nOrder, w.stream, d, w.nOrder); // nColorWork was zeroed by reset_counters at step start
         read_counters(w);
         nCons = w.hostCnt.nConstraints;
+        ensure(w, G_CONS, nCons + 1); // the rows (13 planes of 16 B) are sized by the constraints, not by the contacts
     }
     w.nCons = nCons; w.nColors = 0;
     std::vector<std::pair<unsigned, unsigned>> ranges; // (start, count) per colour, overflow tail last
@@ -400,6 +403,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
                 if (round && (round % 64u) == 0u) PR_LAUNCH(k_color_reset_claims, N, w.stream, d, N);
                 PR_LAUNCH(k_color_claim, nWork, w.stream, d, nWork, round);
                 PR_LAUNCH(k_color_commit, nWork, w.stream, d, nWork, round);
+                ++w.profile.color_rounds;
                 if ((round & 3u) == 3u || nWork < 64u) { // look at the remaining count every 4th round only
                     read_counters(w);
                     if (w.hostCnt.nUncolored == 0) break;
@@ -523,7 +527,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     // homogeneous warps, but a warp's 32 contact ids are no longer consecutive, so every 16-byte row of the seven contact
     // planes drags in a 32-byte sector of its own and the kernel turns bandwidth-bound. Kept for the record and the tests.
     if ((w.debugFlags & 2u) && w.nOrder) {
-        ensure(w, G_CONS, w.nOrder + 1); // (k_tmpKey/k_tmpKey2/k_tmpVal and c_tmp are free scratch at this point of the step)
+        ensure(w, G_CONTACT, w.nOrder + 1); // (k_tmpKey/k_tmpKey2/k_tmpVal and c_tmp are free scratch at this point of the step)
         PR_LAUNCH(k_narrow_keys, w.nOrder, w.stream, d, w.nOrder, 1u, d.k_tmpKey, d.k_tmpVal);
         const bool inB = radix_sort_pairs<unsigned>(d.k_tmpKey, d.k_tmpVal, d.k_tmpKey2, d.c_tmp, w.nOrder, 0, 8, false, w.rs, w.stream);
         PR_LAUNCH(k_update_contacts_binned, w.nOrder, w.stream, d, conf, w.nOrder, inB ? d.k_tmpKey2 : d.k_tmpKey, inB ? d.c_tmp : d.k_tmpVal);
@@ -593,7 +597,9 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     for (;;) {
         if (w.nOrder == 0) { w.stepComplete = true; break; } // nothing can have a TOI
         if (!w.adjValid) build_adjacency(w);
-        ensure(w, G_CONS, std::min(2u * w.nOrder, w.nOrder + (1u << 20)) + 64u); // island rows (VC/PC scratch) of one round's events
+        // island scratch (body / contact lists, VC/PC rows of islands too large for shared memory) of ONE round's events: an
+        // event that does not fit is deferred to the next round (k_toi_solve), so this is a working size, not a worst case
+        ensure(w, G_CONS, std::min(2u * w.nOrder, std::max(1u << 16, 16u * w.toiListBound)) + 64u);
         const unsigned P = w.nProxies;
         // ---- batched rounds: needs an intact tree to refit in place; otherwise one host-driven round (below)
         const bool canBatch = w.bvhValid && w.bvhLeaves == P && P > 1; // (the refit budget is checked by the next regular step)
@@ -834,7 +840,14 @@ int pr_create(const pr_world_conf* conf, pr_world** out)
         ensure(w, G_SHAPE, 64); ensure(w, G_CHILD, 64); ensure(w, G_VERT, std::max(256u, w.conf.vertex_capacity));
         ensure(w, G_PROXY, std::max(64u, w.conf.proxy_capacity));
         ensure(w, G_CONTACT, std::max(256u, w.conf.contact_capacity));
-        ensure(w, G_PAIR, 1024); ensure(w, G_CONS, 256); ensure(w, G_ADJ, 256); ensure(w, G_JOINT, 16);
+        // The derived buffers start in proportion to the configured contact capacity, so that a world sized by its caller
+        // never re-allocates while stepping: a growth is cudaMalloc + copy + cudaFree of up to GBs, measured at 10-400 ms
+        // on a shared B200 host (three such steps in a 50-step timed window cost 10% of the mean step time).
+        const unsigned cc = w.conf.contact_capacity, bc = w.conf.body_capacity;
+        ensure(w, G_PAIR, std::max(1024u, cc / 8u));
+        ensure(w, G_CONS, std::max(256u, cc / 3u));
+        ensure(w, G_ADJ, std::max(256u, cc ? 2u * cc + cc / 2u + 8u * bc + 64u : 0u));
+        ensure(w, G_JOINT, 16);
         ensure(w, G_HASH, next_pow2(2u * w.capContacts));
         reset_counters(w);
         sync(w);
