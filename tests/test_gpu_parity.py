@@ -241,3 +241,68 @@ def test_cuda_large_scene_invariants():
          (np.minimum(px["max_y"][ia], px["max_y"][ib]) >= np.maximum(px["min_y"][ia], px["min_y"][ib]))
     assert ov.all()
     assert len(cs) > 100000
+
+
+def test_cuda_full_size_mixed_world_invariants():
+    """BASELINE config 4 at FULL size (1M mixed disks / 4-8-gons over chain terrain, TOI on, parallel event mode): the
+    size-independent properties of the step. (1) determinism: a clone steps to identical bits (stats, bodies, contacts,
+    manifolds) through the batched TOI rounds; (2) the contact set is exactly the broadphase's: keys unique, A < B, every
+    contact's fat boxes overlap, and for a random sample of proxies EVERY other proxy whose fat box overlaps theirs (other
+    body, either accelerable) has its contact -- completeness of the LBVH query against brute force; (3) touching <=> a
+    manifold with points; (4) nothing re-allocates while stepping a world created with its capacities."""
+    n = 1000000
+    sc = scenes_np.mixed_fast(n, seed=12345)
+    nb = len(sc["bodies"])
+    gw = W.World(sc, device=0, body_capacity=nb + 16, proxy_capacity=nb + 8192, contact_capacity=6 * nb)
+    conf = W.default_step_conf()
+    events = 0
+    for s in range(120):
+        st = gw.step(conf)
+        events += int(st["toi"]["contacts_found"])
+        if s >= 60:
+            assert int(gw.profile()["grow_events"]) == 0, "step %d re-allocated a device buffer" % s
+    assert events > 0
+    other = gw.clone()
+    for _ in range(3):
+        s1 = gw.step(conf); s2 = other.step(conf)
+        assert_bits(np.array([s1]), np.array([s2]), "stats of clone")
+    b1 = gw.bodies()
+    assert_bits(b1, other.bodies(), "clone bodies")
+    c1, m1 = gw.contacts(); c2, m2 = other.contacts()
+    assert_bits(c1, c2, "clone contacts"); assert_bits(m1, m2, "clone manifolds")
+    for f in ("pos1_x", "pos1_y", "pos1_a", "vel_x", "vel_y", "vel_w"):
+        assert np.isfinite(b1[f]).all()
+    gw.step(W.default_step_conf(delta_time=0.0))  # pre-phase only: DestroyContacts + FindContacts (AabbTreeWorld.cpp:2186-2205)
+    cs, ms = gw.contacts()
+    assert len(cs) > n
+    keys = (cs["key_min"].astype(np.uint64) << np.uint64(32)) | cs["key_max"].astype(np.uint64)
+    assert len(np.unique(keys)) == len(keys)
+    assert (cs["key_min"] < cs["key_max"]).all()
+    px = gw.proxies()
+    slot = np.full(int(px["tree_id"].max()) + 1, -1, np.int64)
+    slot[px["tree_id"]] = np.arange(len(px))
+    ia, ib = slot[cs["key_min"]], slot[cs["key_max"]]
+    assert (ia >= 0).all() and (ib >= 0).all()
+    ov = (np.minimum(px["max_x"][ia], px["max_x"][ib]) >= np.maximum(px["min_x"][ia], px["min_x"][ib])) & \
+         (np.minimum(px["max_y"][ia], px["max_y"][ib]) >= np.maximum(px["min_y"][ia], px["min_y"][ib]))
+    assert ov.all()
+    touching = (cs["flags"] & 1) != 0
+    sensor = (cs["flags"] & 0x20) != 0
+    assert np.array_equal(touching[~sensor], ms["count"][~sensor] > 0)
+    # completeness against brute force for a sample of proxies of dynamic bodies
+    rows = gw.bodies()
+    accel = (rows["flags"] & abi.BODY_ACCELERATION) != 0 if hasattr(abi, "BODY_ACCELERATION") else rows["inv_mass"] > 0
+    rng = np.random.default_rng(7)
+    dyn_px = np.nonzero(accel[px["body"]])[0]
+    have = set(keys.tolist())
+    checked = 0
+    for q in rng.choice(dyn_px, 200, replace=False):
+        hit = (np.minimum(px["max_x"], px["max_x"][q]) >= np.maximum(px["min_x"], px["min_x"][q])) & \
+              (np.minimum(px["max_y"], px["max_y"][q]) >= np.maximum(px["min_y"], px["min_y"][q])) & (px["body"] != px["body"][q])
+        tq = int(px["tree_id"][q])
+        for o in np.nonzero(hit)[0]:
+            to = int(px["tree_id"][o])
+            k = (min(tq, to) << 32) | max(tq, to)
+            assert k in have, "overlapping fat boxes of proxies %d and %d have no contact" % (q, o)
+            checked += 1
+    assert checked > 400
