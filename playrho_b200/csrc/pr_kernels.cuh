@@ -422,19 +422,66 @@ PR_D void update_contact(const DV& d, const pr_step_conf& conf, unsigned id, uns
     else if (oldTouching && !newTouching) flags &= ~static_cast<unsigned>(PR_CONTACT_TOUCHING);
     if (flags != oldFlags) d.c_flags[id] = flags;
 }
-// UpdateContacts (AabbTreeWorld.cpp:2333-2421): one thread per contact of order[start, start+n)
-PR_KERNEL k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n, unsigned useMoved, unsigned countIt)
+// UpdateContacts (AabbTreeWorld.cpp:2333-2421): one thread per contact of order[start, start+n).
+// A warp's 32 contacts mix disk-disk, disk-polygon and polygon-polygon pairs, and it used to execute the three paths one
+// after another (ncu: 4.9 of 32 lanes active; every warp paid for the O(vA x vB) polygon search). The block now deals its
+// 256 contacts out again by class -- a counting sort in shared memory, stable, so neighbouring lanes still hold
+// neighbouring contact ids and the global accesses keep their locality (a GLOBAL sort by class lost to sector waste).
+#if !defined(PR_HOST_EMUL)
+#ifndef PR_NARROW_MINBLOCKS
+#define PR_NARROW_MINBLOCKS 4 // latency-bound on its gather chain: 64 registers / 4 CTAs per SM measured 0.77 -> 0.65 ms (5 and 6: 0.68)
+#endif
+__global__ void __launch_bounds__(PR_BLOCK, PR_NARROW_MINBLOCKS)
+#else
+PR_KERNEL
+#endif
+k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n, unsigned useMoved, unsigned countIt)
 {
     const unsigned i = PR_TID;
-    bool updated = false;
+    bool dirty = false;
+    unsigned id = 0u, flags = 0u;
     if (i < n) {
-        const unsigned id = d.c_order[start + i];
-        const unsigned flags = d.c_flags[id];
-        bool dirty = (flags & PR_CONTACT_DIRTY) != 0;
+        id = d.c_order[start + i];
+        flags = d.c_flags[id];
+        dirty = (flags & PR_CONTACT_DIRTY) != 0;
         if (useMoved) { const uint4 ab = d.c_ab[id]; dirty = dirty || (d.b_moved[ab.x] | d.b_moved[ab.y]) != 0u; }
-        if (dirty) { updated = true; update_contact(d, conf, id, flags); }
     }
-    block_add(&d.cnt->contactsUpdated, (updated && countIt) ? 1u : 0u);
+#ifndef PR_HOST_EMUL
+    constexpr unsigned NCLS = 4u; // 0 point-point, 1 point-polygon, 2 polygon-polygon / sensor, 3 nothing to do
+    __shared__ unsigned s_id[PR_BLOCK], s_flags[PR_BLOCK];
+    __shared__ unsigned s_warp[PR_BLOCK / 32][NCLS], s_base[NCLS + 1u];
+    unsigned cls = 3u;
+    if (dirty) {
+        const uint4 ab = d.c_ab[id];
+        const unsigned ca = d.ch_count[ab.z], cb = d.ch_count[ab.w];
+        cls = (flags & PR_CONTACT_SENSOR) ? 2u : (ca == 1u && cb == 1u) ? 0u : (ca == 1u || cb == 1u) ? 1u : 2u;
+    }
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    unsigned rank = 0u;
+#pragma unroll
+    for (unsigned c = 0; c < NCLS; ++c) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+        if (cls == c) rank = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0u) s_warp[wid][c] = __popc(m);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0u) { // (32 numbers: one thread turns the per-warp counts into class-major offsets)
+        unsigned run = 0u;
+        for (unsigned c = 0; c < NCLS; ++c) {
+            s_base[c] = run;
+            for (unsigned w = 0; w < blockDim.x / 32u; ++w) { const unsigned t = s_warp[w][c]; s_warp[w][c] = run; run += t; }
+        }
+        s_base[NCLS] = run;
+    }
+    __syncthreads();
+    const unsigned slot = s_warp[wid][cls] + rank;
+    s_id[slot] = id; s_flags[slot] = flags;
+    __syncthreads();
+    if (threadIdx.x < s_base[3]) update_contact(d, conf, s_id[threadIdx.x], s_flags[threadIdx.x]);
+#else
+    if (dirty) update_contact(d, conf, id, flags);
+#endif
+    block_add(&d.cnt->contactsUpdated, (dirty && countIt) ? 1u : 0u);
 }
 
 // Binned narrowphase (the regular phase's UpdateContacts, where nearly every contact is dirty): a warp of the plain
@@ -1414,7 +1461,15 @@ PR_D float solve_velocity_row(const DV& d, const RS& r, unsigned i, bool& did, b
     r.vc8[i] = make_float4(jn[0], jt[0], jn[1], jt[1]);
     return maxInc;
 }
-PR_KERNEL k_solve_velocity(DV d, unsigned start, unsigned count)
+#if !defined(PR_HOST_EMUL)
+#ifndef PR_VEL_MINBLOCKS
+#define PR_VEL_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(PR_BLOCK, PR_VEL_MINBLOCKS)
+#else
+PR_KERNEL
+#endif
+k_solve_velocity(DV d, unsigned start, unsigned count)
 {
     const unsigned t = PR_TID;
     bool did = false; float inc = 0.0f; unsigned label = 0u;
