@@ -362,6 +362,11 @@ def main():
     rows_in = pinned_in.numpy().view(abi.BODY)
     rows_out = pinned_out.numpy().view(abi.BODY)
     e2e_steps = max(2, min(args.steps, 10))
+    for _ in range(3):  # untimed: the first bulk upload / download allocates the library's staging buffers (cudaMalloc of ~100 MB)
+        gw.set_bodies(ids, rows_in)
+        gw.step(conf)
+        gw.bodies_into(rows_out)
+        rows_in, rows_out = rows_out, rows_in
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev2.record(stream)

@@ -382,12 +382,16 @@ PR_D void update_contact(const DV& d, const pr_step_conf& conf, unsigned id, uns
         newTouching = gjk_test_overlap(child_view(d, ab.z), xfA, child_view(d, ab.w), xfB, conf.max_distance_iters) >= 0.0f;
         manifold_clear(d, id);
     } else {
-        Mf nm = collide_shapes(child_view(d, ab.z), xfA, child_view(d, ab.w), xfB, conf.linear_slop, conf.max_circles_ratio);
+        // the old manifold is fetched BEFORE the collision (it does not depend on it): its round trip overlaps the
+        // vertex fetches instead of following them (a touching contact will need the points and impulses too)
         const uint4 o3 = d.m3[id];
+        float4 o1 = make_float4(0, 0, 0, 0), o2 = make_float4(0, 0, 0, 0);
+        if (oldTouching) { o1 = d.m1[id]; o2 = d.m2[id]; }
+        Mf nm = collide_shapes(child_view(d, ab.z), xfA, child_view(d, ab.w), xfB, conf.linear_slop, conf.max_circles_ratio);
         const unsigned oldCount = o3.w, newCount = nm.count;
         newTouching = newCount > 0u;
         if (newCount > 0u && oldCount > 0u) {
-            const float4 o1 = d.m1[id], o2 = d.m2[id];
+            if (!oldTouching) { o1 = d.m1[id]; o2 = d.m2[id]; } // (old points without the touching flag: not produced by Update, kept for safety)
             const unsigned ocf[2] = {o3.x, o3.y};
             const float ojn[2] = {o2.x, o2.z}, ojt[2] = {o2.y, o2.w};
             const float2 op[2] = {v2(o1.x, o1.y), v2(o1.z, o1.w)};
