@@ -80,6 +80,34 @@ template <class F> PR_D void fused_tail(const DV& d, const SolvePlan& p, F&& fn)
     }
 }
 
+// ---- the trailing SMALL colours of an iteration in one launch ---------------------------------------------------
+// Greedy colouring leaves a tail of nearly empty colours (1M mixed scene: 127k, 125k, ... 21k, 5.4k, 891, 108, 12, 1
+// rows): each still cost a launch per iteration. Colours of at most SMALL_COLOR_ROWS rows are solved by ONE block, a
+// block barrier between colours (same SM: the barrier orders their global writes).
+constexpr unsigned SMALL_COLOR_ROWS = 1024u, SMALL_COLOR_MAX = 24u, SMALL_BLOCK = 1024u;
+struct SmallPlan { unsigned n; unsigned start[SMALL_COLOR_MAX], count[SMALL_COLOR_MAX]; };
+// mode 0 warm start, 1 velocity, 2 position
+__global__ void __launch_bounds__(SMALL_BLOCK, 1) k_solve_small_colors(DV d, SmallPlan p, unsigned mode, float rate, float slop, float maxCorr)
+{
+    const RS r = rs_global(d);
+    const unsigned t = threadIdx.x;
+    for (unsigned c = 0; c < p.n; ++c) {
+        const unsigned start = p.start[c], count = p.count[c];
+        if (mode == 0u) { if (t < count) warm_start_row(r, start + t); }
+        else if (mode == 1u) {
+            bool did = false; float inc = 0.0f; unsigned label = 0u;
+            if (t < count) { inc = solve_velocity_row(d, r, start + t, did); label = d.vc_island[start + t]; }
+            island_max(d.isl_inc, label, f2u(inc), did);
+        } else {
+            bool did = false; float sep = PR_INF; unsigned label = 0u;
+            if (t < count) { sep = solve_position_row(d, r, start + t, rate, slop, maxCorr, did); label = d.vc_island[start + t]; }
+            island_min(d.isl_sep, label, float_flip(sep), did);
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
 constexpr unsigned FUSED_BLOCK = 512u; // 2 CTAs of 512 per SM (<= 64 registers): every colour of the 1M scene is one row per thread
 __global__ void __launch_bounds__(FUSED_BLOCK, 2) k_solve_fused(DV d, pr_step_conf conf, SolvePlan p, unsigned* barrier)
 {

@@ -488,28 +488,43 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     }
 #endif
     if (!fused) {
+        // the trailing colours with at most SMALL_COLOR_ROWS rows go through ONE single-block launch per iteration
+        size_t nBig = ranges.size();
+#ifndef PR_HOST_EMUL
+        SmallPlan sp{};
+        while (nBig > 0 && ranges[nBig - 1].second <= SMALL_COLOR_ROWS && sp.n < SMALL_COLOR_MAX) { --nBig; ++sp.n; }
+        if (sp.n < 2u) { nBig = ranges.size(); sp.n = 0u; } // (one small colour alone is just a launch)
+        for (unsigned c = 0; c < sp.n; ++c) { sp.start[c] = ranges[nBig + c].first; sp.count[c] = ranges[nBig + c].second; }
+#define PR_SMALL_COLORS(mode) do { if (sp.n) PR_LAUNCH_GRID(k_solve_small_colors, 1, SMALL_BLOCK, w.stream, d, sp, mode, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction); } while (0)
+#else
+#define PR_SMALL_COLORS(mode) do { } while (0)
+#endif
         if (nCons && conf.do_warm_start) {
-            for (const auto& r : ranges) PR_LAUNCH(k_warm_start, r.second, w.stream, d, r.first, r.second);
+            for (size_t c = 0; c < nBig; ++c) PR_LAUNCH(k_warm_start, ranges[c].second, w.stream, d, ranges[c].first, ranges[c].second);
+            PR_SMALL_COLORS(0u);
             if (tailCount) PR_LAUNCH(k_warm_start_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
         }
         PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 0u, jSerial); // InitVelocity after the contacts' warm start (:1597)
         tm.mark(w, PR_STAGE_VELOCITY);
         for (unsigned it = 0; it < conf.reg_velocity_iters; ++it) {
             PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 1u, jSerial); // joints first (:1605-1608)
-            for (const auto& r : ranges) PR_LAUNCH(k_solve_velocity, r.second, w.stream, d, r.first, r.second);
+            for (size_t c = 0; c < nBig; ++c) PR_LAUNCH(k_solve_velocity, ranges[c].second, w.stream, d, ranges[c].first, ranges[c].second);
+            PR_SMALL_COLORS(1u);
             if (tailCount) PR_LAUNCH(k_solve_velocity_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
             PR_LAUNCH(k_isl_vel_check, N, w.stream, d, N, it, conf.reg_min_momentum);
         }
         tm.mark(w, PR_STAGE_POSITION);
         PR_LAUNCH(k_integrate_positions, N, w.stream, d, N, conf.delta_time);
         for (unsigned it = 0; it < conf.reg_position_iters; ++it) {
-            for (const auto& r : ranges)
-                PR_LAUNCH(k_solve_position, r.second, w.stream, d, r.first, r.second, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
+            for (size_t c = 0; c < nBig; ++c)
+                PR_LAUNCH(k_solve_position, ranges[c].second, w.stream, d, ranges[c].first, ranges[c].second, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
+            PR_SMALL_COLORS(2u);
             if (tailCount)
                 PR_LAUNCH(k_solve_position_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
             PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 2u, jSerial); // joints after the contacts (:1634-1637)
             PR_LAUNCH(k_isl_pos_check, N, w.stream, d, N, it, conf.reg_min_separation);
         }
+#undef PR_SMALL_COLORS
     }
     tm.mark(w, PR_STAGE_WRITEBACK);
     if (nCons) PR_LAUNCH(k_assign_impulses, nCons, w.stream, d, nCons);
