@@ -1489,22 +1489,34 @@ PR_KERNEL k_solve_velocity_tail(DV d, unsigned tailStart, unsigned tailCount, un
     });
 }
 // per-island early exit of velocity iterations (AabbTreeWorld.cpp:1603-1622)
+PR_D unsigned isl_vel_check_root(const DV& d, unsigned i, unsigned iter, float minMomentum)
+{ // i is an island root; returns 1 if the island must keep iterating
+    const unsigned st = d.isl_state[i];
+    if (!(st & ISL_ACTIVE) || (st & ISL_VEL_DONE)) return 0u;
+    const unsigned incBits = d.isl_inc[i];
+    if (incBits > d.isl_maxInc[i]) d.isl_maxInc[i] = incBits; // non-negative floats order like uints
+    const bool jointsOkay = d.isl_jflag[i] == 0u; // every joint's SolveVelocity left the velocities unchanged
+    unsigned still = 0u;
+    if (jointsOkay && u2f(incBits) <= minMomentum) { d.isl_state[i] = st | ISL_VEL_DONE; d.isl_velIters[i] = iter + 1u; }
+    else still = 1u;
+    d.isl_inc[i] = 0u; d.isl_jflag[i] = 0u;
+    return still;
+}
+// iteration 0 scans all bodies for island roots and LISTS the islands still iterating (k_ulist2): a pile is a handful of
+// islands among hundreds of thousands of single falling bodies, which are done after the first iteration
 PR_KERNEL k_isl_vel_check(DV d, unsigned nBodies, unsigned iter, float minMomentum)
 {
     const unsigned i = PR_TID;
     unsigned stillActive = 0u;
-    if (i < nBodies && d.b_island[i] == i) {
-        const unsigned st = d.isl_state[i];
-        if ((st & ISL_ACTIVE) && !(st & ISL_VEL_DONE)) {
-            const unsigned incBits = d.isl_inc[i];
-            if (incBits > d.isl_maxInc[i]) d.isl_maxInc[i] = incBits; // non-negative floats order like uints
-            const bool jointsOkay = d.isl_jflag[i] == 0u; // every joint's SolveVelocity left the velocities unchanged
-            if (jointsOkay && u2f(incBits) <= minMomentum) { d.isl_state[i] = st | ISL_VEL_DONE; d.isl_velIters[i] = iter + 1u; }
-            else stillActive = 1u;
-            d.isl_inc[i] = 0u; d.isl_jflag[i] = 0u;
-        }
-    }
-    block_add(&d.cnt->nActiveVel, stillActive);
+    if (i < nBodies && d.b_island[i] == i) stillActive = isl_vel_check_root(d, i, iter, minMomentum);
+    const unsigned slot = warp_append(&d.cnt->nActiveVel, stillActive != 0u);
+    if (stillActive) d.isl_active[slot] = i;
+}
+// later iterations: only the listed islands (grid-stride; the list never grows)
+PR_KERNEL k_isl_vel_check_list(DV d, unsigned iter, float minMomentum)
+{
+    const unsigned n = d.cnt->nActiveVel;
+    for (unsigned k = PR_TID; k < n; k += PR_NTHREADS) isl_vel_check_root(d, d.isl_active[k], iter, minMomentum);
 }
 
 // ------------------------------------------------------------------ a11: integrate + NGS position solve
@@ -1634,22 +1646,31 @@ PR_KERNEL k_solve_position_tail(DV d, unsigned tailStart, unsigned tailCount, un
         if (did) atomicMin(&d.isl_sep[d.vc_island[row]], float_flip(sep));
     });
 }
-PR_KERNEL k_isl_pos_check(DV d, unsigned nBodies, unsigned iter, float minSeparation)
+PR_D unsigned isl_pos_check_root(const DV& d, unsigned i, unsigned iter, float minSeparation)
 { // AabbTreeWorld.cpp:1628-1644
+    const unsigned st = d.isl_state[i];
+    if (!(st & ISL_ACTIVE) || (st & ISL_POS_SOLVED)) return 0u;
+    const unsigned sepFlip = d.isl_sep[i];
+    if (sepFlip < d.isl_minSep[i]) d.isl_minSep[i] = sepFlip;
+    const bool jointsOkay = d.isl_jflag[i] == 0u;
+    unsigned still = 0u;
+    if (jointsOkay && float_unflip(sepFlip) >= minSeparation) { d.isl_state[i] = st | ISL_POS_SOLVED; d.isl_posIters[i] = iter + 1u; }
+    else still = 1u;
+    d.isl_sep[i] = float_flip(PR_INF); d.isl_jflag[i] = 0u;
+    return still;
+}
+PR_KERNEL k_isl_pos_check(DV d, unsigned nBodies, unsigned iter, float minSeparation)
+{
     const unsigned i = PR_TID;
     unsigned stillActive = 0u;
-    if (i < nBodies && d.b_island[i] == i) {
-        const unsigned st = d.isl_state[i];
-        if ((st & ISL_ACTIVE) && !(st & ISL_POS_SOLVED)) {
-            const unsigned sepFlip = d.isl_sep[i];
-            if (sepFlip < d.isl_minSep[i]) d.isl_minSep[i] = sepFlip;
-            const bool jointsOkay = d.isl_jflag[i] == 0u;
-            if (jointsOkay && float_unflip(sepFlip) >= minSeparation) { d.isl_state[i] = st | ISL_POS_SOLVED; d.isl_posIters[i] = iter + 1u; }
-            else stillActive = 1u;
-            d.isl_sep[i] = float_flip(PR_INF); d.isl_jflag[i] = 0u;
-        }
-    }
-    block_add(&d.cnt->nActivePos, stillActive);
+    if (i < nBodies && d.b_island[i] == i) stillActive = isl_pos_check_root(d, i, iter, minSeparation);
+    const unsigned slot = warp_append(&d.cnt->nActivePos, stillActive != 0u);
+    if (stillActive) d.isl_active[slot] = i; // (the velocity iterations are over: their list is free)
+}
+PR_KERNEL k_isl_pos_check_list(DV d, unsigned iter, float minSeparation)
+{
+    const unsigned n = d.cnt->nActivePos;
+    for (unsigned k = PR_TID; k < n; k += PR_NTHREADS) isl_pos_check_root(d, d.isl_active[k], iter, minSeparation);
 }
 
 // ------------------------------------------------------------------ a12: write-back, sleep, stats

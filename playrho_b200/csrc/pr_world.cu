@@ -81,7 +81,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(b_lc, G_BODY), A(b_flags, G_BODY), A(s_vel, G_BODY), A(s_pos, G_BODY), A(b_island, G_BODY), A(b_root, G_BODY),
         A(b_moved, G_BODY), A(b_sync, G_BODY), A(isl_state, G_BODY), A(isl_velIters, G_BODY), A(isl_posIters, G_BODY),
         A(isl_inc, G_BODY), A(isl_maxInc, G_BODY), A(isl_sep, G_BODY), A(isl_minSep, G_BODY), A(isl_minUA, G_BODY),
-        A(isl_nbodies, G_BODY), A(b_claim, G_BODY), A(b_cmask, G_BODY),
+        A(isl_nbodies, G_BODY), A(isl_active, G_BODY), A(b_claim, G_BODY), A(b_cmask, G_BODY),
         A(adj_off, G_BODY), A(adj_cnt, G_BODY), A(adj_n, G_BODY), A(b_toiIsl, G_BODY), A(b_toiAlpha, G_BODY), A(b_toiStamp, G_BODY), A(b_inR, G_BODY),
         A(sync_list, G_BODY), A(bp_off, G_BODY), A(bp_list, G_PROXY), A(bv_leafOf, G_PROXY), A(b_world, G_BODY), A(bv_wr, G_PROXY),
         A(c_pos, G_CONTACT), A(c_color, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT), A(toi_list, G_CONTACT), A(toi_cand, G_CONTACT),
@@ -511,7 +511,8 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             for (size_t c = 0; c < nBig; ++c) PR_LAUNCH(k_solve_velocity, ranges[c].second, w.stream, d, ranges[c].first, ranges[c].second);
             PR_SMALL_COLORS(1u);
             if (tailCount) PR_LAUNCH(k_solve_velocity_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
-            PR_LAUNCH(k_isl_vel_check, N, w.stream, d, N, it, conf.reg_min_momentum);
+            if (it == 0u) PR_LAUNCH(k_isl_vel_check, N, w.stream, d, N, it, conf.reg_min_momentum);
+            else PR_LAUNCH(k_isl_vel_check_list, std::min(N, 64u * 256u), w.stream, d, it, conf.reg_min_momentum);
         }
         tm.mark(w, PR_STAGE_POSITION);
         PR_LAUNCH(k_integrate_positions, N, w.stream, d, N, conf.delta_time);
@@ -522,7 +523,8 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             if (tailCount)
                 PR_LAUNCH(k_solve_position_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
             PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 2u, jSerial); // joints after the contacts (:1634-1637)
-            PR_LAUNCH(k_isl_pos_check, N, w.stream, d, N, it, conf.reg_min_separation);
+            if (it == 0u) PR_LAUNCH(k_isl_pos_check, N, w.stream, d, N, it, conf.reg_min_separation);
+            else PR_LAUNCH(k_isl_pos_check_list, std::min(N, 64u * 256u), w.stream, d, it, conf.reg_min_separation);
         }
 #undef PR_SMALL_COLORS
     }

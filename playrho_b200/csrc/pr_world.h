@@ -86,7 +86,7 @@ struct DV {
     unsigned *b_island, *b_root, *b_moved, *b_sync;
     pr_revolute_joint* jt; JointWork* jt_work; unsigned* isl_jflag; // revolute joints (a15)
     unsigned long long* nc_pairs; unsigned nNcPairs;               // body pairs joined by a collideConnected=false joint
-    unsigned *isl_state, *isl_velIters, *isl_posIters, *isl_inc, *isl_maxInc, *isl_sep, *isl_minSep, *isl_minUA, *isl_nbodies;
+    unsigned *isl_state, *isl_velIters, *isl_posIters, *isl_inc, *isl_maxInc, *isl_sep, *isl_minSep, *isl_minUA, *isl_nbodies, *isl_active;
     unsigned long long *b_claim, *b_cmask;
     // shapes / children / vertices
     float4* sh_mat; unsigned* sh_filter; int* sh_group;
