@@ -354,39 +354,70 @@ def main():
     if rank == 0:  # the slowest steps with their stage times (stderr): growth / rebuild steps show up here
         for k in sorted(range(len(profs)), key=lambda k: -float(profs[k]["ms_total"]))[:3]:
             print("slow step %d: %.2f ms colour rounds %d, buffer growths %d  %s" % (k, float(profs[k]["ms_total"]), int(profs[k]["color_rounds"]), int(profs[k]["grow_events"]), {n: round(float(profs[k]["ms_stage"][i]), 2) for i, n in enumerate(abi.STAGE_NAMES) if profs[k]["ms_stage"][i] > 0.3}), file=sys.stderr)
-    # ---------------- end-to-end: host buffers in, host buffers out, every step
+    # ---------------- end-to-end through the C ABI with HOST buffers, every step: the loop a user of the world runs --
+    # upload an acceleration for EVERY body (SetAcceleration), Step, read EVERY body's transformation back (GetTransformation)
+    # -- from / into pinned host memory (pr_set_body_accelerations / pr_get_body_poses).
     rows = gw.bodies()
     ids = np.arange(nb, dtype=np.uint32)
+    pin_acc = torch.from_numpy(np.stack([rows["acc_x"], rows["acc_y"], rows["acc_w"]], axis=1).astype(np.float32).copy()).pin_memory()
+    pin_ids = torch.from_numpy(ids.copy()).pin_memory()
+    pin_xf = torch.empty((nb, 4), dtype=torch.float32).pin_memory()
+    acc_np, ids_np, xf_np = pin_acc.numpy(), pin_ids.numpy(), pin_xf.numpy()
+    e2e_steps = max(2, min(args.steps, 20))
+
+    e2e_host = np.zeros(3)
+
+    def pose_loop(k):
+        for _ in range(k):
+            t_a = time.perf_counter()
+            gw.set_accelerations(None, acc_np)     # H2D: 12 B acceleration per body (bodies 0..n-1: no id array)
+            t_b = time.perf_counter()
+            gw.step(conf)
+            t_c = time.perf_counter()
+            gw.poses_into(xf_np)                   # D2H: 16 B transformation per body
+            e2e_host[:] += [t_b - t_a, t_c - t_b, time.perf_counter() - t_c]
+    pose_loop(3)  # untimed: the first bulk transfers allocate the library's staging buffers
+    e2e_host[:] = 0.0
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev2.record(stream)
+    pose_loop(e2e_steps)
+    ev3.record(stream)
+    barrier()
+    e2e_secs = ev2.elapsed_time(ev3) / 1e3
+    e2e_h2d, e2e_d2h = int(nb * 12), int(nb * 16)
+    # ... and the worst case: every body's WHOLE row (SetBody / GetBody value semantics, 104 B) up and down every step
     pinned_in = torch.from_numpy(rows.view(np.uint8).reshape(-1).copy()).pin_memory()
     pinned_out = torch.empty_like(pinned_in).pin_memory()
     rows_in = pinned_in.numpy().view(abi.BODY)
     rows_out = pinned_out.numpy().view(abi.BODY)
-    e2e_steps = max(2, min(args.steps, 10))
-    for _ in range(3):  # untimed: the first bulk upload / download allocates the library's staging buffers (cudaMalloc of ~100 MB)
-        gw.set_bodies(ids, rows_in)
-        gw.step(conf)
-        gw.bodies_into(rows_out)
-        rows_in, rows_out = rows_out, rows_in
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rows_in[:] = gw.bodies()
+    full_steps = max(2, min(args.steps, 8))
+
+    def row_loop(k):
+        nonlocal rows_in, rows_out
+        for _ in range(k):
+            gw.set_bodies(ids, rows_in)           # H2D: every body row, from pinned host memory
+            gw.step(conf)
+            gw.bodies_into(rows_out)              # D2H: every body row, into pinned host memory
+            rows_in, rows_out = rows_out, rows_in # next step uploads what this step produced
+    row_loop(2)
+    ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev2.record(stream)
-    for _ in range(e2e_steps):
-        gw.set_bodies(ids, rows_in)           # H2D: every body row, from pinned host memory
-        gw.step(conf)
-        gw.bodies_into(rows_out)              # D2H: every body row, into pinned host memory
-        rows_in, rows_out = rows_out, rows_in # next step uploads what this step produced
-    ev3.record(stream)
+    ev4.record(stream)
+    row_loop(full_steps)
+    ev5.record(stream)
     barrier()
-    e2e_secs = ev2.elapsed_time(ev3) / 1e3
+    full_secs = ev4.elapsed_time(ev5) / 1e3
     sampler.stop_flag = True
     sampler.join(timeout=2)
     # ---------------- reduce over ranks (max time; stats summed over NVLink)
-    t = torch.tensor([secs, e2e_secs, wall_secs], device="cuda", dtype=torch.float64)
+    t = torch.tensor([secs, e2e_secs, wall_secs, full_secs], device="cuda", dtype=torch.float64)
     s = torch.tensor(np.concatenate([stats_sum, [nb, launches]]), device="cuda", dtype=torch.float64)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-    secs, e2e_secs, wall_secs = float(t[0]), float(t[1]), float(t[2])
+    secs, e2e_secs, wall_secs, full_secs = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     # the step statistics of all ranks, folded like StepStats.cpp:29-38 (the only NVLink traffic of the sharded path)
     from playrho_b200 import shard
     folded, _, _ = shard.reduce_step_stats(shard.fold_step_stats(step_recs), nb * args.steps, secs, device="cuda")
@@ -434,8 +465,13 @@ def main():
             "higher_is_better": True, "scaling": "strong" if tumblers else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
             "e2e": {"value": total_bodies * e2e_steps / e2e_secs, "unit": "body-steps/s",
-                    "h2d_bytes_per_step": int(nb * abi.BODY.itemsize + 4 * nb), "d2h_bytes_per_step": int(nb * abi.BODY.itemsize),
-                    "ms_per_step": 1e3 * e2e_secs / e2e_steps},
+                    "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h, "ms_per_step": 1e3 * e2e_secs / e2e_steps, "steps": e2e_steps,
+                    "loop": "pr_set_body_accelerations(every body) + pr_step + pr_get_body_poses(every body), pinned host buffers; later steps than the device-timed window (the pile keeps growing: compare host_ms_per_step.step)",
+                    "host_ms_per_step": {"set_accelerations": 1e3 * e2e_host[0] / e2e_steps, "step": 1e3 * e2e_host[1] / e2e_steps, "get_poses": 1e3 * e2e_host[2] / e2e_steps}},
+            "e2e_full_rows": {"value": total_bodies * full_steps / full_secs, "unit": "body-steps/s",
+                              "h2d_bytes_per_step": int(nb * abi.BODY.itemsize + 4 * nb), "d2h_bytes_per_step": int(nb * abi.BODY.itemsize),
+                              "ms_per_step": 1e3 * full_secs / full_steps, "steps": full_steps,
+                              "loop": "pr_set_bodies(every 104-byte row) + pr_step + pr_get_bodies(every row): the worst case of value-semantic SetBody/GetBody"},
             "gpu_launches": int(float(s[5])),
             "roofline": {"bound": "hbm", "kernel": "k_update_contacts (regular-phase narrowphase: CollideShapes + impulse carry-over for every dirty contact, one launch per step)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,

@@ -223,6 +223,17 @@ int pr_create_revolute_joints(pr_world* w, uint32_t n, const pr_revolute_joint* 
 /* ---- dirty-row upload / download (SetBody :2723 / GetBody; value semantics) ---- */
 int pr_set_bodies(pr_world* w, uint32_t n, const uint32_t* ids, const pr_body* rows);
 int pr_get_bodies(const pr_world* w, uint32_t first, uint32_t n, pr_body* rows);
+/* Column accessors for the per-step loop "apply accelerations -> Step -> read poses" (bulk body
+ * get/set instead of one value-semantic SetBody/GetBody per id): a 104-byte row per body each way is 204 MB per step
+ * at 1M bodies, these are 16 + 16 (+12) bytes.
+ * pr_set_body_accelerations: RAW write of (linear x, linear y, angular) for bodies ids[0..n) (ids == NULL: bodies 0..n-1): what SetBody does with a Body
+ * whose only change is the acceleration. Body::SetAcceleration's wake rule (Body.cpp:203-236: awake + underActiveTime = 0 when
+ * the acceleration grows or turns) is the host shim's business -- it runs the reference's own Body::SetAcceleration on its
+ * mirror and uploads whole rows (pr_set_bodies) for the bodies whose flags changed.
+ * pr_get_body_poses: transformation (px, py, cos, sin) of bodies [first, first+n) -- GetTransformation(world, id), Body.hpp --
+ * and, if vel3 != NULL, their velocity (linear x, linear y, angular) -- GetVelocity(world, id). */
+int pr_set_body_accelerations(pr_world* w, uint32_t n, const uint32_t* ids, const float* acc3);
+int pr_get_body_poses(const pr_world* w, uint32_t first, uint32_t n, float* xf4, float* vel3);
 int pr_get_revolute_joints(const pr_world* w, uint32_t first, uint32_t n, pr_revolute_joint* rows);
 int pr_get_counts(const pr_world* w, pr_counts* out);
 /* contacts in m_contacts order (creation order), manifolds[i] belongs to contacts[i] */

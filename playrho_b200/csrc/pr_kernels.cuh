@@ -172,6 +172,19 @@ PR_KERNEL k_put_bodies(DV d, unsigned n, unsigned firstId, const unsigned* ids, 
     }
 }
 
+PR_KERNEL k_put_accelerations(DV d, unsigned n, const unsigned* ids, const float* acc3)
+{
+    const unsigned i = PR_TID;
+    if (i < n) d.b_acc[ids ? ids[i] : i] = make_float4(acc3[3u * i], acc3[3u * i + 1u], acc3[3u * i + 2u], 0.0f);
+}
+PR_KERNEL k_get_poses(DV d, unsigned first, unsigned n, float4* xf, float* vel3)
+{
+    const unsigned i = PR_TID;
+    if (i < n) {
+        xf[i] = d.b_xf[first + i];
+        if (vel3) { const float4 v = d.b_vel[first + i]; vel3[3u * i] = v.x; vel3[3u * i + 1u] = v.y; vel3[3u * i + 2u] = v.z; }
+    }
+}
 PR_KERNEL k_get_bodies(DV d, unsigned first, unsigned n, pr_body* rows)
 {
     const unsigned i = PR_TID;

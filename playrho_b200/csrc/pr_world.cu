@@ -33,6 +33,7 @@ static void dev_free(void* p) { if (p) cudaFree(p); }
 static void h2d(World& w, void* dst, const void* src, size_t n) { if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, w.stream)); }
 static void d2h(World& w, void* dst, const void* src, size_t n) { if (n) { CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, w.stream)); CK(cudaStreamSynchronize(w.stream)); } }
 static void d2d(World& w, void* dst, const void* src, size_t n) { if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, w.stream)); }
+#define CK_COPY_D2H_ASYNC(w, dst, src, n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, (w).stream))
 static void dset(World& w, void* dst, int v, size_t n) { if (n) CK(cudaMemsetAsync(dst, v, n, w.stream)); }
 static void sync(World& w) { CK(cudaStreamSynchronize(w.stream)); }
 static void check_launch() { CK(cudaGetLastError()); }
@@ -62,6 +63,7 @@ static void dev_free(void* p) { std::free(p); }
 static void h2d(World&, void* dst, const void* src, size_t n) { if (n) std::memcpy(dst, src, n); }
 static void d2h(World&, void* dst, const void* src, size_t n) { if (n) std::memcpy(dst, src, n); }
 static void d2d(World&, void* dst, const void* src, size_t n) { if (n) std::memmove(dst, src, n); }
+#define CK_COPY_D2H_ASYNC(w, dst, src, n) std::memcpy(dst, src, n)
 static void dset(World&, void* dst, int v, size_t n) { if (n) std::memset(dst, v, n); }
 static void sync(World&) {}
 static void check_launch() {}
@@ -1077,6 +1079,40 @@ int pr_get_bodies(const pr_world* cpw, uint32_t first, uint32_t n, pr_body* rows
     pr_body* staging = static_cast<pr_body*>(stage_buf(w, 0, sizeof(pr_body) * n));
     PR_LAUNCH(k_get_bodies, n, w.stream, w.d, first, n, staging);
     d2h(w, rows, staging, sizeof(pr_body) * n);
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_set_body_accelerations(pr_world* pw, uint32_t n, const uint32_t* ids, const float* acc3)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    uint32_t maxId = n ? n - 1u : 0u; // ids == NULL: bodies [0, n)
+    if (ids) { maxId = 0; for (uint32_t i = 0; i < n; ++i) maxId = ids[i] > maxId ? ids[i] : maxId; }
+    if (n && maxId >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    if (!n) return PR_OK;
+    float* sacc = static_cast<float*>(stage_buf(w, 0, sizeof(float) * 3u * n));
+    unsigned* dids = ids ? static_cast<unsigned*>(stage_buf(w, 1, 4u * n)) : nullptr;
+    h2d(w, sacc, acc3, sizeof(float) * 3u * n);
+    if (ids) h2d(w, dids, ids, 4u * n);
+    PR_LAUNCH(k_put_accelerations, n, w.stream, w.d, n, dids, sacc);
+    sync(w); // the caller's buffers may be reused once we return
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_get_body_poses(const pr_world* cpw, uint32_t first, uint32_t n, float* xf4, float* vel3)
+{
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    if (first + n > w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    if (!n) return PR_OK;
+    float4* sxf = static_cast<float4*>(stage_buf(w, 0, sizeof(float4) * n));
+    float* svel = vel3 ? static_cast<float*>(stage_buf(w, 1, sizeof(float) * 3u * n)) : nullptr;
+    PR_LAUNCH(k_get_poses, n, w.stream, w.d, first, n, sxf, svel);
+    if (vel3) CK_COPY_D2H_ASYNC(w, vel3, svel, sizeof(float) * 3u * n);
+    d2h(w, xf4, sxf, sizeof(float4) * n);
     return PR_OK;
     API_CATCH(pw)
 }

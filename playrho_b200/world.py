@@ -25,6 +25,7 @@ EXPORTS = [
     "pr_get_inv_dt0", "pr_get_stream", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
     "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
+    "pr_set_body_accelerations", "pr_get_body_poses",
 ]
 
 
@@ -44,6 +45,8 @@ def bind(lib):
     lib.pr_create_revolute_joints.argtypes = [vp, u32, vp, C.POINTER(u32)]
     lib.pr_set_bodies.argtypes = [vp, u32, vp, vp]
     lib.pr_get_bodies.argtypes = [vp, u32, u32, vp]
+    lib.pr_set_body_accelerations.argtypes = [vp, u32, vp, vp]
+    lib.pr_get_body_poses.argtypes = [vp, u32, u32, vp, vp]
     lib.pr_get_revolute_joints.argtypes = [vp, u32, u32, vp]
     lib.pr_get_counts.argtypes = [vp, vp]
     lib.pr_get_contacts.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
@@ -174,6 +177,24 @@ class World:
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         rows = np.ascontiguousarray(rows, dtype=abi.BODY)
         self._chk(self.lib.pr_set_bodies(self.h, len(ids), abi.ptr(ids), abi.ptr(rows)))
+
+    def set_accelerations(self, ids, acc3):
+        """Raw write of (linear x, linear y, angular) acceleration of bodies `ids` (pr_set_body_accelerations)."""
+        acc3 = np.ascontiguousarray(acc3, dtype=np.float32)
+        if ids is None:  # bodies [0, len(acc3))
+            self._chk(self.lib.pr_set_body_accelerations(self.h, acc3.size // 3, None, abi.ptr(acc3)))
+            return
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        assert acc3.size == 3 * len(ids)
+        self._chk(self.lib.pr_set_body_accelerations(self.h, len(ids), abi.ptr(ids), abi.ptr(acc3)))
+
+    def poses_into(self, xf4, vel3=None, first=0):
+        """Transformations (px, py, cos, sin) -- and velocities if vel3 is given -- of bodies [first, first+len(xf4)) into
+        caller-owned float32 arrays (e.g. pinned)."""
+        assert xf4.dtype == np.float32 and xf4.size % 4 == 0
+        n = xf4.size // 4
+        self._chk(self.lib.pr_get_body_poses(self.h, first, n, abi.ptr(xf4), abi.ptr(vel3) if vel3 is not None else None))
+        return xf4
 
     def joints(self):
         n = int(self.counts()["joints"])

@@ -143,3 +143,41 @@ def test_set_bodies_moves_proxies_and_flags_contacts():
         assert refworld.bits_equal(gc, oc) and refworld.bits_equal(gm, om)
         if s == 0:
             assert gs["pre"]["proxies_moved"] == os_["pre"]["proxies_moved"] == 1
+
+
+def _column_accessors_check(lib, device):
+    """pr_set_body_accelerations / pr_get_body_poses against the whole-row accessors (pr_set_bodies / pr_get_bodies)."""
+    sc = scenes_np.disks_box(32, seed=5)
+    a, b = W.World(sc, lib=lib, device=device), W.World(sc, lib=lib, device=device)
+    conf = refworld.default_step_conf(do_toi=0)
+    for _ in range(10):
+        a.step(conf); b.step(conf)
+    rows = a.bodies()
+    ids = np.arange(len(rows), dtype=np.uint32)[1::2]
+    acc = np.stack([np.linspace(-3, 3, len(ids)), np.full(len(ids), -12.5), np.linspace(0.5, -0.5, len(ids))], axis=1).astype(np.float32)
+    new = rows[ids].copy()
+    new["acc_x"], new["acc_y"], new["acc_w"] = acc[:, 0], acc[:, 1], acc[:, 2]
+    a.set_bodies(ids, new)          # SetBody with a Body whose only change is the acceleration
+    b.set_accelerations(ids, acc)   # the column write
+    for _ in range(20):
+        sa, sb = a.step(conf), b.step(conf)
+        assert np.array([sa]).tobytes() == np.array([sb]).tobytes()
+    ra, rb = a.bodies(), b.bodies()
+    assert ra.tobytes() == rb.tobytes()
+    xf, vel = np.zeros((len(rb), 4), np.float32), np.zeros((len(rb), 3), np.float32)
+    b.poses_into(xf, vel)
+    assert np.array_equal(xf.view(np.uint32), np.stack([rb["xf_px"], rb["xf_py"], rb["xf_qc"], rb["xf_qs"]], axis=1).view(np.uint32))
+    assert np.array_equal(vel.view(np.uint32), np.stack([rb["vel_x"], rb["vel_y"], rb["vel_w"]], axis=1).view(np.uint32))
+    xf2 = np.zeros((5, 4), np.float32)
+    b.poses_into(xf2, first=3)
+    assert np.array_equal(xf2, xf[3:8])
+    with pytest.raises(W.PrError):
+        b.set_accelerations(np.array([len(rb)], np.uint32), np.zeros((1, 3), np.float32))
+    allacc = np.stack([rb["acc_x"], rb["acc_y"], rb["acc_w"]], axis=1).astype(np.float32) * 0.5
+    b.set_accelerations(None, allacc)  # ids == NULL: bodies 0..n-1
+    assert np.array_equal(np.stack([b.bodies()[f] for f in ("acc_x", "acc_y", "acc_w")], axis=1), allacc)
+
+
+@need_emul
+def test_emulated_column_accessors_equal_row_accessors():
+    _column_accessors_check(emul_lib(), -1)

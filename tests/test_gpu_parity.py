@@ -306,3 +306,8 @@ def test_cuda_full_size_mixed_world_invariants():
             assert k in have, "overlapping fat boxes of proxies %d and %d have no contact" % (q, o)
             checked += 1
     assert checked > 400
+
+
+def test_cuda_column_accessors_equal_row_accessors():
+    from test_emul_pipeline import _column_accessors_check
+    _column_accessors_check(None, 0)
