@@ -261,7 +261,7 @@ def make_tumbler_arena(args, W, rank, world_size, local_rank):
     unit = scenes_np.tumbler(0)
     per = 2 + args.squares
     gw = W.Batch(n_worlds, device=local_rank, body_capacity=n_worlds * per + 16, proxy_capacity=n_worlds * (4 + args.squares) + 64,
-                 contact_capacity=8 * n_worlds * args.squares)
+                 contact_capacity=12 * n_worlds * args.squares)  # (~9 fat-box pairs per square at 512 squares: no growth while timing)
     gw.set_toi_mode(args.toi_mode)
     gw.create_shapes(unit)  # the 5 shapes (4 enclosure walls + the square) are shared by every world
     nu = len(unit["bodies"])
