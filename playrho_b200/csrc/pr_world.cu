@@ -587,6 +587,11 @@ static void build_adjacency(World& w)
     w.hostCnt.toiListN = 0; w.hostCnt.adjOverflow = 0;
     write_counters(w);
     PR_LAUNCH(k_toi_list_build, w.nOrder, w.stream, d, w.nOrder);
+    read_counters(w);
+    if (w.hostCnt.toiListN == 0u) { // no contact can ever get a TOI (e.g. an arena of tumblers: no static or bullet body touches anything):
+        w.toiListBound = 0; w.adjValid = true; // the set R is empty, so the adjacency (three more passes over every contact) is too
+        return;
+    }
     PR_LAUNCH(k_adj_count, w.nOrder, w.stream, d, w.nOrder);
     PR_LAUNCH(k_adj_cap, N, w.stream, d, N);
     scan_exclusive_u32(d.adj_cnt, d.adj_off, N, d.adj_off + N, w.scanScratch, w.stream);
@@ -620,6 +625,11 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         // event that does not fit is deferred to the next round (k_toi_solve), so this is a working size, not a worst case
         ensure(w, G_CONS, std::min(2u * w.nOrder, std::max(1u << 16, 16u * w.toiListBound)) + 64u);
         const unsigned P = w.nProxies;
+        if (w.toiListBound == 0u) { // no TOI-candidate contact in the world: nothing to compute, no event (:1768-1777)
+            w.stepComplete = true;
+            if (rounds || w.toiAlphaDirty) { PR_LAUNCH(k_toi_finish_bodies, N, w.stream, d, N); w.toiAlphaDirty = false; }
+            break;
+        }
         // ---- batched rounds: needs an intact tree to refit in place; otherwise one host-driven round (below)
         const bool canBatch = w.bvhValid && w.bvhLeaves == P && P > 1; // (the refit budget is checked by the next regular step)
         if (canBatch) {
