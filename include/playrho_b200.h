@@ -254,7 +254,8 @@ int pr_get_solve_order(const pr_world* w, uint32_t cap, uint32_t* contact_ids, u
                        uint32_t* n_out);
 /* debug flags: bit 0 = record the solve order of every step (costs a device->host copy);
  * bit 1 = use the binned narrowphase, bit 2 = use the persistent fused solver kernel (two experiments that did not beat the
- * default kernels on B200; off by default, kept under test) */
+ * default kernels on B200; off by default, kept under test); bit 3 = TOI rounds through the list kernels only (no single-block
+ * late rounds: A/B measurements) */
 int pr_set_debug(pr_world* w, uint32_t flags);
 int pr_get_step_profile(const pr_world* w, pr_step_profile* out);
 int pr_abi_sizeof(int which); /* sizeof of the POD structs above, for foreign-language mirrors */

@@ -90,6 +90,8 @@ inline int __clzll(unsigned long long v) { return v ? __builtin_clzll(v) : 64; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffsll(unsigned long long v) { return __builtin_ffsll(static_cast<long long>(v)); }
 inline void __threadfence() {}
+inline void __threadfence_block() {}
+inline void __syncthreads() {}
 #endif
 
 namespace pr {

@@ -830,6 +830,7 @@ PR_KERNEL k_bvh_query_coop(DV d, unsigned nQueue, unsigned nLeaves, const unsign
 // free stack else by append (ObjectPool::Allocate), is appended to m_contacts in key order.
 PR_D void adj_append(const DV& d, unsigned b, unsigned id, bool eligible);
 PR_D bool toi_static_eligible(unsigned flags);
+PR_D void toi_mark_recompute(const DV& d, unsigned cid);
 PR_D void create_contact_one(const DV& d, unsigned i, const unsigned long long* keys, const unsigned* srcIdx,
                               unsigned nOrder, unsigned nFree, unsigned poolSize, unsigned adjLive)
 {
@@ -852,19 +853,19 @@ PR_D void create_contact_one(const DV& d, unsigned i, const unsigned long long* 
         // MixFriction = sqrt(f1*f2), MixRestitution = max, Contact.hpp:57-69
         d.c_mat[id] = make_float4(sqrtf(matA.x * matB.x), (matA.y > matB.y) ? matA.y : matB.y, 0.0f, 1.0f);
         d.c_flags[id] = flags;
-        d.c_toiIsl[id] = 0u; d.c_color[id] = COLOR_UNSET;
+        d.c_toiIsl[id] = 0u; d.c_color[id] = COLOR_UNSET; d.c_rstamp[id] = 0u;
         manifold_clear(d, id);
         d.c_order[nOrder + i] = id;
         if (adjLive) { // the TOI phase's tables are live: m_bodyContacts push_back + TOI candidate list
             d.c_pos[id] = nOrder + i;
             const bool eligible = toi_static_eligible(flags);
             adj_append(d, bA, id, eligible); adj_append(d, bB, id, eligible);
-            if (eligible) d.toi_list[atomicAdd(&d.cnt->toiListN, 1u)] = id;
+            if (eligible) { d.toi_list[atomicAdd(&d.cnt->toiListN, 1u)] = id; toi_mark_recompute(d, id); }
         }
         hash_insert(d, key);
-        if (!sensor) {
-            if (f_speedable(fA)) atomicOr(&d.b_flags[bA], static_cast<unsigned>(PR_BODY_AWAKE));
-            if (f_speedable(fB)) atomicOr(&d.b_flags[bB], static_cast<unsigned>(PR_BODY_AWAKE));
+        if (!sensor) { // (a body woken while the TOI tables are live: see toi_wake)
+            if (f_speedable(fA) && !(atomicOr(&d.b_flags[bA], static_cast<unsigned>(PR_BODY_AWAKE)) & PR_BODY_AWAKE) && adjLive) d.cnt->toiForceFull = 1u;
+            if (f_speedable(fB) && !(atomicOr(&d.b_flags[bB], static_cast<unsigned>(PR_BODY_AWAKE)) & PR_BODY_AWAKE) && adjLive) d.cnt->toiForceFull = 1u;
         }
     }
 }
@@ -1800,7 +1801,7 @@ PR_KERNEL k_import_contacts(DV d, unsigned n, const pr_contact* in, const pr_man
             d.m0[id] = make_float4(m.ln_x, m.ln_y, m.lp_x, m.lp_y); d.m1[id] = make_float4(m.p0_x, m.p0_y, m.p1_x, m.p1_y);
             d.m2[id] = make_float4(m.jn0, m.jt0, m.jn1, m.jt1); d.m3[id] = make_uint4(m.cf0, m.cf1, m.type, m.count);
         }
-        d.c_toiIsl[id] = 0u; d.c_color[id] = COLOR_UNSET;
+        d.c_toiIsl[id] = 0u; d.c_color[id] = COLOR_UNSET; d.c_rstamp[id] = 0u;
         d.c_order[i] = id;
     }
 }

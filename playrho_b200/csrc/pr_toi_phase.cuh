@@ -128,25 +128,41 @@ PR_KERNEL k_toi_phase_init(DV d, unsigned nBodies)
 // (thread 0 also opens the round: it resets the round's counters, or -- batched rounds -- halts the rest of the batch when
 // the previous round overflowed an adjacency segment or raised an error. A halt that becomes visible to only some threads of
 // THIS kernel is harmless: the atomicMax below is idempotent and k_toi_advance, which consumes it, is skipped.)
-PR_KERNEL k_toi_alpha(DV d, unsigned maxSubSteps)
+// a contact that must get its TOI (re)computed in the round after the current one: stamped so that it is listed once
+PR_D void toi_mark_recompute(const DV& d, unsigned cid)
+{
+    const unsigned next = d.cnt->toiRoundId + 1u;
+    if (atomicExch(&d.c_rstamp[cid], next) != next) {
+        const unsigned slot = atomicAdd(&d.cnt->toiReN[next & 1u], 1u);
+        ((next & 1u) ? d.toi_re1 : d.toi_re0)[slot] = cid;
+    }
+}
+PR_D void toi_open_round(const DV& d, unsigned roundId)
+{ // one thread: the counters of a round, and the (empty) list of what the NEXT round will have to recompute
+    d.cnt->toiRoundId = roundId;
+    d.cnt->toiMinKey = ~0ull; d.cnt->toiEvents = 0u; d.cnt->toiScratchTop = 0u; d.cnt->syncN = 0u;
+    d.cnt->toiReN[(roundId + 1u) & 1u] = 0u;
+}
+PR_D void toi_alpha_one(const DV& d, unsigned id, unsigned maxSubSteps)
+{
+    const uint4 ab = d.c_ab[id];
+    bool atMax;
+    if (toi_eligible(d, d.c_flags[id], ab, maxSubSteps, atMax)) {
+        const float a0 = stdmax(d.b_pos0[ab.x].w, d.b_pos0[ab.y].w);
+        atomicMax(&d.b_toiAlpha[ab.x], f2u(a0)); // alpha in [0,1): non-negative floats order like uints
+        atomicMax(&d.b_toiAlpha[ab.y], f2u(a0));
+    }
+}
+PR_KERNEL k_toi_alpha(DV d, unsigned maxSubSteps, unsigned round)
 {
     const unsigned i = PR_TID;
     if (d.cnt->toiHalt) return;
     if (i == 0u) {
         if (d.cnt->adjOverflow) d.cnt->toiHalt = TB_ADJ;
         else if (d.cnt->error) d.cnt->toiHalt = TB_ERROR;
-        else { d.cnt->toiMinKey = ~0ull; d.cnt->toiEvents = 0u; d.cnt->toiScratchTop = 0u; d.cnt->syncN = 0u; d.cnt->toiCandN = 0u; }
+        else { toi_open_round(d, round); d.cnt->toiCandN = 0u; d.cnt->toiAtMaxLive = 0u; d.cnt->toiForceFull = 0u; }
     }
-    if (i < d.cnt->toiListN) {
-        const unsigned id = d.toi_list[i];
-        const uint4 ab = d.c_ab[id];
-        bool atMax;
-        if (toi_eligible(d, d.c_flags[id], ab, maxSubSteps, atMax)) {
-            const float a0 = stdmax(d.b_pos0[ab.x].w, d.b_pos0[ab.y].w);
-            atomicMax(&d.b_toiAlpha[ab.x], f2u(a0)); // alpha in [0,1): non-negative floats order like uints
-            atomicMax(&d.b_toiAlpha[ab.y], f2u(a0));
-        }
-    }
+    if (i < d.cnt->toiListN) toi_alpha_one(d, d.toi_list[i], maxSubSteps);
 }
 PR_D void advance0(float4& p0, float4 p1, float alpha)
 { // Advance0(Sweep, alpha), Sweep.cpp:30-34
@@ -157,26 +173,27 @@ PR_D void advance0(float4& p0, float4 p1, float alpha)
     p0 = make_float4(r.l.x, r.l.y, r.a, alpha);
 }
 // Advance0(bA, alpha0); Advance0(bB, alpha0) (:1718-1719): once per body per round (stamp = round id)
+PR_D void toi_advance_one(const DV& d, unsigned id, unsigned maxSubSteps, unsigned round)
+{
+    const uint4 ab = d.c_ab[id];
+    bool atMax;
+    if (toi_eligible(d, d.c_flags[id], ab, maxSubSteps, atMax)) {
+        const unsigned two[2] = {ab.x, ab.y};
+        for (int s = 0; s < 2; ++s) {
+            const unsigned b = two[s];
+            const unsigned t = d.b_toiAlpha[b];
+            if (atomicExch(&d.b_toiStamp[b], round) != round) {
+                float4 p0 = d.b_pos0[b];
+                if (f2u(p0.w) != t) { advance0(p0, d.b_pos1[b], u2f(t)); d.b_pos0[b] = p0; }
+            }
+        }
+    }
+}
 PR_KERNEL k_toi_advance(DV d, unsigned maxSubSteps, unsigned round)
 {
     const unsigned i = PR_TID;
     if (d.cnt->toiHalt) return;
-    if (i < d.cnt->toiListN) {
-        const unsigned id = d.toi_list[i];
-        const uint4 ab = d.c_ab[id];
-        bool atMax;
-        if (toi_eligible(d, d.c_flags[id], ab, maxSubSteps, atMax)) {
-            const unsigned two[2] = {ab.x, ab.y};
-            for (int s = 0; s < 2; ++s) {
-                const unsigned b = two[s];
-                const unsigned t = d.b_toiAlpha[b];
-                if (atomicExch(&d.b_toiStamp[b], round) != round) {
-                    float4 p0 = d.b_pos0[b];
-                    if (f2u(p0.w) != t) { advance0(p0, d.b_pos1[b], u2f(t)); d.b_pos0[b] = p0; }
-                }
-            }
-        }
-    }
+    if (i < d.cnt->toiListN) toi_advance_one(d, d.toi_list[i], maxSubSteps, round);
 }
 PR_D float normalized_angle(float value)
 { // GetNormalized(Angle), Math.cpp:30-93 (trunc variant)
@@ -201,40 +218,45 @@ PR_D SweepD normalized_sweep(float4 p0, float4 p1, float2 lc)
 }
 PR_D unsigned long long toi_key(float toi, unsigned pos) { return (static_cast<unsigned long long>(f2u(toi)) << 32) | pos; }
 
+struct ToiComputeOut { unsigned atMax, updated, distIt, toiIt, rootIt; unsigned long long key; };
+// UpdateContactTOIs' body for one listed contact; key != ~0: the contact is a GetSoonestContact candidate (valid TOI < 1)
+PR_D ToiComputeOut toi_compute_one(const DV& d, unsigned id, const pr_step_conf& conf)
+{
+    ToiComputeOut o; o.atMax = o.updated = o.distIt = o.toiIt = o.rootIt = 0u; o.key = ~0ull;
+    unsigned flags = d.c_flags[id];
+    const uint4 ab = d.c_ab[id];
+    bool atMax;
+    float toi = d.c_mat[id].w;
+    if (toi_eligible(d, flags, ab, conf.max_sub_steps, atMax)) {
+        float4 p0A = d.b_pos0[ab.x], p0B = d.b_pos0[ab.y];
+        const float4 p1A = d.b_pos1[ab.x], p1B = d.b_pos1[ab.y];
+        const float alpha0 = stdmax(p0A.w, p0B.w);
+        if (p0A.w != alpha0) advance0(p0A, p1A, alpha0); // not stored: only reachable in parallel mode
+        if (p0B.w != alpha0) advance0(p0B, p1B, alpha0);
+        const SweepD sA = normalized_sweep(p0A, p1A, d.b_lc[ab.x]), sB = normalized_sweep(p0B, p1B, d.b_lc[ab.y]);
+        const ToiResult out = toi_via_sat(child_view(d, ab.z), sA, child_view(d, ab.w), sB, conf.target_depth, conf.tolerance,
+                                          conf.max_toi_iters, conf.max_toi_root_iters, conf.max_distance_iters);
+        toi = (out.state == TOI_TOUCHING) ? stdmin(alpha0 + (1.0f - alpha0) * out.time, 1.0f) : 1.0f; // :1740
+        reinterpret_cast<float*>(&d.c_mat[id])[3] = toi;
+        flags |= PR_CONTACT_TOI;
+        d.c_flags[id] = flags;
+        o.updated = 1u; o.distIt = out.maxDistIters; o.toiIt = out.toiIters; o.rootIt = out.maxRootIters;
+    } else if (atMax) o.atMax = 1u;
+    if ((flags & PR_CONTACT_TOI) && toi < 1.0f) o.key = toi_key(toi, d.c_pos[id]);
+    return o;
+}
 PR_KERNEL k_toi_compute(DV d, pr_step_conf conf)
 {
     const unsigned i = PR_TID;
-    unsigned atMaxCount = 0u, updated = 0u, distIt = 0u, toiIt = 0u, rootIt = 0u;
-    unsigned long long key = ~0ull;
+    ToiComputeOut o; o.atMax = o.updated = o.distIt = o.toiIt = o.rootIt = 0u; o.key = ~0ull;
     if (!d.cnt->toiHalt && i < d.cnt->toiListN) {
         const unsigned id = d.toi_list[i];
-        unsigned flags = d.c_flags[id];
-        const uint4 ab = d.c_ab[id];
-        bool atMax;
-        float toi = d.c_mat[id].w;
-        if (toi_eligible(d, flags, ab, conf.max_sub_steps, atMax)) {
-            float4 p0A = d.b_pos0[ab.x], p0B = d.b_pos0[ab.y];
-            const float4 p1A = d.b_pos1[ab.x], p1B = d.b_pos1[ab.y];
-            const float alpha0 = stdmax(p0A.w, p0B.w);
-            if (p0A.w != alpha0) advance0(p0A, p1A, alpha0); // not stored: only reachable in parallel mode
-            if (p0B.w != alpha0) advance0(p0B, p1B, alpha0);
-            const SweepD sA = normalized_sweep(p0A, p1A, d.b_lc[ab.x]), sB = normalized_sweep(p0B, p1B, d.b_lc[ab.y]);
-            const ToiResult out = toi_via_sat(child_view(d, ab.z), sA, child_view(d, ab.w), sB, conf.target_depth, conf.tolerance,
-                                              conf.max_toi_iters, conf.max_toi_root_iters, conf.max_distance_iters);
-            toi = (out.state == TOI_TOUCHING) ? stdmin(alpha0 + (1.0f - alpha0) * out.time, 1.0f) : 1.0f; // :1740
-            reinterpret_cast<float*>(&d.c_mat[id])[3] = toi;
-            flags |= PR_CONTACT_TOI;
-            d.c_flags[id] = flags;
-            updated = 1u; distIt = out.maxDistIters; toiIt = out.toiIters; rootIt = out.maxRootIters;
-        } else if (atMax) atMaxCount = 1u;
-        if ((flags & PR_CONTACT_TOI) && toi < 1.0f) { // GetSoonestContact candidates: compacted for the selection kernels
-            key = toi_key(toi, d.c_pos[id]);
-            d.toi_cand[atomicAdd(&d.cnt->toiCandN, 1u)] = id;
-        }
+        o = toi_compute_one(d, id, conf);
+        if (o.key != ~0ull) d.toi_cand[atomicAdd(&d.cnt->toiCandN, 1u)] = id; // candidates, compacted for the selection kernels
     }
-    warp_add(&d.cnt->toiAtMaxSub, atMaxCount); warp_add(&d.cnt->toiUpdated, updated);
-    warp_max(&d.cnt->toiMaxDistIters, distIt); warp_max(&d.cnt->toiMaxToiIters, toiIt); warp_max(&d.cnt->toiMaxRootIters, rootIt);
-    if (key != ~0ull) atomicMin(&d.cnt->toiMinKey, key);
+    warp_add(&d.cnt->toiAtMaxSub, o.atMax); warp_add(&d.cnt->toiAtMaxLive, o.atMax); warp_add(&d.cnt->toiUpdated, o.updated);
+    warp_max(&d.cnt->toiMaxDistIters, o.distIt); warp_max(&d.cnt->toiMaxToiIters, o.toiIt); warp_max(&d.cnt->toiMaxRootIters, o.rootIt);
+    if (o.key != ~0ull) atomicMin(&d.cnt->toiMinKey, o.key);
 }
 
 // ------------------------------------------------------------------ event selection
@@ -262,41 +284,49 @@ template <class F> PR_D void toi_for_each_claim_body(const DV& d, uint4 ab, F&& 
         }
     }
 }
+PR_D void toi_claim_cand(const DV& d, unsigned id)
+{
+    const unsigned long long key = toi_key(d.c_mat[id].w, d.c_pos[id]);
+    toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { atomicMin(&d.b_claim[b], key); });
+}
+PR_D void toi_unclaim_cand(const DV& d, unsigned id) { toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { d.b_claim[b] = ~0ull; }); }
+PR_D void toi_select_cand(const DV& d, unsigned id, unsigned parallel)
+{
+    const unsigned long long key = toi_key(d.c_mat[id].w, d.c_pos[id]);
+    bool win;
+    if (parallel) {
+        bool mine = true;
+        toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { if (d.b_claim[b] != key) mine = false; });
+        win = PR_WARP_ALL(mine);
+    } else win = (key == d.cnt->toiMinKey);
+    if (win && PR_LANE == 0u) d.toi_events[atomicAdd(&d.cnt->toiEvents, 1u)] = id;
+}
 PR_KERNEL k_toi_claim(DV d)
 {
     if (d.cnt->toiHalt) return;
     const unsigned n = d.cnt->toiCandN;
-    for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS) {
-        const unsigned id = d.toi_cand[c];
-        const unsigned long long key = toi_key(d.c_mat[id].w, d.c_pos[id]);
-        toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { atomicMin(&d.b_claim[b], key); });
-    }
+    for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS) toi_claim_cand(d, d.toi_cand[c]);
 }
 PR_KERNEL k_toi_unclaim(DV d)
 {
     if (d.cnt->toiHalt) return;
     const unsigned n = d.cnt->toiCandN;
-    for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS)
-        toi_for_each_claim_body(d, d.c_ab[d.toi_cand[c]], [&](unsigned b) { d.b_claim[b] = ~0ull; });
+    for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS) toi_unclaim_cand(d, d.toi_cand[c]);
 }
 PR_KERNEL k_toi_select(DV d, unsigned parallel)
 {
     if (d.cnt->toiHalt) return;
     const unsigned n = d.cnt->toiCandN;
-    for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS) {
-        const unsigned id = d.toi_cand[c];
-        const unsigned long long key = toi_key(d.c_mat[id].w, d.c_pos[id]);
-        bool win;
-        if (parallel) {
-            bool mine = true;
-            toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { if (d.b_claim[b] != key) mine = false; });
-            win = PR_WARP_ALL(mine);
-        } else win = (key == d.cnt->toiMinKey);
-        if (win && PR_LANE == 0u) d.toi_events[atomicAdd(&d.cnt->toiEvents, 1u)] = id;
-    }
+    for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS) toi_select_cand(d, d.toi_cand[c], parallel);
 }
 
 // ------------------------------------------------------------------ SolveToi(contact) (:1833-1955)
+// SetAwake on a body that was asleep makes contacts eligible that no list of "contacts to recompute" holds: the next
+// round must walk the full TOI list again (k_tb_late hands back to the list kernels)
+PR_D void toi_wake(const DV& d, unsigned b)
+{
+    if (!(atomicOr(&d.b_flags[b], static_cast<unsigned>(PR_BODY_AWAKE)) & PR_BODY_AWAKE)) d.cnt->toiForceFull = 1u;
+}
 PR_D void toi_flag_body_contacts(const DV& d, unsigned b)
 { // FlagForUpdating(m_bodyContacts[b]), :459-465
     for (unsigned k = d.adj_off[b], ke = adj_end(d, b); k < ke; ++k) atomicOr(&d.c_flags[d.adj_list[k]], static_cast<unsigned>(PR_CONTACT_DIRTY));
@@ -364,7 +394,7 @@ PR_D void toi_process_contacts(const DV& d, const pr_step_conf& conf, unsigned i
         d.toi_islContacts[isl.base + isl.nC++] = cid;
         d.c_toiIsl[cid] = 1u;
         if (!otherIslanded) {
-            if (otherSpeedable) { atomicOr(&d.b_flags[other], static_cast<unsigned>(PR_BODY_AWAKE)); d.b_toiIsl[other] = 1u; }
+            if (otherSpeedable) { toi_wake(d, other); d.b_toiIsl[other] = 1u; }
             d.toi_islBodies[isl.base + isl.nB++] = other;
         }
     }
@@ -417,6 +447,8 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
         cf &= ~static_cast<unsigned>(PR_CONTACT_TOI); // SetToi(contact, {})
         cf += 0x100u;                                  // IncrementToiCount
         d.c_flags[cid] = cf;
+        if ((cf >> 8) == conf.max_sub_steps) atomicAdd(&d.cnt->toiAtMaxLive, 1u); // from now on UpdateContactTOIs counts it every round
+        toi_mark_recompute(d, cid);                    // (its TOI is gone: next round looks at it again)
         reinterpret_cast<float*>(&d.c_mat[cid])[3] = 1.0f;
         if (!(cf & PR_CONTACT_ENABLED) || !(cf & PR_CONTACT_TOUCHING)) {
             if (touchA) toi_restore(d, A, bkA);
@@ -427,8 +459,8 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
         }
     }
     PR_TT(0);
-    if (f_speedable(fA)) atomicOr(&d.b_flags[A], static_cast<unsigned>(PR_BODY_AWAKE));
-    if (f_speedable(fB)) atomicOr(&d.b_flags[B], static_cast<unsigned>(PR_BODY_AWAKE));
+    if (f_speedable(fA)) toi_wake(d, A);
+    if (f_speedable(fB)) toi_wake(d, B);
     isl.nB = 2u; isl.nC = 1u;
     d.toi_islBodies[isl.base] = A; d.toi_islBodies[isl.base + 1u] = B; d.toi_islContacts[isl.base] = cid;
     if (f_speedable(fA)) d.b_toiIsl[A] = 1u;
@@ -539,7 +571,8 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
             d.sync_list[atomicAdd(&d.cnt->syncN, 1u)] = b;
             for (unsigned q = d.adj_off[b], qe = adj_end(d, b); q < qe; ++q) {
                 const unsigned c2 = d.adj_list[q];
-                atomicAnd(&d.c_flags[c2], ~static_cast<unsigned>(PR_CONTACT_TOI));
+                const unsigned f2 = atomicAnd(&d.c_flags[c2], ~static_cast<unsigned>(PR_CONTACT_TOI));
+                if (toi_static_eligible(f2)) toi_mark_recompute(d, c2);
                 reinterpret_cast<float*>(&d.c_mat[c2])[3] = 1.0f;
                 d.c_toiIsl[c2] = 0u;
             }
@@ -589,29 +622,31 @@ PR_KERNEL k_toi_finish_contacts(DV d)
     if (i < d.cnt->toiListN) {
         const unsigned id = d.toi_list[i];
         d.c_flags[id] = d.c_flags[id] & 0xFFu & ~static_cast<unsigned>(PR_CONTACT_TOI); // SetToi({}) + SetToiCount(0)
+        d.c_rstamp[id] = 0u; // (round ids restart with every step)
         reinterpret_cast<float*>(&d.c_mat[id])[3] = 1.0f;
     }
 }
 // Synchronize (:2564-2585) for the bodies the round's events listed (:1800-1805): grid-stride over sync_list
+PR_D void sync_body_proxies_one(const DV& d, const pr_step_conf& conf, unsigned body)
+{
+    const Xf xf1 = xf_from4(d.b_xf[body]);
+    const Xf xf0 = get_xf(pos_from4(d.b_pos0[body]), d.b_lc[body]);
+    const float2 dsp = conf.displace_multiplier * (xf1.p - xf0.p);
+    for (unsigned k = d.bp_off[body]; k < d.bp_off[body + 1u]; ++k) {
+        const unsigned px = d.bp_list[k];
+        const Box a = compute_aabb(child_view(d, d.p_cg[px]), xf0, xf1);
+        if (!box_contains(box_from4(d.p_fat[px]), a)) {
+            d.p_fat[px] = box_to4(fatten_displace(a, conf.aabb_extension, dsp));
+            if (d.p_moved[px] == 0u) { d.p_moved[px] = 1u; d.q_list[atomicAdd(&d.cnt->nQueue, 1u)] = px; }
+            atomicAdd(&d.cnt->proxiesMoved, 1u);
+        }
+    }
+}
 PR_KERNEL k_sync_body_proxies(DV d, pr_step_conf conf)
 {
     if (d.cnt->toiHalt) return;
     const unsigned n = d.cnt->syncN;
-    for (unsigned i = PR_TID; i < n; i += PR_NTHREADS) {
-        const unsigned body = d.sync_list[i];
-        const Xf xf1 = xf_from4(d.b_xf[body]);
-        const Xf xf0 = get_xf(pos_from4(d.b_pos0[body]), d.b_lc[body]);
-        const float2 dsp = conf.displace_multiplier * (xf1.p - xf0.p);
-        for (unsigned k = d.bp_off[body]; k < d.bp_off[body + 1u]; ++k) {
-            const unsigned px = d.bp_list[k];
-            const Box a = compute_aabb(child_view(d, d.p_cg[px]), xf0, xf1);
-            if (!box_contains(box_from4(d.p_fat[px]), a)) {
-                d.p_fat[px] = box_to4(fatten_displace(a, conf.aabb_extension, dsp));
-                if (d.p_moved[px] == 0u) { d.p_moved[px] = 1u; d.q_list[atomicAdd(&d.cnt->nQueue, 1u)] = px; }
-                atomicAdd(&d.cnt->proxiesMoved, 1u);
-            }
-        }
-    }
+    for (unsigned i = PR_TID; i < n; i += PR_NTHREADS) sync_body_proxies_one(d, conf, d.sync_list[i]);
 }
 
 // ------------------------------------------------------------------ batched rounds (k_tb_*)
@@ -677,24 +712,24 @@ PR_KERNEL k_tb_query(DV d, unsigned nLeaves, const unsigned* sortedIdx, unsigned
 //   update  : AddContacts' Update(contactID) of the new contacts (:2531), then the bookkeeping of the round
 // (four launches before; the block-wide barriers order the global writes of one stage before the reads of the next)
 constexpr unsigned TB_ADD_BLOCK = 512u;
-PR_KERNEL k_tb_add(DV d, pr_step_conf conf, unsigned capPairs, unsigned capContacts, unsigned capHash, unsigned hashTombs)
+// returns false when the host must take over (toiHalt = TB_HOST_FIND); kbuf / vbuf: SMALL_SORT_MAX entries of shared memory
+PR_D bool tb_add_block(const DV& d, const pr_step_conf& conf, unsigned capPairs, unsigned capContacts, unsigned capHash, unsigned hashTombs,
+                       unsigned long long* kbuf, unsigned* vbuf)
 {
-    if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
     const unsigned nP = d.cnt->nPairs, order = d.cnt->devOrder, pool = d.cnt->devPool, nFree = d.cnt->devFree, nQ = d.cnt->nQueue;
     const bool hostMust = (d.cnt->error & ERR_PAIR_OVERFLOW) || nP > capPairs || nP > SMALL_SORT_MAX ||
                           order + nP + 1u > capContacts || pool + nP + 1u > capContacts ||
                           2ull * (static_cast<unsigned long long>(order) + nP + hashTombs) > capHash;
-    if (hostMust) { if (PR_TID == 0u) d.cnt->toiHalt = TB_HOST_FIND; return; }
+    __syncthreads(); // (every thread has read the counters the decision depends on)
+    if (hostMust) { if (PR_TID == 0u) d.cnt->toiHalt = TB_HOST_FIND; return false; }
     for (unsigned t = PR_TID; t < nQ; t += PR_NTHREADS) d.p_moved[d.q_list[t]] = 0u;
-#ifndef PR_HOST_EMUL
-    __shared__ unsigned long long k[SMALL_SORT_MAX];
-    __shared__ unsigned v[SMALL_SORT_MAX];
     __syncthreads();
-    if (threadIdx.x == 0u) { d.cnt->nQueue = 0u; d.cnt->tbPairs += nP; }
-    if (nP == 0u) return;
+    if (PR_TID == 0u) { d.cnt->nQueue = 0u; d.cnt->tbPairs += nP; }
+    if (nP == 0u) return true;
+#ifndef PR_HOST_EMUL
     unsigned N = 32u;
     while (N < nP) N <<= 1;
-    for (unsigned i = threadIdx.x; i < N; i += blockDim.x) { k[i] = (i < nP) ? d.np_key[i] : ~0ull; v[i] = i; }
+    for (unsigned i = threadIdx.x; i < N; i += blockDim.x) { kbuf[i] = (i < nP) ? d.np_key[i] : ~0ull; vbuf[i] = i; }
     __syncthreads();
     for (unsigned size = 2; size <= N; size <<= 1) {
         for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
@@ -702,29 +737,147 @@ PR_KERNEL k_tb_add(DV d, pr_step_conf conf, unsigned capPairs, unsigned capConta
                 const unsigned lo = 2u * t - (t & (stride - 1u));
                 const unsigned hi = lo + stride;
                 const bool asc = ((lo & size) == 0u);
-                const unsigned long long a = k[lo], b = k[hi];
-                if ((a > b) == asc) { k[lo] = b; k[hi] = a; const unsigned tv = v[lo]; v[lo] = v[hi]; v[hi] = tv; }
+                const unsigned long long a = kbuf[lo], b = kbuf[hi];
+                if ((a > b) == asc) { kbuf[lo] = b; kbuf[hi] = a; const unsigned tv = vbuf[lo]; vbuf[lo] = vbuf[hi]; vbuf[hi] = tv; }
             }
             __syncthreads();
         }
     }
-    for (unsigned i = threadIdx.x; i < nP; i += blockDim.x) { d.np_key2[i] = k[i]; d.np_idx2[i] = v[i]; }
+    for (unsigned i = threadIdx.x; i < nP; i += blockDim.x) { d.np_key2[i] = kbuf[i]; d.np_idx2[i] = vbuf[i]; }
     __threadfence_block();
     __syncthreads();
 #else
-    d.cnt->nQueue = 0u; d.cnt->tbPairs += nP;
-    if (nP == 0u) return;
+    (void)kbuf; (void)vbuf;
     sort_pairs_small(d.np_key, d.np_key2, d.np_idx2, nP, 0);
 #endif
     for (unsigned i = PR_TID; i < nP; i += PR_NTHREADS) create_contact_one(d, i, d.np_key2, d.np_idx2, order, nFree, pool, 1u);
-#ifndef PR_HOST_EMUL
     __threadfence_block();
     __syncthreads();
-#endif
     for (unsigned i = PR_TID; i < nP; i += PR_NTHREADS) { const unsigned id = d.c_order[order + i]; update_contact(d, conf, id, d.c_flags[id]); }
     if (PR_TID == 0u) {
         const unsigned used = nP < nFree ? nP : nFree;
         d.cnt->devFree = nFree - used; d.cnt->devPool = pool + (nP - used); d.cnt->devOrder = order + nP; d.cnt->tbAdded += nP;
+    }
+    return true;
+}
+PR_KERNEL k_tb_add(DV d, pr_step_conf conf, unsigned capPairs, unsigned capContacts, unsigned capHash, unsigned hashTombs)
+{
+    if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
+#ifndef PR_HOST_EMUL
+    __shared__ unsigned long long k[SMALL_SORT_MAX];
+    __shared__ unsigned v[SMALL_SORT_MAX];
+    tb_add_block(d, conf, capPairs, capContacts, capHash, hashTombs, k, v);
+#else
+    tb_add_block(d, conf, capPairs, capContacts, capHash, hashTombs, nullptr, nullptr);
+#endif
+}
+
+// ------------------------------------------------------------------ late rounds in ONE block (k_tb_late)
+// After the first round of a step the TOI phase is a handful of events per round (at 1M bodies: <= 8, for the bodies the
+// pile presses into the terrain, one event per sub-step up to maxSubSteps), yet every round cost eleven launches over the
+// full candidate list besides the ~130 us event chain. Here ONE block runs whole rounds back to back, block barriers
+// between the stages, over compact lists: the contacts the previous round's events invalidated (toi_mark_recompute) and the
+// surviving candidates. It hands back to the list kernels (TB_BIG) when a list outgrows it or a sleeping body was woken,
+// and to the host for what only the host can do -- exactly like the batched list rounds.
+constexpr unsigned LATE_BLOCK = 512u, LATE_MAX_LIST = 2048u, LATE_MAX_CAND = 192u, LATE_SOLVE_WARPS = 8u;
+PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratchCap, unsigned nLeaves, const unsigned* sortedIdx,
+                    unsigned capPairs, unsigned capContacts, unsigned capHash, unsigned hashTombs, unsigned maxRounds)
+{
+#ifndef PR_HOST_EMUL
+    // one shared-memory arena, re-used stage by stage: event islands | query stacks | sort buffers
+    __shared__ __align__(16) unsigned char arena[LATE_SOLVE_WARPS * sizeof(ToiSmem)];
+    static_assert(sizeof(arena) >= (LATE_BLOCK / QG) * QSTACK * sizeof(unsigned), "query stacks fit the arena");
+    static_assert(sizeof(arena) >= SMALL_SORT_MAX * (sizeof(unsigned long long) + sizeof(unsigned)), "sort buffers fit the arena");
+    ToiSmem* islands = reinterpret_cast<ToiSmem*>(arena);
+#else
+    ToiSmem local;
+    ToiSmem* islands = &local;
+#endif
+    for (unsigned r = 0; r < maxRounds; ++r) {
+        __syncthreads();
+        if (d.cnt->toiHalt) return;
+        const unsigned roundId = d.cnt->toiRoundId + 1u;
+        const unsigned nR = d.cnt->toiReN[roundId & 1u], nC = d.cnt->toiCandN;
+        const unsigned* R = (roundId & 1u) ? d.toi_re1 : d.toi_re0;
+        const unsigned stop = d.cnt->adjOverflow ? TB_ADJ : d.cnt->error ? TB_ERROR
+                            : (d.cnt->toiForceFull || nR > LATE_MAX_LIST || nC + nR > LATE_MAX_CAND) ? TB_BIG : TB_RUN;
+        __syncthreads();
+        if (stop != TB_RUN) { if (PR_TID == 0u) d.cnt->toiHalt = stop; return; }
+        if (PR_TID == 0u) { toi_open_round(d, roundId); d.cnt->toiCand2N = 0u; d.cnt->toiAtMaxSub += d.cnt->toiAtMaxLive; }
+        // ---- UpdateContactTOIs over the invalidated contacts
+        for (unsigned i = PR_TID; i < nR; i += PR_NTHREADS) toi_alpha_one(d, R[i], conf.max_sub_steps);
+        __threadfence_block(); __syncthreads();
+        for (unsigned i = PR_TID; i < nR; i += PR_NTHREADS) toi_advance_one(d, R[i], conf.max_sub_steps, roundId);
+        // (same stage) candidates that kept their TOI stay candidates; the invalidated ones are re-listed by their computation
+        for (unsigned i = PR_TID; i < nC; i += PR_NTHREADS) {
+            const unsigned id = d.toi_cand[i];
+            const float toi = d.c_mat[id].w;
+            if ((d.c_flags[id] & PR_CONTACT_TOI) && toi < 1.0f) {
+                d.toi_cand2[atomicAdd(&d.cnt->toiCand2N, 1u)] = id;
+                atomicMin(&d.cnt->toiMinKey, toi_key(toi, d.c_pos[id]));
+            }
+        }
+        __threadfence_block(); __syncthreads();
+        for (unsigned i = PR_TID; i < nR; i += PR_NTHREADS) {
+            const unsigned id = R[i];
+            const ToiComputeOut o = toi_compute_one(d, id, conf);
+            if (o.updated) atomicAdd(&d.cnt->toiUpdated, 1u);
+            atomicMax(&d.cnt->toiMaxDistIters, o.distIt); atomicMax(&d.cnt->toiMaxToiIters, o.toiIt); atomicMax(&d.cnt->toiMaxRootIters, o.rootIt);
+            if (o.key != ~0ull) { d.toi_cand2[atomicAdd(&d.cnt->toiCand2N, 1u)] = id; atomicMin(&d.cnt->toiMinKey, o.key); }
+        }
+        __threadfence_block(); __syncthreads();
+        const unsigned nCand = d.cnt->toiCand2N;
+        for (unsigned i = PR_TID; i < nCand; i += PR_NTHREADS) d.toi_cand[i] = d.toi_cand2[i];
+        __syncthreads();
+        if (PR_TID == 0u) d.cnt->toiCandN = nCand;
+        __threadfence_block(); __syncthreads();
+        // ---- GetSoonestContact
+        if (!exactMode) {
+            for (unsigned c = PR_WARP_ID; c < nCand; c += PR_NWARPS) toi_claim_cand(d, d.toi_cand[c]);
+            __threadfence_block(); __syncthreads();
+        }
+        for (unsigned c = PR_WARP_ID; c < nCand; c += PR_NWARPS) toi_select_cand(d, d.toi_cand[c], exactMode ? 0u : 1u);
+        __threadfence_block(); __syncthreads();
+        if (!exactMode) {
+            for (unsigned c = PR_WARP_ID; c < nCand; c += PR_NWARPS) toi_unclaim_cand(d, d.toi_cand[c]);
+        }
+        const unsigned nEvents = d.cnt->toiEvents;
+        __threadfence_block(); __syncthreads();
+        if (nEvents == 0u) { if (PR_TID == 0u) d.cnt->toiHalt = TB_DONE; return; } // :1768
+        if (PR_TID == 0u) { d.cnt->tbRounds += 1u; d.cnt->tbFound += nEvents; }
+        // ---- SolveToi per event: one warp each (lane 0 working), islands in the arena
+        if (PR_LANE == 0u && PR_WARP_ID < LATE_SOLVE_WARPS)
+            for (unsigned e = PR_WARP_ID; e < nEvents; e += (PR_NWARPS < LATE_SOLVE_WARPS ? PR_NWARPS : LATE_SOLVE_WARPS))
+                toi_solve_event(d, conf, e, exactMode, scratchCap, &islands[PR_WARP_ID < LATE_SOLVE_WARPS ? PR_WARP_ID : 0u]);
+        __threadfence_block(); __syncthreads();
+        // ---- Synchronize the moved bodies' proxies, FindContacts, AddContacts
+        {
+            const unsigned n = d.cnt->syncN;
+            for (unsigned i = PR_TID; i < n; i += PR_NTHREADS) sync_body_proxies_one(d, conf, d.sync_list[i]);
+        }
+        __threadfence_block(); __syncthreads();
+        const unsigned nQ = d.cnt->nQueue;
+        if (nQ == 0u) continue;
+        if (8ull * nQ >= nLeaves) { if (PR_TID == 0u) d.cnt->toiHalt = TB_HOST_FIND; return; } // full rebuild: the host's
+        for (unsigned t = PR_TID; t < nQ; t += PR_NTHREADS) bvh_refit_moved_one(d, t, nLeaves);
+        if (PR_TID == 0u) { d.cnt->nPairs = 0u; d.cnt->error &= ~static_cast<unsigned>(ERR_PAIR_OVERFLOW); }
+        __threadfence_block(); __syncthreads();
+#ifndef PR_HOST_EMUL
+        {
+            unsigned (*stk)[QSTACK] = reinterpret_cast<unsigned (*)[QSTACK]>(arena);
+            const unsigned lane = threadIdx.x & 31u, gl = lane & (QG - 1u);
+            const unsigned gmask = ((1u << QG) - 1u) << (lane & ~(QG - 1u));
+            for (unsigned qi = threadIdx.x / QG; qi < nQ; qi += blockDim.x / QG)
+                bvh_query_group(d, d.q_list[qi], sortedIdx, capPairs, stk[threadIdx.x / QG], lane, gl, gmask);
+        }
+        __threadfence_block(); __syncthreads();
+        if (!tb_add_block(d, conf, capPairs, capContacts, capHash, hashTombs, reinterpret_cast<unsigned long long*>(arena),
+                          reinterpret_cast<unsigned*>(arena + SMALL_SORT_MAX * sizeof(unsigned long long)))) return;
+#else
+        for (unsigned t = PR_TID; t < nQ; t += PR_NTHREADS) bvh_query_serial(d, d.q_list[t], nLeaves, sortedIdx, capPairs);
+        if (!tb_add_block(d, conf, capPairs, capContacts, capHash, hashTombs, nullptr, nullptr)) return;
+#endif
+        __threadfence_block();
     }
 }
 

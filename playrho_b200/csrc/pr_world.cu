@@ -86,7 +86,8 @@ static std::vector<ArrDesc> arrays(World& w)
         A(isl_nbodies, G_BODY), A(isl_active, G_BODY), A(b_claim, G_BODY), A(b_cmask, G_BODY),
         A(adj_off, G_BODY), A(adj_cnt, G_BODY), A(adj_n, G_BODY), A(b_toiIsl, G_BODY), A(b_toiAlpha, G_BODY), A(b_toiStamp, G_BODY), A(b_inR, G_BODY),
         A(sync_list, G_BODY), A(bp_off, G_BODY), A(bp_list, G_PROXY), A(bv_leafOf, G_PROXY), A(b_world, G_BODY), A(bv_wr, G_PROXY),
-        A(c_pos, G_CONTACT), A(c_color, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT), A(toi_list, G_CONTACT), A(toi_cand, G_CONTACT),
+        A(c_pos, G_CONTACT), A(c_color, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT), A(toi_list, G_CONTACT), A(toi_cand, G_CONTACT), A(toi_cand2, G_CONTACT), A(toi_re0, G_CONTACT),
+        A(toi_re1, G_CONTACT), A(c_rstamp, G_CONTACT),
         A(adj_list, G_ADJ), A(toi_islBodies, G_ADJ), A(toi_islContacts, G_ADJ),
         A(jt, G_JOINT), A(jt_work, G_JOINT), A(nc_pairs, G_JOINT), A(isl_jflag, G_BODY),
         A(sh_mat, G_SHAPE), A(sh_filter, G_SHAPE), A(sh_group, G_SHAPE),
@@ -613,6 +614,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     w.hostCnt.toiMaxIncBits = 0; w.hostCnt.toiIslandsSolved = w.hostCnt.toiSumPosIters = w.hostCnt.toiSumVelIters = 0;
     w.hostCnt.toiIslandsFound = w.hostCnt.toiUpdTouching = w.hostCnt.toiSkipTouching = 0;
     w.hostCnt.proxiesMoved = 0; w.hostCnt.contactsUpdated = 0; w.hostCnt.toiDeferred = 0;
+    w.hostCnt.toiRoundId = 0; w.hostCnt.toiReN[0] = w.hostCnt.toiReN[1] = 0; w.hostCnt.toiAtMaxLive = 0; w.hostCnt.toiForceFull = 0; w.hostCnt.toiHalt = TB_RUN;
     write_counters(w);
     const bool exact = (w.toiMode == 0u);
     unsigned rounds = 0, round = 0;
@@ -648,9 +650,13 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             write_counters(w);
             const unsigned listBound = w.toiListBound + K * SMALL_SORT_MAX; // contacts created by earlier rounds of the batch join the list
             const unsigned solveWarps = std::min(592u * 8u, std::max(8u, listBound)); // (8 warps per 256-thread block)
-            for (unsigned k = 0; k < K; ++k) {
+            // one round over the full TOI list (list kernels), then -- unless switched off (debug bit 3) or sub-stepping -- up to
+            // K more rounds in ONE block over compact lists (k_tb_late); without it, K list rounds
+            const bool late = !(w.debugFlags & 8u) && !w.subStepping;
+            const unsigned listRounds = late ? 1u : K;
+            for (unsigned k = 0; k < listRounds; ++k) {
                 ++round;
-                PR_LAUNCH(k_toi_alpha, listBound, w.stream, d, conf.max_sub_steps);
+                PR_LAUNCH(k_toi_alpha, listBound, w.stream, d, conf.max_sub_steps, round);
                 PR_LAUNCH(k_toi_advance, listBound, w.stream, d, conf.max_sub_steps, round);
                 PR_LAUNCH(k_toi_compute, listBound, w.stream, d, conf);
                 if (!exact) PR_LAUNCH(k_toi_claim, listBound, w.stream, d);
@@ -669,15 +675,24 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
                 PR_LAUNCH(k_tb_add, 1, w.stream, d, conf, w.capPairs, w.capContacts, w.capHash, w.hashTombs);
 #endif
             }
+            if (late) {
+#ifndef PR_HOST_EMUL
+                PR_LAUNCH_GRID(k_tb_late, 1, LATE_BLOCK, w.stream, d, conf, exact ? 1u : 0u, scratchCap, P, w.bvhSortedIdx, w.capPairs, w.capContacts,
+                               w.capHash, w.hashTombs, K);
+#else
+                PR_LAUNCH(k_tb_late, 1, w.stream, d, conf, exact ? 1u : 0u, scratchCap, P, w.bvhSortedIdx, w.capPairs, w.capContacts, w.capHash,
+                          w.hashTombs, K);
+#endif
+            }
             read_counters(w);
             const Counters c = w.hostCnt;
-            round -= K - std::min(K, c.tbRounds + 1u); // (stamps only need to be unique; keep the count honest)
+            round = c.toiRoundId; // (the device opened this many rounds so far this step)
             w.nOrder = c.devOrder; w.nFree = c.devFree; w.poolSize = c.devPool;
             w.toiListBound += c.tbAdded; w.bvhRefits += c.tbRounds;
             rounds += c.tbRounds;
             st.contacts_found += c.tbFound; st.contacts_added += c.tbAdded;
             w.profile.candidate_pairs += c.tbPairs;
-            const unsigned halt = c.toiHalt;
+            const unsigned halt = (c.toiHalt == TB_BIG) ? static_cast<unsigned>(TB_RUN) : c.toiHalt; // (TB_BIG: the next batch starts with a list round anyway)
             w.hostCnt.toiHalt = TB_RUN;
             if (halt == TB_ERROR) { write_counters(w); throw_device_error(w); throw CudaError{"TOI rounds halted on a device error"}; }
             if (halt == TB_ADJ || c.adjOverflow) { w.adjValid = false; w.hostCnt.adjOverflow = 0; }
@@ -701,7 +716,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         const unsigned nList = w.toiListBound; // >= device toiListN (kernels re-check against it)
         ++round;
         if (nList) {
-            PR_LAUNCH(k_toi_alpha, nList, w.stream, d, conf.max_sub_steps);
+            PR_LAUNCH(k_toi_alpha, nList, w.stream, d, conf.max_sub_steps, round);
             PR_LAUNCH(k_toi_advance, nList, w.stream, d, conf.max_sub_steps, round);
             PR_LAUNCH(k_toi_compute, nList, w.stream, d, conf);
             if (!exact) PR_LAUNCH(k_toi_claim, nList, w.stream, d);

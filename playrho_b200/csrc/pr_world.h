@@ -26,7 +26,7 @@ constexpr unsigned MAX_COLORS = 65u;
 constexpr unsigned LEAF_BIT = 0x80000000u;
 
 enum { ISL_ACTIVE = 1u, ISL_VEL_DONE = 2u, ISL_POS_SOLVED = 4u };
-enum { TB_RUN = 0, TB_DONE = 1, TB_HOST_FIND = 2, TB_ADJ = 3, TB_ERROR = 4 };
+enum { TB_RUN = 0, TB_DONE = 1, TB_HOST_FIND = 2, TB_ADJ = 3, TB_ERROR = 4, TB_BIG = 5 };
 enum { ERR_NONE = 0, ERR_STACK = 1, ERR_SENSOR = 2, ERR_PAIR_OVERFLOW = 4, ERR_HASH_FULL = 8, ERR_TOI_SCRATCH = 16 };
 
 // VelocityConstraint row (Library/include/playrho/d2/VelocityConstraint.hpp), 144 B
@@ -74,6 +74,9 @@ struct Counters {
     unsigned tbRounds, tbFound, tbAdded, tbPairs; // totals of the batch
     unsigned devOrder, devFree, devPool;          // m_contacts size, free-stack height, pool size
     unsigned tbFindSkip, tbAddOld, tbAddN, toiCandN; // toiCandN: candidates (valid TOI < 1) of the round, see k_toi_compute
+    // compact lists for the single-block late rounds (k_tb_late): contacts to recompute in round toiRoundId + 1 (parity
+    // ping-pong), the candidates being compacted, the listed contacts currently at maxSubSteps, "next round needs the full list"
+    unsigned toiRoundId, toiReN[2], toiCand2N, toiAtMaxLive, toiForceFull, tbPad2;
 #ifdef PR_TOI_TIMING
     unsigned long long dbg[16]; // profiling build only: clock64 deltas of the phases of toi_solve_event (event 0 of each round)
 #endif
@@ -100,7 +103,7 @@ struct DV {
     // TOI phase: body -> contact adjacency (m_bodyContacts) as CSR, islanded flags, event list, island scratch
     // (adjacency covers speedable bodies only, each segment has slack for contacts added during the TOI rounds)
     unsigned *adj_off, *adj_cnt, *adj_n, *adj_list, *c_pos, *b_toiIsl, *c_toiIsl, *b_toiAlpha, *b_toiStamp, *b_inR, *toi_events, *toi_islBodies,
-        *toi_islContacts, *toi_list, *toi_cand, *sync_list;
+        *toi_islContacts, *toi_list, *toi_cand, *toi_cand2, *toi_re0, *toi_re1, *c_rstamp, *sync_list;
     unsigned *bp_off, *bp_list; // body -> proxy CSR (m_bodyProxies)
     unsigned long long* ht_keys; unsigned ht_mask;
     // new pairs
