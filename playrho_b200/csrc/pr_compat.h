@@ -41,6 +41,25 @@ typedef cudaEvent_t pr_event_t;
     } while (0)
 #define PR_LAUNCH_GRID(kernel, grid, block, stream, ...)                                           \
     do { kernel<<<grid, block, 0, stream>>>(__VA_ARGS__); pr::count_launch(); } while (0)
+// Programmatic dependent launch (sm_90+): the kernel may START while its predecessor in the stream is still draining; it
+// must call pr_pdl_wait() before touching anything the predecessor writes. Used by the per-colour solver kernels, whose
+// prologue (the row planes, immutable during the solve) then overlaps the previous colour's tail and the launch gap.
+#define PR_LAUNCH_PDL(kernel, n, strm_, ...)                                                       \
+    do {                                                                                           \
+        const unsigned pr_n_ = static_cast<unsigned>(n);                                           \
+        if (pr_n_ > 0) {                                                                           \
+            cudaLaunchConfig_t pr_cfg_ = {};                                                       \
+            pr_cfg_.gridDim = dim3((pr_n_ + PR_BLOCK - 1) / PR_BLOCK); pr_cfg_.blockDim = dim3(PR_BLOCK); pr_cfg_.stream = strm_; \
+            cudaLaunchAttribute pr_at_[1];                                                         \
+            pr_at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                     \
+            pr_at_[0].val.programmaticStreamSerializationAllowed = 1;                              \
+            pr_cfg_.attrs = pr_at_; pr_cfg_.numAttrs = 1;                                          \
+            cudaLaunchKernelEx(&pr_cfg_, kernel, __VA_ARGS__);                                     \
+            pr::count_launch();                                                                    \
+        }                                                                                          \
+    } while (0)
+__device__ __forceinline__ void pr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pr_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 #else
 // ------------------------------------------------------------------ host emulation (tests only)
@@ -74,6 +93,9 @@ typedef int pr_event_t;
         for (unsigned pr_t_ = 0; pr_t_ < pr_n_; ++pr_t_) { pr::emul_tid = pr_t_; kernel(__VA_ARGS__); } \
         if (pr_n_ > 0) pr::count_launch();                                                         \
     } while (0)
+#define PR_LAUNCH_PDL PR_LAUNCH
+inline void pr_pdl_wait() {}
+inline void pr_pdl_launch_dependents() {}
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }

@@ -1157,16 +1157,17 @@ PR_D void vc_load_head(const RS& r, unsigned i, VCRow& v)
     v.invMA = b.x; v.invIA = b.y; v.invMB = b.z; v.invIB = b.w;
     v.island = r.vc_island[i];
 }
-PR_D VCRow vc_load(const RS& r, unsigned i)
+// everything of the row but the accumulated impulses (vc8): immutable between k_build_constraints and the end of the solve
+PR_D VCRow vc_load_static(const RS& r, unsigned i)
 {
     VCRow v;
     vc_load_head(r, i, v);
-    const float4 a = r.vc0[i], c = r.vc3[i], e = r.vc5[i], f = r.vc6[i], h = r.vc8[i];
+    const float4 a = r.vc0[i], c = r.vc3[i], e = r.vc5[i], f = r.vc6[i];
     v.nx = a.x; v.ny = a.y; v.friction = a.z; v.tangentSpeed = a.w;
     v.rA0x = c.x; v.rA0y = c.y; v.rB0x = c.z; v.rB0y = c.w;
     v.nm0 = e.x; v.tm0 = e.y; v.nm1 = e.z; v.tm1 = e.w;
     v.bias0 = f.x; v.bias1 = f.y; v.k00 = f.z; v.k11 = f.w;
-    v.jn0 = h.x; v.jt0 = h.y; v.jn1 = h.z; v.jt1 = h.w;
+    v.jn0 = v.jt0 = v.jn1 = v.jt1 = 0.0f;
     if (v.count == 2u) { // second point and the block-solver matrices only exist for two-point rows
         const float4 dd = r.vc4[i], g = r.vc7[i];
         v.rA1x = dd.x; v.rA1y = dd.y; v.rB1x = dd.z; v.rB1y = dd.w;
@@ -1174,6 +1175,17 @@ PR_D VCRow vc_load(const RS& r, unsigned i)
     } else {
         v.rA1x = v.rA1y = v.rB1x = v.rB1y = 0.0f; v.k01 = v.m00 = v.m11 = v.m01 = 0.0f;
     }
+    return v;
+}
+PR_D void vc_load_impulses(const RS& r, unsigned i, VCRow& v)
+{
+    const float4 h = r.vc8[i];
+    v.jn0 = h.x; v.jt0 = h.y; v.jn1 = h.z; v.jt1 = h.w;
+}
+PR_D VCRow vc_load(const RS& r, unsigned i)
+{
+    VCRow v = vc_load_static(r, i);
+    vc_load_impulses(r, i, v);
     return v;
 }
 PR_D void pc_store(const RS& r, unsigned i, const PCRow& p)
@@ -1328,9 +1340,10 @@ PR_D void apply_pair(float4& vA, float4& vB, float2 P, float2 relA, float2 relB,
     const float2 b = v2(vB.x, vB.y) + imB * P; vB.x = b.x; vB.y = b.y; vB.z += iiB * LB;
 }
 // WarmStartVelocities, AabbTreeWorld.cpp:222-273
-PR_D void warm_start_row(const RS& r, unsigned i)
+PR_D void warm_start_loaded(const RS& r, const VCRow& vc);
+PR_D void warm_start_row(const RS& r, unsigned i) { warm_start_loaded(r, vc_load(r, i)); }
+PR_D void warm_start_loaded(const RS& r, const VCRow& vc)
 {
-    const VCRow vc = vc_load(r, i);
     float4 vA = r.s_vel[vc.bodyA], vB = r.s_vel[vc.bodyB];
     const Rot normal = mkrot(vc.nx, vc.ny), tangent = fwd_perp(normal);
     float2 dAl = v2(0, 0), dBl = v2(0, 0); float dAa = 0.0f, dBa = 0.0f;
@@ -1346,9 +1359,13 @@ PR_D void warm_start_row(const RS& r, unsigned i)
     if (vc.dynB) r.s_vel[vc.bodyB] = make_float4(vB.x + dBl.x, vB.y + dBl.y, vB.z + dBa, 0.0f);
 }
 PR_KERNEL k_warm_start(DV d, unsigned start, unsigned count)
-{
+{ // (launched with PR_LAUNCH_PDL: the row is fetched while the previous colour drains; the bodies after it has)
     const unsigned t = PR_TID;
-    if (t < count) warm_start_row(rs_global(d), start + t);
+    VCRow vc;
+    if (t < count) vc = vc_load(rs_global(d), start + t); // (the stored impulses are k_build_constraints': no colour writes them)
+    pr_pdl_launch_dependents();
+    pr_pdl_wait();
+    if (t < count) warm_start_loaded(rs_global(d), vc);
 }
 // ---- colour-overflow tail (constraints that found no free colour < 64, e.g. the 65th+ contact of one body):
 // the tail is sorted by island label and solved by ONE THREAD PER ISLAND SEGMENT in list order -- a valid
@@ -1391,9 +1408,14 @@ PR_KERNEL k_warm_start_tail(DV d, unsigned tailStart, unsigned tailCount, unsign
 
 // GaussSeidel::SolveVelocityConstraint (ContactSolver.cpp:481): tangent (:395) then normal
 // (block :245 with cases 1-4 :113-243, else sequential :337); points in order 1 then 0.
+PR_D float solve_velocity_loaded(const DV& d, const RS& r, unsigned i, VCRow vc, bool& did, bool checkIsland);
 PR_D float solve_velocity_row(const DV& d, const RS& r, unsigned i, bool& did, bool checkIsland = true)
 {
-    VCRow vc = vc_load(r, i);
+    return solve_velocity_loaded(d, r, i, vc_load(r, i), did, checkIsland);
+}
+// vc: the whole row, impulses included
+PR_D float solve_velocity_loaded(const DV& d, const RS& r, unsigned i, VCRow vc, bool& did, bool checkIsland)
+{
     did = false;
     // (the two body loads are issued before the island test, not behind it: one round trip less in the dependent chain)
     float4 vA = r.s_vel[vc.bodyA], vB = r.s_vel[vc.bodyB];
@@ -1489,9 +1511,15 @@ PR_KERNEL
 #endif
 k_solve_velocity(DV d, unsigned start, unsigned count)
 {
+    // (launched with PR_LAUNCH_PDL) prologue: the immutable planes of the row, while the previous colour drains
     const unsigned t = PR_TID;
+    const RS r = rs_global(d);
     bool did = false; float inc = 0.0f; unsigned label = 0u;
-    if (t < count) { inc = solve_velocity_row(d, rs_global(d), start + t, did); label = d.vc_island[start + t]; }
+    VCRow vc;
+    if (t < count) vc = vc_load_static(r, start + t);
+    pr_pdl_launch_dependents();
+    pr_pdl_wait(); // from here on: what earlier kernels wrote (impulses, body velocities, island flags)
+    if (t < count) { vc_load_impulses(r, start + t, vc); inc = solve_velocity_loaded(d, r, start + t, vc, did, true); label = vc.island; }
     island_max(d.isl_inc, label, f2u(inc), did);
 }
 PR_KERNEL k_solve_velocity_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs)
@@ -1589,16 +1617,21 @@ PR_D PDelta psm_solve(const PSM& psm, float2 pA, float2 pB, float imA, float iiA
     return r;
 }
 // GaussSeidel::SolvePositionConstraint, ContactSolver.cpp:494-643 (moveA = moveB = true)
+PR_D float solve_position_loaded(const DV& d, const RS& r, const VCRow& vch, const PCRow& pc, float rate, float slop, float maxCorr, bool& did, bool checkIsland);
 PR_D float solve_position_row(const DV& d, const RS& r, unsigned i, float rate, float slop, float maxCorr, bool& did, bool checkIsland = true)
 {
     VCRow vch; vc_load_head(r, i, vch);
+    return solve_position_loaded(d, r, vch, pc_load(r, i), rate, slop, maxCorr, did, checkIsland);
+}
+// vch: the row's head (bodies, inverse masses, island), pc: its position-constraint planes -- both immutable during the solve
+PR_D float solve_position_loaded(const DV& d, const RS& r, const VCRow& vch, const PCRow& pc, float rate, float slop, float maxCorr, bool& did, bool checkIsland)
+{
     const VCRow* vcp = &vch;
     const unsigned island = vcp->island;
     did = false;
     const unsigned bA = vcp->bodyA, bB = vcp->bodyB;
     const float imA = vcp->invMA, iiA = vcp->invIA, imB = vcp->invMB, iiB = vcp->invIB;
     const unsigned dynA = vcp->dynA, dynB = vcp->dynB;
-    const PCRow pc = pc_load(r, i);
     float4 a4 = r.s_pos[bA], b4 = r.s_pos[bB]; // (issued before the island test: see solve_velocity_row)
     if (checkIsland && (d.isl_state[island] & ISL_POS_SOLVED)) return PR_INF;
     did = true;
@@ -1647,9 +1680,15 @@ PR_D float solve_position_row(const DV& d, const RS& r, unsigned i, float rate, 
 }
 PR_KERNEL k_solve_position(DV d, unsigned start, unsigned count, float rate, float slop, float maxCorr)
 {
+    // (launched with PR_LAUNCH_PDL: see k_solve_velocity)
     const unsigned t = PR_TID;
+    const RS r = rs_global(d);
     bool did = false; float sep = PR_INF; unsigned label = 0u;
-    if (t < count) { sep = solve_position_row(d, rs_global(d), start + t, rate, slop, maxCorr, did); label = d.vc_island[start + t]; }
+    VCRow vch; PCRow pc;
+    if (t < count) { vc_load_head(r, start + t, vch); pc = pc_load(r, start + t); }
+    pr_pdl_launch_dependents();
+    pr_pdl_wait();
+    if (t < count) { sep = solve_position_loaded(d, r, vch, pc, rate, slop, maxCorr, did, true); label = vch.island; }
     island_min(d.isl_sep, label, float_flip(sep), did);
 }
 PR_KERNEL k_solve_position_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs, float rate, float slop, float maxCorr)

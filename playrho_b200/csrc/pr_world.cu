@@ -503,7 +503,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
 #define PR_SMALL_COLORS(mode) do { } while (0)
 #endif
         if (nCons && conf.do_warm_start) {
-            for (size_t c = 0; c < nBig; ++c) PR_LAUNCH(k_warm_start, ranges[c].second, w.stream, d, ranges[c].first, ranges[c].second);
+            for (size_t c = 0; c < nBig; ++c) PR_LAUNCH_PDL(k_warm_start, ranges[c].second, w.stream, d, ranges[c].first, ranges[c].second);
             PR_SMALL_COLORS(0u);
             if (tailCount) PR_LAUNCH(k_warm_start_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
         }
@@ -511,7 +511,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         tm.mark(w, PR_STAGE_VELOCITY);
         for (unsigned it = 0; it < conf.reg_velocity_iters; ++it) {
             PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 1u, jSerial); // joints first (:1605-1608)
-            for (size_t c = 0; c < nBig; ++c) PR_LAUNCH(k_solve_velocity, ranges[c].second, w.stream, d, ranges[c].first, ranges[c].second);
+            for (size_t c = 0; c < nBig; ++c) PR_LAUNCH_PDL(k_solve_velocity, ranges[c].second, w.stream, d, ranges[c].first, ranges[c].second);
             PR_SMALL_COLORS(1u);
             if (tailCount) PR_LAUNCH(k_solve_velocity_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
             if (it == 0u) PR_LAUNCH(k_isl_vel_check, N, w.stream, d, N, it, conf.reg_min_momentum);
@@ -521,7 +521,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         PR_LAUNCH(k_integrate_positions, N, w.stream, d, N, conf.delta_time);
         for (unsigned it = 0; it < conf.reg_position_iters; ++it) {
             for (size_t c = 0; c < nBig; ++c)
-                PR_LAUNCH(k_solve_position, ranges[c].second, w.stream, d, ranges[c].first, ranges[c].second, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
+                PR_LAUNCH_PDL(k_solve_position, ranges[c].second, w.stream, d, ranges[c].first, ranges[c].second, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
             PR_SMALL_COLORS(2u);
             if (tailCount)
                 PR_LAUNCH(k_solve_position_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
