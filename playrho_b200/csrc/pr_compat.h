@@ -30,36 +30,31 @@ typedef cudaEvent_t pr_event_t;
 #define PR_WARP_ID (PR_TID >> 5)
 #define PR_NWARPS (PR_NTHREADS >> 5)
 #define PR_WARP_ALL(p) (__all_sync(0xffffffffu, (p)) != 0)
-// one thread per element launch
-#define PR_LAUNCH(kernel, n, stream, ...)                                                          \
+// Every kernel launch is a programmatic dependent launch (sm_90+, below): the grid may be SCHEDULED while its predecessor in the
+// stream is still draining, and every kernel body starts with PR_PDL_ENTER() -- let my own dependents be scheduled, then wait
+// for my predecessor to complete (and its writes to be visible) -- before it touches global memory. A step is ~300 dependent
+// launches; this hides the launch gap of each.
+#define PR_LAUNCH(kernel, n, strm_, ...)                                                           \
     do {                                                                                           \
         const unsigned pr_n_ = static_cast<unsigned>(n);                                           \
-        if (pr_n_ > 0) {                                                                           \
-            kernel<<<(pr_n_ + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, 0, stream>>>(__VA_ARGS__);       \
-            pr::count_launch();                                                                    \
-        }                                                                                          \
+        if (pr_n_ > 0) PR_LAUNCH_GRID(kernel, (pr_n_ + PR_BLOCK - 1) / PR_BLOCK, PR_BLOCK, strm_, __VA_ARGS__); \
     } while (0)
-#define PR_LAUNCH_GRID(kernel, grid, block, stream, ...)                                           \
-    do { kernel<<<grid, block, 0, stream>>>(__VA_ARGS__); pr::count_launch(); } while (0)
-// Programmatic dependent launch (sm_90+): the kernel may START while its predecessor in the stream is still draining; it
-// must call pr_pdl_wait() before touching anything the predecessor writes. Used by the per-colour solver kernels, whose
-// prologue (the row planes, immutable during the solve) then overlaps the previous colour's tail and the launch gap.
-#define PR_LAUNCH_PDL(kernel, n, strm_, ...)                                                       \
+#define PR_LAUNCH_GRID(kernel, grid, block, strm_, ...)                                            \
     do {                                                                                           \
-        const unsigned pr_n_ = static_cast<unsigned>(n);                                           \
-        if (pr_n_ > 0) {                                                                           \
-            cudaLaunchConfig_t pr_cfg_ = {};                                                       \
-            pr_cfg_.gridDim = dim3((pr_n_ + PR_BLOCK - 1) / PR_BLOCK); pr_cfg_.blockDim = dim3(PR_BLOCK); pr_cfg_.stream = strm_; \
-            cudaLaunchAttribute pr_at_[1];                                                         \
-            pr_at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                     \
-            pr_at_[0].val.programmaticStreamSerializationAllowed = 1;                              \
-            pr_cfg_.attrs = pr_at_; pr_cfg_.numAttrs = 1;                                          \
-            cudaLaunchKernelEx(&pr_cfg_, kernel, __VA_ARGS__);                                     \
-            pr::count_launch();                                                                    \
-        }                                                                                          \
+        cudaLaunchConfig_t pr_cfg_ = {};                                                           \
+        pr_cfg_.gridDim = dim3(grid); pr_cfg_.blockDim = dim3(block); pr_cfg_.stream = strm_;      \
+        cudaLaunchAttribute pr_at_[1];                                                             \
+        pr_at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                         \
+        pr_at_[0].val.programmaticStreamSerializationAllowed = 1;                                  \
+        pr_cfg_.attrs = pr_at_; pr_cfg_.numAttrs = 1;                                              \
+        cudaLaunchKernelEx(&pr_cfg_, kernel, __VA_ARGS__);                                         \
+        pr::count_launch();                                                                        \
     } while (0)
+// (the per-colour solver kernels go further: they fetch their immutable row planes BEFORE the wait)
+#define PR_LAUNCH_PDL PR_LAUNCH
 __device__ __forceinline__ void pr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pr_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define PR_PDL_ENTER() do { pr_pdl_launch_dependents(); pr_pdl_wait(); } while (0)
 
 #else
 // ------------------------------------------------------------------ host emulation (tests only)
@@ -96,6 +91,7 @@ typedef int pr_event_t;
 #define PR_LAUNCH_PDL PR_LAUNCH
 inline void pr_pdl_wait() {}
 inline void pr_pdl_launch_dependents() {}
+#define PR_PDL_ENTER() do { } while (0)
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }

@@ -218,6 +218,7 @@ PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& con
 // phase: 0 = InitVelocity, 1 = SolveVelocity, 2 = SolvePosition. serial != 0: one thread walks all joints.
 PR_KERNEL k_joints(DV d, pr_step_conf conf, unsigned nJoints, unsigned phase, unsigned serial)
 {
+    PR_PDL_ENTER();
     const unsigned t = PR_TID;
     const unsigned lo = serial ? 0u : t, hi = serial ? (t == 0u ? nJoints : 0u) : (t < nJoints ? t + 1u : 0u);
     for (unsigned ji = lo; ji < hi; ++ji) {
@@ -229,6 +230,7 @@ PR_KERNEL k_joints(DV d, pr_step_conf conf, unsigned nJoints, unsigned phase, un
 // islands: a joint links its two bodies (AddToIsland :1443-1466) when both can be island members
 PR_KERNEL k_isl_union_joints(DV d, unsigned nJoints)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nJoints) {
         const unsigned a = d.jt[i].body_a, b = d.jt[i].body_b;
@@ -238,6 +240,7 @@ PR_KERNEL k_isl_union_joints(DV d, unsigned nJoints)
 // Add(JointID) wakes both bodies (AabbTreeWorld.cpp:1159-1180)
 PR_KERNEL k_joint_wake(DV d, unsigned first, unsigned n)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < n) { body_set_awake(d, d.jt[first + i].body_a); body_set_awake(d, d.jt[first + i].body_b); }
 }

@@ -151,6 +151,7 @@ PR_D Pos pos_from4(float4 p) { Pos r; r.l = v2(p.x, p.y); r.a = p.z; return r; }
 // ------------------------------------------------------------------ bodies: AoS rows <-> SoA
 PR_KERNEL k_put_bodies(DV d, unsigned n, unsigned firstId, const unsigned* ids, const pr_body* rows, unsigned isUpdate)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < n) {
         const unsigned id = ids ? ids[i] : firstId + i;
@@ -174,11 +175,13 @@ PR_KERNEL k_put_bodies(DV d, unsigned n, unsigned firstId, const unsigned* ids, 
 
 PR_KERNEL k_put_accelerations(DV d, unsigned n, const unsigned* ids, const float* acc3)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < n) d.b_acc[ids ? ids[i] : i] = make_float4(acc3[3u * i], acc3[3u * i + 1u], acc3[3u * i + 2u], 0.0f);
 }
 PR_KERNEL k_get_poses(DV d, unsigned first, unsigned n, float4* xf, float* vel3)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < n) {
         xf[i] = d.b_xf[first + i];
@@ -187,6 +190,7 @@ PR_KERNEL k_get_poses(DV d, unsigned first, unsigned n, float4* xf, float* vel3)
 }
 PR_KERNEL k_get_bodies(DV d, unsigned first, unsigned n, pr_body* rows)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < n) {
         const unsigned id = first + i;
@@ -241,6 +245,7 @@ PR_D bool box_overlap(Box a, Box b)
 // CreateProxies (AabbTreeWorld.cpp:557-579) for proxies [first, first+n): fat box + queue for FindContacts
 PR_KERNEL k_create_proxy_aabbs(DV d, pr_step_conf conf, unsigned first, unsigned n)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < n) {
         const unsigned px = first + i;
@@ -258,6 +263,7 @@ PR_KERNEL k_create_proxy_aabbs(DV d, pr_step_conf conf, unsigned first, unsigned
 // Synchronize (AabbTreeWorld.cpp:2564-2585) for every proxy whose body is flagged in b_sync
 PR_KERNEL k_sync_proxies(DV d, pr_step_conf conf, unsigned nProxies)
 {
+    PR_PDL_ENTER();
     const unsigned px = PR_TID;
     bool moved = false;
     if (px < nProxies) {
@@ -282,6 +288,7 @@ PR_KERNEL k_sync_proxies(DV d, pr_step_conf conf, unsigned nProxies)
 
 PR_KERNEL k_clear_queue_flags(DV d, unsigned nQueue)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nQueue) d.p_moved[d.q_list[i]] = 0u;
 }
@@ -327,6 +334,7 @@ PR_D bool hash_contains(const DV& d, unsigned long long key)
 }
 PR_KERNEL k_hash_fill(DV d, unsigned nOrder)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nOrder) hash_insert(d, d.c_key[d.c_order[i]]);
 }
@@ -347,6 +355,7 @@ PR_D void manifold_clear(const DV& d, unsigned id)
 // keep[i] = 1 if the two FAT leaf boxes still overlap (AabbTreeWorld.cpp:2290-2304), else InternalDestroy (:2245)
 PR_KERNEL k_destroy_test(DV d, unsigned nOrder, unsigned* keep, unsigned hashLive)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nOrder) {
         const unsigned id = d.c_order[i];
@@ -367,6 +376,7 @@ PR_KERNEL k_destroy_test(DV d, unsigned nOrder, unsigned* keep, unsigned hashLiv
 // stable compaction: kept ids to newOrder[pos[i]]; destroyed ids pushed on the free stack in order (ObjectPool::Free)
 PR_KERNEL k_destroy_compact(DV d, unsigned nOrder, const unsigned* keep, const unsigned* pos, unsigned* newOrder, unsigned nFree)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nOrder) {
         const unsigned id = d.c_order[i];
@@ -454,6 +464,7 @@ PR_KERNEL
 #endif
 k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n, unsigned useMoved, unsigned countIt)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     bool dirty = false;
     unsigned id = 0u, flags = 0u;
@@ -508,6 +519,7 @@ k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n, unsigned 
 // k_update_contacts_binned runs the same update_contact on homogeneous warps. Results are per contact: order-free.
 PR_KERNEL k_narrow_keys(DV d, unsigned nOrder, unsigned useMoved, unsigned* keys, unsigned* vals)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     bool dirty = false;
     if (i < nOrder) {
@@ -531,6 +543,7 @@ PR_KERNEL k_narrow_keys(DV d, unsigned nOrder, unsigned useMoved, unsigned* keys
 }
 PR_KERNEL k_update_contacts_binned(DV d, pr_step_conf conf, unsigned n, const unsigned* keys, const unsigned* vals)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < n && keys[i] != 0xFFu) { const unsigned id = vals[i]; update_contact(d, conf, id, d.c_flags[id]); }
 }
@@ -538,6 +551,7 @@ PR_KERNEL k_update_contacts_binned(DV d, pr_step_conf conf, unsigned n, const un
 // ------------------------------------------------------------------ a3: LBVH (Morton + Karras build + refit)
 PR_KERNEL k_bvh_bounds(DV d, unsigned nProxies)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     unsigned cx0 = 0xFFFFFFFFu, cy0 = 0xFFFFFFFFu, cx1 = 0u, cy1 = 0u;
     if (i < nProxies) {
@@ -557,6 +571,7 @@ PR_D unsigned expand_bits16(unsigned v)
 }
 PR_KERNEL k_bvh_morton(DV d, unsigned nProxies)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nProxies) {
         const float x0 = float_unflip(d.cnt->boundsMinX), y0 = float_unflip(d.cnt->boundsMinY);
@@ -584,6 +599,7 @@ PR_D int bvh_delta(const unsigned* codes, int n, int i, int j)
 // Karras 2012: one thread per internal node i in [0, n-1)
 PR_KERNEL k_bvh_build(DV d, unsigned nLeaves, const unsigned* codes)
 {
+    PR_PDL_ENTER();
     const int i = static_cast<int>(PR_TID);
     const int n = static_cast<int>(nLeaves);
     if (i < n - 1) {
@@ -627,6 +643,7 @@ PR_D float4 ld_cg4(const float4* p)
 // the child it came from, and the second thread to arrive unions both slots and continues
 PR_KERNEL k_bvh_refit(DV d, unsigned nLeaves, const unsigned* sortedIdx)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nLeaves) d.bv_leafOf[sortedIdx[i]] = i;
     if (i < nLeaves && nLeaves > 1u) {
@@ -693,6 +710,7 @@ PR_D void bvh_refit_moved_one(const DV& d, unsigned t, unsigned nLeaves)
 }
 PR_KERNEL k_bvh_refit_moved(DV d, unsigned nQueue, unsigned nLeaves)
 {
+    PR_PDL_ENTER();
     const unsigned t = PR_TID;
     if (t < nQueue && nLeaves > 1u) bvh_refit_moved_one(d, t, nLeaves);
 }
@@ -763,6 +781,7 @@ PR_D void bvh_query_serial(const DV& d, unsigned q, unsigned nLeaves, const unsi
 }
 PR_KERNEL k_bvh_query(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs, unsigned mortonOrder)
 {
+    PR_PDL_ENTER();
     const unsigned t = PR_TID;
     unsigned q = INVALID;
     if (mortonOrder) { if (t < nLeaves) { const unsigned c = sortedIdx[t]; if (d.p_moved[c]) q = c; } }
@@ -817,6 +836,7 @@ PR_D void bvh_query_group(const DV& d, unsigned q, const unsigned* sortedIdx, un
 }
 PR_KERNEL k_bvh_query_coop(DV d, unsigned nQueue, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs)
 {
+    PR_PDL_ENTER();
     __shared__ unsigned stk[PR_BLOCK / QG][QSTACK];
     const unsigned lane = threadIdx.x & 31u, gl = lane & (QG - 1u);
     const unsigned gmask = ((1u << QG) - 1u) << (lane & ~(QG - 1u));
@@ -872,6 +892,7 @@ PR_D void create_contact_one(const DV& d, unsigned i, const unsigned long long* 
 PR_KERNEL k_create_contacts(DV d, unsigned nNew, const unsigned long long* keys, const unsigned* srcIdx,
                             unsigned nOrder, unsigned nFree, unsigned poolSize, unsigned adjLive)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nNew) create_contact_one(d, i, keys, srcIdx, nOrder, nFree, poolSize, adjLive);
 }
@@ -899,6 +920,7 @@ PR_D void uf_union(unsigned* parent, unsigned a, unsigned b)
 }
 PR_KERNEL k_isl_init(DV d, unsigned nBodies, unsigned velIters, unsigned posIters)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nBodies) {
         const unsigned f = d.b_flags[i];
@@ -917,6 +939,7 @@ PR_D bool contact_solvable(unsigned flags)
 }
 PR_KERNEL k_isl_union(DV d, unsigned nOrder)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nOrder) {
         const unsigned id = d.c_order[i];
@@ -928,6 +951,7 @@ PR_KERNEL k_isl_union(DV d, unsigned nOrder)
 }
 PR_KERNEL k_isl_flatten(DV d, unsigned nBodies)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nBodies) {
         unsigned r = INVALID;
@@ -967,6 +991,7 @@ PR_D float4 body_constraint_velocity(const DV& d, unsigned i, float4 v, unsigned
 // also SolveRegIslandViaGS's pos0 <- pos1 (:1574) and AddToIsland's SetAwakeFlag (:1400).
 PR_KERNEL k_isl_prepare(DV d, unsigned nBodies, pr_step_conf conf)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     unsigned isRoot = 0u, isActive = 0u;
     if (i < nBodies) {
@@ -995,6 +1020,7 @@ PR_KERNEL k_isl_prepare(DV d, unsigned nBodies, pr_step_conf conf)
 // constraint this step loses its persistent colour (it was not in the conflict masks of this step's colouring).
 PR_KERNEL k_mark_constraints(DV d, unsigned nOrder, unsigned* mark)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     unsigned touching = 0u;
     if (i < nOrder) {
@@ -1014,6 +1040,7 @@ PR_KERNEL k_mark_constraints(DV d, unsigned nOrder, unsigned* mark)
 }
 PR_KERNEL k_gather_constraints(DV d, unsigned nOrder, const unsigned* mark, const unsigned* pos, unsigned recolorAll)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nOrder && mark[i]) {
         const unsigned id = d.c_order[i];
@@ -1038,6 +1065,7 @@ PR_D unsigned long long color_key(unsigned round, unsigned cid, unsigned k)
 }
 PR_KERNEL k_color_keep(DV d, unsigned nBound)
 {
+    PR_PDL_ENTER();
     const unsigned k = PR_TID;
     bool todo = false;
     if (k < nBound && k < d.cnt->nConstraints) {
@@ -1054,6 +1082,7 @@ PR_KERNEL k_color_keep(DV d, unsigned nBound)
 }
 PR_KERNEL k_color_claim(DV d, unsigned nWork, unsigned round)
 {
+    PR_PDL_ENTER();
     const unsigned t = PR_TID;
     if (t == 0u) d.cnt->nUncolored = 0u; // (k_color_commit of this round counts what is left)
     if (t < nWork) {
@@ -1069,6 +1098,7 @@ PR_KERNEL k_color_claim(DV d, unsigned nWork, unsigned round)
 }
 PR_KERNEL k_color_commit(DV d, unsigned nWork, unsigned round)
 {
+    PR_PDL_ENTER();
     const unsigned t = PR_TID;
     unsigned remaining = 0u;
     if (t < nWork) {
@@ -1097,11 +1127,13 @@ PR_KERNEL k_color_commit(DV d, unsigned nWork, unsigned round)
 }
 PR_KERNEL k_color_reset_claims(DV d, unsigned nBodies)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nBodies) d.b_claim[i] = ~0ull;
 }
 PR_KERNEL k_color_starts(DV d, unsigned nCons, const unsigned* sortedColor)
 {
+    PR_PDL_ENTER();
     const unsigned k = PR_TID;
     if (k < nCons) {
         const unsigned c = sortedColor[k];
@@ -1323,6 +1355,8 @@ PR_D void build_constraint_rows(const DV& d, const RS& r, unsigned cid, unsigned
 }
 PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtRatio)
 {
+    // (no early trigger: the solver kernels that follow fetch the rows written here BEFORE their own dependency wait)
+    pr_pdl_wait();
     const unsigned i = PR_TID;
     if (i < nCons) {
         const unsigned cid = d.k_contact[d.k_sorted[i]];
@@ -1372,6 +1406,7 @@ PR_KERNEL k_warm_start(DV d, unsigned start, unsigned count)
 // Gauss-Seidel order inside each island, islands in parallel.
 PR_KERNEL k_tail_keys(DV d, unsigned tailStart, unsigned tailCount, unsigned* keys, unsigned* vals)
 {
+    PR_PDL_ENTER();
     const unsigned t = PR_TID;
     if (t < tailCount) {
         const unsigned k = d.k_sorted[tailStart + t];
@@ -1383,6 +1418,7 @@ PR_KERNEL k_tail_keys(DV d, unsigned tailStart, unsigned tailCount, unsigned* ke
 }
 PR_KERNEL k_tail_segments(DV d, unsigned tailStart, unsigned tailCount, const unsigned* keys, const unsigned* vals)
 {
+    PR_PDL_ENTER();
     const unsigned t = PR_TID;
     bool head = false;
     if (t < tailCount) {
@@ -1403,6 +1439,7 @@ template <class F> PR_D void tail_for_each_row(const DV& d, unsigned tailStart, 
 }
 PR_KERNEL k_warm_start_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs)
 {
+    PR_PDL_ENTER();
     tail_for_each_row(d, tailStart, tailCount, nSegs, [&](unsigned row) { warm_start_row(rs_global(d), row); });
 }
 
@@ -1524,6 +1561,7 @@ k_solve_velocity(DV d, unsigned start, unsigned count)
 }
 PR_KERNEL k_solve_velocity_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs)
 {
+    PR_PDL_ENTER();
     tail_for_each_row(d, tailStart, tailCount, nSegs, [&](unsigned row) {
         bool did = false;
         const float inc = solve_velocity_row(d, rs_global(d), row, did);
@@ -1548,6 +1586,7 @@ PR_D unsigned isl_vel_check_root(const DV& d, unsigned i, unsigned iter, float m
 // islands among hundreds of thousands of single falling bodies, which are done after the first iteration
 PR_KERNEL k_isl_vel_check(DV d, unsigned nBodies, unsigned iter, float minMomentum)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     unsigned stillActive = 0u;
     if (i < nBodies && d.b_island[i] == i) stillActive = isl_vel_check_root(d, i, iter, minMomentum);
@@ -1557,13 +1596,15 @@ PR_KERNEL k_isl_vel_check(DV d, unsigned nBodies, unsigned iter, float minMoment
 // later iterations: only the listed islands (grid-stride; the list never grows)
 PR_KERNEL k_isl_vel_check_list(DV d, unsigned iter, float minMomentum)
 {
+    PR_PDL_ENTER();
     const unsigned n = d.cnt->nActiveVel;
     for (unsigned k = PR_TID; k < n; k += PR_NTHREADS) isl_vel_check_root(d, d.isl_active[k], iter, minMomentum);
 }
 
 // ------------------------------------------------------------------ a11: integrate + NGS position solve
 PR_KERNEL k_integrate_positions(DV d, unsigned nBodies, float h)
-{ // IntegratePositions, AabbTreeWorld.cpp:176-189
+{
+    PR_PDL_ENTER(); // IntegratePositions, AabbTreeWorld.cpp:176-189
     const unsigned i = PR_TID;
     if (i < nBodies && d.b_island[i] != INVALID) {
         const float4 v = d.s_vel[i];
@@ -1693,6 +1734,7 @@ PR_KERNEL k_solve_position(DV d, unsigned start, unsigned count, float rate, flo
 }
 PR_KERNEL k_solve_position_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs, float rate, float slop, float maxCorr)
 {
+    PR_PDL_ENTER();
     tail_for_each_row(d, tailStart, tailCount, nSegs, [&](unsigned row) {
         bool did = false;
         const float sep = solve_position_row(d, rs_global(d), row, rate, slop, maxCorr, did);
@@ -1714,6 +1756,7 @@ PR_D unsigned isl_pos_check_root(const DV& d, unsigned i, unsigned iter, float m
 }
 PR_KERNEL k_isl_pos_check(DV d, unsigned nBodies, unsigned iter, float minSeparation)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     unsigned stillActive = 0u;
     if (i < nBodies && d.b_island[i] == i) stillActive = isl_pos_check_root(d, i, iter, minSeparation);
@@ -1722,13 +1765,15 @@ PR_KERNEL k_isl_pos_check(DV d, unsigned nBodies, unsigned iter, float minSepara
 }
 PR_KERNEL k_isl_pos_check_list(DV d, unsigned iter, float minSeparation)
 {
+    PR_PDL_ENTER();
     const unsigned n = d.cnt->nActivePos;
     for (unsigned k = PR_TID; k < n; k += PR_NTHREADS) isl_pos_check_root(d, d.isl_active[k], iter, minSeparation);
 }
 
 // ------------------------------------------------------------------ a12: write-back, sleep, stats
 PR_KERNEL k_assign_impulses(DV d, unsigned nCons)
-{ // AssignImpulses, AabbTreeWorld.cpp:208-230
+{
+    PR_PDL_ENTER(); // AssignImpulses, AabbTreeWorld.cpp:208-230
     const unsigned i = PR_TID;
     if (i < nCons) {
         const float4 head = d.vc1[i], imp = d.vc8[i];
@@ -1740,7 +1785,8 @@ PR_KERNEL k_assign_impulses(DV d, unsigned nCons)
     }
 }
 PR_KERNEL k_writeback_bodies(DV d, unsigned nBodies, pr_step_conf conf)
-{ // AabbTreeWorld.cpp:1652-1664 + UpdateUnderActiveTimes :395-417
+{
+    PR_PDL_ENTER(); // AabbTreeWorld.cpp:1652-1664 + UpdateUnderActiveTimes :395-417
     const unsigned i = PR_TID;
     bool member = false; unsigned label = 0u; unsigned uaFlip = 0xFFFFFFFFu;
     if (i < nBodies) {
@@ -1768,7 +1814,8 @@ PR_KERNEL k_writeback_bodies(DV d, unsigned nBodies, pr_step_conf conf)
     island_min(d.isl_minUA, label, uaFlip, member);
 }
 PR_KERNEL k_sleep_and_stats(DV d, unsigned nBodies, float minStillTime)
-{ // Sleepem :419-430 ; Update(RegStepStats&, IslandStats) StepStats.cpp:29-38
+{
+    PR_PDL_ENTER(); // Sleepem :419-430 ; Update(RegStepStats&, IslandStats) StepStats.cpp:29-38
     const unsigned i = PR_TID;
     unsigned slept = 0u, solved = 0u, posIt = 0u, velIt = 0u, nb = 0u, sepFlip = 0xFFFFFFFFu, incBits = 0u;
     if (i < nBodies) {
@@ -1799,6 +1846,7 @@ PR_KERNEL k_sleep_and_stats(DV d, unsigned nBodies, float minStillTime)
 // ------------------------------------------------------------------ export helpers
 PR_KERNEL k_export_contacts(DV d, unsigned nOrder, pr_contact* out, pr_manifold* mout)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nOrder) {
         const unsigned id = d.c_order[i];
@@ -1823,6 +1871,7 @@ PR_KERNEL k_export_contacts(DV d, unsigned nOrder, pr_contact* out, pr_manifold*
 }
 PR_KERNEL k_import_contacts(DV d, unsigned n, const pr_contact* in, const pr_manifold* min, const unsigned* pxOfTree)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < n) {
         const pr_contact c = in[i];
@@ -1846,6 +1895,7 @@ PR_KERNEL k_import_contacts(DV d, unsigned n, const pr_contact* in, const pr_man
 }
 PR_KERNEL k_export_proxies(DV d, unsigned n, pr_proxy* out)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < n) {
         const float4 f = d.p_fat[i];
@@ -1855,11 +1905,12 @@ PR_KERNEL k_export_proxies(DV d, unsigned n, pr_proxy* out)
         out[i] = p;
     }
 }
-PR_KERNEL k_fill_u32(unsigned* p, unsigned n, unsigned v) { const unsigned i = PR_TID; if (i < n) p[i] = v; }
-PR_KERNEL k_fill_u64(unsigned long long* p, unsigned n, unsigned long long v) { const unsigned i = PR_TID; if (i < n) p[i] = v; }
-PR_KERNEL k_gather_u32(const unsigned* src, const unsigned* idx, unsigned* dst, unsigned n) { const unsigned i = PR_TID; if (i < n) dst[i] = src[idx[i]]; }
+PR_KERNEL k_fill_u32(unsigned* p, unsigned n, unsigned v) { PR_PDL_ENTER(); const unsigned i = PR_TID; if (i < n) p[i] = v; }
+PR_KERNEL k_fill_u64(unsigned long long* p, unsigned n, unsigned long long v) { PR_PDL_ENTER(); const unsigned i = PR_TID; if (i < n) p[i] = v; }
+PR_KERNEL k_gather_u32(const unsigned* src, const unsigned* idx, unsigned* dst, unsigned n) { PR_PDL_ENTER(); const unsigned i = PR_TID; if (i < n) dst[i] = src[idx[i]]; }
 PR_KERNEL k_solve_order(DV d, unsigned nCons, unsigned* ids, unsigned* colors, const unsigned* sortedColor)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nCons) { ids[i] = d.k_contact[d.k_sorted[i]]; colors[i] = sortedColor[i]; }
 }
@@ -1869,6 +1920,7 @@ PR_KERNEL k_collide_batch(unsigned n, const pr_child* children, const float2* ve
                           const unsigned* aChild, const float4* xfA, const unsigned* bChild, const float4* xfB,
                           float linearSlop, float maxCirclesRatio, pr_manifold* out)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < n) {
         const pr_child ca = children[aChild[i]], cb = children[bChild[i]];

@@ -51,6 +51,7 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* smem, 
 
 __global__ void k_scan_tile_sums(const unsigned* __restrict__ in, unsigned* __restrict__ tileSums, unsigned n)
 {
+    PR_PDL_ENTER();
     __shared__ unsigned smem[33];
     const unsigned base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     unsigned s = 0;
@@ -64,6 +65,7 @@ __global__ void k_scan_tile_sums(const unsigned* __restrict__ in, unsigned* __re
 // single block: exclusive scan of tileSums in place (sequential over chunks with a carry)
 __global__ void k_scan_tile_offsets(unsigned* __restrict__ tileSums, unsigned nTiles, unsigned* __restrict__ totalOut)
 {
+    PR_PDL_ENTER();
     __shared__ unsigned smem[33];
     unsigned carry = 0;
     for (unsigned base = 0; base < nTiles; base += blockDim.x) {
@@ -80,6 +82,7 @@ __global__ void k_scan_tile_offsets(unsigned* __restrict__ tileSums, unsigned nT
 __global__ void k_scan_apply(const unsigned* __restrict__ in, unsigned* __restrict__ out,
                              const unsigned* __restrict__ tileOffsets, unsigned n)
 {
+    PR_PDL_ENTER();
     __shared__ unsigned smem[33];
     const unsigned base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     unsigned v[SCAN_ITEMS];
@@ -97,6 +100,7 @@ __global__ void k_scan_apply(const unsigned* __restrict__ in, unsigned* __restri
 constexpr unsigned SCAN_SMALL_MAX = 65536u;
 __global__ void k_scan_small(const unsigned* in, unsigned* out, unsigned n, unsigned* totalOut) // (in may alias out)
 {
+    PR_PDL_ENTER();
     __shared__ unsigned smem[33];
     unsigned carry = 0;
     for (unsigned chunk = 0; chunk < n; chunk += blockDim.x * SCAN_ITEMS) {
@@ -142,6 +146,7 @@ constexpr unsigned RS_SMALL_MAX = 262144u;
 template <class K, int CHUNKS>
 __global__ void k_rs_hist(const K* __restrict__ keys, unsigned n, int shift, unsigned* __restrict__ hist, unsigned nBlocks)
 {
+    PR_PDL_ENTER();
     __shared__ unsigned h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -160,6 +165,7 @@ __global__ void k_rs_scatter(const K* __restrict__ keysIn, const unsigned* __res
                              K* __restrict__ keysOut, unsigned* __restrict__ valsOut, unsigned n, int shift,
                              const unsigned* __restrict__ offsets, unsigned nBlocks)
 {
+    PR_PDL_ENTER();
     __shared__ unsigned running[256];                 // next output slot per digit for this block
     __shared__ unsigned warpCnt[RS_THREADS / 32][256];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -239,6 +245,7 @@ constexpr unsigned SMALL_SORT_MAX = 2048;
 __global__ void k_sort_pairs_small(const unsigned long long* __restrict__ keysIn, unsigned long long* __restrict__ keysOut,
                                    unsigned* __restrict__ valsOut, unsigned n)
 {
+    PR_PDL_ENTER();
     __shared__ unsigned long long k[SMALL_SORT_MAX];
     __shared__ unsigned v[SMALL_SORT_MAX];
     for (unsigned i = threadIdx.x; i < SMALL_SORT_MAX; i += blockDim.x) {

@@ -89,6 +89,7 @@ struct SmallPlan { unsigned n; unsigned start[SMALL_COLOR_MAX], count[SMALL_COLO
 // mode 0 warm start, 1 velocity, 2 position
 __global__ void __launch_bounds__(SMALL_BLOCK, 1) k_solve_small_colors(DV d, SmallPlan p, unsigned mode, float rate, float slop, float maxCorr)
 {
+    PR_PDL_ENTER();
     const RS r = rs_global(d);
     const unsigned t = threadIdx.x;
     for (unsigned c = 0; c < p.n; ++c) {

@@ -35,6 +35,7 @@ PR_D bool toi_static_eligible(unsigned flags)
 // candidate contact -- only those bodies can ever be advanced, walked or flagged by a TOI event
 PR_KERNEL k_toi_list_build(DV d, unsigned nOrder)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     bool listed = false; unsigned id = 0u;
     if (i < nOrder) {
@@ -52,6 +53,7 @@ PR_KERNEL k_toi_list_build(DV d, unsigned nOrder)
 }
 PR_KERNEL k_adj_count(DV d, unsigned nOrder)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nOrder) {
         const uint4 ab = d.c_ab[d.c_order[i]];
@@ -61,6 +63,7 @@ PR_KERNEL k_adj_count(DV d, unsigned nOrder)
 }
 PR_KERNEL k_adj_cap(DV d, unsigned nBodies)
 {
+    PR_PDL_ENTER();
     const unsigned b = PR_TID;
     if (b < nBodies) {
         const unsigned c = d.adj_cnt[b];
@@ -70,6 +73,7 @@ PR_KERNEL k_adj_cap(DV d, unsigned nBodies)
 }
 PR_KERNEL k_adj_fill(DV d, unsigned nOrder)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nOrder) {
         const unsigned id = d.c_order[i];
@@ -96,6 +100,7 @@ PR_D void adj_sort_body(const DV& d, unsigned b)
 }
 PR_KERNEL k_adj_sort(DV d, unsigned nBodies)
 {
+    PR_PDL_ENTER();
     const unsigned b = PR_TID;
     if (b < nBodies && f_speedable(d.b_flags[b])) adj_sort_body(d, b);
 }
@@ -120,6 +125,7 @@ PR_D bool toi_eligible(const DV& d, unsigned flags, uint4 ab, unsigned maxSubSte
 }
 PR_KERNEL k_toi_phase_init(DV d, unsigned nBodies)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nBodies) { d.b_toiAlpha[i] = f2u(d.b_pos0[i].w); d.b_claim[i] = ~0ull; d.b_toiStamp[i] = 0u; d.b_toiIsl[i] = 0u; }
 }
@@ -155,6 +161,7 @@ PR_D void toi_alpha_one(const DV& d, unsigned id, unsigned maxSubSteps)
 }
 PR_KERNEL k_toi_alpha(DV d, unsigned maxSubSteps, unsigned round)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (d.cnt->toiHalt) return;
     if (i == 0u) {
@@ -191,6 +198,7 @@ PR_D void toi_advance_one(const DV& d, unsigned id, unsigned maxSubSteps, unsign
 }
 PR_KERNEL k_toi_advance(DV d, unsigned maxSubSteps, unsigned round)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (d.cnt->toiHalt) return;
     if (i < d.cnt->toiListN) toi_advance_one(d, d.toi_list[i], maxSubSteps, round);
@@ -247,6 +255,7 @@ PR_D ToiComputeOut toi_compute_one(const DV& d, unsigned id, const pr_step_conf&
 }
 PR_KERNEL k_toi_compute(DV d, pr_step_conf conf)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     ToiComputeOut o; o.atMax = o.updated = o.distIt = o.toiIt = o.rootIt = 0u; o.key = ~0ull;
     if (!d.cnt->toiHalt && i < d.cnt->toiListN) {
@@ -303,18 +312,21 @@ PR_D void toi_select_cand(const DV& d, unsigned id, unsigned parallel)
 }
 PR_KERNEL k_toi_claim(DV d)
 {
+    PR_PDL_ENTER();
     if (d.cnt->toiHalt) return;
     const unsigned n = d.cnt->toiCandN;
     for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS) toi_claim_cand(d, d.toi_cand[c]);
 }
 PR_KERNEL k_toi_unclaim(DV d)
 {
+    PR_PDL_ENTER();
     if (d.cnt->toiHalt) return;
     const unsigned n = d.cnt->toiCandN;
     for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS) toi_unclaim_cand(d, d.toi_cand[c]);
 }
 PR_KERNEL k_toi_select(DV d, unsigned parallel)
 {
+    PR_PDL_ENTER();
     if (d.cnt->toiHalt) return;
     const unsigned n = d.cnt->toiCandN;
     for (unsigned c = PR_WARP_ID; c < n; c += PR_NWARPS) toi_select_cand(d, d.toi_cand[c], parallel);
@@ -596,6 +608,7 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
 
 PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactMode, unsigned scratchCap)
 {
+    PR_PDL_ENTER();
     // one WARP per event, lane 0 working: events take wildly different paths (island sizes, manifold cases,
     // iteration counts), so packing 32 of them into one warp serialises them (measured: 3.5 active lanes)
 #ifndef PR_HOST_EMUL
@@ -613,11 +626,13 @@ PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactM
 // no event left (:1768-1777): ResetBodiesForSolveTOI, ResetContactsForSolveTOI
 PR_KERNEL k_toi_finish_bodies(DV d, unsigned nBodies)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < nBodies) { reinterpret_cast<float*>(&d.b_pos0[i])[3] = 0.0f; d.b_toiAlpha[i] = 0u; }
 }
 PR_KERNEL k_toi_finish_contacts(DV d)
-{ // only contacts on the TOI list can carry a TOI or a TOI count
+{
+    PR_PDL_ENTER(); // only contacts on the TOI list can carry a TOI or a TOI count
     const unsigned i = PR_TID;
     if (i < d.cnt->toiListN) {
         const unsigned id = d.toi_list[i];
@@ -644,6 +659,7 @@ PR_D void sync_body_proxies_one(const DV& d, const pr_step_conf& conf, unsigned 
 }
 PR_KERNEL k_sync_body_proxies(DV d, pr_step_conf conf)
 {
+    PR_PDL_ENTER();
     if (d.cnt->toiHalt) return;
     const unsigned n = d.cnt->syncN;
     for (unsigned i = PR_TID; i < n; i += PR_NTHREADS) sync_body_proxies_one(d, conf, d.sync_list[i]);
@@ -659,6 +675,7 @@ PR_KERNEL k_sync_body_proxies(DV d, pr_step_conf conf)
 // The contact-pool bookkeeping (m_contacts size, free stack, pool size) is mirrored in the counters meanwhile.
 PR_KERNEL k_tb_solve(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratchCap)
 {
+    PR_PDL_ENTER();
 #ifndef PR_HOST_EMUL
     __shared__ ToiSmem sm[PR_BLOCK / 32];
     ToiSmem* mine = &sm[threadIdx.x >> 5];
@@ -678,6 +695,7 @@ PR_KERNEL k_tb_solve(DV d, pr_step_conf conf, unsigned exactMode, unsigned scrat
 // FindContacts' tree update for the proxies the round's events moved; decides whether the host must take over
 PR_KERNEL k_tb_refit(DV d, unsigned nLeaves)
 {
+    PR_PDL_ENTER();
     if (d.cnt->toiHalt) return;
     const unsigned nQ = d.cnt->nQueue;
     const bool hostMust = nQ != 0u && 8ull * nQ >= nLeaves; // too many moved proxies for in-place refits: full rebuild
@@ -692,6 +710,7 @@ PR_KERNEL k_tb_refit(DV d, unsigned nLeaves)
 }
 PR_KERNEL k_tb_query(DV d, unsigned nLeaves, const unsigned* sortedIdx, unsigned capPairs)
 {
+    PR_PDL_ENTER();
     if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
     const unsigned nQ = d.cnt->nQueue;
 #ifndef PR_HOST_EMUL
@@ -762,6 +781,7 @@ PR_D bool tb_add_block(const DV& d, const pr_step_conf& conf, unsigned capPairs,
 }
 PR_KERNEL k_tb_add(DV d, pr_step_conf conf, unsigned capPairs, unsigned capContacts, unsigned capHash, unsigned hashTombs)
 {
+    PR_PDL_ENTER();
     if (d.cnt->toiHalt || d.cnt->tbFindSkip) return;
 #ifndef PR_HOST_EMUL
     __shared__ unsigned long long k[SMALL_SORT_MAX];
@@ -783,6 +803,7 @@ constexpr unsigned LATE_BLOCK = 512u, LATE_MAX_LIST = 2048u, LATE_MAX_CAND = 192
 PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratchCap, unsigned nLeaves, const unsigned* sortedIdx,
                     unsigned capPairs, unsigned capContacts, unsigned capHash, unsigned hashTombs, unsigned maxRounds)
 {
+    PR_PDL_ENTER();
 #ifndef PR_HOST_EMUL
     // one shared-memory arena, re-used stage by stage: event islands | query stacks | sort buffers
     __shared__ __align__(16) unsigned char arena[LATE_SOLVE_WARPS * sizeof(ToiSmem)];
@@ -886,6 +907,7 @@ PR_KERNEL k_toi_batch(unsigned n, const pr_child* children, const float2* verts,
                       const float* sweepA, const unsigned* bChild, const float* sweepB, pr_step_conf conf, float* outTime,
                       int* outState, unsigned* outIters)
 {
+    PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (i < n) {
         const pr_child ca = children[aChild[i]], cb = children[bChild[i]];
