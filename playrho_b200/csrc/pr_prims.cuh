@@ -97,7 +97,7 @@ __global__ void k_scan_apply(const unsigned* __restrict__ in, unsigned* __restri
 
 // small inputs: ONE block walks the array in chunks of blockDim.x * SCAN_ITEMS with a running carry (one launch
 // instead of three; the radix passes over a few ten thousand candidate pairs scan 256 x ~100 counters each)
-constexpr unsigned SCAN_SMALL_MAX = 65536u;
+constexpr unsigned SCAN_SMALL_MAX = 8192u; // one chunk of the block (1024 threads x 8): beyond it the three tiled kernels win (31 vs 16 us at 25k, ncu)
 __global__ void k_scan_small(const unsigned* in, unsigned* out, unsigned n, unsigned* totalOut) // (in may alias out)
 {
     PR_PDL_ENTER();

@@ -167,7 +167,9 @@ PR_KERNEL k_toi_alpha(DV d, unsigned maxSubSteps, unsigned round)
     if (i == 0u) {
         if (d.cnt->adjOverflow) d.cnt->toiHalt = TB_ADJ;
         else if (d.cnt->error) d.cnt->toiHalt = TB_ERROR;
-        else { toi_open_round(d, round); d.cnt->toiCandN = 0u; d.cnt->toiAtMaxLive = 0u; d.cnt->toiForceFull = 0u; }
+        else { // (round == 0: the device numbers the rounds itself -- list rounds enqueued behind single-block late rounds)
+            toi_open_round(d, round ? round : d.cnt->toiRoundId + 1u); d.cnt->toiCandN = 0u; d.cnt->toiAtMaxLive = 0u; d.cnt->toiForceFull = 0u;
+        }
     }
     if (i < d.cnt->toiListN) toi_alpha_one(d, d.toi_list[i], maxSubSteps);
 }
@@ -201,7 +203,7 @@ PR_KERNEL k_toi_advance(DV d, unsigned maxSubSteps, unsigned round)
     PR_PDL_ENTER();
     const unsigned i = PR_TID;
     if (d.cnt->toiHalt) return;
-    if (i < d.cnt->toiListN) toi_advance_one(d, d.toi_list[i], maxSubSteps, round);
+    if (i < d.cnt->toiListN) toi_advance_one(d, d.toi_list[i], maxSubSteps, round ? round : d.cnt->toiRoundId);
 }
 PR_D float normalized_angle(float value)
 { // GetNormalized(Angle), Math.cpp:30-93 (trunc variant)
@@ -823,6 +825,7 @@ PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratc
         const unsigned stop = d.cnt->adjOverflow ? TB_ADJ : d.cnt->error ? TB_ERROR
                             : (d.cnt->toiForceFull || nR > LATE_MAX_LIST || nC + nR > LATE_MAX_CAND) ? TB_BIG : TB_RUN;
         __syncthreads();
+        if (stop == TB_BIG) return; // too much for one block (or a body was woken): the list kernels enqueued behind this launch go on
         if (stop != TB_RUN) { if (PR_TID == 0u) d.cnt->toiHalt = stop; return; }
         if (PR_TID == 0u) { toi_open_round(d, roundId); d.cnt->toiCand2N = 0u; d.cnt->toiAtMaxSub += d.cnt->toiAtMaxLive; }
         // ---- UpdateContactTOIs over the invalidated contacts

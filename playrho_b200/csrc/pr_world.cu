@@ -617,7 +617,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     w.hostCnt.toiRoundId = 0; w.hostCnt.toiReN[0] = w.hostCnt.toiReN[1] = 0; w.hostCnt.toiAtMaxLive = 0; w.hostCnt.toiForceFull = 0; w.hostCnt.toiHalt = TB_RUN;
     write_counters(w);
     const bool exact = (w.toiMode == 0u);
-    unsigned rounds = 0, round = 0;
+    unsigned rounds = 0, round = 0, toiBatches = 0;
     upload_body_proxies(w);
     PR_LAUNCH(k_toi_phase_init, N, w.stream, d, N);
     for (;;) {
@@ -638,9 +638,15 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             if (w.hashDirty) rebuild_hash(w);
             // rounds to enqueue: what the last step needed (+1: the round that finds nothing), a few at a time after that
             const unsigned K = w.subStepping ? 1u : std::min(32u, rounds ? 4u : std::max(2u, w.toiRoundsHint + 1u));
+            // late: groups of [one round over the full TOI list][up to K rounds in one block over compact lists]; the block
+            // hands back (too many candidates yet, a woken body) simply by returning, and the next group's list round goes on
+            const bool late = !(w.debugFlags & 8u) && !w.subStepping;
+            const unsigned groups = late ? std::max(1u, std::min(4u, w.toiGroupsHint)) : 1u;
+            const unsigned listRounds = late ? 1u : K;
+            const unsigned batchRounds = groups * (listRounds + (late ? K : 0u)); // every round may add up to SMALL_SORT_MAX contacts
             ensure(w, G_PAIR, SMALL_SORT_MAX);
-            ensure(w, G_CONTACT, std::max(w.poolSize, w.nOrder) + K * SMALL_SORT_MAX + 2u);
-            if (2ull * (static_cast<unsigned long long>(w.nOrder) + K * SMALL_SORT_MAX + w.hashTombs) > w.capHash) rebuild_hash(w);
+            ensure(w, G_CONTACT, std::max(w.poolSize, w.nOrder) + batchRounds * SMALL_SORT_MAX + 2u);
+            if (2ull * (static_cast<unsigned long long>(w.nOrder) + batchRounds * SMALL_SORT_MAX + w.hashTombs) > w.capHash) rebuild_hash(w);
             const unsigned scratchCap = std::min(w.capCons, w.capAdj);
             read_counters(w);
             throw_device_error(w);
@@ -648,42 +654,43 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             w.hostCnt.devOrder = w.nOrder; w.hostCnt.devFree = w.nFree; w.hostCnt.devPool = w.poolSize;
             w.hostCnt.tbFindSkip = 1u; w.hostCnt.tbAddN = w.hostCnt.tbAddOld = 0u;
             write_counters(w);
-            const unsigned listBound = w.toiListBound + K * SMALL_SORT_MAX; // contacts created by earlier rounds of the batch join the list
+            const unsigned listBound = w.toiListBound + batchRounds * SMALL_SORT_MAX; // contacts created by earlier rounds of the batch join the list
             const unsigned solveWarps = std::min(592u * 8u, std::max(8u, listBound)); // (8 warps per 256-thread block)
             // one round over the full TOI list (list kernels), then -- unless switched off (debug bit 3) or sub-stepping -- up to
             // K more rounds in ONE block over compact lists (k_tb_late); without it, K list rounds
-            const bool late = !(w.debugFlags & 8u) && !w.subStepping;
-            const unsigned listRounds = late ? 1u : K;
-            for (unsigned k = 0; k < listRounds; ++k) {
-                ++round;
-                PR_LAUNCH(k_toi_alpha, listBound, w.stream, d, conf.max_sub_steps, round);
-                PR_LAUNCH(k_toi_advance, listBound, w.stream, d, conf.max_sub_steps, round);
-                PR_LAUNCH(k_toi_compute, listBound, w.stream, d, conf);
-                if (!exact) PR_LAUNCH(k_toi_claim, listBound, w.stream, d);
-                PR_LAUNCH(k_toi_select, listBound, w.stream, d, exact ? 0u : 1u);
-                if (!exact) PR_LAUNCH(k_toi_unclaim, listBound, w.stream, d);
-                PR_LAUNCH(k_tb_solve, 32u * solveWarps, w.stream, d, conf, exact ? 1u : 0u, scratchCap);
+            for (unsigned g = 0; g < groups; ++g) {
+                for (unsigned k = 0; k < listRounds; ++k) {
+                    const unsigned rid = late ? 0u : ++round; // (late: the device numbers the rounds)
+                    PR_LAUNCH(k_toi_alpha, listBound, w.stream, d, conf.max_sub_steps, rid);
+                    PR_LAUNCH(k_toi_advance, listBound, w.stream, d, conf.max_sub_steps, rid);
+                    PR_LAUNCH(k_toi_compute, listBound, w.stream, d, conf);
+                    if (!exact) PR_LAUNCH(k_toi_claim, listBound, w.stream, d);
+                    PR_LAUNCH(k_toi_select, listBound, w.stream, d, exact ? 0u : 1u);
+                    if (!exact) PR_LAUNCH(k_toi_unclaim, listBound, w.stream, d);
+                    PR_LAUNCH(k_tb_solve, 32u * solveWarps, w.stream, d, conf, exact ? 1u : 0u, scratchCap);
 #ifndef PR_HOST_EMUL
-                PR_LAUNCH_GRID(k_sync_body_proxies, 148, PR_BLOCK, w.stream, d, conf);
-                PR_LAUNCH_GRID(k_tb_refit, 32, PR_BLOCK, w.stream, d, P);
-                PR_LAUNCH_GRID(k_tb_query, 148, PR_BLOCK, w.stream, d, P, w.bvhSortedIdx, w.capPairs);
-                PR_LAUNCH_GRID(k_tb_add, 1, TB_ADD_BLOCK, w.stream, d, conf, w.capPairs, w.capContacts, w.capHash, w.hashTombs);
+                    PR_LAUNCH_GRID(k_sync_body_proxies, 148, PR_BLOCK, w.stream, d, conf);
+                    PR_LAUNCH_GRID(k_tb_refit, 32, PR_BLOCK, w.stream, d, P);
+                    PR_LAUNCH_GRID(k_tb_query, 148, PR_BLOCK, w.stream, d, P, w.bvhSortedIdx, w.capPairs);
+                    PR_LAUNCH_GRID(k_tb_add, 1, TB_ADD_BLOCK, w.stream, d, conf, w.capPairs, w.capContacts, w.capHash, w.hashTombs);
 #else
-                PR_LAUNCH(k_sync_body_proxies, 1, w.stream, d, conf);
-                PR_LAUNCH(k_tb_refit, 2, w.stream, d, P);
-                PR_LAUNCH(k_tb_query, 2, w.stream, d, P, w.bvhSortedIdx, w.capPairs);
-                PR_LAUNCH(k_tb_add, 1, w.stream, d, conf, w.capPairs, w.capContacts, w.capHash, w.hashTombs);
+                    PR_LAUNCH(k_sync_body_proxies, 1, w.stream, d, conf);
+                    PR_LAUNCH(k_tb_refit, 2, w.stream, d, P);
+                    PR_LAUNCH(k_tb_query, 2, w.stream, d, P, w.bvhSortedIdx, w.capPairs);
+                    PR_LAUNCH(k_tb_add, 1, w.stream, d, conf, w.capPairs, w.capContacts, w.capHash, w.hashTombs);
 #endif
-            }
-            if (late) {
+                }
+                if (late) {
 #ifndef PR_HOST_EMUL
-                PR_LAUNCH_GRID(k_tb_late, 1, LATE_BLOCK, w.stream, d, conf, exact ? 1u : 0u, scratchCap, P, w.bvhSortedIdx, w.capPairs, w.capContacts,
-                               w.capHash, w.hashTombs, K);
+                    PR_LAUNCH_GRID(k_tb_late, 1, LATE_BLOCK, w.stream, d, conf, exact ? 1u : 0u, scratchCap, P, w.bvhSortedIdx, w.capPairs, w.capContacts,
+                                   w.capHash, w.hashTombs, K);
 #else
-                PR_LAUNCH(k_tb_late, 1, w.stream, d, conf, exact ? 1u : 0u, scratchCap, P, w.bvhSortedIdx, w.capPairs, w.capContacts, w.capHash,
-                          w.hashTombs, K);
+                    PR_LAUNCH(k_tb_late, 1, w.stream, d, conf, exact ? 1u : 0u, scratchCap, P, w.bvhSortedIdx, w.capPairs, w.capContacts, w.capHash,
+                              w.hashTombs, K);
 #endif
+                }
             }
+            ++toiBatches;
             read_counters(w);
             const Counters c = w.hostCnt;
             round = c.toiRoundId; // (the device opened this many rounds so far this step)
@@ -747,6 +754,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         if (w.subStepping) { w.stepComplete = false; w.toiAlphaDirty = true; break; }
     }
     w.toiRoundsHint = rounds;
+    if (toiBatches) w.toiGroupsHint = std::min(4u, std::max(1u, w.toiGroupsHint * toiBatches)); // (what one batch should have held)
     // final UpdateContacts (:1825-1827)
     read_counters(w);
     const unsigned movedToi = w.hostCnt.proxiesMoved;

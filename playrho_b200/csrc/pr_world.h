@@ -146,7 +146,7 @@ struct World {
     bool anyBodySet = false, hashDirty = true, stepComplete = true;
     bool recolorAll = true; unsigned colorsAtFull = 0;
     bool subStepping = false, adjValid = false, bvhValid = false, bpDirty = true, toiAlphaDirty = true;
-    unsigned bvhLeaves = 0, bvhRefits = 0, hashTombs = 0, toiListBound = 0, toiRoundsHint = 1;
+    unsigned bvhLeaves = 0, bvhRefits = 0, hashTombs = 0, toiListBound = 0, toiRoundsHint = 1, toiGroupsHint = 1;
     const unsigned* bvhSortedIdx = nullptr;
     std::vector<std::vector<unsigned>> bodyProxies; // m_bodyProxies
     unsigned toiMode = 1; // PR_TOI_PARALLEL (default) or PR_TOI_SERIAL_EXACT (reference order)
