@@ -234,6 +234,14 @@ int pr_get_bodies(const pr_world* w, uint32_t first, uint32_t n, pr_body* rows);
  * and, if vel3 != NULL, their velocity (linear x, linear y, angular) -- GetVelocity(world, id). */
 int pr_set_body_accelerations(pr_world* w, uint32_t n, const uint32_t* ids, const float* acc3);
 int pr_get_body_poses(const pr_world* w, uint32_t first, uint32_t n, float* xf4, float* vel3);
+/* Query(const DynamicTree&, const AABB&, QueryShapeCallback) (DynamicTree.hpp:696-708, DynamicTree.cpp:673-710; SURVEY 8(f)
+ * rank 2) for n_boxes boxes at once, on the device LBVH instead of a materialised DynamicTree: every proxy whose FAT AABB
+ * overlaps box i (closed intervals, TestOverlap) is reported as (i, body, shape, child) -- the leaves the reference's callback
+ * would see, in no particular order. boxes4 = (min x, min y, max x, max y) per box; box_world = world index per box for a batch
+ * arena, NULL for a plain world. *n_out = number of hits; if it exceeds cap only the first cap were written. The tree is the one
+ * of the last Step (like GetTree): bodies created or moved since are seen after the next Step. */
+int pr_query_aabb(const pr_world* w, uint32_t n_boxes, const float* boxes4, const uint32_t* box_world, uint32_t cap,
+                  uint32_t* hit_box, uint32_t* hit_body, uint32_t* hit_shape, uint32_t* hit_child, uint32_t* n_out);
 int pr_get_revolute_joints(const pr_world* w, uint32_t first, uint32_t n, pr_revolute_joint* rows);
 int pr_get_counts(const pr_world* w, pr_counts* out);
 /* contacts in m_contacts order (creation order), manifolds[i] belongs to contacts[i] */

@@ -569,6 +569,21 @@ int ref_export_proxies(void* h, pr_proxy* out, uint32_t cap)
     REF_CATCH(-1)
 }
 
+// Query(const DynamicTree&, const AABB&, QueryShapeCallback) (DynamicTree.hpp:708): the reference's own spatial query over its tree
+int ref_query_aabb(void* h, float min_x, float min_y, float max_x, float max_y, uint32_t* body, uint32_t* shape, uint32_t* child, uint32_t cap)
+{
+    REF_TRY(h)
+    const AABB aabb{LengthInterval{min_x * 1_m, max_x * 1_m}, LengthInterval{min_y * 1_m, max_y * 1_m}};
+    uint32_t n = 0;
+    Query(GetTree(rw->world), aabb, [&](BodyID b, ShapeID s, ChildCounter c) {
+        if (n < cap) { body[n] = to_underlying(b); shape[n] = to_underlying(s); child[n] = c; }
+        ++n;
+        return true;
+    });
+    return static_cast<int>(n);
+    REF_CATCH(-1)
+}
+
 int ref_export_contacts(void* h, pr_contact* out, pr_manifold* manifolds, uint32_t cap)
 {
     REF_TRY(h)

@@ -846,6 +846,79 @@ PR_KERNEL k_bvh_query_coop(DV d, unsigned nQueue, unsigned nLeaves, const unsign
 }
 #endif
 
+// ------------------------------------------------------------------ spatial query: Query(tree, AABB, callback)
+// (DynamicTree.cpp:673-710) every proxy whose FAT box overlaps the query box, closed intervals like
+// TestOverlap -- the leaves the reference's tree query visits. One group of QG lanes per box (the broadphase's walk).
+PR_D void query_box_emit(const DV& d, unsigned qi, unsigned px, unsigned cap, unsigned* out, unsigned* count)
+{
+    const unsigned slot = atomicAdd(count, 1u);
+    if (slot < cap) { out[4u * slot] = qi; out[4u * slot + 1u] = d.p_body[px]; out[4u * slot + 2u] = d.p_shape[px]; out[4u * slot + 3u] = d.p_child[px]; }
+}
+PR_KERNEL k_query_boxes(DV d, unsigned nBoxes, const float4* boxes, const unsigned* boxWorld, unsigned nLeaves, const unsigned* sortedIdx,
+                        unsigned cap, unsigned* out, unsigned* count)
+{
+    PR_PDL_ENTER();
+#ifndef PR_HOST_EMUL
+    __shared__ unsigned stk[PR_BLOCK / QG][QSTACK];
+    const unsigned lane = threadIdx.x & 31u, gl = lane & (QG - 1u);
+    const unsigned gmask = ((1u << QG) - 1u) << (lane & ~(QG - 1u));
+    const unsigned qi = PR_TID / QG;
+    if (qi >= nBoxes) return; // (whole groups leave together)
+    const Box qb = box_from4(boxes[qi]);
+    const unsigned qw = boxWorld ? boxWorld[qi] : 0u;
+    if (nLeaves == 1u) { if (gl == 0u && box_overlap(qb, box_from4(d.p_fat[0])) && (!d.nWorlds || d.b_world[d.p_body[0]] == qw)) query_box_emit(d, qi, 0u, cap, out, count); return; }
+    unsigned* st = stk[threadIdx.x / QG];
+    if (gl == 0u) st[0] = 0u;
+    unsigned n = 1u;
+    __syncwarp(gmask);
+    while (n) {
+        const unsigned take = n < QG ? n : QG;
+        const unsigned node = (gl < take) ? st[n - 1u - gl] : INVALID;
+        __syncwarp(gmask);
+        n -= take;
+        unsigned push0 = INVALID, push1 = INVALID;
+        if (node != INVALID) {
+            const unsigned c0 = d.bv_left[node], c1 = d.bv_right[node];
+            const CBox cb = d.bv_cbox[node];
+            if (box_overlap(qb, box_from4(cb.l))) {
+                if (c0 & LEAF_BIT) { const unsigned px = sortedIdx[c0 & ~LEAF_BIT]; if (!d.nWorlds || d.b_world[d.p_body[px]] == qw) query_box_emit(d, qi, px, cap, out, count); }
+                else if (node_has_world(d, c0, qw)) push0 = c0;
+            }
+            if (box_overlap(qb, box_from4(cb.r))) {
+                if (c1 & LEAF_BIT) { const unsigned px = sortedIdx[c1 & ~LEAF_BIT]; if (!d.nWorlds || d.b_world[d.p_body[px]] == qw) query_box_emit(d, qi, px, cap, out, count); }
+                else if (node_has_world(d, c1, qw)) push1 = c1;
+            }
+        }
+        const unsigned b0 = __ballot_sync(gmask, push0 != INVALID) & gmask, b1 = __ballot_sync(gmask, push1 != INVALID) & gmask;
+        const unsigned below = (1u << lane) - 1u;
+        const unsigned n0 = __popc(b0), total = n0 + __popc(b1);
+        if (n + total > QSTACK) { if (gl == 0u) atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_STACK)); break; }
+        if (push0 != INVALID) st[n + __popc(b0 & below)] = push0;
+        if (push1 != INVALID) st[n + n0 + __popc(b1 & below)] = push1;
+        n += total;
+        __syncwarp(gmask);
+    }
+#else
+    const unsigned qi = PR_TID;
+    if (qi >= nBoxes) return;
+    const Box qb = box_from4(boxes[qi]);
+    const unsigned qw = boxWorld ? boxWorld[qi] : 0u;
+    if (nLeaves == 1u) { if (box_overlap(qb, box_from4(d.p_fat[0])) && (!d.nWorlds || d.b_world[d.p_body[0]] == qw)) query_box_emit(d, qi, 0u, cap, out, count); return; }
+    unsigned stack[64]; int sp = 0; stack[sp++] = 0u;
+    while (sp > 0) {
+        const unsigned node = stack[--sp];
+        const unsigned ch[2] = {d.bv_left[node], d.bv_right[node]};
+        const CBox cb = d.bv_cbox[node];
+        const float4 bx[2] = {cb.l, cb.r};
+        for (int c = 0; c < 2; ++c) {
+            if (!box_overlap(qb, box_from4(bx[c]))) continue;
+            if (ch[c] & LEAF_BIT) { const unsigned px = sortedIdx[ch[c] & ~LEAF_BIT]; if (!d.nWorlds || d.b_world[d.p_body[px]] == qw) query_box_emit(d, qi, px, cap, out, count); }
+            else if (node_has_world(d, ch[c], qw) && sp < 64) stack[sp++] = ch[c];
+        }
+    }
+#endif
+}
+
 // AddContacts (AabbTreeWorld.cpp:2423-2547), creation part: sorted pair i gets its ContactID from the LIFO
 // free stack else by append (ObjectPool::Allocate), is appended to m_contacts in key order.
 PR_D void adj_append(const DV& d, unsigned b, unsigned id, bool eligible);

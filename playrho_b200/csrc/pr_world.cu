@@ -288,6 +288,23 @@ static void rebuild_hash(World& w)
 
 static int key_bits(unsigned maxVal) { int b = 1; while (b < 32 && (maxVal >> b)) ++b; return ((b + 7) / 8) * 8; }
 
+// full LBVH rebuild over the current fat boxes (hostCnt mirrors the device counters on entry)
+static void rebuild_bvh(World& w)
+{
+    DV& d = w.d;
+    const unsigned P = w.nProxies;
+    w.hostCnt.boundsMinX = w.hostCnt.boundsMinY = 0xFFFFFFFFu; w.hostCnt.boundsMaxX = w.hostCnt.boundsMaxY = 0u;
+    write_counters(w);
+    PR_LAUNCH(k_bvh_bounds, P, w.stream, d, P);
+    PR_LAUNCH(k_bvh_morton, P, w.stream, d, P);
+    const bool idxInB = radix_sort_pairs<unsigned>(d.bv_code, d.bv_idx, d.bv_code2, d.bv_idx2, P, 0, 32, true, w.rs, w.stream);
+    const unsigned* codes = idxInB ? d.bv_code2 : d.bv_code;
+    w.bvhSortedIdx = idxInB ? d.bv_idx2 : d.bv_idx;
+    PR_LAUNCH(k_bvh_build, P - 1, w.stream, d, P, codes);
+    PR_LAUNCH(k_bvh_refit, P, w.stream, d, P, w.bvhSortedIdx);
+    w.bvhValid = true; w.bvhLeaves = P; w.bvhRefits = 0;
+}
+
 // FindContacts + AddContacts, AabbTreeWorld.cpp:709-751 and :2423-2547
 static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer& tm, bool toiRound = false)
 {
@@ -303,18 +320,7 @@ static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer
     if (refit) {
         PR_LAUNCH(k_bvh_refit_moved, nQueue, w.stream, d, nQueue, P);
         ++w.bvhRefits;
-    } else if (P > 1) {
-        w.hostCnt.boundsMinX = w.hostCnt.boundsMinY = 0xFFFFFFFFu; w.hostCnt.boundsMaxX = w.hostCnt.boundsMaxY = 0u;
-        write_counters(w);
-        PR_LAUNCH(k_bvh_bounds, P, w.stream, d, P);
-        PR_LAUNCH(k_bvh_morton, P, w.stream, d, P);
-        const bool idxInB = radix_sort_pairs<unsigned>(d.bv_code, d.bv_idx, d.bv_code2, d.bv_idx2, P, 0, 32, true, w.rs, w.stream);
-        const unsigned* codes = idxInB ? d.bv_code2 : d.bv_code;
-        w.bvhSortedIdx = idxInB ? d.bv_idx2 : d.bv_idx;
-        PR_LAUNCH(k_bvh_build, P - 1, w.stream, d, P, codes);
-        PR_LAUNCH(k_bvh_refit, P, w.stream, d, P, w.bvhSortedIdx);
-        w.bvhValid = true; w.bvhLeaves = P; w.bvhRefits = 0;
-    }
+    } else if (P > 1) rebuild_bvh(w);
     if (w.hashDirty) rebuild_hash(w);
     tm.mark(w, PR_STAGE_QUERY);
     unsigned nPairs = 0;
@@ -1146,6 +1152,42 @@ int pr_get_body_poses(const pr_world* cpw, uint32_t first, uint32_t n, float* xf
     PR_LAUNCH(k_get_poses, n, w.stream, w.d, first, n, sxf, svel);
     if (vel3) CK_COPY_D2H_ASYNC(w, vel3, svel, sizeof(float) * 3u * n);
     d2h(w, xf4, sxf, sizeof(float4) * n);
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_query_aabb(const pr_world* cpw, uint32_t n_boxes, const float* boxes4, const uint32_t* box_world, uint32_t cap, uint32_t* hit_box,
+                  uint32_t* hit_body, uint32_t* hit_shape, uint32_t* hit_child, uint32_t* n_out)
+{
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    *n_out = 0;
+    if (w.d.nWorlds && !box_world) { w.error = "pr_query_aabb on a batch arena needs the world index of every box"; return PR_ERR_INVALID_ARGUMENT; }
+    const unsigned P = w.nProxies;
+    if (!n_boxes || !P) return PR_OK;
+    if (P > 1 && (!w.bvhValid || w.bvhLeaves != P)) { read_counters(w); rebuild_bvh(w); }
+    float4* sbox = static_cast<float4*>(stage_buf(w, 0, sizeof(float4) * n_boxes + 4u * n_boxes));
+    unsigned* sworld = box_world ? reinterpret_cast<unsigned*>(sbox + n_boxes) : nullptr;
+    unsigned* sout = static_cast<unsigned*>(stage_buf(w, 1, 16u * static_cast<size_t>(cap) + 16u));
+    unsigned* scount = sout + 4u * static_cast<size_t>(cap);
+    h2d(w, sbox, boxes4, sizeof(float4) * n_boxes);
+    if (box_world) h2d(w, sworld, box_world, 4u * n_boxes);
+    dset(w, scount, 0, 4);
+#ifndef PR_HOST_EMUL
+    PR_LAUNCH(k_query_boxes, static_cast<unsigned long long>(n_boxes) * QG, w.stream, w.d, n_boxes, sbox, sworld, P, w.bvhSortedIdx, cap, sout, scount);
+#else
+    PR_LAUNCH(k_query_boxes, n_boxes, w.stream, w.d, n_boxes, sbox, sworld, P, w.bvhSortedIdx, cap, sout, scount);
+#endif
+    unsigned total = 0;
+    d2h(w, &total, scount, 4);
+    const unsigned got = std::min(total, cap);
+    if (got) {
+        std::vector<unsigned> tmp(4u * static_cast<size_t>(got));
+        d2h(w, tmp.data(), sout, 16u * static_cast<size_t>(got));
+        for (unsigned i = 0; i < got; ++i) { hit_box[i] = tmp[4u * i]; hit_body[i] = tmp[4u * i + 1u]; hit_shape[i] = tmp[4u * i + 2u]; hit_child[i] = tmp[4u * i + 3u]; }
+    }
+    *n_out = total; // > cap: the caller's arrays were too short, the first `cap` hits were written
     return PR_OK;
     API_CATCH(pw)
 }

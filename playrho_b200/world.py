@@ -25,7 +25,7 @@ EXPORTS = [
     "pr_get_inv_dt0", "pr_get_stream", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
     "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
-    "pr_set_body_accelerations", "pr_get_body_poses",
+    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb",
 ]
 
 
@@ -47,6 +47,7 @@ def bind(lib):
     lib.pr_get_bodies.argtypes = [vp, u32, u32, vp]
     lib.pr_set_body_accelerations.argtypes = [vp, u32, vp, vp]
     lib.pr_get_body_poses.argtypes = [vp, u32, u32, vp, vp]
+    lib.pr_query_aabb.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp, vp, C.POINTER(u32)]
     lib.pr_get_revolute_joints.argtypes = [vp, u32, u32, vp]
     lib.pr_get_counts.argtypes = [vp, vp]
     lib.pr_get_contacts.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
@@ -195,6 +196,21 @@ class World:
         n = xf4.size // 4
         self._chk(self.lib.pr_get_body_poses(self.h, first, n, abi.ptr(xf4), abi.ptr(vel3) if vel3 is not None else None))
         return xf4
+
+    def query_aabb(self, boxes, box_world=None, cap=None):
+        """Query(tree, AABB) for many boxes (rows of min x, min y, max x, max y): arrays (box index, body, shape, child) of every
+        proxy whose fat AABB overlaps the box (pr_query_aabb). Order unspecified."""
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
+        bw = None if box_world is None else np.ascontiguousarray(box_world, dtype=np.uint32)
+        cap = cap or max(1024, 64 * len(boxes))
+        while True:
+            out = [np.zeros(cap, np.uint32) for _ in range(4)]
+            k = u32(0)
+            self._chk(self.lib.pr_query_aabb(self.h, len(boxes), abi.ptr(boxes), abi.ptr(bw), cap, abi.ptr(out[0]), abi.ptr(out[1]),
+                                             abi.ptr(out[2]), abi.ptr(out[3]), C.byref(k)))
+            if k.value <= cap:
+                return tuple(o[:k.value] for o in out)
+            cap = k.value
 
     def joints(self):
         n = int(self.counts()["joints"])

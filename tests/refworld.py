@@ -229,6 +229,15 @@ class RefWorld:
         k = self.lib.ref_export_proxies(self.h, abi.ptr(out), len(out))
         return out[:k]
 
+    def query_aabb(self, box):
+        """The reference's Query(GetTree(world), AABB, callback): (body, shape, child) of every leaf it reports."""
+        cap = max(16, int(self.counts()["proxies"]))
+        b, s, c = (np.zeros(cap, np.uint32) for _ in range(3))
+        self.lib.ref_query_aabb.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        k = self.lib.ref_query_aabb(self.h, float(box[0]), float(box[1]), float(box[2]), float(box[3]), abi.ptr(b), abi.ptr(s), abi.ptr(c), cap)
+        assert 0 <= k <= cap
+        return b[:k], s[:k], c[:k]
+
     def contacts(self):
         n = self.counts()
         cs = np.zeros(max(1, n["contacts"]), abi.CONTACT)
