@@ -123,7 +123,7 @@ inline void scan_exclusive_u32(const unsigned* in, unsigned* out, unsigned n, un
                                unsigned* scratch, cudaStream_t stream)
 {
     if (n == 0) {
-        if (totalOut) cudaMemsetAsync(totalOut, 0, sizeof(unsigned), stream);
+        if (totalOut) { cudaMemsetAsync(totalOut, 0, sizeof(unsigned), stream); count_launch(); } // (a device counter changed: see read_counters)
         return;
     }
     if (n <= SCAN_SMALL_MAX) { PR_LAUNCH_GRID(k_scan_small, 1, 1024, stream, in, out, n, totalOut); return; }

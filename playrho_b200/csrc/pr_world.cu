@@ -12,7 +12,8 @@
 namespace pr {
 
 static unsigned g_launches = 0;
-void count_launch() { ++g_launches; }
+static unsigned long long g_launchSerial = 0; // never reset: "has any kernel been launched since ...?"
+void count_launch() { ++g_launches; ++g_launchSerial; }
 unsigned launches_since_reset() { return g_launches; }
 void reset_launch_count() { g_launches = 0; }
 #ifdef PR_HOST_EMUL
@@ -171,10 +172,14 @@ static void* stage_buf(World& w, int which, size_t bytes)
 }
 static void read_counters(World& w)
 {
+    // only kernels change the device counters behind the host's back: if none was launched since the last read (or since the
+    // write that followed it) the host copy IS the device's, and the round trip (a stream drain, ~20 us of idle GPU) is skipped
+    if (w.cntSerialValid && w.cntSerial == g_launchSerial) return;
     CK(cudaMemcpyAsync(&w.pinnedCnt[0], w.d.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, w.stream));
     CK(cudaStreamSynchronize(w.stream));
     w.hostCnt = w.pinnedCnt[0];
     w.pinnedNext = 1; // everything queued before this point has executed: all write slots are free again
+    w.cntSerial = g_launchSerial; w.cntSerialValid = true;
 }
 static void write_counters(World& w)
 {

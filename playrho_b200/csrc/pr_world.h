@@ -160,6 +160,7 @@ struct World {
     RadixScratch rs;
     unsigned* scanScratch = nullptr; size_t scanScratchCap = 0;
     Counters hostCnt{};
+    unsigned long long cntSerial = 0; bool cntSerialValid = false; // launch serial at the last device->host read of the counters
     static constexpr unsigned PINNED_SLOTS = 64;
     Counters* pinnedCnt = nullptr; unsigned pinnedNext = 1;
     pr_step_profile profile{};
