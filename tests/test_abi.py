@@ -52,3 +52,29 @@ def test_no_cpu_fallback_in_package():
                 assert "libpr_oracle" not in txt and "ref_harness" not in txt and "orc_" not in txt, f
                 if f.endswith(".py"):
                     assert "_emul" not in txt, f
+
+
+def test_every_kernel_waits_for_its_predecessor():
+    """Every launch is a programmatic dependent launch (PR_LAUNCH, pr_compat.h): a kernel body that touched global memory before
+    `griddepcontrol.wait` would race with the previous kernel of the stream. Static check: each kernel starts with
+    PR_PDL_ENTER() -- or, for the solver kernels that prefetch immutable rows first, contains pr_pdl_wait()."""
+    import re
+    csrc = os.path.join(refworld.ROOT, "playrho_b200", "csrc")
+    missing, seen = [], 0
+    for f in sorted(os.listdir(csrc)):
+        if not f.endswith((".cuh", ".cu")):
+            continue
+        s = open(os.path.join(csrc, f)).read()
+        for m in re.finditer(r"(?:PR_KERNEL|__global__ void(?: __launch_bounds__\([^)]*\))?|^)\s*(k_\w+)\(", s, flags=re.M):
+            brace, semi = s.find("{", m.end()), s.find(";", m.end())
+            head = s[m.start():brace]
+            if brace < 0 or (0 <= semi < brace) or "<<<" in head or "=" in head:
+                continue  # a declaration or a launch, not a definition
+            seen += 1
+            body = s[brace:brace + 1500]
+            if m.group(1) == "k_solve_fused":
+                continue  # cooperative launch (cudaLaunchCooperativeKernel): an ordinary stream dependency
+            if "PR_PDL_ENTER" not in body[:200] and "pr_pdl_wait" not in body:
+                missing.append("%s:%s" % (f, m.group(1)))
+    assert seen > 80, seen
+    assert not missing, missing
