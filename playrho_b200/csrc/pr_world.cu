@@ -629,6 +629,12 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     write_counters(w);
     const bool exact = (w.toiMode == 0u);
     unsigned rounds = 0, round = 0, toiBatches = 0;
+    if (!w.toiPossible) { // no contact of this world can be a TOI candidate: SolveToi finds nothing (:1768) and its final UpdateContacts skips all
+        w.stepComplete = true;
+        if (w.toiAlphaDirty) { PR_LAUNCH(k_toi_finish_bodies, N, w.stream, d, N); w.toiAlphaDirty = false; }
+        st.contacts_skipped_touching = w.nOrder;
+        return;
+    }
     upload_body_proxies(w);
     PR_LAUNCH(k_toi_phase_init, N, w.stream, d, N);
     for (;;) {
@@ -772,7 +778,8 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     w.hostCnt.contactsUpdated = 0;
     write_counters(w);
     const unsigned nOrderAtUpdate = w.nOrder;
-    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 0u, 1u);
+    // (no event this step: nothing was flagged since the regular phase's UpdateContacts -- every contact is skipped)
+    if (rounds) PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 0u, 1u);
     read_counters(w);
     const Counters c = w.hostCnt;
     st.contacts_at_max_sub_steps = c.toiAtMaxSub; st.contacts_updated_toi = c.toiUpdated;
@@ -952,7 +959,7 @@ int pr_clone(const pr_world* src, pr_world** out)
     d2d(w, w.d.cnt, s.d.cnt, sizeof(Counters));
     w.shapes = s.shapes; w.children = s.children; w.bodyShapes = s.bodyShapes; w.joints = s.joints;
     w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies;
-    w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll;
+    w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll; w.toiPossible = s.toiPossible;
     w.nJoints = s.nJoints; w.jointsSerial = s.jointsSerial; w.d.nNcPairs = s.d.nNcPairs;
     w.d.nWorlds = s.d.nWorlds; w.d.worldBits = s.d.worldBits; w.bodyWorld = s.bodyWorld;
     w.nBodies = s.nBodies; w.nShapes = s.nShapes; w.nChildren = s.nChildren; w.nVerts = s.nVerts; w.nProxies = s.nProxies;
@@ -974,7 +981,7 @@ int pr_clear(pr_world* pw)
     w.bodyProxies.clear(); w.bpDirty = true; w.bvhValid = false; w.hashTombs = 0; w.toiAlphaDirty = true;
     w.nJoints = 0; w.jointsSerial = false; w.d.nNcPairs = 0; w.bodyWorld.clear();
     w.nBodies = w.nShapes = w.nChildren = w.nVerts = w.nProxies = w.nOrder = w.nFree = w.poolSize = 0; w.maxTreeId = 0;
-    w.anyBodySet = false; w.hashDirty = true; w.adjValid = false; w.stepComplete = true;
+    w.anyBodySet = false; w.hashDirty = true; w.adjValid = false; w.stepComplete = true; w.toiPossible = false;
     reset_counters(w);
     return PR_OK;
     API_CATCH(pw)
@@ -1046,6 +1053,7 @@ static int create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const 
     for (uint32_t i = 0; i < n; ++i) {
         std::vector<unsigned> sh(shape_ids + shape_offsets[i], shape_ids + shape_offsets[i + 1]);
         if (bodies[i].flags & PR_BODY_ENABLED) for (unsigned s : sh) w.fixturesForProxies.emplace_back(w.nBodies + i, s); // CreateBody :1046-1052
+        if ((bodies[i].flags & PR_BODY_IMPENETRABLE) && !sh.empty()) w.toiPossible = true;
         w.bodyShapes.push_back(std::move(sh));
     }
     if (first_id) *first_id = w.nBodies;
@@ -1109,6 +1117,9 @@ int pr_set_bodies(pr_world* pw, uint32_t n, const uint32_t* ids, const pr_body* 
     PR_LAUNCH(k_put_bodies, n, w.stream, w.d, n, 0u, dids, staging, 1u);
     sync(w); // the caller's rows / ids may be reused once we return
     w.anyBodySet = true; w.toiAlphaDirty = true;
+    if (!w.toiPossible)
+        for (uint32_t i = 0; i < n; ++i)
+            if ((rows[i].flags & PR_BODY_IMPENETRABLE) && ids[i] < w.bodyShapes.size() && !w.bodyShapes[ids[i]].empty()) { w.toiPossible = true; break; }
     return PR_OK;
     API_CATCH(pw)
 }

@@ -150,6 +150,9 @@ struct World {
     const unsigned* bvhSortedIdx = nullptr;
     std::vector<std::vector<unsigned>> bodyProxies; // m_bodyProxies
     unsigned toiMode = 1; // PR_TOI_PARALLEL (default) or PR_TOI_SERIAL_EXACT (reference order)
+    // some body WITH shapes is (or may be: SetBody, load) impenetrable -- static, kinematic or bullet: only then can a contact be a
+    // TOI candidate (UpdateContactTOIs' filter :1696). An arena of tumblers has none: its TOI phase is skipped outright.
+    bool toiPossible = false;
     float inv_dt0 = 0;
     // capacities
     unsigned capBodies = 0, capShapes = 0, capChildren = 0, capVerts = 0, capProxies = 0, capContacts = 0,
