@@ -1169,7 +1169,7 @@ PR_KERNEL k_color_claim(DV d, unsigned nWork, unsigned round)
         }
     }
 }
-PR_KERNEL k_color_commit(DV d, unsigned nWork, unsigned round)
+PR_KERNEL k_color_commit(DV d, unsigned nWork, unsigned round, unsigned colorCap)
 {
     PR_PDL_ENTER();
     const unsigned t = PR_TID;
@@ -1186,7 +1186,7 @@ PR_KERNEL k_color_commit(DV d, unsigned nWork, unsigned round)
                 const unsigned long long used = (dA ? d.b_cmask[ab.x] : 0ull) | (dB ? d.b_cmask[ab.y] : 0ull);
                 const unsigned long long freeBits = ~used;
                 unsigned c = COLOR_OVERFLOW;
-                if (freeBits) {
+                if (freeBits && static_cast<unsigned>(__ffsll(static_cast<long long>(freeBits))) - 1u < colorCap) { // (colorCap: see World::colorCap)
                     c = static_cast<unsigned>(__ffsll(static_cast<long long>(freeBits))) - 1u;
                     if (dA) d.b_cmask[ab.x] |= (1ull << c);
                     if (dB) d.b_cmask[ab.y] |= (1ull << c);

@@ -416,7 +416,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             for (unsigned round = 0;; ++round) {
                 if (round && (round % 64u) == 0u) PR_LAUNCH(k_color_reset_claims, N, w.stream, d, N);
                 PR_LAUNCH(k_color_claim, nWork, w.stream, d, nWork, round);
-                PR_LAUNCH(k_color_commit, nWork, w.stream, d, nWork, round);
+                PR_LAUNCH(k_color_commit, nWork, w.stream, d, nWork, round, w.colorCap);
                 ++w.profile.color_rounds;
                 if ((round & 3u) == 3u || nWork < 64u) { // look at the remaining count every 4th round only
                     read_counters(w);
@@ -463,6 +463,14 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         w.nColors = static_cast<unsigned>(ranges.size()) + (tailCount ? 1u : 0u);
         if (nWork == nCons) w.colorsAtFull = w.nColors; // (this step coloured everything from scratch)
         else if (w.nColors > 24u && w.nColors > w.colorsAtFull + 8u) w.recolorAll = true; // persistent colours fragmented
+        if (w.colorCap == 64u && ranges.size() > 32u) { // hub rule (World::colorCap): cap the colours from the next step on?
+            unsigned long long beyond = tailCount;
+            for (size_t c = COLOR_CAP_HUBS; c < ranges.size(); ++c) beyond += ranges[c].second;
+            const unsigned islands = std::max(1u, w.hostCnt.islandsFound);
+            if (4ull * beyond <= nCons && beyond / islands <= 256ull) { w.colorCap = COLOR_CAP_HUBS; w.recolorAll = true; }
+        } else if (w.colorCap != 64u && nTailSegs && tailCount / nTailSegs > 512u) { // tails too long for one thread each: back
+            w.colorCap = 64u; w.recolorAll = true;
+        }
         tm.mark(w, PR_STAGE_SETUP);
         PR_LAUNCH(k_build_constraints, nCons, w.stream, d, nCons, conf, conf.do_warm_start ? conf.dt_ratio : 0.0f);
     }
@@ -959,7 +967,7 @@ int pr_clone(const pr_world* src, pr_world** out)
     d2d(w, w.d.cnt, s.d.cnt, sizeof(Counters));
     w.shapes = s.shapes; w.children = s.children; w.bodyShapes = s.bodyShapes; w.joints = s.joints;
     w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies;
-    w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll; w.toiPossible = s.toiPossible;
+    w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll; w.toiPossible = s.toiPossible; w.colorCap = s.colorCap;
     w.nJoints = s.nJoints; w.jointsSerial = s.jointsSerial; w.d.nNcPairs = s.d.nNcPairs;
     w.d.nWorlds = s.d.nWorlds; w.d.worldBits = s.d.worldBits; w.bodyWorld = s.bodyWorld;
     w.nBodies = s.nBodies; w.nShapes = s.nShapes; w.nChildren = s.nChildren; w.nVerts = s.nVerts; w.nProxies = s.nProxies;

@@ -23,6 +23,7 @@ constexpr unsigned INVALID = 0xFFFFFFFFu;
 constexpr unsigned COLOR_UNSET = 0xFFu;
 constexpr unsigned COLOR_OVERFLOW = 64u; // constraints that found no free colour < 64: serial tail
 constexpr unsigned MAX_COLORS = 65u;
+constexpr unsigned COLOR_CAP_HUBS = 24u;
 constexpr unsigned LEAF_BIT = 0x80000000u;
 
 enum { ISL_ACTIVE = 1u, ISL_VEL_DONE = 2u, ISL_POS_SOLVED = 4u };
@@ -145,6 +146,11 @@ struct World {
     unsigned nCons = 0, nColors = 0, maxTreeId = 0, debugFlags = 0;
     bool anyBodySet = false, hashDirty = true, stepComplete = true;
     bool recolorAll = true; unsigned colorsAtFull = 0;
+    // Hub rule: a body touched by many constraints (a tumbler's enclosure carries ~100 squares) needs one colour per constraint,
+    // i.e. one dependent launch per constraint and iteration. When a world needs more than 32 colours and the constraints beyond
+    // colour COLOR_CAP_HUBS are few per island, colours stop at the cap and the rest go to the per-island serial tail (one thread
+    // per island, list order: still a valid Gauss-Seidel order) -- 65 colours + tail become 24 + tail for an arena of tumblers.
+    unsigned colorCap = 64u;
     bool subStepping = false, adjValid = false, bvhValid = false, bpDirty = true, toiAlphaDirty = true;
     unsigned bvhLeaves = 0, bvhRefits = 0, hashTombs = 0, toiListBound = 0, toiRoundsHint = 1, toiGroupsHint = 1;
     const unsigned* bvhSortedIdx = nullptr;
