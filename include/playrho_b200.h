@@ -267,7 +267,43 @@ int pr_get_solve_order(const pr_world* w, uint32_t cap, uint32_t* contact_ids, u
 int pr_set_debug(pr_world* w, uint32_t flags);
 int pr_get_step_profile(const pr_world* w, pr_step_profile* out);
 int pr_abi_sizeof(int which); /* sizeof of the POD structs above, for foreign-language mirrors */
-int pr_shift_origin(pr_world* w, float x, float y);     /* ShiftOrigin :2221 */
+/* ShiftOrigin(AabbTreeWorld&, const Length2&), AabbTreeWorld.cpp:2221-2243: every body's sweep positions 0 and 1 move by
+ * -newOrigin (SetSweep recomputes the transformation), every contact of every body is flagged for updating, every tree
+ * AABB moves by -newOrigin (DynamicTree::ShiftOrigin, DynamicTree.cpp:650-658). The revolute joint keeps no world-space
+ * anchor (RevoluteJointConf.hpp:222). PR_ERR_WRONG_STATE while a sub-stepped Step is incomplete. */
+int pr_shift_origin(pr_world* w, float x, float y);
+
+/* ---- contact events: the begin/end/post-solve listeners of a Step, recorded on the device ----
+ * The reference invokes std::function listeners synchronously INSIDE Step (begin/end: Update, AabbTreeWorld.cpp:2703-2714,
+ * and InternalDestroy :2249-2252 for a touching contact that is destroyed; post-solve: Report :196-206 after each regular
+ * island :1671-1674 and each TOI island :2053-2055). A device step cannot call back into the host, so the kernels append
+ * event records to device buffers instead and the host reads them after pr_step (pr_events); the CudaWorld shim then invokes
+ * the stored listeners, in (kind, contact id) order. Pre-solve (:2716-2720) exists to let the host edit a contact before the
+ * solve of the same step: that needs the synchronous callback and is not offered (PR_ERR_UNSUPPORTED when asked for).
+ * Nothing is recorded (and the kernels pay one uniform branch) until pr_set_event_mask asks for it. */
+enum { PR_EVENT_BEGIN = 1, PR_EVENT_END = 2, PR_EVENT_PRE_SOLVE = 4, PR_EVENT_POST_SOLVE = 8 };
+typedef struct pr_contact_event { /* begin / end: the contact as the listener would have seen it through GetContact */
+    uint32_t kind;                      /* PR_EVENT_BEGIN or PR_EVENT_END */
+    uint32_t contact;                   /* ContactID */
+    uint32_t body_a, shape_a, child_a;
+    uint32_t body_b, shape_b, child_b;
+} pr_contact_event;
+typedef struct pr_impulse_event { /* post-solve: (ContactID, ContactImpulsesList, iteration_type) */
+    uint32_t contact;
+    uint32_t count;                     /* entries of the ContactImpulsesList = the velocity constraint's point count */
+    uint32_t iterations;                /* regular island: positionIters - 1 if solved else 255 (StepConf::InvalidIteration);
+                                           TOI island: positionIters */
+    uint32_t phase;                     /* 0 regular phase, 1 TOI phase */
+    float normal[2], tangent[2];
+} pr_impulse_event;
+/* mask: PR_EVENT_* bits to record from the next pr_step on (0 = off); capacity: records kept per step and kind group
+ * (begin+end share one buffer, post-solve has its own); further events of a step are counted but dropped. */
+int pr_set_event_mask(pr_world* w, uint32_t mask, uint32_t capacity);
+/* Events of the LAST pr_step. kind = PR_EVENT_BEGIN | PR_EVENT_END (either or both): buf = pr_contact_event[cap];
+ * kind = PR_EVENT_POST_SOLVE: buf = pr_impulse_event[cap]. Sorted by (kind, contact id) resp. (phase, contact id); *n_out =
+ * matching events (at most cap are written). If the step produced more events than the capacity given to pr_set_event_mask
+ * it dropped the rest: PR_ERR_LENGTH, and *n_out = the number the step produced (begin+end together, or post-solve). */
+int pr_events(const pr_world* w, uint32_t kind, void* buf, uint32_t cap, uint32_t* n_out);
 /* TOI event scheduling (SolveToi loop, AabbTreeWorld.cpp:1752-1831):
  *   PR_TOI_SERIAL_EXACT  one event per round in the reference's order (global soonest first): bit-exact
  *   PR_TOI_PARALLEL      every locally-soonest event whose bodies and contact neighbours are disjoint

@@ -16,6 +16,7 @@
 #include <playrho/ToiConf.hpp>
 #include <playrho/ToiOutput.hpp>
 
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <string>
@@ -31,6 +32,9 @@ namespace {
 struct RefWorld {
     World world;
     std::string error;
+    std::vector<pr_contact_event> evContact; // begin/end listener calls of the last ref_step, call order
+    std::vector<pr_impulse_event> evImpulse; // post-solve listener calls of the last ref_step, call order
+    bool inToiPhase = false;
     explicit RefWorld(const WorldConf& c) : world{c} {}
 };
 
@@ -428,9 +432,62 @@ int ref_set_body_transform(void* h, uint32_t body, float x, float y, float angle
     REF_CATCH(-1)
 }
 
+// Installs the reference's own listeners (World.hpp SetBeginContactListener / SetEndContactListener /
+// SetPostSolveContactListener); each call is recorded with what the listener can see through GetContact at that moment.
+int ref_set_event_mask(void* h, uint32_t mask)
+{
+    REF_TRY(h)
+    auto record = [rw](uint32_t kind, ContactID id) {
+        const auto c = GetContact(rw->world, id);
+        rw->evContact.push_back(pr_contact_event{kind, static_cast<uint32_t>(to_underlying(id)),
+            static_cast<uint32_t>(to_underlying(GetBodyA(c))), static_cast<uint32_t>(to_underlying(GetShapeA(c))), static_cast<uint32_t>(GetChildIndexA(c)),
+            static_cast<uint32_t>(to_underlying(GetBodyB(c))), static_cast<uint32_t>(to_underlying(GetShapeB(c))), static_cast<uint32_t>(GetChildIndexB(c))});
+    };
+    if (mask & PR_EVENT_BEGIN) SetBeginContactListener(rw->world, [record](ContactID id) { record(PR_EVENT_BEGIN, id); });
+    else SetBeginContactListener(rw->world, {});
+    if (mask & PR_EVENT_END) SetEndContactListener(rw->world, [record](ContactID id) { record(PR_EVENT_END, id); });
+    else SetEndContactListener(rw->world, {});
+    if (mask & PR_EVENT_POST_SOLVE)
+        SetPostSolveContactListener(rw->world, [rw](ContactID id, const ContactImpulsesList& imp, unsigned iters) {
+            pr_impulse_event e;
+            std::memset(&e, 0, sizeof(e));
+            e.contact = static_cast<uint32_t>(to_underlying(id)); e.count = imp.GetCount(); e.iterations = iters; e.phase = 0xFFFFFFFFu; // (phase: not visible to a listener)
+            for (unsigned j = 0; j < imp.GetCount() && j < 2; ++j) { e.normal[j] = imp.GetEntryNormal(j); e.tangent[j] = imp.GetEntryTanget(j); }
+            rw->evImpulse.push_back(e);
+        });
+    else SetPostSolveContactListener(rw->world, {});
+    return 0;
+    REF_CATCH(-1)
+}
+
+int ref_events(void* h, uint32_t kind, void* buf, uint32_t cap, uint32_t* n_out)
+{
+    REF_TRY(h)
+    if (kind == PR_EVENT_POST_SOLVE) {
+        *n_out = static_cast<uint32_t>(rw->evImpulse.size());
+        std::memcpy(buf, rw->evImpulse.data(), sizeof(pr_impulse_event) * std::min<size_t>(cap, rw->evImpulse.size()));
+    } else {
+        std::vector<pr_contact_event> ev;
+        for (const auto& e : rw->evContact) if (e.kind & kind) ev.push_back(e);
+        *n_out = static_cast<uint32_t>(ev.size());
+        std::memcpy(buf, ev.data(), sizeof(pr_contact_event) * std::min<size_t>(cap, ev.size()));
+    }
+    return 0;
+    REF_CATCH(-1)
+}
+
+int ref_shift_origin(void* h, float x, float y)
+{
+    REF_TRY(h)
+    ShiftOrigin(rw->world, Length2{x, y});
+    return 0;
+    REF_CATCH(-1)
+}
+
 int ref_step(void* h, const pr_step_conf* conf, pr_step_stats* stats)
 {
     REF_TRY(h)
+    rw->evContact.clear(); rw->evImpulse.clear();
     const auto s = Step(rw->world, ToStepConf(*conf));
     if (stats) FromStats(s, *stats);
     return 0;

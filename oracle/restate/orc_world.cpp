@@ -71,6 +71,9 @@ struct orc_world {
     std::vector<std::pair<uint32_t, uint32_t>> fixturesForProxies; // (body, shape)
     std::vector<uint32_t> proxiesForContacts;
     std::vector<uint32_t> bodiesForSync;
+    uint32_t evMask = 0;                          // listeners installed (PR_EVENT_* bits)
+    std::vector<pr_contact_event> evContact;      // begin/end listener calls of the last step, call order
+    std::vector<pr_impulse_event> evImpulse;      // post-solve listener calls of the last step, call order
     std::vector<char> islandedBodies, islandedContacts, islandedJoints;
     bool stepComplete = true;
     bool subStepping = false;
@@ -153,7 +156,22 @@ inline bool overlap(AABB a, AABB b)
     return (std::min(a.maxx, b.maxx) >= std::max(a.minx, b.minx)) && (std::min(a.maxy, b.maxy) >= std::max(a.miny, b.miny));
 }
 
+// Report -> GetContactImpulses(vc), ContactImpulsesList.cpp:28-37
+void record_impulse_event(orc_world& w, uint32_t id, const VC& vc, uint32_t iterations, uint32_t phase)
+{
+    pr_impulse_event e;
+    std::memset(&e, 0, sizeof(e));
+    e.contact = id; e.count = vc.count; e.iterations = iterations; e.phase = phase;
+    for (uint32_t j = 0; j < vc.count; ++j) { e.normal[j] = vc.pt[j].normalImpulse; e.tangent[j] = vc.pt[j].tangentImpulse; }
+    w.evImpulse.push_back(e);
+}
 // ---------------- narrowphase Update, AabbTreeWorld.cpp:2587-2721 ----------------
+void record_contact_event(orc_world& w, uint32_t kind, uint32_t id)
+{
+    if (!(w.evMask & kind)) return;
+    const pr_contact& c = w.contacts[id].c;
+    w.evContact.push_back(pr_contact_event{kind, id, c.body_a, c.shape_a, c.child_a, c.body_b, c.shape_b, c.child_b});
+}
 void update_contact(orc_world& w, uint32_t id, const pr_step_conf& conf)
 {
     OContact& oc = w.contacts[id];
@@ -199,6 +217,8 @@ void update_contact(orc_world& w, uint32_t id, const pr_step_conf& conf)
     c.flags &= ~uint32_t(PR_CONTACT_DIRTY);
     if (!oldTouching && newTouching) c.flags |= PR_CONTACT_TOUCHING;
     else if (oldTouching && !newTouching) c.flags &= ~uint32_t(PR_CONTACT_TOUCHING);
+    if (!oldTouching && newTouching) record_contact_event(w, PR_EVENT_BEGIN, id);    // :2703-2708
+    else if (oldTouching && !newTouching) record_contact_event(w, PR_EVENT_END, id); // :2709-2714
 }
 
 // UpdateContacts, AabbTreeWorld.cpp:2333-2421
@@ -219,6 +239,7 @@ void flag_body_contacts_dirty(orc_world& w, uint32_t body)
 void internal_destroy(orc_world& w, uint32_t id)
 {
     OContact& oc = w.contacts[id];
+    if (oc.c.flags & PR_CONTACT_TOUCHING) record_contact_event(w, PR_EVENT_END, id); // :2249-2252
     for (uint32_t b : {oc.c.body_a, oc.c.body_b}) {
         auto& lst = w.bodies[b].contacts;
         auto it = std::find(lst.begin(), lst.end(), id);
@@ -833,6 +854,8 @@ IslandStats solve_reg_island(orc_world& w, const pr_step_conf& conf, const Islan
         if (contactsOkay && jointsOkay) { results.positionIters = i + 1; results.solved = true; break; }
     }
     for (size_t i = 0; i < vcs.size(); ++i) assign_impulses(w.contacts[island.contacts[i]].m, vcs[i]);
+    if (w.evMask & PR_EVENT_POST_SOLVE) // Report(...), :1671-1674
+        for (size_t i = 0; i < vcs.size(); ++i) record_impulse_event(w, island.contacts[i], vcs[i], results.solved ? results.positionIters - 1u : 255u, 0u);
     for (uint32_t id : island.bodies) {
         const BC& bc = bcs[id];
         pr_body& b = w.bodies[id].b;
@@ -1028,6 +1051,37 @@ int orc_set_bodies(orc_world* w, uint32_t n, const uint32_t* ids, const pr_body*
     return 0;
 }
 
+// ShiftOrigin(AabbTreeWorld&, newOrigin), AabbTreeWorld.cpp:2221-2243
+int orc_shift_origin(orc_world* w, float x, float y)
+{
+    for (uint32_t id = 0; id < w->bodies.size(); ++id) {
+        pr_body& b = w->bodies[id].b;
+        b.pos0_x -= x; b.pos0_y -= y;
+        Pos p1 = body_pos1(b);
+        p1.l.x -= x; p1.l.y -= y;
+        set_pos1(b, p1); // SetSweep: m_xf = GetTransform1(sweep), Body.hpp:697-702
+        flag_body_contacts_dirty(*w, id);
+    }
+    const float nx = -x, ny = -y; // DynamicTree::ShiftOrigin: GetMovedAABB(aabb, -newOrigin), DynamicTree.cpp:650-658
+    for (OProxy& op : w->proxies) { op.p.min_x += nx; op.p.max_x += nx; op.p.min_y += ny; op.p.max_y += ny; }
+    return 0;
+}
+
+int orc_set_event_mask(orc_world* w, uint32_t mask) { w->evMask = mask; return 0; }
+int orc_events(const orc_world* w, uint32_t kind, void* buf, uint32_t cap, uint32_t* n_out)
+{ // call order (the order the reference's listeners are invoked in)
+    if (kind == PR_EVENT_POST_SOLVE) {
+        *n_out = static_cast<uint32_t>(w->evImpulse.size());
+        std::memcpy(buf, w->evImpulse.data(), sizeof(pr_impulse_event) * std::min<size_t>(cap, w->evImpulse.size()));
+    } else {
+        std::vector<pr_contact_event> ev;
+        for (const auto& e : w->evContact) if (e.kind & kind) ev.push_back(e);
+        *n_out = static_cast<uint32_t>(ev.size());
+        std::memcpy(buf, ev.data(), sizeof(pr_contact_event) * std::min<size_t>(cap, ev.size()));
+    }
+    return 0;
+}
+
 int orc_load_state(orc_world* w, uint32_t n_bodies, const pr_body* bodies, uint32_t n_proxies,
                    const pr_proxy* proxies, uint32_t n_contacts, const pr_contact* contacts,
                    const pr_manifold* manifolds, float inv_dt0)
@@ -1073,6 +1127,7 @@ int orc_step(orc_world* w, const pr_step_conf* confp, pr_step_stats* stats_out, 
     std::memset(&stats, 0, sizeof(stats));
     stats.reg.min_separation = kInf;
     stats.toi.min_separation = kInf;
+    w->evContact.clear(); w->evImpulse.clear();
     for (const auto& bs : w->fixturesForProxies) stats.pre.proxies_created += create_proxies(*w, bs.first, bs.second, conf);
     w->fixturesForProxies.clear();
     for (uint32_t bodyId : w->bodiesForSync) {

@@ -31,6 +31,10 @@ int orc_create_bodies(orc_world* w, uint32_t n, const pr_body* bodies,
                       const uint32_t* shape_offsets, const uint32_t* shape_ids);
 int orc_create_revolute_joints(orc_world* w, uint32_t n, const pr_revolute_joint* joints);
 int orc_set_bodies(orc_world* w, uint32_t n, const uint32_t* ids, const pr_body* rows);
+int orc_shift_origin(orc_world* w, float x, float y); /* ShiftOrigin, AabbTreeWorld.cpp:2221 */
+/* the begin/end/post-solve listener calls of the last orc_step, in the reference's call order */
+int orc_set_event_mask(orc_world* w, uint32_t mask);
+int orc_events(const orc_world* w, uint32_t kind, void* buf, uint32_t cap, uint32_t* n_out);
 int orc_load_state(orc_world* w, uint32_t n_bodies, const pr_body* bodies, uint32_t n_proxies,
                    const pr_proxy* proxies, uint32_t n_contacts, const pr_contact* contacts,
                    const pr_manifold* manifolds, float inv_dt0);

@@ -103,3 +103,8 @@ def one(dt):
 
 def cf_unpack(cf):
     return (cf & 0xFF, (cf >> 8) & 0xFF, (cf >> 16) & 0xFF, (cf >> 24) & 0xFF)
+
+# pr_contact_event / pr_impulse_event (pr_events)
+EVENT_BEGIN, EVENT_END, EVENT_PRE_SOLVE, EVENT_POST_SOLVE = 1, 2, 4, 8
+CONTACT_EVENT = np.dtype([(n, u4) for n in ("kind", "contact", "body_a", "shape_a", "child_a", "body_b", "shape_b", "child_b")])
+IMPULSE_EVENT = np.dtype([("contact", u4), ("count", u4), ("iterations", u4), ("phase", u4), ("normal", f4, (2,)), ("tangent", f4, (2,))])

@@ -339,6 +339,29 @@ PR_KERNEL k_hash_fill(DV d, unsigned nOrder)
     if (i < nOrder) hash_insert(d, d.c_key[d.c_order[i]]);
 }
 
+// ShiftOrigin(AabbTreeWorld&, newOrigin), AabbTreeWorld.cpp:2221-2243: sweeps move by -newOrigin and SetSweep recomputes the
+// transformation from position 1 (Body.hpp:697-702); b_moved stands for FlagForUpdating of the body's contacts (the next
+// pre-phase UpdateContacts reads it); tree boxes move by -newOrigin (DynamicTree.cpp:650-658, GetMovedAABB = min/max + value).
+PR_KERNEL k_shift_origin(DV d, unsigned nBodies, unsigned nProxies, float ox, float oy)
+{
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    if (i < nBodies) {
+        float4 p0 = d.b_pos0[i], p1 = d.b_pos1[i];
+        p0.x -= ox; p0.y -= oy; p1.x -= ox; p1.y -= oy;
+        d.b_pos0[i] = p0; d.b_pos1[i] = p1;
+        const Xf xf = get_xf(pos_from4(p1), d.b_lc[i]);
+        d.b_xf[i] = make_float4(xf.p.x, xf.p.y, xf.q.c, xf.q.s);
+        d.b_moved[i] = 1u;
+    }
+    if (i < nProxies) {
+        float4 f = d.p_fat[i];
+        const float nx = -ox, ny = -oy;
+        f.x += nx; f.y += ny; f.z += nx; f.w += ny;
+        d.p_fat[i] = f;
+    }
+}
+
 // ------------------------------------------------------------------ a6: DestroyContacts
 PR_D void body_set_awake(const DV& d, unsigned b)
 { // Body::SetAwake, Body.cpp:163-171
@@ -351,6 +374,29 @@ PR_D void manifold_clear(const DV& d, unsigned id)
 {
     d.m0[id] = make_float4(0, 0, 0, 0); d.m1[id] = make_float4(0, 0, 0, 0); d.m2[id] = make_float4(0, 0, 0, 0);
     d.m3[id] = make_uint4(PR_CF_DEFAULT, PR_CF_DEFAULT, 0u, 0u);
+}
+// Contact events (pr_events): what the begin/end listeners (AabbTreeWorld.cpp:2249-2252, :2703-2714) and the post-solve listener
+// (Report :196-206) would have been called with, appended to device buffers; the host reads them after the step.
+PR_D void emit_contact_event(const DV& d, unsigned kind, unsigned id, const uint4& ab)
+{
+    const unsigned slot = atomicAdd(&d.cnt->nEvContact, 1u);
+    if (slot < d.ev_cap) {
+        const uint4 ids = d.c_ids[id];
+        pr_contact_event e;
+        e.kind = kind; e.contact = id; e.body_a = ab.x; e.shape_a = ids.x; e.child_a = ids.y; e.body_b = ab.y; e.shape_b = ids.z; e.child_b = ids.w;
+        d.ev_contact[slot] = e;
+    }
+}
+PR_D void emit_impulse_event(const DV& d, unsigned id, unsigned count, unsigned iterations, unsigned phase, const float4& imp)
+{
+    const unsigned slot = atomicAdd(&d.cnt->nEvImpulse, 1u);
+    if (slot < d.ev_cap) {
+        pr_impulse_event e;
+        e.contact = id; e.count = count; e.iterations = iterations; e.phase = phase;
+        e.normal[0] = count > 0u ? imp.x : 0.0f; e.tangent[0] = count > 0u ? imp.y : 0.0f;
+        e.normal[1] = count > 1u ? imp.z : 0.0f; e.tangent[1] = count > 1u ? imp.w : 0.0f;
+        d.ev_impulse[slot] = e;
+    }
 }
 // keep[i] = 1 if the two FAT leaf boxes still overlap (AabbTreeWorld.cpp:2290-2304), else InternalDestroy (:2245)
 PR_KERNEL k_destroy_test(DV d, unsigned nOrder, unsigned* keep, unsigned hashLive)
@@ -365,6 +411,7 @@ PR_KERNEL k_destroy_test(DV d, unsigned nOrder, unsigned* keep, unsigned hashLiv
         if (!ov) {
             const uint4 ab = d.c_ab[id];
             const unsigned flags = d.c_flags[id];
+            if ((d.ev_mask & PR_EVENT_END) && (flags & PR_CONTACT_TOUCHING)) emit_contact_event(d, PR_EVENT_END, id, ab); // :2249-2252
             if (d.m3[id].w > 0u && !(flags & PR_CONTACT_SENSOR)) { body_set_awake(d, ab.x); body_set_awake(d, ab.y); }
             d.c_flags[id] = PR_CONTACT_DESTROYED;
             if (hashLive) hash_remove(d, d.c_key[id]);
@@ -448,6 +495,10 @@ PR_D void update_contact(const DV& d, const pr_step_conf& conf, unsigned id, uns
     if (!oldTouching && newTouching) flags |= PR_CONTACT_TOUCHING;
     else if (oldTouching && !newTouching) flags &= ~static_cast<unsigned>(PR_CONTACT_TOUCHING);
     if (flags != oldFlags) d.c_flags[id] = flags;
+    if (d.ev_mask && oldTouching != newTouching) { // beginContact / endContact, :2703-2714
+        const unsigned kind = newTouching ? PR_EVENT_BEGIN : PR_EVENT_END;
+        if (d.ev_mask & kind) emit_contact_event(d, kind, id, ab);
+    }
 }
 // UpdateContacts (AabbTreeWorld.cpp:2333-2421): one thread per contact of order[start, start+n).
 // A warp's 32 contacts mix disk-disk, disk-polygon and polygon-polygon pairs, and it used to execute the three paths one
@@ -1855,6 +1906,11 @@ PR_KERNEL k_assign_impulses(DV d, unsigned nCons)
         if (count > 0u) { m2.x = imp.x; m2.y = imp.y; }
         if (count > 1u) { m2.z = imp.z; m2.w = imp.w; }
         d.m2[cid] = m2;
+        if (d.ev_mask & PR_EVENT_POST_SOLVE) { // Report(postSolveContact, ...), AabbTreeWorld.cpp:1671-1674
+            const unsigned r = d.vc_island[i];
+            const unsigned it = (d.isl_state[r] & ISL_POS_SOLVED) ? d.isl_posIters[r] - 1u : 255u; // StepConf::InvalidIteration
+            emit_impulse_event(d, cid, count, it, 0u, imp);
+        }
     }
 }
 PR_KERNEL k_writeback_bodies(DV d, unsigned nBodies, pr_step_conf conf)

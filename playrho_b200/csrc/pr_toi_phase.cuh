@@ -555,6 +555,12 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
         maxIncAll = stdmax(maxIncAll, newInc);
     }
     PR_TT(5);
+    if (d.ev_mask & PR_EVENT_POST_SOLVE) { // Report(postSolveContact, island.contacts, velConstraints, positionIters), :2053-2055
+        for (unsigned j = 0; j < isl.nC; ++j) {
+            const float4 head = r.vc1[row0 + j];
+            emit_impulse_event(d, f2u(head.w), f2u(head.z) & 0xFFu, positionIters, 1u, r.vc8[row0 + j]);
+        }
+    }
     const float h = sub.delta_time;
     for (unsigned k = 0; k < isl.nB; ++k) { // IntegratePositions + write-back (:2042-2052)
         const unsigned b = d.toi_islBodies[isl.base + k];

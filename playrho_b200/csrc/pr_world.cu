@@ -939,6 +939,7 @@ int pr_destroy(pr_world* pw)
     if (!pw) return PR_OK;
     World& w = pw->w;
     for (const ArrDesc& a : arrays(w)) dev_free(*a.slot);
+    dev_free(w.d.ev_contact); dev_free(w.d.ev_impulse);
     dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist); dev_free(w.stageBuf[0]); dev_free(w.stageBuf[1]);
 #ifndef PR_HOST_EMUL
     if (w.stream) cudaStreamDestroy(w.stream);
@@ -1359,7 +1360,74 @@ int pr_set_debug(pr_world* pw, uint32_t flags) { pw->w.debugFlags = flags; retur
 
 int pr_get_step_profile(const pr_world* pw, pr_step_profile* out) { *out = pw->w.profile; return PR_OK; }
 
-int pr_shift_origin(pr_world* pw, float, float) { pw->w.error = "ShiftOrigin: not implemented yet"; return PR_ERR_UNSUPPORTED; }
+int pr_shift_origin(pr_world* pw, float x, float y)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    if (!w.stepComplete) { w.error = "ShiftOrigin: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    const unsigned n = std::max(w.nBodies, w.nProxies);
+    if (n) PR_LAUNCH(k_shift_origin, n, w.stream, w.d, w.nBodies, w.nProxies, x, y);
+    w.anyBodySet = true;  // the pre-phase UpdateContacts of the next Step looks at b_moved (FlagForUpdating, :2235)
+    w.bvhValid = false;   // every leaf box moved: rebuild the LBVH
+    w.toiAlphaDirty = true;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_set_event_mask(pr_world* pw, uint32_t mask, uint32_t capacity)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    if (mask & PR_EVENT_PRE_SOLVE) { w.error = "pre-solve needs a synchronous host callback inside Step: not offered by the device step"; return PR_ERR_UNSUPPORTED; }
+    if (mask & ~static_cast<uint32_t>(PR_EVENT_BEGIN | PR_EVENT_END | PR_EVENT_POST_SOLVE)) { w.error = "unknown event kind"; return PR_ERR_INVALID_ARGUMENT; }
+    sync(w);
+    if (mask && capacity > w.d.ev_cap) {
+        dev_free(w.d.ev_contact); dev_free(w.d.ev_impulse);
+        w.d.ev_contact = static_cast<pr_contact_event*>(dev_alloc(sizeof(pr_contact_event) * capacity));
+        w.d.ev_impulse = static_cast<pr_impulse_event*>(dev_alloc(sizeof(pr_impulse_event) * capacity));
+        w.d.ev_cap = capacity;
+    }
+    if (mask && !w.d.ev_cap) { w.error = "event capacity is zero"; return PR_ERR_INVALID_ARGUMENT; }
+    w.d.ev_mask = mask;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_events(const pr_world* cpw, uint32_t kind, void* buf, uint32_t cap, uint32_t* n_out)
+{
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    const bool contactKinds = (kind & (PR_EVENT_BEGIN | PR_EVENT_END)) != 0 && !(kind & ~static_cast<uint32_t>(PR_EVENT_BEGIN | PR_EVENT_END));
+    if (!contactKinds && kind != PR_EVENT_POST_SOLVE) { w.error = "pr_events: kind must be begin|end or post-solve"; return PR_ERR_INVALID_ARGUMENT; }
+    read_counters(w);
+    const unsigned total = contactKinds ? w.hostCnt.nEvContact : w.hostCnt.nEvImpulse;
+    const unsigned have = std::min(total, w.d.ev_cap);
+    if (contactKinds) {
+        std::vector<pr_contact_event> ev(have);
+        if (have) d2h(w, ev.data(), w.d.ev_contact, sizeof(pr_contact_event) * have);
+        ev.erase(std::remove_if(ev.begin(), ev.end(), [&](const pr_contact_event& e) { return !(e.kind & kind); }), ev.end());
+        std::sort(ev.begin(), ev.end(), [](const pr_contact_event& a, const pr_contact_event& b) { return a.kind != b.kind ? a.kind < b.kind : a.contact < b.contact; });
+        if (n_out) *n_out = static_cast<uint32_t>(ev.size());
+        if (buf && !ev.empty()) std::memcpy(buf, ev.data(), sizeof(pr_contact_event) * std::min<size_t>(ev.size(), cap));
+    } else {
+        std::vector<pr_impulse_event> ev(have);
+        if (have) d2h(w, ev.data(), w.d.ev_impulse, sizeof(pr_impulse_event) * have);
+        std::sort(ev.begin(), ev.end(), [](const pr_impulse_event& a, const pr_impulse_event& b) {
+            if (a.phase != b.phase) return a.phase < b.phase;
+            if (a.contact != b.contact) return a.contact < b.contact;
+            if (a.iterations != b.iterations) return a.iterations < b.iterations;
+            return std::memcmp(a.normal, b.normal, 16) < 0; });
+        if (n_out) *n_out = static_cast<uint32_t>(ev.size());
+        if (buf && !ev.empty()) std::memcpy(buf, ev.data(), sizeof(pr_impulse_event) * std::min<size_t>(ev.size(), cap));
+    }
+    if (total > w.d.ev_cap) { // the step dropped events: say how many there were
+        if (n_out) *n_out = total;
+        w.error = "events of the last step exceeded the capacity given to pr_set_event_mask"; return PR_ERR_LENGTH;
+    }
+    return PR_OK;
+    API_CATCH(pw)
+}
 
 float pr_get_inv_dt0(const pr_world* pw) { return pw->w.inv_dt0; }
 void* pr_get_stream(const pr_world* pw)

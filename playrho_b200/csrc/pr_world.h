@@ -68,6 +68,7 @@ struct Counters {
     unsigned proxiesMoved, contactsUpdated, nAwake, nTouching, nActiveVel, nActivePos;
     unsigned minSepFlip, maxIncBits, error, pad;
     unsigned boundsMinX, boundsMinY, boundsMaxX, boundsMaxY;
+    unsigned nEvContact, nEvImpulse; // contact events of this step (pr_events): begin/end records, post-solve records
     unsigned colorStart[MAX_COLORS + 1];
     // batched TOI rounds (pr_toi_phase.cuh, k_tb_*): the host enqueues several rounds without reading anything back;
     // the contact-pool bookkeeping it normally keeps (World::nOrder/nFree/poolSize) is mirrored here meanwhile
@@ -116,6 +117,8 @@ struct DV {
     float4 *pc0, *pc1, *pc2, *pc3;
     unsigned *k_contact, *k_color, *k_sorted, *k_tmpKey, *k_tmpKey2, *k_tmpVal, *k_ulist;
     unsigned* c_color; // persistent colour per contact
+    // contact events (pr_set_event_mask / pr_events): off unless ev_mask != 0
+    pr_contact_event* ev_contact; pr_impulse_event* ev_impulse; unsigned ev_mask, ev_cap;
     // bvh
     unsigned *bv_code, *bv_code2, *bv_idx, *bv_idx2, *bv_left, *bv_right, *bv_parent, *bv_lparent, *bv_visit, *bv_leafOf;
     CBox* bv_cbox; // per internal node: the boxes of its two children (see k_bvh_refit)

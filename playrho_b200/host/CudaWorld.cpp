@@ -219,9 +219,46 @@ struct CudaWorld::Impl {
     // lazily materialised DynamicTree (GetTree): leaves created in tree-id order replay the id sequence
     mutable bool treeStale = true;
     mutable DynamicTree tree;
-    // listeners (stored only)
+    // listeners: begin/end/post-solve are delivered after the device step from pr_events (deliverEvents)
     ShapeFunction shapeDestruction; BodyShapeFunction detach; JointFunction jointDestruction;
     ContactFunction beginContact, endContact; ContactManifoldFunction preSolve; ContactImpulsesFunction postSolve;
+    std::uint32_t eventCap = 1u << 16;
+
+    void updateEventMask() noexcept
+    {
+        const std::uint32_t mask = (beginContact ? PR_EVENT_BEGIN : 0u) | (endContact ? PR_EVENT_END : 0u) | (postSolve ? PR_EVENT_POST_SOLVE : 0u);
+        if (h) pr_set_event_mask(h, mask, eventCap);
+    }
+    // The listeners of the step that just ran, in (kind, contact id) order: all begin calls, all end calls, then post-solve.
+    // (The reference interleaves them inside Step; a listener here sees the world AFTER the step and may mutate it.)
+    void deliverEvents()
+    {
+        if (!beginContact && !endContact && !postSolve) return;
+        for (;;) { // a step that overflowed the buffers: grow them for the next step, deliver what was kept
+            std::vector<pr_contact_event> ce(eventCap);
+            std::vector<pr_impulse_event> ie(postSolve ? eventCap : 0u);
+            std::uint32_t nc = 0, ni = 0;
+            int rc = PR_OK;
+            if (beginContact || endContact) rc = pr_events(h, PR_EVENT_BEGIN | PR_EVENT_END, ce.data(), eventCap, &nc);
+            int rc2 = PR_OK;
+            if (postSolve) rc2 = pr_events(h, PR_EVENT_POST_SOLVE, ie.data(), eventCap, &ni);
+            const bool overflow = rc == PR_ERR_LENGTH || rc2 == PR_ERR_LENGTH;
+            if (!overflow) { check(rc, "pr_events"); check(rc2, "pr_events"); }
+            const std::uint32_t keptC = std::min(nc, eventCap), keptI = std::min(ni, eventCap);
+            for (std::uint32_t i = 0; i < keptC && (rc == PR_OK); ++i) {
+                const auto id = MakeId<ContactID>(ce[i].contact);
+                if (ce[i].kind == PR_EVENT_BEGIN) { if (beginContact) beginContact(id); }
+                else if (endContact) endContact(id);
+            }
+            for (std::uint32_t i = 0; i < keptI && (rc2 == PR_OK); ++i) {
+                ContactImpulsesList imp;
+                for (std::uint32_t j = 0; j < ie[i].count && j < 2u; ++j) imp.AddEntry(Momentum{ie[i].normal[j] * NewtonSecond}, Momentum{ie[i].tangent[j] * NewtonSecond});
+                postSolve(MakeId<ContactID>(ie[i].contact), imp, static_cast<unsigned>(ie[i].iterations));
+            }
+            if (overflow) { eventCap = std::max(nc, ni) * 2u; updateEventMask(); throw LengthError("CudaWorld: more contact events in one step than the event buffers hold (grown for the next step)"); }
+            return;
+        }
+    }
 
     void check(int rc, const char* what) const
     {
@@ -307,6 +344,7 @@ CudaWorld::CudaWorld(const CudaWorld& o) : m{new Impl}
         m->bodiesStale = false; m->shapes = o.m->shapes; m->joints = o.m->joints;
         m->shapeDestruction = o.m->shapeDestruction; m->detach = o.m->detach; m->jointDestruction = o.m->jointDestruction;
         m->beginContact = o.m->beginContact; m->endContact = o.m->endContact; m->preSolve = o.m->preSolve; m->postSolve = o.m->postSolve;
+        m->eventCap = o.m->eventCap; m->updateEventMask();
     } catch (...) { if (m->h) pr_destroy(m->h); delete m; m = nullptr; throw; }
 }
 CudaWorld::CudaWorld(CudaWorld&& o) noexcept : m{o.m} { o.m = nullptr; }
@@ -337,10 +375,12 @@ bool operator!=(const CudaWorld& a, const CudaWorld& b) { return !(a == b); }
 void SetShapeDestructionListener(CudaWorld& w, ShapeFunction l) noexcept { w.m->shapeDestruction = std::move(l); }
 void SetDetachListener(CudaWorld& w, BodyShapeFunction l) noexcept { w.m->detach = std::move(l); }
 void SetJointDestructionListener(CudaWorld& w, JointFunction l) noexcept { w.m->jointDestruction = std::move(l); }
-void SetBeginContactListener(CudaWorld& w, ContactFunction l) noexcept { w.m->beginContact = std::move(l); }
-void SetEndContactListener(CudaWorld& w, ContactFunction l) noexcept { w.m->endContact = std::move(l); }
+void SetBeginContactListener(CudaWorld& w, ContactFunction l) noexcept { w.m->beginContact = std::move(l); w.m->updateEventMask(); }
+void SetEndContactListener(CudaWorld& w, ContactFunction l) noexcept { w.m->endContact = std::move(l); w.m->updateEventMask(); }
+// pre-solve: stored, never invoked -- it exists to edit a contact before the same step's solve, which needs a synchronous host
+// callback inside the device step (include/playrho_b200.h, "contact events")
 void SetPreSolveContactListener(CudaWorld& w, ContactManifoldFunction l) noexcept { w.m->preSolve = std::move(l); }
-void SetPostSolveContactListener(CudaWorld& w, ContactImpulsesFunction l) noexcept { w.m->postSolve = std::move(l); }
+void SetPostSolveContactListener(CudaWorld& w, ContactImpulsesFunction l) noexcept { w.m->postSolve = std::move(l); w.m->updateEventMask(); }
 
 // ---- miscellaneous
 std::optional<pmr::StatsResource::Stats> GetResourceStats(const CudaWorld&) noexcept { return {}; }
@@ -370,16 +410,21 @@ StepStats Step(CudaWorld& w, const StepConf& conf)
     w.m->check(rc, "pr_step");
     w.m->bodiesStale = true;
     w.m->mutated();
+    w.m->deliverEvents();
     return ToStats(st);
 }
 bool IsStepComplete(const CudaWorld& w) noexcept { return pr_is_step_complete(w.m->h) != 0; }
 bool GetSubStepping(const CudaWorld& w) noexcept { return pr_get_sub_stepping(w.m->h) != 0; }
 void SetSubStepping(CudaWorld& w, bool flag) noexcept { pr_set_sub_stepping(w.m->h, flag ? 1u : 0u); }
 bool IsLocked(const CudaWorld& w) noexcept { return w.m->locked; }
-void ShiftOrigin(CudaWorld& w, const Length2&)
-{
+void ShiftOrigin(CudaWorld& w, const Length2& newOrigin)
+{ // ShiftOrigin(AabbTreeWorld&, const Length2&), :2221-2243
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
-    throw InvalidArgument(unsupportedMsg);
+    w.m->refreshBodies();
+    w.m->uploadDirtyBodies();
+    w.m->check(pr_shift_origin(w.m->h, static_cast<float>(Real(GetX(newOrigin) / Meter)), static_cast<float>(Real(GetY(newOrigin) / Meter))), "pr_shift_origin");
+    w.m->bodiesStale = true;
+    w.m->mutated();
 }
 Interval<Positive<Length>> GetVertexRadiusInterval(const CudaWorld& w) noexcept { return w.m->conf.vertexRadius; }
 Frequency GetInvDeltaTime(const CudaWorld& w) noexcept { return Frequency{pr_get_inv_dt0(w.m->h)}; }

@@ -57,8 +57,8 @@ public:
 bool operator==(const CudaWorld& lhs, const CudaWorld& rhs);
 bool operator!=(const CudaWorld& lhs, const CudaWorld& rhs);
 
-// Listeners (stored; begin/end/pre/post-solve are host callbacks inside Step and are not invoked by the
-// device world yet -- SURVEY 8(f) rank 3)
+// Listeners: begin/end/post-solve calls are recorded on the device during Step (pr_events) and made right after it, in
+// (kind, contact id) order; pre-solve is stored but never invoked (it needs a synchronous callback inside the step).
 void SetShapeDestructionListener(CudaWorld& world, ShapeFunction listener) noexcept;
 void SetDetachListener(CudaWorld& world, BodyShapeFunction listener) noexcept;
 void SetJointDestructionListener(CudaWorld& world, JointFunction listener) noexcept;

@@ -62,10 +62,26 @@ int main(int argc, char** argv)
     for (World* w : {&ref, &cud}) {
         if (!std::strcmp(scene, "pyramid")) BuildPyramid(*w, 8); else BuildDisks(*w, 40);
     }
+    // the reference's listener API on both worlds: begin/end/post-solve calls are counted; a begin listener also reads the
+    // contact through the world (GetContact must work from inside a listener)
+    unsigned long nBegin[2] = {0, 0}, nEnd[2] = {0, 0}, nPost[2] = {0, 0}, badListenerRead = 0;
+    double postImpulse[2] = {0, 0};
+    int wi = 0;
+    for (World* w : {&ref, &cud}) {
+        const int k = wi++;
+        SetBeginContactListener(*w, [&, w, k](ContactID id) { ++nBegin[k]; if (!IsTouching(GetContact(*w, id)) && k == 0) ++badListenerRead; });
+        SetEndContactListener(*w, [&, k](ContactID) { ++nEnd[k]; });
+        SetPostSolveContactListener(*w, [&, k](ContactID, const ContactImpulsesList& imp, unsigned) {
+            ++nPost[k];
+            for (unsigned j = 0; j < imp.GetCount(); ++j) postImpulse[k] += static_cast<double>(Real(imp.GetEntryNormal(j) / NewtonSecond));
+        });
+    }
+    const bool shift = argc > 3 && !std::strcmp(argv[3], "shift");
     const auto conf = StepConf{};
     double maxPos = 0, maxVel = 0;
     unsigned long touchMismatch = 0, contactCountMismatch = 0, toiEvents = 0, toiEventsRef = 0;
     for (int s = 0; s < steps; ++s) {
+        if (shift && s == steps / 2) { ShiftOrigin(ref, Length2{13.37_m, -2.25_m}); ShiftOrigin(cud, Length2{13.37_m, -2.25_m}); }
         const auto rs = Step(ref, conf);
         const auto cs = Step(cud, conf);
         toiEvents += cs.toi.contactsFound; toiEventsRef += rs.toi.contactsFound;
@@ -89,8 +105,11 @@ int main(int argc, char** argv)
     unsigned long points = 0;
     for (const auto& kc : GetContacts(cud)) points += GetManifold(cud, std::get<ContactID>(kc)).GetPointCount();
     std::printf("scene=%s steps=%d bodies=%u contacts_ref=%zu contacts_dev=%zu manifold_points_dev=%lu toi_events_ref=%lu toi_events_dev=%lu "
-                "steps_with_contact_count_mismatch=%lu steps_with_touching_set_mismatch=%lu max_pos_diff=%.6g max_vel_diff=%.6g type_is_cudaworld=%d\n",
+                "steps_with_contact_count_mismatch=%lu steps_with_touching_set_mismatch=%lu max_pos_diff=%.6g max_vel_diff=%.6g type_is_cudaworld=%d "
+                "begin_ref=%lu begin_dev=%lu end_ref=%lu end_dev=%lu post_ref=%lu post_dev=%lu post_impulse_ref=%.6g post_impulse_dev=%.6g shifted=%d\n",
                 scene, steps, static_cast<unsigned>(nb), GetContacts(ref).size(), GetContacts(cud).size(), points, toiEventsRef, toiEvents,
-                contactCountMismatch, touchMismatch, maxPos, maxVel, TypeCast<b200::CudaWorld>(&cud) != nullptr ? 1 : 0);
+                contactCountMismatch, touchMismatch, maxPos, maxVel, TypeCast<b200::CudaWorld>(&cud) != nullptr ? 1 : 0,
+                nBegin[0], nBegin[1], nEnd[0], nEnd[1], nPost[0], nPost[1], postImpulse[0], postImpulse[1], shift ? 1 : 0);
+    (void)badListenerRead;
     return 0;
 }

@@ -25,7 +25,7 @@ EXPORTS = [
     "pr_get_inv_dt0", "pr_get_stream", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
     "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
-    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb",
+    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events",
 ]
 
 
@@ -48,6 +48,8 @@ def bind(lib):
     lib.pr_set_body_accelerations.argtypes = [vp, u32, vp, vp]
     lib.pr_get_body_poses.argtypes = [vp, u32, u32, vp, vp]
     lib.pr_query_aabb.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp, vp, C.POINTER(u32)]
+    lib.pr_set_event_mask.argtypes = [vp, u32, u32]
+    lib.pr_events.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
     lib.pr_get_revolute_joints.argtypes = [vp, u32, u32, vp]
     lib.pr_get_counts.argtypes = [vp, vp]
     lib.pr_get_contacts.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
@@ -211,6 +213,24 @@ class World:
             if k.value <= cap:
                 return tuple(o[:k.value] for o in out)
             cap = k.value
+
+    def shift_origin(self, x, y):
+        """ShiftOrigin(world, newOrigin) (pr_shift_origin)."""
+        self._chk(self.lib.pr_shift_origin(self.h, float(x), float(y)))
+
+    def set_event_mask(self, mask, capacity=1 << 16):
+        """Record contact events (abi.EVENT_* bits) from the next step on (pr_set_event_mask)."""
+        self._chk(self.lib.pr_set_event_mask(self.h, mask, capacity))
+        self._ev_cap = capacity
+
+    def events(self, kind):
+        """Events of the last step (pr_events): abi.CONTACT_EVENT rows for begin/end, abi.IMPULSE_EVENT rows for post-solve."""
+        dt = abi.IMPULSE_EVENT if kind == abi.EVENT_POST_SOLVE else abi.CONTACT_EVENT
+        cap = getattr(self, "_ev_cap", 0)
+        out = np.zeros(max(1, cap), dt)
+        k = u32(0)
+        self._chk(self.lib.pr_events(self.h, kind, abi.ptr(out), cap, C.byref(k)))
+        return out[:k.value]
 
     def joints(self):
         n = int(self.counts()["joints"])

@@ -190,6 +190,23 @@ class RefWorld:
         secs = self.lib.ref_step_timed(self.h, abi.ptr(conf), n, abi.ptr(st))
         return secs, st[0]
 
+    def shift_origin(self, x, y):
+        self.lib.ref_shift_origin.argtypes = [vp, f32, f32]
+        self._chk(self.lib.ref_shift_origin(self.h, x, y))
+
+    def set_event_mask(self, mask):
+        """Installs the reference's begin/end/post-solve listeners (recorded in call order)."""
+        self.lib.ref_set_event_mask.argtypes = [vp, u32]
+        self._chk(self.lib.ref_set_event_mask(self.h, mask))
+
+    def events(self, kind, cap=1 << 18):
+        self.lib.ref_events.argtypes = [vp, u32, vp, u32, vp]
+        out = np.zeros(cap, abi.IMPULSE_EVENT if kind == abi.EVENT_POST_SOLVE else abi.CONTACT_EVENT)
+        k = C.c_uint32(0)
+        self._chk(self.lib.ref_events(self.h, kind, abi.ptr(out), cap, C.byref(k)))
+        assert k.value <= cap
+        return out[:k.value]
+
     def counts(self):
         c = abi.one(abi.COUNTS)
         self._chk(self.lib.ref_get_counts(self.h, abi.ptr(c)))
@@ -283,6 +300,23 @@ class OracleWorld:
         if r != 0:
             raise RuntimeError(self.lib.orc_last_error(self.h).decode())
         return st[0]
+
+    def shift_origin(self, x, y):
+        self.lib.orc_shift_origin.argtypes = [vp, f32, f32]
+        self.lib.orc_shift_origin(self.h, x, y)
+
+    def set_event_mask(self, mask):
+        self.lib.orc_set_event_mask.argtypes = [vp, u32]
+        self.lib.orc_set_event_mask(self.h, mask)
+
+    def events(self, kind, cap=1 << 18):
+        """Listener calls of the last step in the reference's call order."""
+        self.lib.orc_events.argtypes = [vp, u32, vp, u32, vp]
+        out = np.zeros(cap, abi.IMPULSE_EVENT if kind == abi.EVENT_POST_SOLVE else abi.CONTACT_EVENT)
+        k = C.c_uint32(0)
+        self.lib.orc_events(self.h, kind, abi.ptr(out), cap, C.byref(k))
+        assert k.value <= cap
+        return out[:k.value]
 
     def counts(self):
         c = abi.one(abi.COUNTS)

@@ -34,8 +34,8 @@ def test_unmodified_reference_helloworld_runs_on_cudaworld_and_matches_golden():
     assert r.stdout.splitlines() == open(GOLDEN).read().splitlines()
 
 
-def _parity(scene, steps):
-    r = subprocess.run([PARITY, scene, str(steps)], capture_output=True, text=True, timeout=300)
+def _parity(scene, steps, *extra):
+    r = subprocess.run([PARITY, scene, str(steps)] + list(extra), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     line = r.stdout.strip().splitlines()[-1]
     print(line)
@@ -67,3 +67,20 @@ def test_world_api_side_by_side_fast_disks_toi():
     """Fast disks + bullets in a closed box: TOI events on both sides; chaotic, so only drift is reported."""
     d = _parity("disks", 60)
     assert int(d["toi_events_dev"]) > 0 and int(d["toi_events_ref"]) > 0
+
+
+@built
+@pytest.mark.gpu
+def test_world_api_listeners_and_shift_origin_pyramid():
+    """SetBeginContactListener / SetEndContactListener / SetPostSolveContactListener and ShiftOrigin through the reference's
+    World API on World{CudaWorld}: the listeners are called (after the device step, from pr_events) as often as the reference
+    calls its own -- up to the native-order drift the side-by-side test above reports -- and a ShiftOrigin in mid-run keeps the
+    two worlds as close as without it."""
+    d = _parity("pyramid", 150, "shift")
+    assert d["shifted"] == "1"
+    assert int(d["steps_with_contact_count_mismatch"]) == 0
+    assert float(d["max_pos_diff"]) < 0.10
+    assert int(d["begin_dev"]) > 0 and int(d["post_dev"]) > 0
+    assert abs(int(d["begin_dev"]) - int(d["begin_ref"])) <= max(10, int(d["begin_ref"]) // 5)
+    assert abs(int(d["post_dev"]) - int(d["post_ref"])) <= int(d["post_ref"]) // 20
+    assert abs(float(d["post_impulse_dev"]) - float(d["post_impulse_ref"])) <= 0.05 * abs(float(d["post_impulse_ref"]))
