@@ -377,11 +377,11 @@ PR_D void manifold_clear(const DV& d, unsigned id)
 }
 // Contact events (pr_events): what the begin/end listeners (AabbTreeWorld.cpp:2249-2252, :2703-2714) and the post-solve listener
 // (Report :196-206) would have been called with, appended to device buffers; the host reads them after the step.
-PR_D void emit_contact_event(const DV& d, unsigned kind, unsigned id, const uint4& ab)
-{
+PR_D void emit_contact_event(const DV& d, unsigned kind, unsigned id)
+{ // (re-reads the contact's bodies: the callers need not keep them in registers across the collision for this rare path)
     const unsigned slot = atomicAdd(&d.cnt->nEvContact, 1u);
     if (slot < d.ev_cap) {
-        const uint4 ids = d.c_ids[id];
+        const uint4 ab = d.c_ab[id], ids = d.c_ids[id];
         pr_contact_event e;
         e.kind = kind; e.contact = id; e.body_a = ab.x; e.shape_a = ids.x; e.child_a = ids.y; e.body_b = ab.y; e.shape_b = ids.z; e.child_b = ids.w;
         d.ev_contact[slot] = e;
@@ -411,7 +411,7 @@ PR_KERNEL k_destroy_test(DV d, unsigned nOrder, unsigned* keep, unsigned hashLiv
         if (!ov) {
             const uint4 ab = d.c_ab[id];
             const unsigned flags = d.c_flags[id];
-            if ((d.ev_mask & PR_EVENT_END) && (flags & PR_CONTACT_TOUCHING)) emit_contact_event(d, PR_EVENT_END, id, ab); // :2249-2252
+            if ((d.ev_mask & PR_EVENT_END) && (flags & PR_CONTACT_TOUCHING)) emit_contact_event(d, PR_EVENT_END, id); // :2249-2252
             if (d.m3[id].w > 0u && !(flags & PR_CONTACT_SENSOR)) { body_set_awake(d, ab.x); body_set_awake(d, ab.y); }
             d.c_flags[id] = PR_CONTACT_DESTROYED;
             if (hashLive) hash_remove(d, d.c_key[id]);
@@ -497,7 +497,7 @@ PR_D void update_contact(const DV& d, const pr_step_conf& conf, unsigned id, uns
     if (flags != oldFlags) d.c_flags[id] = flags;
     if (d.ev_mask && oldTouching != newTouching) { // beginContact / endContact, :2703-2714
         const unsigned kind = newTouching ? PR_EVENT_BEGIN : PR_EVENT_END;
-        if (d.ev_mask & kind) emit_contact_event(d, kind, id, ab);
+        if (d.ev_mask & kind) emit_contact_event(d, kind, id);
     }
 }
 // UpdateContacts (AabbTreeWorld.cpp:2333-2421): one thread per contact of order[start, start+n).
