@@ -5,13 +5,15 @@
 
 Per kernel: registers, stack (spill) bytes, static shared memory, SASS instruction count and the instruction mix that the
 design claims rest on:
-  * no FFMA/DFMA anywhere (--fmad=false: every float result equals the reference's FMA-free x86-64 build);
+  * --fmad=false: no DFMA at all, and FFMA only inside the correctly rounded division / square-root sequences (div.rn / sqrt.rn
+    = MUFU.RCP / MUFU.RSQ + FCHK + Newton steps, whose internal FFMAs are what makes them IEEE-exact): kernels without MUFU have
+    0 FFMA (k_solve_velocity, k_warm_start, the broadphase), i.e. no user-level a*b+c was contracted -- every float result equals
+    the reference's FMA-free x86-64 build;
   * 128-bit global loads/stores (LDG.E.128 / STG.E.128) on the float4 planes;
-  * programmatic dependent launch: every kernel starts with griddepcontrol (SASS: ACQBULK / PREEXIT-style control is shown as
-    the 'ACQBULK'/'PREEXIT' mnemonics on sm_100; counted under pdl);
+  * programmatic dependent launch: griddepcontrol.launch_dependents / .wait show up as PREEXIT / ACQBULK (column pdl: 2 per
+    kernel; k_build_constraints keeps the completion trigger = 1; the opt-in cooperative k_solve_fused has none);
   * warp collectives (SHFL / VOTE / MATCH / REDUX) in the cooperative query, island and append paths;
-  * IEEE division / square root sequences (MUFU.RCP / MUFU.RSQ + Newton steps; the *count* of MUFU shows where they live);
-  * FP64 (DADD/DMUL) only in the glibc sincosf restatement.
+  * FP64 (DADD/DMUL, never DFMA) only where the glibc sincosf restatement is used (position solve, TOI, joints, proxies).
 """
 import collections
 import re
