@@ -242,6 +242,22 @@ int pr_get_body_poses(const pr_world* w, uint32_t first, uint32_t n, float* xf4,
  * of the last Step (like GetTree): bodies created or moved since are seen after the next Step. */
 int pr_query_aabb(const pr_world* w, uint32_t n_boxes, const float* boxes4, const uint32_t* box_world, uint32_t cap,
                   uint32_t* hit_box, uint32_t* hit_body, uint32_t* hit_shape, uint32_t* hit_child, uint32_t* n_out);
+/* RayCast(const World&, const RayCastInput&, ShapeRayCastCB) (RayCastOutput.cpp:301-337 over RayCast(const DynamicTree&, ...)
+ * :241-299 and RayCast(const DistanceProxy&, ...) :139-233 / the disk case :41-75) for n_rays rays at once on
+ * the device LBVH. rays5 = (p1 x, p1 y, p2 x, p2 y, maxFraction) per ray; ray_world as in pr_query_aabb.
+ *   PR_RAY_ALL      every shape child the ray hits: what a callback returning RayCastOpcode::ResetRay is called with
+ *                   (hits[0..min(*n_out, cap)), no particular order; *n_out > cap: too short, first cap written);
+ *   PR_RAY_CLOSEST  per ray the hit with the least fraction: what a callback returning ClipRay last sees. hits[i] belongs to
+ *                   ray i (cap >= n_rays), body == 0xFFFFFFFF for a miss; equal fractions: the lower proxy index wins.
+ * fraction, normal and point (= p1 + (p2 - p1) * fraction) are the reference's, bit for bit. The tree is the one of the last
+ * Step (like GetTree). */
+enum { PR_RAY_ALL = 0, PR_RAY_CLOSEST = 1 };
+typedef struct pr_ray_hit {
+    uint32_t ray, body, shape, child;
+    float fraction, normal_x, normal_y, point_x, point_y;
+} pr_ray_hit;
+int pr_ray_cast(const pr_world* w, uint32_t n_rays, const float* rays5, const uint32_t* ray_world, uint32_t mode, uint32_t cap,
+                pr_ray_hit* hits, uint32_t* n_out);
 int pr_get_revolute_joints(const pr_world* w, uint32_t first, uint32_t n, pr_revolute_joint* rows);
 int pr_get_counts(const pr_world* w, pr_counts* out);
 /* contacts in m_contacts order (creation order), manifolds[i] belongs to contacts[i] */

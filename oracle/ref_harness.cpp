@@ -13,6 +13,8 @@
 #include <playrho/d2/WorldManifold.hpp>
 #include <playrho/d2/RevoluteJointConf.hpp>
 #include <playrho/d2/TimeOfImpact.hpp>
+#include <playrho/d2/RayCastOutput.hpp>
+#include <playrho/RayCastOpcode.hpp>
 #include <playrho/ToiConf.hpp>
 #include <playrho/ToiOutput.hpp>
 
@@ -472,6 +474,32 @@ int ref_events(void* h, uint32_t kind, void* buf, uint32_t cap, uint32_t* n_out)
         *n_out = static_cast<uint32_t>(ev.size());
         std::memcpy(buf, ev.data(), sizeof(pr_contact_event) * std::min<size_t>(cap, ev.size()));
     }
+    return 0;
+    REF_CATCH(-1)
+}
+
+// RayCast(const World&, const RayCastInput&, ShapeRayCastCB) with a callback that records every call and returns ResetRay
+// (RayCastOutput.cpp:301-337); hits in callback order
+int ref_ray_cast(void* h, uint32_t n_rays, const float* rays5, uint32_t cap, pr_ray_hit* hits, uint32_t* n_out)
+{
+    REF_TRY(h)
+    uint32_t n = 0;
+    for (uint32_t r = 0; r < n_rays; ++r) {
+        const RayCastInput input{Length2{rays5[5 * r] * 1_m, rays5[5 * r + 1] * 1_m}, Length2{rays5[5 * r + 2] * 1_m, rays5[5 * r + 3] * 1_m}, rays5[5 * r + 4]};
+        RayCast(rw->world, input, [&](BodyID b, ShapeID s, ChildCounter c, const Length2& point, const UnitVec& normal) {
+            if (n < cap) {
+                // the fraction is not handed to the callback: recompute the shape cast the way RayCast(world) did
+                const auto shape = GetShape(rw->world, s);
+                const auto out = RayCast(GetChild(shape, c), input, GetTransformation(rw->world, b));
+                hits[n] = pr_ray_hit{r, static_cast<uint32_t>(to_underlying(b)), static_cast<uint32_t>(to_underlying(s)), static_cast<uint32_t>(c),
+                                     out.has_value() ? static_cast<float>(out->fraction) : -1.0f, static_cast<float>(normal.GetX()), static_cast<float>(normal.GetY()),
+                                     static_cast<float>(Real(GetX(point) / Meter)), static_cast<float>(Real(GetY(point) / Meter))};
+            }
+            ++n;
+            return RayCastOpcode::ResetRay;
+        });
+    }
+    *n_out = n;
     return 0;
     REF_CATCH(-1)
 }

@@ -1067,6 +1067,92 @@ int orc_shift_origin(orc_world* w, float x, float y)
     return 0;
 }
 
+// ---------------- RayCast, RayCastOutput.cpp ----------------
+namespace {
+struct RayOut { bool hit; Rot normal; float fraction; };
+// RayCast(Length radius, const Length2& location, const RayCastInput&), :41-75
+RayOut ray_cast_circle(float radius, V2 location, V2 p1, V2 p2, float maxFraction)
+{
+    const V2 s = p1 - location;
+    const float b = magsq(s) - square(radius);
+    const V2 raySegment = p2 - p1;
+    const float c = dot(s, raySegment);
+    const float rr = magsq(raySegment);
+    const float sigma = square(c) - rr * b;
+    if (sigma < 0.0f || almost_zero(rr)) return {false, {0, 0}, 0};
+    const float a = -(c + std::sqrt(sigma));
+    const float fraction = a / rr;
+    if (fraction >= 0.0f && fraction <= maxFraction) return {true, unit_vector(s + fraction * raySegment, Rot{0, 0}), fraction};
+    return {false, {0, 0}, 0};
+}
+// RayCast(const DistanceProxy&, const RayCastInput&, const Transformation&), :139-233
+RayOut ray_cast_proxy(const Proxy& proxy, V2 p1, V2 p2, float maxFraction, Xf xf)
+{
+    const uint32_t count = proxy.count;
+    const float radius = proxy.radius;
+    V2 v0 = proxy.vertex(0);
+    if (count == 1) return ray_cast_circle(radius, transform(v0, xf), p1, p2, maxFraction);
+    const V2 tp1 = inv_transform(p1, xf), tp2 = inv_transform(p2, xf);
+    const V2 ray0 = tp1, ray = tp2 - tp1;
+    float minT = std::nextafter(maxFraction, 2.0f);
+    Rot normalFound{0, 0};
+    for (uint32_t i = 0; i < count; ++i) {
+        const RayOut circle = ray_cast_circle(radius, v0, tp1, tp2, maxFraction);
+        if (circle.hit && minT > circle.fraction) { minT = circle.fraction; normalFound = circle.normal; }
+        const V2 v1 = proxy.vertex(mod_next(i, count));
+        const V2 edge = v1 - v0;
+        const float rayCrossEdge = cross(ray, edge);
+        if (!almost_zero(rayCrossEdge)) {
+            const Rot normal = proxy.normal(i);
+            const V2 offset = normal * radius;
+            const V2 v0off = v0 + offset;
+            const V2 qSubP = v0off - ray0;
+            const float recip = 1.0f / rayCrossEdge;
+            const float t = cross(qSubP, edge) * recip;
+            const float u = cross(qSubP, ray) * recip;
+            if (t >= 0.0f && t <= 1.0f && u >= 0.0f && u <= 1.0f) {
+                if (minT > t) { minT = t; normalFound = normal; }
+            }
+        }
+        v0 = v1;
+    }
+    if (minT <= maxFraction) return {true, rot_rotate(normalFound, xf.q), minT};
+    return {false, {0, 0}, 0};
+}
+} // namespace
+
+int orc_ray_cast(const orc_world* w, uint32_t n_rays, const float* rays5, uint32_t cap, pr_ray_hit* hits, uint32_t* n_out)
+{
+    uint32_t n = 0;
+    for (uint32_t r = 0; r < n_rays; ++r) {
+        const V2 p1{rays5[5 * r], rays5[5 * r + 1]}, p2{rays5[5 * r + 2], rays5[5 * r + 3]};
+        const float maxFraction = rays5[5 * r + 4];
+        // RayCast(const DynamicTree&, RayCastInput, cb), :241-299: the two tests a leaf must pass
+        const Rot v = rev_perp(unit_vector(p2 - p1, Rot{0, 0}));
+        const V2 absV{std::fabs(v.c), std::fabs(v.s)};
+        const V2 fractDelta = maxFraction * (p2 - p1); // GetAABB(RayCastInput), AABB.cpp:107-112
+        const V2 e = p1 + fractDelta;
+        const AABB seg{std::min(p1.x, e.x), std::max(p1.x, e.x), std::min(p1.y, e.y), std::max(p1.y, e.y)};
+        for (const OProxy& op : w->proxies) {
+            const AABB box = fat_of(op.p);
+            if (!overlap(box, seg)) continue;
+            const V2 center{(box.minx + box.maxx) / 2, (box.miny + box.maxy) / 2};
+            const V2 extents{(box.maxx - box.minx) * 0.5f, (box.maxy - box.miny) * 0.5f};
+            const float separation = std::fabs(dot(rotv(v), p1 - center)) - dot(absV, extents);
+            if (separation > 0.0f) continue;
+            const RayOut o = ray_cast_proxy(w->child(op.p.shape, op.p.child), p1, p2, maxFraction, body_xf(w->bodies[op.p.body].b));
+            if (!o.hit) continue;
+            if (n < cap) {
+                const V2 point = p1 + (p2 - p1) * o.fraction;
+                hits[n] = pr_ray_hit{r, op.p.body, op.p.shape, op.p.child, o.fraction, o.normal.c, o.normal.s, point.x, point.y};
+            }
+            ++n;
+        }
+    }
+    *n_out = n;
+    return 0;
+}
+
 int orc_set_event_mask(orc_world* w, uint32_t mask) { w->evMask = mask; return 0; }
 int orc_events(const orc_world* w, uint32_t kind, void* buf, uint32_t cap, uint32_t* n_out)
 { // call order (the order the reference's listeners are invoked in)

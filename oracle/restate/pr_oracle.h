@@ -52,6 +52,10 @@ int orc_get_proxies(const orc_world* w, uint32_t cap, pr_proxy* proxies, uint32_
 int orc_get_revolute_joints(const orc_world* w, uint32_t first, uint32_t n, pr_revolute_joint* rows);
 float orc_get_inv_dt0(const orc_world* w);
 
+/* RayCast(world, input, callback returning ResetRay): every hit, brute force over the proxies with the tree's two leaf tests
+ * (RayCastOutput.cpp:241-337); hits in proxy order per ray */
+int orc_ray_cast(const orc_world* w, uint32_t n_rays, const float* rays5, uint32_t cap, pr_ray_hit* hits, uint32_t* n_out);
+
 /* stage functions on flat arrays */
 int orc_collide_shapes(uint32_t n, const pr_child* children, const pr_vec2* verts,
                        const pr_vec2* normals, const uint32_t* a_child, const float* xf_a,

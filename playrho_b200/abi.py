@@ -108,3 +108,8 @@ def cf_unpack(cf):
 EVENT_BEGIN, EVENT_END, EVENT_PRE_SOLVE, EVENT_POST_SOLVE = 1, 2, 4, 8
 CONTACT_EVENT = np.dtype([(n, u4) for n in ("kind", "contact", "body_a", "shape_a", "child_a", "body_b", "shape_b", "child_b")])
 IMPULSE_EVENT = np.dtype([("contact", u4), ("count", u4), ("iterations", u4), ("phase", u4), ("normal", f4, (2,)), ("tangent", f4, (2,))])
+
+# pr_ray_hit (pr_ray_cast)
+RAY_ALL, RAY_CLOSEST = 0, 1
+RAY_HIT = np.dtype([("ray", u4), ("body", u4), ("shape", u4), ("child", u4), ("fraction", f4), ("normal_x", f4), ("normal_y", f4),
+                    ("point_x", f4), ("point_y", f4)])

@@ -970,6 +970,138 @@ PR_KERNEL k_query_boxes(DV d, unsigned nBoxes, const float4* boxes, const unsign
 #endif
 }
 
+// ------------------------------------------------------------------ RayCast on the LBVH
+struct RayOut { bool hit; Rot normal; float fraction; };
+PR_D RayOut ray_miss() { RayOut o; o.hit = false; o.normal = mkrot(0.0f, 0.0f); o.fraction = 0.0f; return o; }
+// RayCast(Length radius, const Length2& location, const RayCastInput&), RayCastOutput.cpp:41-75
+PR_D RayOut ray_cast_circle(float radius, float2 location, float2 p1, float2 p2, float maxFraction)
+{
+    const float2 s = p1 - location;
+    const float b = magsq(s) - square(radius);
+    const float2 raySegment = p2 - p1;
+    const float c = dot(s, raySegment);
+    const float rr = magsq(raySegment);
+    const float sigma = square(c) - rr * b;
+    if (sigma < 0.0f || almost_zero(rr)) return ray_miss();
+    const float a = -(c + sqrtf(sigma));
+    const float fraction = a / rr;
+    if (fraction >= 0.0f && fraction <= maxFraction) {
+        RayOut o; o.hit = true; o.normal = unit_vector(s + fraction * raySegment, mkrot(0.0f, 0.0f)); o.fraction = fraction; return o;
+    }
+    return ray_miss();
+}
+// RayCast(const DistanceProxy&, const RayCastInput&, const Transformation&), RayCastOutput.cpp:139-233
+PR_D RayOut ray_cast_proxy(const ProxyView& proxy, float2 p1, float2 p2, float maxFraction, Xf xf)
+{
+    const unsigned count = proxy.count;
+    const float radius = proxy.radius;
+    float2 v0 = proxy.vertex(0u);
+    if (count == 1u) return ray_cast_circle(radius, transform(v0, xf), p1, p2, maxFraction);
+    const float2 tp1 = inv_transform(p1, xf), tp2 = inv_transform(p2, xf);
+    const float2 ray0 = tp1, ray = tp2 - tp1;
+    float minT = nextafterf(maxFraction, 2.0f);
+    Rot normalFound = mkrot(0.0f, 0.0f);
+    for (unsigned i = 0; i < count; ++i) {
+        const RayOut circle = ray_cast_circle(radius, v0, tp1, tp2, maxFraction);
+        if (circle.hit && minT > circle.fraction) { minT = circle.fraction; normalFound = circle.normal; }
+        const float2 v1 = proxy.vertex(mod_next(i, count));
+        const float2 edge = v1 - v0;
+        const float rayCrossEdge = cross(ray, edge);
+        if (!almost_zero(rayCrossEdge)) {
+            const Rot normal = proxy.normal(i);
+            const float2 offset = normal * radius;
+            const float2 v0off = v0 + offset;
+            const float2 qSubP = v0off - ray0;
+            const float recip = 1.0f / rayCrossEdge;
+            const float t = cross(qSubP, edge) * recip;
+            const float u = cross(qSubP, ray) * recip;
+            if (t >= 0.0f && t <= 1.0f && u >= 0.0f && u <= 1.0f) {
+                if (minT > t) { minT = t; normalFound = normal; }
+            }
+        }
+        v0 = v1;
+    }
+    if (minT <= maxFraction) { RayOut o; o.hit = true; o.normal = rot_rotate(normalFound, xf.q); o.fraction = minT; return o; }
+    return ray_miss();
+}
+// the two tests of RayCast(const DynamicTree&, RayCastInput, cb) (RayCastOutput.cpp:255-271): the node's box overlaps the
+// segment's box, and the segment's line does not separate from the box (|dot(v, p1 - centre)| <= dot(|v|, extents))
+struct RaySeg { float2 p1; Rot v; float2 absV; Box seg; };
+PR_D Box ray_seg_box(float2 p1, float2 p2, float maxFraction)
+{ // GetAABB(const RayCastInput&), AABB.cpp:107-112
+    const float2 fractDelta = maxFraction * (p2 - p1);
+    const float2 e = p1 + fractDelta;
+    Box b; b.minx = stdmin(p1.x, e.x); b.maxx = stdmax(p1.x, e.x); b.miny = stdmin(p1.y, e.y); b.maxy = stdmax(p1.y, e.y);
+    return b;
+}
+PR_D bool ray_box_test(const RaySeg& r, const Box& box, float slack)
+{
+    if (!box_overlap(box, r.seg)) return false;
+    const float2 center = v2((box.minx + box.maxx) / 2.0f, (box.miny + box.maxy) / 2.0f);
+    const float2 extents = v2((box.maxx - box.minx) * 0.5f, (box.maxy - box.miny) * 0.5f);
+    const float separation = fabsf(dot(rotv(r.v), r.p1 - center)) - dot(r.absV, extents);
+    return !(separation > slack);
+}
+// One thread per ray. A leaf must pass the reference's two tests exactly (slack 0); an internal node -- whose box is the
+// union of its leaves' boxes, so it passes whenever one of them does, up to rounding -- is given a small slack instead.
+// mode PR_RAY_ALL: hits appended to out[]; PR_RAY_CLOSEST: out[ray] = least (fraction, proxy), the segment box shrinks with
+// the best hit so far (what a ClipRay callback makes the reference do).
+PR_D void ray_leaf(const DV& d, unsigned ri, unsigned px, RaySeg& r, float2 p1, float2 p2, float& maxFraction, unsigned qw, unsigned mode,
+                   unsigned cap, pr_ray_hit* out, unsigned* count, pr_ray_hit& best, unsigned& bestPx)
+{
+    if (d.nWorlds && d.b_world[d.p_body[px]] != qw) return;
+    if (!ray_box_test(r, box_from4(d.p_fat[px]), 0.0f)) return;
+    const unsigned body = d.p_body[px];
+    const RayOut o = ray_cast_proxy(child_view(d, d.p_cg[px]), p1, p2, maxFraction, xf_from4(d.b_xf[body]));
+    if (!o.hit) return;
+    const float2 point = p1 + (p2 - p1) * o.fraction;
+    pr_ray_hit h;
+    h.ray = ri; h.body = body; h.shape = d.p_shape[px]; h.child = d.p_child[px];
+    h.fraction = o.fraction; h.normal_x = o.normal.c; h.normal_y = o.normal.s; h.point_x = point.x; h.point_y = point.y;
+    if (mode == PR_RAY_ALL) {
+        const unsigned slot = atomicAdd(count, 1u);
+        if (slot < cap) out[slot] = h;
+    } else if (bestPx == INVALID || o.fraction < best.fraction || (o.fraction == best.fraction && px < bestPx)) {
+        best = h; bestPx = px;
+        maxFraction = o.fraction; r.seg = ray_seg_box(p1, p2, maxFraction); // ClipRay: :290-294
+    }
+}
+PR_KERNEL k_ray_cast(DV d, unsigned nRays, const float* rays5, const unsigned* rayWorld, unsigned nLeaves, const unsigned* sortedIdx,
+                     unsigned mode, unsigned cap, pr_ray_hit* out, unsigned* count)
+{
+    PR_PDL_ENTER();
+    const unsigned ri = PR_TID;
+    if (ri >= nRays) return;
+    const float2 p1 = v2(rays5[5u * ri], rays5[5u * ri + 1u]), p2 = v2(rays5[5u * ri + 2u], rays5[5u * ri + 3u]);
+    float maxFraction = rays5[5u * ri + 4u];
+    const unsigned qw = rayWorld ? rayWorld[ri] : 0u;
+    RaySeg r;
+    r.p1 = p1; r.v = rev_perp(unit_vector(p2 - p1, mkrot(0.0f, 0.0f))); r.absV = v2(fabsf(r.v.c), fabsf(r.v.s));
+    r.seg = ray_seg_box(p1, p2, maxFraction);
+    pr_ray_hit best; best.ray = ri; best.body = INVALID; best.shape = INVALID; best.child = INVALID;
+    best.fraction = 0.0f; best.normal_x = best.normal_y = best.point_x = best.point_y = 0.0f;
+    unsigned bestPx = INVALID;
+    if (nLeaves == 1u) ray_leaf(d, ri, 0u, r, p1, p2, maxFraction, qw, mode, cap, out, count, best, bestPx);
+    else {
+        const float slack = 1e-3f;
+        unsigned stack[64]; int sp = 0; stack[sp++] = 0u;
+        while (sp > 0) {
+            const unsigned node = stack[--sp];
+            const unsigned ch[2] = {d.bv_left[node], d.bv_right[node]};
+            const CBox cb = d.bv_cbox[node];
+            const float4 bx[2] = {cb.l, cb.r};
+            for (int c = 0; c < 2; ++c) {
+                if (ch[c] & LEAF_BIT) ray_leaf(d, ri, sortedIdx[ch[c] & ~LEAF_BIT], r, p1, p2, maxFraction, qw, mode, cap, out, count, best, bestPx);
+                else if (ray_box_test(r, box_from4(bx[c]), slack) && node_has_world(d, ch[c], qw)) {
+                    if (sp < 64) stack[sp++] = ch[c];
+                    else atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_STACK));
+                }
+            }
+        }
+    }
+    if (mode == PR_RAY_CLOSEST) out[ri] = best;
+}
+
 // AddContacts (AabbTreeWorld.cpp:2423-2547), creation part: sorted pair i gets its ContactID from the LIFO
 // free stack else by append (ObjectPool::Allocate), is appended to m_contacts in key order.
 PR_D void adj_append(const DV& d, unsigned b, unsigned id, bool eligible);

@@ -695,7 +695,7 @@ PR_KERNEL k_tb_solve(DV d, pr_step_conf conf, unsigned exactMode, unsigned scrat
     const unsigned nEvents = d.cnt->toiEvents;
     if (PR_TID == 0u) {
         if (nEvents == 0u) d.cnt->toiHalt = TB_DONE; // :1768 (threads that miss this flip see nEvents == 0 and do nothing either)
-        else { d.cnt->tbRounds += 1u; d.cnt->tbFound += nEvents; }
+        else { d.cnt->tbRounds += 1u; d.cnt->tbFound += nEvents; d.cnt->lateWhy[6] = d.cnt->lateWhy[6] * 100000u + nEvents; d.cnt->lateWhy[7] += 1u; }
     }
     if ((PR_TID & 31u) != 0u) return; // one warp per event, lane 0 working (see k_toi_solve)
     for (unsigned e = PR_TID >> 5; e < nEvents; e += PR_NTHREADS >> 5) toi_solve_event(d, conf, e, exactMode, scratchCap, mine);
@@ -831,7 +831,16 @@ PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratc
         const unsigned stop = d.cnt->adjOverflow ? TB_ADJ : d.cnt->error ? TB_ERROR
                             : (d.cnt->toiForceFull || nR > LATE_MAX_LIST || nC + nR > LATE_MAX_CAND) ? TB_BIG : TB_RUN;
         __syncthreads();
-        if (stop == TB_BIG) return; // too much for one block (or a body was woken): the list kernels enqueued behind this launch go on
+        if (stop == TB_BIG) { // (diagnostics: why)
+            if (PR_TID == 0u) {
+                if (d.cnt->toiForceFull) d.cnt->lateWhy[0] += 1u; else if (nR > LATE_MAX_LIST) d.cnt->lateWhy[1] += 1u; else d.cnt->lateWhy[2] += 1u;
+                if (nC > d.cnt->lateWhy[3]) d.cnt->lateWhy[3] = nC;
+                if (nR > d.cnt->lateWhy[4]) d.cnt->lateWhy[4] = nR;
+            }
+            return;
+        }
+        if (PR_TID == 0u && stop == TB_RUN) d.cnt->lateWhy[5] += 1u; // rounds run by the block
+        if (false) return; // too much for one block (or a body was woken): the list kernels enqueued behind this launch go on
         if (stop != TB_RUN) { if (PR_TID == 0u) d.cnt->toiHalt = stop; return; }
         if (PR_TID == 0u) { toi_open_round(d, roundId); d.cnt->toiCand2N = 0u; d.cnt->toiAtMaxSub += d.cnt->toiAtMaxLive; }
         // ---- UpdateContactTOIs over the invalidated contacts

@@ -718,6 +718,9 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             ++toiBatches;
             read_counters(w);
             const Counters c = w.hostCnt;
+            if (getenv("PR_TOI_DEBUG"))
+                std::fprintf(stderr, "toi batch: groups %u K %u rounds %u found %u halt %u | late: woken %u bigR %u bigC %u maxC %u maxR %u lateRounds %u candN %u listRoundEvents(base 1e5) %u listRounds %u\n", groups, K,
+                             c.tbRounds, c.tbFound, c.toiHalt, c.lateWhy[0], c.lateWhy[1], c.lateWhy[2], c.lateWhy[3], c.lateWhy[4], c.lateWhy[5], c.toiCandN, c.lateWhy[6], c.lateWhy[7]);
             round = c.toiRoundId; // (the device opened this many rounds so far this step)
             w.nOrder = c.devOrder; w.nFree = c.devFree; w.poolSize = c.devPool;
             w.toiListBound += c.tbAdded; w.bvhRefits += c.tbRounds;
@@ -1213,6 +1216,45 @@ int pr_query_aabb(const pr_world* cpw, uint32_t n_boxes, const float* boxes4, co
         for (unsigned i = 0; i < got; ++i) { hit_box[i] = tmp[4u * i]; hit_body[i] = tmp[4u * i + 1u]; hit_shape[i] = tmp[4u * i + 2u]; hit_child[i] = tmp[4u * i + 3u]; }
     }
     *n_out = total; // > cap: the caller's arrays were too short, the first `cap` hits were written
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_ray_cast(const pr_world* cpw, uint32_t n_rays, const float* rays5, const uint32_t* ray_world, uint32_t mode, uint32_t cap,
+                pr_ray_hit* hits, uint32_t* n_out)
+{
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    *n_out = 0;
+    if (mode != PR_RAY_ALL && mode != PR_RAY_CLOSEST) { w.error = "pr_ray_cast: unknown mode"; return PR_ERR_INVALID_ARGUMENT; }
+    if (w.d.nWorlds && !ray_world) { w.error = "pr_ray_cast on a batch arena needs the world index of every ray"; return PR_ERR_INVALID_ARGUMENT; }
+    if (mode == PR_RAY_CLOSEST && cap < n_rays) { w.error = "pr_ray_cast: PR_RAY_CLOSEST writes one hit per ray (cap < n_rays)"; return PR_ERR_INVALID_ARGUMENT; }
+    for (uint32_t i = 0; i < n_rays; ++i) // RayCastInput::maxFraction is a UnitInterval<Real>
+        if (!(rays5[5u * i + 4u] >= 0.0f && rays5[5u * i + 4u] <= 1.0f)) { w.error = "pr_ray_cast: maxFraction outside [0, 1]"; return PR_ERR_INVALID_ARGUMENT; }
+    const unsigned P = w.nProxies;
+    if (!n_rays) return PR_OK;
+    if (!P) {
+        if (mode == PR_RAY_CLOSEST) { for (uint32_t i = 0; i < n_rays; ++i) { std::memset(&hits[i], 0, sizeof(pr_ray_hit)); hits[i].ray = i; hits[i].body = hits[i].shape = hits[i].child = INVALID; } *n_out = n_rays; }
+        return PR_OK;
+    }
+    if (P > 1 && (!w.bvhValid || w.bvhLeaves != P)) { read_counters(w); rebuild_bvh(w); }
+    float* srays = static_cast<float*>(stage_buf(w, 0, 20u * static_cast<size_t>(n_rays) + 4u * n_rays));
+    unsigned* sworld = ray_world ? reinterpret_cast<unsigned*>(srays + 5u * static_cast<size_t>(n_rays)) : nullptr;
+    const unsigned outCap = mode == PR_RAY_CLOSEST ? n_rays : cap;
+    pr_ray_hit* sout = static_cast<pr_ray_hit*>(stage_buf(w, 1, sizeof(pr_ray_hit) * static_cast<size_t>(outCap) + 16u));
+    unsigned* scount = reinterpret_cast<unsigned*>(sout + outCap);
+    h2d(w, srays, rays5, 20u * static_cast<size_t>(n_rays));
+    if (ray_world) h2d(w, sworld, ray_world, 4u * n_rays);
+    dset(w, scount, 0, 4);
+    PR_LAUNCH(k_ray_cast, n_rays, w.stream, w.d, n_rays, srays, sworld, P, w.bvhSortedIdx, mode, outCap, sout, scount);
+    unsigned total = n_rays;
+    if (mode == PR_RAY_ALL) d2h(w, &total, scount, 4);
+    const unsigned got = std::min(total, outCap);
+    if (got) d2h(w, hits, sout, sizeof(pr_ray_hit) * static_cast<size_t>(got));
+    *n_out = total; // PR_RAY_ALL and > cap: the caller's array was too short, the first `cap` hits were written
+    read_counters(w);
+    throw_device_error(w);
     return PR_OK;
     API_CATCH(pw)
 }

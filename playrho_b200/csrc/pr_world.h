@@ -69,6 +69,7 @@ struct Counters {
     unsigned minSepFlip, maxIncBits, error, pad;
     unsigned boundsMinX, boundsMinY, boundsMaxX, boundsMaxY;
     unsigned nEvContact, nEvImpulse; // contact events of this step (pr_events): begin/end records, post-solve records
+    unsigned lateWhy[8]; // diagnostics (PR_TOI_DEBUG): hand-backs of k_tb_late by reason, list sizes seen, events per round
     unsigned colorStart[MAX_COLORS + 1];
     // batched TOI rounds (pr_toi_phase.cuh, k_tb_*): the host enqueues several rounds without reading anything back;
     // the contact-pool bookkeeping it normally keeps (World::nOrder/nFree/poolSize) is mirrored here meanwhile

@@ -25,7 +25,7 @@ EXPORTS = [
     "pr_get_inv_dt0", "pr_get_stream", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
     "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
-    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events",
+    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast",
 ]
 
 
@@ -50,6 +50,7 @@ def bind(lib):
     lib.pr_query_aabb.argtypes = [vp, u32, vp, vp, u32, vp, vp, vp, vp, C.POINTER(u32)]
     lib.pr_set_event_mask.argtypes = [vp, u32, u32]
     lib.pr_events.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+    lib.pr_ray_cast.argtypes = [vp, u32, vp, vp, u32, u32, vp, C.POINTER(u32)]
     lib.pr_get_revolute_joints.argtypes = [vp, u32, u32, vp]
     lib.pr_get_counts.argtypes = [vp, vp]
     lib.pr_get_contacts.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
@@ -212,6 +213,20 @@ class World:
                                              abi.ptr(out[2]), abi.ptr(out[3]), C.byref(k)))
             if k.value <= cap:
                 return tuple(o[:k.value] for o in out)
+            cap = k.value
+
+    def ray_cast(self, rays, mode=abi.RAY_ALL, ray_world=None, cap=None):
+        """RayCast(world, input, callback) for many rays (rows of p1 x, p1 y, p2 x, p2 y, maxFraction): abi.RAY_HIT rows --
+        every hit (RAY_ALL, order unspecified) or the closest hit per ray (RAY_CLOSEST, row i = ray i, body 0xFFFFFFFF = miss)."""
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 5)
+        rw = None if ray_world is None else np.ascontiguousarray(ray_world, dtype=np.uint32)
+        cap = len(rays) if mode == abi.RAY_CLOSEST else (cap or max(1024, 16 * len(rays)))
+        while True:
+            out = np.zeros(max(1, cap), abi.RAY_HIT)
+            k = u32(0)
+            self._chk(self.lib.pr_ray_cast(self.h, len(rays), abi.ptr(rays), abi.ptr(rw), mode, cap, abi.ptr(out), C.byref(k)))
+            if k.value <= cap:
+                return out[:k.value]
             cap = k.value
 
     def shift_origin(self, x, y):

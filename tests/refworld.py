@@ -190,6 +190,16 @@ class RefWorld:
         secs = self.lib.ref_step_timed(self.h, abi.ptr(conf), n, abi.ptr(st))
         return secs, st[0]
 
+    def ray_cast(self, rays, cap=1 << 16):
+        """The reference's RayCast(world, input, callback -> ResetRay) per ray: abi.RAY_HIT rows in callback order."""
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 5)
+        self.lib.ref_ray_cast.argtypes = [vp, u32, vp, u32, vp, vp]
+        out = np.zeros(cap, abi.RAY_HIT)
+        k = C.c_uint32(0)
+        self._chk(self.lib.ref_ray_cast(self.h, len(rays), abi.ptr(rays), cap, abi.ptr(out), C.byref(k)))
+        assert k.value <= cap
+        return out[:k.value]
+
     def shift_origin(self, x, y):
         self.lib.ref_shift_origin.argtypes = [vp, f32, f32]
         self._chk(self.lib.ref_shift_origin(self.h, x, y))
@@ -300,6 +310,15 @@ class OracleWorld:
         if r != 0:
             raise RuntimeError(self.lib.orc_last_error(self.h).decode())
         return st[0]
+
+    def ray_cast(self, rays, cap=1 << 16):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 5)
+        self.lib.orc_ray_cast.argtypes = [vp, u32, vp, u32, vp, vp]
+        out = np.zeros(cap, abi.RAY_HIT)
+        k = C.c_uint32(0)
+        self.lib.orc_ray_cast(self.h, len(rays), abi.ptr(rays), cap, abi.ptr(out), C.byref(k))
+        assert k.value <= cap
+        return out[:k.value]
 
     def shift_origin(self, x, y):
         self.lib.orc_shift_origin.argtypes = [vp, f32, f32]
