@@ -264,6 +264,14 @@ int pr_get_counts(const pr_world* w, pr_counts* out);
 int pr_get_contacts(const pr_world* w, uint32_t cap, pr_contact* contacts, pr_manifold* manifolds,
                     uint32_t* n_out);
 int pr_get_proxies(const pr_world* w, uint32_t cap, pr_proxy* proxies, uint32_t* n_out);
+/* SetContact(AabbTreeWorld&, ContactID, Contact) (AabbTreeWorld.cpp:2797-2831) for n contacts, rows[i].id naming the contact:
+ * the value replaces the contact -- i.e. its flag bits (enabled, touching, dirty/needs-updating, filter), friction, restitution
+ * and tangent speed -- after the reference's checks: PR_ERR_OUT_OF_RANGE for an id out of range, PR_ERR_INVALID_ARGUMENT for a
+ * freed id (WasDestroyed) or a change of the is-destroyed flag, either contactable, the impenetrable or sensor flag, the TOI or
+ * the TOI count. All rows are checked before any is applied.
+ * pr_set_manifolds = SetManifold (:2833-2846): type and point count must not change (points, normal and impulses may). */
+int pr_set_contacts(pr_world* w, uint32_t n, const pr_contact* rows);
+int pr_set_manifolds(pr_world* w, uint32_t n, const uint32_t* ids, const pr_manifold* rows);
 /* whole-state restore for stage-parity tests and clone-from-host: replaces every proxy's fat AABB
  * and the complete contact list (ids, flags, manifolds incl. stored impulses). */
 int pr_load_state(pr_world* w, uint32_t n_bodies, const pr_body* bodies, uint32_t n_proxies,

@@ -712,6 +712,35 @@ int ref_export_contacts(void* h, pr_contact* out, pr_manifold* manifolds, uint32
     REF_CATCH(-1)
 }
 
+// SetContact through the reference's API: the current value with the row's mutable fields put in (friction, restitution,
+// tangent speed, enabled / needs-updating flags). Returns 0, or -1 with the reference's exception text in ref_last_error.
+int ref_set_contact(void* h, const pr_contact* row)
+{
+    REF_TRY(h)
+    const auto id = MakeId<ContactID>(row->id);
+    auto c = GetContact(rw->world, id);
+    SetFriction(c, row->friction);
+    SetRestitution(c, row->restitution);
+    SetTangentSpeed(c, row->tangent_speed * 1_mps);
+    if (row->flags & PR_CONTACT_ENABLED) SetEnabled(c); else UnsetEnabled(c);
+    if (row->flags & PR_CONTACT_DIRTY) c.FlagForUpdating(); else c.UnflagForUpdating();
+    SetContact(rw->world, id, c);
+    return 0;
+    REF_CATCH(-1)
+}
+// SetManifold: the current manifold with the row's impulses (the one thing the reference lets a user change)
+int ref_set_manifold_impulses(void* h, uint32_t contact, const pr_manifold* row)
+{
+    REF_TRY(h)
+    const auto id = MakeId<ContactID>(contact);
+    auto m = GetManifold(rw->world, id);
+    if (m.GetPointCount() > 0) m.SetImpulses(0, row->jn0 * NewtonSecond, row->jt0 * NewtonSecond);
+    if (m.GetPointCount() > 1) m.SetImpulses(1, row->jn1 * NewtonSecond, row->jt1 * NewtonSecond);
+    SetManifold(rw->world, id, m);
+    return 0;
+    REF_CATCH(-1)
+}
+
 float ref_get_inv_dt0(void* h) { return GetInvDeltaTime(static_cast<RefWorld*>(h)->world); }
 
 // ---- stage functions of the reference on flat arrays ----

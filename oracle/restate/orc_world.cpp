@@ -1153,6 +1153,38 @@ int orc_ray_cast(const orc_world* w, uint32_t n_rays, const float* rays5, uint32
     return 0;
 }
 
+// SetContact / SetManifold, AabbTreeWorld.cpp:2797-2846 (-2: no such contact, -1: what the reference throws InvalidArgument for)
+int orc_set_contacts(orc_world* w, uint32_t n, const pr_contact* rows)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        const pr_contact& v = rows[i];
+        if (v.id >= w->contacts.size()) { w->error = "no such contact"; return -2; }
+        const pr_contact& e = w->contacts[v.id].c;
+        if (std::find(w->freeContacts.begin(), w->freeContacts.end(), v.id) != w->freeContacts.end()) { w->error = "contact identifier is destroyed"; return -1; }
+        const bool same = (e.flags & PR_CONTACT_DESTROYED) == (v.flags & PR_CONTACT_DESTROYED) && e.body_a == v.body_a && e.shape_a == v.shape_a &&
+                          e.child_a == v.child_a && e.body_b == v.body_b && e.shape_b == v.shape_b && e.child_b == v.child_b &&
+                          (e.flags & PR_CONTACT_IMPENETRABLE) == (v.flags & PR_CONTACT_IMPENETRABLE) && (e.flags & PR_CONTACT_SENSOR) == (v.flags & PR_CONTACT_SENSOR) &&
+                          (e.flags & PR_CONTACT_TOI) == (v.flags & PR_CONTACT_TOI) && (!(e.flags & PR_CONTACT_TOI) || e.toi == v.toi) && e.toi_count == v.toi_count;
+        if (!same) { w->error = "immutable contact field changed"; return -1; }
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        pr_contact& e = w->contacts[rows[i].id].c;
+        e.friction = rows[i].friction; e.restitution = rows[i].restitution; e.tangent_speed = rows[i].tangent_speed; e.flags = rows[i].flags & 0xFFu;
+    }
+    return 0;
+}
+int orc_set_manifolds(orc_world* w, uint32_t n, const uint32_t* ids, const pr_manifold* rows)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        if (ids[i] >= w->contacts.size()) { w->error = "no such contact"; return -2; }
+        const pr_manifold& m = w->contacts[ids[i]].m;
+        if (std::find(w->freeContacts.begin(), w->freeContacts.end(), ids[i]) != w->freeContacts.end()) { w->error = "contact identifier is destroyed"; return -1; }
+        if (m.type != rows[i].type || m.count != rows[i].count) { w->error = "cannot change manifold type / point count"; return -1; }
+    }
+    for (uint32_t i = 0; i < n; ++i) w->contacts[ids[i]].m = rows[i];
+    return 0;
+}
+
 int orc_set_event_mask(orc_world* w, uint32_t mask) { w->evMask = mask; return 0; }
 int orc_events(const orc_world* w, uint32_t kind, void* buf, uint32_t cap, uint32_t* n_out)
 { // call order (the order the reference's listeners are invoked in)

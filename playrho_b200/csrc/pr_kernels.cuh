@@ -2154,6 +2154,59 @@ PR_KERNEL k_import_contacts(DV d, unsigned n, const pr_contact* in, const pr_man
         d.c_order[i] = id;
     }
 }
+// SetContact(AabbTreeWorld&, ContactID, Contact), AabbTreeWorld.cpp:2797-2831: phase 0 validates every row against the device's
+// contact (what the reference throws for, as a code in *err: the least row's code wins), phase 1 applies "elem = value" -- the
+// mutable part: the flag bits, friction, restitution, tangent speed.
+enum { SETC_OK = 0, SETC_NO_SUCH = 1, SETC_DESTROYED = 2, SETC_IS_DESTROYED = 3, SETC_CONTACTABLE_A = 4, SETC_CONTACTABLE_B = 5,
+       SETC_IMPENETRABLE = 6, SETC_SENSOR = 7, SETC_TOI = 8, SETC_TOI_COUNT = 9, SETM_TYPE = 10, SETM_COUNT = 11 };
+PR_KERNEL k_set_contacts(DV d, unsigned n, const pr_contact* rows, unsigned poolSize, unsigned phase, unsigned long long* err)
+{
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    if (i >= n) return;
+    const pr_contact c = rows[i];
+    const unsigned id = c.id;
+    if (phase == 0u) {
+        unsigned code = SETC_OK;
+        if (id >= poolSize) code = SETC_NO_SUCH;
+        else {
+            const unsigned fl = d.c_flags[id];
+            const uint4 ab = d.c_ab[id], ids = d.c_ids[id];
+            if (d.c_key[id] == ~0ull) code = SETC_DESTROYED; // freed id (ObjectPool::FindFree): WasDestroyed
+            else if ((fl & PR_CONTACT_DESTROYED) != (c.flags & PR_CONTACT_DESTROYED)) code = SETC_IS_DESTROYED;
+            else if (ab.x != c.body_a || ids.x != c.shape_a || ids.y != c.child_a) code = SETC_CONTACTABLE_A;
+            else if (ab.y != c.body_b || ids.z != c.shape_b || ids.w != c.child_b) code = SETC_CONTACTABLE_B;
+            else if ((fl & PR_CONTACT_IMPENETRABLE) != (c.flags & PR_CONTACT_IMPENETRABLE)) code = SETC_IMPENETRABLE;
+            else if ((fl & PR_CONTACT_SENSOR) != (c.flags & PR_CONTACT_SENSOR)) code = SETC_SENSOR;
+            else if ((fl & PR_CONTACT_TOI) != (c.flags & PR_CONTACT_TOI) || ((fl & PR_CONTACT_TOI) && d.c_mat[id].w != c.toi)) code = SETC_TOI;
+            else if ((fl >> 8) != c.toi_count) code = SETC_TOI_COUNT;
+        }
+        if (code != SETC_OK) atomicMin(err, (static_cast<unsigned long long>(i) << 32) | code);
+    } else {
+        const float toi = d.c_mat[id].w;
+        d.c_mat[id] = make_float4(c.friction, c.restitution, c.tangent_speed, toi);
+        d.c_flags[id] = (c.flags & 0xFFu) | (d.c_flags[id] & ~0xFFu);
+    }
+}
+// SetManifold(AabbTreeWorld&, ContactID, const Manifold&), AabbTreeWorld.cpp:2833-2846 (same two phases)
+PR_KERNEL k_set_manifolds(DV d, unsigned n, const unsigned* ids, const pr_manifold* rows, unsigned poolSize, unsigned phase, unsigned long long* err)
+{
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    if (i >= n) return;
+    const unsigned id = ids[i];
+    const pr_manifold m = rows[i];
+    if (phase == 0u) {
+        unsigned code = SETC_OK;
+        if (id >= poolSize) code = SETC_NO_SUCH;
+        else if (d.c_key[id] == ~0ull) code = SETC_DESTROYED;
+        else { const uint4 m3 = d.m3[id]; if (m3.z != m.type) code = SETM_TYPE; else if (m3.w != m.count) code = SETM_COUNT; }
+        if (code != SETC_OK) atomicMin(err, (static_cast<unsigned long long>(i) << 32) | code);
+    } else {
+        d.m0[id] = make_float4(m.ln_x, m.ln_y, m.lp_x, m.lp_y); d.m1[id] = make_float4(m.p0_x, m.p0_y, m.p1_x, m.p1_y);
+        d.m2[id] = make_float4(m.jn0, m.jt0, m.jn1, m.jt1); d.m3[id] = make_uint4(m.cf0, m.cf1, m.type, m.count);
+    }
+}
 PR_KERNEL k_export_proxies(DV d, unsigned n, pr_proxy* out)
 {
     PR_PDL_ENTER();

@@ -1220,6 +1220,59 @@ int pr_query_aabb(const pr_world* cpw, uint32_t n_boxes, const float* boxes4, co
     API_CATCH(pw)
 }
 
+static int set_contact_error(World& w, unsigned long long e)
+{
+    const unsigned code = static_cast<unsigned>(e & 0xFFFFFFFFull);
+    static const char* msgs[] = {"", "no such contact", "contact identifier is destroyed", "cannot change is-destroyed value", "cannot change contactable A",
+                                 "cannot change contactable B", "change body A or B being impenetrable to change impenetrable state",
+                                 "change shape A or B being a sensor to change sensor state", "user may not change the TOI",
+                                 "user may not change the TOI count", "cannot change manifold type", "cannot change manifold point count"};
+    w.error = std::string(msgs[code < 12u ? code : 0u]) + " (row " + std::to_string(static_cast<unsigned>(e >> 32)) + ")";
+    return code == SETC_NO_SUCH ? PR_ERR_OUT_OF_RANGE : PR_ERR_INVALID_ARGUMENT;
+}
+
+int pr_set_contacts(pr_world* pw, uint32_t n, const pr_contact* rows)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    if (!w.stepComplete) { w.error = "SetContact: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    if (!n) return PR_OK;
+    pr_contact* srows = static_cast<pr_contact*>(stage_buf(w, 0, sizeof(pr_contact) * n));
+    unsigned long long* serr = static_cast<unsigned long long*>(stage_buf(w, 1, 8));
+    h2d(w, srows, rows, sizeof(pr_contact) * n);
+    dset(w, serr, 0xFF, 8);
+    PR_LAUNCH(k_set_contacts, n, w.stream, w.d, n, srows, w.poolSize, 0u, serr);
+    unsigned long long e = 0;
+    d2h(w, &e, serr, 8);
+    if (e != ~0ull) return set_contact_error(w, e);
+    PR_LAUNCH(k_set_contacts, n, w.stream, w.d, n, srows, w.poolSize, 1u, serr);
+    sync(w);
+    w.adjValid = false; // the enabled flag decides TOI candidacy (toi_static_eligible): rebuild the TOI list
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_set_manifolds(pr_world* pw, uint32_t n, const uint32_t* ids, const pr_manifold* rows)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    if (!w.stepComplete) { w.error = "SetManifold: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    if (!n) return PR_OK;
+    pr_manifold* srows = static_cast<pr_manifold*>(stage_buf(w, 0, sizeof(pr_manifold) * n + 4u * n));
+    unsigned* sids = reinterpret_cast<unsigned*>(srows + n);
+    unsigned long long* serr = static_cast<unsigned long long*>(stage_buf(w, 1, 8));
+    h2d(w, srows, rows, sizeof(pr_manifold) * n); h2d(w, sids, ids, 4u * n);
+    dset(w, serr, 0xFF, 8);
+    PR_LAUNCH(k_set_manifolds, n, w.stream, w.d, n, sids, srows, w.poolSize, 0u, serr);
+    unsigned long long e = 0;
+    d2h(w, &e, serr, 8);
+    if (e != ~0ull) return set_contact_error(w, e);
+    PR_LAUNCH(k_set_manifolds, n, w.stream, w.d, n, sids, srows, w.poolSize, 1u, serr);
+    sync(w);
+    return PR_OK;
+    API_CATCH(pw)
+}
+
 int pr_ray_cast(const pr_world* cpw, uint32_t n_rays, const float* rays5, const uint32_t* ray_world, uint32_t mode, uint32_t cap,
                 pr_ray_hit* hits, uint32_t* n_out)
 {

@@ -652,24 +652,68 @@ Contact GetContact(const CudaWorld& w, ContactID id)
     w.m->refreshContacts();
     return AtId(w.m->contactBuf, id, noSuchContactMsg);
 }
-void SetContact(CudaWorld& w, ContactID id, Contact)
-{
+void SetContact(CudaWorld& w, ContactID id, Contact value)
+{ // SetContact(AabbTreeWorld&, ContactID, Contact), :2797-2831 -- same checks, same exception types, then "elem = value"
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    (void)GetBody(w, GetBodyA(value));
+    (void)GetBody(w, GetBodyB(value));
+    { const auto shapeA = GetShape(w, GetShapeA(value)); (void)GetChild(shapeA, GetChildIndexA(value)); }
+    { const auto shapeB = GetShape(w, GetShapeB(value)); (void)GetChild(shapeB, GetChildIndexB(value)); }
     w.m->refreshContacts();
-    (void)AtId(w.m->contactBuf, id, noSuchContactMsg);
-    throw InvalidArgument(unsupportedMsg);
+    const auto& elem = AtId(w.m->contactBuf, id, noSuchContactMsg);
+    if (!w.m->contactLive[to_underlying(id)]) throw WasDestroyed{id, "ID is destroyed"};
+    if (elem.IsDestroyed() != value.IsDestroyed()) throw InvalidArgument("cannot change is-destroyed value");
+    if (elem.GetContactableA() != value.GetContactableA()) throw InvalidArgument("cannot change contactable A");
+    if (elem.GetContactableB() != value.GetContactableB()) throw InvalidArgument("cannot change contactable B");
+    if (IsImpenetrable(elem) != IsImpenetrable(value)) throw InvalidArgument("change body A or B being impenetrable to change impenetrable state");
+    if (IsSensor(elem) != IsSensor(value)) throw InvalidArgument("change shape A or B being a sensor to change sensor state");
+    if (GetToi(elem) != GetToi(value)) throw InvalidArgument("user may not change the TOI");
+    if (GetToiCount(elem) != GetToiCount(value)) throw InvalidArgument("user may not change the TOI count");
+    pr_contact row{};
+    row.id = static_cast<std::uint32_t>(to_underlying(id));
+    row.body_a = static_cast<std::uint32_t>(to_underlying(GetBodyA(value))); row.shape_a = static_cast<std::uint32_t>(to_underlying(GetShapeA(value)));
+    row.child_a = static_cast<std::uint32_t>(GetChildIndexA(value));
+    row.body_b = static_cast<std::uint32_t>(to_underlying(GetBodyB(value))); row.shape_b = static_cast<std::uint32_t>(to_underlying(GetShapeB(value)));
+    row.child_b = static_cast<std::uint32_t>(GetChildIndexB(value));
+    row.friction = static_cast<float>(GetFriction(value)); row.restitution = static_cast<float>(GetRestitution(value));
+    row.tangent_speed = static_cast<float>(Real(GetTangentSpeed(value) / MeterPerSecond));
+    row.toi = HasValidToi(value) ? static_cast<float>(*GetToi(value)) : 1.0f;
+    row.toi_count = GetToiCount(value);
+    row.flags = (IsTouching(value) ? PR_CONTACT_TOUCHING : 0u) | (IsEnabled(value) ? PR_CONTACT_ENABLED : 0u) | (NeedsFiltering(value) ? PR_CONTACT_FILTER : 0u) |
+                (HasValidToi(value) ? PR_CONTACT_TOI : 0u) | (NeedsUpdating(value) ? PR_CONTACT_DIRTY : 0u) | (IsSensor(value) ? PR_CONTACT_SENSOR : 0u) |
+                (IsDestroyed(value) ? PR_CONTACT_DESTROYED : 0u) | (IsImpenetrable(value) ? PR_CONTACT_IMPENETRABLE : 0u);
+    w.m->check(pr_set_contacts(w.m->h, 1u, &row), "pr_set_contacts");
+    w.m->contactBuf[to_underlying(id)] = value;
 }
 Manifold GetManifold(const CudaWorld& w, ContactID id)
 {
     w.m->refreshContacts();
     return AtId(w.m->manifoldBuf, id, "no such manifold");
 }
-void SetManifold(CudaWorld& w, ContactID id, const Manifold&)
-{
+void SetManifold(CudaWorld& w, ContactID id, const Manifold& value)
+{ // SetManifold(AabbTreeWorld&, ContactID, const Manifold&), :2833-2846
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
     w.m->refreshContacts();
-    (void)AtId(w.m->manifoldBuf, id, "no such manifold");
-    throw InvalidArgument(unsupportedMsg);
+    const auto& manifold = AtId(w.m->manifoldBuf, id, "no such manifold");
+    if (!w.m->contactLive[to_underlying(id)]) throw WasDestroyed{id, "ID is destroyed"};
+    if (manifold.GetType() != value.GetType()) throw InvalidArgument("cannot change manifold type");
+    if (manifold.GetPointCount() != value.GetPointCount()) throw InvalidArgument("cannot change manifold point count");
+    pr_manifold row{};
+    const auto ln = value.GetLocalNormal();
+    const auto lp = value.GetLocalPoint();
+    row.ln_x = static_cast<float>(ln.GetX()); row.ln_y = static_cast<float>(ln.GetY());
+    row.lp_x = static_cast<float>(Real(GetX(lp) / Meter)); row.lp_y = static_cast<float>(Real(GetY(lp) / Meter));
+    row.cf0 = row.cf1 = Pack(ContactFeature{ContactFeature::e_vertex, InvalidVertex, ContactFeature::e_vertex, InvalidVertex});
+    row.type = value.GetType() == Manifold::e_circles ? PR_MANIFOLD_CIRCLES : value.GetType() == Manifold::e_faceA ? PR_MANIFOLD_FACE_A
+             : value.GetType() == Manifold::e_faceB ? PR_MANIFOLD_FACE_B : PR_MANIFOLD_UNSET;
+    row.count = value.GetPointCount();
+    if (row.count > 0) { const auto p = value.GetPoint(0); row.p0_x = static_cast<float>(Real(GetX(p.localPoint) / Meter)); row.p0_y = static_cast<float>(Real(GetY(p.localPoint) / Meter));
+                         row.cf0 = Pack(p.contactFeature); row.jn0 = static_cast<float>(Real(p.normalImpulse / NewtonSecond)); row.jt0 = static_cast<float>(Real(p.tangentImpulse / NewtonSecond)); }
+    if (row.count > 1) { const auto p = value.GetPoint(1); row.p1_x = static_cast<float>(Real(GetX(p.localPoint) / Meter)); row.p1_y = static_cast<float>(Real(GetY(p.localPoint) / Meter));
+                         row.cf1 = Pack(p.contactFeature); row.jn1 = static_cast<float>(Real(p.normalImpulse / NewtonSecond)); row.jt1 = static_cast<float>(Real(p.tangentImpulse / NewtonSecond)); }
+    const std::uint32_t cid = static_cast<std::uint32_t>(to_underlying(id));
+    w.m->check(pr_set_manifolds(w.m->h, 1u, &cid, &row), "pr_set_manifolds");
+    w.m->manifoldBuf[to_underlying(id)] = value;
 }
 
 } // namespace playrho::b200

@@ -76,11 +76,28 @@ int main(int argc, char** argv)
             for (unsigned j = 0; j < imp.GetCount(); ++j) postImpulse[k] += static_cast<double>(Real(imp.GetEntryNormal(j) / NewtonSecond));
         });
     }
+    unsigned long setCalls = 0, setRefused = 0;
     const bool shift = argc > 3 && !std::strcmp(argv[3], "shift");
     const auto conf = StepConf{};
     double maxPos = 0, maxVel = 0;
     unsigned long touchMismatch = 0, contactCountMismatch = 0, toiEvents = 0, toiEventsRef = 0;
     for (int s = 0; s < steps; ++s) {
+        if (shift && s == steps / 3) { // SetContact / SetManifold through the World API on both worlds, and the refusals
+            for (World* w : {&ref, &cud}) {
+                for (const auto& kc : GetContacts(*w)) {
+                    const auto id = std::get<ContactID>(kc);
+                    auto c = GetContact(*w, id);
+                    SetFriction(c, GetFriction(c)); // (value unchanged: this test reports drift; the effect of edits is gated bit for bit in tests/test_set_contact.py)
+                    SetContact(*w, id, c);
+                    SetManifold(*w, id, GetManifold(*w, id));
+                    ++setCalls;
+                    auto bad = c;
+                    bad.SetToiCount(static_cast<Contact::substep_type>(GetToiCount(c) + 1));
+                    try { SetContact(*w, id, bad); } catch (const InvalidArgument&) { ++setRefused; }
+                }
+                try { SetContact(*w, ContactID(60000), Contact{}); } catch (const std::out_of_range&) { ++setRefused; } catch (const InvalidArgument&) { ++setRefused; }
+            }
+        }
         if (shift && s == steps / 2) { ShiftOrigin(ref, Length2{13.37_m, -2.25_m}); ShiftOrigin(cud, Length2{13.37_m, -2.25_m}); }
         const auto rs = Step(ref, conf);
         const auto cs = Step(cud, conf);
@@ -106,10 +123,10 @@ int main(int argc, char** argv)
     for (const auto& kc : GetContacts(cud)) points += GetManifold(cud, std::get<ContactID>(kc)).GetPointCount();
     std::printf("scene=%s steps=%d bodies=%u contacts_ref=%zu contacts_dev=%zu manifold_points_dev=%lu toi_events_ref=%lu toi_events_dev=%lu "
                 "steps_with_contact_count_mismatch=%lu steps_with_touching_set_mismatch=%lu max_pos_diff=%.6g max_vel_diff=%.6g type_is_cudaworld=%d "
-                "begin_ref=%lu begin_dev=%lu end_ref=%lu end_dev=%lu post_ref=%lu post_dev=%lu post_impulse_ref=%.6g post_impulse_dev=%.6g shifted=%d\n",
+                "begin_ref=%lu begin_dev=%lu end_ref=%lu end_dev=%lu post_ref=%lu post_dev=%lu post_impulse_ref=%.6g post_impulse_dev=%.6g shifted=%d set_contact_calls=%lu set_contact_refusals=%lu\n",
                 scene, steps, static_cast<unsigned>(nb), GetContacts(ref).size(), GetContacts(cud).size(), points, toiEventsRef, toiEvents,
                 contactCountMismatch, touchMismatch, maxPos, maxVel, TypeCast<b200::CudaWorld>(&cud) != nullptr ? 1 : 0,
-                nBegin[0], nBegin[1], nEnd[0], nEnd[1], nPost[0], nPost[1], postImpulse[0], postImpulse[1], shift ? 1 : 0);
+                nBegin[0], nBegin[1], nEnd[0], nEnd[1], nPost[0], nPost[1], postImpulse[0], postImpulse[1], shift ? 1 : 0, setCalls, setRefused);
     (void)badListenerRead;
     return 0;
 }

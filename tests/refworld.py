@@ -190,6 +190,20 @@ class RefWorld:
         secs = self.lib.ref_step_timed(self.h, abi.ptr(conf), n, abi.ptr(st))
         return secs, st[0]
 
+    def set_contacts(self, rows):
+        """SetContact per row (friction, restitution, tangent speed, enabled / needs-updating flags); raises with the
+        reference's exception text."""
+        self.lib.ref_set_contact.argtypes = [vp, vp]
+        for r in np.ascontiguousarray(rows, dtype=abi.CONTACT):
+            one = np.array([r], abi.CONTACT)
+            self._chk(self.lib.ref_set_contact(self.h, abi.ptr(one)))
+
+    def set_manifold_impulses(self, ids, rows):
+        self.lib.ref_set_manifold_impulses.argtypes = [vp, u32, vp]
+        for i, r in zip(ids, np.ascontiguousarray(rows, dtype=abi.MANIFOLD)):
+            one = np.array([r], abi.MANIFOLD)
+            self._chk(self.lib.ref_set_manifold_impulses(self.h, int(i), abi.ptr(one)))
+
     def ray_cast(self, rays, cap=1 << 16):
         """The reference's RayCast(world, input, callback -> ResetRay) per ray: abi.RAY_HIT rows in callback order."""
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 5)
@@ -310,6 +324,21 @@ class OracleWorld:
         if r != 0:
             raise RuntimeError(self.lib.orc_last_error(self.h).decode())
         return st[0]
+
+    def set_contacts(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=abi.CONTACT)
+        self.lib.orc_set_contacts.argtypes = [vp, u32, vp]
+        r = self.lib.orc_set_contacts(self.h, len(rows), abi.ptr(rows))
+        if r != 0:
+            raise RuntimeError(self.lib.orc_last_error(self.h).decode())
+
+    def set_manifolds(self, ids, rows):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=abi.MANIFOLD)
+        self.lib.orc_set_manifolds.argtypes = [vp, u32, vp, vp]
+        r = self.lib.orc_set_manifolds(self.h, len(ids), abi.ptr(ids), abi.ptr(rows))
+        if r != 0:
+            raise RuntimeError(self.lib.orc_last_error(self.h).decode())
 
     def ray_cast(self, rays, cap=1 << 16):
         rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 5)

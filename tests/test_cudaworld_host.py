@@ -78,6 +78,8 @@ def test_world_api_listeners_and_shift_origin_pyramid():
     two worlds as close as without it."""
     d = _parity("pyramid", 150, "shift")
     assert d["shifted"] == "1"
+    # SetContact / SetManifold on every contact of both worlds at step 50, plus one refused edit per contact and one unknown id
+    assert int(d["set_contact_calls"]) > 100 and int(d["set_contact_refusals"]) == int(d["set_contact_calls"]) + 2
     assert int(d["steps_with_contact_count_mismatch"]) == 0
     assert float(d["max_pos_diff"]) < 0.10
     assert int(d["begin_dev"]) > 0 and int(d["post_dev"]) > 0
