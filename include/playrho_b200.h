@@ -258,6 +258,12 @@ typedef struct pr_ray_hit {
 } pr_ray_hit;
 int pr_ray_cast(const pr_world* w, uint32_t n_rays, const float* rays5, const uint32_t* ray_world, uint32_t mode, uint32_t cap,
                 pr_ray_hit* hits, uint32_t* n_out);
+/* SetJoint(AabbTreeWorld&, JointID, Joint) (AabbTreeWorld.cpp:1108-1130) for revolute joints: rows[i] replaces joint ids[i] --
+ * anchors, reference angle, limits, motor (enable, speed, max torque) and the solver's stored impulses, exactly as the value
+ * says -- and both bodies are woken (Remove(JointID) :1192-1205). The bodies and collideConnected of a joint must stay what
+ * they are (PR_ERR_UNSUPPORTED otherwise: re-filtering the pair's contacts is not done on the device);
+ * PR_ERR_OUT_OF_RANGE for an unknown joint id. */
+int pr_set_revolute_joints(pr_world* w, uint32_t n, const uint32_t* ids, const pr_revolute_joint* rows);
 int pr_get_revolute_joints(const pr_world* w, uint32_t first, uint32_t n, pr_revolute_joint* rows);
 int pr_get_counts(const pr_world* w, pr_counts* out);
 /* contacts in m_contacts order (creation order), manifolds[i] belongs to contacts[i] */

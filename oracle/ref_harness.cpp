@@ -418,6 +418,19 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
     REF_CATCH(-1)
 }
 
+// SetJoint through the reference's API: the current RevoluteJointConf with the row's motor / limit fields put in
+int ref_set_revolute_joint(void* h, uint32_t joint, const pr_revolute_joint* row)
+{
+    REF_TRY(h)
+    const auto id = MakeId<JointID>(joint);
+    auto jc = TypeCast<RevoluteJointConf>(GetJoint(rw->world, id));
+    jc.enableMotor = row->enable_motor != 0; jc.motorSpeed = row->motor_speed * 1_rad / 1_s; jc.maxMotorTorque = row->max_motor_torque * 1_Nm;
+    jc.enableLimit = row->enable_limit != 0; jc.lowerAngle = row->lower_angle * 1_rad; jc.upperAngle = row->upper_angle * 1_rad;
+    SetJoint(rw->world, id, Joint{jc});
+    return 0;
+    REF_CATCH(-1)
+}
+
 int ref_set_body_velocity(void* h, uint32_t body, float vx, float vy, float w)
 {
     REF_TRY(h)

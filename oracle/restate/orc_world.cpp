@@ -1036,6 +1036,28 @@ int orc_create_revolute_joints(orc_world* w, uint32_t n, const pr_revolute_joint
     return 0;
 }
 
+// SetJoint, AabbTreeWorld.cpp:1108-1130 (same bodies, same collideConnected): Remove(id) wakes both bodies and takes the joint
+// out of their m_bodyJoints lists, Add(id) appends it again
+int orc_set_revolute_joints(orc_world* w, uint32_t n, const uint32_t* ids, const pr_revolute_joint* rows)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t id = ids[i];
+        if (id >= w->joints.size()) { w->error = "no such joint"; return -2; }
+        const pr_revolute_joint old = w->joints[id];
+        if (old.body_a != rows[i].body_a || old.body_b != rows[i].body_b || (old.collide_connected != 0) != (rows[i].collide_connected != 0)) { w->error = "unsupported"; return -6; }
+        for (uint32_t b : {old.body_a, old.body_b}) {
+            set_awake(w->bodies[b].b);
+            auto& lst = w->bodies[b].joints;
+            auto it = std::find(lst.begin(), lst.end(), id);
+            if (it != lst.end()) lst.erase(it);
+        }
+        w->joints[id] = rows[i];
+        w->bodies[rows[i].body_a].joints.push_back(id);
+        w->bodies[rows[i].body_b].joints.push_back(id);
+    }
+    return 0;
+}
+
 int orc_set_bodies(orc_world* w, uint32_t n, const uint32_t* ids, const pr_body* rows)
 {
     // SetBody (transform change path), AabbTreeWorld.cpp:2723-2795

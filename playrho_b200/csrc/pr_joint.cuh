@@ -238,6 +238,12 @@ PR_KERNEL k_isl_union_joints(DV d, unsigned nJoints)
     }
 }
 // Add(JointID) wakes both bodies (AabbTreeWorld.cpp:1159-1180)
+PR_KERNEL k_set_joints(DV d, unsigned n, const unsigned* ids, const pr_revolute_joint* rows)
+{ // SetJoint: Remove(id) wakes both bodies (:1192-1205), joint = def (:1128)
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    if (i < n) { const pr_revolute_joint j = rows[i]; d.jt[ids[i]] = j; body_set_awake(d, j.body_a); body_set_awake(d, j.body_b); }
+}
 PR_KERNEL k_joint_wake(DV d, unsigned first, unsigned n)
 {
     PR_PDL_ENTER();

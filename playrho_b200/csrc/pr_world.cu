@@ -1115,6 +1115,29 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
     API_CATCH(pw)
 }
 
+int pr_set_revolute_joints(pr_world* pw, uint32_t n, const uint32_t* ids, const pr_revolute_joint* rows)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    if (!w.stepComplete) { w.error = "SetJoint: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (ids[i] >= w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
+        const pr_revolute_joint& cur = w.joints[ids[i]];
+        if (cur.body_a != rows[i].body_a || cur.body_b != rows[i].body_b || (cur.collide_connected != 0u) != (rows[i].collide_connected != 0u)) {
+            w.error = "SetJoint: changing a joint's bodies or collideConnected is not supported by the device world"; return PR_ERR_UNSUPPORTED;
+        }
+    }
+    if (!n) return PR_OK;
+    pr_revolute_joint* srows = static_cast<pr_revolute_joint*>(stage_buf(w, 0, sizeof(pr_revolute_joint) * n));
+    unsigned* sids = static_cast<unsigned*>(stage_buf(w, 1, 4u * n));
+    h2d(w, srows, rows, sizeof(pr_revolute_joint) * n); h2d(w, sids, ids, 4u * n);
+    PR_LAUNCH(k_set_joints, n, w.stream, w.d, n, sids, srows);
+    sync(w);
+    for (uint32_t i = 0; i < n; ++i) w.joints[ids[i]] = rows[i];
+    return PR_OK;
+    API_CATCH(pw)
+}
+
 int pr_set_bodies(pr_world* pw, uint32_t n, const uint32_t* ids, const pr_body* rows)
 {
     API_TRY(pw)

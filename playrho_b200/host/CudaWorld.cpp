@@ -534,14 +534,8 @@ std::vector<JointID> GetJoints(const CudaWorld& w)
     for (std::size_t i = 0; i < w.m->joints.size(); ++i) r.push_back(MakeId<JointID>(static_cast<std::uint32_t>(i)));
     return r;
 }
-JointID CreateJoint(CudaWorld& w, Joint def)
-{ // CreateJoint(AabbTreeWorld&, Joint), :1132-1157
-    if (w.m->locked) throw WrongState(worldIsLockedMsg);
-    if (w.m->joints.size() >= MaxJoints) throw LengthError("CreateJoint: operation would exceed MaxJoints");
-    if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
-    if (GetType(def) != GetTypeID<RevoluteJointConf>()) throw InvalidArgument(unsupportedMsg);
-    const auto jc = TypeCast<RevoluteJointConf>(def);
-    (void)AtId(w.m->bodies, jc.bodyA, noSuchBodyMsg); (void)AtId(w.m->bodies, jc.bodyB, noSuchBodyMsg);
+static pr_revolute_joint ToJointRow(const RevoluteJointConf& jc)
+{
     pr_revolute_joint o{};
     o.body_a = static_cast<std::uint32_t>(to_underlying(jc.bodyA)); o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
     o.collide_connected = jc.collideConnected ? 1u : 0u;
@@ -553,6 +547,17 @@ JointID CreateJoint(CudaWorld& w, Joint def)
     o.lower_angle = jc.lowerAngle; o.upper_angle = jc.upperAngle;
     o.motor_speed = jc.motorSpeed; o.max_motor_torque = jc.maxMotorTorque;
     o.limit_state = static_cast<std::uint32_t>(jc.limitState);
+    return o;
+}
+JointID CreateJoint(CudaWorld& w, Joint def)
+{ // CreateJoint(AabbTreeWorld&, Joint), :1132-1157
+    if (w.m->locked) throw WrongState(worldIsLockedMsg);
+    if (w.m->joints.size() >= MaxJoints) throw LengthError("CreateJoint: operation would exceed MaxJoints");
+    if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
+    if (GetType(def) != GetTypeID<RevoluteJointConf>()) throw InvalidArgument(unsupportedMsg);
+    const auto jc = TypeCast<RevoluteJointConf>(def);
+    (void)AtId(w.m->bodies, jc.bodyA, noSuchBodyMsg); (void)AtId(w.m->bodies, jc.bodyB, noSuchBodyMsg);
+    const pr_revolute_joint o = ToJointRow(jc);
     w.m->refreshBodies();       // Add(JointID) wakes both bodies on the device: keep the host values in step
     w.m->uploadDirtyBodies();
     std::uint32_t first = 0;
@@ -572,11 +577,21 @@ Joint GetJoint(const CudaWorld& w, JointID id)
     jc.limitState = static_cast<LimitState>(r.limit_state);
     return Joint{jc};
 }
-void SetJoint(CudaWorld& w, JointID id, Joint)
-{
+void SetJoint(CudaWorld& w, JointID id, Joint def)
+{ // SetJoint(AabbTreeWorld&, JointID, Joint), :1108-1130 (revolute joints; bodies and collideConnected must stay: pr_set_revolute_joints)
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
     (void)AtId(w.m->joints, id, noSuchJointMsg);
-    throw InvalidArgument(unsupportedMsg);
+    if (const auto b = GetBodyA(def); b != InvalidBodyID) (void)AtId(w.m->bodies, b, noSuchBodyMsg);
+    if (const auto b = GetBodyB(def); b != InvalidBodyID) (void)AtId(w.m->bodies, b, noSuchBodyMsg);
+    if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
+    if (GetType(def) != GetTypeID<RevoluteJointConf>()) throw InvalidArgument(unsupportedMsg);
+    const pr_revolute_joint o = ToJointRow(TypeCast<RevoluteJointConf>(def));
+    w.m->refreshBodies();       // Remove(JointID) wakes both bodies on the device: keep the host values in step
+    w.m->uploadDirtyBodies();
+    const std::uint32_t jid = static_cast<std::uint32_t>(to_underlying(id));
+    w.m->check(pr_set_revolute_joints(w.m->h, 1u, &jid, &o), "pr_set_revolute_joints");
+    w.m->joints[to_underlying(id)] = std::move(def);
+    w.m->bodiesStale = true;
 }
 void Destroy(CudaWorld& w, JointID id)
 {

@@ -25,7 +25,7 @@ EXPORTS = [
     "pr_get_inv_dt0", "pr_get_stream", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
     "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
-    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_set_contacts", "pr_set_manifolds",
+    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_set_contacts", "pr_set_manifolds", "pr_set_revolute_joints",
 ]
 
 
@@ -52,6 +52,7 @@ def bind(lib):
     lib.pr_events.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
     lib.pr_ray_cast.argtypes = [vp, u32, vp, vp, u32, u32, vp, C.POINTER(u32)]
     lib.pr_set_contacts.argtypes = [vp, u32, vp]
+    lib.pr_set_revolute_joints.argtypes = [vp, u32, vp, vp]
     lib.pr_set_manifolds.argtypes = [vp, u32, vp, vp]
     lib.pr_get_revolute_joints.argtypes = [vp, u32, u32, vp]
     lib.pr_get_counts.argtypes = [vp, vp]
@@ -230,6 +231,12 @@ class World:
             if k.value <= cap:
                 return out[:k.value]
             cap = k.value
+
+    def set_joints(self, ids, rows):
+        """SetJoint for revolute joints (pr_set_revolute_joints)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=abi.REVOLUTE)
+        self._chk(self.lib.pr_set_revolute_joints(self.h, len(ids), abi.ptr(ids), abi.ptr(rows)))
 
     def set_contacts(self, rows):
         """SetContact for every row of an abi.CONTACT array (row["id"] names the contact)."""

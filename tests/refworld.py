@@ -190,6 +190,13 @@ class RefWorld:
         secs = self.lib.ref_step_timed(self.h, abi.ptr(conf), n, abi.ptr(st))
         return secs, st[0]
 
+    def set_joints(self, ids, rows):
+        """SetJoint per revolute joint (motor and limit fields of the row)."""
+        self.lib.ref_set_revolute_joint.argtypes = [vp, u32, vp]
+        for i, r in zip(ids, np.ascontiguousarray(rows, dtype=abi.REVOLUTE)):
+            one = np.array([r], abi.REVOLUTE)
+            self._chk(self.lib.ref_set_revolute_joint(self.h, int(i), abi.ptr(one)))
+
     def set_contacts(self, rows):
         """SetContact per row (friction, restitution, tangent speed, enabled / needs-updating flags); raises with the
         reference's exception text."""
@@ -324,6 +331,14 @@ class OracleWorld:
         if r != 0:
             raise RuntimeError(self.lib.orc_last_error(self.h).decode())
         return st[0]
+
+    def set_joints(self, ids, rows):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=abi.REVOLUTE)
+        self.lib.orc_set_revolute_joints.argtypes = [vp, u32, vp, vp]
+        r = self.lib.orc_set_revolute_joints(self.h, len(ids), abi.ptr(ids), abi.ptr(rows))
+        if r != 0:
+            raise RuntimeError(self.lib.orc_last_error(self.h).decode())
 
     def set_contacts(self, rows):
         rows = np.ascontiguousarray(rows, dtype=abi.CONTACT)
