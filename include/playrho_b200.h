@@ -220,6 +220,11 @@ int pr_create_bodies(pr_world* w, uint32_t n, const pr_body* bodies, const uint3
 int pr_create_revolute_joints(pr_world* w, uint32_t n, const pr_revolute_joint* joints,
                               uint32_t* first_id);
 
+/* Attach(World&, BodyID, ShapeID) = the SetBody whose new value has MORE shapes than the old one (AabbTreeWorld.cpp:2760-2786,
+ * GetOldAndNewShapeIDs :647-680): the added shapes are queued for proxy creation by the next Step (m_fixturesForProxies), in
+ * the order given (the reference appends them in ShapeID order). The body row itself (mass data after ResetMassData) is
+ * uploaded with pr_set_bodies as for any SetBody. Removing shapes from a body is not supported. */
+int pr_attach_shapes(pr_world* w, uint32_t body, uint32_t n, const uint32_t* shape_ids);
 /* ---- dirty-row upload / download (SetBody :2723 / GetBody; value semantics) ---- */
 int pr_set_bodies(pr_world* w, uint32_t n, const uint32_t* ids, const pr_body* rows);
 int pr_get_bodies(const pr_world* w, uint32_t first, uint32_t n, pr_body* rows);

@@ -418,6 +418,15 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
     REF_CATCH(-1)
 }
 
+// Attach(World&, BodyID, ShapeID, resetMassData = true), WorldBody.cpp
+int ref_attach_shape(void* h, uint32_t body, uint32_t shape)
+{
+    REF_TRY(h)
+    Attach(rw->world, MakeId<BodyID>(body), MakeId<ShapeID>(shape));
+    return 0;
+    REF_CATCH(-1)
+}
+
 // SetJoint through the reference's API: the current RevoluteJointConf with the row's motor / limit fields put in
 int ref_set_revolute_joint(void* h, uint32_t joint, const pr_revolute_joint* row)
 {

@@ -1036,6 +1036,13 @@ int orc_create_revolute_joints(orc_world* w, uint32_t n, const pr_revolute_joint
     return 0;
 }
 
+// SetBody with added shapes, AabbTreeWorld.cpp:2760-2786: Append(m_fixturesForProxies, id, added)
+int orc_attach_shapes(orc_world* w, uint32_t body, uint32_t n, const uint32_t* shape_ids)
+{
+    for (uint32_t i = 0; i < n; ++i) { w->bodies[body].shapes.push_back(shape_ids[i]); w->fixturesForProxies.emplace_back(body, shape_ids[i]); }
+    return 0;
+}
+
 // SetJoint, AabbTreeWorld.cpp:1108-1130 (same bodies, same collideConnected): Remove(id) wakes both bodies and takes the joint
 // out of their m_bodyJoints lists, Add(id) appends it again
 int orc_set_revolute_joints(orc_world* w, uint32_t n, const uint32_t* ids, const pr_revolute_joint* rows)

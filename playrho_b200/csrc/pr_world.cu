@@ -1075,6 +1075,24 @@ static int create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const 
     API_CATCH(pw)
 }
 
+int pr_attach_shapes(pr_world* pw, uint32_t body, uint32_t n, const uint32_t* shape_ids)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    if (!w.stepComplete) { w.error = "SetBody: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    if (body >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    for (uint32_t i = 0; i < n; ++i) if (shape_ids[i] >= w.nShapes) { w.error = "no such shape"; return PR_ERR_OUT_OF_RANGE; }
+    if (!n) return PR_OK;
+    unsigned flags = 0;
+    d2h(w, &flags, w.d.b_flags + body, 4);
+    if (!(flags & PR_BODY_ENABLED)) { w.error = "attaching shapes to a disabled body is not supported by the device world"; return PR_ERR_UNSUPPORTED; }
+    for (uint32_t i = 0; i < n; ++i) { w.fixturesForProxies.emplace_back(body, shape_ids[i]); w.bodyShapes[body].push_back(shape_ids[i]); } // Append(m_fixturesForProxies, ...) :2786
+    if (flags & PR_BODY_IMPENETRABLE) w.toiPossible = true;
+    w.adjValid = false; w.bpDirty = true; w.toiAlphaDirty = true;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
 int pr_create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const uint32_t* shape_offsets, const uint32_t* shape_ids, uint32_t* first_id)
 {
     return create_bodies(pw, n, bodies, shape_offsets, shape_ids, nullptr, first_id);

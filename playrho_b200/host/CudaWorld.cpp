@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <limits>
 #include <stdexcept>
 #include <string>
@@ -492,9 +493,18 @@ void SetBody(CudaWorld& w, BodyID id, Body value)
     if (IsDestroyed(elem)) throw WasDestroyed{id, "ID is destroyed"};
     if (IsDestroyed(value)) throw InvalidArgument("cannot change is-destroyed value");
     for (const auto& sid : value.GetShapes()) (void)AtId(w.m->shapes, sid, noSuchShapeMsg);
-    // what the device world cannot follow yet: changes that create/destroy proxies or contacts
-    if (GetType(elem) != GetType(value) || elem.GetShapes() != value.GetShapes() || IsEnabled(elem) != IsEnabled(value)) {
-        throw InvalidArgument(unsupportedMsg);
+    // what the device world cannot follow yet: changes that destroy proxies or contacts (type, enabled, removed shapes)
+    if (GetType(elem) != GetType(value) || IsEnabled(elem) != IsEnabled(value)) throw InvalidArgument(unsupportedMsg);
+    if (elem.GetShapes() != value.GetShapes()) { // GetOldAndNewShapeIDs, :647-680: multiset difference, in ShapeID order
+        if (!IsEnabled(value)) throw InvalidArgument(unsupportedMsg);
+        std::map<ShapeID, int> oldmap, newmap;
+        for (const auto& i : elem.GetShapes()) { ++oldmap[i]; --newmap[i]; }
+        for (const auto& i : value.GetShapes()) { --oldmap[i]; ++newmap[i]; }
+        for (const auto& e : oldmap) if (e.second > 0) throw InvalidArgument(unsupportedMsg); // a shape was detached
+        std::vector<std::uint32_t> added;
+        for (const auto& e : newmap) for (int i = 0; i < e.second; ++i) added.push_back(static_cast<std::uint32_t>(to_underlying(e.first)));
+        w.m->uploadDirtyBodies(); // (the device reads the body's flags)
+        w.m->check(pr_attach_shapes(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), static_cast<std::uint32_t>(added.size()), added.data()), "pr_attach_shapes");
     }
     elem = std::move(value);
     w.m->bodyDirty[to_underlying(id)] = 1;

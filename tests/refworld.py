@@ -190,6 +190,11 @@ class RefWorld:
         secs = self.lib.ref_step_timed(self.h, abi.ptr(conf), n, abi.ptr(st))
         return secs, st[0]
 
+    def attach_shape(self, body, shape):
+        """Attach(world, body, shape) with the mass data reset (the reference's default)."""
+        self.lib.ref_attach_shape.argtypes = [vp, u32, u32]
+        self._chk(self.lib.ref_attach_shape(self.h, int(body), int(shape)))
+
     def set_joints(self, ids, rows):
         """SetJoint per revolute joint (motor and limit fields of the row)."""
         self.lib.ref_set_revolute_joint.argtypes = [vp, u32, vp]
@@ -331,6 +336,16 @@ class OracleWorld:
         if r != 0:
             raise RuntimeError(self.lib.orc_last_error(self.h).decode())
         return st[0]
+
+    def attach_shapes(self, body, shape_ids):
+        ids = np.ascontiguousarray(shape_ids, dtype=np.uint32)
+        self.lib.orc_attach_shapes.argtypes = [vp, u32, u32, vp]
+        self.lib.orc_attach_shapes(self.h, int(body), len(ids), abi.ptr(ids))
+
+    def set_bodies(self, ids, rows):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        rows = np.ascontiguousarray(rows, dtype=abi.BODY)
+        self.lib.orc_set_bodies(self.h, len(ids), abi.ptr(ids), abi.ptr(rows))
 
     def set_joints(self, ids, rows):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
