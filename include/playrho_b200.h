@@ -220,6 +220,12 @@ int pr_create_bodies(pr_world* w, uint32_t n, const pr_body* bodies, const uint3
 int pr_create_revolute_joints(pr_world* w, uint32_t n, const pr_revolute_joint* joints,
                               uint32_t* first_id);
 
+/* SetShape(AabbTreeWorld&, ShapeID, Shape) (AabbTreeWorld.cpp:1284-1356) for a value whose geometry (children) and filter are
+ * what they were: friction, restitution, density and the sensor flag are replaced; every body using the shape is woken
+ * (:1297-1301); if the sensor flag, friction or restitution changed, every contact of the shape is flagged for updating and
+ * its bodies are woken (:1346-1354). Existing contacts keep their mixed friction / restitution and their sensor flag, like
+ * the reference's (they are set when a contact is created). Geometry or filter changes: not supported on the device. */
+int pr_set_shape_material(pr_world* w, uint32_t shape, float friction, float restitution, float density, uint32_t is_sensor);
 /* Attach(World&, BodyID, ShapeID) = the SetBody whose new value has MORE shapes than the old one (AabbTreeWorld.cpp:2760-2786,
  * GetOldAndNewShapeIDs :647-680): the added shapes are queued for proxy creation by the next Step (m_fixturesForProxies), in
  * the order given (the reference appends them in ShapeID order). The body row itself (mass data after ResetMassData) is
@@ -298,7 +304,8 @@ int pr_get_solve_order(const pr_world* w, uint32_t cap, uint32_t* contact_ids, u
 /* debug flags: bit 0 = record the solve order of every step (costs a device->host copy);
  * bit 1 = use the binned narrowphase, bit 2 = use the persistent fused solver kernel (two experiments that did not beat the
  * default kernels on B200; off by default, kept under test); bit 3 = TOI rounds through the list kernels only (no single-block
- * late rounds: A/B measurements) */
+ * late rounds: A/B measurements); bit 4 = hub rule of the colouring (colours capped at 24 when a few bodies carry very many
+ * constraints, the rest in the per-island serial tail: measured no faster on the tumbler arena) */
 int pr_set_debug(pr_world* w, uint32_t flags);
 int pr_get_step_profile(const pr_world* w, pr_step_profile* out);
 int pr_abi_sizeof(int which); /* sizeof of the POD structs above, for foreign-language mirrors */

@@ -418,6 +418,21 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
     REF_CATCH(-1)
 }
 
+// SetShape through the reference's API: the current shape with friction / restitution / density / sensor put in
+int ref_set_shape_material(void* h, uint32_t shape, float friction, float restitution, float density, uint32_t is_sensor)
+{
+    REF_TRY(h)
+    const auto id = MakeId<ShapeID>(shape);
+    auto s = GetShape(rw->world, id);
+    SetFriction(s, friction);
+    SetRestitution(s, restitution);
+    SetDensity(s, density * 1_kgpm2);
+    SetSensor(s, is_sensor != 0);
+    SetShape(rw->world, id, s);
+    return 0;
+    REF_CATCH(-1)
+}
+
 // Attach(World&, BodyID, ShapeID, resetMassData = true), WorldBody.cpp
 int ref_attach_shape(void* h, uint32_t body, uint32_t shape)
 {

@@ -1036,6 +1036,22 @@ int orc_create_revolute_joints(orc_world* w, uint32_t n, const pr_revolute_joint
     return 0;
 }
 
+// SetShape with unchanged geometry and filter, AabbTreeWorld.cpp:1284-1356
+int orc_set_shape_material(orc_world* w, uint32_t shape, float friction, float restitution, float density, uint32_t is_sensor)
+{
+    pr_shape& cur = w->shapes[shape];
+    for (OBody& ob : w->bodies) // :1297-1301 (m_bodyBuffer order)
+        if (std::find(ob.shapes.begin(), ob.shapes.end(), shape) != ob.shapes.end()) set_awake(ob.b);
+    if ((cur.is_sensor != 0) != (is_sensor != 0) || cur.friction != friction || cur.restitution != restitution) { // :1346-1354
+        for (uint32_t id : w->order) {
+            pr_contact& c = w->contacts[id].c;
+            if (c.shape_a == shape || c.shape_b == shape) { c.flags |= PR_CONTACT_DIRTY; set_awake(w->bodies[c.body_a].b); set_awake(w->bodies[c.body_b].b); }
+        }
+    }
+    cur.friction = friction; cur.restitution = restitution; cur.density = density; cur.is_sensor = is_sensor ? 1 : 0;
+    return 0;
+}
+
 // SetBody with added shapes, AabbTreeWorld.cpp:2760-2786: Append(m_fixturesForProxies, id, added)
 int orc_attach_shapes(orc_world* w, uint32_t body, uint32_t n, const uint32_t* shape_ids)
 {

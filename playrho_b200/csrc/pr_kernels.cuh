@@ -2154,6 +2154,28 @@ PR_KERNEL k_import_contacts(DV d, unsigned n, const pr_contact* in, const pr_man
         d.c_order[i] = id;
     }
 }
+// SetShape, AabbTreeWorld.cpp:1297-1301 and :1346-1354: wake the listed bodies; flag the shape's contacts for updating and wake
+// their bodies
+PR_KERNEL k_wake_bodies(DV d, unsigned n, const unsigned* ids)
+{
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    if (i < n) body_set_awake(d, ids[i]);
+}
+PR_KERNEL k_shape_flag_contacts(DV d, unsigned nOrder, unsigned shape)
+{
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        const uint4 ids = d.c_ids[id];
+        if (ids.x == shape || ids.z == shape) {
+            atomicOr(&d.c_flags[id], static_cast<unsigned>(PR_CONTACT_DIRTY));
+            const uint4 ab = d.c_ab[id];
+            body_set_awake(d, ab.x); body_set_awake(d, ab.y);
+        }
+    }
+}
 // SetContact(AabbTreeWorld&, ContactID, Contact), AabbTreeWorld.cpp:2797-2831: phase 0 validates every row against the device's
 // contact (what the reference throws for, as a code in *err: the least row's code wins), phase 1 applies "elem = value" -- the
 // mutable part: the flag bits, friction, restitution, tangent speed.

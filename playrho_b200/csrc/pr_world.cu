@@ -463,7 +463,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         w.nColors = static_cast<unsigned>(ranges.size()) + (tailCount ? 1u : 0u);
         if (nWork == nCons) w.colorsAtFull = w.nColors; // (this step coloured everything from scratch)
         else if (w.nColors > 24u && w.nColors > w.colorsAtFull + 8u) w.recolorAll = true; // persistent colours fragmented
-        if (w.colorCap == 64u && ranges.size() > 32u) { // hub rule (World::colorCap): cap the colours from the next step on?
+        if ((w.debugFlags & 16u) && w.colorCap == 64u && ranges.size() > 32u) { // hub rule (World::colorCap, opt-in): cap the colours from the next step on?
             unsigned long long beyond = tailCount;
             for (size_t c = COLOR_CAP_HUBS; c < ranges.size(); ++c) beyond += ranges[c].second;
             const unsigned islands = std::max(1u, w.hostCnt.islandsFound);
@@ -1071,6 +1071,31 @@ static int create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const 
     if (first_id) *first_id = w.nBodies;
     w.nBodies += n;
     w.adjValid = false; w.bpDirty = true; w.toiAlphaDirty = true;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_set_shape_material(pr_world* pw, uint32_t shape, float friction, float restitution, float density, uint32_t is_sensor)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    if (!w.stepComplete) { w.error = "SetShape: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    if (shape >= w.nShapes) { w.error = "no such shape"; return PR_ERR_OUT_OF_RANGE; }
+    pr_shape& cur = w.shapes[shape];
+    const bool touch = (cur.is_sensor != 0) != (is_sensor != 0) || cur.friction != friction || cur.restitution != restitution;
+    std::vector<unsigned> users;
+    for (unsigned b = 0; b < w.bodyShapes.size(); ++b)
+        if (std::find(w.bodyShapes[b].begin(), w.bodyShapes[b].end(), shape) != w.bodyShapes[b].end()) users.push_back(b);
+    if (!users.empty()) {
+        unsigned* sids = static_cast<unsigned*>(stage_buf(w, 1, 4u * users.size()));
+        h2d(w, sids, users.data(), 4u * users.size());
+        PR_LAUNCH(k_wake_bodies, static_cast<unsigned>(users.size()), w.stream, w.d, static_cast<unsigned>(users.size()), sids);
+    }
+    if (touch && w.nOrder) PR_LAUNCH(k_shape_flag_contacts, w.nOrder, w.stream, w.d, w.nOrder, shape);
+    cur.friction = friction; cur.restitution = restitution; cur.density = density; cur.is_sensor = is_sensor ? 1 : 0;
+    const float4 mat = make_float4(friction, restitution, is_sensor ? 1.0f : 0.0f, density);
+    h2d(w, w.d.sh_mat + shape, &mat, sizeof(float4));
+    sync(w);
     return PR_OK;
     API_CATCH(pw)
 }

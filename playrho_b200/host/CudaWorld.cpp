@@ -246,6 +246,8 @@ struct CudaWorld::Impl {
             const bool overflow = rc == PR_ERR_LENGTH || rc2 == PR_ERR_LENGTH;
             if (!overflow) { check(rc, "pr_events"); check(rc2, "pr_events"); }
             const std::uint32_t keptC = std::min(nc, eventCap), keptI = std::min(ni, eventCap);
+            // like inside the reference's Step, the world is locked while listeners run: mutators throw WrongState (:2156)
+            struct Lock { bool& f; explicit Lock(bool& b) : f(b) { f = true; } ~Lock() { f = false; } } lock{locked};
             for (std::uint32_t i = 0; i < keptC && (rc == PR_OK); ++i) {
                 const auto id = MakeId<ContactID>(ce[i].contact);
                 if (ce[i].kind == PR_EVENT_BEGIN) { if (beginContact) beginContact(id); }
@@ -653,9 +655,21 @@ Shape GetShape(const CudaWorld& w, ShapeID id) { return AtId(w.m->shapes, id, no
 void SetShape(CudaWorld& w, ShapeID id, Shape def)
 {
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
-    (void)AtId(w.m->shapes, id, noSuchShapeMsg);
+    auto& shape = AtId(w.m->shapes, id, noSuchShapeMsg);
     if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
-    throw InvalidArgument(unsupportedMsg);
+    // SetShape(AabbTreeWorld&, ShapeID, Shape), :1284-1356: the device follows values whose children (IsGeomChanged :778-793) and
+    // filter are unchanged -- friction, restitution, density, sensor
+    bool geometryChanged = GetChildCount(shape) != GetChildCount(def);
+    for (ChildCounter c = 0; !geometryChanged && c < GetChildCount(def); ++c) geometryChanged = GetChild(shape, c) != GetChild(def, c);
+    if (geometryChanged || GetFilter(shape) != GetFilter(def)) throw InvalidArgument(unsupportedMsg);
+    w.m->refreshBodies();       // bodies are woken on the device: keep the host values in step
+    w.m->uploadDirtyBodies();
+    w.m->check(pr_set_shape_material(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), static_cast<float>(Real(GetFriction(def))),
+                                     static_cast<float>(GetRestitution(def)), static_cast<float>(Real(GetDensity(def) / KilogramPerSquareMeter)),
+                                     IsSensor(def) ? 1u : 0u), "pr_set_shape_material");
+    shape = std::move(def);
+    w.m->bodiesStale = true;
+    w.m->mutated();
 }
 void Destroy(CudaWorld& w, ShapeID id)
 {

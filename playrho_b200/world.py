@@ -25,7 +25,7 @@ EXPORTS = [
     "pr_get_inv_dt0", "pr_get_stream", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
     "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
-    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_set_contacts", "pr_set_manifolds", "pr_set_revolute_joints", "pr_attach_shapes",
+    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_set_contacts", "pr_set_manifolds", "pr_set_revolute_joints", "pr_attach_shapes", "pr_set_shape_material",
 ]
 
 
@@ -54,6 +54,7 @@ def bind(lib):
     lib.pr_set_contacts.argtypes = [vp, u32, vp]
     lib.pr_set_revolute_joints.argtypes = [vp, u32, vp, vp]
     lib.pr_attach_shapes.argtypes = [vp, u32, u32, vp]
+    lib.pr_set_shape_material.argtypes = [vp, u32, f32, f32, f32, u32]
     lib.pr_set_manifolds.argtypes = [vp, u32, vp, vp]
     lib.pr_get_revolute_joints.argtypes = [vp, u32, u32, vp]
     lib.pr_get_counts.argtypes = [vp, vp]
@@ -232,6 +233,10 @@ class World:
             if k.value <= cap:
                 return out[:k.value]
             cap = k.value
+
+    def set_shape_material(self, shape, friction, restitution, density, sensor):
+        """SetShape with unchanged geometry and filter (pr_set_shape_material)."""
+        self._chk(self.lib.pr_set_shape_material(self.h, int(shape), friction, restitution, density, int(sensor)))
 
     def attach_shapes(self, body, shape_ids):
         """Attach(world, body, shape) for each shape id (pr_attach_shapes); upload the body row (new mass) with set_bodies."""

@@ -190,6 +190,10 @@ class RefWorld:
         secs = self.lib.ref_step_timed(self.h, abi.ptr(conf), n, abi.ptr(st))
         return secs, st[0]
 
+    def set_shape_material(self, shape, friction, restitution, density, sensor):
+        self.lib.ref_set_shape_material.argtypes = [vp, u32, f32, f32, f32, u32]
+        self._chk(self.lib.ref_set_shape_material(self.h, int(shape), friction, restitution, density, int(sensor)))
+
     def attach_shape(self, body, shape):
         """Attach(world, body, shape) with the mass data reset (the reference's default)."""
         self.lib.ref_attach_shape.argtypes = [vp, u32, u32]
@@ -336,6 +340,10 @@ class OracleWorld:
         if r != 0:
             raise RuntimeError(self.lib.orc_last_error(self.h).decode())
         return st[0]
+
+    def set_shape_material(self, shape, friction, restitution, density, sensor):
+        self.lib.orc_set_shape_material.argtypes = [vp, u32, f32, f32, f32, u32]
+        self.lib.orc_set_shape_material(self.h, int(shape), friction, restitution, density, int(sensor))
 
     def attach_shapes(self, body, shape_ids):
         ids = np.ascontiguousarray(shape_ids, dtype=np.uint32)

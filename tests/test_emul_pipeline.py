@@ -105,6 +105,7 @@ def test_emulated_tumbler_colour_overflow_tail_bit_exact():
     sc = scenes.tumbler(512).export_scene()
     conf = refworld.default_step_conf()
     gw = W.World(sc, lib=emul_lib(), record_solve_order=True)
+    gw.lib.pr_set_debug(gw.h, 1 | 16)  # record the solve order + the (opt-in) hub rule
     gw.set_toi_mode(0)
     orc = refworld.OracleWorld(sc)
     max_colors = last_colors = 0
