@@ -433,6 +433,9 @@ int ref_set_shape_material(void* h, uint32_t shape, float friction, float restit
     REF_CATCH(-1)
 }
 
+int ref_set_sub_stepping(void* h, int flag) { REF_TRY(h) SetSubStepping(rw->world, flag != 0); return 0; REF_CATCH(-1) }
+int ref_is_step_complete(void* h) { return IsStepComplete(static_cast<RefWorld*>(h)->world) ? 1 : 0; }
+
 // Attach(World&, BodyID, ShapeID, resetMassData = true), WorldBody.cpp
 int ref_attach_shape(void* h, uint32_t body, uint32_t shape)
 {

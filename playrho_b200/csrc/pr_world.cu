@@ -635,7 +635,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     w.hostCnt.proxiesMoved = 0; w.hostCnt.contactsUpdated = 0; w.hostCnt.toiDeferred = 0;
     w.hostCnt.toiRoundId = 0; w.hostCnt.toiReN[0] = w.hostCnt.toiReN[1] = 0; w.hostCnt.toiAtMaxLive = 0; w.hostCnt.toiForceFull = 0; w.hostCnt.toiHalt = TB_RUN;
     write_counters(w);
-    const bool exact = (w.toiMode == 0u);
+    const bool exact = (w.toiMode == 0u) || w.subStepping; // (sub-stepping = one TOI event per Step call, in the reference's order: :1779-1824)
     unsigned rounds = 0, round = 0, toiBatches = 0;
     if (!w.toiPossible) { // no contact of this world can be a TOI candidate: SolveToi finds nothing (:1768) and its final UpdateContacts skips all
         w.stepComplete = true;
