@@ -206,6 +206,7 @@ struct CudaWorld::Impl {
     // host mirrors of entity values
     mutable std::vector<Body> bodies;
     std::vector<char> bodyDirty;   // host value newer than the device row
+    std::vector<BodyID> bodiesForSync; // bodies whose transformation was set since the last Step (m_bodiesForSync)
     bool anyBodyDirty = false;
     mutable bool bodiesStale = false; // device rows newer than the host values (after a Step)
     std::vector<Shape> shapes;
@@ -343,7 +344,7 @@ CudaWorld::CudaWorld(const CudaWorld& o) : m{new Impl}
         const_cast<CudaWorld&>(o).m->uploadDirtyBodies();
         m->conf = o.m->conf; m->toiMode = o.m->toiMode;
         m->check(pr_clone(o.m->h, &m->h), "pr_clone");
-        m->bodies = o.m->bodies; m->bodyDirty = o.m->bodyDirty; m->anyBodyDirty = o.m->anyBodyDirty;
+        m->bodies = o.m->bodies; m->bodyDirty = o.m->bodyDirty; m->anyBodyDirty = o.m->anyBodyDirty; m->bodiesForSync = o.m->bodiesForSync;
         m->bodiesStale = false; m->shapes = o.m->shapes; m->joints = o.m->joints;
         m->shapeDestruction = o.m->shapeDestruction; m->detach = o.m->detach; m->jointDestruction = o.m->jointDestruction;
         m->beginContact = o.m->beginContact; m->endContact = o.m->endContact; m->preSolve = o.m->preSolve; m->postSolve = o.m->postSolve;
@@ -395,7 +396,7 @@ void Clear(CudaWorld& w) noexcept
         if (w.m->shapeDestruction) for (std::size_t i = 0; i < w.m->shapes.size(); ++i) w.m->shapeDestruction(MakeId<ShapeID>(static_cast<std::uint32_t>(i)));
     } catch (...) {}
     pr_clear(w.m->h);
-    w.m->bodies.clear(); w.m->bodyDirty.clear(); w.m->anyBodyDirty = false; w.m->bodiesStale = false;
+    w.m->bodies.clear(); w.m->bodyDirty.clear(); w.m->anyBodyDirty = false; w.m->bodiesStale = false; w.m->bodiesForSync.clear();
     w.m->shapes.clear(); w.m->joints.clear();
     w.m->mutated();
 }
@@ -412,6 +413,7 @@ StepStats Step(CudaWorld& w, const StepConf& conf)
     w.m->locked = false;
     w.m->check(rc, "pr_step");
     w.m->bodiesStale = true;
+    w.m->bodiesForSync.clear();
     w.m->mutated();
     w.m->deliverEvents();
     return ToStats(st);
@@ -462,7 +464,7 @@ std::vector<BodyID> GetBodies(const CudaWorld& w)
     for (std::size_t i = 0; i < w.m->bodies.size(); ++i) r.push_back(MakeId<BodyID>(static_cast<std::uint32_t>(i)));
     return r;
 }
-std::vector<BodyID> GetBodiesForProxies(const CudaWorld&) { return {}; }
+std::vector<BodyID> GetBodiesForProxies(const CudaWorld& w) { return w.m->bodiesForSync; } // m_bodiesForSync (:2792, cleared by Step :2181)
 
 BodyID CreateBody(CudaWorld& w, Body body)
 { // CreateBody(AabbTreeWorld&, Body), :1019-1060
@@ -508,6 +510,7 @@ void SetBody(CudaWorld& w, BodyID id, Body value)
         w.m->uploadDirtyBodies(); // (the device reads the body's flags)
         w.m->check(pr_attach_shapes(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), static_cast<std::uint32_t>(added.size()), added.data()), "pr_attach_shapes");
     }
+    if (GetTransformation(elem) != GetTransformation(value)) w.m->bodiesForSync.push_back(id); // :2787-2793
     elem = std::move(value);
     w.m->bodyDirty[to_underlying(id)] = 1;
     w.m->anyBodyDirty = true;
