@@ -275,6 +275,12 @@ int pr_ray_cast(const pr_world* w, uint32_t n_rays, const float* rays5, const ui
  * they are (PR_ERR_UNSUPPORTED otherwise: re-filtering the pair's contacts is not done on the device);
  * PR_ERR_OUT_OF_RANGE for an unknown joint id. */
 int pr_set_revolute_joints(pr_world* w, uint32_t n, const uint32_t* ids, const pr_revolute_joint* rows);
+/* Destroy(AabbTreeWorld&, JointID) (AabbTreeWorld.cpp:1215-1227): both bodies are woken, the joint stops taking part in islands,
+ * solves and the collideConnected filter, its row reads back zeroed with body_a == body_b == 0xFFFFFFFF, and its id is the
+ * next one pr_create_revolute_joints hands out (last freed first, like the reference's joint pool). Destroying a destroyed
+ * joint does nothing. (Contacts between the two bodies that a collideConnected == false joint had kept from forming appear
+ * when the broadphase next looks at their proxies, as in the reference.) */
+int pr_destroy_joints(pr_world* w, uint32_t n, const uint32_t* ids);
 int pr_get_revolute_joints(const pr_world* w, uint32_t first, uint32_t n, pr_revolute_joint* rows);
 int pr_get_counts(const pr_world* w, pr_counts* out);
 /* contacts in m_contacts order (creation order), manifolds[i] belongs to contacts[i] */

@@ -398,10 +398,12 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
 {
     REF_TRY(h)
     const auto n = static_cast<uint32_t>(GetJointRange(rw->world));
+    const auto live = GetJoints(rw->world);
     for (uint32_t i = 0; i < n && i < cap; ++i) {
-        const auto jc = TypeCast<RevoluteJointConf>(GetJoint(rw->world, MakeId<JointID>(i)));
         auto& o = out[i];
         std::memset(&o, 0, sizeof(o));
+        if (std::find(live.begin(), live.end(), MakeId<JointID>(i)) == live.end()) { o.body_a = o.body_b = 0xFFFFFFFFu; continue; } // destroyed
+        const auto jc = TypeCast<RevoluteJointConf>(GetJoint(rw->world, MakeId<JointID>(i)));
         o.body_a = to_underlying(jc.bodyA); o.body_b = to_underlying(jc.bodyB);
         o.collide_connected = jc.collideConnected ? 1u : 0u;
         o.local_anchor_a = pr_vec2{GetX(jc.localAnchorA), GetY(jc.localAnchorA)};
@@ -441,6 +443,14 @@ int ref_attach_shape(void* h, uint32_t body, uint32_t shape)
 {
     REF_TRY(h)
     Attach(rw->world, MakeId<BodyID>(body), MakeId<ShapeID>(shape));
+    return 0;
+    REF_CATCH(-1)
+}
+
+int ref_destroy_joint(void* h, uint32_t joint)
+{
+    REF_TRY(h)
+    Destroy(rw->world, MakeId<JointID>(joint));
     return 0;
     REF_CATCH(-1)
 }

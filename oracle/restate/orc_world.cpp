@@ -67,6 +67,7 @@ struct orc_world {
     std::vector<uint32_t> freeContacts;  // ObjectPool free list (LIFO), ObjectPool.hpp
     std::vector<uint32_t> order;         // m_contacts (ids, creation order)
     std::vector<pr_revolute_joint> joints;
+    std::vector<uint32_t> freeJoints;            // joint pool free list (LIFO)
     std::vector<orc::RevoluteWork> jointWork;
     std::vector<std::pair<uint32_t, uint32_t>> fixturesForProxies; // (body, shape)
     std::vector<uint32_t> proxiesForContacts;
@@ -1024,9 +1025,9 @@ int orc_create_bodies(orc_world* w, uint32_t n, const pr_body* bodies, const uin
 int orc_create_revolute_joints(orc_world* w, uint32_t n, const pr_revolute_joint* joints)
 {
     for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t id = static_cast<uint32_t>(w->joints.size());
-        w->joints.push_back(joints[i]);
-        w->jointWork.emplace_back();
+        uint32_t id;
+        if (!w->freeJoints.empty()) { id = w->freeJoints.back(); w->freeJoints.pop_back(); w->joints[id] = joints[i]; }
+        else { id = static_cast<uint32_t>(w->joints.size()); w->joints.push_back(joints[i]); w->jointWork.emplace_back(); }
         w->bodies[joints[i].body_a].joints.push_back(id);
         w->bodies[joints[i].body_b].joints.push_back(id);
         // Add(JointID) :1159-1180: set awake both bodies
@@ -1056,6 +1057,27 @@ int orc_set_shape_material(orc_world* w, uint32_t shape, float friction, float r
 int orc_attach_shapes(orc_world* w, uint32_t body, uint32_t n, const uint32_t* shape_ids)
 {
     for (uint32_t i = 0; i < n; ++i) { w->bodies[body].shapes.push_back(shape_ids[i]); w->fixturesForProxies.emplace_back(body, shape_ids[i]); }
+    return 0;
+}
+
+// Destroy(AabbTreeWorld&, JointID), :1215-1227 + Remove(JointID) :1177-1213
+int orc_destroy_joints(orc_world* w, uint32_t n, const uint32_t* ids)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t id = ids[i];
+        if (id >= w->joints.size()) { w->error = "no such joint"; return -2; }
+        pr_revolute_joint& j = w->joints[id];
+        if (j.body_a == 0xFFFFFFFFu) continue;
+        for (uint32_t b : {j.body_a, j.body_b}) {
+            set_awake(w->bodies[b].b);
+            auto& lst = w->bodies[b].joints;
+            auto it = std::find(lst.begin(), lst.end(), id);
+            if (it != lst.end()) lst.erase(it);
+        }
+        std::memset(&j, 0, sizeof(j));
+        j.body_a = j.body_b = 0xFFFFFFFFu;
+        w->freeJoints.push_back(id);
+    }
     return 0;
 }
 

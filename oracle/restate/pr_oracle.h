@@ -33,6 +33,7 @@ int orc_create_revolute_joints(orc_world* w, uint32_t n, const pr_revolute_joint
 int orc_set_bodies(orc_world* w, uint32_t n, const uint32_t* ids, const pr_body* rows);
 int orc_set_shape_material(orc_world* w, uint32_t shape, float friction, float restitution, float density, uint32_t is_sensor); /* SetShape :1284 */
 int orc_attach_shapes(orc_world* w, uint32_t body, uint32_t n, const uint32_t* shape_ids); /* SetBody with added shapes :2760-2786 */
+int orc_destroy_joints(orc_world* w, uint32_t n, const uint32_t* ids); /* Destroy(JointID) :1215 */
 int orc_set_revolute_joints(orc_world* w, uint32_t n, const uint32_t* ids, const pr_revolute_joint* rows); /* SetJoint :1108 */
 int orc_set_contacts(orc_world* w, uint32_t n, const pr_contact* rows);                 /* SetContact :2797 */
 int orc_set_manifolds(orc_world* w, uint32_t n, const uint32_t* ids, const pr_manifold* rows); /* SetManifold :2833 */

@@ -36,6 +36,7 @@ enum { LS_INACTIVE = 0, LS_AT_LOWER = 1, LS_AT_UPPER = 2, LS_EQUAL = 3 };
 // INVALID when no active island reached it or the other body is disabled
 PR_D unsigned joint_island(const DV& d, const pr_revolute_joint& j)
 {
+    if (j.body_a == INVALID) return INVALID; // destroyed joint
     const unsigned ia = d.b_island[j.body_a], ib = d.b_island[j.body_b];
     if (ia != INVALID) return f_enabled(d.b_flags[j.body_b]) ? ia : INVALID;
     if (ib != INVALID) return f_enabled(d.b_flags[j.body_a]) ? ib : INVALID;
@@ -234,7 +235,7 @@ PR_KERNEL k_isl_union_joints(DV d, unsigned nJoints)
     const unsigned i = PR_TID;
     if (i < nJoints) {
         const unsigned a = d.jt[i].body_a, b = d.jt[i].body_b;
-        if (d.b_island[a] != INVALID && d.b_island[b] != INVALID) uf_union(d.b_island, a, b);
+        if (a != INVALID && d.b_island[a] != INVALID && d.b_island[b] != INVALID) uf_union(d.b_island, a, b);
     }
 }
 // Add(JointID) wakes both bodies (AabbTreeWorld.cpp:1159-1180)

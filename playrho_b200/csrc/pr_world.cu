@@ -969,7 +969,7 @@ int pr_clone(const pr_world* src, pr_world** out)
     auto da = arrays(w); auto sa = arrays(s);
     for (size_t i = 0; i < da.size(); ++i) d2d(w, *da[i].slot, *sa[i].slot, da[i].elem * *cap_of(s, sa[i].g));
     d2d(w, w.d.cnt, s.d.cnt, sizeof(Counters));
-    w.shapes = s.shapes; w.children = s.children; w.bodyShapes = s.bodyShapes; w.joints = s.joints;
+    w.shapes = s.shapes; w.children = s.children; w.bodyShapes = s.bodyShapes; w.joints = s.joints; w.freeJoints = s.freeJoints;
     w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies;
     w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll; w.toiPossible = s.toiPossible; w.colorCap = s.colorCap;
     w.nJoints = s.nJoints; w.jointsSerial = s.jointsSerial; w.d.nNcPairs = s.d.nNcPairs;
@@ -991,7 +991,7 @@ int pr_clear(pr_world* pw)
     World& w = pw->w;
     w.shapes.clear(); w.children.clear(); w.bodyShapes.clear(); w.joints.clear(); w.fixturesForProxies.clear();
     w.bodyProxies.clear(); w.bpDirty = true; w.bvhValid = false; w.hashTombs = 0; w.toiAlphaDirty = true;
-    w.nJoints = 0; w.jointsSerial = false; w.d.nNcPairs = 0; w.bodyWorld.clear();
+    w.nJoints = 0; w.jointsSerial = false; w.d.nNcPairs = 0; w.bodyWorld.clear(); w.freeJoints.clear();
     w.nBodies = w.nShapes = w.nChildren = w.nVerts = w.nProxies = w.nOrder = w.nFree = w.poolSize = 0; w.maxTreeId = 0;
     w.anyBodySet = false; w.hashDirty = true; w.adjValid = false; w.stepComplete = true; w.toiPossible = false;
     reset_counters(w);
@@ -1100,6 +1100,26 @@ int pr_set_shape_material(pr_world* pw, uint32_t shape, float friction, float re
     API_CATCH(pw)
 }
 
+// joints that share a body cannot be solved by concurrent threads (one thread in id order then); body pairs joined by a
+// collideConnected == false joint, sorted, for the broadphase's ShouldCollide. Destroyed joints (bodies == INVALID) are skipped.
+static void refresh_joint_tables(World& w)
+{
+    std::unordered_map<unsigned, unsigned> uses;
+    std::vector<unsigned long long> nc;
+    for (const auto& j : w.joints) {
+        if (j.body_a == INVALID) continue;
+        ++uses[j.body_a]; ++uses[j.body_b];
+        if (!j.collide_connected) nc.push_back((static_cast<unsigned long long>(std::min(j.body_a, j.body_b)) << 32) | std::max(j.body_a, j.body_b));
+    }
+    w.jointsSerial = false;
+    for (const auto& u : uses) if (u.second > 1u) w.jointsSerial = true;
+    std::sort(nc.begin(), nc.end());
+    nc.erase(std::unique(nc.begin(), nc.end()), nc.end());
+    ensure(w, G_JOINT, static_cast<unsigned>(std::max<size_t>(nc.size(), w.joints.size()) + 1));
+    h2d(w, w.d.nc_pairs, nc.data(), sizeof(unsigned long long) * nc.size());
+    w.d.nNcPairs = static_cast<unsigned>(nc.size());
+}
+
 int pr_attach_shapes(pr_world* pw, uint32_t body, uint32_t n, const uint32_t* shape_ids)
 {
     API_TRY(pw)
@@ -1133,27 +1153,53 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
     if (w.d.nWorlds)
         for (uint32_t i = 0; i < n; ++i)
             if (w.bodyWorld[joints[i].body_a] != w.bodyWorld[joints[i].body_b]) { w.error = "joint between bodies of different worlds"; return PR_ERR_INVALID_ARGUMENT; }
+    if (!w.freeJoints.empty()) { // ids of destroyed joints are handed out again first, last freed first (ObjectPool::Allocate)
+        if (n != 1u) { w.error = "CreateJoint: create joints one at a time while destroyed joint ids are free"; return PR_ERR_UNSUPPORTED; }
+        const unsigned id = w.freeJoints.back();
+        w.freeJoints.pop_back();
+        w.joints[id] = joints[0];
+        h2d(w, w.d.jt + id, joints, sizeof(pr_revolute_joint));
+        refresh_joint_tables(w);
+        PR_LAUNCH(k_joint_wake, 1u, w.stream, w.d, id, 1u);
+        sync(w);
+        if (first_id) *first_id = id;
+        return PR_OK;
+    }
     w.joints.insert(w.joints.end(), joints, joints + n);
     ensure(w, G_JOINT, w.nJoints + n + 1);
     h2d(w, w.d.jt + w.nJoints, joints, sizeof(pr_revolute_joint) * n);
-    // joints that share a body cannot be solved by concurrent threads: fall back to one thread in id order
-    std::unordered_map<unsigned, unsigned> uses;
-    std::vector<unsigned long long> nc;
-    for (const auto& j : w.joints) {
-        ++uses[j.body_a]; ++uses[j.body_b];
-        if (!j.collide_connected) nc.push_back((static_cast<unsigned long long>(std::min(j.body_a, j.body_b)) << 32) | std::max(j.body_a, j.body_b));
-    }
-    w.jointsSerial = false;
-    for (const auto& u : uses) if (u.second > 1u) w.jointsSerial = true;
-    std::sort(nc.begin(), nc.end());
-    nc.erase(std::unique(nc.begin(), nc.end()), nc.end());
-    ensure(w, G_JOINT, static_cast<unsigned>(std::max<size_t>(nc.size(), w.nJoints + n) + 1));
-    h2d(w, w.d.nc_pairs, nc.data(), sizeof(unsigned long long) * nc.size());
-    w.d.nNcPairs = static_cast<unsigned>(nc.size());
+    refresh_joint_tables(w);
     PR_LAUNCH(k_joint_wake, n, w.stream, w.d, w.nJoints, n);
     sync(w);
     if (first_id) *first_id = w.nJoints;
     w.nJoints += n;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_destroy_joints(pr_world* pw, uint32_t n, const uint32_t* ids)
+{ // Destroy(AabbTreeWorld&, JointID), :1215-1227: Remove(id) wakes both bodies (:1192-1205), the id goes to the free list
+    API_TRY(pw)
+    World& w = pw->w;
+    if (!w.stepComplete) { w.error = "Destroy: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    for (uint32_t i = 0; i < n; ++i) if (ids[i] >= w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
+    std::vector<unsigned> wake;
+    for (uint32_t i = 0; i < n; ++i) {
+        pr_revolute_joint& j = w.joints[ids[i]];
+        if (j.body_a == INVALID) continue; // already destroyed: not in m_joints, nothing happens (:1222)
+        wake.push_back(j.body_a); wake.push_back(j.body_b);
+        std::memset(&j, 0, sizeof(j));
+        j.body_a = j.body_b = INVALID;
+        h2d(w, w.d.jt + ids[i], &j, sizeof(j));
+        w.freeJoints.push_back(ids[i]);
+    }
+    if (!wake.empty()) {
+        unsigned* sids = static_cast<unsigned*>(stage_buf(w, 1, 4u * wake.size()));
+        h2d(w, sids, wake.data(), 4u * wake.size());
+        PR_LAUNCH(k_wake_bodies, static_cast<unsigned>(wake.size()), w.stream, w.d, static_cast<unsigned>(wake.size()), sids);
+    }
+    refresh_joint_tables(w);
+    sync(w);
     return PR_OK;
     API_CATCH(pw)
 }
@@ -1166,6 +1212,7 @@ int pr_set_revolute_joints(pr_world* pw, uint32_t n, const uint32_t* ids, const 
     for (uint32_t i = 0; i < n; ++i) {
         if (ids[i] >= w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
         const pr_revolute_joint& cur = w.joints[ids[i]];
+        if (cur.body_a == INVALID) { w.error = "joint identifier is destroyed"; return PR_ERR_INVALID_ARGUMENT; }
         if (cur.body_a != rows[i].body_a || cur.body_b != rows[i].body_b || (cur.collide_connected != 0u) != (rows[i].collide_connected != 0u)) {
             w.error = "SetJoint: changing a joint's bodies or collideConnected is not supported by the device world"; return PR_ERR_UNSUPPORTED;
         }

@@ -143,7 +143,7 @@ struct World {
     std::vector<pr_shape> shapes;       // child_offset is global
     std::vector<pr_child> children;     // vertex_offset is global
     std::vector<std::vector<unsigned>> bodyShapes;
-    std::vector<pr_revolute_joint> joints;
+    std::vector<pr_revolute_joint> joints; std::vector<unsigned> freeJoints; // (a destroyed joint: bodies == INVALID; its id is re-used LIFO, ObjectPool)
     std::vector<std::pair<unsigned, unsigned>> fixturesForProxies;
     unsigned nBodies = 0, nShapes = 0, nChildren = 0, nVerts = 0, nProxies = 0;
     unsigned nOrder = 0, nFree = 0, poolSize = 0;  // contacts

@@ -210,7 +210,8 @@ struct CudaWorld::Impl {
     bool anyBodyDirty = false;
     mutable bool bodiesStale = false; // device rows newer than the host values (after a Step)
     std::vector<Shape> shapes;
-    std::vector<Joint> joints;
+    std::vector<Joint> joints;         // an empty Joint = destroyed (its id is in freeJoints and is handed out again, last freed first)
+    std::vector<std::uint32_t> freeJoints;
     // lazily downloaded contact state
     mutable bool contactsStale = true;
     mutable std::vector<KeyedContactID> contactIds;            // m_contacts order
@@ -345,7 +346,7 @@ CudaWorld::CudaWorld(const CudaWorld& o) : m{new Impl}
         m->conf = o.m->conf; m->toiMode = o.m->toiMode;
         m->check(pr_clone(o.m->h, &m->h), "pr_clone");
         m->bodies = o.m->bodies; m->bodyDirty = o.m->bodyDirty; m->anyBodyDirty = o.m->anyBodyDirty; m->bodiesForSync = o.m->bodiesForSync;
-        m->bodiesStale = false; m->shapes = o.m->shapes; m->joints = o.m->joints;
+        m->bodiesStale = false; m->shapes = o.m->shapes; m->joints = o.m->joints; m->freeJoints = o.m->freeJoints;
         m->shapeDestruction = o.m->shapeDestruction; m->detach = o.m->detach; m->jointDestruction = o.m->jointDestruction;
         m->beginContact = o.m->beginContact; m->endContact = o.m->endContact; m->preSolve = o.m->preSolve; m->postSolve = o.m->postSolve;
         m->eventCap = o.m->eventCap; m->updateEventMask();
@@ -397,7 +398,7 @@ void Clear(CudaWorld& w) noexcept
     } catch (...) {}
     pr_clear(w.m->h);
     w.m->bodies.clear(); w.m->bodyDirty.clear(); w.m->anyBodyDirty = false; w.m->bodiesStale = false; w.m->bodiesForSync.clear();
-    w.m->shapes.clear(); w.m->joints.clear();
+    w.m->shapes.clear(); w.m->joints.clear(); w.m->freeJoints.clear();
     w.m->mutated();
 }
 
@@ -527,6 +528,7 @@ std::vector<std::pair<BodyID, JointID>> GetJoints(const CudaWorld& w, BodyID id)
     (void)AtId(w.m->bodies, id, noSuchBodyMsg);
     std::vector<std::pair<BodyID, JointID>> r;
     for (std::size_t i = 0; i < w.m->joints.size(); ++i) {
+        if (!w.m->joints[i].has_value()) continue;
         const auto a = GetBodyA(w.m->joints[i]), b = GetBodyB(w.m->joints[i]);
         if (a == id) r.emplace_back(b, MakeId<JointID>(static_cast<std::uint32_t>(i)));
         else if (b == id) r.emplace_back(a, MakeId<JointID>(static_cast<std::uint32_t>(i)));
@@ -546,7 +548,7 @@ JointCounter GetJointRange(const CudaWorld& w) noexcept { return static_cast<Joi
 std::vector<JointID> GetJoints(const CudaWorld& w)
 {
     std::vector<JointID> r;
-    for (std::size_t i = 0; i < w.m->joints.size(); ++i) r.push_back(MakeId<JointID>(static_cast<std::uint32_t>(i)));
+    for (std::size_t i = 0; i < w.m->joints.size(); ++i) if (w.m->joints[i].has_value()) r.push_back(MakeId<JointID>(static_cast<std::uint32_t>(i)));
     return r;
 }
 static pr_revolute_joint ToJointRow(const RevoluteJointConf& jc)
@@ -577,13 +579,17 @@ JointID CreateJoint(CudaWorld& w, Joint def)
     w.m->uploadDirtyBodies();
     std::uint32_t first = 0;
     w.m->check(pr_create_revolute_joints(w.m->h, 1, &o, &first), "pr_create_revolute_joints");
-    w.m->joints.push_back(std::move(def));
+    if (first < w.m->joints.size()) { // a destroyed joint's id came back
+        w.m->joints[first] = std::move(def);
+        w.m->freeJoints.erase(std::remove(w.m->freeJoints.begin(), w.m->freeJoints.end(), first), w.m->freeJoints.end());
+    } else w.m->joints.push_back(std::move(def));
     w.m->bodiesStale = true;
     return MakeId<JointID>(first);
 }
 Joint GetJoint(const CudaWorld& w, JointID id)
 { // the solver-written fields (impulses, limit state) come back from the device
     auto& elem = AtId(w.m->joints, id, noSuchJointMsg);
+    if (!elem.has_value()) throw WasDestroyed{id, "ID is destroyed"};
     pr_revolute_joint r{};
     w.m->check(pr_get_revolute_joints(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), 1, &r), "pr_get_revolute_joints");
     auto jc = TypeCast<RevoluteJointConf>(elem);
@@ -595,7 +601,7 @@ Joint GetJoint(const CudaWorld& w, JointID id)
 void SetJoint(CudaWorld& w, JointID id, Joint def)
 { // SetJoint(AabbTreeWorld&, JointID, Joint), :1108-1130 (revolute joints; bodies and collideConnected must stay: pr_set_revolute_joints)
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
-    (void)AtId(w.m->joints, id, noSuchJointMsg);
+    if (!AtId(w.m->joints, id, noSuchJointMsg).has_value()) throw WasDestroyed{id, "ID is destroyed"};
     if (const auto b = GetBodyA(def); b != InvalidBodyID) (void)AtId(w.m->bodies, b, noSuchBodyMsg);
     if (const auto b = GetBodyB(def); b != InvalidBodyID) (void)AtId(w.m->bodies, b, noSuchBodyMsg);
     if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
@@ -609,10 +615,17 @@ void SetJoint(CudaWorld& w, JointID id, Joint def)
     w.m->bodiesStale = true;
 }
 void Destroy(CudaWorld& w, JointID id)
-{
+{ // Destroy(AabbTreeWorld&, JointID), :1215-1227
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
-    (void)AtId(w.m->joints, id, noSuchJointMsg);
-    throw InvalidArgument(unsupportedMsg);
+    auto& elem = AtId(w.m->joints, id, noSuchJointMsg);
+    if (!elem.has_value()) return; // not in m_joints any more: nothing happens
+    w.m->refreshBodies();       // Remove(JointID) wakes both bodies on the device: keep the host values in step
+    w.m->uploadDirtyBodies();
+    const std::uint32_t jid = static_cast<std::uint32_t>(to_underlying(id));
+    w.m->check(pr_destroy_joints(w.m->h, 1u, &jid), "pr_destroy_joints");
+    elem = Joint{};
+    w.m->freeJoints.push_back(jid);
+    w.m->bodiesStale = true;
 }
 
 // ---- shapes

@@ -25,7 +25,7 @@ EXPORTS = [
     "pr_get_inv_dt0", "pr_get_stream", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
     "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
-    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_set_contacts", "pr_set_manifolds", "pr_set_revolute_joints", "pr_attach_shapes", "pr_set_shape_material",
+    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_set_contacts", "pr_set_manifolds", "pr_set_revolute_joints", "pr_attach_shapes", "pr_set_shape_material", "pr_destroy_joints",
 ]
 
 
@@ -54,6 +54,7 @@ def bind(lib):
     lib.pr_set_contacts.argtypes = [vp, u32, vp]
     lib.pr_set_revolute_joints.argtypes = [vp, u32, vp, vp]
     lib.pr_attach_shapes.argtypes = [vp, u32, u32, vp]
+    lib.pr_destroy_joints.argtypes = [vp, u32, vp]
     lib.pr_set_shape_material.argtypes = [vp, u32, f32, f32, f32, u32]
     lib.pr_set_manifolds.argtypes = [vp, u32, vp, vp]
     lib.pr_get_revolute_joints.argtypes = [vp, u32, u32, vp]
@@ -242,6 +243,16 @@ class World:
         """Attach(world, body, shape) for each shape id (pr_attach_shapes); upload the body row (new mass) with set_bodies."""
         ids = np.ascontiguousarray(shape_ids, dtype=np.uint32)
         self._chk(self.lib.pr_attach_shapes(self.h, int(body), len(ids), abi.ptr(ids)))
+
+    def destroy_joints(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._chk(self.lib.pr_destroy_joints(self.h, len(ids), abi.ptr(ids)))
+
+    def create_joints(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=abi.REVOLUTE)
+        first = u32(0)
+        self._chk(self.lib.pr_create_revolute_joints(self.h, len(rows), abi.ptr(rows), C.byref(first)))
+        return first.value
 
     def set_joints(self, ids, rows):
         """SetJoint for revolute joints (pr_set_revolute_joints)."""

@@ -199,6 +199,10 @@ class RefWorld:
         self.lib.ref_attach_shape.argtypes = [vp, u32, u32]
         self._chk(self.lib.ref_attach_shape(self.h, int(body), int(shape)))
 
+    def destroy_joint(self, joint):
+        self.lib.ref_destroy_joint.argtypes = [vp, u32]
+        self._chk(self.lib.ref_destroy_joint(self.h, int(joint)))
+
     def set_joints(self, ids, rows):
         """SetJoint per revolute joint (motor and limit fields of the row)."""
         self.lib.ref_set_revolute_joint.argtypes = [vp, u32, vp]
@@ -354,6 +358,15 @@ class OracleWorld:
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         rows = np.ascontiguousarray(rows, dtype=abi.BODY)
         self.lib.orc_set_bodies(self.h, len(ids), abi.ptr(ids), abi.ptr(rows))
+
+    def destroy_joints(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self.lib.orc_destroy_joints.argtypes = [vp, u32, vp]
+        self.lib.orc_destroy_joints(self.h, len(ids), abi.ptr(ids))
+
+    def create_joints(self, rows):
+        rows = np.ascontiguousarray(rows, dtype=abi.REVOLUTE)
+        self.lib.orc_create_revolute_joints(self.h, len(rows), abi.ptr(rows))
 
     def set_joints(self, ids, rows):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
