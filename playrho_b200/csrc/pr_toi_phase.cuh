@@ -831,16 +831,15 @@ PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratc
         const unsigned stop = d.cnt->adjOverflow ? TB_ADJ : d.cnt->error ? TB_ERROR
                             : (d.cnt->toiForceFull || nR > LATE_MAX_LIST || nC + nR > LATE_MAX_CAND) ? TB_BIG : TB_RUN;
         __syncthreads();
-        if (stop == TB_BIG) { // (diagnostics: why)
-            if (PR_TID == 0u) {
+        if (stop == TB_BIG) { // too much for one block (or a body was woken): the list kernels enqueued behind this launch go on
+            if (PR_TID == 0u) { // diagnostics for PR_TOI_DEBUG: why, and how long the lists were
                 if (d.cnt->toiForceFull) d.cnt->lateWhy[0] += 1u; else if (nR > LATE_MAX_LIST) d.cnt->lateWhy[1] += 1u; else d.cnt->lateWhy[2] += 1u;
                 if (nC > d.cnt->lateWhy[3]) d.cnt->lateWhy[3] = nC;
                 if (nR > d.cnt->lateWhy[4]) d.cnt->lateWhy[4] = nR;
             }
             return;
         }
-        if (PR_TID == 0u && stop == TB_RUN) d.cnt->lateWhy[5] += 1u; // rounds run by the block
-        if (false) return; // too much for one block (or a body was woken): the list kernels enqueued behind this launch go on
+        if (PR_TID == 0u && stop == TB_RUN) d.cnt->lateWhy[5] += 1u; // (diagnostics: rounds run by the block)
         if (stop != TB_RUN) { if (PR_TID == 0u) d.cnt->toiHalt = stop; return; }
         if (PR_TID == 0u) { toi_open_round(d, roundId); d.cnt->toiCand2N = 0u; d.cnt->toiAtMaxSub += d.cnt->toiAtMaxLive; }
         // ---- UpdateContactTOIs over the invalidated contacts
