@@ -119,3 +119,63 @@ def test_cuda_batch_arena_at_scale_invariants():
     assert islands >= n_worlds  # at least the enclosure's island in every world
     gw2, _, _ = _big_arena(n_worlds, n_sq, steps, add_steps)
     assert gw2.bodies().tobytes() == rows.tobytes()
+
+
+def _arena_queries_vs_oracle(lib, device, n_worlds=4, n_squares=25, steps=90):
+    """Contact events and ray casts on an arena: events of the arena == events of the filter-layered oracle world; a ray cast
+    in world w reports exactly the oracle's hits on bodies of world w (shapes of other worlds overlap it in space)."""
+    units = [scenes_np.tumbler(n_squares, seed=12345 + w) for w in range(n_worlds)]
+    plain, world = scenes_np.merge_worlds(units)
+    layered, _ = scenes_np.merge_worlds(units, layer_filters=True)
+    conf = scenes_np.tumbler_step_conf(refworld.default_step_conf())
+    gw = W.Batch(n_worlds, lib=lib, device=device, record_solve_order=True)
+    gw.set_toi_mode(0)
+    gw.create_shapes(plain)
+    gw.create_bodies(plain["bodies"], world, plain["shape_offsets"], plain["shape_ids"])
+    gw.create_joints(plain["joints"])
+    orc = refworld.OracleWorld(layered)
+    mask = abi.EVENT_BEGIN | abi.EVENT_END | abi.EVENT_POST_SOLVE
+    gw.set_event_mask(mask, 1 << 16); orc.set_event_mask(mask)
+    n_begin = n_post = 0
+    for s in range(steps):
+        gw.step(conf)
+        orc.step(conf, order=gw.solve_order()[0])
+        ge = gw.events(abi.EVENT_BEGIN | abi.EVENT_END)
+        oe = orc.events(abi.EVENT_BEGIN | abi.EVENT_END)
+        oe = oe[np.lexsort((oe["contact"], oe["kind"]))]
+        assert_bits(ge, oe, "step %d begin/end events" % s)
+        gi, oi = gw.events(abi.EVENT_POST_SOLVE), orc.events(abi.EVENT_POST_SOLVE)
+        key = lambda e: e[np.lexsort((np.ascontiguousarray(e["normal"]).view(np.uint32)[:, 0], e["iterations"], e["contact"], e["phase"]))]
+        assert_bits(key(gi), key(oi), "step %d post-solve events" % s)
+        n_begin += int((oe["kind"] == abi.EVENT_BEGIN).sum()); n_post += len(oi)
+    assert n_begin > n_worlds and n_post > 100
+    assert_bits(gw.bodies(), orc.bodies(), "bodies")
+    px = gw.proxies()
+    rng = np.random.default_rng(3)
+    lo = np.array([px["min_x"].min(), px["min_y"].min()]) - 0.5
+    hi = np.array([px["max_x"].max(), px["max_y"].max()]) + 0.5
+    n = 40 * n_worlds
+    rays = np.concatenate([rng.uniform(lo, hi, (n, 2)), rng.uniform(lo, hi, (n, 2)), np.ones((n, 1))], axis=1).astype(np.float32)
+    rw = (np.arange(n) % n_worlds).astype(np.uint32)
+    gh = gw.ray_cast(rays, ray_world=rw)
+    oh = orc.ray_cast(rays)
+    oh = oh[world[oh["body"]] == rw[oh["ray"]]]          # the oracle world holds every world's bodies: keep the ray's world
+    srt = lambda h: h[np.lexsort((h["child"], h["shape"], h["body"], h["ray"]))]
+    assert len(oh) > n_worlds
+    assert_bits(srt(gh), srt(oh), "arena ray hits")
+    assert (world[gh["body"]] == rw[gh["ray"]]).all()
+    import ctypes as C
+    out = np.zeros(4, abi.RAY_HIT); k = C.c_uint32(0)
+    assert gw.lib.pr_ray_cast(gw.h, 1, abi.ptr(rays), None, abi.RAY_ALL, 4, abi.ptr(out), C.byref(k)) == -1  # arena: world index needed
+
+
+@need_oracle
+@need_emul
+def test_emulated_batch_arena_events_and_ray_casts():
+    _arena_queries_vs_oracle(emul_lib(), -1)
+
+
+@pytest.mark.gpu
+@need_oracle
+def test_cuda_batch_arena_events_and_ray_casts():
+    _arena_queries_vs_oracle(None, 0, n_worlds=8, n_squares=40, steps=120)
