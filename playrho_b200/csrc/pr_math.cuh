@@ -77,9 +77,19 @@ PR_HD bool almost_equal(float a, float b)
 // s_sincosf_data.c; ARM optimized-routines algorithm by Szabolcs Nagy). Third-party code not under
 // /root/reference: restated from its published algorithm; the same restatement is
 // checked exhaustively (all 2^32 inputs) against the image's libm in tests/ (oracle/restate).
-// glibc is built with -ffp-contract=off, so even its -mfma ifunc variant evaluates every a*b+c as
-// two roundings; verified: 0 mismatches over all 2^32 inputs for this un-contracted form (the
-// contracted form differs from libm in 34 inputs). --fmad=false keeps nvcc from contracting it.
+// glibc ships sincosf (and sinf / cosf, same polynomial) in ifunc variants: the generic one evaluates every a*b+c of the
+// polynomial and of the range reduction with two roundings; the x86-64 "-fma" variant, which the dynamic loader selects on CPUs
+// with usable FMA + AVX2, contracts them into fused multiply-adds. The two differ, by one ulp of the float result, for 34 of the
+// 2^32 inputs (tools/sincos_exhaustive.cpp checks all of them against the libm of the machine it runs on; results in
+// profiles/r01h_sincosf_exhaustive.txt). So the reference's own bits depend on the CPU it runs on. This restatement is the
+// GENERIC form by default (0 mismatches against a libm that selected the generic variant; --fmad=false keeps nvcc from
+// contracting it); -DPR_SINCOSF_FMA builds the contracted form with explicit fma() (0 mismatches against a libm that selected
+// the fma variant). Run-time selection by the host's CPU features, like the loader's, is a next step.
+#ifdef PR_SINCOSF_FMA
+#define PR_MAD(a, b, c) fma((a), (b), (c))
+#else
+#define PR_MAD(a, b, c) ((c) + (a) * (b))
+#endif
 struct SinCosTab { double c0, c1, c2, c3, c4, s1, s2, s3; };
 PR_HD void sincosf_poly(double x, double x2, bool alt, int n, float* sinp, float* cosp)
 {
@@ -89,15 +99,15 @@ PR_HD void sincosf_poly(double x, double x2, bool alt, int n, float* sinp, float
     const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
     const double x4 = x2 * x2;
     const double x3 = x2 * x;
-    const double c2 = C3 + x2 * C4;
-    const double s1 = S2 + x2 * S3;
-    const double c1 = C0 + x2 * C1;
+    const double c2 = PR_MAD(x2, C4, C3);
+    const double s1 = PR_MAD(x2, S3, S2);
+    const double c1 = PR_MAD(x2, C1, C0);
     const double x5 = x3 * x2;
     const double x6 = x4 * x2;
-    const double s = x + x3 * S1;
-    const double c = c1 + x4 * C2;
-    const float rs = static_cast<float>(s + x5 * s1);
-    const float rc = static_cast<float>(c + x6 * c2);
+    const double s = PR_MAD(x3, S1, x);
+    const double c = PR_MAD(x4, C2, c1);
+    const float rs = static_cast<float>(PR_MAD(x5, s1, s));
+    const float rc = static_cast<float>(PR_MAD(x6, c2, c));
     if (n & 1) { *cosp = rs; *sinp = rc; } else { *sinp = rs; *cosp = rc; }
 }
 PR_HD unsigned abstop12(float x) { return (f2u(x) >> 20) & 0x7ffu; }
@@ -113,7 +123,7 @@ PR_HD void glibc_sincosf(float y, float* sinp, float* cosp)
     } else if (abstop12(y) < 0x42fu) { // |y| < 120
         const double r = x * 0x1.45F306DC9C883p+23;
         const int n = (static_cast<int>(r) + 0x800000) >> 24;
-        x = x - static_cast<double>(n) * 0x1.921FB54442D18p0;
+        x = PR_MAD(-static_cast<double>(n), 0x1.921FB54442D18p0, x); // x - n * hpi
         const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0; // sign[] = {1,-1,-1,1}
         sincosf_poly(x * s, x * x, (n & 2) != 0, n, sinp, cosp);
     } else if (abstop12(y) < 0x7f8u) { // finite
