@@ -199,6 +199,12 @@ typedef struct pr_world pr_world; /* opaque */
 
 /* ---- lifetime (replaces AabbTreeWorld ctor/copy/Clear: AabbTreeWorld.cpp:780-1017) ---- */
 int pr_abi_version(void);
+/* UnitVec::Get(Angle) (Library/source/playrho/d2/UnitVec.cpp:27-30: cos(angle), sin(angle) -- libm's sincosf / sinf / cosf, one
+ * polynomial) gives bits that depend on the ifunc variant glibc's loader picked for the host CPU: generic, or "-fma" on CPUs with
+ * usable FMA + AVX2; 34 of the 2^32 inputs differ by one ulp (profiles/r01h_sincosf_exhaustive.txt). Each build of this library
+ * restates ONE variant: 0 = generic (libplayrho_b200.so), 1 = fma (libplayrho_b200_fma.so, -DPR_SINCOSF_FMA). The host loads
+ * the build that matches the reference's libm on the same machine ("sincosf variant"). */
+int pr_sincosf_variant(void);
 void pr_world_conf_default(pr_world_conf* conf);
 void pr_step_conf_default(pr_step_conf* conf);          /* StepConf{} defaults */
 int pr_create(const pr_world_conf* conf, pr_world** out);

@@ -872,6 +872,15 @@ struct pr_world { World w; };
 extern "C" {
 
 int pr_abi_version(void) { return PR_ABI_VERSION; }
+// which glibc sincosf ifunc variant pr::glibc_sincosf restates in this build (pr_math.cuh): 0 = generic, 1 = x86-64 "-fma"
+int pr_sincosf_variant(void)
+{
+#ifdef PR_SINCOSF_FMA
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 void pr_world_conf_default(pr_world_conf* c)
 {

@@ -12,12 +12,46 @@ from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # PLAYRHO_B200_LIB: an alternative build of the SAME CUDA library (e.g. a -DPR_TOI_TIMING profiling build)
-LIB_PATH = os.environ.get("PLAYRHO_B200_LIB") or os.path.join(_HERE, "libplayrho_b200.so")
+LIB_PATH_GENERIC = os.path.join(_HERE, "libplayrho_b200.so")
+LIB_PATH_FMA = os.path.join(_HERE, "libplayrho_b200_fma.so")  # same sources, -DPR_SINCOSF_FMA (pr_math.cuh)
+
+
+def host_sincosf_variant():
+    """Which sincosf glibc's loader binds on THIS host: "fma" when the CPU has usable FMA and AVX2 (glibc 2.39
+    sysdeps/x86_64/fpu/multiarch/ifunc-fma.h: CPU_FEATURE_USABLE_P(FMA) && CPU_FEATURE_USABLE_P(AVX2)), else "generic".
+    The reference's UnitVec::Get(angle) (UnitVec.cpp:27-30) inherits that choice; 34 of the 2^32 angles differ by one ulp."""
+    if "-FMA" in os.environ.get("GLIBC_TUNABLES", "").upper() or "-AVX2" in os.environ.get("GLIBC_TUNABLES", "").upper():
+        return "generic"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = set(line.split(":", 1)[1].split())
+                    return "fma" if {"fma", "avx2"} <= flags else "generic"
+    except OSError:
+        pass
+    return "generic"
+
+
+def _select_lib_path():
+    """PLAYRHO_B200_LIB = explicit path; else PLAYRHO_B200_SINCOSF = generic (default) | fma | auto (= host_sincosf_variant())."""
+    explicit = os.environ.get("PLAYRHO_B200_LIB")
+    if explicit:
+        return explicit
+    want = os.environ.get("PLAYRHO_B200_SINCOSF", "generic").lower()
+    if want == "auto":
+        want = host_sincosf_variant()
+    if want not in ("generic", "fma"):
+        raise RuntimeError("PLAYRHO_B200_SINCOSF must be generic, fma or auto (got %r)" % want)
+    return LIB_PATH_FMA if want == "fma" else LIB_PATH_GENERIC
+
+
+LIB_PATH = _select_lib_path()
 
 vp, u32, f32, i32 = C.c_void_p, C.c_uint32, C.c_float, C.c_int
 
 EXPORTS = [
-    "pr_abi_version", "pr_world_conf_default", "pr_step_conf_default", "pr_create", "pr_destroy",
+    "pr_abi_version", "pr_sincosf_variant", "pr_world_conf_default", "pr_step_conf_default", "pr_create", "pr_destroy",
     "pr_clone", "pr_clear", "pr_last_error", "pr_create_shapes", "pr_create_bodies",
     "pr_create_revolute_joints", "pr_set_bodies", "pr_get_bodies", "pr_get_revolute_joints",
     "pr_get_counts", "pr_get_contacts", "pr_get_proxies", "pr_load_state", "pr_step",
@@ -32,6 +66,7 @@ EXPORTS = [
 def bind(lib):
     """Attach argtypes/restypes to a loaded library exposing the pr_* C ABI."""
     lib.pr_abi_version.restype = i32
+    lib.pr_sincosf_variant.restype = i32
     lib.pr_world_conf_default.argtypes = [vp]
     lib.pr_step_conf_default.argtypes = [vp]
     lib.pr_create.argtypes = [vp, C.POINTER(vp)]
@@ -99,7 +134,7 @@ def load_library(path=None):
     if path is None:
         if _lib is None:
             if not os.path.exists(LIB_PATH):
-                raise RuntimeError("libplayrho_b200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                raise RuntimeError(os.path.basename(LIB_PATH) + " not built: run `python -c 'import __graft_entry__ as g; g.build()'`. "
                                    "There is no CPU fallback.")
             _lib = bind(C.CDLL(LIB_PATH))
         return _lib
