@@ -454,6 +454,7 @@ def main():
                "toi_events_per_step": float(np.mean([p["toi_events"] for p in profs])), "toi_rounds_per_step": float(np.mean([p["toi_rounds"] for p in profs])),
                "step_conf": "default StepConf (8 vel / 3 pos iters, doToi=%s)%s" % (not args.no_toi, " + TumblerPlayRho's displaceMultiplier 4, maxRotation pi/2" if tumblers else ""),
                "l2": "working set (>1 GB) exceeds the 126 MB L2",
+               "sincosf_variant": "fma" if W.load_library().pr_sincosf_variant() else "generic",
                "contacts": int(last["c_total"]), "touching": int(last["c_touching"]), "colors": int(last["n_colors"]),
                "islands": int(last["n_islands"]), "awake_bodies": int(last["n_awake"]),
                "proxies": int(last["p_total"]), "proxies_moved": int(last["p_moved"]), "contacts_dirty": int(last["c_dirty"]),
