@@ -49,6 +49,10 @@ PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf
     JointWork wk;
     wk.island = joint_island(d, j);
     if (wk.island == INVALID) { d.jt_work[ji] = wk; return; }
+    // AddJointsToIsland (:1443-1466) puts the other body on the island's stack whatever its type: a body that cannot move is
+    // the island's guest (maxIslandBodies, see island_count_static)
+    if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
+    if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
     const float4 pA = d.s_pos[j.body_a], pB = d.s_pos[j.body_b];

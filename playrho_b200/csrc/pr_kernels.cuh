@@ -338,6 +338,22 @@ PR_KERNEL k_hash_fill(DV d, unsigned nOrder)
     const unsigned i = PR_TID;
     if (i < nOrder) hash_insert(d, d.c_key[d.c_order[i]]);
 }
+// SolveReg's maxIslandBodies (AabbTreeWorld.cpp:1510) counts a body that cannot move once for every island that reaches it
+// (AddToIsland pushes it, does not propagate through it, and RemoveUnspeedablesFromIslanded frees it for the next island,
+// :1395-1403): the first thread to insert (island root, body) into the step's pair set counts it. A full probe window is
+// reported (islStatOverflow) and the host recounts from the constraint rows with a larger set (recount_island_statics).
+PR_D void island_count_static(const DV& d, unsigned root, unsigned body)
+{
+    const unsigned long long key = (static_cast<unsigned long long>(root) << 32) | body;
+    unsigned h = static_cast<unsigned>(mix64(key)) & d.is_mask;
+    for (unsigned probe = 0; probe < 64u; ++probe) {
+        const unsigned long long old = atomicCAS(&d.is_keys[h], ~0ull, key);
+        if (old == ~0ull) { atomicAdd(&d.isl_nstat[root], 1u); return; }
+        if (old == key) return;
+        h = (h + 1u) & d.is_mask;
+    }
+    d.cnt->islStatOverflow = 1u;
+}
 
 // ShiftOrigin(AabbTreeWorld&, newOrigin), AabbTreeWorld.cpp:2221-2243: sweeps move by -newOrigin and SetSweep recomputes the
 // transformation from position 1 (Body.hpp:697-702); b_moved stands for FlagForUpdating of the body's contacts (the next
@@ -1184,7 +1200,7 @@ PR_KERNEL k_isl_init(DV d, unsigned nBodies, unsigned velIters, unsigned posIter
         d.isl_state[i] = 0u; d.isl_velIters[i] = velIters; d.isl_posIters[i] = posIters;
         d.isl_inc[i] = 0u; d.isl_maxInc[i] = 0u; d.isl_jflag[i] = 0u;
         d.isl_sep[i] = float_flip(PR_INF); d.isl_minSep[i] = float_flip(PR_INF); d.isl_minUA[i] = float_flip(PR_INF);
-        d.isl_nbodies[i] = 0u;
+        d.isl_nbodies[i] = 0u; d.isl_nstat[i] = 0u;
         d.b_cmask[i] = 0ull; d.b_claim[i] = ~0ull;
         d.b_sync[i] = 0u;
     }
@@ -1278,7 +1294,7 @@ PR_KERNEL k_mark_constraints(DV d, unsigned nOrder, unsigned* mark)
 {
     PR_PDL_ENTER();
     const unsigned i = PR_TID;
-    unsigned touching = 0u;
+    unsigned touching = 0u, statTouch = 0u;
     if (i < nOrder) {
         const unsigned id = d.c_order[i];
         unsigned m = 0u;
@@ -1288,11 +1304,14 @@ PR_KERNEL k_mark_constraints(DV d, unsigned nOrder, unsigned* mark)
             const uint4 ab = d.c_ab[id];
             const unsigned rA = d.b_island[ab.x], rB = d.b_island[ab.y];
             m = (rA != INVALID || rB != INVALID) ? 1u : 0u;
+            // the body without a label cannot move (a speedable one would have been united with the other): the island's guest
+            if (m && (rA == INVALID || rB == INVALID)) { statTouch = 1u; island_count_static(d, rA != INVALID ? rA : rB, rA != INVALID ? ab.y : ab.x); }
         }
         mark[i] = m;
         if (!m) d.c_color[id] = COLOR_UNSET;
     }
     block_add(&d.cnt->nTouching, touching);
+    block_add(&d.cnt->nStaticTouch, statTouch);
 }
 PR_KERNEL k_gather_constraints(DV d, unsigned nOrder, const unsigned* mark, const unsigned* pos, unsigned recolorAll)
 {
@@ -2094,7 +2113,7 @@ PR_KERNEL k_sleep_and_stats(DV d, unsigned nBodies, float minStillTime)
             }
             if (r == i) {
                 solved = (st & ISL_POS_SOLVED) ? 1u : 0u;
-                posIt = d.isl_posIters[i]; velIt = d.isl_velIters[i]; nb = d.isl_nbodies[i];
+                posIt = d.isl_posIters[i]; velIt = d.isl_velIters[i]; nb = d.isl_nbodies[i] + d.isl_nstat[i];
                 sepFlip = d.isl_minSep[i]; incBits = d.isl_maxInc[i];
             }
         }
@@ -2102,6 +2121,36 @@ PR_KERNEL k_sleep_and_stats(DV d, unsigned nBodies, float minStillTime)
     block_add(&d.cnt->bodiesSlept, slept); block_add(&d.cnt->islandsSolved, solved);
     block_add(&d.cnt->sumPosIters, posIt); block_add(&d.cnt->sumVelIters, velIt);
     block_max(&d.cnt->maxIslandBodies, nb); block_min(&d.cnt->minSepFlip, sepFlip); block_max(&d.cnt->maxIncBits, incBits);
+}
+
+// The rare recount after an overflow of the (island, body) pair set: the step's constraint rows and joint work data still
+// name every island's guests (a row's body without a label; labels live until the next step's k_isl_init).
+PR_KERNEL k_isl_recount_statics(DV d, unsigned nCons, unsigned nJoints)
+{
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    if (i < nCons) {
+        const float4 head = d.vc1[i];
+        const unsigned bA = f2u(head.x), bB = f2u(head.y);
+        const unsigned rA = d.b_island[bA], rB = d.b_island[bB];
+        if (rA == INVALID || rB == INVALID) island_count_static(d, d.vc_island[i], rA == INVALID ? bA : bB);
+    }
+    if (i < nJoints) {
+        const unsigned isl = d.jt_work[i].island;
+        if (isl != INVALID) {
+            const unsigned a = d.jt[i].body_a, b = d.jt[i].body_b;
+            if (d.b_island[a] == INVALID) island_count_static(d, isl, a);
+            if (d.b_island[b] == INVALID) island_count_static(d, isl, b);
+        }
+    }
+}
+PR_KERNEL k_isl_max_bodies(DV d, unsigned nBodies)
+{
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    unsigned nb = 0u;
+    if (i < nBodies && d.b_island[i] == i) nb = d.isl_nbodies[i] + d.isl_nstat[i];
+    block_max(&d.cnt->maxIslandBodies, nb);
 }
 
 // ------------------------------------------------------------------ export helpers

@@ -84,7 +84,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(b_lc, G_BODY), A(b_flags, G_BODY), A(s_vel, G_BODY), A(s_pos, G_BODY), A(b_island, G_BODY), A(b_root, G_BODY),
         A(b_moved, G_BODY), A(b_sync, G_BODY), A(isl_state, G_BODY), A(isl_velIters, G_BODY), A(isl_posIters, G_BODY),
         A(isl_inc, G_BODY), A(isl_maxInc, G_BODY), A(isl_sep, G_BODY), A(isl_minSep, G_BODY), A(isl_minUA, G_BODY),
-        A(isl_nbodies, G_BODY), A(isl_active, G_BODY), A(b_claim, G_BODY), A(b_cmask, G_BODY),
+        A(isl_nbodies, G_BODY), A(isl_nstat, G_BODY), A(isl_active, G_BODY), A(b_claim, G_BODY), A(b_cmask, G_BODY),
         A(adj_off, G_BODY), A(adj_cnt, G_BODY), A(adj_n, G_BODY), A(b_toiIsl, G_BODY), A(b_toiAlpha, G_BODY), A(b_toiStamp, G_BODY), A(b_inR, G_BODY),
         A(sync_list, G_BODY), A(bp_off, G_BODY), A(bp_list, G_PROXY), A(bv_leafOf, G_PROXY), A(b_world, G_BODY), A(bv_wr, G_PROXY),
         A(c_pos, G_CONTACT), A(c_color, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT), A(toi_list, G_CONTACT), A(toi_cand, G_CONTACT), A(toi_cand2, G_CONTACT), A(toi_re0, G_CONTACT),
@@ -383,11 +383,39 @@ static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer
 }
 
 // ------------------------------------------------------------------ regular phase (SolveReg :1472-1561)
+// the step's (island, non-speedable body) pair set (island_count_static): sized from what the last step inserted, emptied
+static void prepare_island_statics(World& w, unsigned want)
+{
+    const unsigned cap = next_pow2(std::max(1024u, want));
+    if (cap > w.isCap) {
+        sync(w);
+        dev_free(w.d.is_keys);
+        w.d.is_keys = static_cast<unsigned long long*>(dev_alloc(sizeof(unsigned long long) * cap));
+        w.isCap = cap;
+    }
+    w.d.is_mask = cap - 1u;
+    dset(w, w.d.is_keys, 0xFF, sizeof(unsigned long long) * cap);
+}
+// islStatOverflow: the set was too small for this step (the pile just landed): count again from the rows with a larger one
+static void recount_island_statics(World& w)
+{
+    for (unsigned want = 8u * (w.hostCnt.nStaticTouch + 256u);; want *= 4u) {
+        prepare_island_statics(w, want);
+        dset(w, w.d.isl_nstat, 0, sizeof(unsigned) * w.nBodies);
+        w.hostCnt.islStatOverflow = 0u; w.hostCnt.maxIslandBodies = 0u;
+        write_counters(w);
+        PR_LAUNCH(k_isl_recount_statics, std::max(w.nCons, w.nJoints), w.stream, w.d, w.nCons, w.nJoints);
+        PR_LAUNCH(k_isl_max_bodies, w.nBodies, w.stream, w.d, w.nBodies);
+        read_counters(w);
+        if (!w.hostCnt.islStatOverflow) return;
+    }
+}
 static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, StageTimer& tm)
 {
     DV& d = w.d;
     const unsigned N = w.nBodies;
     tm.mark(w, PR_STAGE_ISLANDS);
+    prepare_island_statics(w, 4u * (w.isHint + 256u));
     PR_LAUNCH(k_isl_init, N, w.stream, d, N, conf.reg_velocity_iters, conf.reg_position_iters);
     PR_LAUNCH(k_isl_union, w.nOrder, w.stream, d, w.nOrder);
     PR_LAUNCH(k_isl_union_joints, w.nJoints, w.stream, d, w.nJoints);
@@ -575,6 +603,8 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     dset(w, d.b_moved, 0, sizeof(unsigned) * N);
     dset(w, d.b_sync, 0, sizeof(unsigned) * N);
     read_counters(w);
+    if (w.hostCnt.islStatOverflow) recount_island_statics(w);
+    w.isHint = w.hostCnt.nStaticTouch;
     const Counters c = w.hostCnt;
     stats.reg.proxies_moved = c.proxiesMoved;
     stats.reg.contacts_updated = c.contactsUpdated;
@@ -952,7 +982,7 @@ int pr_destroy(pr_world* pw)
     World& w = pw->w;
     for (const ArrDesc& a : arrays(w)) dev_free(*a.slot);
     dev_free(w.d.ev_contact); dev_free(w.d.ev_impulse);
-    dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist); dev_free(w.stageBuf[0]); dev_free(w.stageBuf[1]);
+    dev_free(w.d.is_keys); dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist); dev_free(w.stageBuf[0]); dev_free(w.stageBuf[1]);
 #ifndef PR_HOST_EMUL
     if (w.stream) cudaStreamDestroy(w.stream);
     if (w.pinnedCnt) cudaFreeHost(w.pinnedCnt);

@@ -67,6 +67,7 @@ struct Counters {
     unsigned islandsFound, islandsSolved, bodiesSlept, sumVelIters, sumPosIters, maxIslandBodies;
     unsigned proxiesMoved, contactsUpdated, nAwake, nTouching, nActiveVel, nActivePos;
     unsigned minSepFlip, maxIncBits, error, pad;
+    unsigned nStaticTouch, islStatOverflow; // (island, non-speedable body) pairs: constraints/joints seen, set overflow (see island_count_static)
     unsigned boundsMinX, boundsMinY, boundsMaxX, boundsMaxY;
     unsigned nEvContact, nEvImpulse; // contact events of this step (pr_events): begin/end records, post-solve records
     unsigned lateWhy[8]; // diagnostics (PR_TOI_DEBUG): hand-backs of k_tb_late by reason, list sizes seen, events per round
@@ -94,6 +95,9 @@ struct DV {
     unsigned long long* nc_pairs; unsigned nNcPairs;               // body pairs joined by a collideConnected=false joint
     unsigned *isl_state, *isl_velIters, *isl_posIters, *isl_inc, *isl_maxInc, *isl_sep, *isl_minSep, *isl_minUA, *isl_nbodies, *isl_active;
     unsigned long long *b_claim, *b_cmask;
+    // SolveReg's maxIslandBodies counts every non-speedable body an island touches once (AabbTreeWorld.cpp:1395-1403, :1510):
+    // isl_nstat[root] = distinct such bodies, deduplicated through a per-step hash set of (root, body) keys
+    unsigned* isl_nstat; unsigned long long* is_keys; unsigned is_mask;
     // shapes / children / vertices
     float4* sh_mat; unsigned* sh_filter; int* sh_group;
     float* ch_radius; unsigned *ch_voff, *ch_count; float2 *vtx, *nrm;
@@ -181,6 +185,7 @@ struct World {
     pr_step_profile profile{};
     std::vector<unsigned> solveOrderIds, solveOrderColors;
     std::vector<void*> allocs;
+    unsigned isCap = 0, isHint = 0; // island-static pair set: capacity (power of two), pairs seen last step
     unsigned* gridBar = nullptr; unsigned fusedGrid = 0; bool fusedProbed = false; // persistent solver kernel (pr_solve_fused.cuh)
     void* stageBuf[2] = {nullptr, nullptr}; size_t stageCap[2] = {0, 0}; // persistent device staging for row upload/download
 };

@@ -35,7 +35,6 @@ def run_vs_oracle(scene, steps, lib=None, conf=None, device=-1, check_every=1, t
         if (s % check_every) and s != steps - 1:
             continue
         gsa, osa = np.array([gs]), np.array([os_])
-        gsa["reg"]["max_island_bodies"] = osa["reg"]["max_island_bodies"]  # known gap: statics not counted
         where = "step %d" % s
         assert_bits(gw.bodies(), orc.bodies(), where + " bodies")
         gc, gm = gw.contacts()
