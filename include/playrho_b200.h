@@ -313,6 +313,10 @@ int pr_step(pr_world* w, const pr_step_conf* conf, pr_step_stats* stats_out);
  * contact ids in solve order, their colour and island label. For the parity oracle. */
 int pr_get_solve_order(const pr_world* w, uint32_t cap, uint32_t* contact_ids, uint32_t* colors,
                        uint32_t* n_out);
+/* the TOI event schedule of the last Step (recorded while debug bit 0 is set): (round, contact id) pairs ordered by round then
+ * id. In PR_TOI_SERIAL_EXACT every round holds the one event GetSoonestContact picks (AabbTreeWorld.cpp:2870-2890); in
+ * PR_TOI_PARALLEL a round holds every locally-soonest event. The parity oracle derives the same rounds by rule and must agree. */
+int pr_get_toi_schedule(const pr_world* w, uint32_t cap, uint32_t* round_contact_pairs, uint32_t* n_out);
 /* debug flags: bit 0 = record the solve order of every step (costs a device->host copy);
  * bit 1 = use the binned narrowphase, bit 2 = use the persistent fused solver kernel (two experiments that did not beat the
  * default kernels on B200; off by default, kept under test); bit 3 = TOI rounds through the list kernels only (no single-block

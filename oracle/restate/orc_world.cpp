@@ -80,6 +80,10 @@ struct orc_world {
     bool subStepping = false;
     float inv_dt0 = 0;
     std::string error;
+    uint32_t toiMode = 0;                                        // 0: the reference's event order; 1: PR_TOI_PARALLEL rounds (orc_toi_phase.inc)
+    std::vector<BC> bcScratch;
+    std::vector<uint32_t> lastToiIslandBodies;
+    std::vector<std::pair<uint32_t, uint32_t>> toiSchedule;      // (round, contact id) of the last step's TOI events, toiMode 1
 
     Proxy child(uint32_t shape, uint32_t childIdx) const
     {
@@ -296,16 +300,56 @@ uint32_t find_and_add_contacts(orc_world& w, const pr_step_conf& conf)
     std::vector<uint32_t> queued;
     queued.swap(w.proxiesForContacts);
     const uint32_t P = static_cast<uint32_t>(w.proxies.size());
-    for (uint32_t q : queued) {
+    auto test_pair = [&](uint32_t q, uint32_t o) {
+        if (o == q) return;
         const pr_proxy& pq = w.proxies[q].p;
-        const AABB aq = fat_of(pq);
-        for (uint32_t o = 0; o < P; ++o) {
-            if (o == q) continue;
-            const pr_proxy& po = w.proxies[o].p;
-            if (po.body == pq.body) continue;
-            if (!overlap(aq, fat_of(po))) continue;
-            if (pq.tree_id < po.tree_id) keys.push_back({pq.tree_id, po.tree_id, q, o});
-            else keys.push_back({po.tree_id, pq.tree_id, o, q});
+        const pr_proxy& po = w.proxies[o].p;
+        if (po.body == pq.body) return;
+        if (!overlap(fat_of(pq), fat_of(po))) return;
+        if (pq.tree_id < po.tree_id) keys.push_back({pq.tree_id, po.tree_id, q, o});
+        else keys.push_back({po.tree_id, pq.tree_id, o, q});
+    };
+    if (static_cast<uint64_t>(queued.size()) * P <= 4000000ull) {
+        for (uint32_t q : queued) for (uint32_t o = 0; o < P; ++o) test_pair(q, o);
+    } else {
+        // Same pair set as the all-pairs loop, found through a uniform grid (the oracle only has to finish in seconds at
+        // BASELINE sizes; the keys are sorted and made unique below either way). Closed intervals: two boxes that overlap share
+        // a cell because the cell index is a monotone function of the coordinate. Boxes spanning many cells go to a side list.
+        std::vector<float> ext(P);
+        float x0 = kInf, y0 = kInf;
+        for (uint32_t i = 0; i < P; ++i) {
+            const AABB a = fat_of(w.proxies[i].p);
+            ext[i] = std::max(a.maxx - a.minx, a.maxy - a.miny);
+            x0 = std::min(x0, a.minx); y0 = std::min(y0, a.miny);
+        }
+        std::vector<float> tmp = ext;
+        std::nth_element(tmp.begin(), tmp.begin() + P / 2, tmp.end());
+        const float cell = std::max(tmp[P / 2] * 2.0f, 1e-3f);
+        auto ci = [&](float v, float o) { return static_cast<int64_t>(std::floor((v - o) / cell)); };
+        std::vector<uint32_t> large;
+        std::vector<std::pair<uint64_t, uint32_t>> cells;
+        auto span = [&](uint32_t i, int64_t& cx0, int64_t& cx1, int64_t& cy0, int64_t& cy1) {
+            const AABB a = fat_of(w.proxies[i].p);
+            cx0 = ci(a.minx, x0); cx1 = ci(a.maxx, x0); cy0 = ci(a.miny, y0); cy1 = ci(a.maxy, y0);
+            return (cx1 - cx0 + 1) * (cy1 - cy0 + 1) <= 16;
+        };
+        auto ckey = [](int64_t cx, int64_t cy) { return (static_cast<uint64_t>(cx) << 32) ^ (static_cast<uint64_t>(cy) & 0xFFFFFFFFull); };
+        std::vector<char> isLarge(P, 0);
+        for (uint32_t i = 0; i < P; ++i) {
+            int64_t cx0, cx1, cy0, cy1;
+            if (!span(i, cx0, cx1, cy0, cy1)) { large.push_back(i); isLarge[i] = 1; continue; }
+            for (int64_t cx = cx0; cx <= cx1; ++cx) for (int64_t cy = cy0; cy <= cy1; ++cy) cells.emplace_back(ckey(cx, cy), i);
+        }
+        std::sort(cells.begin(), cells.end());
+        for (uint32_t q : queued) {
+            if (isLarge[q]) { for (uint32_t o = 0; o < P; ++o) test_pair(q, o); continue; }
+            int64_t cx0, cx1, cy0, cy1;
+            span(q, cx0, cx1, cy0, cy1);
+            for (int64_t cx = cx0; cx <= cx1; ++cx) for (int64_t cy = cy0; cy <= cy1; ++cy) {
+                const uint64_t k = ckey(cx, cy);
+                for (auto it = std::lower_bound(cells.begin(), cells.end(), std::make_pair(k, 0u)); it != cells.end() && it->first == k; ++it) test_pair(q, it->second);
+            }
+            for (uint32_t o : large) test_pair(q, o);
         }
     }
     std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.mn != b.mn ? a.mn < b.mn : a.mx < b.mx; });
@@ -806,7 +850,10 @@ IslandStats solve_reg_island(orc_world& w, const pr_step_conf& conf, const Islan
     results.positionIters = conf.reg_position_iters;
     const float h = conf.delta_time;
     for (uint32_t id : island.bodies) { pr_body& b = w.bodies[id].b; set_pos0(b, body_pos1(b)); }
-    std::vector<BC> bcs(w.bodies.size());
+    // (BodyConstraints indexed by body id: a world-owned scratch; every body an island's constraints or joints name is set by
+    // build_constraints first -- one vector per island made a 100k-island step quadratic)
+    std::vector<BC>& bcs = w.bcScratch;
+    if (bcs.size() < w.bodies.size()) bcs.resize(w.bodies.size());
     std::vector<VC> vcs; std::vector<PC> pcs;
     build_constraints(w, island, bcs, vcs, pcs, h, conf, conf.do_warm_start ? conf.dt_ratio : 0.0f);
     if (conf.do_warm_start) for (const VC& vc : vcs) warm_start(vc, bcs);
@@ -1381,6 +1428,14 @@ int orc_get_revolute_joints(const orc_world* w, uint32_t first, uint32_t n, pr_r
 }
 
 float orc_get_inv_dt0(const orc_world* w) { return w->inv_dt0; }
+int orc_set_toi_mode(orc_world* w, uint32_t mode) { if (mode > 1u) return 1; w->toiMode = mode; return 0; }
+int orc_get_toi_schedule(const orc_world* w, uint32_t cap, uint32_t* round_contact_pairs, uint32_t* n_out)
+{
+    const uint32_t n = static_cast<uint32_t>(w->toiSchedule.size());
+    *n_out = n;
+    for (uint32_t i = 0; i < n && i < cap; ++i) { round_contact_pairs[2u * i] = w->toiSchedule[i].first; round_contact_pairs[2u * i + 1u] = w->toiSchedule[i].second; }
+    return n <= cap ? 0 : 1;
+}
 
 int orc_collide_shapes(uint32_t n, const pr_child* children, const pr_vec2* verts, const pr_vec2* normals,
                        const uint32_t* a_child, const float* xf_a, const uint32_t* b_child, const float* xf_b,

@@ -57,6 +57,11 @@ int orc_get_contacts(const orc_world* w, uint32_t cap, pr_contact* contacts, pr_
 int orc_get_proxies(const orc_world* w, uint32_t cap, pr_proxy* proxies, uint32_t* n_out);
 int orc_get_revolute_joints(const orc_world* w, uint32_t first, uint32_t n, pr_revolute_joint* rows);
 float orc_get_inv_dt0(const orc_world* w);
+/* TOI event schedule: 0 = the reference's (one globally soonest contact per loop turn, AabbTreeWorld.cpp:1752-1831);
+ * 1 = the product's PR_TOI_PARALLEL rounds, derived here by the documented rule (orc_toi_phase.inc, solve_toi_parallel).
+ * orc_get_toi_schedule: (round, contact id) of every event of the last step, mode 1. */
+int orc_set_toi_mode(orc_world* w, uint32_t mode);
+int orc_get_toi_schedule(const orc_world* w, uint32_t cap, uint32_t* round_contact_pairs, uint32_t* n_out);
 
 /* RayCast(world, input, callback returning ResetRay): every hit, brute force over the proxies with the tree's two leaf tests
  * (RayCastOutput.cpp:241-337); hits in proxy order per ray */

@@ -310,7 +310,13 @@ PR_D void toi_select_cand(const DV& d, unsigned id, unsigned parallel)
         toi_for_each_claim_body(d, d.c_ab[id], [&](unsigned b) { if (d.b_claim[b] != key) mine = false; });
         win = PR_WARP_ALL(mine);
     } else win = (key == d.cnt->toiMinKey);
-    if (win && PR_LANE == 0u) d.toi_events[atomicAdd(&d.cnt->toiEvents, 1u)] = id;
+    if (win && PR_LANE == 0u) {
+        d.toi_events[atomicAdd(&d.cnt->toiEvents, 1u)] = id;
+        if (d.toi_log) { // the schedule, for the parity oracle (pr_get_toi_schedule)
+            const unsigned slot = atomicAdd(&d.cnt->toiLogN, 1u);
+            if (slot < d.toi_logCap) d.toi_log[slot] = make_uint2(d.cnt->toiRoundId, id);
+        }
+    }
 }
 PR_KERNEL k_toi_claim(DV d)
 {

@@ -674,6 +674,11 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         return;
     }
     upload_body_proxies(w);
+    if (w.debugFlags & 1u) { // record the event schedule (pr_get_toi_schedule)
+        const unsigned want = std::max(1u << 16, 4u * w.capContacts / 8u);
+        if (want > d.toi_logCap) { sync(w); dev_free(d.toi_log); d.toi_log = static_cast<uint2*>(dev_alloc(sizeof(uint2) * want)); d.toi_logCap = want; }
+    } else if (d.toi_log) { sync(w); dev_free(d.toi_log); d.toi_log = nullptr; d.toi_logCap = 0u; }
+    w.toiScheduleN = 0; w.toiSchedule.clear();
     PR_LAUNCH(k_toi_phase_init, N, w.stream, d, N);
     for (;;) {
         if (w.nOrder == 0) { w.stepComplete = true; break; } // nothing can have a TOI
@@ -832,6 +837,12 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     st.contacts_skipped_touching = c.toiSkipTouching + (nOrderAtUpdate - c.contactsUpdated);
     st.proxies_moved = movedToi;
     st.contacts_found -= c.toiDeferred;
+    if (d.toi_log) {
+        w.toiScheduleN = c.toiLogN;
+        w.toiSchedule.resize(std::min(c.toiLogN, d.toi_logCap));
+        d2h(w, w.toiSchedule.data(), d.toi_log, sizeof(uint2) * w.toiSchedule.size());
+        std::sort(w.toiSchedule.begin(), w.toiSchedule.end(), [](const uint2& a, const uint2& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    }
     w.profile.toi_rounds = rounds; w.profile.toi_events = st.contacts_found;
 #ifdef PR_TOI_TIMING
     std::fprintf(stderr, "toi_timing rounds=%u ev0=%llu | cyc: head %llu procA %llu procB %llu build %llu pos %llu vel %llu tailwb %llu | nC %llu nB %llu posIt %llu velIt %llu upd %llu skip %llu\n",
@@ -982,7 +993,7 @@ int pr_destroy(pr_world* pw)
     World& w = pw->w;
     for (const ArrDesc& a : arrays(w)) dev_free(*a.slot);
     dev_free(w.d.ev_contact); dev_free(w.d.ev_impulse);
-    dev_free(w.d.is_keys); dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist); dev_free(w.stageBuf[0]); dev_free(w.stageBuf[1]);
+    dev_free(w.d.is_keys); dev_free(w.d.toi_log); dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist); dev_free(w.stageBuf[0]); dev_free(w.stageBuf[1]);
 #ifndef PR_HOST_EMUL
     if (w.stream) cudaStreamDestroy(w.stream);
     if (w.pinnedCnt) cudaFreeHost(w.pinnedCnt);
@@ -1601,6 +1612,15 @@ int pr_get_solve_order(const pr_world* pw, uint32_t cap, uint32_t* contact_ids, 
     const unsigned n = std::min<unsigned>(cap, static_cast<unsigned>(std::min<size_t>(w.nCons, w.solveOrderIds.size())));
     for (unsigned i = 0; i < n; ++i) { contact_ids[i] = w.solveOrderIds[i]; if (colors) colors[i] = w.solveOrderColors[i]; }
     return PR_OK;
+}
+
+int pr_get_toi_schedule(const pr_world* pw, uint32_t cap, uint32_t* round_contact_pairs, uint32_t* n_out)
+{
+    const World& w = pw->w;
+    *n_out = w.toiScheduleN;
+    const unsigned n = std::min<unsigned>(cap, static_cast<unsigned>(w.toiSchedule.size()));
+    for (unsigned i = 0; i < n; ++i) { round_contact_pairs[2u * i] = w.toiSchedule[i].x; round_contact_pairs[2u * i + 1u] = w.toiSchedule[i].y; }
+    return w.toiScheduleN <= cap && w.toiSchedule.size() == w.toiScheduleN ? PR_OK : PR_ERR_LENGTH;
 }
 
 int pr_set_debug(pr_world* pw, uint32_t flags) { pw->w.debugFlags = flags; return PR_OK; }

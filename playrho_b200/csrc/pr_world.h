@@ -67,6 +67,7 @@ struct Counters {
     unsigned islandsFound, islandsSolved, bodiesSlept, sumVelIters, sumPosIters, maxIslandBodies;
     unsigned proxiesMoved, contactsUpdated, nAwake, nTouching, nActiveVel, nActivePos;
     unsigned minSepFlip, maxIncBits, error, pad;
+    unsigned toiLogN; // TOI events logged this step (pr_get_toi_schedule)
     unsigned nStaticTouch, islStatOverflow; // (island, non-speedable body) pairs: constraints/joints seen, set overflow (see island_count_static)
     unsigned boundsMinX, boundsMinY, boundsMaxX, boundsMaxY;
     unsigned nEvContact, nEvImpulse; // contact events of this step (pr_events): begin/end records, post-solve records
@@ -112,6 +113,7 @@ struct DV {
     unsigned *adj_off, *adj_cnt, *adj_n, *adj_list, *c_pos, *b_toiIsl, *c_toiIsl, *b_toiAlpha, *b_toiStamp, *b_inR, *toi_events, *toi_islBodies,
         *toi_islContacts, *toi_list, *toi_cand, *toi_cand2, *toi_re0, *toi_re1, *c_rstamp, *sync_list;
     unsigned *bp_off, *bp_list; // body -> proxy CSR (m_bodyProxies)
+    uint2* toi_log; unsigned toi_logCap; // (round, contact id) of every TOI event of the step; only while the solve order is recorded
     unsigned long long* ht_keys; unsigned ht_mask;
     // new pairs
     unsigned long long *np_key, *np_key2; uint2* np_px; unsigned *np_idx, *np_idx2;
@@ -184,6 +186,7 @@ struct World {
     Counters* pinnedCnt = nullptr; unsigned pinnedNext = 1;
     pr_step_profile profile{};
     std::vector<unsigned> solveOrderIds, solveOrderColors;
+    std::vector<uint2> toiSchedule; unsigned toiScheduleN = 0; // last step's TOI events by round (debug bit 0)
     std::vector<void*> allocs;
     unsigned isCap = 0, isHint = 0; // island-static pair set: capacity (power of two), pairs seen last step
     unsigned* gridBar = nullptr; unsigned fusedGrid = 0; bool fusedProbed = false; // persistent solver kernel (pr_solve_fused.cuh)

@@ -55,7 +55,7 @@ EXPORTS = [
     "pr_clone", "pr_clear", "pr_last_error", "pr_create_shapes", "pr_create_bodies",
     "pr_create_revolute_joints", "pr_set_bodies", "pr_get_bodies", "pr_get_revolute_joints",
     "pr_get_counts", "pr_get_contacts", "pr_get_proxies", "pr_load_state", "pr_step",
-    "pr_get_solve_order", "pr_set_debug", "pr_get_step_profile", "pr_abi_sizeof", "pr_shift_origin",
+    "pr_get_solve_order", "pr_get_toi_schedule", "pr_set_debug", "pr_get_step_profile", "pr_abi_sizeof", "pr_shift_origin",
     "pr_get_inv_dt0", "pr_get_stream", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
     "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
@@ -99,6 +99,7 @@ def bind(lib):
     lib.pr_load_state.argtypes = [vp, u32, vp, u32, vp, u32, vp, vp, f32]
     lib.pr_step.argtypes = [vp, vp, vp]
     lib.pr_get_solve_order.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
+    lib.pr_get_toi_schedule.argtypes = [vp, u32, vp, C.POINTER(u32)]
     lib.pr_set_debug.argtypes = [vp, u32]
     lib.pr_get_step_profile.argtypes = [vp, vp]
     lib.pr_abi_sizeof.argtypes = [i32]
@@ -359,6 +360,14 @@ class World:
         ids, cols = np.zeros(max(1, k.value), np.uint32), np.zeros(max(1, k.value), np.uint32)
         self.lib.pr_get_solve_order(self.h, len(ids), abi.ptr(ids), abi.ptr(cols), C.byref(k))
         return ids[:k.value], cols[:k.value]
+
+    def toi_schedule(self):
+        """(round, contact id) rows of the last step's TOI events (needs record_solve_order)."""
+        k = u32(0)
+        self.lib.pr_get_toi_schedule(self.h, 0, None, C.byref(k))
+        rows = np.zeros((max(1, k.value), 2), np.uint32)
+        self._chk(self.lib.pr_get_toi_schedule(self.h, len(rows), abi.ptr(rows), C.byref(k)))
+        return rows[:k.value]
 
     def profile(self):
         p = abi.one(abi.STEP_PROFILE)

@@ -25,17 +25,25 @@ def run_vs_oracle(scene, steps, lib=None, conf=None, device=-1, check_every=1, t
     proxies (fat AABBs) and step statistics after every step."""
     conf = conf if conf is not None else refworld.default_step_conf(do_toi=0)
     gw = W.World(scene, lib=lib, device=device, record_solve_order=True, large_variants=large_variants)
-    gw.set_toi_mode(toi_mode)  # 0 = serial-exact: the reference's TOI event order
+    gw.set_toi_mode(toi_mode)  # 0 = serial-exact: the reference's TOI event order; 1 = PR_TOI_PARALLEL rounds (product default)
     orc = refworld.OracleWorld(scene)
+    orc.set_toi_mode(toi_mode)  # (mode 1: the oracle derives the rounds by rule; the two schedules must be the same)
     last = None
     for s in range(steps):
         gs = gw.step(conf)
         ids, cols = gw.solve_order()
         os_ = orc.step(conf, order=ids)
+        where = "step %d" % s
+        if toi_mode == 1 and conf["do_toi"]:
+            gsch, osch = gw.toi_schedule(), orc.toi_schedule()
+            assert gsch.shape == osch.shape and np.array_equal(gsch, osch), "%s TOI schedule differs: device %s oracle %s" % (
+                where, gsch[:8].tolist(), osch[:8].tolist())
+            run_vs_oracle.toi_events = getattr(run_vs_oracle, "toi_events", 0) + len(gsch)
+            run_vs_oracle.toi_multi_rounds = getattr(run_vs_oracle, "toi_multi_rounds", 0) + int(
+                (np.bincount(gsch[:, 0]) > 1).sum() if len(gsch) else 0)
         if (s % check_every) and s != steps - 1:
             continue
         gsa, osa = np.array([gs]), np.array([os_])
-        where = "step %d" % s
         assert_bits(gw.bodies(), orc.bodies(), where + " bodies")
         gc, gm = gw.contacts()
         oc, om = orc.contacts()

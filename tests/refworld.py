@@ -345,6 +345,19 @@ class OracleWorld:
             raise RuntimeError(self.lib.orc_last_error(self.h).decode())
         return st[0]
 
+    def set_toi_mode(self, mode):
+        self.lib.orc_set_toi_mode.argtypes = [vp, u32]
+        assert self.lib.orc_set_toi_mode(self.h, int(mode)) == 0
+
+    def toi_schedule(self):
+        self.lib.orc_get_toi_schedule.argtypes = [vp, u32, vp, C.POINTER(u32)]
+        k = u32(0)
+        self.lib.orc_get_toi_schedule(self.h, 0, None, C.byref(k))
+        rows = np.zeros((max(1, k.value), 2), np.uint32)
+        self.lib.orc_get_toi_schedule(self.h, len(rows), abi.ptr(rows), C.byref(k))
+        rows = rows[:k.value]
+        return rows[np.lexsort((rows[:, 1], rows[:, 0]))] if len(rows) else rows
+
     def set_shape_material(self, shape, friction, restitution, density, sensor):
         self.lib.orc_set_shape_material.argtypes = [vp, u32, f32, f32, f32, u32]
         self.lib.orc_set_shape_material(self.h, int(shape), friction, restitution, density, int(sensor))

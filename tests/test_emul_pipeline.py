@@ -183,3 +183,34 @@ def _column_accessors_check(lib, device):
 @need_emul
 def test_emulated_column_accessors_equal_row_accessors():
     _column_accessors_check(emul_lib(), -1)
+
+
+@need_oracle
+@need_emul
+@pytest.mark.parametrize("name,builder,steps", [
+    ("disks64", lambda: scenes_np.disks_box(64, seed=7), 120),
+    ("pyramid6", lambda: scenes_np.pyramid(6), 150),
+    ("mixed80", lambda: scenes_np.mixed(80, seed=11, tile_segments=16, tile_width=8.0), 150),
+    ("mixed400", lambda: scenes_np.mixed(400, seed=3, tile_segments=32, tile_width=16.0), 120),
+])
+def test_emulated_parallel_toi_mode_bit_exact(name, builder, steps):
+    """PR_TOI_PARALLEL (the product default and the benchmarked mode): the oracle derives the rounds by the documented rule
+    (oracle/restate/orc_toi_phase.inc, solve_toi_parallel); event schedule, every state array and every StepStats field
+    must agree bit for bit."""
+    run_vs_oracle.toi_events = 0
+    gs, ncontacts, prof = run_vs_oracle(builder(), steps, lib=emul_lib(), conf=refworld.default_step_conf(), toi_mode=1)
+    assert ncontacts > 0
+    if name.startswith("mixed"):
+        assert run_vs_oracle.toi_events > 0
+
+
+@need_oracle
+@need_emul
+@need_ref
+def test_emulated_parallel_toi_mode_shooter_bit_exact():
+    """The TOI stress scene (bullets, kinematic bar, sensor) in PR_TOI_PARALLEL: many rounds hold several events."""
+    import scenes
+    run_vs_oracle.toi_events = 0; run_vs_oracle.toi_multi_rounds = 0
+    run_vs_oracle(scenes.shooter().export_scene(), 200, lib=emul_lib(), conf=refworld.default_step_conf(), toi_mode=1)
+    assert run_vs_oracle.toi_events > 100
+    assert run_vs_oracle.toi_multi_rounds > 0

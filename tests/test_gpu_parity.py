@@ -41,6 +41,56 @@ def test_cuda_step_with_toi_bit_exact_vs_oracle(name, builder, steps, every):
 
 
 @need_oracle
+@pytest.mark.parametrize("name,builder,steps,every", [
+    ("disks64", lambda: scenes_np.disks_box(64, seed=7), 120, 1),
+    ("pyramid10", lambda: scenes_np.pyramid(10), 200, 1),
+    ("mixed80", lambda: scenes_np.mixed(80, seed=11, tile_segments=16, tile_width=8.0), 150, 1),
+    ("mixed1500", lambda: scenes_np.mixed(1500, seed=12345, tile_segments=64, tile_width=32.0), 100, 5),
+    ("mixed20000", lambda: scenes_np.mixed_fast(20000, seed=7), 80, 10),
+])
+def test_cuda_parallel_toi_mode_bit_exact_vs_oracle(name, builder, steps, every):
+    """PR_TOI_PARALLEL -- the product default and the mode bench.py times -- with the default StepConf: the oracle derives
+    the rounds by the documented rule (oracle/restate/orc_toi_phase.inc solve_toi_parallel: every locally-soonest event with
+    a disjoint body neighbourhood runs in the same round) and must agree with the device on the event schedule of EVERY
+    step (pr_get_toi_schedule), and bit for bit on bodies, contacts, manifolds, proxies and every StepStats field."""
+    run_vs_oracle.toi_events = 0
+    gs, ncontacts, prof = run_vs_oracle(builder(), steps, device=0, check_every=every, conf=refworld.default_step_conf(), toi_mode=1)
+    assert ncontacts > 0
+    if name.startswith("mixed"):
+        assert run_vs_oracle.toi_events > 0
+
+
+@need_oracle
+@need_ref
+def test_cuda_parallel_toi_mode_shooter_bit_exact_vs_oracle():
+    """The TOI stress scene (bullets, spinning kinematic bar, sensor) in PR_TOI_PARALLEL: rounds with several events."""
+    import scenes
+    run_vs_oracle.toi_events = 0; run_vs_oracle.toi_multi_rounds = 0
+    run_vs_oracle(scenes.shooter().export_scene(), 300, device=0, conf=refworld.default_step_conf(), toi_mode=1)
+    assert run_vs_oracle.toi_events > 300
+    assert run_vs_oracle.toi_multi_rounds > 0
+
+
+@need_oracle
+@pytest.mark.parametrize("toi_mode", [0, 1])
+def test_cuda_config2_full_size_pyramid40_bit_exact_vs_oracle(toi_mode):
+    """BASELINE config 2 at its stated size: the 40-row pyramid (820 boxes on edge ground), 600 steps, default StepConf with
+    TOI on, in both TOI modes."""
+    gs, ncontacts, prof = run_vs_oracle(scenes_np.pyramid(40), 600, device=0, check_every=20, conf=refworld.default_step_conf(),
+                                        toi_mode=toi_mode)
+    assert ncontacts > 2000
+
+
+@need_oracle
+def test_cuda_config3_full_size_100k_disks_bit_exact_vs_oracle():
+    """BASELINE config 3 at its stated size: 100k disks dropped into the static 4-edge container, default StepConf (TOI on,
+    the benchmarked parallel mode), 60 steps from the drop: pair set / contact ids / manifolds / bodies / stats bit-exact."""
+    gs, ncontacts, prof = run_vs_oracle(scenes_np.disks_box(100000, seed=12345), 60, device=0, check_every=15,
+                                        conf=refworld.default_step_conf(), toi_mode=1)
+    assert ncontacts > 100000
+
+
+@need_oracle
 def test_cuda_binned_narrowphase_variant_bit_exact_vs_oracle():
     """The opt-in kernel variants (narrowphase binned by shape-pair class; the persistent cooperative solver kernel with
     grid barriers between colours) on small scenes: same bits as the oracle, incl. joints and the colour-overflow tail."""
