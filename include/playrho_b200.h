@@ -205,6 +205,8 @@ int pr_abi_version(void);
  * restates ONE variant: 0 = generic (libplayrho_b200.so), 1 = fma (libplayrho_b200_fma.so, -DPR_SINCOSF_FMA). The host loads
  * the build that matches the reference's libm on the same machine ("sincosf variant"). */
 int pr_sincosf_variant(void);
+/* the variant this host's glibc selects (usable FMA + AVX2 -> 1, else 0): what pr_sincosf_variant() of the loaded build should be */
+int pr_host_sincosf_variant(void);
 void pr_world_conf_default(pr_world_conf* conf);
 void pr_step_conf_default(pr_step_conf* conf);          /* StepConf{} defaults */
 int pr_create(const pr_world_conf* conf, pr_world** out);

@@ -828,9 +828,16 @@ PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratc
     ToiSmem local;
     ToiSmem* islands = &local;
 #endif
+#ifdef PR_TOI_TIMING
+    long long lt_ = clock64();
+#define PR_LT(k) do { if (PR_TID == 0u) { const long long t_ = clock64(); d.cnt->dbgLate[k] += static_cast<unsigned long long>(t_ - lt_); lt_ = t_; } } while (0)
+#else
+#define PR_LT(k) do { } while (0)
+#endif
     for (unsigned r = 0; r < maxRounds; ++r) {
         __syncthreads();
         if (d.cnt->toiHalt) return;
+        PR_LT(0);
         const unsigned roundId = d.cnt->toiRoundId + 1u;
         const unsigned nR = d.cnt->toiReN[roundId & 1u], nC = d.cnt->toiCandN;
         const unsigned* R = (roundId & 1u) ? d.toi_re1 : d.toi_re0;
@@ -870,6 +877,7 @@ PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratc
             if (o.key != ~0ull) { d.toi_cand2[atomicAdd(&d.cnt->toiCand2N, 1u)] = id; atomicMin(&d.cnt->toiMinKey, o.key); }
         }
         __threadfence_block(); __syncthreads();
+        PR_LT(1); // UpdateContactTOIs
         const unsigned nCand = d.cnt->toiCand2N;
         for (unsigned i = PR_TID; i < nCand; i += PR_NTHREADS) d.toi_cand[i] = d.toi_cand2[i];
         __syncthreads();
@@ -887,13 +895,18 @@ PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratc
         }
         const unsigned nEvents = d.cnt->toiEvents;
         __threadfence_block(); __syncthreads();
+        PR_LT(2); // selection
         if (nEvents == 0u) { if (PR_TID == 0u) d.cnt->toiHalt = TB_DONE; return; } // :1768
         if (PR_TID == 0u) { d.cnt->tbRounds += 1u; d.cnt->tbFound += nEvents; }
+#ifdef PR_TOI_TIMING
+        if (PR_TID == 0u) { d.cnt->dbgLate[8] += 1ull; d.cnt->dbgLate[9] += nEvents; d.cnt->dbgLate[10] += nR; d.cnt->dbgLate[11] += nCand; }
+#endif
         // ---- SolveToi per event: one warp each (lane 0 working), islands in the arena
         if (PR_LANE == 0u && PR_WARP_ID < LATE_SOLVE_WARPS)
             for (unsigned e = PR_WARP_ID; e < nEvents; e += (PR_NWARPS < LATE_SOLVE_WARPS ? PR_NWARPS : LATE_SOLVE_WARPS))
                 toi_solve_event(d, conf, e, exactMode, scratchCap, &islands[PR_WARP_ID < LATE_SOLVE_WARPS ? PR_WARP_ID : 0u]);
         __threadfence_block(); __syncthreads();
+        PR_LT(3); // event solve
         // ---- Synchronize the moved bodies' proxies, FindContacts, AddContacts
         {
             const unsigned n = d.cnt->syncN;
@@ -901,6 +914,7 @@ PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratc
         }
         __threadfence_block(); __syncthreads();
         const unsigned nQ = d.cnt->nQueue;
+        PR_LT(4); // Synchronize
         if (nQ == 0u) continue;
         if (8ull * nQ >= nLeaves) { if (PR_TID == 0u) d.cnt->toiHalt = TB_HOST_FIND; return; } // full rebuild: the host's
         for (unsigned t = PR_TID; t < nQ; t += PR_NTHREADS) bvh_refit_moved_one(d, t, nLeaves);
@@ -915,8 +929,10 @@ PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratc
                 bvh_query_group(d, d.q_list[qi], sortedIdx, capPairs, stk[threadIdx.x / QG], lane, gl, gmask);
         }
         __threadfence_block(); __syncthreads();
+        PR_LT(5); // refit + query
         if (!tb_add_block(d, conf, capPairs, capContacts, capHash, hashTombs, reinterpret_cast<unsigned long long*>(arena),
                           reinterpret_cast<unsigned*>(arena + SMALL_SORT_MAX * sizeof(unsigned long long)))) return;
+        PR_LT(6); // add
 #else
         for (unsigned t = PR_TID; t < nQ; t += PR_NTHREADS) bvh_query_serial(d, d.q_list[t], nLeaves, sortedIdx, capPairs);
         if (!tb_add_block(d, conf, capPairs, capContacts, capHash, hashTombs, nullptr, nullptr)) return;

@@ -4,6 +4,7 @@
 #include "pr_kernels.cuh"
 #include "pr_solve_fused.cuh"
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <limits>
@@ -11,9 +12,11 @@
 
 namespace pr {
 
-static unsigned g_launches = 0;
-static unsigned long long g_launchSerial = 0; // never reset: "has any kernel been launched since ...?"
-void count_launch() { ++g_launches; ++g_launchSerial; }
+// (launch count of the step running on this thread; the serial is process-wide and atomic: worlds stepped from several threads
+// can only make each other re-read their counters, never skip a read)
+static thread_local unsigned g_launches = 0;
+static std::atomic<unsigned long long> g_launchSerial{0}; // never reset: "has any kernel been launched since ...?"
+void count_launch() { ++g_launches; g_launchSerial.fetch_add(1ull, std::memory_order_relaxed); }
 unsigned launches_since_reset() { return g_launches; }
 void reset_launch_count() { g_launches = 0; }
 #ifdef PR_HOST_EMUL
@@ -39,7 +42,7 @@ static void dset(World& w, void* dst, int v, size_t n) { if (n) CK(cudaMemsetAsy
 static void sync(World& w) { CK(cudaStreamSynchronize(w.stream)); }
 static void check_launch() { CK(cudaGetLastError()); }
 struct StageTimer {
-    static constexpr int MAXEV = 2048;
+    static constexpr int MAXEV = 1024;
     cudaEvent_t ev[MAXEV]; int stage[MAXEV]; int n = 0; bool on = true;
     StageTimer() { for (auto& e : ev) cudaEventCreate(&e); }
     ~StageTimer() { for (auto& e : ev) cudaEventDestroy(e); }
@@ -174,12 +177,12 @@ static void read_counters(World& w)
 {
     // only kernels change the device counters behind the host's back: if none was launched since the last read (or since the
     // write that followed it) the host copy IS the device's, and the round trip (a stream drain, ~20 us of idle GPU) is skipped
-    if (w.cntSerialValid && w.cntSerial == g_launchSerial) return;
+    if (w.cntSerialValid && w.cntSerial == g_launchSerial.load(std::memory_order_relaxed)) return;
     CK(cudaMemcpyAsync(&w.pinnedCnt[0], w.d.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, w.stream));
     CK(cudaStreamSynchronize(w.stream));
     w.hostCnt = w.pinnedCnt[0];
     w.pinnedNext = 1; // everything queued before this point has executed: all write slots are free again
-    w.cntSerial = g_launchSerial; w.cntSerialValid = true;
+    w.cntSerial = g_launchSerial.load(std::memory_order_relaxed); w.cntSerialValid = true;
 }
 static void write_counters(World& w)
 {
@@ -845,6 +848,8 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     }
     w.profile.toi_rounds = rounds; w.profile.toi_events = st.contacts_found;
 #ifdef PR_TOI_TIMING
+    std::fprintf(stderr, "late_timing rounds %llu events %llu nR %llu nCand %llu | cyc: entry %llu tois %llu select %llu solve %llu sync %llu refitquery %llu add %llu\n",
+                 c.dbgLate[8], c.dbgLate[9], c.dbgLate[10], c.dbgLate[11], c.dbgLate[0], c.dbgLate[1], c.dbgLate[2], c.dbgLate[3], c.dbgLate[4], c.dbgLate[5], c.dbgLate[6]);
     std::fprintf(stderr, "toi_timing rounds=%u ev0=%llu | cyc: head %llu procA %llu procB %llu build %llu pos %llu vel %llu tailwb %llu | nC %llu nB %llu posIt %llu velIt %llu upd %llu skip %llu\n",
                  rounds, c.dbg[8], c.dbg[0], c.dbg[1], c.dbg[2], c.dbg[3], c.dbg[4], c.dbg[5], c.dbg[6], c.dbg[9], c.dbg[10], c.dbg[11], c.dbg[12], c.dbg[13], c.dbg[14]);
 #endif
@@ -860,9 +865,8 @@ static void reset_counters(World& w)
 static void step_impl(World& w, const pr_step_conf& conf, pr_step_stats& stats)
 {
     DV& d = w.d;
-    static thread_local StageTimer* tmp = nullptr;
-    if (!tmp) tmp = new StageTimer();
-    StageTimer& tm = *tmp;
+    if (!w.timer) w.timer = new StageTimer(); // (the world's own: its CUDA events belong to the world's device)
+    StageTimer& tm = *static_cast<StageTimer*>(w.timer);
     std::memset(&stats, 0, sizeof(stats));
     stats.reg.min_separation = std::numeric_limits<float>::infinity();
     stats.toi.min_separation = std::numeric_limits<float>::infinity();
@@ -905,7 +909,18 @@ static void step_impl(World& w, const pr_step_conf& conf, pr_step_stats& stats)
 using namespace pr;
 struct pr_world { World w; };
 
-#define API_TRY(wptr) try {
+// every entry point runs with the world's device current and puts the caller's device back (two worlds on two GPUs in one
+// process, or a caller -- torch -- that changed the current device since pr_create)
+#ifndef PR_HOST_EMUL
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess || prev == dev) prev = -1; else cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#else
+struct DeviceGuard { explicit DeviceGuard(int) {} };
+#endif
+#define API_TRY(wptr) try { DeviceGuard pr_guard_((wptr)->w.device);
 #define API_CATCH(wptr)                                                                            \
     } catch (const CudaError& e) { (wptr)->w.error = e.msg; return PR_ERR_CUDA; }                  \
     catch (const std::exception& e) { (wptr)->w.error = e.what(); return PR_ERR_CUDA; }
@@ -918,6 +933,18 @@ int pr_sincosf_variant(void)
 {
 #ifdef PR_SINCOSF_FMA
     return 1;
+#else
+    return 0;
+#endif
+}
+
+// which variant this host's glibc selects for sincosf (sysdeps/x86_64/fpu/multiarch/ifunc-fma.h: the "-fma" one on CPUs with
+// usable FMA and AVX2, else the generic one) -- i.e. the bits the reference computes when it runs on this host
+int pr_host_sincosf_variant(void)
+{
+#if defined(__x86_64__) && !defined(__CUDA_ARCH__)
+    __builtin_cpu_init();
+    return (__builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2")) ? 1 : 0;
 #else
     return 0;
 #endif
@@ -991,6 +1018,8 @@ int pr_destroy(pr_world* pw)
 {
     if (!pw) return PR_OK;
     World& w = pw->w;
+    DeviceGuard guard(w.device);
+    delete static_cast<StageTimer*>(w.timer);
     for (const ArrDesc& a : arrays(w)) dev_free(*a.slot);
     dev_free(w.d.ev_contact); dev_free(w.d.ev_impulse);
     dev_free(w.d.is_keys); dev_free(w.d.toi_log); dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist); dev_free(w.stageBuf[0]); dev_free(w.stageBuf[1]);
@@ -1007,7 +1036,9 @@ const char* pr_last_error(const pr_world* pw) { return pw ? pw->w.error.c_str() 
 int pr_clone(const pr_world* src, pr_world** out)
 {
     pr_world* pw = nullptr;
-    const int rc = pr_create(&src->w.conf, &pw);
+    pr_world_conf conf = src->w.conf;
+    conf.device = src->w.device; // (the clone lives where its source lives, whatever device is current)
+    const int rc = pr_create(&conf, &pw);
     if (rc != PR_OK) return rc;
     API_TRY(pw)
     World& w = pw->w;
@@ -1044,6 +1075,9 @@ int pr_clear(pr_world* pw)
     w.nJoints = 0; w.jointsSerial = false; w.d.nNcPairs = 0; w.bodyWorld.clear(); w.freeJoints.clear();
     w.nBodies = w.nShapes = w.nChildren = w.nVerts = w.nProxies = w.nOrder = w.nFree = w.poolSize = 0; w.maxTreeId = 0;
     w.anyBodySet = false; w.hashDirty = true; w.adjValid = false; w.stepComplete = true; w.toiPossible = false;
+    w.inv_dt0 = 0.0f; // m_inv_dt0 = 0_Hz (AabbTreeWorld.cpp:982)
+    w.recolorAll = true; w.colorsAtFull = 0; w.colorCap = 64u; w.nCons = w.nColors = 0; w.toiRoundsHint = 1; w.toiGroupsHint = 1; w.isHint = 0;
+    if (w.d.ev_mask) { w.hostCnt.nEvContact = w.hostCnt.nEvImpulse = 0u; }
     reset_counters(w);
     return PR_OK;
     API_CATCH(pw)
@@ -1060,13 +1094,14 @@ int pr_create_shapes(pr_world* pw, uint32_t n, const pr_shape* shapes, const pr_
         if (!(children[i].vertex_radius >= w.conf.min_vertex_radius && children[i].vertex_radius <= w.conf.max_vertex_radius)) {
             w.error = "vertex radius outside world interval"; return PR_ERR_INVALID_ARGUMENT;
         }
-        if (children[i].vertex_offset + children[i].vertex_count > n_vertices) { w.error = "child vertex range"; return PR_ERR_OUT_OF_RANGE; }
+        if (children[i].vertex_offset > n_vertices || children[i].vertex_count > n_vertices - children[i].vertex_offset) { w.error = "child vertex range"; return PR_ERR_OUT_OF_RANGE; }
     }
+    for (uint32_t i = 0; i < n; ++i) // (every row is checked before any is applied)
+        if (shapes[i].child_offset > n_children || shapes[i].child_count > n_children - shapes[i].child_offset) { w.error = "shape child range"; return PR_ERR_OUT_OF_RANGE; }
     ensure(w, G_SHAPE, w.nShapes + n); ensure(w, G_CHILD, w.nChildren + n_children); ensure(w, G_VERT, w.nVerts + n_vertices);
     std::vector<float4> mat(n); std::vector<unsigned> filt(n); std::vector<int> grp(n);
     for (uint32_t i = 0; i < n; ++i) {
         pr_shape s = shapes[i];
-        if (s.child_offset + s.child_count > n_children) { w.error = "shape child range"; return PR_ERR_OUT_OF_RANGE; }
         s.child_offset += w.nChildren;
         w.shapes.push_back(s);
         mat[i] = make_float4(s.friction, s.restitution, s.is_sensor ? 1.0f : 0.0f, s.density);
@@ -1304,7 +1339,7 @@ int pr_get_bodies(const pr_world* cpw, uint32_t first, uint32_t n, pr_body* rows
     pr_world* pw = const_cast<pr_world*>(cpw);
     API_TRY(pw)
     World& w = pw->w;
-    if (first + n > w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    if (first > w.nBodies || n > w.nBodies - first) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
     if (!n) return PR_OK;
     pr_body* staging = static_cast<pr_body*>(stage_buf(w, 0, sizeof(pr_body) * n));
     PR_LAUNCH(k_get_bodies, n, w.stream, w.d, first, n, staging);
@@ -1336,7 +1371,7 @@ int pr_get_body_poses(const pr_world* cpw, uint32_t first, uint32_t n, float* xf
     pr_world* pw = const_cast<pr_world*>(cpw);
     API_TRY(pw)
     World& w = pw->w;
-    if (first + n > w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    if (first > w.nBodies || n > w.nBodies - first) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
     if (!n) return PR_OK;
     float4* sxf = static_cast<float4*>(stage_buf(w, 0, sizeof(float4) * n));
     float* svel = vel3 ? static_cast<float*>(stage_buf(w, 1, sizeof(float) * 3u * n)) : nullptr;
@@ -1480,7 +1515,7 @@ int pr_get_revolute_joints(const pr_world* cpw, uint32_t first, uint32_t n, pr_r
     pr_world* pw = const_cast<pr_world*>(cpw);
     API_TRY(pw)
     World& w = pw->w;
-    if (first + n > w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
+    if (first > w.nJoints || n > w.nJoints - first) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
     d2h(w, rows, w.d.jt + first, sizeof(pr_revolute_joint) * n);
     return PR_OK;
     API_CATCH(pw)
@@ -1553,6 +1588,7 @@ int pr_load_state(pr_world* pw, uint32_t n_bodies, const pr_body* bodies, uint32
     for (unsigned i = 0; i < n_proxies; ++i) {
         const pr_proxy& p = proxies[i];
         if (p.shape >= w.nShapes || p.body >= w.nBodies) { w.error = "proxy refers to unknown body/shape"; return PR_ERR_OUT_OF_RANGE; }
+        if (p.child >= w.shapes[p.shape].child_count) { w.error = "proxy refers to a child its shape does not have"; return PR_ERR_OUT_OF_RANGE; }
         body[i] = p.body; shape[i] = p.shape; child[i] = p.child; cg[i] = w.shapes[p.shape].child_offset + p.child; tree[i] = p.tree_id;
         fat[i] = make_float4(p.min_x, p.min_y, p.max_x, p.max_y);
         maxTree = std::max(maxTree, p.tree_id);
@@ -1568,6 +1604,13 @@ int pr_load_state(pr_world* pw, uint32_t n_bodies, const pr_body* bodies, uint32
     w.fixturesForProxies.clear();
     // contacts
     unsigned maxId = 0;
+    std::vector<char> treeKnown(static_cast<size_t>(maxTree) + 1u, 0);
+    for (unsigned i = 0; i < n_proxies; ++i) treeKnown[tree[i]] = 1;
+    for (unsigned i = 0; i < n_contacts; ++i) { // (validated before anything is uploaded: the import kernel indexes pxOfTree with the keys)
+        const pr_contact& c = contacts[i];
+        if (c.key_min > maxTree || c.key_max > maxTree || !treeKnown[c.key_min] || !treeKnown[c.key_max]) { w.error = "contact key names no proxy"; return PR_ERR_OUT_OF_RANGE; }
+        if (c.id == 0xFFFFFFFFu) { w.error = "invalid contact id"; return PR_ERR_OUT_OF_RANGE; }
+    }
     for (unsigned i = 0; i < n_contacts; ++i) maxId = std::max(maxId, contacts[i].id + 1);
     ensure(w, G_CONTACT, std::max(maxId, n_contacts) + 1);
     std::vector<unsigned> pxOfTree(maxTree + 1, 0u);
@@ -1819,7 +1862,7 @@ int pr_batch_step(pr_batch* b, const pr_step_conf* conf, pr_step_stats* sum) { r
 int pr_batch_get_body_worlds(const pr_batch* b, uint32_t first, uint32_t n, uint32_t* world_index)
 {
     const World& w = b->arena->w;
-    if (first + n > w.nBodies) return PR_ERR_OUT_OF_RANGE;
+    if (first > w.nBodies || n > w.nBodies - first) return PR_ERR_OUT_OF_RANGE;
     std::memcpy(world_index, w.bodyWorld.data() + first, sizeof(uint32_t) * n);
     return PR_OK;
 }

@@ -84,6 +84,7 @@ struct Counters {
     unsigned toiRoundId, toiReN[2], toiCand2N, toiAtMaxLive, toiForceFull, tbPad2;
 #ifdef PR_TOI_TIMING
     unsigned long long dbg[16]; // profiling build only: clock64 deltas of the phases of toi_solve_event (event 0 of each round)
+    unsigned long long dbgLate[12]; // profiling build only: clock64 deltas of the stages of a k_tb_late round (thread 0)
 #endif
 };
 
@@ -190,6 +191,7 @@ struct World {
     std::vector<void*> allocs;
     unsigned isCap = 0, isHint = 0; // island-static pair set: capacity (power of two), pairs seen last step
     unsigned* gridBar = nullptr; unsigned fusedGrid = 0; bool fusedProbed = false; // persistent solver kernel (pr_solve_fused.cuh)
+    void* timer = nullptr; // StageTimer (pr_world.cu): per-stage CUDA events of this world's device
     void* stageBuf[2] = {nullptr, nullptr}; size_t stageCap[2] = {0, 0}; // persistent device staging for row upload/download
 };
 

@@ -226,6 +226,7 @@ struct CudaWorld::Impl {
     ShapeFunction shapeDestruction; BodyShapeFunction detach; JointFunction jointDestruction;
     ContactFunction beginContact, endContact; ContactManifoldFunction preSolve; ContactImpulsesFunction postSolve;
     std::uint32_t eventCap = 1u << 16;
+    std::uint64_t droppedEvents = 0; // listener calls lost to a full device event buffer (it is grown after such a step)
 
     void updateEventMask() noexcept
     {
@@ -250,17 +251,21 @@ struct CudaWorld::Impl {
             const std::uint32_t keptC = std::min(nc, eventCap), keptI = std::min(ni, eventCap);
             // like inside the reference's Step, the world is locked while listeners run: mutators throw WrongState (:2156)
             struct Lock { bool& f; explicit Lock(bool& b) : f(b) { f = true; } ~Lock() { f = false; } } lock{locked};
-            for (std::uint32_t i = 0; i < keptC && (rc == PR_OK); ++i) {
+            for (std::uint32_t i = 0; i < keptC; ++i) {
                 const auto id = MakeId<ContactID>(ce[i].contact);
                 if (ce[i].kind == PR_EVENT_BEGIN) { if (beginContact) beginContact(id); }
                 else if (endContact) endContact(id);
             }
-            for (std::uint32_t i = 0; i < keptI && (rc2 == PR_OK); ++i) {
+            for (std::uint32_t i = 0; i < keptI; ++i) {
                 ContactImpulsesList imp;
                 for (std::uint32_t j = 0; j < ie[i].count && j < 2u; ++j) imp.AddEntry(Momentum{ie[i].normal[j] * NewtonSecond}, Momentum{ie[i].tangent[j] * NewtonSecond});
                 postSolve(MakeId<ContactID>(ie[i].contact), imp, static_cast<unsigned>(ie[i].iterations));
             }
-            if (overflow) { eventCap = std::max(nc, ni) * 2u; updateEventMask(); throw LengthError("CudaWorld: more contact events in one step than the event buffers hold (grown for the next step)"); }
+            if (overflow) { // the step is applied and its kept events are delivered: count what was dropped, hold more from now on
+                droppedEvents += (nc > keptC ? nc - keptC : 0u) + (ni > keptI ? ni - keptI : 0u);
+                eventCap = std::max(nc, ni) * 2u;
+                updateEventMask();
+            }
             return;
         }
     }
@@ -356,6 +361,7 @@ CudaWorld::CudaWorld(CudaWorld&& o) noexcept : m{o.m} { o.m = nullptr; }
 CudaWorld& CudaWorld::operator=(const CudaWorld& o) { if (this != &o) { CudaWorld tmp{o}; std::swap(m, tmp.m); } return *this; }
 CudaWorld& CudaWorld::operator=(CudaWorld&& o) noexcept { if (this != &o) { std::swap(m, o.m); } return *this; }
 CudaWorld::~CudaWorld() noexcept { if (m) { if (m->h) pr_destroy(m->h); delete m; } }
+std::uint64_t CudaWorld::GetDroppedEventCount() const noexcept { return m ? m->droppedEvents : 0u; }
 void CudaWorld::SetToiMode(ToiMode mode) { m->toiMode = static_cast<unsigned>(mode); m->check(pr_set_toi_mode(m->h, m->toiMode), "pr_set_toi_mode"); }
 
 bool operator==(const CudaWorld& a, const CudaWorld& b)
@@ -393,9 +399,16 @@ std::optional<pmr::StatsResource::Stats> GetResourceStats(const CudaWorld&) noex
 void Clear(CudaWorld& w) noexcept
 { // Clear(AabbTreeWorld&), :949-1017 (destruction listeners are told about joints and shapes first)
     if (!w.m || !w.m->h) return;
-    try {
-        if (w.m->shapeDestruction) for (std::size_t i = 0; i < w.m->shapes.size(); ++i) w.m->shapeDestruction(MakeId<ShapeID>(static_cast<std::uint32_t>(i)));
-    } catch (...) {}
+    if (w.m->jointDestruction) // every live joint (:955-965); an exception of one call does not stop the others
+        for (std::size_t i = 0; i < w.m->joints.size(); ++i) {
+            if (!w.m->joints[i].has_value()) continue;
+            try { w.m->jointDestruction(MakeId<JointID>(static_cast<std::uint32_t>(i))); } catch (...) {}
+        }
+    if (w.m->shapeDestruction) // every non-empty shape slot (:966-980)
+        for (std::size_t i = 0; i < w.m->shapes.size(); ++i) {
+            if (w.m->shapes[i] == Shape{}) continue;
+            try { w.m->shapeDestruction(MakeId<ShapeID>(static_cast<std::uint32_t>(i))); } catch (...) {}
+        }
     pr_clear(w.m->h);
     w.m->bodies.clear(); w.m->bodyDirty.clear(); w.m->anyBodyDirty = false; w.m->bodiesStale = false; w.m->bodiesForSync.clear();
     w.m->shapes.clear(); w.m->joints.clear(); w.m->freeJoints.clear();

@@ -48,6 +48,9 @@ public:
     ~CudaWorld() noexcept;
 
     void SetToiMode(ToiMode mode);
+    /// Listener calls lost because a step produced more contact events than the device event buffers held (the step itself is
+    /// applied, the events that were kept are delivered, and the buffers are grown for the following steps).
+    std::uint64_t GetDroppedEventCount() const noexcept;
 
     // ---- implementation detail (public for the free functions below; not part of the World API)
     struct Impl;

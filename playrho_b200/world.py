@@ -34,11 +34,12 @@ def host_sincosf_variant():
 
 
 def _select_lib_path():
-    """PLAYRHO_B200_LIB = explicit path; else PLAYRHO_B200_SINCOSF = generic (default) | fma | auto (= host_sincosf_variant())."""
+    """PLAYRHO_B200_LIB = explicit path; else PLAYRHO_B200_SINCOSF = auto (default: host_sincosf_variant(), the variant this
+    host's glibc -- hence the reference running here -- uses) | generic | fma."""
     explicit = os.environ.get("PLAYRHO_B200_LIB")
     if explicit:
         return explicit
-    want = os.environ.get("PLAYRHO_B200_SINCOSF", "generic").lower()
+    want = os.environ.get("PLAYRHO_B200_SINCOSF", "auto").lower()
     if want == "auto":
         want = host_sincosf_variant()
     if want not in ("generic", "fma"):
@@ -51,7 +52,7 @@ LIB_PATH = _select_lib_path()
 vp, u32, f32, i32 = C.c_void_p, C.c_uint32, C.c_float, C.c_int
 
 EXPORTS = [
-    "pr_abi_version", "pr_sincosf_variant", "pr_world_conf_default", "pr_step_conf_default", "pr_create", "pr_destroy",
+    "pr_abi_version", "pr_sincosf_variant", "pr_host_sincosf_variant", "pr_world_conf_default", "pr_step_conf_default", "pr_create", "pr_destroy",
     "pr_clone", "pr_clear", "pr_last_error", "pr_create_shapes", "pr_create_bodies",
     "pr_create_revolute_joints", "pr_set_bodies", "pr_get_bodies", "pr_get_revolute_joints",
     "pr_get_counts", "pr_get_contacts", "pr_get_proxies", "pr_load_state", "pr_step",
@@ -67,6 +68,7 @@ def bind(lib):
     """Attach argtypes/restypes to a loaded library exposing the pr_* C ABI."""
     lib.pr_abi_version.restype = i32
     lib.pr_sincosf_variant.restype = i32
+    lib.pr_host_sincosf_variant.restype = i32
     lib.pr_world_conf_default.argtypes = [vp]
     lib.pr_step_conf_default.argtypes = [vp]
     lib.pr_create.argtypes = [vp, C.POINTER(vp)]

@@ -5,7 +5,9 @@ import pytest
 import refworld
 from playrho_b200 import abi, world as W
 
-EMUL_SO = os.path.join(refworld.ROOT, "tests", "_emul", "libplayrho_b200_emul.so")
+# (the emulated-kernel build of the sincosf variant this host's libm -- hence the oracle -- uses, like the product's default)
+EMUL_SO = os.path.join(refworld.ROOT, "tests", "_emul",
+                       "libplayrho_b200_emul_fma.so" if W.host_sincosf_variant() == "fma" else "libplayrho_b200_emul.so")
 need_ref = pytest.mark.skipif(not refworld.have_ref(), reason="oracle/_ref not built (no /root/reference at build time)")
 need_oracle = pytest.mark.skipif(not refworld.have_oracle(), reason="oracle/libpr_oracle.so not built")
 need_emul = pytest.mark.skipif(not os.path.exists(EMUL_SO), reason="tests/_emul not built")

@@ -48,7 +48,10 @@ def test_host_rule_picks_the_variant_this_libm_uses():
 def test_library_selection_by_environment(monkeypatch):
     monkeypatch.delenv("PLAYRHO_B200_LIB", raising=False)
     monkeypatch.delenv("PLAYRHO_B200_SINCOSF", raising=False)
-    assert W._select_lib_path() == W.LIB_PATH_GENERIC  # the default stays the generic build
+    auto = W.LIB_PATH_FMA if _libm_variant() == "fma" else W.LIB_PATH_GENERIC
+    assert W._select_lib_path() == auto  # the default: the build that restates what this host's libm (the reference here) computes
+    monkeypatch.setenv("PLAYRHO_B200_SINCOSF", "generic")
+    assert W._select_lib_path() == W.LIB_PATH_GENERIC
     monkeypatch.setenv("PLAYRHO_B200_SINCOSF", "fma")
     assert W._select_lib_path() == W.LIB_PATH_FMA
     monkeypatch.setenv("PLAYRHO_B200_SINCOSF", "auto")
@@ -66,6 +69,7 @@ def test_product_builds_report_their_variant(path, variant):
         pytest.skip(os.path.basename(path) + " not built")
     lib = W.load_library(path)
     assert lib.pr_sincosf_variant() == variant
+    assert lib.pr_host_sincosf_variant() == (1 if _libm_variant() == "fma" else 0)  # the C ABI's own statement of the host rule
     for name in W.EXPORTS:
         assert hasattr(lib, name), name
 
