@@ -21,7 +21,14 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _checker_path():
+    """tests/ holds the reference-side harness (refworld, scenes: oracle/_ref bindings). Only the reference arm and the
+    cpu_baseline leg put it on the path; the product arm imports nothing from tests/ or oracle/."""
+    t = os.path.join(ROOT, "tests")
+    if t not in sys.path:
+        sys.path.insert(0, t)
 
 import numpy as np  # noqa: E402
 
@@ -33,7 +40,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--bodies", type=int, default=1000000)
-    ap.add_argument("--workload", default="mixed")
+    ap.add_argument("--workload", default=None, help="mixed (BASELINE config 4: the N=1 default) | disks | tumblers (BASELINE config 5, "
+                    "--worlds independent worlds sharded over the GPUs: the default for --gpus > 1, the split north_star names)")
     ap.add_argument("--settle", type=int, default=300, help="untimed steps so that the dropped bodies have piled up and are in contact")
     ap.add_argument("--worlds", type=int, default=8192, help="tumblers: total number of independent worlds (sharded over the ranks)")
     ap.add_argument("--squares", type=int, default=512, help="tumblers: squares added one per step per world before timing")
@@ -42,9 +50,13 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-toi", action="store_true", help="StepConf.doToi=false (default: TOI enabled as BASELINE config 4 says)")
     ap.add_argument("--toi-mode", type=int, default=1, help="1 = parallel independent TOI events (product default), 0 = serial-exact")
-    ap.add_argument("--debug-flags", type=int, default=0, help="pr_set_debug flags (4 = plain narrowphase instead of the binned one)")
+    ap.add_argument("--debug-flags", type=int, default=0, help="pr_set_debug flags (see include/playrho_b200.h; 32 = tumbler arena through the arena-wide per-colour launches instead of the block solver)")
     ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra measurements of the N=1 mixed line (tumbler arena at N=1, serial-exact TOI mode)")
+    args = ap.parse_args()
+    if args.workload is None:  # one world runs on one GPU (config 4); what shards over the GPUs of a box is the batch of worlds (config 5)
+        args.workload = "mixed" if args.gpus <= 1 else "tumblers"
+    return args
 
 
 def peaks():
@@ -147,7 +159,7 @@ def algorithmic_bytes(prof, nv, np_):
 
 
 def build_scene(args, seed):
-    import scenes_np
+    from playrho_b200 import scenes_np
     if args.workload == "disks":
         return scenes_np.disks_box(args.bodies, seed=seed)
     return scenes_np.mixed_fast(args.bodies, seed=seed)
@@ -155,6 +167,7 @@ def build_scene(args, seed):
 
 # ---------------------------------------------------------------- reference arm (CPU)
 def ref_scene(args, n):
+    _checker_path()
     import refworld
     import scenes
     ids32 = refworld.have_ref(True)
@@ -163,6 +176,7 @@ def ref_scene(args, n):
 
 def ref_tumbler_world(n_squares, conf):
     """One TumblerPlayRho (Benchmark/BenchmarkMain.cpp:2614-2722) in the real reference: Step(); AddSquare() x n."""
+    _checker_path()
     import refworld
     import scenes
     w = scenes.tumbler(0)
@@ -177,7 +191,7 @@ def time_reference_tumblers(args, steps, warmup):
     """Reference Step on `cores` host threads, one independent tumbler world each (the reference is single-threaded
     per world; ctypes releases the GIL inside ref_step_timed). Returns (body-steps/s, cores, bodies per world)."""
     import refworld
-    import scenes_np
+    from playrho_b200 import scenes_np
     cores = args.ref_worlds or max(1, len(os.sched_getaffinity(0)))
     conf = scenes_np.tumbler_step_conf(refworld.default_step_conf(do_toi=0 if args.no_toi else 1))
     worlds = [None] * cores
@@ -255,7 +269,7 @@ def make_mixed_world(args, W, rank, local_rank):
 
 def make_tumbler_arena(args, W, rank, world_size, local_rank):
     """BASELINE config 5: this rank's share of --worlds tumbler worlds in one device arena; Step(); AddSquare() x --squares."""
-    import scenes_np
+    from playrho_b200 import scenes_np
     from playrho_b200 import shard
     _, n_worlds = shard.world_block(args.worlds, rank, world_size)  # this rank's contiguous block of worlds
     unit = scenes_np.tumbler(0)
@@ -263,6 +277,8 @@ def make_tumbler_arena(args, W, rank, world_size, local_rank):
     gw = W.Batch(n_worlds, device=local_rank, body_capacity=n_worlds * per + 16, proxy_capacity=n_worlds * (4 + args.squares) + 64,
                  contact_capacity=12 * n_worlds * args.squares)  # (~9 fat-box pairs per square at 512 squares: no growth while timing)
     gw.set_toi_mode(args.toi_mode)
+    if args.debug_flags:
+        gw.lib.pr_set_debug(gw.h, args.debug_flags)
     gw.create_shapes(unit)  # the 5 shapes (4 enclosure walls + the square) are shared by every world
     nu = len(unit["bodies"])
     offs = np.concatenate([[0], (unit["shape_offsets"][1:][None, :] + int(unit["shape_offsets"][-1]) * np.arange(n_worlds)[:, None]).reshape(-1)])
@@ -283,6 +299,21 @@ def make_tumbler_arena(args, W, rank, world_size, local_rank):
            "motorised revolute joint + %d squares added one per step before timing, Benchmark/BenchmarkMain.cpp:2614-2759)" \
            % (args.worlds, n_worlds, per, args.squares)
     return gw, conf, desc, {"worlds": args.worlds, "worlds_per_gpu": n_worlds, "bodies_per_world": per}
+
+
+def time_steps(gw, conf, stream, steps, warmup=3):
+    """Device time of `steps` steps of an already-built world (CUDA events on the world's stream)."""
+    import torch
+    for _ in range(warmup):
+        gw.step(conf)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        gw.step(conf)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
 
 
 def main():
@@ -448,6 +479,13 @@ def main():
                 {"algorithmic_bytes": terms["a9_setup"], "ms": stage["setup"],
                  "achieved": (terms["a9_setup"] / 1e9) / (stage["setup"] / 1e3) if stage["setup"] > 0 else 0.0},
         }
+        def entry(nbytes, ms):
+            return {"algorithmic_bytes": nbytes, "ms": ms, "achieved": (nbytes / 1e9) / (ms / 1e3) if ms > 0 else 0.0}
+        # broadphase: proxy AABBs + fat-box policy, LBVH refit/rebuild, overlap query -- per stage and together
+        others["k_sync_proxies (a2: proxy AABB + fat-box policy)"] = entry(terms["a2_proxies"], stage["sync"])
+        others["k_bvh_* (a3: Morton sort + LBVH build/refit)"] = entry(terms["a3_bvh"], stage["bvh"])
+        others["k_bvh_query* (a4: overlap query)"] = entry(terms["a4_query"], stage["query"])
+        others["broadphase a2-a4 together"] = entry(terms["a2_proxies"] + terms["a3_bvh"] + terms["a4_query"], stage["sync"] + stage["bvh"] + stage["query"])
         for v in others.values():
             v["frac"] = v["achieved"] / peak
         cfg = {"workload": desc, "toi": not args.no_toi, "toi_mode": "parallel" if args.toi_mode else "serial-exact",
@@ -491,8 +529,37 @@ def main():
                                      "toi_events": int(folded["toi"]["contacts_found"]), "min_separation": float(min(folded["reg"]["min_separation"], folded["toi"]["min_separation"])),
                                      "max_inc_impulse": float(max(folded["reg"]["max_inc_impulse"], folded["toi"]["max_inc_impulse"]))},
         }
+        if world_size == 1 and not tumblers and not args.no_extras and not args.no_toi and args.toi_mode == 1:
+            # the same world with the reference's own TOI event order (PR_TOI_SERIAL_EXACT: one event per round): on record
+            # beside the parallel rounds the headline times (both modes are pinned bit for bit to the oracle by the GPU tests)
+            try:
+                other = gw.clone()
+                other.set_toi_mode(0)
+                ostream = torch.cuda.ExternalStream(other.stream(), device=torch.device("cuda", local_rank))
+                ms0 = time_steps(other, conf, ostream, 2, warmup=1)
+                line["toi_serial_exact"] = {"ms_per_step": ms0, "steps": 2, "rounds_per_step": int(other.profile()["toi_rounds"]),
+                                            "note": "same state, TOI events one per round in the reference's order"}
+                del other
+            except Exception as e:  # noqa: BLE001
+                line["toi_serial_exact"] = {"ms_per_step": None, "note": "failed: %s" % e}
+        if world_size == 1 and not tumblers and not args.no_extras:
+            # BASELINE config 5 at N=1: the base of the strong-scaling runs (bench.py --gpus N > 1 shards these worlds)
+            try:
+                del gw
+                targs = argparse.Namespace(**vars(args))
+                targs.workload = "tumblers"
+                tw, tconf, tdesc, textra = make_tumbler_arena(targs, W, 0, 1, local_rank)
+                tstream = torch.cuda.ExternalStream(tw.stream(), device=torch.device("cuda", local_rank))
+                tms = time_steps(tw, tconf, tstream, 10)
+                tnb = int(tw.counts()["bodies"])
+                line["tumblers_n1"] = {"workload": tdesc, "ms_per_step": tms, "value": tnb / (tms / 1e3), "unit": "body-steps/s", "steps": 10,
+                                       "note": "the N=1 point of the strong-scaling series that --gpus 2/4/8 continue (same 8192 worlds, sharded)"}
+                del tw
+            except Exception as e:  # noqa: BLE001
+                line["tumblers_n1"] = {"value": None, "note": "failed: %s" % e}
         if not args.no_cpu_baseline and world_size == 1:
             try:
+                _checker_path()
                 import refworld
                 if refworld.have_ref(refworld.have_ref(True)):
                     if tumblers:

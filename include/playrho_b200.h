@@ -323,7 +323,8 @@ int pr_get_toi_schedule(const pr_world* w, uint32_t cap, uint32_t* round_contact
  * bit 1 = use the binned narrowphase, bit 2 = use the persistent fused solver kernel (two experiments that did not beat the
  * default kernels on B200; off by default, kept under test); bit 3 = TOI rounds through the list kernels only (no single-block
  * late rounds: A/B measurements); bit 4 = hub rule of the colouring (colours capped at 24 when a few bodies carry very many
- * constraints, the rest in the per-island serial tail: measured no faster on the tumbler arena) */
+ * constraints, the rest in the per-island serial tail: measured no faster on the tumbler arena); bit 5 = a batch arena solves
+ * through the arena-wide per-colour launches instead of the block solver (one CTA per world, pr_block_solve.cuh): A/B runs */
 int pr_set_debug(pr_world* w, uint32_t flags);
 int pr_get_step_profile(const pr_world* w, pr_step_profile* out);
 int pr_abi_sizeof(int which); /* sizeof of the POD structs above, for foreign-language mirrors */

@@ -50,6 +50,18 @@ typedef cudaEvent_t pr_event_t;
         cudaLaunchKernelEx(&pr_cfg_, kernel, __VA_ARGS__);                                         \
         pr::count_launch();                                                                        \
     } while (0)
+#define PR_LAUNCH_GRID_SMEM(kernel, grid, block, smemBytes, strm_, ...)                            \
+    do {                                                                                           \
+        cudaLaunchConfig_t pr_cfg_ = {};                                                           \
+        pr_cfg_.gridDim = dim3(grid); pr_cfg_.blockDim = dim3(block); pr_cfg_.stream = strm_;      \
+        pr_cfg_.dynamicSmemBytes = smemBytes;                                                      \
+        cudaLaunchAttribute pr_at_[1];                                                             \
+        pr_at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                         \
+        pr_at_[0].val.programmaticStreamSerializationAllowed = 1;                                  \
+        pr_cfg_.attrs = pr_at_; pr_cfg_.numAttrs = 1;                                              \
+        cudaLaunchKernelEx(&pr_cfg_, kernel, __VA_ARGS__);                                         \
+        pr::count_launch();                                                                        \
+    } while (0)
 // (the per-colour solver kernels go further: they fetch their immutable row planes BEFORE the wait)
 #define PR_LAUNCH_PDL PR_LAUNCH
 __device__ __forceinline__ void pr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -43,20 +43,33 @@ PR_D unsigned joint_island(const DV& d, const pr_revolute_joint& j)
     return INVALID;
 }
 
-PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf)
+// Where a joint's BodyConstraints and its island's flags live: the world's HBM arrays indexed by body id / island label
+// (jview_global), or a block's shared-memory arrays indexed by slot (pr_block_solve.cuh; slot[] maps a body id to its slot).
+// slotV / slotP / slotI: body id -> index into s_vel / s_pos / isl_state (nullptr: the id itself). isl_jflag is always the
+// world's array, indexed by island label.
+struct JView { float4 *s_vel, *s_pos; const unsigned* isl_state; unsigned* isl_jflag; const unsigned *slotV, *slotP, *slotI; };
+PR_D JView jview_global(const DV& d)
+{
+    JView v; v.s_vel = d.s_vel; v.s_pos = d.s_pos; v.isl_state = d.isl_state; v.isl_jflag = d.isl_jflag; v.slotV = v.slotP = v.slotI = nullptr;
+    return v;
+}
+PR_D unsigned jv_idx(const unsigned* slot, unsigned id) { return slot ? slot[id] : id; }
+
+PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf, const JView& v)
 {
     pr_revolute_joint j = d.jt[ji];
     JointWork wk;
     wk.island = joint_island(d, j);
     if (wk.island == INVALID) { d.jt_work[ji] = wk; return; }
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
     // AddJointsToIsland (:1443-1466) puts the other body on the island's stack whatever its type: a body that cannot move is
     // the island's guest (maxIslandBodies, see island_count_static)
     if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
     if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
-    const float4 pA = d.s_pos[j.body_a], pB = d.s_pos[j.body_b];
-    float4 velA = d.s_vel[j.body_a], velB = d.s_vel[j.body_b];
+    const float4 pA = v.s_pos[jv_idx(v.slotP, j.body_a)], pB = v.s_pos[jv_idx(v.slotP, j.body_b)];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
     const float aA = pA.z, aB = pB.z;
     const Rot qA = rot_from_angle(aA), qB = rot_from_angle(aB);
     const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
@@ -99,19 +112,21 @@ PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf
         j.impulse_x = j.impulse_y = j.impulse_z = 0.0f;
         j.angular_motor_impulse = 0.0f;
     }
-    d.s_vel[j.body_a] = velA; d.s_vel[j.body_b] = velB; // bodyConstraint.SetVelocity (:224-225)
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB; // bodyConstraint.SetVelocity (:224-225)
     d.jt[ji] = j;
     d.jt_work[ji] = wk;
 }
 
-PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& conf)
+PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& conf, const JView& v)
 {
     const JointWork wk = d.jt_work[ji];
-    if (wk.island == INVALID || (d.isl_state[wk.island] & ISL_VEL_DONE)) return;
+    if (wk.island == INVALID) return;
+    if (v.isl_state[jv_idx(v.slotI, wk.island)] & ISL_VEL_DONE) return;
     pr_revolute_joint j = d.jt[ji];
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
-    const float4 oldA = d.s_vel[j.body_a], oldB = d.s_vel[j.body_b];
+    const float4 oldA = v.s_vel[ia], oldB = v.s_vel[ib];
     float4 velA = oldA, velB = oldB;
     const float2 rA = v2(wk.rAx, wk.rAy), rB = v2(wk.rBx, wk.rBy);
     const bool fixedRotation = (iiA + iiB == 0.0f);
@@ -159,19 +174,21 @@ PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& con
     d.jt[ji] = j;
     const bool changed = velA.x != oldA.x || velA.y != oldA.y || velA.z != oldA.z || velB.x != oldB.x || velB.y != oldB.y || velB.z != oldB.z;
     if (changed) {
-        d.s_vel[j.body_a] = velA; d.s_vel[j.body_b] = velB;
-        d.isl_jflag[wk.island] = 1u; // jointsOkay = false for this island this iteration (:1604-1608)
+        v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+        v.isl_jflag[wk.island] = 1u; // jointsOkay = false for this island this iteration (:1604-1608)
     }
 }
 
-PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& conf)
+PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& conf, const JView& v)
 {
     const JointWork wk = d.jt_work[ji];
-    if (wk.island == INVALID || (d.isl_state[wk.island] & ISL_POS_SOLVED)) return;
+    if (wk.island == INVALID) return;
+    if (v.isl_state[jv_idx(v.slotI, wk.island)] & ISL_POS_SOLVED) return;
     const pr_revolute_joint j = d.jt[ji];
+    const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
-    float4 posA = d.s_pos[j.body_a], posB = d.s_pos[j.body_b];
+    float4 posA = v.s_pos[ia], posB = v.s_pos[ib];
     const bool fixedRotation = ((iiA + iiB) == 0.0f);
     float angularError = 0.0f;
     if (j.enable_limit && (j.limit_state != LS_INACTIVE) && !fixedRotation) {
@@ -215,9 +232,9 @@ PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& con
         const float2 la = v2(posA.x, posA.y) - imA * P; posA.x = la.x; posA.y = la.y; posA.z -= iiA * cross(rA, P) / 1.0f;
         const float2 lb = v2(posB.x, posB.y) + imB * P; posB.x = lb.x; posB.y = lb.y; posB.z += iiB * cross(rB, P) / 1.0f;
     }
-    d.s_pos[j.body_a] = posA; d.s_pos[j.body_b] = posB;
+    v.s_pos[ia] = posA; v.s_pos[ib] = posB;
     const bool ok = (positionError <= square(conf.linear_slop)) && (angularError <= conf.angular_slop);
-    if (!ok) d.isl_jflag[wk.island] = 1u;
+    if (!ok) v.isl_jflag[wk.island] = 1u;
 }
 
 // phase: 0 = InitVelocity, 1 = SolveVelocity, 2 = SolvePosition. serial != 0: one thread walks all joints.
@@ -226,10 +243,11 @@ PR_KERNEL k_joints(DV d, pr_step_conf conf, unsigned nJoints, unsigned phase, un
     PR_PDL_ENTER();
     const unsigned t = PR_TID;
     const unsigned lo = serial ? 0u : t, hi = serial ? (t == 0u ? nJoints : 0u) : (t < nJoints ? t + 1u : 0u);
+    const JView v = jview_global(d);
     for (unsigned ji = lo; ji < hi; ++ji) {
-        if (phase == 0u) joint_init_velocity(d, ji, conf);
-        else if (phase == 1u) joint_solve_velocity(d, ji, conf);
-        else joint_solve_position(d, ji, conf);
+        if (phase == 0u) joint_init_velocity(d, ji, conf, v);
+        else if (phase == 1u) joint_solve_velocity(d, ji, conf, v);
+        else joint_solve_position(d, ji, conf, v);
     }
 }
 // islands: a joint links its two bodies (AddToIsland :1443-1466) when both can be island members

@@ -1434,10 +1434,12 @@ struct RS {
     float4 *vc0, *vc1, *vc2, *vc3, *vc4, *vc5, *vc6, *vc7, *vc8; unsigned* vc_island;
     float4 *pc0, *pc1, *pc2, *pc3;
     float4 *s_vel, *s_pos;
+    const unsigned* isl_state; // per-island early-exit flags, indexed by the rows' island field (HBM, or a block's shared memory)
 };
 PR_D RS rs_global(const DV& d)
 {
     RS r;
+    r.isl_state = d.isl_state;
     r.vc0 = d.vc0; r.vc1 = d.vc1; r.vc2 = d.vc2; r.vc3 = d.vc3; r.vc4 = d.vc4; r.vc5 = d.vc5; r.vc6 = d.vc6; r.vc7 = d.vc7; r.vc8 = d.vc8;
     r.vc_island = d.vc_island; r.pc0 = d.pc0; r.pc1 = d.pc1; r.pc2 = d.pc2; r.pc3 = d.pc3; r.s_vel = d.s_vel; r.s_pos = d.s_pos;
     return r;
@@ -1517,8 +1519,10 @@ PR_D PCRow pc_load(const RS& r, unsigned i)
 // + PositionConstraint (AabbTreeWorld.cpp:289-312) for sorted constraint row i
 // r: where the rows and the BodyConstraint arrays live (HBM for the regular phase, shared memory for a TOI mini island);
 // sA/sB: the two bodies' indices into r.s_vel / r.s_pos (the body ids themselves in the regular phase)
+// storeA/storeB: what the row keeps as its bodies' indices (the block solver, pr_block_solve.cuh, keeps slots of the block's
+// shared-memory arrays; everyone else the indices the row was built from)
 PR_D void build_constraint_rows(const DV& d, const RS& r, unsigned cid, unsigned i, const pr_step_conf& conf, float dtRatio, unsigned islandLabel,
-                                unsigned sA, unsigned sB)
+                                unsigned sA, unsigned sB, unsigned storeA = INVALID, unsigned storeB = INVALID)
 {
     {
         const uint4 ab = d.c_ab[cid];
@@ -1574,7 +1578,7 @@ PR_D void build_constraint_rows(const DV& d, const RS& r, unsigned cid, unsigned
         }
         VCRow vc;
         vc.nx = normal.c; vc.ny = normal.s; vc.friction = mat.x; vc.tangentSpeed = mat.z;
-        vc.bodyA = sA; vc.bodyB = sB; vc.count = count; vc.contact = cid;
+        vc.bodyA = (storeA != INVALID) ? storeA : sA; vc.bodyB = (storeB != INVALID) ? storeB : sB; vc.count = count; vc.contact = cid;
         vc.invMA = mA.x; vc.invIA = mA.y; vc.invMB = mB.x; vc.invIB = mB.y;
         vc.island = islandLabel;
         vc.dynA = (mA.x != 0.0f || mA.y != 0.0f) ? 1u : 0u; vc.dynB = (mB.x != 0.0f || mB.y != 0.0f) ? 1u : 0u; vc.pad = 0u;
@@ -1628,7 +1632,9 @@ PR_D void build_constraint_rows(const DV& d, const RS& r, unsigned cid, unsigned
         vc_store(r, i, vc);
     }
 }
-PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtRatio)
+// blockMode: the rows are for the block solver (pr_block_solve.cuh) -- they keep their bodies' slots and the slot of the
+// island's root instead of body ids and the island's label
+PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtRatio, unsigned blockMode)
 {
     // (no early trigger: the solver kernels that follow fetch the rows written here BEFORE their own dependency wait)
     pr_pdl_wait();
@@ -1637,7 +1643,9 @@ PR_KERNEL k_build_constraints(DV d, unsigned nCons, pr_step_conf conf, float dtR
         const unsigned cid = d.k_contact[d.k_sorted[i]];
         const uint4 ab = d.c_ab[cid];
         const unsigned rAi = d.b_island[ab.x], rBi = d.b_island[ab.y];
-        build_constraint_rows(d, rs_global(d), cid, i, conf, dtRatio, (rAi != INVALID) ? rAi : rBi, ab.x, ab.y);
+        const unsigned label = (rAi != INVALID) ? rAi : rBi;
+        if (blockMode) build_constraint_rows(d, rs_global(d), cid, i, conf, dtRatio, d.b_slot[label], ab.x, ab.y, d.b_slot[ab.x], d.b_slot[ab.y]);
+        else build_constraint_rows(d, rs_global(d), cid, i, conf, dtRatio, label, ab.x, ab.y);
     }
 }
 
@@ -1731,7 +1739,7 @@ PR_D float solve_velocity_loaded(const DV& d, const RS& r, unsigned i, VCRow vc,
     did = false;
     // (the two body loads are issued before the island test, not behind it: one round trip less in the dependent chain)
     float4 vA = r.s_vel[vc.bodyA], vB = r.s_vel[vc.bodyB];
-    if (checkIsland && (d.isl_state[vc.island] & ISL_VEL_DONE)) return 0.0f;
+    if (checkIsland && (r.isl_state[vc.island] & ISL_VEL_DONE)) return 0.0f;
     did = true;
     const Rot normal = mkrot(vc.nx, vc.ny), tangent = fwd_perp(normal);
     const float2 relA[2] = {v2(vc.rA0x, vc.rA0y), v2(vc.rA1x, vc.rA1y)}, relB[2] = {v2(vc.rB0x, vc.rB0y), v2(vc.rB1x, vc.rB1y)};
@@ -1949,7 +1957,7 @@ PR_D float solve_position_loaded(const DV& d, const RS& r, const VCRow& vch, con
     const float imA = vcp->invMA, iiA = vcp->invIA, imB = vcp->invMB, iiB = vcp->invIB;
     const unsigned dynA = vcp->dynA, dynB = vcp->dynB;
     float4 a4 = r.s_pos[bA], b4 = r.s_pos[bB]; // (issued before the island test: see solve_velocity_row)
-    if (checkIsland && (d.isl_state[island] & ISL_POS_SOLVED)) return PR_INF;
+    if (checkIsland && (r.isl_state[island] & ISL_POS_SOLVED)) return PR_INF;
     did = true;
     Pos posA = pos_from4(a4), posB = pos_from4(b4);
     const float2 lcA = v2(pc.lcAx, pc.lcAy), lcB = v2(pc.lcBx, pc.lcBy);
@@ -2058,7 +2066,9 @@ PR_KERNEL k_assign_impulses(DV d, unsigned nCons)
         if (count > 1u) { m2.z = imp.z; m2.w = imp.w; }
         d.m2[cid] = m2;
         if (d.ev_mask & PR_EVENT_POST_SOLVE) { // Report(postSolveContact, ...), AabbTreeWorld.cpp:1671-1674
-            const unsigned r = d.vc_island[i];
+            const uint4 ab = d.c_ab[cid]; // (the island's label from the bodies: the block solver's rows keep slots, not labels)
+            const unsigned rA = d.b_island[ab.x];
+            const unsigned r = (rA != INVALID) ? rA : d.b_island[ab.y];
             const unsigned it = (d.isl_state[r] & ISL_POS_SOLVED) ? d.isl_posIters[r] - 1u : 255u; // StepConf::InvalidIteration
             emit_impulse_event(d, cid, count, it, 0u, imp);
         }
@@ -2129,11 +2139,10 @@ PR_KERNEL k_isl_recount_statics(DV d, unsigned nCons, unsigned nJoints)
 {
     PR_PDL_ENTER();
     const unsigned i = PR_TID;
-    if (i < nCons) {
-        const float4 head = d.vc1[i];
-        const unsigned bA = f2u(head.x), bB = f2u(head.y);
-        const unsigned rA = d.b_island[bA], rB = d.b_island[bB];
-        if (rA == INVALID || rB == INVALID) island_count_static(d, d.vc_island[i], rA == INVALID ? bA : bB);
+    if (i < nCons) { // (bodies and label through the row's contact: the block solver's rows keep slots)
+        const uint4 ab = d.c_ab[f2u(d.vc1[i].w)];
+        const unsigned rA = d.b_island[ab.x], rB = d.b_island[ab.y];
+        if (rA == INVALID || rB == INVALID) island_count_static(d, rA != INVALID ? rA : rB, rA == INVALID ? ab.x : ab.y);
     }
     if (i < nJoints) {
         const unsigned isl = d.jt_work[i].island;
@@ -2297,7 +2306,7 @@ PR_KERNEL k_solve_order(DV d, unsigned nCons, unsigned* ids, unsigned* colors, c
 {
     PR_PDL_ENTER();
     const unsigned i = PR_TID;
-    if (i < nCons) { ids[i] = d.k_contact[d.k_sorted[i]]; colors[i] = sortedColor[i]; }
+    if (i < nCons) { ids[i] = d.k_contact[d.k_sorted[i]]; colors[i] = sortedColor[i] & 127u; } // (block solver keys: world << 7 | colour)
 }
 
 // standalone CollideShapes over arrays (pr_collide_shapes)
@@ -2322,4 +2331,5 @@ PR_KERNEL k_collide_batch(unsigned n, const pr_child* children, const float2* ve
 
 } // namespace pr
 #include "pr_toi_phase.cuh"
+#include "pr_block_solve.cuh"
 #endif

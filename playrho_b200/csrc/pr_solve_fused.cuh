@@ -59,15 +59,15 @@ PR_D void fused_joints(const DV& d, const pr_step_conf& conf, const SolvePlan& p
     if (p.jointsSerial) {
         if (PR_TID == 0u)
             for (unsigned ji = 0; ji < p.nJoints; ++ji) {
-                if (phase == 0u) joint_init_velocity(d, ji, conf);
-                else if (phase == 1u) joint_solve_velocity(d, ji, conf);
-                else joint_solve_position(d, ji, conf);
+                if (phase == 0u) joint_init_velocity(d, ji, conf, jview_global(d));
+                else if (phase == 1u) joint_solve_velocity(d, ji, conf, jview_global(d));
+                else joint_solve_position(d, ji, conf, jview_global(d));
             }
     } else {
         for (unsigned ji = PR_TID; ji < p.nJoints; ji += PR_NTHREADS) {
-            if (phase == 0u) joint_init_velocity(d, ji, conf);
-            else if (phase == 1u) joint_solve_velocity(d, ji, conf);
-            else joint_solve_position(d, ji, conf);
+            if (phase == 0u) joint_init_velocity(d, ji, conf, jview_global(d));
+            else if (phase == 1u) joint_solve_velocity(d, ji, conf, jview_global(d));
+            else joint_solve_position(d, ji, conf, jview_global(d));
         }
     }
 }

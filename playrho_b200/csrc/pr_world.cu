@@ -89,7 +89,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(isl_inc, G_BODY), A(isl_maxInc, G_BODY), A(isl_sep, G_BODY), A(isl_minSep, G_BODY), A(isl_minUA, G_BODY),
         A(isl_nbodies, G_BODY), A(isl_nstat, G_BODY), A(isl_active, G_BODY), A(b_claim, G_BODY), A(b_cmask, G_BODY),
         A(adj_off, G_BODY), A(adj_cnt, G_BODY), A(adj_n, G_BODY), A(b_toiIsl, G_BODY), A(b_toiAlpha, G_BODY), A(b_toiStamp, G_BODY), A(b_inR, G_BODY),
-        A(sync_list, G_BODY), A(bp_off, G_BODY), A(bp_list, G_PROXY), A(bv_leafOf, G_PROXY), A(b_world, G_BODY), A(bv_wr, G_PROXY),
+        A(sync_list, G_BODY), A(blk_body, G_BODY), A(b_slot, G_BODY), A(blk_joint, G_JOINT), A(bp_off, G_BODY), A(bp_list, G_PROXY), A(bv_leafOf, G_PROXY), A(b_world, G_BODY), A(bv_wr, G_PROXY),
         A(c_pos, G_CONTACT), A(c_color, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT), A(toi_list, G_CONTACT), A(toi_cand, G_CONTACT), A(toi_cand2, G_CONTACT), A(toi_re0, G_CONTACT),
         A(toi_re1, G_CONTACT), A(c_rstamp, G_CONTACT),
         A(adj_list, G_ADJ), A(toi_islBodies, G_ADJ), A(toi_islContacts, G_ADJ),
@@ -385,6 +385,78 @@ static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer
     return nPairs;
 }
 
+// ------------------------------------------------------------------ block solver plumbing (pr_block_solve.cuh)
+static unsigned block_color_cap()
+{ // colours a block walks with barriers; the rest of a world's rows (a hub's) is its serial tail. PR_BLK_COLORS overrides.
+    static const unsigned cap = [] { const char* e = getenv("PR_BLK_COLORS"); const unsigned v = e ? static_cast<unsigned>(atoi(e)) : 16u; return std::min(64u, std::max(1u, v)); }();
+    return cap;
+}
+static void ensure_block_tables(World& w)
+{
+    const unsigned need = w.d.nWorlds + 2u;
+    if (need <= w.blkWorldCap) return;
+    sync(w);
+    dev_free(w.d.blk_off); dev_free(w.d.blk_rowOff); dev_free(w.d.blk_jOff);
+    w.d.blk_off = static_cast<unsigned*>(dev_alloc(sizeof(unsigned) * need));
+    w.d.blk_rowOff = static_cast<unsigned*>(dev_alloc(sizeof(unsigned) * need));
+    w.d.blk_jOff = static_cast<unsigned*>(dev_alloc(sizeof(unsigned) * need));
+    w.blkWorldCap = need; w.blocksDirty = true; w.blkJointsDirty = true;
+}
+// bodies grouped by world: counting sort on the device (world index = key, ids ascending inside a world)
+static void rebuild_blocks(World& w)
+{
+    DV& d = w.d;
+    const unsigned N = w.nBodies, W = d.nWorlds;
+    ensure_block_tables(w);
+    if (w.blocksDirty) {
+        dset(w, d.blk_off, 0, sizeof(unsigned) * (W + 1u));
+        PR_LAUNCH(k_blk_count, N, w.stream, d, N, d.blk_off);
+        scan_exclusive_u32(d.blk_off, d.blk_off, W + 1u, nullptr, w.scanScratch, w.stream);
+        if (N) {
+            unsigned* buf = static_cast<unsigned*>(stage_buf(w, 0, sizeof(unsigned) * 4ull * N));
+            unsigned *kA = buf, *vA = buf + N, *kB = buf + 2ull * N, *vB = buf + 3ull * N;
+            d2d(w, kA, d.b_world, sizeof(unsigned) * N);
+            const bool inB = radix_sort_pairs<unsigned>(kA, vA, kB, vB, N, 0, static_cast<int>(d.worldBits), true, w.rs, w.stream);
+            PR_LAUNCH(k_blk_fill, N, w.stream, d, N, inB ? kB : kA, inB ? vB : vA);
+        }
+        read_counters(w);
+        w.hostCnt.blkMaxBodies = 0u;
+        write_counters(w);
+        PR_LAUNCH(k_blk_max, W, w.stream, d, W);
+        read_counters(w);
+        w.blkMaxBodies = w.hostCnt.blkMaxBodies;
+        w.blocksDirty = false;
+    }
+    if (w.blkJointsDirty) { // the joints of every world, ids ascending (few: built on the host)
+        std::vector<unsigned> off(W + 1u, 0u), list;
+        std::vector<std::pair<unsigned, unsigned>> wj;
+        for (unsigned j = 0; j < w.joints.size(); ++j) if (w.joints[j].body_a != INVALID) wj.emplace_back(w.bodyWorld[w.joints[j].body_a], j);
+        std::sort(wj.begin(), wj.end());
+        for (const auto& e : wj) { ++off[e.first + 1u]; list.push_back(e.second); }
+        for (unsigned k = 0; k < W; ++k) off[k + 1u] += off[k];
+        ensure(w, G_JOINT, static_cast<unsigned>(list.size()) + 1u);
+        h2d(w, d.blk_jOff, off.data(), sizeof(unsigned) * (W + 1u));
+        h2d(w, d.blk_joint, list.data(), sizeof(unsigned) * list.size());
+        sync(w);
+        w.blkJointsDirty = false;
+    }
+}
+static unsigned block_threads()
+{
+    static const unsigned t = [] { const char* e = getenv("PR_BLK_THREADS"); const unsigned v = e ? static_cast<unsigned>(atoi(e)) : BLK_THREADS; return std::min(BLK_MAX_THREADS, std::max(32u, v / 32u * 32u)); }();
+    return t;
+}
+// The block solver wins while the worlds of one GPU are few enough to be latency-bound (B200, 514-body tumblers: 512 worlds 1.8
+// vs 3.6 ms, 1 024 worlds 2.3 vs 4.9 ms for the whole solve); from ~2 500 worlds up the arena-wide per-colour launches, which
+// run every world's hub rows side by side in full warps, have the higher throughput (8 192 worlds: 9.2 vs 15.7 ms).
+// PR_BLK_MAX_WORLDS moves the crossover; debug bit 5 switches the block solver off.
+static unsigned block_max_worlds()
+{
+    static const unsigned v = [] { const char* e = getenv("PR_BLK_MAX_WORLDS"); return e ? static_cast<unsigned>(atoi(e)) : 2560u; }();
+    return v;
+}
+static bool use_block_solver(const World& w) { return w.d.nWorlds != 0u && w.d.nWorlds <= block_max_worlds() && !(w.debugFlags & (4u | 32u)); }
+
 // ------------------------------------------------------------------ regular phase (SolveReg :1472-1561)
 // the step's (island, non-speedable body) pair set (island_count_static): sized from what the last step inserted, emptied
 static void prepare_island_statics(World& w, unsigned want)
@@ -418,6 +490,14 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     DV& d = w.d;
     const unsigned N = w.nBodies;
     tm.mark(w, PR_STAGE_ISLANDS);
+    bool blockMode = use_block_solver(w);
+    if (blockMode) {
+        if (w.blocksDirty || w.blkJointsDirty || w.blkWorldCap < d.nWorlds + 2u) rebuild_blocks(w);
+        if (w.blkMaxBodies > BLK_MAX_BODIES) blockMode = false; // a world too large for one CTA's shared memory: arena-wide launches
+    }
+    // colours: a block walks few of them with barriers and runs the rest of its world's rows (a hub's) as its serial tail
+    if (blockMode) { if (w.colorCap != block_color_cap()) { w.colorCap = block_color_cap(); w.recolorAll = true; } }
+    else if (!(w.debugFlags & 16u) && w.colorCap != 64u) { w.colorCap = 64u; w.recolorAll = true; }
     prepare_island_statics(w, 4u * (w.isHint + 256u));
     PR_LAUNCH(k_isl_init, N, w.stream, d, N, conf.reg_velocity_iters, conf.reg_position_iters);
     PR_LAUNCH(k_isl_union, w.nOrder, w.stream, d, w.nOrder);
@@ -456,10 +536,19 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
                 if (round > 100000u) throw CudaError{"colouring did not converge"};
             }
         }
+        const unsigned* sortedColor = nullptr;
+        if (blockMode) { // rows sorted by (world, colour); every world's first row: histogram + scan (pr_block_solve.cuh)
+            dset(w, d.blk_rowOff, 0, sizeof(unsigned) * (d.nWorlds + 1u));
+            PR_LAUNCH(k_blk_row_keys, nCons, w.stream, d, nCons, d.k_tmpKey, d.blk_rowOff);
+            scan_exclusive_u32(d.blk_rowOff, d.blk_rowOff, d.nWorlds + 1u, nullptr, w.scanScratch, w.stream);
+            const bool inB = radix_sort_pairs<unsigned>(d.k_tmpKey, d.k_sorted, d.k_tmpKey2, d.k_tmpVal, nCons, 0, 7 + static_cast<int>(d.worldBits), true, w.rs, w.stream);
+            sortedColor = inB ? d.k_tmpKey2 : d.k_tmpKey;
+            if (inB) d2d(w, d.k_sorted, d.k_tmpVal, nCons * sizeof(unsigned));
+        } else {
         // stable sort by colour (one 8-bit radix pass): k_sorted = permutation of the base constraint list
         d2d(w, d.k_tmpKey, d.k_color, nCons * sizeof(unsigned));
         const bool inB = radix_sort_pairs<unsigned>(d.k_tmpKey, d.k_sorted, d.k_tmpKey2, d.k_tmpVal, nCons, 0, 8, true, w.rs, w.stream);
-        const unsigned* sortedColor = inB ? d.k_tmpKey2 : d.k_tmpKey;
+        sortedColor = inB ? d.k_tmpKey2 : d.k_tmpKey;
         if (inB) d2d(w, d.k_sorted, d.k_tmpVal, nCons * sizeof(unsigned));
         for (unsigned c = 0; c <= MAX_COLORS; ++c) w.hostCnt.colorStart[c] = INVALID;
         write_counters(w);
@@ -484,6 +573,8 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             read_counters(w);
             nTailSegs = w.hostCnt.nTailSegs;
         }
+        } // (!blockMode)
+        w.blkSortedKey = sortedColor;
         if (w.debugFlags & 1u) { // solve order for the parity oracle (pr_get_solve_order)
             w.solveOrderIds.resize(nCons); w.solveOrderColors.resize(nCons);
             // c_tmp (marks, consumed) and c_tmp2 (stale ping-pong copy of c_order) are free scratch here
@@ -492,9 +583,11 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             d2h(w, w.solveOrderColors.data(), d.c_tmp2, nCons * sizeof(unsigned));
         }
         w.nColors = static_cast<unsigned>(ranges.size()) + (tailCount ? 1u : 0u);
-        if (nWork == nCons) w.colorsAtFull = w.nColors; // (this step coloured everything from scratch)
+        if (blockMode) w.nColors = 0u; // (filled from the device's count at the end of the step)
+        else if (nWork == nCons) w.colorsAtFull = w.nColors; // (this step coloured everything from scratch)
         else if (w.nColors > 24u && w.nColors > w.colorsAtFull + 8u) w.recolorAll = true; // persistent colours fragmented
-        if ((w.debugFlags & 16u) && w.colorCap == 64u && ranges.size() > 32u) { // hub rule (World::colorCap, opt-in): cap the colours from the next step on?
+        if (blockMode) { }
+        else if ((w.debugFlags & 16u) && w.colorCap == 64u && ranges.size() > 32u) { // hub rule (World::colorCap, opt-in): cap the colours from the next step on?
             unsigned long long beyond = tailCount;
             for (size_t c = COLOR_CAP_HUBS; c < ranges.size(); ++c) beyond += ranges[c].second;
             const unsigned islands = std::max(1u, w.hostCnt.islandsFound);
@@ -503,8 +596,9 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             w.colorCap = 64u; w.recolorAll = true;
         }
         tm.mark(w, PR_STAGE_SETUP);
-        PR_LAUNCH(k_build_constraints, nCons, w.stream, d, nCons, conf, conf.do_warm_start ? conf.dt_ratio : 0.0f);
+        PR_LAUNCH(k_build_constraints, nCons, w.stream, d, nCons, conf, conf.do_warm_start ? conf.dt_ratio : 0.0f, blockMode ? 1u : 0u);
     }
+    if (blockMode && !nCons) dset(w, d.blk_rowOff, 0, sizeof(unsigned) * (d.nWorlds + 1u)); // (no world has a row)
     const unsigned jSerial = w.jointsSerial ? 1u : 0u, jThreads = w.jointsSerial ? (w.nJoints ? 1u : 0u) : w.nJoints;
     bool fused = false;
 #ifndef PR_HOST_EMUL
@@ -540,7 +634,18 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         }
     }
 #endif
-    if (!fused) {
+    if (blockMode) { // one CTA per world runs the whole solve (pr_block_solve.cuh)
+        tm.mark(w, PR_STAGE_VELOCITY);
+        const unsigned maxB = std::max(1u, w.blkMaxBodies);
+#ifndef PR_HOST_EMUL
+        const unsigned smem = maxB * BLK_BYTES_PER_BODY;
+        if (smem > w.blkSmemSet) { CK(cudaFuncSetAttribute(k_block_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); w.blkSmemSet = smem; }
+        PR_LAUNCH_GRID_SMEM(k_block_solve, d.nWorlds, block_threads(), smem, w.stream, d, conf, w.blkSortedKey, maxB, (nCons && conf.do_warm_start) ? 1u : 0u);
+#else
+        PR_LAUNCH(k_block_solve, d.nWorlds, w.stream, d, conf, w.blkSortedKey, maxB, (nCons && conf.do_warm_start) ? 1u : 0u);
+#endif
+        tm.mark(w, PR_STAGE_POSITION);
+    } else if (!fused) {
         // the trailing colours with at most SMALL_COLOR_ROWS rows go through ONE single-block launch per iteration
         size_t nBig = ranges.size();
 #ifndef PR_HOST_EMUL
@@ -621,6 +726,11 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     stats.reg.min_separation = float_unflip(c.minSepFlip);
     stats.reg.max_inc_impulse = u2f(c.maxIncBits);
     w.profile.n_awake = c.nAwake; w.profile.c_touching = c.nTouching; w.profile.c_dirty = c.contactsUpdated;
+    if (blockMode) w.nColors = c.blkColors;
+#ifdef PR_TOI_TIMING
+    if (blockMode) std::fprintf(stderr, "blk_timing world 0: rows %llu tail %llu bodies %llu | cyc: warm colours %llu tail %llu | vel colours %llu tail %llu | pos colours %llu tail %llu | other %llu\n",
+                                c.dbgBlk[8], c.dbgBlk[9], c.dbgBlk[10], c.dbgBlk[0], c.dbgBlk[1], c.dbgBlk[2], c.dbgBlk[3], c.dbgBlk[4], c.dbgBlk[5], c.dbgBlk[11]);
+#endif
     w.profile.p_moved = c.proxiesMoved; w.profile.n_islands = c.islandsFound; w.profile.n_colors = w.nColors;
     w.profile.vel_iters = conf.reg_velocity_iters; w.profile.pos_iters = conf.reg_position_iters;
     stats.reg.contacts_added = find_add_contacts(w, conf, tm);
@@ -1022,7 +1132,7 @@ int pr_destroy(pr_world* pw)
     delete static_cast<StageTimer*>(w.timer);
     for (const ArrDesc& a : arrays(w)) dev_free(*a.slot);
     dev_free(w.d.ev_contact); dev_free(w.d.ev_impulse);
-    dev_free(w.d.is_keys); dev_free(w.d.toi_log); dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist); dev_free(w.stageBuf[0]); dev_free(w.stageBuf[1]);
+    dev_free(w.d.is_keys); dev_free(w.d.blk_off); dev_free(w.d.blk_rowOff); dev_free(w.d.blk_jOff); dev_free(w.d.toi_log); dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist); dev_free(w.stageBuf[0]); dev_free(w.stageBuf[1]);
 #ifndef PR_HOST_EMUL
     if (w.stream) cudaStreamDestroy(w.stream);
     if (w.pinnedCnt) cudaFreeHost(w.pinnedCnt);
@@ -1054,7 +1164,7 @@ int pr_clone(const pr_world* src, pr_world** out)
     w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies;
     w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll; w.toiPossible = s.toiPossible; w.colorCap = s.colorCap;
     w.nJoints = s.nJoints; w.jointsSerial = s.jointsSerial; w.d.nNcPairs = s.d.nNcPairs;
-    w.d.nWorlds = s.d.nWorlds; w.d.worldBits = s.d.worldBits; w.bodyWorld = s.bodyWorld;
+    w.d.nWorlds = s.d.nWorlds; w.d.worldBits = s.d.worldBits; w.bodyWorld = s.bodyWorld; w.blocksDirty = w.blkJointsDirty = true;
     w.nBodies = s.nBodies; w.nShapes = s.nShapes; w.nChildren = s.nChildren; w.nVerts = s.nVerts; w.nProxies = s.nProxies;
     w.maxTreeId = s.maxTreeId; w.debugFlags = s.debugFlags;
     w.nOrder = s.nOrder; w.nFree = s.nFree; w.poolSize = s.poolSize; w.anyBodySet = s.anyBodySet; w.hashDirty = true;
@@ -1144,7 +1254,7 @@ static int create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const 
     h2d(w, staging, bodies, sizeof(pr_body) * n);
     PR_LAUNCH(k_put_bodies, n, w.stream, w.d, n, w.nBodies, static_cast<const unsigned*>(nullptr), staging, 0u);
     dset(w, w.d.b_moved + w.nBodies, 0, 4 * n); dset(w, w.d.b_sync + w.nBodies, 0, 4 * n);
-    if (w.d.nWorlds) { h2d(w, w.d.b_world + w.nBodies, world_index, 4 * n); w.bodyWorld.insert(w.bodyWorld.end(), world_index, world_index + n); }
+    if (w.d.nWorlds) { h2d(w, w.d.b_world + w.nBodies, world_index, 4 * n); w.bodyWorld.insert(w.bodyWorld.end(), world_index, world_index + n); w.blocksDirty = true; }
     sync(w);
     dev_free(staging);
     for (uint32_t i = 0; i < n; ++i) {
@@ -1189,6 +1299,7 @@ int pr_set_shape_material(pr_world* pw, uint32_t shape, float friction, float re
 // collideConnected == false joint, sorted, for the broadphase's ShouldCollide. Destroyed joints (bodies == INVALID) are skipped.
 static void refresh_joint_tables(World& w)
 {
+    w.blkJointsDirty = true; // (block solver: the joints of every world are listed again before the next solve)
     std::unordered_map<unsigned, unsigned> uses;
     std::vector<unsigned long long> nc;
     for (const auto& j : w.joints) {

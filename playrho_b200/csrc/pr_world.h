@@ -68,6 +68,7 @@ struct Counters {
     unsigned proxiesMoved, contactsUpdated, nAwake, nTouching, nActiveVel, nActivePos;
     unsigned minSepFlip, maxIncBits, error, pad;
     unsigned toiLogN; // TOI events logged this step (pr_get_toi_schedule)
+    unsigned blkMaxBodies, blkColors; // block solver (pr_block_solve.cuh): bodies of the largest world, colours in use this step
     unsigned nStaticTouch, islStatOverflow; // (island, non-speedable body) pairs: constraints/joints seen, set overflow (see island_count_static)
     unsigned boundsMinX, boundsMinY, boundsMaxX, boundsMaxY;
     unsigned nEvContact, nEvImpulse; // contact events of this step (pr_events): begin/end records, post-solve records
@@ -84,6 +85,7 @@ struct Counters {
     unsigned toiRoundId, toiReN[2], toiCand2N, toiAtMaxLive, toiForceFull, tbPad2;
 #ifdef PR_TOI_TIMING
     unsigned long long dbg[16]; // profiling build only: clock64 deltas of the phases of toi_solve_event (event 0 of each round)
+    unsigned long long dbgBlk[12]; // profiling build only: clock64 deltas of the phases of k_block_solve (block 0, thread 0)
     unsigned long long dbgLate[12]; // profiling build only: clock64 deltas of the stages of a k_tb_late round (thread 0)
 #endif
 };
@@ -133,6 +135,9 @@ struct DV {
     // batched independent worlds (config 5): every body carries the index of the world it lives in; the world index is
     // the high bits of the LBVH sort key, so each internal node covers a contiguous world range [bv_wr.x, bv_wr.y]
     unsigned* b_world; uint2* bv_wr; unsigned nWorlds, worldBits; // nWorlds == 0: a plain single world
+    // block solver (pr_block_solve.cuh): bodies grouped by world (CSR blk_off/blk_body, b_slot = index of a body inside its
+    // world), this step's first constraint row of every world, the joints of every world
+    unsigned *blk_off, *blk_body, *b_slot, *blk_rowOff, *blk_jOff, *blk_joint;
     Counters* cnt;
 };
 
@@ -189,6 +194,8 @@ struct World {
     std::vector<unsigned> solveOrderIds, solveOrderColors;
     std::vector<uint2> toiSchedule; unsigned toiScheduleN = 0; // last step's TOI events by round (debug bit 0)
     std::vector<void*> allocs;
+    const unsigned* blkSortedKey = nullptr; // this step's sorted (world << 7 | colour) keys
+    bool blocksDirty = true, blkJointsDirty = true; unsigned blkMaxBodies = 0, blkWorldCap = 0, blkSmemSet = 0; // block solver
     unsigned isCap = 0, isHint = 0; // island-static pair set: capacity (power of two), pairs seen last step
     unsigned* gridBar = nullptr; unsigned fusedGrid = 0; bool fusedProbed = false; // persistent solver kernel (pr_solve_fused.cuh)
     void* timer = nullptr; // StageTimer (pr_world.cu): per-stage CUDA events of this world's device
