@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--toi-mode", type=int, default=1, help="1 = parallel independent TOI events (product default), 0 = serial-exact")
     ap.add_argument("--debug-flags", type=int, default=0, help="pr_set_debug flags (see include/playrho_b200.h; 32 = tumbler arena through the arena-wide per-colour launches instead of the block solver)")
     ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
+    ap.add_argument("--strip", type=float, default=None, help="mixed: width (m) of the terrain strip the bodies are dropped over (default: a 4:1 lattice, 2 200 m at 1M bodies)")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra measurements of the N=1 mixed line (tumbler arena at N=1, serial-exact TOI mode)")
     args = ap.parse_args()
     if args.workload is None:  # one world runs on one GPU (config 4); what shards over the GPUs of a box is the batch of worlds (config 5)
@@ -162,7 +163,7 @@ def build_scene(args, seed):
     from playrho_b200 import scenes_np
     if args.workload == "disks":
         return scenes_np.disks_box(args.bodies, seed=seed)
-    return scenes_np.mixed_fast(args.bodies, seed=seed)
+    return scenes_np.mixed_fast(args.bodies, seed=seed, strip_width=args.strip)
 
 
 # ---------------------------------------------------------------- reference arm (CPU)

@@ -277,6 +277,12 @@ typedef struct pr_ray_hit {
 } pr_ray_hit;
 int pr_ray_cast(const pr_world* w, uint32_t n_rays, const float* rays5, const uint32_t* ray_world, uint32_t mode, uint32_t cap,
                 pr_ray_hit* hits, uint32_t* n_out);
+/* TestPoint(const World&, BodyID, ShapeID, const Length2&) (WorldShape.cpp:178-181; DistanceProxy.cpp:107-158) for n (body, shape,
+ * world-space point) triples at once: out[i] = 1 if the point, taken into the body's frame, lies in a child of the shape. */
+int pr_test_points(const pr_world* w, uint32_t n, const uint32_t* body_ids, const uint32_t* shape_ids, const float* points_xy, uint32_t* out);
+/* FindClosestBody(const World&, const Length2&) (WorldBody.cpp:576-592) for n locations at once: the body whose location is
+ * nearest, the lowest id on a tie; 0xFFFFFFFF in a world without bodies. */
+int pr_find_closest_bodies(const pr_world* w, uint32_t n, const float* points_xy, uint32_t* out_body_ids);
 /* SetJoint(AabbTreeWorld&, JointID, Joint) (AabbTreeWorld.cpp:1108-1130) for revolute joints: rows[i] replaces joint ids[i] --
  * anchors, reference angle, limits, motor (enable, speed, max torque) and the solver's stored impulses, exactly as the value
  * says -- and both bodies are woken (Remove(JointID) :1192-1205). The bodies and collideConnected of a joint must stay what

@@ -484,6 +484,18 @@ int ref_set_body_transform(void* h, uint32_t body, float x, float y, float angle
     REF_CATCH(-1)
 }
 
+// Body::SetSweep(Sweep{Position{(x, y), angle}, localCenter}) through SetBody: pos0 = pos1 = the given position, the
+// transformation recomputed from it (Body.hpp:697-702) -- how tests give the reference world another world's poses
+int ref_set_body_sweep(void* h, uint32_t body, float x, float y, float angle)
+{
+    REF_TRY(h)
+    auto b = GetBody(rw->world, MakeId<BodyID>(body));
+    SetSweep(b, Sweep{Position{Length2{x * 1_m, y * 1_m}, angle * 1_rad}, GetLocalCenter(b)});
+    SetBody(rw->world, MakeId<BodyID>(body), b);
+    return 0;
+    REF_CATCH(-1)
+}
+
 // Installs the reference's own listeners (World.hpp SetBeginContactListener / SetEndContactListener /
 // SetPostSolveContactListener); each call is recorded with what the listener can see through GetContact at that moment.
 int ref_set_event_mask(void* h, uint32_t mask)
@@ -550,6 +562,26 @@ int ref_ray_cast(void* h, uint32_t n_rays, const float* rays5, uint32_t cap, pr_
         });
     }
     *n_out = n;
+    return 0;
+    REF_CATCH(-1)
+}
+
+// TestPoint(const World&, BodyID, ShapeID, const Length2&), WorldShape.cpp:178; FindClosestBody(const World&, const Length2&), WorldBody.cpp:576
+int ref_test_points(void* h, uint32_t n, const uint32_t* body, const uint32_t* shape, const float* xy, uint32_t* out)
+{
+    REF_TRY(h)
+    for (uint32_t i = 0; i < n; ++i)
+        out[i] = TestPoint(rw->world, MakeId<BodyID>(body[i]), MakeId<ShapeID>(shape[i]), Length2{xy[2 * i] * 1_m, xy[2 * i + 1] * 1_m}) ? 1u : 0u;
+    return 0;
+    REF_CATCH(-1)
+}
+int ref_find_closest_bodies(void* h, uint32_t n, const float* xy, uint32_t* out)
+{
+    REF_TRY(h)
+    for (uint32_t i = 0; i < n; ++i) {
+        const auto id = FindClosestBody(rw->world, Length2{xy[2 * i] * 1_m, xy[2 * i + 1] * 1_m});
+        out[i] = (id == InvalidBodyID) ? 0xFFFFFFFFu : static_cast<uint32_t>(to_underlying(id));
+    }
     return 0;
     REF_CATCH(-1)
 }

@@ -1118,6 +1118,81 @@ PR_KERNEL k_ray_cast(DV d, unsigned nRays, const float* rays5, const unsigned* r
     if (mode == PR_RAY_CLOSEST) out[ri] = best;
 }
 
+// ------------------------------------------------------------------ TestPoint / FindClosestBody
+// TestPoint(const DistanceProxy&, const Length2&), DistanceProxy.cpp:107-158
+PR_D bool test_point_proxy(const ProxyView& proxy, float2 point)
+{
+    const unsigned count = proxy.count;
+    const float vr = proxy.radius;
+    if (count == 0u) return false;
+    if (count == 1u) return magsq(point - proxy.vertex(0u)) <= square(vr);
+    float maxDot = -3.402823466e+38f; // -MaxFloat
+    unsigned maxIdx = 0u;
+    for (unsigned i = 0; i < count; ++i) {
+        const float2 delta = point - proxy.vertex(i);
+        const float dt = dot(rotv(proxy.normal(i)), delta);
+        if (dt > vr) return false;
+        if (maxDot < dt) { maxDot = dt; maxIdx = i; }
+    }
+    const float2 v0 = proxy.vertex(maxIdx), v1 = proxy.vertex(mod_next(maxIdx, count));
+    const float2 edge = v1 - v0;
+    const float2 delta0 = v0 - point;
+    if (dot(edge, delta0) >= 0.0f) return magsq(delta0) <= square(vr);
+    const float2 delta1 = point - v1;
+    if (dot(edge, delta1) >= 0.0f) return magsq(delta1) <= square(vr);
+    return true;
+}
+// TestPoint(const World&, BodyID, ShapeID, const Length2&), WorldShape.cpp:178-181: the point in the body's frame against every
+// child of the shape (Shape.cpp:32-41). q4[i] = (body, first child, child count, -), one thread per query.
+PR_KERNEL k_test_points(DV d, unsigned n, const uint4* q4, const float2* points, unsigned* out)
+{
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    if (i < n) {
+        const uint4 q = q4[i];
+        const float2 local = inv_transform(points[i], xf_from4(d.b_xf[q.x]));
+        unsigned hit = 0u;
+        for (unsigned c = 0; c < q.z && !hit; ++c) hit = test_point_proxy(child_view(d, q.y + c), local) ? 1u : 0u;
+        out[i] = hit;
+    }
+}
+// FindClosestBody(const World&, const Length2&), WorldBody.cpp:576-592: least squared distance of the body's location, the first
+// body in m_bodies order on a tie (strictly-less update). One BLOCK per query: a min over (distance bits, body id) keys --
+// squared distances are non-negative, so their bit patterns order like the floats.
+PR_KERNEL k_find_closest_bodies(DV d, unsigned nBodies, const float2* points, unsigned* out)
+{
+    PR_PDL_ENTER();
+#ifndef PR_HOST_EMUL
+    __shared__ unsigned long long best[PR_BLOCK / 32];
+    const float2 p = points[blockIdx.x];
+    unsigned long long key = ~0ull;
+    for (unsigned b = threadIdx.x; b < nBodies; b += blockDim.x) {
+        if (!(d.b_flags[b] & PR_BODY_DESTROYED)) {
+            const float4 xf = d.b_xf[b];
+            const float lsq = magsq(v2(xf.x, xf.y) - p);
+            if (lsq == lsq) { const unsigned long long k = (static_cast<unsigned long long>(f2u(lsq + 0.0f)) << 32) | b; key = k < key ? k : key; }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, key, o); key = t < key ? t : key; }
+    if ((threadIdx.x & 31u) == 0u) best[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0u) {
+        for (unsigned w = 1; w < blockDim.x / 32u; ++w) key = best[w] < key ? best[w] : key;
+        out[blockIdx.x] = (key == ~0ull) ? INVALID : static_cast<unsigned>(key & 0xFFFFFFFFull);
+    }
+#else
+    const float2 p = points[PR_TID];
+    unsigned long long key = ~0ull;
+    for (unsigned b = 0; b < nBodies; ++b) {
+        if (d.b_flags[b] & PR_BODY_DESTROYED) continue;
+        const float4 xf = d.b_xf[b];
+        const float lsq = magsq(v2(xf.x, xf.y) - p);
+        if (lsq == lsq) { const unsigned long long k = (static_cast<unsigned long long>(f2u(lsq + 0.0f)) << 32) | b; key = k < key ? k : key; }
+    }
+    out[PR_TID] = (key == ~0ull) ? INVALID : static_cast<unsigned>(key & 0xFFFFFFFFull);
+#endif
+}
+
 // AddContacts (AabbTreeWorld.cpp:2423-2547), creation part: sorted pair i gets its ContactID from the LIFO
 // free stack else by append (ObjectPool::Allocate), is appended to m_contacts in key order.
 PR_D void adj_append(const DV& d, unsigned b, unsigned id, bool eligible);

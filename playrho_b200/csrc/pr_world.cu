@@ -1529,6 +1529,49 @@ int pr_query_aabb(const pr_world* cpw, uint32_t n_boxes, const float* boxes4, co
     API_CATCH(pw)
 }
 
+int pr_test_points(const pr_world* cpw, uint32_t n, const uint32_t* body_ids, const uint32_t* shape_ids, const float* points_xy, uint32_t* out)
+{ // TestPoint(const World&, BodyID, ShapeID, const Length2&), WorldShape.cpp:178-181, for many (body, shape, point) at once
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    if (!n) return PR_OK;
+    std::vector<uint4> q(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (body_ids[i] >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+        if (shape_ids[i] >= w.nShapes) { w.error = "no such shape"; return PR_ERR_OUT_OF_RANGE; }
+        const pr_shape& sh = w.shapes[shape_ids[i]];
+        q[i] = make_uint4(body_ids[i], sh.child_offset, sh.child_count, 0u);
+    }
+    unsigned char* in = static_cast<unsigned char*>(stage_buf(w, 0, (sizeof(uint4) + sizeof(float2)) * static_cast<size_t>(n)));
+    unsigned* sout = static_cast<unsigned*>(stage_buf(w, 1, sizeof(unsigned) * static_cast<size_t>(n)));
+    uint4* sq = reinterpret_cast<uint4*>(in);
+    float2* sp = reinterpret_cast<float2*>(in + sizeof(uint4) * static_cast<size_t>(n));
+    h2d(w, sq, q.data(), sizeof(uint4) * n); h2d(w, sp, points_xy, sizeof(float2) * n);
+    PR_LAUNCH(k_test_points, n, w.stream, w.d, n, sq, sp, sout);
+    d2h(w, out, sout, sizeof(unsigned) * n);
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_find_closest_bodies(const pr_world* cpw, uint32_t n, const float* points_xy, uint32_t* out_body_ids)
+{ // FindClosestBody(const World&, const Length2&), WorldBody.cpp:576-592, for many locations at once (0xFFFFFFFF: no body)
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    if (!n) return PR_OK;
+    float2* sp = static_cast<float2*>(stage_buf(w, 0, sizeof(float2) * static_cast<size_t>(n)));
+    unsigned* sout = static_cast<unsigned*>(stage_buf(w, 1, sizeof(unsigned) * static_cast<size_t>(n)));
+    h2d(w, sp, points_xy, sizeof(float2) * n);
+#ifndef PR_HOST_EMUL
+    PR_LAUNCH_GRID(k_find_closest_bodies, n, PR_BLOCK, w.stream, w.d, w.nBodies, sp, sout);
+#else
+    PR_LAUNCH(k_find_closest_bodies, n, w.stream, w.d, w.nBodies, sp, sout);
+#endif
+    d2h(w, out_body_ids, sout, sizeof(unsigned) * n);
+    return PR_OK;
+    API_CATCH(pw)
+}
+
 static int set_contact_error(World& w, unsigned long long e)
 {
     const unsigned code = static_cast<unsigned>(e & 0xFFFFFFFFull);

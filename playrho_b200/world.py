@@ -60,7 +60,7 @@ EXPORTS = [
     "pr_get_inv_dt0", "pr_get_stream", "pr_collide_shapes", "pr_set_toi_mode", "pr_set_sub_stepping", "pr_get_sub_stepping",
     "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
-    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_set_contacts", "pr_set_manifolds", "pr_set_revolute_joints", "pr_attach_shapes", "pr_set_shape_material", "pr_destroy_joints",
+    "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_test_points", "pr_find_closest_bodies", "pr_set_contacts", "pr_set_manifolds", "pr_set_revolute_joints", "pr_attach_shapes", "pr_set_shape_material", "pr_destroy_joints",
 ]
 
 
@@ -89,6 +89,8 @@ def bind(lib):
     lib.pr_events.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
     lib.pr_ray_cast.argtypes = [vp, u32, vp, vp, u32, u32, vp, C.POINTER(u32)]
     lib.pr_set_contacts.argtypes = [vp, u32, vp]
+    lib.pr_test_points.argtypes = [vp, u32, vp, vp, vp, vp]
+    lib.pr_find_closest_bodies.argtypes = [vp, u32, vp, vp]
     lib.pr_set_revolute_joints.argtypes = [vp, u32, vp, vp]
     lib.pr_attach_shapes.argtypes = [vp, u32, u32, vp]
     lib.pr_destroy_joints.argtypes = [vp, u32, vp]
@@ -272,6 +274,21 @@ class World:
             if k.value <= cap:
                 return out[:k.value]
             cap = k.value
+
+    def test_points(self, body_ids, shape_ids, points):
+        """TestPoint(world, body, shape, point) for many triples (pr_test_points): uint32 array of 0/1."""
+        b = np.ascontiguousarray(body_ids, dtype=np.uint32); s_ = np.ascontiguousarray(shape_ids, dtype=np.uint32)
+        p = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
+        out = np.zeros(len(b), np.uint32)
+        self._chk(self.lib.pr_test_points(self.h, len(b), abi.ptr(b), abi.ptr(s_), abi.ptr(p), abi.ptr(out)))
+        return out
+
+    def find_closest_bodies(self, points):
+        """FindClosestBody(world, location) for many locations (pr_find_closest_bodies)."""
+        p = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
+        out = np.zeros(len(p), np.uint32)
+        self._chk(self.lib.pr_find_closest_bodies(self.h, len(p), abi.ptr(p), abi.ptr(out)))
+        return out
 
     def set_shape_material(self, shape, friction, restitution, density, sensor):
         """SetShape with unchanged geometry and filter (pr_set_shape_material)."""

@@ -21,12 +21,12 @@ def assert_bits(a, b, what):
     assert refworld.bits_equal(a, b), "%s differ: %s" % (what, refworld.diff_fields(a, b))
 
 
-def run_vs_oracle(scene, steps, lib=None, conf=None, device=-1, check_every=1, toi_mode=0, large_variants=False):
+def run_vs_oracle(scene, steps, lib=None, conf=None, device=-1, check_every=1, toi_mode=0, large_variants=False, world_kwargs=None):
     """Step the device world and the oracle (fed the device's colour-sorted order) side by side and
     require BIT-EXACT bodies, contacts (ids, keys, flags), manifolds (points, feature ids, impulses),
     proxies (fat AABBs) and step statistics after every step."""
     conf = conf if conf is not None else refworld.default_step_conf(do_toi=0)
-    gw = W.World(scene, lib=lib, device=device, record_solve_order=True, large_variants=large_variants)
+    gw = W.World(scene, lib=lib, device=device, record_solve_order=True, large_variants=large_variants, **(world_kwargs or {}))
     gw.set_toi_mode(toi_mode)  # 0 = serial-exact: the reference's TOI event order; 1 = PR_TOI_PARALLEL rounds (product default)
     orc = refworld.OracleWorld(scene)
     orc.set_toi_mode(toi_mode)  # (mode 1: the oracle derives the rounds by rule; the two schedules must be the same)

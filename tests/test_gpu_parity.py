@@ -91,6 +91,20 @@ def test_cuda_config3_full_size_100k_disks_bit_exact_vs_oracle():
 
 
 @need_oracle
+def test_cuda_config4_full_size_1m_mixed_bit_exact_vs_oracle():
+    """BASELINE config 4 at its stated size: 1M mixed disks / 4-8-gons dropped on the tiled chain terrain, default StepConf, TOI on
+    in the benchmarked parallel mode, the first 64 steps (the lattice lands and starts to pile up: ~1.4M contacts, TOI events
+    against the terrain): bodies, contacts, manifolds, proxies, every StepStats field and the TOI schedule bit-exact."""
+    sc = scenes_np.mixed_fast(1000000, seed=12345)
+    nb = len(sc["bodies"])
+    run_vs_oracle.toi_events = 0
+    gs, ncontacts, prof = run_vs_oracle(sc, 64, device=0, check_every=16, conf=refworld.default_step_conf(), toi_mode=1,
+                                        world_kwargs=dict(body_capacity=nb + 16, proxy_capacity=nb + 8192, contact_capacity=6 * nb))
+    assert ncontacts > 1000000
+    assert run_vs_oracle.toi_events > 100
+
+
+@need_oracle
 def test_cuda_binned_narrowphase_variant_bit_exact_vs_oracle():
     """The opt-in kernel variants (narrowphase binned by shape-pair class; the persistent cooperative solver kernel with
     grid barriers between colours) on small scenes: same bits as the oracle, incl. joints and the colour-overflow tail."""
