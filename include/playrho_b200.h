@@ -211,7 +211,15 @@ void pr_world_conf_default(pr_world_conf* conf);
 void pr_step_conf_default(pr_step_conf* conf);          /* StepConf{} defaults */
 int pr_create(const pr_world_conf* conf, pr_world** out);
 int pr_destroy(pr_world* w);
-int pr_clone(const pr_world* w, pr_world** out);        /* WorldModel::Clone_, WorldModel.hpp:96-99 */
+int pr_clone(const pr_world* w, pr_world** out);
+/* Snapshot / restore (the reference's world is a value: copy construction AabbTreeWorld.cpp:842-880, here to and from host
+ * memory, e.g. a file). pr_snapshot_save writes the whole device world -- every array of every pool, the counters, the contact
+ * pool's free stack and list order, the persistent colours, joints, queued proxies -- into buf (buf == NULL: only the size
+ * is reported in *bytes_out; PR_ERR_LENGTH if cap is too small). pr_snapshot_load creates a world from such a buffer on
+ * `device` (-1: the current one): it continues bit for bit like the saved world (like a pr_clone). The buffer is only valid
+ * for the library version and sincosf build that wrote it. */
+int pr_snapshot_save(const pr_world* w, void* buf, uint64_t cap, uint64_t* bytes_out);
+int pr_snapshot_load(const void* buf, uint64_t bytes, int device, pr_world** out);        /* WorldModel::Clone_, WorldModel.hpp:96-99 */
 int pr_clear(pr_world* w);                              /* Clear(AabbTreeWorld&), AabbTreeWorld.cpp:949 */
 const char* pr_last_error(const pr_world* w);           /* w may be NULL: last create error */
 

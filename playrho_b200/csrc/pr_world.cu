@@ -1176,6 +1176,162 @@ int pr_clone(const pr_world* src, pr_world** out)
     API_CATCH(pw)
 }
 
+// ------------------------------------------------------------------ snapshot / restore
+// What pr_clone copies device to device -- every array of every group, the counters, the host-side tables and scalars -- goes
+// through one self-describing byte stream instead: a world restored from it continues exactly like a clone does (= like the
+// source: tests/test_snapshot.py), which a pr_load_state of bodies/proxies/contacts cannot (the contact pool's free stack,
+// the persistent colours and the m_contacts order are history). Layout: header | scalars | host tables | counters | arrays
+// (element size, used count, bytes; groups that the next step rebuilds anyway -- hash, candidate pairs, constraint rows,
+// adjacency -- are left out and flagged dirty on load, like pr_clone flags them).
+extern "C++" {
+namespace {
+constexpr unsigned long long SNAP_MAGIC = 0x30325042524e5350ull; // "PSNRBP20"
+struct SnapHeader {
+    unsigned long long magic; unsigned version, abi, variant, nArrays;
+    unsigned szBody, szContact, szCounters, pad;
+};
+struct SnapScalars {
+    pr_world_conf conf;
+    unsigned nBodies, nShapes, nChildren, nVerts, nProxies, nOrder, nFree, poolSize, maxTreeId, debugFlags, nJoints, nWorlds, worldBits, nNcPairs;
+    unsigned colorsAtFull, colorCap, toiMode, toiRoundsHint, toiGroupsHint, isHint, evMask, evCap;
+    unsigned anyBodySet, stepComplete, recolorAll, subStepping, jointsSerial, toiPossible;
+    float inv_dt0;
+};
+struct SnapWriter {
+    unsigned char* p; unsigned long long cap, n = 0; bool ok = true;
+    void put(const void* src, size_t bytes) { if (p && n + bytes <= cap) std::memcpy(p + n, src, bytes); else if (p) ok = false; n += bytes; }
+    template <class T> void pod(const T& v) { put(&v, sizeof(T)); }
+    template <class T> void vec(const std::vector<T>& v) { const unsigned long long k = v.size(); pod(k); if (k) put(v.data(), sizeof(T) * k); }
+};
+struct SnapReader {
+    const unsigned char* p; unsigned long long cap, n = 0; bool ok = true;
+    void get(void* dst, size_t bytes) { if (n + bytes <= cap) std::memcpy(dst, p + n, bytes); else ok = false; n += bytes; }
+    template <class T> void pod(T& v) { get(&v, sizeof(T)); }
+    template <class T> void vec(std::vector<T>& v) { unsigned long long k = 0; pod(k); if (!ok || k > (cap - n) / sizeof(T) + 1ull) { ok = false; return; } v.resize(static_cast<size_t>(k)); if (k) get(v.data(), sizeof(T) * k); }
+};
+// elements of group g that carry state across steps (0: the group is rebuilt by the next step)
+unsigned snap_used(const World& w, Group g)
+{
+    switch (g) {
+    case G_BODY: return w.nBodies + 1u; case G_SHAPE: return w.nShapes; case G_CHILD: return w.nChildren; case G_VERT: return w.nVerts;
+    case G_PROXY: return w.nProxies + 1u; case G_CONTACT: return std::max(w.poolSize, w.nOrder) + 1u; case G_JOINT: return static_cast<unsigned>(w.joints.size()) + 1u;
+    default: return 0u; // G_HASH, G_PAIR, G_CONS, G_ADJ
+    }
+}
+void snap_scalars(const World& w, SnapScalars& s)
+{
+    std::memset(&s, 0, sizeof(s));
+    s.conf = w.conf;
+    s.nBodies = w.nBodies; s.nShapes = w.nShapes; s.nChildren = w.nChildren; s.nVerts = w.nVerts; s.nProxies = w.nProxies;
+    s.nOrder = w.nOrder; s.nFree = w.nFree; s.poolSize = w.poolSize; s.maxTreeId = w.maxTreeId; s.debugFlags = w.debugFlags; s.nJoints = w.nJoints;
+    s.nWorlds = w.d.nWorlds; s.worldBits = w.d.worldBits; s.nNcPairs = w.d.nNcPairs;
+    s.colorsAtFull = w.colorsAtFull; s.colorCap = w.colorCap; s.toiMode = w.toiMode; s.toiRoundsHint = w.toiRoundsHint; s.toiGroupsHint = w.toiGroupsHint;
+    s.isHint = w.isHint; s.evMask = w.d.ev_mask; s.evCap = w.d.ev_cap;
+    s.anyBodySet = w.anyBodySet; s.stepComplete = w.stepComplete; s.recolorAll = w.recolorAll; s.subStepping = w.subStepping;
+    s.jointsSerial = w.jointsSerial; s.toiPossible = w.toiPossible; s.inv_dt0 = w.inv_dt0;
+}
+template <class T> void snap_nested(SnapWriter& o, const std::vector<std::vector<T>>& v)
+{
+    const unsigned long long k = v.size(); o.pod(k);
+    for (const auto& e : v) o.vec(e);
+}
+template <class T> void snap_nested(SnapReader& in, std::vector<std::vector<T>>& v)
+{
+    unsigned long long k = 0; in.pod(k);
+    if (!in.ok || k > in.cap) { in.ok = false; return; }
+    v.resize(static_cast<size_t>(k));
+    for (auto& e : v) { in.vec(e); if (!in.ok) return; }
+}
+} // namespace
+} // extern "C++"
+
+int pr_snapshot_save(const pr_world* cpw, void* buf, uint64_t cap, uint64_t* bytes_out)
+{
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    sync(w);
+    SnapWriter o{static_cast<unsigned char*>(buf), cap};
+    auto arrs = arrays(w);
+    SnapHeader h{SNAP_MAGIC, 1u, static_cast<unsigned>(PR_ABI_VERSION), static_cast<unsigned>(pr_sincosf_variant()), static_cast<unsigned>(arrs.size()),
+                 static_cast<unsigned>(sizeof(pr_body)), static_cast<unsigned>(sizeof(pr_contact)), static_cast<unsigned>(sizeof(Counters)), 0u};
+    o.pod(h);
+    SnapScalars sc; snap_scalars(w, sc); o.pod(sc);
+    o.vec(w.shapes); o.vec(w.children); snap_nested(o, w.bodyShapes); o.vec(w.joints); o.vec(w.freeJoints);
+    { std::vector<unsigned> flat; for (const auto& f : w.fixturesForProxies) { flat.push_back(f.first); flat.push_back(f.second); } o.vec(flat); }
+    snap_nested(o, w.bodyProxies); o.vec(w.bodyWorld);
+    read_counters(w);
+    o.pod(w.hostCnt);
+    std::vector<unsigned char> tmp;
+    for (const ArrDesc& a : arrs) {
+        const unsigned long long used = snap_used(w, a.g), elem = a.elem;
+        o.pod(elem); o.pod(used);
+        const size_t bytes = static_cast<size_t>(elem * used);
+        if (bytes) {
+            if (o.p && o.n + bytes <= o.cap) d2h(w, o.p + o.n, *a.slot, bytes);
+            else if (o.p) o.ok = false;
+            o.n += bytes;
+        }
+    }
+    if (bytes_out) *bytes_out = o.n;
+    if (buf && !o.ok) { w.error = "pr_snapshot_save: buffer too small"; return PR_ERR_LENGTH; }
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_snapshot_load(const void* buf, uint64_t bytes, int device, pr_world** out)
+{
+    *out = nullptr;
+    SnapReader in{static_cast<const unsigned char*>(buf), bytes};
+    SnapHeader h{}; in.pod(h);
+    SnapScalars sc{}; in.pod(sc);
+    if (!in.ok || h.magic != SNAP_MAGIC || h.version != 1u || h.abi != static_cast<unsigned>(PR_ABI_VERSION) || h.szBody != sizeof(pr_body) ||
+        h.szContact != sizeof(pr_contact) || h.szCounters != sizeof(Counters)) { g_createError = "pr_snapshot_load: not a snapshot of this library version"; return PR_ERR_INVALID_ARGUMENT; }
+    if (h.variant != static_cast<unsigned>(pr_sincosf_variant())) { g_createError = "pr_snapshot_load: the snapshot was taken by the other sincosf build of the library"; return PR_ERR_INVALID_ARGUMENT; }
+    pr_world* pw = nullptr;
+    pr_world_conf conf = sc.conf;
+    conf.device = device;
+    const int rc = pr_create(&conf, &pw);
+    if (rc != PR_OK) return rc;
+    try {
+        DeviceGuard guard(pw->w.device);
+        World& w = pw->w;
+        in.vec(w.shapes); in.vec(w.children); snap_nested(in, w.bodyShapes); in.vec(w.joints); in.vec(w.freeJoints);
+        { std::vector<unsigned> flat; in.vec(flat); for (size_t i = 0; i + 1 < flat.size(); i += 2) w.fixturesForProxies.emplace_back(flat[i], flat[i + 1]); }
+        snap_nested(in, w.bodyProxies); in.vec(w.bodyWorld);
+        in.pod(w.hostCnt);
+        if (!in.ok) throw CudaError{"pr_snapshot_load: truncated snapshot"};
+        w.nBodies = sc.nBodies; w.nShapes = sc.nShapes; w.nChildren = sc.nChildren; w.nVerts = sc.nVerts; w.nProxies = sc.nProxies;
+        w.nOrder = sc.nOrder; w.nFree = sc.nFree; w.poolSize = sc.poolSize; w.maxTreeId = sc.maxTreeId; w.debugFlags = sc.debugFlags; w.nJoints = sc.nJoints;
+        w.d.nWorlds = sc.nWorlds; w.d.worldBits = sc.worldBits; w.d.nNcPairs = sc.nNcPairs;
+        w.colorsAtFull = sc.colorsAtFull; w.colorCap = sc.colorCap; w.toiMode = sc.toiMode; w.toiRoundsHint = sc.toiRoundsHint; w.toiGroupsHint = sc.toiGroupsHint;
+        w.isHint = sc.isHint;
+        w.anyBodySet = sc.anyBodySet != 0; w.stepComplete = sc.stepComplete != 0; w.recolorAll = sc.recolorAll != 0; w.subStepping = sc.subStepping != 0;
+        w.jointsSerial = sc.jointsSerial != 0; w.toiPossible = sc.toiPossible != 0; w.inv_dt0 = sc.inv_dt0;
+        ensure(w, G_BODY, w.nBodies + 2u); ensure(w, G_SHAPE, w.nShapes + 1u); ensure(w, G_CHILD, w.nChildren + 1u); ensure(w, G_VERT, w.nVerts + 1u);
+        ensure(w, G_PROXY, w.nProxies + 2u); ensure(w, G_CONTACT, std::max(w.poolSize, w.nOrder) + 2u); ensure(w, G_JOINT, static_cast<unsigned>(w.joints.size()) + 2u);
+        auto arrs = arrays(w);
+        if (arrs.size() != h.nArrays) throw CudaError{"pr_snapshot_load: array table mismatch"};
+        for (const ArrDesc& a : arrs) {
+            unsigned long long elem = 0, used = 0; in.pod(elem); in.pod(used);
+            if (!in.ok || elem != a.elem || used > *cap_of(w, a.g)) throw CudaError{"pr_snapshot_load: array does not fit this build"};
+            const size_t nbytes = static_cast<size_t>(elem * used);
+            if (nbytes) {
+                if (in.n + nbytes > in.cap) throw CudaError{"pr_snapshot_load: truncated snapshot"};
+                h2d(w, *a.slot, in.p + in.n, nbytes);
+                in.n += nbytes;
+            }
+        }
+        write_counters(w);
+        if (sc.evMask) { const int erc = pr_set_event_mask(pw, sc.evMask, std::max(1u, sc.evCap)); if (erc != PR_OK) throw CudaError{"pr_snapshot_load: event buffers"}; }
+        w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.hashDirty = true; w.adjValid = false; w.blocksDirty = w.blkJointsDirty = true;
+        sync(w);
+    } catch (const CudaError& e) { g_createError = e.msg; pr_destroy(pw); return PR_ERR_INVALID_ARGUMENT; }
+    catch (const std::exception& e) { g_createError = e.what(); pr_destroy(pw); return PR_ERR_INVALID_ARGUMENT; }
+    *out = pw;
+    return PR_OK;
+}
+
 int pr_clear(pr_world* pw)
 {
     API_TRY(pw)

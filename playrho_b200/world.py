@@ -53,7 +53,7 @@ vp, u32, f32, i32 = C.c_void_p, C.c_uint32, C.c_float, C.c_int
 
 EXPORTS = [
     "pr_abi_version", "pr_sincosf_variant", "pr_host_sincosf_variant", "pr_world_conf_default", "pr_step_conf_default", "pr_create", "pr_destroy",
-    "pr_clone", "pr_clear", "pr_last_error", "pr_create_shapes", "pr_create_bodies",
+    "pr_clone", "pr_snapshot_save", "pr_snapshot_load", "pr_clear", "pr_last_error", "pr_create_shapes", "pr_create_bodies",
     "pr_create_revolute_joints", "pr_set_bodies", "pr_get_bodies", "pr_get_revolute_joints",
     "pr_get_counts", "pr_get_contacts", "pr_get_proxies", "pr_load_state", "pr_step",
     "pr_get_solve_order", "pr_get_toi_schedule", "pr_set_debug", "pr_get_step_profile", "pr_abi_sizeof", "pr_shift_origin",
@@ -75,6 +75,8 @@ def bind(lib):
     lib.pr_destroy.argtypes = [vp]
     lib.pr_clone.argtypes = [vp, C.POINTER(vp)]
     lib.pr_clear.argtypes = [vp]
+    lib.pr_snapshot_save.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.pr_snapshot_load.argtypes = [vp, C.c_uint64, i32, C.POINTER(vp)]
     lib.pr_last_error.restype = C.c_char_p
     lib.pr_last_error.argtypes = [vp]
     lib.pr_create_shapes.argtypes = [vp, u32, vp, vp, u32, vp, vp, u32, C.POINTER(u32)]
@@ -415,6 +417,26 @@ class World:
         self._chk(self.lib.pr_clone(self.h, C.byref(h)))
         other = World.__new__(World)
         other.lib, other.h = self.lib, h
+        return other
+
+    def snapshot(self):
+        """The whole world as bytes (pr_snapshot_save): World.restore(bytes) continues bit for bit like this world."""
+        n = C.c_uint64(0)
+        self._chk(self.lib.pr_snapshot_save(self.h, None, 0, C.byref(n)))
+        buf = np.zeros(n.value, np.uint8)
+        self._chk(self.lib.pr_snapshot_save(self.h, abi.ptr(buf), buf.nbytes, C.byref(n)))
+        return buf[:n.value]
+
+    @classmethod
+    def restore(cls, buf, lib=None, device=-1):
+        lib = lib or load_library()
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        h = vp()
+        rc = lib.pr_snapshot_load(abi.ptr(buf), buf.nbytes, device, C.byref(h))
+        if rc != 0:
+            raise PrError(rc, lib.pr_last_error(None).decode())
+        other = World.__new__(World)
+        other.lib, other.h = lib, h
         return other
 
 
