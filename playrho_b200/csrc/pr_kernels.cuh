@@ -458,14 +458,20 @@ PR_D void store_manifold(const DV& d, unsigned id, const Mf& m)
 }
 // Update(ContactID), AabbTreeWorld.cpp:2587-2721: collide (or sensor TestOverlap), carry impulses over by
 // ContactFeature equality else nearest old point, touching flag. Called with the contact's flags word.
+// (pvA / pvB: the two children's vertex sets -- the shape pool in HBM, or a block's shared-memory copy of them: k_update_contacts_tma)
+PR_D void update_contact_v(const DV& d, const pr_step_conf& conf, unsigned id, unsigned flags, const uint4 ab, const ProxyView& pvA, const ProxyView& pvB);
 PR_D void update_contact(const DV& d, const pr_step_conf& conf, unsigned id, unsigned flags)
 {
     const uint4 ab = d.c_ab[id];
+    update_contact_v(d, conf, id, flags, ab, child_view(d, ab.z), child_view(d, ab.w));
+}
+PR_D void update_contact_v(const DV& d, const pr_step_conf& conf, unsigned id, unsigned flags, const uint4 ab, const ProxyView& pvA, const ProxyView& pvB)
+{
     const bool oldTouching = (flags & PR_CONTACT_TOUCHING) != 0;
     bool newTouching = false;
     const Xf xfA = xf_from4(d.b_xf[ab.x]), xfB = xf_from4(d.b_xf[ab.y]);
     if (flags & PR_CONTACT_SENSOR) { // TestOverlap(...) >= 0, AabbTreeWorld.cpp:2622-2626
-        newTouching = gjk_test_overlap(child_view(d, ab.z), xfA, child_view(d, ab.w), xfB, conf.max_distance_iters) >= 0.0f;
+        newTouching = gjk_test_overlap(pvA, xfA, pvB, xfB, conf.max_distance_iters) >= 0.0f;
         manifold_clear(d, id);
     } else {
         // the old manifold is fetched BEFORE the collision (it does not depend on it): its round trip overlaps the
@@ -473,7 +479,7 @@ PR_D void update_contact(const DV& d, const pr_step_conf& conf, unsigned id, uns
         const uint4 o3 = d.m3[id];
         float4 o1 = make_float4(0, 0, 0, 0), o2 = make_float4(0, 0, 0, 0);
         if (oldTouching) { o1 = d.m1[id]; o2 = d.m2[id]; }
-        Mf nm = collide_shapes(child_view(d, ab.z), xfA, child_view(d, ab.w), xfB, conf.linear_slop, conf.max_circles_ratio);
+        Mf nm = collide_shapes(pvA, xfA, pvB, xfB, conf.linear_slop, conf.max_circles_ratio);
         const unsigned oldCount = o3.w, newCount = nm.count;
         newTouching = newCount > 0u;
         if (newCount > 0u && oldCount > 0u) {
@@ -578,6 +584,129 @@ k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n, unsigned 
 #endif
     block_add(&d.cnt->contactsUpdated, (dirty && countIt) ? 1u : 0u);
 }
+
+#ifndef PR_HOST_EMUL
+// ---- TMA staging of the vertex sets (BASELINE north_star (2); opt-in, debug bit 6 -- measured) ----------------
+// Same kernel, but before the collision every thread whose pair has a polygon / edge child has the bulk-copy engine
+// (cp.async.bulk, the non-tensor TMA path: UBLKCP in SASS) bring that child's vertices and normals from the shape pool into the
+// block's shared memory, completion counted on one mbarrier; collide_shapes then reads shared memory. A run starts on an
+// 8-byte boundary in the pool and the engine wants 16: the copy starts at the aligned address below it and the view skips the
+// first element where needed (the pool has slack at its end).
+constexpr unsigned TMA_STAGE_BYTES = 40960u;
+PR_D unsigned tma_run_bytes(unsigned voff, unsigned count) { return (((voff & 1u) + count) * 8u + 15u) & ~15u; }
+PR_D unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__global__ void __launch_bounds__(PR_BLOCK, 3)
+k_update_contacts_tma(DV d, pr_step_conf conf, unsigned start, unsigned n, unsigned useMoved, unsigned countIt)
+{
+    PR_PDL_ENTER();
+    extern __shared__ __align__(128) unsigned char tma_stage[];
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned i = PR_TID;
+    bool dirty = false;
+    unsigned id = 0u, flags = 0u;
+    if (i < n) {
+        id = d.c_order[start + i];
+        flags = d.c_flags[id];
+        dirty = (flags & PR_CONTACT_DIRTY) != 0;
+        if (useMoved) { const uint4 ab = d.c_ab[id]; dirty = dirty || (d.b_moved[ab.x] | d.b_moved[ab.y]) != 0u; }
+    }
+    constexpr unsigned NCLS = 4u;
+    __shared__ unsigned s_id[PR_BLOCK], s_flags[PR_BLOCK];
+    __shared__ unsigned s_warp[PR_BLOCK / 32][NCLS], s_base[NCLS + 1u], s_scan[PR_BLOCK / 32];
+    unsigned cls = 3u;
+    if (dirty) {
+        const uint4 ab = d.c_ab[id];
+        const unsigned ca = d.ch_count[ab.z], cb = d.ch_count[ab.w];
+        cls = (flags & PR_CONTACT_SENSOR) ? 2u : (ca == 1u && cb == 1u) ? 0u : (ca == 1u || cb == 1u) ? 1u : 2u;
+    }
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    unsigned rank = 0u;
+#pragma unroll
+    for (unsigned c = 0; c < NCLS; ++c) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+        if (cls == c) rank = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0u) s_warp[wid][c] = __popc(m);
+    }
+    if (threadIdx.x == 0u) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(static_cast<unsigned>(PR_BLOCK)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0u) {
+        unsigned run = 0u;
+        for (unsigned c = 0; c < NCLS; ++c) {
+            s_base[c] = run;
+            for (unsigned w = 0; w < blockDim.x / 32u; ++w) { const unsigned t = s_warp[w][c]; s_warp[w][c] = run; run += t; }
+        }
+        s_base[NCLS] = run;
+    }
+    __syncthreads();
+    const unsigned slot = s_warp[wid][cls] + rank;
+    s_id[slot] = id; s_flags[slot] = flags;
+    __syncthreads();
+    // ---- thread t now owns the t-th dirty contact of the block (by class): what must be staged for it
+    const bool work = threadIdx.x < s_base[3];
+    unsigned myId = 0u, myFlags = 0u, need = 0u;
+    uint4 ab = make_uint4(0u, 0u, 0u, 0u);
+    unsigned voff[2] = {0u, 0u}, cnt[2] = {0u, 0u};
+    float rad[2] = {0.0f, 0.0f};
+    if (work) {
+        myId = s_id[threadIdx.x]; myFlags = s_flags[threadIdx.x];
+        ab = d.c_ab[myId];
+        const unsigned cg[2] = {ab.z, ab.w};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            voff[k] = d.ch_voff[cg[k]]; cnt[k] = d.ch_count[cg[k]]; rad[k] = d.ch_radius[cg[k]];
+            if (cnt[k] >= 2u) need += 2u * tma_run_bytes(voff[k], cnt[k]); // vertices + normals
+        }
+    }
+    // block-wide exclusive scan of the staging sizes
+    unsigned incl = need;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= static_cast<unsigned>(o)) incl += t; }
+    if (lane == 31u) s_scan[wid] = incl;
+    __syncthreads();
+    unsigned off = incl - need;
+    for (unsigned w = 0; w < wid; ++w) off += s_scan[w];
+    const bool staged = need != 0u && off + need <= TMA_STAGE_BYTES;
+    const unsigned barAddr = smem_u32(&bar);
+    ProxyView pv[2];
+    if (staged) {
+        unsigned long long st;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 %0, [%1], %2;" : "=l"(st) : "r"(barAddr), "r"(need) : "memory");
+        (void)st;
+        unsigned cur = off;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            pv[k].radius = rad[k]; pv[k].count = cnt[k];
+            if (cnt[k] >= 2u) {
+                const unsigned bytes = tma_run_bytes(voff[k], cnt[k]);
+                const float2* gv = d.vtx + (voff[k] & ~1u);
+                const float2* gn = d.nrm + (voff[k] & ~1u);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(tma_stage + cur)), "l"(gv), "r"(bytes), "r"(barAddr) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(tma_stage + cur + bytes)), "l"(gn), "r"(bytes), "r"(barAddr) : "memory");
+                pv[k].v = reinterpret_cast<const float2*>(tma_stage + cur) + (voff[k] & 1u);
+                pv[k].n = reinterpret_cast<const float2*>(tma_stage + cur + bytes) + (voff[k] & 1u);
+                cur += 2u * bytes;
+            } else { pv[k].v = d.vtx + voff[k]; pv[k].n = d.nrm + voff[k]; }
+        }
+    } else {
+        unsigned long long st;
+        asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(barAddr) : "memory");
+        (void)st;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { pv[k].radius = rad[k]; pv[k].count = cnt[k]; pv[k].v = d.vtx + voff[k]; pv[k].n = d.nrm + voff[k]; }
+    }
+    { // every thread arrived once; the phase completes when the engine has delivered every expected byte
+        unsigned done = 0u;
+        while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(barAddr) : "memory");
+    }
+    if (work) update_contact_v(d, conf, myId, myFlags, ab, pv[0], pv[1]);
+    block_add(&d.cnt->contactsUpdated, (dirty && countIt) ? 1u : 0u);
+}
+#endif
 
 // Binned narrowphase (the regular phase's UpdateContacts, where nearly every contact is dirty): a warp of the plain
 // kernel mixes disk-disk, disk-polygon and k-gon/m-gon pairs and executes them one after another (measured: 4.9 of

@@ -706,7 +706,14 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         PR_LAUNCH(k_narrow_keys, w.nOrder, w.stream, d, w.nOrder, 1u, d.k_tmpKey, d.k_tmpVal);
         const bool inB = radix_sort_pairs<unsigned>(d.k_tmpKey, d.k_tmpVal, d.k_tmpKey2, d.c_tmp, w.nOrder, 0, 8, false, w.rs, w.stream);
         PR_LAUNCH(k_update_contacts_binned, w.nOrder, w.stream, d, conf, w.nOrder, inB ? d.k_tmpKey2 : d.k_tmpKey, inB ? d.c_tmp : d.k_tmpVal);
-    } else
+    }
+#ifndef PR_HOST_EMUL
+    else if ((w.debugFlags & 64u) && w.nOrder) { // TMA-staged vertex sets (k_update_contacts_tma): opt-in, measured slower
+        if (!w.tmaSmemSet) { CK(cudaFuncSetAttribute(k_update_contacts_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TMA_STAGE_BYTES))); w.tmaSmemSet = true; }
+        PR_LAUNCH_GRID_SMEM(k_update_contacts_tma, (w.nOrder + PR_BLOCK - 1u) / PR_BLOCK, PR_BLOCK, TMA_STAGE_BYTES, w.stream, d, conf, 0u, w.nOrder, 1u, 1u);
+    }
+#endif
+    else
         PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 1u, 1u);
     dset(w, d.b_moved, 0, sizeof(unsigned) * N);
     dset(w, d.b_sync, 0, sizeof(unsigned) * N);
@@ -993,9 +1000,13 @@ static void step_impl(World& w, const pr_step_conf& conf, pr_step_stats& stats)
     if (w.anyBodySet) PR_LAUNCH(k_sync_proxies, w.nProxies, w.stream, d, conf, w.nProxies);
     stats.pre.contacts_destroyed = destroy_contacts(w);
     const unsigned nOrderAtUpdate = w.nOrder;
-    PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, w.anyBodySet ? 1u : 0u, 1u);
+    // UpdateContacts of the pre-phase (:2190): nothing to look at when the last Step ended with every contact updated and no
+    // mutator ran since (the usual step-after-step loop): every contact is skipped, as the reference finds out one by one
+    const bool preClean = w.contactsClean && !w.anyBodySet;
+    if (!preClean) PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, w.anyBodySet ? 1u : 0u, 1u);
     if (w.anyBodySet) { dset(w, d.b_moved, 0, sizeof(unsigned) * w.nBodies); dset(w, d.b_sync, 0, sizeof(unsigned) * w.nBodies); }
     w.anyBodySet = false;
+    w.contactsClean = false;
     read_counters(w);
     stats.pre.proxies_moved = w.hostCnt.proxiesMoved;
     stats.pre.contacts_updated = w.hostCnt.contactsUpdated;
@@ -1006,6 +1017,9 @@ static void step_impl(World& w, const pr_step_conf& conf, pr_step_stats& stats)
         if (w.stepComplete) solve_reg(w, conf, stats, tm);
         if (conf.do_toi) solve_toi(w, conf, stats, tm);
     }
+    // every contact that was flagged or whose body moved has been updated by now (regular phase :1547, the TOI phase's final
+    // UpdateContacts :1825, AddContacts' own Update) unless a sub-stepped TOI phase is still open
+    w.contactsClean = w.stepComplete;
     check_launch();
     w.profile.p_total = w.nProxies; w.profile.c_total = w.nOrder;
     tm.finish(w, w.profile);
@@ -1336,6 +1350,7 @@ int pr_clear(pr_world* pw)
 {
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     w.shapes.clear(); w.children.clear(); w.bodyShapes.clear(); w.joints.clear(); w.fixturesForProxies.clear();
     w.bodyProxies.clear(); w.bpDirty = true; w.bvhValid = false; w.hashTombs = 0; w.toiAlphaDirty = true;
     w.nJoints = 0; w.jointsSerial = false; w.d.nNcPairs = 0; w.bodyWorld.clear(); w.freeJoints.clear();
@@ -1354,6 +1369,7 @@ int pr_create_shapes(pr_world* pw, uint32_t n, const pr_shape* shapes, const pr_
 {
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     // CreateShape validation (AabbTreeWorld.cpp:1234-1255): every child's vertex radius within the world interval
     for (uint32_t i = 0; i < n_children; ++i) {
         if (children[i].vertex_count == 0 || children[i].vertex_count > 254) { w.error = "child vertex count out of range"; return PR_ERR_INVALID_ARGUMENT; }
@@ -1364,7 +1380,7 @@ int pr_create_shapes(pr_world* pw, uint32_t n, const pr_shape* shapes, const pr_
     }
     for (uint32_t i = 0; i < n; ++i) // (every row is checked before any is applied)
         if (shapes[i].child_offset > n_children || shapes[i].child_count > n_children - shapes[i].child_offset) { w.error = "shape child range"; return PR_ERR_OUT_OF_RANGE; }
-    ensure(w, G_SHAPE, w.nShapes + n); ensure(w, G_CHILD, w.nChildren + n_children); ensure(w, G_VERT, w.nVerts + n_vertices);
+    ensure(w, G_SHAPE, w.nShapes + n); ensure(w, G_CHILD, w.nChildren + n_children); ensure(w, G_VERT, w.nVerts + n_vertices + 4u); // (+4: the TMA-staged narrowphase copies whole 16-byte lines)
     std::vector<float4> mat(n); std::vector<unsigned> filt(n); std::vector<int> grp(n);
     for (uint32_t i = 0; i < n; ++i) {
         pr_shape s = shapes[i];
@@ -1398,6 +1414,7 @@ static int create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const 
 {
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false;
     if (w.d.nWorlds) { // batch arena: every body names the world it lives in
         if (!world_index) { w.error = "batch arena: bodies are created with pr_batch_create_bodies (a world index per body)"; return PR_ERR_INVALID_ARGUMENT; }
         for (uint32_t i = 0; i < n; ++i) if (world_index[i] >= w.d.nWorlds) { w.error = "no such world"; return PR_ERR_OUT_OF_RANGE; }
@@ -1430,6 +1447,7 @@ int pr_set_shape_material(pr_world* pw, uint32_t shape, float friction, float re
 {
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     if (!w.stepComplete) { w.error = "SetShape: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
     if (shape >= w.nShapes) { w.error = "no such shape"; return PR_ERR_OUT_OF_RANGE; }
     pr_shape& cur = w.shapes[shape];
@@ -1476,6 +1494,7 @@ int pr_attach_shapes(pr_world* pw, uint32_t body, uint32_t n, const uint32_t* sh
 {
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     if (!w.stepComplete) { w.error = "SetBody: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
     if (body >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
     for (uint32_t i = 0; i < n; ++i) if (shape_ids[i] >= w.nShapes) { w.error = "no such shape"; return PR_ERR_OUT_OF_RANGE; }
@@ -1499,6 +1518,7 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
 { // CreateJoint (:1132-1157) + Add(JointID) (:1159-1180) for RevoluteJointConf values
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     if (n == 0) return PR_OK;
     for (uint32_t i = 0; i < n; ++i)
         if (joints[i].body_a >= w.nBodies || joints[i].body_b >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
@@ -1533,6 +1553,7 @@ int pr_destroy_joints(pr_world* pw, uint32_t n, const uint32_t* ids)
 { // Destroy(AabbTreeWorld&, JointID), :1215-1227: Remove(id) wakes both bodies (:1192-1205), the id goes to the free list
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     if (!w.stepComplete) { w.error = "Destroy: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
     for (uint32_t i = 0; i < n; ++i) if (ids[i] >= w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
     std::vector<unsigned> wake;
@@ -1560,6 +1581,7 @@ int pr_set_revolute_joints(pr_world* pw, uint32_t n, const uint32_t* ids, const 
 {
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     if (!w.stepComplete) { w.error = "SetJoint: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
     for (uint32_t i = 0; i < n; ++i) {
         if (ids[i] >= w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
@@ -1584,6 +1606,7 @@ int pr_set_bodies(pr_world* pw, uint32_t n, const uint32_t* ids, const pr_body* 
 {
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     uint32_t maxId = 0; // (branch-free so that it vectorises: a bulk SetBody of 1M rows spent ~1 ms in an early-exit loop here)
     for (uint32_t i = 0; i < n; ++i) maxId = ids[i] > maxId ? ids[i] : maxId;
     if (n && maxId >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
@@ -1743,6 +1766,7 @@ int pr_set_contacts(pr_world* pw, uint32_t n, const pr_contact* rows)
 {
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     if (!w.stepComplete) { w.error = "SetContact: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
     if (!n) return PR_OK;
     pr_contact* srows = static_cast<pr_contact*>(stage_buf(w, 0, sizeof(pr_contact) * n));
@@ -1764,6 +1788,7 @@ int pr_set_manifolds(pr_world* pw, uint32_t n, const uint32_t* ids, const pr_man
 {
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     if (!w.stepComplete) { w.error = "SetManifold: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
     if (!n) return PR_OK;
     pr_manifold* srows = static_cast<pr_manifold*>(stage_buf(w, 0, sizeof(pr_manifold) * n + 4u * n));
@@ -1883,6 +1908,7 @@ int pr_load_state(pr_world* pw, uint32_t n_bodies, const pr_body* bodies, uint32
 {
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     if (n_bodies != w.nBodies) { w.error = "body count mismatch"; return PR_ERR_INVALID_ARGUMENT; }
     std::vector<unsigned> ids(n_bodies);
     for (unsigned i = 0; i < n_bodies; ++i) ids[i] = i;
@@ -1984,6 +2010,7 @@ int pr_shift_origin(pr_world* pw, float x, float y)
 {
     API_TRY(pw)
     World& w = pw->w;
+    w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     if (!w.stepComplete) { w.error = "ShiftOrigin: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
     const unsigned n = std::max(w.nBodies, w.nProxies);
     if (n) PR_LAUNCH(k_shift_origin, n, w.stream, w.d, w.nBodies, w.nProxies, x, y);

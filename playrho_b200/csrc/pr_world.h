@@ -195,6 +195,8 @@ struct World {
     std::vector<uint2> toiSchedule; unsigned toiScheduleN = 0; // last step's TOI events by round (debug bit 0)
     std::vector<void*> allocs;
     const unsigned* blkSortedKey = nullptr; // this step's sorted (world << 7 | colour) keys
+    bool tmaSmemSet = false;
+    bool contactsClean = false; // no contact is flagged for updating and no body moved since the last Step ended (step_impl)
     bool blocksDirty = true, blkJointsDirty = true; unsigned blkMaxBodies = 0, blkWorldCap = 0, blkSmemSet = 0; // block solver
     unsigned isCap = 0, isHint = 0; // island-static pair set: capacity (power of two), pairs seen last step
     unsigned* gridBar = nullptr; unsigned fusedGrid = 0; bool fusedProbed = false; // persistent solver kernel (pr_solve_fused.cuh)

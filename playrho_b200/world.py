@@ -167,7 +167,7 @@ class World:
     """Device-resident world. Mirrors the reference's World usage: create shapes/bodies, Step, read back."""
 
     def __init__(self, scene=None, lib=None, device=-1, body_capacity=0, contact_capacity=0, proxy_capacity=0,
-                 record_solve_order=False, large_variants=False):
+                 record_solve_order=False, large_variants=False, debug_flags=0):
         self.lib = lib or load_library()
         conf = abi.one(abi.WORLD_CONF)
         self.lib.pr_world_conf_default(abi.ptr(conf))
@@ -181,8 +181,8 @@ class World:
             raise PrError(rc, self.lib.pr_last_error(None).decode())
         self.h = h
         # bit 0: record the solve order; bits 1,2: the opt-in kernel variants (binned narrowphase, persistent fused solver)
-        if record_solve_order or large_variants:
-            self.lib.pr_set_debug(self.h, (1 if record_solve_order else 0) | (6 if large_variants else 0))
+        if record_solve_order or large_variants or debug_flags:
+            self.lib.pr_set_debug(self.h, (1 if record_solve_order else 0) | (6 if large_variants else 0) | debug_flags)
         if scene is not None:
             self.create(scene)
 

@@ -119,6 +119,17 @@ def test_cuda_binned_narrowphase_variant_bit_exact_vs_oracle():
 
 
 @need_oracle
+def test_cuda_tma_staged_narrowphase_variant_bit_exact_vs_oracle():
+    """k_update_contacts_tma (debug bit 6): the regular phase's narrowphase with the pair's vertex sets brought into shared
+    memory by the bulk-copy engine (cp.async.bulk + mbarrier) -- same bits as the oracle on polygon-heavy scenes."""
+    sc = scenes_np.mixed(1500, seed=12345, tile_segments=64, tile_width=32.0)
+    gs, ncontacts, prof = run_vs_oracle(sc, 100, device=0, check_every=5, conf=refworld.default_step_conf(), toi_mode=1, world_kwargs=dict(debug_flags=64))
+    assert ncontacts > 0
+    gs, ncontacts, prof = run_vs_oracle(scenes_np.pyramid(10), 120, device=0, check_every=5, world_kwargs=dict(debug_flags=64))
+    assert ncontacts > 0
+
+
+@need_oracle
 @need_ref
 def test_cuda_shooter_toi_bit_exact_vs_oracle():
     """Fast bodies, bullets, spinning kinematic bar, sensor shape: hundreds of TOI events (SolveToi mini
