@@ -18,6 +18,7 @@
 #define PR_HD __host__ __device__ __forceinline__
 #define PR_D __device__ __forceinline__
 #define PR_KERNEL __global__ void
+#define PR_KERNEL_LB(threads, blocks) __global__ void __launch_bounds__(threads, blocks)
 #define PR_TID (blockIdx.x * blockDim.x + threadIdx.x)
 #define PR_NTHREADS (gridDim.x * blockDim.x)
 typedef cudaStream_t pr_stream_t;
@@ -30,6 +31,14 @@ typedef cudaEvent_t pr_event_t;
 #define PR_WARP_ID (PR_TID >> 5)
 #define PR_NWARPS (PR_NTHREADS >> 5)
 #define PR_WARP_ALL(p) (__all_sync(0xffffffffu, (p)) != 0)
+#define PR_WARP_ANY(p) (__any_sync(0xffffffffu, (p)) != 0)
+#define PR_BALLOT(p) __ballot_sync(0xffffffffu, (p))
+#define PR_SHFL(v, src) __shfl_sync(0xffffffffu, (v), (src))
+#define PR_SYNCWARP() __syncwarp()
+#define PR_LANEMASK_LT ((1u << (threadIdx.x & 31u)) - 1u)
+#define PR_WARP_SUM(v) __reduce_add_sync(0xffffffffu, (v))
+#define PR_DN __device__ __noinline__
+#define PR_GRID_CONST const __grid_constant__ // (a kernel parameter whose address may be taken without a local copy)
 // Every kernel launch is a programmatic dependent launch (sm_90+, below): the grid may be SCHEDULED while its predecessor in the
 // stream is still draining, and every kernel body starts with PR_PDL_ENTER() -- let my own dependents be scheduled, then wait
 // for my predecessor to complete (and its writes to be visible) -- before it touches global memory. A step is ~300 dependent
@@ -75,6 +84,7 @@ __device__ __forceinline__ void pr_pdl_launch_dependents() { asm volatile("gridd
 #define PR_HD inline
 #define PR_D inline
 #define PR_KERNEL void
+#define PR_KERNEL_LB(threads, blocks) void
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct uint2 { unsigned x, y; };
@@ -91,6 +101,14 @@ namespace pr { extern thread_local unsigned emul_tid, emul_nthreads; }
 #define PR_WARP_ID (pr::emul_tid)
 #define PR_NWARPS (pr::emul_nthreads)
 #define PR_WARP_ALL(p) (p)
+#define PR_WARP_ANY(p) (p)
+#define PR_BALLOT(p) ((p) ? 1u : 0u)
+#define PR_SHFL(v, src) (v)
+#define PR_SYNCWARP() do { } while (0)
+#define PR_LANEMASK_LT 0u
+#define PR_WARP_SUM(v) (v)
+#define PR_DN inline
+#define PR_GRID_CONST const
 typedef int pr_stream_t;
 typedef int pr_event_t;
 #define PR_LAUNCH(kernel, n, stream, ...)                                                          \
@@ -118,6 +136,7 @@ inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); retu
 inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 inline int __clzll(unsigned long long v) { return v ? __builtin_clzll(v) : 64; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __ffsll(unsigned long long v) { return __builtin_ffsll(static_cast<long long>(v)); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}

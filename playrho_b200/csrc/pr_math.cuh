@@ -156,6 +156,13 @@ PR_HD void glibc_sincosf(float y, float* sinp, float* cosp)
 // UnitVec::Get(angle), Library/source/playrho/d2/UnitVec.cpp:27-30
 PR_HD Rot rot_from_angle(float a) { Rot r; glibc_sincosf(a, &r.s, &r.c); return r; }
 // GetTransformation(pos, localCenter), d2/Math.hpp:232-245
+// the same function as ONE out-of-line copy: for code that is a single lane's serial chain (the TOI event solve), where
+// twenty inlined copies of the double-precision polynomial only inflate the kernel
+#ifndef PR_HOST_EMUL
+__device__ __noinline__ Rot rot_from_angle_call(float a) { return rot_from_angle(a); }
+#else
+inline Rot rot_from_angle_call(float a) { return rot_from_angle(a); }
+#endif
 PR_HD Xf get_xf(float2 ctr, Rot rot, float2 lc) { return mkxf(ctr - rotate(lc, rot), rot); }
 PR_HD Xf get_xf(Pos pos, float2 lc) { return get_xf(pos.l, rot_from_angle(pos.a), lc); }
 

@@ -369,8 +369,7 @@ PR_D bool toi_advance_body(const DV& d, unsigned b, float toi)
     advance0(p0, p1, toi);
     p1.x = p0.x; p1.y = p0.y; p1.z = p0.z;
     d.b_pos0[b] = p0; d.b_pos1[b] = p1; d.b_toiAlpha[b] = f2u(toi);
-    Pos p; p.l = v2(p1.x, p1.y); p.a = p1.z;
-    const Xf xf = get_xf(p, d.b_lc[b]);
+    const Xf xf = get_xf(v2(p1.x, p1.y), rot_from_angle_call(p1.z), d.b_lc[b]);
     d.b_xf[b] = make_float4(xf.p.x, xf.p.y, xf.q.c, xf.q.s);
     return pos_differs(p0, o0) || pos_differs(p1, o1);
 }
@@ -381,42 +380,127 @@ PR_D bool toi_body_islanded(const DV& d, const ToiIsland& isl, unsigned b, bool 
     for (unsigned k = 0; k < isl.nB; ++k) if (d.toi_islBodies[isl.base + k] == b) return true; // non-speedable: this event's list
     return false;
 }
-// ProcessContactsForTOI, :2060-2142
+// Update(contactID) as the TOI phase calls it: ONE copy of the narrowphase per kernel (it used to be inlined four times into
+// the event solve, 23 000 instructions of which a single lane walked a few hundred)
+PR_DN void toi_update_contact(const DV& d, const pr_step_conf& conf, unsigned cid, unsigned cf) { update_contact(d, conf, cid, cf); }
+// one entry of ProcessContactsForTOI's loop (:2079-2140), everything in the reference's order: used when the entries of a
+// chunk may depend on each other (serial-exact mode, or two contacts of the chunk share their other body)
+PR_D void toi_process_entry(const DV& d, const pr_step_conf& conf, unsigned id, bool bodyImpenetrable, unsigned cid, ToiIsland& isl,
+                            float toi, bool exactMode, unsigned& updatedN, unsigned& skippedN)
+{
+    if (d.c_toiIsl[cid]) return;
+    unsigned cf = d.c_flags[cid];
+    if (cf & PR_CONTACT_SENSOR) return;
+    const uint4 ab = d.c_ab[cid];
+    const unsigned other = (ab.x == id) ? ab.y : ab.x;
+    const unsigned of = d.b_flags[other];
+    if (!(bodyImpenetrable || (of & PR_BODY_IMPENETRABLE))) return;
+    const bool otherSpeedable = f_speedable(of);
+    const bool otherIslanded = toi_body_islanded(d, isl, other, otherSpeedable);
+    const SweepBk backup = toi_backup(d, other);
+    const bool touchOther = !otherIslanded && (otherSpeedable || exactMode);
+    if (touchOther) {
+        if (toi_advance_body(d, other, toi)) toi_flag_body_contacts(d, other);
+    }
+    cf = d.c_flags[cid];
+    if (cf & PR_CONTACT_DIRTY) { toi_update_contact(d, conf, cid, cf); ++updatedN; }
+    else ++skippedN;
+    cf = d.c_flags[cid];
+    if (!(cf & PR_CONTACT_ENABLED) || !(cf & PR_CONTACT_TOUCHING)) {
+        if (touchOther) toi_restore(d, other, backup);
+        return;
+    }
+    d.toi_islContacts[isl.base + isl.nC++] = cid;
+    d.c_toiIsl[cid] = 1u;
+    if (!otherIslanded) {
+        if (otherSpeedable) { toi_wake(d, other); d.b_toiIsl[other] = 1u; }
+        d.toi_islBodies[isl.base + isl.nB++] = other;
+    }
+}
+// ProcessContactsForTOI, :2060-2142 -- the whole WARP: a chunk of 32 entries of the body's contact list at a time. Each lane
+// advances its entry's other body, updates the contact and restores the body if the contact turned out not to touch -- the
+// entries are independent of each other as long as no two of them share a body that can be moved (then, and in serial-exact
+// mode, where unspeedable bodies are advanced too, the chunk runs entry by entry) -- and the island lists are appended in lane
+// order (= list order) by ballot ranks. isl and the two counts are warp-uniform on entry and on exit... the counts are
+// per-lane partial sums (the caller adds them up).
 PR_D void toi_process_contacts(const DV& d, const pr_step_conf& conf, unsigned id, ToiIsland& isl, float toi, bool exactMode,
                                unsigned& updatedN, unsigned& skippedN)
 {
     const bool bodyImpenetrable = (d.b_flags[id] & PR_BODY_IMPENETRABLE) != 0u;
-    adj_sort_body(d, id); // contacts appended since the table was built go to their m_bodyContacts position
-    for (unsigned k = d.adj_off[id], ke = adj_end(d, id); k < ke; ++k) {
-        const unsigned cid = d.adj_list[k];
-        if (d.c_toiIsl[cid]) continue;
-        unsigned cf = d.c_flags[cid];
-        if (cf & PR_CONTACT_SENSOR) continue;
-        const uint4 ab = d.c_ab[cid];
-        const unsigned other = (ab.x == id) ? ab.y : ab.x;
-        const unsigned of = d.b_flags[other];
-        if (!(bodyImpenetrable || (of & PR_BODY_IMPENETRABLE))) continue;
-        const bool otherSpeedable = f_speedable(of);
-        const bool otherIslanded = toi_body_islanded(d, isl, other, otherSpeedable);
-        const SweepBk backup = toi_backup(d, other);
-        const bool touchOther = !otherIslanded && (otherSpeedable || exactMode);
-        if (touchOther) {
-            if (toi_advance_body(d, other, toi)) toi_flag_body_contacts(d, other);
+    const unsigned lo = d.adj_off[id], hi = adj_end(d, id);
+    { // contacts appended since the table was built go to their m_bodyContacts position (rare: check first, all lanes)
+        bool sorted = true;
+        for (unsigned k = lo + 1u + PR_LANE; k < hi; k += PR_WARP) if (d.c_pos[d.adj_list[k - 1u]] > d.c_pos[d.adj_list[k]]) sorted = false;
+        if (!PR_WARP_ALL(sorted)) { if (PR_LANE == 0u) adj_sort_body(d, id); }
+        PR_SYNCWARP();
+    }
+    for (unsigned k0 = lo; k0 < hi; k0 += PR_WARP) {
+        const unsigned k = k0 + PR_LANE;
+        bool cand = false;
+        unsigned cid = 0u, other = 0u, of = 0u;
+        if (k < hi) {
+            cid = d.adj_list[k];
+            if (!d.c_toiIsl[cid] && !(d.c_flags[cid] & PR_CONTACT_SENSOR)) {
+                const uint4 ab = d.c_ab[cid];
+                other = (ab.x == id) ? ab.y : ab.x;
+                of = d.b_flags[other];
+                cand = bodyImpenetrable || (of & PR_BODY_IMPENETRABLE);
+            }
         }
-        cf = d.c_flags[cid];
-        if (cf & PR_CONTACT_DIRTY) { update_contact(d, conf, cid, cf); ++updatedN; }
-        else ++skippedN;
-        cf = d.c_flags[cid];
-        if (!(cf & PR_CONTACT_ENABLED) || !(cf & PR_CONTACT_TOUCHING)) {
-            if (touchOther) toi_restore(d, other, backup);
+        const bool otherSpeedable = f_speedable(of);
+        bool serial = exactMode;
+#ifndef PR_HOST_EMUL
+        if (!serial) { // two movable entries of the chunk with the same other body?
+            const unsigned m = PR_BALLOT(cand && otherSpeedable);
+            bool dup = false;
+            if (cand && otherSpeedable) dup = __popc(__match_any_sync(m, other)) > 1;
+            serial = PR_WARP_ANY(dup);
+        }
+#endif
+        if (serial) {
+            for (unsigned l = 0; l < PR_WARP; ++l) {
+                if (PR_LANE == l && k < hi) toi_process_entry(d, conf, id, bodyImpenetrable, d.adj_list[k], isl, toi, exactMode, updatedN, skippedN);
+                PR_SYNCWARP();
+                isl.nB = PR_SHFL(isl.nB, l); isl.nC = PR_SHFL(isl.nC, l);
+            }
             continue;
         }
-        d.toi_islContacts[isl.base + isl.nC++] = cid;
-        d.c_toiIsl[cid] = 1u;
-        if (!otherIslanded) {
-            if (otherSpeedable) { toi_wake(d, other); d.b_toiIsl[other] = 1u; }
-            d.toi_islBodies[isl.base + isl.nB++] = other;
+        bool touching = false, otherIslanded = false;
+        if (cand) {
+            if (otherSpeedable) otherIslanded = d.b_toiIsl[other] != 0u; // (an unspeedable body is never touched here: looked up below)
+            const bool touchOther = otherSpeedable && !otherIslanded;
+            SweepBk backup;
+            if (touchOther) {
+                backup = toi_backup(d, other);
+                if (toi_advance_body(d, other, toi)) toi_flag_body_contacts(d, other);
+            }
+            unsigned cf = d.c_flags[cid];
+            if (cf & PR_CONTACT_DIRTY) { toi_update_contact(d, conf, cid, cf); ++updatedN; }
+            else ++skippedN;
+            cf = d.c_flags[cid];
+            touching = (cf & PR_CONTACT_ENABLED) && (cf & PR_CONTACT_TOUCHING);
+            if (!touching && touchOther) toi_restore(d, other, backup);
         }
+        const unsigned mC = PR_BALLOT(touching);
+        if (touching) { d.toi_islContacts[isl.base + isl.nC + __popc(mC & PR_LANEMASK_LT)] = cid; d.c_toiIsl[cid] = 1u; }
+        bool addBody = false;
+        if (touching) {
+            if (otherSpeedable) addBody = !otherIslanded;
+            else { addBody = true; for (unsigned q = 0; q < isl.nB; ++q) if (d.toi_islBodies[isl.base + q] == other) addBody = false; }
+        }
+#ifndef PR_HOST_EMUL
+        { // an unspeedable body (the terrain) that several entries of the chunk touch joins the list once, with the first of them
+            const unsigned m = PR_BALLOT(addBody && !otherSpeedable);
+            if (addBody && !otherSpeedable && PR_LANE != static_cast<unsigned>(__ffs(__match_any_sync(m, other)) - 1)) addBody = false;
+        }
+#endif
+        const unsigned mB = PR_BALLOT(addBody);
+        if (addBody) {
+            if (otherSpeedable) { toi_wake(d, other); d.b_toiIsl[other] = 1u; }
+            d.toi_islBodies[isl.base + isl.nB + __popc(mB & PR_LANEMASK_LT)] = other;
+        }
+        isl.nC += __popc(mC); isl.nB += __popc(mB);
+        PR_SYNCWARP();
     }
 }
 
@@ -428,10 +512,30 @@ struct ToiSmem {
     float4 rows[13][TOI_SM_NC];
     float4 svel[TOI_SM_NB], spos[TOI_SM_NB];
     unsigned island[TOI_SM_NC], bodies[TOI_SM_NB];
+    unsigned changed[2], pad[2];
 };
-// SolveToi(contact) for event e (one thread; see k_toi_solve)
+// the two serial chains of an event (lane 0 runs them; the rows sit in shared memory)
+// (measured on B200, 1M mixed scene: as out-of-line calls the two passes are 10-15% SLOWER -- the row store's pointers then
+// live on the stack -- and a per-body cache of UnitVec::Get(angle) loses too: 7 950 vs 6 560 cycles per position pass)
+PR_D float toi_position_pass(const DV& d, const RS& r, unsigned row0, unsigned nC, float rate, float slop, float maxCorr)
+{
+    float minSeparation = PR_INF;
+    for (unsigned j = 0; j < nC; ++j) {
+        bool did;
+        minSeparation = stdmin(minSeparation, solve_position_row(d, r, row0 + j, rate, slop, maxCorr, did, false));
+    }
+    return minSeparation;
+}
+PR_D float toi_velocity_pass(const DV& d, const RS& r, unsigned row0, unsigned nC)
+{
+    float newInc = 0.0f;
+    for (unsigned j = 0; j < nC; ++j) { bool did; newInc = stdmax(newInc, solve_velocity_row(d, r, row0 + j, did, false)); }
+    return newInc;
+}
+// SolveToi(contact) for event e -- the whole WARP (see k_toi_solve): the two bodies, the entries of their contact lists, the
+// island's bodies and rows are dealt out to the lanes; only the Gauss-Seidel iterations themselves run on lane 0
 #ifdef PR_TOI_TIMING
-#define PR_TT(k) do { if (e == 0u) { const long long t_ = clock64(); atomicAdd(&d.cnt->dbg[k], static_cast<unsigned long long>(t_ - tt_)); tt_ = t_; } } while (0)
+#define PR_TT(k) do { if (e == 0u && PR_LANE == 0u) { const long long t_ = clock64(); atomicAdd(&d.cnt->dbg[k], static_cast<unsigned long long>(t_ - tt_)); tt_ = t_; } } while (0)
 #else
 #define PR_TT(k) do { } while (0)
 #endif
@@ -444,52 +548,77 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
     const uint4 ab = d.c_ab[cid];
     const unsigned A = ab.x, B = ab.y;
     const float toi = d.c_mat[cid].w;
-    unsigned numUpdated = 0u, numSkipped = 0u;
+    unsigned numUpdated = 0u, numSkipped = 0u; // (per-lane partial sums)
     const unsigned fA = d.b_flags[A], fB = d.b_flags[B];
     // island scratch (body list, contact list, VC/PC rows): sized by the two contact lists. An event that does
     // not fit this round's arena is left untouched (still the soonest of its neighbourhood) for the next round.
     ToiIsland isl;
     const unsigned need = 2u + (f_speedable(fA) ? d.adj_n[A] : 0u) + (f_speedable(fB) ? d.adj_n[B] : 0u);
-    isl.base = atomicAdd(&d.cnt->toiScratchTop, need);
+    isl.base = 0u;
+    if (PR_LANE == 0u) isl.base = atomicAdd(&d.cnt->toiScratchTop, need);
+    isl.base = PR_SHFL(isl.base, 0);
     if (isl.base + need > scratchCap) {
-        if (isl.base == 0u) atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_TOI_SCRATCH));
-        atomicAdd(&d.cnt->toiDeferred, 1u);
+        if (PR_LANE == 0u) {
+            if (isl.base == 0u) atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_TOI_SCRATCH));
+            atomicAdd(&d.cnt->toiDeferred, 1u);
+        }
         return;
     }
     {
-        const SweepBk bkA = toi_backup(d, A), bkB = toi_backup(d, B);
-        const bool touchA = f_speedable(fA) || exactMode, touchB = f_speedable(fB) || exactMode;
-        if (touchA && toi_advance_body(d, A, toi)) toi_flag_body_contacts(d, A);
-        if (touchB && toi_advance_body(d, B, toi)) toi_flag_body_contacts(d, B);
-        unsigned cf = d.c_flags[cid];
-        if (cf & PR_CONTACT_DIRTY) { update_contact(d, conf, cid, cf); ++numUpdated; }
-        cf = d.c_flags[cid];
-        cf &= ~static_cast<unsigned>(PR_CONTACT_TOI); // SetToi(contact, {})
-        cf += 0x100u;                                  // IncrementToiCount
-        d.c_flags[cid] = cf;
-        if ((cf >> 8) == conf.max_sub_steps) atomicAdd(&d.cnt->toiAtMaxLive, 1u); // from now on UpdateContactTOIs counts it every round
-        toi_mark_recompute(d, cid);                    // (its TOI is gone: next round looks at it again)
-        reinterpret_cast<float*>(&d.c_mat[cid])[3] = 1.0f;
-        if (!(cf & PR_CONTACT_ENABLED) || !(cf & PR_CONTACT_TOUCHING)) {
-            if (touchA) toi_restore(d, A, bkA);
-            if (touchB) toi_restore(d, B, bkB);
-            atomicAdd(&d.cnt->toiUpdTouching, numUpdated);
-            atomicAdd(&d.cnt->toiSkipTouching, numUpdated ? 0u : 1u);
+        // lanes 0 and 1 advance A and B (the host emulation's single lane takes them one after the other)
+        constexpr unsigned NS = (PR_WARP >= 2u) ? 1u : 2u;
+        SweepBk bk[NS]; bool touch[NS];
+        for (unsigned s = PR_LANE; s < 2u; s += PR_WARP) {
+            const unsigned X = s ? B : A, fX = s ? fB : fA;
+            bk[s % NS] = toi_backup(d, X);
+            touch[s % NS] = f_speedable(fX) || exactMode;
+            sm->changed[s] = (touch[s % NS] && toi_advance_body(d, X, toi)) ? 1u : 0u;
+        }
+        PR_SYNCWARP();
+        for (unsigned s = 0; s < 2u; ++s) { // FlagForUpdating of a body that moved: its list over the lanes
+            const unsigned X = s ? B : A;
+            if (sm->changed[s]) for (unsigned k = d.adj_off[X] + PR_LANE, ke = adj_end(d, X); k < ke; k += PR_WARP) atomicOr(&d.c_flags[d.adj_list[k]], static_cast<unsigned>(PR_CONTACT_DIRTY));
+        }
+        PR_SYNCWARP();
+        unsigned proceed = 0u;
+        if (PR_LANE == 0u) {
+            unsigned cf = d.c_flags[cid];
+            if (cf & PR_CONTACT_DIRTY) { toi_update_contact(d, conf, cid, cf); ++numUpdated; }
+            cf = d.c_flags[cid];
+            cf &= ~static_cast<unsigned>(PR_CONTACT_TOI); // SetToi(contact, {})
+            cf += 0x100u;                                  // IncrementToiCount
+            d.c_flags[cid] = cf;
+            if ((cf >> 8) == conf.max_sub_steps) atomicAdd(&d.cnt->toiAtMaxLive, 1u); // from now on UpdateContactTOIs counts it every round
+            toi_mark_recompute(d, cid);                    // (its TOI is gone: next round looks at it again)
+            reinterpret_cast<float*>(&d.c_mat[cid])[3] = 1.0f;
+            proceed = ((cf & PR_CONTACT_ENABLED) && (cf & PR_CONTACT_TOUCHING)) ? 1u : 0u;
+            if (!proceed) {
+                atomicAdd(&d.cnt->toiUpdTouching, numUpdated);
+                atomicAdd(&d.cnt->toiSkipTouching, numUpdated ? 0u : 1u);
+            }
+        }
+        proceed = PR_SHFL(proceed, 0);
+        if (!proceed) {
+            for (unsigned s = PR_LANE; s < 2u; s += PR_WARP) if (touch[s % NS]) toi_restore(d, s ? B : A, bk[s % NS]);
             return;
         }
     }
     PR_TT(0);
-    if (f_speedable(fA)) toi_wake(d, A);
-    if (f_speedable(fB)) toi_wake(d, B);
+    if (PR_LANE == 0u) {
+        if (f_speedable(fA)) toi_wake(d, A);
+        if (f_speedable(fB)) toi_wake(d, B);
+        d.toi_islBodies[isl.base] = A; d.toi_islBodies[isl.base + 1u] = B; d.toi_islContacts[isl.base] = cid;
+        if (f_speedable(fA)) d.b_toiIsl[A] = 1u;
+        if (f_speedable(fB)) d.b_toiIsl[B] = 1u;
+        d.c_toiIsl[cid] = 1u;
+    }
     isl.nB = 2u; isl.nC = 1u;
-    d.toi_islBodies[isl.base] = A; d.toi_islBodies[isl.base + 1u] = B; d.toi_islContacts[isl.base] = cid;
-    if (f_speedable(fA)) d.b_toiIsl[A] = 1u;
-    if (f_speedable(fB)) d.b_toiIsl[B] = 1u;
-    d.c_toiIsl[cid] = 1u;
-    if (f_accelerable(fA)) toi_process_contacts(d, conf, A, isl, toi, exactMode != 0u, numUpdated, numSkipped);
-    PR_TT(1);
-    if (f_accelerable(fB)) toi_process_contacts(d, conf, B, isl, toi, exactMode != 0u, numUpdated, numSkipped);
-    PR_TT(2);
+    PR_SYNCWARP();
+    for (unsigned s = 0; s < 2u; ++s) { // (a loop: one copy of the code)
+        if (f_accelerable(s ? fB : fA)) toi_process_contacts(d, conf, s ? B : A, isl, toi, exactMode != 0u, numUpdated, numSkipped);
+        PR_TT(1u + s);
+    }
+    numUpdated = PR_WARP_SUM(numUpdated); numSkipped = PR_WARP_SUM(numSkipped);
 
     // ---- SolveToiViaGS (:1957-2058) with subConf.deltaTime = (1 - toi) * deltaTime (:1952-1953)
     pr_step_conf sub = conf;
@@ -503,7 +632,8 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
         r.pc0 = sm->rows[9]; r.pc1 = sm->rows[10]; r.pc2 = sm->rows[11]; r.pc3 = sm->rows[12];
         r.s_vel = sm->svel; r.s_pos = sm->spos;
         row0 = 0u;
-        for (unsigned k = 0; k < isl.nB; ++k) sm->bodies[k] = d.toi_islBodies[isl.base + k];
+        for (unsigned k = PR_LANE; k < isl.nB; k += PR_WARP) { sm->bodies[k] = d.toi_islBodies[isl.base + k]; }
+        PR_SYNCWARP();
     }
     // index of island body k (id b) in r.s_vel / r.s_pos, and of a contact's body there
     auto slot_of_k = [&](unsigned k, unsigned b) { return small ? k : b; };
@@ -513,89 +643,107 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
         while (k + 1u < isl.nB && sm->bodies[k] != b) ++k;
         return k;
     };
-    auto build_rows = [&]() {
-        for (unsigned j = 0; j < isl.nC; ++j) {
+    float minSepAll = PR_INF;
+    unsigned positionIters = conf.toi_position_iters, velocityIters = conf.toi_velocity_iters;
+    unsigned solved = 0u;
+    float maxIncAll = 0.0f;
+    for (unsigned pass = 0; pass < 2u; ++pass) { // position pass, velocity pass (a loop: one copy of the row builder)
+        if (pass == 0u) {
+            for (unsigned k = PR_LANE; k < isl.nB; k += PR_WARP) { // GetBodyConstraints(h = 0)
+                const unsigned b = d.toi_islBodies[isl.base + k];
+                const float4 p1 = d.b_pos1[b];
+                float4 v = body_constraint_velocity(d, b, d.b_vel[b], d.b_flags[b], 0.0f, sub);
+                v.w = 0.0f;
+                r.s_vel[slot_of_k(k, b)] = v;
+                r.s_pos[slot_of_k(k, b)] = make_float4(p1.x, p1.y, p1.z, 0.0f);
+            }
+            PR_SYNCWARP();
+        }
+        for (unsigned j = PR_LANE; j < isl.nC; j += PR_WARP) { // (one row per lane)
             const unsigned c2 = d.toi_islContacts[isl.base + j];
             const uint4 ab2 = d.c_ab[c2];
             build_constraint_rows(d, r, c2, row0 + j, sub, 0.0f, 0u, slot_of_body(ab2.x), slot_of_body(ab2.y));
         }
-    };
-    for (unsigned k = 0; k < isl.nB; ++k) { // GetBodyConstraints(h = 0)
-        const unsigned b = d.toi_islBodies[isl.base + k];
-        const float4 p1 = d.b_pos1[b];
-        float4 v = body_constraint_velocity(d, b, d.b_vel[b], d.b_flags[b], 0.0f, sub);
-        v.w = 0.0f;
-        r.s_vel[slot_of_k(k, b)] = v;
-        r.s_pos[slot_of_k(k, b)] = make_float4(p1.x, p1.y, p1.z, 0.0f);
-    }
-    build_rows();
-    PR_TT(3);
-    float minSepAll = PR_INF;
-    unsigned positionIters = conf.toi_position_iters;
-    unsigned solved = 0u;
-    for (unsigned it = 0; it < conf.toi_position_iters; ++it) {
-        float minSeparation = PR_INF;
-        for (unsigned j = 0; j < isl.nC; ++j) {
-            bool did;
-            minSeparation = stdmin(minSeparation, solve_position_row(d, r, row0 + j, conf.toi_resolution_rate, conf.linear_slop,
-                                                                     conf.max_linear_correction, did, false));
+        PR_SYNCWARP();
+        if (pass == 0u) {
+            PR_TT(3);
+            if (PR_LANE == 0u) {
+                for (unsigned it = 0; it < conf.toi_position_iters; ++it) {
+                    const float minSeparation = toi_position_pass(d, r, row0, isl.nC, conf.toi_resolution_rate, conf.linear_slop, conf.max_linear_correction);
+                    minSepAll = stdmin(minSepAll, minSeparation);
+                    if (minSeparation >= conf.toi_min_separation) { positionIters = it + 1u; solved = 1u; break; }
+                }
+            }
+            PR_SYNCWARP();
+            PR_TT(4);
+            for (unsigned k = PR_LANE; k < isl.nB; k += PR_WARP) { // "leap of faith": pos0 <- solved position (:2006-2012)
+                const unsigned b = d.toi_islBodies[isl.base + k];
+                if (f_speedable(d.b_flags[b])) {
+                    const float4 sp = r.s_pos[slot_of_k(k, b)];
+                    float4 p0 = d.b_pos0[b]; p0.x = sp.x; p0.y = sp.y; p0.z = sp.z; d.b_pos0[b] = p0;
+                }
+            }
+        } else {
+            if (PR_LANE == 0u) {
+                for (unsigned it = 0; it < conf.toi_velocity_iters; ++it) {
+                    const float newInc = toi_velocity_pass(d, r, row0, isl.nC);
+                    if (newInc <= conf.toi_min_momentum) { velocityIters = it + 1u; break; }
+                    maxIncAll = stdmax(maxIncAll, newInc);
+                }
+            }
+            PR_SYNCWARP();
         }
-        minSepAll = stdmin(minSepAll, minSeparation);
-        if (minSeparation >= conf.toi_min_separation) { positionIters = it + 1u; solved = 1u; break; }
-    }
-    PR_TT(4);
-    for (unsigned k = 0; k < isl.nB; ++k) { // "leap of faith": pos0 <- solved position (:2006-2012)
-        const unsigned b = d.toi_islBodies[isl.base + k];
-        if (f_speedable(d.b_flags[b])) {
-            const float4 sp = r.s_pos[slot_of_k(k, b)];
-            float4 p0 = d.b_pos0[b]; p0.x = sp.x; p0.y = sp.y; p0.z = sp.z; d.b_pos0[b] = p0;
-        }
-    }
-    build_rows();
-    unsigned velocityIters = conf.toi_velocity_iters;
-    float maxIncAll = 0.0f;
-    for (unsigned it = 0; it < conf.toi_velocity_iters; ++it) {
-        float newInc = 0.0f;
-        for (unsigned j = 0; j < isl.nC; ++j) { bool did; newInc = stdmax(newInc, solve_velocity_row(d, r, row0 + j, did, false)); }
-        if (newInc <= conf.toi_min_momentum) { velocityIters = it + 1u; break; }
-        maxIncAll = stdmax(maxIncAll, newInc);
     }
     PR_TT(5);
+    positionIters = PR_SHFL(positionIters, 0);
     if (d.ev_mask & PR_EVENT_POST_SOLVE) { // Report(postSolveContact, island.contacts, velConstraints, positionIters), :2053-2055
-        for (unsigned j = 0; j < isl.nC; ++j) {
+        for (unsigned j = PR_LANE; j < isl.nC; j += PR_WARP) {
             const float4 head = r.vc1[row0 + j];
             emit_impulse_event(d, f2u(head.w), f2u(head.z) & 0xFFu, positionIters, 1u, r.vc8[row0 + j]);
         }
     }
     const float h = sub.delta_time;
-    for (unsigned k = 0; k < isl.nB; ++k) { // IntegratePositions + write-back (:2042-2052)
-        const unsigned b = d.toi_islBodies[isl.base + k];
-        const unsigned f = d.b_flags[b];
-        if (!f_speedable(f)) continue;
-        const float4 v = r.s_vel[slot_of_k(k, b)];
-        float4 sp = r.s_pos[slot_of_k(k, b)];
-        const float2 tr = h * v2(v.x, v.y);
-        const float rot = h * v.z;
-        sp.x += tr.x; sp.y += tr.y; sp.z += rot;
-        d.b_vel[b] = make_float4(v.x, v.y, v.z, 0.0f);
-        float4 p1 = d.b_pos1[b];
-        if (pos_differs(p1, sp)) {
-            p1.x = sp.x; p1.y = sp.y; p1.z = sp.z;
-            d.b_pos1[b] = p1;
-            Pos p; p.l = v2(sp.x, sp.y); p.a = sp.z;
-            const Xf xf = get_xf(p, d.b_lc[b]);
-            d.b_xf[b] = make_float4(xf.p.x, xf.p.y, xf.q.c, xf.q.s);
-            toi_flag_body_contacts(d, b);
+    for (unsigned k0 = 0; k0 < isl.nB; k0 += PR_WARP) { // IntegratePositions + write-back (:2042-2052): a body per lane ...
+        const unsigned k = k0 + PR_LANE;
+        bool moved = false; unsigned b = 0u;
+        if (k < isl.nB) {
+            b = d.toi_islBodies[isl.base + k];
+            const unsigned f = d.b_flags[b];
+            if (f_speedable(f)) {
+                const float4 v = r.s_vel[slot_of_k(k, b)];
+                float4 sp = r.s_pos[slot_of_k(k, b)];
+                const float2 tr = h * v2(v.x, v.y);
+                const float rot = h * v.z;
+                sp.x += tr.x; sp.y += tr.y; sp.z += rot;
+                d.b_vel[b] = make_float4(v.x, v.y, v.z, 0.0f);
+                float4 p1 = d.b_pos1[b];
+                if (pos_differs(p1, sp)) {
+                    p1.x = sp.x; p1.y = sp.y; p1.z = sp.z;
+                    d.b_pos1[b] = p1;
+                    const Xf xf = get_xf(v2(sp.x, sp.y), rot_from_angle_call(sp.z), d.b_lc[b]);
+                    d.b_xf[b] = make_float4(xf.p.x, xf.p.y, xf.q.c, xf.q.s);
+                    moved = true;
+                }
+            }
+        }
+        // ... then FlagForUpdating of the moved ones, each list over the lanes
+        for (unsigned m = PR_BALLOT(moved); m; m &= m - 1u) {
+            const unsigned bm = PR_SHFL(b, static_cast<unsigned>(__ffs(static_cast<int>(m)) - 1));
+            for (unsigned q = d.adj_off[bm] + PR_LANE, qe = adj_end(d, bm); q < qe; q += PR_WARP) atomicOr(&d.c_flags[d.adj_list[q]], static_cast<unsigned>(PR_CONTACT_DIRTY));
         }
     }
+    PR_SYNCWARP();
     // ---- :1797-1811: reset island flags; accelerable bodies get their proxies synchronised and their contacts' TOIs reset
+    // (body after body, each one's contact list over the lanes: every entry is a chain of three returning atomics)
     for (unsigned k = 0; k < isl.nB; ++k) {
         const unsigned b = d.toi_islBodies[isl.base + k];
         const unsigned f = d.b_flags[b];
-        if (f_speedable(f)) d.b_toiIsl[b] = 0u;
+        if (PR_LANE == 0u) {
+            if (f_speedable(f)) d.b_toiIsl[b] = 0u;
+            if (f_accelerable(f)) d.sync_list[atomicAdd(&d.cnt->syncN, 1u)] = b;
+        }
         if (f_accelerable(f)) {
-            d.sync_list[atomicAdd(&d.cnt->syncN, 1u)] = b;
-            for (unsigned q = d.adj_off[b], qe = adj_end(d, b); q < qe; ++q) {
+            for (unsigned q = d.adj_off[b] + PR_LANE, qe = adj_end(d, b); q < qe; q += PR_WARP) {
                 const unsigned c2 = d.adj_list[q];
                 const unsigned f2 = atomicAnd(&d.c_flags[c2], ~static_cast<unsigned>(PR_CONTACT_TOI));
                 if (toi_static_eligible(f2)) toi_mark_recompute(d, c2);
@@ -604,7 +752,9 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
             }
         }
     }
+    PR_SYNCWARP();
     PR_TT(6);
+    if (PR_LANE != 0u) return;
 #ifdef PR_TOI_TIMING
     if (e == 0u) { atomicAdd(&d.cnt->dbg[8], 1ull); atomicAdd(&d.cnt->dbg[9], isl.nC); atomicAdd(&d.cnt->dbg[10], isl.nB);
                    atomicAdd(&d.cnt->dbg[11], positionIters); atomicAdd(&d.cnt->dbg[12], velocityIters);
@@ -620,11 +770,12 @@ PR_D void toi_solve_event(const DV& d, const pr_step_conf& conf, unsigned e, uns
     atomicAdd(&d.cnt->toiSkipTouching, numSkipped);
 }
 
-PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactMode, unsigned scratchCap)
+PR_KERNEL_LB(PR_BLOCK, 2) k_toi_solve(PR_GRID_CONST DV d, PR_GRID_CONST pr_step_conf conf, unsigned nEvents, unsigned exactMode, unsigned scratchCap)
 {
     PR_PDL_ENTER();
-    // one WARP per event, lane 0 working: events take wildly different paths (island sizes, manifold cases,
-    // iteration counts), so packing 32 of them into one warp serialises them (measured: 3.5 active lanes)
+    // one WARP per event (toi_solve_event deals the event's bodies, contact-list entries and rows out to the lanes): events take
+    // wildly different paths (island sizes, manifold cases, iteration counts), so packing 32 of them into one warp serialises
+    // them (measured: 3.5 active lanes)
 #ifndef PR_HOST_EMUL
     __shared__ ToiSmem sm[PR_BLOCK / 32];
     ToiSmem* mine = &sm[threadIdx.x >> 5];
@@ -633,7 +784,10 @@ PR_KERNEL k_toi_solve(DV d, pr_step_conf conf, unsigned nEvents, unsigned exactM
     ToiSmem* mine = &local;
 #endif
     const unsigned e = PR_TID >> 5;
-    if ((PR_TID & 31u) != 0u || e >= nEvents) return;
+#ifdef PR_HOST_EMUL
+    if ((PR_TID & 31u) != 0u) return; // (a warp of the emulation is one thread)
+#endif
+    if (e >= nEvents) return;
     toi_solve_event(d, conf, e, exactMode, scratchCap, mine);
 }
 
@@ -687,7 +841,7 @@ PR_KERNEL k_sync_body_proxies(DV d, pr_step_conf conf)
 // no event (TB_DONE) or meets something only the host can do (grow a buffer, rebuild the tree or the hash:
 // TB_HOST_FIND -- the round is then completed by the host's find_add_contacts -- or rebuild the adjacency: TB_ADJ).
 // The contact-pool bookkeeping (m_contacts size, free stack, pool size) is mirrored in the counters meanwhile.
-PR_KERNEL k_tb_solve(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratchCap)
+PR_KERNEL_LB(PR_BLOCK, 2) k_tb_solve(PR_GRID_CONST DV d, PR_GRID_CONST pr_step_conf conf, unsigned exactMode, unsigned scratchCap)
 {
     PR_PDL_ENTER();
 #ifndef PR_HOST_EMUL
@@ -703,8 +857,10 @@ PR_KERNEL k_tb_solve(DV d, pr_step_conf conf, unsigned exactMode, unsigned scrat
         if (nEvents == 0u) d.cnt->toiHalt = TB_DONE; // :1768 (threads that miss this flip see nEvents == 0 and do nothing either)
         else { d.cnt->tbRounds += 1u; d.cnt->tbFound += nEvents; d.cnt->lateWhy[6] = d.cnt->lateWhy[6] * 100000u + nEvents; d.cnt->lateWhy[7] += 1u; }
     }
-    if ((PR_TID & 31u) != 0u) return; // one warp per event, lane 0 working (see k_toi_solve)
-    for (unsigned e = PR_TID >> 5; e < nEvents; e += PR_NTHREADS >> 5) toi_solve_event(d, conf, e, exactMode, scratchCap, mine);
+#ifdef PR_HOST_EMUL
+    if ((PR_TID & 31u) != 0u) return; // (a warp of the emulation is one thread)
+#endif
+    for (unsigned e = PR_TID >> 5; e < nEvents; e += PR_NTHREADS >> 5) { toi_solve_event(d, conf, e, exactMode, scratchCap, mine); PR_SYNCWARP(); } // one warp per event
 }
 // FindContacts' tree update for the proxies the round's events moved; decides whether the host must take over
 PR_KERNEL k_tb_refit(DV d, unsigned nLeaves)
@@ -814,7 +970,7 @@ PR_KERNEL k_tb_add(DV d, pr_step_conf conf, unsigned capPairs, unsigned capConta
 // surviving candidates. It hands back to the list kernels (TB_BIG) when a list outgrows it or a sleeping body was woken,
 // and to the host for what only the host can do -- exactly like the batched list rounds.
 constexpr unsigned LATE_BLOCK = 512u, LATE_MAX_LIST = 2048u, LATE_MAX_CAND = 192u, LATE_SOLVE_WARPS = 8u;
-PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratchCap, unsigned nLeaves, const unsigned* sortedIdx,
+PR_KERNEL_LB(LATE_BLOCK, 1) k_tb_late(PR_GRID_CONST DV d, PR_GRID_CONST pr_step_conf conf, unsigned exactMode, unsigned scratchCap, unsigned nLeaves, const unsigned* sortedIdx,
                     unsigned capPairs, unsigned capContacts, unsigned capHash, unsigned hashTombs, unsigned maxRounds)
 {
     PR_PDL_ENTER();
@@ -901,10 +1057,12 @@ PR_KERNEL k_tb_late(DV d, pr_step_conf conf, unsigned exactMode, unsigned scratc
 #ifdef PR_TOI_TIMING
         if (PR_TID == 0u) { d.cnt->dbgLate[8] += 1ull; d.cnt->dbgLate[9] += nEvents; d.cnt->dbgLate[10] += nR; d.cnt->dbgLate[11] += nCand; }
 #endif
-        // ---- SolveToi per event: one warp each (lane 0 working), islands in the arena
-        if (PR_LANE == 0u && PR_WARP_ID < LATE_SOLVE_WARPS)
-            for (unsigned e = PR_WARP_ID; e < nEvents; e += (PR_NWARPS < LATE_SOLVE_WARPS ? PR_NWARPS : LATE_SOLVE_WARPS))
+        // ---- SolveToi per event: one warp each, islands in the arena
+        if (PR_WARP_ID < LATE_SOLVE_WARPS)
+            for (unsigned e = PR_WARP_ID; e < nEvents; e += (PR_NWARPS < LATE_SOLVE_WARPS ? PR_NWARPS : LATE_SOLVE_WARPS)) {
                 toi_solve_event(d, conf, e, exactMode, scratchCap, &islands[PR_WARP_ID < LATE_SOLVE_WARPS ? PR_WARP_ID : 0u]);
+                PR_SYNCWARP();
+            }
         __threadfence_block(); __syncthreads();
         PR_LT(3); // event solve
         // ---- Synchronize the moved bodies' proxies, FindContacts, AddContacts
