@@ -136,6 +136,7 @@ inline float __uint_as_float(unsigned i) { float f; std::memcpy(&f, &i, 4); retu
 inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 inline int __clzll(unsigned long long v) { return v ? __builtin_clzll(v) : 64; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __ffsll(unsigned long long v) { return __builtin_ffsll(static_cast<long long>(v)); }
 inline void __threadfence() {}

@@ -1863,9 +1863,16 @@ PR_D void apply_pair(float4& vA, float4& vB, float2 P, float2 relA, float2 relB,
 // WarmStartVelocities, AabbTreeWorld.cpp:222-273
 PR_D void warm_start_loaded(const RS& r, const VCRow& vc);
 PR_D void warm_start_row(const RS& r, unsigned i) { warm_start_loaded(r, vc_load(r, i)); }
+PR_D void warm_start_core(const VCRow& vc, float4& vA, float4& vB);
 PR_D void warm_start_loaded(const RS& r, const VCRow& vc)
 {
     float4 vA = r.s_vel[vc.bodyA], vB = r.s_vel[vc.bodyB];
+    warm_start_core(vc, vA, vB);
+    if (vc.dynA) r.s_vel[vc.bodyA] = vA;
+    if (vc.dynB) r.s_vel[vc.bodyB] = vB;
+}
+PR_D void warm_start_core(const VCRow& vc, float4& vA, float4& vB)
+{
     const Rot normal = mkrot(vc.nx, vc.ny), tangent = fwd_perp(normal);
     float2 dAl = v2(0, 0), dBl = v2(0, 0); float dAa = 0.0f, dBa = 0.0f;
     const float2 relA[2] = {v2(vc.rA0x, vc.rA0y), v2(vc.rA1x, vc.rA1y)}, relB[2] = {v2(vc.rB0x, vc.rB0y), v2(vc.rB1x, vc.rB1y)};
@@ -1876,8 +1883,8 @@ PR_D void warm_start_loaded(const RS& r, const VCRow& vc)
         dAl = dAl - vc.invMA * P; dAa -= vc.invIA * LA;
         dBl = dBl + vc.invMB * P; dBa += vc.invIB * LB;
     }
-    if (vc.dynA) r.s_vel[vc.bodyA] = make_float4(vA.x + dAl.x, vA.y + dAl.y, vA.z + dAa, 0.0f);
-    if (vc.dynB) r.s_vel[vc.bodyB] = make_float4(vB.x + dBl.x, vB.y + dBl.y, vB.z + dBa, 0.0f);
+    vA = make_float4(vA.x + dAl.x, vA.y + dAl.y, vA.z + dAa, vA.w); // (.w: the dataflow solver's row count, else 0)
+    vB = make_float4(vB.x + dBl.x, vB.y + dBl.y, vB.z + dBa, vB.w);
 }
 PR_KERNEL k_warm_start(DV d, unsigned start, unsigned count)
 { // (launched with PR_LAUNCH_PDL: the row is fetched while the previous colour drains; the bodies after it has)
@@ -1938,6 +1945,7 @@ PR_D float solve_velocity_row(const DV& d, const RS& r, unsigned i, bool& did, b
     return solve_velocity_loaded(d, r, i, vc_load(r, i), did, checkIsland);
 }
 // vc: the whole row, impulses included
+PR_D float solve_velocity_core(const VCRow& vc, float4& vA, float4& vB, float4& impulses);
 PR_D float solve_velocity_loaded(const DV& d, const RS& r, unsigned i, VCRow vc, bool& did, bool checkIsland)
 {
     did = false;
@@ -1945,6 +1953,16 @@ PR_D float solve_velocity_loaded(const DV& d, const RS& r, unsigned i, VCRow vc,
     float4 vA = r.s_vel[vc.bodyA], vB = r.s_vel[vc.bodyB];
     if (checkIsland && (r.isl_state[vc.island] & ISL_VEL_DONE)) return 0.0f;
     did = true;
+    float4 impulses;
+    const float maxInc = solve_velocity_core(vc, vA, vB, impulses);
+    if (vc.dynA) r.s_vel[vc.bodyA] = vA;
+    if (vc.dynB) r.s_vel[vc.bodyB] = vB;
+    r.vc8[i] = impulses;
+    return maxInc;
+}
+// the row's arithmetic on registers: the two bodies' velocities in and out, the new accumulated impulses out
+PR_D float solve_velocity_core(const VCRow& vc, float4& vA, float4& vB, float4& impulses)
+{
     const Rot normal = mkrot(vc.nx, vc.ny), tangent = fwd_perp(normal);
     const float2 relA[2] = {v2(vc.rA0x, vc.rA0y), v2(vc.rA1x, vc.rA1y)}, relB[2] = {v2(vc.rB0x, vc.rB0y), v2(vc.rB1x, vc.rB1y)};
     float jn[2] = {vc.jn0, vc.jn1}, jt[2] = {vc.jt0, vc.jt1};
@@ -2020,9 +2038,7 @@ PR_D float solve_velocity_loaded(const DV& d, const RS& r, unsigned i, VCRow vc,
             maxInc = stdmax(maxInc, stdmax(fabsf(n0), fabsf(n1)));
         }
     }
-    if (vc.dynA) r.s_vel[vc.bodyA] = vA;
-    if (vc.dynB) r.s_vel[vc.bodyB] = vB;
-    r.vc8[i] = make_float4(jn[0], jt[0], jn[1], jt[1]);
+    impulses = make_float4(jn[0], jt[0], jn[1], jt[1]);
     return maxInc;
 }
 #if !defined(PR_HOST_EMUL)
@@ -2146,6 +2162,7 @@ PR_D PDelta psm_solve(const PSM& psm, float2 pA, float2 pB, float imA, float iiA
 }
 // GaussSeidel::SolvePositionConstraint, ContactSolver.cpp:494-643 (moveA = moveB = true)
 PR_D float solve_position_loaded(const DV& d, const RS& r, const VCRow& vch, const PCRow& pc, float rate, float slop, float maxCorr, bool& did, bool checkIsland);
+PR_D float solve_position_core(const VCRow& vch, const PCRow& pc, float4& a4, float4& b4, float rate, float slop, float maxCorr);
 PR_D float solve_position_row(const DV& d, const RS& r, unsigned i, float rate, float slop, float maxCorr, bool& did, bool checkIsland = true)
 {
     VCRow vch; vc_load_head(r, i, vch);
@@ -2154,15 +2171,19 @@ PR_D float solve_position_row(const DV& d, const RS& r, unsigned i, float rate, 
 // vch: the row's head (bodies, inverse masses, island), pc: its position-constraint planes -- both immutable during the solve
 PR_D float solve_position_loaded(const DV& d, const RS& r, const VCRow& vch, const PCRow& pc, float rate, float slop, float maxCorr, bool& did, bool checkIsland)
 {
-    const VCRow* vcp = &vch;
-    const unsigned island = vcp->island;
     did = false;
-    const unsigned bA = vcp->bodyA, bB = vcp->bodyB;
-    const float imA = vcp->invMA, iiA = vcp->invIA, imB = vcp->invMB, iiB = vcp->invIB;
-    const unsigned dynA = vcp->dynA, dynB = vcp->dynB;
-    float4 a4 = r.s_pos[bA], b4 = r.s_pos[bB]; // (issued before the island test: see solve_velocity_row)
-    if (checkIsland && (r.isl_state[island] & ISL_POS_SOLVED)) return PR_INF;
+    float4 a4 = r.s_pos[vch.bodyA], b4 = r.s_pos[vch.bodyB]; // (issued before the island test: see solve_velocity_row)
+    if (checkIsland && (r.isl_state[vch.island] & ISL_POS_SOLVED)) return PR_INF;
     did = true;
+    const float minSep = solve_position_core(vch, pc, a4, b4, rate, slop, maxCorr);
+    if (vch.dynA) r.s_pos[vch.bodyA] = a4;
+    if (vch.dynB) r.s_pos[vch.bodyB] = b4;
+    return minSep;
+}
+// the row's arithmetic on registers: the two bodies' positions (x, y, angle, 0) in and out
+PR_D float solve_position_core(const VCRow& vch, const PCRow& pc, float4& a4, float4& b4, float rate, float slop, float maxCorr)
+{
+    const float imA = vch.invMA, iiA = vch.invIA, imB = vch.invMB, iiB = vch.invIB;
     Pos posA = pos_from4(a4), posB = pos_from4(b4);
     const float2 lcA = v2(pc.lcAx, pc.lcAy), lcB = v2(pc.lcBx, pc.lcBy);
     const unsigned count = (pc.typeCount >> 8) & 0xFFu;
@@ -2202,8 +2223,8 @@ PR_D float solve_position_loaded(const DV& d, const RS& r, const VCRow& vch, con
             minSep = s1.sep;
         }
     }
-    if (dynA) r.s_pos[bA] = make_float4(posA.l.x, posA.l.y, posA.a, 0.0f);
-    if (dynB) r.s_pos[bB] = make_float4(posB.l.x, posB.l.y, posB.a, 0.0f);
+    a4 = make_float4(posA.l.x, posA.l.y, posA.a, a4.w); // (.w: the dataflow solver's row count, else 0)
+    b4 = make_float4(posB.l.x, posB.l.y, posB.a, b4.w);
     return minSep;
 }
 PR_KERNEL k_solve_position(DV d, unsigned start, unsigned count, float rate, float slop, float maxCorr)
@@ -2219,6 +2240,103 @@ PR_KERNEL k_solve_position(DV d, unsigned start, unsigned count, float rate, flo
     if (t < count) { sep = solve_position_loaded(d, r, vch, pc, rate, slop, maxCorr, did, true); label = vch.island; }
     island_min(d.isl_sep, label, float_flip(sep), did);
 }
+// ------------------------------------------------------------------ a10/a11 as ONE launch per pass: the dataflow solver
+// The coloured solve is a launch per colour and pass: 15 colours x (1 + 8 + 3) passes = 180 dependent launches of a few
+// microseconds each, although a row only ever depends on the rows of LOWER colour that share one of its two bodies. Here a
+// pass (warm start, one velocity iteration, one position iteration) is one launch over all coloured rows in solve order:
+//   * every BodyConstraint row carries, in its unused fourth word, the number of rows applied to it so far (s_vel.w during
+//     the warm start and the velocity iterations, s_pos.w during the position iterations). A row knows from the colour masks
+//     how many rows of lower colour each of its bodies has (vc_flow: rank and row count per body), hence the count each body
+//     must show before the row may run -- pass * rows(body) + rank(row, body) -- and it stores count + 1 WITH the new
+//     velocity / position in one 16-byte store. Per body the rows therefore run in colour order: exactly the order of the
+//     per-colour launches, bit for bit, with the waiting confined to true dependencies -- and without a fence: the 16-byte
+//     row is the message and the flag at once (aligned 128-bit accesses to L2 are single transactions).
+//   * blocks take their 256 rows by a ticket (atomic counter per pass), so rows START in solve order: a waiting row only
+//     waits for rows that are already running or done, whatever order the hardware dispatches blocks in -- no deadlock.
+// Bodies that carry no mass are never written by the solver and are not waited for (the colouring ignores them as well).
+constexpr unsigned FLOW_SPIN_LIMIT = 1u << 22;
+#ifndef PR_HOST_EMUL
+PR_D float4 flow_ld(const float4* p)
+{ // one 128-bit load from L2 (never L1: other SMs write these rows during the kernel)
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+PR_D void flow_st(float4* p, float4 v) { asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory"); }
+#else
+PR_D float4 flow_ld(const float4* p) { return *p; }
+PR_D void flow_st(float4* p, float4 v) { *p = v; }
+#endif
+// rank | rows << 8 per body (a body's rows all have different colours: the colour mask counts them), body B's << 16
+PR_KERNEL k_flow_words(DV d, unsigned nRows, const unsigned* sortedColor)
+{
+    pr_pdl_wait(); // (no early trigger: the first pass reads vc_flow BEFORE its own dependency wait)
+    const unsigned i = PR_TID;
+    if (i < nRows) {
+        const float4 head = d.vc1[i];
+        const unsigned cf = f2u(head.z), color = sortedColor[i];
+        const unsigned long long below = (1ull << color) - 1ull;
+        const unsigned long long mA = ((cf >> 8) & 1u) ? d.b_cmask[f2u(head.x)] : 0ull, mB = ((cf >> 9) & 1u) ? d.b_cmask[f2u(head.y)] : 0ull;
+        d.vc_flow[i] = static_cast<unsigned>(__popcll(mA & below)) | (static_cast<unsigned>(__popcll(mA)) << 8) |
+                       (static_cast<unsigned>(__popcll(mB & below)) << 16) | (static_cast<unsigned>(__popcll(mB)) << 24);
+    }
+}
+// mode 0: WarmStartVelocities, 1: one velocity iteration, 2: one position iteration; nRows: the coloured rows (the overflow
+// tail, if any, follows in its own launch); pass: how many passes ran on the same array (s_vel / s_pos) before this one
+template <unsigned mode> PR_KERNEL_LB(PR_BLOCK, 3) k_flow_pass(DV d, unsigned nRows, unsigned ticket, unsigned pass, float rate, float slop, float maxCorr)
+{
+    pr_pdl_launch_dependents();
+#ifndef PR_HOST_EMUL
+    __shared__ unsigned s_chunk;
+    if (threadIdx.x == 0u) s_chunk = atomicAdd(&d.cnt->flowTicket[ticket & 31u], 1u);
+    __syncthreads();
+    const unsigned i = s_chunk * PR_BLOCK + threadIdx.x;
+#else
+    const unsigned i = PR_TID;
+#endif
+    const RS r = rs_global(d);
+    const bool valid = i < nRows;
+    VCRow vc; PCRow pc;
+    unsigned tA = 0u, tB = 0u;
+    if (valid) { // the immutable part of the row, while the previous pass drains
+        if (mode == 2u) { vc_load_head(r, i, vc); pc = pc_load(r, i); }
+        else vc = vc_load_static(r, i);
+        const unsigned fw = d.vc_flow[i];
+        tA = pass * ((fw >> 8) & 0xFFu) + (fw & 0xFFu);
+        tB = pass * (fw >> 24) + ((fw >> 16) & 0xFFu);
+    }
+    pr_pdl_wait();
+    if (valid && mode != 2u) vc_load_impulses(r, i, vc);
+    float4* const rows = (mode == 2u) ? d.s_pos : d.s_vel;
+    bool done = !valid, did = false;
+    float result = (mode == 2u) ? PR_INF : 0.0f;
+    bool skip = false;
+    if (valid) skip = (mode == 1u) ? (d.isl_state[vc.island] & ISL_VEL_DONE) != 0u : (mode == 2u) ? (d.isl_state[vc.island] & ISL_POS_SOLVED) != 0u : false;
+    for (unsigned spins = 0;; ++spins) {
+        if (!done) {
+            float4 a = flow_ld(&rows[vc.bodyA]), b = flow_ld(&rows[vc.bodyB]);
+            if ((!vc.dynA || f2u(a.w) == tA) && (!vc.dynB || f2u(b.w) == tB)) {
+                if (!skip) {
+                    if (mode == 0u) warm_start_core(vc, a, b);
+                    else if (mode == 1u) { float4 imp; result = solve_velocity_core(vc, a, b, imp); d.vc8[i] = imp; did = true; }
+                    else { result = solve_position_core(vc, pc, a, b, rate, slop, maxCorr); did = true; }
+                }
+                if (vc.dynA) { a.w = u2f(tA + 1u); flow_st(&rows[vc.bodyA], a); }
+                if (vc.dynB) { b.w = u2f(tB + 1u); flow_st(&rows[vc.bodyB], b); }
+                done = true;
+            }
+        }
+        if (PR_WARP_ALL(done)) break;
+#ifdef PR_HOST_EMUL
+        if (spins > 2u && getenv("PR_FLOW_DEBUG")) { const float4 a = rows[vc.bodyA], b = rows[vc.bodyB]; fprintf(stderr, "flow stall: mode %u row %u pass %u bodies %u(dyn %u) %u(dyn %u) want %u %u have %u %u flow %08x color %u\n", mode, i, pass, vc.bodyA, vc.dynA, vc.bodyB, vc.dynB, tA, tB, f2u(a.w), f2u(b.w), d.vc_flow[i], d.k_color[d.k_sorted[i]]); }
+#endif
+        if (spins > FLOW_SPIN_LIMIT) { atomicOr(&d.cnt->error, static_cast<unsigned>(ERR_FLOW_STALL)); break; } // (never seen: a guard against a hung GPU)
+    }
+    const unsigned label = valid ? vc.island : 0u;
+    if (mode == 1u) island_max(d.isl_inc, label, f2u(result), did);
+    else if (mode == 2u) island_min(d.isl_sep, label, float_flip(result), did);
+}
+
 PR_KERNEL k_solve_position_tail(DV d, unsigned tailStart, unsigned tailCount, unsigned nSegs, float rate, float slop, float maxCorr)
 {
     PR_PDL_ENTER();

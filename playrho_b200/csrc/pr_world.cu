@@ -105,7 +105,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(ht_keys, G_HASH),
         A(np_key, G_PAIR), A(np_key2, G_PAIR), A(np_px, G_PAIR), A(np_idx, G_PAIR), A(np_idx2, G_PAIR),
         A(vc0, G_CONS), A(vc1, G_CONS), A(vc2, G_CONS), A(vc3, G_CONS), A(vc4, G_CONS), A(vc5, G_CONS), A(vc6, G_CONS), A(vc7, G_CONS),
-        A(vc8, G_CONS), A(vc_island, G_CONS), A(pc0, G_CONS), A(pc1, G_CONS), A(pc2, G_CONS), A(pc3, G_CONS), A(k_sorted, G_CONS),
+        A(vc8, G_CONS), A(vc_island, G_CONS), A(vc_flow, G_CONS), A(pc0, G_CONS), A(pc1, G_CONS), A(pc2, G_CONS), A(pc3, G_CONS), A(k_sorted, G_CONS),
         // per-contact scratch of the constraint-list build (sized like m_contacts: written before the constraint count is known)
         A(k_contact, G_CONTACT), A(k_color, G_CONTACT), A(k_tmpKey, G_CONTACT), A(k_tmpKey2, G_CONTACT), A(k_tmpVal, G_CONTACT), A(k_ulist, G_CONTACT),
     };
@@ -210,6 +210,7 @@ static void throw_device_error(World& w)
     if (e & ERR_SENSOR) m += " sensor contacts (GJK TestOverlap) not supported yet;";
     if (e & ERR_HASH_FULL) m += " contact hash full;";
     if (e & ERR_TOI_SCRATCH) m += " one TOI island needs more scratch rows than the arena holds;";
+    if (e & ERR_FLOW_STALL) m += " dataflow solver: a row waited for its bodies beyond the spin limit;";
     throw CudaError{m};
 }
 
@@ -645,6 +646,35 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         PR_LAUNCH(k_block_solve, d.nWorlds, w.stream, d, conf, w.blkSortedKey, maxB, (nCons && conf.do_warm_start) ? 1u : 0u);
 #endif
         tm.mark(w, PR_STAGE_POSITION);
+    } else if (!fused && !(w.debugFlags & 128u) && 1u + conf.reg_velocity_iters + conf.reg_position_iters <= 32u) {
+        // dataflow solver (k_flow_pass, pr_kernels.cuh): ONE launch per pass over all coloured rows; debug bit 7 = the per-colour launches below
+        const unsigned nFlow = tailCount ? tailStart : nCons; // (the overflow tail sorts last)
+        unsigned ticket = 0u, pass = 0u; // ticket: launches so far; pass: passes so far over the same array (s_vel, then s_pos)
+        if (nFlow) PR_LAUNCH(k_flow_words, nFlow, w.stream, d, nFlow, w.blkSortedKey);
+        if (nCons && conf.do_warm_start) {
+            if (nFlow) { PR_LAUNCH(k_flow_pass<0u>, nFlow, w.stream, d, nFlow, ticket, pass, 0.0f, 0.0f, 0.0f); ++ticket; ++pass; } // (no ++ inside the macro's arguments)
+            if (tailCount) PR_LAUNCH(k_warm_start_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
+        }
+        PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 0u, jSerial); // InitVelocity after the contacts' warm start (:1597)
+        tm.mark(w, PR_STAGE_VELOCITY);
+        for (unsigned it = 0; it < conf.reg_velocity_iters; ++it) {
+            PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 1u, jSerial); // joints first (:1605-1608)
+            if (nFlow) { PR_LAUNCH(k_flow_pass<1u>, nFlow, w.stream, d, nFlow, ticket, pass, 0.0f, 0.0f, 0.0f); ++ticket; ++pass; }
+            if (tailCount) PR_LAUNCH(k_solve_velocity_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
+            if (it == 0u) PR_LAUNCH(k_isl_vel_check, N, w.stream, d, N, it, conf.reg_min_momentum);
+            else PR_LAUNCH(k_isl_vel_check_list, std::min(N, 64u * 256u), w.stream, d, it, conf.reg_min_momentum);
+        }
+        tm.mark(w, PR_STAGE_POSITION);
+        PR_LAUNCH(k_integrate_positions, N, w.stream, d, N, conf.delta_time);
+        pass = 0u;
+        for (unsigned it = 0; it < conf.reg_position_iters; ++it) {
+            if (nFlow) { PR_LAUNCH(k_flow_pass<2u>, nFlow, w.stream, d, nFlow, ticket, pass, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction); ++ticket; ++pass; }
+            if (tailCount)
+                PR_LAUNCH(k_solve_position_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
+            PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 2u, jSerial); // joints after the contacts (:1634-1637)
+            if (it == 0u) PR_LAUNCH(k_isl_pos_check, N, w.stream, d, N, it, conf.reg_min_separation);
+            else PR_LAUNCH(k_isl_pos_check_list, std::min(N, 64u * 256u), w.stream, d, it, conf.reg_min_separation);
+        }
     } else if (!fused) {
         // the trailing colours with at most SMALL_COLOR_ROWS rows go through ONE single-block launch per iteration
         size_t nBig = ranges.size();

@@ -28,7 +28,7 @@ constexpr unsigned LEAF_BIT = 0x80000000u;
 
 enum { ISL_ACTIVE = 1u, ISL_VEL_DONE = 2u, ISL_POS_SOLVED = 4u };
 enum { TB_RUN = 0, TB_DONE = 1, TB_HOST_FIND = 2, TB_ADJ = 3, TB_ERROR = 4, TB_BIG = 5 };
-enum { ERR_NONE = 0, ERR_STACK = 1, ERR_SENSOR = 2, ERR_PAIR_OVERFLOW = 4, ERR_HASH_FULL = 8, ERR_TOI_SCRATCH = 16 };
+enum { ERR_NONE = 0, ERR_STACK = 1, ERR_SENSOR = 2, ERR_PAIR_OVERFLOW = 4, ERR_HASH_FULL = 8, ERR_TOI_SCRATCH = 16, ERR_FLOW_STALL = 32 };
 
 // VelocityConstraint row (Library/include/playrho/d2/VelocityConstraint.hpp), 144 B
 struct VCRow {
@@ -83,6 +83,7 @@ struct Counters {
     // compact lists for the single-block late rounds (k_tb_late): contacts to recompute in round toiRoundId + 1 (parity
     // ping-pong), the candidates being compacted, the listed contacts currently at maxSubSteps, "next round needs the full list"
     unsigned toiRoundId, toiReN[2], toiCand2N, toiAtMaxLive, toiForceFull, tbPad2;
+    unsigned flowTicket[32]; // dataflow solver (k_flow_pass): the next block of rows of each pass
 #ifdef PR_TOI_TIMING
     unsigned long long dbg[16]; // profiling build only: clock64 deltas of the phases of toi_solve_event (event 0 of each round)
     unsigned long long dbgBlk[12]; // profiling build only: clock64 deltas of the phases of k_block_solve (block 0, thread 0)
@@ -125,6 +126,7 @@ struct DV {
     // 32 consecutive rows is one coalesced 512 B transaction): see vc_load / vc_store in pr_kernels.cuh
     float4 *vc0, *vc1, *vc2, *vc3, *vc4, *vc5, *vc6, *vc7, *vc8; unsigned* vc_island;
     float4 *pc0, *pc1, *pc2, *pc3;
+    unsigned* vc_flow; // dataflow solver: per row, rank | rows << 8 of body A, the same << 16 of body B (flow_word)
     unsigned *k_contact, *k_color, *k_sorted, *k_tmpKey, *k_tmpKey2, *k_tmpVal, *k_ulist;
     unsigned* c_color; // persistent colour per contact
     // contact events (pr_set_event_mask / pr_events): off unless ev_mask != 0
