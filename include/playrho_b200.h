@@ -240,12 +240,12 @@ int pr_create_revolute_joints(pr_world* w, uint32_t n, const pr_revolute_joint* 
  * what they were: friction, restitution, density and the sensor flag are replaced; every body using the shape is woken
  * (:1297-1301); if the sensor flag, friction or restitution changed, every contact of the shape is flagged for updating and
  * its bodies are woken (:1346-1354). Existing contacts keep their mixed friction / restitution and their sensor flag, like
- * the reference's (they are set when a contact is created). Geometry or filter changes: not supported on the device. */
+ * the reference's (they are set when a contact is created). Geometry or filter changes: pr_set_shape. */
 int pr_set_shape_material(pr_world* w, uint32_t shape, float friction, float restitution, float density, uint32_t is_sensor);
 /* Attach(World&, BodyID, ShapeID) = the SetBody whose new value has MORE shapes than the old one (AabbTreeWorld.cpp:2760-2786,
  * GetOldAndNewShapeIDs :647-680): the added shapes are queued for proxy creation by the next Step (m_fixturesForProxies), in
  * the order given (the reference appends them in ShapeID order). The body row itself (mass data after ResetMassData) is
- * uploaded with pr_set_bodies as for any SetBody. Removing shapes from a body is not supported. */
+ * uploaded with pr_set_bodies as for any SetBody. Removing shapes: pr_detach_shapes. */
 int pr_attach_shapes(pr_world* w, uint32_t body, uint32_t n, const uint32_t* shape_ids);
 /* ---- dirty-row upload / download (SetBody :2723 / GetBody; value semantics) ---- */
 int pr_set_bodies(pr_world* w, uint32_t n, const uint32_t* ids, const pr_body* rows);
@@ -303,6 +303,38 @@ int pr_set_revolute_joints(pr_world* w, uint32_t n, const uint32_t* ids, const p
  * joint does nothing. (Contacts between the two bodies that a collideConnected == false joint had kept from forming appear
  * when the broadphase next looks at their proxies, as in the reference.) */
 int pr_destroy_joints(pr_world* w, uint32_t n, const uint32_t* ids);
+/* Destroy(AabbTreeWorld&, BodyID) (AabbTreeWorld.cpp:1062-1106), one body after the other: the joints attached to the body are
+ * destroyed (pr_destroy_joints; in id order), its contacts are destroyed in the body's contact-list order (end-contact events
+ * for touching ones when the event mask asks for them; the other body is woken when the manifold had points, :2245-2279), its
+ * pending (body, shape) pairs leave the proxy queue, its proxies leave the broadphase in leaf-id order (FindProxies :617) and
+ * the body id is the next one pr_create_bodies hands out (last freed first, ObjectPool). Leaf ids are recycled like
+ * DynamicTree's free list hands them out (DynamicTree.cpp:517-569), so later contact keys stay the reference's. The row of a
+ * destroyed body reads back with flags == PR_BODY_DESTROYED. PR_ERR_OUT_OF_RANGE: unknown id; PR_ERR_INVALID_ARGUMENT: the id
+ * is destroyed already (the reference's WasDestroyed). */
+int pr_destroy_bodies(pr_world* w, uint32_t n, const uint32_t* ids);
+/* Detach(World&, BodyID, ShapeID) = the SetBody whose new value has FEWER shapes (AabbTreeWorld.cpp:2760-2785): one entry of
+ * shape_ids per attachment to remove. The proxies of the (body, shape) pairs leave the broadphase in the body's proxy-list
+ * order, the contacts of each pair are destroyed, the pairs leave the proxy queue. The body row (new mass data) is uploaded
+ * with pr_set_bodies as for any SetBody. */
+int pr_detach_shapes(pr_world* w, uint32_t body, uint32_t n, const uint32_t* shape_ids);
+/* Destroy(AabbTreeWorld&, ShapeID) (:1259-1277): the shape is detached from every body that has it (body-id order, like
+ * pr_detach_shapes) and its id is the next one pr_create_shapes hands out. Destroying a destroyed shape does nothing. */
+int pr_destroy_shapes(pr_world* w, uint32_t n, const uint32_t* ids);
+/* SetShape(AabbTreeWorld&, ShapeID, Shape) (:1284-1356) for ANY new value. def: the new material / sensor flag / filter and,
+ * when geometry_changed != 0, child_count children (vertex offsets relative to `vertices`, n_vertices entries; def->child_offset
+ * is ignored). Every body using the shape is woken; with new geometry every ENABLED user loses the shape's proxies and contacts
+ * and is queued for new proxies at the next Step; with another filter the shape's contacts are flagged for filtering (tested
+ * again by the next Step's DestroyContacts, :2305-2328) and the shape's proxies are queued for contact finding; when the sensor
+ * flag, friction, restitution or the geometry changed the shape's contacts are flagged for updating and their bodies woken. */
+int pr_set_shape(pr_world* w, uint32_t shape, const pr_shape* def, const pr_child* children, const pr_vec2* vertices,
+                 const pr_vec2* normals, uint32_t n_vertices, uint32_t geometry_changed);
+/* The SetBody whose value differs in IsEnabled (GetOldAndNewShapeIDs, AabbTreeWorld.cpp:647-680): disabling destroys the body's
+ * proxies and contacts (its shapes stay attached), enabling queues every attached shape for proxy creation at the next Step. */
+int pr_set_body_enabled(pr_world* w, uint32_t body, uint32_t enabled);
+/* The SetBody whose value has another BodyType (:2738-2758): the body's contacts are destroyed, then row replaces the body (flags
+ * carry the new type's velocity / acceleration bits, mass data as the caller computed them); a body turned static has its
+ * proxies synchronised by the next Step (m_bodiesForSync). */
+int pr_set_body_type(pr_world* w, uint32_t body, const pr_body* row);
 int pr_get_revolute_joints(const pr_world* w, uint32_t first, uint32_t n, pr_revolute_joint* rows);
 int pr_get_counts(const pr_world* w, pr_counts* out);
 /* contacts in m_contacts order (creation order), manifolds[i] belongs to contacts[i] */

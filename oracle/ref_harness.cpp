@@ -447,6 +447,53 @@ int ref_attach_shape(void* h, uint32_t body, uint32_t shape)
     REF_CATCH(-1)
 }
 
+// the structural mutators, through the reference's own API (World.hpp / WorldBody.hpp / WorldShape.hpp)
+int ref_destroy_body(void* h, uint32_t body) { REF_TRY(h) Destroy(rw->world, MakeId<BodyID>(body)); return 0; REF_CATCH(-1) }
+int ref_destroy_shape(void* h, uint32_t shape) { REF_TRY(h) Destroy(rw->world, MakeId<ShapeID>(shape)); return 0; REF_CATCH(-1) }
+int ref_detach_shape(void* h, uint32_t body, uint32_t shape) { REF_TRY(h) Detach(rw->world, MakeId<BodyID>(body), MakeId<ShapeID>(shape)); return 0; REF_CATCH(-1) }
+int ref_set_body_enabled(void* h, uint32_t body, int flag) { REF_TRY(h) SetEnabled(rw->world, MakeId<BodyID>(body), flag != 0); return 0; REF_CATCH(-1) }
+int ref_set_body_type(void* h, uint32_t body, int type)
+{
+    REF_TRY(h)
+    SetType(rw->world, MakeId<BodyID>(body), type == 0 ? BodyType::Static : type == 1 ? BodyType::Kinematic : BodyType::Dynamic);
+    return 0;
+    REF_CATCH(-1)
+}
+int ref_set_shape_filter(void* h, uint32_t shape, uint32_t category, uint32_t mask, int group)
+{
+    REF_TRY(h)
+    Filter f; f.categoryBits = static_cast<Filter::bits_type>(category); f.maskBits = static_cast<Filter::bits_type>(mask); f.groupIndex = static_cast<Filter::index_type>(group);
+    SetFilterData(rw->world, MakeId<ShapeID>(shape), f);
+    return 0;
+    REF_CATCH(-1)
+}
+int ref_translate_shape(void* h, uint32_t shape, float dx, float dy) { REF_TRY(h) Translate(rw->world, MakeId<ShapeID>(shape), Length2{dx * 1_m, dy * 1_m}); return 0; REF_CATCH(-1) }
+// one shape flattened like ref_export_shapes does all of them (child_offset 0, vertex offsets relative to verts); returns the vertex count
+int ref_export_shape(void* h, uint32_t sid, pr_shape* o, pr_child* children, uint32_t capChildren, pr_vec2* verts, pr_vec2* normals, uint32_t capVerts)
+{
+    REF_TRY(h)
+    const auto& shape = GetShape(rw->world, MakeId<ShapeID>(sid));
+    o->friction = GetFriction(shape); o->restitution = GetRestitution(shape); o->density = GetDensity(shape);
+    const auto f = GetFilter(shape);
+    o->filter_category = f.categoryBits; o->filter_mask = f.maskBits; o->filter_group = f.groupIndex;
+    o->is_sensor = IsSensor(shape) ? 1 : 0;
+    o->child_offset = 0; o->child_count = GetChildCount(shape);
+    uint32_t vi = 0;
+    for (ChildCounter c = 0; c < o->child_count; ++c) {
+        const auto dp = GetChild(shape, c);
+        if (c < capChildren) { children[c].vertex_offset = vi; children[c].vertex_count = dp.GetVertexCount(); children[c].vertex_radius = dp.GetVertexRadius(); }
+        for (VertexCounter v = 0; v < dp.GetVertexCount(); ++v) {
+            if (vi < capVerts) {
+                verts[vi] = pr_vec2{GetX(dp.GetVertex(v)), GetY(dp.GetVertex(v))};
+                normals[vi] = dp.GetVertexCount() > 1 ? pr_vec2{dp.GetNormal(v).GetX(), dp.GetNormal(v).GetY()} : pr_vec2{0, 0};
+            }
+            ++vi;
+        }
+    }
+    return static_cast<int>(vi);
+    REF_CATCH(-1)
+}
+
 int ref_destroy_joint(void* h, uint32_t joint)
 {
     REF_TRY(h)

@@ -70,6 +70,15 @@ struct orc_world {
     std::vector<uint32_t> freeJoints;            // joint pool free list (LIFO)
     std::vector<orc::RevoluteWork> jointWork;
     std::vector<std::pair<uint32_t, uint32_t>> fixturesForProxies; // (body, shape)
+    // ids of destroyed bodies / shapes (ObjectPool free lists, LIFO) and the DynamicTree's free list as the LEAVES see it:
+    // DestroyLeaf frees the leaf's parent node and then the leaf (DynamicTree.cpp:539-569), CreateLeaf takes a leaf and then a
+    // parent (:517-537), so the k-th new leaf gets the k-th last destroyed leaf id; with the list empty a leaf takes the
+    // next fresh node and its parent the one after it (the first leaf of an empty tree has no parent)
+    std::vector<uint32_t> bodyFree, shapeFree, treeFree;
+    std::vector<uint32_t> bodyOrder; // m_bodies: live body ids in creation order (a re-used id goes to the END: SolveReg seeds its islands in this order)
+    uint32_t treeNextFresh = 0;
+    std::vector<char> bodyDead, shapeDead;
+    bool needsFiltering = false; // e_needsContactFiltering
     std::vector<uint32_t> proxiesForContacts;
     std::vector<uint32_t> bodiesForSync;
     uint32_t evMask = 0;                          // listeners installed (PR_EVENT_* bits)
@@ -289,7 +298,62 @@ uint32_t destroy_contacts(orc_world& w)
         else keep.push_back(id);
     }
     w.order.swap(keep);
+    if (w.needsFiltering) { // :2305-2328
+        keep.clear();
+        for (uint32_t id : w.order) {
+            OContact& oc = w.contacts[id];
+            if (oc.c.flags & PR_CONTACT_FILTER) {
+                const pr_body& bA = w.bodies[oc.c.body_a].b; const pr_body& bB = w.bodies[oc.c.body_b].b;
+                if (!(accelerable(bA) || accelerable(bB)) || !joints_allow_collision(w, oc.c.body_a, oc.c.body_b) ||
+                    !filters_allow(w.shapes[oc.c.shape_a], w.shapes[oc.c.shape_b])) { internal_destroy(w, id); ++destroyed; continue; }
+                oc.c.flags &= ~static_cast<uint32_t>(PR_CONTACT_FILTER);
+            }
+            keep.push_back(id);
+        }
+        w.order.swap(keep);
+        w.needsFiltering = false;
+    }
     return destroyed;
+}
+// Destroy(ContactID, from), :2281-2288
+void destroy_contact(orc_world& w, uint32_t id)
+{
+    auto it = std::find(w.order.begin(), w.order.end(), id);
+    if (it != w.order.end()) w.order.erase(it);
+    internal_destroy(w, id);
+}
+// DestroyLeaf for the proxy slots listed, in that order; the dense proxy table and everything that indexes it are renumbered
+void destroy_proxy_slots(orc_world& w, const std::vector<uint32_t>& slots)
+{
+    if (slots.empty()) return;
+    const uint32_t P = static_cast<uint32_t>(w.proxies.size());
+    std::vector<uint32_t> map(P, 0u);
+    for (uint32_t s : slots) { map[s] = 0xFFFFFFFFu; w.treeFree.push_back(w.proxies[s].p.tree_id); }
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < P; ++i) if (map[i] != 0xFFFFFFFFu) { w.proxies[k] = w.proxies[i]; map[i] = k++; }
+    w.proxies.resize(k);
+    for (uint32_t id : w.order) { OContact& oc = w.contacts[id]; oc.pxA = map[oc.pxA]; oc.pxB = map[oc.pxB]; }
+    auto remap = [&](std::vector<uint32_t>& v) { uint32_t m = 0; for (uint32_t e : v) if (map[e] != 0xFFFFFFFFu) v[m++] = map[e]; v.resize(m); };
+    remap(w.proxiesForContacts);
+    for (OBody& ob : w.bodies) remap(ob.proxies);
+}
+// the SetBody whose value lost shapes (:2760-2785): proxies in m_bodyProxies order, then per shape its contacts and queue entries
+void body_remove_shapes(orc_world& w, uint32_t body, const std::vector<uint32_t>& shapeIds, bool keepInList)
+{
+    OBody& ob = w.bodies[body];
+    std::vector<uint32_t> slots;
+    for (uint32_t s : ob.proxies) if (std::find(shapeIds.begin(), shapeIds.end(), w.proxies[s].p.shape) != shapeIds.end()) slots.push_back(s);
+    for (uint32_t sid : shapeIds) {
+        const std::vector<uint32_t> list = ob.contacts;
+        for (uint32_t id : list) {
+            const pr_contact& c = w.contacts[id].c;
+            if ((c.body_a == body && c.shape_a == sid) || (c.body_b == body && c.shape_b == sid)) destroy_contact(w, id);
+        }
+        auto& f = w.fixturesForProxies;
+        f.erase(std::remove(f.begin(), f.end(), std::make_pair(body, sid)), f.end());
+    }
+    destroy_proxy_slots(w, slots);
+    if (!keepInList) for (uint32_t sid : shapeIds) { auto it = std::find(ob.shapes.begin(), ob.shapes.end(), sid); if (it != ob.shapes.end()) ob.shapes.erase(it); }
 }
 
 // FindContacts + AddContacts, AabbTreeWorld.cpp:709-751, 2423-2547
@@ -413,7 +477,8 @@ uint32_t create_proxies(orc_world& w, uint32_t bodyId, uint32_t shapeId, const p
         const AABB a = fatten_displace(compute_aabb(w.child(shapeId, ci), xf0, xf1), conf.aabb_extension, displacement);
         OProxy op;
         const uint32_t k = static_cast<uint32_t>(w.proxies.size());
-        op.p.tree_id = (k == 0) ? 0u : 2u * k - 1u;
+        if (!w.treeFree.empty()) { op.p.tree_id = w.treeFree.back(); w.treeFree.pop_back(); }
+        else { op.p.tree_id = w.treeNextFresh; w.treeNextFresh += (k == 0) ? 1u : 2u; }
         op.p.body = bodyId; op.p.shape = shapeId; op.p.child = ci;
         set_fat(op.p, a);
         w.proxies.push_back(op);
@@ -971,7 +1036,7 @@ void solve_reg(orc_world& w, const pr_step_conf& conf, pr_step_stats& stats,
     w.islandedBodies.assign(w.bodies.size(), 0);
     w.islandedContacts.assign(w.contacts.size(), 0);
     w.islandedJoints.assign(w.joints.size(), 0);
-    for (uint32_t bodyId = 0; bodyId < w.bodies.size(); ++bodyId) {
+    for (uint32_t bodyId : w.bodyOrder) { // (m_bodies order, :1493)
         if (w.islandedBodies[bodyId]) continue;
         const pr_body& b = w.bodies[bodyId].b;
         if (!(awake(b) && enabled(b))) continue;
@@ -997,7 +1062,7 @@ void solve_reg(orc_world& w, const pr_step_conf& conf, pr_step_stats& stats,
         stats.reg.sum_vel_iters += r.velocityIters;
         stats.reg.bodies_slept += r.bodiesSlept;
     }
-    for (uint32_t bodyId = 0; bodyId < w.bodies.size(); ++bodyId) {
+    for (uint32_t bodyId : w.bodyOrder) {
         if (!w.islandedBodies[bodyId]) continue;
         const pr_body& b = w.bodies[bodyId].b;
         if (speedable(b)) {
@@ -1046,7 +1111,11 @@ int orc_create_shapes(orc_world* w, uint32_t n, const pr_shape* shapes, const pr
 {
     const uint32_t cbase = static_cast<uint32_t>(w->children.size());
     const uint32_t vbase = static_cast<uint32_t>(w->verts.size());
-    for (uint32_t i = 0; i < n; ++i) { pr_shape s = shapes[i]; s.child_offset += cbase; w->shapes.push_back(s); }
+    for (uint32_t i = 0; i < n; ++i) {
+        pr_shape s = shapes[i]; s.child_offset += cbase;
+        if (!w->shapeFree.empty()) { const uint32_t id = w->shapeFree.back(); w->shapeFree.pop_back(); w->shapeDead[id] = 0; w->shapes[id] = s; } // ObjectPool::Allocate
+        else w->shapes.push_back(s);
+    }
     for (uint32_t i = 0; i < n_children; ++i) { pr_child c = children[i]; c.vertex_offset += vbase; w->children.push_back(c); }
     w->verts.insert(w->verts.end(), vertices, vertices + n_vertices);
     w->normals.insert(w->normals.end(), normals, normals + n_vertices);
@@ -1059,12 +1128,15 @@ int orc_create_bodies(orc_world* w, uint32_t n, const pr_body* bodies, const uin
     for (uint32_t i = 0; i < n; ++i) {
         OBody ob;
         ob.b = bodies[i];
-        const uint32_t id = static_cast<uint32_t>(w->bodies.size());
+        const bool reuse = !w->bodyFree.empty(); // ObjectPool::Allocate: the last freed id first
+        const uint32_t id = reuse ? w->bodyFree.back() : static_cast<uint32_t>(w->bodies.size());
+        if (reuse) { w->bodyFree.pop_back(); w->bodyDead[id] = 0; }
         for (uint32_t k = shape_offsets[i]; k < shape_offsets[i + 1]; ++k) {
             ob.shapes.push_back(shape_ids[k]);
             if (enabled(ob.b)) w->fixturesForProxies.emplace_back(id, shape_ids[k]); // CreateBody :1046-1052
         }
-        w->bodies.push_back(ob);
+        if (reuse) w->bodies[id] = ob; else w->bodies.push_back(ob);
+        w->bodyOrder.push_back(id);
     }
     return 0;
 }
@@ -1104,6 +1176,125 @@ int orc_set_shape_material(orc_world* w, uint32_t shape, float friction, float r
 int orc_attach_shapes(orc_world* w, uint32_t body, uint32_t n, const uint32_t* shape_ids)
 {
     for (uint32_t i = 0; i < n; ++i) { w->bodies[body].shapes.push_back(shape_ids[i]); w->fixturesForProxies.emplace_back(body, shape_ids[i]); }
+    return 0;
+}
+
+int orc_destroy_joints(orc_world* w, uint32_t n, const uint32_t* ids);
+// Destroy(AabbTreeWorld&, BodyID), :1062-1106
+int orc_destroy_bodies(orc_world* w, uint32_t n, const uint32_t* ids)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t id = ids[i];
+        if (id >= w->bodies.size()) { w->error = "no such body"; return -2; }
+        if (id < w->bodyDead.size() && w->bodyDead[id]) { w->error = "destroyed"; return -3; }
+        OBody& ob = w->bodies[id];
+        { std::vector<uint32_t> js = ob.joints; std::sort(js.begin(), js.end()); js.erase(std::unique(js.begin(), js.end()), js.end()); if (!js.empty()) orc_destroy_joints(w, static_cast<uint32_t>(js.size()), js.data()); }
+        { const std::vector<uint32_t> list = ob.contacts; for (uint32_t c : list) destroy_contact(*w, c); }
+        { auto& f = w->fixturesForProxies; f.erase(std::remove_if(f.begin(), f.end(), [id](const std::pair<uint32_t, uint32_t>& e) { return e.first == id; }), f.end()); }
+        std::vector<uint32_t> slots = ob.proxies; // FindProxies: ascending leaf id (:617-630)
+        std::sort(slots.begin(), slots.end(), [w](uint32_t a, uint32_t b) { return w->proxies[a].p.tree_id < w->proxies[b].p.tree_id; });
+        destroy_proxy_slots(*w, slots);
+        { auto& bs = w->bodiesForSync; bs.erase(std::remove(bs.begin(), bs.end(), id), bs.end()); } // Remove(BodyID) :1046-1060
+        w->bodyOrder.erase(std::remove(w->bodyOrder.begin(), w->bodyOrder.end(), id), w->bodyOrder.end());
+        OBody gone; std::memset(&gone.b, 0, sizeof(gone.b)); gone.b.xf_qc = 1.0f; gone.b.flags = PR_BODY_DESTROYED;
+        w->bodies[id] = gone;
+        if (w->bodyDead.size() <= id) w->bodyDead.resize(id + 1u, 0);
+        w->bodyDead[id] = 1; w->bodyFree.push_back(id);
+    }
+    return 0;
+}
+// Detach = the SetBody whose value has fewer shapes (:2760-2785)
+int orc_detach_shapes(orc_world* w, uint32_t body, uint32_t n, const uint32_t* shape_ids)
+{
+    std::vector<uint32_t> ids(shape_ids, shape_ids + n);
+    std::sort(ids.begin(), ids.end()); // (GetOldAndNewShapeIDs walks a std::map)
+    if (enabled(w->bodies[body].b)) body_remove_shapes(*w, body, ids, false);
+    else for (uint32_t sid : ids) { auto& l = w->bodies[body].shapes; auto it = std::find(l.begin(), l.end(), sid); if (it != l.end()) l.erase(it); }
+    return 0;
+}
+// Destroy(AabbTreeWorld&, ShapeID), :1259-1277
+int orc_destroy_shapes(orc_world* w, uint32_t n, const uint32_t* ids)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t sid = ids[i];
+        if (sid >= w->shapes.size()) { w->error = "no such shape"; return -2; }
+        if (sid < w->shapeDead.size() && w->shapeDead[sid]) continue;
+        for (uint32_t b = 0; b < w->bodies.size(); ++b) {
+            const uint32_t cnt = static_cast<uint32_t>(std::count(w->bodies[b].shapes.begin(), w->bodies[b].shapes.end(), sid));
+            if (!cnt) continue;
+            const std::vector<uint32_t> rm(cnt, sid);
+            orc_detach_shapes(w, b, cnt, rm.data());
+        }
+        if (w->shapeDead.size() <= sid) w->shapeDead.resize(sid + 1u, 0);
+        w->shapeDead[sid] = 1; w->shapeFree.push_back(sid);
+        w->shapes[sid].child_count = 0;
+    }
+    return 0;
+}
+// the SetBody whose value differs in IsEnabled (GetOldAndNewShapeIDs :671-676)
+int orc_set_body_enabled(orc_world* w, uint32_t body, uint32_t en)
+{
+    OBody& ob = w->bodies[body];
+    if (enabled(ob.b) == (en != 0)) return 0;
+    if (!en) {
+        std::vector<uint32_t> ids = ob.shapes; std::sort(ids.begin(), ids.end());
+        body_remove_shapes(*w, body, ids, true);
+        ob.b.flags &= ~static_cast<uint32_t>(PR_BODY_ENABLED);
+    } else {
+        for (uint32_t sid : ob.shapes) w->fixturesForProxies.emplace_back(body, sid);
+        ob.b.flags |= PR_BODY_ENABLED;
+    }
+    return 0;
+}
+// the SetBody whose value has another BodyType (:2738-2758)
+int orc_set_body_type(orc_world* w, uint32_t body, const pr_body* row)
+{
+    OBody& ob = w->bodies[body];
+    { const std::vector<uint32_t> list = ob.contacts; for (uint32_t c : list) destroy_contact(*w, c); }
+    const pr_body old = ob.b;
+    ob.b = *row;
+    bool sync = !(row->flags & (PR_BODY_VELOCITY | PR_BODY_ACCELERATION));
+    if (old.xf_px != ob.b.xf_px || old.xf_py != ob.b.xf_py || old.xf_qc != ob.b.xf_qc || old.xf_qs != ob.b.xf_qs) { flag_body_contacts_dirty(*w, body); sync = true; }
+    if (sync) w->bodiesForSync.push_back(body);
+    return 0;
+}
+// SetShape(AabbTreeWorld&, ShapeID, Shape), :1284-1356, any new value
+int orc_set_shape(orc_world* w, uint32_t shape, const pr_shape* def, const pr_child* children, const pr_vec2* vertices, const pr_vec2* normals,
+                  uint32_t n_vertices, uint32_t geometry_changed)
+{
+    pr_shape cur = w->shapes[shape];
+    for (uint32_t b = 0; b < w->bodies.size(); ++b) {
+        OBody& ob = w->bodies[b];
+        if (std::find(ob.shapes.begin(), ob.shapes.end(), shape) == ob.shapes.end()) continue;
+        set_awake(ob.b);
+        if (geometry_changed && enabled(ob.b)) {
+            body_remove_shapes(*w, b, std::vector<uint32_t>{shape}, true);
+            w->fixturesForProxies.emplace_back(b, shape);
+        }
+    }
+    if (geometry_changed) {
+        const uint32_t cbase = static_cast<uint32_t>(w->children.size()), vbase = static_cast<uint32_t>(w->verts.size());
+        for (uint32_t i = 0; i < def->child_count; ++i) { pr_child c = children[i]; c.vertex_offset += vbase; w->children.push_back(c); }
+        w->verts.insert(w->verts.end(), vertices, vertices + n_vertices);
+        w->normals.insert(w->normals.end(), normals, normals + n_vertices);
+        cur.child_offset = cbase; cur.child_count = def->child_count;
+    }
+    if (cur.filter_category != def->filter_category || cur.filter_mask != def->filter_mask || cur.filter_group != def->filter_group) { // :1330-1345
+        for (uint32_t id : w->order) {
+            pr_contact& c = w->contacts[id].c;
+            if (c.shape_a == shape || c.shape_b == shape) { c.flags |= PR_CONTACT_FILTER; set_awake(w->bodies[c.body_a].b); set_awake(w->bodies[c.body_b].b); w->needsFiltering = true; }
+        }
+        for (uint32_t k = 0; k < w->proxies.size(); ++k) if (w->proxies[k].p.shape == shape) w->proxiesForContacts.push_back(k);
+    }
+    if ((cur.is_sensor != 0) != (def->is_sensor != 0) || cur.friction != def->friction || cur.restitution != def->restitution || geometry_changed) { // :1346-1354
+        for (uint32_t id : w->order) {
+            pr_contact& c = w->contacts[id].c;
+            if (c.shape_a == shape || c.shape_b == shape) { c.flags |= PR_CONTACT_DIRTY; set_awake(w->bodies[c.body_a].b); set_awake(w->bodies[c.body_b].b); }
+        }
+    }
+    cur.friction = def->friction; cur.restitution = def->restitution; cur.density = def->density; cur.is_sensor = def->is_sensor ? 1 : 0;
+    cur.filter_category = def->filter_category; cur.filter_mask = def->filter_mask; cur.filter_group = def->filter_group;
+    w->shapes[shape] = cur;
     return 0;
 }
 

@@ -3,6 +3,7 @@
 // (Library/source/playrho/d2/AabbTreeWorld.cpp:2144-2219): pre-phase, SolveReg (:1472), SolveToi.
 #include "pr_kernels.cuh"
 #include "pr_solve_fused.cuh"
+#include "pr_mutate.cuh"
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
@@ -214,6 +215,11 @@ static void throw_device_error(World& w)
     throw CudaError{m};
 }
 
+// ids of destroyed bodies / shapes (World::Pools)
+static bool body_dead(const World& w, unsigned id) { return id < w.pools.bodyDead.size() && w.pools.bodyDead[id]; }
+static bool shape_dead(const World& w, unsigned id) { return id < w.pools.shapeDead.size() && w.pools.shapeDead[id]; }
+static unsigned body_flags(World& w, unsigned id) { unsigned f = 0; d2h(w, &f, w.d.b_flags + id, 4); return f; }
+
 // ------------------------------------------------------------------ pre-phase pieces
 static unsigned create_queued_proxies(World& w, const pr_step_conf& conf)
 { // Step: CreateProxies for m_fixturesForProxies, AabbTreeWorld.cpp:2158-2168
@@ -226,7 +232,12 @@ static unsigned create_queued_proxies(World& w, const pr_step_conf& conf)
             body.push_back(bs.first); shape.push_back(bs.second); child.push_back(c); cg.push_back(s.child_offset + c);
             if (w.bodyProxies.size() <= bs.first) w.bodyProxies.resize(bs.first + 1u);
             w.bodyProxies[bs.first].push_back(k);
-            tree.push_back(k == 0 ? 0u : 2u * k - 1u); // DynamicTree leaf id sequence
+            // DynamicTree leaf id: the last destroyed leaf's, else the next fresh node (World::Pools)
+            unsigned leaf;
+            if (!w.pools.treeFree.empty()) { leaf = w.pools.treeFree.back(); w.pools.treeFree.pop_back(); }
+            else { leaf = w.pools.treeNextFresh; w.pools.treeNextFresh += (k == 0 ? 1u : 2u); }
+            tree.push_back(leaf);
+            w.pools.pxBody.push_back(bs.first); w.pools.pxShape.push_back(bs.second); w.pools.pxTree.push_back(leaf);
             w.maxTreeId = std::max(w.maxTreeId, tree.back());
         }
     }
@@ -266,12 +277,39 @@ static void upload_body_proxies(World& w)
     w.bpDirty = false;
 }
 
-static unsigned destroy_contacts(World& w)
-{ // DestroyContacts (overlap part), AabbTreeWorld.cpp:2290-2304
+// m_contacts without the contacts whose keep flag (c_tmp) is 0: stable; their ids go onto the pool's free stack in list order
+static unsigned compact_destroyed_contacts(World& w)
+{
+    DV& d = w.d;
+    scan_exclusive_u32(d.c_tmp, d.k_tmpVal, w.nOrder, &d.cnt->nNew, w.scanScratch, w.stream);
+    read_counters(w);
+    const unsigned kept = w.hostCnt.nNew;
+    const unsigned destroyed = w.nOrder - kept;
+    if (destroyed) {
+        PR_LAUNCH(k_destroy_compact, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, d.k_tmpVal, d.c_tmp2, w.nFree);
+        std::swap(d.c_order, d.c_tmp2);
+        w.nFree += destroyed;
+        w.nOrder = kept;
+        w.hashTombs += destroyed; w.adjValid = false;
+        if (2ull * (static_cast<unsigned long long>(w.nOrder) + w.hashTombs) > w.capHash) w.hashDirty = true;
+    }
+    return destroyed;
+}
+// Destroy(ContactID, from) for every contact that matches (k_destroy_mark, pr_mutate.cuh)
+static unsigned destroy_contacts_where(World& w, unsigned mode, unsigned a, unsigned b, const unsigned* dead = nullptr)
+{
     if (w.nOrder == 0) return 0;
+    ensure(w, G_CONTACT, w.nOrder + 1);
+    PR_LAUNCH(k_destroy_mark, w.nOrder, w.stream, w.d, w.nOrder, w.d.c_tmp, mode, a, b, dead, w.hashDirty ? 0u : 1u);
+    return compact_destroyed_contacts(w);
+}
+static unsigned destroy_contacts(World& w)
+{ // DestroyContacts, AabbTreeWorld.cpp:2290-2331: the overlap test and, when some contact is flagged for it, the filter test
+    if (w.nOrder == 0) { w.needsFiltering = false; return 0; }
     DV& d = w.d;
     ensure(w, G_CONTACT, w.nOrder + 1);
     PR_LAUNCH(k_destroy_test, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, w.hashDirty ? 0u : 1u);
+    if (w.needsFiltering) { PR_LAUNCH(k_destroy_filter, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, w.hashDirty ? 0u : 1u); w.needsFiltering = false; }
     scan_exclusive_u32(d.c_tmp, d.k_tmpVal, w.nOrder, &d.cnt->nNew, w.scanScratch, w.stream);
     read_counters(w);
     const unsigned kept = w.hostCnt.nNew;
@@ -1205,7 +1243,7 @@ int pr_clone(const pr_world* src, pr_world** out)
     for (size_t i = 0; i < da.size(); ++i) d2d(w, *da[i].slot, *sa[i].slot, da[i].elem * *cap_of(s, sa[i].g));
     d2d(w, w.d.cnt, s.d.cnt, sizeof(Counters));
     w.shapes = s.shapes; w.children = s.children; w.bodyShapes = s.bodyShapes; w.joints = s.joints; w.freeJoints = s.freeJoints;
-    w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies;
+    w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies; w.pools = s.pools; w.needsFiltering = s.needsFiltering;
     w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll; w.toiPossible = s.toiPossible; w.colorCap = s.colorCap;
     w.nJoints = s.nJoints; w.jointsSerial = s.jointsSerial; w.d.nNcPairs = s.d.nNcPairs;
     w.d.nWorlds = s.d.nWorlds; w.d.worldBits = s.d.worldBits; w.bodyWorld = s.bodyWorld; w.blocksDirty = w.blkJointsDirty = true;
@@ -1297,13 +1335,16 @@ int pr_snapshot_save(const pr_world* cpw, void* buf, uint64_t cap, uint64_t* byt
     sync(w);
     SnapWriter o{static_cast<unsigned char*>(buf), cap};
     auto arrs = arrays(w);
-    SnapHeader h{SNAP_MAGIC, 1u, static_cast<unsigned>(PR_ABI_VERSION), static_cast<unsigned>(pr_sincosf_variant()), static_cast<unsigned>(arrs.size()),
+    SnapHeader h{SNAP_MAGIC, 2u, static_cast<unsigned>(PR_ABI_VERSION), static_cast<unsigned>(pr_sincosf_variant()), static_cast<unsigned>(arrs.size()),
                  static_cast<unsigned>(sizeof(pr_body)), static_cast<unsigned>(sizeof(pr_contact)), static_cast<unsigned>(sizeof(Counters)), 0u};
     o.pod(h);
     SnapScalars sc; snap_scalars(w, sc); o.pod(sc);
     o.vec(w.shapes); o.vec(w.children); snap_nested(o, w.bodyShapes); o.vec(w.joints); o.vec(w.freeJoints);
     { std::vector<unsigned> flat; for (const auto& f : w.fixturesForProxies) { flat.push_back(f.first); flat.push_back(f.second); } o.vec(flat); }
     snap_nested(o, w.bodyProxies); o.vec(w.bodyWorld);
+    o.vec(w.pools.bodyFree); o.vec(w.pools.shapeFree); o.vec(w.pools.treeFree); o.vec(w.pools.bodyDead); o.vec(w.pools.shapeDead);
+    o.vec(w.pools.pxBody); o.vec(w.pools.pxShape); o.vec(w.pools.pxTree);
+    { const unsigned extra[2] = {w.pools.treeNextFresh, w.needsFiltering ? 1u : 0u}; o.pod(extra); }
     read_counters(w);
     o.pod(w.hostCnt);
     std::vector<unsigned char> tmp;
@@ -1329,7 +1370,7 @@ int pr_snapshot_load(const void* buf, uint64_t bytes, int device, pr_world** out
     SnapReader in{static_cast<const unsigned char*>(buf), bytes};
     SnapHeader h{}; in.pod(h);
     SnapScalars sc{}; in.pod(sc);
-    if (!in.ok || h.magic != SNAP_MAGIC || h.version != 1u || h.abi != static_cast<unsigned>(PR_ABI_VERSION) || h.szBody != sizeof(pr_body) ||
+    if (!in.ok || h.magic != SNAP_MAGIC || h.version != 2u || h.abi != static_cast<unsigned>(PR_ABI_VERSION) || h.szBody != sizeof(pr_body) ||
         h.szContact != sizeof(pr_contact) || h.szCounters != sizeof(Counters)) { g_createError = "pr_snapshot_load: not a snapshot of this library version"; return PR_ERR_INVALID_ARGUMENT; }
     if (h.variant != static_cast<unsigned>(pr_sincosf_variant())) { g_createError = "pr_snapshot_load: the snapshot was taken by the other sincosf build of the library"; return PR_ERR_INVALID_ARGUMENT; }
     pr_world* pw = nullptr;
@@ -1343,6 +1384,9 @@ int pr_snapshot_load(const void* buf, uint64_t bytes, int device, pr_world** out
         in.vec(w.shapes); in.vec(w.children); snap_nested(in, w.bodyShapes); in.vec(w.joints); in.vec(w.freeJoints);
         { std::vector<unsigned> flat; in.vec(flat); for (size_t i = 0; i + 1 < flat.size(); i += 2) w.fixturesForProxies.emplace_back(flat[i], flat[i + 1]); }
         snap_nested(in, w.bodyProxies); in.vec(w.bodyWorld);
+        in.vec(w.pools.bodyFree); in.vec(w.pools.shapeFree); in.vec(w.pools.treeFree); in.vec(w.pools.bodyDead); in.vec(w.pools.shapeDead);
+        in.vec(w.pools.pxBody); in.vec(w.pools.pxShape); in.vec(w.pools.pxTree);
+        { unsigned extra[2] = {0u, 0u}; in.pod(extra); w.pools.treeNextFresh = extra[0]; w.needsFiltering = extra[1] != 0u; }
         in.pod(w.hostCnt);
         if (!in.ok) throw CudaError{"pr_snapshot_load: truncated snapshot"};
         w.nBodies = sc.nBodies; w.nShapes = sc.nShapes; w.nChildren = sc.nChildren; w.nVerts = sc.nVerts; w.nProxies = sc.nProxies;
@@ -1384,6 +1428,7 @@ int pr_clear(pr_world* pw)
     w.shapes.clear(); w.children.clear(); w.bodyShapes.clear(); w.joints.clear(); w.fixturesForProxies.clear();
     w.bodyProxies.clear(); w.bpDirty = true; w.bvhValid = false; w.hashTombs = 0; w.toiAlphaDirty = true;
     w.nJoints = 0; w.jointsSerial = false; w.d.nNcPairs = 0; w.bodyWorld.clear(); w.freeJoints.clear();
+    w.pools = World::Pools{}; w.needsFiltering = false;
     w.nBodies = w.nShapes = w.nChildren = w.nVerts = w.nProxies = w.nOrder = w.nFree = w.poolSize = 0; w.maxTreeId = 0;
     w.anyBodySet = false; w.hashDirty = true; w.adjValid = false; w.stepComplete = true; w.toiPossible = false;
     w.inv_dt0 = 0.0f; // m_inv_dt0 = 0_Hz (AabbTreeWorld.cpp:982)
@@ -1411,11 +1456,16 @@ int pr_create_shapes(pr_world* pw, uint32_t n, const pr_shape* shapes, const pr_
     for (uint32_t i = 0; i < n; ++i) // (every row is checked before any is applied)
         if (shapes[i].child_offset > n_children || shapes[i].child_count > n_children - shapes[i].child_offset) { w.error = "shape child range"; return PR_ERR_OUT_OF_RANGE; }
     ensure(w, G_SHAPE, w.nShapes + n); ensure(w, G_CHILD, w.nChildren + n_children); ensure(w, G_VERT, w.nVerts + n_vertices + 4u); // (+4: the TMA-staged narrowphase copies whole 16-byte lines)
+    // ids of destroyed shapes are handed out again first, last freed first (ObjectPool::Allocate)
+    const bool reuse = !w.pools.shapeFree.empty();
+    if (reuse && n != 1u) { w.error = "CreateShape: create shapes one at a time while destroyed shape ids are free"; return PR_ERR_UNSUPPORTED; }
+    const unsigned firstShape = reuse ? w.pools.shapeFree.back() : w.nShapes;
+    if (reuse) { w.pools.shapeFree.pop_back(); w.pools.shapeDead[firstShape] = 0; }
     std::vector<float4> mat(n); std::vector<unsigned> filt(n); std::vector<int> grp(n);
     for (uint32_t i = 0; i < n; ++i) {
         pr_shape s = shapes[i];
         s.child_offset += w.nChildren;
-        w.shapes.push_back(s);
+        if (reuse) w.shapes[firstShape] = s; else w.shapes.push_back(s);
         mat[i] = make_float4(s.friction, s.restitution, s.is_sensor ? 1.0f : 0.0f, s.density);
         filt[i] = static_cast<unsigned>(s.filter_category) | (static_cast<unsigned>(s.filter_mask) << 16);
         grp[i] = s.filter_group;
@@ -1427,14 +1477,15 @@ int pr_create_shapes(pr_world* pw, uint32_t n, const pr_shape* shapes, const pr_
         w.children.push_back(c);
         rad[i] = c.vertex_radius; voff[i] = c.vertex_offset; cnt[i] = c.vertex_count;
     }
-    h2d(w, w.d.sh_mat + w.nShapes, mat.data(), n * sizeof(float4)); h2d(w, w.d.sh_filter + w.nShapes, filt.data(), n * 4);
-    h2d(w, w.d.sh_group + w.nShapes, grp.data(), n * 4);
+    h2d(w, w.d.sh_mat + firstShape, mat.data(), n * sizeof(float4)); h2d(w, w.d.sh_filter + firstShape, filt.data(), n * 4);
+    h2d(w, w.d.sh_group + firstShape, grp.data(), n * 4);
     h2d(w, w.d.ch_radius + w.nChildren, rad.data(), n_children * 4); h2d(w, w.d.ch_voff + w.nChildren, voff.data(), n_children * 4);
     h2d(w, w.d.ch_count + w.nChildren, cnt.data(), n_children * 4);
     h2d(w, w.d.vtx + w.nVerts, vertices, n_vertices * sizeof(pr_vec2)); h2d(w, w.d.nrm + w.nVerts, normals, n_vertices * sizeof(pr_vec2));
     sync(w);
-    if (first_id) *first_id = w.nShapes;
-    w.nShapes += n; w.nChildren += n_children; w.nVerts += n_vertices;
+    if (first_id) *first_id = firstShape;
+    if (!reuse) w.nShapes += n;
+    w.nChildren += n_children; w.nVerts += n_vertices;
     return PR_OK;
     API_CATCH(pw)
 }
@@ -1452,6 +1503,27 @@ static int create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const 
     for (uint32_t i = 0; i < n; ++i)
         for (uint32_t k = shape_offsets[i]; k < shape_offsets[i + 1]; ++k)
             if (shape_ids[k] >= w.nShapes) { w.error = "no such shape"; return PR_ERR_OUT_OF_RANGE; }
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t k = shape_offsets[i]; k < shape_offsets[i + 1]; ++k)
+            if (shape_dead(w, shape_ids[k])) { w.error = "shape identifier is destroyed"; return PR_ERR_INVALID_ARGUMENT; }
+    if (!w.pools.bodyFree.empty()) { // ids of destroyed bodies are handed out again first, last freed first (ObjectPool::Allocate)
+        if (n != 1u) { w.error = "CreateBody: create bodies one at a time while destroyed body ids are free"; return PR_ERR_UNSUPPORTED; }
+        const unsigned id = w.pools.bodyFree.back();
+        w.pools.bodyFree.pop_back(); w.pools.bodyDead[id] = 0;
+        const int rc = pr_set_bodies(pw, 1u, &id, bodies);
+        if (rc != PR_OK) return rc;
+        const unsigned z = 0u;
+        h2d(w, w.d.b_moved + id, &z, 4); h2d(w, w.d.b_sync + id, &z, 4);
+        if (w.d.nWorlds) { h2d(w, w.d.b_world + id, world_index, 4); w.bodyWorld[id] = world_index[0]; w.blocksDirty = true; }
+        sync(w);
+        std::vector<unsigned> sh(shape_ids + shape_offsets[0], shape_ids + shape_offsets[1]);
+        if (bodies[0].flags & PR_BODY_ENABLED) for (unsigned s : sh) w.fixturesForProxies.emplace_back(id, s);
+        if ((bodies[0].flags & PR_BODY_IMPENETRABLE) && !sh.empty()) w.toiPossible = true;
+        w.bodyShapes[id] = std::move(sh);
+        if (first_id) *first_id = id;
+        w.adjValid = false; w.bpDirty = true; w.toiAlphaDirty = true; w.recolorAll = true;
+        return PR_OK;
+    }
     ensure(w, G_BODY, w.nBodies + n);
     pr_body* staging = static_cast<pr_body*>(dev_alloc(sizeof(pr_body) * n));
     h2d(w, staging, bodies, sizeof(pr_body) * n);
@@ -1542,6 +1614,273 @@ int pr_attach_shapes(pr_world* pw, uint32_t body, uint32_t n, const uint32_t* sh
 int pr_create_bodies(pr_world* pw, uint32_t n, const pr_body* bodies, const uint32_t* shape_offsets, const uint32_t* shape_ids, uint32_t* first_id)
 {
     return create_bodies(pw, n, bodies, shape_offsets, shape_ids, nullptr, first_id);
+}
+
+} // extern "C" (helpers of the structural mutators)
+// DestroyLeaf for the proxy slots listed, in the order given (= the order the reference destroys the leaves in: their ids go
+// onto the leaf free list in that order); the proxy table, the queue, the contacts' slot pairs and m_bodyProxies are renumbered.
+// Contacts on these leaves were destroyed by the caller (the reference destroys them around the DestroyLeaf calls too).
+static void destroy_proxy_slots(World& w, const std::vector<unsigned>& slots)
+{
+    if (slots.empty()) return;
+    DV& d = w.d;
+    const unsigned P = w.nProxies;
+    std::vector<unsigned> map(P, 0u);
+    for (unsigned s : slots) { map[s] = INVALID; w.pools.treeFree.push_back(w.pools.pxTree[s]); }
+    unsigned k = 0;
+    for (unsigned i = 0; i < P; ++i) if (map[i] != INVALID) map[i] = k++;
+    // device: the columns only the device holds
+    unsigned char* tmp = static_cast<unsigned char*>(stage_buf(w, 0, static_cast<size_t>(P) * 28u + 64u));
+    unsigned* dmap = static_cast<unsigned*>(stage_buf(w, 1, static_cast<size_t>(P) * 4u + 16u));
+    unsigned* tChild = reinterpret_cast<unsigned*>(tmp + static_cast<size_t>(P) * 16u); unsigned* tCg = tChild + P; unsigned* tMoved = tCg + P;
+    float4* tFat = reinterpret_cast<float4*>(tmp);
+    h2d(w, dmap, map.data(), 4u * P);
+    PR_LAUNCH(k_px_compact, P, w.stream, d, P, dmap, tChild, tCg, tMoved, tFat);
+    d2d(w, d.p_child, tChild, 4u * k); d2d(w, d.p_cg, tCg, 4u * k); d2d(w, d.p_moved, tMoved, 4u * k); d2d(w, d.p_fat, tFat, sizeof(float4) * k);
+    if (w.nOrder) PR_LAUNCH(k_px_remap_contacts, w.nOrder, w.stream, d, w.nOrder, dmap);
+    // the queue (m_proxiesForContacts): EraseFirst of the destroyed ones, the others renumbered
+    read_counters(w);
+    if (w.hostCnt.nQueue) {
+        std::vector<unsigned> q(w.hostCnt.nQueue);
+        d2h(w, q.data(), d.q_list, 4u * q.size());
+        unsigned m = 0;
+        for (unsigned e : q) if (map[e] != INVALID) q[m++] = map[e];
+        h2d(w, d.q_list, q.data(), 4u * m);
+        w.hostCnt.nQueue = m; write_counters(w);
+    }
+    { // host mirrors
+        auto& pl = w.pools;
+        for (unsigned i = 0; i < P; ++i) if (map[i] != INVALID) { pl.pxBody[map[i]] = pl.pxBody[i]; pl.pxShape[map[i]] = pl.pxShape[i]; pl.pxTree[map[i]] = pl.pxTree[i]; }
+        pl.pxBody.resize(k); pl.pxShape.resize(k); pl.pxTree.resize(k);
+        h2d(w, d.p_body, pl.pxBody.data(), 4u * k); h2d(w, d.p_shape, pl.pxShape.data(), 4u * k); h2d(w, d.p_tree, pl.pxTree.data(), 4u * k);
+    }
+    for (auto& list : w.bodyProxies) {
+        unsigned m = 0;
+        for (unsigned e : list) if (map[e] != INVALID) list[m++] = map[e];
+        list.resize(m);
+    }
+    sync(w);
+    w.nProxies = k; w.bvhValid = false; w.bpDirty = true; w.toiAlphaDirty = true;
+}
+// the SetBody whose value has lost shapes (AabbTreeWorld.cpp:2760-2785; Detach, Destroy(ShapeID), a body being disabled): the
+// proxies of the (body, shape) pairs leave the tree in m_bodyProxies order, then per shape the contacts of that pair are
+// destroyed and the pair leaves m_fixturesForProxies. shapeIds: ascending (the reference walks a std::map).
+static void body_remove_shapes(World& w, unsigned body, const std::vector<unsigned>& shapeIds, bool keepInList)
+{
+    std::vector<unsigned> slots;
+    if (body < w.bodyProxies.size())
+        for (unsigned s : w.bodyProxies[body])
+            if (std::find(shapeIds.begin(), shapeIds.end(), w.pools.pxShape[s]) != shapeIds.end()) slots.push_back(s);
+    for (unsigned sid : shapeIds) {
+        destroy_contacts_where(w, 1u, body, sid);
+        auto& f = w.fixturesForProxies;
+        f.erase(std::remove(f.begin(), f.end(), std::make_pair(body, sid)), f.end());
+    }
+    destroy_proxy_slots(w, slots);
+    if (!keepInList) {
+        auto& list = w.bodyShapes[body];
+        for (unsigned sid : shapeIds) { const auto it = std::find(list.begin(), list.end(), sid); if (it != list.end()) list.erase(it); }
+    }
+}
+extern "C" {
+
+int pr_destroy_bodies(pr_world* pw, uint32_t n, const uint32_t* ids)
+{ // Destroy(AabbTreeWorld&, BodyID), :1062-1106
+    API_TRY(pw)
+    World& w = pw->w;
+    w.contactsClean = false;
+    if (!w.stepComplete) { w.error = "Destroy: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (ids[i] >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+        if (body_dead(w, ids[i])) { w.error = "body identifier is destroyed"; return PR_ERR_INVALID_ARGUMENT; }
+        for (uint32_t k = 0; k < i; ++k) if (ids[k] == ids[i]) { w.error = "body listed twice"; return PR_ERR_INVALID_ARGUMENT; }
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const unsigned id = ids[i];
+        // the attached joints (:1072-1085), in id order
+        std::vector<unsigned> js;
+        for (unsigned j = 0; j < w.joints.size(); ++j) if (w.joints[j].body_a != INVALID && (w.joints[j].body_a == id || w.joints[j].body_b == id)) js.push_back(j);
+        if (!js.empty()) { const int rc = pr_destroy_joints(pw, static_cast<uint32_t>(js.size()), js.data()); if (rc != PR_OK) return rc; }
+        destroy_contacts_where(w, 0u, id, 0u); // the attached contacts (:1087-1091), in m_bodyContacts order
+        { auto& f = w.fixturesForProxies; f.erase(std::remove_if(f.begin(), f.end(), [id](const std::pair<unsigned, unsigned>& e) { return e.first == id; }), f.end()); }
+        std::vector<unsigned> slots = id < w.bodyProxies.size() ? w.bodyProxies[id] : std::vector<unsigned>{};
+        std::sort(slots.begin(), slots.end(), [&w](unsigned a, unsigned b) { return w.pools.pxTree[a] < w.pools.pxTree[b]; }); // FindProxies: by leaf id (:617-630)
+        destroy_proxy_slots(w, slots);
+        // Remove(BodyID) (:1046-1060): the slot reads back destroyed and is the next id a CreateBody hands out
+        pr_body zero{};
+        zero.xf_qc = 1.0f; zero.flags = PR_BODY_DESTROYED;
+        const int rc = pr_set_bodies(pw, 1u, &id, &zero);
+        if (rc != PR_OK) return rc;
+        const unsigned z = 0u;
+        h2d(w, w.d.b_sync + id, &z, 4); h2d(w, w.d.b_moved + id, &z, 4);
+        sync(w);
+        w.bodyShapes[id].clear();
+        if (w.pools.bodyDead.size() <= id) w.pools.bodyDead.resize(id + 1u, 0);
+        w.pools.bodyDead[id] = 1; w.pools.bodyFree.push_back(id);
+        w.recolorAll = true; w.blocksDirty = true;
+    }
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_detach_shapes(pr_world* pw, uint32_t body, uint32_t n, const uint32_t* shape_ids)
+{ // the SetBody whose value has fewer shapes (:2760-2785); shape_ids: one entry per attachment to remove
+    API_TRY(pw)
+    World& w = pw->w;
+    w.contactsClean = false;
+    if (!w.stepComplete) { w.error = "SetBody: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    if (body >= w.nBodies || body_dead(w, body)) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    std::vector<unsigned> ids(shape_ids, shape_ids + n), have = w.bodyShapes[body];
+    std::sort(ids.begin(), ids.end());
+    for (unsigned sid : ids) { const auto it = std::find(have.begin(), have.end(), sid); if (it == have.end()) { w.error = "shape is not attached to the body"; return PR_ERR_INVALID_ARGUMENT; } have.erase(it); }
+    if (!n) return PR_OK;
+    if (body_flags(w, body) & PR_BODY_ENABLED) body_remove_shapes(w, body, ids, false);
+    else w.bodyShapes[body] = have; // (a disabled body has no proxies and no contacts)
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_destroy_shapes(pr_world* pw, uint32_t n, const uint32_t* ids)
+{ // Destroy(AabbTreeWorld&, ShapeID), :1259-1277: detached from every body (in body order), then the id is free
+    API_TRY(pw)
+    World& w = pw->w;
+    w.contactsClean = false;
+    if (!w.stepComplete) { w.error = "Destroy: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    for (uint32_t i = 0; i < n; ++i) if (ids[i] >= w.nShapes) { w.error = "no such shape"; return PR_ERR_OUT_OF_RANGE; }
+    for (uint32_t i = 0; i < n; ++i) {
+        const unsigned sid = ids[i];
+        if (shape_dead(w, sid)) continue; // (Free of a freed id: nothing)
+        for (unsigned b = 0; b < w.bodyShapes.size(); ++b) {
+            const unsigned cnt = static_cast<unsigned>(std::count(w.bodyShapes[b].begin(), w.bodyShapes[b].end(), sid));
+            if (!cnt) continue;
+            const std::vector<unsigned> rm(cnt, sid);
+            const int rc = pr_detach_shapes(pw, b, cnt, rm.data());
+            if (rc != PR_OK) return rc;
+        }
+        if (w.pools.shapeDead.size() <= sid) w.pools.shapeDead.resize(sid + 1u, 0);
+        w.pools.shapeDead[sid] = 1; w.pools.shapeFree.push_back(sid);
+        w.shapes[sid].child_count = 0;
+    }
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_set_body_enabled(pr_world* pw, uint32_t body, uint32_t enabled)
+{ // the SetBody whose value differs in IsEnabled (GetOldAndNewShapeIDs :671-676): all proxies and contacts go / all shapes are queued
+    API_TRY(pw)
+    World& w = pw->w;
+    w.contactsClean = false;
+    if (!w.stepComplete) { w.error = "SetBody: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    if (body >= w.nBodies || body_dead(w, body)) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    unsigned f = body_flags(w, body);
+    const bool was = (f & PR_BODY_ENABLED) != 0u, now = enabled != 0u;
+    if (was == now) return PR_OK;
+    if (!now) {
+        std::vector<unsigned> ids = w.bodyShapes[body];
+        std::sort(ids.begin(), ids.end());
+        body_remove_shapes(w, body, ids, true);
+        f &= ~static_cast<unsigned>(PR_BODY_ENABLED);
+    } else {
+        for (unsigned sid : w.bodyShapes[body]) w.fixturesForProxies.emplace_back(body, sid);
+        f |= PR_BODY_ENABLED;
+        if ((f & PR_BODY_IMPENETRABLE) && !w.bodyShapes[body].empty()) w.toiPossible = true;
+    }
+    h2d(w, w.d.b_flags + body, &f, 4);
+    sync(w);
+    w.adjValid = false; w.bpDirty = true; w.toiAlphaDirty = true; w.recolorAll = true;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_set_body_type(pr_world* pw, uint32_t body, const pr_body* row)
+{ // the SetBody whose value has another BodyType (:2738-2758): the body's contacts are destroyed; a body turned static is
+  // synchronised by the next Step (m_bodiesForSync); then "elem = value"
+    API_TRY(pw)
+    World& w = pw->w;
+    w.contactsClean = false;
+    if (!w.stepComplete) { w.error = "SetBody: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    if (body >= w.nBodies || body_dead(w, body)) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    destroy_contacts_where(w, 0u, body, 0u);
+    const int rc = pr_set_bodies(pw, 1u, &body, row);
+    if (rc != PR_OK) return rc;
+    if (!(row->flags & (PR_BODY_VELOCITY | PR_BODY_ACCELERATION))) { const unsigned one = 1u; h2d(w, w.d.b_sync + body, &one, 4); sync(w); }
+    w.recolorAll = true; w.adjValid = false;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
+int pr_set_shape(pr_world* pw, uint32_t shape, const pr_shape* def, const pr_child* children, const pr_vec2* vertices, const pr_vec2* normals,
+                 uint32_t n_vertices, uint32_t geometry_changed)
+{ // SetShape(AabbTreeWorld&, ShapeID, Shape), :1284-1356, for any new value
+    API_TRY(pw)
+    World& w = pw->w;
+    w.contactsClean = false;
+    if (!w.stepComplete) { w.error = "SetShape: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    if (shape >= w.nShapes) { w.error = "no such shape"; return PR_ERR_OUT_OF_RANGE; }
+    if (shape_dead(w, shape)) { w.error = "shape identifier is destroyed"; return PR_ERR_INVALID_ARGUMENT; }
+    pr_shape cur = w.shapes[shape];
+    if (geometry_changed) {
+        for (uint32_t i = 0; i < def->child_count; ++i) {
+            const pr_child& c = children[i];
+            if (c.vertex_count == 0 || c.vertex_count > 254) { w.error = "child vertex count out of range"; return PR_ERR_INVALID_ARGUMENT; }
+            if (!(c.vertex_radius >= w.conf.min_vertex_radius && c.vertex_radius <= w.conf.max_vertex_radius)) { w.error = "vertex radius outside world interval"; return PR_ERR_INVALID_ARGUMENT; }
+            if (c.vertex_offset > n_vertices || c.vertex_count > n_vertices - c.vertex_offset) { w.error = "child vertex range"; return PR_ERR_OUT_OF_RANGE; }
+        }
+    }
+    std::vector<unsigned> users;
+    for (unsigned b = 0; b < w.bodyShapes.size(); ++b)
+        if (std::find(w.bodyShapes[b].begin(), w.bodyShapes[b].end(), shape) != w.bodyShapes[b].end()) users.push_back(b);
+    if (!users.empty()) { // SetAwake(b) for every body that has the shape (:1301)
+        unsigned* sids = static_cast<unsigned*>(stage_buf(w, 1, 4u * users.size()));
+        h2d(w, sids, users.data(), 4u * users.size());
+        PR_LAUNCH(k_wake_bodies, static_cast<unsigned>(users.size()), w.stream, w.d, static_cast<unsigned>(users.size()), sids);
+        sync(w);
+    }
+    if (geometry_changed) {
+        for (unsigned b : users) { // :1302-1328: the enabled users lose the shape's proxies and contacts and are queued for new proxies
+            if (!(body_flags(w, b) & PR_BODY_ENABLED)) continue;
+            body_remove_shapes(w, b, std::vector<unsigned>{shape}, true);
+            w.fixturesForProxies.emplace_back(b, shape);
+        }
+        // the new children and vertices go to the end of the pools (the old ones are dead storage)
+        ensure(w, G_CHILD, w.nChildren + def->child_count); ensure(w, G_VERT, w.nVerts + n_vertices + 4u);
+        std::vector<float> rad(def->child_count); std::vector<unsigned> voff(def->child_count), cnt(def->child_count);
+        for (uint32_t i = 0; i < def->child_count; ++i) {
+            pr_child c = children[i];
+            c.vertex_offset += w.nVerts;
+            w.children.push_back(c);
+            rad[i] = c.vertex_radius; voff[i] = c.vertex_offset; cnt[i] = c.vertex_count;
+        }
+        h2d(w, w.d.ch_radius + w.nChildren, rad.data(), def->child_count * 4u); h2d(w, w.d.ch_voff + w.nChildren, voff.data(), def->child_count * 4u);
+        h2d(w, w.d.ch_count + w.nChildren, cnt.data(), def->child_count * 4u);
+        h2d(w, w.d.vtx + w.nVerts, vertices, n_vertices * sizeof(pr_vec2)); h2d(w, w.d.nrm + w.nVerts, normals, n_vertices * sizeof(pr_vec2));
+        cur.child_offset = w.nChildren; cur.child_count = def->child_count;
+        w.nChildren += def->child_count; w.nVerts += n_vertices;
+    }
+    const bool filterChanged = cur.filter_category != def->filter_category || cur.filter_mask != def->filter_mask || cur.filter_group != def->filter_group;
+    if (filterChanged) { // :1330-1345 (the shape's NEW filter is what the next DestroyContacts tests with)
+        if (w.nOrder) {
+            read_counters(w); w.hostCnt.nDestroyed = 0u; write_counters(w);
+            PR_LAUNCH(k_shape_flag_filter, w.nOrder, w.stream, w.d, w.nOrder, shape);
+            read_counters(w);
+            if (w.hostCnt.nDestroyed) w.needsFiltering = true;
+            w.hostCnt.nDestroyed = 0u; write_counters(w);
+        }
+        if (w.nProxies) { ensure(w, G_PROXY, w.nProxies + 1u); PR_LAUNCH(k_queue_shape_proxies, w.nProxies, w.stream, w.d, w.nProxies, shape); }
+    }
+    const bool touch = (cur.is_sensor != 0) != (def->is_sensor != 0) || cur.friction != def->friction || cur.restitution != def->restitution || geometry_changed;
+    if (touch && w.nOrder) PR_LAUNCH(k_shape_flag_contacts, w.nOrder, w.stream, w.d, w.nOrder, shape); // :1346-1354
+    cur.friction = def->friction; cur.restitution = def->restitution; cur.density = def->density; cur.is_sensor = def->is_sensor ? 1 : 0;
+    cur.filter_category = def->filter_category; cur.filter_mask = def->filter_mask; cur.filter_group = def->filter_group;
+    w.shapes[shape] = cur;
+    const float4 mat = make_float4(cur.friction, cur.restitution, cur.is_sensor ? 1.0f : 0.0f, cur.density);
+    const unsigned filt = static_cast<unsigned>(cur.filter_category) | (static_cast<unsigned>(cur.filter_mask) << 16);
+    const int grp = cur.filter_group;
+    h2d(w, w.d.sh_mat + shape, &mat, sizeof(float4)); h2d(w, w.d.sh_filter + shape, &filt, 4); h2d(w, w.d.sh_group + shape, &grp, 4);
+    sync(w);
+    w.adjValid = false;
+    return PR_OK;
+    API_CATCH(pw)
 }
 
 int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint* joints, uint32_t* first_id)
@@ -1964,6 +2303,15 @@ int pr_load_state(pr_world* pw, uint32_t n_bodies, const pr_body* bodies, uint32
     h2d(w, w.d.p_tree, tree.data(), 4 * n_proxies); h2d(w, w.d.p_fat, fat.data(), sizeof(float4) * n_proxies);
     dset(w, w.d.p_moved, 0, 4 * w.capProxies);
     w.nProxies = n_proxies; w.maxTreeId = maxTree;
+    w.pools.pxBody = body; w.pools.pxShape = shape; w.pools.pxTree = tree;
+    { // the leaf allocator as a tree with these leaves and no destroyed node between them would stand (2k - 1 sequence)
+        std::vector<char> used(static_cast<size_t>(maxTree) + 2u, 0);
+        for (unsigned t : tree) used[t] = 1;
+        w.pools.treeFree.clear();
+        w.pools.treeNextFresh = n_proxies ? maxTree + 2u : 0u;
+        if (n_proxies) for (unsigned t = maxTree; t-- > 0u;) if ((t & 1u) && !used[t]) w.pools.treeFree.push_back(t); // (odd ids below the maximum that no proxy holds: freed leaves)
+        if (n_proxies && !used[0] ) w.pools.treeFree.push_back(0u);
+    }
     w.bodyProxies.assign(w.nBodies, {});
     for (unsigned i = 0; i < n_proxies; ++i) w.bodyProxies[body[i]].push_back(i);
     w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true;

@@ -159,6 +159,18 @@ struct World {
     std::vector<std::vector<unsigned>> bodyShapes;
     std::vector<pr_revolute_joint> joints; std::vector<unsigned> freeJoints; // (a destroyed joint: bodies == INVALID; its id is re-used LIFO, ObjectPool)
     std::vector<std::pair<unsigned, unsigned>> fixturesForProxies;
+    // Destroy(BodyID / ShapeID), Detach, SetShape with new geometry (AabbTreeWorld.cpp:1062, :1259, :1284, :2760): ids of destroyed
+    // bodies and shapes are handed out again last-freed-first (ObjectPool), and so are the DynamicTree's leaf ids -- a leaf's
+    // destruction frees its parent node and then the leaf (DynamicTree.cpp:539-569), a creation takes a leaf and then a parent
+    // (:517-537), so the free list pairs up and the k-th new leaf gets the k-th last destroyed LEAF id whatever the internal
+    // nodes were; with the list empty a leaf takes the next fresh node, and its parent the one after it.
+    struct Pools {
+        std::vector<unsigned> bodyFree, shapeFree, treeFree;
+        unsigned treeNextFresh = 0;
+        std::vector<unsigned char> bodyDead, shapeDead;          // by id (shorter than the pool: the rest is live)
+        std::vector<unsigned> pxBody, pxShape, pxTree;           // host mirror of p_body / p_shape / p_tree, by proxy slot
+    } pools;
+    bool needsFiltering = false; // e_needsContactFiltering: some contact is flagged for filtering (SetShape with another filter)
     unsigned nBodies = 0, nShapes = 0, nChildren = 0, nVerts = 0, nProxies = 0;
     unsigned nOrder = 0, nFree = 0, poolSize = 0;  // contacts
     unsigned nCons = 0, nColors = 0, maxTreeId = 0, debugFlags = 0;

@@ -206,6 +206,9 @@ struct CudaWorld::Impl {
     // host mirrors of entity values
     mutable std::vector<Body> bodies;
     std::vector<char> bodyDirty;   // host value newer than the device row
+    std::vector<char> bodyLive;    // 0: destroyed (its id is handed out again by the device, last freed first)
+    std::vector<BodyID> bodyOrder; // m_bodies: live ids in creation order
+    std::vector<char> shapeLive;
     std::vector<BodyID> bodiesForSync; // bodies whose transformation was set since the last Step (m_bodiesForSync)
     bool anyBodyDirty = false;
     mutable bool bodiesStale = false; // device rows newer than the host values (after a Step)
@@ -300,14 +303,14 @@ struct CudaWorld::Impl {
         if (!bodiesStale) return;
         std::vector<pr_body> rows(bodies.size());
         if (!rows.empty()) check(pr_get_bodies(h, 0, static_cast<std::uint32_t>(rows.size()), rows.data()), "pr_get_bodies");
-        for (std::size_t i = 0; i < rows.size(); ++i) if (!bodyDirty[i]) FromRow(rows[i], bodies[i]);
+        for (std::size_t i = 0; i < rows.size(); ++i) if (!bodyDirty[i] && bodyLive[i]) FromRow(rows[i], bodies[i]);
         bodiesStale = false;
     }
     void uploadDirtyBodies()
     {
         if (!anyBodyDirty) return;
         std::vector<std::uint32_t> ids; std::vector<pr_body> rows;
-        for (std::size_t i = 0; i < bodies.size(); ++i) if (bodyDirty[i]) { ids.push_back(static_cast<std::uint32_t>(i)); rows.push_back(ToRow(bodies[i])); bodyDirty[i] = 0; }
+        for (std::size_t i = 0; i < bodies.size(); ++i) if (bodyDirty[i] && bodyLive[i]) { ids.push_back(static_cast<std::uint32_t>(i)); rows.push_back(ToRow(bodies[i])); bodyDirty[i] = 0; }
         if (!ids.empty()) check(pr_set_bodies(h, static_cast<std::uint32_t>(ids.size()), ids.data(), rows.data()), "pr_set_bodies");
         anyBodyDirty = false;
     }
@@ -351,6 +354,7 @@ CudaWorld::CudaWorld(const CudaWorld& o) : m{new Impl}
         m->conf = o.m->conf; m->toiMode = o.m->toiMode;
         m->check(pr_clone(o.m->h, &m->h), "pr_clone");
         m->bodies = o.m->bodies; m->bodyDirty = o.m->bodyDirty; m->anyBodyDirty = o.m->anyBodyDirty; m->bodiesForSync = o.m->bodiesForSync;
+        m->bodyLive = o.m->bodyLive; m->bodyOrder = o.m->bodyOrder; m->shapeLive = o.m->shapeLive;
         m->bodiesStale = false; m->shapes = o.m->shapes; m->joints = o.m->joints; m->freeJoints = o.m->freeJoints;
         m->shapeDestruction = o.m->shapeDestruction; m->detach = o.m->detach; m->jointDestruction = o.m->jointDestruction;
         m->beginContact = o.m->beginContact; m->endContact = o.m->endContact; m->preSolve = o.m->preSolve; m->postSolve = o.m->postSolve;
@@ -410,7 +414,7 @@ void Clear(CudaWorld& w) noexcept
             try { w.m->shapeDestruction(MakeId<ShapeID>(static_cast<std::uint32_t>(i))); } catch (...) {}
         }
     pr_clear(w.m->h);
-    w.m->bodies.clear(); w.m->bodyDirty.clear(); w.m->anyBodyDirty = false; w.m->bodiesStale = false; w.m->bodiesForSync.clear();
+    w.m->bodies.clear(); w.m->bodyDirty.clear(); w.m->bodyLive.clear(); w.m->bodyOrder.clear(); w.m->shapeLive.clear(); w.m->anyBodyDirty = false; w.m->bodiesStale = false; w.m->bodiesForSync.clear();
     w.m->shapes.clear(); w.m->joints.clear(); w.m->freeJoints.clear();
     w.m->mutated();
 }
@@ -474,16 +478,14 @@ const DynamicTree& GetTree(const CudaWorld& w) noexcept
 BodyCounter GetBodyRange(const CudaWorld& w) noexcept { return static_cast<BodyCounter>(w.m->bodies.size()); }
 std::vector<BodyID> GetBodies(const CudaWorld& w)
 {
-    std::vector<BodyID> r; r.reserve(w.m->bodies.size());
-    for (std::size_t i = 0; i < w.m->bodies.size(); ++i) r.push_back(MakeId<BodyID>(static_cast<std::uint32_t>(i)));
-    return r;
+    return w.m->bodyOrder; // m_bodies (creation order; a re-used id sits where its new body was created)
 }
 std::vector<BodyID> GetBodiesForProxies(const CudaWorld& w) { return w.m->bodiesForSync; } // m_bodiesForSync (:2792, cleared by Step :2181)
 
 BodyID CreateBody(CudaWorld& w, Body body)
 { // CreateBody(AabbTreeWorld&, Body), :1019-1060
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
-    if (w.m->bodies.size() >= MaxBodies) throw LengthError("CreateBody: operation would exceed MaxBodies");
+    if (w.m->bodyOrder.size() >= MaxBodies) throw LengthError("CreateBody: operation would exceed MaxBodies");
     for (const auto& sid : body.GetShapes()) (void)AtId(w.m->shapes, sid, noSuchShapeMsg); // :1030 validates shape ids
     const pr_body row = ToRow(body);
     std::vector<std::uint32_t> sh;
@@ -492,8 +494,9 @@ BodyID CreateBody(CudaWorld& w, Body body)
     const std::uint32_t dummy = 0;
     std::uint32_t first = 0;
     w.m->check(pr_create_bodies(w.m->h, 1, &row, offs, sh.empty() ? &dummy : sh.data(), &first), "pr_create_bodies");
-    w.m->bodies.push_back(std::move(body));
-    w.m->bodyDirty.push_back(0);
+    if (first < w.m->bodies.size()) { w.m->bodies[first] = std::move(body); w.m->bodyDirty[first] = 0; w.m->bodyLive[first] = 1; } // a destroyed body's id came back
+    else { w.m->bodies.push_back(std::move(body)); w.m->bodyDirty.push_back(0); w.m->bodyLive.push_back(1); }
+    w.m->bodyOrder.push_back(MakeId<BodyID>(first));
     w.m->mutated();
     return MakeId<BodyID>(first);
 }
@@ -511,19 +514,48 @@ void SetBody(CudaWorld& w, BodyID id, Body value)
     if (IsDestroyed(elem)) throw WasDestroyed{id, "ID is destroyed"};
     if (IsDestroyed(value)) throw InvalidArgument("cannot change is-destroyed value");
     for (const auto& sid : value.GetShapes()) (void)AtId(w.m->shapes, sid, noSuchShapeMsg);
-    // what the device world cannot follow yet: changes that destroy proxies or contacts (type, enabled, removed shapes)
-    if (GetType(elem) != GetType(value) || IsEnabled(elem) != IsEnabled(value)) throw InvalidArgument(unsupportedMsg);
-    if (elem.GetShapes() != value.GetShapes()) { // GetOldAndNewShapeIDs, :647-680: multiset difference, in ShapeID order
-        if (!IsEnabled(value)) throw InvalidArgument(unsupportedMsg);
-        std::map<ShapeID, int> oldmap, newmap;
-        for (const auto& i : elem.GetShapes()) { ++oldmap[i]; --newmap[i]; }
-        for (const auto& i : value.GetShapes()) { --oldmap[i]; ++newmap[i]; }
-        for (const auto& e : oldmap) if (e.second > 0) throw InvalidArgument(unsupportedMsg); // a shape was detached
-        std::vector<std::uint32_t> added;
-        for (const auto& e : newmap) for (int i = 0; i < e.second; ++i) added.push_back(static_cast<std::uint32_t>(to_underlying(e.first)));
-        w.m->uploadDirtyBodies(); // (the device reads the body's flags)
-        w.m->check(pr_attach_shapes(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), static_cast<std::uint32_t>(added.size()), added.data()), "pr_attach_shapes");
+    const auto bid = static_cast<std::uint32_t>(to_underlying(id));
+    bool rowUploaded = false;
+    if (GetType(elem) != GetType(value)) { // :2738-2758: the body's contacts are destroyed; a body turned static is synchronised by the next Step
+        w.m->uploadDirtyBodies();
+        const pr_body row = ToRow(value);
+        w.m->check(pr_set_body_type(w.m->h, bid, &row), "pr_set_body_type");
+        if (GetType(value) == BodyType::Static) w.m->bodiesForSync.push_back(id);
+        rowUploaded = true;
+        w.m->bodiesStale = true; // (the other bodies of destroyed contacts were woken)
     }
+    if (IsEnabled(elem) != IsEnabled(value) || elem.GetShapes() != value.GetShapes()) { // GetOldAndNewShapeIDs, :647-680
+        w.m->uploadDirtyBodies(); // (the device reads the body's flags)
+        std::vector<std::uint32_t> removed, added;
+        if (IsEnabled(elem) && IsEnabled(value)) { // multiset difference, in ShapeID order
+            std::map<ShapeID, int> oldmap, newmap;
+            for (const auto& i : elem.GetShapes()) { ++oldmap[i]; --newmap[i]; }
+            for (const auto& i : value.GetShapes()) { --oldmap[i]; ++newmap[i]; }
+            for (const auto& e : oldmap) for (int i = 0; i < e.second; ++i) removed.push_back(static_cast<std::uint32_t>(to_underlying(e.first)));
+            for (const auto& e : newmap) for (int i = 0; i < e.second; ++i) added.push_back(static_cast<std::uint32_t>(to_underlying(e.first)));
+            if (!removed.empty()) w.m->check(pr_detach_shapes(w.m->h, bid, static_cast<std::uint32_t>(removed.size()), removed.data()), "pr_detach_shapes");
+            if (!added.empty()) w.m->check(pr_attach_shapes(w.m->h, bid, static_cast<std::uint32_t>(added.size()), added.data()), "pr_attach_shapes");
+        } else { // enabled <-> disabled: the device's shape list follows the value's first (no proxies involved either way), then the switch
+            if (IsEnabled(elem)) w.m->check(pr_set_body_enabled(w.m->h, bid, 0u), "pr_set_body_enabled"); // all proxies and contacts go (:674-676)
+            if (elem.GetShapes() != value.GetShapes()) {
+                std::map<ShapeID, int> oldmap;
+                for (const auto& i : elem.GetShapes()) ++oldmap[i];
+                for (const auto& i : value.GetShapes()) --oldmap[i];
+                for (const auto& e : oldmap) { for (int i = 0; i < e.second; ++i) removed.push_back(static_cast<std::uint32_t>(to_underlying(e.first)));
+                                               for (int i = 0; i > e.second; --i) added.push_back(static_cast<std::uint32_t>(to_underlying(e.first))); }
+                if (!removed.empty()) w.m->check(pr_detach_shapes(w.m->h, bid, static_cast<std::uint32_t>(removed.size()), removed.data()), "pr_detach_shapes");
+                if (!added.empty()) { // (pr_attach_shapes wants an enabled body: attach after the switch below when the value is enabled)
+                    if (!IsEnabled(value)) throw InvalidArgument(unsupportedMsg);
+                }
+            }
+            if (IsEnabled(value)) {
+                w.m->check(pr_set_body_enabled(w.m->h, bid, 1u), "pr_set_body_enabled"); // every attached shape is queued (:671-673)
+                if (!added.empty()) w.m->check(pr_attach_shapes(w.m->h, bid, static_cast<std::uint32_t>(added.size()), added.data()), "pr_attach_shapes");
+            }
+        }
+        w.m->bodiesStale = true;
+    }
+    (void)rowUploaded;
     if (GetTransformation(elem) != GetTransformation(value)) w.m->bodiesForSync.push_back(id); // :2787-2793
     elem = std::move(value);
     w.m->bodyDirty[to_underlying(id)] = 1;
@@ -531,10 +563,37 @@ void SetBody(CudaWorld& w, BodyID id, Body value)
     w.m->mutated();
 }
 void Destroy(CudaWorld& w, BodyID id)
-{
+{ // Destroy(AabbTreeWorld&, BodyID), :1062-1106
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
-    (void)AtId(w.m->bodies, id, noSuchBodyMsg);
-    throw InvalidArgument(unsupportedMsg);
+    const auto& body = AtId(w.m->bodies, id, noSuchBodyMsg);
+    const auto bid = static_cast<std::uint32_t>(to_underlying(id));
+    if (!w.m->bodyLive[bid]) throw WasDestroyed{id, "ID is destroyed"};
+    w.m->refreshBodies();
+    w.m->uploadDirtyBodies();
+    // the attached joints (:1072-1085): the listener hears of each, then the device destroys them with the body
+    for (std::size_t i = 0; i < w.m->joints.size(); ++i) {
+        if (!w.m->joints[i].has_value()) continue;
+        if (GetBodyA(w.m->joints[i]) != id && GetBodyB(w.m->joints[i]) != id) continue;
+        if (w.m->jointDestruction) w.m->jointDestruction(MakeId<JointID>(static_cast<std::uint32_t>(i)));
+        w.m->joints[i] = Joint{};
+        w.m->freeJoints.push_back(static_cast<std::uint32_t>(i));
+    }
+    if (w.m->endContact) { // InternalDestroy (:2249-2252): end-contact for the touching contacts that go with the body
+        w.m->refreshContacts();
+        const auto list = w.m->bodyContacts[bid];
+        for (const auto& kc : list) if (IsTouching(w.m->contactBuf[to_underlying(std::get<ContactID>(kc))])) w.m->endContact(std::get<ContactID>(kc));
+    }
+    const auto shapes = body.GetShapes();
+    w.m->check(pr_destroy_bodies(w.m->h, 1u, &bid), "pr_destroy_bodies");
+    if (w.m->detach) for (const auto& sid : shapes) w.m->detach(std::make_pair(id, sid)); // :1100-1104
+    // Remove(BodyID), :1046-1060
+    w.m->bodiesForSync.erase(std::remove(w.m->bodiesForSync.begin(), w.m->bodiesForSync.end(), id), w.m->bodiesForSync.end());
+    w.m->bodyOrder.erase(std::remove(w.m->bodyOrder.begin(), w.m->bodyOrder.end(), id), w.m->bodyOrder.end());
+    w.m->bodies[bid] = Body{};
+    w.m->bodies[bid].SetDestroyed();
+    w.m->bodyDirty[bid] = 0; w.m->bodyLive[bid] = 0;
+    w.m->bodiesStale = true; // (bodies of the destroyed contacts and joints were woken)
+    w.m->mutated();
 }
 std::vector<std::pair<BodyID, JointID>> GetJoints(const CudaWorld& w, BodyID id)
 { // m_bodyJoints: (other body, joint) pairs
@@ -677,7 +736,8 @@ ShapeID CreateShape(CudaWorld& w, Shape def)
     w.m->check(pr_create_shapes(w.m->h, 1, &s, children.empty() ? &noChild : children.data(), static_cast<std::uint32_t>(children.size()),
                                 verts.empty() ? &noVert : verts.data(), normals.empty() ? &noVert : normals.data(),
                                 static_cast<std::uint32_t>(verts.size()), &first), "pr_create_shapes");
-    w.m->shapes.push_back(std::move(def));
+    if (first < w.m->shapes.size()) { w.m->shapes[first] = std::move(def); w.m->shapeLive[first] = 1; } // a destroyed shape's id came back
+    else { w.m->shapes.push_back(std::move(def)); w.m->shapeLive.push_back(1); }
     return MakeId<ShapeID>(first);
 }
 Shape GetShape(const CudaWorld& w, ShapeID id) { return AtId(w.m->shapes, id, noSuchShapeMsg); }
@@ -686,25 +746,66 @@ void SetShape(CudaWorld& w, ShapeID id, Shape def)
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
     auto& shape = AtId(w.m->shapes, id, noSuchShapeMsg);
     if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
-    // SetShape(AabbTreeWorld&, ShapeID, Shape), :1284-1356: the device follows values whose children (IsGeomChanged :778-793) and
-    // filter are unchanged -- friction, restitution, density, sensor
-    bool geometryChanged = GetChildCount(shape) != GetChildCount(def);
+    // SetShape(AabbTreeWorld&, ShapeID, Shape), :1284-1356
+    if (!shape.has_value()) throw WasDestroyed{id, "ID is destroyed"};
+    bool geometryChanged = GetChildCount(shape) != GetChildCount(def); // IsGeomChanged, :778-793
     for (ChildCounter c = 0; !geometryChanged && c < GetChildCount(def); ++c) geometryChanged = GetChild(shape, c) != GetChild(def, c);
-    if (geometryChanged || GetFilter(shape) != GetFilter(def)) throw InvalidArgument(unsupportedMsg);
     w.m->refreshBodies();       // bodies are woken on the device: keep the host values in step
     w.m->uploadDirtyBodies();
-    w.m->check(pr_set_shape_material(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), static_cast<float>(Real(GetFriction(def))),
-                                     static_cast<float>(GetRestitution(def)), static_cast<float>(Real(GetDensity(def) / KilogramPerSquareMeter)),
-                                     IsSensor(def) ? 1u : 0u), "pr_set_shape_material");
+    if (!geometryChanged && GetFilter(shape) == GetFilter(def)) {
+        w.m->check(pr_set_shape_material(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), static_cast<float>(Real(GetFriction(def))),
+                                         static_cast<float>(GetRestitution(def)), static_cast<float>(Real(GetDensity(def) / KilogramPerSquareMeter)),
+                                         IsSensor(def) ? 1u : 0u), "pr_set_shape_material");
+    } else {
+        pr_shape row{};
+        row.friction = static_cast<float>(Real(GetFriction(def))); row.restitution = GetRestitution(def);
+        row.density = static_cast<float>(Real(GetDensity(def) / KilogramPerSquareMeter));
+        const auto f = GetFilter(def);
+        row.filter_category = f.categoryBits; row.filter_mask = f.maskBits; row.filter_group = f.groupIndex;
+        row.is_sensor = IsSensor(def) ? 1 : 0;
+        row.child_offset = 0; row.child_count = GetChildCount(def);
+        std::vector<pr_child> children; std::vector<pr_vec2> verts, normals;
+        if (geometryChanged) {
+            const auto vmin = w.m->conf.vertexRadius.GetMin();
+            const auto vmax = w.m->conf.vertexRadius.GetMax();
+            for (ChildCounter c = 0; c < GetChildCount(def); ++c) {
+                const auto dp = GetChild(def, c);
+                const auto vr = dp.GetVertexRadius();
+                if (!(vr >= vmin) || !(vr <= vmax)) throw InvalidArgument("SetShape: vertex radius outside the world's interval");
+                pr_child ch{};
+                ch.vertex_offset = static_cast<std::uint32_t>(verts.size()); ch.vertex_count = dp.GetVertexCount(); ch.vertex_radius = vr;
+                for (VertexCounter v = 0; v < dp.GetVertexCount(); ++v) {
+                    verts.push_back(pr_vec2{GetX(dp.GetVertex(v)), GetY(dp.GetVertex(v))});
+                    normals.push_back(dp.GetVertexCount() > 1 ? pr_vec2{dp.GetNormal(v).GetX(), dp.GetNormal(v).GetY()} : pr_vec2{0, 0});
+                }
+                children.push_back(ch);
+            }
+        }
+        const pr_child noChild{}; const pr_vec2 noVert{};
+        w.m->check(pr_set_shape(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), &row, children.empty() ? &noChild : children.data(),
+                                verts.empty() ? &noVert : verts.data(), normals.empty() ? &noVert : normals.data(),
+                                static_cast<std::uint32_t>(verts.size()), geometryChanged ? 1u : 0u), "pr_set_shape");
+    }
     shape = std::move(def);
     w.m->bodiesStale = true;
     w.m->mutated();
 }
 void Destroy(CudaWorld& w, ShapeID id)
-{
+{ // Destroy(AabbTreeWorld&, ShapeID), :1259-1277: detached from every body that has it, then the id is free
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
     (void)AtId(w.m->shapes, id, noSuchShapeMsg);
-    throw InvalidArgument(unsupportedMsg);
+    w.m->refreshBodies();
+    w.m->uploadDirtyBodies();
+    const auto sid = static_cast<std::uint32_t>(to_underlying(id));
+    w.m->check(pr_destroy_shapes(w.m->h, 1u, &sid), "pr_destroy_shapes");
+    for (std::size_t b = 0; b < w.m->bodies.size(); ++b) { // the values follow: body.Detach(id) until it has none left (:1266-1275)
+        if (!w.m->bodyLive[b]) continue;
+        while (w.m->bodies[b].Detach(id)) {}
+    }
+    w.m->shapes[sid] = Shape{};
+    w.m->shapeLive[sid] = 0;
+    w.m->bodiesStale = true;
+    w.m->mutated();
 }
 
 // ---- contacts

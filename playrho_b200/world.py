@@ -61,6 +61,7 @@ EXPORTS = [
     "pr_is_step_complete", "pr_toi_batch", "pr_batch_create", "pr_batch_destroy", "pr_batch_arena",
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
     "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_test_points", "pr_find_closest_bodies", "pr_set_contacts", "pr_set_manifolds", "pr_set_revolute_joints", "pr_attach_shapes", "pr_set_shape_material", "pr_destroy_joints",
+    "pr_destroy_bodies", "pr_detach_shapes", "pr_destroy_shapes", "pr_set_shape", "pr_set_body_enabled", "pr_set_body_type",
 ]
 
 
@@ -96,6 +97,12 @@ def bind(lib):
     lib.pr_set_revolute_joints.argtypes = [vp, u32, vp, vp]
     lib.pr_attach_shapes.argtypes = [vp, u32, u32, vp]
     lib.pr_destroy_joints.argtypes = [vp, u32, vp]
+    lib.pr_destroy_bodies.argtypes = [vp, u32, vp]
+    lib.pr_detach_shapes.argtypes = [vp, u32, u32, vp]
+    lib.pr_destroy_shapes.argtypes = [vp, u32, vp]
+    lib.pr_set_shape.argtypes = [vp, u32, vp, vp, vp, vp, u32, u32]
+    lib.pr_set_body_enabled.argtypes = [vp, u32, u32]
+    lib.pr_set_body_type.argtypes = [vp, u32, vp]
     lib.pr_set_shape_material.argtypes = [vp, u32, f32, f32, f32, u32]
     lib.pr_set_manifolds.argtypes = [vp, u32, vp, vp]
     lib.pr_get_revolute_joints.argtypes = [vp, u32, u32, vp]
@@ -304,6 +311,60 @@ class World:
     def destroy_joints(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         self._chk(self.lib.pr_destroy_joints(self.h, len(ids), abi.ptr(ids)))
+
+    def add_body(self, row, shape_ids=()):
+        """CreateBody for one body row with the shapes listed; returns its id (a destroyed body's id first, last freed first)."""
+        row = np.ascontiguousarray(row, dtype=abi.BODY).reshape(1)
+        off = np.array([0, len(shape_ids)], np.uint32)
+        ids = np.ascontiguousarray(shape_ids, dtype=np.uint32)
+        first = u32(0)
+        self._chk(self.lib.pr_create_bodies(self.h, 1, abi.ptr(row), abi.ptr(off), abi.ptr(ids), C.byref(first)))
+        return first.value
+
+    def add_shape(self, row, children, vertices, normals):
+        """CreateShape for one flattened shape; returns its id (a destroyed shape's id first)."""
+        row = np.ascontiguousarray(row, dtype=abi.SHAPE).reshape(1).copy()
+        children = np.ascontiguousarray(children, dtype=abi.CHILD)
+        vertices = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 2)
+        normals = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 2)
+        row["child_offset"] = 0; row["child_count"] = len(children)
+        first = u32(0)
+        self._chk(self.lib.pr_create_shapes(self.h, 1, abi.ptr(row), abi.ptr(children), len(children), abi.ptr(vertices), abi.ptr(normals), len(vertices), C.byref(first)))
+        return first.value
+
+    def destroy_bodies(self, ids):
+        """Destroy(world, BodyID) for each id (pr_destroy_bodies)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._chk(self.lib.pr_destroy_bodies(self.h, len(ids), abi.ptr(ids)))
+
+    def detach_shapes(self, body, shape_ids):
+        """Detach(world, body, shape) for each shape id (pr_detach_shapes); upload the body row (new mass) with set_bodies."""
+        ids = np.ascontiguousarray(shape_ids, dtype=np.uint32)
+        self._chk(self.lib.pr_detach_shapes(self.h, int(body), len(ids), abi.ptr(ids)))
+
+    def destroy_shapes(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._chk(self.lib.pr_destroy_shapes(self.h, len(ids), abi.ptr(ids)))
+
+    def set_shape(self, shape, row, children=None, vertices=None, normals=None):
+        """SetShape with any new value (pr_set_shape); children/vertices/normals given = new geometry."""
+        row = np.ascontiguousarray(row, dtype=abi.SHAPE).reshape(1).copy()
+        geom = children is not None
+        if geom:
+            children = np.ascontiguousarray(children, dtype=abi.CHILD)
+            vertices = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 2)
+            normals = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 2)
+            row["child_count"] = len(children)
+            self._chk(self.lib.pr_set_shape(self.h, int(shape), abi.ptr(row), abi.ptr(children), abi.ptr(vertices), abi.ptr(normals), len(vertices), 1))
+        else:
+            self._chk(self.lib.pr_set_shape(self.h, int(shape), abi.ptr(row), None, None, None, 0, 0))
+
+    def set_body_enabled(self, body, enabled):
+        self._chk(self.lib.pr_set_body_enabled(self.h, int(body), 1 if enabled else 0))
+
+    def set_body_type(self, body, row):
+        row = np.ascontiguousarray(row, dtype=abi.BODY).reshape(1)
+        self._chk(self.lib.pr_set_body_type(self.h, int(body), abi.ptr(row)))
 
     def create_joints(self, rows):
         rows = np.ascontiguousarray(rows, dtype=abi.REVOLUTE)

@@ -9,7 +9,16 @@ COLS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
         ("l1tex__t_sector_hit_rate.pct", "L1hit%"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"),
         ("launch__registers_per_thread", "regs"), ("smsp__thread_inst_executed_per_inst_executed.ratio", "thr/inst"),
         ("launch__grid_size", "grid"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
-        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%")]
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_lsb"),
+        ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "st_wait"),
+        ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "st_ssb"),
+        ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "st_br"),
+        ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "st_noinst"),
+        ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "st_bar"),
+        ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "st_lg"),
+        ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "st_math"),
+        ("smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "st_membar")]
 
 
 def main(paths):

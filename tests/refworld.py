@@ -203,6 +203,43 @@ class RefWorld:
         self.lib.ref_destroy_joint.argtypes = [vp, u32]
         self._chk(self.lib.ref_destroy_joint(self.h, int(joint)))
 
+    # ---- structural mutators through the reference's own API
+    def destroy_body(self, body):
+        self.lib.ref_destroy_body.argtypes = [vp, u32]
+        self._chk(self.lib.ref_destroy_body(self.h, int(body)))
+
+    def destroy_shape(self, shape):
+        self.lib.ref_destroy_shape.argtypes = [vp, u32]
+        self._chk(self.lib.ref_destroy_shape(self.h, int(shape)))
+
+    def detach_shape(self, body, shape):
+        self.lib.ref_detach_shape.argtypes = [vp, u32, u32]
+        self._chk(self.lib.ref_detach_shape(self.h, int(body), int(shape)))
+
+    def set_body_enabled(self, body, flag):
+        self.lib.ref_set_body_enabled.argtypes = [vp, u32, i32]
+        self._chk(self.lib.ref_set_body_enabled(self.h, int(body), 1 if flag else 0))
+
+    def set_body_type(self, body, btype):
+        self.lib.ref_set_body_type.argtypes = [vp, u32, i32]
+        self._chk(self.lib.ref_set_body_type(self.h, int(body), int(btype)))
+
+    def set_shape_filter(self, shape, cat, mask, group):
+        self.lib.ref_set_shape_filter.argtypes = [vp, u32, u32, u32, i32]
+        self._chk(self.lib.ref_set_shape_filter(self.h, int(shape), int(cat), int(mask), int(group)))
+
+    def translate_shape(self, shape, dx, dy):
+        self.lib.ref_translate_shape.argtypes = [vp, u32, f32, f32]
+        self._chk(self.lib.ref_translate_shape(self.h, int(shape), dx, dy))
+
+    def export_shape(self, shape):
+        """(row, children, vertices, normals) of one shape, as pr_set_shape takes them."""
+        self.lib.ref_export_shape.argtypes = [vp, u32, vp, vp, u32, vp, vp, u32]
+        row = np.zeros(1, abi.SHAPE); ch = np.zeros(64, abi.CHILD); vt = np.zeros((4096, 2), np.float32); nm = np.zeros((4096, 2), np.float32)
+        nv = self._chk(self.lib.ref_export_shape(self.h, int(shape), abi.ptr(row), abi.ptr(ch), 64, abi.ptr(vt), abi.ptr(nm), 4096))
+        nc = int(row["child_count"][0])
+        return row, ch[:nc].copy(), vt[:nv].copy(), nm[:nv].copy()
+
     def set_joints(self, ids, rows):
         """SetJoint per revolute joint (motor and limit fields of the row)."""
         self.lib.ref_set_revolute_joint.argtypes = [vp, u32, vp]
@@ -376,6 +413,56 @@ class OracleWorld:
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         self.lib.orc_destroy_joints.argtypes = [vp, u32, vp]
         self.lib.orc_destroy_joints(self.h, len(ids), abi.ptr(ids))
+
+    def add_body(self, row, shape_ids=()):
+        row = np.ascontiguousarray(row, dtype=abi.BODY).reshape(1)
+        off = np.array([0, len(shape_ids)], np.uint32)
+        ids = np.ascontiguousarray(shape_ids, dtype=np.uint32)
+        self.lib.orc_create_bodies(self.h, 1, abi.ptr(row), abi.ptr(off), abi.ptr(ids))
+
+    def add_shape(self, row, children, vertices, normals):
+        row = np.ascontiguousarray(row, dtype=abi.SHAPE).reshape(1).copy()
+        children = np.ascontiguousarray(children, dtype=abi.CHILD)
+        vertices = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 2)
+        normals = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 2)
+        row["child_offset"] = 0; row["child_count"] = len(children)
+        self.lib.orc_create_shapes(self.h, 1, abi.ptr(row), abi.ptr(children), len(children), abi.ptr(vertices), abi.ptr(normals), len(vertices))
+
+    def destroy_bodies(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self.lib.orc_destroy_bodies.argtypes = [vp, u32, vp]
+        assert self.lib.orc_destroy_bodies(self.h, len(ids), abi.ptr(ids)) == 0
+
+    def detach_shapes(self, body, shape_ids):
+        ids = np.ascontiguousarray(shape_ids, dtype=np.uint32)
+        self.lib.orc_detach_shapes.argtypes = [vp, u32, u32, vp]
+        self.lib.orc_detach_shapes(self.h, int(body), len(ids), abi.ptr(ids))
+
+    def destroy_shapes(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self.lib.orc_destroy_shapes.argtypes = [vp, u32, vp]
+        assert self.lib.orc_destroy_shapes(self.h, len(ids), abi.ptr(ids)) == 0
+
+    def set_body_enabled(self, body, flag):
+        self.lib.orc_set_body_enabled.argtypes = [vp, u32, u32]
+        self.lib.orc_set_body_enabled(self.h, int(body), 1 if flag else 0)
+
+    def set_body_type(self, body, row):
+        row = np.ascontiguousarray(row, dtype=abi.BODY).reshape(1)
+        self.lib.orc_set_body_type.argtypes = [vp, u32, vp]
+        self.lib.orc_set_body_type(self.h, int(body), abi.ptr(row))
+
+    def set_shape(self, shape, row, children=None, vertices=None, normals=None):
+        self.lib.orc_set_shape.argtypes = [vp, u32, vp, vp, vp, vp, u32, u32]
+        row = np.ascontiguousarray(row, dtype=abi.SHAPE).reshape(1).copy()
+        if children is not None:
+            children = np.ascontiguousarray(children, dtype=abi.CHILD)
+            vertices = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 2)
+            normals = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 2)
+            row["child_count"] = len(children)
+            self.lib.orc_set_shape(self.h, int(shape), abi.ptr(row), abi.ptr(children), abi.ptr(vertices), abi.ptr(normals), len(vertices), 1)
+        else:
+            self.lib.orc_set_shape(self.h, int(shape), abi.ptr(row), None, None, None, 0, 0)
 
     def create_joints(self, rows):
         rows = np.ascontiguousarray(rows, dtype=abi.REVOLUTE)
