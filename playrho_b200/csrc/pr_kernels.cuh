@@ -1559,50 +1559,140 @@ PR_KERNEL k_color_keep(DV d, unsigned nBound)
     const unsigned slot = warp_append(&d.cnt->nColorWork, todo);
     if (todo) d.k_ulist[slot] = k;
 }
+PR_D void color_claim_one(const DV& d, unsigned t, unsigned round)
+{
+    const unsigned k = d.k_ulist[t];
+    if (d.k_color[k] == COLOR_UNSET) {
+        const unsigned cid = d.k_contact[k];
+        const uint4 ab = d.c_ab[cid];
+        const unsigned long long key = color_key(round, cid, k);
+        if (body_dyn(d, ab.x)) atomicMin(&d.b_claim[ab.x], key);
+        if (body_dyn(d, ab.y)) atomicMin(&d.b_claim[ab.y], key);
+    }
+}
+// returns 1 when the constraint is still without a colour after this round
+PR_D unsigned color_commit_one(const DV& d, unsigned t, unsigned round, unsigned colorCap)
+{
+    const unsigned k = d.k_ulist[t];
+    if (d.k_color[k] != COLOR_UNSET) return 0u;
+    const unsigned cid = d.k_contact[k];
+    const uint4 ab = d.c_ab[cid];
+    const unsigned long long key = color_key(round, cid, k);
+    const bool dA = body_dyn(d, ab.x), dB = body_dyn(d, ab.y);
+    const bool win = (!dA || d.b_claim[ab.x] == key) && (!dB || d.b_claim[ab.y] == key);
+    if (!win) return 1u;
+    const unsigned long long used = (dA ? d.b_cmask[ab.x] : 0ull) | (dB ? d.b_cmask[ab.y] : 0ull);
+    const unsigned long long freeBits = ~used;
+    unsigned c = COLOR_OVERFLOW;
+    if (freeBits && static_cast<unsigned>(__ffsll(static_cast<long long>(freeBits))) - 1u < colorCap) { // (colorCap: see World::colorCap)
+        c = static_cast<unsigned>(__ffsll(static_cast<long long>(freeBits))) - 1u;
+        if (dA) d.b_cmask[ab.x] |= (1ull << c);
+        if (dB) d.b_cmask[ab.y] |= (1ull << c);
+    }
+    d.k_color[k] = c;
+    d.c_color[cid] = c;
+    return 0u;
+}
 PR_KERNEL k_color_claim(DV d, unsigned nWork, unsigned round)
 {
     PR_PDL_ENTER();
     const unsigned t = PR_TID;
     if (t == 0u) d.cnt->nUncolored = 0u; // (k_color_commit of this round counts what is left)
-    if (t < nWork) {
-        const unsigned k = d.k_ulist[t];
-        if (d.k_color[k] == COLOR_UNSET) {
-            const unsigned cid = d.k_contact[k];
-            const uint4 ab = d.c_ab[cid];
-            const unsigned long long key = color_key(round, cid, k);
-            if (body_dyn(d, ab.x)) atomicMin(&d.b_claim[ab.x], key);
-            if (body_dyn(d, ab.y)) atomicMin(&d.b_claim[ab.y], key);
-        }
-    }
+    if (t < nWork) color_claim_one(d, t, round);
 }
 PR_KERNEL k_color_commit(DV d, unsigned nWork, unsigned round, unsigned colorCap)
 {
     PR_PDL_ENTER();
     const unsigned t = PR_TID;
     unsigned remaining = 0u;
-    if (t < nWork) {
-        const unsigned k = d.k_ulist[t];
-        if (d.k_color[k] == COLOR_UNSET) {
+    if (t < nWork) remaining = color_commit_one(d, t, round, colorCap);
+    block_add(&d.cnt->nUncolored, remaining);
+}
+// A step of a settled world colours a few thousand NEW constraints in a dozen Jones-Plassmann rounds: as two launches per
+// round that was ~25 launches of 7-9 us each, most of them for a few hundred leftover constraints (profiles/r02e). After the first
+// COLOR_LAUNCH_ROUNDS rounds ONE block runs the remaining rounds back to back (same keys, same winners, same colours: the rounds
+// are what they were, only the barriers are block barriers) over a compacted work list; it stops before the claim keys' round
+// field would wrap (the host loop goes on). (All rounds in the block: measured slower -- 0.40 vs 0.33 ms for the colour stage --
+// a round over 11 000 constraints is a dozen dependent gathers per thread in one block and one per thread across the chip.)
+constexpr unsigned COLOR_BLOCK = 1024u, COLOR_BLOCK_MAX_WORK = 1u << 20, COLOR_BLOCK_MAX_ROUNDS = 60u, COLOR_LAUNCH_ROUNDS = 3u, COLOR_BLOCK_TAIL_MAX = 8192u;
+PR_KERNEL k_color_rounds_block(DV d, unsigned colorCap, unsigned* scratch, unsigned firstRound)
+{
+    PR_PDL_ENTER();
+#ifndef PR_HOST_EMUL
+    __shared__ unsigned s_n;
+    const unsigned tid = threadIdx.x, nth = blockDim.x;
+#else
+    unsigned s_n = 0u;
+    const unsigned tid = 0u, nth = 1u;
+#endif
+    unsigned n = d.cnt->nColorWork;
+    unsigned* cur = d.k_ulist; unsigned* nxt = scratch;
+    if (firstRound) { // the first rounds ran as launches over the whole list: what they left, compacted
+        if (tid == 0u) s_n = 0u;
+        __syncthreads();
+        for (unsigned t0 = 0; t0 < n; t0 += nth) {
+            const unsigned t = t0 + tid;
+            unsigned k = 0u;
+            const bool left = t < n && d.k_color[k = cur[t]] == COLOR_UNSET;
+            const unsigned slot = warp_append(&s_n, left);
+            if (left) nxt[slot] = k;
+        }
+        __threadfence_block(); __syncthreads();
+        n = s_n;
+        unsigned* tmp = cur; cur = nxt; nxt = tmp;
+        __syncthreads();
+        if (n > COLOR_BLOCK_TAIL_MAX) { // too much left for one block (a world's first step): the launches go on where they stopped
+            if (tid == 0u) { d.cnt->nUncolored = n; d.cnt->colorRoundsDev = firstRound; }
+            return;
+        }
+    }
+    unsigned round = firstRound;
+    for (; round < COLOR_BLOCK_MAX_ROUNDS && n; ++round) {
+        for (unsigned t = tid; t < n; t += nth) {
+            const unsigned k = cur[t];
             const unsigned cid = d.k_contact[k];
             const uint4 ab = d.c_ab[cid];
             const unsigned long long key = color_key(round, cid, k);
-            const bool dA = body_dyn(d, ab.x), dB = body_dyn(d, ab.y);
-            const bool win = (!dA || d.b_claim[ab.x] == key) && (!dB || d.b_claim[ab.y] == key);
-            if (win) {
-                const unsigned long long used = (dA ? d.b_cmask[ab.x] : 0ull) | (dB ? d.b_cmask[ab.y] : 0ull);
-                const unsigned long long freeBits = ~used;
-                unsigned c = COLOR_OVERFLOW;
-                if (freeBits && static_cast<unsigned>(__ffsll(static_cast<long long>(freeBits))) - 1u < colorCap) { // (colorCap: see World::colorCap)
-                    c = static_cast<unsigned>(__ffsll(static_cast<long long>(freeBits))) - 1u;
-                    if (dA) d.b_cmask[ab.x] |= (1ull << c);
-                    if (dB) d.b_cmask[ab.y] |= (1ull << c);
-                }
-                d.k_color[k] = c;
-                d.c_color[cid] = c;
-            } else remaining = 1u;
+            if (body_dyn(d, ab.x)) atomicMin(&d.b_claim[ab.x], key);
+            if (body_dyn(d, ab.y)) atomicMin(&d.b_claim[ab.y], key);
         }
+        if (tid == 0u) s_n = 0u;
+        __threadfence_block(); __syncthreads();
+        for (unsigned t0 = 0; t0 < n; t0 += nth) { // (every thread of the block walks every stripe: the appends below are warp-wide)
+            const unsigned t = t0 + tid;
+            bool left = false; unsigned k = 0u;
+            if (t < n) {
+                k = cur[t];
+                const unsigned cid = d.k_contact[k];
+                const uint4 ab = d.c_ab[cid];
+                const unsigned long long key = color_key(round, cid, k);
+                const bool dA = body_dyn(d, ab.x), dB = body_dyn(d, ab.y);
+                const bool win = (!dA || d.b_claim[ab.x] == key) && (!dB || d.b_claim[ab.y] == key);
+                if (win) {
+                    const unsigned long long used = (dA ? d.b_cmask[ab.x] : 0ull) | (dB ? d.b_cmask[ab.y] : 0ull);
+                    const unsigned long long freeBits = ~used;
+                    unsigned c = COLOR_OVERFLOW;
+                    if (freeBits && static_cast<unsigned>(__ffsll(static_cast<long long>(freeBits))) - 1u < colorCap) {
+                        c = static_cast<unsigned>(__ffsll(static_cast<long long>(freeBits))) - 1u;
+                        if (dA) d.b_cmask[ab.x] |= (1ull << c);
+                        if (dB) d.b_cmask[ab.y] |= (1ull << c);
+                    }
+                    d.k_color[k] = c;
+                    d.c_color[cid] = c;
+                } else left = true;
+            }
+            const unsigned slot = warp_append(&s_n, left);
+            if (left) nxt[slot] = k;
+        }
+        __threadfence_block(); __syncthreads();
+        n = s_n;
+        unsigned* tmp = cur; cur = nxt; nxt = tmp;
+        __syncthreads();
     }
-    block_add(&d.cnt->nUncolored, remaining);
+    if (tid == 0u) { d.cnt->nUncolored = n; d.cnt->colorRoundsDev = round; }
+    // what is left (only when the round budget ran out) goes back to the head of k_ulist for the host-driven rounds
+    if (n && cur != d.k_ulist) for (unsigned t = tid; t < n; t += nth) d.k_ulist[t] = cur[t];
+    if (tid == 0u && n) d.cnt->nColorWork = n;
 }
 PR_KERNEL k_color_reset_claims(DV d, unsigned nBodies)
 {
@@ -2283,7 +2373,10 @@ PR_KERNEL k_flow_words(DV d, unsigned nRows, const unsigned* sortedColor)
 }
 // mode 0: WarmStartVelocities, 1: one velocity iteration, 2: one position iteration; nRows: the coloured rows (the overflow
 // tail, if any, follows in its own launch); pass: how many passes ran on the same array (s_vel / s_pos) before this one
-template <unsigned mode> PR_KERNEL_LB(PR_BLOCK, 3) k_flow_pass(DV d, unsigned nRows, unsigned ticket, unsigned pass, float rate, float slop, float maxCorr)
+#ifndef PR_FLOW_MINBLOCKS
+#define PR_FLOW_MINBLOCKS 2 // (measured on B200, 1M mixed: 2 -> velocity 0.60 + position 0.33 ms, 3 -> 0.62 + 0.36 (80 registers, spills), 4 -> 0.66 + 0.37)
+#endif
+template <unsigned mode> PR_KERNEL_LB(PR_BLOCK, PR_FLOW_MINBLOCKS) k_flow_pass(DV d, unsigned nRows, unsigned ticket, unsigned pass, float rate, float slop, float maxCorr)
 {
     pr_pdl_launch_dependents();
 #ifndef PR_HOST_EMUL

@@ -562,8 +562,29 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     if (nCons) {
         const unsigned nWork = w.hostCnt.nColorWork;
         w.recolorAll = false;
-        if (nWork) {
-            for (unsigned round = 0;; ++round) {
+        unsigned nWorkLeft = nWork, firstRound = 0u;
+        if (nWork && nWork <= COLOR_BLOCK_MAX_WORK && !(w.debugFlags & 256u)) { // the first rounds as launches, the tail in one block (debug bit 8: launches only)
+            for (unsigned round = 0; round < COLOR_LAUNCH_ROUNDS; ++round) {
+                PR_LAUNCH(k_color_claim, nWork, w.stream, d, nWork, round);
+                PR_LAUNCH(k_color_commit, nWork, w.stream, d, nWork, round, w.colorCap);
+            }
+            ensure(w, G_PAIR, nWork); // (np_idx: the block's second work list; the candidate-pair buffers are idle here)
+#ifndef PR_HOST_EMUL
+            PR_LAUNCH_GRID(k_color_rounds_block, 1, COLOR_BLOCK, w.stream, d, w.colorCap, d.np_idx, COLOR_LAUNCH_ROUNDS);
+#else
+            PR_LAUNCH(k_color_rounds_block, 1, w.stream, d, w.colorCap, d.np_idx, COLOR_LAUNCH_ROUNDS);
+#endif
+            read_counters(w);
+            w.profile.color_rounds += w.hostCnt.colorRoundsDev;
+            // 0 left; or the block handed back at once (too much left: the launches go on over the whole list), or its round
+            // budget ran out (the rest, compacted to the head of the list, goes on after a reset of the claims)
+            const bool handedBack = w.hostCnt.colorRoundsDev == COLOR_LAUNCH_ROUNDS;
+            nWorkLeft = !w.hostCnt.nUncolored ? 0u : handedBack ? nWork : w.hostCnt.nUncolored;
+            firstRound = handedBack ? COLOR_LAUNCH_ROUNDS : 64u;
+        }
+        if (nWorkLeft) {
+            const unsigned nWork = nWorkLeft;
+            for (unsigned round = firstRound;; ++round) {
                 if (round && (round % 64u) == 0u) PR_LAUNCH(k_color_reset_claims, N, w.stream, d, N);
                 PR_LAUNCH(k_color_claim, nWork, w.stream, d, nWork, round);
                 PR_LAUNCH(k_color_commit, nWork, w.stream, d, nWork, round, w.colorCap);

@@ -83,6 +83,7 @@ struct Counters {
     // compact lists for the single-block late rounds (k_tb_late): contacts to recompute in round toiRoundId + 1 (parity
     // ping-pong), the candidates being compacted, the listed contacts currently at maxSubSteps, "next round needs the full list"
     unsigned toiRoundId, toiReN[2], toiCand2N, toiAtMaxLive, toiForceFull, tbPad2;
+    unsigned colorRoundsDev; // rounds k_color_rounds_block ran this step
     unsigned flowTicket[32]; // dataflow solver (k_flow_pass): the next block of rows of each pass
 #ifdef PR_TOI_TIMING
     unsigned long long dbg[16]; // profiling build only: clock64 deltas of the phases of toi_solve_event (event 0 of each round)

@@ -338,6 +338,7 @@ struct CudaWorld::Impl {
             bodyContacts[cs[i].body_a].emplace_back(key, id); // m_bodyContacts: append order == m_contacts order
             bodyContacts[cs[i].body_b].emplace_back(key, id);
         }
+        for (std::size_t i = 0; i < contactBuf.size(); ++i) if (!contactLive[i]) contactBuf[i].SetDestroyed(); // (m_contactBuffer.Free(id).SetDestroyed(), :2277)
         contactsStale = false;
     }
     void mutated() { contactsStale = true; treeStale = true; }
