@@ -141,8 +141,9 @@ PR_D bool f_enabled(unsigned f) { return (f & PR_BODY_ENABLED) != 0; }
 PR_D ProxyView child_view(const DV& d, unsigned cg)
 {
     ProxyView v;
-    v.radius = d.ch_radius[cg]; v.count = d.ch_count[cg];
-    const unsigned off = d.ch_voff[cg];
+    const float4 c = d.ch_pack[cg]; // (radius, vertex offset, vertex count) in ONE 16-byte gather instead of three
+    v.radius = c.x; v.count = f2u(c.z);
+    const unsigned off = f2u(c.y);
     v.v = d.vtx + off; v.n = d.nrm + off;
     return v;
 }
@@ -554,7 +555,7 @@ k_update_contacts(DV d, pr_step_conf conf, unsigned start, unsigned n, unsigned 
     unsigned cls = 3u;
     if (dirty) {
         const uint4 ab = d.c_ab[id];
-        const unsigned ca = d.ch_count[ab.z], cb = d.ch_count[ab.w];
+        const unsigned ca = f2u(d.ch_pack[ab.z].z), cb = f2u(d.ch_pack[ab.w].z);
         cls = (flags & PR_CONTACT_SENSOR) ? 2u : (ca == 1u && cb == 1u) ? 0u : (ca == 1u || cb == 1u) ? 1u : 2u;
     }
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -616,7 +617,7 @@ k_update_contacts_tma(DV d, pr_step_conf conf, unsigned start, unsigned n, unsig
     unsigned cls = 3u;
     if (dirty) {
         const uint4 ab = d.c_ab[id];
-        const unsigned ca = d.ch_count[ab.z], cb = d.ch_count[ab.w];
+        const unsigned ca = f2u(d.ch_pack[ab.z].z), cb = f2u(d.ch_pack[ab.w].z);
         cls = (flags & PR_CONTACT_SENSOR) ? 2u : (ca == 1u && cb == 1u) ? 0u : (ca == 1u || cb == 1u) ? 1u : 2u;
     }
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -656,7 +657,7 @@ k_update_contacts_tma(DV d, pr_step_conf conf, unsigned start, unsigned n, unsig
         const unsigned cg[2] = {ab.z, ab.w};
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            voff[k] = d.ch_voff[cg[k]]; cnt[k] = d.ch_count[cg[k]]; rad[k] = d.ch_radius[cg[k]];
+            { const float4 c = d.ch_pack[cg[k]]; voff[k] = f2u(c.y); cnt[k] = f2u(c.z); rad[k] = c.x; }
             if (cnt[k] >= 2u) need += 2u * tma_run_bytes(voff[k], cnt[k]); // vertices + normals
         }
     }
@@ -726,7 +727,7 @@ PR_KERNEL k_narrow_keys(DV d, unsigned nOrder, unsigned useMoved, unsigned* keys
         if (useMoved) dirty = dirty || (d.b_moved[ab.x] | d.b_moved[ab.y]) != 0u;
         unsigned key = 0xFFu; // not dirty: sorted to the end, skipped
         if (dirty) {
-            unsigned ca = d.ch_count[ab.z], cb = d.ch_count[ab.w];
+            unsigned ca = f2u(d.ch_pack[ab.z].z), cb = f2u(d.ch_pack[ab.w].z);
             ca = ca > 8u ? 8u : ca; cb = cb > 8u ? 8u : cb;
             if (flags & PR_CONTACT_SENSOR) key = 0xC0u;
             else if (ca == 1u && cb == 1u) key = 0u;
@@ -1823,7 +1824,7 @@ PR_D void build_constraint_rows(const DV& d, const RS& r, unsigned cid, unsigned
         const float4 mat = d.c_mat[cid];
         const float4 q0 = d.m0[cid], q1 = d.m1[cid], q2 = d.m2[cid];
         const uint4 q3 = d.m3[cid];
-        const float rA = d.ch_radius[ab.z], rB = d.ch_radius[ab.w];
+        const float rA = d.ch_pack[ab.z].x, rB = d.ch_pack[ab.w].x;
         const float4 pA = r.s_pos[sA], pB = r.s_pos[sB];
         const float4 vA = r.s_vel[sA], vB = r.s_vel[sB];
         const float4 mA = d.b_mass[ab.x], mB = d.b_mass[ab.y];

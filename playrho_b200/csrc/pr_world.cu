@@ -96,7 +96,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(adj_list, G_ADJ), A(toi_islBodies, G_ADJ), A(toi_islContacts, G_ADJ),
         A(jt, G_JOINT), A(jt_work, G_JOINT), A(nc_pairs, G_JOINT), A(isl_jflag, G_BODY),
         A(sh_mat, G_SHAPE), A(sh_filter, G_SHAPE), A(sh_group, G_SHAPE),
-        A(ch_radius, G_CHILD), A(ch_voff, G_CHILD), A(ch_count, G_CHILD), A(vtx, G_VERT), A(nrm, G_VERT),
+        A(ch_radius, G_CHILD), A(ch_voff, G_CHILD), A(ch_count, G_CHILD), A(ch_pack, G_CHILD), A(vtx, G_VERT), A(nrm, G_VERT),
         A(p_body, G_PROXY), A(p_shape, G_PROXY), A(p_child, G_PROXY), A(p_cg, G_PROXY), A(p_tree, G_PROXY), A(p_moved, G_PROXY),
         A(p_fat, G_PROXY), A(q_list, G_PROXY), A(bv_code, G_PROXY), A(bv_code2, G_PROXY), A(bv_idx, G_PROXY), A(bv_idx2, G_PROXY),
         A(bv_left, G_PROXY), A(bv_right, G_PROXY), A(bv_parent, G_PROXY), A(bv_lparent, G_PROXY), A(bv_visit, G_PROXY), A(bv_cbox, G_PROXY),
@@ -875,7 +875,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     w.hostCnt.toiRoundId = 0; w.hostCnt.toiReN[0] = w.hostCnt.toiReN[1] = 0; w.hostCnt.toiAtMaxLive = 0; w.hostCnt.toiForceFull = 0; w.hostCnt.toiHalt = TB_RUN;
     write_counters(w);
     const bool exact = (w.toiMode == 0u) || w.subStepping; // (sub-stepping = one TOI event per Step call, in the reference's order: :1779-1824)
-    unsigned rounds = 0, round = 0, toiBatches = 0;
+    unsigned rounds = 0, round = 0, toiBatches = 0, listRoundsUsed = 0;
     if (!w.toiPossible) { // no contact of this world can be a TOI candidate: SolveToi finds nothing (:1768) and its final UpdateContacts skips all
         w.stepComplete = true;
         if (w.toiAlphaDirty) { PR_LAUNCH(k_toi_finish_bodies, N, w.stream, d, N); w.toiAlphaDirty = false; }
@@ -965,6 +965,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             if (getenv("PR_TOI_DEBUG"))
                 std::fprintf(stderr, "toi batch: groups %u K %u rounds %u found %u halt %u | late: woken %u bigR %u bigC %u maxC %u maxR %u lateRounds %u candN %u listRoundEvents(base 1e5) %u listRounds %u\n", groups, K,
                              c.tbRounds, c.tbFound, c.toiHalt, c.lateWhy[0], c.lateWhy[1], c.lateWhy[2], c.lateWhy[3], c.lateWhy[4], c.lateWhy[5], c.toiCandN, c.lateWhy[6], c.lateWhy[7]);
+            listRoundsUsed = c.lateWhy[7]; // (list rounds of this step that had events)
             round = c.toiRoundId; // (the device opened this many rounds so far this step)
             w.nOrder = c.devOrder; w.nFree = c.devFree; w.poolSize = c.devPool;
             w.toiListBound += c.tbAdded; w.bvhRefits += c.tbRounds;
@@ -1026,7 +1027,8 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         if (w.subStepping) { w.stepComplete = false; w.toiAlphaDirty = true; break; }
     }
     w.toiRoundsHint = rounds;
-    if (toiBatches) w.toiGroupsHint = std::min(4u, std::max(1u, w.toiGroupsHint * toiBatches)); // (what one batch should have held)
+    // groups to enqueue next step = list rounds this step needed (a group beyond that is ~12 launches that find the halt flag set)
+    if (toiBatches) w.toiGroupsHint = std::min(4u, std::max(1u, listRoundsUsed));
     // final UpdateContacts (:1825-1827)
     read_counters(w);
     const unsigned movedToi = w.hostCnt.proxiesMoved;
@@ -1502,6 +1504,9 @@ int pr_create_shapes(pr_world* pw, uint32_t n, const pr_shape* shapes, const pr_
     h2d(w, w.d.sh_group + firstShape, grp.data(), n * 4);
     h2d(w, w.d.ch_radius + w.nChildren, rad.data(), n_children * 4); h2d(w, w.d.ch_voff + w.nChildren, voff.data(), n_children * 4);
     h2d(w, w.d.ch_count + w.nChildren, cnt.data(), n_children * 4);
+    std::vector<float4> pack(n_children);
+    for (uint32_t i = 0; i < n_children; ++i) pack[i] = make_float4(rad[i], u2f(voff[i]), u2f(cnt[i]), 0.0f);
+    h2d(w, w.d.ch_pack + w.nChildren, pack.data(), n_children * sizeof(float4));
     h2d(w, w.d.vtx + w.nVerts, vertices, n_vertices * sizeof(pr_vec2)); h2d(w, w.d.nrm + w.nVerts, normals, n_vertices * sizeof(pr_vec2));
     sync(w);
     if (first_id) *first_id = firstShape;
@@ -1874,6 +1879,9 @@ int pr_set_shape(pr_world* pw, uint32_t shape, const pr_shape* def, const pr_chi
         }
         h2d(w, w.d.ch_radius + w.nChildren, rad.data(), def->child_count * 4u); h2d(w, w.d.ch_voff + w.nChildren, voff.data(), def->child_count * 4u);
         h2d(w, w.d.ch_count + w.nChildren, cnt.data(), def->child_count * 4u);
+        std::vector<float4> pack(def->child_count);
+        for (uint32_t i = 0; i < def->child_count; ++i) pack[i] = make_float4(rad[i], u2f(voff[i]), u2f(cnt[i]), 0.0f);
+        h2d(w, w.d.ch_pack + w.nChildren, pack.data(), def->child_count * sizeof(float4));
         h2d(w, w.d.vtx + w.nVerts, vertices, n_vertices * sizeof(pr_vec2)); h2d(w, w.d.nrm + w.nVerts, normals, n_vertices * sizeof(pr_vec2));
         cur.child_offset = w.nChildren; cur.child_count = def->child_count;
         w.nChildren += def->child_count; w.nVerts += n_vertices;

@@ -106,7 +106,7 @@ struct DV {
     unsigned* isl_nstat; unsigned long long* is_keys; unsigned is_mask;
     // shapes / children / vertices
     float4* sh_mat; unsigned* sh_filter; int* sh_group;
-    float* ch_radius; unsigned *ch_voff, *ch_count; float2 *vtx, *nrm;
+    float* ch_radius; unsigned *ch_voff, *ch_count; float4* ch_pack; float2 *vtx, *nrm; // ch_pack: (radius, offset, count) per child, one gather
     // proxies
     unsigned *p_body, *p_shape, *p_child, *p_cg, *p_tree, *p_moved; float4* p_fat; unsigned* q_list;
     // contacts
