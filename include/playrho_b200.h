@@ -385,8 +385,10 @@ int pr_shift_origin(pr_world* w, float x, float y);
  * and InternalDestroy :2249-2252 for a touching contact that is destroyed; post-solve: Report :196-206 after each regular
  * island :1671-1674 and each TOI island :2053-2055). A device step cannot call back into the host, so the kernels append
  * event records to device buffers instead and the host reads them after pr_step (pr_events); the CudaWorld shim then invokes
- * the stored listeners, in (kind, contact id) order. Pre-solve (:2716-2720) exists to let the host edit a contact before the
- * solve of the same step: that needs the synchronous callback and is not offered (PR_ERR_UNSUPPORTED when asked for).
+ * the stored listeners, in (kind, contact id) order. Pre-solve (:2716-2720) is recorded the same way -- the contact id and the
+ * manifold it had BEFORE the update, for every Update that left a non-sensor contact touching -- and delivered after the step:
+ * a listener can observe it, but what it does to the contact (the reference lets it disable the contact for the solve of the
+ * same step) takes effect from the next step on.
  * Nothing is recorded (and the kernels pay one uniform branch) until pr_set_event_mask asks for it. */
 enum { PR_EVENT_BEGIN = 1, PR_EVENT_END = 2, PR_EVENT_PRE_SOLVE = 4, PR_EVENT_POST_SOLVE = 8 };
 typedef struct pr_contact_event { /* begin / end: the contact as the listener would have seen it through GetContact */
@@ -403,11 +405,17 @@ typedef struct pr_impulse_event { /* post-solve: (ContactID, ContactImpulsesList
     uint32_t phase;                     /* 0 regular phase, 1 TOI phase */
     float normal[2], tangent[2];
 } pr_impulse_event;
+typedef struct pr_presolve_event { /* pre-solve: (ContactID, const Manifold& oldManifold) */
+    uint32_t contact;
+    uint32_t pad;
+    pr_manifold old_manifold;
+} pr_presolve_event;
 /* mask: PR_EVENT_* bits to record from the next pr_step on (0 = off); capacity: records kept per step and kind group
- * (begin+end share one buffer, post-solve has its own); further events of a step are counted but dropped. */
+ * (begin+end share one buffer, post-solve and pre-solve have their own); further events of a step are counted but dropped. */
 int pr_set_event_mask(pr_world* w, uint32_t mask, uint32_t capacity);
 /* Events of the LAST pr_step. kind = PR_EVENT_BEGIN | PR_EVENT_END (either or both): buf = pr_contact_event[cap];
- * kind = PR_EVENT_POST_SOLVE: buf = pr_impulse_event[cap]. Sorted by (kind, contact id) resp. (phase, contact id); *n_out =
+ * kind = PR_EVENT_POST_SOLVE: buf = pr_impulse_event[cap]; kind = PR_EVENT_PRE_SOLVE: buf = pr_presolve_event[cap] (a contact updated
+ * in the regular phase and again in the TOI phase has a record for each). Sorted by (kind, contact id) resp. (phase, contact id); *n_out =
  * matching events (at most cap are written). If the step produced more events than the capacity given to pr_set_event_mask
  * it dropped the rest: PR_ERR_LENGTH, and *n_out = the number the step produced (begin+end together, or post-solve). */
 int pr_events(const pr_world* w, uint32_t kind, void* buf, uint32_t cap, uint32_t* n_out);

@@ -36,6 +36,7 @@ struct RefWorld {
     std::string error;
     std::vector<pr_contact_event> evContact; // begin/end listener calls of the last ref_step, call order
     std::vector<pr_impulse_event> evImpulse; // post-solve listener calls of the last ref_step, call order
+    std::vector<pr_presolve_event> evPre;    // pre-solve listener calls of the last ref_step, call order
     bool inToiPhase = false;
     explicit RefWorld(const WorldConf& c) : world{c} {}
 };
@@ -567,6 +568,15 @@ int ref_set_event_mask(void* h, uint32_t mask)
             rw->evImpulse.push_back(e);
         });
     else SetPostSolveContactListener(rw->world, {});
+    if (mask & PR_EVENT_PRE_SOLVE)
+        SetPreSolveContactListener(rw->world, [rw](ContactID id, const Manifold& oldManifold) {
+            pr_presolve_event e;
+            std::memset(&e, 0, sizeof(e));
+            e.contact = static_cast<uint32_t>(to_underlying(id));
+            FromManifold(oldManifold, e.old_manifold);
+            rw->evPre.push_back(e);
+        });
+    else SetPreSolveContactListener(rw->world, {});
     return 0;
     REF_CATCH(-1)
 }
@@ -574,7 +584,10 @@ int ref_set_event_mask(void* h, uint32_t mask)
 int ref_events(void* h, uint32_t kind, void* buf, uint32_t cap, uint32_t* n_out)
 {
     REF_TRY(h)
-    if (kind == PR_EVENT_POST_SOLVE) {
+    if (kind == PR_EVENT_PRE_SOLVE) {
+        *n_out = static_cast<uint32_t>(rw->evPre.size());
+        std::memcpy(buf, rw->evPre.data(), sizeof(pr_presolve_event) * std::min<size_t>(cap, rw->evPre.size()));
+    } else if (kind == PR_EVENT_POST_SOLVE) {
         *n_out = static_cast<uint32_t>(rw->evImpulse.size());
         std::memcpy(buf, rw->evImpulse.data(), sizeof(pr_impulse_event) * std::min<size_t>(cap, rw->evImpulse.size()));
     } else {
@@ -644,7 +657,7 @@ int ref_shift_origin(void* h, float x, float y)
 int ref_step(void* h, const pr_step_conf* conf, pr_step_stats* stats)
 {
     REF_TRY(h)
-    rw->evContact.clear(); rw->evImpulse.clear();
+    rw->evContact.clear(); rw->evImpulse.clear(); rw->evPre.clear();
     const auto s = Step(rw->world, ToStepConf(*conf));
     if (stats) FromStats(s, *stats);
     return 0;

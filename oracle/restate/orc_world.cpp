@@ -84,6 +84,7 @@ struct orc_world {
     uint32_t evMask = 0;                          // listeners installed (PR_EVENT_* bits)
     std::vector<pr_contact_event> evContact;      // begin/end listener calls of the last step, call order
     std::vector<pr_impulse_event> evImpulse;      // post-solve listener calls of the last step, call order
+    std::vector<pr_presolve_event> evPre;         // pre-solve listener calls of the last step, call order
     std::vector<char> islandedBodies, islandedContacts, islandedJoints;
     bool stepComplete = true;
     bool subStepping = false;
@@ -233,6 +234,11 @@ void update_contact(orc_world& w, uint32_t id, const pr_step_conf& conf)
     else if (oldTouching && !newTouching) c.flags &= ~uint32_t(PR_CONTACT_TOUCHING);
     if (!oldTouching && newTouching) record_contact_event(w, PR_EVENT_BEGIN, id);    // :2703-2708
     else if (oldTouching && !newTouching) record_contact_event(w, PR_EVENT_END, id); // :2709-2714
+    if (!(c.flags & PR_CONTACT_SENSOR) && newTouching && (w.evMask & PR_EVENT_PRE_SOLVE)) { // :2716-2720
+        pr_presolve_event e; std::memset(&e, 0, sizeof(e));
+        e.contact = id; e.old_manifold = oldM;
+        w.evPre.push_back(e);
+    }
 }
 
 // UpdateContacts, AabbTreeWorld.cpp:2333-2421
@@ -1493,7 +1499,10 @@ int orc_set_manifolds(orc_world* w, uint32_t n, const uint32_t* ids, const pr_ma
 int orc_set_event_mask(orc_world* w, uint32_t mask) { w->evMask = mask; return 0; }
 int orc_events(const orc_world* w, uint32_t kind, void* buf, uint32_t cap, uint32_t* n_out)
 { // call order (the order the reference's listeners are invoked in)
-    if (kind == PR_EVENT_POST_SOLVE) {
+    if (kind == PR_EVENT_PRE_SOLVE) {
+        *n_out = static_cast<uint32_t>(w->evPre.size());
+        std::memcpy(buf, w->evPre.data(), sizeof(pr_presolve_event) * std::min<size_t>(cap, w->evPre.size()));
+    } else if (kind == PR_EVENT_POST_SOLVE) {
         *n_out = static_cast<uint32_t>(w->evImpulse.size());
         std::memcpy(buf, w->evImpulse.data(), sizeof(pr_impulse_event) * std::min<size_t>(cap, w->evImpulse.size()));
     } else {
@@ -1550,7 +1559,7 @@ int orc_step(orc_world* w, const pr_step_conf* confp, pr_step_stats* stats_out, 
     std::memset(&stats, 0, sizeof(stats));
     stats.reg.min_separation = kInf;
     stats.toi.min_separation = kInf;
-    w->evContact.clear(); w->evImpulse.clear();
+    w->evContact.clear(); w->evImpulse.clear(); w->evPre.clear();
     for (const auto& bs : w->fixturesForProxies) stats.pre.proxies_created += create_proxies(*w, bs.first, bs.second, conf);
     w->fixturesForProxies.clear();
     for (uint32_t bodyId : w->bodiesForSync) {

@@ -108,6 +108,7 @@ def cf_unpack(cf):
 EVENT_BEGIN, EVENT_END, EVENT_PRE_SOLVE, EVENT_POST_SOLVE = 1, 2, 4, 8
 CONTACT_EVENT = np.dtype([(n, u4) for n in ("kind", "contact", "body_a", "shape_a", "child_a", "body_b", "shape_b", "child_b")])
 IMPULSE_EVENT = np.dtype([("contact", u4), ("count", u4), ("iterations", u4), ("phase", u4), ("normal", f4, (2,)), ("tangent", f4, (2,))])
+PRESOLVE_EVENT = np.dtype([("contact", u4), ("pad", u4), ("old_manifold", MANIFOLD)])
 
 # pr_ray_hit (pr_ray_cast)
 RAY_ALL, RAY_CLOSEST = 0, 1

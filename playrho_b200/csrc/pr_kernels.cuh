@@ -415,6 +415,21 @@ PR_D void emit_impulse_event(const DV& d, unsigned id, unsigned count, unsigned 
         d.ev_impulse[slot] = e;
     }
 }
+PR_D void emit_presolve_event(const DV& d, unsigned id)
+{ // preSolveContact(contactID, oldManifold), AabbTreeWorld.cpp:2716-2720: called BEFORE the new manifold is stored
+    const unsigned slot = atomicAdd(&d.cnt->nEvPre, 1u);
+    if (slot < d.ev_cap) {
+        const float4 a = d.m0[id], b = d.m1[id], c = d.m2[id];
+        const uint4 e = d.m3[id];
+        pr_presolve_event ev;
+        ev.contact = id; ev.pad = 0u;
+        ev.old_manifold.ln_x = a.x; ev.old_manifold.ln_y = a.y; ev.old_manifold.lp_x = a.z; ev.old_manifold.lp_y = a.w;
+        ev.old_manifold.p0_x = b.x; ev.old_manifold.p0_y = b.y; ev.old_manifold.p1_x = b.z; ev.old_manifold.p1_y = b.w;
+        ev.old_manifold.jn0 = c.x; ev.old_manifold.jt0 = c.y; ev.old_manifold.jn1 = c.z; ev.old_manifold.jt1 = c.w;
+        ev.old_manifold.cf0 = e.x; ev.old_manifold.cf1 = e.y; ev.old_manifold.type = e.z; ev.old_manifold.count = e.w;
+        d.ev_presolve[slot] = ev;
+    }
+}
 // keep[i] = 1 if the two FAT leaf boxes still overlap (AabbTreeWorld.cpp:2290-2304), else InternalDestroy (:2245)
 PR_KERNEL k_destroy_test(DV d, unsigned nOrder, unsigned* keep, unsigned hashLive)
 {
@@ -510,6 +525,7 @@ PR_D void update_contact_v(const DV& d, const pr_step_conf& conf, unsigned id, u
         }
         // an empty manifold over an empty manifold (3 of 4 contacts of a pile are fat-box overlaps only) is the same
         // 64 bytes again (mf_unset() == manifold_clear()): skip the stores
+        if ((d.ev_mask & PR_EVENT_PRE_SOLVE) && newTouching) emit_presolve_event(d, id); // (the old manifold is still in place)
         const bool sameEmpty = newCount == 0u && oldCount == 0u && o3.x == PR_CF_DEFAULT && o3.y == PR_CF_DEFAULT && o3.z == MF_UNSET;
         if (!sameEmpty) store_manifold(d, id, nm);
     }

@@ -1236,7 +1236,7 @@ int pr_destroy(pr_world* pw)
     DeviceGuard guard(w.device);
     delete static_cast<StageTimer*>(w.timer);
     for (const ArrDesc& a : arrays(w)) dev_free(*a.slot);
-    dev_free(w.d.ev_contact); dev_free(w.d.ev_impulse);
+    dev_free(w.d.ev_contact); dev_free(w.d.ev_impulse); dev_free(w.d.ev_presolve);
     dev_free(w.d.is_keys); dev_free(w.d.blk_off); dev_free(w.d.blk_rowOff); dev_free(w.d.blk_jOff); dev_free(w.d.toi_log); dev_free(w.d.cnt); dev_free(w.scanScratch); dev_free(w.rs.hist); dev_free(w.stageBuf[0]); dev_free(w.stageBuf[1]);
 #ifndef PR_HOST_EMUL
     if (w.stream) cudaStreamDestroy(w.stream);
@@ -2432,11 +2432,11 @@ int pr_set_event_mask(pr_world* pw, uint32_t mask, uint32_t capacity)
 {
     API_TRY(pw)
     World& w = pw->w;
-    if (mask & PR_EVENT_PRE_SOLVE) { w.error = "pre-solve needs a synchronous host callback inside Step: not offered by the device step"; return PR_ERR_UNSUPPORTED; }
-    if (mask & ~static_cast<uint32_t>(PR_EVENT_BEGIN | PR_EVENT_END | PR_EVENT_POST_SOLVE)) { w.error = "unknown event kind"; return PR_ERR_INVALID_ARGUMENT; }
+    if (mask & ~static_cast<uint32_t>(PR_EVENT_BEGIN | PR_EVENT_END | PR_EVENT_PRE_SOLVE | PR_EVENT_POST_SOLVE)) { w.error = "unknown event kind"; return PR_ERR_INVALID_ARGUMENT; }
     sync(w);
     if (mask && capacity > w.d.ev_cap) {
-        dev_free(w.d.ev_contact); dev_free(w.d.ev_impulse);
+        dev_free(w.d.ev_contact); dev_free(w.d.ev_impulse); dev_free(w.d.ev_presolve);
+        w.d.ev_presolve = static_cast<pr_presolve_event*>(dev_alloc(sizeof(pr_presolve_event) * capacity));
         w.d.ev_contact = static_cast<pr_contact_event*>(dev_alloc(sizeof(pr_contact_event) * capacity));
         w.d.ev_impulse = static_cast<pr_impulse_event*>(dev_alloc(sizeof(pr_impulse_event) * capacity));
         w.d.ev_cap = capacity;
@@ -2453,11 +2453,18 @@ int pr_events(const pr_world* cpw, uint32_t kind, void* buf, uint32_t cap, uint3
     API_TRY(pw)
     World& w = pw->w;
     const bool contactKinds = (kind & (PR_EVENT_BEGIN | PR_EVENT_END)) != 0 && !(kind & ~static_cast<uint32_t>(PR_EVENT_BEGIN | PR_EVENT_END));
-    if (!contactKinds && kind != PR_EVENT_POST_SOLVE) { w.error = "pr_events: kind must be begin|end or post-solve"; return PR_ERR_INVALID_ARGUMENT; }
+    if (!contactKinds && kind != PR_EVENT_POST_SOLVE && kind != PR_EVENT_PRE_SOLVE) { w.error = "pr_events: kind must be begin|end, pre-solve or post-solve"; return PR_ERR_INVALID_ARGUMENT; }
     read_counters(w);
-    const unsigned total = contactKinds ? w.hostCnt.nEvContact : w.hostCnt.nEvImpulse;
+    const unsigned total = contactKinds ? w.hostCnt.nEvContact : kind == PR_EVENT_PRE_SOLVE ? w.hostCnt.nEvPre : w.hostCnt.nEvImpulse;
     const unsigned have = std::min(total, w.d.ev_cap);
-    if (contactKinds) {
+    if (kind == PR_EVENT_PRE_SOLVE) {
+        std::vector<pr_presolve_event> ev(have);
+        if (have) d2h(w, ev.data(), w.d.ev_presolve, sizeof(pr_presolve_event) * have);
+        std::sort(ev.begin(), ev.end(), [](const pr_presolve_event& a, const pr_presolve_event& b) {
+            return a.contact != b.contact ? a.contact < b.contact : std::memcmp(&a.old_manifold, &b.old_manifold, sizeof(pr_manifold)) < 0; });
+        if (n_out) *n_out = static_cast<uint32_t>(ev.size());
+        if (buf && !ev.empty()) std::memcpy(buf, ev.data(), sizeof(pr_presolve_event) * std::min<size_t>(ev.size(), cap));
+    } else if (contactKinds) {
         std::vector<pr_contact_event> ev(have);
         if (have) d2h(w, ev.data(), w.d.ev_contact, sizeof(pr_contact_event) * have);
         ev.erase(std::remove_if(ev.begin(), ev.end(), [&](const pr_contact_event& e) { return !(e.kind & kind); }), ev.end());

@@ -71,7 +71,7 @@ struct Counters {
     unsigned blkMaxBodies, blkColors; // block solver (pr_block_solve.cuh): bodies of the largest world, colours in use this step
     unsigned nStaticTouch, islStatOverflow; // (island, non-speedable body) pairs: constraints/joints seen, set overflow (see island_count_static)
     unsigned boundsMinX, boundsMinY, boundsMaxX, boundsMaxY;
-    unsigned nEvContact, nEvImpulse; // contact events of this step (pr_events): begin/end records, post-solve records
+    unsigned nEvContact, nEvImpulse, nEvPre, evPad; // contact events of this step (pr_events): begin/end, post-solve, pre-solve records
     unsigned lateWhy[8]; // diagnostics (PR_TOI_DEBUG): hand-backs of k_tb_late by reason, list sizes seen, events per round
     unsigned colorStart[MAX_COLORS + 1];
     // batched TOI rounds (pr_toi_phase.cuh, k_tb_*): the host enqueues several rounds without reading anything back;
@@ -131,7 +131,7 @@ struct DV {
     unsigned *k_contact, *k_color, *k_sorted, *k_tmpKey, *k_tmpKey2, *k_tmpVal, *k_ulist;
     unsigned* c_color; // persistent colour per contact
     // contact events (pr_set_event_mask / pr_events): off unless ev_mask != 0
-    pr_contact_event* ev_contact; pr_impulse_event* ev_impulse; unsigned ev_mask, ev_cap;
+    pr_contact_event* ev_contact; pr_impulse_event* ev_impulse; pr_presolve_event* ev_presolve; unsigned ev_mask, ev_cap;
     // bvh
     unsigned *bv_code, *bv_code2, *bv_idx, *bv_idx2, *bv_left, *bv_right, *bv_parent, *bv_lparent, *bv_visit, *bv_leafOf;
     CBox* bv_cbox; // per internal node: the boxes of its two children (see k_bvh_refit)

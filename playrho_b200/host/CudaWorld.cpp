@@ -233,25 +233,30 @@ struct CudaWorld::Impl {
 
     void updateEventMask() noexcept
     {
-        const std::uint32_t mask = (beginContact ? PR_EVENT_BEGIN : 0u) | (endContact ? PR_EVENT_END : 0u) | (postSolve ? PR_EVENT_POST_SOLVE : 0u);
+        const std::uint32_t mask = (beginContact ? PR_EVENT_BEGIN : 0u) | (endContact ? PR_EVENT_END : 0u) | (preSolve ? PR_EVENT_PRE_SOLVE : 0u) |
+                                   (postSolve ? PR_EVENT_POST_SOLVE : 0u);
         if (h) pr_set_event_mask(h, mask, eventCap);
     }
-    // The listeners of the step that just ran, in (kind, contact id) order: all begin calls, all end calls, then post-solve.
-    // (The reference interleaves them inside Step; a listener here sees the world AFTER the step and may mutate it.)
+    // The listeners of the step that just ran, in (kind, contact id) order: all begin calls, all end calls, pre-solve, then post-solve.
+    // (The reference interleaves them inside Step; a listener here sees the world AFTER the step -- a pre-solve listener gets the
+    // contact id and the manifold the contact had before its update, like in the reference, but cannot change this step's solve.)
     void deliverEvents()
     {
-        if (!beginContact && !endContact && !postSolve) return;
+        if (!beginContact && !endContact && !postSolve && !preSolve) return;
         for (;;) { // a step that overflowed the buffers: grow them for the next step, deliver what was kept
             std::vector<pr_contact_event> ce(eventCap);
             std::vector<pr_impulse_event> ie(postSolve ? eventCap : 0u);
-            std::uint32_t nc = 0, ni = 0;
+            std::vector<pr_presolve_event> pe(preSolve ? eventCap : 0u);
+            std::uint32_t nc = 0, ni = 0, np = 0;
             int rc = PR_OK;
             if (beginContact || endContact) rc = pr_events(h, PR_EVENT_BEGIN | PR_EVENT_END, ce.data(), eventCap, &nc);
             int rc2 = PR_OK;
             if (postSolve) rc2 = pr_events(h, PR_EVENT_POST_SOLVE, ie.data(), eventCap, &ni);
-            const bool overflow = rc == PR_ERR_LENGTH || rc2 == PR_ERR_LENGTH;
-            if (!overflow) { check(rc, "pr_events"); check(rc2, "pr_events"); }
-            const std::uint32_t keptC = std::min(nc, eventCap), keptI = std::min(ni, eventCap);
+            int rc3 = PR_OK;
+            if (preSolve) rc3 = pr_events(h, PR_EVENT_PRE_SOLVE, pe.data(), eventCap, &np);
+            const bool overflow = rc == PR_ERR_LENGTH || rc2 == PR_ERR_LENGTH || rc3 == PR_ERR_LENGTH;
+            if (!overflow) { check(rc, "pr_events"); check(rc2, "pr_events"); check(rc3, "pr_events"); }
+            const std::uint32_t keptC = std::min(nc, eventCap), keptI = std::min(ni, eventCap), keptP = std::min(np, eventCap);
             // like inside the reference's Step, the world is locked while listeners run: mutators throw WrongState (:2156)
             struct Lock { bool& f; explicit Lock(bool& b) : f(b) { f = true; } ~Lock() { f = false; } } lock{locked};
             for (std::uint32_t i = 0; i < keptC; ++i) {
@@ -259,14 +264,15 @@ struct CudaWorld::Impl {
                 if (ce[i].kind == PR_EVENT_BEGIN) { if (beginContact) beginContact(id); }
                 else if (endContact) endContact(id);
             }
+            for (std::uint32_t i = 0; i < keptP; ++i) preSolve(MakeId<ContactID>(pe[i].contact), ToManifold(pe[i].old_manifold));
             for (std::uint32_t i = 0; i < keptI; ++i) {
                 ContactImpulsesList imp;
                 for (std::uint32_t j = 0; j < ie[i].count && j < 2u; ++j) imp.AddEntry(Momentum{ie[i].normal[j] * NewtonSecond}, Momentum{ie[i].tangent[j] * NewtonSecond});
                 postSolve(MakeId<ContactID>(ie[i].contact), imp, static_cast<unsigned>(ie[i].iterations));
             }
             if (overflow) { // the step is applied and its kept events are delivered: count what was dropped, hold more from now on
-                droppedEvents += (nc > keptC ? nc - keptC : 0u) + (ni > keptI ? ni - keptI : 0u);
-                eventCap = std::max(nc, ni) * 2u;
+                droppedEvents += (nc > keptC ? nc - keptC : 0u) + (ni > keptI ? ni - keptI : 0u) + (np > keptP ? np - keptP : 0u);
+                eventCap = std::max(std::max(nc, ni), np) * 2u;
                 updateEventMask();
             }
             return;
@@ -393,9 +399,9 @@ void SetDetachListener(CudaWorld& w, BodyShapeFunction l) noexcept { w.m->detach
 void SetJointDestructionListener(CudaWorld& w, JointFunction l) noexcept { w.m->jointDestruction = std::move(l); }
 void SetBeginContactListener(CudaWorld& w, ContactFunction l) noexcept { w.m->beginContact = std::move(l); w.m->updateEventMask(); }
 void SetEndContactListener(CudaWorld& w, ContactFunction l) noexcept { w.m->endContact = std::move(l); w.m->updateEventMask(); }
-// pre-solve: stored, never invoked -- it exists to edit a contact before the same step's solve, which needs a synchronous host
-// callback inside the device step (include/playrho_b200.h, "contact events")
-void SetPreSolveContactListener(CudaWorld& w, ContactManifoldFunction l) noexcept { w.m->preSolve = std::move(l); }
+// pre-solve: recorded on the device like the others and delivered after the step (contact id + the manifold before the update);
+// what the listener does to the contact takes effect from the next step on (include/playrho_b200.h, "contact events")
+void SetPreSolveContactListener(CudaWorld& w, ContactManifoldFunction l) noexcept { w.m->preSolve = std::move(l); w.m->updateEventMask(); }
 void SetPostSolveContactListener(CudaWorld& w, ContactImpulsesFunction l) noexcept { w.m->postSolve = std::move(l); w.m->updateEventMask(); }
 
 // ---- miscellaneous

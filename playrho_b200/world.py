@@ -398,8 +398,8 @@ class World:
         self._ev_cap = capacity
 
     def events(self, kind):
-        """Events of the last step (pr_events): abi.CONTACT_EVENT rows for begin/end, abi.IMPULSE_EVENT rows for post-solve."""
-        dt = abi.IMPULSE_EVENT if kind == abi.EVENT_POST_SOLVE else abi.CONTACT_EVENT
+        """Events of the last step (pr_events): abi.CONTACT_EVENT rows for begin/end, abi.IMPULSE_EVENT for post-solve, abi.PRESOLVE_EVENT for pre-solve."""
+        dt = abi.IMPULSE_EVENT if kind == abi.EVENT_POST_SOLVE else abi.PRESOLVE_EVENT if kind == abi.EVENT_PRE_SOLVE else abi.CONTACT_EVENT
         cap = getattr(self, "_ev_cap", 0)
         out = np.zeros(max(1, cap), dt)
         k = u32(0)

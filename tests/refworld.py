@@ -282,7 +282,7 @@ class RefWorld:
 
     def events(self, kind, cap=1 << 18):
         self.lib.ref_events.argtypes = [vp, u32, vp, u32, vp]
-        out = np.zeros(cap, abi.IMPULSE_EVENT if kind == abi.EVENT_POST_SOLVE else abi.CONTACT_EVENT)
+        out = np.zeros(cap, abi.IMPULSE_EVENT if kind == abi.EVENT_POST_SOLVE else abi.PRESOLVE_EVENT if kind == abi.EVENT_PRE_SOLVE else abi.CONTACT_EVENT)
         k = C.c_uint32(0)
         self._chk(self.lib.ref_events(self.h, kind, abi.ptr(out), cap, C.byref(k)))
         assert k.value <= cap
@@ -511,7 +511,7 @@ class OracleWorld:
     def events(self, kind, cap=1 << 18):
         """Listener calls of the last step in the reference's call order."""
         self.lib.orc_events.argtypes = [vp, u32, vp, u32, vp]
-        out = np.zeros(cap, abi.IMPULSE_EVENT if kind == abi.EVENT_POST_SOLVE else abi.CONTACT_EVENT)
+        out = np.zeros(cap, abi.IMPULSE_EVENT if kind == abi.EVENT_POST_SOLVE else abi.PRESOLVE_EVENT if kind == abi.EVENT_PRE_SOLVE else abi.CONTACT_EVENT)
         k = C.c_uint32(0)
         self.lib.orc_events(self.h, kind, abi.ptr(out), cap, C.byref(k))
         assert k.value <= cap

@@ -1,4 +1,4 @@
-"""Contact events (pr_events: begin / end / post-solve) and ShiftOrigin (pr_shift_origin).
+"""Contact events (pr_events: begin / end / pre-solve / post-solve) and ShiftOrigin (pr_shift_origin).
 
 Three links, like the rest of the suite:
   1. the REAL reference with its own listeners installed (oracle/ref_harness.cpp: SetBeginContactListener,
@@ -18,11 +18,18 @@ from common import need_ref, need_oracle, need_emul, emul_lib, assert_bits
 from playrho_b200 import abi
 from playrho_b200 import world as W
 
-ALL = abi.EVENT_BEGIN | abi.EVENT_END | abi.EVENT_POST_SOLVE
+ALL = abi.EVENT_BEGIN | abi.EVENT_END | abi.EVENT_PRE_SOLVE | abi.EVENT_POST_SOLVE
 
 
 def _sorted_contact_events(ev):
     return ev[np.lexsort((ev["contact"], ev["kind"]))]
+
+
+def _sorted_presolve_events(ev):
+    if not len(ev):
+        return ev
+    raw = np.ascontiguousarray(ev).view(np.uint32).reshape(len(ev), -1).astype(np.uint64)
+    return ev[np.lexsort(tuple(raw[:, k] for k in range(raw.shape[1] - 1, -1, -1)))]
 
 
 def _sorted_impulse_events(ev):
@@ -50,10 +57,13 @@ def test_restatement_listener_calls_equal_reference(name, steps):
         toi_reports += int((oi["phase"] == 1).sum())
         oi = oi.copy(); oi["phase"] = 0xFFFFFFFF  # a listener cannot see the phase; the harness stores ~0
         assert_bits(ri, oi, "%s step %d post-solve" % (name, s))
+        rp_, op_ = ref.events(abi.EVENT_PRE_SOLVE), orc.events(abi.EVENT_PRE_SOLVE)  # (contact, old manifold), call order
+        assert_bits(rp_, op_, "%s step %d pre-solve" % (name, s))
+        seen[abi.EVENT_PRE_SOLVE] = seen.get(abi.EVENT_PRE_SOLVE, 0) + len(rp_)
         seen[abi.EVENT_BEGIN] += len(ref.events(abi.EVENT_BEGIN))
         seen[abi.EVENT_END] += len(ref.events(abi.EVENT_END))
         seen[abi.EVENT_POST_SOLVE] += len(ri)
-    assert seen[abi.EVENT_BEGIN] > 0 and seen[abi.EVENT_POST_SOLVE] > 0
+    assert seen[abi.EVENT_BEGIN] > 0 and seen[abi.EVENT_POST_SOLVE] > 0 and seen[abi.EVENT_PRE_SOLVE] > 0
     if name in ("disks100", "mixed100", "shooter"):
         assert seen[abi.EVENT_END] > 0
     if name == "shooter":
@@ -114,6 +124,10 @@ def run_events_vs_oracle(sc, steps, lib=None, device=-1, shift_at=()):
         gi = _sorted_impulse_events(gw.events(abi.EVENT_POST_SOLVE))
         oi = _sorted_impulse_events(orc.events(abi.EVENT_POST_SOLVE))
         assert_bits(gi, oi, "step %d post-solve events" % s)
+        gp_ = _sorted_presolve_events(gw.events(abi.EVENT_PRE_SOLVE))
+        op_ = _sorted_presolve_events(orc.events(abi.EVENT_PRE_SOLVE))
+        assert_bits(gp_, op_, "step %d pre-solve events" % s)
+        n["pre"] = n.get("pre", 0) + len(op_)
         n[abi.EVENT_BEGIN] += int((oe["kind"] == abi.EVENT_BEGIN).sum()); n[abi.EVENT_END] += int((oe["kind"] == abi.EVENT_END).sum())
         n[abi.EVENT_POST_SOLVE] += len(oi); n["toi"] += int((oi["phase"] == 1).sum())
     return n
@@ -127,7 +141,7 @@ def run_events_vs_oracle(sc, steps, lib=None, device=-1, shift_at=()):
 ])
 def test_emulated_events_equal_oracle(name, builder, steps):
     n = run_events_vs_oracle(builder(), steps, lib=emul_lib())
-    assert n[abi.EVENT_BEGIN] > 0 and n[abi.EVENT_END] > 0 and n[abi.EVENT_POST_SOLVE] > 0
+    assert n[abi.EVENT_BEGIN] > 0 and n[abi.EVENT_END] > 0 and n[abi.EVENT_POST_SOLVE] > 0 and n["pre"] > 0
 
 
 @need_oracle
@@ -150,7 +164,6 @@ def test_emulated_shift_origin_equals_oracle():
 def test_event_mask_errors_and_overflow():
     sc = scenes_np.disks_box(64, seed=7)
     gw = W.World(sc, lib=emul_lib())
-    assert gw.lib.pr_set_event_mask(gw.h, abi.EVENT_PRE_SOLVE, 16) == -6   # PR_ERR_UNSUPPORTED: needs a synchronous callback
     assert gw.lib.pr_set_event_mask(gw.h, 64, 16) == -1                     # PR_ERR_INVALID_ARGUMENT
     conf = refworld.default_step_conf()
     gw.step(conf)
