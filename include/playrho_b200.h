@@ -105,6 +105,25 @@ typedef struct pr_revolute_joint {
     uint32_t limit_state;
 } pr_revolute_joint;
 
+/* Joint rows share one table (JointIDs are one id space in the reference): every row has pr_revolute_joint's size and leading
+ * fields, and bits 8..15 of collide_connected say which joint type it is (bit 0 is the flag itself). */
+enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1 };
+#define PR_JOINT_TYPE(row) (((row).collide_connected >> 8) & 0xFFu)
+/* DistanceJointConf (Library/include/playrho/d2/DistanceJointConf.hpp): rod or spring between two anchor points.
+ * Solver: Library/source/playrho/d2/DistanceJointConf.cpp:81-246 (InitVelocity, SolveVelocity, SolvePosition). */
+typedef struct pr_distance_joint {
+    uint32_t body_a, body_b;
+    uint32_t collide_connected;          /* bit 0: collideConnected; bits 8..15: PR_JOINT_DISTANCE */
+    pr_vec2 local_anchor_a, local_anchor_b;
+    float impulse;                       /* accumulated impulse (warm start) */
+    float reserved0[3];
+    float length;                        /* rest length */
+    uint32_t reserved1[2];
+    float frequency, damping_ratio;      /* frequency 0: rigid rod (position-corrected); > 0: soft spring */
+    float reserved2[2];
+    uint32_t reserved3;
+} pr_distance_joint;
+
 /* ContactFeature packed little-endian: typeA | indexA<<8 | typeB<<16 | indexB<<24 */
 typedef uint32_t pr_contact_feature;
 
@@ -235,6 +254,10 @@ int pr_create_bodies(pr_world* w, uint32_t n, const pr_body* bodies, const uint3
                      const uint32_t* shape_ids, uint32_t* first_id);
 int pr_create_revolute_joints(pr_world* w, uint32_t n, const pr_revolute_joint* joints,
                               uint32_t* first_id);
+/* CreateJoint for DistanceJointConf values (the type tag is set by the call). Ids come from the same pool as the revolute
+ * joints'; pr_get_revolute_joints / pr_set_revolute_joints / pr_destroy_joints work on any row of the table (read a row's
+ * type with PR_JOINT_TYPE and view it as the matching struct). */
+int pr_create_distance_joints(pr_world* w, uint32_t n, const pr_distance_joint* joints, uint32_t* first_id);
 
 /* SetShape(AabbTreeWorld&, ShapeID, Shape) (AabbTreeWorld.cpp:1284-1356) for a value whose geometry (children) and filter are
  * what they were: friction, restitution, density and the sensor flag are replaced; every body using the shape is woken

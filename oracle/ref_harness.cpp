@@ -394,7 +394,17 @@ uint32_t ref_add_revolute(void* h, uint32_t bodyA, uint32_t bodyB, float ax, flo
     REF_CATCH(PR_INVALID_ID)
 }
 
-// every joint as a pr_revolute_joint (only revolute joints exist in the scenes built through this harness)
+// every joint as a row of the joint table (revolute and distance joints: PR_JOINT_TYPE says which)
+// CreateJoint(world, GetDistanceJointConf(world, bodyA, bodyB, anchorA, anchorB)) with frequency / damping ratio put in
+uint32_t ref_add_distance(void* h, uint32_t bodyA, uint32_t bodyB, float ax, float ay, float bx, float by, float frequency, float dampingRatio,
+                          int collideConnected)
+{
+    REF_TRY(h)
+    auto jc = GetDistanceJointConf(rw->world, MakeId<BodyID>(bodyA), MakeId<BodyID>(bodyB), Length2{ax * 1_m, ay * 1_m}, Length2{bx * 1_m, by * 1_m});
+    jc.frequency = frequency * 1_Hz; jc.dampingRatio = dampingRatio; jc.collideConnected = collideConnected != 0;
+    return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
+    REF_CATCH(0xFFFFFFFFu)
+}
 int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
 {
     REF_TRY(h)
@@ -404,7 +414,17 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
         auto& o = out[i];
         std::memset(&o, 0, sizeof(o));
         if (std::find(live.begin(), live.end(), MakeId<JointID>(i)) == live.end()) { o.body_a = o.body_b = 0xFFFFFFFFu; continue; } // destroyed
-        const auto jc = TypeCast<RevoluteJointConf>(GetJoint(rw->world, MakeId<JointID>(i)));
+        const auto joint = GetJoint(rw->world, MakeId<JointID>(i));
+        if (GetType(joint) == GetTypeID<DistanceJointConf>()) { // the same row, viewed as pr_distance_joint
+            const auto dc = TypeCast<DistanceJointConf>(joint);
+            o.body_a = to_underlying(dc.bodyA); o.body_b = to_underlying(dc.bodyB);
+            o.collide_connected = (dc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_DISTANCE) << 8);
+            o.local_anchor_a = pr_vec2{GetX(dc.localAnchorA), GetY(dc.localAnchorA)};
+            o.local_anchor_b = pr_vec2{GetX(dc.localAnchorB), GetY(dc.localAnchorB)};
+            o.impulse_x = dc.impulse; o.reference_angle = dc.length; o.lower_angle = dc.frequency; o.upper_angle = dc.dampingRatio;
+            continue;
+        }
+        const auto jc = TypeCast<RevoluteJointConf>(joint);
         o.body_a = to_underlying(jc.bodyA); o.body_b = to_underlying(jc.bodyB);
         o.collide_connected = jc.collideConnected ? 1u : 0u;
         o.local_anchor_a = pr_vec2{GetX(jc.localAnchorA), GetY(jc.localAnchorA)};

@@ -518,6 +518,108 @@ bool revolute_solve_position(const pr_revolute_joint& j, float imA, float iiA, V
     pA = posA; pB = posB;
     return (positionError <= square(c.linearSlop)) && (angularError <= c.angularSlop);
 }
+
+// ---------------- DistanceJointConf.cpp:81-246 ----------------
+namespace {
+// UnitVec::Get(x, y) with the magnitude, UnitVec.hpp:176-232 (default fallback: the zero vector)
+Rot unit_vector_mag(V2 v, float& mag)
+{
+    const float x = v.x, y = v.y;
+    const float ms = x * x + y * y;
+    if (std::isnormal(ms)) { mag = std::sqrt(ms); const float inv = 1.0f / mag; return Rot{x * inv, y * inv}; }
+    mag = std::hypot(x, y);
+    if (!std::isnormal(mag)) { mag = 0.0f; return Rot{0.0f, 0.0f}; }
+    return Rot{x / mag, y / mag};
+}
+void distance_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
+                            float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
+{
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    wk.rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    wk.rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    const V2 delta = (posB.l + wk.rB) - (posA.l + wk.rA);
+    float length;
+    const Rot u = unit_vector_mag(delta, length);
+    const V2 uv{u.c, u.s};
+    const float crAu = cross(wk.rA, uv) / 1.0f, crBu = cross(wk.rB, uv) / 1.0f;
+    const float invRotMassA = iiA * square(crAu), invRotMassB = iiB * square(crBu);
+    float invMass = imA + invRotMassA + imB + invRotMassB;
+    float mass = (invMass != 0.0f) ? 1.0f / invMass : 0.0f;
+    float invGamma = 0.0f, bias = 0.0f;
+    const float frequency = j.lower_angle, dampingRatio = j.upper_angle, restLength = j.reference_angle;
+    if (frequency > 0.0f) {
+        const float C = length - restLength;
+        const float omega = 2.0f * 3.14159265358979323846264338327950288f * frequency;
+        const float d = 2.0f * mass * dampingRatio * omega;
+        const float k = mass * square(omega);
+        const float h = c.dt;
+        const float gamma = h * (d + h * k);
+        invGamma = (gamma != 0.0f) ? 1.0f / gamma : 0.0f;
+        bias = C * h * k * invGamma;
+        invMass += invGamma;
+        mass = (invMass != 0.0f) ? 1.0f / invMass : 0.0f;
+    }
+    wk.mass[0] = u.c; wk.mass[1] = u.s; wk.mass[2] = invGamma; wk.mass[3] = bias; wk.mass[4] = mass;
+    if (c.warmStart) {
+        j.impulse_x *= c.dtRatio;
+        const V2 P = j.impulse_x * uv;
+        const float LA = cross(wk.rA, P) / 1.0f, LB = cross(wk.rB, P) / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    } else j.impulse_x = 0.0f;
+}
+bool distance_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& velA, float imB, float iiB, Vel& velB)
+{
+    const V2 uv{wk.mass[0], wk.mass[1]};
+    const V2 vpA = velA.l + rev_perp(wk.rA) * (velA.a / 1.0f);
+    const V2 vpB = velB.l + rev_perp(wk.rB) * (velB.a / 1.0f);
+    const float Cdot = dot(uv, vpB - vpA);
+    const float impulse = -wk.mass[4] * (Cdot + wk.mass[3] + wk.mass[2] * j.impulse_x);
+    j.impulse_x += impulse;
+    const V2 P = impulse * uv;
+    const float LA = cross(wk.rA, P) / 1.0f, LB = cross(wk.rB, P) / 1.0f;
+    velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+    velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    return impulse == 0.0f;
+}
+bool distance_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos& posA,
+                             float imB, float iiB, V2 lcB, Pos& posB, const JointSolverConf& c)
+{
+    if (j.lower_angle > 0.0f) return true; // soft constraint: no position correction
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    const V2 rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    const V2 rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    const V2 relLoc = (posB.l + rB) - (posA.l + rA);
+    float length;
+    const Rot u = unit_vector_mag(relLoc, length);
+    const V2 uv{u.c, u.s};
+    const float deltaLength = length - j.reference_angle;
+    const float C = std::clamp(deltaLength, -c.maxLinearCorrection, c.maxLinearCorrection);
+    const float impulse = -wk.mass[4] * C;
+    const V2 P = impulse * uv;
+    const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+    posA.l = posA.l - imA * P; posA.a -= iiA * LA;
+    posB.l = posB.l + imB * P; posB.a += iiB * LB;
+    return std::fabs(C) < c.linearSlop;
+}
+} // namespace
+void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
+                         float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
+{
+    if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) distance_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
+    else revolute_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
+}
+bool joint_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& velA, float imB, float iiB, Vel& velB, const JointSolverConf& c)
+{
+    if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) return distance_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB);
+    return revolute_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
+}
+bool joint_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos& posA,
+                          float imB, float iiB, V2 lcB, Pos& posB, const JointSolverConf& c)
+{
+    if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) return distance_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
+    return revolute_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
+}
 }
 
 #include "pr_oracle.h"

@@ -21,5 +21,13 @@ bool revolute_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, 
                              float imB, float iiB, Vel& velB, const JointSolverConf& c);
 bool revolute_solve_position(const pr_revolute_joint& j, float imA, float iiA, V2 lcA, Pos& posA,
                              float imB, float iiB, V2 lcB, Pos& posB, const JointSolverConf& c);
+// the joint table's rows carry their type (PR_JOINT_TYPE): these dispatch to the revolute or the distance joint
+// (DistanceJointConf.cpp:81-246; work: rA, rB, mass[0..1] = u, mass[2] = invGamma, mass[3] = bias, mass[4] = mass)
+void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
+                         float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c);
+bool joint_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& velA,
+                          float imB, float iiB, Vel& velB, const JointSolverConf& c);
+bool joint_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos& posA,
+                          float imB, float iiB, V2 lcB, Pos& posB, const JointSolverConf& c);
 } // namespace orc
 #endif

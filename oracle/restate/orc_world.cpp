@@ -281,7 +281,7 @@ bool joints_allow_collision(const orc_world& w, uint32_t a, uint32_t b)
     for (uint32_t j : w.bodies[a].joints) {
         const auto& jt = w.joints[j];
         const uint32_t other = (jt.body_a == a) ? jt.body_b : jt.body_a;
-        if (other == b && !jt.collide_connected) return false;
+        if (other == b && !(jt.collide_connected & 1u)) return false;
     }
     return true;
 }
@@ -932,7 +932,7 @@ IslandStats solve_reg_island(orc_world& w, const pr_step_conf& conf, const Islan
                             conf.max_linear_correction, conf.max_angular_correction};
     for (uint32_t j : island.joints) {
         auto& jt = w.joints[j];
-        orc::revolute_init_velocity(jt, w.jointWork[j], bcs[jt.body_a].invM, bcs[jt.body_a].invI, bcs[jt.body_a].lc, bcs[jt.body_a].pos, bcs[jt.body_a].vel,
+        orc::joint_init_velocity(jt, w.jointWork[j], bcs[jt.body_a].invM, bcs[jt.body_a].invI, bcs[jt.body_a].lc, bcs[jt.body_a].pos, bcs[jt.body_a].vel,
                                     bcs[jt.body_b].invM, bcs[jt.body_b].invI, bcs[jt.body_b].lc, bcs[jt.body_b].pos, bcs[jt.body_b].vel, jc);
     }
     results.velocityIters = conf.reg_velocity_iters;
@@ -940,7 +940,7 @@ IslandStats solve_reg_island(orc_world& w, const pr_step_conf& conf, const Islan
         bool jointsOkay = true;
         for (uint32_t j : island.joints) {
             auto& jt = w.joints[j];
-            jointsOkay &= orc::revolute_solve_velocity(jt, w.jointWork[j], bcs[jt.body_a].invM, bcs[jt.body_a].invI, bcs[jt.body_a].vel,
+            jointsOkay &= orc::joint_solve_velocity(jt, w.jointWork[j], bcs[jt.body_a].invM, bcs[jt.body_a].invI, bcs[jt.body_a].vel,
                                                        bcs[jt.body_b].invM, bcs[jt.body_b].invI, bcs[jt.body_b].vel, jc);
         }
         float newInc = 0;
@@ -967,7 +967,7 @@ IslandStats solve_reg_island(orc_world& w, const pr_step_conf& conf, const Islan
         bool jointsOkay = true;
         for (uint32_t j : island.joints) {
             auto& jt = w.joints[j];
-            jointsOkay &= orc::revolute_solve_position(jt, bcs[jt.body_a].invM, bcs[jt.body_a].invI, bcs[jt.body_a].lc, bcs[jt.body_a].pos,
+            jointsOkay &= orc::joint_solve_position(jt, w.jointWork[j], bcs[jt.body_a].invM, bcs[jt.body_a].invI, bcs[jt.body_a].lc, bcs[jt.body_a].pos,
                                                        bcs[jt.body_b].invM, bcs[jt.body_b].invI, bcs[jt.body_b].lc, bcs[jt.body_b].pos, jc);
         }
         if (contactsOkay && jointsOkay) { results.positionIters = i + 1; results.solved = true; break; }
@@ -1333,7 +1333,7 @@ int orc_set_revolute_joints(orc_world* w, uint32_t n, const uint32_t* ids, const
         const uint32_t id = ids[i];
         if (id >= w->joints.size()) { w->error = "no such joint"; return -2; }
         const pr_revolute_joint old = w->joints[id];
-        if (old.body_a != rows[i].body_a || old.body_b != rows[i].body_b || (old.collide_connected != 0) != (rows[i].collide_connected != 0)) { w->error = "unsupported"; return -6; }
+        if (old.body_a != rows[i].body_a || old.body_b != rows[i].body_b || (old.collide_connected & 1u) != (rows[i].collide_connected & 1u) || PR_JOINT_TYPE(old) != PR_JOINT_TYPE(rows[i])) { w->error = "unsupported"; return -6; }
         for (uint32_t b : {old.body_a, old.body_b}) {
             set_awake(w->bodies[b].b);
             auto& lst = w->bodies[b].joints;

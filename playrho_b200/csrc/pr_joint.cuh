@@ -1,4 +1,5 @@
-// pr_joint.cuh -- the revolute joint on the device: InitVelocity / SolveVelocity / SolvePosition
+// pr_joint.cuh -- joints on the device: the revolute joint and the distance joint (below):
+// InitVelocity / SolveVelocity / SolvePosition
 // of Library/source/playrho/d2/RevoluteJointConf.cpp:127-435 (GetMat33 :35-62, Solve33 / Solve22 Math.hpp:447-474),
 // one thread per joint. Joints run before the contact colours in every velocity iteration and after them in
 // every position iteration, exactly where SolveRegIslandViaGS calls them (AabbTreeWorld.cpp:1597-1644).
@@ -43,6 +44,22 @@ PR_D unsigned joint_island(const DV& d, const pr_revolute_joint& j)
     return INVALID;
 }
 
+PR_D unsigned joint_type(const pr_revolute_joint& j) { return (j.collide_connected >> 8) & 0xFFu; }
+// UnitVec::Get(x, y) with the magnitude (UnitVec.hpp:176-232, default fallback = the zero vector)
+PR_D Rot unit_vector_mag(float2 v, float& mag)
+{
+    const float x = v.x, y = v.y;
+    const float ms = x * x + y * y;
+    if (is_normal(ms)) {
+        mag = sqrtf(ms);
+        const float inv = 1.0f / mag;
+        return mkrot(x * inv, y * inv);
+    }
+    mag = hypotf(x, y);
+    if (!is_normal(mag)) { mag = 0.0f; return mkrot(0.0f, 0.0f); }
+    return mkrot(x / mag, y / mag);
+}
+
 // Where a joint's BodyConstraints and its island's flags live: the world's HBM arrays indexed by body id / island label
 // (jview_global), or a block's shared-memory arrays indexed by slot (pr_block_solve.cuh; slot[] maps a body id to its slot).
 // slotV / slotP / slotI: body id -> index into s_vel / s_pos / isl_state (nullptr: the id itself). isl_jflag is always the
@@ -55,12 +72,107 @@ PR_D JView jview_global(const DV& d)
 }
 PR_D unsigned jv_idx(const unsigned* slot, unsigned id) { return slot ? slot[id] : id; }
 
+// ---- DistanceJointConf.cpp:81-246. Row overlay (pr_distance_joint): impulse = impulse_x, length = reference_angle, frequency =
+// lower_angle, dampingRatio = upper_angle; work: rA, rB, m[0..1] = u, m[2] = invGamma, m[3] = bias, m[4] = mass
+PR_D void distance_init_velocity(const DV& d, unsigned ji, pr_revolute_joint j, JointWork wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 pA = v.s_pos[jv_idx(v.slotP, j.body_a)], pB = v.s_pos[jv_idx(v.slotP, j.body_b)];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
+    const Rot qA = rot_from_angle(pA.z), qB = rot_from_angle(pB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    wk.rAx = rA.x; wk.rAy = rA.y; wk.rBx = rB.x; wk.rBy = rB.y;
+    const float2 delta = (v2(pB.x, pB.y) + rB) - (v2(pA.x, pA.y) + rA);
+    float length;
+    const Rot u = unit_vector_mag(delta, length);
+    const float crAu = cross(rA, u) / 1.0f, crBu = cross(rB, u) / 1.0f;
+    const float invRotMassA = iiA * square(crAu), invRotMassB = iiB * square(crBu);
+    float invMass = imA + invRotMassA + imB + invRotMassB;
+    float mass = (invMass != 0.0f) ? 1.0f / invMass : 0.0f;
+    float invGamma = 0.0f, bias = 0.0f;
+    const float frequency = j.lower_angle, dampingRatio = j.upper_angle, restLength = j.reference_angle;
+    if (frequency > 0.0f) {
+        const float C = length - restLength;
+        const float omega = 2.0f * 3.14159265358979323846264338327950288f * frequency;
+        const float dd = 2.0f * mass * dampingRatio * omega;
+        const float k = mass * square(omega);
+        const float h = conf.delta_time;
+        const float gamma = h * (dd + h * k);
+        invGamma = (gamma != 0.0f) ? 1.0f / gamma : 0.0f;
+        bias = C * h * k * invGamma;
+        invMass += invGamma;
+        mass = (invMass != 0.0f) ? 1.0f / invMass : 0.0f;
+    }
+    wk.m[0] = u.c; wk.m[1] = u.s; wk.m[2] = invGamma; wk.m[3] = bias; wk.m[4] = mass;
+    if (conf.do_warm_start) {
+        j.impulse_x *= conf.dt_ratio;
+        const float2 P = j.impulse_x * u;
+        const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    } else j.impulse_x = 0.0f;
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    d.jt_work[ji] = wk;
+}
+PR_D void distance_solve_velocity(const DV& d, unsigned ji, pr_revolute_joint j, const JointWork& wk, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
+    const float2 rA = v2(wk.rAx, wk.rAy), rB = v2(wk.rBx, wk.rBy);
+    const Rot u = mkrot(wk.m[0], wk.m[1]);
+    const float2 vpA = v2(velA.x, velA.y) + rev_perp(rA) * (velA.z / 1.0f);
+    const float2 vpB = v2(velB.x, velB.y) + rev_perp(rB) * (velB.z / 1.0f);
+    const float Cdot = dot(u, vpB - vpA);
+    const float impulse = -wk.m[4] * (Cdot + wk.m[3] + wk.m[2] * j.impulse_x);
+    j.impulse_x += impulse;
+    const float2 P = impulse * u;
+    const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+    const float2 la = v2(velA.x, velA.y) - mA.x * P; velA.x = la.x; velA.y = la.y; velA.z -= mA.y * LA;
+    const float2 lb = v2(velB.x, velB.y) + mB.x * P; velB.x = lb.x; velB.y = lb.y; velB.z += mB.y * LB;
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    if (!(impulse == 0.0f)) v.isl_jflag[wk.island] = 1u; // (:190: solved when the impulse is zero)
+}
+PR_D void distance_solve_position(const DV& d, const pr_revolute_joint& j, const JointWork& wk, const pr_step_conf& conf, const JView& v)
+{
+    if (j.lower_angle > 0.0f) return; // no position correction for soft distance constraints (:203-206)
+    const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    float4 posA = v.s_pos[ia], posB = v.s_pos[ib];
+    const Rot qA = rot_from_angle(posA.z), qB = rot_from_angle(posB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    const float2 relLoc = (v2(posB.x, posB.y) + rB) - (v2(posA.x, posA.y) + rA);
+    float length;
+    const Rot u = unit_vector_mag(relLoc, length);
+    const float deltaLength = length - j.reference_angle;
+    const float C = stdclamp(deltaLength, -conf.max_linear_correction, conf.max_linear_correction);
+    const float impulse = -wk.m[4] * C;
+    const float2 P = impulse * u;
+    const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+    const float2 la = v2(posA.x, posA.y) - mA.x * P; posA.x = la.x; posA.y = la.y; posA.z -= mA.y * LA;
+    const float2 lb = v2(posB.x, posB.y) + mB.x * P; posB.x = lb.x; posB.y = lb.y; posB.z += mB.y * LB;
+    v.s_pos[ia] = posA; v.s_pos[ib] = posB;
+    if (!(fabsf(C) < conf.linear_slop)) v.isl_jflag[wk.island] = 1u;
+}
+
 PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf, const JView& v)
 {
     pr_revolute_joint j = d.jt[ji];
     JointWork wk;
     wk.island = joint_island(d, j);
     if (wk.island == INVALID) { d.jt_work[ji] = wk; return; }
+    if (joint_type(j) == PR_JOINT_DISTANCE) {
+        if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
+        if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
+        distance_init_velocity(d, ji, j, wk, conf, v);
+        return;
+    }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
     // AddJointsToIsland (:1443-1466) puts the other body on the island's stack whatever its type: a body that cannot move is
     // the island's guest (maxIslandBodies, see island_count_static)
@@ -123,6 +235,7 @@ PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& con
     if (wk.island == INVALID) return;
     if (v.isl_state[jv_idx(v.slotI, wk.island)] & ISL_VEL_DONE) return;
     pr_revolute_joint j = d.jt[ji];
+    if (joint_type(j) == PR_JOINT_DISTANCE) { distance_solve_velocity(d, ji, j, wk, v); return; }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
@@ -185,6 +298,7 @@ PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& con
     if (wk.island == INVALID) return;
     if (v.isl_state[jv_idx(v.slotI, wk.island)] & ISL_POS_SOLVED) return;
     const pr_revolute_joint j = d.jt[ji];
+    if (joint_type(j) == PR_JOINT_DISTANCE) { distance_solve_position(d, j, wk, conf, v); return; }
     const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;

@@ -1607,7 +1607,7 @@ static void refresh_joint_tables(World& w)
     for (const auto& j : w.joints) {
         if (j.body_a == INVALID) continue;
         ++uses[j.body_a]; ++uses[j.body_b];
-        if (!j.collide_connected) nc.push_back((static_cast<unsigned long long>(std::min(j.body_a, j.body_b)) << 32) | std::max(j.body_a, j.body_b));
+        if (!(j.collide_connected & 1u)) nc.push_back((static_cast<unsigned long long>(std::min(j.body_a, j.body_b)) << 32) | std::max(j.body_a, j.body_b));
     }
     w.jointsSerial = false;
     for (const auto& u : uses) if (u.second > 1u) w.jointsSerial = true;
@@ -1947,6 +1947,19 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
     API_CATCH(pw)
 }
 
+int pr_create_distance_joints(pr_world* pw, uint32_t n, const pr_distance_joint* joints, uint32_t* first_id)
+{ // CreateJoint for DistanceJointConf values: rows of the one joint table, tagged
+    static_assert(sizeof(pr_distance_joint) == sizeof(pr_revolute_joint), "joint rows share one table");
+    std::vector<pr_revolute_joint> rows(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        std::memcpy(&rows[i], &joints[i], sizeof(pr_revolute_joint));
+        rows[i].collide_connected = (joints[i].collide_connected & 1u) | (static_cast<uint32_t>(PR_JOINT_DISTANCE) << 8);
+        rows[i].impulse_y = rows[i].impulse_z = rows[i].angular_motor_impulse = 0.0f;
+        rows[i].enable_limit = rows[i].enable_motor = 0u; rows[i].motor_speed = rows[i].max_motor_torque = 0.0f; rows[i].limit_state = 0u;
+    }
+    return pr_create_revolute_joints(pw, n, rows.data(), first_id);
+}
+
 int pr_destroy_joints(pr_world* pw, uint32_t n, const uint32_t* ids)
 { // Destroy(AabbTreeWorld&, JointID), :1215-1227: Remove(id) wakes both bodies (:1192-1205), the id goes to the free list
     API_TRY(pw)
@@ -1985,7 +1998,7 @@ int pr_set_revolute_joints(pr_world* pw, uint32_t n, const uint32_t* ids, const 
         if (ids[i] >= w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
         const pr_revolute_joint& cur = w.joints[ids[i]];
         if (cur.body_a == INVALID) { w.error = "joint identifier is destroyed"; return PR_ERR_INVALID_ARGUMENT; }
-        if (cur.body_a != rows[i].body_a || cur.body_b != rows[i].body_b || (cur.collide_connected != 0u) != (rows[i].collide_connected != 0u)) {
+        if (cur.body_a != rows[i].body_a || cur.body_b != rows[i].body_b || ((cur.collide_connected & 1u) != (rows[i].collide_connected & 1u) || PR_JOINT_TYPE(cur) != PR_JOINT_TYPE(rows[i]))) {
             w.error = "SetJoint: changing a joint's bodies or collideConnected is not supported by the device world"; return PR_ERR_UNSUPPORTED;
         }
     }

@@ -10,6 +10,7 @@
 #include <playrho/WrongState.hpp>
 #include <playrho/d2/DistanceProxy.hpp>
 #include <playrho/d2/RevoluteJointConf.hpp>
+#include <playrho/d2/DistanceJointConf.hpp>
 #include <playrho/to_underlying.hpp>
 
 #include <algorithm>
@@ -645,15 +646,34 @@ static pr_revolute_joint ToJointRow(const RevoluteJointConf& jc)
     o.limit_state = static_cast<std::uint32_t>(jc.limitState);
     return o;
 }
+static pr_revolute_joint ToJointRow(const DistanceJointConf& jc)
+{ // the same table row viewed as pr_distance_joint (include/playrho_b200.h)
+    pr_distance_joint o{};
+    o.body_a = static_cast<std::uint32_t>(to_underlying(jc.bodyA)); o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.collide_connected = (jc.collideConnected ? 1u : 0u) | (static_cast<std::uint32_t>(PR_JOINT_DISTANCE) << 8);
+    o.local_anchor_a = pr_vec2{GetX(jc.localAnchorA), GetY(jc.localAnchorA)};
+    o.local_anchor_b = pr_vec2{GetX(jc.localAnchorB), GetY(jc.localAnchorB)};
+    o.impulse = jc.impulse; o.length = jc.length; o.frequency = jc.frequency; o.damping_ratio = jc.dampingRatio;
+    pr_revolute_joint r{};
+    static_assert(sizeof(r) == sizeof(o), "joint rows share one table");
+    std::memcpy(&r, &o, sizeof(r));
+    return r;
+}
+// the joint types the device solves (SURVEY a15 + the first of 8(f) rank 1); the others are rejected
+static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, BodyID& b)
+{
+    if (GetType(def) == GetTypeID<RevoluteJointConf>()) { const auto jc = TypeCast<RevoluteJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
+    if (GetType(def) == GetTypeID<DistanceJointConf>()) { const auto jc = TypeCast<DistanceJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
+    return false;
+}
 JointID CreateJoint(CudaWorld& w, Joint def)
 { // CreateJoint(AabbTreeWorld&, Joint), :1132-1157
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
     if (w.m->joints.size() >= MaxJoints) throw LengthError("CreateJoint: operation would exceed MaxJoints");
     if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
-    if (GetType(def) != GetTypeID<RevoluteJointConf>()) throw InvalidArgument(unsupportedMsg);
-    const auto jc = TypeCast<RevoluteJointConf>(def);
-    (void)AtId(w.m->bodies, jc.bodyA, noSuchBodyMsg); (void)AtId(w.m->bodies, jc.bodyB, noSuchBodyMsg);
-    const pr_revolute_joint o = ToJointRow(jc);
+    pr_revolute_joint o{}; BodyID bA{}, bB{};
+    if (!ToAnyJointRow(def, o, bA, bB)) throw InvalidArgument(unsupportedMsg);
+    (void)AtId(w.m->bodies, bA, noSuchBodyMsg); (void)AtId(w.m->bodies, bB, noSuchBodyMsg);
     w.m->refreshBodies();       // Add(JointID) wakes both bodies on the device: keep the host values in step
     w.m->uploadDirtyBodies();
     std::uint32_t first = 0;
@@ -671,6 +691,11 @@ Joint GetJoint(const CudaWorld& w, JointID id)
     if (!elem.has_value()) throw WasDestroyed{id, "ID is destroyed"};
     pr_revolute_joint r{};
     w.m->check(pr_get_revolute_joints(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), 1, &r), "pr_get_revolute_joints");
+    if (GetType(elem) == GetTypeID<DistanceJointConf>()) {
+        auto dc = TypeCast<DistanceJointConf>(elem);
+        dc.impulse = Momentum{r.impulse_x * NewtonSecond};
+        return Joint{dc};
+    }
     auto jc = TypeCast<RevoluteJointConf>(elem);
     jc.impulse = Vec3{r.impulse_x, r.impulse_y, r.impulse_z};
     jc.angularMotorImpulse = r.angular_motor_impulse;
@@ -684,8 +709,8 @@ void SetJoint(CudaWorld& w, JointID id, Joint def)
     if (const auto b = GetBodyA(def); b != InvalidBodyID) (void)AtId(w.m->bodies, b, noSuchBodyMsg);
     if (const auto b = GetBodyB(def); b != InvalidBodyID) (void)AtId(w.m->bodies, b, noSuchBodyMsg);
     if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
-    if (GetType(def) != GetTypeID<RevoluteJointConf>()) throw InvalidArgument(unsupportedMsg);
-    const pr_revolute_joint o = ToJointRow(TypeCast<RevoluteJointConf>(def));
+    pr_revolute_joint o{}; BodyID bA{}, bB{};
+    if (!ToAnyJointRow(def, o, bA, bB)) throw InvalidArgument(unsupportedMsg);
     w.m->refreshBodies();       // Remove(JointID) wakes both bodies on the device: keep the host values in step
     w.m->uploadDirtyBodies();
     const std::uint32_t jid = static_cast<std::uint32_t>(to_underlying(id));

@@ -199,6 +199,14 @@ class RefWorld:
         self.lib.ref_attach_shape.argtypes = [vp, u32, u32]
         self._chk(self.lib.ref_attach_shape(self.h, int(body), int(shape)))
 
+    def add_distance(self, body_a, body_b, anchor_a, anchor_b, frequency=0.0, damping_ratio=0.0, collide_connected=False):
+        self.lib.ref_add_distance.argtypes = [vp, u32, u32, f32, f32, f32, f32, f32, f32, i32]
+        self.lib.ref_add_distance.restype = u32
+        jid = self.lib.ref_add_distance(self.h, int(body_a), int(body_b), anchor_a[0], anchor_a[1], anchor_b[0], anchor_b[1],
+                                        frequency, damping_ratio, 1 if collide_connected else 0)
+        assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
+        return jid
+
     def destroy_joint(self, joint):
         self.lib.ref_destroy_joint.argtypes = [vp, u32]
         self._chk(self.lib.ref_destroy_joint(self.h, int(joint)))
