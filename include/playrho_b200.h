@@ -283,6 +283,10 @@ int pr_get_bodies(const pr_world* w, uint32_t first, uint32_t n, pr_body* rows);
  * pr_get_body_poses: transformation (px, py, cos, sin) of bodies [first, first+n) -- GetTransformation(world, id), Body.hpp --
  * and, if vel3 != NULL, their velocity (linear x, linear y, angular) -- GetVelocity(world, id). */
 int pr_set_body_accelerations(pr_world* w, uint32_t n, const uint32_t* ids, const float* acc3);
+/* pr_set_body_velocities: Body::SetVelocity (Body.cpp:184-194) of (linear x, linear y, angular) for bodies ids[0..n) (ids == NULL:
+ * bodies 0..n-1): a non-zero velocity is ignored for a body that cannot move (no velocity flag) and otherwise wakes the body and
+ * resets its under-active time; a zero velocity is just stored. The RL loop's "set actions" call when actions are velocities. */
+int pr_set_body_velocities(pr_world* w, uint32_t n, const uint32_t* ids, const float* vel3);
 int pr_get_body_poses(const pr_world* w, uint32_t first, uint32_t n, float* xf4, float* vel3);
 /* Query(const DynamicTree&, const AABB&, QueryShapeCallback) (DynamicTree.hpp:696-708, DynamicTree.cpp:673-710; SURVEY 8(f)
  * rank 2) for n_boxes boxes at once, on the device LBVH instead of a materialised DynamicTree: every proxy whose FAT AABB
@@ -491,6 +495,12 @@ int pr_batch_create_bodies(pr_batch* b, uint32_t n, const pr_body* bodies, const
                            const uint32_t* shape_offsets, const uint32_t* shape_ids, uint32_t* first_id);
 int pr_batch_step(pr_batch* b, const pr_step_conf* conf, pr_step_stats* stats_sum_out);
 int pr_batch_get_body_worlds(const pr_batch* b, uint32_t first, uint32_t n, uint32_t* world_index);
+/* pr_batch_create(n_worlds, device_mask) / pr_batch_stats. One process drives one GPU (the batch's worlds of the
+ * other GPUs belong to the other ranks, playrho_b200/shard.py): pr_batch_create_masked creates the arena on the LOWEST device
+ * whose bit is set in device_mask (PR_ERR_INVALID_ARGUMENT if none of the mask's devices exists); pr_batch_stats returns the
+ * statistics of the last pr_batch_step again (the sums over this arena's worlds that the ranks all-reduce). */
+int pr_batch_create_masked(const pr_world_conf* conf, uint32_t n_worlds, uint64_t device_mask, pr_batch** out);
+int pr_batch_stats(const pr_batch* b, pr_step_stats* stats_sum_out);
 
 #ifdef __cplusplus
 }

@@ -180,6 +180,23 @@ PR_KERNEL k_put_accelerations(DV d, unsigned n, const unsigned* ids, const float
     const unsigned i = PR_TID;
     if (i < n) d.b_acc[ids ? ids[i] : i] = make_float4(acc3[3u * i], acc3[3u * i + 1u], acc3[3u * i + 2u], 0.0f);
 }
+// Body::SetVelocity, Body.cpp:184-194
+PR_KERNEL k_put_velocities(DV d, unsigned n, const unsigned* ids, const float* vel3)
+{
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    if (i < n) {
+        const unsigned b = ids ? ids[i] : i;
+        const float x = vel3[3u * i], y = vel3[3u * i + 1u], w = vel3[3u * i + 2u];
+        if (x != 0.0f || y != 0.0f || w != 0.0f) {
+            const unsigned f = d.b_flags[b];
+            if (!f_speedable(f)) return;
+            if (!f_awake(f)) d.b_flags[b] = f | PR_BODY_AWAKE;
+            reinterpret_cast<float*>(&d.b_pos1[b])[3] = 0.0f; // m_underActiveTime = 0
+        }
+        d.b_vel[b] = make_float4(x, y, w, 0.0f);
+    }
+}
 PR_KERNEL k_get_poses(DV d, unsigned first, unsigned n, float4* xf, float* vel3)
 {
     PR_PDL_ENTER();

@@ -2067,6 +2067,25 @@ int pr_set_body_accelerations(pr_world* pw, uint32_t n, const uint32_t* ids, con
     API_CATCH(pw)
 }
 
+int pr_set_body_velocities(pr_world* pw, uint32_t n, const uint32_t* ids, const float* vel3)
+{
+    API_TRY(pw)
+    World& w = pw->w;
+    uint32_t maxId = n ? n - 1u : 0u; // ids == NULL: bodies [0, n)
+    if (ids) { maxId = 0; for (uint32_t i = 0; i < n; ++i) maxId = ids[i] > maxId ? ids[i] : maxId; }
+    if (n && maxId >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+    if (!n) return PR_OK;
+    float* svel = static_cast<float*>(stage_buf(w, 0, sizeof(float) * 3u * n));
+    unsigned* dids = ids ? static_cast<unsigned*>(stage_buf(w, 1, 4u * n)) : nullptr;
+    h2d(w, svel, vel3, sizeof(float) * 3u * n);
+    if (ids) h2d(w, dids, ids, 4u * n);
+    PR_LAUNCH(k_put_velocities, n, w.stream, w.d, n, dids, svel);
+    sync(w); // the caller's buffers may be reused once we return
+    w.anyBodySet = true;
+    return PR_OK;
+    API_CATCH(pw)
+}
+
 int pr_get_body_poses(const pr_world* cpw, uint32_t first, uint32_t n, float* xf4, float* vel3)
 {
     pr_world* pw = const_cast<pr_world*>(cpw);
@@ -2599,7 +2618,7 @@ int pr_abi_sizeof(int which)
 // the queried proxy's world (k_bvh_query / query_emit). No contact ever joins two worlds, hence islands, colours, the
 // solver's per-island early exits, sleeping and TOI events are per world by construction, and one pr_step of the arena
 // is one Step of every world: each kernel launch is n_worlds wide instead of one launch train per world.
-struct pr_batch { pr_world* arena; uint32_t nWorlds; };
+struct pr_batch { pr_world* arena; uint32_t nWorlds; pr_step_stats lastStats{}; };
 int pr_batch_create(const pr_world_conf* conf, uint32_t n_worlds, pr_batch** out)
 {
     *out = nullptr;
@@ -2614,6 +2633,19 @@ int pr_batch_create(const pr_world_conf* conf, uint32_t n_worlds, pr_batch** out
     *out = b;
     return PR_OK;
 }
+int pr_batch_create_masked(const pr_world_conf* conf, uint32_t n_worlds, uint64_t device_mask, pr_batch** out)
+{
+    *out = nullptr;
+    int count = 1;
+#ifndef PR_HOST_EMUL
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); count = 0; }
+#endif
+    for (int dev = 0; dev < count && dev < 64; ++dev)
+        if (device_mask & (1ull << dev)) { pr_world_conf c = *conf; c.device = dev; return pr_batch_create(&c, n_worlds, out); }
+    g_createError = "pr_batch_create_masked: no device of the mask exists";
+    return PR_ERR_INVALID_ARGUMENT;
+}
+int pr_batch_stats(const pr_batch* b, pr_step_stats* out) { if (!b || !out) return PR_ERR_INVALID_ARGUMENT; *out = b->lastStats; return PR_OK; }
 int pr_batch_destroy(pr_batch* b) { if (b) { pr_destroy(b->arena); delete b; } return PR_OK; }
 pr_world* pr_batch_arena(pr_batch* b) { return b ? b->arena : nullptr; }
 uint32_t pr_batch_world_count(const pr_batch* b) { return b ? b->nWorlds : 0u; }
@@ -2622,7 +2654,12 @@ int pr_batch_create_bodies(pr_batch* b, uint32_t n, const pr_body* bodies, const
 {
     return create_bodies(b->arena, n, bodies, shape_offsets, shape_ids, world_index, first_id);
 }
-int pr_batch_step(pr_batch* b, const pr_step_conf* conf, pr_step_stats* sum) { return pr_step(b->arena, conf, sum); }
+int pr_batch_step(pr_batch* b, const pr_step_conf* conf, pr_step_stats* sum)
+{
+    const int rc = pr_step(b->arena, conf, &b->lastStats);
+    if (sum) *sum = b->lastStats;
+    return rc;
+}
 int pr_batch_get_body_worlds(const pr_batch* b, uint32_t first, uint32_t n, uint32_t* world_index)
 {
     const World& w = b->arena->w;

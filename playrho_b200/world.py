@@ -62,6 +62,7 @@ EXPORTS = [
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
     "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_test_points", "pr_find_closest_bodies", "pr_set_contacts", "pr_set_manifolds", "pr_set_revolute_joints", "pr_attach_shapes", "pr_set_shape_material", "pr_destroy_joints",
     "pr_destroy_bodies", "pr_detach_shapes", "pr_destroy_shapes", "pr_set_shape", "pr_set_body_enabled", "pr_set_body_type",
+    "pr_create_distance_joints", "pr_set_body_velocities", "pr_batch_create_masked", "pr_batch_stats",
 ]
 
 
@@ -103,6 +104,10 @@ def bind(lib):
     lib.pr_set_shape.argtypes = [vp, u32, vp, vp, vp, vp, u32, u32]
     lib.pr_set_body_enabled.argtypes = [vp, u32, u32]
     lib.pr_set_body_type.argtypes = [vp, u32, vp]
+    lib.pr_create_distance_joints.argtypes = [vp, u32, vp, C.POINTER(u32)]
+    lib.pr_set_body_velocities.argtypes = [vp, u32, vp, vp]
+    lib.pr_batch_create_masked.argtypes = [vp, u32, C.c_uint64, C.POINTER(vp)]
+    lib.pr_batch_stats.argtypes = [vp, vp]
     lib.pr_set_shape_material.argtypes = [vp, u32, f32, f32, f32, u32]
     lib.pr_set_manifolds.argtypes = [vp, u32, vp, vp]
     lib.pr_get_revolute_joints.argtypes = [vp, u32, u32, vp]
@@ -358,6 +363,13 @@ class World:
             self._chk(self.lib.pr_set_shape(self.h, int(shape), abi.ptr(row), abi.ptr(children), abi.ptr(vertices), abi.ptr(normals), len(vertices), 1))
         else:
             self._chk(self.lib.pr_set_shape(self.h, int(shape), abi.ptr(row), None, None, None, 0, 0))
+
+    def set_body_velocities(self, vel3, ids=None):
+        """Body::SetVelocity for many bodies at once (pr_set_body_velocities); vel3: (n, 3) linear x, y, angular."""
+        vel3 = np.ascontiguousarray(vel3, dtype=np.float32).reshape(-1, 3)
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._chk(self.lib.pr_set_body_velocities(self.h, len(vel3), abi.ptr(ids) if ids is not None else None, abi.ptr(vel3)))
 
     def set_body_enabled(self, body, enabled):
         self._chk(self.lib.pr_set_body_enabled(self.h, int(body), 1 if enabled else 0))
