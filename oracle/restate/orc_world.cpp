@@ -1147,6 +1147,15 @@ int orc_create_bodies(orc_world* w, uint32_t n, const pr_body* bodies, const uin
     return 0;
 }
 
+// FlagForFiltering, AabbTreeWorld.cpp:436-451
+static void flag_pair_for_filtering(orc_world& w, uint32_t a, uint32_t b)
+{
+    for (uint32_t id : w.bodies[b].contacts) {
+        pr_contact& c = w.contacts[id].c;
+        const uint32_t other = (c.body_a == b) ? c.body_b : c.body_a;
+        if (other == a) { c.flags |= PR_CONTACT_FILTER; w.needsFiltering = true; }
+    }
+}
 int orc_create_revolute_joints(orc_world* w, uint32_t n, const pr_revolute_joint* joints)
 {
     for (uint32_t i = 0; i < n; ++i) {
@@ -1155,9 +1164,8 @@ int orc_create_revolute_joints(orc_world* w, uint32_t n, const pr_revolute_joint
         else { id = static_cast<uint32_t>(w->joints.size()); w->joints.push_back(joints[i]); w->jointWork.emplace_back(); }
         w->bodies[joints[i].body_a].joints.push_back(id);
         w->bodies[joints[i].body_b].joints.push_back(id);
-        // Add(JointID) :1159-1180: set awake both bodies
-        set_awake(w->bodies[joints[i].body_a].b);
-        set_awake(w->bodies[joints[i].body_b].b);
+        // Add(JointID, !collideConnected) :1159-1175: creating a joint does not wake its bodies; the pair's contacts are flagged for filtering
+        if (!(joints[i].collide_connected & 1u)) flag_pair_for_filtering(*w, joints[i].body_a, joints[i].body_b);
     }
     return 0;
 }
@@ -1312,6 +1320,7 @@ int orc_destroy_joints(orc_world* w, uint32_t n, const uint32_t* ids)
         if (id >= w->joints.size()) { w->error = "no such joint"; return -2; }
         pr_revolute_joint& j = w->joints[id];
         if (j.body_a == 0xFFFFFFFFu) continue;
+        if (!(j.collide_connected & 1u)) flag_pair_for_filtering(*w, j.body_a, j.body_b); // Remove(JointID), :1184-1190
         for (uint32_t b : {j.body_a, j.body_b}) {
             set_awake(w->bodies[b].b);
             auto& lst = w->bodies[b].joints;
@@ -1340,9 +1349,11 @@ int orc_set_revolute_joints(orc_world* w, uint32_t n, const uint32_t* ids, const
             auto it = std::find(lst.begin(), lst.end(), id);
             if (it != lst.end()) lst.erase(it);
         }
+        if (!(old.collide_connected & 1u)) flag_pair_for_filtering(*w, old.body_a, old.body_b); // Remove
         w->joints[id] = rows[i];
         w->bodies[rows[i].body_a].joints.push_back(id);
         w->bodies[rows[i].body_b].joints.push_back(id);
+        if (!(rows[i].collide_connected & 1u)) flag_pair_for_filtering(*w, rows[i].body_a, rows[i].body_b); // Add(id, true)
     }
     return 0;
 }

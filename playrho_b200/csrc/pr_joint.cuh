@@ -381,6 +381,21 @@ PR_KERNEL k_set_joints(DV d, unsigned n, const unsigned* ids, const pr_revolute_
     const unsigned i = PR_TID;
     if (i < n) { const pr_revolute_joint j = rows[i]; d.jt[ids[i]] = j; body_set_awake(d, j.body_a); body_set_awake(d, j.body_b); }
 }
+// Add(JointID, flagForFiltering) / Remove(JointID) of a joint with collideConnected == false (AabbTreeWorld.cpp:1159-1191, FlagForFiltering
+// :436-451): the contacts between its two bodies are flagged for the next Step's filter test (pr_mutate.cuh: k_destroy_filter)
+PR_KERNEL k_pair_flag_filter(DV d, unsigned nOrder, unsigned n, const unsigned* pairs)
+{
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    if (i < nOrder) {
+        const unsigned id = d.c_order[i];
+        const uint4 ab = d.c_ab[id];
+        for (unsigned k = 0; k < n; ++k) {
+            const unsigned a = pairs[2u * k], b = pairs[2u * k + 1u];
+            if ((ab.x == a && ab.y == b) || (ab.x == b && ab.y == a)) { atomicOr(&d.c_flags[id], static_cast<unsigned>(PR_CONTACT_FILTER)); break; }
+        }
+    }
+}
 PR_KERNEL k_joint_wake(DV d, unsigned first, unsigned n)
 {
     PR_PDL_ENTER();

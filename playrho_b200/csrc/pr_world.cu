@@ -1912,8 +1912,20 @@ int pr_set_shape(pr_world* pw, uint32_t shape, const pr_shape* def, const pr_chi
     API_CATCH(pw)
 }
 
+} // extern "C"
+// FlagForFiltering (:436-451) for the body pairs of joints with collideConnected == false that are being added or removed
+static void flag_joint_pairs_for_filtering(World& w, const std::vector<unsigned>& pairs)
+{
+    if (pairs.empty() || !w.nOrder) return;
+    unsigned* dp = static_cast<unsigned*>(stage_buf(w, 1, 4u * pairs.size()));
+    h2d(w, dp, pairs.data(), 4u * pairs.size());
+    PR_LAUNCH(k_pair_flag_filter, w.nOrder, w.stream, w.d, w.nOrder, static_cast<unsigned>(pairs.size() / 2u), dp);
+    sync(w);
+    w.needsFiltering = true; // (the filter pass only looks at flagged contacts: harmless when none was)
+}
+extern "C" {
 int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint* joints, uint32_t* first_id)
-{ // CreateJoint (:1132-1157) + Add(JointID) (:1159-1180) for RevoluteJointConf values
+{ // CreateJoint (:1132-1157) + Add(JointID, !collideConnected) (:1159-1175) for rows of the joint table; creating a joint does not wake its bodies
     API_TRY(pw)
     World& w = pw->w;
     w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
@@ -1930,7 +1942,7 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
         w.joints[id] = joints[0];
         h2d(w, w.d.jt + id, joints, sizeof(pr_revolute_joint));
         refresh_joint_tables(w);
-        PR_LAUNCH(k_joint_wake, 1u, w.stream, w.d, id, 1u);
+        if (!(joints[0].collide_connected & 1u)) flag_joint_pairs_for_filtering(w, {joints[0].body_a, joints[0].body_b});
         sync(w);
         if (first_id) *first_id = id;
         return PR_OK;
@@ -1939,7 +1951,8 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
     ensure(w, G_JOINT, w.nJoints + n + 1);
     h2d(w, w.d.jt + w.nJoints, joints, sizeof(pr_revolute_joint) * n);
     refresh_joint_tables(w);
-    PR_LAUNCH(k_joint_wake, n, w.stream, w.d, w.nJoints, n);
+    { std::vector<unsigned> pairs; for (uint32_t i = 0; i < n; ++i) if (!(joints[i].collide_connected & 1u)) { pairs.push_back(joints[i].body_a); pairs.push_back(joints[i].body_b); }
+      flag_joint_pairs_for_filtering(w, pairs); }
     sync(w);
     if (first_id) *first_id = w.nJoints;
     w.nJoints += n;
@@ -1967,10 +1980,11 @@ int pr_destroy_joints(pr_world* pw, uint32_t n, const uint32_t* ids)
     w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     if (!w.stepComplete) { w.error = "Destroy: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
     for (uint32_t i = 0; i < n; ++i) if (ids[i] >= w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
-    std::vector<unsigned> wake;
+    std::vector<unsigned> wake, pairs;
     for (uint32_t i = 0; i < n; ++i) {
         pr_revolute_joint& j = w.joints[ids[i]];
         if (j.body_a == INVALID) continue; // already destroyed: not in m_joints, nothing happens (:1222)
+        if (!(j.collide_connected & 1u)) { pairs.push_back(j.body_a); pairs.push_back(j.body_b); } // Remove(JointID), :1184-1190
         wake.push_back(j.body_a); wake.push_back(j.body_b);
         std::memset(&j, 0, sizeof(j));
         j.body_a = j.body_b = INVALID;
@@ -1982,6 +1996,7 @@ int pr_destroy_joints(pr_world* pw, uint32_t n, const uint32_t* ids)
         h2d(w, sids, wake.data(), 4u * wake.size());
         PR_LAUNCH(k_wake_bodies, static_cast<unsigned>(wake.size()), w.stream, w.d, static_cast<unsigned>(wake.size()), sids);
     }
+    flag_joint_pairs_for_filtering(w, pairs);
     refresh_joint_tables(w);
     sync(w);
     return PR_OK;
@@ -2008,6 +2023,8 @@ int pr_set_revolute_joints(pr_world* pw, uint32_t n, const uint32_t* ids, const 
     h2d(w, srows, rows, sizeof(pr_revolute_joint) * n); h2d(w, sids, ids, 4u * n);
     PR_LAUNCH(k_set_joints, n, w.stream, w.d, n, sids, srows);
     sync(w);
+    { std::vector<unsigned> pairs; for (uint32_t i = 0; i < n; ++i) if (!(rows[i].collide_connected & 1u)) { pairs.push_back(rows[i].body_a); pairs.push_back(rows[i].body_b); }
+      flag_joint_pairs_for_filtering(w, pairs); } // Remove(id) and Add(id, true) both flag the pair's contacts (:1122-1129)
     for (uint32_t i = 0; i < n; ++i) w.joints[ids[i]] = rows[i];
     return PR_OK;
     API_CATCH(pw)

@@ -688,7 +688,7 @@ JointID CreateJoint(CudaWorld& w, Joint def)
 Joint GetJoint(const CudaWorld& w, JointID id)
 { // the solver-written fields (impulses, limit state) come back from the device
     auto& elem = AtId(w.m->joints, id, noSuchJointMsg);
-    if (!elem.has_value()) throw WasDestroyed{id, "ID is destroyed"};
+    if (!elem.has_value()) return Joint{}; // GetJoint = At(m_jointBuffer, id) (:1103): a freed slot reads back empty
     pr_revolute_joint r{};
     w.m->check(pr_get_revolute_joints(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), 1, &r), "pr_get_revolute_joints");
     if (GetType(elem) == GetTypeID<DistanceJointConf>()) {

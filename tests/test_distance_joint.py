@@ -28,7 +28,9 @@ def _build():
     ref.add_distance(hub, c, (2.0, 10.0), (2.0, 6.2))
     ref.add_distance(c, e, (2.3, 6.0), (3.5, 5.0), collide_connected=True)                 # rod between two dynamic bodies
     ref.add_revolute(hub, f, (6.0, 9.0))                                                   # and a revolute joint in the same table
-    return ref, hub, (a, b, c, e, f)
+    g1 = ref.add_body(DYNAMIC, pos=(10.0, 0.31), acc=(0.0, -9.8), shapes=[box])            # two boxes stacked on the ground, touching
+    g2 = ref.add_body(DYNAMIC, pos=(10.0, 0.92), acc=(0.0, -9.8), shapes=[box])
+    return ref, hub, (a, b, c, e, f, g1, g2)
 
 
 def _run(lib=None, device=-1, with_device=True):
@@ -44,6 +46,24 @@ def _run(lib=None, device=-1, with_device=True):
         twins = [gw, orc2]
     conf = refworld.default_step_conf()
     for s in range(220):
+        if s == 60:  # a joint with collideConnected == false between two bodies in contact: Add(JointID, true) flags their contact
+            # for filtering (AabbTreeWorld.cpp:1159-1175) and the next Step's DestroyContacts drops it (:2305-2328)
+            g1, g2 = bodies[5], bodies[6]
+            def pair_contacts(w):
+                c, _ = w.contacts()
+                return int((((c["body_a"] == g1) & (c["body_b"] == g2)) | ((c["body_a"] == g2) & (c["body_b"] == g1))).sum())
+            assert pair_contacts(ref) == 1
+            jid = ref.add_distance(g1, g2, (10.0, 0.31), (10.0, 0.92))
+            row = ref.joints()[jid:jid + 1]
+            orc.create_joints(row)
+            for t in twins:
+                t.create_joints(row)
+            c, _ = ref.contacts()
+            sel = ((c["body_a"] == g1) & (c["body_b"] == g2)) | ((c["body_a"] == g2) & (c["body_b"] == g1))
+            assert (c["flags"][sel] & abi.CONTACT_FILTER).all()
+            filtered_at = s
+        if s == 62:
+            assert pair_contacts(ref) == 0 and all(pair_contacts(t) == 0 for t in twins)
         if s == 90:  # the spring is cut; later a new rod takes its id
             ref.destroy_joint(1); orc.destroy_joints([1])
             for t in twins:
