@@ -107,7 +107,7 @@ typedef struct pr_revolute_joint {
 
 /* Joint rows share one table (JointIDs are one id space in the reference): every row has pr_revolute_joint's size and leading
  * fields, and bits 8..15 of collide_connected say which joint type it is (bit 0 is the flag itself). */
-enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1 };
+enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2 };
 #define PR_JOINT_TYPE(row) (((row).collide_connected >> 8) & 0xFFu)
 /* DistanceJointConf (Library/include/playrho/d2/DistanceJointConf.hpp): rod or spring between two anchor points.
  * Solver: Library/source/playrho/d2/DistanceJointConf.cpp:81-246 (InitVelocity, SolveVelocity, SolvePosition). */
@@ -123,6 +123,20 @@ typedef struct pr_distance_joint {
     float reserved2[2];
     uint32_t reserved3;
 } pr_distance_joint;
+
+/* RopeJointConf (Library/include/playrho/d2/RopeJointConf.hpp): the two anchor points are never further apart than max_length.
+ * Solver: Library/source/playrho/d2/RopeJointConf.cpp:58-214. */
+typedef struct pr_rope_joint {
+    uint32_t body_a, body_b;
+    uint32_t collide_connected;          /* bit 0: collideConnected; bits 8..15: PR_JOINT_ROPE */
+    pr_vec2 local_anchor_a, local_anchor_b;
+    float impulse;                       /* accumulated impulse (warm start), <= 0 */
+    float reserved0[3];
+    float max_length;
+    uint32_t reserved1[2];
+    float reserved2[4];
+    uint32_t limit_state;                /* LimitState: 0 inactive, 2 at the upper limit (InitVelocity writes it) */
+} pr_rope_joint;
 
 /* ContactFeature packed little-endian: typeA | indexA<<8 | typeB<<16 | indexB<<24 */
 typedef uint32_t pr_contact_feature;
@@ -258,6 +272,7 @@ int pr_create_revolute_joints(pr_world* w, uint32_t n, const pr_revolute_joint* 
  * joints'; pr_get_revolute_joints / pr_set_revolute_joints / pr_destroy_joints work on any row of the table (read a row's
  * type with PR_JOINT_TYPE and view it as the matching struct). */
 int pr_create_distance_joints(pr_world* w, uint32_t n, const pr_distance_joint* joints, uint32_t* first_id);
+int pr_create_rope_joints(pr_world* w, uint32_t n, const pr_rope_joint* joints, uint32_t* first_id);
 
 /* SetShape(AabbTreeWorld&, ShapeID, Shape) (AabbTreeWorld.cpp:1284-1356) for a value whose geometry (children) and filter are
  * what they were: friction, restitution, density and the sensor flag are replaced; every body using the shape is woken

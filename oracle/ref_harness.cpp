@@ -405,6 +405,16 @@ uint32_t ref_add_distance(void* h, uint32_t bodyA, uint32_t bodyB, float ax, flo
     return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
     REF_CATCH(0xFFFFFFFFu)
 }
+// CreateJoint(world, RopeJointConf{bodyA, bodyB}) with local anchors and the maximum length put in
+uint32_t ref_add_rope(void* h, uint32_t bodyA, uint32_t bodyB, float lax, float lay, float lbx, float lby, float maxLength, int collideConnected)
+{
+    REF_TRY(h)
+    auto jc = RopeJointConf{MakeId<BodyID>(bodyA), MakeId<BodyID>(bodyB)};
+    jc.localAnchorA = Length2{lax * 1_m, lay * 1_m}; jc.localAnchorB = Length2{lbx * 1_m, lby * 1_m};
+    jc.maxLength = maxLength * 1_m; jc.collideConnected = collideConnected != 0;
+    return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
+    REF_CATCH(0xFFFFFFFFu)
+}
 int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
 {
     REF_TRY(h)
@@ -422,6 +432,15 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
             o.local_anchor_a = pr_vec2{GetX(dc.localAnchorA), GetY(dc.localAnchorA)};
             o.local_anchor_b = pr_vec2{GetX(dc.localAnchorB), GetY(dc.localAnchorB)};
             o.impulse_x = dc.impulse; o.reference_angle = dc.length; o.lower_angle = dc.frequency; o.upper_angle = dc.dampingRatio;
+            continue;
+        }
+        if (GetType(joint) == GetTypeID<RopeJointConf>()) { // the same row, viewed as pr_rope_joint
+            const auto rc = TypeCast<RopeJointConf>(joint);
+            o.body_a = to_underlying(rc.bodyA); o.body_b = to_underlying(rc.bodyB);
+            o.collide_connected = (rc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_ROPE) << 8);
+            o.local_anchor_a = pr_vec2{GetX(rc.localAnchorA), GetY(rc.localAnchorA)};
+            o.local_anchor_b = pr_vec2{GetX(rc.localAnchorB), GetY(rc.localAnchorB)};
+            o.impulse_x = rc.impulse; o.reference_angle = rc.maxLength; o.limit_state = static_cast<uint32_t>(rc.limitState);
             continue;
         }
         const auto jc = TypeCast<RevoluteJointConf>(joint);

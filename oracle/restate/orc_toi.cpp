@@ -602,22 +602,89 @@ bool distance_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk,
     posB.l = posB.l + imB * P; posB.a += iiB * LB;
     return std::fabs(C) < c.linearSlop;
 }
+// ---------------- RopeJointConf.cpp:58-214 (mass[0..1] = u, mass[4] = mass, mass[5] = length) ----------------
+void rope_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
+                        float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
+{
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    wk.rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    wk.rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    const V2 posDelta = (posB.l + wk.rB) - (posA.l + wk.rA);
+    float length;
+    const Rot u = unit_vector_mag(posDelta, length);
+    wk.mass[5] = length;
+    const float C = length - j.reference_angle;
+    j.limit_state = (C > 0.0f) ? LS_AT_UPPER : LS_INACTIVE;
+    if (!(length > c.linearSlop)) { wk.mass[0] = wk.mass[1] = 0.0f; wk.mass[4] = 0.0f; j.impulse_x = 0.0f; return; }
+    wk.mass[0] = u.c; wk.mass[1] = u.s;
+    const V2 uv{u.c, u.s};
+    const float crA = cross(wk.rA, uv) / 1.0f, crB = cross(wk.rB, uv) / 1.0f;
+    const float invRotMassA = iiA * square(crA), invRotMassB = iiB * square(crB);
+    const float invMass = imA + imB + invRotMassA + invRotMassB;
+    wk.mass[4] = (invMass != 0.0f) ? 1.0f / invMass : 0.0f;
+    if (c.warmStart) {
+        j.impulse_x *= c.dtRatio;
+        const V2 P = j.impulse_x * uv;
+        const float LA = cross(wk.rA, P) / 1.0f, LB = cross(wk.rB, P) / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    } else j.impulse_x = 0.0f;
+}
+bool rope_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& velA, float imB, float iiB, Vel& velB, const JointSolverConf& c)
+{
+    const V2 uv{wk.mass[0], wk.mass[1]};
+    const V2 vpA = velA.l + rev_perp(wk.rA) * (velA.a / 1.0f);
+    const V2 vpB = velB.l + rev_perp(wk.rB) * (velB.a / 1.0f);
+    const float C = wk.mass[5] - j.reference_angle;
+    const float inv_h = (c.dt != 0.0f) ? 1.0f / c.dt : 0.0f;
+    const float Cdot = dot(uv, vpB - vpA) + ((C < 0.0f) ? inv_h * C : 0.0f);
+    float localImpulse = -wk.mass[4] * Cdot;
+    const float oldImpulse = j.impulse_x;
+    j.impulse_x = std::min(0.0f, j.impulse_x + localImpulse);
+    localImpulse = j.impulse_x - oldImpulse;
+    const V2 P = localImpulse * uv;
+    const float LA = cross(wk.rA, P) / 1.0f, LB = cross(wk.rB, P) / 1.0f;
+    velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+    velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    return localImpulse == 0.0f;
+}
+bool rope_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos& posA,
+                         float imB, float iiB, V2 lcB, Pos& posB, const JointSolverConf& c)
+{
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    const V2 rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    const V2 rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    const V2 posDelta = (posB.l + rB) - (posA.l + rA);
+    float length;
+    const Rot u = unit_vector_mag(posDelta, length);
+    const V2 uv{u.c, u.s};
+    const float C = std::clamp(length - j.reference_angle, 0.0f, c.maxLinearCorrection);
+    const float localImpulse = -wk.mass[4] * C;
+    const V2 P = localImpulse * uv;
+    const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+    posA.l = posA.l - imA * P; posA.a -= iiA * LA;
+    posB.l = posB.l + imB * P; posB.a += iiB * LB;
+    return (length - j.reference_angle) < c.linearSlop;
+}
 } // namespace
 void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
                          float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
 {
     if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) distance_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
+    else if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) rope_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
     else revolute_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
 }
 bool joint_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& velA, float imB, float iiB, Vel& velB, const JointSolverConf& c)
 {
     if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) return distance_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB);
+    if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) return rope_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
     return revolute_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
 }
 bool joint_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos& posA,
                           float imB, float iiB, V2 lcB, Pos& posB, const JointSolverConf& c)
 {
     if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) return distance_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
+    if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) return rope_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     return revolute_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
 }
 }

@@ -161,6 +161,93 @@ PR_D void distance_solve_position(const DV& d, const pr_revolute_joint& j, const
     if (!(fabsf(C) < conf.linear_slop)) v.isl_jflag[wk.island] = 1u;
 }
 
+// ---- RopeJointConf.cpp:58-214. Row overlay (pr_rope_joint): impulse = impulse_x, maxLength = reference_angle, limitState = limit_state;
+// work: rA, rB, m[0..1] = u, m[4] = mass, m[5] = length
+PR_D void rope_init_velocity(const DV& d, unsigned ji, pr_revolute_joint j, JointWork wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 pA = v.s_pos[jv_idx(v.slotP, j.body_a)], pB = v.s_pos[jv_idx(v.slotP, j.body_b)];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
+    const Rot qA = rot_from_angle(pA.z), qB = rot_from_angle(pB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    wk.rAx = rA.x; wk.rAy = rA.y; wk.rBx = rB.x; wk.rBy = rB.y;
+    const float2 posDelta = (v2(pB.x, pB.y) + rB) - (v2(pA.x, pA.y) + rA);
+    float length;
+    const Rot uv = unit_vector_mag(posDelta, length);
+    wk.m[5] = length;
+    const float C = length - j.reference_angle;
+    j.limit_state = (C > 0.0f) ? LS_AT_UPPER : LS_INACTIVE;
+    if (!(length > conf.linear_slop)) { // (:96-104: the bodies' velocities are left as they are)
+        wk.m[0] = 0.0f; wk.m[1] = 0.0f; wk.m[4] = 0.0f;
+        j.impulse_x = 0.0f;
+        d.jt[ji] = j; d.jt_work[ji] = wk;
+        return;
+    }
+    const Rot u = uv;
+    wk.m[0] = u.c; wk.m[1] = u.s;
+    const float crA = cross(rA, u) / 1.0f, crB = cross(rB, u) / 1.0f;
+    const float invRotMassA = iiA * square(crA), invRotMassB = iiB * square(crB);
+    const float invMass = imA + imB + invRotMassA + invRotMassB;
+    wk.m[4] = (invMass != 0.0f) ? 1.0f / invMass : 0.0f;
+    if (conf.do_warm_start) {
+        j.impulse_x *= conf.dt_ratio;
+        const float2 P = j.impulse_x * u;
+        const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    } else j.impulse_x = 0.0f;
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    d.jt_work[ji] = wk;
+}
+PR_D void rope_solve_velocity(const DV& d, unsigned ji, pr_revolute_joint j, const JointWork& wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
+    const float2 rA = v2(wk.rAx, wk.rAy), rB = v2(wk.rBx, wk.rBy);
+    const Rot u = mkrot(wk.m[0], wk.m[1]);
+    const float2 vpA = v2(velA.x, velA.y) + rev_perp(rA) * (velA.z / 1.0f);
+    const float2 vpB = v2(velB.x, velB.y) + rev_perp(rB) * (velB.z / 1.0f);
+    const float C = wk.m[5] - j.reference_angle;
+    const float inv_h = (conf.delta_time != 0.0f) ? 1.0f / conf.delta_time : 0.0f;
+    const float Cdot = dot(u, vpB - vpA) + ((C < 0.0f) ? inv_h * C : 0.0f);
+    float localImpulse = -wk.m[4] * Cdot;
+    const float oldImpulse = j.impulse_x;
+    j.impulse_x = stdmin(0.0f, j.impulse_x + localImpulse);
+    localImpulse = j.impulse_x - oldImpulse;
+    const float2 P = localImpulse * u;
+    const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+    const float2 la = v2(velA.x, velA.y) - mA.x * P; velA.x = la.x; velA.y = la.y; velA.z -= mA.y * LA;
+    const float2 lb = v2(velB.x, velB.y) + mB.x * P; velB.x = lb.x; velB.y = lb.y; velB.z += mB.y * LB;
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    if (!(localImpulse == 0.0f)) v.isl_jflag[wk.island] = 1u;
+}
+PR_D void rope_solve_position(const DV& d, const pr_revolute_joint& j, const JointWork& wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    float4 posA = v.s_pos[ia], posB = v.s_pos[ib];
+    const Rot qA = rot_from_angle(posA.z), qB = rot_from_angle(posB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    const float2 posDelta = (v2(posB.x, posB.y) + rB) - (v2(posA.x, posA.y) + rA);
+    float length;
+    const Rot uv = unit_vector_mag(posDelta, length);
+    const float C = stdclamp(length - j.reference_angle, 0.0f, conf.max_linear_correction);
+    const float localImpulse = -wk.m[4] * C;
+    const float2 P = localImpulse * uv;
+    const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+    const float2 la = v2(posA.x, posA.y) - mA.x * P; posA.x = la.x; posA.y = la.y; posA.z -= mA.y * LA;
+    const float2 lb = v2(posB.x, posB.y) + mB.x * P; posB.x = lb.x; posB.y = lb.y; posB.z += mB.y * LB;
+    v.s_pos[ia] = posA; v.s_pos[ib] = posB;
+    if (!((length - j.reference_angle) < conf.linear_slop)) v.isl_jflag[wk.island] = 1u;
+}
+
 PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf, const JView& v)
 {
     pr_revolute_joint j = d.jt[ji];
@@ -171,6 +258,12 @@ PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf
         if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
         if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
         distance_init_velocity(d, ji, j, wk, conf, v);
+        return;
+    }
+    if (joint_type(j) == PR_JOINT_ROPE) {
+        if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
+        if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
+        rope_init_velocity(d, ji, j, wk, conf, v);
         return;
     }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
@@ -236,6 +329,7 @@ PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& con
     if (v.isl_state[jv_idx(v.slotI, wk.island)] & ISL_VEL_DONE) return;
     pr_revolute_joint j = d.jt[ji];
     if (joint_type(j) == PR_JOINT_DISTANCE) { distance_solve_velocity(d, ji, j, wk, v); return; }
+    if (joint_type(j) == PR_JOINT_ROPE) { rope_solve_velocity(d, ji, j, wk, conf, v); return; }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
@@ -299,6 +393,7 @@ PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& con
     if (v.isl_state[jv_idx(v.slotI, wk.island)] & ISL_POS_SOLVED) return;
     const pr_revolute_joint j = d.jt[ji];
     if (joint_type(j) == PR_JOINT_DISTANCE) { distance_solve_position(d, j, wk, conf, v); return; }
+    if (joint_type(j) == PR_JOINT_ROPE) { rope_solve_position(d, j, wk, conf, v); return; }
     const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;

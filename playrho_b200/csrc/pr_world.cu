@@ -1941,7 +1941,7 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
         w.freeJoints.pop_back();
         w.joints[id] = joints[0];
         h2d(w, w.d.jt + id, joints, sizeof(pr_revolute_joint));
-        refresh_joint_tables(w);
+        w.jointTablesDirty = true;
         if (!(joints[0].collide_connected & 1u)) flag_joint_pairs_for_filtering(w, {joints[0].body_a, joints[0].body_b});
         sync(w);
         if (first_id) *first_id = id;
@@ -1950,7 +1950,7 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
     w.joints.insert(w.joints.end(), joints, joints + n);
     ensure(w, G_JOINT, w.nJoints + n + 1);
     h2d(w, w.d.jt + w.nJoints, joints, sizeof(pr_revolute_joint) * n);
-    refresh_joint_tables(w);
+    w.jointTablesDirty = true;
     { std::vector<unsigned> pairs; for (uint32_t i = 0; i < n; ++i) if (!(joints[i].collide_connected & 1u)) { pairs.push_back(joints[i].body_a); pairs.push_back(joints[i].body_b); }
       flag_joint_pairs_for_filtering(w, pairs); }
     sync(w);
@@ -1969,6 +1969,20 @@ int pr_create_distance_joints(pr_world* pw, uint32_t n, const pr_distance_joint*
         rows[i].collide_connected = (joints[i].collide_connected & 1u) | (static_cast<uint32_t>(PR_JOINT_DISTANCE) << 8);
         rows[i].impulse_y = rows[i].impulse_z = rows[i].angular_motor_impulse = 0.0f;
         rows[i].enable_limit = rows[i].enable_motor = 0u; rows[i].motor_speed = rows[i].max_motor_torque = 0.0f; rows[i].limit_state = 0u;
+    }
+    return pr_create_revolute_joints(pw, n, rows.data(), first_id);
+}
+
+int pr_create_rope_joints(pr_world* pw, uint32_t n, const pr_rope_joint* joints, uint32_t* first_id)
+{
+    static_assert(sizeof(pr_rope_joint) == sizeof(pr_revolute_joint), "joint rows share one table");
+    std::vector<pr_revolute_joint> rows(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        std::memset(&rows[i], 0, sizeof(pr_revolute_joint));
+        rows[i].body_a = joints[i].body_a; rows[i].body_b = joints[i].body_b;
+        rows[i].collide_connected = (joints[i].collide_connected & 1u) | (static_cast<uint32_t>(PR_JOINT_ROPE) << 8);
+        rows[i].local_anchor_a = joints[i].local_anchor_a; rows[i].local_anchor_b = joints[i].local_anchor_b;
+        rows[i].impulse_x = joints[i].impulse; rows[i].reference_angle = joints[i].max_length; rows[i].limit_state = joints[i].limit_state;
     }
     return pr_create_revolute_joints(pw, n, rows.data(), first_id);
 }
@@ -1997,7 +2011,7 @@ int pr_destroy_joints(pr_world* pw, uint32_t n, const uint32_t* ids)
         PR_LAUNCH(k_wake_bodies, static_cast<unsigned>(wake.size()), w.stream, w.d, static_cast<unsigned>(wake.size()), sids);
     }
     flag_joint_pairs_for_filtering(w, pairs);
-    refresh_joint_tables(w);
+    w.jointTablesDirty = true;
     sync(w);
     return PR_OK;
     API_CATCH(pw)
@@ -2434,6 +2448,7 @@ int pr_step(pr_world* pw, const pr_step_conf* conf, pr_step_stats* stats_out)
 {
     API_TRY(pw)
     pr_step_stats st;
+    if (pw->w.jointTablesDirty) { refresh_joint_tables(pw->w); pw->w.jointTablesDirty = false; } // (built when a Step needs them, not per CreateJoint / Destroy)
     step_impl(pw->w, *conf, st);
     if (stats_out) *stats_out = st;
     return PR_OK;

@@ -196,7 +196,7 @@ struct World {
     // capacities
     unsigned capBodies = 0, capShapes = 0, capChildren = 0, capVerts = 0, capProxies = 0, capContacts = 0,
              capPairs = 0, capCons = 0, capHash = 0, capAdj = 0, capJoints = 0;
-    unsigned nJoints = 0; bool jointsSerial = false;
+    unsigned nJoints = 0; bool jointsSerial = false, jointTablesDirty = true; // (tables: jointsSerial, the collideConnected == false pair list)
     std::vector<unsigned> bodyWorld; // batch arena only: world index of each body
     DV d{};
     RadixScratch rs;

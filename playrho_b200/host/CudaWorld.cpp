@@ -11,6 +11,7 @@
 #include <playrho/d2/DistanceProxy.hpp>
 #include <playrho/d2/RevoluteJointConf.hpp>
 #include <playrho/d2/DistanceJointConf.hpp>
+#include <playrho/d2/RopeJointConf.hpp>
 #include <playrho/to_underlying.hpp>
 
 #include <algorithm>
@@ -659,11 +660,25 @@ static pr_revolute_joint ToJointRow(const DistanceJointConf& jc)
     std::memcpy(&r, &o, sizeof(r));
     return r;
 }
+static pr_revolute_joint ToJointRow(const RopeJointConf& jc)
+{ // the same table row viewed as pr_rope_joint
+    pr_rope_joint o{};
+    o.body_a = static_cast<std::uint32_t>(to_underlying(jc.bodyA)); o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.collide_connected = (jc.collideConnected ? 1u : 0u) | (static_cast<std::uint32_t>(PR_JOINT_ROPE) << 8);
+    o.local_anchor_a = pr_vec2{GetX(jc.localAnchorA), GetY(jc.localAnchorA)};
+    o.local_anchor_b = pr_vec2{GetX(jc.localAnchorB), GetY(jc.localAnchorB)};
+    o.impulse = jc.impulse; o.max_length = jc.maxLength; o.limit_state = static_cast<std::uint32_t>(jc.limitState);
+    pr_revolute_joint r{};
+    static_assert(sizeof(r) == sizeof(o), "joint rows share one table");
+    std::memcpy(&r, &o, sizeof(r));
+    return r;
+}
 // the joint types the device solves (SURVEY a15 + the first of 8(f) rank 1); the others are rejected
 static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, BodyID& b)
 {
     if (GetType(def) == GetTypeID<RevoluteJointConf>()) { const auto jc = TypeCast<RevoluteJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     if (GetType(def) == GetTypeID<DistanceJointConf>()) { const auto jc = TypeCast<DistanceJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
+    if (GetType(def) == GetTypeID<RopeJointConf>()) { const auto jc = TypeCast<RopeJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     return false;
 }
 JointID CreateJoint(CudaWorld& w, Joint def)
@@ -695,6 +710,12 @@ Joint GetJoint(const CudaWorld& w, JointID id)
         auto dc = TypeCast<DistanceJointConf>(elem);
         dc.impulse = Momentum{r.impulse_x * NewtonSecond};
         return Joint{dc};
+    }
+    if (GetType(elem) == GetTypeID<RopeJointConf>()) {
+        auto rc = TypeCast<RopeJointConf>(elem);
+        rc.impulse = Momentum{r.impulse_x * NewtonSecond};
+        rc.limitState = static_cast<LimitState>(r.limit_state);
+        return Joint{rc};
     }
     auto jc = TypeCast<RevoluteJointConf>(elem);
     jc.impulse = Vec3{r.impulse_x, r.impulse_y, r.impulse_z};

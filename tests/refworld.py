@@ -207,6 +207,14 @@ class RefWorld:
         assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
         return jid
 
+    def add_rope(self, body_a, body_b, local_a, local_b, max_length, collide_connected=False):
+        self.lib.ref_add_rope.argtypes = [vp, u32, u32, f32, f32, f32, f32, f32, i32]
+        self.lib.ref_add_rope.restype = u32
+        jid = self.lib.ref_add_rope(self.h, int(body_a), int(body_b), local_a[0], local_a[1], local_b[0], local_b[1], max_length,
+                                    1 if collide_connected else 0)
+        assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
+        return jid
+
     def destroy_joint(self, joint):
         self.lib.ref_destroy_joint.argtypes = [vp, u32]
         self._chk(self.lib.ref_destroy_joint(self.h, int(joint)))

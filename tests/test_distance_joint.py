@@ -1,4 +1,5 @@
-"""DistanceJointConf on the device (the first of the ten other joint types; DistanceJointConf.cpp:81-246):
+"""DistanceJointConf and RopeJointConf on the device (the first two of the ten other joint types;
+DistanceJointConf.cpp:81-246, RopeJointConf.cpp:58-214):
 a rigid rod, a soft spring, a rod between two dynamic bodies and a revolute joint in one world -- the joint table holds both
 types, PR_JOINT_TYPE says which row is which. Reference (its own CreateJoint / Destroy) == restatement == emulated kernels ==
 GPU, bit for bit, incl. the joints' accumulated impulses."""
@@ -28,15 +29,18 @@ def _build():
     ref.add_distance(hub, c, (2.0, 10.0), (2.0, 6.2))
     ref.add_distance(c, e, (2.3, 6.0), (3.5, 5.0), collide_connected=True)                 # rod between two dynamic bodies
     ref.add_revolute(hub, f, (6.0, 9.0))                                                   # and a revolute joint in the same table
+    r1 = ref.add_body(DYNAMIC, pos=(-10.0, 8.0), vel=(4.0, 0.0), acc=(0.0, -9.8), shapes=[disk])   # on a rope: slack at first, then taut
+    ref.add_rope(hub, r1, (-10.0, 0.0), (0.0, 0.0), 3.0)
     g1 = ref.add_body(DYNAMIC, pos=(10.0, 0.31), acc=(0.0, -9.8), shapes=[box])            # two boxes stacked on the ground, touching
     g2 = ref.add_body(DYNAMIC, pos=(10.0, 0.92), acc=(0.0, -9.8), shapes=[box])
+    ref.rope_body = r1
     return ref, hub, (a, b, c, e, f, g1, g2)
 
 
 def _run(lib=None, device=-1, with_device=True):
     ref, hub, bodies = _build()
     sc = ref.export_scene()
-    assert [int(j["collide_connected"]) >> 8 for j in sc["joints"]] == [1, 1, 1, 1, 0]
+    assert [int(j["collide_connected"]) >> 8 for j in sc["joints"]] == [1, 1, 1, 1, 0, 2]
     orc = refworld.OracleWorld(sc)
     twins = []
     if with_device:
@@ -97,6 +101,8 @@ def _run(lib=None, device=-1, with_device=True):
     assert b[bodies[0]]["xf_py"] > 5.0          # the rod holds its box up
     j = ref.joints()
     assert abs(float(j[0]["impulse_x"])) > 0.0  # and carries load
+    assert float(j[5]["impulse_x"]) < 0.0 and int(j[5]["limit_state"]) in (0, 2)   # the rope went taut
+    assert b[ref.rope_body]["xf_py"] > 6.0
     return twins[0] if twins else None
 
 
