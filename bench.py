@@ -220,6 +220,7 @@ def run_reference(args, rank, world_size):
     """--impl reference: the reference's own Step (oracle/_ref, built from /root/reference) on the host."""
     if rank != 0:
         return
+    _checker_path()
     import refworld
     from playrho_b200 import abi  # noqa: F401
     if not refworld.have_ref(refworld.have_ref(True)):
