@@ -107,7 +107,7 @@ typedef struct pr_revolute_joint {
 
 /* Joint rows share one table (JointIDs are one id space in the reference): every row has pr_revolute_joint's size and leading
  * fields, and bits 8..15 of collide_connected say which joint type it is (bit 0 is the flag itself). */
-enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2 };
+enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2, PR_JOINT_FRICTION = 3, PR_JOINT_MOTOR = 4 };
 #define PR_JOINT_TYPE(row) (((row).collide_connected >> 8) & 0xFFu)
 /* DistanceJointConf (Library/include/playrho/d2/DistanceJointConf.hpp): rod or spring between two anchor points.
  * Solver: Library/source/playrho/d2/DistanceJointConf.cpp:81-246 (InitVelocity, SolveVelocity, SolvePosition). */
@@ -137,6 +137,33 @@ typedef struct pr_rope_joint {
     float reserved2[4];
     uint32_t limit_state;                /* LimitState: 0 inactive, 2 at the upper limit (InitVelocity writes it) */
 } pr_rope_joint;
+
+/* FrictionJointConf (FrictionJointConf.hpp; solver FrictionJointConf.cpp:76-239): top-down friction, force and torque capped. */
+typedef struct pr_friction_joint {
+    uint32_t body_a, body_b;
+    uint32_t collide_connected;          /* bit 0: collideConnected; bits 8..15: PR_JOINT_FRICTION */
+    pr_vec2 local_anchor_a, local_anchor_b;
+    float linear_impulse_x, linear_impulse_y, angular_impulse; /* accumulated impulses (warm start) */
+    float reserved0[2];
+    uint32_t reserved1[2];
+    float reserved2[2];
+    float max_force, max_torque;
+    uint32_t reserved3;
+} pr_friction_joint;
+/* MotorJointConf (MotorJointConf.hpp; solver MotorJointConf.cpp:77-235): drives body B towards an offset pose relative to A. */
+typedef struct pr_motor_joint {
+    uint32_t body_a, body_b;
+    uint32_t collide_connected;          /* bit 0: collideConnected; bits 8..15: PR_JOINT_MOTOR */
+    pr_vec2 linear_offset;               /* in body A's frame */
+    pr_vec2 reserved0;
+    float linear_impulse_x, linear_impulse_y, angular_impulse;
+    float reserved1;
+    float angular_offset;
+    uint32_t reserved2[2];
+    float correction_factor, reserved3;
+    float max_force, max_torque;
+    uint32_t reserved4;
+} pr_motor_joint;
 
 /* ContactFeature packed little-endian: typeA | indexA<<8 | typeB<<16 | indexB<<24 */
 typedef uint32_t pr_contact_feature;
@@ -273,6 +300,8 @@ int pr_create_revolute_joints(pr_world* w, uint32_t n, const pr_revolute_joint* 
  * type with PR_JOINT_TYPE and view it as the matching struct). */
 int pr_create_distance_joints(pr_world* w, uint32_t n, const pr_distance_joint* joints, uint32_t* first_id);
 int pr_create_rope_joints(pr_world* w, uint32_t n, const pr_rope_joint* joints, uint32_t* first_id);
+int pr_create_friction_joints(pr_world* w, uint32_t n, const pr_friction_joint* joints, uint32_t* first_id);
+int pr_create_motor_joints(pr_world* w, uint32_t n, const pr_motor_joint* joints, uint32_t* first_id);
 
 /* SetShape(AabbTreeWorld&, ShapeID, Shape) (AabbTreeWorld.cpp:1284-1356) for a value whose geometry (children) and filter are
  * what they were: friction, restitution, density and the sensor flag are replaced; every body using the shape is woken

@@ -415,6 +415,22 @@ uint32_t ref_add_rope(void* h, uint32_t bodyA, uint32_t bodyB, float lax, float 
     return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
     REF_CATCH(0xFFFFFFFFu)
 }
+uint32_t ref_add_friction(void* h, uint32_t bodyA, uint32_t bodyB, float ax, float ay, float maxForce, float maxTorque)
+{
+    REF_TRY(h)
+    auto jc = GetFrictionJointConf(rw->world, MakeId<BodyID>(bodyA), MakeId<BodyID>(bodyB), Length2{ax * 1_m, ay * 1_m});
+    jc.maxForce = maxForce * 1_N; jc.maxTorque = maxTorque * 1_Nm;
+    return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
+    REF_CATCH(0xFFFFFFFFu)
+}
+uint32_t ref_add_motor(void* h, uint32_t bodyA, uint32_t bodyB, float ox, float oy, float angularOffset, float maxForce, float maxTorque, float correctionFactor)
+{
+    REF_TRY(h)
+    auto jc = MotorJointConf{MakeId<BodyID>(bodyA), MakeId<BodyID>(bodyB), Length2{ox * 1_m, oy * 1_m}, angularOffset * 1_rad};
+    jc.maxForce = maxForce * 1_N; jc.maxTorque = maxTorque * 1_Nm; jc.correctionFactor = correctionFactor;
+    return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
+    REF_CATCH(0xFFFFFFFFu)
+}
 int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
 {
     REF_TRY(h)
@@ -432,6 +448,26 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
             o.local_anchor_a = pr_vec2{GetX(dc.localAnchorA), GetY(dc.localAnchorA)};
             o.local_anchor_b = pr_vec2{GetX(dc.localAnchorB), GetY(dc.localAnchorB)};
             o.impulse_x = dc.impulse; o.reference_angle = dc.length; o.lower_angle = dc.frequency; o.upper_angle = dc.dampingRatio;
+            continue;
+        }
+        if (GetType(joint) == GetTypeID<FrictionJointConf>()) { // the same row, viewed as pr_friction_joint
+            const auto fc = TypeCast<FrictionJointConf>(joint);
+            o.body_a = to_underlying(fc.bodyA); o.body_b = to_underlying(fc.bodyB);
+            o.collide_connected = (fc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_FRICTION) << 8);
+            o.local_anchor_a = pr_vec2{GetX(fc.localAnchorA), GetY(fc.localAnchorA)};
+            o.local_anchor_b = pr_vec2{GetX(fc.localAnchorB), GetY(fc.localAnchorB)};
+            o.impulse_x = GetX(fc.linearImpulse); o.impulse_y = GetY(fc.linearImpulse); o.impulse_z = fc.angularImpulse;
+            o.motor_speed = fc.maxForce; o.max_motor_torque = fc.maxTorque;
+            continue;
+        }
+        if (GetType(joint) == GetTypeID<MotorJointConf>()) { // the same row, viewed as pr_motor_joint
+            const auto mc = TypeCast<MotorJointConf>(joint);
+            o.body_a = to_underlying(mc.bodyA); o.body_b = to_underlying(mc.bodyB);
+            o.collide_connected = (mc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_MOTOR) << 8);
+            o.local_anchor_a = pr_vec2{GetX(mc.linearOffset), GetY(mc.linearOffset)};
+            o.impulse_x = GetX(mc.linearImpulse); o.impulse_y = GetY(mc.linearImpulse); o.impulse_z = mc.angularImpulse;
+            o.reference_angle = mc.angularOffset; o.lower_angle = mc.correctionFactor;
+            o.motor_speed = mc.maxForce; o.max_motor_torque = mc.maxTorque;
             continue;
         }
         if (GetType(joint) == GetTypeID<RopeJointConf>()) { // the same row, viewed as pr_rope_joint

@@ -666,18 +666,110 @@ bool rope_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, flo
     posB.l = posB.l + imB * P; posB.a += iiB * LB;
     return (length - j.reference_angle) < c.linearSlop;
 }
+// ---------------- FrictionJointConf.cpp:76-239, MotorJointConf.cpp:77-235 ----------------
+// (mass[0..3] = linearMass rows, angularMass; motor: mass[4..5] = linearError, mass[6] = angularError)
+V2 mat22_transform(const float* m, V2 v)
+{ // Transform(v, M) = M * v, Vector.hpp:458-472
+    float x = 0.0f; x += m[0] * v.x; x += m[1] * v.y;
+    float y = 0.0f; y += m[2] * v.x; y += m[3] * v.y;
+    return {x, y};
+}
+void fm_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
+                      float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c, bool motor)
+{
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    wk.rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    wk.rB = motor ? rotate(-lcB, qB) : rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    const V2 rA = wk.rA, rB = wk.rB;
+    float exx, exy, eyy;
+    if (motor) {
+        exx = imA + imB + iiA * square(rA.y) / 1.0f + iiB * square(rB.y) / 1.0f;
+        exy = -iiA * rA.x * rA.y / 1.0f + -iiB * rB.x * rB.y / 1.0f;
+        eyy = imA + imB + iiA * square(rA.x) / 1.0f + iiB * square(rB.x) / 1.0f;
+    } else {
+        exx = imA + iiA * square(rA.y) / 1.0f + imB + iiB * square(rB.y) / 1.0f;
+        exy = -iiA * rA.x * rA.y / 1.0f + -iiB * rB.x * rB.y / 1.0f;
+        eyy = imA + iiA * square(rA.x) / 1.0f + imB + iiB * square(rB.x) / 1.0f;
+    }
+    const float cp = exx * eyy - exy * exy; // Invert(Matrix22), Math.hpp:430-442
+    if (!almost_zero(cp)) {
+        const float inverse = 1 / cp;
+        wk.mass[0] = eyy * inverse; wk.mass[1] = -exy * inverse; wk.mass[2] = -exy * inverse; wk.mass[3] = exx * inverse;
+    } else wk.mass[0] = wk.mass[1] = wk.mass[2] = wk.mass[3] = 0.0f;
+    const float invRotInertia = iiA + iiB;
+    wk.angularMass = (invRotInertia > 0.0f) ? 1.0f / invRotInertia : 0.0f;
+    if (motor) {
+        const V2 le = (posB.l + rB) - (posA.l + rA);
+        wk.mass[4] = le.x; wk.mass[5] = le.y;
+        wk.mass[6] = (posB.a - posA.a) - j.reference_angle;
+    }
+    if (c.warmStart) {
+        j.impulse_x *= c.dtRatio; j.impulse_y *= c.dtRatio; j.impulse_z *= c.dtRatio;
+        const V2 P{j.impulse_x, j.impulse_y};
+        const float crossAP = cross(rA, P) / 1.0f, crossBP = cross(rB, P) / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * (crossAP + j.impulse_z);
+        velB.l = velB.l + imB * P; velB.a += iiB * (crossBP + j.impulse_z);
+    } else { j.impulse_x = j.impulse_y = 0.0f; j.impulse_z = 0.0f; }
+}
+bool fm_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& vA, float imB, float iiB, Vel& vB,
+                       const JointSolverConf& c, bool motor)
+{
+    Vel velA = vA, velB = vB;
+    const V2 rA = wk.rA, rB = wk.rB;
+    const float h = c.dt;
+    const float inv_h = (h != 0.0f) ? 1.0f / h : 0.0f;
+    const float maxForce = j.motor_speed, maxTorque = j.max_motor_torque, correction = j.lower_angle;
+    bool solved = true;
+    {
+        const float Cdot = motor ? (velB.a - velA.a) + inv_h * correction * wk.mass[6] : (velB.a - velA.a);
+        const float angularImpulse = -wk.angularMass * Cdot;
+        const float oldAngularImpulse = j.impulse_z;
+        const float maxAngularImpulse = h * maxTorque;
+        j.impulse_z = std::clamp(oldAngularImpulse + angularImpulse, -maxAngularImpulse, maxAngularImpulse);
+        const float inc = j.impulse_z - oldAngularImpulse;
+        if (inc != 0.0f) solved = false;
+        if (!motor || inc != 0.0f) { velA.a -= iiA * inc; velB.a += iiB * inc; }
+    }
+    {
+        const V2 vb = velB.l + (rev_perp(rB) * (velB.a / 1.0f));
+        const V2 va = velA.l + (rev_perp(rA) * (velA.a / 1.0f));
+        const V2 Cdot = motor ? (vb - va) + (inv_h * correction) * V2{wk.mass[4], wk.mass[5]} : vb - va;
+        const V2 t = mat22_transform(wk.mass, Cdot);
+        const V2 impulse{-t.x, -t.y};
+        const V2 oldImpulse{j.impulse_x, j.impulse_y};
+        V2 acc = oldImpulse + impulse;
+        const float maxImpulse = h * maxForce;
+        if (magsq(acc) > square(maxImpulse)) { const Rot u = unit_vector(acc, Rot{0.0f, 0.0f}); acc = V2{u.c * maxImpulse, u.s * maxImpulse}; }
+        j.impulse_x = acc.x; j.impulse_y = acc.y;
+        const V2 inc = acc - oldImpulse;
+        const float angImpulseA = cross(rA, inc) / 1.0f, angImpulseB = cross(rB, inc) / 1.0f;
+        const bool any = motor ? (inc.x != 0.0f || inc.y != 0.0f || angImpulseA != 0.0f || angImpulseB != 0.0f) : (inc.x != 0.0f || inc.y != 0.0f);
+        if (any) solved = false;
+        if (!motor || any) {
+            velA.l = velA.l - imA * inc; velA.a -= iiA * angImpulseA;
+            velB.l = velB.l + imB * inc; velB.a += iiB * angImpulseB;
+        }
+    }
+    if (motor && solved) return true;
+    vA = velA; vB = velB;
+    return solved;
+}
 } // namespace
 void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
                          float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
 {
     if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) distance_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
     else if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) rope_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
+    else if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR)
+        fm_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c, PR_JOINT_TYPE(j) == PR_JOINT_MOTOR);
     else revolute_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
 }
 bool joint_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& velA, float imB, float iiB, Vel& velB, const JointSolverConf& c)
 {
     if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) return distance_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB);
     if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) return rope_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
+    if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR)
+        return fm_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c, PR_JOINT_TYPE(j) == PR_JOINT_MOTOR);
     return revolute_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
 }
 bool joint_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos& posA,
@@ -685,6 +777,7 @@ bool joint_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, fl
 {
     if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) return distance_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) return rope_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
+    if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR) return true;
     return revolute_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
 }
 }

@@ -248,6 +248,108 @@ PR_D void rope_solve_position(const DV& d, const pr_revolute_joint& j, const Joi
     if (!((length - j.reference_angle) < conf.linear_slop)) v.isl_jflag[wk.island] = 1u;
 }
 
+// ---- FrictionJointConf.cpp:76-239 and MotorJointConf.cpp:77-235 (one code path: the motor joint is the friction joint with a
+// pose error fed back). Row overlay: linearImpulse = impulse_x/y, angularImpulse = impulse_z, maxForce = motor_speed, maxTorque =
+// max_motor_torque; motor: linearOffset = local_anchor_a, angularOffset = reference_angle, correctionFactor = lower_angle.
+// work: rA, rB, m[0..3] = linearMass (rows), angularMass; motor: m[4..5] = linearError, m[6] = angularError
+PR_D float2 mat22_transform(const float* m, float2 v)
+{ // Transform(v, M) = M * v, Vector.hpp:458-472 (each element accumulated from zero)
+    float x = 0.0f; x += m[0] * v.x; x += m[1] * v.y;
+    float y = 0.0f; y += m[2] * v.x; y += m[3] * v.y;
+    return v2(x, y);
+}
+PR_D void fm_init_velocity(const DV& d, unsigned ji, pr_revolute_joint j, JointWork wk, const pr_step_conf& conf, const JView& v, bool motor)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 pA = v.s_pos[jv_idx(v.slotP, j.body_a)], pB = v.s_pos[jv_idx(v.slotP, j.body_b)];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
+    const Rot qA = rot_from_angle(pA.z), qB = rot_from_angle(pB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = motor ? rotate(-d.b_lc[j.body_b], qB) : rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    wk.rAx = rA.x; wk.rAy = rA.y; wk.rBx = rB.x; wk.rBy = rB.y;
+    float exx, exy, eyy;
+    if (motor) {
+        exx = imA + imB + iiA * square(rA.y) / 1.0f + iiB * square(rB.y) / 1.0f;
+        exy = -iiA * rA.x * rA.y / 1.0f + -iiB * rB.x * rB.y / 1.0f;
+        eyy = imA + imB + iiA * square(rA.x) / 1.0f + iiB * square(rB.x) / 1.0f;
+    } else {
+        exx = imA + iiA * square(rA.y) / 1.0f + imB + iiB * square(rB.y) / 1.0f;
+        exy = -iiA * rA.x * rA.y / 1.0f + -iiB * rB.x * rB.y / 1.0f;
+        eyy = imA + iiA * square(rA.x) / 1.0f + imB + iiB * square(rB.x) / 1.0f;
+    }
+    { // Invert(Matrix22), Math.hpp:430-442: columns (exx, exy), (exy, eyy)
+        const float cp = exx * eyy - exy * exy;
+        if (!almost_zero(cp)) {
+            const float inverse = 1 / cp;
+            wk.m[0] = eyy * inverse; wk.m[1] = -exy * inverse; wk.m[2] = -exy * inverse; wk.m[3] = exx * inverse;
+        } else wk.m[0] = wk.m[1] = wk.m[2] = wk.m[3] = 0.0f;
+    }
+    const float invRotInertia = iiA + iiB;
+    wk.angularMass = (invRotInertia > 0.0f) ? 1.0f / invRotInertia : 0.0f;
+    if (motor) {
+        const float2 le = (v2(pB.x, pB.y) + rB) - (v2(pA.x, pA.y) + rA);
+        wk.m[4] = le.x; wk.m[5] = le.y;
+        wk.m[6] = (pB.z - pA.z) - j.reference_angle;
+    }
+    if (conf.do_warm_start) {
+        j.impulse_x *= conf.dt_ratio; j.impulse_y *= conf.dt_ratio; j.impulse_z *= conf.dt_ratio;
+        const float2 P = v2(j.impulse_x, j.impulse_y);
+        const float crossAP = cross(rA, P) / 1.0f, crossBP = cross(rB, P) / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * (crossAP + j.impulse_z);
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * (crossBP + j.impulse_z);
+    } else { j.impulse_x = j.impulse_y = 0.0f; j.impulse_z = 0.0f; }
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    d.jt_work[ji] = wk;
+}
+PR_D void fm_solve_velocity(const DV& d, unsigned ji, pr_revolute_joint j, const JointWork& wk, const pr_step_conf& conf, const JView& v, bool motor)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
+    const float2 rA = v2(wk.rAx, wk.rAy), rB = v2(wk.rBx, wk.rBy);
+    const float h = conf.delta_time;
+    const float inv_h = (h != 0.0f) ? 1.0f / h : 0.0f;
+    const float maxForce = j.motor_speed, maxTorque = j.max_motor_torque, correction = j.lower_angle;
+    bool solved = true;
+    { // angular
+        const float Cdot = motor ? (velB.z - velA.z) + inv_h * correction * wk.m[6] : (velB.z - velA.z);
+        const float angularImpulse = -wk.angularMass * Cdot;
+        const float oldAngularImpulse = j.impulse_z;
+        const float maxAngularImpulse = h * maxTorque;
+        j.impulse_z = stdclamp(oldAngularImpulse + angularImpulse, -maxAngularImpulse, maxAngularImpulse);
+        const float inc = j.impulse_z - oldAngularImpulse;
+        if (inc != 0.0f) solved = false;
+        if (!motor || inc != 0.0f) { velA.z -= iiA * inc; velB.z += iiB * inc; }
+    }
+    { // linear
+        const float2 vb = v2(velB.x, velB.y) + (rev_perp(rB) * (velB.z / 1.0f));
+        const float2 va = v2(velA.x, velA.y) + (rev_perp(rA) * (velA.z / 1.0f));
+        const float2 Cdot = motor ? (vb - va) + (inv_h * correction) * v2(wk.m[4], wk.m[5]) : vb - va;
+        const float2 impulse = -mat22_transform(wk.m, Cdot);
+        const float2 oldImpulse = v2(j.impulse_x, j.impulse_y);
+        float2 acc = oldImpulse + impulse;
+        const float maxImpulse = h * maxForce;
+        if (magsq(acc) > square(maxImpulse)) { const Rot u = unit_vector(acc, mkrot(0.0f, 0.0f)); acc = u * maxImpulse; }
+        j.impulse_x = acc.x; j.impulse_y = acc.y;
+        const float2 inc = acc - oldImpulse;
+        const float angImpulseA = cross(rA, inc) / 1.0f, angImpulseB = cross(rB, inc) / 1.0f;
+        const bool any = motor ? (inc.x != 0.0f || inc.y != 0.0f || angImpulseA != 0.0f || angImpulseB != 0.0f) : (inc.x != 0.0f || inc.y != 0.0f);
+        if (any) solved = false;
+        if (!motor || any) {
+            const float2 la = v2(velA.x, velA.y) - imA * inc; velA.x = la.x; velA.y = la.y; velA.z -= iiA * angImpulseA;
+            const float2 lb = v2(velB.x, velB.y) + imB * inc; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * angImpulseB;
+        }
+    }
+    d.jt[ji] = j;
+    if (motor && solved) return; // (:222-224: the velocities are what they were)
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+    if (!solved) v.isl_jflag[wk.island] = 1u;
+}
+
 PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf, const JView& v)
 {
     pr_revolute_joint j = d.jt[ji];
@@ -264,6 +366,12 @@ PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf
         if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
         if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
         rope_init_velocity(d, ji, j, wk, conf, v);
+        return;
+    }
+    if (joint_type(j) == PR_JOINT_FRICTION || joint_type(j) == PR_JOINT_MOTOR) {
+        if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
+        if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
+        fm_init_velocity(d, ji, j, wk, conf, v, joint_type(j) == PR_JOINT_MOTOR);
         return;
     }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
@@ -330,6 +438,7 @@ PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& con
     pr_revolute_joint j = d.jt[ji];
     if (joint_type(j) == PR_JOINT_DISTANCE) { distance_solve_velocity(d, ji, j, wk, v); return; }
     if (joint_type(j) == PR_JOINT_ROPE) { rope_solve_velocity(d, ji, j, wk, conf, v); return; }
+    if (joint_type(j) == PR_JOINT_FRICTION || joint_type(j) == PR_JOINT_MOTOR) { fm_solve_velocity(d, ji, j, wk, conf, v, joint_type(j) == PR_JOINT_MOTOR); return; }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
@@ -394,6 +503,7 @@ PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& con
     const pr_revolute_joint j = d.jt[ji];
     if (joint_type(j) == PR_JOINT_DISTANCE) { distance_solve_position(d, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_ROPE) { rope_solve_position(d, j, wk, conf, v); return; }
+    if (joint_type(j) == PR_JOINT_FRICTION || joint_type(j) == PR_JOINT_MOTOR) return; // SolvePosition: nothing to do, always solved
     const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;

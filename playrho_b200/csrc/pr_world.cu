@@ -352,6 +352,11 @@ static void rebuild_bvh(World& w)
     w.bvhValid = true; w.bvhLeaves = P; w.bvhRefits = 0;
 }
 
+static unsigned bvh_refit_steps()
+{
+    static const unsigned v = [] { const char* e = getenv("PR_BVH_REFIT_STEPS"); return e ? static_cast<unsigned>(atoi(e)) : 3u; }();
+    return v;
+}
 // FindContacts + AddContacts, AabbTreeWorld.cpp:709-751 and :2423-2547
 static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer& tm, bool toiRound = false)
 {
@@ -364,10 +369,18 @@ static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer
     tm.mark(w, PR_STAGE_BVH);
     // few moved proxies and an intact tree: grow the ancestors' boxes in place instead of rebuilding
     const bool refit = w.bvhValid && w.bvhLeaves == P && P > 1 && 8ull * nQueue < P && w.bvhRefits < 256u;
+    // many moved proxies, but bodies move a fraction of their size per step: the Morton order of the last rebuild is still a good
+    // tree for a few steps -- recompute every box bottom-up over the SAME topology (k_bvh_refit alone: no bounds pass, no sort,
+    // no build) and rebuild every bvh_refit_steps()-th time (PR_BVH_REFIT_STEPS, 0 = always rebuild; debug bit 10 too)
+    const bool fullRefit = !refit && w.bvhValid && w.bvhLeaves == P && P > 1 && w.bvhFullRefits < bvh_refit_steps() && !(w.debugFlags & 1024u);
     if (refit) {
         PR_LAUNCH(k_bvh_refit_moved, nQueue, w.stream, d, nQueue, P);
         ++w.bvhRefits;
-    } else if (P > 1) rebuild_bvh(w);
+    } else if (fullRefit) {
+        dset(w, d.bv_visit, 0, sizeof(unsigned) * P);
+        PR_LAUNCH(k_bvh_refit, P, w.stream, d, P, w.bvhSortedIdx);
+        ++w.bvhFullRefits;
+    } else if (P > 1) { rebuild_bvh(w); w.bvhFullRefits = 0; }
     if (w.hashDirty) rebuild_hash(w);
     tm.mark(w, PR_STAGE_QUERY);
     unsigned nPairs = 0;
@@ -1986,6 +1999,21 @@ int pr_create_rope_joints(pr_world* pw, uint32_t n, const pr_rope_joint* joints,
     }
     return pr_create_revolute_joints(pw, n, rows.data(), first_id);
 }
+
+} // extern "C"
+template <class Row> static int create_tagged_joints(pr_world* pw, uint32_t n, const Row* joints, uint32_t type, uint32_t* first_id)
+{ // rows of the one joint table: same size and leading fields as pr_revolute_joint, tagged with their type
+    static_assert(sizeof(Row) == sizeof(pr_revolute_joint), "joint rows share one table");
+    std::vector<pr_revolute_joint> rows(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        std::memcpy(&rows[i], &joints[i], sizeof(pr_revolute_joint));
+        rows[i].collide_connected = (joints[i].collide_connected & 1u) | (type << 8);
+    }
+    return pr_create_revolute_joints(pw, n, rows.data(), first_id);
+}
+extern "C" {
+int pr_create_friction_joints(pr_world* pw, uint32_t n, const pr_friction_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_FRICTION, first_id); }
+int pr_create_motor_joints(pr_world* pw, uint32_t n, const pr_motor_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_MOTOR, first_id); }
 
 int pr_destroy_joints(pr_world* pw, uint32_t n, const uint32_t* ids)
 { // Destroy(AabbTreeWorld&, JointID), :1215-1227: Remove(id) wakes both bodies (:1192-1205), the id goes to the free list

@@ -185,6 +185,7 @@ struct World {
     // the 40 saved launches per iteration cost): opt-in (pr_set_debug bit 4), bit-exact, under test.
     unsigned colorCap = 64u;
     bool subStepping = false, adjValid = false, bvhValid = false, bpDirty = true, toiAlphaDirty = true;
+    unsigned bvhFullRefits = 0; // steps since the last rebuild that only re-fitted the boxes over the same topology
     unsigned bvhLeaves = 0, bvhRefits = 0, hashTombs = 0, toiListBound = 0, toiRoundsHint = 1, toiGroupsHint = 1;
     const unsigned* bvhSortedIdx = nullptr;
     std::vector<std::vector<unsigned>> bodyProxies; // m_bodyProxies

@@ -12,6 +12,8 @@
 #include <playrho/d2/RevoluteJointConf.hpp>
 #include <playrho/d2/DistanceJointConf.hpp>
 #include <playrho/d2/RopeJointConf.hpp>
+#include <playrho/d2/FrictionJointConf.hpp>
+#include <playrho/d2/MotorJointConf.hpp>
 #include <playrho/to_underlying.hpp>
 
 #include <algorithm>
@@ -673,11 +675,41 @@ static pr_revolute_joint ToJointRow(const RopeJointConf& jc)
     std::memcpy(&r, &o, sizeof(r));
     return r;
 }
+static pr_revolute_joint ToJointRow(const FrictionJointConf& jc)
+{ // the same table row viewed as pr_friction_joint
+    pr_friction_joint o{};
+    o.body_a = static_cast<std::uint32_t>(to_underlying(jc.bodyA)); o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.collide_connected = (jc.collideConnected ? 1u : 0u) | (static_cast<std::uint32_t>(PR_JOINT_FRICTION) << 8);
+    o.local_anchor_a = pr_vec2{GetX(jc.localAnchorA), GetY(jc.localAnchorA)};
+    o.local_anchor_b = pr_vec2{GetX(jc.localAnchorB), GetY(jc.localAnchorB)};
+    o.linear_impulse_x = GetX(jc.linearImpulse); o.linear_impulse_y = GetY(jc.linearImpulse); o.angular_impulse = jc.angularImpulse;
+    o.max_force = jc.maxForce; o.max_torque = jc.maxTorque;
+    pr_revolute_joint r{};
+    static_assert(sizeof(r) == sizeof(o), "joint rows share one table");
+    std::memcpy(&r, &o, sizeof(r));
+    return r;
+}
+static pr_revolute_joint ToJointRow(const MotorJointConf& jc)
+{ // the same table row viewed as pr_motor_joint
+    pr_motor_joint o{};
+    o.body_a = static_cast<std::uint32_t>(to_underlying(jc.bodyA)); o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.collide_connected = (jc.collideConnected ? 1u : 0u) | (static_cast<std::uint32_t>(PR_JOINT_MOTOR) << 8);
+    o.linear_offset = pr_vec2{GetX(jc.linearOffset), GetY(jc.linearOffset)};
+    o.linear_impulse_x = GetX(jc.linearImpulse); o.linear_impulse_y = GetY(jc.linearImpulse); o.angular_impulse = jc.angularImpulse;
+    o.angular_offset = jc.angularOffset; o.correction_factor = jc.correctionFactor;
+    o.max_force = jc.maxForce; o.max_torque = jc.maxTorque;
+    pr_revolute_joint r{};
+    static_assert(sizeof(r) == sizeof(o), "joint rows share one table");
+    std::memcpy(&r, &o, sizeof(r));
+    return r;
+}
 // the joint types the device solves (SURVEY a15 + the first of 8(f) rank 1); the others are rejected
 static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, BodyID& b)
 {
     if (GetType(def) == GetTypeID<RevoluteJointConf>()) { const auto jc = TypeCast<RevoluteJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     if (GetType(def) == GetTypeID<DistanceJointConf>()) { const auto jc = TypeCast<DistanceJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
+    if (GetType(def) == GetTypeID<FrictionJointConf>()) { const auto jc = TypeCast<FrictionJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
+    if (GetType(def) == GetTypeID<MotorJointConf>()) { const auto jc = TypeCast<MotorJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     if (GetType(def) == GetTypeID<RopeJointConf>()) { const auto jc = TypeCast<RopeJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     return false;
 }
@@ -710,6 +742,18 @@ Joint GetJoint(const CudaWorld& w, JointID id)
         auto dc = TypeCast<DistanceJointConf>(elem);
         dc.impulse = Momentum{r.impulse_x * NewtonSecond};
         return Joint{dc};
+    }
+    if (GetType(elem) == GetTypeID<FrictionJointConf>()) {
+        auto fc = TypeCast<FrictionJointConf>(elem);
+        fc.linearImpulse = Momentum2{r.impulse_x * NewtonSecond, r.impulse_y * NewtonSecond};
+        fc.angularImpulse = AngularMomentum{r.impulse_z * NewtonMeterSecond};
+        return Joint{fc};
+    }
+    if (GetType(elem) == GetTypeID<MotorJointConf>()) {
+        auto mc = TypeCast<MotorJointConf>(elem);
+        mc.linearImpulse = Momentum2{r.impulse_x * NewtonSecond, r.impulse_y * NewtonSecond};
+        mc.angularImpulse = AngularMomentum{r.impulse_z * NewtonMeterSecond};
+        return Joint{mc};
     }
     if (GetType(elem) == GetTypeID<RopeJointConf>()) {
         auto rc = TypeCast<RopeJointConf>(elem);

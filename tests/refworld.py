@@ -215,6 +215,21 @@ class RefWorld:
         assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
         return jid
 
+    def add_friction(self, body_a, body_b, anchor, max_force, max_torque):
+        self.lib.ref_add_friction.argtypes = [vp, u32, u32, f32, f32, f32, f32]
+        self.lib.ref_add_friction.restype = u32
+        jid = self.lib.ref_add_friction(self.h, int(body_a), int(body_b), anchor[0], anchor[1], max_force, max_torque)
+        assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
+        return jid
+
+    def add_motor(self, body_a, body_b, linear_offset, angular_offset, max_force, max_torque, correction_factor=0.3):
+        self.lib.ref_add_motor.argtypes = [vp, u32, u32, f32, f32, f32, f32, f32, f32]
+        self.lib.ref_add_motor.restype = u32
+        jid = self.lib.ref_add_motor(self.h, int(body_a), int(body_b), linear_offset[0], linear_offset[1], angular_offset, max_force, max_torque,
+                                     correction_factor)
+        assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
+        return jid
+
     def destroy_joint(self, joint):
         self.lib.ref_destroy_joint.argtypes = [vp, u32]
         self._chk(self.lib.ref_destroy_joint(self.h, int(joint)))
