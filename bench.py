@@ -475,7 +475,8 @@ def main():
         solve_ms = stage["velocity"] + stage["position"]
         others = {
             ("k_solve_fused (warm start + %d velocity + %d position iterations, all colours, one persistent kernel)" % (nv, npi)) if fused
-            else ("k_solve_velocity/k_solve_position (one launch per colour and iteration)"):
+            else ("k_solve_velocity/k_solve_position (one launch per colour and iteration)" if (args.debug_flags & 128) else
+                  "k_flow_pass (dataflow solver: one launch per warm-start / velocity / position pass over all coloured rows)"):
                 {"algorithmic_bytes": solve_bytes, "ms": solve_ms, "achieved": (solve_bytes / 1e9) / (solve_ms / 1e3) if solve_ms > 0 else 0.0},
             "k_build_constraints (setup)":
                 {"algorithmic_bytes": terms["a9_setup"], "ms": stage["setup"],

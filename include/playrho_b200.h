@@ -107,7 +107,7 @@ typedef struct pr_revolute_joint {
 
 /* Joint rows share one table (JointIDs are one id space in the reference): every row has pr_revolute_joint's size and leading
  * fields, and bits 8..15 of collide_connected say which joint type it is (bit 0 is the flag itself). */
-enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2, PR_JOINT_FRICTION = 3, PR_JOINT_MOTOR = 4 };
+enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2, PR_JOINT_FRICTION = 3, PR_JOINT_MOTOR = 4, PR_JOINT_WELD = 5 };
 #define PR_JOINT_TYPE(row) (((row).collide_connected >> 8) & 0xFFu)
 /* DistanceJointConf (Library/include/playrho/d2/DistanceJointConf.hpp): rod or spring between two anchor points.
  * Solver: Library/source/playrho/d2/DistanceJointConf.cpp:81-246 (InitVelocity, SolveVelocity, SolvePosition). */
@@ -164,6 +164,19 @@ typedef struct pr_motor_joint {
     float max_force, max_torque;
     uint32_t reserved4;
 } pr_motor_joint;
+/* WeldJointConf (WeldJointConf.hpp; solver WeldJointConf.cpp:35-371): glues two bodies together (rigid, or with a soft angular spring). */
+typedef struct pr_weld_joint {
+    uint32_t body_a, body_b;
+    uint32_t collide_connected;          /* bit 0: collideConnected; bits 8..15: PR_JOINT_WELD */
+    pr_vec2 local_anchor_a, local_anchor_b;
+    float impulse_x, impulse_y, impulse_z; /* accumulated impulse (warm start) */
+    float reserved0;
+    float reference_angle;               /* angle of body B minus angle of body A */
+    uint32_t reserved1[2];
+    float frequency, damping_ratio;      /* frequency 0: rigid; > 0: the angular constraint is a soft spring */
+    float reserved2[2];
+    uint32_t reserved3;
+} pr_weld_joint;
 
 /* ContactFeature packed little-endian: typeA | indexA<<8 | typeB<<16 | indexB<<24 */
 typedef uint32_t pr_contact_feature;
@@ -302,6 +315,7 @@ int pr_create_distance_joints(pr_world* w, uint32_t n, const pr_distance_joint* 
 int pr_create_rope_joints(pr_world* w, uint32_t n, const pr_rope_joint* joints, uint32_t* first_id);
 int pr_create_friction_joints(pr_world* w, uint32_t n, const pr_friction_joint* joints, uint32_t* first_id);
 int pr_create_motor_joints(pr_world* w, uint32_t n, const pr_motor_joint* joints, uint32_t* first_id);
+int pr_create_weld_joints(pr_world* w, uint32_t n, const pr_weld_joint* joints, uint32_t* first_id);
 
 /* SetShape(AabbTreeWorld&, ShapeID, Shape) (AabbTreeWorld.cpp:1284-1356) for a value whose geometry (children) and filter are
  * what they were: friction, restitution, density and the sensor flag are replaced; every body using the shape is woken

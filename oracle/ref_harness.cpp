@@ -431,6 +431,14 @@ uint32_t ref_add_motor(void* h, uint32_t bodyA, uint32_t bodyB, float ox, float 
     return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
     REF_CATCH(0xFFFFFFFFu)
 }
+uint32_t ref_add_weld(void* h, uint32_t bodyA, uint32_t bodyB, float ax, float ay, float frequency, float dampingRatio)
+{
+    REF_TRY(h)
+    auto jc = GetWeldJointConf(rw->world, MakeId<BodyID>(bodyA), MakeId<BodyID>(bodyB), Length2{ax * 1_m, ay * 1_m});
+    jc.frequency = frequency * 1_Hz; jc.dampingRatio = dampingRatio;
+    return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
+    REF_CATCH(0xFFFFFFFFu)
+}
 int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
 {
     REF_TRY(h)
@@ -468,6 +476,16 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
             o.impulse_x = GetX(mc.linearImpulse); o.impulse_y = GetY(mc.linearImpulse); o.impulse_z = mc.angularImpulse;
             o.reference_angle = mc.angularOffset; o.lower_angle = mc.correctionFactor;
             o.motor_speed = mc.maxForce; o.max_motor_torque = mc.maxTorque;
+            continue;
+        }
+        if (GetType(joint) == GetTypeID<WeldJointConf>()) { // the same row, viewed as pr_weld_joint
+            const auto wc = TypeCast<WeldJointConf>(joint);
+            o.body_a = to_underlying(wc.bodyA); o.body_b = to_underlying(wc.bodyB);
+            o.collide_connected = (wc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_WELD) << 8);
+            o.local_anchor_a = pr_vec2{GetX(wc.localAnchorA), GetY(wc.localAnchorA)};
+            o.local_anchor_b = pr_vec2{GetX(wc.localAnchorB), GetY(wc.localAnchorB)};
+            o.impulse_x = GetX(wc.impulse); o.impulse_y = GetY(wc.impulse); o.impulse_z = GetZ(wc.impulse);
+            o.reference_angle = wc.referenceAngle; o.lower_angle = wc.frequency; o.upper_angle = wc.dampingRatio;
             continue;
         }
         if (GetType(joint) == GetTypeID<RopeJointConf>()) { // the same row, viewed as pr_rope_joint

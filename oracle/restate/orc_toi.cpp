@@ -754,6 +754,150 @@ bool fm_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float 
     vA = velA; vB = velB;
     return solved;
 }
+// ---------------- WeldJointConf.cpp:35-371 (mass[3 * i + k] = mass[i][k], angularMass = gamma, ex[0] = bias) ----------------
+void weld_k(float* m, float imA, V2 rA, float iiA, float imB, V2 rB, float iiB)
+{ // GetMat33, :35-62
+    const float exx = imA + square(rA.y) * iiA / 1.0f + imB + square(rB.y) * iiB / 1.0f;
+    const float eyx = -rA.y * rA.x * iiA / 1.0f + -rB.y * rB.x * iiB / 1.0f;
+    const float ezx = -rA.y * iiA * 1.0f / 1.0f + -rB.y * iiB * 1.0f / 1.0f;
+    const float eyy = imA + square(rA.x) * iiA / 1.0f + imB + square(rB.x) * iiB / 1.0f;
+    const float ezy = rA.x * iiA * 1.0f / 1.0f + rB.x * iiB * 1.0f / 1.0f;
+    const float ezz = (iiA + iiB) * 1.0f / 1.0f;
+    m[0] = exx; m[3] = eyx; m[6] = ezx;
+    m[1] = m[3]; m[4] = eyy; m[7] = ezy;
+    m[2] = m[6]; m[5] = m[7]; m[8] = ezz;
+}
+void inverse22_of33(const float* k, float* r)
+{ // GetInverse22, Math.hpp:478-489
+    const float a = k[0], b = k[3], c = k[1], d = k[4];
+    float det = (a * d) - (b * c);
+    if (det != 0.0f) det = 1.0f / det;
+    const float out[9] = {det * d, -det * c, 0.0f, -det * b, det * a, 0.0f, 0.0f, 0.0f, 0.0f};
+    for (int i = 0; i < 9; ++i) r[i] = out[i];
+}
+void sym_inverse33(const float* k, float* r)
+{ // GetSymInverse33, Math.hpp:493-509
+    const float invDet = dot3(col(k, 0), cross3(col(k, 1), col(k, 2)));
+    const float det = (invDet != 0.0f) ? (1.0f / invDet) : invDet;
+    const float a11 = k[0], a12 = k[3], a13 = k[6], a22 = k[4], a23 = k[7], a33 = k[8];
+    const float ex_y = det * (a13 * a23 - a12 * a33);
+    const float ey_z = det * (a13 * a12 - a11 * a23);
+    const float ex_z = det * (a12 * a23 - a13 * a22);
+    const float out[9] = {det * (a22 * a33 - a23 * a23), ex_y, ex_z, ex_y, det * (a11 * a33 - a13 * a13), ey_z, ex_z, ey_z, det * (a11 * a22 - a12 * a12)};
+    for (int i = 0; i < 9; ++i) r[i] = out[i];
+}
+V2 transform2_by33(const float* A, V2 v) { return {A[0] * v.x + A[3] * v.y, A[1] * v.x + A[4] * v.y}; } // Math.hpp:522-526
+V3 transform3_by33(const float* m, V3 v)
+{ // m * v, Vector.hpp:458-472
+    float e[3];
+    const float vv[3] = {v.x, v.y, v.z};
+    for (int b = 0; b < 3; ++b) { float el = 0.0f; for (int a = 0; a < 3; ++a) el += m[3 * b + a] * vv[a]; e[b] = el; }
+    return {e[0], e[1], e[2]};
+}
+void weld_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
+                        float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
+{
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    wk.rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    wk.rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    float K[9];
+    weld_k(K, imA, wk.rA, iiA, imB, wk.rB, iiB);
+    const float frequency = j.lower_angle, dampingRatio = j.upper_angle;
+    if (frequency > 0.0f) {
+        inverse22_of33(K, wk.mass);
+        float invRotInertia = iiA + iiB;
+        const float rotInertia = (invRotInertia > 0.0f) ? 1.0f / invRotInertia : 0.0f;
+        const float C = posB.a - posA.a - j.reference_angle;
+        const float omega = 2.0f * 3.14159265358979323846264338327950288f * frequency;
+        const float d = 2.0f * rotInertia * dampingRatio * omega;
+        const float k = rotInertia * omega * omega;
+        const float h = c.dt;
+        const float invGamma = h * (d + h * k);
+        wk.angularMass = (invGamma != 0.0f) ? 1.0f / invGamma : 0.0f;
+        wk.ex[0] = C * h * k * wk.angularMass;
+        invRotInertia += wk.angularMass;
+        wk.mass[8] = (invRotInertia != 0.0f) ? 1.0f / invRotInertia : 0.0f;
+    } else if (K[8] == 0.0f) { inverse22_of33(K, wk.mass); wk.angularMass = 0.0f; wk.ex[0] = 0.0f; }
+    else { sym_inverse33(K, wk.mass); wk.angularMass = 0.0f; wk.ex[0] = 0.0f; }
+    if (c.warmStart) {
+        j.impulse_x *= c.dtRatio; j.impulse_y *= c.dtRatio; j.impulse_z *= c.dtRatio;
+        const V2 P{j.impulse_x * 1.0f, j.impulse_y * 1.0f};
+        const float L = j.impulse_z * 1.0f * 1.0f / (1.0f * 1.0f);
+        const float LA = L + cross(wk.rA, P) / 1.0f, LB = L + cross(wk.rB, P) / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    } else j.impulse_x = j.impulse_y = j.impulse_z = 0.0f;
+}
+bool weld_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& vA, float imB, float iiB, Vel& vB)
+{
+    const Vel oldA = vA, oldB = vB;
+    Vel velA = vA, velB = vB;
+    if (j.lower_angle > 0.0f) {
+        const float Cdot2 = velB.a - velA.a;
+        const float gamma = wk.angularMass * j.impulse_z * 1.0f * 1.0f / (1.0f * 1.0f);
+        const float impulse2 = -wk.mass[8] * (Cdot2 + wk.ex[0] + gamma);
+        j.impulse_z += impulse2;
+        velA.a -= iiA * impulse2 * 1.0f * 1.0f / (1.0f * 1.0f);
+        velB.a += iiB * impulse2 * 1.0f * 1.0f / (1.0f * 1.0f);
+        const V2 vb = velB.l + rev_perp(wk.rB) * (velB.a / 1.0f);
+        const V2 va = velA.l + rev_perp(wk.rA) * (velA.a / 1.0f);
+        const V2 Cdot1 = vb - va;
+        const V2 t = transform2_by33(wk.mass, V2{Cdot1.x / 1.0f, Cdot1.y / 1.0f});
+        const V2 impulse1{-t.x, -t.y};
+        j.impulse_x += impulse1.x; j.impulse_y += impulse1.y;
+        const V2 P{impulse1.x * 1.0f, impulse1.y * 1.0f};
+        const float LA = cross(wk.rA, P) / 1.0f, LB = cross(wk.rB, P) / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    } else {
+        const V2 vb = velB.l + rev_perp(wk.rB) * (velB.a / 1.0f);
+        const V2 va = velA.l + rev_perp(wk.rA) * (velA.a / 1.0f);
+        const V2 Cdot1 = vb - va;
+        const V3 Cdot{Cdot1.x / 1.0f, Cdot1.y / 1.0f, (velB.a - velA.a) / 1.0f};
+        const V3 t = transform3_by33(wk.mass, Cdot);
+        const V3 impulse{-t.x, -t.y, -t.z};
+        j.impulse_x += impulse.x; j.impulse_y += impulse.y; j.impulse_z += impulse.z;
+        const V2 P{impulse.x * 1.0f, impulse.y * 1.0f};
+        const float L = impulse.z * 1.0f * 1.0f / (1.0f * 1.0f);
+        const float LA = L + cross(wk.rA, P) / 1.0f, LB = L + cross(wk.rB, P) / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    }
+    const bool changed = (velA.l != oldA.l) || (velA.a != oldA.a) || (velB.l != oldB.l) || (velB.a != oldB.a);
+    if (changed) { vA = velA; vB = velB; return false; }
+    return true;
+}
+bool weld_solve_position(const pr_revolute_joint& j, float imA, float iiA, V2 lcA, Pos& posA, float imB, float iiB, V2 lcB, Pos& posB,
+                         const JointSolverConf& c)
+{
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    const V2 rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    const V2 rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    float K[9];
+    weld_k(K, imA, rA, iiA, imB, rB, iiB);
+    const V2 C1 = (posB.l + rB) - (posA.l + rA);
+    const float positionError = std::sqrt(magsq(C1));
+    float angularError = 0.0f;
+    if (j.lower_angle > 0.0f) {
+        const V2 s = solve22(K, C1);
+        const V2 P = V2{-s.x, -s.y} * 1.0f;
+        const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+        posA.l = posA.l - imA * P; posA.a -= iiA * LA;
+        posB.l = posB.l + imB * P; posB.a += iiB * LB;
+    } else {
+        const float C2 = posB.a - posA.a - j.reference_angle;
+        angularError = std::fabs(C2);
+        V3 impulse;
+        if (K[8] > 0.0f) { const V3 s = solve33(K, V3{C1.x, C1.y, C2}); impulse = V3{-s.x, -s.y, -s.z}; }
+        else { const V2 s = solve22(K, C1); impulse = V3{-s.x, -s.y, 0.0f}; }
+        const V2 P = V2{impulse.x * 1.0f, impulse.y * 1.0f} * 1.0f;
+        const float L = impulse.z * 1.0f * 1.0f / 1.0f;
+        const float LA = L + cross(rA, P) / 1.0f, LB = L + cross(rB, P) / 1.0f;
+        posA.l = posA.l - imA * P; posA.a -= iiA * LA;
+        posB.l = posB.l + imB * P; posB.a += iiB * LB;
+    }
+    return (positionError <= c.linearSlop) && (angularError <= c.angularSlop);
+}
 } // namespace
 void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
                          float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
@@ -762,6 +906,7 @@ void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, floa
     else if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) rope_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
     else if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR)
         fm_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c, PR_JOINT_TYPE(j) == PR_JOINT_MOTOR);
+    else if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) weld_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
     else revolute_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
 }
 bool joint_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& velA, float imB, float iiB, Vel& velB, const JointSolverConf& c)
@@ -770,6 +915,7 @@ bool joint_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, flo
     if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) return rope_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR)
         return fm_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c, PR_JOINT_TYPE(j) == PR_JOINT_MOTOR);
+    if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) return weld_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB);
     return revolute_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
 }
 bool joint_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos& posA,
@@ -778,6 +924,7 @@ bool joint_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, fl
     if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) return distance_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) return rope_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR) return true;
+    if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) return weld_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     return revolute_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
 }
 }

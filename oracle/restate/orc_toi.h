@@ -14,7 +14,7 @@ struct Sweep { Pos pos0, pos1; V2 lc; float alpha0; };
 ToiOut toi_via_sat(const Proxy& a, const Sweep& sA, const Proxy& b, const Sweep& sB, const pr_step_conf& conf);
 
 struct JointSolverConf { float dt, dtRatio; bool warmStart; float linearSlop, angularSlop, maxLinearCorrection, maxAngularCorrection; };
-struct RevoluteWork { V2 rA{0, 0}, rB{0, 0}; float mass[9] = {0}; float angularMass = 0; };
+struct RevoluteWork { V2 rA{0, 0}, rB{0, 0}; float mass[9] = {0}; float angularMass = 0; float ex[8] = {0}; };
 void revolute_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
                             float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c);
 bool revolute_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& velA,

@@ -350,6 +350,185 @@ PR_D void fm_solve_velocity(const DV& d, unsigned ji, pr_revolute_joint j, const
     if (!solved) v.isl_jflag[wk.island] = 1u;
 }
 
+// ---- WeldJointConf.cpp:35-371. Row overlay (pr_weld_joint): impulse = impulse_x/y/z, referenceAngle = reference_angle, frequency =
+// lower_angle, dampingRatio = upper_angle; work: rA, rB, m[3 * i + k] = mass[i][k], angularMass = gamma, ex[0] = bias
+PR_D void weld_k(float* m, float imA, float2 rA, float iiA, float imB, float2 rB, float iiB)
+{ // GetMat33, :35-62
+    const float exx = imA + square(rA.y) * iiA / 1.0f + imB + square(rB.y) * iiB / 1.0f;
+    const float eyx = -rA.y * rA.x * iiA / 1.0f + -rB.y * rB.x * iiB / 1.0f;
+    const float ezx = -rA.y * iiA * 1.0f / 1.0f + -rB.y * iiB * 1.0f / 1.0f;
+    const float eyy = imA + square(rA.x) * iiA / 1.0f + imB + square(rB.x) * iiB / 1.0f;
+    const float ezy = rA.x * iiA * 1.0f / 1.0f + rB.x * iiB * 1.0f / 1.0f;
+    const float ezz = (iiA + iiB) * 1.0f / 1.0f;
+    m[0] = exx; m[3] = eyx; m[6] = ezx;
+    m[1] = m[3]; m[4] = eyy; m[7] = ezy;
+    m[2] = m[6]; m[5] = m[7]; m[8] = ezz;
+}
+PR_D void mat33_inverse22(const float* k, float* r)
+{ // GetInverse22, Math.hpp:478-489
+    const float a = k[0], b = k[3], c = k[1], dd = k[4];
+    float det = (a * dd) - (b * c);
+    if (det != 0.0f) det = 1.0f / det;
+    r[0] = det * dd; r[1] = -det * c; r[2] = 0.0f;
+    r[3] = -det * b; r[4] = det * a; r[5] = 0.0f;
+    r[6] = 0.0f; r[7] = 0.0f; r[8] = 0.0f;
+}
+PR_D void mat33_sym_inverse33(const float* k, float* r)
+{ // GetSymInverse33, Math.hpp:493-509
+    const float invDet = dot3(mcol(k, 0), cross3(mcol(k, 1), mcol(k, 2)));
+    const float det = (invDet != 0.0f) ? (1.0f / invDet) : invDet;
+    const float a11 = k[0], a12 = k[3], a13 = k[6], a22 = k[4], a23 = k[7], a33 = k[8];
+    const float ex_y = det * (a13 * a23 - a12 * a33);
+    const float ey_z = det * (a13 * a12 - a11 * a23);
+    const float ex_z = det * (a12 * a23 - a13 * a22);
+    r[0] = det * (a22 * a33 - a23 * a23); r[1] = ex_y; r[2] = ex_z;
+    r[3] = ex_y; r[4] = det * (a11 * a33 - a13 * a13); r[5] = ey_z;
+    r[6] = ex_z; r[7] = ey_z; r[8] = det * (a11 * a22 - a12 * a12);
+}
+PR_D float2 mat33_transform2(const float* A, float2 v)
+{ // Transform(const Vec2&, const Mat33&), Math.hpp:522-526
+    return v2(A[0] * v.x + A[3] * v.y, A[1] * v.x + A[4] * v.y);
+}
+PR_D V3 mat33_transform3(const float* m, V3 v)
+{ // Transform(Vec3, Mat33) = m * v, Vector.hpp:458-472 (each element accumulated from zero)
+    V3 r;
+    r.x = 0.0f; r.x += m[0] * v.x; r.x += m[1] * v.y; r.x += m[2] * v.z;
+    r.y = 0.0f; r.y += m[3] * v.x; r.y += m[4] * v.y; r.y += m[5] * v.z;
+    r.z = 0.0f; r.z += m[6] * v.x; r.z += m[7] * v.y; r.z += m[8] * v.z;
+    return r;
+}
+PR_D void weld_init_velocity(const DV& d, unsigned ji, pr_revolute_joint j, JointWork wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 pA = v.s_pos[jv_idx(v.slotP, j.body_a)], pB = v.s_pos[jv_idx(v.slotP, j.body_b)];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
+    const Rot qA = rot_from_angle(pA.z), qB = rot_from_angle(pB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    wk.rAx = rA.x; wk.rAy = rA.y; wk.rBx = rB.x; wk.rBy = rB.y;
+    float K[9];
+    weld_k(K, imA, rA, iiA, imB, rB, iiB);
+    const float frequency = j.lower_angle, dampingRatio = j.upper_angle;
+    if (frequency > 0.0f) {
+        mat33_inverse22(K, wk.m);
+        float invRotInertia = iiA + iiB;
+        const float rotInertia = (invRotInertia > 0.0f) ? 1.0f / invRotInertia : 0.0f;
+        const float C = pB.z - pA.z - j.reference_angle;
+        const float omega = 2.0f * 3.14159265358979323846264338327950288f * frequency;
+        const float dd = 2.0f * rotInertia * dampingRatio * omega;
+        const float k = rotInertia * omega * omega;
+        const float h = conf.delta_time;
+        const float invGamma = h * (dd + h * k);
+        wk.angularMass = (invGamma != 0.0f) ? 1.0f / invGamma : 0.0f;
+        wk.ex[0] = C * h * k * wk.angularMass;
+        invRotInertia += wk.angularMass;
+        wk.m[8] = (invRotInertia != 0.0f) ? 1.0f / invRotInertia : 0.0f;
+    } else if (K[8] == 0.0f) {
+        mat33_inverse22(K, wk.m); wk.angularMass = 0.0f; wk.ex[0] = 0.0f;
+    } else {
+        mat33_sym_inverse33(K, wk.m); wk.angularMass = 0.0f; wk.ex[0] = 0.0f;
+    }
+    if (conf.do_warm_start) {
+        j.impulse_x *= conf.dt_ratio; j.impulse_y *= conf.dt_ratio; j.impulse_z *= conf.dt_ratio;
+        const float2 P = v2(j.impulse_x * 1.0f, j.impulse_y * 1.0f);
+        const float L = j.impulse_z * 1.0f * 1.0f / (1.0f * 1.0f);
+        const float LA = L + cross(rA, P) / 1.0f;
+        const float LB = L + cross(rB, P) / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    } else j.impulse_x = j.impulse_y = j.impulse_z = 0.0f;
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    d.jt_work[ji] = wk;
+}
+PR_D void weld_solve_velocity(const DV& d, unsigned ji, pr_revolute_joint j, const JointWork& wk, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 oldA = v.s_vel[ia], oldB = v.s_vel[ib];
+    float4 velA = oldA, velB = oldB;
+    const float2 rA = v2(wk.rAx, wk.rAy), rB = v2(wk.rBx, wk.rBy);
+    if (j.lower_angle > 0.0f) {
+        const float Cdot2 = velB.z - velA.z;
+        const float gamma = wk.angularMass * j.impulse_z * 1.0f * 1.0f / (1.0f * 1.0f);
+        const float impulse2 = -wk.m[8] * (Cdot2 + wk.ex[0] + gamma);
+        j.impulse_z += impulse2;
+        velA.z -= iiA * impulse2 * 1.0f * 1.0f / (1.0f * 1.0f);
+        velB.z += iiB * impulse2 * 1.0f * 1.0f / (1.0f * 1.0f);
+        const float2 vb = v2(velB.x, velB.y) + rev_perp(rB) * (velB.z / 1.0f);
+        const float2 va = v2(velA.x, velA.y) + rev_perp(rA) * (velA.z / 1.0f);
+        const float2 Cdot1 = vb - va;
+        const float2 impulse1 = -mat33_transform2(wk.m, v2(Cdot1.x / 1.0f, Cdot1.y / 1.0f));
+        j.impulse_x += impulse1.x; j.impulse_y += impulse1.y;
+        const float2 P = v2(impulse1.x * 1.0f, impulse1.y * 1.0f);
+        const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    } else {
+        const float2 vb = v2(velB.x, velB.y) + rev_perp(rB) * (velB.z / 1.0f);
+        const float2 va = v2(velA.x, velA.y) + rev_perp(rA) * (velA.z / 1.0f);
+        const float2 Cdot1 = vb - va;
+        V3 Cdot; Cdot.x = Cdot1.x / 1.0f; Cdot.y = Cdot1.y / 1.0f; Cdot.z = (velB.z - velA.z) / 1.0f;
+        const V3 t = mat33_transform3(wk.m, Cdot);
+        V3 impulse; impulse.x = -t.x; impulse.y = -t.y; impulse.z = -t.z;
+        j.impulse_x += impulse.x; j.impulse_y += impulse.y; j.impulse_z += impulse.z;
+        const float2 P = v2(impulse.x * 1.0f, impulse.y * 1.0f);
+        const float L = impulse.z * 1.0f * 1.0f / (1.0f * 1.0f);
+        const float LA = L + cross(rA, P) / 1.0f;
+        const float LB = L + cross(rB, P) / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    }
+    d.jt[ji] = j;
+    const bool changed = velA.x != oldA.x || velA.y != oldA.y || velA.z != oldA.z || velB.x != oldB.x || velB.y != oldB.y || velB.z != oldB.z;
+    if (changed) { v.s_vel[ia] = velA; v.s_vel[ib] = velB; v.isl_jflag[wk.island] = 1u; }
+}
+PR_D void weld_solve_position(const DV& d, const pr_revolute_joint& j, const JointWork& wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    float4 posA = v.s_pos[ia], posB = v.s_pos[ib];
+    const Rot qA = rot_from_angle(posA.z), qB = rot_from_angle(posB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    float positionError, angularError;
+    float K[9];
+    weld_k(K, imA, rA, iiA, imB, rB, iiB);
+    const float2 C1 = (v2(posB.x, posB.y) + rB) - (v2(posA.x, posA.y) + rA);
+    positionError = sqrtf(magsq(C1));
+    if (j.lower_angle > 0.0f) {
+        angularError = 0.0f;
+        const float2 P = -solve22(K, C1) * 1.0f;
+        const float LA = cross(rA, P) / 1.0f, LB = cross(rB, P) / 1.0f;
+        const float2 la = v2(posA.x, posA.y) - imA * P; posA.x = la.x; posA.y = la.y; posA.z -= iiA * LA;
+        const float2 lb = v2(posB.x, posB.y) + imB * P; posB.x = lb.x; posB.y = lb.y; posB.z += iiB * LB;
+    } else {
+        const float C2 = posB.z - posA.z - j.reference_angle;
+        angularError = fabsf(C2);
+        V3 impulse;
+        if (K[8] > 0.0f) {
+            V3 C; C.x = C1.x; C.y = C1.y; C.z = C2;
+            const V3 s = solve33(K, C);
+            impulse.x = -s.x; impulse.y = -s.y; impulse.z = -s.z;
+        } else {
+            const float2 impulse2 = -solve22(K, C1);
+            impulse.x = impulse2.x; impulse.y = impulse2.y; impulse.z = 0.0f;
+        }
+        const float2 P = v2(impulse.x * 1.0f, impulse.y * 1.0f) * 1.0f;
+        const float L = impulse.z * 1.0f * 1.0f / 1.0f;
+        const float LA = L + cross(rA, P) / 1.0f;
+        const float LB = L + cross(rB, P) / 1.0f;
+        const float2 la = v2(posA.x, posA.y) - imA * P; posA.x = la.x; posA.y = la.y; posA.z -= iiA * LA;
+        const float2 lb = v2(posB.x, posB.y) + imB * P; posB.x = lb.x; posB.y = lb.y; posB.z += iiB * LB;
+    }
+    v.s_pos[ia] = posA; v.s_pos[ib] = posB;
+    if (!((positionError <= conf.linear_slop) && (angularError <= conf.angular_slop))) v.isl_jflag[wk.island] = 1u;
+}
+
 PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf, const JView& v)
 {
     pr_revolute_joint j = d.jt[ji];
@@ -372,6 +551,12 @@ PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf
         if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
         if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
         fm_init_velocity(d, ji, j, wk, conf, v, joint_type(j) == PR_JOINT_MOTOR);
+        return;
+    }
+    if (joint_type(j) == PR_JOINT_WELD) {
+        if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
+        if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
+        weld_init_velocity(d, ji, j, wk, conf, v);
         return;
     }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
@@ -439,6 +624,7 @@ PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& con
     if (joint_type(j) == PR_JOINT_DISTANCE) { distance_solve_velocity(d, ji, j, wk, v); return; }
     if (joint_type(j) == PR_JOINT_ROPE) { rope_solve_velocity(d, ji, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_FRICTION || joint_type(j) == PR_JOINT_MOTOR) { fm_solve_velocity(d, ji, j, wk, conf, v, joint_type(j) == PR_JOINT_MOTOR); return; }
+    if (joint_type(j) == PR_JOINT_WELD) { weld_solve_velocity(d, ji, j, wk, v); return; }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
@@ -504,6 +690,7 @@ PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& con
     if (joint_type(j) == PR_JOINT_DISTANCE) { distance_solve_position(d, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_ROPE) { rope_solve_position(d, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_FRICTION || joint_type(j) == PR_JOINT_MOTOR) return; // SolvePosition: nothing to do, always solved
+    if (joint_type(j) == PR_JOINT_WELD) { weld_solve_position(d, j, wk, conf, v); return; }
     const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;

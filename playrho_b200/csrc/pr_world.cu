@@ -2014,6 +2014,7 @@ template <class Row> static int create_tagged_joints(pr_world* pw, uint32_t n, c
 extern "C" {
 int pr_create_friction_joints(pr_world* pw, uint32_t n, const pr_friction_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_FRICTION, first_id); }
 int pr_create_motor_joints(pr_world* pw, uint32_t n, const pr_motor_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_MOTOR, first_id); }
+int pr_create_weld_joints(pr_world* pw, uint32_t n, const pr_weld_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_WELD, first_id); }
 
 int pr_destroy_joints(pr_world* pw, uint32_t n, const uint32_t* ids)
 { // Destroy(AabbTreeWorld&, JointID), :1215-1227: Remove(id) wakes both bodies (:1192-1205), the id goes to the free list

@@ -53,7 +53,7 @@ struct PCRow {
 };
 
 // per-step work data of a revolute joint (RevoluteJointConf's rA, rB, mass, angularMass) + its island label
-struct JointWork { float rAx, rAy, rBx, rBy; float m[9]; float angularMass; unsigned island; unsigned pad; };
+struct JointWork { float rAx, rAy, rBx, rBy; float m[9]; float angularMass; unsigned island; unsigned pad; float ex[8]; };
 
 // the boxes of an LBVH node's two children, stored with the node
 struct CBox { float4 l, r; };

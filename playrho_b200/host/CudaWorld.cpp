@@ -14,6 +14,7 @@
 #include <playrho/d2/RopeJointConf.hpp>
 #include <playrho/d2/FrictionJointConf.hpp>
 #include <playrho/d2/MotorJointConf.hpp>
+#include <playrho/d2/WeldJointConf.hpp>
 #include <playrho/to_underlying.hpp>
 
 #include <algorithm>
@@ -703,6 +704,20 @@ static pr_revolute_joint ToJointRow(const MotorJointConf& jc)
     std::memcpy(&r, &o, sizeof(r));
     return r;
 }
+static pr_revolute_joint ToJointRow(const WeldJointConf& jc)
+{ // the same table row viewed as pr_weld_joint
+    pr_weld_joint o{};
+    o.body_a = static_cast<std::uint32_t>(to_underlying(jc.bodyA)); o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.collide_connected = (jc.collideConnected ? 1u : 0u) | (static_cast<std::uint32_t>(PR_JOINT_WELD) << 8);
+    o.local_anchor_a = pr_vec2{GetX(jc.localAnchorA), GetY(jc.localAnchorA)};
+    o.local_anchor_b = pr_vec2{GetX(jc.localAnchorB), GetY(jc.localAnchorB)};
+    o.impulse_x = GetX(jc.impulse); o.impulse_y = GetY(jc.impulse); o.impulse_z = GetZ(jc.impulse);
+    o.reference_angle = jc.referenceAngle; o.frequency = jc.frequency; o.damping_ratio = jc.dampingRatio;
+    pr_revolute_joint r{};
+    static_assert(sizeof(r) == sizeof(o), "joint rows share one table");
+    std::memcpy(&r, &o, sizeof(r));
+    return r;
+}
 // the joint types the device solves (SURVEY a15 + the first of 8(f) rank 1); the others are rejected
 static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, BodyID& b)
 {
@@ -711,6 +726,7 @@ static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, B
     if (GetType(def) == GetTypeID<FrictionJointConf>()) { const auto jc = TypeCast<FrictionJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     if (GetType(def) == GetTypeID<MotorJointConf>()) { const auto jc = TypeCast<MotorJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     if (GetType(def) == GetTypeID<RopeJointConf>()) { const auto jc = TypeCast<RopeJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
+    if (GetType(def) == GetTypeID<WeldJointConf>()) { const auto jc = TypeCast<WeldJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     return false;
 }
 JointID CreateJoint(CudaWorld& w, Joint def)
@@ -754,6 +770,11 @@ Joint GetJoint(const CudaWorld& w, JointID id)
         mc.linearImpulse = Momentum2{r.impulse_x * NewtonSecond, r.impulse_y * NewtonSecond};
         mc.angularImpulse = AngularMomentum{r.impulse_z * NewtonMeterSecond};
         return Joint{mc};
+    }
+    if (GetType(elem) == GetTypeID<WeldJointConf>()) {
+        auto wc = TypeCast<WeldJointConf>(elem);
+        wc.impulse = Vec3{r.impulse_x, r.impulse_y, r.impulse_z};
+        return Joint{wc};
     }
     if (GetType(elem) == GetTypeID<RopeJointConf>()) {
         auto rc = TypeCast<RopeJointConf>(elem);

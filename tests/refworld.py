@@ -215,6 +215,13 @@ class RefWorld:
         assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
         return jid
 
+    def add_weld(self, body_a, body_b, anchor, frequency=0.0, damping_ratio=0.0):
+        self.lib.ref_add_weld.argtypes = [vp, u32, u32, f32, f32, f32, f32]
+        self.lib.ref_add_weld.restype = u32
+        jid = self.lib.ref_add_weld(self.h, int(body_a), int(body_b), anchor[0], anchor[1], frequency, damping_ratio)
+        assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
+        return jid
+
     def add_friction(self, body_a, body_b, anchor, max_force, max_torque):
         self.lib.ref_add_friction.argtypes = [vp, u32, u32, f32, f32, f32, f32]
         self.lib.ref_add_friction.restype = u32

@@ -1,0 +1,94 @@
+"""The joint types of SURVEY 8(f) rank 1 added after the distance / rope / friction / motor joints, each as a scene stepped by
+the real reference, the restatement, the emulated kernels and the GPU -- bit for bit, incl. the joints' accumulated impulses:
+  weld  (WeldJointConf.cpp:35-371): a cantilever of boxes welded to a static wall (rigid), a soft-welded pair, a welded pair with
+        fixed rotation (K.ez.z == 0 -> the 2x2 branch), all under gravity and hit by a falling disk."""
+import numpy as np
+import pytest
+import refworld
+from refworld import RefWorld, STATIC, DYNAMIC
+from common import need_ref, need_oracle, need_emul, emul_lib, assert_bits
+from playrho_b200 import world as W
+
+
+G = (0.0, -10.0)
+
+
+def _weld_scene():
+    ref = RefWorld()
+    wall = ref.add_body(STATIC, pos=(0.0, 0.0))
+    box = ref.add_box(0.5, 0.125, density=20.0)
+    disk = ref.add_disk(0.3, density=5.0)
+    prev = wall
+    for i in range(4):                                     # cantilever: rigid welds
+        b = ref.add_body(DYNAMIC, acc=G, pos=(0.5 + 1.0 * i, 5.0), shapes=[box])
+        ref.add_weld(prev, b, (1.0 * i, 5.0))
+        prev = b
+    s1 = ref.add_body(DYNAMIC, acc=G, pos=(-3.0, 5.0), shapes=[box])
+    s2 = ref.add_body(DYNAMIC, acc=G, pos=(-4.0, 5.0), shapes=[box])
+    ref.add_weld(wall, s1, (-2.5, 5.0), frequency=5.0, damping_ratio=0.7)   # soft angular spring
+    ref.add_weld(s1, s2, (-3.5, 5.0), frequency=8.0, damping_ratio=0.2)
+    f1 = ref.add_body(DYNAMIC, acc=G, pos=(0.0, 9.0), shapes=[box], fixed_rotation=True)
+    f2 = ref.add_body(DYNAMIC, acc=G, pos=(1.0, 9.0), shapes=[box], fixed_rotation=True)
+    ref.add_weld(f1, f2, (0.5, 9.0))                       # no rotational inertia at all: GetInverse22
+    ref.add_body(DYNAMIC, acc=G, pos=(3.2, 8.0), shapes=[disk])   # falls on the cantilever's tip
+    ref.add_body(DYNAMIC, acc=G, pos=(-3.9, 8.0), shapes=[disk])  # and on the soft one
+    return ref, [5, 5, 5, 5, 5, 5, 5]
+
+
+SCENES = {"weld": (_weld_scene, 200)}
+
+
+def _run(name, lib=None, device=-1, with_device=True):
+    build, steps = SCENES[name]
+    ref, types = build()
+    sc = ref.export_scene()
+    assert [int(j["collide_connected"]) >> 8 for j in sc["joints"]] == types
+    orc = refworld.OracleWorld(sc)
+    twins = []
+    if with_device:
+        gw = W.World(sc, lib=lib, device=device, record_solve_order=True)
+        gw.set_toi_mode(0)
+        twins = [gw, refworld.OracleWorld(sc)]
+    conf = refworld.default_step_conf()
+    for s in range(steps):
+        rs, os_ = ref.step(conf), orc.step(conf)
+        assert_bits(np.array([rs]), np.array([os_]), "step %d stats (reference vs restatement)" % s)
+        assert_bits(ref.bodies(), orc.bodies(), "step %d bodies (reference vs restatement)" % s)
+        assert_bits(ref.joints(), orc.joints(), "step %d joints (reference vs restatement)" % s)
+        rc, rm = ref.contacts(); oc, om = orc.contacts()
+        assert_bits(rc, oc, "step %d contacts (reference vs restatement)" % s)
+        assert_bits(rm, om, "step %d manifolds (reference vs restatement)" % s)
+        if twins:
+            gw, orc2 = twins
+            gs = gw.step(conf)
+            o2 = orc2.step(conf, order=gw.solve_order()[0])
+            assert_bits(np.array([gs]), np.array([o2]), "step %d stats" % s)
+            assert_bits(gw.bodies(), orc2.bodies(), "step %d bodies" % s)
+            assert_bits(gw.joints(), orc2.joints(), "step %d joints" % s)
+            gc, gm = gw.contacts(); oc2, om2 = orc2.contacts()
+            assert_bits(gc, oc2, "step %d contacts" % s)
+            assert_bits(gm, om2, "step %d manifolds" % s)
+    return ref
+
+
+@need_ref
+@need_oracle
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_restatement_equals_reference(name):
+    _run(name, with_device=False)
+
+
+@need_ref
+@need_oracle
+@need_emul
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_emulated_kernels_equal_oracle(name):
+    _run(name, lib=emul_lib())
+
+
+@pytest.mark.gpu
+@need_ref
+@need_oracle
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_gpu_equals_oracle(name):
+    _run(name, device=0)
