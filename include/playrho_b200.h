@@ -107,7 +107,7 @@ typedef struct pr_revolute_joint {
 
 /* Joint rows share one table (JointIDs are one id space in the reference): every row has pr_revolute_joint's size and leading
  * fields, and bits 8..15 of collide_connected say which joint type it is (bit 0 is the flag itself). */
-enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2, PR_JOINT_FRICTION = 3, PR_JOINT_MOTOR = 4, PR_JOINT_WELD = 5 };
+enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2, PR_JOINT_FRICTION = 3, PR_JOINT_MOTOR = 4, PR_JOINT_WELD = 5, PR_JOINT_TARGET = 6 };
 #define PR_JOINT_TYPE(row) (((row).collide_connected >> 8) & 0xFFu)
 /* DistanceJointConf (Library/include/playrho/d2/DistanceJointConf.hpp): rod or spring between two anchor points.
  * Solver: Library/source/playrho/d2/DistanceJointConf.cpp:81-246 (InitVelocity, SolveVelocity, SolvePosition). */
@@ -177,6 +177,20 @@ typedef struct pr_weld_joint {
     float reserved2[2];
     uint32_t reserved3;
 } pr_weld_joint;
+/* TargetJointConf (TargetJointConf.hpp; solver TargetJointConf.cpp:52-243): drags a point of ONE body towards a world target
+ * (the reference's "mouse joint"). The reference's bodyA is InvalidBodyID; in the table row body_a repeats body_b. */
+typedef struct pr_target_joint {
+    uint32_t body_a, body_b;             /* body_a == body_b: the dragged body */
+    uint32_t collide_connected;          /* bits 8..15: PR_JOINT_TARGET */
+    pr_vec2 target;                      /* world coordinates */
+    pr_vec2 local_anchor_b;
+    float impulse_x, impulse_y;          /* accumulated impulse (warm start) */
+    float reserved0[3];
+    uint32_t reserved1[2];
+    float frequency, damping_ratio;
+    float max_force, reserved2;
+    uint32_t reserved3;
+} pr_target_joint;
 
 /* ContactFeature packed little-endian: typeA | indexA<<8 | typeB<<16 | indexB<<24 */
 typedef uint32_t pr_contact_feature;
@@ -316,6 +330,7 @@ int pr_create_rope_joints(pr_world* w, uint32_t n, const pr_rope_joint* joints, 
 int pr_create_friction_joints(pr_world* w, uint32_t n, const pr_friction_joint* joints, uint32_t* first_id);
 int pr_create_motor_joints(pr_world* w, uint32_t n, const pr_motor_joint* joints, uint32_t* first_id);
 int pr_create_weld_joints(pr_world* w, uint32_t n, const pr_weld_joint* joints, uint32_t* first_id);
+int pr_create_target_joints(pr_world* w, uint32_t n, const pr_target_joint* joints, uint32_t* first_id);
 
 /* SetShape(AabbTreeWorld&, ShapeID, Shape) (AabbTreeWorld.cpp:1284-1356) for a value whose geometry (children) and filter are
  * what they were: friction, restitution, density and the sensor flag are replaced; every body using the shape is woken

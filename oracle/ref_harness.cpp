@@ -439,6 +439,27 @@ uint32_t ref_add_weld(void* h, uint32_t bodyA, uint32_t bodyB, float ax, float a
     return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
     REF_CATCH(0xFFFFFFFFu)
 }
+uint32_t ref_add_target(void* h, uint32_t bodyB, float tx, float ty, float ax, float ay, float frequency, float dampingRatio, float maxForce)
+{
+    REF_TRY(h)
+    auto jc = TargetJointConf{};
+    jc.bodyB = MakeId<BodyID>(bodyB);
+    jc.target = Length2{tx * 1_m, ty * 1_m};
+    jc.localAnchorB = GetLocalPoint(rw->world, jc.bodyB, Length2{ax * 1_m, ay * 1_m});
+    jc.frequency = frequency * 1_Hz; jc.dampingRatio = dampingRatio; jc.maxForce = maxForce * 1_N;
+    return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
+    REF_CATCH(0xFFFFFFFFu)
+}
+int ref_set_target(void* h, uint32_t joint, float tx, float ty)
+{
+    REF_TRY(h)
+    const auto id = MakeId<JointID>(joint);
+    auto jc = TypeCast<TargetJointConf>(GetJoint(rw->world, id));
+    jc.target = Length2{tx * 1_m, ty * 1_m};
+    SetJoint(rw->world, id, Joint{jc});
+    return 0;
+    REF_CATCH(-1)
+}
 int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
 {
     REF_TRY(h)
@@ -486,6 +507,16 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
             o.local_anchor_b = pr_vec2{GetX(wc.localAnchorB), GetY(wc.localAnchorB)};
             o.impulse_x = GetX(wc.impulse); o.impulse_y = GetY(wc.impulse); o.impulse_z = GetZ(wc.impulse);
             o.reference_angle = wc.referenceAngle; o.lower_angle = wc.frequency; o.upper_angle = wc.dampingRatio;
+            continue;
+        }
+        if (GetType(joint) == GetTypeID<TargetJointConf>()) { // the same row, viewed as pr_target_joint (body_a repeats body_b)
+            const auto tc = TypeCast<TargetJointConf>(joint);
+            o.body_a = o.body_b = to_underlying(tc.bodyB);
+            o.collide_connected = (tc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_TARGET) << 8);
+            o.local_anchor_a = pr_vec2{GetX(tc.target), GetY(tc.target)};
+            o.local_anchor_b = pr_vec2{GetX(tc.localAnchorB), GetY(tc.localAnchorB)};
+            o.impulse_x = GetX(tc.impulse); o.impulse_y = GetY(tc.impulse);
+            o.lower_angle = tc.frequency; o.upper_angle = tc.dampingRatio; o.motor_speed = tc.maxForce;
             continue;
         }
         if (GetType(joint) == GetTypeID<RopeJointConf>()) { // the same row, viewed as pr_rope_joint

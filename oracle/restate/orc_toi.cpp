@@ -898,6 +898,53 @@ bool weld_solve_position(const pr_revolute_joint& j, float imA, float iiA, V2 lc
     }
     return (positionError <= c.linearSlop) && (angularError <= c.angularSlop);
 }
+// ---------------- TargetJointConf.cpp:52-243 (one body: the row's body_a repeats body_b; mass[0..3] = mass, angularMass = gamma, ex[0..1] = C) ----
+void target_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
+{
+    const Rot qB = rot_from_angle(posB.a);
+    const float mass = (imB != 0.0f) ? (1.0f / imB) : 0.0f;
+    const float omega = 2.0f * 3.14159265358979323846264338327950288f * j.lower_angle;
+    const float d = 2.0f * mass * j.upper_angle * omega;
+    const float k = mass * square(omega);
+    const float h = c.dt;
+    const float tmp = d + h * k;
+    const float invGamma = h * tmp;
+    wk.angularMass = (invGamma != 0.0f) ? 1.0f / invGamma : 0.0f;
+    const float beta = h * k * wk.angularMass;
+    wk.rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    const float exx = imB + (iiB * square(wk.rB.y) / 1.0f) + wk.angularMass;
+    const float exy = -iiB * wk.rB.x * wk.rB.y / 1.0f;
+    const float eyy = imB + (iiB * square(wk.rB.x) / 1.0f) + wk.angularMass;
+    const float cp = exx * eyy - exy * exy;
+    if (!almost_zero(cp)) {
+        const float inverse = 1 / cp;
+        wk.mass[0] = eyy * inverse; wk.mass[1] = -exy * inverse; wk.mass[2] = -exy * inverse; wk.mass[3] = exx * inverse;
+    } else wk.mass[0] = wk.mass[1] = wk.mass[2] = wk.mass[3] = 0.0f;
+    const V2 C = ((posB.l + wk.rB) - V2{j.local_anchor_a.x, j.local_anchor_a.y}) * beta;
+    wk.ex[0] = C.x; wk.ex[1] = C.y;
+    velB.a *= 0.98f;
+    if (c.warmStart) {
+        j.impulse_x *= c.dtRatio; j.impulse_y *= c.dtRatio;
+        const V2 P{j.impulse_x, j.impulse_y};
+        const float crossBP = cross(wk.rB, P) / 1.0f;
+        velB.l = velB.l + imB * P; velB.a += iiB * crossBP;
+    } else j.impulse_x = j.impulse_y = 0.0f;
+}
+bool target_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imB, float iiB, Vel& velB, const JointSolverConf& c)
+{
+    const V2 Cdot = velB.l + (rev_perp(wk.rB) * (velB.a / 1.0f));
+    const V2 ev = Cdot + (V2{wk.ex[0], wk.ex[1]} + (wk.angularMass * V2{j.impulse_x, j.impulse_y}));
+    const V2 oldImpulse{j.impulse_x, j.impulse_y};
+    const V2 addImpulse = mat22_transform(wk.mass, V2{-ev.x, -ev.y});
+    V2 impulse = oldImpulse + addImpulse;
+    const float maxImpulse = c.dt * j.motor_speed;
+    if (magsq(impulse) > square(maxImpulse)) { const Rot u = unit_vector(impulse, Rot{0.0f, 0.0f}); impulse = V2{u.c * maxImpulse, u.s * maxImpulse}; }
+    j.impulse_x = impulse.x; j.impulse_y = impulse.y;
+    const V2 inc = impulse - oldImpulse;
+    const float angImpulseB = cross(wk.rB, inc) / 1.0f;
+    velB.l = velB.l + imB * inc; velB.a += iiB * angImpulseB;
+    return inc.x == 0.0f && inc.y == 0.0f;
+}
 } // namespace
 void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
                          float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
@@ -906,6 +953,7 @@ void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, floa
     else if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) rope_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
     else if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR)
         fm_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c, PR_JOINT_TYPE(j) == PR_JOINT_MOTOR);
+    else if (PR_JOINT_TYPE(j) == PR_JOINT_TARGET) target_init_velocity(j, wk, imB, iiB, lcB, posB, velB, c);
     else if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) weld_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
     else revolute_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
 }
@@ -915,6 +963,7 @@ bool joint_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, flo
     if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) return rope_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR)
         return fm_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c, PR_JOINT_TYPE(j) == PR_JOINT_MOTOR);
+    if (PR_JOINT_TYPE(j) == PR_JOINT_TARGET) return target_solve_velocity(j, wk, imB, iiB, velB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) return weld_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB);
     return revolute_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
 }
@@ -923,7 +972,7 @@ bool joint_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, fl
 {
     if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) return distance_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) return rope_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
-    if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR) return true;
+    if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR || PR_JOINT_TYPE(j) == PR_JOINT_TARGET) return true;
     if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) return weld_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     return revolute_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
 }

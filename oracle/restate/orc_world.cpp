@@ -1163,7 +1163,7 @@ int orc_create_revolute_joints(orc_world* w, uint32_t n, const pr_revolute_joint
         if (!w->freeJoints.empty()) { id = w->freeJoints.back(); w->freeJoints.pop_back(); w->joints[id] = joints[i]; }
         else { id = static_cast<uint32_t>(w->joints.size()); w->joints.push_back(joints[i]); w->jointWork.emplace_back(); }
         w->bodies[joints[i].body_a].joints.push_back(id);
-        w->bodies[joints[i].body_b].joints.push_back(id);
+        if (joints[i].body_b != joints[i].body_a) w->bodies[joints[i].body_b].joints.push_back(id); // (target joint: one body, :1164-1169)
         // Add(JointID, !collideConnected) :1159-1175: creating a joint does not wake its bodies; the pair's contacts are flagged for filtering
         if (!(joints[i].collide_connected & 1u)) flag_pair_for_filtering(*w, joints[i].body_a, joints[i].body_b);
     }
@@ -1352,7 +1352,7 @@ int orc_set_revolute_joints(orc_world* w, uint32_t n, const uint32_t* ids, const
         if (!(old.collide_connected & 1u)) flag_pair_for_filtering(*w, old.body_a, old.body_b); // Remove
         w->joints[id] = rows[i];
         w->bodies[rows[i].body_a].joints.push_back(id);
-        w->bodies[rows[i].body_b].joints.push_back(id);
+        if (rows[i].body_b != rows[i].body_a) w->bodies[rows[i].body_b].joints.push_back(id);
         if (!(rows[i].collide_connected & 1u)) flag_pair_for_filtering(*w, rows[i].body_a, rows[i].body_b); // Add(id, true)
     }
     return 0;

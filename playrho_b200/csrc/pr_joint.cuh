@@ -529,6 +529,74 @@ PR_D void weld_solve_position(const DV& d, const pr_revolute_joint& j, const Joi
     if (!((positionError <= conf.linear_slop) && (angularError <= conf.angular_slop))) v.isl_jflag[wk.island] = 1u;
 }
 
+// ---- TargetJointConf.cpp:52-243. One body: the row has body_a == body_b (the reference's bodyA is InvalidBodyID). Row overlay
+// (pr_target_joint): target = local_anchor_a, localAnchorB = local_anchor_b, impulse = impulse_x/y, frequency = lower_angle,
+// dampingRatio = upper_angle, maxForce = motor_speed; work: rB, m[0..3] = mass, angularMass = gamma, ex[0..1] = C
+PR_D void target_init_velocity(const DV& d, unsigned ji, pr_revolute_joint j, JointWork wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ib = jv_idx(v.slotV, j.body_b);
+    const float4 mB = d.b_mass[j.body_b];
+    const float imB = mB.x, iiB = mB.y;
+    const float4 pB = v.s_pos[jv_idx(v.slotP, j.body_b)];
+    float4 velB = v.s_vel[ib];
+    const Rot qB = rot_from_angle(pB.z);
+    const float mass = (imB != 0.0f) ? (1.0f / imB) : 0.0f;
+    const float omega = 2.0f * 3.14159265358979323846264338327950288f * j.lower_angle;
+    const float dd = 2.0f * mass * j.upper_angle * omega;
+    const float k = mass * square(omega);
+    const float h = conf.delta_time;
+    const float tmp = dd + h * k;
+    const float invGamma = h * tmp;
+    const float gamma = (invGamma != 0.0f) ? 1.0f / invGamma : 0.0f;
+    wk.angularMass = gamma;
+    const float beta = h * k * gamma;
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    wk.rAx = 0.0f; wk.rAy = 0.0f; wk.rBx = rB.x; wk.rBy = rB.y;
+    { // GetEffectiveMassMatrix, :52-75
+        const float exx = imB + (iiB * square(rB.y) / 1.0f) + gamma;
+        const float exy = -iiB * rB.x * rB.y / 1.0f;
+        const float eyy = imB + (iiB * square(rB.x) / 1.0f) + gamma;
+        const float cp = exx * eyy - exy * exy; // Invert(Matrix22), Math.hpp:430-442
+        if (!almost_zero(cp)) {
+            const float inverse = 1 / cp;
+            wk.m[0] = eyy * inverse; wk.m[1] = -exy * inverse; wk.m[2] = -exy * inverse; wk.m[3] = exx * inverse;
+        } else wk.m[0] = wk.m[1] = wk.m[2] = wk.m[3] = 0.0f;
+    }
+    const float2 C = ((v2(pB.x, pB.y) + rB) - v2(j.local_anchor_a.x, j.local_anchor_a.y)) * beta;
+    wk.ex[0] = C.x; wk.ex[1] = C.y;
+    velB.z *= 0.98f; // "cheat with some damping" (:125-127)
+    if (conf.do_warm_start) {
+        j.impulse_x *= conf.dt_ratio; j.impulse_y *= conf.dt_ratio;
+        const float2 P = v2(j.impulse_x, j.impulse_y);
+        const float crossBP = cross(rB, P) / 1.0f;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * crossBP;
+    } else j.impulse_x = j.impulse_y = 0.0f;
+    v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    d.jt_work[ji] = wk;
+}
+PR_D void target_solve_velocity(const DV& d, unsigned ji, pr_revolute_joint j, const JointWork& wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ib = jv_idx(v.slotV, j.body_b);
+    const float4 mB = d.b_mass[j.body_b];
+    float4 velB = v.s_vel[ib];
+    const float2 rB = v2(wk.rBx, wk.rBy);
+    const float2 Cdot = v2(velB.x, velB.y) + (rev_perp(rB) * (velB.z / 1.0f));
+    const float2 ev = Cdot + (v2(wk.ex[0], wk.ex[1]) + (wk.angularMass * v2(j.impulse_x, j.impulse_y)));
+    const float2 oldImpulse = v2(j.impulse_x, j.impulse_y);
+    const float2 addImpulse = mat22_transform(wk.m, -ev);
+    float2 impulse = oldImpulse + addImpulse;
+    const float maxImpulse = conf.delta_time * j.motor_speed;
+    if (magsq(impulse) > square(maxImpulse)) { const Rot u = unit_vector(impulse, mkrot(0.0f, 0.0f)); impulse = u * maxImpulse; }
+    j.impulse_x = impulse.x; j.impulse_y = impulse.y;
+    const float2 inc = impulse - oldImpulse;
+    const float angImpulseB = cross(rB, inc) / 1.0f;
+    const float2 lb = v2(velB.x, velB.y) + mB.x * inc; velB.x = lb.x; velB.y = lb.y; velB.z += mB.y * angImpulseB;
+    v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    if (!(inc.x == 0.0f && inc.y == 0.0f)) v.isl_jflag[wk.island] = 1u;
+}
+
 PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf, const JView& v)
 {
     pr_revolute_joint j = d.jt[ji];
@@ -553,6 +621,7 @@ PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf
         fm_init_velocity(d, ji, j, wk, conf, v, joint_type(j) == PR_JOINT_MOTOR);
         return;
     }
+    if (joint_type(j) == PR_JOINT_TARGET) { target_init_velocity(d, ji, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_WELD) {
         if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
         if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
@@ -625,6 +694,7 @@ PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& con
     if (joint_type(j) == PR_JOINT_ROPE) { rope_solve_velocity(d, ji, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_FRICTION || joint_type(j) == PR_JOINT_MOTOR) { fm_solve_velocity(d, ji, j, wk, conf, v, joint_type(j) == PR_JOINT_MOTOR); return; }
     if (joint_type(j) == PR_JOINT_WELD) { weld_solve_velocity(d, ji, j, wk, v); return; }
+    if (joint_type(j) == PR_JOINT_TARGET) { target_solve_velocity(d, ji, j, wk, conf, v); return; }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
@@ -689,7 +759,7 @@ PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& con
     const pr_revolute_joint j = d.jt[ji];
     if (joint_type(j) == PR_JOINT_DISTANCE) { distance_solve_position(d, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_ROPE) { rope_solve_position(d, j, wk, conf, v); return; }
-    if (joint_type(j) == PR_JOINT_FRICTION || joint_type(j) == PR_JOINT_MOTOR) return; // SolvePosition: nothing to do, always solved
+    if (joint_type(j) == PR_JOINT_FRICTION || joint_type(j) == PR_JOINT_MOTOR || joint_type(j) == PR_JOINT_TARGET) return; // SolvePosition: nothing to do, always solved
     if (joint_type(j) == PR_JOINT_WELD) { weld_solve_position(d, j, wk, conf, v); return; }
     const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];

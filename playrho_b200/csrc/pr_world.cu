@@ -1619,8 +1619,8 @@ static void refresh_joint_tables(World& w)
     std::vector<unsigned long long> nc;
     for (const auto& j : w.joints) {
         if (j.body_a == INVALID) continue;
-        ++uses[j.body_a]; ++uses[j.body_b];
-        if (!(j.collide_connected & 1u)) nc.push_back((static_cast<unsigned long long>(std::min(j.body_a, j.body_b)) << 32) | std::max(j.body_a, j.body_b));
+        ++uses[j.body_a]; if (j.body_b != j.body_a) ++uses[j.body_b]; // (a target joint's row has body_a == body_b)
+        if (!(j.collide_connected & 1u) && j.body_a != j.body_b) nc.push_back((static_cast<unsigned long long>(std::min(j.body_a, j.body_b)) << 32) | std::max(j.body_a, j.body_b));
     }
     w.jointsSerial = false;
     for (const auto& u : uses) if (u.second > 1u) w.jointsSerial = true;
@@ -2015,6 +2015,11 @@ extern "C" {
 int pr_create_friction_joints(pr_world* pw, uint32_t n, const pr_friction_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_FRICTION, first_id); }
 int pr_create_motor_joints(pr_world* pw, uint32_t n, const pr_motor_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_MOTOR, first_id); }
 int pr_create_weld_joints(pr_world* pw, uint32_t n, const pr_weld_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_WELD, first_id); }
+int pr_create_target_joints(pr_world* pw, uint32_t n, const pr_target_joint* joints, uint32_t* first_id)
+{
+    for (uint32_t i = 0; i < n; ++i) if (joints[i].body_a != joints[i].body_b) { if (pw) pw->w.error = "target joint: body_a must repeat body_b"; return PR_ERR_INVALID_ARGUMENT; }
+    return create_tagged_joints(pw, n, joints, PR_JOINT_TARGET, first_id);
+}
 
 int pr_destroy_joints(pr_world* pw, uint32_t n, const uint32_t* ids)
 { // Destroy(AabbTreeWorld&, JointID), :1215-1227: Remove(id) wakes both bodies (:1192-1205), the id goes to the free list

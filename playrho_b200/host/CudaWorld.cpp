@@ -15,6 +15,7 @@
 #include <playrho/d2/FrictionJointConf.hpp>
 #include <playrho/d2/MotorJointConf.hpp>
 #include <playrho/d2/WeldJointConf.hpp>
+#include <playrho/d2/TargetJointConf.hpp>
 #include <playrho/to_underlying.hpp>
 
 #include <algorithm>
@@ -718,6 +719,21 @@ static pr_revolute_joint ToJointRow(const WeldJointConf& jc)
     std::memcpy(&r, &o, sizeof(r));
     return r;
 }
+static pr_revolute_joint ToJointRow(const TargetJointConf& jc)
+{ // the same table row viewed as pr_target_joint: one body, the row's body_a repeats body_b
+    pr_target_joint o{};
+    o.body_a = o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.collide_connected = (jc.collideConnected ? 1u : 0u) | (static_cast<std::uint32_t>(PR_JOINT_TARGET) << 8);
+    o.target = pr_vec2{GetX(jc.target), GetY(jc.target)};
+    o.local_anchor_b = pr_vec2{GetX(jc.localAnchorB), GetY(jc.localAnchorB)};
+    o.impulse_x = GetX(jc.impulse); o.impulse_y = GetY(jc.impulse);
+    o.frequency = static_cast<float>(Real(Frequency(jc.frequency) / Hertz)); o.damping_ratio = static_cast<float>(Real(jc.dampingRatio));
+    o.max_force = static_cast<float>(Real(Force(jc.maxForce) / Newton));
+    pr_revolute_joint r{};
+    static_assert(sizeof(r) == sizeof(o), "joint rows share one table");
+    std::memcpy(&r, &o, sizeof(r));
+    return r;
+}
 // the joint types the device solves (SURVEY a15 + the first of 8(f) rank 1); the others are rejected
 static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, BodyID& b)
 {
@@ -727,6 +743,11 @@ static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, B
     if (GetType(def) == GetTypeID<MotorJointConf>()) { const auto jc = TypeCast<MotorJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     if (GetType(def) == GetTypeID<RopeJointConf>()) { const auto jc = TypeCast<RopeJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     if (GetType(def) == GetTypeID<WeldJointConf>()) { const auto jc = TypeCast<WeldJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
+    if (GetType(def) == GetTypeID<TargetJointConf>()) { // (bodyA is ignored by the target joint's solver)
+        const auto jc = TypeCast<TargetJointConf>(def);
+        if (jc.bodyB == InvalidBodyID || jc.bodyA != InvalidBodyID) return false;
+        row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true;
+    }
     return false;
 }
 JointID CreateJoint(CudaWorld& w, Joint def)
@@ -736,7 +757,8 @@ JointID CreateJoint(CudaWorld& w, Joint def)
     if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
     pr_revolute_joint o{}; BodyID bA{}, bB{};
     if (!ToAnyJointRow(def, o, bA, bB)) throw InvalidArgument(unsupportedMsg);
-    (void)AtId(w.m->bodies, bA, noSuchBodyMsg); (void)AtId(w.m->bodies, bB, noSuchBodyMsg);
+    if (bA != InvalidBodyID) (void)AtId(w.m->bodies, bA, noSuchBodyMsg); // (:1144-1149)
+    if (bB != InvalidBodyID) (void)AtId(w.m->bodies, bB, noSuchBodyMsg);
     w.m->refreshBodies();       // Add(JointID) wakes both bodies on the device: keep the host values in step
     w.m->uploadDirtyBodies();
     std::uint32_t first = 0;
@@ -775,6 +797,11 @@ Joint GetJoint(const CudaWorld& w, JointID id)
         auto wc = TypeCast<WeldJointConf>(elem);
         wc.impulse = Vec3{r.impulse_x, r.impulse_y, r.impulse_z};
         return Joint{wc};
+    }
+    if (GetType(elem) == GetTypeID<TargetJointConf>()) {
+        auto tc = TypeCast<TargetJointConf>(elem);
+        tc.impulse = Momentum2{r.impulse_x * NewtonSecond, r.impulse_y * NewtonSecond};
+        return Joint{tc};
     }
     if (GetType(elem) == GetTypeID<RopeJointConf>()) {
         auto rc = TypeCast<RopeJointConf>(elem);

@@ -222,6 +222,17 @@ class RefWorld:
         assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
         return jid
 
+    def add_target(self, body_b, target, anchor, frequency=5.0, damping_ratio=0.7, max_force=1000.0):
+        self.lib.ref_add_target.argtypes = [vp, u32, f32, f32, f32, f32, f32, f32, f32]
+        self.lib.ref_add_target.restype = u32
+        jid = self.lib.ref_add_target(self.h, int(body_b), target[0], target[1], anchor[0], anchor[1], frequency, damping_ratio, max_force)
+        assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
+        return jid
+
+    def set_target(self, joint, target):
+        self.lib.ref_set_target.argtypes = [vp, u32, f32, f32]
+        self._chk(self.lib.ref_set_target(self.h, int(joint), target[0], target[1]))
+
     def add_friction(self, body_a, body_b, anchor, max_force, max_torque):
         self.lib.ref_add_friction.argtypes = [vp, u32, u32, f32, f32, f32, f32]
         self.lib.ref_add_friction.restype = u32

@@ -1,7 +1,9 @@
 """The joint types of SURVEY 8(f) rank 1 added after the distance / rope / friction / motor joints, each as a scene stepped by
 the real reference, the restatement, the emulated kernels and the GPU -- bit for bit, incl. the joints' accumulated impulses:
   weld  (WeldJointConf.cpp:35-371): a cantilever of boxes welded to a static wall (rigid), a soft-welded pair, a welded pair with
-        fixed rotation (K.ez.z == 0 -> the 2x2 branch), all under gravity and hit by a falling disk."""
+        fixed rotation (K.ez.z == 0 -> the 2x2 branch), all under gravity and hit by a falling disk.
+  target (TargetJointConf.cpp:52-243): one-body "mouse" joints dragging boxes through a pile of disks -- a strong one, one
+        whose force cap saturates, one on a body that also hangs from a weld; the targets are moved with SetJoint in mid-run."""
 import numpy as np
 import pytest
 import refworld
@@ -35,7 +37,34 @@ def _weld_scene():
     return ref, [5, 5, 5, 5, 5, 5, 5]
 
 
-SCENES = {"weld": (_weld_scene, 200)}
+def _target_scene():
+    ref = RefWorld()
+    ground = ref.add_body(STATIC, pos=(0.0, 0.0), shapes=[ref.add_box(10.0, 0.5, center=(0.0, -0.5))])
+    box = ref.add_box(0.4, 0.3, density=4.0)
+    disk = ref.add_disk(0.25, density=1.0)
+    for i in range(12):
+        ref.add_body(DYNAMIC, acc=G, pos=(-2.0 + 0.55 * (i % 6), 0.3 + 0.55 * (i // 6)), shapes=[disk])
+    b1 = ref.add_body(DYNAMIC, acc=G, pos=(-5.0, 0.35), shapes=[box])
+    b2 = ref.add_body(DYNAMIC, acc=G, pos=(5.0, 0.35), shapes=[box])
+    b3 = ref.add_body(DYNAMIC, acc=G, pos=(0.0, 4.0), shapes=[box])
+    b4 = ref.add_body(DYNAMIC, acc=G, pos=(0.8, 4.0), shapes=[box])
+    ref.add_target(b1, (-5.0, 0.35), (-5.0, 0.35), max_force=2000.0)                       # strong: pulled through the pile
+    ref.add_target(b2, (5.0, 0.35), (5.2, 0.5), frequency=3.0, damping_ratio=0.3, max_force=30.0)   # saturates
+    ref.add_weld(b3, b4, (0.4, 4.0))
+    ref.add_target(b3, (0.0, 4.0), (-0.3, 4.2), frequency=4.0, damping_ratio=1.0, max_force=500.0)
+    return ref, [6, 6, 5, 6]
+
+
+def _target_moves(step):
+    """(joint id, new target) pairs to apply before the given step"""
+    if step % 10 == 0 and step < 160:
+        k = step // 10
+        return [(0, (-5.0 + 0.6 * k, 0.35 + 0.02 * k)), (1, (5.0 - 0.5 * k, 0.35)), (3, (0.3 * k, 4.0 - 0.1 * k))]
+    return []
+
+
+SCENES = {"weld": (_weld_scene, 200), "target": (_target_scene, 220)}
+MOVES = {"target": _target_moves}
 
 
 def _run(name, lib=None, device=-1, with_device=True):
@@ -51,6 +80,16 @@ def _run(name, lib=None, device=-1, with_device=True):
         twins = [gw, refworld.OracleWorld(sc)]
     conf = refworld.default_step_conf()
     for s in range(steps):
+        for jid, tgt in (MOVES[name](s) if name in MOVES else []):
+            rows = orc.joints()[[jid]].copy()
+            rows["local_anchor_a"] = tgt          # (pr_target_joint: the target sits where the other rows have local_anchor_a)
+            ids = np.array([jid], np.uint32)
+            ref.set_target(jid, tgt)
+            orc.set_joints(ids, rows)
+            for t in twins:
+                rows2 = t.joints()[[jid]].copy()
+                rows2["local_anchor_a"] = tgt
+                t.set_joints(ids, rows2)
         rs, os_ = ref.step(conf), orc.step(conf)
         assert_bits(np.array([rs]), np.array([os_]), "step %d stats (reference vs restatement)" % s)
         assert_bits(ref.bodies(), orc.bodies(), "step %d bodies (reference vs restatement)" % s)
