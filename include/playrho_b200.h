@@ -107,7 +107,10 @@ typedef struct pr_revolute_joint {
 
 /* Joint rows share one table (JointIDs are one id space in the reference): every row has pr_revolute_joint's size and leading
  * fields, and bits 8..15 of collide_connected say which joint type it is (bit 0 is the flag itself). */
-enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2, PR_JOINT_FRICTION = 3, PR_JOINT_MOTOR = 4, PR_JOINT_WELD = 5, PR_JOINT_TARGET = 6 };
+enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2, PR_JOINT_FRICTION = 3, PR_JOINT_MOTOR = 4, PR_JOINT_WELD = 5, PR_JOINT_TARGET = 6, PR_JOINT_PRISMATIC = 7, PR_JOINT_WHEEL = 8 };
+/* prismatic and wheel rows keep their enable flags in collide_connected (their enable_limit / enable_motor words hold the local axis) */
+#define PR_JOINT_ENABLE_LIMIT 0x10000u
+#define PR_JOINT_ENABLE_MOTOR 0x20000u
 #define PR_JOINT_TYPE(row) (((row).collide_connected >> 8) & 0xFFu)
 /* DistanceJointConf (Library/include/playrho/d2/DistanceJointConf.hpp): rod or spring between two anchor points.
  * Solver: Library/source/playrho/d2/DistanceJointConf.cpp:81-246 (InitVelocity, SolveVelocity, SolvePosition). */
@@ -191,6 +194,33 @@ typedef struct pr_target_joint {
     float max_force, reserved2;
     uint32_t reserved3;
 } pr_target_joint;
+/* PrismaticJointConf (PrismaticJointConf.hpp; solver PrismaticJointConf.cpp:150-533): body B slides along an axis fixed in body A,
+ * no relative rotation; optional translation limits and a linear motor. localYAxisA is the reverse perpendicular of local_x_axis_a. */
+typedef struct pr_prismatic_joint {
+    uint32_t body_a, body_b;
+    uint32_t collide_connected;          /* bit 0: collideConnected; bits 8..15: PR_JOINT_PRISMATIC; PR_JOINT_ENABLE_LIMIT / _MOTOR */
+    pr_vec2 local_anchor_a, local_anchor_b;
+    float impulse_x, impulse_y, impulse_z; /* accumulated impulse: perpendicular, angular, limit (warm start) */
+    float motor_impulse;
+    float reference_angle;
+    pr_vec2 local_x_axis_a;              /* unit vector in body A's frame */
+    float lower_translation, upper_translation;
+    float motor_speed, max_motor_force;
+    uint32_t limit_state;                /* LimitState (InitVelocity writes it) */
+} pr_prismatic_joint;
+/* WheelJointConf (WheelJointConf.hpp; solver WheelJointConf.cpp:103-362): body B's anchor stays on a line fixed in body A, with a
+ * spring along the line and a rotational motor -- a vehicle suspension. */
+typedef struct pr_wheel_joint {
+    uint32_t body_a, body_b;
+    uint32_t collide_connected;          /* bit 0: collideConnected; bits 8..15: PR_JOINT_WHEEL; PR_JOINT_ENABLE_MOTOR */
+    pr_vec2 local_anchor_a, local_anchor_b;
+    float impulse, spring_impulse, angular_impulse; /* accumulated impulses (warm start) */
+    float reserved0[2];
+    pr_vec2 local_x_axis_a;              /* unit vector in body A's frame */
+    float frequency, damping_ratio;
+    float motor_speed, max_motor_torque;
+    uint32_t reserved1;
+} pr_wheel_joint;
 
 /* ContactFeature packed little-endian: typeA | indexA<<8 | typeB<<16 | indexB<<24 */
 typedef uint32_t pr_contact_feature;
@@ -331,6 +361,8 @@ int pr_create_friction_joints(pr_world* w, uint32_t n, const pr_friction_joint* 
 int pr_create_motor_joints(pr_world* w, uint32_t n, const pr_motor_joint* joints, uint32_t* first_id);
 int pr_create_weld_joints(pr_world* w, uint32_t n, const pr_weld_joint* joints, uint32_t* first_id);
 int pr_create_target_joints(pr_world* w, uint32_t n, const pr_target_joint* joints, uint32_t* first_id);
+int pr_create_prismatic_joints(pr_world* w, uint32_t n, const pr_prismatic_joint* joints, uint32_t* first_id);
+int pr_create_wheel_joints(pr_world* w, uint32_t n, const pr_wheel_joint* joints, uint32_t* first_id);
 
 /* SetShape(AabbTreeWorld&, ShapeID, Shape) (AabbTreeWorld.cpp:1284-1356) for a value whose geometry (children) and filter are
  * what they were: friction, restitution, density and the sensor flag are replaced; every body using the shape is woken

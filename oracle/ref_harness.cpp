@@ -460,6 +460,26 @@ int ref_set_target(void* h, uint32_t joint, float tx, float ty)
     return 0;
     REF_CATCH(-1)
 }
+uint32_t ref_add_prismatic(void* h, uint32_t bodyA, uint32_t bodyB, float ax, float ay, float dirx, float diry, int enableLimit, float lower, float upper,
+                           int enableMotor, float motorSpeed, float maxMotorForce)
+{
+    REF_TRY(h)
+    auto jc = GetPrismaticJointConf(rw->world, MakeId<BodyID>(bodyA), MakeId<BodyID>(bodyB), Length2{ax * 1_m, ay * 1_m}, UnitVec::Get(dirx, diry).first);
+    jc.enableLimit = enableLimit != 0; jc.lowerTranslation = lower * 1_m; jc.upperTranslation = upper * 1_m;
+    jc.enableMotor = enableMotor != 0; jc.motorSpeed = motorSpeed * 1_rad / 1_s; jc.maxMotorForce = maxMotorForce * 1_N;
+    return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
+    REF_CATCH(0xFFFFFFFFu)
+}
+uint32_t ref_add_wheel(void* h, uint32_t bodyA, uint32_t bodyB, float ax, float ay, float dirx, float diry, float frequency, float dampingRatio,
+                       int enableMotor, float motorSpeed, float maxMotorTorque)
+{
+    REF_TRY(h)
+    auto jc = GetWheelJointConf(rw->world, MakeId<BodyID>(bodyA), MakeId<BodyID>(bodyB), Length2{ax * 1_m, ay * 1_m}, UnitVec::Get(dirx, diry).first);
+    jc.frequency = frequency * 1_Hz; jc.dampingRatio = dampingRatio;
+    jc.enableMotor = enableMotor != 0; jc.motorSpeed = motorSpeed * 1_rad / 1_s; jc.maxMotorTorque = maxMotorTorque * 1_Nm;
+    return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
+    REF_CATCH(0xFFFFFFFFu)
+}
 int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
 {
     REF_TRY(h)
@@ -517,6 +537,37 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
             o.local_anchor_b = pr_vec2{GetX(tc.localAnchorB), GetY(tc.localAnchorB)};
             o.impulse_x = GetX(tc.impulse); o.impulse_y = GetY(tc.impulse);
             o.lower_angle = tc.frequency; o.upper_angle = tc.dampingRatio; o.motor_speed = tc.maxForce;
+            continue;
+        }
+        if (GetType(joint) == GetTypeID<PrismaticJointConf>()) { // the same row, viewed as pr_prismatic_joint
+            const auto pc = TypeCast<PrismaticJointConf>(joint);
+            pr_prismatic_joint p{};
+            p.body_a = to_underlying(pc.bodyA); p.body_b = to_underlying(pc.bodyB);
+            p.collide_connected = (pc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_PRISMATIC) << 8) |
+                                  (pc.enableLimit ? PR_JOINT_ENABLE_LIMIT : 0u) | (pc.enableMotor ? PR_JOINT_ENABLE_MOTOR : 0u);
+            p.local_anchor_a = pr_vec2{GetX(pc.localAnchorA), GetY(pc.localAnchorA)};
+            p.local_anchor_b = pr_vec2{GetX(pc.localAnchorB), GetY(pc.localAnchorB)};
+            p.impulse_x = GetX(pc.impulse); p.impulse_y = GetY(pc.impulse); p.impulse_z = GetZ(pc.impulse);
+            p.motor_impulse = pc.motorImpulse; p.reference_angle = pc.referenceAngle;
+            p.local_x_axis_a = pr_vec2{pc.localXAxisA.GetX(), pc.localXAxisA.GetY()};
+            p.lower_translation = pc.lowerTranslation; p.upper_translation = pc.upperTranslation;
+            p.motor_speed = pc.motorSpeed; p.max_motor_force = pc.maxMotorForce;
+            p.limit_state = static_cast<uint32_t>(pc.limitState);
+            std::memcpy(&o, &p, sizeof(o));
+            continue;
+        }
+        if (GetType(joint) == GetTypeID<WheelJointConf>()) { // the same row, viewed as pr_wheel_joint
+            const auto wc = TypeCast<WheelJointConf>(joint);
+            pr_wheel_joint p{};
+            p.body_a = to_underlying(wc.bodyA); p.body_b = to_underlying(wc.bodyB);
+            p.collide_connected = (wc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_WHEEL) << 8) | (wc.enableMotor ? PR_JOINT_ENABLE_MOTOR : 0u);
+            p.local_anchor_a = pr_vec2{GetX(wc.localAnchorA), GetY(wc.localAnchorA)};
+            p.local_anchor_b = pr_vec2{GetX(wc.localAnchorB), GetY(wc.localAnchorB)};
+            p.impulse = wc.impulse; p.spring_impulse = wc.springImpulse; p.angular_impulse = wc.angularImpulse;
+            p.local_x_axis_a = pr_vec2{wc.localXAxisA.GetX(), wc.localXAxisA.GetY()};
+            p.frequency = wc.frequency; p.damping_ratio = wc.dampingRatio;
+            p.motor_speed = wc.motorSpeed; p.max_motor_torque = wc.maxMotorTorque;
+            std::memcpy(&o, &p, sizeof(o));
             continue;
         }
         if (GetType(joint) == GetTypeID<RopeJointConf>()) { // the same row, viewed as pr_rope_joint

@@ -1,6 +1,7 @@
 // orc_toi.cpp -- TEST INFRASTRUCTURE ONLY (oracle restatement): GJK Distance (Distance.cpp, Simplex.cpp),
 // SeparationScenario.cpp, GetToiViaSat (TimeOfImpact.cpp) and the revolute joint (RevoluteJointConf.cpp).
 #include <algorithm>
+#include <cstring>
 #include "orc_toi.h"
 namespace orc {
 namespace {
@@ -945,6 +946,299 @@ bool target_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imB, fl
     velB.l = velB.l + imB * inc; velB.a += iiB * angImpulseB;
     return inc.x == 0.0f && inc.y == 0.0f;
 }
+// ---------------- PrismaticJointConf.cpp:150-533 ----------------
+// (mass[3 * i + k] = K[i][k], angularMass = motorMass, ex[0..1] = axis, ex[2..3] = perp, ex[4] = s1, ex[5] = s2, ex[6] = a1, ex[7] = a2)
+inline float bits_to_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline Rot local_x_axis(const pr_revolute_joint& j) { return Rot{bits_to_float(j.enable_limit), bits_to_float(j.enable_motor)}; }
+inline bool has_limit(const pr_revolute_joint& j) { return (j.collide_connected & PR_JOINT_ENABLE_LIMIT) != 0u; }
+inline bool has_motor(const pr_revolute_joint& j) { return (j.collide_connected & PR_JOINT_ENABLE_MOTOR) != 0u; }
+void prismatic_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
+                             float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
+{
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    const V2 rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    const V2 rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    wk.rA = rA; wk.rB = rB;
+    const V2 d = (posB.l - posA.l) + rB - rA;
+    const Rot axis = rot_rotate(local_x_axis(j), qA);
+    const float a1 = cross(d + rA, axis), a2 = cross(rB, axis);
+    const float invRotMassA = iiA * square(a1) / 1.0f, invRotMassB = iiB * square(a2) / 1.0f;
+    const float totalInvMass = imA + imB + invRotMassA + invRotMassB;
+    wk.angularMass = (totalInvMass > 0.0f) ? 1.0f / totalInvMass : 0.0f;
+    const Rot perp = rot_rotate(rev_perp(local_x_axis(j)), qA);
+    const float s1 = cross(d + rA, perp), s2 = cross(rB, perp);
+    const float invRotMassA2 = iiA * square(s1) / 1.0f, invRotMassB2 = iiB * square(s2) / 1.0f;
+    const float k11 = imA + imB + invRotMassA2 + invRotMassB2;
+    const float k12 = (iiA * s1 + iiB * s2) * 1.0f * 1.0f / 1.0f;
+    const float k13 = (iiA * s1 * a1 + iiB * s2 * a2) / 1.0f;
+    const float totalInvRotInertia = iiA + iiB;
+    const float k22 = (totalInvRotInertia == 0.0f) ? 1.0f : totalInvRotInertia;
+    const float k23 = (iiA * a1 + iiB * a2) * 1.0f * 1.0f / 1.0f;
+    const float k33 = totalInvMass;
+    const float K[9] = {k11, k12, k13, k12, k22, k23, k13, k23, k33};
+    for (int i = 0; i < 9; ++i) wk.mass[i] = K[i];
+    wk.ex[0] = axis.c; wk.ex[1] = axis.s; wk.ex[2] = perp.c; wk.ex[3] = perp.s; wk.ex[4] = s1; wk.ex[5] = s2; wk.ex[6] = a1; wk.ex[7] = a2;
+    if (has_limit(j)) {
+        const float jointTranslation = dot(axis, d);
+        if (std::fabs(j.upper_angle - j.lower_angle) < (c.linearSlop * 2.0f)) j.limit_state = LS_EQUAL;
+        else if (jointTranslation <= j.lower_angle) {
+            if (j.limit_state != LS_AT_LOWER) { j.limit_state = LS_AT_LOWER; j.impulse_z = 0; }
+        } else if (jointTranslation >= j.upper_angle) {
+            if (j.limit_state != LS_AT_UPPER) { j.limit_state = LS_AT_UPPER; j.impulse_z = 0; }
+        } else { j.limit_state = LS_INACTIVE; j.impulse_z = 0; }
+    } else { j.limit_state = LS_INACTIVE; j.impulse_z = 0; }
+    if (!has_motor(j)) j.angular_motor_impulse = 0.0f;
+    if (c.warmStart) {
+        j.impulse_x *= c.dtRatio; j.impulse_y *= c.dtRatio; j.impulse_z *= c.dtRatio;
+        j.angular_motor_impulse *= c.dtRatio;
+        const V2 ul = j.impulse_x * perp;
+        const V2 Px{ul.x * 1.0f, ul.y * 1.0f};
+        const float Pxs1 = j.impulse_x * s1 * 1.0f / 1.0f, Pxs2 = j.impulse_x * s2 * 1.0f / 1.0f;
+        const float PzLength = j.angular_motor_impulse + j.impulse_z * 1.0f;
+        const V2 Pz = PzLength * axis;
+        const V2 P = Px + Pz;
+        const float L = j.impulse_y * 1.0f * 1.0f / (1.0f * 1.0f);
+        const float LA = L + (Pxs1 * 1.0f + PzLength * a1) / 1.0f;
+        const float LB = L + (Pxs2 * 1.0f + PzLength * a2) / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    } else { j.impulse_x = j.impulse_y = j.impulse_z = 0.0f; j.angular_motor_impulse = 0.0f; }
+}
+bool prismatic_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& vA, float imB, float iiB, Vel& vB, const JointSolverConf& c)
+{
+    const Vel oldA = vA, oldB = vB;
+    Vel velA = vA, velB = vB;
+    const Rot axis{wk.ex[0], wk.ex[1]}, perp{wk.ex[2], wk.ex[3]};
+    const float s1 = wk.ex[4], s2 = wk.ex[5], a1 = wk.ex[6], a2 = wk.ex[7];
+    if (has_motor(j) && j.limit_state != LS_EQUAL) {
+        const float vDot = dot(axis, velB.l - velA.l);
+        const float Cdot = vDot + (a2 * velB.a - a1 * velA.a) / 1.0f;
+        float impulse = wk.angularMass * (j.motor_speed * 1.0f / 1.0f - Cdot);
+        const float oldImpulse = j.angular_motor_impulse;
+        const float maxImpulse = c.dt * j.max_motor_torque;
+        j.angular_motor_impulse = std::clamp(j.angular_motor_impulse + impulse, -maxImpulse, maxImpulse);
+        impulse = j.angular_motor_impulse - oldImpulse;
+        const V2 P = impulse * axis;
+        const float LA = impulse * a1 / 1.0f, LB = impulse * a2 / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    }
+    const V2 velDelta = velB.l - velA.l;
+    const float sRotSpeed = (s2 * velB.a - s1 * velA.a) / 1.0f;
+    const V2 Cdot1{dot(perp, velDelta) + sRotSpeed, velB.a - velA.a};
+    if (has_limit(j) && (j.limit_state != LS_INACTIVE)) {
+        const float deltaDot = dot(axis, velDelta);
+        const float aRotSpeed = (a2 * velB.a - a1 * velA.a) / 1.0f;
+        const float Cdot2 = deltaDot + aRotSpeed;
+        const V3 f1{j.impulse_x, j.impulse_y, j.impulse_z};
+        const V3 sol = solve33(wk.mass, V3{-Cdot1.x, -Cdot1.y, -Cdot2});
+        V3 imp{f1.x + sol.x, f1.y + sol.y, f1.z + sol.z};
+        if (j.limit_state == LS_AT_LOWER) imp.z = std::max(imp.z, 0.0f);
+        else if (j.limit_state == LS_AT_UPPER) imp.z = std::min(imp.z, 0.0f);
+        const V2 b = -Cdot1 - (imp.z - f1.z) * V2{wk.mass[6], wk.mass[7]};
+        const V2 f2r = solve22(wk.mass, b) + V2{f1.x, f1.y};
+        imp.x = f2r.x; imp.y = f2r.y;
+        j.impulse_x = imp.x; j.impulse_y = imp.y; j.impulse_z = imp.z;
+        const V3 df{imp.x - f1.x, imp.y - f1.y, imp.z - f1.z};
+        const V2 ulP = df.x * perp + df.z * axis;
+        const V2 P{ulP.x * 1.0f, ulP.y * 1.0f};
+        const float LA = (df.x * s1 + df.y * 1.0f + df.z * a1) * 1.0f / 1.0f;
+        const float LB = (df.x * s2 + df.y * 1.0f + df.z * a2) * 1.0f / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    } else {
+        const V2 df = solve22(wk.mass, -Cdot1);
+        j.impulse_x += df.x; j.impulse_y += df.y;
+        const V2 ulP = df.x * perp;
+        const V2 P{ulP.x * 1.0f, ulP.y * 1.0f};
+        const float LA = (df.x * s1 + df.y * 1.0f) * 1.0f / 1.0f;
+        const float LB = (df.x * s2 + df.y * 1.0f) * 1.0f / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    }
+    const bool changed = (velA.l != oldA.l) || (velA.a != oldA.a) || (velB.l != oldB.l) || (velB.a != oldB.a);
+    if (changed) { vA = velA; vB = velB; return false; }
+    return true;
+}
+bool prismatic_solve_position(const pr_revolute_joint& j, float imA, float iiA, V2 lcA, Pos& posA, float imB, float iiB, V2 lcB, Pos& posB,
+                              const JointSolverConf& c)
+{
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    const V2 rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    const V2 rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    const V2 d = (posB.l + rB) - (posA.l + rA);
+    const Rot axis = rot_rotate(local_x_axis(j), qA);
+    const float a1 = cross(d + rA, axis), a2 = cross(rB, axis);
+    const Rot perp = rot_rotate(rev_perp(local_x_axis(j)), qA);
+    const float s1 = cross(d + rA, perp), s2 = cross(rB, perp);
+    const V2 C1{dot(perp, d) / 1.0f, (posB.a - posA.a - j.reference_angle) / 1.0f};
+    float linearError = std::fabs(C1.x) * 1.0f;
+    const float angularError = std::fabs(C1.y) * 1.0f;
+    bool active = false;
+    float C2 = 0.0f;
+    if (has_limit(j)) {
+        const float translation = dot(axis, d);
+        if (std::fabs(j.upper_angle - j.lower_angle) < (2.0f * c.linearSlop)) {
+            C2 = std::clamp(translation, -c.maxLinearCorrection, c.maxLinearCorrection);
+            linearError = std::max(linearError, std::fabs(translation));
+            active = true;
+        } else if (translation <= j.lower_angle) {
+            C2 = std::clamp(translation - j.lower_angle + c.linearSlop, -c.maxLinearCorrection, 0.0f);
+            linearError = std::max(linearError, j.lower_angle - translation);
+            active = true;
+        } else if (translation >= j.upper_angle) {
+            C2 = std::clamp(translation - j.upper_angle - c.linearSlop, 0.0f, c.maxLinearCorrection);
+            linearError = std::max(linearError, translation - j.upper_angle);
+            active = true;
+        }
+    }
+    V3 impulse;
+    if (active) {
+        const float k11 = imA + iiA * square(s1) / 1.0f + imB + iiB * square(s2) / 1.0f;
+        const float k12 = iiA * s1 * 1.0f / 1.0f + iiB * s2 * 1.0f / 1.0f;
+        const float k13 = iiA * s1 * a1 / 1.0f + iiB * s2 * a2 / 1.0f;
+        float k22 = iiA + iiB;
+        if (k22 == 0.0f) k22 = 1.0f * 1.0f / (1.0f * 1.0f);
+        const float k23 = iiA * a1 * 1.0f / 1.0f + iiB * a2 * 1.0f / 1.0f;
+        const float k33 = imA + iiA * square(a1) / 1.0f + imB + iiB * square(a2) / 1.0f;
+        const float K[9] = {k11, k12, k13, k12, k22, k23, k13, k23, k33};
+        impulse = solve33(K, V3{-C1.x, -C1.y, -C2});
+    } else {
+        const float k11 = imA + iiA * s1 * s1 / 1.0f + imB + iiB * s2 * s2 / 1.0f;
+        const float k12 = iiA * s1 * 1.0f / 1.0f + iiB * s2 * 1.0f / 1.0f;
+        float k22 = iiA + iiB;
+        if (k22 == 0.0f) k22 = 1.0f;
+        const float cp = cross(V2{k11, k12}, V2{k12, k22}); // Solve(Matrix22, Vector2), Math.hpp:414-426
+        const V2 b = -C1;
+        V2 impulse1{0.0f, 0.0f};
+        if (!almost_zero(cp)) {
+            const float inverse = 1 / cp;
+            impulse1 = V2{(k22 * b.x - k12 * b.y) * inverse, (k11 * b.y - k12 * b.x) * inverse};
+        }
+        impulse = V3{impulse1.x, impulse1.y, 0.0f};
+    }
+    const V2 P = (impulse.x * perp + impulse.z * axis) * 1.0f * 1.0f;
+    const float LA = (impulse.x * s1 + impulse.y * 1.0f + impulse.z * a1) * 1.0f * 1.0f / 1.0f;
+    const float LB = (impulse.x * s2 + impulse.y * 1.0f + impulse.z * a2) * 1.0f * 1.0f / 1.0f;
+    posA.l = posA.l - imA * P; posA.a -= iiA * LA;
+    posB.l = posB.l + imB * P; posB.a += iiB * LB;
+    return (linearError <= c.linearSlop) && (angularError <= c.angularSlop);
+}
+// ---------------- WheelJointConf.cpp:103-362 ----------------
+// (mass[0..1] = ay, mass[2] = sAy, mass[3] = sBy, mass[4] = mass, mass[5..6] = ax, mass[7] = sAx, mass[8] = sBx, ex[0] = springMass, ex[1] = bias,
+//  ex[2] = gamma, angularMass)
+void wheel_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
+                         float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
+{
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    const V2 rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    const V2 rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    wk.rA = rA; wk.rB = rB;
+    const V2 dd = (posB.l + rB) - (posA.l + rA);
+    const Rot ay = rot_rotate(rev_perp(local_x_axis(j)), qA);
+    const float sAy = cross(dd + rA, ay), sBy = cross(rB, ay);
+    {
+        const float invRotMassA = iiA * square(sAy) / 1.0f, invRotMassB = iiB * square(sBy) / 1.0f;
+        const float invMass = imA + imB + invRotMassA + invRotMassB;
+        wk.mass[4] = (invMass > 0.0f) ? 1.0f / invMass : 0.0f;
+    }
+    wk.mass[0] = ay.c; wk.mass[1] = ay.s; wk.mass[2] = sAy; wk.mass[3] = sBy;
+    float springMass = 0.0f, bias = 0.0f, gamma = 0.0f;
+    Rot ax{0.0f, 0.0f};
+    float sAx = 0.0f, sBx = 0.0f;
+    if (j.lower_angle > 0.0f) {
+        ax = rot_rotate(local_x_axis(j), qA);
+        sAx = cross(dd + rA, ax); sBx = cross(rB, ax);
+        const float invRotMassA = iiA * square(sAx) / 1.0f, invRotMassB = iiB * square(sBx) / 1.0f;
+        const float invMass = imA + imB + invRotMassA + invRotMassB;
+        if (invMass > 0.0f) {
+            springMass = 1.0f / invMass;
+            const float C = dot(dd, ax);
+            const float omega = 2.0f * 3.14159265358979323846264338327950288f * j.lower_angle;
+            const float d = 2.0f * springMass * j.upper_angle * omega;
+            const float k = springMass * omega * omega;
+            const float h = c.dt;
+            const float invGamma = h * (d + h * k);
+            gamma = (invGamma > 0.0f) ? 1.0f / invGamma : 0.0f;
+            bias = C * h * k * gamma;
+            const float totalInvMass = invMass + gamma;
+            springMass = (totalInvMass > 0.0f) ? 1.0f / totalInvMass : 0.0f;
+        }
+    } else j.impulse_y = 0.0f;
+    wk.mass[5] = ax.c; wk.mass[6] = ax.s; wk.mass[7] = sAx; wk.mass[8] = sBx;
+    wk.ex[0] = springMass; wk.ex[1] = bias; wk.ex[2] = gamma;
+    if (has_motor(j)) {
+        const float invRotInertia = iiA + iiB;
+        wk.angularMass = (invRotInertia > 0.0f) ? 1.0f / invRotInertia : 0.0f;
+    } else { wk.angularMass = 0.0f; j.impulse_z = 0.0f; }
+    if (c.warmStart) {
+        j.impulse_x *= c.dtRatio; j.impulse_y *= c.dtRatio; j.impulse_z *= c.dtRatio;
+        const V2 P = j.impulse_x * ay + j.impulse_y * ax;
+        const float LA = (j.impulse_x * sAy + j.impulse_y * sAx) / 1.0f + j.impulse_z;
+        const float LB = (j.impulse_x * sBy + j.impulse_y * sBx) / 1.0f + j.impulse_z;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    } else j.impulse_x = j.impulse_y = j.impulse_z = 0.0f;
+}
+bool wheel_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& vA, float imB, float iiB, Vel& vB, const JointSolverConf& c)
+{
+    const Vel oldA = vA, oldB = vB;
+    Vel velA = vA, velB = vB;
+    const Rot ay{wk.mass[0], wk.mass[1]}, ax{wk.mass[5], wk.mass[6]};
+    const float sAy = wk.mass[2], sBy = wk.mass[3], sAx = wk.mass[7], sBx = wk.mass[8];
+    {
+        const float dt = dot(ax, velB.l - velA.l);
+        const float Cdot = dt + sBx * velB.a / 1.0f - sAx * velA.a / 1.0f;
+        const float impulse = -wk.ex[0] * (Cdot + wk.ex[1] + wk.ex[2] * j.impulse_y);
+        j.impulse_y += impulse;
+        const V2 P = impulse * ax;
+        const float LA = impulse * sAx / 1.0f, LB = impulse * sBx / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    }
+    {
+        const float Cdot = (velB.a - velA.a - j.motor_speed);
+        float impulse = -wk.angularMass * Cdot;
+        const float oldImpulse = j.impulse_z;
+        const float maxImpulse = c.dt * j.max_motor_torque;
+        j.impulse_z = std::clamp(j.impulse_z + impulse, -maxImpulse, maxImpulse);
+        impulse = j.impulse_z - oldImpulse;
+        velA.a -= iiA * impulse;
+        velB.a += iiB * impulse;
+    }
+    {
+        const float dt = dot(ay, velB.l - velA.l);
+        const float Cdot = dt + sBy * velB.a / 1.0f - sAy * velA.a / 1.0f;
+        const float impulse = -wk.mass[4] * Cdot;
+        j.impulse_x += impulse;
+        const V2 P = impulse * ay;
+        const float LA = impulse * sAy / 1.0f, LB = impulse * sBy / 1.0f;
+        velA.l = velA.l - imA * P; velA.a -= iiA * LA;
+        velB.l = velB.l + imB * P; velB.a += iiB * LB;
+    }
+    const bool changed = (velA.l != oldA.l) || (velA.a != oldA.a) || (velB.l != oldB.l) || (velB.a != oldB.a);
+    if (changed) { vA = velA; vB = velB; return false; }
+    return true;
+}
+bool wheel_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos& posA, float imB, float iiB, V2 lcB,
+                          Pos& posB, const JointSolverConf& c)
+{
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    const V2 rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    const V2 rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    const V2 d = (posB.l - posA.l) + (rB - rA);
+    const Rot ay = rot_rotate(rev_perp(local_x_axis(j)), qA);
+    const float sAy = cross(d + rA, ay), sBy = cross(rB, ay);
+    const float C = dot(d, ay);
+    const float invRotMassA = iiA * square(wk.mass[2]) / 1.0f, invRotMassB = iiB * square(wk.mass[3]) / 1.0f; // (:339-340: the stored sAy / sBy)
+    const float k = imA + imB + invRotMassA + invRotMassB;
+    const float impulse = (k != 0.0f) ? -(C / k) : 0.0f * 1.0f * 1.0f;
+    const V2 P = impulse * ay;
+    const float LA = impulse * sAy / 1.0f, LB = impulse * sBy / 1.0f;
+    posA.l = posA.l - imA * P; posA.a -= iiA * LA;
+    posB.l = posB.l + imB * P; posB.a += iiB * LB;
+    return std::fabs(C) <= c.linearSlop;
+}
 } // namespace
 void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
                          float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
@@ -954,6 +1248,8 @@ void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, floa
     else if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR)
         fm_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c, PR_JOINT_TYPE(j) == PR_JOINT_MOTOR);
     else if (PR_JOINT_TYPE(j) == PR_JOINT_TARGET) target_init_velocity(j, wk, imB, iiB, lcB, posB, velB, c);
+    else if (PR_JOINT_TYPE(j) == PR_JOINT_PRISMATIC) prismatic_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
+    else if (PR_JOINT_TYPE(j) == PR_JOINT_WHEEL) wheel_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
     else if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) weld_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
     else revolute_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
 }
@@ -964,6 +1260,8 @@ bool joint_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, flo
     if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR)
         return fm_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c, PR_JOINT_TYPE(j) == PR_JOINT_MOTOR);
     if (PR_JOINT_TYPE(j) == PR_JOINT_TARGET) return target_solve_velocity(j, wk, imB, iiB, velB, c);
+    if (PR_JOINT_TYPE(j) == PR_JOINT_PRISMATIC) return prismatic_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
+    if (PR_JOINT_TYPE(j) == PR_JOINT_WHEEL) return wheel_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) return weld_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB);
     return revolute_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
 }
@@ -973,6 +1271,8 @@ bool joint_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, fl
     if (PR_JOINT_TYPE(j) == PR_JOINT_DISTANCE) return distance_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_ROPE) return rope_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR || PR_JOINT_TYPE(j) == PR_JOINT_TARGET) return true;
+    if (PR_JOINT_TYPE(j) == PR_JOINT_PRISMATIC) return prismatic_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
+    if (PR_JOINT_TYPE(j) == PR_JOINT_WHEEL) return wheel_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) return weld_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     return revolute_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
 }

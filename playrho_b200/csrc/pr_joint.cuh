@@ -597,6 +597,342 @@ PR_D void target_solve_velocity(const DV& d, unsigned ji, pr_revolute_joint j, c
     if (!(inc.x == 0.0f && inc.y == 0.0f)) v.isl_jflag[wk.island] = 1u;
 }
 
+// ---- PrismaticJointConf.cpp:150-533. Row overlay (pr_prismatic_joint): impulse = impulse_x/y/z, motorImpulse = angular_motor_impulse,
+// localXAxisA = the bits of enable_limit / enable_motor (localYAxisA is its reverse perpendicular), enableLimit / enableMotor = bits
+// 16 / 17 of collide_connected, lower / upperTranslation = lower_angle / upper_angle, motorSpeed, maxMotorForce = max_motor_torque;
+// work: m[3 * i + k] = K[i][k], angularMass = motorMass, ex[0..1] = axis, ex[2..3] = perp, ex[4] = s1, ex[5] = s2, ex[6] = a1, ex[7] = a2
+PR_D bool j_enable_limit(const pr_revolute_joint& j) { return (j.collide_connected & PR_JOINT_ENABLE_LIMIT) != 0u; }
+PR_D bool j_enable_motor(const pr_revolute_joint& j) { return (j.collide_connected & PR_JOINT_ENABLE_MOTOR) != 0u; }
+PR_D Rot j_local_x_axis(const pr_revolute_joint& j) { return mkrot(u2f(j.enable_limit), u2f(j.enable_motor)); }
+PR_D void prismatic_init_velocity(const DV& d, unsigned ji, pr_revolute_joint j, JointWork wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 pA = v.s_pos[jv_idx(v.slotP, j.body_a)], pB = v.s_pos[jv_idx(v.slotP, j.body_b)];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
+    const Rot qA = rot_from_angle(pA.z), qB = rot_from_angle(pB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    wk.rAx = rA.x; wk.rAy = rA.y; wk.rBx = rB.x; wk.rBy = rB.y;
+    const float2 dd = (v2(pB.x, pB.y) - v2(pA.x, pA.y)) + rB - rA;
+    const Rot lx = j_local_x_axis(j);
+    const Rot axis = rot_rotate(lx, qA);
+    const float a1 = cross(dd + rA, axis), a2 = cross(rB, axis);
+    const float invRotMassA = iiA * square(a1) / 1.0f, invRotMassB = iiB * square(a2) / 1.0f;
+    const float totalInvMass = imA + imB + invRotMassA + invRotMassB;
+    wk.angularMass = (totalInvMass > 0.0f) ? 1.0f / totalInvMass : 0.0f;
+    const Rot perp = rot_rotate(rev_perp(lx), qA);
+    const float s1 = cross(dd + rA, perp), s2 = cross(rB, perp);
+    {
+        const float invRotMassA2 = iiA * square(s1) / 1.0f, invRotMassB2 = iiB * square(s2) / 1.0f;
+        const float k11 = imA + imB + invRotMassA2 + invRotMassB2;
+        const float k12 = (iiA * s1 + iiB * s2) * 1.0f * 1.0f / 1.0f;
+        const float k13 = (iiA * s1 * a1 + iiB * s2 * a2) / 1.0f;
+        const float totalInvRotInertia = iiA + iiB;
+        const float k22 = (totalInvRotInertia == 0.0f) ? 1.0f : totalInvRotInertia;
+        const float k23 = (iiA * a1 + iiB * a2) * 1.0f * 1.0f / 1.0f;
+        const float k33 = totalInvMass;
+        float* m = wk.m;
+        m[0] = k11; m[1] = k12; m[2] = k13;
+        m[3] = k12; m[4] = k22; m[5] = k23;
+        m[6] = k13; m[7] = k23; m[8] = k33;
+    }
+    wk.ex[0] = axis.c; wk.ex[1] = axis.s; wk.ex[2] = perp.c; wk.ex[3] = perp.s; wk.ex[4] = s1; wk.ex[5] = s2; wk.ex[6] = a1; wk.ex[7] = a2;
+    if (j_enable_limit(j)) {
+        const float jointTranslation = dot(axis, dd);
+        if (fabsf(j.upper_angle - j.lower_angle) < (conf.linear_slop * 2.0f)) j.limit_state = LS_EQUAL;
+        else if (jointTranslation <= j.lower_angle) {
+            if (j.limit_state != LS_AT_LOWER) { j.limit_state = LS_AT_LOWER; j.impulse_z = 0; }
+        } else if (jointTranslation >= j.upper_angle) {
+            if (j.limit_state != LS_AT_UPPER) { j.limit_state = LS_AT_UPPER; j.impulse_z = 0; }
+        } else { j.limit_state = LS_INACTIVE; j.impulse_z = 0; }
+    } else { j.limit_state = LS_INACTIVE; j.impulse_z = 0; }
+    if (!j_enable_motor(j)) j.angular_motor_impulse = 0.0f;
+    if (conf.do_warm_start) {
+        j.impulse_x *= conf.dt_ratio; j.impulse_y *= conf.dt_ratio; j.impulse_z *= conf.dt_ratio;
+        j.angular_motor_impulse *= conf.dt_ratio;
+        const float2 ulImpulseX = j.impulse_x * perp;
+        const float2 Px = v2(ulImpulseX.x * 1.0f, ulImpulseX.y * 1.0f);
+        const float Pxs1 = j.impulse_x * s1 * 1.0f / 1.0f, Pxs2 = j.impulse_x * s2 * 1.0f / 1.0f;
+        const float PzLength = j.angular_motor_impulse + j.impulse_z * 1.0f;
+        const float2 Pz = PzLength * axis;
+        const float2 P = Px + Pz;
+        const float L = j.impulse_y * 1.0f * 1.0f / (1.0f * 1.0f);
+        const float LA = L + (Pxs1 * 1.0f + PzLength * a1) / 1.0f;
+        const float LB = L + (Pxs2 * 1.0f + PzLength * a2) / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    } else { j.impulse_x = j.impulse_y = j.impulse_z = 0.0f; j.angular_motor_impulse = 0.0f; }
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    d.jt_work[ji] = wk;
+}
+PR_D void prismatic_solve_velocity(const DV& d, unsigned ji, pr_revolute_joint j, const JointWork& wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 oldA = v.s_vel[ia], oldB = v.s_vel[ib];
+    float4 velA = oldA, velB = oldB;
+    const Rot axis = mkrot(wk.ex[0], wk.ex[1]), perp = mkrot(wk.ex[2], wk.ex[3]);
+    const float s1 = wk.ex[4], s2 = wk.ex[5], a1 = wk.ex[6], a2 = wk.ex[7];
+    if (j_enable_motor(j) && j.limit_state != LS_EQUAL) {
+        const float vDot = dot(axis, v2(velB.x, velB.y) - v2(velA.x, velA.y));
+        const float Cdot = vDot + (a2 * velB.z - a1 * velA.z) / 1.0f;
+        float impulse = wk.angularMass * (j.motor_speed * 1.0f / 1.0f - Cdot);
+        const float oldImpulse = j.angular_motor_impulse;
+        const float maxImpulse = conf.delta_time * j.max_motor_torque;
+        j.angular_motor_impulse = stdclamp(j.angular_motor_impulse + impulse, -maxImpulse, maxImpulse);
+        impulse = j.angular_motor_impulse - oldImpulse;
+        const float2 P = impulse * axis;
+        const float LA = impulse * a1 / 1.0f, LB = impulse * a2 / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    }
+    const float2 velDelta = v2(velB.x, velB.y) - v2(velA.x, velA.y);
+    const float sRotSpeed = (s2 * velB.z - s1 * velA.z) / 1.0f;
+    const float2 Cdot1 = v2(dot(perp, velDelta) + sRotSpeed, velB.z - velA.z);
+    if (j_enable_limit(j) && (j.limit_state != LS_INACTIVE)) {
+        const float deltaDot = dot(axis, velDelta);
+        const float aRotSpeed = (a2 * velB.z - a1 * velA.z) / 1.0f;
+        const float Cdot2 = deltaDot + aRotSpeed;
+        V3 nC; nC.x = -Cdot1.x; nC.y = -Cdot1.y; nC.z = -Cdot2;
+        V3 f1; f1.x = j.impulse_x; f1.y = j.impulse_y; f1.z = j.impulse_z;
+        const V3 sol = solve33(wk.m, nC);
+        V3 imp; imp.x = f1.x + sol.x; imp.y = f1.y + sol.y; imp.z = f1.z + sol.z;
+        if (j.limit_state == LS_AT_LOWER) imp.z = stdmax(imp.z, 0.0f);
+        else if (j.limit_state == LS_AT_UPPER) imp.z = stdmin(imp.z, 0.0f);
+        const float2 b = -Cdot1 - (imp.z - f1.z) * v2(wk.m[6], wk.m[7]);
+        const float2 f2r = solve22(wk.m, b) + v2(f1.x, f1.y);
+        imp.x = f2r.x; imp.y = f2r.y;
+        j.impulse_x = imp.x; j.impulse_y = imp.y; j.impulse_z = imp.z;
+        V3 df; df.x = imp.x - f1.x; df.y = imp.y - f1.y; df.z = imp.z - f1.z;
+        const float2 ulP = df.x * perp + df.z * axis;
+        const float2 P = v2(ulP.x * 1.0f, ulP.y * 1.0f);
+        const float LA = (df.x * s1 + df.y * 1.0f + df.z * a1) * 1.0f / 1.0f;
+        const float LB = (df.x * s2 + df.y * 1.0f + df.z * a2) * 1.0f / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    } else {
+        const float2 df = solve22(wk.m, -Cdot1);
+        j.impulse_x += df.x; j.impulse_y += df.y;
+        const float2 ulP = df.x * perp;
+        const float2 P = v2(ulP.x * 1.0f, ulP.y * 1.0f);
+        const float LA = (df.x * s1 + df.y * 1.0f) * 1.0f / 1.0f;
+        const float LB = (df.x * s2 + df.y * 1.0f) * 1.0f / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    }
+    d.jt[ji] = j;
+    const bool changed = velA.x != oldA.x || velA.y != oldA.y || velA.z != oldA.z || velB.x != oldB.x || velB.y != oldB.y || velB.z != oldB.z;
+    if (changed) { v.s_vel[ia] = velA; v.s_vel[ib] = velB; v.isl_jflag[wk.island] = 1u; }
+}
+PR_D void prismatic_solve_position(const DV& d, const pr_revolute_joint& j, const JointWork& wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    float4 posA = v.s_pos[ia], posB = v.s_pos[ib];
+    const Rot qA = rot_from_angle(posA.z), qB = rot_from_angle(posB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    const float2 dd = (v2(posB.x, posB.y) + rB) - (v2(posA.x, posA.y) + rA);
+    const Rot lx = j_local_x_axis(j);
+    const Rot axis = rot_rotate(lx, qA);
+    const float a1 = cross(dd + rA, axis), a2 = cross(rB, axis);
+    const Rot perp = rot_rotate(rev_perp(lx), qA);
+    const float s1 = cross(dd + rA, perp), s2 = cross(rB, perp);
+    const float2 C1 = v2(dot(perp, dd) / 1.0f, (posB.z - posA.z - j.reference_angle) / 1.0f);
+    float linearError = fabsf(C1.x) * 1.0f;
+    const float angularError = fabsf(C1.y) * 1.0f;
+    bool active = false;
+    float C2 = 0.0f;
+    if (j_enable_limit(j)) {
+        const float translation = dot(axis, dd);
+        if (fabsf(j.upper_angle - j.lower_angle) < (2.0f * conf.linear_slop)) {
+            C2 = stdclamp(translation, -conf.max_linear_correction, conf.max_linear_correction);
+            linearError = stdmax(linearError, fabsf(translation));
+            active = true;
+        } else if (translation <= j.lower_angle) {
+            C2 = stdclamp(translation - j.lower_angle + conf.linear_slop, -conf.max_linear_correction, 0.0f);
+            linearError = stdmax(linearError, j.lower_angle - translation);
+            active = true;
+        } else if (translation >= j.upper_angle) {
+            C2 = stdclamp(translation - j.upper_angle - conf.linear_slop, 0.0f, conf.max_linear_correction);
+            linearError = stdmax(linearError, translation - j.upper_angle);
+            active = true;
+        }
+    }
+    V3 impulse;
+    if (active) {
+        const float k11 = imA + iiA * square(s1) / 1.0f + imB + iiB * square(s2) / 1.0f;
+        const float k12 = iiA * s1 * 1.0f / 1.0f + iiB * s2 * 1.0f / 1.0f;
+        const float k13 = iiA * s1 * a1 / 1.0f + iiB * s2 * a2 / 1.0f;
+        float k22 = iiA + iiB;
+        if (k22 == 0.0f) k22 = 1.0f * 1.0f / (1.0f * 1.0f);
+        const float k23 = iiA * a1 * 1.0f / 1.0f + iiB * a2 * 1.0f / 1.0f;
+        const float k33 = imA + iiA * square(a1) / 1.0f + imB + iiB * square(a2) / 1.0f;
+        float K[9];
+        K[0] = k11; K[1] = k12; K[2] = k13; K[3] = k12; K[4] = k22; K[5] = k23; K[6] = k13; K[7] = k23; K[8] = k33;
+        V3 nC; nC.x = -C1.x; nC.y = -C1.y; nC.z = -C2;
+        impulse = solve33(K, nC);
+    } else {
+        const float k11 = imA + iiA * s1 * s1 / 1.0f + imB + iiB * s2 * s2 / 1.0f;
+        const float k12 = iiA * s1 * 1.0f / 1.0f + iiB * s2 * 1.0f / 1.0f;
+        float k22 = iiA + iiB;
+        if (k22 == 0.0f) k22 = 1.0f;
+        const float cp = cross(v2(k11, k12), v2(k12, k22)); // Solve(Matrix22, Vector2), Math.hpp:414-426
+        const float2 b = -C1;
+        float2 impulse1 = v2(0.0f, 0.0f);
+        if (!almost_zero(cp)) {
+            const float inverse = 1 / cp;
+            impulse1 = v2((k22 * b.x - k12 * b.y) * inverse, (k11 * b.y - k12 * b.x) * inverse);
+        }
+        impulse.x = impulse1.x; impulse.y = impulse1.y; impulse.z = 0.0f;
+    }
+    const float2 P = (impulse.x * perp + impulse.z * axis) * 1.0f * 1.0f;
+    const float LA = (impulse.x * s1 + impulse.y * 1.0f + impulse.z * a1) * 1.0f * 1.0f / 1.0f;
+    const float LB = (impulse.x * s2 + impulse.y * 1.0f + impulse.z * a2) * 1.0f * 1.0f / 1.0f;
+    const float2 la = v2(posA.x, posA.y) - imA * P; posA.x = la.x; posA.y = la.y; posA.z -= iiA * LA;
+    const float2 lb = v2(posB.x, posB.y) + imB * P; posB.x = lb.x; posB.y = lb.y; posB.z += iiB * LB;
+    v.s_pos[ia] = posA; v.s_pos[ib] = posB;
+    if (!((linearError <= conf.linear_slop) && (angularError <= conf.angular_slop))) v.isl_jflag[wk.island] = 1u;
+}
+
+// ---- WheelJointConf.cpp:103-362. Row overlay (pr_wheel_joint): impulse = impulse_x, springImpulse = impulse_y, angularImpulse = impulse_z,
+// localXAxisA = the bits of enable_limit / enable_motor, enableMotor = bit 17 of collide_connected, frequency = lower_angle, dampingRatio =
+// upper_angle, motorSpeed, maxMotorTorque; work: m[0..1] = ay, m[2] = sAy, m[3] = sBy, m[4] = mass, m[5..6] = ax, m[7] = sAx, m[8] = sBx,
+// ex[0] = springMass, ex[1] = bias, ex[2] = gamma, angularMass
+PR_D void wheel_init_velocity(const DV& d, unsigned ji, pr_revolute_joint j, JointWork wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 pA = v.s_pos[jv_idx(v.slotP, j.body_a)], pB = v.s_pos[jv_idx(v.slotP, j.body_b)];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
+    const Rot qA = rot_from_angle(pA.z), qB = rot_from_angle(pB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    wk.rAx = rA.x; wk.rAy = rA.y; wk.rBx = rB.x; wk.rBy = rB.y;
+    const float2 dd = (v2(pB.x, pB.y) + rB) - (v2(pA.x, pA.y) + rA);
+    const Rot lx = j_local_x_axis(j);
+    const Rot ay = rot_rotate(rev_perp(lx), qA);
+    const float sAy = cross(dd + rA, ay), sBy = cross(rB, ay);
+    {
+        const float invRotMassA = iiA * square(sAy) / 1.0f, invRotMassB = iiB * square(sBy) / 1.0f;
+        const float invMass = imA + imB + invRotMassA + invRotMassB;
+        wk.m[4] = (invMass > 0.0f) ? 1.0f / invMass : 0.0f;
+    }
+    wk.m[0] = ay.c; wk.m[1] = ay.s; wk.m[2] = sAy; wk.m[3] = sBy;
+    float springMass = 0.0f, bias = 0.0f, gamma = 0.0f;
+    Rot ax = mkrot(0.0f, 0.0f);
+    float sAx = 0.0f, sBx = 0.0f;
+    if (j.lower_angle > 0.0f) {
+        ax = rot_rotate(lx, qA);
+        sAx = cross(dd + rA, ax); sBx = cross(rB, ax);
+        const float invRotMassA = iiA * square(sAx) / 1.0f, invRotMassB = iiB * square(sBx) / 1.0f;
+        const float invMass = imA + imB + invRotMassA + invRotMassB;
+        if (invMass > 0.0f) {
+            springMass = 1.0f / invMass;
+            const float C = dot(dd, ax);
+            const float omega = 2.0f * 3.14159265358979323846264338327950288f * j.lower_angle;
+            const float dc = 2.0f * springMass * j.upper_angle * omega;
+            const float k = springMass * omega * omega;
+            const float h = conf.delta_time;
+            const float invGamma = h * (dc + h * k);
+            gamma = (invGamma > 0.0f) ? 1.0f / invGamma : 0.0f;
+            bias = C * h * k * gamma;
+            const float totalInvMass = invMass + gamma;
+            springMass = (totalInvMass > 0.0f) ? 1.0f / totalInvMass : 0.0f;
+        }
+    } else j.impulse_y = 0.0f;
+    wk.m[5] = ax.c; wk.m[6] = ax.s; wk.m[7] = sAx; wk.m[8] = sBx;
+    wk.ex[0] = springMass; wk.ex[1] = bias; wk.ex[2] = gamma;
+    if (j_enable_motor(j)) {
+        const float invRotInertia = iiA + iiB;
+        wk.angularMass = (invRotInertia > 0.0f) ? 1.0f / invRotInertia : 0.0f;
+    } else { wk.angularMass = 0.0f; j.impulse_z = 0.0f; }
+    if (conf.do_warm_start) {
+        j.impulse_x *= conf.dt_ratio; j.impulse_y *= conf.dt_ratio; j.impulse_z *= conf.dt_ratio;
+        const float2 P = j.impulse_x * ay + j.impulse_y * ax;
+        const float LA = (j.impulse_x * sAy + j.impulse_y * sAx) / 1.0f + j.impulse_z;
+        const float LB = (j.impulse_x * sBy + j.impulse_y * sBx) / 1.0f + j.impulse_z;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    } else j.impulse_x = j.impulse_y = j.impulse_z = 0.0f;
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    d.jt_work[ji] = wk;
+}
+PR_D void wheel_solve_velocity(const DV& d, unsigned ji, pr_revolute_joint j, const JointWork& wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 oldA = v.s_vel[ia], oldB = v.s_vel[ib];
+    float4 velA = oldA, velB = oldB;
+    const Rot ay = mkrot(wk.m[0], wk.m[1]), ax = mkrot(wk.m[5], wk.m[6]);
+    const float sAy = wk.m[2], sBy = wk.m[3], sAx = wk.m[7], sBx = wk.m[8];
+    { // spring
+        const float dt = dot(ax, v2(velB.x, velB.y) - v2(velA.x, velA.y));
+        const float Cdot = dt + sBx * velB.z / 1.0f - sAx * velA.z / 1.0f;
+        const float impulse = -wk.ex[0] * (Cdot + wk.ex[1] + wk.ex[2] * j.impulse_y);
+        j.impulse_y += impulse;
+        const float2 P = impulse * ax;
+        const float LA = impulse * sAx / 1.0f, LB = impulse * sBx / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    }
+    { // rotational motor
+        const float Cdot = (velB.z - velA.z - j.motor_speed);
+        float impulse = -wk.angularMass * Cdot;
+        const float oldImpulse = j.impulse_z;
+        const float maxImpulse = conf.delta_time * j.max_motor_torque;
+        j.impulse_z = stdclamp(j.impulse_z + impulse, -maxImpulse, maxImpulse);
+        impulse = j.impulse_z - oldImpulse;
+        velA.z -= iiA * impulse;
+        velB.z += iiB * impulse;
+    }
+    { // point to line
+        const float dt = dot(ay, v2(velB.x, velB.y) - v2(velA.x, velA.y));
+        const float Cdot = dt + sBy * velB.z / 1.0f - sAy * velA.z / 1.0f;
+        const float impulse = -wk.m[4] * Cdot;
+        j.impulse_x += impulse;
+        const float2 P = impulse * ay;
+        const float LA = impulse * sAy / 1.0f, LB = impulse * sBy / 1.0f;
+        const float2 la = v2(velA.x, velA.y) - imA * P; velA.x = la.x; velA.y = la.y; velA.z -= iiA * LA;
+        const float2 lb = v2(velB.x, velB.y) + imB * P; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * LB;
+    }
+    d.jt[ji] = j;
+    const bool changed = velA.x != oldA.x || velA.y != oldA.y || velA.z != oldA.z || velB.x != oldB.x || velB.y != oldB.y || velB.z != oldB.z;
+    if (changed) { v.s_vel[ia] = velA; v.s_vel[ib] = velB; v.isl_jflag[wk.island] = 1u; }
+}
+PR_D void wheel_solve_position(const DV& d, const pr_revolute_joint& j, const JointWork& wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    float4 posA = v.s_pos[ia], posB = v.s_pos[ib];
+    const Rot qA = rot_from_angle(posA.z), qB = rot_from_angle(posB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    const float2 dd = (v2(posB.x, posB.y) - v2(posA.x, posA.y)) + (rB - rA);
+    const Rot ay = rot_rotate(rev_perp(j_local_x_axis(j)), qA);
+    const float sAy = cross(dd + rA, ay), sBy = cross(rB, ay);
+    const float C = dot(dd, ay);
+    // (:339-340: the inverse rotational masses come from the sAy / sBy InitVelocity stored, not from the fresh ones)
+    const float invRotMassA = iiA * square(wk.m[2]) / 1.0f, invRotMassB = iiB * square(wk.m[3]) / 1.0f;
+    const float k = imA + imB + invRotMassA + invRotMassB;
+    const float impulse = (k != 0.0f) ? -(C / k) : 0.0f * 1.0f * 1.0f;
+    const float2 P = impulse * ay;
+    const float LA = impulse * sAy / 1.0f, LB = impulse * sBy / 1.0f;
+    const float2 la = v2(posA.x, posA.y) - imA * P; posA.x = la.x; posA.y = la.y; posA.z -= iiA * LA;
+    const float2 lb = v2(posB.x, posB.y) + imB * P; posB.x = lb.x; posB.y = lb.y; posB.z += iiB * LB;
+    v.s_pos[ia] = posA; v.s_pos[ib] = posB;
+    if (!(fabsf(C) <= conf.linear_slop)) v.isl_jflag[wk.island] = 1u;
+}
+
 PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf, const JView& v)
 {
     pr_revolute_joint j = d.jt[ji];
@@ -622,10 +958,12 @@ PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf
         return;
     }
     if (joint_type(j) == PR_JOINT_TARGET) { target_init_velocity(d, ji, j, wk, conf, v); return; }
-    if (joint_type(j) == PR_JOINT_WELD) {
+    if (joint_type(j) == PR_JOINT_WELD || joint_type(j) == PR_JOINT_PRISMATIC || joint_type(j) == PR_JOINT_WHEEL) {
         if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
         if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
-        weld_init_velocity(d, ji, j, wk, conf, v);
+        if (joint_type(j) == PR_JOINT_WELD) weld_init_velocity(d, ji, j, wk, conf, v);
+        else if (joint_type(j) == PR_JOINT_PRISMATIC) prismatic_init_velocity(d, ji, j, wk, conf, v);
+        else wheel_init_velocity(d, ji, j, wk, conf, v);
         return;
     }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
@@ -695,6 +1033,8 @@ PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& con
     if (joint_type(j) == PR_JOINT_FRICTION || joint_type(j) == PR_JOINT_MOTOR) { fm_solve_velocity(d, ji, j, wk, conf, v, joint_type(j) == PR_JOINT_MOTOR); return; }
     if (joint_type(j) == PR_JOINT_WELD) { weld_solve_velocity(d, ji, j, wk, v); return; }
     if (joint_type(j) == PR_JOINT_TARGET) { target_solve_velocity(d, ji, j, wk, conf, v); return; }
+    if (joint_type(j) == PR_JOINT_PRISMATIC) { prismatic_solve_velocity(d, ji, j, wk, conf, v); return; }
+    if (joint_type(j) == PR_JOINT_WHEEL) { wheel_solve_velocity(d, ji, j, wk, conf, v); return; }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
@@ -761,6 +1101,8 @@ PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& con
     if (joint_type(j) == PR_JOINT_ROPE) { rope_solve_position(d, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_FRICTION || joint_type(j) == PR_JOINT_MOTOR || joint_type(j) == PR_JOINT_TARGET) return; // SolvePosition: nothing to do, always solved
     if (joint_type(j) == PR_JOINT_WELD) { weld_solve_position(d, j, wk, conf, v); return; }
+    if (joint_type(j) == PR_JOINT_PRISMATIC) { prismatic_solve_position(d, j, wk, conf, v); return; }
+    if (joint_type(j) == PR_JOINT_WHEEL) { wheel_solve_position(d, j, wk, conf, v); return; }
     const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;

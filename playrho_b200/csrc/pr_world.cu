@@ -2007,7 +2007,7 @@ template <class Row> static int create_tagged_joints(pr_world* pw, uint32_t n, c
     std::vector<pr_revolute_joint> rows(n);
     for (uint32_t i = 0; i < n; ++i) {
         std::memcpy(&rows[i], &joints[i], sizeof(pr_revolute_joint));
-        rows[i].collide_connected = (joints[i].collide_connected & 1u) | (type << 8);
+        rows[i].collide_connected = (joints[i].collide_connected & (1u | PR_JOINT_ENABLE_LIMIT | PR_JOINT_ENABLE_MOTOR)) | (type << 8);
     }
     return pr_create_revolute_joints(pw, n, rows.data(), first_id);
 }
@@ -2015,6 +2015,8 @@ extern "C" {
 int pr_create_friction_joints(pr_world* pw, uint32_t n, const pr_friction_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_FRICTION, first_id); }
 int pr_create_motor_joints(pr_world* pw, uint32_t n, const pr_motor_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_MOTOR, first_id); }
 int pr_create_weld_joints(pr_world* pw, uint32_t n, const pr_weld_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_WELD, first_id); }
+int pr_create_prismatic_joints(pr_world* pw, uint32_t n, const pr_prismatic_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_PRISMATIC, first_id); }
+int pr_create_wheel_joints(pr_world* pw, uint32_t n, const pr_wheel_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_WHEEL, first_id); }
 int pr_create_target_joints(pr_world* pw, uint32_t n, const pr_target_joint* joints, uint32_t* first_id)
 {
     for (uint32_t i = 0; i < n; ++i) if (joints[i].body_a != joints[i].body_b) { if (pw) pw->w.error = "target joint: body_a must repeat body_b"; return PR_ERR_INVALID_ARGUMENT; }

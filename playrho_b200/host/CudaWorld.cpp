@@ -16,6 +16,8 @@
 #include <playrho/d2/MotorJointConf.hpp>
 #include <playrho/d2/WeldJointConf.hpp>
 #include <playrho/d2/TargetJointConf.hpp>
+#include <playrho/d2/PrismaticJointConf.hpp>
+#include <playrho/d2/WheelJointConf.hpp>
 #include <playrho/to_underlying.hpp>
 
 #include <algorithm>
@@ -734,6 +736,41 @@ static pr_revolute_joint ToJointRow(const TargetJointConf& jc)
     std::memcpy(&r, &o, sizeof(r));
     return r;
 }
+static pr_revolute_joint ToJointRow(const PrismaticJointConf& jc)
+{ // the same table row viewed as pr_prismatic_joint
+    pr_prismatic_joint o{};
+    o.body_a = static_cast<std::uint32_t>(to_underlying(jc.bodyA)); o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.collide_connected = (jc.collideConnected ? 1u : 0u) | (static_cast<std::uint32_t>(PR_JOINT_PRISMATIC) << 8) |
+                          (jc.enableLimit ? PR_JOINT_ENABLE_LIMIT : 0u) | (jc.enableMotor ? PR_JOINT_ENABLE_MOTOR : 0u);
+    o.local_anchor_a = pr_vec2{GetX(jc.localAnchorA), GetY(jc.localAnchorA)};
+    o.local_anchor_b = pr_vec2{GetX(jc.localAnchorB), GetY(jc.localAnchorB)};
+    o.impulse_x = GetX(jc.impulse); o.impulse_y = GetY(jc.impulse); o.impulse_z = GetZ(jc.impulse);
+    o.motor_impulse = jc.motorImpulse; o.reference_angle = jc.referenceAngle;
+    o.local_x_axis_a = pr_vec2{jc.localXAxisA.GetX(), jc.localXAxisA.GetY()};
+    o.lower_translation = jc.lowerTranslation; o.upper_translation = jc.upperTranslation;
+    o.motor_speed = jc.motorSpeed; o.max_motor_force = jc.maxMotorForce;
+    o.limit_state = static_cast<std::uint32_t>(jc.limitState);
+    pr_revolute_joint r{};
+    static_assert(sizeof(r) == sizeof(o), "joint rows share one table");
+    std::memcpy(&r, &o, sizeof(r));
+    return r;
+}
+static pr_revolute_joint ToJointRow(const WheelJointConf& jc)
+{ // the same table row viewed as pr_wheel_joint
+    pr_wheel_joint o{};
+    o.body_a = static_cast<std::uint32_t>(to_underlying(jc.bodyA)); o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.collide_connected = (jc.collideConnected ? 1u : 0u) | (static_cast<std::uint32_t>(PR_JOINT_WHEEL) << 8) | (jc.enableMotor ? PR_JOINT_ENABLE_MOTOR : 0u);
+    o.local_anchor_a = pr_vec2{GetX(jc.localAnchorA), GetY(jc.localAnchorA)};
+    o.local_anchor_b = pr_vec2{GetX(jc.localAnchorB), GetY(jc.localAnchorB)};
+    o.impulse = jc.impulse; o.spring_impulse = jc.springImpulse; o.angular_impulse = jc.angularImpulse;
+    o.local_x_axis_a = pr_vec2{jc.localXAxisA.GetX(), jc.localXAxisA.GetY()};
+    o.frequency = jc.frequency; o.damping_ratio = jc.dampingRatio;
+    o.motor_speed = jc.motorSpeed; o.max_motor_torque = jc.maxMotorTorque;
+    pr_revolute_joint r{};
+    static_assert(sizeof(r) == sizeof(o), "joint rows share one table");
+    std::memcpy(&r, &o, sizeof(r));
+    return r;
+}
 // the joint types the device solves (SURVEY a15 + the first of 8(f) rank 1); the others are rejected
 static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, BodyID& b)
 {
@@ -743,6 +780,16 @@ static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, B
     if (GetType(def) == GetTypeID<MotorJointConf>()) { const auto jc = TypeCast<MotorJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     if (GetType(def) == GetTypeID<RopeJointConf>()) { const auto jc = TypeCast<RopeJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     if (GetType(def) == GetTypeID<WeldJointConf>()) { const auto jc = TypeCast<WeldJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
+    if (GetType(def) == GetTypeID<PrismaticJointConf>()) { // (the device derives localYAxisA from localXAxisA, like the reference's constructor)
+        const auto jc = TypeCast<PrismaticJointConf>(def);
+        if (jc.localYAxisA != GetRevPerpendicular(jc.localXAxisA)) return false;
+        row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true;
+    }
+    if (GetType(def) == GetTypeID<WheelJointConf>()) {
+        const auto jc = TypeCast<WheelJointConf>(def);
+        if (jc.localYAxisA != GetRevPerpendicular(jc.localXAxisA)) return false;
+        row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true;
+    }
     if (GetType(def) == GetTypeID<TargetJointConf>()) { // (bodyA is ignored by the target joint's solver)
         const auto jc = TypeCast<TargetJointConf>(def);
         if (jc.bodyB == InvalidBodyID || jc.bodyA != InvalidBodyID) return false;
@@ -802,6 +849,22 @@ Joint GetJoint(const CudaWorld& w, JointID id)
         auto tc = TypeCast<TargetJointConf>(elem);
         tc.impulse = Momentum2{r.impulse_x * NewtonSecond, r.impulse_y * NewtonSecond};
         return Joint{tc};
+    }
+    if (GetType(elem) == GetTypeID<PrismaticJointConf>()) {
+        auto pc = TypeCast<PrismaticJointConf>(elem);
+        pr_prismatic_joint p{}; std::memcpy(&p, &r, sizeof(p));
+        pc.impulse = Vec3{p.impulse_x, p.impulse_y, p.impulse_z};
+        pc.motorImpulse = Momentum{p.motor_impulse * NewtonSecond};
+        pc.limitState = static_cast<LimitState>(p.limit_state);
+        return Joint{pc};
+    }
+    if (GetType(elem) == GetTypeID<WheelJointConf>()) {
+        auto wc = TypeCast<WheelJointConf>(elem);
+        pr_wheel_joint p{}; std::memcpy(&p, &r, sizeof(p));
+        wc.impulse = Momentum{p.impulse * NewtonSecond};
+        wc.springImpulse = Momentum{p.spring_impulse * NewtonSecond};
+        wc.angularImpulse = AngularMomentum{p.angular_impulse * NewtonMeterSecond};
+        return Joint{wc};
     }
     if (GetType(elem) == GetTypeID<RopeJointConf>()) {
         auto rc = TypeCast<RopeJointConf>(elem);

@@ -233,6 +233,26 @@ class RefWorld:
         self.lib.ref_set_target.argtypes = [vp, u32, f32, f32]
         self._chk(self.lib.ref_set_target(self.h, int(joint), target[0], target[1]))
 
+    def add_prismatic(self, body_a, body_b, anchor, axis, limits=None, motor=None):
+        """limits = (lower, upper) or None; motor = (speed, max force) or None"""
+        self.lib.ref_add_prismatic.argtypes = [vp, u32, u32, f32, f32, f32, f32, i32, f32, f32, i32, f32, f32]
+        self.lib.ref_add_prismatic.restype = u32
+        lo, hi = limits if limits else (0.0, 0.0)
+        sp, mf = motor if motor else (0.0, 0.0)
+        jid = self.lib.ref_add_prismatic(self.h, int(body_a), int(body_b), anchor[0], anchor[1], axis[0], axis[1], 1 if limits else 0, lo, hi,
+                                         1 if motor else 0, sp, mf)
+        assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
+        return jid
+
+    def add_wheel(self, body_a, body_b, anchor, axis, frequency=2.0, damping_ratio=0.7, motor=None):
+        self.lib.ref_add_wheel.argtypes = [vp, u32, u32, f32, f32, f32, f32, f32, f32, i32, f32, f32]
+        self.lib.ref_add_wheel.restype = u32
+        sp, mt = motor if motor else (0.0, 0.0)
+        jid = self.lib.ref_add_wheel(self.h, int(body_a), int(body_b), anchor[0], anchor[1], axis[0], axis[1], frequency, damping_ratio,
+                                     1 if motor else 0, sp, mt)
+        assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
+        return jid
+
     def add_friction(self, body_a, body_b, anchor, max_force, max_torque):
         self.lib.ref_add_friction.argtypes = [vp, u32, u32, f32, f32, f32, f32]
         self.lib.ref_add_friction.restype = u32

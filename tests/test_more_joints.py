@@ -3,7 +3,11 @@ the real reference, the restatement, the emulated kernels and the GPU -- bit for
   weld  (WeldJointConf.cpp:35-371): a cantilever of boxes welded to a static wall (rigid), a soft-welded pair, a welded pair with
         fixed rotation (K.ez.z == 0 -> the 2x2 branch), all under gravity and hit by a falling disk.
   target (TargetJointConf.cpp:52-243): one-body "mouse" joints dragging boxes through a pile of disks -- a strong one, one
-        whose force cap saturates, one on a body that also hangs from a weld; the targets are moved with SetJoint in mid-run."""
+        whose force cap saturates, one on a body that also hangs from a weld; the targets are moved with SetJoint in mid-run.
+  prismatic (PrismaticJointConf.cpp:150-533): sliders on a static rail -- free, with limits (lower hit under gravity, upper hit by a motor),
+        equal limits, a motor that saturates, a slider between two dynamic bodies, one with fixed rotation (k22 == 0 -> 1).
+  wheel (WheelJointConf.cpp:103-362): a car (chassis + two wheels on sprung wheel joints, one driven by a motor) on a bumpy ground,
+        and a rigid (frequency 0) wheel joint."""
 import numpy as np
 import pytest
 import refworld
@@ -63,7 +67,46 @@ def _target_moves(step):
     return []
 
 
-SCENES = {"weld": (_weld_scene, 200), "target": (_target_scene, 220)}
+def _prismatic_scene():
+    ref = RefWorld()
+    ground = ref.add_body(STATIC, pos=(0.0, 0.0), shapes=[ref.add_box(20.0, 0.5, center=(0.0, -0.5))])
+    box = ref.add_box(0.4, 0.3, density=3.0)
+    disk = ref.add_disk(0.25, density=2.0)
+    def dyn(pos, **kw):
+        return ref.add_body(DYNAMIC, acc=G, pos=pos, shapes=[box], **kw)
+    s0 = dyn((-8.0, 3.0)); ref.add_prismatic(ground, s0, (-8.0, 3.0), (0.0, 1.0))                                   # free vertical slider: falls to the ground
+    s1 = dyn((-6.0, 3.0)); ref.add_prismatic(ground, s1, (-6.0, 3.0), (0.0, 1.0), limits=(-1.0, 1.0))               # lower limit stops it
+    s2 = dyn((-4.0, 3.0)); ref.add_prismatic(ground, s2, (-4.0, 3.0), (0.6, 0.8), limits=(-0.5, 1.5), motor=(2.0, 500.0))   # motor drives it to the upper limit
+    s3 = dyn((-2.0, 3.0)); ref.add_prismatic(ground, s3, (-2.0, 3.0), (1.0, 0.0), limits=(0.0, 0.0))                # equal limits
+    s4 = dyn((0.0, 3.0)); ref.add_prismatic(ground, s4, (0.0, 3.0), (0.0, 1.0), motor=(5.0, 10.0))                  # motor too weak against gravity: saturates
+    s5 = dyn((2.0, 2.0)); s6 = dyn((3.0, 2.6))
+    ref.add_prismatic(s5, s6, (2.5, 2.3), (0.8, 0.6), limits=(-0.3, 0.6))                                           # two dynamic bodies
+    s7 = dyn((5.0, 3.0), fixed_rotation=True); s8 = dyn((5.0, 4.0), fixed_rotation=True)
+    ref.add_prismatic(s7, s8, (5.0, 3.5), (1.0, 0.0), limits=(-0.4, 0.4))                                           # no rotational inertia
+    ref.add_body(DYNAMIC, acc=G, pos=(-5.9, 6.0), shapes=[disk])
+    ref.add_body(DYNAMIC, acc=G, pos=(2.6, 6.0), shapes=[disk])
+    ref.add_body(DYNAMIC, acc=G, pos=(5.3, 7.0), shapes=[disk])
+    return ref, [7] * 7
+
+
+def _wheel_scene():
+    ref = RefWorld()
+    gs = [ref.add_box(30.0, 0.5, center=(0.0, -0.5))] + [ref.add_box(0.3, 0.08, center=(2.0 + 1.7 * i, 0.08)) for i in range(8)]
+    ground = ref.add_body(STATIC, pos=(0.0, 0.0), shapes=gs)
+    chassis = ref.add_box(1.5, 0.25, density=1.0)
+    wheel = ref.add_disk(0.4, density=1.0, friction=0.9)
+    car = ref.add_body(DYNAMIC, acc=G, pos=(0.0, 1.0), shapes=[chassis])
+    w1 = ref.add_body(DYNAMIC, acc=G, pos=(-1.0, 0.45), shapes=[wheel])
+    w2 = ref.add_body(DYNAMIC, acc=G, pos=(1.0, 0.45), shapes=[wheel])
+    ref.add_wheel(car, w1, (-1.0, 0.45), (0.0, 1.0), frequency=4.0, damping_ratio=0.7, motor=(-12.0, 20.0))     # driven
+    ref.add_wheel(car, w2, (1.0, 0.45), (0.0, 1.0), frequency=4.0, damping_ratio=0.7)                           # free-rolling
+    cart = ref.add_body(DYNAMIC, acc=G, pos=(-6.0, 1.0), shapes=[chassis])
+    w3 = ref.add_body(DYNAMIC, acc=G, pos=(-6.0, 0.45), shapes=[wheel])
+    ref.add_wheel(cart, w3, (-6.0, 0.45), (0.6, 0.8), frequency=0.0, motor=(3.0, 1.0))                          # no spring; weak motor saturates
+    return ref, [8, 8, 8]
+
+
+SCENES = {"weld": (_weld_scene, 200), "target": (_target_scene, 220), "prismatic": (_prismatic_scene, 240), "wheel": (_wheel_scene, 300)}
 MOVES = {"target": _target_moves}
 
 
@@ -71,7 +114,7 @@ def _run(name, lib=None, device=-1, with_device=True):
     build, steps = SCENES[name]
     ref, types = build()
     sc = ref.export_scene()
-    assert [int(j["collide_connected"]) >> 8 for j in sc["joints"]] == types
+    assert [(int(j["collide_connected"]) >> 8) & 0xFF for j in sc["joints"]] == types
     orc = refworld.OracleWorld(sc)
     twins = []
     if with_device:
