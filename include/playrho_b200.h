@@ -107,7 +107,7 @@ typedef struct pr_revolute_joint {
 
 /* Joint rows share one table (JointIDs are one id space in the reference): every row has pr_revolute_joint's size and leading
  * fields, and bits 8..15 of collide_connected say which joint type it is (bit 0 is the flag itself). */
-enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2, PR_JOINT_FRICTION = 3, PR_JOINT_MOTOR = 4, PR_JOINT_WELD = 5, PR_JOINT_TARGET = 6, PR_JOINT_PRISMATIC = 7, PR_JOINT_WHEEL = 8 };
+enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2, PR_JOINT_FRICTION = 3, PR_JOINT_MOTOR = 4, PR_JOINT_WELD = 5, PR_JOINT_TARGET = 6, PR_JOINT_PRISMATIC = 7, PR_JOINT_WHEEL = 8, PR_JOINT_PULLEY = 9 };
 /* prismatic and wheel rows keep their enable flags in collide_connected (their enable_limit / enable_motor words hold the local axis) */
 #define PR_JOINT_ENABLE_LIMIT 0x10000u
 #define PR_JOINT_ENABLE_MOTOR 0x20000u
@@ -221,6 +221,19 @@ typedef struct pr_wheel_joint {
     float motor_speed, max_motor_torque;
     uint32_t reserved1;
 } pr_wheel_joint;
+/* PulleyJointConf (PulleyJointConf.hpp; solver PulleyJointConf.cpp:91-282): length_a + ratio * length_b stays constant, each length
+ * measured from a body's anchor to its ground anchor (world points; pr_shift_origin moves them). */
+typedef struct pr_pulley_joint {
+    uint32_t body_a, body_b;
+    uint32_t collide_connected;          /* bit 0: collideConnected (the reference's default for this type: true); bits 8..15: PR_JOINT_PULLEY */
+    pr_vec2 local_anchor_a, local_anchor_b;
+    float impulse;                       /* accumulated impulse (warm start) */
+    pr_vec2 ground_anchor_a, ground_anchor_b;
+    float length_a, length_b;            /* rest lengths */
+    float ratio;
+    float reserved0[3];
+    uint32_t reserved1;
+} pr_pulley_joint;
 
 /* ContactFeature packed little-endian: typeA | indexA<<8 | typeB<<16 | indexB<<24 */
 typedef uint32_t pr_contact_feature;
@@ -363,6 +376,7 @@ int pr_create_weld_joints(pr_world* w, uint32_t n, const pr_weld_joint* joints, 
 int pr_create_target_joints(pr_world* w, uint32_t n, const pr_target_joint* joints, uint32_t* first_id);
 int pr_create_prismatic_joints(pr_world* w, uint32_t n, const pr_prismatic_joint* joints, uint32_t* first_id);
 int pr_create_wheel_joints(pr_world* w, uint32_t n, const pr_wheel_joint* joints, uint32_t* first_id);
+int pr_create_pulley_joints(pr_world* w, uint32_t n, const pr_pulley_joint* joints, uint32_t* first_id);
 
 /* SetShape(AabbTreeWorld&, ShapeID, Shape) (AabbTreeWorld.cpp:1284-1356) for a value whose geometry (children) and filter are
  * what they were: friction, restitution, density and the sensor flag are replaced; every body using the shape is woken

@@ -480,6 +480,15 @@ uint32_t ref_add_wheel(void* h, uint32_t bodyA, uint32_t bodyB, float ax, float 
     return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
     REF_CATCH(0xFFFFFFFFu)
 }
+uint32_t ref_add_pulley(void* h, uint32_t bodyA, uint32_t bodyB, float gax, float gay, float gbx, float gby, float ax, float ay, float bx, float by, float ratio)
+{
+    REF_TRY(h)
+    auto jc = GetPulleyJointConf(rw->world, MakeId<BodyID>(bodyA), MakeId<BodyID>(bodyB), Length2{gax * 1_m, gay * 1_m}, Length2{gbx * 1_m, gby * 1_m},
+                                 Length2{ax * 1_m, ay * 1_m}, Length2{bx * 1_m, by * 1_m});
+    jc.ratio = ratio;
+    return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
+    REF_CATCH(0xFFFFFFFFu)
+}
 int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
 {
     REF_TRY(h)
@@ -567,6 +576,20 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
             p.local_x_axis_a = pr_vec2{wc.localXAxisA.GetX(), wc.localXAxisA.GetY()};
             p.frequency = wc.frequency; p.damping_ratio = wc.dampingRatio;
             p.motor_speed = wc.motorSpeed; p.max_motor_torque = wc.maxMotorTorque;
+            std::memcpy(&o, &p, sizeof(o));
+            continue;
+        }
+        if (GetType(joint) == GetTypeID<PulleyJointConf>()) { // the same row, viewed as pr_pulley_joint
+            const auto pc = TypeCast<PulleyJointConf>(joint);
+            pr_pulley_joint p{};
+            p.body_a = to_underlying(pc.bodyA); p.body_b = to_underlying(pc.bodyB);
+            p.collide_connected = (pc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_PULLEY) << 8);
+            p.local_anchor_a = pr_vec2{GetX(pc.localAnchorA), GetY(pc.localAnchorA)};
+            p.local_anchor_b = pr_vec2{GetX(pc.localAnchorB), GetY(pc.localAnchorB)};
+            p.impulse = pc.impulse;
+            p.ground_anchor_a = pr_vec2{GetX(pc.groundAnchorA), GetY(pc.groundAnchorA)};
+            p.ground_anchor_b = pr_vec2{GetX(pc.groundAnchorB), GetY(pc.groundAnchorB)};
+            p.length_a = pc.lengthA; p.length_b = pc.lengthB; p.ratio = pc.ratio;
             std::memcpy(&o, &p, sizeof(o));
             continue;
         }

@@ -1239,6 +1239,75 @@ bool wheel_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, fl
     posB.l = posB.l + imB * P; posB.a += iiB * LB;
     return std::fabs(C) <= c.linearSlop;
 }
+// ---------------- PulleyJointConf.cpp:91-282 (mass[0..1] = uA, mass[2..3] = uB, mass[4] = mass) ----------------
+// row: impulse = impulse_x, groundAnchorA = (impulse_y, impulse_z), groundAnchorB = (angular_motor_impulse, reference_angle),
+// lengthA / lengthB = the bits of enable_limit / enable_motor, ratio = lower_angle
+void pulley_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
+                          float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
+{
+    const Rot qA = rot_from_angle(posA.a), qB = rot_from_angle(posB.a);
+    wk.rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, qA);
+    wk.rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, qB);
+    const float ratio = j.lower_angle;
+    const V2 pulleyAxisA = posA.l + wk.rA - V2{j.impulse_y, j.impulse_z};
+    const V2 pulleyAxisB = posB.l + wk.rB - V2{j.angular_motor_impulse, j.reference_angle};
+    const Rot uA = unit_vector(pulleyAxisA, Rot{0.0f, 0.0f}), uB = unit_vector(pulleyAxisB, Rot{0.0f, 0.0f});
+    const float ruA = cross(wk.rA, uA), ruB = cross(wk.rB, uB);
+    const float totInvMassA = imA + (iiA * square(ruA)) / 1.0f;
+    const float totInvMassB = imB + (iiB * square(ruB)) / 1.0f;
+    const float totalInvMass = totInvMassA + ratio * ratio * totInvMassB;
+    wk.mass[0] = uA.c; wk.mass[1] = uA.s; wk.mass[2] = uB.c; wk.mass[3] = uB.s;
+    wk.mass[4] = (totalInvMass > 0.0f) ? 1.0f / totalInvMass : 0.0f;
+    if (c.warmStart) {
+        j.impulse_x *= c.dtRatio;
+        const V2 PA = -(j.impulse_x) * uA;
+        const V2 PB = (-ratio * j.impulse_x) * uB;
+        velA.l = velA.l + imA * PA; velA.a += iiA * cross(wk.rA, PA) / 1.0f;
+        velB.l = velB.l + imB * PB; velB.a += iiB * cross(wk.rB, PB) / 1.0f;
+    } else j.impulse_x = 0.0f;
+}
+bool pulley_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, Vel& velA, float imB, float iiB, Vel& velB)
+{
+    const Rot uA{wk.mass[0], wk.mass[1]}, uB{wk.mass[2], wk.mass[3]};
+    const float ratio = j.lower_angle;
+    const V2 vpA = velA.l + rev_perp(wk.rA) * (velA.a / 1.0f);
+    const V2 vpB = velB.l + rev_perp(wk.rB) * (velB.a / 1.0f);
+    const float Cdot = -dot(uA, vpA) - ratio * dot(uB, vpB);
+    const float impulse = -wk.mass[4] * Cdot;
+    j.impulse_x += impulse;
+    const V2 PA = -impulse * uA;
+    const V2 PB = -ratio * impulse * uB;
+    velA.l = velA.l + imA * PA; velA.a += iiA * cross(wk.rA, PA) / 1.0f;
+    velB.l = velB.l + imB * PB; velB.a += iiB * cross(wk.rB, PB) / 1.0f;
+    return impulse == 0.0f;
+}
+bool pulley_solve_position(const pr_revolute_joint& j, float imA, float iiA, V2 lcA, Pos& posA, float imB, float iiB, V2 lcB, Pos& posB,
+                           const JointSolverConf& c)
+{
+    const V2 rA = rotate(V2{j.local_anchor_a.x, j.local_anchor_a.y} - lcA, rot_from_angle(posA.a));
+    const V2 rB = rotate(V2{j.local_anchor_b.x, j.local_anchor_b.y} - lcB, rot_from_angle(posB.a));
+    const float ratio = j.lower_angle;
+    float lengthA, lengthB;
+    const V2 pA = posA.l + rA - V2{j.impulse_y, j.impulse_z};
+    const Rot uA = unit_vector_mag(pA, lengthA);
+    const V2 pB = posB.l + rB - V2{j.angular_motor_impulse, j.reference_angle};
+    const Rot uB = unit_vector_mag(pB, lengthB);
+    const float ruA = cross(rA, uA), ruB = cross(rB, uB);
+    const float totalInvMassA = imA + iiA * square(ruA) / 1.0f;
+    const float totalInvMassB = imB + iiB * square(ruB) / 1.0f;
+    const float totalInvMass = totalInvMassA + square(ratio) * totalInvMassB;
+    const float mass = (totalInvMass > 0.0f) ? 1.0f / totalInvMass : 0.0f;
+    const float srcLengthRatio = bits_to_float(j.enable_limit) + ratio * bits_to_float(j.enable_motor);
+    const float dstLengthRatio = lengthA + ratio * lengthB;
+    const float C = srcLengthRatio - dstLengthRatio;
+    const float linearError = std::fabs(C);
+    const float impulse = -mass * C;
+    const V2 PA = -impulse * uA;
+    const V2 PB = -ratio * impulse * uB;
+    posA.l = posA.l + imA * PA; posA.a += iiA * cross(rA, PA) / 1.0f;
+    posB.l = posB.l + imB * PB; posB.a += iiB * cross(rB, PB) / 1.0f;
+    return linearError < c.linearSlop;
+}
 } // namespace
 void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
                          float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
@@ -1250,6 +1319,7 @@ void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, floa
     else if (PR_JOINT_TYPE(j) == PR_JOINT_TARGET) target_init_velocity(j, wk, imB, iiB, lcB, posB, velB, c);
     else if (PR_JOINT_TYPE(j) == PR_JOINT_PRISMATIC) prismatic_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
     else if (PR_JOINT_TYPE(j) == PR_JOINT_WHEEL) wheel_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
+    else if (PR_JOINT_TYPE(j) == PR_JOINT_PULLEY) pulley_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
     else if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) weld_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
     else revolute_init_velocity(j, wk, imA, iiA, lcA, posA, velA, imB, iiB, lcB, posB, velB, c);
 }
@@ -1262,6 +1332,7 @@ bool joint_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, flo
     if (PR_JOINT_TYPE(j) == PR_JOINT_TARGET) return target_solve_velocity(j, wk, imB, iiB, velB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_PRISMATIC) return prismatic_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_WHEEL) return wheel_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
+    if (PR_JOINT_TYPE(j) == PR_JOINT_PULLEY) return pulley_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB);
     if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) return weld_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB);
     return revolute_solve_velocity(j, wk, imA, iiA, velA, imB, iiB, velB, c);
 }
@@ -1273,6 +1344,7 @@ bool joint_solve_position(const pr_revolute_joint& j, const RevoluteWork& wk, fl
     if (PR_JOINT_TYPE(j) == PR_JOINT_FRICTION || PR_JOINT_TYPE(j) == PR_JOINT_MOTOR || PR_JOINT_TYPE(j) == PR_JOINT_TARGET) return true;
     if (PR_JOINT_TYPE(j) == PR_JOINT_PRISMATIC) return prismatic_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_WHEEL) return wheel_solve_position(j, wk, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
+    if (PR_JOINT_TYPE(j) == PR_JOINT_PULLEY) return pulley_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     if (PR_JOINT_TYPE(j) == PR_JOINT_WELD) return weld_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
     return revolute_solve_position(j, imA, iiA, lcA, posA, imB, iiB, lcB, posB, c);
 }

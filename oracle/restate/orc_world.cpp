@@ -1384,6 +1384,11 @@ int orc_shift_origin(orc_world* w, float x, float y)
         set_pos1(b, p1); // SetSweep: m_xf = GetTransform1(sweep), Body.hpp:697-702
         flag_body_contacts_dirty(*w, id);
     }
+    for (pr_revolute_joint& j : w->joints) { // ShiftOrigin(Joint&, newOrigin), AabbTreeWorld.cpp:2237-2240: target joint's target, pulley joint's ground anchors
+        if (j.body_a == 0xFFFFFFFFu && j.body_b == 0xFFFFFFFFu) continue;
+        if (PR_JOINT_TYPE(j) == PR_JOINT_TARGET) { j.local_anchor_a.x -= x; j.local_anchor_a.y -= y; }
+        else if (PR_JOINT_TYPE(j) == PR_JOINT_PULLEY) { j.impulse_y -= x; j.impulse_z -= y; j.angular_motor_impulse -= x; j.reference_angle -= y; }
+    }
     const float nx = -x, ny = -y; // DynamicTree::ShiftOrigin: GetMovedAABB(aabb, -newOrigin), DynamicTree.cpp:650-658
     for (OProxy& op : w->proxies) { op.p.min_x += nx; op.p.max_x += nx; op.p.min_y += ny; op.p.max_y += ny; }
     return 0;

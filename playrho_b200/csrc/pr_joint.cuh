@@ -933,6 +933,94 @@ PR_D void wheel_solve_position(const DV& d, const pr_revolute_joint& j, const Jo
     if (!(fabsf(C) <= conf.linear_slop)) v.isl_jflag[wk.island] = 1u;
 }
 
+// ---- PulleyJointConf.cpp:91-282. Row overlay (pr_pulley_joint): impulse = impulse_x, groundAnchorA = impulse_y / impulse_z, groundAnchorB =
+// angular_motor_impulse / reference_angle, lengthA / lengthB = the bits of enable_limit / enable_motor, ratio = lower_angle;
+// work: rA, rB, m[0..1] = uA, m[2..3] = uB, m[4] = mass
+PR_D void pulley_init_velocity(const DV& d, unsigned ji, pr_revolute_joint j, JointWork wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    const float4 pA = v.s_pos[jv_idx(v.slotP, j.body_a)], pB = v.s_pos[jv_idx(v.slotP, j.body_b)];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
+    const Rot qA = rot_from_angle(pA.z), qB = rot_from_angle(pB.z);
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], qA);
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], qB);
+    wk.rAx = rA.x; wk.rAy = rA.y; wk.rBx = rB.x; wk.rBy = rB.y;
+    const float ratio = j.lower_angle;
+    const float2 pulleyAxisA = v2(pA.x, pA.y) + rA - v2(j.impulse_y, j.impulse_z);
+    const float2 pulleyAxisB = v2(pB.x, pB.y) + rB - v2(j.angular_motor_impulse, j.reference_angle);
+    const Rot uA = unit_vector(pulleyAxisA, mkrot(0.0f, 0.0f)), uB = unit_vector(pulleyAxisB, mkrot(0.0f, 0.0f));
+    const float ruA = cross(rA, uA), ruB = cross(rB, uB);
+    const float totInvMassA = imA + (iiA * square(ruA)) / 1.0f;
+    const float totInvMassB = imB + (iiB * square(ruB)) / 1.0f;
+    const float totalInvMass = totInvMassA + ratio * ratio * totInvMassB;
+    wk.m[0] = uA.c; wk.m[1] = uA.s; wk.m[2] = uB.c; wk.m[3] = uB.s;
+    wk.m[4] = (totalInvMass > 0.0f) ? 1.0f / totalInvMass : 0.0f;
+    if (conf.do_warm_start) {
+        j.impulse_x *= conf.dt_ratio;
+        const float2 PA = -(j.impulse_x) * uA;
+        const float2 PB = (-ratio * j.impulse_x) * uB;
+        const float2 la = v2(velA.x, velA.y) + imA * PA; velA.x = la.x; velA.y = la.y; velA.z += iiA * cross(rA, PA) / 1.0f;
+        const float2 lb = v2(velB.x, velB.y) + imB * PB; velB.x = lb.x; velB.y = lb.y; velB.z += iiB * cross(rB, PB) / 1.0f;
+    } else j.impulse_x = 0.0f;
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    d.jt_work[ji] = wk;
+}
+PR_D void pulley_solve_velocity(const DV& d, unsigned ji, pr_revolute_joint j, const JointWork& wk, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib];
+    const float2 rA = v2(wk.rAx, wk.rAy), rB = v2(wk.rBx, wk.rBy);
+    const Rot uA = mkrot(wk.m[0], wk.m[1]), uB = mkrot(wk.m[2], wk.m[3]);
+    const float ratio = j.lower_angle;
+    const float2 vpA = v2(velA.x, velA.y) + rev_perp(rA) * (velA.z / 1.0f);
+    const float2 vpB = v2(velB.x, velB.y) + rev_perp(rB) * (velB.z / 1.0f);
+    const float Cdot = -dot(uA, vpA) - ratio * dot(uB, vpB);
+    const float impulse = -wk.m[4] * Cdot;
+    j.impulse_x += impulse;
+    const float2 PA = -impulse * uA;
+    const float2 PB = -ratio * impulse * uB;
+    const float2 la = v2(velA.x, velA.y) + mA.x * PA; velA.x = la.x; velA.y = la.y; velA.z += mA.y * cross(rA, PA) / 1.0f;
+    const float2 lb = v2(velB.x, velB.y) + mB.x * PB; velB.x = lb.x; velB.y = lb.y; velB.z += mB.y * cross(rB, PB) / 1.0f;
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB;
+    d.jt[ji] = j;
+    if (!(impulse == 0.0f)) v.isl_jflag[wk.island] = 1u;
+}
+PR_D void pulley_solve_position(const DV& d, const pr_revolute_joint& j, const JointWork& wk, const pr_step_conf& conf, const JView& v)
+{
+    const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
+    const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
+    float4 posA = v.s_pos[ia], posB = v.s_pos[ib];
+    const float2 rA = rotate(v2(j.local_anchor_a.x, j.local_anchor_a.y) - d.b_lc[j.body_a], rot_from_angle(posA.z));
+    const float2 rB = rotate(v2(j.local_anchor_b.x, j.local_anchor_b.y) - d.b_lc[j.body_b], rot_from_angle(posB.z));
+    const float ratio = j.lower_angle;
+    float lengthA, lengthB;
+    const float2 pA = v2(posA.x, posA.y) + rA - v2(j.impulse_y, j.impulse_z);
+    const Rot uA = unit_vector_mag(pA, lengthA);
+    const float2 pB = v2(posB.x, posB.y) + rB - v2(j.angular_motor_impulse, j.reference_angle);
+    const Rot uB = unit_vector_mag(pB, lengthB);
+    const float ruA = cross(rA, uA), ruB = cross(rB, uB);
+    const float totalInvMassA = imA + iiA * square(ruA) / 1.0f;
+    const float totalInvMassB = imB + iiB * square(ruB) / 1.0f;
+    const float totalInvMass = totalInvMassA + square(ratio) * totalInvMassB;
+    const float mass = (totalInvMass > 0.0f) ? 1.0f / totalInvMass : 0.0f;
+    const float srcLengthRatio = u2f(j.enable_limit) + ratio * u2f(j.enable_motor);
+    const float dstLengthRatio = lengthA + ratio * lengthB;
+    const float C = srcLengthRatio - dstLengthRatio;
+    const float linearError = fabsf(C);
+    const float impulse = -mass * C;
+    const float2 PA = -impulse * uA;
+    const float2 PB = -ratio * impulse * uB;
+    const float2 la = v2(posA.x, posA.y) + imA * PA; posA.x = la.x; posA.y = la.y; posA.z += iiA * cross(rA, PA) / 1.0f;
+    const float2 lb = v2(posB.x, posB.y) + imB * PB; posB.x = lb.x; posB.y = lb.y; posB.z += iiB * cross(rB, PB) / 1.0f;
+    v.s_pos[ia] = posA; v.s_pos[ib] = posB;
+    if (!(linearError < conf.linear_slop)) v.isl_jflag[wk.island] = 1u;
+}
+
 PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf, const JView& v)
 {
     pr_revolute_joint j = d.jt[ji];
@@ -958,11 +1046,12 @@ PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf
         return;
     }
     if (joint_type(j) == PR_JOINT_TARGET) { target_init_velocity(d, ji, j, wk, conf, v); return; }
-    if (joint_type(j) == PR_JOINT_WELD || joint_type(j) == PR_JOINT_PRISMATIC || joint_type(j) == PR_JOINT_WHEEL) {
+    if (joint_type(j) == PR_JOINT_WELD || joint_type(j) == PR_JOINT_PRISMATIC || joint_type(j) == PR_JOINT_WHEEL || joint_type(j) == PR_JOINT_PULLEY) {
         if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
         if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
         if (joint_type(j) == PR_JOINT_WELD) weld_init_velocity(d, ji, j, wk, conf, v);
         else if (joint_type(j) == PR_JOINT_PRISMATIC) prismatic_init_velocity(d, ji, j, wk, conf, v);
+        else if (joint_type(j) == PR_JOINT_PULLEY) pulley_init_velocity(d, ji, j, wk, conf, v);
         else wheel_init_velocity(d, ji, j, wk, conf, v);
         return;
     }
@@ -1035,6 +1124,7 @@ PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& con
     if (joint_type(j) == PR_JOINT_TARGET) { target_solve_velocity(d, ji, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_PRISMATIC) { prismatic_solve_velocity(d, ji, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_WHEEL) { wheel_solve_velocity(d, ji, j, wk, conf, v); return; }
+    if (joint_type(j) == PR_JOINT_PULLEY) { pulley_solve_velocity(d, ji, j, wk, v); return; }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
@@ -1103,6 +1193,7 @@ PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& con
     if (joint_type(j) == PR_JOINT_WELD) { weld_solve_position(d, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_PRISMATIC) { prismatic_solve_position(d, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_WHEEL) { wheel_solve_position(d, j, wk, conf, v); return; }
+    if (joint_type(j) == PR_JOINT_PULLEY) { pulley_solve_position(d, j, wk, conf, v); return; }
     const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
@@ -1198,6 +1289,19 @@ PR_KERNEL k_pair_flag_filter(DV d, unsigned nOrder, unsigned n, const unsigned* 
             const unsigned a = pairs[2u * k], b = pairs[2u * k + 1u];
             if ((ab.x == a && ab.y == b) || (ab.x == b && ab.y == a)) { atomicOr(&d.c_flags[id], static_cast<unsigned>(PR_CONTACT_FILTER)); break; }
         }
+    }
+}
+// ShiftOrigin(Joint&, newOrigin) (AabbTreeWorld.cpp:2237-2240): the joints that hold world points move them -- the target joint's target
+// (TargetJointConf.hpp:200-204) and the pulley joint's ground anchors (PulleyJointConf.cpp:284-289)
+PR_KERNEL k_shift_joints(DV d, unsigned nJoints, float x, float y)
+{
+    PR_PDL_ENTER();
+    const unsigned i = PR_TID;
+    if (i < nJoints) {
+        pr_revolute_joint j = d.jt[i];
+        if (j.body_a == INVALID && j.body_b == INVALID) return;
+        if (joint_type(j) == PR_JOINT_TARGET) { j.local_anchor_a.x -= x; j.local_anchor_a.y -= y; d.jt[i] = j; }
+        else if (joint_type(j) == PR_JOINT_PULLEY) { j.impulse_y -= x; j.impulse_z -= y; j.angular_motor_impulse -= x; j.reference_angle -= y; d.jt[i] = j; }
     }
 }
 PR_KERNEL k_joint_wake(DV d, unsigned first, unsigned n)

@@ -2017,6 +2017,7 @@ int pr_create_motor_joints(pr_world* pw, uint32_t n, const pr_motor_joint* joint
 int pr_create_weld_joints(pr_world* pw, uint32_t n, const pr_weld_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_WELD, first_id); }
 int pr_create_prismatic_joints(pr_world* pw, uint32_t n, const pr_prismatic_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_PRISMATIC, first_id); }
 int pr_create_wheel_joints(pr_world* pw, uint32_t n, const pr_wheel_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_WHEEL, first_id); }
+int pr_create_pulley_joints(pr_world* pw, uint32_t n, const pr_pulley_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_PULLEY, first_id); }
 int pr_create_target_joints(pr_world* pw, uint32_t n, const pr_target_joint* joints, uint32_t* first_id)
 {
     for (uint32_t i = 0; i < n; ++i) if (joints[i].body_a != joints[i].body_b) { if (pw) pw->w.error = "target joint: body_a must repeat body_b"; return PR_ERR_INVALID_ARGUMENT; }
@@ -2521,6 +2522,7 @@ int pr_shift_origin(pr_world* pw, float x, float y)
     if (!w.stepComplete) { w.error = "ShiftOrigin: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
     const unsigned n = std::max(w.nBodies, w.nProxies);
     if (n) PR_LAUNCH(k_shift_origin, n, w.stream, w.d, w.nBodies, w.nProxies, x, y);
+    if (w.nJoints) PR_LAUNCH(k_shift_joints, w.nJoints, w.stream, w.d, w.nJoints, x, y);
     w.anyBodySet = true;  // the pre-phase UpdateContacts of the next Step looks at b_moved (FlagForUpdating, :2235)
     w.bvhValid = false;   // every leaf box moved: rebuild the LBVH
     w.toiAlphaDirty = true;

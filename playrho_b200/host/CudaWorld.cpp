@@ -18,6 +18,7 @@
 #include <playrho/d2/TargetJointConf.hpp>
 #include <playrho/d2/PrismaticJointConf.hpp>
 #include <playrho/d2/WheelJointConf.hpp>
+#include <playrho/d2/PulleyJointConf.hpp>
 #include <playrho/to_underlying.hpp>
 
 #include <algorithm>
@@ -461,6 +462,7 @@ void ShiftOrigin(CudaWorld& w, const Length2& newOrigin)
     w.m->refreshBodies();
     w.m->uploadDirtyBodies();
     w.m->check(pr_shift_origin(w.m->h, static_cast<float>(Real(GetX(newOrigin) / Meter)), static_cast<float>(Real(GetY(newOrigin) / Meter))), "pr_shift_origin");
+    for (auto& j : w.m->joints) if (j.has_value()) ::playrho::d2::ShiftOrigin(j, newOrigin); // (:2237-2240: target joints' targets, pulley joints' ground anchors)
     w.m->bodiesStale = true;
     w.m->mutated();
 }
@@ -771,6 +773,22 @@ static pr_revolute_joint ToJointRow(const WheelJointConf& jc)
     std::memcpy(&r, &o, sizeof(r));
     return r;
 }
+static pr_revolute_joint ToJointRow(const PulleyJointConf& jc)
+{ // the same table row viewed as pr_pulley_joint
+    pr_pulley_joint o{};
+    o.body_a = static_cast<std::uint32_t>(to_underlying(jc.bodyA)); o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.collide_connected = (jc.collideConnected ? 1u : 0u) | (static_cast<std::uint32_t>(PR_JOINT_PULLEY) << 8);
+    o.local_anchor_a = pr_vec2{GetX(jc.localAnchorA), GetY(jc.localAnchorA)};
+    o.local_anchor_b = pr_vec2{GetX(jc.localAnchorB), GetY(jc.localAnchorB)};
+    o.impulse = jc.impulse;
+    o.ground_anchor_a = pr_vec2{GetX(jc.groundAnchorA), GetY(jc.groundAnchorA)};
+    o.ground_anchor_b = pr_vec2{GetX(jc.groundAnchorB), GetY(jc.groundAnchorB)};
+    o.length_a = jc.lengthA; o.length_b = jc.lengthB; o.ratio = jc.ratio;
+    pr_revolute_joint r{};
+    static_assert(sizeof(r) == sizeof(o), "joint rows share one table");
+    std::memcpy(&r, &o, sizeof(r));
+    return r;
+}
 // the joint types the device solves (SURVEY a15 + the first of 8(f) rank 1); the others are rejected
 static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, BodyID& b)
 {
@@ -790,6 +808,7 @@ static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, B
         if (jc.localYAxisA != GetRevPerpendicular(jc.localXAxisA)) return false;
         row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true;
     }
+    if (GetType(def) == GetTypeID<PulleyJointConf>()) { const auto jc = TypeCast<PulleyJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     if (GetType(def) == GetTypeID<TargetJointConf>()) { // (bodyA is ignored by the target joint's solver)
         const auto jc = TypeCast<TargetJointConf>(def);
         if (jc.bodyB == InvalidBodyID || jc.bodyA != InvalidBodyID) return false;
@@ -865,6 +884,11 @@ Joint GetJoint(const CudaWorld& w, JointID id)
         wc.springImpulse = Momentum{p.spring_impulse * NewtonSecond};
         wc.angularImpulse = AngularMomentum{p.angular_impulse * NewtonMeterSecond};
         return Joint{wc};
+    }
+    if (GetType(elem) == GetTypeID<PulleyJointConf>()) {
+        auto pc = TypeCast<PulleyJointConf>(elem);
+        pc.impulse = Momentum{r.impulse_x * NewtonSecond};
+        return Joint{pc};
     }
     if (GetType(elem) == GetTypeID<RopeJointConf>()) {
         auto rc = TypeCast<RopeJointConf>(elem);

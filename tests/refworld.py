@@ -253,6 +253,14 @@ class RefWorld:
         assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
         return jid
 
+    def add_pulley(self, body_a, body_b, ground_a, ground_b, anchor_a, anchor_b, ratio=1.0):
+        self.lib.ref_add_pulley.argtypes = [vp, u32, u32] + [f32] * 9
+        self.lib.ref_add_pulley.restype = u32
+        jid = self.lib.ref_add_pulley(self.h, int(body_a), int(body_b), ground_a[0], ground_a[1], ground_b[0], ground_b[1],
+                                      anchor_a[0], anchor_a[1], anchor_b[0], anchor_b[1], ratio)
+        assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
+        return jid
+
     def add_friction(self, body_a, body_b, anchor, max_force, max_torque):
         self.lib.ref_add_friction.argtypes = [vp, u32, u32, f32, f32, f32, f32]
         self.lib.ref_add_friction.restype = u32

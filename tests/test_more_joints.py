@@ -7,7 +7,9 @@ the real reference, the restatement, the emulated kernels and the GPU -- bit for
   prismatic (PrismaticJointConf.cpp:150-533): sliders on a static rail -- free, with limits (lower hit under gravity, upper hit by a motor),
         equal limits, a motor that saturates, a slider between two dynamic bodies, one with fixed rotation (k22 == 0 -> 1).
   wheel (WheelJointConf.cpp:103-362): a car (chassis + two wheels on sprung wheel joints, one driven by a motor) on a bumpy ground,
-        and a rigid (frequency 0) wheel joint."""
+        and a rigid (frequency 0) wheel joint.
+  pulley (PulleyJointConf.cpp:91-282): two unequal weights over a pulley (ratio 1), a ratio-2 block and tackle, a pulley between a
+        body and a static one; ShiftOrigin in mid-run moves the ground anchors (and a target joint's target)."""
 import numpy as np
 import pytest
 import refworld
@@ -106,7 +108,26 @@ def _wheel_scene():
     return ref, [8, 8, 8]
 
 
-SCENES = {"weld": (_weld_scene, 200), "target": (_target_scene, 220), "prismatic": (_prismatic_scene, 240), "wheel": (_wheel_scene, 300)}
+def _pulley_scene():
+    ref = RefWorld()
+    ground = ref.add_body(STATIC, pos=(0.0, 0.0), shapes=[ref.add_box(20.0, 0.5, center=(0.0, -0.5))])
+    light = ref.add_box(0.4, 0.4, density=1.0)
+    heavy = ref.add_box(0.4, 0.4, density=2.5)
+    a = ref.add_body(DYNAMIC, acc=G, pos=(-3.0, 3.0), shapes=[light])
+    b = ref.add_body(DYNAMIC, acc=G, pos=(-1.0, 3.0), shapes=[heavy])
+    ref.add_pulley(a, b, (-3.0, 8.0), (-1.0, 8.0), (-3.0, 3.4), (-1.0, 3.4))                   # the heavy one sinks to the ground, lifting the light one
+    c = ref.add_body(DYNAMIC, acc=G, pos=(2.0, 4.0), shapes=[light])
+    d = ref.add_body(DYNAMIC, acc=G, pos=(4.0, 4.0), shapes=[light])
+    ref.add_pulley(c, d, (2.0, 9.0), (4.5, 9.0), (2.0, 4.4), (4.2, 4.3), ratio=2.0)            # block and tackle, slanted rope
+    e = ref.add_body(DYNAMIC, acc=G, pos=(7.0, 3.0), vel=(1.0, 0.0), shapes=[heavy])
+    ref.add_pulley(e, ground, (7.0, 8.0), (9.0, 8.0), (7.0, 3.4), (9.0, 0.0))                  # the other end is static: a pendulum of fixed length
+    f = ref.add_body(DYNAMIC, acc=G, pos=(-7.0, 2.0), shapes=[light])
+    ref.add_target(f, (-7.0, 2.0), (-6.0, 4.0), max_force=200.0)
+    return ref, [9, 9, 9, 6]
+
+
+SHIFTS = {"pulley": {60: (1.5, -0.75), 130: (-100.0, 33.3)}}
+SCENES = {"pulley": (_pulley_scene, 200), "weld": (_weld_scene, 200), "target": (_target_scene, 220), "prismatic": (_prismatic_scene, 240), "wheel": (_wheel_scene, 300)}
 MOVES = {"target": _target_moves}
 
 
@@ -133,6 +154,9 @@ def _run(name, lib=None, device=-1, with_device=True):
                 rows2 = t.joints()[[jid]].copy()
                 rows2["local_anchor_a"] = tgt
                 t.set_joints(ids, rows2)
+        if name in SHIFTS and s in SHIFTS[name]:
+            for t in [ref, orc] + twins:
+                t.shift_origin(*SHIFTS[name][s])
         rs, os_ = ref.step(conf), orc.step(conf)
         assert_bits(np.array([rs]), np.array([os_]), "step %d stats (reference vs restatement)" % s)
         assert_bits(ref.bodies(), orc.bodies(), "step %d bodies (reference vs restatement)" % s)
