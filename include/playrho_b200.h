@@ -107,7 +107,7 @@ typedef struct pr_revolute_joint {
 
 /* Joint rows share one table (JointIDs are one id space in the reference): every row has pr_revolute_joint's size and leading
  * fields, and bits 8..15 of collide_connected say which joint type it is (bit 0 is the flag itself). */
-enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2, PR_JOINT_FRICTION = 3, PR_JOINT_MOTOR = 4, PR_JOINT_WELD = 5, PR_JOINT_TARGET = 6, PR_JOINT_PRISMATIC = 7, PR_JOINT_WHEEL = 8, PR_JOINT_PULLEY = 9 };
+enum { PR_JOINT_REVOLUTE = 0, PR_JOINT_DISTANCE = 1, PR_JOINT_ROPE = 2, PR_JOINT_FRICTION = 3, PR_JOINT_MOTOR = 4, PR_JOINT_WELD = 5, PR_JOINT_TARGET = 6, PR_JOINT_PRISMATIC = 7, PR_JOINT_WHEEL = 8, PR_JOINT_PULLEY = 9, PR_JOINT_GEAR = 10 };
 /* prismatic and wheel rows keep their enable flags in collide_connected (their enable_limit / enable_motor words hold the local axis) */
 #define PR_JOINT_ENABLE_LIMIT 0x10000u
 #define PR_JOINT_ENABLE_MOTOR 0x20000u
@@ -181,9 +181,11 @@ typedef struct pr_weld_joint {
     uint32_t reserved3;
 } pr_weld_joint;
 /* TargetJointConf (TargetJointConf.hpp; solver TargetJointConf.cpp:52-243): drags a point of ONE body towards a world target
- * (the reference's "mouse joint"). The reference's bodyA is InvalidBodyID; in the table row body_a repeats body_b. */
+ * (the reference's "mouse joint"). The solver only touches body B. When the reference's bodyA is InvalidBodyID the table row's body_a
+ * repeats body_b; a valid bodyA only takes part in the island rules (a joint whose other body is disabled is not solved,
+ * AabbTreeWorld.cpp:1443-1466). */
 typedef struct pr_target_joint {
-    uint32_t body_a, body_b;             /* body_a == body_b: the dragged body */
+    uint32_t body_a, body_b;             /* body_b: the dragged body; body_a: body_b again, or the reference's bodyA */
     uint32_t collide_connected;          /* bits 8..15: PR_JOINT_TARGET */
     pr_vec2 target;                      /* world coordinates */
     pr_vec2 local_anchor_b;
@@ -234,6 +236,27 @@ typedef struct pr_pulley_joint {
     float reserved0[3];
     uint32_t reserved1;
 } pr_pulley_joint;
+/* GearJointConf (GearJointConf.hpp; solver GearJointConf.cpp:171-468): couples the coordinate of one revolute or prismatic joint (between
+ * bodies C and A) to that of another (between D and B): coordinate1 + ratio * coordinate2 = constant. The reference copies what it needs
+ * from the two geared joints when the conf is made (GetGearJointConf, :91-169); this struct carries those copies. It is wider than a
+ * row of the joint table: the table row (pr_get_revolute_joints) holds body_a, body_b, collide_connected, impulse, ratio and constant,
+ * pr_get_gear_joints reads the whole value. */
+enum { PR_GEAR_NONE = 0, PR_GEAR_PRISMATIC = 1, PR_GEAR_REVOLUTE = 2 };
+typedef struct pr_gear_side {
+    uint32_t type;                       /* PR_GEAR_*: the geared joint's type */
+    pr_vec2 local_anchor_a;              /* prismatic: the geared joint's localAnchorA (on body C / D) */
+    pr_vec2 local_anchor_b;              /* prismatic: its localAnchorB (on body A / B) */
+    pr_vec2 local_axis;                  /* prismatic: its localXAxisA */
+    float reference_angle;               /* revolute: its referenceAngle */
+} pr_gear_side;
+typedef struct pr_gear_joint {
+    uint32_t body_a, body_b;             /* the geared joints' bodyB's */
+    uint32_t collide_connected;          /* bit 0: collideConnected; bits 8..15: PR_JOINT_GEAR */
+    uint32_t body_c, body_d;             /* the geared joints' bodyA's */
+    float impulse;                       /* accumulated impulse (warm start) */
+    float ratio, constant;
+    pr_gear_side ac, bd;
+} pr_gear_joint;
 
 /* ContactFeature packed little-endian: typeA | indexA<<8 | typeB<<16 | indexB<<24 */
 typedef uint32_t pr_contact_feature;
@@ -377,6 +400,9 @@ int pr_create_target_joints(pr_world* w, uint32_t n, const pr_target_joint* join
 int pr_create_prismatic_joints(pr_world* w, uint32_t n, const pr_prismatic_joint* joints, uint32_t* first_id);
 int pr_create_wheel_joints(pr_world* w, uint32_t n, const pr_wheel_joint* joints, uint32_t* first_id);
 int pr_create_pulley_joints(pr_world* w, uint32_t n, const pr_pulley_joint* joints, uint32_t* first_id);
+int pr_create_gear_joints(pr_world* w, uint32_t n, const pr_gear_joint* joints, uint32_t* first_id);
+/* the gear joints among joints [first, first + n): out[i] is filled for a gear joint, zeroed with body_a == 0xFFFFFFFF for any other row */
+int pr_get_gear_joints(const pr_world* w, uint32_t first, uint32_t n, pr_gear_joint* out);
 
 /* SetShape(AabbTreeWorld&, ShapeID, Shape) (AabbTreeWorld.cpp:1284-1356) for a value whose geometry (children) and filter are
  * what they were: friction, restitution, density and the sensor flag are replaced; every body using the shape is woken

@@ -22,6 +22,7 @@
 #include <chrono>
 #include <cstring>
 #include <string>
+#include <variant>
 #include <vector>
 
 #include "../include/playrho_b200.h"
@@ -439,10 +440,11 @@ uint32_t ref_add_weld(void* h, uint32_t bodyA, uint32_t bodyB, float ax, float a
     return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
     REF_CATCH(0xFFFFFFFFu)
 }
-uint32_t ref_add_target(void* h, uint32_t bodyB, float tx, float ty, float ax, float ay, float frequency, float dampingRatio, float maxForce)
-{
+uint32_t ref_add_target(void* h, uint32_t bodyA, uint32_t bodyB, float tx, float ty, float ax, float ay, float frequency, float dampingRatio, float maxForce)
+{ // bodyA: 0xFFFFFFFF = none (the usual target joint), else the conf's bodyA (it only takes part in the island rules)
     REF_TRY(h)
     auto jc = TargetJointConf{};
+    if (bodyA != 0xFFFFFFFFu) jc.bodyA = MakeId<BodyID>(bodyA);
     jc.bodyB = MakeId<BodyID>(bodyB);
     jc.target = Length2{tx * 1_m, ty * 1_m};
     jc.localAnchorB = GetLocalPoint(rw->world, jc.bodyB, Length2{ax * 1_m, ay * 1_m});
@@ -488,6 +490,47 @@ uint32_t ref_add_pulley(void* h, uint32_t bodyA, uint32_t bodyB, float gax, floa
     jc.ratio = ratio;
     return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
     REF_CATCH(0xFFFFFFFFu)
+}
+uint32_t ref_add_gear(void* h, uint32_t joint1, uint32_t joint2, float ratio)
+{
+    REF_TRY(h)
+    const auto jc = GetGearJointConf(rw->world, MakeId<JointID>(joint1), MakeId<JointID>(joint2), ratio);
+    return static_cast<uint32_t>(to_underlying(CreateJoint(rw->world, Joint{jc})));
+    REF_CATCH(0xFFFFFFFFu)
+}
+static void export_gear_side(const GearJointConf::TypeData& td, pr_gear_side& o)
+{
+    if (std::holds_alternative<GearJointConf::PrismaticData>(td)) {
+        const auto& d = std::get<GearJointConf::PrismaticData>(td);
+        o.type = PR_GEAR_PRISMATIC;
+        o.local_anchor_a = pr_vec2{GetX(d.localAnchorA), GetY(d.localAnchorA)};
+        o.local_anchor_b = pr_vec2{GetX(d.localAnchorB), GetY(d.localAnchorB)};
+        o.local_axis = pr_vec2{d.localAxis.GetX(), d.localAxis.GetY()};
+    } else if (std::holds_alternative<GearJointConf::RevoluteData>(td)) {
+        o.type = PR_GEAR_REVOLUTE;
+        o.reference_angle = std::get<GearJointConf::RevoluteData>(td).referenceAngle;
+    } else o.type = PR_GEAR_NONE;
+}
+int ref_export_gear_joints(void* h, pr_gear_joint* out, uint32_t cap)
+{
+    REF_TRY(h)
+    const auto n = static_cast<uint32_t>(GetJointRange(rw->world));
+    const auto live = GetJoints(rw->world);
+    for (uint32_t i = 0; i < n && i < cap; ++i) {
+        auto& o = out[i];
+        std::memset(&o, 0, sizeof(o));
+        o.body_a = o.body_b = o.body_c = o.body_d = 0xFFFFFFFFu;
+        if (std::find(live.begin(), live.end(), MakeId<JointID>(i)) == live.end()) continue;
+        const auto joint = GetJoint(rw->world, MakeId<JointID>(i));
+        if (GetType(joint) != GetTypeID<GearJointConf>()) continue;
+        const auto gc = TypeCast<GearJointConf>(joint);
+        o.body_a = to_underlying(gc.bodyA); o.body_b = to_underlying(gc.bodyB); o.body_c = to_underlying(gc.bodyC); o.body_d = to_underlying(gc.bodyD);
+        o.collide_connected = (gc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_GEAR) << 8);
+        o.impulse = gc.impulse; o.ratio = gc.ratio; o.constant = gc.constant;
+        export_gear_side(gc.typeDataAC, o.ac); export_gear_side(gc.typeDataBD, o.bd);
+    }
+    return static_cast<int>(n);
+    REF_CATCH(-1)
 }
 int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
 {
@@ -540,7 +583,7 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
         }
         if (GetType(joint) == GetTypeID<TargetJointConf>()) { // the same row, viewed as pr_target_joint (body_a repeats body_b)
             const auto tc = TypeCast<TargetJointConf>(joint);
-            o.body_a = o.body_b = to_underlying(tc.bodyB);
+            o.body_b = to_underlying(tc.bodyB); o.body_a = (tc.bodyA != InvalidBodyID) ? to_underlying(tc.bodyA) : o.body_b;
             o.collide_connected = (tc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_TARGET) << 8);
             o.local_anchor_a = pr_vec2{GetX(tc.target), GetY(tc.target)};
             o.local_anchor_b = pr_vec2{GetX(tc.localAnchorB), GetY(tc.localAnchorB)};
@@ -591,6 +634,13 @@ int ref_export_revolute_joints(void* h, pr_revolute_joint* out, uint32_t cap)
             p.ground_anchor_b = pr_vec2{GetX(pc.groundAnchorB), GetY(pc.groundAnchorB)};
             p.length_a = pc.lengthA; p.length_b = pc.lengthB; p.ratio = pc.ratio;
             std::memcpy(&o, &p, sizeof(o));
+            continue;
+        }
+        if (GetType(joint) == GetTypeID<GearJointConf>()) { // the table row of a gear joint (the whole value: ref_export_gear_joints)
+            const auto gc = TypeCast<GearJointConf>(joint);
+            o.body_a = to_underlying(gc.bodyA); o.body_b = to_underlying(gc.bodyB);
+            o.collide_connected = (gc.collideConnected ? 1u : 0u) | (static_cast<uint32_t>(PR_JOINT_GEAR) << 8);
+            o.impulse_x = gc.impulse; o.lower_angle = gc.ratio; o.upper_angle = gc.constant;
             continue;
         }
         if (GetType(joint) == GetTypeID<RopeJointConf>()) { // the same row, viewed as pr_rope_joint

@@ -1309,6 +1309,142 @@ bool pulley_solve_position(const pr_revolute_joint& j, float imA, float iiA, V2 
     return linearError < c.linearSlop;
 }
 } // namespace
+// ---------------- GearJointConf.cpp:171-468 ----------------
+// (mass[0..1] = JvAC, mass[2..3] = JvBD, mass[4] = JwA, mass[5] = JwB, mass[6] = JwC, mass[7] = JwD, mass[8] = mass)
+void gear_init_velocity(pr_revolute_joint& j, const pr_gear_joint& g, RevoluteWork& wk, GearBody A, GearBody B, GearBody C, GearBody D, const JointSolverConf& c)
+{
+    Vel velA = *A.vel, velB = *B.vel, velC = *C.vel, velD = *D.vel;
+    const float ratio = j.lower_angle;
+    V2 JvAC, JvBD; float JwA, JwB, JwC, JwD;
+    float invMass = 0.0f;
+    if (g.ac.type == PR_GEAR_PRISMATIC) {
+        const Rot qA = rot_from_angle(A.pos->a), qC = rot_from_angle(C.pos->a);
+        const Rot u = rot_rotate(Rot{g.ac.local_axis.x, g.ac.local_axis.y}, qC);
+        const V2 rC = rotate(V2{g.ac.local_anchor_a.x, g.ac.local_anchor_a.y} - C.lc, qC);
+        const V2 rA = rotate(V2{g.ac.local_anchor_b.x, g.ac.local_anchor_b.y} - A.lc, qA);
+        JvAC = 1.0f * u;
+        JwC = cross(rC, u); JwA = cross(rA, u);
+        const float invRotMassC = C.invI * square(JwC) / 1.0f, invRotMassA = A.invI * square(JwA) / 1.0f;
+        invMass += C.invM + A.invM + invRotMassC + invRotMassA;
+    } else {
+        JvAC = V2{0.0f, 0.0f}; JwA = 1.0f; JwC = 1.0f;
+        invMass += A.invI + C.invI;
+    }
+    if (g.bd.type == PR_GEAR_PRISMATIC) {
+        const Rot qB = rot_from_angle(B.pos->a), qD = rot_from_angle(D.pos->a);
+        const Rot u = rot_rotate(Rot{g.bd.local_axis.x, g.bd.local_axis.y}, qD);
+        const V2 rD = rotate(V2{g.bd.local_anchor_a.x, g.bd.local_anchor_a.y} - D.lc, qD);
+        const V2 rB = rotate(V2{g.bd.local_anchor_b.x, g.bd.local_anchor_b.y} - B.lc, qB);
+        JvBD = ratio * u;
+        JwD = ratio * cross(rD, u); JwB = ratio * cross(rB, u);
+        const float invRotMassD = D.invI * square(JwD) / 1.0f, invRotMassB = B.invI * square(JwB) / 1.0f;
+        invMass += square(ratio) * (D.invM + B.invM) + invRotMassD + invRotMassB;
+    } else {
+        JvBD = V2{0.0f, 0.0f}; JwB = ratio * 1.0f; JwD = ratio * 1.0f;
+        invMass += square(ratio) * (B.invI + D.invI);
+    }
+    wk.mass[0] = JvAC.x; wk.mass[1] = JvAC.y; wk.mass[2] = JvBD.x; wk.mass[3] = JvBD.y; wk.mass[4] = JwA; wk.mass[5] = JwB; wk.mass[6] = JwC; wk.mass[7] = JwD;
+    wk.mass[8] = (invMass > 0.0f) ? 1.0f / invMass : 0.0f;
+    if (c.warmStart) {
+        const float imp = j.impulse_x;
+        velA.l = velA.l + (A.invM * imp) * JvAC; velA.a += A.invI * imp * JwA / 1.0f;
+        velB.l = velB.l + (B.invM * imp) * JvBD; velB.a += B.invI * imp * JwB / 1.0f;
+        velC.l = velC.l - (C.invM * imp) * JvAC; velC.a -= C.invI * imp * JwC / 1.0f;
+        velD.l = velD.l - (D.invM * imp) * JvBD; velD.a -= D.invI * imp * JwD / 1.0f;
+    } else j.impulse_x = 0.0f;
+    *A.vel = velA; *B.vel = velB; *C.vel = velC; *D.vel = velD;
+}
+bool gear_solve_velocity(pr_revolute_joint& j, RevoluteWork& wk, GearBody A, GearBody B, GearBody C, GearBody D)
+{
+    Vel velA = *A.vel, velB = *B.vel, velC = *C.vel, velD = *D.vel;
+    const V2 JvAC{wk.mass[0], wk.mass[1]}, JvBD{wk.mass[2], wk.mass[3]};
+    const float JwA = wk.mass[4], JwB = wk.mass[5], JwC = wk.mass[6], JwD = wk.mass[7];
+    const float acDot = dot(JvAC, velA.l - velC.l);
+    const float bdDot = dot(JvBD, velB.l - velD.l);
+    const float Cdot = acDot + bdDot + (JwA * velA.a - JwC * velC.a) / 1.0f + (JwB * velB.a - JwD * velD.a) / 1.0f;
+    const float impulse = -wk.mass[8] * 1.0f * Cdot;
+    j.impulse_x += impulse;
+    velA.l = velA.l + (A.invM * impulse) * JvAC; velA.a += A.invI * impulse * JwA / 1.0f;
+    velB.l = velB.l + (B.invM * impulse) * JvBD; velB.a += B.invI * impulse * JwB / 1.0f;
+    velC.l = velC.l - (C.invM * impulse) * JvAC; velC.a -= C.invI * impulse * JwC / 1.0f;
+    velD.l = velD.l - (D.invM * impulse) * JvBD; velD.a -= D.invI * impulse * JwD / 1.0f;
+    *A.vel = velA; *B.vel = velB; *C.vel = velC; *D.vel = velD;
+    return impulse == 0.0f;
+}
+namespace {
+Pos cap_position(V2 lin, float ang, const JointSolverConf& c)
+{ // Cap(Position, ConstraintSolverConf), d2/Math.cpp:63-71
+    const float lsquared = magsq(lin);
+    if (lsquared > square(c.maxLinearCorrection)) { const float sc = c.maxLinearCorrection / std::sqrt(lsquared); lin.x *= sc; lin.y *= sc; }
+    return Pos{lin, std::clamp(ang, -c.maxAngularCorrection, +c.maxAngularCorrection)};
+}
+}
+bool gear_solve_position(const pr_revolute_joint& j, const pr_gear_joint& g, GearBody A, GearBody B, GearBody C, GearBody D, const JointSolverConf& c)
+{
+    const Pos posA = *A.pos, posB = *B.pos, posC = *C.pos, posD = *D.pos;
+    const float ratio = j.lower_angle, constant = j.upper_angle;
+    if (!std::isfinite(constant)) return true;
+    V2 JvAC{0.0f, 0.0f}, JvBD{0.0f, 0.0f};
+    float JwA = 0.0f, JwB = 0.0f, JwC = 0.0f, JwD = 0.0f, coordinateA = 0.0f, coordinateB = 0.0f, invMass = 0.0f;
+    if (g.ac.type == PR_GEAR_PRISMATIC) {
+        const Rot qA = rot_from_angle(posA.a), qC = rot_from_angle(posC.a);
+        const Rot lax{g.ac.local_axis.x, g.ac.local_axis.y};
+        const Rot u = rot_rotate(lax, qC);
+        const V2 rC = rotate(V2{g.ac.local_anchor_a.x, g.ac.local_anchor_a.y} - C.lc, qC);
+        const V2 rA = rotate(V2{g.ac.local_anchor_b.x, g.ac.local_anchor_b.y} - A.lc, qA);
+        JvAC = u * 1.0f;
+        JwC = cross(rC, u); JwA = cross(rA, u);
+        const float invLinMass = C.invM + A.invM;
+        const float invRotMassC = C.invI * square(JwC * 1.0f / 1.0f), invRotMassA = A.invI * square(JwA * 1.0f / 1.0f);
+        invMass += invLinMass + invRotMassC + invRotMassA;
+        const V2 pC = V2{g.ac.local_anchor_a.x, g.ac.local_anchor_a.y} - C.lc;
+        const V2 pA = inv_rotate(rA + (posA.l - posC.l), qC);
+        coordinateA = dot(pA - pC, lax) / 1.0f;
+    } else if (g.ac.type == PR_GEAR_REVOLUTE) {
+        JwA = 1.0f; JwC = 1.0f;
+        invMass += A.invI + C.invI;
+        coordinateA = ((posA.a - posC.a) - g.ac.reference_angle) / 1.0f;
+    }
+    if (g.bd.type == PR_GEAR_PRISMATIC) {
+        const Rot qB = rot_from_angle(posB.a), qD = rot_from_angle(posD.a);
+        const Rot lax{g.bd.local_axis.x, g.bd.local_axis.y};
+        const Rot u = rot_rotate(lax, qD);
+        const V2 rD = rotate(V2{g.bd.local_anchor_a.x, g.bd.local_anchor_a.y} - D.lc, qD);
+        const V2 rB = rotate(V2{g.bd.local_anchor_b.x, g.bd.local_anchor_b.y} - B.lc, qB);
+        JvBD = ratio * u;
+        JwD = ratio * cross(rD, u); JwB = ratio * cross(rB, u);
+        const float invLinMass = square(ratio) * (D.invM + B.invM);
+        const float invRotMassD = D.invI * square(JwD * 1.0f / 1.0f), invRotMassB = B.invI * square(JwB * 1.0f / 1.0f);
+        invMass += invLinMass + invRotMassD + invRotMassB;
+        const V2 pD = V2{g.bd.local_anchor_a.x, g.bd.local_anchor_a.y} - D.lc;
+        const V2 pB = inv_rotate(rB + (posB.l - posD.l), qD);
+        coordinateB = dot(pB - pD, lax) / 1.0f;
+    } else if (g.bd.type == PR_GEAR_REVOLUTE) {
+        JwB = ratio; JwD = ratio;
+        invMass += square(ratio) * (B.invI + D.invI);
+        coordinateB = ((posB.a - posD.a) - g.bd.reference_angle) / 1.0f;
+    }
+    const float Cc = ((coordinateA + ratio * coordinateB) - constant) * c.resolutionRate;
+    const float impulse = ((invMass > 0.0f) ? -Cc / invMass : 0.0f) * 1.0f * 1.0f;
+    const Pos deltaA = cap_position(A.invM * impulse * JvAC, A.invI * impulse * JwA * 1.0f / 1.0f, c);
+    const Pos deltaC = cap_position(C.invM * impulse * JvAC, C.invI * impulse * JwC * 1.0f / 1.0f, c);
+    const Pos deltaB = cap_position(B.invM * impulse * JvBD, B.invI * impulse * JwB * 1.0f / 1.0f, c);
+    const Pos deltaD = cap_position(D.invM * impulse * JvBD, D.invI * impulse * JwD * 1.0f / 1.0f, c);
+    *A.pos = Pos{posA.l + deltaA.l, posA.a + deltaA.a};
+    *B.pos = Pos{posB.l + deltaB.l, posB.a + deltaB.a};
+    *C.pos = Pos{posC.l - deltaC.l, posC.a - deltaC.a};
+    *D.pos = Pos{posD.l - deltaD.l, posD.a - deltaD.a};
+    float linearError = 0.0f, angularError = 0.0f;
+    linearError = std::max(linearError, magsq(deltaA.l));
+    linearError = std::max(linearError, magsq(deltaB.l));
+    linearError = std::max(linearError, magsq(deltaC.l));
+    linearError = std::max(linearError, magsq(deltaD.l));
+    angularError = std::max(angularError, std::fabs(deltaA.a));
+    angularError = std::max(angularError, std::fabs(deltaB.a));
+    angularError = std::max(angularError, std::fabs(deltaC.a));
+    angularError = std::max(angularError, std::fabs(deltaD.a));
+    return (linearError <= square(c.linearSlop)) && (angularError <= c.angularSlop);
+}
 void joint_init_velocity(pr_revolute_joint& j, RevoluteWork& wk, float imA, float iiA, V2 lcA, Pos posA, Vel& velA,
                          float imB, float iiB, V2 lcB, Pos posB, Vel& velB, const JointSolverConf& c)
 {

@@ -69,6 +69,7 @@ struct orc_world {
     std::vector<pr_revolute_joint> joints;
     std::vector<uint32_t> freeJoints;            // joint pool free list (LIFO)
     std::vector<orc::RevoluteWork> jointWork;
+    std::vector<pr_gear_joint> gears;   // by joint id: the whole value of a gear joint (GearJointConf), zeroed for other types
     std::vector<std::pair<uint32_t, uint32_t>> fixturesForProxies; // (body, shape)
     // ids of destroyed bodies / shapes (ObjectPool free lists, LIFO) and the DynamicTree's free list as the LEAVES see it:
     // DestroyLeaf frees the leaf's parent node and then the leaf (DynamicTree.cpp:539-569), CreateLeaf takes a leaf and then a
@@ -929,9 +930,11 @@ IslandStats solve_reg_island(orc_world& w, const pr_step_conf& conf, const Islan
     build_constraints(w, island, bcs, vcs, pcs, h, conf, conf.do_warm_start ? conf.dt_ratio : 0.0f);
     if (conf.do_warm_start) for (const VC& vc : vcs) warm_start(vc, bcs);
     orc::JointSolverConf jc{conf.delta_time, conf.dt_ratio, conf.do_warm_start != 0, conf.linear_slop, conf.angular_slop,
-                            conf.max_linear_correction, conf.max_angular_correction};
+                            conf.max_linear_correction, conf.max_angular_correction, conf.reg_resolution_rate};
+    auto gb = [&](uint32_t id) { return orc::GearBody{bcs[id].invM, bcs[id].invI, bcs[id].lc, &bcs[id].pos, &bcs[id].vel}; };
     for (uint32_t j : island.joints) {
         auto& jt = w.joints[j];
+        if (PR_JOINT_TYPE(jt) == PR_JOINT_GEAR) { const auto& g = w.gears[j]; orc::gear_init_velocity(jt, g, w.jointWork[j], gb(jt.body_a), gb(jt.body_b), gb(g.body_c), gb(g.body_d), jc); continue; }
         orc::joint_init_velocity(jt, w.jointWork[j], bcs[jt.body_a].invM, bcs[jt.body_a].invI, bcs[jt.body_a].lc, bcs[jt.body_a].pos, bcs[jt.body_a].vel,
                                     bcs[jt.body_b].invM, bcs[jt.body_b].invI, bcs[jt.body_b].lc, bcs[jt.body_b].pos, bcs[jt.body_b].vel, jc);
     }
@@ -940,6 +943,7 @@ IslandStats solve_reg_island(orc_world& w, const pr_step_conf& conf, const Islan
         bool jointsOkay = true;
         for (uint32_t j : island.joints) {
             auto& jt = w.joints[j];
+            if (PR_JOINT_TYPE(jt) == PR_JOINT_GEAR) { const auto& g = w.gears[j]; jointsOkay &= orc::gear_solve_velocity(jt, w.jointWork[j], gb(jt.body_a), gb(jt.body_b), gb(g.body_c), gb(g.body_d)); continue; }
             jointsOkay &= orc::joint_solve_velocity(jt, w.jointWork[j], bcs[jt.body_a].invM, bcs[jt.body_a].invI, bcs[jt.body_a].vel,
                                                        bcs[jt.body_b].invM, bcs[jt.body_b].invI, bcs[jt.body_b].vel, jc);
         }
@@ -967,6 +971,7 @@ IslandStats solve_reg_island(orc_world& w, const pr_step_conf& conf, const Islan
         bool jointsOkay = true;
         for (uint32_t j : island.joints) {
             auto& jt = w.joints[j];
+            if (PR_JOINT_TYPE(jt) == PR_JOINT_GEAR) { const auto& g = w.gears[j]; jointsOkay &= orc::gear_solve_position(jt, g, gb(jt.body_a), gb(jt.body_b), gb(g.body_c), gb(g.body_d), jc); continue; }
             jointsOkay &= orc::joint_solve_position(jt, w.jointWork[j], bcs[jt.body_a].invM, bcs[jt.body_a].invI, bcs[jt.body_a].lc, bcs[jt.body_a].pos,
                                                        bcs[jt.body_b].invM, bcs[jt.body_b].invI, bcs[jt.body_b].lc, bcs[jt.body_b].pos, jc);
         }
@@ -1056,6 +1061,9 @@ void solve_reg(orc_world& w, const pr_step_conf& conf, pr_step_stats& stats,
                 const uint32_t rb = ib == rank->end() ? 0xFFFFFFFFu : ib->second;
                 return ra < rb;
             });
+            // the device walks joints in id order (one thread when joints share a body, pr_joint.cuh); the reference in the island's
+            // discovery order (AddJointsToIsland :1443-1466). As the device's twin the restatement takes the device's order, like for contacts.
+            std::sort(island.joints.begin(), island.joints.end());
         }
         stats.reg.max_island_bodies = std::max(stats.reg.max_island_bodies, static_cast<uint32_t>(island.bodies.size()));
         for (uint32_t id : island.bodies) if (!speedable(w.bodies[id].b)) w.islandedBodies[id] = 0;
@@ -1637,6 +1645,21 @@ int orc_get_proxies(const orc_world* w, uint32_t cap, pr_proxy* proxies, uint32_
     return 0;
 }
 
+// CreateJoint of GearJointConf values: the table row (bodies A and B, impulse, ratio, constant) + the whole value by joint id
+int orc_create_gear_joints(orc_world* w, uint32_t n, const pr_gear_joint* joints)
+{
+    for (uint32_t i = 0; i < n; ++i) {
+        pr_revolute_joint r{};
+        r.body_a = joints[i].body_a; r.body_b = joints[i].body_b;
+        r.collide_connected = (joints[i].collide_connected & 1u) | (static_cast<uint32_t>(PR_JOINT_GEAR) << 8);
+        r.impulse_x = joints[i].impulse; r.lower_angle = joints[i].ratio; r.upper_angle = joints[i].constant;
+        const uint32_t id = w->freeJoints.empty() ? static_cast<uint32_t>(w->joints.size()) : w->freeJoints.back();
+        orc_create_revolute_joints(w, 1, &r);
+        if (w->gears.size() < w->joints.size()) w->gears.resize(w->joints.size());
+        w->gears[id] = joints[i];
+    }
+    return 0;
+}
 int orc_get_revolute_joints(const orc_world* w, uint32_t first, uint32_t n, pr_revolute_joint* rows)
 {
     for (uint32_t i = 0; i < n; ++i) rows[i] = w->joints[first + i];

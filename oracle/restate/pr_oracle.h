@@ -30,6 +30,7 @@ int orc_create_shapes(orc_world* w, uint32_t n, const pr_shape* shapes, const pr
 int orc_create_bodies(orc_world* w, uint32_t n, const pr_body* bodies,
                       const uint32_t* shape_offsets, const uint32_t* shape_ids);
 int orc_create_revolute_joints(orc_world* w, uint32_t n, const pr_revolute_joint* joints);
+int orc_create_gear_joints(orc_world* w, uint32_t n, const pr_gear_joint* joints);
 int orc_set_bodies(orc_world* w, uint32_t n, const uint32_t* ids, const pr_body* rows);
 int orc_set_shape_material(orc_world* w, uint32_t shape, float friction, float restitution, float density, uint32_t is_sensor); /* SetShape :1284 */
 int orc_attach_shapes(orc_world* w, uint32_t body, uint32_t n, const uint32_t* shape_ids); /* SetBody with added shapes :2760-2786 */

@@ -29,6 +29,31 @@ REVOLUTE = np.dtype([("body_a", u4), ("body_b", u4), ("collide_connected", u4),
                      ("upper_angle", f4), ("motor_speed", f4), ("max_motor_torque", f4),
                      ("limit_state", u4)])
 
+GEAR_SIDE = np.dtype([("type", u4), ("local_anchor_a", VEC2), ("local_anchor_b", VEC2), ("local_axis", VEC2), ("reference_angle", f4)])
+GEAR = np.dtype([("body_a", u4), ("body_b", u4), ("collide_connected", u4), ("body_c", u4), ("body_d", u4),
+                 ("impulse", f4), ("ratio", f4), ("constant", f4), ("ac", GEAR_SIDE), ("bd", GEAR_SIDE)])
+JOINT_GEAR = 10
+
+
+def joint_type(row):
+    return (int(row["collide_connected"]) >> 8) & 0xFF
+
+
+def joint_batches(rows):
+    """(start, end, is_gear) runs of a joint table in id order: gear joints one by one (their value is wider than a row), the others in runs"""
+    i, n = 0, len(rows)
+    while i < n:
+        if joint_type(rows[i]) == JOINT_GEAR:
+            yield i, i + 1, True
+            i += 1
+        else:
+            j = i
+            while j < n and joint_type(rows[j]) != JOINT_GEAR:
+                j += 1
+            yield i, j, False
+            i = j
+
+
 MANIFOLD = np.dtype([(n, f4) for n in ("ln_x", "ln_y", "lp_x", "lp_y", "p0_x", "p0_y", "p1_x", "p1_y",
                                         "jn0", "jt0", "jn1", "jt1")] +
                     [("cf0", u4), ("cf1", u4), ("type", u4), ("count", u4)])

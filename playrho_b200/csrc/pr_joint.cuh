@@ -1021,6 +1021,159 @@ PR_D void pulley_solve_position(const DV& d, const pr_revolute_joint& j, const J
     if (!(linearError < conf.linear_slop)) v.isl_jflag[wk.island] = 1u;
 }
 
+// ---- GearJointConf.cpp:171-468: four bodies -- A and B (the row's bodies) geared through their joints to C and D (GearExt). Row overlay:
+// impulse = impulse_x, ratio = lower_angle, constant = upper_angle; work: m[0..1] = JvAC, m[2..3] = JvBD, m[4] = JwA, m[5] = JwB, m[6] = JwC,
+// m[7] = JwD, m[8] = mass. (A body C or D the island did not reach reads a default BodyConstraint in the reference, :282-285; here it reads the body's own.)
+PR_D void gear_init_velocity(const DV& d, unsigned ji, pr_revolute_joint j, JointWork wk, const pr_step_conf& conf, const JView& v)
+{
+    const GearExt g = d.jt_gear[ji];
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b), ic = jv_idx(v.slotV, g.body_c), id = jv_idx(v.slotV, g.body_d);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b], mC = d.b_mass[g.body_c], mD = d.b_mass[g.body_d];
+    const float ratio = j.lower_angle;
+    float2 JvAC, JvBD; float JwA, JwB, JwC, JwD;
+    float invMass = 0.0f;
+    if (g.type_ac == 1u) {
+        const Rot qA = rot_from_angle(v.s_pos[jv_idx(v.slotP, j.body_a)].z), qC = rot_from_angle(v.s_pos[jv_idx(v.slotP, g.body_c)].z);
+        const Rot u = rot_rotate(mkrot(g.ac[4], g.ac[5]), qC);
+        const float2 rC = rotate(v2(g.ac[0], g.ac[1]) - d.b_lc[g.body_c], qC);
+        const float2 rA = rotate(v2(g.ac[2], g.ac[3]) - d.b_lc[j.body_a], qA);
+        JvAC = 1.0f * u;
+        JwC = cross(rC, u); JwA = cross(rA, u);
+        const float invRotMassC = mC.y * square(JwC) / 1.0f, invRotMassA = mA.y * square(JwA) / 1.0f;
+        const float invLinMass = mC.x + mA.x + invRotMassC + invRotMassA;
+        invMass += invLinMass;
+    } else {
+        JvAC = v2(0.0f, 0.0f); JwA = 1.0f; JwC = 1.0f;
+        invMass += mA.y + mC.y;
+    }
+    if (g.type_bd == 1u) {
+        const Rot qB = rot_from_angle(v.s_pos[jv_idx(v.slotP, j.body_b)].z), qD = rot_from_angle(v.s_pos[jv_idx(v.slotP, g.body_d)].z);
+        const Rot u = rot_rotate(mkrot(g.bd[4], g.bd[5]), qD);
+        const float2 rD = rotate(v2(g.bd[0], g.bd[1]) - d.b_lc[g.body_d], qD);
+        const float2 rB = rotate(v2(g.bd[2], g.bd[3]) - d.b_lc[j.body_b], qB);
+        JvBD = ratio * u;
+        JwD = ratio * cross(rD, u); JwB = ratio * cross(rB, u);
+        const float invRotMassD = mD.y * square(JwD) / 1.0f, invRotMassB = mB.y * square(JwB) / 1.0f;
+        const float invLinMass = square(ratio) * (mD.x + mB.x) + invRotMassD + invRotMassB;
+        invMass += invLinMass;
+    } else {
+        JvBD = v2(0.0f, 0.0f); JwB = ratio * 1.0f; JwD = ratio * 1.0f;
+        invMass += square(ratio) * (mB.y + mD.y);
+    }
+    wk.m[0] = JvAC.x; wk.m[1] = JvAC.y; wk.m[2] = JvBD.x; wk.m[3] = JvBD.y; wk.m[4] = JwA; wk.m[5] = JwB; wk.m[6] = JwC; wk.m[7] = JwD;
+    wk.m[8] = (invMass > 0.0f) ? 1.0f / invMass : 0.0f;
+    if (conf.do_warm_start) { // (:244-253: each body's velocity is read, changed and written in turn -- the four need not be different bodies)
+        const float imp = j.impulse_x;
+        float4 vel = v.s_vel[ia];
+        { const float2 l = v2(vel.x, vel.y) + (mA.x * imp) * JvAC; vel.x = l.x; vel.y = l.y; vel.z += mA.y * imp * JwA / 1.0f; }
+        float4 velB = v.s_vel[ib], velC = v.s_vel[ic], velD = v.s_vel[id];
+        { const float2 l = v2(velB.x, velB.y) + (mB.x * imp) * JvBD; velB.x = l.x; velB.y = l.y; velB.z += mB.y * imp * JwB / 1.0f; }
+        { const float2 l = v2(velC.x, velC.y) - (mC.x * imp) * JvAC; velC.x = l.x; velC.y = l.y; velC.z -= mC.y * imp * JwC / 1.0f; }
+        { const float2 l = v2(velD.x, velD.y) - (mD.x * imp) * JvBD; velD.x = l.x; velD.y = l.y; velD.z -= mD.y * imp * JwD / 1.0f; }
+        v.s_vel[ia] = vel; v.s_vel[ib] = velB; v.s_vel[ic] = velC; v.s_vel[id] = velD;
+    } else j.impulse_x = 0.0f;
+    d.jt[ji] = j;
+    d.jt_work[ji] = wk;
+}
+PR_D void gear_solve_velocity(const DV& d, unsigned ji, pr_revolute_joint j, const JointWork& wk, const JView& v)
+{
+    const GearExt g = d.jt_gear[ji];
+    const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b), ic = jv_idx(v.slotV, g.body_c), id = jv_idx(v.slotV, g.body_d);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b], mC = d.b_mass[g.body_c], mD = d.b_mass[g.body_d];
+    float4 velA = v.s_vel[ia], velB = v.s_vel[ib], velC = v.s_vel[ic], velD = v.s_vel[id];
+    const float2 JvAC = v2(wk.m[0], wk.m[1]), JvBD = v2(wk.m[2], wk.m[3]);
+    const float JwA = wk.m[4], JwB = wk.m[5], JwC = wk.m[6], JwD = wk.m[7];
+    const float acDot = dot(JvAC, v2(velA.x, velA.y) - v2(velC.x, velC.y));
+    const float bdDot = dot(JvBD, v2(velB.x, velB.y) - v2(velD.x, velD.y));
+    const float Cdot = acDot + bdDot + (JwA * velA.z - JwC * velC.z) / 1.0f + (JwB * velB.z - JwD * velD.z) / 1.0f;
+    const float impulse = -wk.m[8] * 1.0f * Cdot;
+    j.impulse_x += impulse;
+    { const float2 l = v2(velA.x, velA.y) + (mA.x * impulse) * JvAC; velA.x = l.x; velA.y = l.y; velA.z += mA.y * impulse * JwA / 1.0f; }
+    { const float2 l = v2(velB.x, velB.y) + (mB.x * impulse) * JvBD; velB.x = l.x; velB.y = l.y; velB.z += mB.y * impulse * JwB / 1.0f; }
+    { const float2 l = v2(velC.x, velC.y) - (mC.x * impulse) * JvAC; velC.x = l.x; velC.y = l.y; velC.z -= mC.y * impulse * JwC / 1.0f; }
+    { const float2 l = v2(velD.x, velD.y) - (mD.x * impulse) * JvBD; velD.x = l.x; velD.y = l.y; velD.z -= mD.y * impulse * JwD / 1.0f; }
+    v.s_vel[ia] = velA; v.s_vel[ib] = velB; v.s_vel[ic] = velC; v.s_vel[id] = velD;
+    d.jt[ji] = j;
+    if (!(impulse == 0.0f)) v.isl_jflag[wk.island] = 1u;
+}
+PR_D float4 gear_cap(float2 lin, float ang, const pr_step_conf& conf)
+{ // Cap(Position, ConstraintSolverConf), d2/Math.cpp:63-71
+    const float lsquared = magsq(lin);
+    if (lsquared > square(conf.max_linear_correction)) { const float sc = conf.max_linear_correction / sqrtf(lsquared); lin.x *= sc; lin.y *= sc; }
+    ang = stdclamp(ang, -conf.max_angular_correction, +conf.max_angular_correction);
+    return make_float4(lin.x, lin.y, ang, 0.0f);
+}
+PR_D void gear_solve_position(const DV& d, unsigned ji, const pr_revolute_joint& j, const JointWork& wk, const pr_step_conf& conf, const JView& v)
+{
+    const GearExt g = d.jt_gear[ji];
+    const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b), ic = jv_idx(v.slotP, g.body_c), id = jv_idx(v.slotP, g.body_d);
+    const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b], mC = d.b_mass[g.body_c], mD = d.b_mass[g.body_d];
+    const float4 posA = v.s_pos[ia], posB = v.s_pos[ib], posC = v.s_pos[ic], posD = v.s_pos[id];
+    const float ratio = j.lower_angle, constant = j.upper_angle;
+    if (((f2u(constant) >> 23) & 0xFFu) == 0xFFu) return; // (!isfinite(constant), :300-302)
+    float2 JvAC = v2(0.0f, 0.0f), JvBD = v2(0.0f, 0.0f);
+    float JwA = 0.0f, JwB = 0.0f, JwC = 0.0f, JwD = 0.0f, coordinateA = 0.0f, coordinateB = 0.0f, invMass = 0.0f;
+    if (g.type_ac == 1u) {
+        const Rot qA = rot_from_angle(posA.z), qC = rot_from_angle(posC.z);
+        const Rot lax = mkrot(g.ac[4], g.ac[5]);
+        const Rot u = rot_rotate(lax, qC);
+        const float2 rC = rotate(v2(g.ac[0], g.ac[1]) - d.b_lc[g.body_c], qC);
+        const float2 rA = rotate(v2(g.ac[2], g.ac[3]) - d.b_lc[j.body_a], qA);
+        JvAC = u * 1.0f;
+        JwC = cross(rC, u); JwA = cross(rA, u);
+        const float invLinMass = mC.x + mA.x;
+        const float invRotMassC = mC.y * square(JwC * 1.0f / 1.0f), invRotMassA = mA.y * square(JwA * 1.0f / 1.0f);
+        invMass += invLinMass + invRotMassC + invRotMassA;
+        const float2 pC = v2(g.ac[0], g.ac[1]) - d.b_lc[g.body_c];
+        const float2 pA = inv_rotate(rA + (v2(posA.x, posA.y) - v2(posC.x, posC.y)), qC);
+        coordinateA = dot(pA - pC, lax) / 1.0f;
+    } else if (g.type_ac == 2u) {
+        JwA = 1.0f; JwC = 1.0f;
+        invMass += mA.y + mC.y;
+        coordinateA = ((posA.z - posC.z) - g.ac[0]) / 1.0f;
+    }
+    if (g.type_bd == 1u) {
+        const Rot qB = rot_from_angle(posB.z), qD = rot_from_angle(posD.z);
+        const Rot lax = mkrot(g.bd[4], g.bd[5]);
+        const Rot u = rot_rotate(lax, qD);
+        const float2 rD = rotate(v2(g.bd[0], g.bd[1]) - d.b_lc[g.body_d], qD);
+        const float2 rB = rotate(v2(g.bd[2], g.bd[3]) - d.b_lc[j.body_b], qB);
+        JvBD = ratio * u;
+        JwD = ratio * cross(rD, u); JwB = ratio * cross(rB, u);
+        const float invLinMass = square(ratio) * (mD.x + mB.x);
+        const float invRotMassD = mD.y * square(JwD * 1.0f / 1.0f), invRotMassB = mB.y * square(JwB * 1.0f / 1.0f);
+        invMass += invLinMass + invRotMassD + invRotMassB;
+        const float2 pD = v2(g.bd[0], g.bd[1]) - d.b_lc[g.body_d];
+        const float2 pB = inv_rotate(rB + (v2(posB.x, posB.y) - v2(posD.x, posD.y)), qD);
+        coordinateB = dot(pB - pD, lax) / 1.0f;
+    } else if (g.type_bd == 2u) {
+        JwB = ratio; JwD = ratio;
+        invMass += square(ratio) * (mB.y + mD.y);
+        coordinateB = ((posB.z - posD.z) - g.bd[0]) / 1.0f;
+    }
+    const float C = ((coordinateA + ratio * coordinateB) - constant) * conf.reg_resolution_rate;
+    const float impulse = ((invMass > 0.0f) ? -C / invMass : 0.0f) * 1.0f * 1.0f;
+    const float4 deltaA = gear_cap(mA.x * impulse * JvAC, mA.y * impulse * JwA * 1.0f / 1.0f, conf);
+    const float4 deltaC = gear_cap(mC.x * impulse * JvAC, mC.y * impulse * JwC * 1.0f / 1.0f, conf);
+    const float4 deltaB = gear_cap(mB.x * impulse * JvBD, mB.y * impulse * JwB * 1.0f / 1.0f, conf);
+    const float4 deltaD = gear_cap(mD.x * impulse * JvBD, mD.y * impulse * JwD * 1.0f / 1.0f, conf);
+    // (:453-456: SetPosition(posX +/- deltaX) from the positions read at the top, in the order A, B, C, D)
+    { float4 p = v.s_pos[ia]; p.x = posA.x + deltaA.x; p.y = posA.y + deltaA.y; p.z = posA.z + deltaA.z; v.s_pos[ia] = p; }
+    { float4 p = v.s_pos[ib]; p.x = posB.x + deltaB.x; p.y = posB.y + deltaB.y; p.z = posB.z + deltaB.z; v.s_pos[ib] = p; }
+    { float4 p = v.s_pos[ic]; p.x = posC.x - deltaC.x; p.y = posC.y - deltaC.y; p.z = posC.z - deltaC.z; v.s_pos[ic] = p; }
+    { float4 p = v.s_pos[id]; p.x = posD.x - deltaD.x; p.y = posD.y - deltaD.y; p.z = posD.z - deltaD.z; v.s_pos[id] = p; }
+    float linearError = 0.0f, angularError = 0.0f;
+    linearError = stdmax(linearError, magsq(v2(deltaA.x, deltaA.y)));
+    linearError = stdmax(linearError, magsq(v2(deltaB.x, deltaB.y)));
+    linearError = stdmax(linearError, magsq(v2(deltaC.x, deltaC.y)));
+    linearError = stdmax(linearError, magsq(v2(deltaD.x, deltaD.y)));
+    angularError = stdmax(angularError, fabsf(deltaA.z));
+    angularError = stdmax(angularError, fabsf(deltaB.z));
+    angularError = stdmax(angularError, fabsf(deltaC.z));
+    angularError = stdmax(angularError, fabsf(deltaD.z));
+    if (!((linearError <= square(conf.linear_slop)) && (angularError <= conf.angular_slop))) v.isl_jflag[wk.island] = 1u;
+}
+
 PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf, const JView& v)
 {
     pr_revolute_joint j = d.jt[ji];
@@ -1045,7 +1198,13 @@ PR_D void joint_init_velocity(const DV& d, unsigned ji, const pr_step_conf& conf
         fm_init_velocity(d, ji, j, wk, conf, v, joint_type(j) == PR_JOINT_MOTOR);
         return;
     }
-    if (joint_type(j) == PR_JOINT_TARGET) { target_init_velocity(d, ji, j, wk, conf, v); return; }
+    if (joint_type(j) == PR_JOINT_TARGET) {
+        if (j.body_a != j.body_b && d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
+        if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
+        target_init_velocity(d, ji, j, wk, conf, v);
+        return;
+    }
+    if (joint_type(j) == PR_JOINT_GEAR) { gear_init_velocity(d, ji, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_WELD || joint_type(j) == PR_JOINT_PRISMATIC || joint_type(j) == PR_JOINT_WHEEL || joint_type(j) == PR_JOINT_PULLEY) {
         if (d.b_island[j.body_a] == INVALID) island_count_static(d, wk.island, j.body_a);
         if (d.b_island[j.body_b] == INVALID) island_count_static(d, wk.island, j.body_b);
@@ -1125,6 +1284,7 @@ PR_D void joint_solve_velocity(const DV& d, unsigned ji, const pr_step_conf& con
     if (joint_type(j) == PR_JOINT_PRISMATIC) { prismatic_solve_velocity(d, ji, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_WHEEL) { wheel_solve_velocity(d, ji, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_PULLEY) { pulley_solve_velocity(d, ji, j, wk, v); return; }
+    if (joint_type(j) == PR_JOINT_GEAR) { gear_solve_velocity(d, ji, j, wk, v); return; }
     const unsigned ia = jv_idx(v.slotV, j.body_a), ib = jv_idx(v.slotV, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;
@@ -1194,6 +1354,7 @@ PR_D void joint_solve_position(const DV& d, unsigned ji, const pr_step_conf& con
     if (joint_type(j) == PR_JOINT_PRISMATIC) { prismatic_solve_position(d, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_WHEEL) { wheel_solve_position(d, j, wk, conf, v); return; }
     if (joint_type(j) == PR_JOINT_PULLEY) { pulley_solve_position(d, j, wk, conf, v); return; }
+    if (joint_type(j) == PR_JOINT_GEAR) { gear_solve_position(d, ji, j, wk, conf, v); return; }
     const unsigned ia = jv_idx(v.slotP, j.body_a), ib = jv_idx(v.slotP, j.body_b);
     const float4 mA = d.b_mass[j.body_a], mB = d.b_mass[j.body_b];
     const float imA = mA.x, iiA = mA.y, imB = mB.x, iiB = mB.y;

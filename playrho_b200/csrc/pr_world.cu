@@ -94,7 +94,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(c_pos, G_CONTACT), A(c_color, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT), A(toi_list, G_CONTACT), A(toi_cand, G_CONTACT), A(toi_cand2, G_CONTACT), A(toi_re0, G_CONTACT),
         A(toi_re1, G_CONTACT), A(c_rstamp, G_CONTACT),
         A(adj_list, G_ADJ), A(toi_islBodies, G_ADJ), A(toi_islContacts, G_ADJ),
-        A(jt, G_JOINT), A(jt_work, G_JOINT), A(nc_pairs, G_JOINT), A(isl_jflag, G_BODY),
+        A(jt, G_JOINT), A(jt_work, G_JOINT), A(jt_gear, G_JOINT), A(nc_pairs, G_JOINT), A(isl_jflag, G_BODY),
         A(sh_mat, G_SHAPE), A(sh_filter, G_SHAPE), A(sh_group, G_SHAPE),
         A(ch_radius, G_CHILD), A(ch_voff, G_CHILD), A(ch_count, G_CHILD), A(ch_pack, G_CHILD), A(vtx, G_VERT), A(nrm, G_VERT),
         A(p_body, G_PROXY), A(p_shape, G_PROXY), A(p_child, G_PROXY), A(p_cg, G_PROXY), A(p_tree, G_PROXY), A(p_moved, G_PROXY),
@@ -1371,7 +1371,7 @@ int pr_snapshot_save(const pr_world* cpw, void* buf, uint64_t cap, uint64_t* byt
     sync(w);
     SnapWriter o{static_cast<unsigned char*>(buf), cap};
     auto arrs = arrays(w);
-    SnapHeader h{SNAP_MAGIC, 2u, static_cast<unsigned>(PR_ABI_VERSION), static_cast<unsigned>(pr_sincosf_variant()), static_cast<unsigned>(arrs.size()),
+    SnapHeader h{SNAP_MAGIC, 3u, static_cast<unsigned>(PR_ABI_VERSION), static_cast<unsigned>(pr_sincosf_variant()), static_cast<unsigned>(arrs.size()),
                  static_cast<unsigned>(sizeof(pr_body)), static_cast<unsigned>(sizeof(pr_contact)), static_cast<unsigned>(sizeof(Counters)), 0u};
     o.pod(h);
     SnapScalars sc; snap_scalars(w, sc); o.pod(sc);
@@ -1406,7 +1406,7 @@ int pr_snapshot_load(const void* buf, uint64_t bytes, int device, pr_world** out
     SnapReader in{static_cast<const unsigned char*>(buf), bytes};
     SnapHeader h{}; in.pod(h);
     SnapScalars sc{}; in.pod(sc);
-    if (!in.ok || h.magic != SNAP_MAGIC || h.version != 2u || h.abi != static_cast<unsigned>(PR_ABI_VERSION) || h.szBody != sizeof(pr_body) ||
+    if (!in.ok || h.magic != SNAP_MAGIC || h.version != 3u || h.abi != static_cast<unsigned>(PR_ABI_VERSION) || h.szBody != sizeof(pr_body) ||
         h.szContact != sizeof(pr_contact) || h.szCounters != sizeof(Counters)) { g_createError = "pr_snapshot_load: not a snapshot of this library version"; return PR_ERR_INVALID_ARGUMENT; }
     if (h.variant != static_cast<unsigned>(pr_sincosf_variant())) { g_createError = "pr_snapshot_load: the snapshot was taken by the other sincosf build of the library"; return PR_ERR_INVALID_ARGUMENT; }
     pr_world* pw = nullptr;
@@ -1624,6 +1624,7 @@ static void refresh_joint_tables(World& w)
     }
     w.jointsSerial = false;
     for (const auto& u : uses) if (u.second > 1u) w.jointsSerial = true;
+    for (const auto& j : w.joints) if (j.body_a != INVALID && PR_JOINT_TYPE(j) == PR_JOINT_GEAR) w.jointsSerial = true; // (a gear joint shares its bodies with the joints it gears)
     std::sort(nc.begin(), nc.end());
     nc.erase(std::unique(nc.begin(), nc.end()), nc.end());
     ensure(w, G_JOINT, static_cast<unsigned>(std::max<size_t>(nc.size(), w.joints.size()) + 1));
@@ -2018,11 +2019,80 @@ int pr_create_weld_joints(pr_world* pw, uint32_t n, const pr_weld_joint* joints,
 int pr_create_prismatic_joints(pr_world* pw, uint32_t n, const pr_prismatic_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_PRISMATIC, first_id); }
 int pr_create_wheel_joints(pr_world* pw, uint32_t n, const pr_wheel_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_WHEEL, first_id); }
 int pr_create_pulley_joints(pr_world* pw, uint32_t n, const pr_pulley_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_PULLEY, first_id); }
-int pr_create_target_joints(pr_world* pw, uint32_t n, const pr_target_joint* joints, uint32_t* first_id)
+static GearExt gear_ext_of(const pr_gear_joint& g)
 {
-    for (uint32_t i = 0; i < n; ++i) if (joints[i].body_a != joints[i].body_b) { if (pw) pw->w.error = "target joint: body_a must repeat body_b"; return PR_ERR_INVALID_ARGUMENT; }
-    return create_tagged_joints(pw, n, joints, PR_JOINT_TARGET, first_id);
+    GearExt e{};
+    e.body_c = g.body_c; e.body_d = g.body_d; e.type_ac = g.ac.type; e.type_bd = g.bd.type;
+    const pr_gear_side* sides[2] = {&g.ac, &g.bd};
+    float* dst[2] = {e.ac, e.bd};
+    for (int k = 0; k < 2; ++k) {
+        if (sides[k]->type == PR_GEAR_PRISMATIC) {
+            dst[k][0] = sides[k]->local_anchor_a.x; dst[k][1] = sides[k]->local_anchor_a.y; dst[k][2] = sides[k]->local_anchor_b.x; dst[k][3] = sides[k]->local_anchor_b.y;
+            dst[k][4] = sides[k]->local_axis.x; dst[k][5] = sides[k]->local_axis.y;
+        } else if (sides[k]->type == PR_GEAR_REVOLUTE) dst[k][0] = sides[k]->reference_angle;
+    }
+    return e;
 }
+int pr_create_gear_joints(pr_world* pw, uint32_t n, const pr_gear_joint* joints, uint32_t* first_id)
+{ // CreateJoint of GearJointConf values: a row of the joint table + the GearExt entry of the same id
+    API_TRY(pw)
+    World& w = pw->w;
+    std::vector<pr_revolute_joint> rows(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const pr_gear_joint& g = joints[i];
+        if (g.body_c >= w.nBodies || g.body_d >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+        if (g.ac.type > PR_GEAR_REVOLUTE || g.bd.type > PR_GEAR_REVOLUTE) { w.error = "gear joint: unknown geared joint type"; return PR_ERR_INVALID_ARGUMENT; }
+        if (w.d.nWorlds && g.body_a < w.nBodies && (w.bodyWorld[g.body_c] != w.bodyWorld[g.body_a] || w.bodyWorld[g.body_d] != w.bodyWorld[g.body_a])) {
+            w.error = "joint between bodies of different worlds"; return PR_ERR_INVALID_ARGUMENT;
+        }
+        pr_revolute_joint r{};
+        r.body_a = g.body_a; r.body_b = g.body_b;
+        r.collide_connected = (g.collide_connected & 1u) | (static_cast<uint32_t>(PR_JOINT_GEAR) << 8);
+        r.impulse_x = g.impulse; r.lower_angle = g.ratio; r.upper_angle = g.constant;
+        rows[i] = r;
+    }
+    uint32_t first = 0;
+    const int rc = pr_create_revolute_joints(pw, n, rows.data(), &first);
+    if (rc != PR_OK) return rc;
+    std::vector<GearExt> ext(n);
+    for (uint32_t i = 0; i < n; ++i) ext[i] = gear_ext_of(joints[i]);
+    if (n) { h2d(w, w.d.jt_gear + first, ext.data(), sizeof(GearExt) * n); sync(w); }
+    if (first_id) *first_id = first;
+    return PR_OK;
+    API_CATCH(pw)
+}
+int pr_get_gear_joints(const pr_world* cpw, uint32_t first, uint32_t n, pr_gear_joint* out)
+{
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    if (first + n > w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
+    if (n == 0) return PR_OK;
+    std::vector<pr_revolute_joint> rows(n); std::vector<GearExt> ext(n);
+    d2h(w, rows.data(), w.d.jt + first, sizeof(pr_revolute_joint) * n);
+    d2h(w, ext.data(), w.d.jt_gear + first, sizeof(GearExt) * n);
+    sync(w);
+    for (uint32_t i = 0; i < n; ++i) {
+        pr_gear_joint g{};
+        const pr_revolute_joint& r = rows[i];
+        if (r.body_a == INVALID || PR_JOINT_TYPE(r) != PR_JOINT_GEAR) { g.body_a = g.body_b = g.body_c = g.body_d = INVALID; out[i] = g; continue; }
+        g.body_a = r.body_a; g.body_b = r.body_b; g.collide_connected = r.collide_connected;
+        g.body_c = ext[i].body_c; g.body_d = ext[i].body_d; g.impulse = r.impulse_x; g.ratio = r.lower_angle; g.constant = r.upper_angle;
+        pr_gear_side* sides[2] = {&g.ac, &g.bd};
+        const float* src[2] = {ext[i].ac, ext[i].bd};
+        const unsigned types[2] = {ext[i].type_ac, ext[i].type_bd};
+        for (int k = 0; k < 2; ++k) {
+            sides[k]->type = types[k];
+            if (types[k] == PR_GEAR_PRISMATIC) {
+                sides[k]->local_anchor_a = pr_vec2{src[k][0], src[k][1]}; sides[k]->local_anchor_b = pr_vec2{src[k][2], src[k][3]}; sides[k]->local_axis = pr_vec2{src[k][4], src[k][5]};
+            } else if (types[k] == PR_GEAR_REVOLUTE) sides[k]->reference_angle = src[k][0];
+        }
+        out[i] = g;
+    }
+    return PR_OK;
+    API_CATCH(pw)
+}
+int pr_create_target_joints(pr_world* pw, uint32_t n, const pr_target_joint* joints, uint32_t* first_id) { return create_tagged_joints(pw, n, joints, PR_JOINT_TARGET, first_id); }
 
 int pr_destroy_joints(pr_world* pw, uint32_t n, const uint32_t* ids)
 { // Destroy(AabbTreeWorld&, JointID), :1215-1227: Remove(id) wakes both bodies (:1192-1205), the id goes to the free list

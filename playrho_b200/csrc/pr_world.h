@@ -53,6 +53,10 @@ struct PCRow {
 };
 
 // per-step work data of a revolute joint (RevoluteJointConf's rA, rB, mass, angularMass) + its island label
+// the part of a gear joint's row that does not fit the shared 76-byte layout: the two other bodies and what the reference copies from the two
+// geared joints (GearJointConf.hpp:70-83: PrismaticData / RevoluteData). type: 0 = none (std::monostate), 1 = prismatic, 2 = revolute.
+// prismatic: v[0..1] = localAnchorA (on C / D), v[2..3] = localAnchorB (on A / B), v[4..5] = localAxis; revolute: v[0] = referenceAngle
+struct GearExt { unsigned body_c, body_d, type_ac, type_bd; float ac[6], bd[6]; };
 struct JointWork { float rAx, rAy, rBx, rBy; float m[9]; float angularMass; unsigned island; unsigned pad; float ex[8]; };
 
 // the boxes of an LBVH node's two children, stored with the node
@@ -97,7 +101,7 @@ struct DV {
     float4 *b_xf, *b_pos0, *b_pos1, *b_vel, *b_acc, *b_mass; float2* b_lc; unsigned* b_flags;
     float4 *s_vel, *s_pos;
     unsigned *b_island, *b_root, *b_moved, *b_sync;
-    pr_revolute_joint* jt; JointWork* jt_work; unsigned* isl_jflag; // revolute joints (a15)
+    pr_revolute_joint* jt; JointWork* jt_work; GearExt* jt_gear; unsigned* isl_jflag; // revolute joints (a15)
     unsigned long long* nc_pairs; unsigned nNcPairs;               // body pairs joined by a collideConnected=false joint
     unsigned *isl_state, *isl_velIters, *isl_posIters, *isl_inc, *isl_maxInc, *isl_sep, *isl_minSep, *isl_minUA, *isl_nbodies, *isl_active;
     unsigned long long *b_claim, *b_cmask;

@@ -19,6 +19,8 @@
 #include <playrho/d2/PrismaticJointConf.hpp>
 #include <playrho/d2/WheelJointConf.hpp>
 #include <playrho/d2/PulleyJointConf.hpp>
+#include <playrho/d2/GearJointConf.hpp>
+#include <variant>
 #include <playrho/to_underlying.hpp>
 
 #include <algorithm>
@@ -726,7 +728,8 @@ static pr_revolute_joint ToJointRow(const WeldJointConf& jc)
 static pr_revolute_joint ToJointRow(const TargetJointConf& jc)
 { // the same table row viewed as pr_target_joint: one body, the row's body_a repeats body_b
     pr_target_joint o{};
-    o.body_a = o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.body_a = (jc.bodyA != InvalidBodyID) ? static_cast<std::uint32_t>(to_underlying(jc.bodyA)) : o.body_b;
     o.collide_connected = (jc.collideConnected ? 1u : 0u) | (static_cast<std::uint32_t>(PR_JOINT_TARGET) << 8);
     o.target = pr_vec2{GetX(jc.target), GetY(jc.target)};
     o.local_anchor_b = pr_vec2{GetX(jc.localAnchorB), GetY(jc.localAnchorB)};
@@ -789,6 +792,29 @@ static pr_revolute_joint ToJointRow(const PulleyJointConf& jc)
     std::memcpy(&r, &o, sizeof(r));
     return r;
 }
+static void ToGearSide(const GearJointConf::TypeData& td, pr_gear_side& o)
+{
+    if (std::holds_alternative<GearJointConf::PrismaticData>(td)) {
+        const auto& d = std::get<GearJointConf::PrismaticData>(td);
+        o.type = PR_GEAR_PRISMATIC;
+        o.local_anchor_a = pr_vec2{GetX(d.localAnchorA), GetY(d.localAnchorA)};
+        o.local_anchor_b = pr_vec2{GetX(d.localAnchorB), GetY(d.localAnchorB)};
+        o.local_axis = pr_vec2{d.localAxis.GetX(), d.localAxis.GetY()};
+    } else if (std::holds_alternative<GearJointConf::RevoluteData>(td)) {
+        o.type = PR_GEAR_REVOLUTE;
+        o.reference_angle = std::get<GearJointConf::RevoluteData>(td).referenceAngle;
+    } else o.type = PR_GEAR_NONE;
+}
+static pr_gear_joint ToGearJoint(const GearJointConf& jc)
+{ // a gear joint's value is wider than a row of the joint table: pr_create_gear_joints
+    pr_gear_joint o{};
+    o.body_a = static_cast<std::uint32_t>(to_underlying(jc.bodyA)); o.body_b = static_cast<std::uint32_t>(to_underlying(jc.bodyB));
+    o.body_c = static_cast<std::uint32_t>(to_underlying(jc.bodyC)); o.body_d = static_cast<std::uint32_t>(to_underlying(jc.bodyD));
+    o.collide_connected = (jc.collideConnected ? 1u : 0u) | (static_cast<std::uint32_t>(PR_JOINT_GEAR) << 8);
+    o.impulse = jc.impulse; o.ratio = jc.ratio; o.constant = jc.constant;
+    ToGearSide(jc.typeDataAC, o.ac); ToGearSide(jc.typeDataBD, o.bd);
+    return o;
+}
 // the joint types the device solves (SURVEY a15 + the first of 8(f) rank 1); the others are rejected
 static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, BodyID& b)
 {
@@ -811,7 +837,7 @@ static bool ToAnyJointRow(const Joint& def, pr_revolute_joint& row, BodyID& a, B
     if (GetType(def) == GetTypeID<PulleyJointConf>()) { const auto jc = TypeCast<PulleyJointConf>(def); row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true; }
     if (GetType(def) == GetTypeID<TargetJointConf>()) { // (bodyA is ignored by the target joint's solver)
         const auto jc = TypeCast<TargetJointConf>(def);
-        if (jc.bodyB == InvalidBodyID || jc.bodyA != InvalidBodyID) return false;
+        if (jc.bodyB == InvalidBodyID) return false;
         row = ToJointRow(jc); a = jc.bodyA; b = jc.bodyB; return true;
     }
     return false;
@@ -821,6 +847,24 @@ JointID CreateJoint(CudaWorld& w, Joint def)
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
     if (w.m->joints.size() >= MaxJoints) throw LengthError("CreateJoint: operation would exceed MaxJoints");
     if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
+    if (GetType(def) == GetTypeID<GearJointConf>()) { // four bodies: its own entry point
+        const auto gc = TypeCast<GearJointConf>(def);
+        for (const auto b : {gc.bodyA, gc.bodyB, gc.bodyC, gc.bodyD}) {
+            if (b == InvalidBodyID) throw InvalidArgument(unsupportedMsg); // (the reference's gear solver does nothing then; not built here)
+            (void)AtId(w.m->bodies, b, noSuchBodyMsg);
+        }
+        const auto g = ToGearJoint(gc);
+        w.m->refreshBodies();
+        w.m->uploadDirtyBodies();
+        std::uint32_t first = 0;
+        w.m->check(pr_create_gear_joints(w.m->h, 1, &g, &first), "pr_create_gear_joints");
+        if (first < w.m->joints.size()) {
+            w.m->joints[first] = std::move(def);
+            w.m->freeJoints.erase(std::remove(w.m->freeJoints.begin(), w.m->freeJoints.end(), first), w.m->freeJoints.end());
+        } else w.m->joints.push_back(std::move(def));
+        w.m->bodiesStale = true;
+        return MakeId<JointID>(first);
+    }
     pr_revolute_joint o{}; BodyID bA{}, bB{};
     if (!ToAnyJointRow(def, o, bA, bB)) throw InvalidArgument(unsupportedMsg);
     if (bA != InvalidBodyID) (void)AtId(w.m->bodies, bA, noSuchBodyMsg); // (:1144-1149)
@@ -890,6 +934,11 @@ Joint GetJoint(const CudaWorld& w, JointID id)
         pc.impulse = Momentum{r.impulse_x * NewtonSecond};
         return Joint{pc};
     }
+    if (GetType(elem) == GetTypeID<GearJointConf>()) {
+        auto gc = TypeCast<GearJointConf>(elem);
+        gc.impulse = Momentum{r.impulse_x * NewtonSecond};
+        return Joint{gc};
+    }
     if (GetType(elem) == GetTypeID<RopeJointConf>()) {
         auto rc = TypeCast<RopeJointConf>(elem);
         rc.impulse = Momentum{r.impulse_x * NewtonSecond};
@@ -910,7 +959,15 @@ void SetJoint(CudaWorld& w, JointID id, Joint def)
     if (const auto b = GetBodyB(def); b != InvalidBodyID) (void)AtId(w.m->bodies, b, noSuchBodyMsg);
     if (!def.has_value()) throw WasDestroyed{def, "cannot be empty"};
     pr_revolute_joint o{}; BodyID bA{}, bB{};
-    if (!ToAnyJointRow(def, o, bA, bB)) throw InvalidArgument(unsupportedMsg);
+    if (GetType(def) == GetTypeID<GearJointConf>()) { // the row part (impulse, ratio, constant) can change; the geared bodies and joint data cannot
+        const auto& old = w.m->joints[to_underlying(id)];
+        if (GetType(old) != GetTypeID<GearJointConf>()) throw InvalidArgument(unsupportedMsg);
+        const auto gn = ToGearJoint(TypeCast<GearJointConf>(def)), go = ToGearJoint(TypeCast<GearJointConf>(old));
+        if (gn.body_c != go.body_c || gn.body_d != go.body_d || std::memcmp(&gn.ac, &go.ac, sizeof(gn.ac)) != 0 || std::memcmp(&gn.bd, &go.bd, sizeof(gn.bd)) != 0)
+            throw InvalidArgument(unsupportedMsg);
+        o.body_a = gn.body_a; o.body_b = gn.body_b; o.collide_connected = gn.collide_connected;
+        o.impulse_x = gn.impulse; o.lower_angle = gn.ratio; o.upper_angle = gn.constant;
+    } else if (!ToAnyJointRow(def, o, bA, bB)) throw InvalidArgument(unsupportedMsg);
     w.m->refreshBodies();       // Remove(JointID) wakes both bodies on the device: keep the host values in step
     w.m->uploadDirtyBodies();
     const std::uint32_t jid = static_cast<std::uint32_t>(to_underlying(id));

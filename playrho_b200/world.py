@@ -62,7 +62,7 @@ EXPORTS = [
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
     "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_test_points", "pr_find_closest_bodies", "pr_set_contacts", "pr_set_manifolds", "pr_set_revolute_joints", "pr_attach_shapes", "pr_set_shape_material", "pr_destroy_joints",
     "pr_destroy_bodies", "pr_detach_shapes", "pr_destroy_shapes", "pr_set_shape", "pr_set_body_enabled", "pr_set_body_type",
-    "pr_create_distance_joints", "pr_create_rope_joints", "pr_create_friction_joints", "pr_create_motor_joints", "pr_create_weld_joints", "pr_create_target_joints", "pr_create_prismatic_joints", "pr_create_wheel_joints", "pr_create_pulley_joints", "pr_set_body_velocities", "pr_batch_create_masked", "pr_batch_stats",
+    "pr_create_distance_joints", "pr_create_rope_joints", "pr_create_friction_joints", "pr_create_motor_joints", "pr_create_weld_joints", "pr_create_target_joints", "pr_create_prismatic_joints", "pr_create_wheel_joints", "pr_create_pulley_joints", "pr_create_gear_joints", "pr_get_gear_joints", "pr_set_body_velocities", "pr_batch_create_masked", "pr_batch_stats",
 ]
 
 
@@ -113,6 +113,8 @@ def bind(lib):
     lib.pr_create_prismatic_joints.argtypes = [vp, u32, vp, C.POINTER(u32)]
     lib.pr_create_wheel_joints.argtypes = [vp, u32, vp, C.POINTER(u32)]
     lib.pr_create_pulley_joints.argtypes = [vp, u32, vp, C.POINTER(u32)]
+    lib.pr_create_gear_joints.argtypes = [vp, u32, vp, C.POINTER(u32)]
+    lib.pr_get_gear_joints.argtypes = [vp, u32, u32, vp]
     lib.pr_set_body_velocities.argtypes = [vp, u32, vp, vp]
     lib.pr_batch_create_masked.argtypes = [vp, u32, C.c_uint64, C.POINTER(vp)]
     lib.pr_batch_stats.argtypes = [vp, vp]
@@ -226,7 +228,13 @@ class World:
         self._chk(self.lib.pr_create_bodies(self.h, len(sc["bodies"]), abi.ptr(sc["bodies"]), abi.ptr(sc["shape_offsets"]),
                                             abi.ptr(sc["shape_ids"]), C.byref(first)))
         if "joints" in sc and len(sc["joints"]):
-            self._chk(self.lib.pr_create_revolute_joints(self.h, len(sc["joints"]), abi.ptr(sc["joints"]), C.byref(first)))
+            for a, b, gear in abi.joint_batches(sc["joints"]):
+                if gear:
+                    g = np.ascontiguousarray(sc["gears"][a:b], dtype=abi.GEAR)
+                    self._chk(self.lib.pr_create_gear_joints(self.h, 1, abi.ptr(g), C.byref(first)))
+                else:
+                    rows = np.ascontiguousarray(sc["joints"][a:b])
+                    self._chk(self.lib.pr_create_revolute_joints(self.h, len(rows), abi.ptr(rows), C.byref(first)))
 
     def step(self, conf):
         st = abi.one(abi.STEP_STATS)
@@ -320,6 +328,14 @@ class World:
         """Attach(world, body, shape) for each shape id (pr_attach_shapes); upload the body row (new mass) with set_bodies."""
         ids = np.ascontiguousarray(shape_ids, dtype=np.uint32)
         self._chk(self.lib.pr_attach_shapes(self.h, int(body), len(ids), abi.ptr(ids)))
+
+    def gear_joints(self):
+        """pr_get_gear_joints over the whole joint table (non-gear rows read back with body_a == 0xFFFFFFFF)"""
+        n = int(self.counts()["joints"])
+        out = np.zeros(n, abi.GEAR)
+        if n:
+            self._chk(self.lib.pr_get_gear_joints(self.h, 0, n, abi.ptr(out)))
+        return out
 
     def destroy_joints(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)

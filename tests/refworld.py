@@ -222,10 +222,10 @@ class RefWorld:
         assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
         return jid
 
-    def add_target(self, body_b, target, anchor, frequency=5.0, damping_ratio=0.7, max_force=1000.0):
-        self.lib.ref_add_target.argtypes = [vp, u32, f32, f32, f32, f32, f32, f32, f32]
+    def add_target(self, body_b, target, anchor, frequency=5.0, damping_ratio=0.7, max_force=1000.0, body_a=0xFFFFFFFF):
+        self.lib.ref_add_target.argtypes = [vp, u32, u32, f32, f32, f32, f32, f32, f32, f32]
         self.lib.ref_add_target.restype = u32
-        jid = self.lib.ref_add_target(self.h, int(body_b), target[0], target[1], anchor[0], anchor[1], frequency, damping_ratio, max_force)
+        jid = self.lib.ref_add_target(self.h, int(body_a), int(body_b), target[0], target[1], anchor[0], anchor[1], frequency, damping_ratio, max_force)
         assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
         return jid
 
@@ -260,6 +260,22 @@ class RefWorld:
                                       anchor_a[0], anchor_a[1], anchor_b[0], anchor_b[1], ratio)
         assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
         return jid
+
+    def add_gear(self, joint1, joint2, ratio=1.0):
+        """GetGearJointConf(world, joint1, joint2, ratio): joint1 / joint2 are revolute or prismatic joints"""
+        self.lib.ref_add_gear.argtypes = [vp, u32, u32, f32]
+        self.lib.ref_add_gear.restype = u32
+        jid = self.lib.ref_add_gear(self.h, int(joint1), int(joint2), ratio)
+        assert jid != 0xFFFFFFFF, self.lib.ref_last_error(self.h)
+        return jid
+
+    def gears(self):
+        """the whole values of the gear joints by joint id (zeroed with body_a == 0xFFFFFFFF for other joints)"""
+        out = np.zeros(max(1, int(self.counts()["joints"])), abi.GEAR)
+        self.lib.ref_export_gear_joints.argtypes = [vp, vp, u32]
+        k = self.lib.ref_export_gear_joints(self.h, abi.ptr(out), len(out))
+        assert k >= 0
+        return out[:k]
 
     def add_friction(self, body_a, body_b, anchor, max_force, max_torque):
         self.lib.ref_add_friction.argtypes = [vp, u32, u32, f32, f32, f32, f32]
@@ -385,7 +401,7 @@ class RefWorld:
         k = self.lib.ref_export_body_shapes(self.h, abi.ptr(offs), abi.ptr(ids), cap)
         assert 0 <= k <= cap
         return dict(shapes=shapes, children=children, verts=verts[:n["vertices"]], normals=normals[:n["vertices"]],
-                    bodies=bodies, shape_offsets=offs, shape_ids=ids[:k], joints=self.joints())
+                    bodies=bodies, shape_offsets=offs, shape_ids=ids[:k], joints=self.joints(), gears=self.gears())
 
     def joints(self):
         out = np.zeros(64, abi.REVOLUTE)
@@ -447,7 +463,14 @@ class OracleWorld:
         self.lib.orc_create_bodies(self.h, len(sc["bodies"]), abi.ptr(sc["bodies"]), abi.ptr(sc["shape_offsets"]),
                                    abi.ptr(sc["shape_ids"]))
         if "joints" in sc and len(sc["joints"]):
-            self.lib.orc_create_revolute_joints(self.h, len(sc["joints"]), abi.ptr(sc["joints"]))
+            for a, b, gear in abi.joint_batches(sc["joints"]):
+                if gear:
+                    g = np.ascontiguousarray(sc["gears"][a:b], dtype=abi.GEAR)
+                    self.lib.orc_create_gear_joints.argtypes = [vp, u32, vp]
+                    self.lib.orc_create_gear_joints(self.h, 1, abi.ptr(g))
+                else:
+                    rows = np.ascontiguousarray(sc["joints"][a:b])
+                    self.lib.orc_create_revolute_joints(self.h, len(rows), abi.ptr(rows))
 
     def step(self, conf, order=None):
         st = abi.one(abi.STEP_STATS)

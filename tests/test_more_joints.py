@@ -9,7 +9,9 @@ the real reference, the restatement, the emulated kernels and the GPU -- bit for
   wheel (WheelJointConf.cpp:103-362): a car (chassis + two wheels on sprung wheel joints, one driven by a motor) on a bumpy ground,
         and a rigid (frequency 0) wheel joint.
   pulley (PulleyJointConf.cpp:91-282): two unequal weights over a pulley (ratio 1), a ratio-2 block and tackle, a pulley between a
-        body and a static one; ShiftOrigin in mid-run moves the ground anchors (and a target joint's target)."""
+        body and a static one; ShiftOrigin in mid-run moves the ground anchors (and a target joint's target).
+  gear (GearJointConf.cpp:171-468; four bodies): two wheels on revolute joints geared 2:1 (one driven by a motor), a rack and pinion
+        (revolute + prismatic), two sliders geared against each other (prismatic + prismatic), disks dropped on them."""
 import numpy as np
 import pytest
 import refworld
@@ -58,7 +60,14 @@ def _target_scene():
     ref.add_target(b2, (5.0, 0.35), (5.2, 0.5), frequency=3.0, damping_ratio=0.3, max_force=30.0)   # saturates
     ref.add_weld(b3, b4, (0.4, 4.0))
     ref.add_target(b3, (0.0, 4.0), (-0.3, 4.2), frequency=4.0, damping_ratio=1.0, max_force=500.0)
-    return ref, [6, 6, 5, 6]
+    # a target joint whose conf names a bodyA: it only takes part in the island rules -- a disabled one keeps the joint from being solved
+    # (AabbTreeWorld.cpp:1443-1466; UnitTests/World.cpp:3377-3396), an enabled static one does not
+    spare = ref.add_body(STATIC, pos=(9.0, 9.0), enabled=False)
+    b5 = ref.add_body(DYNAMIC, acc=G, pos=(-8.0, 3.0), shapes=[box])
+    b6 = ref.add_body(DYNAMIC, acc=G, pos=(8.0, 3.0), shapes=[box])
+    ref.add_target(b5, (-8.0, 6.0), (-8.0, 3.0), max_force=500.0, body_a=spare)
+    ref.add_target(b6, (8.0, 6.0), (8.0, 3.0), max_force=500.0, body_a=ground)
+    return ref, [6, 6, 5, 6, 6, 6]
 
 
 def _target_moves(step):
@@ -126,8 +135,36 @@ def _pulley_scene():
     return ref, [9, 9, 9, 6]
 
 
+def _gear_scene():
+    ref = RefWorld()
+    ground = ref.add_body(STATIC, pos=(0.0, 0.0), shapes=[ref.add_box(20.0, 0.5, center=(0.0, -0.5))])
+    big = ref.add_disk(1.0, density=1.0)
+    small = ref.add_disk(0.5, density=1.0)
+    bar = ref.add_box(0.25, 1.0, density=2.0)
+    pebble = ref.add_disk(0.2, density=3.0)
+    w1 = ref.add_body(DYNAMIC, acc=G, pos=(-6.0, 4.0), shapes=[big])
+    w2 = ref.add_body(DYNAMIC, acc=G, pos=(-4.5, 4.0), shapes=[small])
+    r1 = ref.add_revolute(ground, w1, (-6.0, 4.0), enable_motor=True, motor_speed=1.5, max_motor_torque=50.0)
+    r2 = ref.add_revolute(ground, w2, (-4.5, 4.0))
+    ref.add_gear(r1, r2, ratio=0.5)                                       # revolute + revolute: w2 turns twice as fast, the other way
+    w3 = ref.add_body(DYNAMIC, acc=G, pos=(0.0, 4.0), w=2.0, shapes=[big])
+    rack = ref.add_body(DYNAMIC, acc=G, pos=(1.25, 4.0), shapes=[bar])
+    r3 = ref.add_revolute(ground, w3, (0.0, 4.0))
+    p1 = ref.add_prismatic(ground, rack, (1.25, 4.0), (0.0, 1.0), limits=(-2.0, 2.0))
+    ref.add_gear(r3, p1, ratio=-1.0)                                      # rack and pinion: the rack's weight turns the wheel
+    s1 = ref.add_body(DYNAMIC, acc=G, pos=(5.0, 3.0), shapes=[bar])
+    s2 = ref.add_body(DYNAMIC, acc=G, pos=(7.0, 3.0), shapes=[ref.add_box(0.25, 1.0, density=3.0)])
+    p2 = ref.add_prismatic(ground, s1, (5.0, 3.0), (0.0, 1.0), limits=(-1.5, 3.0))
+    p3 = ref.add_prismatic(ground, s2, (7.0, 3.0), (0.6, 0.8), limits=(-1.5, 3.0))
+    ref.add_gear(p2, p3, ratio=1.0)                                       # a counterweight: the heavier slider sinks, lifting the other
+    ref.add_body(DYNAMIC, acc=G, pos=(-6.4, 7.0), shapes=[pebble])
+    ref.add_body(DYNAMIC, acc=G, pos=(0.3, 7.5), shapes=[pebble])
+    ref.add_body(DYNAMIC, acc=G, pos=(5.0, 7.0), shapes=[pebble])
+    return ref, [0, 0, 10, 0, 7, 10, 7, 7, 10]
+
+
 SHIFTS = {"pulley": {60: (1.5, -0.75), 130: (-100.0, 33.3)}}
-SCENES = {"pulley": (_pulley_scene, 200), "weld": (_weld_scene, 200), "target": (_target_scene, 220), "prismatic": (_prismatic_scene, 240), "wheel": (_wheel_scene, 300)}
+SCENES = {"gear": (_gear_scene, 240), "pulley": (_pulley_scene, 200), "weld": (_weld_scene, 200), "target": (_target_scene, 220), "prismatic": (_prismatic_scene, 240), "wheel": (_wheel_scene, 300)}
 MOVES = {"target": _target_moves}
 
 
