@@ -862,7 +862,7 @@ JointID CreateJoint(CudaWorld& w, Joint def)
             w.m->joints[first] = std::move(def);
             w.m->freeJoints.erase(std::remove(w.m->freeJoints.begin(), w.m->freeJoints.end(), first), w.m->freeJoints.end());
         } else w.m->joints.push_back(std::move(def));
-        w.m->bodiesStale = true;
+        w.m->bodiesStale = true; w.m->contactsStale = true;
         return MakeId<JointID>(first);
     }
     pr_revolute_joint o{}; BodyID bA{}, bB{};
@@ -877,7 +877,7 @@ JointID CreateJoint(CudaWorld& w, Joint def)
         w.m->joints[first] = std::move(def);
         w.m->freeJoints.erase(std::remove(w.m->freeJoints.begin(), w.m->freeJoints.end(), first), w.m->freeJoints.end());
     } else w.m->joints.push_back(std::move(def));
-    w.m->bodiesStale = true;
+    w.m->bodiesStale = true; w.m->contactsStale = true; // (Add(JointID, flagForFiltering) flags the pair's contacts, :1170-1174)
     return MakeId<JointID>(first);
 }
 Joint GetJoint(const CudaWorld& w, JointID id)
@@ -973,7 +973,7 @@ void SetJoint(CudaWorld& w, JointID id, Joint def)
     const std::uint32_t jid = static_cast<std::uint32_t>(to_underlying(id));
     w.m->check(pr_set_revolute_joints(w.m->h, 1u, &jid, &o), "pr_set_revolute_joints");
     w.m->joints[to_underlying(id)] = std::move(def);
-    w.m->bodiesStale = true;
+    w.m->bodiesStale = true; w.m->contactsStale = true;
 }
 void Destroy(CudaWorld& w, JointID id)
 { // Destroy(AabbTreeWorld&, JointID), :1215-1227
@@ -986,7 +986,7 @@ void Destroy(CudaWorld& w, JointID id)
     w.m->check(pr_destroy_joints(w.m->h, 1u, &jid), "pr_destroy_joints");
     elem = Joint{};
     w.m->freeJoints.push_back(jid);
-    w.m->bodiesStale = true;
+    w.m->bodiesStale = true; w.m->contactsStale = true; // (Remove(JointID) flags the pair's contacts, :1184-1190)
 }
 
 // ---- shapes
