@@ -1420,6 +1420,18 @@ PR_KERNEL k_joints(DV d, pr_step_conf conf, unsigned nJoints, unsigned phase, un
         else joint_solve_position(d, ji, conf, v);
     }
 }
+// one level of joints that share no movable body (pr_world.cu: refresh_joint_tables): one thread per joint of d.jt_order[start, start + count)
+PR_KERNEL k_joints_level(DV d, pr_step_conf conf, unsigned start, unsigned count, unsigned phase)
+{
+    PR_PDL_ENTER();
+    const unsigned t = PR_TID;
+    if (t >= count) return;
+    const unsigned ji = d.jt_order[start + t];
+    const JView v = jview_global(d);
+    if (phase == 0u) joint_init_velocity(d, ji, conf, v);
+    else if (phase == 1u) joint_solve_velocity(d, ji, conf, v);
+    else joint_solve_position(d, ji, conf, v);
+}
 // islands: a joint links its two bodies (AddToIsland :1443-1466) when both can be island members
 PR_KERNEL k_isl_union_joints(DV d, unsigned nJoints)
 {

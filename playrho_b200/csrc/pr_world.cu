@@ -94,7 +94,7 @@ static std::vector<ArrDesc> arrays(World& w)
         A(c_pos, G_CONTACT), A(c_color, G_CONTACT), A(c_toiIsl, G_CONTACT), A(toi_events, G_CONTACT), A(toi_list, G_CONTACT), A(toi_cand, G_CONTACT), A(toi_cand2, G_CONTACT), A(toi_re0, G_CONTACT),
         A(toi_re1, G_CONTACT), A(c_rstamp, G_CONTACT),
         A(adj_list, G_ADJ), A(toi_islBodies, G_ADJ), A(toi_islContacts, G_ADJ),
-        A(jt, G_JOINT), A(jt_work, G_JOINT), A(jt_gear, G_JOINT), A(nc_pairs, G_JOINT), A(isl_jflag, G_BODY),
+        A(jt, G_JOINT), A(jt_work, G_JOINT), A(jt_gear, G_JOINT), A(jt_order, G_JOINT), A(nc_pairs, G_JOINT), A(isl_jflag, G_BODY),
         A(sh_mat, G_SHAPE), A(sh_filter, G_SHAPE), A(sh_group, G_SHAPE),
         A(ch_radius, G_CHILD), A(ch_voff, G_CHILD), A(ch_count, G_CHILD), A(ch_pack, G_CHILD), A(vtx, G_VERT), A(nrm, G_VERT),
         A(p_body, G_PROXY), A(p_shape, G_PROXY), A(p_child, G_PROXY), A(p_cg, G_PROXY), A(p_tree, G_PROXY), A(p_moved, G_PROXY),
@@ -673,6 +673,15 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     }
     if (blockMode && !nCons) dset(w, d.blk_rowOff, 0, sizeof(unsigned) * (d.nWorlds + 1u)); // (no world has a row)
     const unsigned jSerial = w.jointsSerial ? 1u : 0u, jThreads = w.jointsSerial ? (w.nJoints ? 1u : 0u) : w.nJoints;
+    // joints: one thread per joint when no two share a movable body, else level by level (refresh_joint_tables), else one thread for all
+    auto launch_joints = [&](unsigned phase) {
+        if (w.jointLevelOff.size() > 2u) {
+            for (size_t l = 0; l + 1u < w.jointLevelOff.size(); ++l) {
+                const unsigned off = w.jointLevelOff[l], cnt = w.jointLevelOff[l + 1u] - off;
+                if (cnt) PR_LAUNCH(k_joints_level, cnt, w.stream, d, conf, off, cnt, phase);
+            }
+        } else PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, phase, jSerial);
+    };
     bool fused = false;
 #ifndef PR_HOST_EMUL
     // The whole solve as ONE persistent cooperative kernel (pr_solve_fused.cuh): opt-in (debug bit 2). Measured on B200 it
@@ -727,10 +736,10 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             if (nFlow) { PR_LAUNCH(k_flow_pass<0u>, nFlow, w.stream, d, nFlow, ticket, pass, 0.0f, 0.0f, 0.0f); ++ticket; ++pass; } // (no ++ inside the macro's arguments)
             if (tailCount) PR_LAUNCH(k_warm_start_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
         }
-        PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 0u, jSerial); // InitVelocity after the contacts' warm start (:1597)
+        launch_joints(0u); // InitVelocity after the contacts' warm start (:1597)
         tm.mark(w, PR_STAGE_VELOCITY);
         for (unsigned it = 0; it < conf.reg_velocity_iters; ++it) {
-            PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 1u, jSerial); // joints first (:1605-1608)
+            launch_joints(1u); // joints first (:1605-1608)
             if (nFlow) { PR_LAUNCH(k_flow_pass<1u>, nFlow, w.stream, d, nFlow, ticket, pass, 0.0f, 0.0f, 0.0f); ++ticket; ++pass; }
             if (tailCount) PR_LAUNCH(k_solve_velocity_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
             if (it == 0u) PR_LAUNCH(k_isl_vel_check, N, w.stream, d, N, it, conf.reg_min_momentum);
@@ -743,7 +752,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             if (nFlow) { PR_LAUNCH(k_flow_pass<2u>, nFlow, w.stream, d, nFlow, ticket, pass, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction); ++ticket; ++pass; }
             if (tailCount)
                 PR_LAUNCH(k_solve_position_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
-            PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 2u, jSerial); // joints after the contacts (:1634-1637)
+            launch_joints(2u); // joints after the contacts (:1634-1637)
             if (it == 0u) PR_LAUNCH(k_isl_pos_check, N, w.stream, d, N, it, conf.reg_min_separation);
             else PR_LAUNCH(k_isl_pos_check_list, std::min(N, 64u * 256u), w.stream, d, it, conf.reg_min_separation);
         }
@@ -764,10 +773,10 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             PR_SMALL_COLORS(0u);
             if (tailCount) PR_LAUNCH(k_warm_start_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
         }
-        PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 0u, jSerial); // InitVelocity after the contacts' warm start (:1597)
+        launch_joints(0u); // InitVelocity after the contacts' warm start (:1597)
         tm.mark(w, PR_STAGE_VELOCITY);
         for (unsigned it = 0; it < conf.reg_velocity_iters; ++it) {
-            PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 1u, jSerial); // joints first (:1605-1608)
+            launch_joints(1u); // joints first (:1605-1608)
             for (size_t c = 0; c < nBig; ++c) PR_LAUNCH_PDL(k_solve_velocity, ranges[c].second, w.stream, d, ranges[c].first, ranges[c].second);
             PR_SMALL_COLORS(1u);
             if (tailCount) PR_LAUNCH(k_solve_velocity_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs);
@@ -782,7 +791,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             PR_SMALL_COLORS(2u);
             if (tailCount)
                 PR_LAUNCH(k_solve_position_tail, nTailSegs, w.stream, d, tailStart, tailCount, nTailSegs, conf.reg_resolution_rate, conf.linear_slop, conf.max_linear_correction);
-            PR_LAUNCH(k_joints, jThreads, w.stream, d, conf, w.nJoints, 2u, jSerial); // joints after the contacts (:1634-1637)
+            launch_joints(2u); // joints after the contacts (:1634-1637)
             if (it == 0u) PR_LAUNCH(k_isl_pos_check, N, w.stream, d, N, it, conf.reg_min_separation);
             else PR_LAUNCH(k_isl_pos_check_list, std::min(N, 64u * 256u), w.stream, d, it, conf.reg_min_separation);
         }
@@ -1281,7 +1290,7 @@ int pr_clone(const pr_world* src, pr_world** out)
     w.shapes = s.shapes; w.children = s.children; w.bodyShapes = s.bodyShapes; w.joints = s.joints; w.freeJoints = s.freeJoints;
     w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies; w.pools = s.pools; w.needsFiltering = s.needsFiltering;
     w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll; w.toiPossible = s.toiPossible; w.colorCap = s.colorCap;
-    w.nJoints = s.nJoints; w.jointsSerial = s.jointsSerial; w.d.nNcPairs = s.d.nNcPairs;
+    w.nJoints = s.nJoints; w.jointsSerial = s.jointsSerial; w.jointLevelOff = s.jointLevelOff; w.d.nNcPairs = s.d.nNcPairs;
     w.d.nWorlds = s.d.nWorlds; w.d.worldBits = s.d.worldBits; w.bodyWorld = s.bodyWorld; w.blocksDirty = w.blkJointsDirty = true;
     w.nBodies = s.nBodies; w.nShapes = s.nShapes; w.nChildren = s.nChildren; w.nVerts = s.nVerts; w.nProxies = s.nProxies;
     w.maxTreeId = s.maxTreeId; w.debugFlags = s.debugFlags;
@@ -1432,6 +1441,7 @@ int pr_snapshot_load(const void* buf, uint64_t bytes, int device, pr_world** out
         w.isHint = sc.isHint;
         w.anyBodySet = sc.anyBodySet != 0; w.stepComplete = sc.stepComplete != 0; w.recolorAll = sc.recolorAll != 0; w.subStepping = sc.subStepping != 0;
         w.jointsSerial = sc.jointsSerial != 0; w.toiPossible = sc.toiPossible != 0; w.inv_dt0 = sc.inv_dt0;
+        w.jointLevelOff.clear(); w.jointTablesDirty = true; // (the level lists are rebuilt by the next Step)
         ensure(w, G_BODY, w.nBodies + 2u); ensure(w, G_SHAPE, w.nShapes + 1u); ensure(w, G_CHILD, w.nChildren + 1u); ensure(w, G_VERT, w.nVerts + 1u);
         ensure(w, G_PROXY, w.nProxies + 2u); ensure(w, G_CONTACT, std::max(w.poolSize, w.nOrder) + 2u); ensure(w, G_JOINT, static_cast<unsigned>(w.joints.size()) + 2u);
         auto arrs = arrays(w);
@@ -1463,7 +1473,7 @@ int pr_clear(pr_world* pw)
     w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     w.shapes.clear(); w.children.clear(); w.bodyShapes.clear(); w.joints.clear(); w.fixturesForProxies.clear();
     w.bodyProxies.clear(); w.bpDirty = true; w.bvhValid = false; w.hashTombs = 0; w.toiAlphaDirty = true;
-    w.nJoints = 0; w.jointsSerial = false; w.d.nNcPairs = 0; w.bodyWorld.clear(); w.freeJoints.clear();
+    w.nJoints = 0; w.jointsSerial = false; w.jointLevelOff.clear(); w.d.nNcPairs = 0; w.bodyWorld.clear(); w.freeJoints.clear();
     w.pools = World::Pools{}; w.needsFiltering = false;
     w.nBodies = w.nShapes = w.nChildren = w.nVerts = w.nProxies = w.nOrder = w.nFree = w.poolSize = 0; w.maxTreeId = 0;
     w.anyBodySet = false; w.hashDirty = true; w.adjValid = false; w.stepComplete = true; w.toiPossible = false;
@@ -1610,21 +1620,52 @@ int pr_set_shape_material(pr_world* pw, uint32_t shape, float friction, float re
     API_CATCH(pw)
 }
 
-// joints that share a body cannot be solved by concurrent threads (one thread in id order then); body pairs joined by a
-// collideConnected == false joint, sorted, for the broadphase's ShouldCollide. Destroyed joints (bodies == INVALID) are skipped.
+// Joints that share a MOVABLE body cannot be solved by concurrent threads, and the device's joint order is id order. Level of a joint
+// = 1 + the highest level among the earlier joints it shares a movable body with: joints of one level touch disjoint movable bodies
+// (a body that cannot move is only ever written back unchanged), and launching the levels in turn keeps every conflicting pair in id
+// order -- the same bits as one thread walking all joints in id order, which is what runs when the chains are longer than
+// JOINT_MAX_LEVELS. Also: the body pairs joined by a collideConnected == false joint, sorted, for the broadphase's ShouldCollide.
+// Destroyed joints (bodies == INVALID) are skipped.
+constexpr unsigned JOINT_MAX_LEVELS = 48u;
 static void refresh_joint_tables(World& w)
 {
     w.blkJointsDirty = true; // (block solver: the joints of every world are listed again before the next solve)
-    std::unordered_map<unsigned, unsigned> uses;
     std::vector<unsigned long long> nc;
-    for (const auto& j : w.joints) {
+    const unsigned nJ = static_cast<unsigned>(w.joints.size());
+    std::vector<unsigned> flags; std::vector<GearExt> gext;
+    bool anyGear = false;
+    for (const auto& j : w.joints) if (j.body_a != INVALID && PR_JOINT_TYPE(j) == PR_JOINT_GEAR) anyGear = true;
+    if (nJ) { flags.resize(w.nBodies); d2h(w, flags.data(), w.d.b_flags, sizeof(unsigned) * w.nBodies); }
+    if (anyGear) { gext.resize(nJ); d2h(w, gext.data(), w.d.jt_gear, sizeof(GearExt) * nJ); }
+    std::unordered_map<unsigned, unsigned> last; // movable body -> level of the last joint on it
+    std::vector<unsigned> level(nJ, 0u);
+    unsigned nLevels = 0u;
+    for (unsigned i = 0; i < nJ; ++i) {
+        const auto& j = w.joints[i];
         if (j.body_a == INVALID) continue;
-        ++uses[j.body_a]; if (j.body_b != j.body_a) ++uses[j.body_b]; // (a target joint's row has body_a == body_b)
+        unsigned bodies[4] = {j.body_a, j.body_b, INVALID, INVALID};
+        if (PR_JOINT_TYPE(j) == PR_JOINT_GEAR) { bodies[2] = gext[i].body_c; bodies[3] = gext[i].body_d; }
+        unsigned lvl = 0u;
+        for (unsigned b : bodies) if (b != INVALID && b < w.nBodies && (flags[b] & PR_BODY_VELOCITY)) { const auto it = last.find(b); if (it != last.end()) lvl = std::max(lvl, it->second); }
+        ++lvl;
+        for (unsigned b : bodies) if (b != INVALID && b < w.nBodies && (flags[b] & PR_BODY_VELOCITY)) last[b] = lvl;
+        level[i] = lvl; nLevels = std::max(nLevels, lvl);
         if (!(j.collide_connected & 1u) && j.body_a != j.body_b) nc.push_back((static_cast<unsigned long long>(std::min(j.body_a, j.body_b)) << 32) | std::max(j.body_a, j.body_b));
     }
-    w.jointsSerial = false;
-    for (const auto& u : uses) if (u.second > 1u) w.jointsSerial = true;
-    for (const auto& j : w.joints) if (j.body_a != INVALID && PR_JOINT_TYPE(j) == PR_JOINT_GEAR) w.jointsSerial = true; // (a gear joint shares its bodies with the joints it gears)
+    w.jointsSerial = nLevels > 1u;
+    w.jointLevelOff.clear();
+    if (nLevels > 1u && nLevels <= JOINT_MAX_LEVELS) { // the joint ids sorted by (level, id) + where each level starts
+        std::vector<unsigned> order; order.reserve(nJ);
+        w.jointLevelOff.assign(nLevels + 1u, 0u);
+        for (unsigned i = 0; i < nJ; ++i) if (level[i]) ++w.jointLevelOff[level[i]];
+        for (unsigned l = 1; l <= nLevels; ++l) w.jointLevelOff[l] += w.jointLevelOff[l - 1u];
+        order.resize(w.jointLevelOff[nLevels]);
+        std::vector<unsigned> fill(w.jointLevelOff.begin(), w.jointLevelOff.end() - 1);
+        for (unsigned i = 0; i < nJ; ++i) if (level[i]) order[fill[level[i] - 1u]++] = i;
+        ensure(w, G_JOINT, nJ + 1u);
+        h2d(w, w.d.jt_order, order.data(), sizeof(unsigned) * order.size());
+        sync(w);
+    }
     std::sort(nc.begin(), nc.end());
     nc.erase(std::unique(nc.begin(), nc.end()), nc.end());
     ensure(w, G_JOINT, static_cast<unsigned>(std::max<size_t>(nc.size(), w.joints.size()) + 1));
@@ -1845,6 +1886,7 @@ int pr_set_body_type(pr_world* pw, uint32_t body, const pr_body* row)
     if (rc != PR_OK) return rc;
     if (!(row->flags & (PR_BODY_VELOCITY | PR_BODY_ACCELERATION))) { const unsigned one = 1u; h2d(w, w.d.b_sync + body, &one, 4); sync(w); }
     w.recolorAll = true; w.adjValid = false;
+    if (w.nJoints) w.jointTablesDirty = true; // (the joint levels depend on which bodies can move)
     return PR_OK;
     API_CATCH(pw)
 }

@@ -101,7 +101,7 @@ struct DV {
     float4 *b_xf, *b_pos0, *b_pos1, *b_vel, *b_acc, *b_mass; float2* b_lc; unsigned* b_flags;
     float4 *s_vel, *s_pos;
     unsigned *b_island, *b_root, *b_moved, *b_sync;
-    pr_revolute_joint* jt; JointWork* jt_work; GearExt* jt_gear; unsigned* isl_jflag; // revolute joints (a15)
+    pr_revolute_joint* jt; JointWork* jt_work; GearExt* jt_gear; unsigned* jt_order; unsigned* isl_jflag; // revolute joints (a15)
     unsigned long long* nc_pairs; unsigned nNcPairs;               // body pairs joined by a collideConnected=false joint
     unsigned *isl_state, *isl_velIters, *isl_posIters, *isl_inc, *isl_maxInc, *isl_sep, *isl_minSep, *isl_minUA, *isl_nbodies, *isl_active;
     unsigned long long *b_claim, *b_cmask;
@@ -201,6 +201,7 @@ struct World {
     // capacities
     unsigned capBodies = 0, capShapes = 0, capChildren = 0, capVerts = 0, capProxies = 0, capContacts = 0,
              capPairs = 0, capCons = 0, capHash = 0, capAdj = 0, capJoints = 0;
+    std::vector<unsigned> jointLevelOff; // joints that share a movable body are solved level by level (refresh_joint_tables): offsets into d.jt_order
     unsigned nJoints = 0; bool jointsSerial = false, jointTablesDirty = true; // (tables: jointsSerial, the collideConnected == false pair list)
     std::vector<unsigned> bodyWorld; // batch arena only: world index of each body
     DV d{};

@@ -406,6 +406,9 @@ class RefWorld:
     def joints(self):
         out = np.zeros(64, abi.REVOLUTE)
         k = self.lib.ref_export_revolute_joints(self.h, abi.ptr(out), len(out))
+        if k > len(out):  # (the call returns the joint range: a bigger table is read again)
+            out = np.zeros(k, abi.REVOLUTE)
+            k = self.lib.ref_export_revolute_joints(self.h, abi.ptr(out), len(out))
         return out[:max(0, k)].copy()
 
     def bodies(self):

@@ -163,8 +163,24 @@ def _gear_scene():
     return ref, [0, 0, 10, 0, 7, 10, 7, 7, 10]
 
 
+def _chains_scene():
+    ref = RefWorld()
+    ground = ref.add_body(STATIC, pos=(0.0, 10.0))
+    link = ref.add_box(0.3, 0.05, density=5.0)
+    types = []
+    for c in range(40):
+        prev = ground
+        x0 = -20.0 + 1.0 * c
+        for k in range(3):
+            b = ref.add_body(DYNAMIC, acc=G, pos=(x0 + 0.3 + 0.6 * k, 10.0 - 0.01 * c), w=0.1 * (c % 5), shapes=[link])
+            ref.add_revolute(prev, b, (x0 + 0.6 * k, 10.0 - 0.01 * c))
+            types.append(0)
+            prev = b
+    return ref, types
+
+
 SHIFTS = {"pulley": {60: (1.5, -0.75), 130: (-100.0, 33.3)}}
-SCENES = {"gear": (_gear_scene, 240), "pulley": (_pulley_scene, 200), "weld": (_weld_scene, 200), "target": (_target_scene, 220), "prismatic": (_prismatic_scene, 240), "wheel": (_wheel_scene, 300)}
+SCENES = {"chains": (_chains_scene, 120), "gear": (_gear_scene, 240), "pulley": (_pulley_scene, 200), "weld": (_weld_scene, 200), "target": (_target_scene, 220), "prismatic": (_prismatic_scene, 240), "wheel": (_wheel_scene, 300)}
 MOVES = {"target": _target_moves}
 
 
