@@ -675,7 +675,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     const unsigned jSerial = w.jointsSerial ? 1u : 0u, jThreads = w.jointsSerial ? (w.nJoints ? 1u : 0u) : w.nJoints;
     // joints: one thread per joint when no two share a movable body, else level by level (refresh_joint_tables), else one thread for all
     auto launch_joints = [&](unsigned phase) {
-        if (w.jointLevelOff.size() > 2u) {
+        if (w.jointLevelOff.size() > 2u && !(w.debugFlags & 2048u)) { // (debug bit 11: one thread for all joints, the A/B of tools/bench_joints.py)
             for (size_t l = 0; l + 1u < w.jointLevelOff.size(); ++l) {
                 const unsigned off = w.jointLevelOff[l], cnt = w.jointLevelOff[l + 1u] - off;
                 if (cnt) PR_LAUNCH(k_joints_level, cnt, w.stream, d, conf, off, cnt, phase);
