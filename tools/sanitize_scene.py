@@ -38,4 +38,19 @@ b.create_shapes(plain); b.create_bodies(plain["bodies"], world, plain["shape_off
 tconf = scenes_np.tumbler_step_conf(W.default_step_conf())
 for _ in range(steps):
     b.step(tconf)
+# 4. every joint type (the scenes of tests/test_more_joints.py, built through the reference harness): level-by-level joint launches,
+#    the gear joints' extension table, ShiftOrigin over joints
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+try:
+    import test_more_joints as tmj  # noqa: E402
+    for name in sorted(tmj.SCENES):
+        ref, _ = tmj.SCENES[name][0]()
+        jw = W.World(ref.export_scene(), device=0)
+        for s in range(steps):
+            if s == steps // 2:
+                jw.shift_origin(1.5, -0.75)
+            jw.step(conf)
+        jw.gear_joints()
+except Exception as e:  # (the reference harness is not built: the joint scenes are skipped)
+    print("joint scenes skipped:", e)
 print("sanitize scene done: %d + %d + %d bodies, %d steps each" % (len(gw.bodies()), len(gw2.bodies()), len(b.bodies()), steps))
