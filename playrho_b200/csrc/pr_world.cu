@@ -33,7 +33,8 @@ struct CudaError { std::string msg; };
         const cudaError_t e_ = (call);                                                             \
         if (e_ != cudaSuccess) throw CudaError{std::string(#call) + ": " + cudaGetErrorString(e_)}; \
     } while (0)
-static void* dev_alloc(size_t bytes) { void* p = nullptr; CK(cudaMalloc(&p, bytes ? bytes : 16)); return p; }
+// (zeroed, like the emulation build's calloc: growing a group copies its whole old capacity, and no kernel ever reads never-written memory)
+static void* dev_alloc(size_t bytes) { void* p = nullptr; CK(cudaMalloc(&p, bytes ? bytes : 16)); CK(cudaMemset(p, 0, bytes ? bytes : 16)); return p; }
 static void dev_free(void* p) { if (p) cudaFree(p); }
 static void h2d(World& w, void* dst, const void* src, size_t n) { if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, w.stream)); }
 static void d2h(World& w, void* dst, const void* src, size_t n) { if (n) { CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, w.stream)); CK(cudaStreamSynchronize(w.stream)); } }
@@ -2108,7 +2109,7 @@ int pr_get_gear_joints(const pr_world* cpw, uint32_t first, uint32_t n, pr_gear_
     pr_world* pw = const_cast<pr_world*>(cpw);
     API_TRY(pw)
     World& w = pw->w;
-    if (first + n > w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
+    if (first > w.nJoints || n > w.nJoints - first) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
     if (n == 0) return PR_OK;
     std::vector<pr_revolute_joint> rows(n); std::vector<GearExt> ext(n);
     d2h(w, rows.data(), w.d.jt + first, sizeof(pr_revolute_joint) * n);

@@ -50,7 +50,7 @@ def main():
         res[t] = (st, detail)
         per_suite[t.split(".")[0]][st.split("(")[0]] += 1
     tot = collections.Counter(v[0].split("(")[0] for v in res.values())
-    print("# the reference's unmodified UnitTests/{World,WorldBody,WorldContact,WorldShape,WorldJoint,RevoluteJoint}.cpp on World{CudaWorld} (seam link), one process per test")
+    print("# the reference's unmodified UnitTests/{World,WorldBody,WorldContact,WorldShape,WorldJoint,<eleven joint types>,Joint,Dump,WorldManifold}.cpp on World{CudaWorld} (seam link), one process per test")
     print("# total %d: %s" % (len(res), ", ".join("%s %d" % kv for kv in sorted(tot.items()))))
     for s, c in per_suite.items():
         print("%-16s %s" % (s, ", ".join("%s %d" % kv for kv in sorted(c.items()))))
