@@ -257,6 +257,19 @@ typedef struct pr_gear_joint {
     float ratio, constant;
     pr_gear_side ac, bd;
 } pr_gear_joint;
+/* What InitVelocity computes for a joint and the reference keeps in the JointConf value ("solver temporaries": rA, rB, effective masses,
+ * axes...; GetJoint returns them, e.g. GetAngularMass(world, joint)). One entry per joint id; which word means what for which type is
+ * listed at each type's solver in playrho_b200/csrc/pr_joint.cuh ("work:" comments), e.g. revolute: m = the 3x3 mass matrix
+ * (m[3 * i + k] = mass[i][k]), angular_mass; wheel: m[0..1] = ay, m[2] = sAy, m[3] = sBy, m[4] = mass, m[5..6] = ax, m[7] = sAx,
+ * m[8] = sBx, ex[0] = springMass, ex[1] = bias, ex[2] = gamma, angular_mass. Valid after a Step that solved the joint's island. */
+typedef struct pr_joint_work {
+    float r_a[2], r_b[2];
+    float m[9];
+    float angular_mass;
+    uint32_t island;                     /* the island the joint was solved with in the last Step, 0xFFFFFFFF: not solved */
+    uint32_t reserved;
+    float ex[8];
+} pr_joint_work;
 
 /* ContactFeature packed little-endian: typeA | indexA<<8 | typeB<<16 | indexB<<24 */
 typedef uint32_t pr_contact_feature;
@@ -403,6 +416,7 @@ int pr_create_pulley_joints(pr_world* w, uint32_t n, const pr_pulley_joint* join
 int pr_create_gear_joints(pr_world* w, uint32_t n, const pr_gear_joint* joints, uint32_t* first_id);
 /* the gear joints among joints [first, first + n): out[i] is filled for a gear joint, zeroed with body_a == 0xFFFFFFFF for any other row */
 int pr_get_gear_joints(const pr_world* w, uint32_t first, uint32_t n, pr_gear_joint* out);
+int pr_get_joint_work(const pr_world* w, uint32_t first, uint32_t n, pr_joint_work* out);
 
 /* SetShape(AabbTreeWorld&, ShapeID, Shape) (AabbTreeWorld.cpp:1284-1356) for a value whose geometry (children) and filter are
  * what they were: friction, restitution, density and the sensor flag are replaced; every body using the shape is woken

@@ -37,11 +37,12 @@ struct CudaError { std::string msg; };
 static void* dev_alloc(size_t bytes) { void* p = nullptr; CK(cudaMalloc(&p, bytes ? bytes : 16)); CK(cudaMemset(p, 0, bytes ? bytes : 16)); return p; }
 static void dev_free(void* p) { if (p) cudaFree(p); }
 static void h2d(World& w, void* dst, const void* src, size_t n) { if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, w.stream)); }
-static void d2h(World& w, void* dst, const void* src, size_t n) { if (n) { CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, w.stream)); CK(cudaStreamSynchronize(w.stream)); } }
+static unsigned g_hostSyncs = 0; // (diagnostics, PR_SYNC_DEBUG: stream synchronisations since the last report)
+static void d2h(World& w, void* dst, const void* src, size_t n) { if (n) { CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, w.stream)); CK(cudaStreamSynchronize(w.stream)); ++g_hostSyncs; } }
 static void d2d(World& w, void* dst, const void* src, size_t n) { if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, w.stream)); }
 #define CK_COPY_D2H_ASYNC(w, dst, src, n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, (w).stream))
 static void dset(World& w, void* dst, int v, size_t n) { if (n) CK(cudaMemsetAsync(dst, v, n, w.stream)); }
-static void sync(World& w) { CK(cudaStreamSynchronize(w.stream)); }
+static void sync(World& w) { CK(cudaStreamSynchronize(w.stream)); ++g_hostSyncs; }
 static void check_launch() { CK(cudaGetLastError()); }
 struct StageTimer {
     static constexpr int MAXEV = 1024;
@@ -182,6 +183,7 @@ static void read_counters(World& w)
     if (w.cntSerialValid && w.cntSerial == g_launchSerial.load(std::memory_order_relaxed)) return;
     CK(cudaMemcpyAsync(&w.pinnedCnt[0], w.d.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, w.stream));
     CK(cudaStreamSynchronize(w.stream));
+    ++g_hostSyncs;
     w.hostCnt = w.pinnedCnt[0];
     w.pinnedNext = 1; // everything queued before this point has executed: all write slots are free again
     w.cntSerial = g_launchSerial.load(std::memory_order_relaxed); w.cntSerialValid = true;
@@ -1998,6 +2000,7 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
         w.freeJoints.pop_back();
         w.joints[id] = joints[0];
         h2d(w, w.d.jt + id, joints, sizeof(pr_revolute_joint));
+        { JointWork fresh{}; fresh.island = INVALID; h2d(w, w.d.jt_work + id, &fresh, sizeof(fresh)); sync(w); } // (not solved yet: pr_get_joint_work)
         w.jointTablesDirty = true;
         if (!(joints[0].collide_connected & 1u)) flag_joint_pairs_for_filtering(w, {joints[0].body_a, joints[0].body_b});
         sync(w);
@@ -2007,6 +2010,7 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
     w.joints.insert(w.joints.end(), joints, joints + n);
     ensure(w, G_JOINT, w.nJoints + n + 1);
     h2d(w, w.d.jt + w.nJoints, joints, sizeof(pr_revolute_joint) * n);
+    { JointWork one{}; one.island = INVALID; std::vector<JointWork> fresh(n, one); h2d(w, w.d.jt_work + w.nJoints, fresh.data(), sizeof(JointWork) * n); sync(w); } // (not solved yet: pr_get_joint_work)
     w.jointTablesDirty = true;
     { std::vector<unsigned> pairs; for (uint32_t i = 0; i < n; ++i) if (!(joints[i].collide_connected & 1u)) { pairs.push_back(joints[i].body_a); pairs.push_back(joints[i].body_b); }
       flag_joint_pairs_for_filtering(w, pairs); }
@@ -2132,6 +2136,17 @@ int pr_get_gear_joints(const pr_world* cpw, uint32_t first, uint32_t n, pr_gear_
         }
         out[i] = g;
     }
+    return PR_OK;
+    API_CATCH(pw)
+}
+int pr_get_joint_work(const pr_world* cpw, uint32_t first, uint32_t n, pr_joint_work* out)
+{
+    static_assert(sizeof(pr_joint_work) == sizeof(JointWork), "pr_joint_work mirrors JointWork");
+    pr_world* pw = const_cast<pr_world*>(cpw);
+    API_TRY(pw)
+    World& w = pw->w;
+    if (first > w.nJoints || n > w.nJoints - first) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
+    if (n) d2h(w, out, w.d.jt_work + first, sizeof(JointWork) * n);
     return PR_OK;
     API_CATCH(pw)
 }
@@ -2600,6 +2615,9 @@ int pr_step(pr_world* pw, const pr_step_conf* conf, pr_step_stats* stats_out)
     pr_step_stats st;
     if (pw->w.jointTablesDirty) { refresh_joint_tables(pw->w); pw->w.jointTablesDirty = false; } // (built when a Step needs them, not per CreateJoint / Destroy)
     step_impl(pw->w, *conf, st);
+#ifndef PR_HOST_EMUL
+    if (getenv("PR_SYNC_DEBUG")) { std::fprintf(stderr, "step: %u host syncs\n", g_hostSyncs); g_hostSyncs = 0; }
+#endif
     if (stats_out) *stats_out = st;
     return PR_OK;
     API_CATCH(pw)

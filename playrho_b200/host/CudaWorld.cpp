@@ -880,37 +880,57 @@ JointID CreateJoint(CudaWorld& w, Joint def)
     w.m->bodiesStale = true; w.m->contactsStale = true; // (Add(JointID, flagForFiltering) flags the pair's contacts, :1170-1174)
     return MakeId<JointID>(first);
 }
+// the solver temporaries InitVelocity leaves in the JointConf value (pr_get_joint_work; layout per type: pr_joint.cuh)
+static UnitVec MakeUnit(float c, float s)
+{
+    if (c == 0.0f && s == 0.0f) return UnitVec::GetZero();
+    try { return UnitVec{Vec2{c, s}}; } catch (...) { return std::get<0>(UnitVec::Get(c, s)); }
+}
+static Mat33 MakeMat33(const float* m) { return Mat33{Vec3{m[0], m[1], m[2]}, Vec3{m[3], m[4], m[5]}, Vec3{m[6], m[7], m[8]}}; }
+static Mass22 MakeMass22(const float* m) { return Mass22{Vector2<Mass>{m[0] * Kilogram, m[1] * Kilogram}, Vector2<Mass>{m[2] * Kilogram, m[3] * Kilogram}}; }
 Joint GetJoint(const CudaWorld& w, JointID id)
 { // the solver-written fields (impulses, limit state) come back from the device
     auto& elem = AtId(w.m->joints, id, noSuchJointMsg);
     if (!elem.has_value()) return Joint{}; // GetJoint = At(m_jointBuffer, id) (:1103): a freed slot reads back empty
     pr_revolute_joint r{};
     w.m->check(pr_get_revolute_joints(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), 1, &r), "pr_get_revolute_joints");
+    pr_joint_work k{};
+    w.m->check(pr_get_joint_work(w.m->h, static_cast<std::uint32_t>(to_underlying(id)), 1, &k), "pr_get_joint_work");
+    const bool solved = k.island != 0xFFFFFFFFu; // (never solved: the conf's temporaries stay what the caller gave)
+    const auto rA = Length2{k.r_a[0] * Meter, k.r_a[1] * Meter}, rB = Length2{k.r_b[0] * Meter, k.r_b[1] * Meter};
     if (GetType(elem) == GetTypeID<DistanceJointConf>()) {
         auto dc = TypeCast<DistanceJointConf>(elem);
         dc.impulse = Momentum{r.impulse_x * NewtonSecond};
+        if (solved) { dc.u = MakeUnit(k.m[0], k.m[1]); dc.rA = rA; dc.rB = rB; dc.invGamma = InvMass{k.m[2] / Kilogram}; dc.bias = LinearVelocity{k.m[3] * MeterPerSecond}; dc.mass = Mass{k.m[4] * Kilogram}; }
         return Joint{dc};
     }
     if (GetType(elem) == GetTypeID<FrictionJointConf>()) {
         auto fc = TypeCast<FrictionJointConf>(elem);
         fc.linearImpulse = Momentum2{r.impulse_x * NewtonSecond, r.impulse_y * NewtonSecond};
         fc.angularImpulse = AngularMomentum{r.impulse_z * NewtonMeterSecond};
+        if (solved) { fc.rA = rA; fc.rB = rB; fc.linearMass = MakeMass22(k.m); fc.angularMass = RotInertia{k.angular_mass * SquareMeter * Kilogram / SquareRadian}; }
         return Joint{fc};
     }
     if (GetType(elem) == GetTypeID<MotorJointConf>()) {
         auto mc = TypeCast<MotorJointConf>(elem);
         mc.linearImpulse = Momentum2{r.impulse_x * NewtonSecond, r.impulse_y * NewtonSecond};
         mc.angularImpulse = AngularMomentum{r.impulse_z * NewtonMeterSecond};
+        if (solved) {
+            mc.rA = rA; mc.rB = rB; mc.linearMass = MakeMass22(k.m); mc.angularMass = RotInertia{k.angular_mass * SquareMeter * Kilogram / SquareRadian};
+            mc.linearError = Length2{k.m[4] * Meter, k.m[5] * Meter}; mc.angularError = Angle{k.m[6] * Radian};
+        }
         return Joint{mc};
     }
     if (GetType(elem) == GetTypeID<WeldJointConf>()) {
         auto wc = TypeCast<WeldJointConf>(elem);
         wc.impulse = Vec3{r.impulse_x, r.impulse_y, r.impulse_z};
+        if (solved) { wc.rA = rA; wc.rB = rB; wc.mass = MakeMat33(k.m); wc.gamma = InvRotInertia{k.angular_mass * SquareRadian / (SquareMeter * Kilogram)}; wc.bias = AngularVelocity{k.ex[0] * RadianPerSecond}; }
         return Joint{wc};
     }
     if (GetType(elem) == GetTypeID<TargetJointConf>()) {
         auto tc = TypeCast<TargetJointConf>(elem);
         tc.impulse = Momentum2{r.impulse_x * NewtonSecond, r.impulse_y * NewtonSecond};
+        if (solved) { tc.rB = rB; tc.mass = MakeMass22(k.m); tc.gamma = InvMass{k.angular_mass / Kilogram}; tc.C = LinearVelocity2{k.ex[0] * MeterPerSecond, k.ex[1] * MeterPerSecond}; }
         return Joint{tc};
     }
     if (GetType(elem) == GetTypeID<PrismaticJointConf>()) {
@@ -919,6 +939,11 @@ Joint GetJoint(const CudaWorld& w, JointID id)
         pc.impulse = Vec3{p.impulse_x, p.impulse_y, p.impulse_z};
         pc.motorImpulse = Momentum{p.motor_impulse * NewtonSecond};
         pc.limitState = static_cast<LimitState>(p.limit_state);
+        if (solved) {
+            pc.axis = MakeUnit(k.ex[0], k.ex[1]); pc.perp = MakeUnit(k.ex[2], k.ex[3]);
+            pc.s1 = Length{k.ex[4] * Meter}; pc.s2 = Length{k.ex[5] * Meter}; pc.a1 = Length{k.ex[6] * Meter}; pc.a2 = Length{k.ex[7] * Meter};
+            pc.K = MakeMat33(k.m); pc.motorMass = Mass{k.angular_mass * Kilogram};
+        }
         return Joint{pc};
     }
     if (GetType(elem) == GetTypeID<WheelJointConf>()) {
@@ -927,28 +952,41 @@ Joint GetJoint(const CudaWorld& w, JointID id)
         wc.impulse = Momentum{p.impulse * NewtonSecond};
         wc.springImpulse = Momentum{p.spring_impulse * NewtonSecond};
         wc.angularImpulse = AngularMomentum{p.angular_impulse * NewtonMeterSecond};
+        if (solved) {
+            wc.ay = MakeUnit(k.m[0], k.m[1]); wc.sAy = Length{k.m[2] * Meter}; wc.sBy = Length{k.m[3] * Meter}; wc.mass = Mass{k.m[4] * Kilogram};
+            wc.ax = MakeUnit(k.m[5], k.m[6]); wc.sAx = Length{k.m[7] * Meter}; wc.sBx = Length{k.m[8] * Meter};
+            wc.springMass = Mass{k.ex[0] * Kilogram}; wc.bias = LinearVelocity{k.ex[1] * MeterPerSecond}; wc.gamma = InvMass{k.ex[2] / Kilogram};
+            wc.angularMass = RotInertia{k.angular_mass * SquareMeter * Kilogram / SquareRadian};
+        }
         return Joint{wc};
     }
     if (GetType(elem) == GetTypeID<PulleyJointConf>()) {
         auto pc = TypeCast<PulleyJointConf>(elem);
         pc.impulse = Momentum{r.impulse_x * NewtonSecond};
+        if (solved) { pc.uA = MakeUnit(k.m[0], k.m[1]); pc.uB = MakeUnit(k.m[2], k.m[3]); pc.rA = rA; pc.rB = rB; pc.mass = Mass{k.m[4] * Kilogram}; }
         return Joint{pc};
     }
     if (GetType(elem) == GetTypeID<GearJointConf>()) {
         auto gc = TypeCast<GearJointConf>(elem);
         gc.impulse = Momentum{r.impulse_x * NewtonSecond};
+        if (solved) {
+            gc.JvAC = Vec2{k.m[0], k.m[1]}; gc.JvBD = Vec2{k.m[2], k.m[3]};
+            gc.JwA = Length{k.m[4] * Meter}; gc.JwB = Length{k.m[5] * Meter}; gc.JwC = Length{k.m[6] * Meter}; gc.JwD = Length{k.m[7] * Meter}; gc.mass = k.m[8];
+        }
         return Joint{gc};
     }
     if (GetType(elem) == GetTypeID<RopeJointConf>()) {
         auto rc = TypeCast<RopeJointConf>(elem);
         rc.impulse = Momentum{r.impulse_x * NewtonSecond};
         rc.limitState = static_cast<LimitState>(r.limit_state);
+        if (solved) { rc.u = MakeUnit(k.m[0], k.m[1]); rc.rA = rA; rc.rB = rB; rc.mass = Mass{k.m[4] * Kilogram}; rc.length = Length{k.m[5] * Meter}; }
         return Joint{rc};
     }
     auto jc = TypeCast<RevoluteJointConf>(elem);
     jc.impulse = Vec3{r.impulse_x, r.impulse_y, r.impulse_z};
     jc.angularMotorImpulse = r.angular_motor_impulse;
     jc.limitState = static_cast<LimitState>(r.limit_state);
+    if (solved) { jc.rA = rA; jc.rB = rB; jc.mass = MakeMat33(k.m); jc.angularMass = RotInertia{k.angular_mass * SquareMeter * Kilogram / SquareRadian}; }
     return Joint{jc};
 }
 void SetJoint(CudaWorld& w, JointID id, Joint def)

@@ -62,7 +62,7 @@ EXPORTS = [
     "pr_batch_world_count", "pr_batch_create_bodies", "pr_batch_step", "pr_batch_get_body_worlds",
     "pr_set_body_accelerations", "pr_get_body_poses", "pr_query_aabb", "pr_set_event_mask", "pr_events", "pr_ray_cast", "pr_test_points", "pr_find_closest_bodies", "pr_set_contacts", "pr_set_manifolds", "pr_set_revolute_joints", "pr_attach_shapes", "pr_set_shape_material", "pr_destroy_joints",
     "pr_destroy_bodies", "pr_detach_shapes", "pr_destroy_shapes", "pr_set_shape", "pr_set_body_enabled", "pr_set_body_type",
-    "pr_create_distance_joints", "pr_create_rope_joints", "pr_create_friction_joints", "pr_create_motor_joints", "pr_create_weld_joints", "pr_create_target_joints", "pr_create_prismatic_joints", "pr_create_wheel_joints", "pr_create_pulley_joints", "pr_create_gear_joints", "pr_get_gear_joints", "pr_set_body_velocities", "pr_batch_create_masked", "pr_batch_stats",
+    "pr_create_distance_joints", "pr_create_rope_joints", "pr_create_friction_joints", "pr_create_motor_joints", "pr_create_weld_joints", "pr_create_target_joints", "pr_create_prismatic_joints", "pr_create_wheel_joints", "pr_create_pulley_joints", "pr_create_gear_joints", "pr_get_gear_joints", "pr_get_joint_work", "pr_set_body_velocities", "pr_batch_create_masked", "pr_batch_stats",
 ]
 
 
@@ -115,6 +115,7 @@ def bind(lib):
     lib.pr_create_pulley_joints.argtypes = [vp, u32, vp, C.POINTER(u32)]
     lib.pr_create_gear_joints.argtypes = [vp, u32, vp, C.POINTER(u32)]
     lib.pr_get_gear_joints.argtypes = [vp, u32, u32, vp]
+    lib.pr_get_joint_work.argtypes = [vp, u32, u32, vp]
     lib.pr_set_body_velocities.argtypes = [vp, u32, vp, vp]
     lib.pr_batch_create_masked.argtypes = [vp, u32, C.c_uint64, C.POINTER(vp)]
     lib.pr_batch_stats.argtypes = [vp, vp]
