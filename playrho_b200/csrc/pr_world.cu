@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <limits>
+#include <map>
 #include <unordered_map>
 
 namespace pr {
@@ -38,11 +39,13 @@ static void* dev_alloc(size_t bytes) { void* p = nullptr; CK(cudaMalloc(&p, byte
 static void dev_free(void* p) { if (p) cudaFree(p); }
 static void h2d(World& w, void* dst, const void* src, size_t n) { if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, w.stream)); }
 static unsigned g_hostSyncs = 0; // (diagnostics, PR_SYNC_DEBUG: stream synchronisations since the last report)
-static void d2h(World& w, void* dst, const void* src, size_t n) { if (n) { CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, w.stream)); CK(cudaStreamSynchronize(w.stream)); ++g_hostSyncs; } }
+static int g_syncTag = 0; static std::map<int, int> g_syncHist; // (which source lines they came from)
+static void count_sync() { ++g_hostSyncs; ++g_syncHist[g_syncTag]; g_syncTag = 0; }
+static void d2h(World& w, void* dst, const void* src, size_t n) { if (n) { CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, w.stream)); CK(cudaStreamSynchronize(w.stream)); count_sync(); } }
 static void d2d(World& w, void* dst, const void* src, size_t n) { if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, w.stream)); }
 #define CK_COPY_D2H_ASYNC(w, dst, src, n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, (w).stream))
 static void dset(World& w, void* dst, int v, size_t n) { if (n) CK(cudaMemsetAsync(dst, v, n, w.stream)); }
-static void sync(World& w) { CK(cudaStreamSynchronize(w.stream)); ++g_hostSyncs; }
+static void sync(World& w) { CK(cudaStreamSynchronize(w.stream)); count_sync(); }
 static void check_launch() { CK(cudaGetLastError()); }
 struct StageTimer {
     static constexpr int MAXEV = 1024;
@@ -183,7 +186,7 @@ static void read_counters(World& w)
     if (w.cntSerialValid && w.cntSerial == g_launchSerial.load(std::memory_order_relaxed)) return;
     CK(cudaMemcpyAsync(&w.pinnedCnt[0], w.d.cnt, sizeof(Counters), cudaMemcpyDeviceToHost, w.stream));
     CK(cudaStreamSynchronize(w.stream));
-    ++g_hostSyncs;
+    count_sync();
     w.hostCnt = w.pinnedCnt[0];
     w.pinnedNext = 1; // everything queued before this point has executed: all write slots are free again
     w.cntSerial = g_launchSerial.load(std::memory_order_relaxed); w.cntSerialValid = true;
@@ -205,6 +208,17 @@ static void read_counters(World& w) { d2h(w, &w.hostCnt, w.d.cnt, sizeof(Counter
 static void write_counters(World& w) { h2d(w, w.d.cnt, &w.hostCnt, sizeof(Counters)); }
 #endif
 
+#ifndef PR_HOST_EMUL
+#define read_counters(w) (g_syncTag = __LINE__, read_counters(w))
+#define sync(w) (g_syncTag = __LINE__, sync(w))
+#endif
+// zero single counters on the device without a round trip: what "read, clear a field, write back" did with a stream drain (~20 us of idle
+// GPU per drain). The host copy's fields are cleared too, so a host copy that mirrored the device still does.
+static void zero_counter(World& w, unsigned Counters::*field)
+{
+    dset(w, &(w.d.cnt->*field), 0, sizeof(unsigned));
+    w.hostCnt.*field = 0u;
+}
 static void throw_device_error(World& w)
 {
     const unsigned e = w.hostCnt.error;
@@ -805,10 +819,7 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     PR_LAUNCH(k_writeback_bodies, N, w.stream, d, N, conf);
     PR_LAUNCH(k_sleep_and_stats, N, w.stream, d, N, conf.min_still_time_to_sleep);
     tm.mark(w, PR_STAGE_SYNC);
-    w.hostCnt.proxiesMoved = 0; // (device copy is refreshed below)
-    read_counters(w);
-    w.hostCnt.proxiesMoved = 0; w.hostCnt.contactsUpdated = 0;
-    write_counters(w);
+    zero_counter(w, &Counters::proxiesMoved); zero_counter(w, &Counters::contactsUpdated); // (no read: the solve's counters are read after the narrowphase)
     PR_LAUNCH(k_sync_proxies, w.nProxies, w.stream, d, conf, w.nProxies);
     tm.mark(w, PR_STAGE_NARROW);
     const unsigned nOrderAtUpdate = w.nOrder;
@@ -867,14 +878,14 @@ static void build_adjacency(World& w)
     ensure(w, G_ADJ, 2u * w.nOrder + 2u * w.nOrder / 4u + 8u * N + 64u);
     dset(w, d.adj_cnt, 0, sizeof(unsigned) * N);
     dset(w, d.b_inR, 0, sizeof(unsigned) * N);
-    read_counters(w);
-    w.hostCnt.toiListN = 0; w.hostCnt.adjOverflow = 0;
-    write_counters(w);
+    zero_counter(w, &Counters::toiListN); zero_counter(w, &Counters::adjOverflow);
     PR_LAUNCH(k_toi_list_build, w.nOrder, w.stream, d, w.nOrder);
-    read_counters(w);
-    if (w.hostCnt.toiListN == 0u) { // no contact can ever get a TOI (e.g. an arena of tumblers: no static or bullet body touches anything):
-        w.toiListBound = 0; w.adjValid = true; // the set R is empty, so the adjacency (three more passes over every contact) is too
-        return;
+    if (w.toiListBound == 0u) { // (the last list was empty, or there was none: look before the three adjacency passes; a world that had TOI candidates
+        read_counters(w);       //  last time has them now, almost surely -- no drain for the look)
+        if (w.hostCnt.toiListN == 0u) { // no contact can ever get a TOI (e.g. an arena of tumblers: no static or bullet body touches anything):
+            w.toiListBound = 0; w.adjValid = true; // the set R is empty, so the adjacency (three more passes over every contact) is too
+            return;
+        }
     }
     PR_LAUNCH(k_adj_count, w.nOrder, w.stream, d, w.nOrder);
     PR_LAUNCH(k_adj_cap, N, w.stream, d, N);
@@ -1055,10 +1066,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     // groups to enqueue next step = list rounds this step needed (a group beyond that is ~12 launches that find the halt flag set)
     if (toiBatches) w.toiGroupsHint = std::min(4u, std::max(1u, listRoundsUsed));
     // final UpdateContacts (:1825-1827)
-    read_counters(w);
-    const unsigned movedToi = w.hostCnt.proxiesMoved;
-    w.hostCnt.contactsUpdated = 0;
-    write_counters(w);
+    zero_counter(w, &Counters::contactsUpdated); // (proxiesMoved is read below: the final UpdateContacts does not touch it)
     const unsigned nOrderAtUpdate = w.nOrder;
     // (no event this step: nothing was flagged since the regular phase's UpdateContacts -- every contact is skipped)
     if (rounds) PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, 0u, 1u);
@@ -1071,7 +1079,7 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     st.sum_pos_iters = c.toiSumPosIters; st.sum_vel_iters = c.toiSumVelIters;
     st.contacts_updated_touching = c.toiUpdTouching + c.contactsUpdated;
     st.contacts_skipped_touching = c.toiSkipTouching + (nOrderAtUpdate - c.contactsUpdated);
-    st.proxies_moved = movedToi;
+    st.proxies_moved = c.proxiesMoved;
     st.contacts_found -= c.toiDeferred;
     if (d.toi_log) {
         w.toiScheduleN = c.toiLogN;
@@ -2616,7 +2624,12 @@ int pr_step(pr_world* pw, const pr_step_conf* conf, pr_step_stats* stats_out)
     if (pw->w.jointTablesDirty) { refresh_joint_tables(pw->w); pw->w.jointTablesDirty = false; } // (built when a Step needs them, not per CreateJoint / Destroy)
     step_impl(pw->w, *conf, st);
 #ifndef PR_HOST_EMUL
-    if (getenv("PR_SYNC_DEBUG")) { std::fprintf(stderr, "step: %u host syncs\n", g_hostSyncs); g_hostSyncs = 0; }
+    if (getenv("PR_SYNC_DEBUG")) {
+        std::fprintf(stderr, "step: %u host syncs:", g_hostSyncs);
+        for (const auto& kv : g_syncHist) std::fprintf(stderr, " L%d x%d", kv.first, kv.second);
+        std::fprintf(stderr, "\n");
+        g_hostSyncs = 0; g_syncHist.clear();
+    }
 #endif
     if (stats_out) *stats_out = st;
     return PR_OK;
