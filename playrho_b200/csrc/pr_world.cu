@@ -375,9 +375,10 @@ static unsigned bvh_refit_steps()
     return v;
 }
 // FindContacts + AddContacts, AabbTreeWorld.cpp:709-751 and :2423-2547
-static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer& tm, bool toiRound = false)
+static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer& tm, bool toiRound = false, bool queueKnownEmpty = false)
 {
     DV& d = w.d;
+    if (queueKnownEmpty) return 0; // (the caller read nQueue == 0 and nothing has queued a proxy since: no drain to find that out again)
     read_counters(w);
     throw_device_error(w);
     const unsigned nQueue = w.hostCnt.nQueue;
@@ -1122,20 +1123,26 @@ static void step_impl(World& w, const pr_step_conf& conf, pr_step_stats& stats)
     w.hostCnt.nQueue = keepQueue; w.hostCnt.toiListN = keepToiList; write_counters(w);
     stats.pre.proxies_created = create_queued_proxies(w, conf);
     if (w.anyBodySet) PR_LAUNCH(k_sync_proxies, w.nProxies, w.stream, d, conf, w.nProxies);
+    const bool queueSeen = w.nOrder != 0u; // (destroy_contacts reads the counters then, after the last kernel of the pre-phase that queues a proxy)
     stats.pre.contacts_destroyed = destroy_contacts(w);
+    const unsigned queueN = w.hostCnt.nQueue;
     const unsigned nOrderAtUpdate = w.nOrder;
     // UpdateContacts of the pre-phase (:2190): nothing to look at when the last Step ended with every contact updated and no
     // mutator ran since (the usual step-after-step loop): every contact is skipped, as the reference finds out one by one
     const bool preClean = w.contactsClean && !w.anyBodySet;
+    const bool hadBodySet = w.anyBodySet;
     if (!preClean) PR_LAUNCH(k_update_contacts, w.nOrder, w.stream, d, conf, 0u, w.nOrder, w.anyBodySet ? 1u : 0u, 1u);
     if (w.anyBodySet) { dset(w, d.b_moved, 0, sizeof(unsigned) * w.nBodies); dset(w, d.b_sync, 0, sizeof(unsigned) * w.nBodies); }
+    // the usual step-after-step loop: no proxy was synchronised and no contact updated in this pre-phase (both counters are what the
+    // reset above left: 0) and the proxy queue is what destroy_contacts' read saw -- nothing to read back
+    const bool quietPre = preClean && !hadBodySet && queueSeen && queueN == 0u;
     w.anyBodySet = false;
     w.contactsClean = false;
-    read_counters(w);
-    stats.pre.proxies_moved = w.hostCnt.proxiesMoved;
-    stats.pre.contacts_updated = w.hostCnt.contactsUpdated;
-    stats.pre.contacts_skipped = nOrderAtUpdate - w.hostCnt.contactsUpdated;
-    stats.pre.contacts_added = find_add_contacts(w, conf, tm);
+    if (!quietPre) read_counters(w);
+    stats.pre.proxies_moved = quietPre ? 0u : w.hostCnt.proxiesMoved;
+    stats.pre.contacts_updated = quietPre ? 0u : w.hostCnt.contactsUpdated;
+    stats.pre.contacts_skipped = nOrderAtUpdate - stats.pre.contacts_updated;
+    stats.pre.contacts_added = find_add_contacts(w, conf, tm, false, quietPre);
     if (conf.delta_time != 0.0f) {
         w.inv_dt0 = 1.0f / conf.delta_time;
         if (w.stepComplete) solve_reg(w, conf, stats, tm);
