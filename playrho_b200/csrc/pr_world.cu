@@ -35,7 +35,9 @@ struct CudaError { std::string msg; };
         if (e_ != cudaSuccess) throw CudaError{std::string(#call) + ": " + cudaGetErrorString(e_)}; \
     } while (0)
 // (zeroed, like the emulation build's calloc: growing a group copies its whole old capacity, and no kernel ever reads never-written memory)
-static void* dev_alloc(size_t bytes) { void* p = nullptr; CK(cudaMalloc(&p, bytes ? bytes : 16)); CK(cudaMemset(p, 0, bytes ? bytes : 16)); return p; }
+// The fill runs on the default stream, which is not ordered with a world's (non-blocking) stream: it is waited for here, or a copy the
+// caller enqueues into the new buffer could be overtaken by it.
+static void* dev_alloc(size_t bytes) { void* p = nullptr; CK(cudaMalloc(&p, bytes ? bytes : 16)); CK(cudaMemset(p, 0, bytes ? bytes : 16)); CK(cudaStreamSynchronize(0)); return p; }
 static void dev_free(void* p) { if (p) cudaFree(p); }
 static void h2d(World& w, void* dst, const void* src, size_t n) { if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, w.stream)); }
 static unsigned g_hostSyncs = 0; // (diagnostics, PR_SYNC_DEBUG: stream synchronisations since the last report)
@@ -594,6 +596,30 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
         const unsigned nWork = w.hostCnt.nColorWork;
         w.recolorAll = false;
         unsigned nWorkLeft = nWork, firstRound = 0u;
+        // the rounds the one-block tail could not finish (rare): launches over the list, the count looked at every 4th round
+        auto finish_rounds = [&]() {
+            const unsigned nW = nWorkLeft;
+            for (unsigned round = firstRound;; ++round) {
+                if (round && (round % 64u) == 0u) PR_LAUNCH(k_color_reset_claims, N, w.stream, d, N);
+                PR_LAUNCH(k_color_claim, nW, w.stream, d, nW, round);
+                PR_LAUNCH(k_color_commit, nW, w.stream, d, nW, round, w.colorCap);
+                ++w.profile.color_rounds;
+                if ((round & 3u) == 3u || nW < 64u) { // look at the remaining count every 4th round only
+                    read_counters(w);
+                    if (w.hostCnt.nUncolored == 0) break;
+                }
+                if (round > 100000u) throw CudaError{"colouring did not converge"};
+            }
+        };
+        // what the one-block tail reported: 0 left; or it handed back at once (too much left: the launches go on over the whole list), or
+        // its round budget ran out (the rest, compacted to the head of the list, goes on after a reset of the claims)
+        auto after_block = [&]() {
+            w.profile.color_rounds += w.hostCnt.colorRoundsDev;
+            const bool handedBack = w.hostCnt.colorRoundsDev == COLOR_LAUNCH_ROUNDS;
+            nWorkLeft = !w.hostCnt.nUncolored ? 0u : handedBack ? nWork : w.hostCnt.nUncolored;
+            firstRound = handedBack ? COLOR_LAUNCH_ROUNDS : 64u;
+        };
+        bool blockPending = false; // the one-block tail is enqueued and its verdict not read yet
         if (nWork && nWork <= COLOR_BLOCK_MAX_WORK && !(w.debugFlags & 256u)) { // the first rounds as launches, the tail in one block (debug bit 8: launches only)
             for (unsigned round = 0; round < COLOR_LAUNCH_ROUNDS; ++round) {
                 PR_LAUNCH(k_color_claim, nWork, w.stream, d, nWork, round);
@@ -605,28 +631,12 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
 #else
             PR_LAUNCH(k_color_rounds_block, 1, w.stream, d, w.colorCap, d.np_idx, COLOR_LAUNCH_ROUNDS);
 #endif
-            read_counters(w);
-            w.profile.color_rounds += w.hostCnt.colorRoundsDev;
-            // 0 left; or the block handed back at once (too much left: the launches go on over the whole list), or its round
-            // budget ran out (the rest, compacted to the head of the list, goes on after a reset of the claims)
-            const bool handedBack = w.hostCnt.colorRoundsDev == COLOR_LAUNCH_ROUNDS;
-            nWorkLeft = !w.hostCnt.nUncolored ? 0u : handedBack ? nWork : w.hostCnt.nUncolored;
-            firstRound = handedBack ? COLOR_LAUNCH_ROUNDS : 64u;
+            // the block almost always finishes: outside the block solver the colour sort and the colour starts are enqueued behind it
+            // and ONE read fetches both its verdict and the starts (no drain here); if something was left the sort is done again
+            if (!blockMode) { blockPending = true; nWorkLeft = 0u; }
+            else { read_counters(w); after_block(); }
         }
-        if (nWorkLeft) {
-            const unsigned nWork = nWorkLeft;
-            for (unsigned round = firstRound;; ++round) {
-                if (round && (round % 64u) == 0u) PR_LAUNCH(k_color_reset_claims, N, w.stream, d, N);
-                PR_LAUNCH(k_color_claim, nWork, w.stream, d, nWork, round);
-                PR_LAUNCH(k_color_commit, nWork, w.stream, d, nWork, round, w.colorCap);
-                ++w.profile.color_rounds;
-                if ((round & 3u) == 3u || nWork < 64u) { // look at the remaining count every 4th round only
-                    read_counters(w);
-                    if (w.hostCnt.nUncolored == 0) break;
-                }
-                if (round > 100000u) throw CudaError{"colouring did not converge"};
-            }
-        }
+        if (nWorkLeft) finish_rounds();
         const unsigned* sortedColor = nullptr;
         if (blockMode) { // rows sorted by (world, colour); every world's first row: histogram + scan (pr_block_solve.cuh)
             dset(w, d.blk_rowOff, 0, sizeof(unsigned) * (d.nWorlds + 1u));
@@ -637,14 +647,20 @@ static void solve_reg(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
             if (inB) d2d(w, d.k_sorted, d.k_tmpVal, nCons * sizeof(unsigned));
         } else {
         // stable sort by colour (one 8-bit radix pass): k_sorted = permutation of the base constraint list
-        d2d(w, d.k_tmpKey, d.k_color, nCons * sizeof(unsigned));
-        const bool inB = radix_sort_pairs<unsigned>(d.k_tmpKey, d.k_sorted, d.k_tmpKey2, d.k_tmpVal, nCons, 0, 8, true, w.rs, w.stream);
-        sortedColor = inB ? d.k_tmpKey2 : d.k_tmpKey;
-        if (inB) d2d(w, d.k_sorted, d.k_tmpVal, nCons * sizeof(unsigned));
-        for (unsigned c = 0; c <= MAX_COLORS; ++c) w.hostCnt.colorStart[c] = INVALID;
-        write_counters(w);
-        PR_LAUNCH(k_color_starts, nCons, w.stream, d, nCons, sortedColor);
-        read_counters(w);
+        auto sort_and_starts = [&]() {
+            d2d(w, d.k_tmpKey, d.k_color, nCons * sizeof(unsigned));
+            const bool inB = radix_sort_pairs<unsigned>(d.k_tmpKey, d.k_sorted, d.k_tmpKey2, d.k_tmpVal, nCons, 0, 8, true, w.rs, w.stream);
+            sortedColor = inB ? d.k_tmpKey2 : d.k_tmpKey;
+            if (inB) d2d(w, d.k_sorted, d.k_tmpVal, nCons * sizeof(unsigned));
+            dset(w, d.cnt->colorStart, 0xFF, sizeof(unsigned) * (MAX_COLORS + 1u)); // (INVALID everywhere, on the device: the host copy may be stale here)
+            PR_LAUNCH(k_color_starts, nCons, w.stream, d, nCons, sortedColor);
+            read_counters(w);
+        };
+        sort_and_starts();
+        if (blockPending) {
+            after_block();
+            if (nWorkLeft) { finish_rounds(); sort_and_starts(); }
+        }
         unsigned prevStart = nCons;
         for (int c = static_cast<int>(MAX_COLORS) - 1; c >= 0; --c) {
             const unsigned s = w.hostCnt.colorStart[c];
