@@ -134,7 +134,7 @@ class ClockSampler(threading.Thread):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE regular-phase k_update_contacts launch on this workload, from the
 # `ncu --set full` capture summarised under profiles/ (None until a capture of the current kernel exists)
-ROOFLINE_TRAFFIC = {"mixed": int(1.259e9 + 0.2397e9)}  # profiles/r02h_ncu_full_mixed1m.txt, k_update_contacts (586 us row; round 2 final build)
+ROOFLINE_TRAFFIC = {"mixed": int(1.27e9 + 0.2387e9)}  # profiles/r02k_ncu_full_mixed1m.txt, k_update_contacts (590 us row; round 2 final build)
 
 
 def algorithmic_bytes(prof, nv, np_):
