@@ -9,15 +9,17 @@ import pytest
 
 import refworld
 import scenes_np
-from common import need_oracle, need_emul, emul_lib, assert_bits
+from common import need_ref, need_oracle, need_emul, emul_lib, assert_bits
 from playrho_b200 import abi, world as W
 
 
-def _arena_vs_oracle(lib, device, n_worlds, n_squares, steps, every, toi_mode=0):
-    units = [scenes_np.tumbler(n_squares, seed=12345 + w) for w in range(n_worlds)]
+def _arena_vs_oracle(lib, device, n_worlds, n_squares, steps, every, toi_mode=0, units=None, conf=None, min_contacts=None):
+    if units is None:
+        units = [scenes_np.tumbler(n_squares, seed=12345 + w) for w in range(n_worlds)]
     plain, world = scenes_np.merge_worlds(units)
     layered, _ = scenes_np.merge_worlds(units, layer_filters=True)
-    conf = scenes_np.tumbler_step_conf(refworld.default_step_conf())
+    if conf is None:
+        conf = scenes_np.tumbler_step_conf(refworld.default_step_conf())
     gw = W.Batch(n_worlds, lib=lib, device=device, record_solve_order=True)
     gw.set_toi_mode(toi_mode)
     gw.create_shapes(plain)
@@ -44,8 +46,37 @@ def _arena_vs_oracle(lib, device, n_worlds, n_squares, steps, every, toi_mode=0)
         # no contact ever joins two worlds
         assert np.array_equal(world[gc["body_a"]], world[gc["body_b"]])
         n_contacts = max(n_contacts, len(gc))
-    assert n_contacts > n_worlds * n_squares // 2
+    assert n_contacts > (n_worlds * n_squares // 2 if min_contacts is None else min_contacts)
     return gw
+
+
+def _joint_units():
+    """one world per joint type: the scenes of test_more_joints.py (the gear scene is left out: a gear joint's value is wider than a table row,
+    and merge_worlds moves rows)"""
+    import test_more_joints as tmj
+    units = []
+    for name in ("weld", "prismatic", "wheel", "pulley", "target", "chains"):
+        ref, _ = tmj.SCENES[name][0]()
+        units.append(ref.export_scene())
+    return units
+
+
+@need_ref
+@need_oracle
+@need_emul
+def test_emulated_batch_arena_of_jointed_worlds_equals_filter_layered_oracle():
+    """every joint type but the gear joint in worlds of one arena: the arena's joint kernels (and, on the GPU, the block solver's) against the
+    restatement with the worlds on filter layers"""
+    units = _joint_units()
+    _arena_vs_oracle(emul_lib(), -1, n_worlds=len(units), n_squares=0, steps=120, every=10, units=units, conf=refworld.default_step_conf(), min_contacts=4)
+
+
+@pytest.mark.gpu
+@need_ref
+@need_oracle
+def test_cuda_batch_arena_of_jointed_worlds_equals_filter_layered_oracle():
+    units = _joint_units()
+    _arena_vs_oracle(None, 0, n_worlds=len(units), n_squares=0, steps=160, every=10, units=units, conf=refworld.default_step_conf(), min_contacts=4)
 
 
 @need_oracle
