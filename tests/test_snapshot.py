@@ -42,10 +42,23 @@ def _roundtrip(lib, device, scene, conf, before, after, tmp_path, with_oracle=Tr
     return gw, twin
 
 
+def _joint_scene(name):
+    """a scene of tests/test_more_joints.py (built through the reference harness): gear joints carry an extension entry per joint, chains the
+    level lists of joints that share a body -- both must come back from a snapshot"""
+    if not refworld.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference at build time)")
+    import test_more_joints as tmj
+    ref, _ = tmj.SCENES[name][0]()
+    return ref.export_scene()
+
+
 SCENES = [
     ("mixed400", lambda: scenes_np.mixed(400, seed=3, tile_segments=32, tile_width=16.0), refworld.default_step_conf, 60, 40),
     ("pyramid10", lambda: scenes_np.pyramid(10), refworld.default_step_conf, 50, 40),
     ("tumbler80", lambda: scenes_np.tumbler(80), lambda: scenes_np.tumbler_step_conf(refworld.default_step_conf()), 60, 40),
+    ("gear", lambda: _joint_scene("gear"), refworld.default_step_conf, 40, 40),
+    ("chains", lambda: _joint_scene("chains"), refworld.default_step_conf, 30, 30),
+    ("wheel", lambda: _joint_scene("wheel"), refworld.default_step_conf, 50, 40),
 ]
 
 
