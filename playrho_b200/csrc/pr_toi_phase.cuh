@@ -123,6 +123,20 @@ PR_D bool toi_eligible(const DV& d, unsigned flags, uint4 ab, unsigned maxSubSte
     if ((flags >> 8) >= maxSubSteps) { atMax = true; return false; }
     return f_awake(d.b_flags[ab.x]) || f_awake(d.b_flags[ab.y]);
 }
+// the TOI phase's statistics and round state, reset on the device (the host used to read the counters, clear these and write them back:
+// a stream drain per Step)
+PR_KERNEL k_toi_step_counters(DV d)
+{
+    PR_PDL_ENTER();
+    if (PR_TID != 0u) return;
+    Counters* c = d.cnt;
+    c->toiAtMaxSub = c->toiUpdated = c->toiMaxDistIters = c->toiMaxToiIters = c->toiMaxRootIters = 0u;
+    c->toiMinSepFlip = float_flip(PR_INF);
+    c->toiMaxIncBits = 0u; c->toiIslandsSolved = c->toiSumPosIters = c->toiSumVelIters = 0u;
+    c->toiIslandsFound = c->toiUpdTouching = c->toiSkipTouching = 0u;
+    c->proxiesMoved = 0u; c->contactsUpdated = 0u; c->toiDeferred = 0u;
+    c->toiRoundId = 0u; c->toiReN[0] = c->toiReN[1] = 0u; c->toiAtMaxLive = 0u; c->toiForceFull = 0u; c->toiHalt = TB_RUN;
+}
 PR_KERNEL k_toi_phase_init(DV d, unsigned nBodies)
 {
     PR_PDL_ENTER();

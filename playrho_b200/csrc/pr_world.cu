@@ -451,6 +451,7 @@ static unsigned find_add_contacts(World& w, const pr_step_conf& conf, StageTimer
     if (adjLive) w.toiListBound += nPairs; else w.adjValid = false;
     // AddContacts ends with Update(contactID) for each new contact (:2531); not part of UpdateContacts' stats
     PR_LAUNCH(k_update_contacts, nPairs, w.stream, d, conf, oldOrder, nPairs, 0u, 0u);
+    if (!toiRound) return nPairs; // (no drain: a device error surfaces at the next read of the counters, the adjacency is not live outside the TOI rounds)
     read_counters(w);
     throw_device_error(w);
     if (w.hostCnt.adjOverflow) { w.adjValid = false; w.hostCnt.adjOverflow = 0; write_counters(w); }
@@ -919,14 +920,13 @@ static void solve_toi(World& w, const pr_step_conf& conf, pr_step_stats& stats, 
     const unsigned N = w.nBodies;
     tm.mark(w, PR_STAGE_TOI);
     auto& st = stats.toi;
-    read_counters(w);
+    PR_LAUNCH(k_toi_step_counters, 1, w.stream, d); // (no read: the host copy below is only kept alike; the next read refreshes it)
     w.hostCnt.toiAtMaxSub = w.hostCnt.toiUpdated = w.hostCnt.toiMaxDistIters = w.hostCnt.toiMaxToiIters = w.hostCnt.toiMaxRootIters = 0;
     w.hostCnt.toiMinSepFlip = float_flip(std::numeric_limits<float>::infinity());
     w.hostCnt.toiMaxIncBits = 0; w.hostCnt.toiIslandsSolved = w.hostCnt.toiSumPosIters = w.hostCnt.toiSumVelIters = 0;
     w.hostCnt.toiIslandsFound = w.hostCnt.toiUpdTouching = w.hostCnt.toiSkipTouching = 0;
     w.hostCnt.proxiesMoved = 0; w.hostCnt.contactsUpdated = 0; w.hostCnt.toiDeferred = 0;
     w.hostCnt.toiRoundId = 0; w.hostCnt.toiReN[0] = w.hostCnt.toiReN[1] = 0; w.hostCnt.toiAtMaxLive = 0; w.hostCnt.toiForceFull = 0; w.hostCnt.toiHalt = TB_RUN;
-    write_counters(w);
     const bool exact = (w.toiMode == 0u) || w.subStepping; // (sub-stepping = one TOI event per Step call, in the reference's order: :1779-1824)
     unsigned rounds = 0, round = 0, toiBatches = 0, listRoundsUsed = 0;
     if (!w.toiPossible) { // no contact of this world can be a TOI candidate: SolveToi finds nothing (:1768) and its final UpdateContacts skips all
