@@ -33,6 +33,7 @@ GEAR_SIDE = np.dtype([("type", u4), ("local_anchor_a", VEC2), ("local_anchor_b",
 GEAR = np.dtype([("body_a", u4), ("body_b", u4), ("collide_connected", u4), ("body_c", u4), ("body_d", u4),
                  ("impulse", f4), ("ratio", f4), ("constant", f4), ("ac", GEAR_SIDE), ("bd", GEAR_SIDE)])
 JOINT_GEAR = 10
+JOINT_WORK = np.dtype([("r_a", f4, 2), ("r_b", f4, 2), ("m", f4, 9), ("angular_mass", f4), ("island", u4), ("reserved", u4), ("ex", f4, 8)])
 
 
 def joint_type(row):

@@ -330,6 +330,14 @@ class World:
         ids = np.ascontiguousarray(shape_ids, dtype=np.uint32)
         self._chk(self.lib.pr_attach_shapes(self.h, int(body), len(ids), abi.ptr(ids)))
 
+    def joint_work(self):
+        """pr_get_joint_work over the whole joint table: what InitVelocity left for each joint in the last Step (island == 0xFFFFFFFF: not solved)"""
+        n = int(self.counts()["joints"])
+        out = np.zeros(n, abi.JOINT_WORK)
+        if n:
+            self._chk(self.lib.pr_get_joint_work(self.h, 0, n, abi.ptr(out)))
+        return out
+
     def gear_joints(self):
         """pr_get_gear_joints over the whole joint table (non-gear rows read back with body_a == 0xFFFFFFFF)"""
         n = int(self.counts()["joints"])

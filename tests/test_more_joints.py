@@ -251,3 +251,32 @@ def test_emulated_kernels_equal_oracle(name):
 @pytest.mark.parametrize("name", sorted(SCENES))
 def test_gpu_equals_oracle(name):
     _run(name, device=0)
+
+
+@need_ref
+@need_emul
+def test_joint_work_reads_back_what_init_velocity_left():
+    """pr_get_joint_work: a fresh joint reads back unsolved; after a Step the wheel scene's driven joint carries its motor mass
+    (1 / (invI_A + invI_B)), the point-to-line mass and the unit axes -- the values the reference keeps in the JointConf (GetAngularMass...)"""
+    ref, _ = _wheel_scene()
+    sc = ref.export_scene()
+    gw = W.World(sc, lib=emul_lib(), device=-1)
+    wk = gw.joint_work()
+    assert (wk["island"] == 0xFFFFFFFF).all()
+    gw.step(refworld.default_step_conf())
+    wk = gw.joint_work()
+    assert (wk["island"] != 0xFFFFFFFF).all()
+    b = gw.bodies()
+    j = gw.joints()
+    ii = b["inv_rot_i"]
+    expect = np.float32(1.0) / (ii[j["body_a"][0]] + ii[j["body_b"][0]])
+    assert wk["angular_mass"][0] == expect            # the driven wheel: motor enabled
+    assert wk["angular_mass"][1] == 0.0               # the free-rolling one: no motor mass
+    for k in range(3):
+        ay, ax = wk["m"][k][0:2], wk["m"][k][5:7]
+        assert abs(float(np.hypot(*ay)) - 1.0) < 1e-6
+        assert wk["m"][k][4] > 0.0                    # point-to-line mass
+        if k < 2:
+            assert abs(float(np.hypot(*ax)) - 1.0) < 1e-6 and abs(float(ay @ ax)) < 1e-6   # sprung: ax set, perpendicular to ay
+        else:
+            assert ax[0] == 0.0 and ax[1] == 0.0     # frequency 0: UnitVec::GetZero()
