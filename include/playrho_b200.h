@@ -477,11 +477,12 @@ int pr_test_points(const pr_world* w, uint32_t n, const uint32_t* body_ids, cons
 /* FindClosestBody(const World&, const Length2&) (WorldBody.cpp:576-592) for n locations at once: the body whose location is
  * nearest, the lowest id on a tie; 0xFFFFFFFF in a world without bodies. */
 int pr_find_closest_bodies(const pr_world* w, uint32_t n, const float* points_xy, uint32_t* out_body_ids);
-/* SetJoint(AabbTreeWorld&, JointID, Joint) (AabbTreeWorld.cpp:1108-1130) for revolute joints: rows[i] replaces joint ids[i] --
- * anchors, reference angle, limits, motor (enable, speed, max torque) and the solver's stored impulses, exactly as the value
- * says -- and both bodies are woken (Remove(JointID) :1192-1205). The bodies and collideConnected of a joint must stay what
- * they are (PR_ERR_UNSUPPORTED otherwise: re-filtering the pair's contacts is not done on the device);
- * PR_ERR_OUT_OF_RANGE for an unknown joint id. */
+/* SetJoint(AabbTreeWorld&, JointID, Joint) (AabbTreeWorld.cpp:1108-1130) for any row of the joint table: rows[i] replaces joint ids[i] --
+ * every field exactly as the value says, the solver's stored impulses included. The joint's OLD bodies are woken and, when the old value
+ * kept them from colliding, their contacts flagged for filtering (Remove(JointID) :1177-1213); the NEW value's bodies are not woken, their
+ * contacts flagged when collideConnected is false (Add(JointID, flag) :1159-1175). The new value may name other bodies, another
+ * collideConnected or another joint type (not to or from a gear joint: PR_ERR_UNSUPPORTED, its value is wider than a row).
+ * PR_ERR_OUT_OF_RANGE for an unknown joint or body id, PR_ERR_INVALID_ARGUMENT for a destroyed joint or an id named twice. */
 int pr_set_revolute_joints(pr_world* w, uint32_t n, const uint32_t* ids, const pr_revolute_joint* rows);
 /* Destroy(AabbTreeWorld&, JointID) (AabbTreeWorld.cpp:1215-1227): both bodies are woken, the joint stops taking part in islands,
  * solves and the collideConnected filter, its row reads back zeroed with body_a == body_b == 0xFFFFFFFF, and its id is the

@@ -757,6 +757,11 @@ int ref_set_revolute_joint(void* h, uint32_t joint, const pr_revolute_joint* row
     REF_TRY(h)
     const auto id = MakeId<JointID>(joint);
     auto jc = TypeCast<RevoluteJointConf>(GetJoint(rw->world, id));
+    // the whole value as the row says: bodies, collideConnected and anchors too (SetJoint = Remove + assign + Add, :1108-1130)
+    jc.bodyA = MakeId<BodyID>(row->body_a); jc.bodyB = MakeId<BodyID>(row->body_b); jc.collideConnected = (row->collide_connected & 1u) != 0;
+    jc.localAnchorA = Length2{row->local_anchor_a.x * 1_m, row->local_anchor_a.y * 1_m};
+    jc.localAnchorB = Length2{row->local_anchor_b.x * 1_m, row->local_anchor_b.y * 1_m};
+    jc.referenceAngle = row->reference_angle * 1_rad;
     jc.enableMotor = row->enable_motor != 0; jc.motorSpeed = row->motor_speed * 1_rad / 1_s; jc.maxMotorTorque = row->max_motor_torque * 1_Nm;
     jc.enableLimit = row->enable_limit != 0; jc.lowerAngle = row->lower_angle * 1_rad; jc.upperAngle = row->upper_angle * 1_rad;
     SetJoint(rw->world, id, Joint{jc});

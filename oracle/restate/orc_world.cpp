@@ -1350,14 +1350,17 @@ int orc_set_revolute_joints(orc_world* w, uint32_t n, const uint32_t* ids, const
         const uint32_t id = ids[i];
         if (id >= w->joints.size()) { w->error = "no such joint"; return -2; }
         const pr_revolute_joint old = w->joints[id];
-        if (old.body_a != rows[i].body_a || old.body_b != rows[i].body_b || (old.collide_connected & 1u) != (rows[i].collide_connected & 1u) || PR_JOINT_TYPE(old) != PR_JOINT_TYPE(rows[i])) { w->error = "unsupported"; return -6; }
+        if (old.body_a == 0xFFFFFFFFu) { w->error = "joint identifier is destroyed"; return -1; }
+        if (rows[i].body_a >= w->bodies.size() || rows[i].body_b >= w->bodies.size()) { w->error = "no such body"; return -2; }
+        if (PR_JOINT_TYPE(old) != PR_JOINT_TYPE(rows[i]) && (PR_JOINT_TYPE(old) == PR_JOINT_GEAR || PR_JOINT_TYPE(rows[i]) == PR_JOINT_GEAR)) { w->error = "unsupported"; return -6; }
+        // Remove(id), :1177-1213: the old pair's contacts flagged, the old bodies woken and the joint taken out of their lists
+        if (!(old.collide_connected & 1u)) flag_pair_for_filtering(*w, old.body_a, old.body_b);
         for (uint32_t b : {old.body_a, old.body_b}) {
             set_awake(w->bodies[b].b);
             auto& lst = w->bodies[b].joints;
             auto it = std::find(lst.begin(), lst.end(), id);
             if (it != lst.end()) lst.erase(it);
         }
-        if (!(old.collide_connected & 1u)) flag_pair_for_filtering(*w, old.body_a, old.body_b); // Remove
         w->joints[id] = rows[i];
         w->bodies[rows[i].body_a].joints.push_back(id);
         if (rows[i].body_b != rows[i].body_a) w->bodies[rows[i].body_b].joints.push_back(id);

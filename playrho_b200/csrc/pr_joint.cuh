@@ -1447,7 +1447,11 @@ PR_KERNEL k_set_joints(DV d, unsigned n, const unsigned* ids, const pr_revolute_
 { // SetJoint: Remove(id) wakes both bodies (:1192-1205), joint = def (:1128)
     PR_PDL_ENTER();
     const unsigned i = PR_TID;
-    if (i < n) { const pr_revolute_joint j = rows[i]; d.jt[ids[i]] = j; body_set_awake(d, j.body_a); body_set_awake(d, j.body_b); }
+    if (i < n) { // (the OLD row's bodies are the ones Remove(id) wakes: the same bodies unless the new value names others)
+        const pr_revolute_joint old = d.jt[ids[i]];
+        body_set_awake(d, old.body_a); body_set_awake(d, old.body_b);
+        d.jt[ids[i]] = rows[i];
+    }
 }
 // Add(JointID, flagForFiltering) / Remove(JointID) of a joint with collideConnected == false (AabbTreeWorld.cpp:1159-1191, FlagForFiltering
 // :436-451): the contacts between its two bodies are flagged for the next Step's filter test (pr_mutate.cuh: k_destroy_filter)

@@ -2219,22 +2219,36 @@ int pr_set_revolute_joints(pr_world* pw, uint32_t n, const uint32_t* ids, const 
     World& w = pw->w;
     w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     if (!w.stepComplete) { w.error = "SetJoint: world is locked (sub-stepped Step incomplete)"; return PR_ERR_WRONG_STATE; }
+    bool structural = false; // bodies, collideConnected or type of some joint change: the joint tables (pairs that must not collide, levels) are rebuilt
     for (uint32_t i = 0; i < n; ++i) {
         if (ids[i] >= w.nJoints) { w.error = "no such joint"; return PR_ERR_OUT_OF_RANGE; }
+        for (uint32_t k = 0; k < i; ++k) if (ids[k] == ids[i]) { w.error = "SetJoint: a joint id is named twice"; return PR_ERR_INVALID_ARGUMENT; }
         const pr_revolute_joint& cur = w.joints[ids[i]];
         if (cur.body_a == INVALID) { w.error = "joint identifier is destroyed"; return PR_ERR_INVALID_ARGUMENT; }
-        if (cur.body_a != rows[i].body_a || cur.body_b != rows[i].body_b || ((cur.collide_connected & 1u) != (rows[i].collide_connected & 1u) || PR_JOINT_TYPE(cur) != PR_JOINT_TYPE(rows[i]))) {
-            w.error = "SetJoint: changing a joint's bodies or collideConnected is not supported by the device world"; return PR_ERR_UNSUPPORTED;
+        if (rows[i].body_a >= w.nBodies || rows[i].body_b >= w.nBodies) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+        if (body_dead(w, rows[i].body_a) || body_dead(w, rows[i].body_b)) { w.error = "no such body"; return PR_ERR_OUT_OF_RANGE; }
+        const bool typeChange = PR_JOINT_TYPE(cur) != PR_JOINT_TYPE(rows[i]);
+        if (typeChange && (PR_JOINT_TYPE(cur) == PR_JOINT_GEAR || PR_JOINT_TYPE(rows[i]) == PR_JOINT_GEAR)) {
+            w.error = "SetJoint: a gear joint's value is wider than a table row (pr_create_gear_joints)"; return PR_ERR_UNSUPPORTED;
         }
+        if (w.d.nWorlds && w.bodyWorld[rows[i].body_a] != w.bodyWorld[rows[i].body_b]) { w.error = "joint between bodies of different worlds"; return PR_ERR_INVALID_ARGUMENT; }
+        if (typeChange || cur.body_a != rows[i].body_a || cur.body_b != rows[i].body_b || (cur.collide_connected & 1u) != (rows[i].collide_connected & 1u)) structural = true;
     }
     if (!n) return PR_OK;
+    // Remove(id) flags the OLD pair's contacts and wakes the OLD bodies, Add(id, !collideConnected) flags the NEW pair's (:1127-1129)
+    std::vector<unsigned> pairs;
+    for (uint32_t i = 0; i < n; ++i) {
+        const pr_revolute_joint& cur = w.joints[ids[i]];
+        if (!(cur.collide_connected & 1u)) { pairs.push_back(cur.body_a); pairs.push_back(cur.body_b); }
+        if (!(rows[i].collide_connected & 1u)) { pairs.push_back(rows[i].body_a); pairs.push_back(rows[i].body_b); }
+    }
     pr_revolute_joint* srows = static_cast<pr_revolute_joint*>(stage_buf(w, 0, sizeof(pr_revolute_joint) * n));
     unsigned* sids = static_cast<unsigned*>(stage_buf(w, 1, 4u * n));
     h2d(w, srows, rows, sizeof(pr_revolute_joint) * n); h2d(w, sids, ids, 4u * n);
     PR_LAUNCH(k_set_joints, n, w.stream, w.d, n, sids, srows);
     sync(w);
-    { std::vector<unsigned> pairs; for (uint32_t i = 0; i < n; ++i) if (!(rows[i].collide_connected & 1u)) { pairs.push_back(rows[i].body_a); pairs.push_back(rows[i].body_b); }
-      flag_joint_pairs_for_filtering(w, pairs); } // Remove(id) and Add(id, true) both flag the pair's contacts (:1122-1129)
+    flag_joint_pairs_for_filtering(w, pairs);
+    if (structural) w.jointTablesDirty = true;
     for (uint32_t i = 0; i < n; ++i) w.joints[ids[i]] = rows[i];
     return PR_OK;
     API_CATCH(pw)

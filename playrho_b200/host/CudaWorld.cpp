@@ -990,7 +990,7 @@ Joint GetJoint(const CudaWorld& w, JointID id)
     return Joint{jc};
 }
 void SetJoint(CudaWorld& w, JointID id, Joint def)
-{ // SetJoint(AabbTreeWorld&, JointID, Joint), :1108-1130 (revolute joints; bodies and collideConnected must stay: pr_set_revolute_joints)
+{ // SetJoint(AabbTreeWorld&, JointID, Joint), :1108-1130 (any row of the joint table; the value may name other bodies or another collideConnected: pr_set_revolute_joints)
     if (w.m->locked) throw WrongState(worldIsLockedMsg);
     if (!AtId(w.m->joints, id, noSuchJointMsg).has_value()) throw WasDestroyed{id, "ID is destroyed"};
     if (const auto b = GetBodyA(def); b != InvalidBodyID) (void)AtId(w.m->bodies, b, noSuchBodyMsg);
