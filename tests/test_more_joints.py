@@ -179,8 +179,21 @@ def _chains_scene():
     return ref, types
 
 
+def _longchain_scene():
+    """one chain of 60 links: more joint levels than the device launches (48) -- one thread walks the joints"""
+    ref = RefWorld()
+    ground = ref.add_body(STATIC, pos=(0.0, 10.0))
+    link = ref.add_box(0.2, 0.05, density=5.0)
+    prev = ground
+    for k in range(60):
+        b = ref.add_body(DYNAMIC, acc=G, pos=(0.2 + 0.4 * k, 10.0), shapes=[link])
+        ref.add_revolute(prev, b, (0.4 * k, 10.0))
+        prev = b
+    return ref, [0] * 60
+
+
 SHIFTS = {"pulley": {60: (1.5, -0.75), 130: (-100.0, 33.3)}}
-SCENES = {"chains": (_chains_scene, 120), "gear": (_gear_scene, 240), "pulley": (_pulley_scene, 200), "weld": (_weld_scene, 200), "target": (_target_scene, 220), "prismatic": (_prismatic_scene, 240), "wheel": (_wheel_scene, 300)}
+SCENES = {"chains": (_chains_scene, 120), "longchain": (_longchain_scene, 60), "gear": (_gear_scene, 240), "pulley": (_pulley_scene, 200), "weld": (_weld_scene, 200), "target": (_target_scene, 220), "prismatic": (_prismatic_scene, 240), "wheel": (_wheel_scene, 300)}
 MOVES = {"target": _target_moves}
 
 
