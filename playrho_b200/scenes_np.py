@@ -335,6 +335,7 @@ def merge_worlds(scenes, layer_filters=False):
     each body). layer_filters=True gives world w's shapes the collision Filter {category = mask = 1 << w}: in a plain
     (reference / oracle) world that is what keeps the worlds apart; the batch arena does not need it."""
     out = dict(shapes=[], children=[], verts=[], normals=[], bodies=[], shape_ids=[], joints=[])
+    gears = []  # the whole values of gear joints, by joint id of the merged table (abi.GEAR; rows of other types stay zeroed)
     offs, world = [0], []
     ns = nc = nv = nb = 0
     for wi, sc in enumerate(scenes):
@@ -356,9 +357,17 @@ def merge_worlds(scenes, layer_filters=False):
             j = sc["joints"].copy()
             j["body_a"] += nb; j["body_b"] += nb
             out["joints"].append(j)
+            g = np.zeros(len(j), abi.GEAR)
+            if "gears" in sc and len(sc["gears"]) == len(j):
+                g = np.ascontiguousarray(sc["gears"], dtype=abi.GEAR).copy()
+                live = g["body_a"] != 0xFFFFFFFF
+                for f in ("body_a", "body_b", "body_c", "body_d"):
+                    g[f][live] += nb
+            gears.append(g)
         world.extend([wi] * len(sc["bodies"]))
         ns += len(sc["shapes"]); nc += len(sc["children"]); nv += len(sc["verts"]); nb += len(sc["bodies"])
     merged = {k: np.concatenate(v) if len(v) else np.zeros(0, abi.REVOLUTE) for k, v in out.items()}
+    merged["gears"] = np.concatenate(gears) if gears else np.zeros(0, abi.GEAR)
     merged["shape_offsets"] = np.array(offs, dtype=np.uint32)
     merged["shape_ids"] = merged["shape_ids"].astype(np.uint32)
     if len(merged["shape_ids"]) == 0:

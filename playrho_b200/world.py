@@ -593,11 +593,20 @@ class Batch(World):
                                                   abi.ptr(shape_offsets), abi.ptr(shape_ids), C.byref(first)))
         return first.value
 
-    def create_joints(self, joints):
+    def create_joints(self, joints, gears=None):
+        """rows of the joint table in id order; gears: the whole values of the gear joints among them (abi.GEAR, same length), if any"""
         first = u32(0)
         joints = np.ascontiguousarray(joints, dtype=abi.REVOLUTE)
-        self._chk(self.lib.pr_create_revolute_joints(self.h, len(joints), abi.ptr(joints), C.byref(first)))
-        return first.value
+        start = None
+        for a, b, gear in abi.joint_batches(joints):
+            if gear:
+                g = np.ascontiguousarray(gears[a:b], dtype=abi.GEAR)
+                self._chk(self.lib.pr_create_gear_joints(self.h, 1, abi.ptr(g), C.byref(first)))
+            else:
+                rows = np.ascontiguousarray(joints[a:b])
+                self._chk(self.lib.pr_create_revolute_joints(self.h, len(rows), abi.ptr(rows), C.byref(first)))
+            start = first.value if start is None else start
+        return 0 if start is None else start
 
     def step(self, conf):
         st = abi.one(abi.STEP_STATS)

@@ -24,7 +24,7 @@ def _arena_vs_oracle(lib, device, n_worlds, n_squares, steps, every, toi_mode=0,
     gw.set_toi_mode(toi_mode)
     gw.create_shapes(plain)
     gw.create_bodies(plain["bodies"], world, plain["shape_offsets"], plain["shape_ids"])
-    gw.create_joints(plain["joints"])
+    gw.create_joints(plain["joints"], plain.get("gears"))
     assert np.array_equal(gw.body_worlds(), world)
     orc = refworld.OracleWorld(layered)
     n_contacts = 0
@@ -51,11 +51,10 @@ def _arena_vs_oracle(lib, device, n_worlds, n_squares, steps, every, toi_mode=0,
 
 
 def _joint_units():
-    """one world per joint type: the scenes of test_more_joints.py (the gear scene is left out: a gear joint's value is wider than a table row,
-    and merge_worlds moves rows)"""
+    """one world per joint type: the scenes of test_more_joints.py"""
     import test_more_joints as tmj
     units = []
-    for name in ("weld", "prismatic", "wheel", "pulley", "target", "chains"):
+    for name in ("weld", "prismatic", "wheel", "pulley", "target", "chains", "gear"):
         ref, _ = tmj.SCENES[name][0]()
         units.append(ref.export_scene())
     return units
@@ -65,7 +64,7 @@ def _joint_units():
 @need_oracle
 @need_emul
 def test_emulated_batch_arena_of_jointed_worlds_equals_filter_layered_oracle():
-    """every joint type but the gear joint in worlds of one arena: the arena's joint kernels (and, on the GPU, the block solver's) against the
+    """every joint type in worlds of one arena: the arena's joint kernels (and, on the GPU, the block solver's) against the
     restatement with the worlds on filter layers"""
     units = _joint_units()
     _arena_vs_oracle(emul_lib(), -1, n_worlds=len(units), n_squares=0, steps=120, every=10, units=units, conf=refworld.default_step_conf(), min_contacts=4)
