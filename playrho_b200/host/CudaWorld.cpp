@@ -226,6 +226,8 @@ struct CudaWorld::Impl {
     std::vector<Shape> shapes;
     std::vector<Joint> joints;         // an empty Joint = destroyed (its id is in freeJoints and is handed out again, last freed first)
     std::vector<std::uint32_t> freeJoints;
+    std::vector<JointID> jointOrder;   // m_joints: creation order, erased on destroy (GetJoints(world), :1132-1157, :1215-1227)
+    std::vector<std::vector<std::pair<BodyID, JointID>>> bodyJoints; // m_bodyJoints: (other body, joint) in Add order (:1159-1175)
     // lazily downloaded contact state
     mutable bool contactsStale = true;
     mutable std::vector<KeyedContactID> contactIds;            // m_contacts order
@@ -373,7 +375,7 @@ CudaWorld::CudaWorld(const CudaWorld& o) : m{new Impl}
         m->check(pr_clone(o.m->h, &m->h), "pr_clone");
         m->bodies = o.m->bodies; m->bodyDirty = o.m->bodyDirty; m->anyBodyDirty = o.m->anyBodyDirty; m->bodiesForSync = o.m->bodiesForSync;
         m->bodyLive = o.m->bodyLive; m->bodyOrder = o.m->bodyOrder; m->shapeLive = o.m->shapeLive;
-        m->bodiesStale = false; m->shapes = o.m->shapes; m->joints = o.m->joints; m->freeJoints = o.m->freeJoints;
+        m->bodiesStale = false; m->shapes = o.m->shapes; m->joints = o.m->joints; m->freeJoints = o.m->freeJoints; m->jointOrder = o.m->jointOrder; m->bodyJoints = o.m->bodyJoints;
         m->shapeDestruction = o.m->shapeDestruction; m->detach = o.m->detach; m->jointDestruction = o.m->jointDestruction;
         m->beginContact = o.m->beginContact; m->endContact = o.m->endContact; m->preSolve = o.m->preSolve; m->postSolve = o.m->postSolve;
         m->eventCap = o.m->eventCap; m->updateEventMask();
@@ -422,9 +424,8 @@ void Clear(CudaWorld& w) noexcept
 { // Clear(AabbTreeWorld&), :949-1017 (destruction listeners are told about joints and shapes first)
     if (!w.m || !w.m->h) return;
     if (w.m->jointDestruction) // every live joint (:955-965); an exception of one call does not stop the others
-        for (std::size_t i = 0; i < w.m->joints.size(); ++i) {
-            if (!w.m->joints[i].has_value()) continue;
-            try { w.m->jointDestruction(MakeId<JointID>(static_cast<std::uint32_t>(i))); } catch (...) {}
+        for (const auto jid : std::vector<JointID>(w.m->jointOrder)) { // (m_joints order; a copy: a listener may not mutate, but stay safe)
+            try { w.m->jointDestruction(jid); } catch (...) {}
         }
     if (w.m->shapeDestruction) // every non-empty shape slot (:966-980)
         for (std::size_t i = 0; i < w.m->shapes.size(); ++i) {
@@ -433,7 +434,7 @@ void Clear(CudaWorld& w) noexcept
         }
     pr_clear(w.m->h);
     w.m->bodies.clear(); w.m->bodyDirty.clear(); w.m->bodyLive.clear(); w.m->bodyOrder.clear(); w.m->shapeLive.clear(); w.m->anyBodyDirty = false; w.m->bodiesStale = false; w.m->bodiesForSync.clear();
-    w.m->shapes.clear(); w.m->joints.clear(); w.m->freeJoints.clear();
+    w.m->shapes.clear(); w.m->joints.clear(); w.m->freeJoints.clear(); w.m->jointOrder.clear(); w.m->bodyJoints.clear();
     w.m->mutated();
 }
 
@@ -589,13 +590,14 @@ void Destroy(CudaWorld& w, BodyID id)
     if (!w.m->bodyLive[bid]) throw WasDestroyed{id, "ID is destroyed"};
     w.m->refreshBodies();
     w.m->uploadDirtyBodies();
-    // the attached joints (:1072-1085): the listener hears of each, then the device destroys them with the body
-    for (std::size_t i = 0; i < w.m->joints.size(); ++i) {
-        if (!w.m->joints[i].has_value()) continue;
-        if (GetBodyA(w.m->joints[i]) != id && GetBodyB(w.m->joints[i]) != id) continue;
-        if (w.m->jointDestruction) w.m->jointDestruction(MakeId<JointID>(static_cast<std::uint32_t>(i)));
-        w.m->joints[i] = Joint{};
-        w.m->freeJoints.push_back(static_cast<std::uint32_t>(i));
+    // the attached joints (:1072-1085), in the order of the body's joint list: the listener hears of each, then the joint is destroyed
+    // (its id is freed in that order: the next CreateJoint gets the last of them)
+    while (bid < w.m->bodyJoints.size() && !w.m->bodyJoints[bid].empty()) {
+        const auto jointID = std::get<JointID>(w.m->bodyJoints[bid].front());
+        if (w.m->jointDestruction) w.m->jointDestruction(jointID);
+        const auto before = w.m->bodyJoints[bid].size();
+        Destroy(w, jointID);
+        if (w.m->bodyJoints[bid].size() == before) w.m->bodyJoints[bid].erase(w.m->bodyJoints[bid].begin()); // (a stale entry: never loop on it)
     }
     if (w.m->endContact) { // InternalDestroy (:2249-2252): end-contact for the touching contacts that go with the body
         w.m->refreshContacts();
@@ -615,16 +617,10 @@ void Destroy(CudaWorld& w, BodyID id)
     w.m->mutated();
 }
 std::vector<std::pair<BodyID, JointID>> GetJoints(const CudaWorld& w, BodyID id)
-{ // m_bodyJoints: (other body, joint) pairs
+{ // m_bodyJoints: (other body, joint) pairs in the order the joints were added to the body
     (void)AtId(w.m->bodies, id, noSuchBodyMsg);
-    std::vector<std::pair<BodyID, JointID>> r;
-    for (std::size_t i = 0; i < w.m->joints.size(); ++i) {
-        if (!w.m->joints[i].has_value()) continue;
-        const auto a = GetBodyA(w.m->joints[i]), b = GetBodyB(w.m->joints[i]);
-        if (a == id) r.emplace_back(b, MakeId<JointID>(static_cast<std::uint32_t>(i)));
-        else if (b == id) r.emplace_back(a, MakeId<JointID>(static_cast<std::uint32_t>(i)));
-    }
-    return r;
+    const auto i = static_cast<std::size_t>(to_underlying(id));
+    return i < w.m->bodyJoints.size() ? w.m->bodyJoints[i] : std::vector<std::pair<BodyID, JointID>>{};
 }
 std::vector<std::tuple<ContactKey, ContactID>> GetContacts(const CudaWorld& w, BodyID id)
 {
@@ -636,12 +632,28 @@ std::vector<ShapeID> GetShapes(const CudaWorld& w, BodyID id) { return AtId(w.m-
 
 // ---- joints: the device solver runs RevoluteJointConf; other joint types are rejected
 JointCounter GetJointRange(const CudaWorld& w) noexcept { return static_cast<JointCounter>(w.m->joints.size()); }
-std::vector<JointID> GetJoints(const CudaWorld& w)
+// m_joints / m_bodyJoints bookkeeping on the host: Add(JointID) appends (:1162-1169), Remove(JointID) erases (:1192-1212)
+static void AddJointLinks(CudaWorld& w, JointID id, const Joint& joint)
 {
-    std::vector<JointID> r;
-    for (std::size_t i = 0; i < w.m->joints.size(); ++i) if (w.m->joints[i].has_value()) r.push_back(MakeId<JointID>(static_cast<std::uint32_t>(i)));
-    return r;
+    const auto a = GetBodyA(joint), b = GetBodyB(joint);
+    auto& bj = w.m->bodyJoints;
+    const auto need = [&](BodyID x) { const auto i = static_cast<std::size_t>(to_underlying(x)); if (bj.size() <= i) bj.resize(i + 1u); return i; };
+    if (a != InvalidBodyID) bj[need(a)].emplace_back(b, id);
+    if (b != InvalidBodyID) bj[need(b)].emplace_back(a, id);
 }
+static void RemoveJointLinks(CudaWorld& w, JointID id, const Joint& joint)
+{
+    auto& bj = w.m->bodyJoints;
+    for (const auto x : {GetBodyA(joint), GetBodyB(joint)}) {
+        if (x == InvalidBodyID) continue;
+        const auto i = static_cast<std::size_t>(to_underlying(x));
+        if (i >= bj.size()) continue;
+        auto& lst = bj[i];
+        const auto it = std::find_if(lst.begin(), lst.end(), [&](const auto& e) { return std::get<JointID>(e) == id; });
+        if (it != lst.end()) lst.erase(it);
+    }
+}
+std::vector<JointID> GetJoints(const CudaWorld& w) { return w.m->jointOrder; }
 static pr_revolute_joint ToJointRow(const RevoluteJointConf& jc)
 {
     pr_revolute_joint o{};
@@ -862,6 +874,7 @@ JointID CreateJoint(CudaWorld& w, Joint def)
             w.m->joints[first] = std::move(def);
             w.m->freeJoints.erase(std::remove(w.m->freeJoints.begin(), w.m->freeJoints.end(), first), w.m->freeJoints.end());
         } else w.m->joints.push_back(std::move(def));
+        w.m->jointOrder.push_back(MakeId<JointID>(first)); AddJointLinks(w, MakeId<JointID>(first), w.m->joints[first]);
         w.m->bodiesStale = true; w.m->contactsStale = true;
         return MakeId<JointID>(first);
     }
@@ -877,6 +890,7 @@ JointID CreateJoint(CudaWorld& w, Joint def)
         w.m->joints[first] = std::move(def);
         w.m->freeJoints.erase(std::remove(w.m->freeJoints.begin(), w.m->freeJoints.end(), first), w.m->freeJoints.end());
     } else w.m->joints.push_back(std::move(def));
+    w.m->jointOrder.push_back(MakeId<JointID>(first)); AddJointLinks(w, MakeId<JointID>(first), w.m->joints[first]);
     w.m->bodiesStale = true; w.m->contactsStale = true; // (Add(JointID, flagForFiltering) flags the pair's contacts, :1170-1174)
     return MakeId<JointID>(first);
 }
@@ -1010,7 +1024,9 @@ void SetJoint(CudaWorld& w, JointID id, Joint def)
     w.m->uploadDirtyBodies();
     const std::uint32_t jid = static_cast<std::uint32_t>(to_underlying(id));
     w.m->check(pr_set_revolute_joints(w.m->h, 1u, &jid, &o), "pr_set_revolute_joints");
+    RemoveJointLinks(w, id, w.m->joints[to_underlying(id)]); // Remove(id) ... Add(id): the joint moves to the end of its bodies' lists
     w.m->joints[to_underlying(id)] = std::move(def);
+    AddJointLinks(w, id, w.m->joints[to_underlying(id)]);
     w.m->bodiesStale = true; w.m->contactsStale = true;
 }
 void Destroy(CudaWorld& w, JointID id)
@@ -1022,6 +1038,8 @@ void Destroy(CudaWorld& w, JointID id)
     w.m->uploadDirtyBodies();
     const std::uint32_t jid = static_cast<std::uint32_t>(to_underlying(id));
     w.m->check(pr_destroy_joints(w.m->h, 1u, &jid), "pr_destroy_joints");
+    RemoveJointLinks(w, id, elem);
+    w.m->jointOrder.erase(std::remove(w.m->jointOrder.begin(), w.m->jointOrder.end(), id), w.m->jointOrder.end());
     elem = Joint{};
     w.m->freeJoints.push_back(jid);
     w.m->bodiesStale = true; w.m->contactsStale = true; // (Remove(JointID) flags the pair's contacts, :1184-1190)
