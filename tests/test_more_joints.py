@@ -192,9 +192,65 @@ def _longchain_scene():
     return ref, [0] * 60
 
 
+def _fuzz_scene(seed):
+    """random joints of every type (but gear, which needs two geared joints) between random bodies of a small pile: limits, motors, soft and
+    rigid variants, joints sharing bodies in any order -- whatever the generator comes up with must be the reference's bits"""
+    def build():
+        rng = np.random.RandomState(1000 + seed)
+        ref = RefWorld()
+        ground = ref.add_body(STATIC, pos=(0.0, 0.0), shapes=[ref.add_box(12.0, 0.5, center=(0.0, -0.5))])
+        shapes = [ref.add_box(0.3, 0.2, density=2.0), ref.add_disk(0.25, density=1.5), ref.add_box(0.15, 0.4, density=3.0)]
+        bodies = []
+        for i in range(10):
+            pos = (float(rng.uniform(-5.0, 5.0)), float(rng.uniform(0.4, 4.0)))
+            bodies.append(ref.add_body(DYNAMIC, acc=G, pos=pos, angle=float(rng.uniform(-0.5, 0.5)), vel=(float(rng.uniform(-1, 1)), 0.0),
+                                       w=float(rng.uniform(-1, 1)), shapes=[shapes[int(rng.randint(3))]], fixed_rotation=bool(rng.rand() < 0.15)))
+        types = []
+        rows = ref.bodies()
+        def p(b):
+            return (float(rows[b]["xf_px"]), float(rows[b]["xf_py"]))
+        for _ in range(9):
+            kind = int(rng.randint(10))
+            a = ground if rng.rand() < 0.3 else bodies[int(rng.randint(10))]
+            b = bodies[int(rng.randint(10))]
+            if a == b:
+                continue
+            pa, pb = p(a) if a != ground else (p(b)[0], p(b)[1] + 1.0), p(b)
+            mid = ((pa[0] + pb[0]) / 2.0, (pa[1] + pb[1]) / 2.0)
+            ax = rng.uniform(-1, 1, 2); ax = ax / max(1e-3, float(np.hypot(*ax)))
+            axis = (float(ax[0]), float(ax[1]))
+            if kind == 0:
+                ref.add_revolute(a, b, mid, enable_motor=bool(rng.rand() < 0.5), motor_speed=float(rng.uniform(-2, 2)), max_motor_torque=float(rng.uniform(0, 20))); types.append(0)
+            elif kind == 1:
+                ref.add_distance(a, b, pa, pb, frequency=float(rng.choice([0.0, 3.0])), damping_ratio=0.4); types.append(1)
+            elif kind == 2:
+                ref.add_weld(a, b, mid, frequency=float(rng.choice([0.0, 4.0])), damping_ratio=0.5); types.append(5)
+            elif kind == 3:
+                ref.add_friction(a, b, mid, float(rng.uniform(0.5, 20)), float(rng.uniform(0.1, 5))); types.append(3)
+            elif kind == 4:
+                ref.add_motor(a, b, (float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1))), float(rng.uniform(-1, 1)), float(rng.uniform(1, 40)), float(rng.uniform(0.5, 20))); types.append(4)
+            elif kind == 5:
+                lim = (float(rng.uniform(-1.0, -0.1)), float(rng.uniform(0.1, 1.0))) if rng.rand() < 0.6 else None
+                mot = (float(rng.uniform(-2, 2)), float(rng.uniform(1, 60))) if rng.rand() < 0.5 else None
+                ref.add_prismatic(a, b, mid, axis, limits=lim, motor=mot); types.append(7)
+            elif kind == 6:
+                mot = (float(rng.uniform(-6, 6)), float(rng.uniform(0.5, 20))) if rng.rand() < 0.5 else None
+                ref.add_wheel(a, b, pb, axis, frequency=float(rng.choice([0.0, 3.0])), damping_ratio=0.6, motor=mot); types.append(8)
+            elif kind == 7:
+                ref.add_pulley(a, b, (pa[0], pa[1] + 3.0), (pb[0], pb[1] + 3.0), pa, pb, ratio=float(rng.choice([1.0, 1.5]))); types.append(9)
+            elif kind == 8:
+                ref.add_target(b, (pb[0] + float(rng.uniform(-1, 1)), pb[1] + float(rng.uniform(0, 1.5))), pb, frequency=float(rng.uniform(2, 6)), max_force=float(rng.uniform(20, 400))); types.append(6)
+            else:
+                ref.add_rope(a, b, (0.0, 0.0), (0.0, 0.0), float(np.hypot(pb[0] - pa[0], pb[1] - pa[1]) + rng.uniform(0.0, 0.5))); types.append(2)
+        return ref, types
+    return build
+
+
 SHIFTS = {"pulley": {60: (1.5, -0.75), 130: (-100.0, 33.3)}}
 SCENES = {"chains": (_chains_scene, 120), "longchain": (_longchain_scene, 60), "gear": (_gear_scene, 240), "pulley": (_pulley_scene, 200), "weld": (_weld_scene, 200), "target": (_target_scene, 220), "prismatic": (_prismatic_scene, 240), "wheel": (_wheel_scene, 300)}
 MOVES = {"target": _target_moves}
+for _seed in range(6):
+    SCENES["fuzz%d" % _seed] = (_fuzz_scene(_seed), 150)
 
 
 def _run(name, lib=None, device=-1, with_device=True):
