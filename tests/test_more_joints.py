@@ -249,8 +249,23 @@ def _fuzz_scene(seed):
 SHIFTS = {"pulley": {60: (1.5, -0.75), 130: (-100.0, 33.3)}}
 SCENES = {"chains": (_chains_scene, 120), "longchain": (_longchain_scene, 60), "gear": (_gear_scene, 240), "pulley": (_pulley_scene, 200), "weld": (_weld_scene, 200), "target": (_target_scene, 220), "prismatic": (_prismatic_scene, 240), "wheel": (_wheel_scene, 300)}
 MOVES = {"target": _target_moves}
+def _fuzz_gear_scene(seed):
+    """a fuzz scene plus a gear joint between two of its revolute / prismatic joints (whatever bodies those tie)"""
+    def build():
+        ref, types = _fuzz_scene(seed)()
+        rng = np.random.RandomState(seed)
+        cand = [i for i, ty in enumerate(types) if ty in (0, 7)]
+        assert len(cand) >= 2
+        a, b = rng.choice(cand, 2, replace=False)
+        ref.add_gear(int(a), int(b), ratio=float(rng.choice([1.0, -1.0, 2.0, 0.5])))
+        return ref, types + [10]
+    return build
+
+
 for _seed in range(6):
     SCENES["fuzz%d" % _seed] = (_fuzz_scene(_seed), 150)
+for _seed in (103, 110):
+    SCENES["fuzzgear%d" % _seed] = (_fuzz_gear_scene(_seed), 120)
 
 
 def _run(name, lib=None, device=-1, with_device=True):
