@@ -491,7 +491,7 @@ int pr_set_revolute_joints(pr_world* w, uint32_t n, const uint32_t* ids, const p
  * when the broadphase next looks at their proxies, as in the reference.) */
 int pr_destroy_joints(pr_world* w, uint32_t n, const uint32_t* ids);
 /* Destroy(AabbTreeWorld&, BodyID) (AabbTreeWorld.cpp:1062-1106), one body after the other: the joints attached to the body are
- * destroyed (pr_destroy_joints; in id order), its contacts are destroyed in the body's contact-list order (end-contact events
+ * destroyed (pr_destroy_joints; in the order they were added to the body, m_bodyJoints -- the order their ids are freed in), its contacts are destroyed in the body's contact-list order (end-contact events
  * for touching ones when the event mask asks for them; the other body is woken when the manifold had points, :2245-2279), its
  * pending (body, shape) pairs leave the proxy queue, its proxies leave the broadphase in leaf-id order (FindProxies :617) and
  * the body id is the next one pr_create_bodies hands out (last freed first, ObjectPool). Leaf ids are recycled like

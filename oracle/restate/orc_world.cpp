@@ -1210,7 +1210,7 @@ int orc_destroy_bodies(orc_world* w, uint32_t n, const uint32_t* ids)
         if (id >= w->bodies.size()) { w->error = "no such body"; return -2; }
         if (id < w->bodyDead.size() && w->bodyDead[id]) { w->error = "destroyed"; return -3; }
         OBody& ob = w->bodies[id];
-        { std::vector<uint32_t> js = ob.joints; std::sort(js.begin(), js.end()); js.erase(std::unique(js.begin(), js.end()), js.end()); if (!js.empty()) orc_destroy_joints(w, static_cast<uint32_t>(js.size()), js.data()); }
+        { const std::vector<uint32_t> js = ob.joints; for (uint32_t j : js) orc_destroy_joints(w, 1u, &j); } // the attached joints in the body's list order (:1072-1085)
         { const std::vector<uint32_t> list = ob.contacts; for (uint32_t c : list) destroy_contact(*w, c); }
         { auto& f = w->fixturesForProxies; f.erase(std::remove_if(f.begin(), f.end(), [id](const std::pair<uint32_t, uint32_t>& e) { return e.first == id; }), f.end()); }
         std::vector<uint32_t> slots = ob.proxies; // FindProxies: ascending leaf id (:617-630)

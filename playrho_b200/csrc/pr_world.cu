@@ -1322,7 +1322,7 @@ int pr_clone(const pr_world* src, pr_world** out)
     for (size_t i = 0; i < da.size(); ++i) d2d(w, *da[i].slot, *sa[i].slot, da[i].elem * *cap_of(s, sa[i].g));
     d2d(w, w.d.cnt, s.d.cnt, sizeof(Counters));
     w.shapes = s.shapes; w.children = s.children; w.bodyShapes = s.bodyShapes; w.joints = s.joints; w.freeJoints = s.freeJoints;
-    w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies; w.pools = s.pools; w.needsFiltering = s.needsFiltering;
+    w.fixturesForProxies = s.fixturesForProxies; w.bodyProxies = s.bodyProxies; w.bodyJointList = s.bodyJointList; w.pools = s.pools; w.needsFiltering = s.needsFiltering;
     w.bpDirty = true; w.bvhValid = false; w.toiAlphaDirty = true; w.recolorAll = s.recolorAll; w.toiPossible = s.toiPossible; w.colorCap = s.colorCap;
     w.nJoints = s.nJoints; w.jointsSerial = s.jointsSerial; w.jointLevelOff = s.jointLevelOff; w.d.nNcPairs = s.d.nNcPairs;
     w.d.nWorlds = s.d.nWorlds; w.d.worldBits = s.d.worldBits; w.bodyWorld = s.bodyWorld; w.blocksDirty = w.blkJointsDirty = true;
@@ -1420,7 +1420,7 @@ int pr_snapshot_save(const pr_world* cpw, void* buf, uint64_t cap, uint64_t* byt
     SnapScalars sc; snap_scalars(w, sc); o.pod(sc);
     o.vec(w.shapes); o.vec(w.children); snap_nested(o, w.bodyShapes); o.vec(w.joints); o.vec(w.freeJoints);
     { std::vector<unsigned> flat; for (const auto& f : w.fixturesForProxies) { flat.push_back(f.first); flat.push_back(f.second); } o.vec(flat); }
-    snap_nested(o, w.bodyProxies); o.vec(w.bodyWorld);
+    snap_nested(o, w.bodyProxies); snap_nested(o, w.bodyJointList); o.vec(w.bodyWorld);
     o.vec(w.pools.bodyFree); o.vec(w.pools.shapeFree); o.vec(w.pools.treeFree); o.vec(w.pools.bodyDead); o.vec(w.pools.shapeDead);
     o.vec(w.pools.pxBody); o.vec(w.pools.pxShape); o.vec(w.pools.pxTree);
     { const unsigned extra[2] = {w.pools.treeNextFresh, w.needsFiltering ? 1u : 0u}; o.pod(extra); }
@@ -1462,7 +1462,7 @@ int pr_snapshot_load(const void* buf, uint64_t bytes, int device, pr_world** out
         World& w = pw->w;
         in.vec(w.shapes); in.vec(w.children); snap_nested(in, w.bodyShapes); in.vec(w.joints); in.vec(w.freeJoints);
         { std::vector<unsigned> flat; in.vec(flat); for (size_t i = 0; i + 1 < flat.size(); i += 2) w.fixturesForProxies.emplace_back(flat[i], flat[i + 1]); }
-        snap_nested(in, w.bodyProxies); in.vec(w.bodyWorld);
+        snap_nested(in, w.bodyProxies); snap_nested(in, w.bodyJointList); in.vec(w.bodyWorld);
         in.vec(w.pools.bodyFree); in.vec(w.pools.shapeFree); in.vec(w.pools.treeFree); in.vec(w.pools.bodyDead); in.vec(w.pools.shapeDead);
         in.vec(w.pools.pxBody); in.vec(w.pools.pxShape); in.vec(w.pools.pxTree);
         { unsigned extra[2] = {0u, 0u}; in.pod(extra); w.pools.treeNextFresh = extra[0]; w.needsFiltering = extra[1] != 0u; }
@@ -1506,7 +1506,7 @@ int pr_clear(pr_world* pw)
     World& w = pw->w;
     w.contactsClean = false; // (a mutator: the next Step's pre-phase UpdateContacts must look at every contact)
     w.shapes.clear(); w.children.clear(); w.bodyShapes.clear(); w.joints.clear(); w.fixturesForProxies.clear();
-    w.bodyProxies.clear(); w.bpDirty = true; w.bvhValid = false; w.hashTombs = 0; w.toiAlphaDirty = true;
+    w.bodyProxies.clear(); w.bodyJointList.clear(); w.bpDirty = true; w.bvhValid = false; w.hashTombs = 0; w.toiAlphaDirty = true;
     w.nJoints = 0; w.jointsSerial = false; w.jointLevelOff.clear(); w.d.nNcPairs = 0; w.bodyWorld.clear(); w.freeJoints.clear();
     w.pools = World::Pools{}; w.needsFiltering = false;
     w.nBodies = w.nShapes = w.nChildren = w.nVerts = w.nProxies = w.nOrder = w.nFree = w.poolSize = 0; w.maxTreeId = 0;
@@ -1660,6 +1660,24 @@ int pr_set_shape_material(pr_world* pw, uint32_t shape, float friction, float re
 // order -- the same bits as one thread walking all joints in id order, which is what runs when the chains are longer than
 // JOINT_MAX_LEVELS. Also: the body pairs joined by a collideConnected == false joint, sorted, for the broadphase's ShouldCollide.
 // Destroyed joints (bodies == INVALID) are skipped.
+// m_bodyJoints on the host: Add(JointID) appends to both bodies' lists (:1162-1169), Remove(JointID) erases (:1192-1212)
+static void joint_links_add(World& w, unsigned jid, const pr_revolute_joint& j)
+{
+    auto& l = w.bodyJointList;
+    const unsigned hi = std::max(j.body_a, j.body_b);
+    if (l.size() <= hi) l.resize(hi + 1u);
+    l[j.body_a].push_back(jid);
+    if (j.body_b != j.body_a) l[j.body_b].push_back(jid); // (a target joint's row repeats its one body)
+}
+static void joint_links_remove(World& w, unsigned jid, const pr_revolute_joint& j)
+{
+    for (unsigned b : {j.body_a, j.body_b}) {
+        if (b >= w.bodyJointList.size()) continue;
+        auto& lst = w.bodyJointList[b];
+        const auto it = std::find(lst.begin(), lst.end(), jid);
+        if (it != lst.end()) lst.erase(it);
+    }
+}
 constexpr unsigned JOINT_MAX_LEVELS = 48u;
 static void refresh_joint_tables(World& w)
 {
@@ -1812,9 +1830,8 @@ int pr_destroy_bodies(pr_world* pw, uint32_t n, const uint32_t* ids)
     }
     for (uint32_t i = 0; i < n; ++i) {
         const unsigned id = ids[i];
-        // the attached joints (:1072-1085), in id order
-        std::vector<unsigned> js;
-        for (unsigned j = 0; j < w.joints.size(); ++j) if (w.joints[j].body_a != INVALID && (w.joints[j].body_a == id || w.joints[j].body_b == id)) js.push_back(j);
+        // the attached joints (:1072-1085), in the order of the body's joint list (the order their ids are freed in)
+        const std::vector<unsigned> js = id < w.bodyJointList.size() ? w.bodyJointList[id] : std::vector<unsigned>{};
         if (!js.empty()) { const int rc = pr_destroy_joints(pw, static_cast<uint32_t>(js.size()), js.data()); if (rc != PR_OK) return rc; }
         destroy_contacts_where(w, 0u, id, 0u); // the attached contacts (:1087-1091), in m_bodyContacts order
         { auto& f = w.fixturesForProxies; f.erase(std::remove_if(f.begin(), f.end(), [id](const std::pair<unsigned, unsigned>& e) { return e.first == id; }), f.end()); }
@@ -2030,6 +2047,7 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
         const unsigned id = w.freeJoints.back();
         w.freeJoints.pop_back();
         w.joints[id] = joints[0];
+        joint_links_add(w, id, joints[0]);
         h2d(w, w.d.jt + id, joints, sizeof(pr_revolute_joint));
         { JointWork fresh{}; fresh.island = INVALID; h2d(w, w.d.jt_work + id, &fresh, sizeof(fresh)); sync(w); } // (not solved yet: pr_get_joint_work)
         w.jointTablesDirty = true;
@@ -2039,6 +2057,7 @@ int pr_create_revolute_joints(pr_world* pw, uint32_t n, const pr_revolute_joint*
         return PR_OK;
     }
     w.joints.insert(w.joints.end(), joints, joints + n);
+    for (uint32_t i = 0; i < n; ++i) joint_links_add(w, w.nJoints + i, joints[i]);
     ensure(w, G_JOINT, w.nJoints + n + 1);
     h2d(w, w.d.jt + w.nJoints, joints, sizeof(pr_revolute_joint) * n);
     { JointWork one{}; one.island = INVALID; std::vector<JointWork> fresh(n, one); h2d(w, w.d.jt_work + w.nJoints, fresh.data(), sizeof(JointWork) * n); sync(w); } // (not solved yet: pr_get_joint_work)
@@ -2196,6 +2215,7 @@ int pr_destroy_joints(pr_world* pw, uint32_t n, const uint32_t* ids)
         if (j.body_a == INVALID) continue; // already destroyed: not in m_joints, nothing happens (:1222)
         if (!(j.collide_connected & 1u)) { pairs.push_back(j.body_a); pairs.push_back(j.body_b); } // Remove(JointID), :1184-1190
         wake.push_back(j.body_a); wake.push_back(j.body_b);
+        joint_links_remove(w, ids[i], j);
         std::memset(&j, 0, sizeof(j));
         j.body_a = j.body_b = INVALID;
         h2d(w, w.d.jt + ids[i], &j, sizeof(j));
@@ -2249,7 +2269,7 @@ int pr_set_revolute_joints(pr_world* pw, uint32_t n, const uint32_t* ids, const 
     sync(w);
     flag_joint_pairs_for_filtering(w, pairs);
     if (structural) w.jointTablesDirty = true;
-    for (uint32_t i = 0; i < n; ++i) w.joints[ids[i]] = rows[i];
+    for (uint32_t i = 0; i < n; ++i) { joint_links_remove(w, ids[i], w.joints[ids[i]]); w.joints[ids[i]] = rows[i]; joint_links_add(w, ids[i], rows[i]); } // (Remove + Add: to the end of the lists)
     return PR_OK;
     API_CATCH(pw)
 }

@@ -193,6 +193,7 @@ struct World {
     unsigned bvhLeaves = 0, bvhRefits = 0, hashTombs = 0, toiListBound = 0, toiRoundsHint = 1, toiGroupsHint = 1;
     const unsigned* bvhSortedIdx = nullptr;
     std::vector<std::vector<unsigned>> bodyProxies; // m_bodyProxies
+    std::vector<std::vector<unsigned>> bodyJointList; // m_bodyJoints: a body's joints in the order they were added to it (Destroy(BodyID) frees them in it)
     unsigned toiMode = 1; // PR_TOI_PARALLEL (default) or PR_TOI_SERIAL_EXACT (reference order)
     // some body WITH shapes is (or may be: SetBody, load) impenetrable -- static, kinematic or bullet: only then can a contact be a
     // TOI candidate (UpdateContactTOIs' filter :1696). An arena of tumblers has none: its TOI phase is skipped outright.
