@@ -1197,7 +1197,8 @@ int orc_set_shape_material(orc_world* w, uint32_t shape, float friction, float r
 // SetBody with added shapes, AabbTreeWorld.cpp:2760-2786: Append(m_fixturesForProxies, id, added)
 int orc_attach_shapes(orc_world* w, uint32_t body, uint32_t n, const uint32_t* shape_ids)
 {
-    for (uint32_t i = 0; i < n; ++i) { w->bodies[body].shapes.push_back(shape_ids[i]); w->fixturesForProxies.emplace_back(body, shape_ids[i]); }
+    const bool on = enabled(w->bodies[body].b); // (a disabled body has no proxies: GetOldAndNewShapeIDs :677-680)
+    for (uint32_t i = 0; i < n; ++i) { w->bodies[body].shapes.push_back(shape_ids[i]); if (on) w->fixturesForProxies.emplace_back(body, shape_ids[i]); }
     return 0;
 }
 

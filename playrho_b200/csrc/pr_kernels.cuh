@@ -2627,6 +2627,9 @@ PR_KERNEL k_export_contacts(DV d, unsigned nOrder, pr_contact* out, pr_manifold*
         c.body_a = ab.x; c.shape_a = ids.x; c.child_a = ids.y; c.body_b = ab.y; c.shape_b = ids.z; c.child_b = ids.w;
         c.friction = mat.x; c.restitution = mat.y; c.tangent_speed = mat.z; c.toi = mat.w;
         c.toi_count = fl >> 8; c.flags = fl & 0xFFu;
+        // a SetBody that changed the transformation flags the body's contacts for updating (AabbTreeWorld.cpp:2787-2790); on the device that is
+        // the body's moved mark until the next Step's UpdateContacts consumes it: the value read back carries the flag either way
+        if (d.b_moved[ab.x] | d.b_moved[ab.y]) c.flags |= PR_CONTACT_DIRTY;
         out[i] = c;
         if (mout) {
             const float4 q0 = d.m0[id], q1 = d.m1[id], q2 = d.m2[id]; const uint4 q3 = d.m3[id];

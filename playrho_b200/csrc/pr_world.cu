@@ -328,18 +328,16 @@ static unsigned destroy_contacts(World& w)
     DV& d = w.d;
     ensure(w, G_CONTACT, w.nOrder + 1);
     PR_LAUNCH(k_destroy_test, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, w.hashDirty ? 0u : 1u);
-    if (w.needsFiltering) { PR_LAUNCH(k_destroy_filter, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, w.hashDirty ? 0u : 1u); w.needsFiltering = false; }
-    scan_exclusive_u32(d.c_tmp, d.k_tmpVal, w.nOrder, &d.cnt->nNew, w.scanScratch, w.stream);
-    read_counters(w);
-    const unsigned kept = w.hostCnt.nNew;
-    const unsigned destroyed = w.nOrder - kept;
-    if (destroyed) {
-        PR_LAUNCH(k_destroy_compact, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, d.k_tmpVal, d.c_tmp2, w.nFree);
-        std::swap(d.c_order, d.c_tmp2);
-        w.nFree += destroyed;
-        w.nOrder = kept;
-        w.hashTombs += destroyed; w.adjValid = false;
-        if (2ull * (static_cast<unsigned long long>(w.nOrder) + w.hashTombs) > w.capHash) w.hashDirty = true;
+    unsigned destroyed = compact_destroyed_contacts(w);
+    // the filter half is a SECOND pass over what the overlap half left (:2305-2328): the contacts it destroys are freed after all of the
+    // first pass's, whatever their places in the list -- the next contacts created get their ids in that order
+    if (w.needsFiltering) {
+        w.needsFiltering = false;
+        if (w.nOrder) {
+            PR_LAUNCH(k_destroy_mark, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, 0u, INVALID, 0u, static_cast<const unsigned*>(nullptr), w.hashDirty ? 0u : 1u); // (keep = 1 everywhere: no body has this id)
+            PR_LAUNCH(k_destroy_filter, w.nOrder, w.stream, d, w.nOrder, d.c_tmp, w.hashDirty ? 0u : 1u);
+            destroyed += compact_destroyed_contacts(w);
+        }
     }
     return destroyed;
 }
@@ -1736,7 +1734,10 @@ int pr_attach_shapes(pr_world* pw, uint32_t body, uint32_t n, const uint32_t* sh
     if (!n) return PR_OK;
     unsigned flags = 0;
     d2h(w, &flags, w.d.b_flags + body, 4);
-    if (!(flags & PR_BODY_ENABLED)) { w.error = "attaching shapes to a disabled body is not supported by the device world"; return PR_ERR_UNSUPPORTED; }
+    if (!(flags & PR_BODY_ENABLED)) { // a disabled body has no proxies: the shapes only join its list (GetOldAndNewShapeIDs :677-680); enabling it queues them all
+        for (uint32_t i = 0; i < n; ++i) w.bodyShapes[body].push_back(shape_ids[i]);
+        return PR_OK;
+    }
     for (uint32_t i = 0; i < n; ++i) { w.fixturesForProxies.emplace_back(body, shape_ids[i]); w.bodyShapes[body].push_back(shape_ids[i]); } // Append(m_fixturesForProxies, ...) :2786
     if (flags & PR_BODY_IMPENETRABLE) w.toiPossible = true;
     w.adjValid = false; w.bpDirty = true; w.toiAlphaDirty = true;
